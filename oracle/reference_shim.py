@@ -1,0 +1,130 @@
+"""Import the UNMODIFIED upstream HOISDF reference (read-only at /root/reference) on a GPU-less host.
+
+TEST INFRASTRUCTURE ONLY.  This file exists so that (a) `oracle/make_golden.py` can generate the
+committed golden vectors under `tests/golden/` and (b) `tests/test_oracle_vs_reference.py` can pin the
+CPU restatement in `oracle/hoisdf_oracle.py` against the real thing.  Nothing in `hoisdf_b200/`
+(the product) may import it, and it is never used on the GPU box (`/root/reference` does not exist
+there -> `available()` is False and the callers skip).
+
+Shims, all applied outside the read-only tree:
+  1. `torchvision.models.resnet.model_urls = {}`  (common/nets/resnet.py:9 imports a removed name)
+  2. `torch.Tensor.cuda = identity` on a host without CUDA (main/model.py:132,275-281,301-302;
+     common/nets/sdf_net.py:122 hard-code `.cuda()`)
+  3. a synthetic `ManoLayer` (manopth/manopth/manolayer.py:14 needs chumpy + the licensed MANO pkl):
+     built with `ManoLayer.__new__` + the buffers `forward` reads (manolayer.py:74-106).
+"""
+from __future__ import annotations
+
+import os
+import sys
+import tempfile
+
+REFERENCE_ROOT = os.environ.get("HOISDF_REFERENCE_ROOT", "/root/reference")
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "main", "model.py"))
+
+
+_loaded = {}
+
+
+def load(setting: str = "ho3d"):
+    """Return a namespace dict {cfg, M (main.model), modules...} for the reference."""
+    if "ns" in _loaded:
+        ns = _loaded["ns"]
+        _apply_setting(ns["cfg"], setting)
+        return ns
+    if not available():
+        raise RuntimeError("upstream reference not present at %s" % REFERENCE_ROOT)
+    import torch
+    import torchvision.models.resnet as tv_resnet
+
+    if not hasattr(tv_resnet, "model_urls"):
+        tv_resnet.model_urls = {}
+    if not torch.cuda.is_available():
+        torch.Tensor.cuda = lambda self, *a, **k: self  # shim 2
+    # main/config.py:197 creates ./outputs/log relative to the CWD at import time
+    scratch = tempfile.mkdtemp(prefix="hoisdf_ref_cwd_")
+    old = os.getcwd()
+    os.chdir(scratch)
+    try:
+        if REFERENCE_ROOT not in sys.path:
+            sys.path.insert(0, REFERENCE_ROOT)
+        # manopth's ManoLayer module imports chumpy-dependent code at import time; stub the loader
+        import types
+
+        stub = types.ModuleType("manopth.mano.webuser.smpl_handpca_wrapper_HAND_only")
+        stub.ready_arguments = lambda *a, **k: (_ for _ in ()).throw(
+            RuntimeError("MANO pkl not available in this container")
+        )
+        sys.modules.setdefault("manopth.mano.webuser.smpl_handpca_wrapper_HAND_only", stub)
+        from main.config import cfg  # noqa
+
+        _apply_setting(cfg, setting)
+        import main.model as M  # noqa
+        from manopth.manopth.manolayer import ManoLayer  # noqa
+    finally:
+        os.chdir(old)
+    ns = {"cfg": cfg, "M": M, "ManoLayer": ManoLayer}
+    _loaded["ns"] = ns
+    return ns
+
+
+def _apply_setting(cfg, setting):
+    cls = type(cfg)
+    if setting == "ho3d":
+        cls.setting = "ho3d"
+        cls.dataset = "ho3d"
+        cls.use_big_decoder = True
+    elif setting == "dexycb":
+        cls.setting = "dexycb"
+        cls.dataset = "dexycb"
+        cls.use_big_decoder = False
+    else:
+        raise ValueError(setting)
+    cls.use_inverse_kinematics = False
+    cfg.calc_mutliscale_dim(cls.use_big_decoder, cls.resnet_type)
+
+
+def synthetic_mano_layer(ns, mano_buffers):
+    """Shim 3: a ManoLayer carrying caller-provided buffers (no pkl, no chumpy)."""
+    import torch
+
+    ManoLayer = ns["ManoLayer"]
+    layer = ManoLayer.__new__(ManoLayer)
+    torch.nn.Module.__init__(layer)
+    layer.center_idx = 0
+    layer.robust_rot = False
+    layer.rot = 3
+    layer.flat_hand_mean = True
+    layer.side = "right"
+    layer.use_pca = False
+    layer.joint_rot_mode = "axisang"
+    layer.root_rot_mode = "axisang"
+    layer.ncomps = 45
+    for k, v in mano_buffers.items():
+        layer.register_buffer(k, v.clone())
+    layer.kintree_parents = [-1, 0, 1, 2, 0, 4, 5, 0, 7, 8, 0, 10, 11, 0, 13, 14]
+    return layer
+
+
+def build_model(ns, mano_buffers):
+    """Mirror of main/model.py:683-760 (`get_model`) without the pkl-dependent ManoLayer."""
+    cfg, M = ns["cfg"], ns["M"]
+    backbone = M.BackboneNet()
+    decoder = M.DecoderNet_big() if cfg.use_big_decoder else M.DecoderNet()
+    hand_sdf = M.SDFDecoder(latent_size=cfg.hidden_dim, point_feat_size=cfg.PointFeatSize,
+                            use_classifier=cfg.ClassifierBranch)
+    obj_sdf = M.SDFDecoder(latent_size=cfg.hidden_dim, point_feat_size=cfg.PointFeatSize,
+                           use_classifier=cfg.ClassifierBranch)
+    hand_tr = M.Transformer(d_model=cfg.hidden_dim, dropout=cfg.dropout, nhead=cfg.nheads,
+                            dim_feedforward=cfg.dim_feedforward, num_encoder_layers=cfg.enc_layers,
+                            num_decoder_layers=cfg.dec_layers, normalize_before=cfg.pre_norm,
+                            return_intermediate_dec=True)
+    obj_tr = M.VoteTransformer(d_model=cfg.hidden_dim, dropout=cfg.dropout, nhead=cfg.nheads,
+                               dim_feedforward=cfg.dim_feedforward,
+                               num_encoder_layers=cfg.enc_layers // 2,
+                               normalize_before=cfg.pre_norm, return_intermediate_dec=True)
+    mano = synthetic_mano_layer(ns, mano_buffers)
+    return M.Model(backbone, decoder, hand_sdf, obj_sdf, hand_tr, obj_tr, mano)
