@@ -1,0 +1,94 @@
+"""ctypes binding of libhoisdf_b200.so (declared in include/hoisdf_b200.h).
+
+There is NO fallback: if the CUDA library is missing or does not export a declared symbol, importing
+this module raises.  Build it with `python -m hoisdf_b200.csrc.build` (or `__graft_entry__.build()`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhoisdf_b200.so")
+
+ABI_VERSION = 1
+ACT_NONE, ACT_RELU = 0, 1
+GATHER_CONCAT, GATHER_SUM = 0, 1
+
+c_float_p = C.c_void_p  # device pointers are passed as integers (tensor.data_ptr())
+i64, i32, f32, vp = C.c_int64, C.c_int32, C.c_float, C.c_void_p
+
+
+class LinearArgs(C.Structure):
+    _fields_ = [
+        ("x", vp), ("ldx", i64), ("x_rows_per_batch", i64), ("x_batch_stride", i64),
+        ("w", vp), ("ldw", i64), ("bias", vp), ("residual", vp),
+        ("y", vp), ("ldy", i64), ("y_rows_per_batch", i64), ("y_batch_stride", i64),
+        ("m", i64), ("n", i64), ("k", i64), ("act", i32),
+    ]
+
+
+class Pyramid(C.Structure):
+    _fields_ = [
+        ("map", vp * 5), ("c", i32 * 5), ("h", i32 * 5), ("w", i32 * 5),
+        ("levels", i32), ("img_h", i32), ("img_w", i32),
+    ]
+
+
+class SdfWeights(C.Structure):
+    _fields_ = [(n, vp) for n in ("w0", "b0", "w1", "b1", "w2", "b2", "w3", "b3", "w4", "b4")]
+
+
+class ManoModel(C.Structure):
+    _fields_ = [(n, vp) for n in ("shapedirs", "posedirs", "v_template", "j_regressor", "weights", "hands_mean")]
+
+
+# name -> (restype, argtypes); mirrors include/hoisdf_b200.h one to one
+SIGNATURES = {
+    "hoisdf_abi_version": (C.c_int, []),
+    "hoisdf_status_string": (C.c_char_p, [C.c_int]),
+    "hoisdf_linear_fwd": (C.c_int, [C.POINTER(LinearArgs), vp]),
+    "hoisdf_fold_weight_norm": (C.c_int, [vp, vp, i64, i64, vp, i64, vp, i64, vp]),
+    "hoisdf_nchw_to_nhwc": (C.c_int, [vp, vp, i64, i64, i64, i64, vp]),
+    "hoisdf_lattice_chunks": (C.c_int, [i32]),
+    "hoisdf_lattice_count": (C.c_int, [vp, vp, vp, f32, i64, i32, vp, vp, vp]),
+    "hoisdf_lattice_compact": (C.c_int, [vp, vp, vp, f32, i64, i32, vp, vp, vp, vp, vp]),
+    "hoisdf_project_points": (C.c_int, [vp, vp, vp, f32, i64, i64, vp, vp, vp]),
+    "hoisdf_gather_fwd": (C.c_int, [C.POINTER(Pyramid), vp, i64, vp, i64, i64, i32, vp, i32, vp, i64, vp]),
+    "hoisdf_posenc_fwd": (C.c_int, [vp, vp, i64, i32, vp, i64, i64, vp]),
+    "hoisdf_sdf_decoder_fwd": (C.c_int, [C.POINTER(SdfWeights), vp, i64, i64, vp, vp, vp, f32, vp]),
+    "hoisdf_sdf_pad_input": (C.c_int, [vp, i64, vp, i64, vp]),
+    "hoisdf_select_points": (C.c_int, [vp, vp, vp, i64, i64, i32, f32, vp, vp, vp, vp, vp, vp]),
+    "hoisdf_tokens_fwd": (C.c_int, [vp, vp, vp, i64, vp, vp, i64, i64, vp, i64, i64, vp]),
+    "hoisdf_attention_fwd": (C.c_int, [vp, i64, vp, vp, i64, vp, i64, i64, i64, i64, i64, i64, vp, vp]),
+    "hoisdf_add_layernorm_fwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp]),
+    "hoisdf_vote_joints_fwd": (C.c_int, [vp, vp, vp, i64, i64, i64, vp, vp]),
+    "hoisdf_mano_fwd": (C.c_int, [C.POINTER(ManoModel), vp, vp, i64, vp, vp, vp]),
+}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "hoisdf_b200: %s is missing -- there is no CPU or PyTorch fallback; build the CUDA library with "
+            "`python -m hoisdf_b200.csrc.build`" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.hoisdf_abi_version() != ABI_VERSION:
+        raise ImportError("hoisdf_b200: ABI mismatch (library %d, binding %d)" % (lib.hoisdf_abi_version(), ABI_VERSION))
+    return lib
+
+
+lib = _load()
+
+
+class HoisdfError(RuntimeError):
+    pass
+
+
+def check(status: int, what: str):
+    if status != 0:
+        raise HoisdfError("%s failed: %s (status %d)" % (what, lib.hoisdf_status_string(status).decode(), status))

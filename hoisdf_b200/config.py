@@ -1,0 +1,66 @@
+"""Configuration singleton with the attribute names of upstream main/config.py:38-151 (only what the hot path
+reads; dataset paths, optimiser and logging knobs belong to the upstream harness and are not mirrored).
+
+Like upstream, point counts and scales are read at CALL time, so `cfg.num_samp_hand = 1536` before a forward
+changes the number of selected points without rebuilding the model.
+"""
+from __future__ import annotations
+
+
+class Config:
+    setting = "ho3d"            # "ho3d" (Decoder_big, C=3968) | "dexycb" (Decoder, C=992)
+    dataset = "ho3d"
+    num_samp_hand = 600
+    num_samp_obj = 200
+    hand_sdf_scale = 3.1
+    obj_sdf_scale = 3.1
+    hand_cls_dist = 0.04
+    obj_cls_dist = 0.05
+    # SDF config (upstream config.py:88-93)
+    bins_n = 64
+    num_class = 6
+    PointFeatSize = 33
+    ClassifierBranch = False
+    ClampingDistance = 0.15
+    # model (upstream config.py:96-126)
+    use_big_decoder = True
+    use_inverse_kinematics = False
+    resnet_type = 50
+    mutliscale_layers = ["stride2", "stride4", "stride8", "stride16", "stride32"]
+    input_img_shape = (256, 256)
+    output_hm_shape = (128, 128, 128)
+    sigma = 2.5 / 2
+    hidden_dim = 256
+    dropout = 0.1
+    nheads = 4
+    dim_feedforward = 1024
+    enc_layers = 6
+    dec_layers = 4
+    pre_norm = False
+    mano_num_queries = 15 + 1 + 1
+    mano_shape_indx = 16
+    # training-time knobs read inside Model.forward (upstream config.py:64-66,129)
+    point_sampling_epoch = 40
+    random_ratio = [0.3, 0.7]
+    random_move_dist = [0.03, 0.05, 0.07]
+    # hoisdf_b200 additions
+    eval_losses = True          # keep the (unused by main/test.py) loss entries in the eval output dict
+    max_rows_per_pass = 1 << 21 # candidate rows processed per pass (bounds the activation workspace)
+
+    def calc_mutliscale_dim(self, use_big_decoder_l, resnet_type_l):
+        # upstream config.py:101-108 (sic: "mutliscale")
+        self.mutliscale_dim = 128 + 256 + 512 + 1024 + 2048 if use_big_decoder_l else 32 + 64 + 128 + 256 + 512
+
+    def set_setting(self, setting: str):
+        """Switch architecture ('ho3d' | 'dexycb'); upstream freezes this at import (config.py:39-44,96-97)."""
+        if setting not in ("ho3d", "dexycb"):
+            raise ValueError("setting must be 'ho3d' or 'dexycb' (ho3d_render / inverse kinematics is out of scope)")
+        cls = type(self)
+        cls.setting = setting
+        cls.dataset = "ho3d" if setting == "ho3d" else "dexycb"
+        cls.use_big_decoder = setting == "ho3d"
+        self.calc_mutliscale_dim(cls.use_big_decoder, cls.resnet_type)
+
+
+cfg = Config()
+cfg.calc_mutliscale_dim(cfg.use_big_decoder, cfg.resnet_type)

@@ -1,0 +1,51 @@
+// Shared helpers for the hoisdf_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/hoisdf_b200.h"
+
+#define HOISDF_API extern "C" __attribute__((visibility("default")))
+
+namespace hoisdf {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+static inline int launch_status() {
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? HOISDF_OK : static_cast<int>(e);
+}
+
+__host__ __device__ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// The sheared lattice of upstream main/model.py:260-273, op for op (each step separately rounded).
+//   col2 = idx % n ; col1 = (idx / n) mod n (TRUE division) ; col0 = ((idx / n) / n) mod n
+//   s = col * (2/(n-1)) + (-1)
+__device__ __forceinline__ void lattice_point(int idx, int bins, float& s0, float& s1, float& s2) {
+  const float fn = static_cast<float>(bins);
+  const float vs = static_cast<float>(2.0 / static_cast<double>(bins - 1));
+  const float fi = static_cast<float>(idx);  // idx < 2^24: exact
+  const float c2 = static_cast<float>(idx % bins);
+  const float d1 = __fdiv_rn(fi, fn);
+  const float c1 = fmodf(d1, fn);
+  const float c0 = fmodf(__fdiv_rn(d1, fn), fn);
+  s0 = __fadd_rn(__fmul_rn(c0, vs), -1.0f);
+  s1 = __fadd_rn(__fmul_rn(c1, vs), -1.0f);
+  s2 = __fadd_rn(__fmul_rn(c2, vs), -1.0f);
+}
+
+}  // namespace hoisdf

@@ -1,0 +1,359 @@
+"""`Model` -- the drop-in boundary: same constructor, method signatures, parameter names and output dict as
+upstream main/model.py:28-665, with the hot path (sdf_infer -> sdf_forward -> get_input_transformer ->
+transformers -> heads -> MANO / vote) running on the hoisdf_b200 sm_100a kernels.
+
+What is different by design (B200-first):
+  * no per-sample Python loop and no `.cpu()` round trips: the whole batch goes through a handful of launches;
+    the only host read-back is the per-sample candidate COUNT (needed to size the row buffers), issued before
+    the backbone so that it never stalls the GPU;
+  * `linear_sdfin` layer 0 is applied to the pyramid once per image (a 1x1 projection of every level) and the
+    bilinear gather then interpolates 512 projected channels instead of 3968 raw ones -- interpolation is
+    linear, so  W.(sum_t w_t F_t) = sum_t w_t (W.F_t); 37x fewer FLOPs for that layer at N_f ~ 19k;
+  * the pyramid is read channels-last (NHWC), which cuDNN emits directly when the U-Net runs in channels_last.
+Inference only for now (mode != "train"); training needs the backward kernels.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .config import cfg
+from .nets.layer import MLP, _require_inference
+from .nets.loss import eval_losses
+from .nets.mano_head import ManoHead, ManoLayer
+from .nets.module import BackboneNet, DecoderNet, DecoderNet_big
+from .nets.sdf_net import SDFDecoder
+from .nets.transformer import Transformer, VoteTransformer
+from .utils.misc import get_mano_memory_mask, get_mano_tgt_mask
+
+
+class PyramidContext:
+    """Channels-last views of one forward's feature pyramid + the per-level projection through
+    `linear_sdfin.layers[0]` (computed lazily, once, shared by every SDF query of the forward)."""
+
+    def __init__(self, feature_pyramid: Dict[str, torch.Tensor], model: "Model"):
+        self.maps = [ops.to_nhwc(feature_pyramid[name]) for name in cfg.mutliscale_layers]
+        self.batch = self.maps[0].shape[0]
+        self.channels = sum(m.shape[3] for m in self.maps)
+        self._model = model
+        self._gmaps = None
+
+    @property
+    def gmaps(self):
+        if self._gmaps is None:
+            w0 = self._model.linear_sdfin.packed()[0]
+            if w0.k != self.channels:
+                raise RuntimeError("pyramid has %d channels, linear_sdfin expects %d" % (self.channels, w0.k))
+            g, off = [], 0
+            for m in self.maps:
+                b, h, w, c = m.shape
+                out = torch.empty(b, h, w, w0.n, device=m.device, dtype=torch.float32)
+                ops.linear(m.view(b * h * w, c), w0.cols(off, off + c), ops.ACT_NONE, out=out.view(b * h * w, w0.n))
+                g.append(out)
+                off += c
+            self._gmaps = g
+        return self._gmaps
+
+
+class CandidatePlan:
+    """Result of pass 1 of the candidate generation: device chunk offsets + host copy of the sample offsets."""
+
+    def __init__(self, center, cam_intr, bbox, sdf_scale):
+        self.center = center.detach().to(torch.float32).contiguous()
+        self.cam_intr = cam_intr.detach().to(torch.float32).contiguous()
+        self.bbox = bbox.detach().to(torch.float32).contiguous()
+        self.sdf_scale = float(sdf_scale)
+        self.counts, self.offsets = ops.lattice_count(self.center, self.cam_intr, self.bbox, self.sdf_scale, cfg.bins_n)
+        self._host = torch.empty(self.offsets.shape, dtype=torch.int64, pin_memory=True)
+        self._host.copy_(self.offsets, non_blocking=True)
+        self._event = torch.cuda.Event()
+        self._event.record()
+
+    def host_offsets(self):
+        self._event.synchronize()
+        return self._host
+
+
+class Model(nn.Module):
+    def __init__(self, backbone_net, decoder_net, hand_sdf_decoder, obj_sdf_decoder, hand_transformer,
+                 obj_transformer, mano_layer):
+        super().__init__()
+        self.backbone_net = backbone_net
+        self.decoder_net = decoder_net
+        self.hand_sdf_decoder = hand_sdf_decoder
+        self.obj_sdf_decoder = obj_sdf_decoder
+        self.hand_transformer = hand_transformer
+        self.obj_transformer = obj_transformer
+
+        self.hand_sigmoid_beta = nn.Parameter(0.1 * torch.ones(1))
+        self.obj_sigmoid_beta = nn.Parameter(0.1 * torch.ones(1))
+
+        d = cfg.hidden_dim
+        self.norm1 = nn.LayerNorm(cfg.mutliscale_dim)  # unused upstream too (model.py:55); kept for strict loading
+        self.linear_transformerin = MLP(cfg.mutliscale_dim, [1024, 512, 256], d - cfg.PointFeatSize, 4, True)
+        self.linear_sdfin = MLP(cfg.mutliscale_dim, [512], int(d), 2, True)
+        if cfg.use_inverse_kinematics:
+            raise NotImplementedError("the ho3d_render / inverse-kinematics setting is out of scope")
+        self.mano_query_embed = nn.Embedding(cfg.mano_num_queries, d)
+        self.mano_head = ManoHead(mano_layer, coord_change_mat=torch.tensor(
+            [[1.0, 0.0, 0.0], [0.0, -1.0, 0.0], [0.0, 0.0, -1.0]], dtype=torch.float32))
+        self.linear_pose = MLP(d, d, 6, 3)
+        self.linear_shape = MLP(d, d, 10, 3)
+        self.linear_handvote = MLP(d, d, 20 * 3, 4)
+        self.linear_handcls = MLP(d, d, 20, 3)
+        self.linear_objvote = MLP(d, d, 8 * 3, 4)   # dead upstream as well (model.py:86-87)
+        self.linear_objcls = MLP(d, d, 8, 3)
+        self.linear_obj_rel_trans = MLP(d, d, 3, 3)
+        self.linear_obj_rot = MLP(d, d, 3, 3)
+        self.last_taps = None      # diagnostics of the most recent forward (selected lattice indices, N_f, ...)
+
+    # ------------------------------------------------------------------------------------------------
+    # layout helper
+    # ------------------------------------------------------------------------------------------------
+    def channels_last_(self):
+        """Run ResNet + U-Net in channels_last so the pyramid comes out NHWC (no transpose before the gather)."""
+        self.backbone_net.to(memory_format=torch.channels_last)
+        self.decoder_net.to(memory_format=torch.channels_last)
+        self._channels_last = True
+        return self
+
+    # ------------------------------------------------------------------------------------------------
+    # upstream-signature operators
+    # ------------------------------------------------------------------------------------------------
+    def sdf_activation(self, input, beta):
+        """upstream model.py:123-126 (in-place floor of beta, then sigmoid(sdf/beta)/beta)."""
+        beta.data.clamp_(min=2e-3)
+        return torch.sigmoid(input / beta) / beta
+
+    def _ctx(self, feature_pyramid):
+        return feature_pyramid if isinstance(feature_pyramid, PyramidContext) else PyramidContext(feature_pyramid, self)
+
+    def get_input_transformer(self, feature_pyramid, sdf_points, center_joint, cam_intr, sdf_scale):
+        """upstream model.py:145-179 -> (transformer_latent (B,P,223), cam_sdf_points (B,P,3))."""
+        _require_inference(self, sdf_points)
+        ctx = self._ctx(feature_pyramid)
+        pts = sdf_points.detach().to(torch.float32).contiguous()
+        b, p, _ = pts.shape
+        cam, uv = ops.project_points(pts, center_joint.contiguous(), cam_intr.contiguous(), sdf_scale)
+        feats = torch.empty(b * p, ctx.channels, device=pts.device, dtype=torch.float32)
+        ops.gather(ctx.maps, uv, b, mode=ops.GATHER_CONCAT, out=feats, rows_per_sample=p, img_hw=cfg.input_img_shape)
+        latent = self.linear_transformerin.forward_rows(feats)
+        return latent.view(b, p, -1) if latent.is_contiguous() else latent.unflatten(0, (b, p)), cam
+
+    def sdf_forward(self, feature_pyramid, sdf_points, center_joint, cam_intr, sdf_scale, type="hand"):
+        """upstream model.py:181-244 -> (pred_sdf (B,P,1) clamped, pred_class, pos_enc3d (B,P,30))."""
+        _require_inference(self, sdf_points)
+        ctx = self._ctx(feature_pyramid)
+        pts = sdf_points.detach().to(torch.float32).contiguous()
+        b, p, _ = pts.shape
+        dev = pts.device
+        _, uv = ops.project_points(pts, center_joint.contiguous(), cam_intr.contiguous(), sdf_scale, want_cam=False)
+        sdfin = self.linear_sdfin.packed()
+        h = torch.empty(b * p, 512, device=dev, dtype=torch.float32)
+        ops.gather(ctx.gmaps, uv, b, mode=ops.GATHER_SUM, out=h, rows_per_sample=p, bias=sdfin[0].b,
+                   act=ops.ACT_RELU, img_hw=cfg.input_img_shape)
+        rows = torch.empty(b * p, ops.ROW_LD, device=dev, dtype=torch.float32)
+        ops.linear(h, sdfin[1], ops.ACT_RELU, out=rows[:, :256])
+        ops.posenc(rows, points=pts.view(b * p, 3), bins=cfg.bins_n)
+        dec = self.hand_sdf_decoder if type == "hand" else self.obj_sdf_decoder
+        sdf = ops.sdf_decoder(dec.packed(), rows, h_a=h, clamp=cfg.ClampingDistance)
+        pe = rows[:, 256:286].reshape(b, p, 30)
+        return sdf.view(b, p, 1), (None if not cfg.ClassifierBranch else None), pe
+
+    def plan_candidates(self, center_joint, cam_intr, bbox, sdf_scale) -> CandidatePlan:
+        return CandidatePlan(center_joint, cam_intr, bbox, sdf_scale)
+
+    def sdf_infer(self, feature_pyramid, center_joint, cam_intr, bbox, sdf_scale, num_points, type="hand",
+                  plan: Optional[CandidatePlan] = None, taps: Optional[dict] = None):
+        """upstream model.py:246-355 -> (pose_points (B,P,3), pose_sdf (B,P,1), pose_posenc3d (B,P,30), None).
+
+        Candidate lattice points of the whole batch are compacted into one row buffer (sample-major, ascending
+        lattice index -- the order upstream's boolean-mask indexing yields), pushed through the projected-map
+        gather + linear_sdfin + SDF decoder, and the `num_points` smallest |sdf| per sample are selected.
+        """
+        ctx = self._ctx(feature_pyramid)
+        if plan is None:
+            plan = self.plan_candidates(center_joint, cam_intr, bbox, sdf_scale)
+        b = plan.center.shape[0]
+        dev = plan.center.device
+        host = plan.host_offsets()
+        total = int(host[-1])
+        n_f = host[1:] - host[:-1]
+        if int(n_f.min()) < num_points:
+            # upstream fails here too (model.py:348: shape mismatch when N_f < num_points)
+            raise RuntimeError("sdf_infer: sample %d has %d lattice points inside its bbox, fewer than num_points=%d"
+                               % (int(n_f.argmin()), int(n_f.min()), num_points))
+        cand_index, cand_uv = ops.lattice_compact(plan.center, plan.cam_intr, plan.bbox, plan.sdf_scale, cfg.bins_n,
+                                                  plan.counts, plan.offsets, total)
+        sdfin = self.linear_sdfin.packed()
+        dec = self.hand_sdf_decoder if type == "hand" else self.obj_sdf_decoder
+        packed = dec.packed()
+        gmaps = ctx.gmaps
+        sdf = torch.empty(total, device=dev, dtype=torch.float32)
+        step = int(cfg.max_rows_per_pass)
+        cap = min(step, total)
+        h = torch.empty(cap, 512, device=dev, dtype=torch.float32)
+        h2 = torch.empty(cap, 512, device=dev, dtype=torch.float32)
+        rows = torch.empty(cap, ops.ROW_LD, device=dev, dtype=torch.float32)
+        for r0 in range(0, total, step):
+            n = min(step, total - r0)
+            offs = plan.offsets if r0 == 0 else plan.offsets - r0
+            ops.gather(gmaps, cand_uv[r0:r0 + n], b, mode=ops.GATHER_SUM, out=h[:n], row_offsets=offs,
+                       bias=sdfin[0].b, act=ops.ACT_RELU, img_hw=cfg.input_img_shape)
+            ops.linear(h[:n], sdfin[1], ops.ACT_RELU, out=rows[:n, :256])
+            ops.posenc(rows[:n], lattice_index=cand_index[r0:r0 + n], bins=cfg.bins_n)
+            ops.sdf_decoder(packed, rows[:n], h_a=h[:n], h_b=h2[:n], out=sdf[r0:r0 + n])
+        sel, pts, out_sdf, pe, _flag = ops.select_points(sdf, plan.offsets, cand_index, b, num_points, cfg.bins_n,
+                                                         cfg.ClampingDistance)
+        if taps is not None:
+            taps.update(index=sel, n_f=n_f.clone(), cand_index=cand_index, cand_sdf=sdf, offsets=host.clone())
+        return pts, out_sdf, pe, None
+
+    # ------------------------------------------------------------------------------------------------
+    # forward
+    # ------------------------------------------------------------------------------------------------
+    def forward(self, inputs, targets, meta_info, mode, epoch_cnt=1e8, batch_ratio=0):
+        if mode == "train":
+            raise NotImplementedError("hoisdf_b200 builds the inference hot path; the training step "
+                                      "(backward kernels, SURVEY.md section 8 f-2) is not built yet")
+        if cfg.dataset == "dexycb":
+            raise NotImplementedError("the dexycb eval extras (GT-point SDF supervision, GT MANO forward, "
+                                      "model.py:370-422,606-620) are not built yet; use hot_path() for the shared path")
+        with torch.no_grad():
+            img = inputs["img"]
+            plans = self._plans(meta_info)
+            if getattr(self, "_channels_last", False):
+                img = img.contiguous(memory_format=torch.channels_last)
+            img_feat, skips = self.backbone_net(img)
+            feature_pyramid, _decoder_out = self.decoder_net(img_feat, skips)
+            out = self.hot_path(feature_pyramid, meta_info, plans)
+            if cfg.eval_losses:
+                out = {**eval_losses(self.last_taps, targets, meta_info), **out}
+        return out
+
+    def _plans(self, meta_info):
+        K = meta_info["cam_intr"]
+        return (self.plan_candidates(meta_info["mano_root"], K, meta_info["bbox_hand"], cfg.hand_sdf_scale),
+                self.plan_candidates(meta_info["obj_center_cam"], K, meta_info["bbox_obj"], cfg.obj_sdf_scale))
+
+    def hot_path(self, feature_pyramid, meta_info, plans=None):
+        """Everything of upstream Model.forward(mode='eval') after the U-Net (model.py:424-638), on our kernels.
+        Returns the `*_out` entries; intermediate tensors are left in `self.last_taps`."""
+        with torch.no_grad():
+            return self._hot_path(feature_pyramid, meta_info, plans)
+
+    def _hot_path(self, feature_pyramid, meta_info, plans):
+        root = meta_info["mano_root"].to(torch.float32).contiguous()
+        objc = meta_info["obj_center_cam"].to(torch.float32).contiguous()
+        K = meta_info["cam_intr"].to(torch.float32).contiguous()
+        if plans is None:
+            plans = self._plans(meta_info)
+        ctx = self._ctx(feature_pyramid)
+        b = ctx.batch
+        dev = root.device
+        Ph, Po = int(cfg.num_samp_hand), int(cfg.num_samp_obj)
+        S = Ph + Po
+        hs_scale, os_scale = cfg.hand_sdf_scale, cfg.obj_sdf_scale
+        th, to = {}, {}
+        hand_points, hand_sdf, hand_pe, _ = self.sdf_infer(ctx, root, K, None, hs_scale, Ph, "hand", plans[0], th)
+        obj_points, obj_sdf, obj_pe, _ = self.sdf_infer(ctx, objc, K, None, os_scale, Po, "obj", plans[1], to)
+
+        self.hand_sigmoid_beta.data.clamp_(min=2e-3)   # upstream model.py:124 (side effect on the parameter)
+        self.obj_sigmoid_beta.data.clamp_(min=2e-3)
+        beta_h, beta_o = self.hand_sigmoid_beta.data, self.obj_sigmoid_beta.data
+
+        hand_fea, hand_cam = self.get_input_transformer(ctx, hand_points, root, K, hs_scale)
+        obj_fea, obj_cam = self.get_input_transformer(ctx, obj_points, objc, K, os_scale)
+        hand_nt = hand_cam - root[:, None, :]
+        obj_nt = obj_cam - objc[:, None, :]
+        hand_o_nt = hand_cam - objc[:, None, :]          # upstream model.py:498 ("bug": unscaled coords, kept)
+        obj_h_nt = obj_cam - root[:, None, :]            # upstream model.py:508
+        hand_o_sdf, _, hand_o_pe = self.sdf_forward(ctx, hand_o_nt * os_scale, objc, K, os_scale, "obj")
+        obj_h_sdf, _, obj_h_pe = self.sdf_forward(ctx, obj_h_nt * hs_scale, root, K, hs_scale, "hand")
+
+        hand_in = torch.empty(b, S, 256, device=dev, dtype=torch.float32)
+        ops.tokens(hand_nt, hand_pe, hand_fea, hand_sdf, beta_h, hand_in, 0)
+        ops.tokens(obj_h_nt, obj_h_pe, obj_fea, obj_h_sdf, beta_h, hand_in, Ph)
+        obj_in = torch.empty(b, S, 256, device=dev, dtype=torch.float32)
+        ops.tokens(obj_nt, obj_pe, obj_fea, obj_sdf, beta_o, obj_in, 0)
+        ops.tokens(hand_o_nt, hand_o_pe, hand_fea, hand_o_sdf, beta_o, obj_in, Po)
+
+        tgt_mask = get_mano_tgt_mask().to(dev)
+        memory_mask = get_mano_memory_mask().to(dev)
+        hs, memory, hand_enc = self.hand_transformer.forward_bm(hand_in, self.mano_query_embed.weight, None,
+                                                                tgt_mask, memory_mask)
+        _, obj_enc = self.obj_transformer.forward_bm(obj_in, None)
+
+        Le, Lo, Ld = hand_enc.shape[0], obj_enc.shape[0], hs.shape[0]
+        hand_off = self._head_rows(self.linear_handvote, hand_enc, Le * b, Ph, S).view(Le, b, Ph, 60)
+        hand_cls = self._head_rows(self.linear_handcls, hand_enc, Le * b, Ph, S).view(Le, b, Ph, 20)
+        obj_rot = self._head_rows(self.linear_obj_rot, obj_enc, Lo * b, Po, S).view(Lo, b, Po, 3)
+        obj_trans = self._head_rows(self.linear_obj_rel_trans, obj_enc, Lo * b, Po, S).view(Lo, b, Po, 3)
+        nq = hs.shape[2]
+        pose6d = self._head_rows(self.linear_pose, hs, Ld * b, cfg.mano_shape_indx, nq).view(Ld, b, cfg.mano_shape_indx, 6)
+        shape = self._head_rows(self.linear_shape, hs, Ld * b, 1, nq, first=cfg.mano_shape_indx).view(Ld, b, 10)
+        verts, joints = self.mano_head.forward_bm(pose6d, shape)
+        hand_joints = ops.vote_joints(hand_nt.contiguous(), hand_off, hand_cls)
+
+        out = {
+            "mano_mesh_out": verts[-1],
+            "mano_joints_out": joints[-1],
+            "obj_rot_out": obj_rot[-1],
+            "obj_trans_out": obj_trans[-1],
+            "hand_joints_out": hand_joints[-1],
+        }
+        self.last_taps = dict(
+            hand=th, obj=to, hand_points=hand_points, hand_sdf=hand_sdf, hand_posenc=hand_pe, obj_points=obj_points,
+            obj_sdf=obj_sdf, obj_posenc=obj_pe, hand_fea=hand_fea, obj_fea=obj_fea, hand_o_sdf=hand_o_sdf,
+            obj_h_sdf=obj_h_sdf, hand_transformer_in=hand_in, obj_transformer_in=obj_in, hs=hs, memory=memory,
+            hand_encoder_out=hand_enc, obj_encoder_out=obj_enc, hand_off=hand_off, hand_cls=hand_cls, obj_rot=obj_rot,
+            obj_trans=obj_trans, mano_pose6d=pose6d, mano_shape=shape, hand_joints=hand_joints, mano_verts=verts,
+            mano_joints=joints, hand_points_notrans=hand_nt)
+        return out
+
+    @staticmethod
+    def _head_rows(mlp: MLP, x: torch.Tensor, groups: int, rows_per_group: int, group_len: int, first: int = 0):
+        """Run `mlp` on tokens [first, first+rows_per_group) of every (layer, sample) group of a (L,B,T,256) tensor
+        without gathering them first: the Linear kernel walks the strided row groups itself."""
+        pk = mlp.packed()
+        d = x.shape[-1]
+        m = groups * rows_per_group
+        base = x.data_ptr() + first * d * 4
+        h_ptr, ld, batch = base, d, (rows_per_group, group_len * d)
+        keep = []
+        for i, pw in enumerate(pk):
+            last = i == len(pk) - 1
+            n_ld = ops.round_up(pw.n, 4)
+            alloc = torch.empty if n_ld == pw.n else torch.zeros
+            y = alloc(m, n_ld, device=x.device, dtype=torch.float32)
+            ops.linear_raw(h_ptr, ld, m, pw, y.data_ptr(), n_ld,
+                           ops.ACT_NONE if (last and not mlp.is_activation_last) else ops.ACT_RELU, None,
+                           x_batch=batch)
+            keep.append(y)
+            h_ptr, ld, batch = y.data_ptr(), n_ld, (0, 0)
+        y = keep[-1]
+        return y if y.shape[1] == pk[-1].n else y[:, :pk[-1].n].contiguous()
+
+
+def get_model(mode, mano_buffers=None, mano_root="tool/mano_models"):
+    """upstream main/model.py:682-766.  `mano_buffers` (dict of th_* tensors) replaces the licensed pkl."""
+    backbone_net = BackboneNet(cfg.resnet_type)
+    decoder_net = DecoderNet_big() if cfg.use_big_decoder else DecoderNet()
+    hand_sdf_decoder = SDFDecoder(latent_size=cfg.hidden_dim, point_feat_size=cfg.PointFeatSize,
+                                  use_classifier=cfg.ClassifierBranch)
+    obj_sdf_decoder = SDFDecoder(latent_size=cfg.hidden_dim, point_feat_size=cfg.PointFeatSize,
+                                 use_classifier=cfg.ClassifierBranch)
+    hand_transformer = Transformer(d_model=cfg.hidden_dim, dropout=cfg.dropout, nhead=cfg.nheads,
+                                   dim_feedforward=cfg.dim_feedforward, num_encoder_layers=cfg.enc_layers,
+                                   num_decoder_layers=cfg.dec_layers, normalize_before=cfg.pre_norm,
+                                   return_intermediate_dec=True)
+    obj_transformer = VoteTransformer(d_model=cfg.hidden_dim, dropout=cfg.dropout, nhead=cfg.nheads,
+                                      dim_feedforward=cfg.dim_feedforward, num_encoder_layers=cfg.enc_layers // 2,
+                                      normalize_before=cfg.pre_norm, return_intermediate_dec=True)
+    mano_layer = ManoLayer(ncomps=45, center_idx=0, flat_hand_mean=True, side="right", mano_root=mano_root,
+                           use_pca=False, buffers=mano_buffers)
+    return Model(backbone_net, decoder_net, hand_sdf_decoder, obj_sdf_decoder, hand_transformer, obj_transformer,
+                 mano_layer)

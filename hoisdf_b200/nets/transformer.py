@@ -1,0 +1,287 @@
+"""`Transformer` / `VoteTransformer` with the upstream constructor, forward signature and state-dict keys
+(common/nets/transformer.py:15-459), running on the hoisdf_b200 kernels: fused QKV projection, streaming
+softmax attention, out-projection with fused residual, fused (add +) LayerNorm (+ the shared inter_norm).
+
+Activations are kept BATCH-MAJOR (B, S, d) internally so that one sample's tokens are contiguous; the public
+`forward` accepts and returns the upstream sequence-major (S, B, d) layout.  Post-norm only
+(`normalize_before=False`, upstream main/config.py:122), ReLU FFN, eval mode (dropout off).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .layer import _require_inference
+
+
+class MultiheadAttentionParams(nn.Module):
+    """Parameter container with nn.MultiheadAttention's names: in_proj_weight [q;k;v], in_proj_bias, out_proj."""
+
+    def __init__(self, d_model, nhead):
+        super().__init__()
+        if d_model // nhead != 64 or d_model % nhead:
+            raise NotImplementedError("hoisdf_b200 attention kernels are built for head_dim 64")
+        self.embed_dim = d_model
+        self.num_heads = nhead
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * d_model, d_model))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * d_model))
+        self.out_proj = nn.Linear(d_model, d_model)
+        nn.init.xavier_uniform_(self.in_proj_weight)
+        nn.init.zeros_(self.out_proj.bias)
+        self._packed = None
+        self._key = None
+
+    def packed(self):
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._packed is None or self._key != key:
+            d = self.embed_dim
+            full = ops.PackedLinear.pack(self.in_proj_weight, self.in_proj_bias)
+            self._packed = {
+                "qkv": full, "q": full.rows(0, d), "k": full.rows(d, 2 * d), "v": full.rows(2 * d, 3 * d),
+                "qk": full.rows(0, 2 * d), "kv": full.rows(d, 3 * d),
+                "out": ops.PackedLinear.pack(self.out_proj.weight, self.out_proj.bias),
+            }
+            self._key = key
+        return self._packed
+
+
+class _LayerBase(nn.Module):
+    def __init__(self, d_model, nhead, dim_feedforward, dropout, activation, normalize_before):
+        super().__init__()
+        if normalize_before:
+            raise NotImplementedError("pre-norm transformer layers are not used upstream (config.py:122)")
+        if activation != "relu":
+            raise NotImplementedError("only the ReLU feed-forward of upstream config is built")
+        self.d_model = d_model
+        self.nhead = nhead
+        self.normalize_before = normalize_before
+        self._ffn = None
+        self._ffn_key = None
+
+    def ffn_packed(self):
+        ps = (self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias)
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if self._ffn is None or self._ffn_key != key:
+            self._ffn = (ops.PackedLinear.pack(self.linear1.weight, self.linear1.bias),
+                         ops.PackedLinear.pack(self.linear2.weight, self.linear2.bias))
+            self._ffn_key = key
+        return self._ffn
+
+    def _ffn_block(self, x2d, norm, norm2=None, out2=None):
+        l1, l2 = self.ffn_packed()
+        h = ops.linear(x2d, l1, ops.ACT_RELU)
+        y = ops.linear(h, l2, ops.ACT_NONE, residual=x2d)
+        if norm2 is None:
+            return ops.add_layernorm(y, None, norm.weight, norm.bias)
+        return ops.add_layernorm(y, None, norm.weight, norm.bias, gamma2=norm2.weight, beta2=norm2.bias, out2=out2)
+
+
+class TransformerEncoderLayer(_LayerBase):
+    def __init__(self, d_model, nhead, dim_feedforward=2048, dropout=0.1, activation="relu", normalize_before=False):
+        super().__init__(d_model, nhead, dim_feedforward, dropout, activation, normalize_before)
+        self.self_attn = MultiheadAttentionParams(d_model, nhead)
+        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+
+    def forward_bm(self, x: torch.Tensor, pos: Optional[torch.Tensor], inter_norm=None, inter_out=None):
+        """x (B, S, d) batch-major contiguous -> same shape; upstream transformer.py:279-302 (forward_post)."""
+        b, s, d = x.shape
+        x2d = x.view(b * s, d)
+        pk = self.self_attn.packed()
+        if pos is None:
+            qkv = ops.linear(x2d, pk["qkv"])                       # (rows, 3d): q | k | v
+            q, k, v, ld = qkv, qkv[:, d:], qkv[:, 2 * d:], 3 * d
+            ldq = ld
+        else:
+            qk_in = (x + pos).view(b * s, d)
+            qk = ops.linear(qk_in, pk["qk"])
+            vv = ops.linear(x2d, pk["v"])
+            # the attention entry point takes one pitch for k and v: copy v next to k
+            kv = torch.empty(b * s, 2 * d, device=x.device, dtype=torch.float32)
+            kv[:, :d] = qk[:, d:]
+            kv[:, d:] = vv
+            q, ldq, k, v, ld = qk, 2 * d, kv, kv[:, d:], 2 * d
+        att = torch.empty(b * s, d, device=x.device, dtype=torch.float32)
+        ops.attention(q, ldq, k, v, ld, att, d, b, self.nhead, s, s)
+        y = ops.linear(att, pk["out"], ops.ACT_NONE, residual=x2d)
+        x1 = ops.add_layernorm(y, None, self.norm1.weight, self.norm1.bias)
+        out = self._ffn_block(x1, self.norm2, inter_norm, inter_out)
+        return out.view(b, s, d)
+
+
+class TransformerDecoderLayer(_LayerBase):
+    def __init__(self, d_model, nhead, dim_feedforward=2048, dropout=0.1, activation="relu", normalize_before=False):
+        super().__init__(d_model, nhead, dim_feedforward, dropout, activation, normalize_before)
+        self.self_attn = MultiheadAttentionParams(d_model, nhead)
+        self.multihead_attn = MultiheadAttentionParams(d_model, nhead)
+        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.norm3 = nn.LayerNorm(d_model)
+
+    def forward_bm(self, tgt, memory, pos, query_pos, tgt_mask, memory_mask, final_norm, final_out):
+        """tgt (B, Lq, d), memory (B, S, d), query_pos (B, Lq, d) batch-major; masks uint8 (1 = blocked).
+        upstream transformer.py:366-395 (forward_post)."""
+        b, lq, d = tgt.shape
+        s = memory.shape[1]
+        dev = tgt.device
+        t2d = tgt.view(b * lq, d)
+        # masked self-attention over the queries
+        sa = self.self_attn.packed()
+        qk_in = (tgt + query_pos).view(b * lq, d)
+        qk = ops.linear(qk_in, sa["qk"])
+        kv = torch.empty(b * lq, 2 * d, device=dev, dtype=torch.float32)
+        ops.linear(t2d, sa["v"], out=kv[:, d:])
+        kv[:, :d] = qk[:, d:]
+        att = torch.empty(b * lq, d, device=dev, dtype=torch.float32)
+        ops.attention(qk, 2 * d, kv, kv[:, d:], 2 * d, att, d, b, self.nhead, lq, lq, mask=tgt_mask)
+        y = ops.linear(att, sa["out"], ops.ACT_NONE, residual=t2d)
+        t1 = ops.add_layernorm(y, None, self.norm1.weight, self.norm1.bias)
+        # cross-attention to the encoder memory
+        ca = self.multihead_attn.packed()
+        q = ops.linear((t1.view(b, lq, d) + query_pos).view(b * lq, d), ca["q"])
+        m2d = memory.view(b * s, d)
+        if pos is None:
+            mkv = ops.linear(m2d, ca["kv"])                       # (B*S, 2d): k | v
+        else:
+            mkv = torch.empty(b * s, 2 * d, device=dev, dtype=torch.float32)
+            ops.linear((memory + pos).view(b * s, d), ca["k"], out=mkv[:, :d])
+            ops.linear(m2d, ca["v"], out=mkv[:, d:])
+        att2 = torch.empty(b * lq, d, device=dev, dtype=torch.float32)
+        ops.attention(q, d, mkv, mkv[:, d:], 2 * d, att2, d, b, self.nhead, lq, s, mask=memory_mask)
+        y2 = ops.linear(att2, ca["out"], ops.ACT_NONE, residual=t1)
+        t2 = ops.add_layernorm(y2, None, self.norm2.weight, self.norm2.bias)
+        out = self._ffn_block(t2, self.norm3, final_norm, final_out)
+        return out.view(b, lq, d)
+
+
+def _clones(make, n):
+    return nn.ModuleList([make() for _ in range(n)])
+
+
+class TransformerEncoder(nn.Module):
+    def __init__(self, make_layer, num_layers, norm=None, inter_norm=None, return_intermediate=False):
+        super().__init__()
+        self.layers = _clones(make_layer, num_layers)
+        self.num_layers = num_layers
+        self.norm = norm
+        self.inter_norm = inter_norm
+        self.return_intermediate = return_intermediate
+
+    def forward_bm(self, x, pos):
+        """(B,S,d) -> (last (B,S,d), intermediate (L,B,S,d) = inter_norm of every layer output);
+        upstream transformer.py:175-202."""
+        b, s, d = x.shape
+        inter = torch.empty(self.num_layers, b, s, d, device=x.device, dtype=torch.float32) \
+            if self.return_intermediate else None
+        for i, layer in enumerate(self.layers):
+            if inter is not None:
+                x = layer.forward_bm(x, pos, self.inter_norm, inter[i])
+            else:
+                x = layer.forward_bm(x, pos)
+        return x, inter
+
+
+class TransformerDecoder(nn.Module):
+    def __init__(self, make_layer, num_layers, norm=None, return_intermediate=False):
+        super().__init__()
+        self.layers = _clones(make_layer, num_layers)
+        self.num_layers = num_layers
+        self.norm = norm
+        self.return_intermediate = return_intermediate
+
+    def forward_bm(self, tgt, memory, pos, query_pos, tgt_mask, memory_mask):
+        """-> hs (L, B, Lq, d) = norm(out_l) for every layer (upstream transformer.py:214-252)."""
+        b, lq, d = tgt.shape
+        hs = torch.empty(self.num_layers, b, lq, d, device=tgt.device, dtype=torch.float32)
+        x = tgt
+        for i, layer in enumerate(self.layers):
+            x = layer.forward_bm(x, memory, pos, query_pos, tgt_mask, memory_mask, self.norm, hs[i])
+        return hs
+
+
+def _mask_u8(mask: Optional[torch.Tensor], device):
+    if mask is None:
+        return None
+    return mask.to(device=device, dtype=torch.uint8).contiguous()
+
+
+def _xavier(module):
+    for p in module.parameters():
+        if p.dim() > 1:
+            nn.init.xavier_uniform_(p)
+
+
+class VoteTransformer(nn.Module):
+    """Encoder-only transformer (upstream transformer.py:15-65)."""
+
+    def __init__(self, d_model=512, nhead=8, num_encoder_layers=6, dim_feedforward=2048, dropout=0.1,
+                 activation="relu", normalize_before=False, return_intermediate_dec=False):
+        super().__init__()
+        self.encoder = TransformerEncoder(
+            lambda: TransformerEncoderLayer(d_model, nhead, dim_feedforward, dropout, activation, normalize_before),
+            num_encoder_layers, None, nn.LayerNorm(d_model), return_intermediate_dec)
+        _xavier(self)
+        self.d_model = d_model
+        self.nhead = nhead
+
+    def forward_bm(self, src_bm, pos_bm=None):
+        x = src_bm if pos_bm is None else src_bm + pos_bm
+        return self.encoder.forward_bm(x.contiguous(), pos_bm)
+
+    def forward(self, src, mask, pos_embed, src_mask=None):
+        """src (S,B,d), pos_embed (S,B,d) -> (memory (S,B,d), intermediate (L,S,B,d))."""
+        _require_inference(self, src)
+        if mask is not None or src_mask is not None:
+            raise NotImplementedError("key-padding / source masks are never passed upstream (model.py:582-584)")
+        pos = None if pos_embed is None else pos_embed.transpose(0, 1).contiguous()
+        mem, inter = self.forward_bm(src.transpose(0, 1).contiguous(), pos)
+        return mem.transpose(0, 1).contiguous(), (inter.transpose(1, 2).contiguous() if inter is not None else [])
+
+
+class Transformer(nn.Module):
+    """Encoder-decoder transformer (upstream transformer.py:68-155)."""
+
+    def __init__(self, d_model=512, nhead=8, num_encoder_layers=6, num_decoder_layers=6, dim_feedforward=2048,
+                 dropout=0.1, activation="relu", normalize_before=False, return_intermediate_dec=False):
+        super().__init__()
+        self.encoder = TransformerEncoder(
+            lambda: TransformerEncoderLayer(d_model, nhead, dim_feedforward, dropout, activation, normalize_before),
+            num_encoder_layers, None, nn.LayerNorm(d_model), return_intermediate_dec)
+        self.decoder = TransformerDecoder(
+            lambda: TransformerDecoderLayer(d_model, nhead, dim_feedforward, dropout, activation, normalize_before),
+            num_decoder_layers, nn.LayerNorm(d_model), return_intermediate=return_intermediate_dec)
+        _xavier(self)
+        self.d_model = d_model
+        self.nhead = nhead
+
+    def forward_bm(self, src_bm, query_embed, pos_bm, tgt_mask, memory_mask):
+        """src (B,S,d), query_embed (Lq,d) -> hs (L,B,Lq,d), memory (B,S,d), intermediate (Le,B,S,d)."""
+        b = src_bm.shape[0]
+        x = src_bm if pos_bm is None else src_bm + pos_bm
+        memory, inter = self.encoder.forward_bm(x.contiguous(), pos_bm)
+        qpos = query_embed.detach().unsqueeze(0).expand(b, -1, -1).contiguous()
+        tgt = torch.zeros_like(qpos)
+        dev = src_bm.device
+        hs = self.decoder.forward_bm(tgt, memory, pos_bm, qpos, _mask_u8(tgt_mask, dev), _mask_u8(memory_mask, dev))
+        return hs, memory, inter
+
+    def forward(self, src, mask, query_embed, pos_embed, tgt_mask=None, src_mask=None, memory_mask=None):
+        """Upstream layout: src/pos_embed (S,B,d) -> (hs (L,Lq,B,d), memory (S,B,d), intermediate (Le,S,B,d), None).
+
+        The fourth return value (per-layer averaged attention maps upstream) is never consumed by the model
+        (main/model.py:571) and is returned as None instead of materialising Lq x S maps.
+        """
+        _require_inference(self, src)
+        if mask is not None or src_mask is not None:
+            raise NotImplementedError("key-padding / source masks are never passed upstream (model.py:571-581)")
+        pos = None if pos_embed is None else pos_embed.transpose(0, 1).contiguous()
+        hs, memory, inter = self.forward_bm(src.transpose(0, 1).contiguous(), query_embed, pos, tgt_mask, memory_mask)
+        inter_sm = inter.transpose(1, 2).contiguous() if inter is not None else []
+        return hs.transpose(1, 2).contiguous(), memory.transpose(0, 1).contiguous(), inter_sm, None

@@ -1,0 +1,309 @@
+"""Thin torch-tensor wrappers over the C ABI (include/hoisdf_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the current stream; every kernel that runs is one of
+ours, launched through `libhoisdf_b200.so`.  Nothing in this file computes with torch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _capi
+from ._capi import ACT_NONE, ACT_RELU, GATHER_CONCAT, GATHER_SUM, check, lib
+
+ROW_LD = 516          # padded SDF row-buffer pitch (see csrc/sdf.cu)
+DEC_IN = 289
+DEC_IN_PAD = 292
+SKIP_OFF = 292
+H1 = 223
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _f32c(t: torch.Tensor, what: str) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError("%s must be float32, got %s" % (what, t.dtype))
+    if not t.is_cuda:
+        raise RuntimeError("%s must live on a CUDA device: hoisdf_b200 has no CPU path" % what)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+# ----------------------------------------------------------------------------------------------------
+# Linear
+# ----------------------------------------------------------------------------------------------------
+@dataclass
+class PackedLinear:
+    """(N, ldw) fp32 weight with K zero-padded to a multiple of 4, plus bias."""
+    w: torch.Tensor
+    b: Optional[torch.Tensor]
+    n: int
+    k: int        # padded K the kernel contracts over (input rows must expose this many columns)
+    ldw: int
+
+    @staticmethod
+    def pack(weight: torch.Tensor, bias: Optional[torch.Tensor]) -> "PackedLinear":
+        weight = weight.detach()
+        n, k = weight.shape
+        kp = round_up(k, 4)
+        if kp == k and weight.is_contiguous() and weight.dtype == torch.float32 and weight.data_ptr() % 16 == 0:
+            w = weight
+        else:
+            w = torch.zeros(n, kp, device=weight.device, dtype=torch.float32)
+            w[:, :k] = weight
+        b = None if bias is None else bias.detach().to(torch.float32).contiguous()
+        return PackedLinear(w, b, n, kp, kp)
+
+    def cols(self, start: int, stop: int) -> "PackedLinear":
+        """A K-slice W[:, start:stop] (no copy; start must be a multiple of 4). Bias dropped."""
+        assert start % 4 == 0 and (stop - start) % 4 == 0
+        return PackedLinear(self.w[:, start:stop], None, self.n, stop - start, self.ldw)
+
+    def rows(self, start: int, stop: int) -> "PackedLinear":
+        b = None if self.b is None else self.b[start:stop]
+        return PackedLinear(self.w[start:stop], b, stop - start, self.k, self.ldw)
+
+
+def linear_raw(x_ptr: int, ldx: int, m: int, pw: PackedLinear, y_ptr: int, ldy: int, act: int = ACT_NONE,
+               residual_ptr: Optional[int] = None, x_batch=(0, 0), y_batch=(0, 0)):
+    if m == 0:
+        return
+    a = _capi.LinearArgs(
+        x_ptr, ldx, x_batch[0], x_batch[1], pw.w.data_ptr(), pw.ldw, _ptr(pw.b), residual_ptr,
+        y_ptr, ldy, y_batch[0], y_batch[1], m, pw.n, pw.k, act)
+    check(lib.hoisdf_linear_fwd(C.byref(a), _stream()), "hoisdf_linear_fwd")
+
+
+def linear(x: torch.Tensor, pw: PackedLinear, act: int = ACT_NONE, out: Optional[torch.Tensor] = None,
+           residual: Optional[torch.Tensor] = None, out_ld: Optional[int] = None) -> torch.Tensor:
+    """x: (M, >=K) 2-D, unit inner stride.  Returns (M, N) (a view of a (M, out_ld) buffer if padded)."""
+    assert x.dim() == 2 and x.stride(1) == 1 and x.shape[1] >= pw.k, (x.shape, x.stride(), pw.k)
+    m = x.shape[0]
+    if out is None:
+        ld = out_ld or round_up(pw.n, 4)
+        # padded tail columns are zeroed so a following layer can contract over them (times zero weights)
+        alloc = torch.empty if ld == pw.n else torch.zeros
+        buf = alloc(m, ld, device=x.device, dtype=torch.float32)
+        out = buf[:, :pw.n]
+    assert out.stride(1) == 1
+    if residual is not None:
+        assert residual.shape == out.shape and residual.stride() == out.stride()
+    linear_raw(x.data_ptr(), x.stride(0), m, pw, out.data_ptr(), out.stride(0), act, _ptr(residual))
+    return out
+
+
+def fold_weight_norm(g: Optional[torch.Tensor], v: torch.Tensor, cols_out: Optional[int] = None,
+                     src_col: Optional[torch.Tensor] = None) -> torch.Tensor:
+    v = _f32c(v.detach(), "weight_v")
+    rows, cols = v.shape
+    cols_out = cols_out or round_up(cols, 4)
+    out = torch.empty(rows, cols_out, device=v.device, dtype=torch.float32)
+    gg = None if g is None else _f32c(g.detach().reshape(-1), "weight_g")
+    if src_col is None:
+        src_col = torch.arange(cols_out, device=v.device, dtype=torch.int32)
+        src_col[cols:] = -1
+    check(lib.hoisdf_fold_weight_norm(_ptr(gg), v.data_ptr(), rows, cols, out.data_ptr(), cols_out,
+                                      src_col.data_ptr(), cols_out, _stream()), "hoisdf_fold_weight_norm")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# Pyramid / gather
+# ----------------------------------------------------------------------------------------------------
+def to_nhwc(x: torch.Tensor) -> torch.Tensor:
+    """(B,C,H,W) logical NCHW tensor -> (B,H,W,C) contiguous; zero-copy when x is already channels_last."""
+    assert x.dim() == 4 and x.dtype == torch.float32 and x.is_cuda
+    b, c, h, w = x.shape
+    p = x.permute(0, 2, 3, 1)
+    if p.is_contiguous():
+        return p
+    x = x.contiguous()
+    out = torch.empty(b, h, w, c, device=x.device, dtype=torch.float32)
+    check(lib.hoisdf_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), b, c, h, w, _stream()), "hoisdf_nchw_to_nhwc")
+    return out
+
+
+def make_pyramid(maps: Sequence[torch.Tensor], img_hw=(256, 256)) -> _capi.Pyramid:
+    """maps: list of (B,H,W,C) contiguous fp32 tensors."""
+    p = _capi.Pyramid()
+    p.levels = len(maps)
+    p.img_h, p.img_w = int(img_hw[0]), int(img_hw[1])
+    for i, m in enumerate(maps):
+        assert m.is_contiguous() and m.dtype == torch.float32 and m.is_cuda
+        p.map[i] = m.data_ptr()
+        p.h[i], p.w[i], p.c[i] = m.shape[1], m.shape[2], m.shape[3]
+    return p
+
+
+def gather(maps: Sequence[torch.Tensor], uv: torch.Tensor, batch: int, *, mode: int, out: torch.Tensor,
+           row_offsets: Optional[torch.Tensor] = None, rows_per_sample: int = 0,
+           bias: Optional[torch.Tensor] = None, act: int = ACT_NONE, img_hw=(256, 256)):
+    rows = uv.shape[0]
+    assert uv.is_contiguous() and uv.shape[1] == 2 and out.stride(1) == 1
+    pyr = make_pyramid(maps, img_hw)
+    check(lib.hoisdf_gather_fwd(C.byref(pyr), uv.data_ptr(), rows, _ptr(row_offsets), batch, rows_per_sample, mode,
+                                _ptr(bias), act, out.data_ptr(), out.stride(0), _stream()), "hoisdf_gather_fwd")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# Lattice / projection
+# ----------------------------------------------------------------------------------------------------
+def lattice_count(center, cam_intr, bbox, sdf_scale: float, bins: int):
+    b = center.shape[0]
+    chunks = lib.hoisdf_lattice_chunks(bins)
+    counts = torch.empty(b, chunks, device=center.device, dtype=torch.int32)
+    offsets = torch.empty(b + 1, device=center.device, dtype=torch.int64)
+    check(lib.hoisdf_lattice_count(center.data_ptr(), cam_intr.data_ptr(), bbox.data_ptr(), float(sdf_scale), b,
+                                   bins, counts.data_ptr(), offsets.data_ptr(), _stream()), "hoisdf_lattice_count")
+    return counts, offsets
+
+
+def lattice_compact(center, cam_intr, bbox, sdf_scale: float, bins: int, counts, offsets, total: int):
+    b = center.shape[0]
+    cand_index = torch.empty(max(total, 1), device=center.device, dtype=torch.int32)
+    cand_uv = torch.empty(max(total, 1), 2, device=center.device, dtype=torch.float32)
+    check(lib.hoisdf_lattice_compact(center.data_ptr(), cam_intr.data_ptr(), bbox.data_ptr(), float(sdf_scale), b,
+                                     bins, counts.data_ptr(), offsets.data_ptr(), cand_index.data_ptr(),
+                                     cand_uv.data_ptr(), _stream()), "hoisdf_lattice_compact")
+    return cand_index, cand_uv
+
+
+def project_points(points, center, cam_intr, sdf_scale: float, want_cam: bool = True):
+    b, p, _ = points.shape
+    cam = torch.empty(b, p, 3, device=points.device, dtype=torch.float32) if want_cam else None
+    uv = torch.empty(b * p, 2, device=points.device, dtype=torch.float32)
+    check(lib.hoisdf_project_points(points.data_ptr(), center.data_ptr(), cam_intr.data_ptr(), float(sdf_scale), b, p,
+                                    _ptr(cam), uv.data_ptr(), _stream()), "hoisdf_project_points")
+    return cam, uv
+
+
+# ----------------------------------------------------------------------------------------------------
+# SDF decoder
+# ----------------------------------------------------------------------------------------------------
+@dataclass
+class PackedSdfDecoder:
+    tensors: List[torch.Tensor]      # keeps the packed buffers alive
+    struct: _capi.SdfWeights
+
+
+def pack_sdf_decoder(dec_params: dict) -> PackedSdfDecoder:
+    """dec_params: {'linh0.weight_g': ..., 'linh0.weight_v': ..., 'linh0.bias': ..., ..., 'linh4.weight', 'linh4.bias'}.
+
+    Folds weight-norm (upstream sdf_net.py:57-62) and lays linh2's columns out for the padded row buffer:
+    upstream input of linh2 is cat[h1 (223), input (289)]; ours is [input (289), 0 0 0, h1 (223), 0].
+    """
+    dev = dec_params["linh0.weight_v"].device
+    w0 = fold_weight_norm(dec_params["linh0.weight_g"], dec_params["linh0.weight_v"], DEC_IN_PAD)
+    w1 = fold_weight_norm(dec_params["linh1.weight_g"], dec_params["linh1.weight_v"], 512)
+    src = torch.full((ROW_LD,), -1, dtype=torch.int32)
+    src[0:DEC_IN] = torch.arange(H1, H1 + DEC_IN, dtype=torch.int32)
+    src[SKIP_OFF:SKIP_OFF + H1] = torch.arange(0, H1, dtype=torch.int32)
+    w2 = fold_weight_norm(dec_params["linh2.weight_g"], dec_params["linh2.weight_v"], ROW_LD, src.to(dev))
+    w3 = fold_weight_norm(dec_params["linh3.weight_g"], dec_params["linh3.weight_v"], 512)
+    w4 = _f32c(dec_params["linh4.weight"].detach().reshape(-1).clone(), "linh4.weight")
+    bs = [_f32c(dec_params["linh%d.bias" % i].detach().clone(), "bias") for i in range(5)]
+    s = _capi.SdfWeights(w0.data_ptr(), bs[0].data_ptr(), w1.data_ptr(), bs[1].data_ptr(), w2.data_ptr(),
+                         bs[2].data_ptr(), w3.data_ptr(), bs[3].data_ptr(), w4.data_ptr(), bs[4].data_ptr())
+    return PackedSdfDecoder([w0, w1, w2, w3, w4] + bs, s)
+
+
+def posenc(rows_buf: torch.Tensor, *, lattice_index=None, points=None, bins: int = 64):
+    rows = rows_buf.shape[0]
+    check(lib.hoisdf_posenc_fwd(_ptr(lattice_index), _ptr(points), rows, bins, rows_buf.data_ptr(),
+                                rows_buf.stride(0), 256, _stream()), "hoisdf_posenc_fwd")
+
+
+def sdf_decoder(packed: PackedSdfDecoder, rows_buf: torch.Tensor, h_a=None, h_b=None, clamp: float = 0.0,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    rows = rows_buf.shape[0]
+    dev = rows_buf.device
+    h_a = h_a if h_a is not None else torch.empty(rows, 512, device=dev, dtype=torch.float32)
+    h_b = h_b if h_b is not None else torch.empty(rows, 512, device=dev, dtype=torch.float32)
+    out = out if out is not None else torch.empty(rows, device=dev, dtype=torch.float32)
+    check(lib.hoisdf_sdf_decoder_fwd(C.byref(packed.struct), rows_buf.data_ptr(), rows_buf.stride(0), rows,
+                                     h_a.data_ptr(), h_b.data_ptr(), out.data_ptr(), float(clamp), _stream()),
+          "hoisdf_sdf_decoder_fwd")
+    return out
+
+
+def sdf_pad_input(x: torch.Tensor) -> torch.Tensor:
+    x = _f32c(x, "SDFDecoder input")
+    rows = x.shape[0]
+    buf = torch.empty(rows, ROW_LD, device=x.device, dtype=torch.float32)
+    check(lib.hoisdf_sdf_pad_input(x.data_ptr(), rows, buf.data_ptr(), ROW_LD, _stream()), "hoisdf_sdf_pad_input")
+    return buf
+
+
+def select_points(sdf, offsets, cand_index, batch: int, num_points: int, bins: int, clamp: float):
+    dev = sdf.device
+    sel = torch.empty(batch, num_points, device=dev, dtype=torch.int32)
+    pts = torch.empty(batch, num_points, 3, device=dev, dtype=torch.float32)
+    out_sdf = torch.empty(batch, num_points, 1, device=dev, dtype=torch.float32)
+    pe = torch.empty(batch, num_points, 30, device=dev, dtype=torch.float32)
+    flag = torch.zeros(1, device=dev, dtype=torch.int32)
+    check(lib.hoisdf_select_points(sdf.data_ptr(), offsets.data_ptr(), cand_index.data_ptr(),
+                                   batch, num_points, bins, float(clamp), sel.data_ptr(),
+                                   pts.data_ptr(), out_sdf.data_ptr(), pe.data_ptr(), flag.data_ptr(), _stream()),
+          "hoisdf_select_points")
+    return sel, pts, out_sdf, pe, flag
+
+
+def tokens(xyz, pe, fea, sdf, beta, out_tokens: torch.Tensor, t0: int):
+    b, p, _ = xyz.shape
+    assert fea.stride(-1) == 1
+    check(lib.hoisdf_tokens_fwd(xyz.data_ptr(), pe.data_ptr(), fea.data_ptr(), fea.stride(-2), sdf.data_ptr(),
+                                beta.data_ptr(), b, p, out_tokens.data_ptr(), out_tokens.shape[1], t0, _stream()),
+          "hoisdf_tokens_fwd")
+
+
+# ----------------------------------------------------------------------------------------------------
+# Transformer pieces
+# ----------------------------------------------------------------------------------------------------
+def attention(q, ldq, k, v, ldk, out, ldo, batch, heads, lq, lk, kv_valid=None, mask=None):
+    """q/k/v/out are tensors whose data_ptr is the first element of head 0 (may be column-offset views)."""
+    check(lib.hoisdf_attention_fwd(q.data_ptr(), ldq, k.data_ptr(), v.data_ptr(), ldk, out.data_ptr(), ldo, batch,
+                                   heads, lq, lk, lk if kv_valid is None else kv_valid, _ptr(mask), _stream()),
+          "hoisdf_attention_fwd")
+    return out
+
+
+def add_layernorm(x, res, gamma, beta, out=None, gamma2=None, beta2=None, out2=None):
+    rows = x.numel() // x.shape[-1]
+    d = x.shape[-1]
+    out = out if out is not None else torch.empty_like(x)
+    check(lib.hoisdf_add_layernorm_fwd(x.data_ptr(), _ptr(res), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
+                                       _ptr(gamma2), _ptr(beta2), _ptr(out2), rows, d, _stream()),
+          "hoisdf_add_layernorm_fwd")
+    return out
+
+
+def vote_joints(points, off, cls) -> torch.Tensor:
+    """points (B,P,3), off (L,B,P,60), cls (L,B,P,20) contiguous -> (L,B,20,3)."""
+    l, b, p, _ = cls.shape
+    out = torch.empty(l, b, 20, 3, device=cls.device, dtype=torch.float32)
+    check(lib.hoisdf_vote_joints_fwd(points.data_ptr(), off.data_ptr(), cls.data_ptr(), l, b, p, out.data_ptr(),
+                                     _stream()), "hoisdf_vote_joints_fwd")
+    return out
+
+
+def mano(model_struct, pose6d, betas):
+    """pose6d (N,16,6), betas (N,10) contiguous -> verts (N,778,3), joints (N,21,3) [m]."""
+    n = pose6d.shape[0]
+    verts = torch.empty(n, 778, 3, device=pose6d.device, dtype=torch.float32)
+    joints = torch.empty(n, 21, 3, device=pose6d.device, dtype=torch.float32)
+    check(lib.hoisdf_mano_fwd(C.byref(model_struct), pose6d.data_ptr(), betas.data_ptr(), n, verts.data_ptr(),
+                              joints.data_ptr(), _stream()), "hoisdf_mano_fwd")
+    return verts, joints

@@ -1,0 +1,219 @@
+/*
+ * hoisdf_b200 -- C ABI of the B200-native (sm_100a) HOISDF hot path.
+ *
+ * The upstream project (amathislab/HOISDF) has no FFI layer: its operator surface is the Python code
+ * in main/model.py and common/nets/*.  Each entry point below replaces the stock-PyTorch call sites
+ * of one upstream operator (cited per function); `hoisdf_b200/` binds them with ctypes and re-exposes
+ * the upstream signatures (see INTEGRATION.md for the binding a maintainer would add upstream).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 unless stated otherwise; the caller owns all buffers
+ *     (inputs, outputs, workspaces); the library allocates nothing and keeps no pointer after return;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no internal synchronisation,
+ *     no host read-back;
+ *   - sizes are int64_t, leading dimensions are in ELEMENTS;
+ *   - return value: 0 = ok, negative = HOISDF_E_* (bad argument), positive = cudaError_t observed after
+ *     the launch.  Nothing throws or exits across the boundary.
+ */
+#ifndef HOISDF_B200_H
+#define HOISDF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HOISDF_ABI_VERSION 1
+
+enum {
+  HOISDF_OK = 0,
+  HOISDF_E_NULL = -1,      /* required pointer is NULL */
+  HOISDF_E_SHAPE = -2,     /* size out of the supported range */
+  HOISDF_E_ALIGN = -3,     /* pointer or leading dimension not 16-byte aligned */
+  HOISDF_E_UNSUPPORTED = -4
+};
+
+enum { HOISDF_ACT_NONE = 0, HOISDF_ACT_RELU = 1 };
+
+int hoisdf_abi_version(void);
+const char* hoisdf_status_string(int status);
+
+/* ---------------------------------------------------------------------------------------------------
+ * nn.Linear (+ReLU) over rows -- upstream common/nets/layer.py:192-201 (MLP.forward), every
+ * `nn.Linear` of common/nets/sdf_net.py:95-107 and common/nets/transformer.py:294-299,378-392.
+ *   Y[r, 0:N] = act( X[r, 0:K] . W[0:N, 0:K]^T + bias ) (+ residual[r, 0:N])
+ * Rows may be "batched": row r lives at  base + (r / rows_per_batch) * batch_stride + (r % rows_per_batch) * ld
+ * (rows_per_batch = 0 means plain `base + r * ld`).  K, ldx, ldw must be multiples of 4 and X, W 16-byte
+ * aligned; columns K..ldw of W are never read.  `residual` (optional) shares Y's addressing.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* x; int64_t ldx; int64_t x_rows_per_batch; int64_t x_batch_stride;
+  const float* w; int64_t ldw;
+  const float* bias;                 /* may be NULL */
+  const float* residual;             /* may be NULL */
+  float* y; int64_t ldy; int64_t y_rows_per_batch; int64_t y_batch_stride;
+  int64_t m; int64_t n; int64_t k;
+  int32_t act;
+} hoisdf_linear_args;
+
+int hoisdf_linear_fwd(const hoisdf_linear_args* args, void* stream);
+
+/* nn.utils.weight_norm(dim=0) fold  W = g * v / ||v||_row  (upstream common/nets/sdf_net.py:57-62),
+ * written into a (rows, ld_out) matrix at column offset 0; optional column permutation `src_col`
+ * (int32[cols_out], -1 = write 0) lets the caller lay the skip-concat layer out for the padded
+ * activation layout used by hoisdf_sdf_decoder_fwd. g may be NULL (plain copy/permutation of v). */
+int hoisdf_fold_weight_norm(const float* g, const float* v, int64_t rows, int64_t cols, float* out,
+                            int64_t ld_out, const int32_t* src_col, int64_t cols_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Layout: NCHW -> NHWC copy of one pyramid level (upstream keeps NCHW: common/nets/module.py:172-218).
+ * ------------------------------------------------------------------------------------------------- */
+int hoisdf_nchw_to_nhwc(const float* src, float* dst, int64_t n, int64_t c, int64_t h, int64_t w, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * sdf_infer candidate generation -- upstream main/model.py:257-302: the sheared 64^3 lattice,
+ * p_cam = s / sdf_scale + center, pinhole projection with K, STRICT bbox test, stable compaction.
+ * Bit-exact with the upstream CPU arithmetic (separately rounded mul/add, IEEE division, fma chain of
+ * the 3-term dot products).
+ *   center (B,3), cam_intr (B,3,3), bbox (B,4) xyxy.
+ * Pass 1 (`_count`): chunk_counts int32 (B, hoisdf_lattice_chunks(bins)) -- per-1024-index chunk counts, turned in
+ * place into exclusive global row offsets; offsets int64 (B+1) exclusive prefix of the per-sample N_f.
+ * The caller reads offsets[B] (total rows) to size the row buffers, then pass 2 (`_compact`) writes
+ *   cand_index int32 (M)   lattice index of every surviving point, sample-major, ascending
+ *   cand_uv    fp32  (M,2) its projection in pixels
+ * ------------------------------------------------------------------------------------------------- */
+int hoisdf_lattice_chunks(int32_t bins);
+int hoisdf_lattice_count(const float* center, const float* cam_intr, const float* bbox, float sdf_scale,
+                         int64_t batch, int32_t bins, int32_t* chunk_counts, int64_t* offsets, void* stream);
+int hoisdf_lattice_compact(const float* center, const float* cam_intr, const float* bbox, float sdf_scale,
+                           int64_t batch, int32_t bins, const int32_t* chunk_counts, const int64_t* offsets,
+                           int32_t* cand_index, float* cand_uv, void* stream);
+
+/* Pinhole projection of given points -- upstream main/model.py:148-150 / 190-192.
+ *   points (B,P,3) normalised coords -> cam (B,P,3) = points/scale + center, uv (B,P,2) */
+int hoisdf_project_points(const float* points, const float* center, const float* cam_intr, float sdf_scale,
+                          int64_t batch, int64_t p, float* cam, float* uv, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Multi-scale bilinear gather -- upstream F.grid_sample(bilinear, border, align_corners=True) x5 + cat
+ * (main/model.py:164-175, 203-214, 316-328).  Maps are NHWC.  Pixel coords use the IMAGE size for every
+ * level: g = (uv - (img-1)/2) / ((img-1)/2), x = (g + 1)/2 * (W_l - 1), clamped to [0, W_l - 1].
+ * mode CONCAT: out[r, off_l : off_l + C_l] = sample of level l  (the (N, C) matrix upstream feeds its MLPs)
+ * mode SUM   : out[r, 0:C] = act(bias + sum_l sample of level l) (all levels carry C channels; used with
+ *              the per-level projected maps  G_l = F_l . W0_l^T , which is linear_sdfin layer 0 applied
+ *              before instead of after the interpolation -- bilinear sampling is linear)
+ * Row r belongs to sample  b = (row_offsets ? upper_bound(row_offsets, r) - 1 : r / rows_per_sample).
+ * ------------------------------------------------------------------------------------------------- */
+enum { HOISDF_GATHER_CONCAT = 0, HOISDF_GATHER_SUM = 1 };
+typedef struct {
+  const float* map[5];  /* NHWC (B, H_l, W_l, C_l) */
+  int32_t c[5]; int32_t h[5]; int32_t w[5];
+  int32_t levels;
+  int32_t img_h, img_w;
+} hoisdf_pyramid;
+
+int hoisdf_gather_fwd(const hoisdf_pyramid* pyr, const float* uv, int64_t rows, const int64_t* row_offsets,
+                      int64_t batch, int64_t rows_per_sample, int32_t mode, const float* bias, int32_t act,
+                      float* out, int64_t ld_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * SDF decoder input tail: NeRF embedding (upstream common/utils/sdf_utils.py:96-141, 5 octaves, sin then
+ * cos per octave) and xyz written at columns [col0, col0+36) of the row buffer: 30 posenc, 3 xyz, 3 zero.
+ * Points come either from lattice indices (sdf_infer) or from an explicit (rows,3) array.
+ * ------------------------------------------------------------------------------------------------- */
+int hoisdf_posenc_fwd(const int32_t* lattice_index, const float* points, int64_t rows, int32_t bins,
+                      float* out, int64_t ld_out, int64_t col0, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * SDFDecoder.forward -- upstream common/nets/sdf_net.py:87-122 (eval: dropout off):
+ *   289 -> 512 -> 223 (+289 skip) -> 512 -> 512 -> 1, ReLU after layers 0..3, tanh.
+ * x is the padded row buffer (rows, ldx>=516): cols [0,289) decoder input, [289,292) zero,
+ * [292,515) scratch for relu(linh1), col 515 zero.  Weights are packed by hoisdf_fold_weight_norm:
+ *   w0 (512,292), w1 (223,512), w2 (512,516) [skip-permuted], w3 (512,512), w4 (512).
+ * h_a, h_b: two (rows,512) scratch buffers.  out_sdf (rows): tanh output, clamped to +-clamp when clamp > 0
+ * (upstream main/model.py:241; sdf_infer clamps after the selection instead, model.py:354).
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* w0; const float* b0;
+  const float* w1; const float* b1;
+  const float* w2; const float* b2;
+  const float* w3; const float* b3;
+  const float* w4; const float* b4;
+} hoisdf_sdf_weights;
+
+int hoisdf_sdf_decoder_fwd(const hoisdf_sdf_weights* wts, float* x, int64_t ldx, int64_t rows, float* h_a,
+                           float* h_b, float* out_sdf, float clamp, void* stream);
+
+/* Expand a plain (rows, 289) decoder input (the upstream SDFDecoder.forward argument) into the padded
+ * row buffer layout above. */
+int hoisdf_sdf_pad_input(const float* in, int64_t rows, float* x, int64_t ldx, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Near-surface point selection -- upstream main/model.py:345-354: per sample, the `num_points` rows with
+ * the smallest |sdf| in ascending order (ties: lower row first), then gather of lattice coords, posenc
+ * and the clamped SDF value.
+ *   sdf (M) raw decoder output, offsets int64 (B+1), cand_index int32 (M)
+ *   -> sel_index int32 (B,P) lattice indices, points (B,P,3), out_sdf (B,P) clamped to +-clamp,
+ *      posenc (B,P,30).  Samples with fewer than P candidates set *status_flag (int32, device) to 1.
+ * ------------------------------------------------------------------------------------------------- */
+int hoisdf_select_points(const float* sdf, const int64_t* offsets, const int32_t* cand_index,
+                         int64_t batch, int64_t num_points, int32_t bins, float clamp,
+                         int32_t* sel_index, float* points, float* out_sdf, float* posenc,
+                         int32_t* status_flag, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Token assembly -- upstream main/model.py:123-126 (sdf_activation) + :520-562:
+ *   tokens[b, t, :] = cat[ xyz (3), posenc (30), fea (223) * sigmoid(sdf/beta)/beta ]
+ * written batch-major (B, S, 256) at token offset t0 .. t0+P.  beta is a device scalar (already floored).
+ * ------------------------------------------------------------------------------------------------- */
+int hoisdf_tokens_fwd(const float* xyz, const float* posenc, const float* fea, int64_t ld_fea, const float* sdf,
+                      const float* beta, int64_t batch, int64_t p, float* tokens, int64_t s_total, int64_t t0,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Multi-head attention core -- upstream nn.MultiheadAttention inside common/nets/transformer.py:294,378,383.
+ *   q (B, Lq, ldq) , k/v (B, Lk, ldk) batch-major with heads as contiguous 64-wide column slices;
+ *   out (B, Lq, ldo).  scores = q.k^T / sqrt(64); keys >= kv_valid are masked (memory_mask of
+ *   common/utils/misc.py:42-47); optional dense bool mask (Lq, Lk) uint8, 1 = blocked (misc.py:11-31).
+ *   Streaming (flash-style) softmax: the Lq x Lk score matrix is never materialised.
+ * ------------------------------------------------------------------------------------------------- */
+int hoisdf_attention_fwd(const float* q, int64_t ldq, const float* k, const float* v, int64_t ldk, float* out,
+                         int64_t ldo, int64_t batch, int64_t heads, int64_t lq, int64_t lk, int64_t kv_valid,
+                         const uint8_t* mask, void* stream);
+
+/* y = LayerNorm(x (+ res)) * gamma + beta, eps 1e-5, rows of 256 (transformer.py:296-301); optional second
+ * output y2 = LayerNorm(y) with (gamma2, beta2) -- the shared `inter_norm` of transformer.py:196-197. */
+int hoisdf_add_layernorm_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* y,
+                             const float* gamma2, const float* beta2, float* y2, int64_t rows, int64_t d,
+                             void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Joint voting -- upstream common/nets/loss.py:31-36,54-57 (the part of JointvoteLoss that produces
+ * `hand_joints`): softmax over points of the class logits, weighted sum of point + offset.
+ *   points (B,P,3), off (L,B,P,60), cls (L,B,P,20) batch-major -> joints (L,B,20,3)
+ * ------------------------------------------------------------------------------------------------- */
+int hoisdf_vote_joints_fwd(const float* points, const float* off, const float* cls, int64_t layers,
+                           int64_t batch, int64_t p, float* joints, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * ManoHead + ManoLayer -- upstream common/nets/mano_head.py:185-256 and
+ * manopth/manopth/manolayer.py:111-276 (axis-angle, flat hand mean, centre on joint 0, right hand):
+ *   pose6d (N,16,6), betas (N,10) -> verts (N,778,3), joints (N,21,3) in metres.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* shapedirs;   /* (778,3,10) */
+  const float* posedirs;    /* (778,3,135) */
+  const float* v_template;  /* (778,3) */
+  const float* j_regressor; /* (16,778) */
+  const float* weights;     /* (778,16) */
+  const float* hands_mean;  /* (45) */
+} hoisdf_mano_model;
+
+int hoisdf_mano_fwd(const hoisdf_mano_model* model, const float* pose6d, const float* betas, int64_t n,
+                    float* verts, float* joints, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HOISDF_B200_H */

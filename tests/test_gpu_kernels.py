@@ -1,0 +1,310 @@
+"""Stage-isolated parity of every hoisdf_b200 kernel against the CPU oracle (oracle/hoisdf_oracle.py), called
+through the C ABI.  Bit-exact for index/mask work, fp32 tolerances (stated per test) for the arithmetic."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from hoisdf_b200 import synthetic as syn
+from oracle import hoisdf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return float((a - b).abs().max() / max(b.abs().max(), 1e-30))
+
+
+def rnd(seed, *shape, lo=-1.0, hi=1.0):
+    g = np.random.Generator(np.random.PCG64(seed))
+    return torch.from_numpy((g.random(size=shape, dtype=np.float32) * (hi - lo) + lo).astype(np.float32))
+
+
+# ---------------------------------------------------------------- linear
+@pytest.mark.parametrize("m,n,k", [(1, 1, 4), (127, 60, 256), (128, 128, 16), (333, 223, 512), (1000, 512, 292),
+                                   (257, 1024, 3968), (64, 3, 256), (513, 768, 256)])
+@pytest.mark.parametrize("act", [0, 1])
+def test_linear_matches_fp64(cuda, m, n, k, act):
+    from hoisdf_b200 import ops
+    x, w, b = rnd(1, m, k), rnd(2, n, k, lo=-0.1, hi=0.1), rnd(3, n)
+    res = rnd(4, m, ops.round_up(n, 4))[:, :n]
+    pw = ops.PackedLinear.pack(w.to(cuda), b.to(cuda))
+    y = ops.linear(x.to(cuda), pw, act)
+    ref = x.double() @ w.double().T + b.double()
+    if act:
+        ref = ref.relu()
+    assert rel_err(y, ref) < 2e-6          # fp32 FMA accumulation over K <= 3968
+    # with fused residual (same pitch as the output)
+    resd = res.to(cuda)
+    out = torch.zeros(m, ops.round_up(n, 4), device=cuda)[:, :n]
+    resd_p = torch.zeros(m, ops.round_up(n, 4), device=cuda)
+    resd_p[:, :n] = resd
+    y2 = ops.linear(x.to(cuda), pw, 0, out=out, residual=resd_p[:, :n])
+    ref2 = x.double() @ w.double().T + b.double() + res.double()
+    assert rel_err(y2, ref2) < 2e-6
+
+
+def test_linear_batched_rows_and_errors(cuda):
+    from hoisdf_b200 import ops, _capi
+    L, T, P, d = 3, 10, 7, 256
+    x = rnd(5, L, T, d).to(cuda)
+    w, b = rnd(6, 20, d, lo=-0.1, hi=0.1), rnd(7, 20)
+    pw = ops.PackedLinear.pack(w.to(cuda), b.to(cuda))
+    y = torch.empty(L * P, 20, device=cuda)
+    ops.linear_raw(x.data_ptr() + 2 * d * 4, d, L * P, pw, y.data_ptr(), 20, 0, None, x_batch=(P, T * d))
+    ref = x[:, 2:2 + P].reshape(-1, d).cpu().double() @ w.double().T + b.double()
+    assert rel_err(y, ref) < 2e-6
+    # error convention: misaligned K -> HOISDF_E_ALIGN (-3), raised as HoisdfError by the binding
+    bad = ops.PackedLinear(pw.w, pw.b, 20, 254, 256)
+    with pytest.raises(_capi.HoisdfError):
+        ops.linear_raw(x.data_ptr(), d, 4, bad, y.data_ptr(), 20)
+
+
+def test_fold_weight_norm(cuda):
+    from hoisdf_b200 import ops
+    v, g = rnd(8, 223, 512), rnd(9, 223, 1, lo=0.5, hi=1.5)
+    w = ops.fold_weight_norm(g.to(cuda), v.to(cuda))
+    assert rel_err(w, O.fold_weight_norm(g, v)) < 1e-6
+
+
+# ---------------------------------------------------------------- lattice (bit-exact)
+def test_lattice_candidates_bit_exact(cuda):
+    from hoisdf_b200 import ops
+    B = 6
+    meta = syn.camera_meta(11, B)
+    samples = O.lattice(64)
+    for key_c, key_b in (("mano_root", "bbox_hand"), ("obj_center_cam", "bbox_obj")):
+        c, K, bb = meta[key_c], meta["cam_intr"], meta[key_b]
+        counts, offsets = ops.lattice_count(c.to(cuda), K.to(cuda), bb.to(cuda), 3.1, 64)
+        total = int(offsets[-1])
+        idx, uv = ops.lattice_compact(c.to(cuda), K.to(cuda), bb.to(cuda), 3.1, 64, counts, offsets, total)
+        offs = offsets.cpu()
+        all_idx = torch.arange(64 ** 3)
+        for b in range(B):
+            m, ouv = O.candidate_mask(samples, c[b], K[b], bb[b], 3.1)
+            got = idx[offs[b]:offs[b + 1]].cpu().long()
+            assert torch.equal(got, all_idx[m]), "candidate index mask differs for sample %d" % b
+            assert torch.equal(uv[offs[b]:offs[b + 1]].cpu(), ouv[m]), "projected uv not bit-identical"
+
+
+def test_lattice_known_answers(cuda):
+    """the lattice is sheared -- samples[1] = (2.4414e-4*2/63-1 ...); column maxima 1.0317/1.03125/1."""
+    from hoisdf_b200 import ops
+    s = O.lattice(64)
+    assert abs(float(s[:, 0].max()) - 1.0317) < 1e-3 and abs(float(s[:, 1].max()) - 1.03125) < 1e-4
+    # device lattice == oracle lattice, bit for bit, through the posenc kernel's xyz columns
+    idx = torch.arange(0, 64 ** 3, 37, dtype=torch.int32, device=cuda)
+    rows = torch.zeros(idx.numel(), ops.ROW_LD, device=cuda)
+    ops.posenc(rows, lattice_index=idx, bins=64)
+    assert torch.equal(rows[:, 286:289].cpu(), s[idx.cpu().long()])
+    pe = O.nerf_embed(s[idx.cpu().long()])
+    assert (rows[:, 256:286].cpu() - pe).abs().max() < 2e-6     # sinf/cosf vs ATen CPU: <= 2 ulp near 1
+    assert float(rows[:, 289:292].abs().max()) == 0.0 and float(rows[:, 515].abs().max()) == 0.0
+
+
+def test_project_points(cuda):
+    from hoisdf_b200 import ops
+    B, P = 3, 50
+    meta = syn.camera_meta(12, B)
+    pts = rnd(13, B, P, 3)
+    cam, uv = ops.project_points(pts.to(cuda), meta["mano_root"].to(cuda), meta["cam_intr"].to(cuda), 3.1)
+    ocam = pts / 3.1 + meta["mano_root"][:, None]
+    ouv = O.project(ocam, meta["cam_intr"])
+    assert torch.equal(cam.cpu(), ocam)
+    assert (uv.cpu().view(B, P, 2) - ouv).abs().max() < 1e-3   # pixels; bmm accumulation order is unspecified
+
+
+# ---------------------------------------------------------------- gather
+@pytest.mark.parametrize("arch", ["dexycb", "ho3d"])
+def test_gather_concat_matches_grid_sample(cuda, arch):
+    from hoisdf_b200 import ops
+    B, P = 2, 300
+    pyr = syn.feature_pyramid(21, B, arch)
+    uv = rnd(22, B, P, 2, lo=-20.0, hi=275.0)      # includes out-of-image projections (border padding)
+    uv[0, 0] = torch.tensor([0.0, 255.0]); uv[0, 1] = torch.tensor([255.0, 0.0]); uv[0, 2] = torch.tensor([127.5, 127.5])
+    cfg = O.default_cfg()
+    ref = O.gather_pyramid(pyr, O.grid_from_uv(uv, cfg))
+    maps = [ops.to_nhwc(pyr[n].to(cuda)) for n in O.LEVELS]
+    C = sum(m.shape[3] for m in maps)
+    out = torch.empty(B * P, C, device=cuda)
+    ops.gather(maps, uv.view(-1, 2).to(cuda).contiguous(), B, mode=ops.GATHER_CONCAT, out=out, rows_per_sample=P)
+    assert (out.cpu().view(B, P, C) - ref).abs().max() < 5e-6
+    # channels_last input is consumed zero-copy
+    cl = pyr["stride4"].to(cuda).contiguous(memory_format=torch.channels_last)
+    assert ops.to_nhwc(cl).data_ptr() == cl.data_ptr()
+
+
+def test_gather_sum_is_projected_linear(cuda):
+    """SUM mode over per-level projected maps == linear_sdfin layer 0 applied after the upstream gather."""
+    from hoisdf_b200 import ops
+    B, P, arch = 2, 257, "dexycb"
+    pyr = syn.feature_pyramid(23, B, arch)
+    C = syn.multiscale_dim(arch)
+    w, bias = rnd(24, 512, C, lo=-0.03, hi=0.03), rnd(25, 512)
+    uv = rnd(26, B, P, 2, lo=0.0, hi=255.0)
+    cfg = O.default_cfg()
+    feats = O.gather_pyramid(pyr, O.grid_from_uv(uv, cfg))
+    ref = F.relu(feats.double() @ w.double().T + bias.double())
+    maps = [ops.to_nhwc(pyr[n].to(cuda)) for n in O.LEVELS]
+    pw = ops.PackedLinear.pack(w.to(cuda), bias.to(cuda))
+    gm, off = [], 0
+    for m in maps:
+        b, h, ww, c = m.shape
+        g = torch.empty(b, h, ww, 512, device=cuda)
+        ops.linear(m.view(-1, c), pw.cols(off, off + c), 0, out=g.view(-1, 512))
+        gm.append(g); off += c
+    out = torch.empty(B * P, 512, device=cuda)
+    uv2 = uv.view(-1, 2).to(cuda).contiguous()
+    ops.gather(gm, uv2, B, mode=ops.GATHER_SUM, out=out, rows_per_sample=P, bias=pw.b, act=1)
+    assert rel_err(out.view(B, P, 512), ref) < 3e-6
+    # ragged rows through row_offsets: sample 0 owns the first 100 rows, sample 1 all the others
+    n0 = 100
+    offsets = torch.tensor([0, n0, B * P], dtype=torch.int64, device=cuda)
+    ops.gather(gm, uv2, B, mode=ops.GATHER_SUM, out=out, row_offsets=offsets, bias=pw.b, act=1)
+    flat = uv.view(1, -1, 2)
+    f0 = O.gather_pyramid(pyr, O.grid_from_uv(flat[:, :n0], cfg), sample=0)[0]
+    f1 = O.gather_pyramid(pyr, O.grid_from_uv(flat[:, n0:], cfg), sample=1)[0]
+    ref2 = F.relu(torch.cat([f0, f1]).double() @ w.double().T + bias.double())
+    assert rel_err(out, ref2) < 3e-6
+
+
+# ---------------------------------------------------------------- SDF decoder
+def test_sdf_decoder_matches_oracle(cuda):
+    from hoisdf_b200.nets.sdf_net import SDFDecoder
+    sd = syn.hot_path_state_dict(31, "dexycb")
+    dec = SDFDecoder(256, 33).to(cuda).eval()
+    dec.load_state_dict({k[len("hand_sdf_decoder."):]: v for k, v in sd.items() if k.startswith("hand_sdf_decoder.")})
+    x = rnd(32, 1000, 289)
+    with torch.no_grad():
+        got, _ = dec(x.to(cuda))
+    ref = O.sdf_decoder(sd, "hand_sdf_decoder", x)
+    assert got.shape == (1000, 1)
+    assert (got.cpu() - ref).abs().max() < 2e-6      # |sdf| < 1; fp32 accumulation-order differences only
+
+
+# ---------------------------------------------------------------- selection (bit-exact)
+@pytest.mark.parametrize("P", [1, 37, 600, 4096])
+def test_select_points_bit_exact(cuda, P):
+    from hoisdf_b200 import ops
+    B = 3
+    n_f = [5000, P, 70000]
+    g = np.random.Generator(np.random.PCG64(41 + P))
+    sdf = torch.from_numpy(np.tanh(g.standard_normal(sum(n_f)).astype(np.float32) * 0.05))
+    sdf[10] = sdf[20]                                  # a tie: lower row must win
+    offsets = torch.tensor(np.concatenate([[0], np.cumsum(n_f)]), dtype=torch.int64)
+    cand = torch.cat([torch.sort(torch.from_numpy(g.choice(64 ** 3, n, replace=False)))[0] for n in n_f]).int()
+    sel, pts, osdf, pe, flag = ops.select_points(sdf.to(cuda), offsets.to(cuda), cand.to(cuda), B, P, 64, 0.15)
+    assert int(flag) == 0
+    lat = O.lattice(64)
+    for b in range(B):
+        s = sdf[offsets[b]:offsets[b + 1]]
+        order = torch.sort(s.abs(), stable=True)[1][:P]
+        want = cand[offsets[b]:offsets[b + 1]][order].long()
+        assert torch.equal(sel[b].cpu().long(), want)
+        assert torch.equal(pts[b].cpu(), lat[want])
+        assert torch.equal(osdf[b, :, 0].cpu(), s[order].clamp(-0.15, 0.15))
+        assert (pe[b].cpu() - O.nerf_embed(lat[want])).abs().max() < 2e-6
+    # too few candidates -> flag, like the upstream shape-mismatch failure (model.py:348)
+    if P + 1 <= 4096:
+        _, _, _, _, flag = ops.select_points(sdf.to(cuda), offsets.to(cuda), cand.to(cuda), B, P + 1, 64, 0.15)
+        assert int(flag) == 1
+
+
+# ---------------------------------------------------------------- attention / layernorm / transformer layers
+@pytest.mark.parametrize("S", [64, 200, 801])
+def test_attention_flash_matches_softmax(cuda, S):
+    from hoisdf_b200 import ops
+    B, H, d = 2, 4, 256
+    qkv = rnd(51, B, S, 3 * d).to(cuda)
+    out = torch.empty(B * S, d, device=cuda)
+    q2 = qkv.view(B * S, 3 * d)
+    ops.attention(q2, 3 * d, q2[:, d:], q2[:, 2 * d:], 3 * d, out, d, B, H, S, S)
+    q, k, v = [t.cpu().double().view(B, S, H, 64).transpose(1, 2) for t in qkv.split(d, dim=2)]
+    ref = torch.softmax(q @ k.transpose(-1, -2) / 8.0, -1) @ v
+    ref = ref.transpose(1, 2).reshape(B, S, d)
+    assert rel_err(out.view(B, S, d), ref) < 2e-6
+
+
+def test_attention_small_masks(cuda):
+    from hoisdf_b200 import ops
+    B, H, d, Lq, S, valid = 2, 4, 256, 17, 150, 90
+    q, kv = rnd(52, B, Lq, d).to(cuda), rnd(53, B, S, 2 * d).to(cuda)
+    mask = torch.zeros(Lq, S, dtype=torch.bool); mask[:, valid:] = True; mask[3, 5] = True
+    out = torch.empty(B * Lq, d, device=cuda)
+    kv2 = kv.view(B * S, 2 * d)
+    ops.attention(q.view(-1, d), d, kv2, kv2[:, d:], 2 * d, out, d, B, H, Lq, S, mask=mask.to(cuda).to(torch.uint8))
+    qq = q.cpu().double().view(B, Lq, H, 64).transpose(1, 2)
+    kk = kv[..., :d].cpu().double().view(B, S, H, 64).transpose(1, 2)
+    vv = kv[..., d:].cpu().double().view(B, S, H, 64).transpose(1, 2)
+    sc = (qq @ kk.transpose(-1, -2) / 8.0).masked_fill(mask, float("-inf"))
+    ref = (torch.softmax(sc, -1) @ vv).transpose(1, 2).reshape(B, Lq, d)
+    assert rel_err(out.view(B, Lq, d), ref) < 2e-6
+
+
+def test_add_layernorm(cuda):
+    from hoisdf_b200 import ops
+    x, r = rnd(54, 1001, 256), rnd(55, 1001, 256)
+    g, b, g2, b2 = rnd(56, 256), rnd(57, 256), rnd(58, 256), rnd(59, 256)
+    y2 = torch.empty(1001, 256, device=cuda)
+    y = ops.add_layernorm(x.to(cuda), r.to(cuda), g.to(cuda), b.to(cuda), gamma2=g2.to(cuda), beta2=b2.to(cuda), out2=y2)
+    ref = F.layer_norm((x + r).double(), (256,), g.double(), b.double(), 1e-5)
+    ref2 = F.layer_norm(ref, (256,), g2.double(), b2.double(), 1e-5)
+    assert rel_err(y, ref) < 2e-6 and rel_err(y2, ref2) < 2e-6
+
+
+def _load_prefix(module, sd, prefix):
+    module.load_state_dict({k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}, strict=True)
+
+
+def test_transformer_matches_oracle(cuda):
+    from hoisdf_b200.config import cfg
+    from hoisdf_b200.nets.transformer import Transformer, VoteTransformer
+    from hoisdf_b200.utils.misc import get_mano_memory_mask, get_mano_tgt_mask
+    sd = syn.hot_path_state_dict(61, "dexycb")
+    ocfg = O.default_cfg(num_samp_hand=70, num_samp_obj=30)
+    old = (cfg.num_samp_hand, cfg.num_samp_obj)
+    type(cfg).num_samp_hand, type(cfg).num_samp_obj = 70, 30
+    try:
+        S, B = 100, 2
+        src = rnd(62, S, B, 256)
+        tr = Transformer(256, 4, 6, 4, 1024, 0.1, "relu", False, True).to(cuda).eval()
+        _load_prefix(tr, sd, "hand_transformer.")
+        with torch.no_grad():
+            hs, mem, inter, attn = tr(src.to(cuda), None, sd["mano_query_embed.weight"].to(cuda), None,
+                                      tgt_mask=get_mano_tgt_mask().to(cuda), memory_mask=get_mano_memory_mask().to(cuda))
+        ohs, omem, ointer = O.transformer(sd, "hand_transformer", src, sd["mano_query_embed.weight"],
+                                          torch.zeros_like(src), O.mano_tgt_mask(ocfg), O.mano_memory_mask(ocfg), ocfg)
+        assert attn is None and hs.shape == ohs.shape and inter.shape == ointer.shape
+        assert rel_err(mem, omem) < 2e-5 and rel_err(inter, ointer) < 2e-5 and rel_err(hs, ohs) < 2e-5
+        # non-zero positional embedding path
+        pos = rnd(63, S, B, 256) * 0.1
+        vt = VoteTransformer(256, 4, 3, 1024, 0.1, "relu", False, True).to(cuda).eval()
+        _load_prefix(vt, sd, "obj_transformer.")
+        with torch.no_grad():
+            m2, i2 = vt(src.to(cuda), None, pos.to(cuda))
+        om2, oi2 = O.vote_transformer(sd, "obj_transformer", src, pos, ocfg)
+        assert rel_err(m2, om2) < 2e-5 and rel_err(i2, oi2) < 2e-5
+    finally:
+        type(cfg).num_samp_hand, type(cfg).num_samp_obj = old
+
+
+# ---------------------------------------------------------------- heads
+def test_vote_and_mano(cuda):
+    from hoisdf_b200 import ops
+    from hoisdf_b200.nets.mano_head import ManoHead, ManoLayer
+    L, B, P = 3, 2, 333
+    pts, off, cls = rnd(71, B, P, 3, lo=-0.1, hi=0.1), rnd(72, L, B, P, 60, lo=-0.05, hi=0.05), rnd(73, L, B, P, 20, lo=-3, hi=3)
+    got = ops.vote_joints(pts.to(cuda), off.to(cuda), cls.to(cuda))
+    ref = O.vote_joints(pts, off.permute(0, 2, 1, 3), cls.permute(0, 2, 1, 3))
+    assert rel_err(got, ref) < 2e-6
+    sd = syn.hot_path_state_dict(74, "dexycb")
+    head = ManoHead(ManoLayer.from_buffers(syn.mano_buffers(74))).to(cuda)
+    pose6d, shape = rnd(75, L, 16, B, 6), rnd(76, L, B, 10, lo=-2, hi=2)
+    pose6d[0, 3, 0] = torch.tensor([1.0, 0, 0, 0, 1.0, 0])       # identity rotation -> the NaN->0 branch
+    res, _ = head(pose6d.to(cuda), shape.to(cuda))
+    overts, ojoints = O.mano_head(sd, pose6d, shape)
+    assert (res["verts3d"].cpu() - overts).abs().max() < 2e-6    # metres; hand extent ~0.2
+    assert (res["joints3d"].cpu() - ojoints).abs().max() < 2e-6
