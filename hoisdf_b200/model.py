@@ -160,7 +160,7 @@ class Model(nn.Module):
         ops.posenc(rows, points=pts.view(b * p, 3), bins=cfg.bins_n)
         dec = self.hand_sdf_decoder if type == "hand" else self.obj_sdf_decoder
         sdf = ops.sdf_decoder(dec.packed(), rows, h_a=h, clamp=cfg.ClampingDistance)
-        pe = rows[:, 256:286].reshape(b, p, 30)
+        pe = rows[:, 256:286].contiguous().view(b, p, 30)
         return sdf.view(b, p, 1), (None if not cfg.ClassifierBranch else None), pe
 
     def plan_candidates(self, center_joint, cam_intr, bbox, sdf_scale) -> CandidatePlan:

@@ -263,7 +263,8 @@ def select_points(sdf, offsets, cand_index, batch: int, num_points: int, bins: i
 
 def tokens(xyz, pe, fea, sdf, beta, out_tokens: torch.Tensor, t0: int):
     b, p, _ = xyz.shape
-    assert fea.stride(-1) == 1
+    assert xyz.is_contiguous() and pe.is_contiguous() and sdf.is_contiguous() and out_tokens.is_contiguous()
+    assert fea.stride(-1) == 1 and fea.stride(0) == p * fea.stride(-2)
     check(lib.hoisdf_tokens_fwd(xyz.data_ptr(), pe.data_ptr(), fea.data_ptr(), fea.stride(-2), sdf.data_ptr(),
                                 beta.data_ptr(), b, p, out_tokens.data_ptr(), out_tokens.shape[1], t0, _stream()),
           "hoisdf_tokens_fwd")

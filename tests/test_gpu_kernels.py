@@ -36,7 +36,8 @@ def test_linear_matches_fp64(cuda, m, n, k, act):
     ref = x.double() @ w.double().T + b.double()
     if act:
         ref = ref.relu()
-    assert rel_err(y, ref) < 2e-6          # fp32 FMA accumulation over K <= 3968
+    tol = 2e-6 * max(1.0, math.sqrt(k / 256.0))   # sequential fp32 FMA accumulation: error ~ sqrt(K) * 2^-24
+    assert rel_err(y, ref) < tol
     # with fused residual (same pitch as the output)
     resd = res.to(cuda)
     out = torch.zeros(m, ops.round_up(n, 4), device=cuda)[:, :n]
@@ -44,7 +45,7 @@ def test_linear_matches_fp64(cuda, m, n, k, act):
     resd_p[:, :n] = resd
     y2 = ops.linear(x.to(cuda), pw, 0, out=out, residual=resd_p[:, :n])
     ref2 = x.double() @ w.double().T + b.double() + res.double()
-    assert rel_err(y2, ref2) < 2e-6
+    assert rel_err(y2, ref2) < tol
 
 
 def test_linear_batched_rows_and_errors(cuda):
