@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""Headline benchmark of the hoisdf_b200 hot path (contract: see the task prompt / DESIGN.md section 6).
+
+    python bench.py --gpus N --steps K --warmup W            # our B200 path (N > 1: launched under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU cores
+
+Workload = BASELINE.json configs[1]: per GPU a batch of 32 synthetic 256x256 images, 2048 SDF points per
+sample (1536 hand + 512 object), `ho3d` architecture (C = 3968), random weights, full
+backbone + U-Net + SDF query + pose-decode eval forward.  A "step" is one such forward.  Weak scaling:
+every rank owns its own 32 samples, results are all-gathered once per step.
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "samples/sec (SDF query + pose decode, 2048 pts, 256² input) @1/2/4/8 B200"
+UNIT = "samples/s"
+P_HAND, P_OBJ = 1536, 512
+ARCH = "ho3d"
+WEIGHT_SEED = 0
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json, sustained bf16)"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.lower() == "active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_inputs(seed: int, batch: int):
+    from hoisdf_b200 import synthetic as syn
+    return {"img": syn.image_batch(seed, batch)}, syn.eval_targets(batch), syn.camera_meta(seed, batch)
+
+
+# ----------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port of the upstream algorithm on the host cores
+# ----------------------------------------------------------------------------------------------------
+def cpu_forward_fn(sample_batch: int):
+    import torch
+
+    from hoisdf_b200 import synthetic as syn
+    from oracle import hoisdf_oracle as O
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = syn.full_state_dict(WEIGHT_SEED, ARCH)
+    ocfg = O.default_cfg(num_samp_hand=P_HAND, num_samp_obj=P_OBJ)
+    inputs, _, meta = make_inputs(1000, sample_batch)
+
+    def step():
+        with torch.no_grad():
+            return O.model_eval(sd, inputs["img"], meta, ocfg, ARCH)
+
+    return step, torch.get_num_threads()
+
+
+def time_cpu(sample_batch: int, steps: int, warmup: int):
+    step, threads = cpu_forward_fn(sample_batch)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return sample_batch * steps / dt, dt / steps, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_batch = 2
+    value, sec_per_step, threads = time_cpu(sample_batch, args.steps, args.warmup)
+    sample = ("oracle port (oracle/hoisdf_oracle.py, PyTorch-CPU fp32) of the upstream Model.forward(eval): "
+              "%d samples per step of the configs[1] workload" % sample_batch)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus, sample_batch_note=sample_batch),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus, batch=32, sample_batch_note=None):
+    cfg = {
+        "workload": "BASELINE configs[1]: batch=32 per GPU, synthetic 256x256 images, 2048 SDF points/sample "
+                    "(1536 hand + 512 object), ho3d arch (C=3968), full backbone+U-Net+SDF+decoder eval forward",
+        "global_batch": batch * n_gpus, "per_gpu_batch": batch, "points_hand": P_HAND, "points_obj": P_OBJ,
+        "parallelism": "sample-sharded x%d, one all-gather of packed results per step" % n_gpus,
+        "l2": "no explicit flush: each step streams > 10 GB of activations/weights (>> 126 MB L2), "
+              "so nothing of a previous step survives",
+        "cudnn_tf32": False,
+    }
+    if sample_batch_note is not None:
+        cfg["reference_sample_batch"] = sample_batch_note
+    return cfg
+
+
+# ----------------------------------------------------------------------------------------------------
+# native arm
+# ----------------------------------------------------------------------------------------------------
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hoisdf_b200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from hoisdf_b200.csrc.build import build
+    build()
+    from hoisdf_b200 import ops, synthetic as syn
+    from hoisdf_b200.config import cfg
+    from hoisdf_b200.dist import pack_outputs, packed_width
+    from hoisdf_b200.model import get_model
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True
+    cfg.set_setting(ARCH)
+    type(cfg).num_samp_hand, type(cfg).num_samp_obj = P_HAND, P_OBJ
+    B = args.batch
+    model = get_model("test", mano_buffers=syn.mano_buffers(WEIGHT_SEED))
+    model.load_state_dict(syn.full_state_dict(WEIGHT_SEED, ARCH), strict=True)
+    model = model.to(dev).eval().channels_last_()
+
+    inputs, targets, meta = make_inputs(100 + rank, B)
+    pin = lambda d: {k: v.pin_memory() for k, v in d.items()}  # noqa
+    h_inputs, h_targets, h_meta = pin(inputs), pin(targets), pin(meta)
+    to_dev = lambda d: {k: v.to(dev, non_blocking=True) for k, v in d.items()}  # noqa
+    d_inputs, d_targets, d_meta = to_dev(h_inputs), to_dev(h_targets), to_dev(h_meta)
+    width = packed_width(P_OBJ)
+    gathered = torch.empty(world * B, width, device=dev) if world > 1 else None
+    h_result = torch.empty(B, width).pin_memory()
+    h2d_bytes = sum(v.numel() * v.element_size() for d in (h_inputs, h_targets, h_meta) for v in d.values())
+    d2h_bytes = h_result.numel() * 4
+
+    def step_device():
+        out = model(d_inputs, d_targets, d_meta, "eval")
+        packed = pack_outputs(out, P_OBJ)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, packed)
+        return packed
+
+    def step_e2e():
+        di, dt, dm = to_dev(h_inputs), to_dev(h_targets), to_dev(h_meta)
+        out = model(di, dt, dm, "eval")
+        packed = pack_outputs(out, P_OBJ)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, packed)
+        h_result.copy_(packed, non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the caller consumes the result of every step
+
+    def fence():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        fence()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        fence()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    fence()
+    if args.profile_step:
+        torch.cuda.profiler.start()
+        step_device()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
+    n_f = None
+    if model.last_taps is not None:
+        n_f = (model.last_taps["hand"]["n_f"].double().mean().item(), model.last_taps["obj"]["n_f"].double().mean().item())
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ops.STATS["launches"] = 0
+    ops.PROFILE = []
+    ms_total = timed(step_device, args.steps)
+    prof, ops.PROFILE = ops.PROFILE, None
+    launches = ops.STATS["launches"]
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    value = world * B * 1000.0 / ms_step
+
+    # dominant kernel: the fp32 Linear kernel (stand-alone launches + the four inside every SDF-decoder call)
+    torch.cuda.synchronize()
+    lin_flops = sum(p[1] for p in prof)
+    lin_ms = sum(p[2].elapsed_time(p[3]) for p in prof)
+    peaks = load_peaks()
+    achieved = lin_flops / (lin_ms * 1e-3) / 1e12 if lin_ms > 0 else 0.0
+    roofline = {
+        "kernel": "hoisdf::linear_fp32_kernel<128,128|64> (all launches of the step, incl. the 4 GEMMs of every "
+                  "SDF-decoder call; fp32 FMA path)",
+        "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+        "frac": achieved / peaks["tflops"], "traffic": None, "peak_source": peaks["source"],
+        "launches_per_step": len(prof) / args.steps, "share_of_step": lin_ms / ms_total,
+        "fp32_fma_peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12,
+        "frac_of_fp32_fma_peak": achieved / (148 * 128 * 2 * 1.965e9 / 1e12),
+        "algorithmic_flops_per_step": lin_flops / args.steps,
+    }
+
+    for _ in range(3):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps) / args.steps
+    e2e = {"value": world * B * 1000.0 / ms_e2e, "unit": UNIT, "ms_per_step": ms_e2e,
+           "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, sec, threads = time_cpu(2, 3, 1)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": "oracle port of the upstream eval forward, 2 samples/step of the same workload, "
+                                  "1 warm-up + 3 timed steps (%.1f s/step)" % sec}
+    if rank == 0:
+        conf = workload_config(world, B)
+        if n_f is not None:
+            conf["mean_candidates_per_sample"] = {"hand": n_f[0], "obj": n_f[1]}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": conf, "clocks": clocks, "e2e": e2e,
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="samples per GPU per step (configs[1]: 32)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="for ncu --profile-from-start off: warm up, bracket ONE step with cudaProfilerStart/Stop, exit")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

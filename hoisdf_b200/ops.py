@@ -19,6 +19,18 @@ DEC_IN = 289
 DEC_IN_PAD = 292
 SKIP_OFF = 292
 H1 = 223
+# algorithmic FLOPs of one SDFDecoder row (2*(289*512+512*223+512*512+512*512+512))
+SDF_DECODER_FLOPS = 2.0 * (289 * 512 + 512 * 223 + 512 * 512 + 512 * 512 + 512)
+
+
+# Launch accounting (bench.py reports it as `gpu_launches`) and optional per-launch CUDA-event profiling of the
+# Linear kernel (bench.py's roofline leg): PROFILE is None or a list receiving (tag, flops, start_evt, end_evt).
+STATS = {"launches": 0}
+PROFILE = None
+
+
+def _count(n: int = 1):
+    STATS["launches"] += n
 
 
 def _stream() -> int:
@@ -83,7 +95,15 @@ def linear_raw(x_ptr: int, ldx: int, m: int, pw: PackedLinear, y_ptr: int, ldy: 
     a = _capi.LinearArgs(
         x_ptr, ldx, x_batch[0], x_batch[1], pw.w.data_ptr(), pw.ldw, _ptr(pw.b), residual_ptr,
         y_ptr, ldy, y_batch[0], y_batch[1], m, pw.n, pw.k, act)
-    check(lib.hoisdf_linear_fwd(C.byref(a), _stream()), "hoisdf_linear_fwd")
+    _count()
+    if PROFILE is None:
+        check(lib.hoisdf_linear_fwd(C.byref(a), _stream()), "hoisdf_linear_fwd")
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(lib.hoisdf_linear_fwd(C.byref(a), _stream()), "hoisdf_linear_fwd")
+        e1.record()
+        PROFILE.append(("linear", 2.0 * m * pw.n * pw.k, e0, e1))
 
 
 def linear(x: torch.Tensor, pw: PackedLinear, act: int = ACT_NONE, out: Optional[torch.Tensor] = None,
@@ -114,6 +134,7 @@ def fold_weight_norm(g: Optional[torch.Tensor], v: torch.Tensor, cols_out: Optio
     if src_col is None:
         src_col = torch.arange(cols_out, device=v.device, dtype=torch.int32)
         src_col[cols:] = -1
+    _count(1)
     check(lib.hoisdf_fold_weight_norm(_ptr(gg), v.data_ptr(), rows, cols, out.data_ptr(), cols_out,
                                       src_col.data_ptr(), cols_out, _stream()), "hoisdf_fold_weight_norm")
     return out
@@ -131,6 +152,7 @@ def to_nhwc(x: torch.Tensor) -> torch.Tensor:
         return p
     x = x.contiguous()
     out = torch.empty(b, h, w, c, device=x.device, dtype=torch.float32)
+    _count(1)
     check(lib.hoisdf_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), b, c, h, w, _stream()), "hoisdf_nchw_to_nhwc")
     return out
 
@@ -153,6 +175,7 @@ def gather(maps: Sequence[torch.Tensor], uv: torch.Tensor, batch: int, *, mode: 
     rows = uv.shape[0]
     assert uv.is_contiguous() and uv.shape[1] == 2 and out.stride(1) == 1
     pyr = make_pyramid(maps, img_hw)
+    _count(1)
     check(lib.hoisdf_gather_fwd(C.byref(pyr), uv.data_ptr(), rows, _ptr(row_offsets), batch, rows_per_sample, mode,
                                 _ptr(bias), act, out.data_ptr(), out.stride(0), _stream()), "hoisdf_gather_fwd")
     return out
@@ -166,6 +189,7 @@ def lattice_count(center, cam_intr, bbox, sdf_scale: float, bins: int):
     chunks = lib.hoisdf_lattice_chunks(bins)
     counts = torch.empty(b, chunks, device=center.device, dtype=torch.int32)
     offsets = torch.empty(b + 1, device=center.device, dtype=torch.int64)
+    _count(2)
     check(lib.hoisdf_lattice_count(center.data_ptr(), cam_intr.data_ptr(), bbox.data_ptr(), float(sdf_scale), b,
                                    bins, counts.data_ptr(), offsets.data_ptr(), _stream()), "hoisdf_lattice_count")
     return counts, offsets
@@ -175,6 +199,7 @@ def lattice_compact(center, cam_intr, bbox, sdf_scale: float, bins: int, counts,
     b = center.shape[0]
     cand_index = torch.empty(max(total, 1), device=center.device, dtype=torch.int32)
     cand_uv = torch.empty(max(total, 1), 2, device=center.device, dtype=torch.float32)
+    _count(1)
     check(lib.hoisdf_lattice_compact(center.data_ptr(), cam_intr.data_ptr(), bbox.data_ptr(), float(sdf_scale), b,
                                      bins, counts.data_ptr(), offsets.data_ptr(), cand_index.data_ptr(),
                                      cand_uv.data_ptr(), _stream()), "hoisdf_lattice_compact")
@@ -185,6 +210,7 @@ def project_points(points, center, cam_intr, sdf_scale: float, want_cam: bool = 
     b, p, _ = points.shape
     cam = torch.empty(b, p, 3, device=points.device, dtype=torch.float32) if want_cam else None
     uv = torch.empty(b * p, 2, device=points.device, dtype=torch.float32)
+    _count(1)
     check(lib.hoisdf_project_points(points.data_ptr(), center.data_ptr(), cam_intr.data_ptr(), float(sdf_scale), b, p,
                                     _ptr(cam), uv.data_ptr(), _stream()), "hoisdf_project_points")
     return cam, uv
@@ -222,6 +248,7 @@ def pack_sdf_decoder(dec_params: dict) -> PackedSdfDecoder:
 
 def posenc(rows_buf: torch.Tensor, *, lattice_index=None, points=None, bins: int = 64):
     rows = rows_buf.shape[0]
+    _count(1)
     check(lib.hoisdf_posenc_fwd(_ptr(lattice_index), _ptr(points), rows, bins, rows_buf.data_ptr(),
                                 rows_buf.stride(0), 256, _stream()), "hoisdf_posenc_fwd")
 
@@ -233,9 +260,16 @@ def sdf_decoder(packed: PackedSdfDecoder, rows_buf: torch.Tensor, h_a=None, h_b=
     h_a = h_a if h_a is not None else torch.empty(rows, 512, device=dev, dtype=torch.float32)
     h_b = h_b if h_b is not None else torch.empty(rows, 512, device=dev, dtype=torch.float32)
     out = out if out is not None else torch.empty(rows, device=dev, dtype=torch.float32)
+    _count(5)
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(lib.hoisdf_sdf_decoder_fwd(C.byref(packed.struct), rows_buf.data_ptr(), rows_buf.stride(0), rows,
                                      h_a.data_ptr(), h_b.data_ptr(), out.data_ptr(), float(clamp), _stream()),
           "hoisdf_sdf_decoder_fwd")
+    if PROFILE is not None:
+        e1.record()
+        PROFILE.append(("sdf_decoder", SDF_DECODER_FLOPS * rows, e0, e1))
     return out
 
 
@@ -243,6 +277,7 @@ def sdf_pad_input(x: torch.Tensor) -> torch.Tensor:
     x = _f32c(x, "SDFDecoder input")
     rows = x.shape[0]
     buf = torch.empty(rows, ROW_LD, device=x.device, dtype=torch.float32)
+    _count(1)
     check(lib.hoisdf_sdf_pad_input(x.data_ptr(), rows, buf.data_ptr(), ROW_LD, _stream()), "hoisdf_sdf_pad_input")
     return buf
 
@@ -254,6 +289,7 @@ def select_points(sdf, offsets, cand_index, batch: int, num_points: int, bins: i
     out_sdf = torch.empty(batch, num_points, 1, device=dev, dtype=torch.float32)
     pe = torch.empty(batch, num_points, 30, device=dev, dtype=torch.float32)
     flag = torch.zeros(1, device=dev, dtype=torch.int32)
+    _count(1)
     check(lib.hoisdf_select_points(sdf.data_ptr(), offsets.data_ptr(), cand_index.data_ptr(),
                                    batch, num_points, bins, float(clamp), sel.data_ptr(),
                                    pts.data_ptr(), out_sdf.data_ptr(), pe.data_ptr(), flag.data_ptr(), _stream()),
@@ -265,6 +301,7 @@ def tokens(xyz, pe, fea, sdf, beta, out_tokens: torch.Tensor, t0: int):
     b, p, _ = xyz.shape
     assert xyz.is_contiguous() and pe.is_contiguous() and sdf.is_contiguous() and out_tokens.is_contiguous()
     assert fea.stride(-1) == 1 and fea.stride(0) == p * fea.stride(-2)
+    _count(1)
     check(lib.hoisdf_tokens_fwd(xyz.data_ptr(), pe.data_ptr(), fea.data_ptr(), fea.stride(-2), sdf.data_ptr(),
                                 beta.data_ptr(), b, p, out_tokens.data_ptr(), out_tokens.shape[1], t0, _stream()),
           "hoisdf_tokens_fwd")
@@ -275,6 +312,7 @@ def tokens(xyz, pe, fea, sdf, beta, out_tokens: torch.Tensor, t0: int):
 # ----------------------------------------------------------------------------------------------------
 def attention(q, ldq, k, v, ldk, out, ldo, batch, heads, lq, lk, kv_valid=None, mask=None):
     """q/k/v/out are tensors whose data_ptr is the first element of head 0 (may be column-offset views)."""
+    _count(1)
     check(lib.hoisdf_attention_fwd(q.data_ptr(), ldq, k.data_ptr(), v.data_ptr(), ldk, out.data_ptr(), ldo, batch,
                                    heads, lq, lk, lk if kv_valid is None else kv_valid, _ptr(mask), _stream()),
           "hoisdf_attention_fwd")
@@ -285,6 +323,7 @@ def add_layernorm(x, res, gamma, beta, out=None, gamma2=None, beta2=None, out2=N
     rows = x.numel() // x.shape[-1]
     d = x.shape[-1]
     out = out if out is not None else torch.empty_like(x)
+    _count(1)
     check(lib.hoisdf_add_layernorm_fwd(x.data_ptr(), _ptr(res), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
                                        _ptr(gamma2), _ptr(beta2), _ptr(out2), rows, d, _stream()),
           "hoisdf_add_layernorm_fwd")
@@ -295,6 +334,7 @@ def vote_joints(points, off, cls) -> torch.Tensor:
     """points (B,P,3), off (L,B,P,60), cls (L,B,P,20) contiguous -> (L,B,20,3)."""
     l, b, p, _ = cls.shape
     out = torch.empty(l, b, 20, 3, device=cls.device, dtype=torch.float32)
+    _count(1)
     check(lib.hoisdf_vote_joints_fwd(points.data_ptr(), off.data_ptr(), cls.data_ptr(), l, b, p, out.data_ptr(),
                                      _stream()), "hoisdf_vote_joints_fwd")
     return out
@@ -305,6 +345,7 @@ def mano(model_struct, pose6d, betas):
     n = pose6d.shape[0]
     verts = torch.empty(n, 778, 3, device=pose6d.device, dtype=torch.float32)
     joints = torch.empty(n, 21, 3, device=pose6d.device, dtype=torch.float32)
+    _count(1)
     check(lib.hoisdf_mano_fwd(C.byref(model_struct), pose6d.data_ptr(), betas.data_ptr(), n, verts.data_ptr(),
                               joints.data_ptr(), _stream()), "hoisdf_mano_fwd")
     return verts, joints
