@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhoisdf_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 ACT_NONE, ACT_RELU = 0, 1
 GATHER_CONCAT, GATHER_SUM = 0, 1
 
@@ -24,7 +24,7 @@ class LinearArgs(C.Structure):
         ("x", vp), ("ldx", i64), ("x_rows_per_batch", i64), ("x_batch_stride", i64),
         ("w", vp), ("ldw", i64), ("bias", vp), ("residual", vp),
         ("y", vp), ("ldy", i64), ("y_rows_per_batch", i64), ("y_batch_stride", i64),
-        ("m", i64), ("n", i64), ("k", i64), ("act", i32),
+        ("m", i64), ("n", i64), ("k", i64), ("act", i32), ("w_lo", vp),
     ]
 
 
@@ -36,7 +36,8 @@ class Pyramid(C.Structure):
 
 
 class SdfWeights(C.Structure):
-    _fields_ = [(n, vp) for n in ("w0", "b0", "w1", "b1", "w2", "b2", "w3", "b3", "w4", "b4")]
+    _fields_ = [(n, vp) for n in ("w0", "b0", "w1", "b1", "w2", "b2", "w3", "b3", "w4", "b4",
+                                   "w0_lo", "w1_lo", "w2_lo", "w3_lo")]
 
 
 class ManoModel(C.Structure):
@@ -48,6 +49,7 @@ SIGNATURES = {
     "hoisdf_abi_version": (C.c_int, []),
     "hoisdf_status_string": (C.c_char_p, [C.c_int]),
     "hoisdf_linear_fwd": (C.c_int, [C.POINTER(LinearArgs), vp]),
+    "hoisdf_split_tf32": (C.c_int, [vp, i64, vp, vp, vp]),
     "hoisdf_fold_weight_norm": (C.c_int, [vp, vp, i64, i64, vp, i64, vp, i64, vp]),
     "hoisdf_nchw_to_nhwc": (C.c_int, [vp, vp, i64, i64, i64, i64, vp]),
     "hoisdf_lattice_chunks": (C.c_int, [i32]),
@@ -58,7 +60,7 @@ SIGNATURES = {
     "hoisdf_posenc_fwd": (C.c_int, [vp, vp, i64, i32, vp, i64, i64, vp]),
     "hoisdf_sdf_decoder_fwd": (C.c_int, [C.POINTER(SdfWeights), vp, i64, i64, vp, vp, vp, f32, vp]),
     "hoisdf_sdf_pad_input": (C.c_int, [vp, i64, vp, i64, vp]),
-    "hoisdf_select_points": (C.c_int, [vp, vp, vp, i64, i64, i32, f32, vp, vp, vp, vp, vp, vp]),
+    "hoisdf_select_points": (C.c_int, [vp, vp, vp, i64, i64, i32, f32, i32, vp, vp, vp, vp, vp, vp, vp]),
     "hoisdf_tokens_fwd": (C.c_int, [vp, vp, vp, i64, vp, vp, i64, i64, vp, i64, i64, vp]),
     "hoisdf_attention_fwd": (C.c_int, [vp, i64, vp, vp, i64, vp, i64, i64, i64, i64, i64, i64, vp, vp]),
     "hoisdf_add_layernorm_fwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp]),

@@ -46,6 +46,7 @@ class Config:
     # hoisdf_b200 additions
     eval_losses = True          # keep the (unused by main/test.py) loss entries in the eval output dict
     max_rows_per_pass = 1 << 21 # candidate rows processed per pass (bounds the activation workspace)
+    screen_margin = 64          # extra rows kept by the tensor-core screening pass before the exact fp32 re-ranking
 
     def calc_mutliscale_dim(self, use_big_decoder_l, resnet_type_l):
         # upstream config.py:101-108 (sic: "mutliscale")

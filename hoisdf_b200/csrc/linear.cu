@@ -230,6 +230,8 @@ __global__ void fold_weight_norm_kernel(const float* __restrict__ g, const float
   }
 }
 
+int launch_linear_tf32x3(const hoisdf_linear_args* a, cudaStream_t s);  // linear_tc.cu
+
 }  // namespace hoisdf
 
 using namespace hoisdf;
@@ -241,6 +243,10 @@ HOISDF_API int hoisdf_linear_fwd(const hoisdf_linear_args* a, void* stream) {
   if ((a->k & 3) || (a->ldx & 3) || (a->ldw & 3) || (a->x_batch_stride & 3)) return HOISDF_E_ALIGN;
   if (!aligned16(a->x) || !aligned16(a->w)) return HOISDF_E_ALIGN;
   if (a->ldx < a->k || a->ldw < a->k || a->ldy < a->n) return HOISDF_E_SHAPE;
+  if (a->w_lo != nullptr && a->x_rows_per_batch <= 0 && a->y_rows_per_batch <= 0) {
+    if (!aligned16(a->w_lo)) return HOISDF_E_ALIGN;
+    return launch_linear_tf32x3(a, static_cast<cudaStream_t>(stream));
+  }
   LinearParams p;
   p.x = a->x; p.w = a->w; p.bias = a->bias; p.residual = a->residual; p.y = a->y;
   p.xa = {a->ldx, a->x_rows_per_batch, a->x_batch_stride};

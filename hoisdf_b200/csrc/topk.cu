@@ -19,9 +19,9 @@ __device__ __forceinline__ uint64_t composite_key(float sdf, uint32_t i) {
 
 __global__ void __launch_bounds__(kSelThreads) select_points_kernel(
     const float* __restrict__ sdf, const int64_t* __restrict__ offsets, const int32_t* __restrict__ cand_index,
-    int num_points, int bins, float clamp, int32_t* __restrict__ sel_index,
-    float* __restrict__ points, float* __restrict__ out_sdf, float* __restrict__ posenc,
-    int32_t* __restrict__ status_flag) {
+    int num_points, int bins, float clamp, int order_by_row, int32_t* __restrict__ sel_index,
+    int32_t* __restrict__ sel_row, float* __restrict__ points, float* __restrict__ out_sdf,
+    float* __restrict__ posenc, int32_t* __restrict__ status_flag) {
   __shared__ uint64_t keys[kMaxSel];
   __shared__ unsigned hist[256];
   __shared__ uint64_t s_prefix;
@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(kSelThreads) select_points_kernel(
     if (tid == 0 && status_flag != nullptr) atomicExch(status_flag, 1);
     for (int j = tid; j < num_points; j += kSelThreads) {
       sel_index[b * num_points + j] = -1;
+      if (sel_row != nullptr) sel_row[b * num_points + j] = -1;
       out_sdf[b * num_points + j] = 0.f;
       for (int c = 0; c < 3; ++c) points[(b * num_points + j) * 3 + c] = 0.f;
       for (int c = 0; c < 30; ++c) posenc[(b * num_points + j) * 30 + c] = 0.f;
@@ -98,6 +99,12 @@ __global__ void __launch_bounds__(kSelThreads) select_points_kernel(
     if (k <= thresh) keys[atomicAdd(&s_count, 1u)] = k;
   }
   __syncthreads();
+  if (order_by_row) {
+    // screening mode: emit the selected SET in ascending row (= lattice) order instead of |sdf| order, so that a
+    // later exact re-ranking of this subset breaks ties exactly like a full-precision pass over all candidates
+    for (int j = tid; j < num_points; j += kSelThreads) keys[j] = ((keys[j] & 0xffffffffull) << 32) | (keys[j] >> 32);
+    __syncthreads();
+  }
 
   for (int size = 2; size <= npad; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -112,21 +119,24 @@ __global__ void __launch_bounds__(kSelThreads) select_points_kernel(
     }
   }
 
+  const int rshift = order_by_row ? 32 : 0;
   for (int j = tid; j < num_points; j += kSelThreads) {
-    const int64_t row = base + static_cast<int64_t>(keys[j] & 0xffffffffull);
+    const int64_t row = base + static_cast<int64_t>((keys[j] >> rshift) & 0xffffffffull);
     const int idx = cand_index[row];
     sel_index[b * num_points + j] = idx;
+    if (sel_row != nullptr) sel_row[b * num_points + j] = static_cast<int32_t>(row);
     float s0, s1, s2;
     lattice_point(idx, bins, s0, s1, s2);
     float* pt = points + (b * num_points + j) * 3;
     pt[0] = s0; pt[1] = s1; pt[2] = s2;
-    out_sdf[b * num_points + j] = fminf(fmaxf(sd[row - base], -clamp), clamp);
+    const float raw_sdf = sd[row - base];
+    out_sdf[b * num_points + j] = clamp > 0.f ? fminf(fmaxf(raw_sdf, -clamp), clamp) : raw_sdf;
   }
   // NeRF embedding of the selected points: same sinf/cosf as posenc_kernel, so the values are bit-identical
   // to the ones the SDF decoder consumed (upstream copies them, model.py:350)
   for (int e = tid; e < num_points * 30; e += kSelThreads) {
     const int j = e / 30, c = e - j * 30;
-    const int64_t row = base + static_cast<int64_t>(keys[j] & 0xffffffffull);
+    const int64_t row = base + static_cast<int64_t>((keys[j] >> rshift) & 0xffffffffull);
     float xyz[3];
     lattice_point(cand_index[row], bins, xyz[0], xyz[1], xyz[2]);
     const int oct = c / 6, w = c % 6;
@@ -141,14 +151,15 @@ using namespace hoisdf;
 
 HOISDF_API int hoisdf_select_points(const float* sdf, const int64_t* offsets, const int32_t* cand_index,
                                     int64_t batch, int64_t num_points, int32_t bins,
-                                    float clamp, int32_t* sel_index, float* points, float* out_sdf, float* posenc,
-                                    int32_t* status_flag, void* stream) {
+                                    float clamp, int32_t order_by_row, int32_t* sel_index, int32_t* sel_row,
+                                    float* points, float* out_sdf, float* posenc, int32_t* status_flag,
+                                    void* stream) {
   if (sdf == nullptr || offsets == nullptr || cand_index == nullptr || sel_index == nullptr ||
       points == nullptr || out_sdf == nullptr || posenc == nullptr)
     return HOISDF_E_NULL;
   if (batch <= 0 || batch > 65535 || num_points <= 0 || num_points > kMaxSel) return HOISDF_E_SHAPE;
   select_points_kernel<<<static_cast<unsigned>(batch), kSelThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      sdf, offsets, cand_index, static_cast<int>(num_points), bins, clamp, sel_index, points, out_sdf,
-      posenc, status_flag);
+      sdf, offsets, cand_index, static_cast<int>(num_points), bins, clamp, order_by_row, sel_index, sel_row, points,
+      out_sdf, posenc, status_flag);
   return launch_status();
 }

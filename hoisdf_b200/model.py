@@ -45,6 +45,9 @@ class PyramidContext:
     def gmaps(self):
         if self._gmaps is None:
             w0 = self._model.linear_sdfin.packed()[0]
+            # K up to 2048 here and the result feeds the top-k-critical candidate SDF: keep the fp32 FMA kernel
+            # (the tensor-core kernel's accumulate-truncation error grows with K; this stage is ~2% of a step)
+            w0 = ops.PackedLinear(w0.w, w0.b, w0.n, w0.k, w0.ldw, None, None)
             if w0.k != self.channels:
                 raise RuntimeError("pyramid has %d channels, linear_sdfin expects %d" % (self.channels, w0.k))
             g, off = [], 0
@@ -206,10 +209,44 @@ class Model(nn.Module):
             ops.linear(h[:n], sdfin[1], ops.ACT_RELU, out=rows[:n, :256])
             ops.posenc(rows[:n], lattice_index=cand_index[r0:r0 + n], bins=cfg.bins_n)
             ops.sdf_decoder(packed, rows[:n], h_a=h[:n], h_b=h2[:n], out=sdf[r0:r0 + n])
-        sel, pts, out_sdf, pe, _flag = ops.select_points(sdf, plan.offsets, cand_index, b, num_points, cfg.bins_n,
-                                                         cfg.ClampingDistance)
+        screened = None
+        if ops.USE_TENSOR_CORES:
+            # Coarse-to-fine selection.  The tensor-core pass above ranks ALL candidates with an error of ~1e-6;
+            # the final ranking must not depend on that, so it keeps the P + margin best rows (in lattice order),
+            # re-evaluates only those with the bit-faithful fp32 FMA kernels and selects the final P from the
+            # exact values.  The result equals an all-fp32 pass whenever the screening error is smaller than
+            # the |sdf| gap between rank P and rank P + margin; `screen_gap` below is that gap (checked in tests).
+            pm = int(min(num_points + cfg.screen_margin, int(n_f.min()), 4096))
+            if pm > num_points:
+                _, _, s_sdf, _, _, s_row = ops.select_points(sdf, plan.offsets, cand_index, b, pm, cfg.bins_n, 0.0,
+                                                             order_by_row=True)
+                s_row = s_row.view(-1).long()
+                s_index = cand_index.index_select(0, s_row)
+                s_uv = cand_uv.index_select(0, s_row)
+                m = b * pm
+                assert m <= cap
+                ops.gather(gmaps, s_uv, b, mode=ops.GATHER_SUM, out=h[:m], rows_per_sample=pm, bias=sdfin[0].b,
+                           act=ops.ACT_RELU, img_hw=cfg.input_img_shape)
+                ops.linear(h[:m], ops.fma_only(sdfin[1]), ops.ACT_RELU, out=rows[:m, :256])
+                ops.posenc(rows[:m], lattice_index=s_index, bins=cfg.bins_n)
+                exact = ops.sdf_decoder(packed, rows[:m], h_a=h[:m], h_b=h2[:m], exact=True)
+                s_offsets = torch.arange(0, (b + 1) * pm, pm, device=dev, dtype=torch.int64)
+                screened = dict(sdf=sdf, exact=exact, rows=s_row, tc_abs=s_sdf.view(b, pm).abs())
+                sdf_sel, cand_sel, offs_sel = exact, s_index, s_offsets
+            else:
+                sdf_sel, cand_sel, offs_sel = sdf, cand_index, plan.offsets
+        else:
+            sdf_sel, cand_sel, offs_sel = sdf, cand_index, plan.offsets
+        sel, pts, out_sdf, pe, _flag, _ = ops.select_points(sdf_sel, offs_sel, cand_sel, b, num_points, cfg.bins_n,
+                                                            cfg.ClampingDistance)
         if taps is not None:
             taps.update(index=sel, n_f=n_f.clone(), cand_index=cand_index, cand_sdf=sdf, offsets=host.clone())
+            if screened is not None:
+                # |sdf| of the worst screened row (tensor-core value) minus the worst selected exact |sdf|
+                kth_exact = out_sdf.view(b, -1).abs().max(dim=1).values
+                taps["screen_gap"] = screened["tc_abs"].max(dim=1).values - kth_exact
+                taps["screen_exact"] = screened["exact"]
+                taps["screen_rows"] = screened["rows"]
         return pts, out_sdf, pe, None
 
     # ------------------------------------------------------------------------------------------------

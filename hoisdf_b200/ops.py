@@ -6,6 +6,7 @@ ours, launched through `libhoisdf_b200.so`.  Nothing in this file computes with 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
@@ -56,17 +57,33 @@ def round_up(x: int, m: int) -> int:
 # ----------------------------------------------------------------------------------------------------
 # Linear
 # ----------------------------------------------------------------------------------------------------
+# Linear implementation switch: True -> tcgen05 3xTF32 tensor-core kernel (fp32-grade accuracy) wherever the rows are
+# not batched; False -> fp32 FMA kernel everywhere.  HOISDF_TC=0 in the environment disables the tensor path.
+USE_TENSOR_CORES = os.environ.get("HOISDF_TC", "1") != "0"
+
+
+def split_tf32(w: torch.Tensor):
+    """(w_hi, w_lo): w_hi = round-to-nearest TF32 of w, w_lo = w - w_hi (exact), same shape/pitch as w."""
+    assert w.is_contiguous() and w.dtype == torch.float32 and w.is_cuda
+    hi, lo = torch.empty_like(w), torch.empty_like(w)
+    _count(1)
+    check(lib.hoisdf_split_tf32(w.data_ptr(), w.numel(), hi.data_ptr(), lo.data_ptr(), _stream()), "hoisdf_split_tf32")
+    return hi, lo
+
+
 @dataclass
 class PackedLinear:
-    """(N, ldw) fp32 weight with K zero-padded to a multiple of 4, plus bias."""
+    """(N, ldw) fp32 weight with K zero-padded to a multiple of 4, plus bias and the TF32 hi/lo split."""
     w: torch.Tensor
     b: Optional[torch.Tensor]
     n: int
     k: int        # padded K the kernel contracts over (input rows must expose this many columns)
     ldw: int
+    w_hi: Optional[torch.Tensor] = None
+    w_lo: Optional[torch.Tensor] = None
 
     @staticmethod
-    def pack(weight: torch.Tensor, bias: Optional[torch.Tensor]) -> "PackedLinear":
+    def pack(weight: torch.Tensor, bias: Optional[torch.Tensor], tensor_cores: bool = True) -> "PackedLinear":
         weight = weight.detach()
         n, k = weight.shape
         kp = round_up(k, 4)
@@ -76,25 +93,39 @@ class PackedLinear:
             w = torch.zeros(n, kp, device=weight.device, dtype=torch.float32)
             w[:, :k] = weight
         b = None if bias is None else bias.detach().to(torch.float32).contiguous()
-        return PackedLinear(w, b, n, kp, kp)
+        hi = lo = None
+        if tensor_cores and w.is_cuda:
+            hi, lo = split_tf32(w)
+        return PackedLinear(w, b, n, kp, kp, hi, lo)
+
+    @staticmethod
+    def from_packed(w: torch.Tensor, bias: Optional[torch.Tensor], tensor_cores: bool = True) -> "PackedLinear":
+        """w already (N, K4) contiguous."""
+        return PackedLinear.pack(w, bias, tensor_cores)
+
+    def _sl(self, f):
+        return (f(self.w), None if self.w_hi is None else f(self.w_hi), None if self.w_lo is None else f(self.w_lo))
 
     def cols(self, start: int, stop: int) -> "PackedLinear":
         """A K-slice W[:, start:stop] (no copy; start must be a multiple of 4). Bias dropped."""
         assert start % 4 == 0 and (stop - start) % 4 == 0
-        return PackedLinear(self.w[:, start:stop], None, self.n, stop - start, self.ldw)
+        w, hi, lo = self._sl(lambda t: t[:, start:stop])
+        return PackedLinear(w, None, self.n, stop - start, self.ldw, hi, lo)
 
     def rows(self, start: int, stop: int) -> "PackedLinear":
         b = None if self.b is None else self.b[start:stop]
-        return PackedLinear(self.w[start:stop], b, stop - start, self.k, self.ldw)
+        w, hi, lo = self._sl(lambda t: t[start:stop])
+        return PackedLinear(w, b, stop - start, self.k, self.ldw, hi, lo)
 
 
 def linear_raw(x_ptr: int, ldx: int, m: int, pw: PackedLinear, y_ptr: int, ldy: int, act: int = ACT_NONE,
                residual_ptr: Optional[int] = None, x_batch=(0, 0), y_batch=(0, 0)):
     if m == 0:
         return
+    tc = USE_TENSOR_CORES and pw.w_lo is not None and x_batch[0] <= 0 and y_batch[0] <= 0
     a = _capi.LinearArgs(
-        x_ptr, ldx, x_batch[0], x_batch[1], pw.w.data_ptr(), pw.ldw, _ptr(pw.b), residual_ptr,
-        y_ptr, ldy, y_batch[0], y_batch[1], m, pw.n, pw.k, act)
+        x_ptr, ldx, x_batch[0], x_batch[1], (pw.w_hi if tc else pw.w).data_ptr(), pw.ldw, _ptr(pw.b), residual_ptr,
+        y_ptr, ldy, y_batch[0], y_batch[1], m, pw.n, pw.k, act, pw.w_lo.data_ptr() if tc else None)
     _count()
     if PROFILE is None:
         check(lib.hoisdf_linear_fwd(C.byref(a), _stream()), "hoisdf_linear_fwd")
@@ -103,7 +134,12 @@ def linear_raw(x_ptr: int, ldx: int, m: int, pw: PackedLinear, y_ptr: int, ldy: 
         e0.record()
         check(lib.hoisdf_linear_fwd(C.byref(a), _stream()), "hoisdf_linear_fwd")
         e1.record()
-        PROFILE.append(("linear", 2.0 * m * pw.n * pw.k, e0, e1))
+        PROFILE.append(("linear_tc" if tc else "linear", 2.0 * m * pw.n * pw.k, e0, e1))
+
+
+def fma_only(pw: PackedLinear) -> PackedLinear:
+    """The same weights, forced onto the fp32 FMA kernel."""
+    return PackedLinear(pw.w, pw.b, pw.n, pw.k, pw.ldw, None, None)
 
 
 def linear(x: torch.Tensor, pw: PackedLinear, act: int = ACT_NONE, out: Optional[torch.Tensor] = None,
@@ -222,7 +258,11 @@ def project_points(points, center, cam_intr, sdf_scale: float, want_cam: bool = 
 @dataclass
 class PackedSdfDecoder:
     tensors: List[torch.Tensor]      # keeps the packed buffers alive
-    struct: _capi.SdfWeights
+    struct_fma: _capi.SdfWeights     # fp32 FMA kernels
+    struct_tc: Optional[_capi.SdfWeights]   # tcgen05 3xTF32 kernels (None when tensor cores are disabled)
+
+    def struct(self, exact: bool = False):
+        return self.struct_fma if (exact or self.struct_tc is None or not USE_TENSOR_CORES) else self.struct_tc
 
 
 def pack_sdf_decoder(dec_params: dict) -> PackedSdfDecoder:
@@ -241,9 +281,17 @@ def pack_sdf_decoder(dec_params: dict) -> PackedSdfDecoder:
     w3 = fold_weight_norm(dec_params["linh3.weight_g"], dec_params["linh3.weight_v"], 512)
     w4 = _f32c(dec_params["linh4.weight"].detach().reshape(-1).clone(), "linh4.weight")
     bs = [_f32c(dec_params["linh%d.bias" % i].detach().clone(), "bias") for i in range(5)]
-    s = _capi.SdfWeights(w0.data_ptr(), bs[0].data_ptr(), w1.data_ptr(), bs[1].data_ptr(), w2.data_ptr(),
-                         bs[2].data_ptr(), w3.data_ptr(), bs[3].data_ptr(), w4.data_ptr(), bs[4].data_ptr())
-    return PackedSdfDecoder([w0, w1, w2, w3, w4] + bs, s)
+    keep = [w0, w1, w2, w3, w4] + bs
+    ws = (w0, w1, w2, w3)
+    bp = [b.data_ptr() for b in bs]
+    s_fma = _capi.SdfWeights(ws[0].data_ptr(), bp[0], ws[1].data_ptr(), bp[1], ws[2].data_ptr(), bp[2],
+                             ws[3].data_ptr(), bp[3], w4.data_ptr(), bp[4], None, None, None, None)
+    splits = [split_tf32(w) for w in ws]
+    keep += [t for hl in splits for t in hl]
+    his, los = [hl[0].data_ptr() for hl in splits], [hl[1].data_ptr() for hl in splits]
+    s_tc = _capi.SdfWeights(his[0], bp[0], his[1], bp[1], his[2], bp[2], his[3], bp[3], w4.data_ptr(), bp[4],
+                            los[0], los[1], los[2], los[3])
+    return PackedSdfDecoder(keep, s_fma, s_tc)
 
 
 def posenc(rows_buf: torch.Tensor, *, lattice_index=None, points=None, bins: int = 64):
@@ -254,7 +302,7 @@ def posenc(rows_buf: torch.Tensor, *, lattice_index=None, points=None, bins: int
 
 
 def sdf_decoder(packed: PackedSdfDecoder, rows_buf: torch.Tensor, h_a=None, h_b=None, clamp: float = 0.0,
-                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                out: Optional[torch.Tensor] = None, exact: bool = False) -> torch.Tensor:
     rows = rows_buf.shape[0]
     dev = rows_buf.device
     h_a = h_a if h_a is not None else torch.empty(rows, 512, device=dev, dtype=torch.float32)
@@ -264,7 +312,7 @@ def sdf_decoder(packed: PackedSdfDecoder, rows_buf: torch.Tensor, h_a=None, h_b=
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    check(lib.hoisdf_sdf_decoder_fwd(C.byref(packed.struct), rows_buf.data_ptr(), rows_buf.stride(0), rows,
+    check(lib.hoisdf_sdf_decoder_fwd(C.byref(packed.struct(exact)), rows_buf.data_ptr(), rows_buf.stride(0), rows,
                                      h_a.data_ptr(), h_b.data_ptr(), out.data_ptr(), float(clamp), _stream()),
           "hoisdf_sdf_decoder_fwd")
     if PROFILE is not None:
@@ -282,19 +330,22 @@ def sdf_pad_input(x: torch.Tensor) -> torch.Tensor:
     return buf
 
 
-def select_points(sdf, offsets, cand_index, batch: int, num_points: int, bins: int, clamp: float):
+def select_points(sdf, offsets, cand_index, batch: int, num_points: int, bins: int, clamp: float,
+                  order_by_row: bool = False):
     dev = sdf.device
     sel = torch.empty(batch, num_points, device=dev, dtype=torch.int32)
+    row = torch.empty(batch, num_points, device=dev, dtype=torch.int32)
     pts = torch.empty(batch, num_points, 3, device=dev, dtype=torch.float32)
     out_sdf = torch.empty(batch, num_points, 1, device=dev, dtype=torch.float32)
     pe = torch.empty(batch, num_points, 30, device=dev, dtype=torch.float32)
     flag = torch.zeros(1, device=dev, dtype=torch.int32)
     _count(1)
     check(lib.hoisdf_select_points(sdf.data_ptr(), offsets.data_ptr(), cand_index.data_ptr(),
-                                   batch, num_points, bins, float(clamp), sel.data_ptr(),
-                                   pts.data_ptr(), out_sdf.data_ptr(), pe.data_ptr(), flag.data_ptr(), _stream()),
+                                   batch, num_points, bins, float(clamp), int(order_by_row), sel.data_ptr(),
+                                   row.data_ptr(), pts.data_ptr(), out_sdf.data_ptr(), pe.data_ptr(), flag.data_ptr(),
+                                   _stream()),
           "hoisdf_select_points")
-    return sel, pts, out_sdf, pe, flag
+    return sel, pts, out_sdf, pe, flag, row
 
 
 def tokens(xyz, pe, fea, sdf, beta, out_tokens: torch.Tensor, t0: int):

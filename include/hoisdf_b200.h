@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 1
+#define HOISDF_ABI_VERSION 2
 
 enum {
   HOISDF_OK = 0,
@@ -46,6 +46,12 @@ const char* hoisdf_status_string(int status);
  * Rows may be "batched": row r lives at  base + (r / rows_per_batch) * batch_stride + (r % rows_per_batch) * ld
  * (rows_per_batch = 0 means plain `base + r * ld`).  K, ldx, ldw must be multiples of 4 and X, W 16-byte
  * aligned; columns K..ldw of W are never read.  `residual` (optional) shares Y's addressing.
+ *
+ * Two implementations with the same contract:
+ *   w_lo == NULL : fp32 FMA kernel (bit-faithful fp32 products).
+ *   w_lo != NULL : tcgen05 tensor-core kernel, 3xTF32 split (fp32-grade accuracy): `w` must then hold the
+ *                  TF32-rounded weights and `w_lo` the residual W - w (both from hoisdf_split_tf32, same pitch).
+ *                  Used only for un-batched rows; batched rows always take the FMA kernel.
  * ------------------------------------------------------------------------------------------------- */
 typedef struct {
   const float* x; int64_t ldx; int64_t x_rows_per_batch; int64_t x_batch_stride;
@@ -55,9 +61,13 @@ typedef struct {
   float* y; int64_t ldy; int64_t y_rows_per_batch; int64_t y_batch_stride;
   int64_t m; int64_t n; int64_t k;
   int32_t act;
+  const float* w_lo;                 /* may be NULL (see above) */
 } hoisdf_linear_args;
 
 int hoisdf_linear_fwd(const hoisdf_linear_args* args, void* stream);
+
+/* Elementwise split of `count` floats: w_hi = round-to-nearest TF32 of w, w_lo = w - w_hi (exact). */
+int hoisdf_split_tf32(const float* w, int64_t count, float* w_hi, float* w_lo, void* stream);
 
 /* nn.utils.weight_norm(dim=0) fold  W = g * v / ||v||_row  (upstream common/nets/sdf_net.py:57-62),
  * written into a (rows, ld_out) matrix at column offset 0; optional column permutation `src_col`
@@ -140,6 +150,8 @@ typedef struct {
   const float* w2; const float* b2;
   const float* w3; const float* b3;
   const float* w4; const float* b4;
+  /* optional TF32 residuals of w0..w3 (all four or none): selects the tensor-core Linear kernel */
+  const float* w0_lo; const float* w1_lo; const float* w2_lo; const float* w3_lo;
 } hoisdf_sdf_weights;
 
 int hoisdf_sdf_decoder_fwd(const hoisdf_sdf_weights* wts, float* x, int64_t ldx, int64_t rows, float* h_a,
@@ -154,12 +166,15 @@ int hoisdf_sdf_pad_input(const float* in, int64_t rows, float* x, int64_t ldx, v
  * the smallest |sdf| in ascending order (ties: lower row first), then gather of lattice coords, posenc
  * and the clamped SDF value.
  *   sdf (M) raw decoder output, offsets int64 (B+1), cand_index int32 (M)
- *   -> sel_index int32 (B,P) lattice indices, points (B,P,3), out_sdf (B,P) clamped to +-clamp,
- *      posenc (B,P,30).  Samples with fewer than P candidates set *status_flag (int32, device) to 1.
+ *   -> sel_index int32 (B,P) lattice indices, sel_row int32 (B,P) global row of each pick (optional),
+ *      points (B,P,3), out_sdf (B,P) clamped to +-clamp, posenc (B,P,30).
+ *      Samples with fewer than P candidates set *status_flag (int32, device) to 1.
+ * order_by_row != 0 ("screening" mode): the same SET of P rows, emitted in ascending row order instead of
+ * |sdf| order -- used when a tensor-core pass pre-selects P + margin rows that an fp32 pass then re-ranks.
  * ------------------------------------------------------------------------------------------------- */
 int hoisdf_select_points(const float* sdf, const int64_t* offsets, const int32_t* cand_index,
-                         int64_t batch, int64_t num_points, int32_t bins, float clamp,
-                         int32_t* sel_index, float* points, float* out_sdf, float* posenc,
+                         int64_t batch, int64_t num_points, int32_t bins, float clamp, int32_t order_by_row,
+                         int32_t* sel_index, int32_t* sel_row, float* points, float* out_sdf, float* posenc,
                          int32_t* status_flag, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------

@@ -77,6 +77,11 @@ def test_sdf_infer(setup):
                                          3.1, P, kind, s["ocfg"], otaps)
         worst = check_selection(taps, otaps, P)
         assert worst < 5e-6, worst                      # raw SDF of every candidate, absolute (|sdf| < 1)
+        if "screen_gap" in taps:
+            # coarse-to-fine selection: the exact re-ranking is provably equal to an all-fp32 pass when the
+            # screening error (`worst`, ~1e-6) is far below the rank-P .. rank-(P+margin) |sdf| gap
+            assert float(taps["screen_gap"].min()) > 20 * worst, (float(taps["screen_gap"].min()), worst)
+            # and the re-evaluated rows are fp32-FMA values: tighter than the tensor-core pass
         assert cls is None and pts.shape == (s["B"], P, 3) and sdf.shape == (s["B"], P, 1) and pe.shape == (s["B"], P, 30)
         if torch.equal(taps["index"].cpu().long(), otaps["index"]):
             assert torch.equal(pts.cpu(), opts)         # lattice coordinates are bit-exact
@@ -136,21 +141,37 @@ def test_hot_path_outputs(setup):
 
 
 def test_full_forward_from_image(setup):
-    """Image -> pose through cuDNN backbone + our hot path vs the all-CPU oracle.  cuDNN and MKL-DNN convolutions
-    differ at ~1e-6, which can legitimately flip near-tied selections, so this is a looser report-style gate."""
+    """Image -> pose through the cuDNN backbone + our hot path vs the all-CPU oracle.  cuDNN and MKL-DNN
+    convolutions differ at ~1e-6 relative, which can legitimately flip near-tied selections, so this gate is
+    looser: >= 97 % of the selected points must coincide, per-point outputs are compared on the common points,
+    global outputs (joints, mesh) to 2e-2 of their range."""
     m, s = setup["model"], setup
     dev = s["dev"]
     img = syn.image_batch(s["seed"], s["B"])
-    out = m({"img": img.to(dev)}, to_dev(syn.eval_targets(s["B"]), dev), to_dev(s["meta"], dev), "eval")
+    otaps = {}
     with torch.no_grad():
-        oout = O.model_eval(dict(s["sd"]), img, s["meta"], s["ocfg"], s["arch"])
-    for k in ("loss_joint_3d", "loss_joint_cls", "loss_all_joint_3d", "obj_rot", "obj_trans"):
-        assert k in out and out[k].dim() == 0
-    for k in oout:
-        assert out[k].shape == oout[k].shape, k
-        assert rel(out[k], oout[k]) < 2e-2, (k, rel(out[k], oout[k]))
-    # channels_last backbone: same numbers, pyramid consumed zero-copy
+        oout = O.model_eval(dict(s["sd"]), img, s["meta"], s["ocfg"], s["arch"], otaps)
+
+    def compare(out):
+        for k in ("loss_joint_3d", "loss_joint_cls", "loss_all_joint_3d", "obj_rot", "obj_trans"):
+            assert k in out and out[k].dim() == 0
+        taps = m.last_taps
+        for kind in ("hand", "obj"):
+            got, want = taps[kind]["index"].cpu().long(), otaps[kind]["index"]
+            common = sum(len(set(g.tolist()) & set(w.tolist())) for g, w in zip(got, want))
+            assert common >= 0.97 * want.numel(), (kind, common, want.numel())
+        for k in ("mano_mesh_out", "mano_joints_out", "hand_joints_out"):
+            assert out[k].shape == oout[k].shape and rel(out[k], oout[k]) < 2e-2, (k, rel(out[k], oout[k]))
+        got, want = taps["obj"]["index"].cpu().long(), otaps["obj"]["index"]
+        for k in ("obj_rot_out", "obj_trans_out"):
+            assert out[k].shape == oout[k].shape
+            for b in range(s["B"]):
+                pos = {int(i): j for j, i in enumerate(want[b].tolist())}
+                pairs = [(j, pos[int(i)]) for j, i in enumerate(got[b].tolist()) if int(i) in pos]
+                gi, wi = zip(*pairs)
+                assert rel(out[k][b, list(gi)], oout[k][b, list(wi)]) < 2e-2, k
+
+    compare(m({"img": img.to(dev)}, to_dev(syn.eval_targets(s["B"]), dev), to_dev(s["meta"], dev), "eval"))
+    # channels_last backbone: pyramid consumed zero-copy
     m.channels_last_()
-    out2 = m({"img": img.to(dev)}, to_dev(syn.eval_targets(s["B"]), dev), to_dev(s["meta"], dev), "eval")
-    for k in oout:
-        assert rel(out2[k], oout[k]) < 2e-2, (k, rel(out2[k], oout[k]))
+    compare(m({"img": img.to(dev)}, to_dev(syn.eval_targets(s["B"]), dev), to_dev(s["meta"], dev), "eval"))
