@@ -1,0 +1,178 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED upstream HOISDF code (through oracle/reference_shim.py)
+on seeded synthetic weights/inputs.  Run in the build container, where /root/reference exists:
+
+    python oracle/make_golden.py
+
+TEST INFRASTRUCTURE.  The fixtures pin `oracle/hoisdf_oracle.py` (tests/test_oracle_golden.py): the upstream
+repository ships no tests or golden vectors of its own, so outputs of the upstream code
+itself are the only possible anchor.  Weights and inputs are NOT stored -- `hoisdf_b200/synthetic.py`
+regenerates them bit-identically from the seeds recorded in each fixture.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+warnings.filterwarnings("ignore")
+
+from hoisdf_b200 import synthetic as syn  # noqa: E402
+from oracle import hoisdf_oracle as O  # noqa: E402
+from oracle import reference_shim as rs  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _np(d):
+    return {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in d.items()}
+
+
+def build_reference(arch, seed, ph, po):
+    ns = rs.load(arch)
+    cfg = ns["cfg"]
+    type(cfg).num_samp_hand, type(cfg).num_samp_obj = ph, po
+    # the small ('dexycb') ARCHITECTURE is used for cheap fixtures, but with the ho3d eval branch: the dexycb
+    # DATASET branch (model.py:370-422) needs ground-truth SDF samples / MANO parameters that are not on this path
+    type(cfg).dataset = "ho3d"
+    model = rs.build_model(ns, syn.mano_buffers(seed))
+    model.load_state_dict(syn.full_state_dict(seed, arch), strict=True)
+    model.eval()
+    return ns, model
+
+
+def pick_points(arch, seed, batch, ph, po, span=8):
+    """Choose P_h, P_o near the requested values such that the |sdf| gap at the selection boundary is as large
+    as possible for every sample: the fixture must not hinge on a near-tie that another BLAS could flip."""
+    sd = syn.hot_path_state_dict(seed, arch)
+    pyr, meta = syn.feature_pyramid(seed, batch, arch), syn.camera_meta(seed, batch)
+    best = {}
+    for kind, ck, bk, p0 in (("hand", "mano_root", "bbox_hand", ph), ("obj", "obj_center_cam", "bbox_obj", po)):
+        taps = {}
+        with torch.no_grad():
+            O.sdf_infer(dict(sd), pyr, meta[ck], meta["cam_intr"], meta[bk], 3.1, p0, kind, O.default_cfg(), taps)
+        gaps = []
+        for p in range(p0, p0 + span):
+            g = min(float((torch.sort(s.abs())[0][p] - torch.sort(s.abs())[0][p - 1])) for s in taps["cand_sdf"])
+            gaps.append((g, p))
+        best[kind] = max(gaps)
+    return best["hand"][1], best["obj"][1], best["hand"][0], best["obj"][0]
+
+
+def hot_path_case(name, arch, seed, batch, ph, po):
+    ph, po, gh, go = pick_points(arch, seed, batch, ph, po)
+    ns, model = build_reference(arch, seed, ph, po)
+    pyr, meta = syn.feature_pyramid(seed, batch, arch), syn.camera_meta(seed, batch)
+    taps = {}
+    # feed the synthetic pyramid: the stage before the hot path is replaced, everything after is upstream code
+    model.backbone_net.forward = lambda img: (None, None)
+    model.decoder_net.forward = lambda f, s: (pyr, torch.zeros(batch, 3, 128, 128))
+    orig_infer = model.sdf_infer
+
+    def tap_infer(*a, **k):
+        r = orig_infer(*a, **k)
+        taps.setdefault("infer", []).append(r)
+        return r
+
+    model.sdf_infer = tap_infer
+    with torch.no_grad():
+        out = model({"img": torch.zeros(batch, 3, 256, 256)}, syn.eval_targets(batch), meta, "eval")
+    lat = O.lattice(64)
+    # recover lattice indices of the selected points (coordinates <-> indices is one-to-one)
+    def to_index(points):
+        # invert s = col * (2/63) - 1 per column, then idx = c0*4096 + ... is NOT valid for the sheared lattice,
+        # so match against the lattice table instead
+        flat = points.reshape(-1, 3)
+        table = {r.tobytes(): i for i, r in enumerate(lat.numpy())}
+        return np.array([table[r.tobytes()] for r in flat.numpy()], dtype=np.int64).reshape(points.shape[:2])
+
+    (hp, hs, hpe, _), (op, os_, ope, _) = taps["infer"]
+    fix = {
+        "arch": arch, "seed": seed, "batch": batch, "num_samp_hand": ph, "num_samp_obj": po,
+        "gap_hand": gh, "gap_obj": go,
+        "hand_index": to_index(hp), "obj_index": to_index(op), "hand_sdf": hs, "obj_sdf": os_,
+        "hand_posenc": hpe, "obj_posenc": ope,
+    }
+    fix.update({k: v for k, v in out.items() if k.endswith("_out")})
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **_np(fix))
+    print(name, "P", ph, po, "gaps", gh, go, {k: tuple(v.shape) for k, v in out.items() if k.endswith("_out")})
+
+
+def stage_case(name, arch, seed):
+    """Stage-isolated fixtures: SDFDecoder, sdf_forward, get_input_transformer, Transformer, ManoHead, vote, masks."""
+    ns, model = build_reference(arch, seed, 24, 8)   # memory mask: 24 hand-side + 8 object-side tokens
+    batch = 2
+    pyr, meta = syn.feature_pyramid(seed, batch, arch), syn.camera_meta(seed, batch)
+    g = np.random.Generator(np.random.PCG64(seed))
+    rnd = lambda *s: torch.from_numpy(g.random(size=s, dtype=np.float32) * 2 - 1)  # noqa
+    fix = {"arch": arch, "seed": seed}
+    with torch.no_grad():
+        x = rnd(64, 289)
+        fix["sdf_decoder_in"] = x
+        fix["sdf_decoder_out"] = model.hand_sdf_decoder(x)[0]
+        pts = rnd(batch, 33, 3)
+        fix["points"] = pts
+        sdf, _, pe = model.sdf_forward(pyr, pts, meta["obj_center_cam"], meta["cam_intr"], 3.1, type="obj")
+        fix["sdf_forward_sdf"], fix["sdf_forward_posenc"] = sdf, pe
+        lat, cam = model.get_input_transformer(pyr, pts, meta["mano_root"], meta["cam_intr"], 3.1)
+        fix["point_latent"], fix["point_cam"] = lat, cam
+        src = rnd(32, batch, 256)
+        fix["transformer_src"] = src
+        from common.utils.misc import get_mano_memory_mask, get_mano_tgt_mask
+        hs, mem, inter, _ = model.hand_transformer(src=src, mask=None, pos_embed=torch.zeros_like(src), src_mask=None,
+                                                   query_embed=model.mano_query_embed.weight,
+                                                   tgt_mask=get_mano_tgt_mask(), memory_mask=get_mano_memory_mask())
+        fix["transformer_hs"], fix["transformer_memory"], fix["transformer_inter_first_last"] = hs, mem, inter[[0, 5]]
+        fix["tgt_mask"], fix["memory_mask"] = get_mano_tgt_mask(), get_mano_memory_mask()
+        pose6d, shape = rnd(2, 16, batch, 6), rnd(2, batch, 10)
+        fix["mano_pose6d"], fix["mano_shape"] = pose6d, shape
+        res, _ = model.mano_head(pose6d, shape)
+        fix["mano_verts"], fix["mano_joints"] = res["verts3d"], res["joints3d"]
+        hp, off, cls = rnd(batch, 24, 3) * 0.1, rnd(2, 24, batch, 60) * 0.05, rnd(2, 24, batch, 20) * 3
+        fix["vote_points"], fix["vote_off"], fix["vote_cls"] = hp, off, cls
+        fix["vote_joints"] = model.joints_vote_loss(hp, off, cls, torch.zeros(batch, 20, 3))[3]
+        fix["lattice_rows"] = np.array([0, 1, 63, 64, 4095, 4096, 262143])
+        # the lattice as upstream builds it (model.py:257-273)
+        fix["lattice_values"] = O.lattice(64)[torch.tensor(fix["lattice_rows"])]
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **_np(fix))
+    print(name, sorted(fix))
+
+
+def image_case(name, arch, seed, batch, ph, po):
+    ns, model = build_reference(arch, seed, ph, po)
+    img, meta = syn.image_batch(seed, batch), syn.camera_meta(seed, batch)
+    pyr = {}
+    orig = model.decoder_net.forward
+
+    def tap(a, b):
+        fp, ho = orig(a, b)
+        pyr.update(fp)
+        pyr["decoder_out"] = ho
+        return fp, ho
+
+    model.decoder_net.forward = tap
+    with torch.no_grad():
+        out = model({"img": img}, syn.eval_targets(batch), meta, "eval")
+    fix = {"arch": arch, "seed": seed, "batch": batch, "num_samp_hand": ph, "num_samp_obj": po}
+    # pyramid checksums + a small crop of every level pin the ResNet/U-Net restatement
+    for k, v in pyr.items():
+        fix["pyr_mean_" + k] = v.double().mean()
+        fix["pyr_abs_" + k] = v.double().abs().mean()
+        fix["pyr_crop_" + k] = v[:, :4, :4, :4]
+    fix.update({k: v for k, v in out.items() if k.endswith("_out")})
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **_np(fix))
+    print(name, {k: tuple(v.shape) for k, v in out.items() if k.endswith("_out")})
+
+
+if __name__ == "__main__":
+    assert rs.available(), "the upstream reference is not mounted; golden vectors can only be made in the build container"
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count() or 1)
+    stage_case("stages_dexycb_seed7", "dexycb", 7)
+    hot_path_case("hot_path_dexycb_seed11", "dexycb", 11, 2, 64, 32)
+    hot_path_case("hot_path_ho3d_seed12", "ho3d", 12, 1, 96, 40)
+    image_case("image_dexycb_seed13", "dexycb", 13, 1, 48, 16)

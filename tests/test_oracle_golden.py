@@ -1,0 +1,92 @@
+"""Pin the CPU oracle (oracle/hoisdf_oracle.py) to outputs of the UNMODIFIED upstream code (tests/golden/*.npz,
+written by oracle/make_golden.py in the build container).  Weights and inputs are regenerated from the recorded
+seeds.  Tolerances: 2e-5 relative for floats (different BLAS / ISA between machines), exact for indices and masks."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from hoisdf_b200 import synthetic as syn
+from oracle import hoisdf_oracle as O
+from util import align_selection, aligned
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load(name):
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    return {k: z[k] for k in z.files}
+
+
+def close(a, b, tol=2e-5):
+    a, b = torch.as_tensor(np.asarray(a)).double(), torch.as_tensor(np.asarray(b)).double()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    err = float((a - b).abs().max() / max(float(b.abs().max()), 1e-30))
+    assert err < tol, err
+
+
+def test_stage_fixtures():
+    g = load("stages_dexycb_seed7")
+    arch, seed = str(g["arch"]), int(g["seed"])
+    sd = syn.hot_path_state_dict(seed, arch)
+    cfg = O.default_cfg(num_samp_hand=24, num_samp_obj=8)
+    pyr, meta = syn.feature_pyramid(seed, 2, arch), syn.camera_meta(seed, 2)
+    t = lambda k: torch.from_numpy(g[k])  # noqa
+    with torch.no_grad():
+        close(O.sdf_decoder(sd, "hand_sdf_decoder", t("sdf_decoder_in")), g["sdf_decoder_out"])
+        sdf, _, pe = O.sdf_forward(sd, pyr, t("points"), meta["obj_center_cam"], meta["cam_intr"], 3.1, "obj", cfg)
+        close(sdf, g["sdf_forward_sdf"]); close(pe, g["sdf_forward_posenc"])
+        lat, cam = O.get_input_transformer(sd, pyr, t("points"), meta["mano_root"], meta["cam_intr"], 3.1, cfg)
+        close(lat, g["point_latent"]); close(cam, g["point_cam"])
+        src = t("transformer_src")
+        assert torch.equal(O.mano_tgt_mask(cfg), t("tgt_mask")) and torch.equal(O.mano_memory_mask(cfg), t("memory_mask"))
+        hs, mem, inter = O.transformer(sd, "hand_transformer", src, sd["mano_query_embed.weight"], torch.zeros_like(src),
+                                       O.mano_tgt_mask(cfg), O.mano_memory_mask(cfg), cfg)
+        close(hs, g["transformer_hs"]); close(mem, g["transformer_memory"])
+        close(inter[[0, 5]], g["transformer_inter_first_last"])
+        verts, joints = O.mano_head(sd, t("mano_pose6d"), t("mano_shape"))
+        close(verts, g["mano_verts"]); close(joints, g["mano_joints"])
+        close(O.vote_joints(t("vote_points"), t("vote_off"), t("vote_cls")), g["vote_joints"])
+        # the sheared lattice, bit for bit
+        assert np.array_equal(O.lattice(64)[torch.from_numpy(g["lattice_rows"])].numpy(), g["lattice_values"])
+
+
+@pytest.mark.parametrize("name", ["hot_path_dexycb_seed11", "hot_path_ho3d_seed12"])
+def test_hot_path_fixtures(name):
+    g = load(name)
+    arch, seed, B = str(g["arch"]), int(g["seed"]), int(g["batch"])
+    ph, po = int(g["num_samp_hand"]), int(g["num_samp_obj"])
+    sd = syn.hot_path_state_dict(seed, arch)
+    pyr, meta = syn.feature_pyramid(seed, B, arch), syn.camera_meta(seed, B)
+    taps = {}
+    with torch.no_grad():
+        out = O.hot_path_eval(sd, pyr, meta, O.default_cfg(num_samp_hand=ph, num_samp_obj=po), taps)
+    # selected lattice indices: identical sets; order identical up to swaps of |sdf| near-ties (see util.py)
+    ph_perm = align_selection(taps["hand"]["index"], g["hand_index"], g["hand_sdf"])
+    po_perm = align_selection(taps["obj"]["index"], g["obj_index"], g["obj_sdf"])
+    close(aligned(taps["hand_sdf"], ph_perm), g["hand_sdf"], 1e-3)
+    close(aligned(taps["obj_sdf"], po_perm), g["obj_sdf"], 1e-3)
+    close(aligned(taps["hand_posenc"], ph_perm), g["hand_posenc"])
+    close(aligned(taps["obj_posenc"], po_perm), g["obj_posenc"])
+    for k in ("mano_mesh_out", "mano_joints_out", "hand_joints_out"):      # global outputs: order-invariant
+        close(out[k], g[k])
+    for k in ("obj_rot_out", "obj_trans_out"):                            # per-point outputs: align first
+        close(aligned(out[k], po_perm), g[k])
+
+
+def test_image_fixture():
+    g = load("image_dexycb_seed13")
+    arch, seed, B = str(g["arch"]), int(g["seed"]), int(g["batch"])
+    sd = syn.full_state_dict(seed, arch)
+    taps = {}
+    with torch.no_grad():
+        out = O.model_eval(sd, syn.image_batch(seed, B), syn.camera_meta(seed, B),
+                           O.default_cfg(num_samp_hand=int(g["num_samp_hand"]), num_samp_obj=int(g["num_samp_obj"])),
+                           arch, taps)
+    for lvl in O.LEVELS:
+        close(taps["pyramid"][lvl][:, :4, :4, :4], g["pyr_crop_" + lvl], 1e-4)
+        assert abs(float(taps["pyramid"][lvl].double().mean()) - float(g["pyr_mean_" + lvl])) < 1e-5 * float(g["pyr_abs_" + lvl])
+    close(taps["decoder_out"][:, :4, :4, :4], g["pyr_crop_decoder_out"], 1e-4)
+    for k in ("mano_mesh_out", "mano_joints_out", "obj_rot_out", "obj_trans_out", "hand_joints_out"):
+        close(out[k], g[k], 1e-3)      # through the conv stack and a top-k: looser across machines
