@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhoisdf_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 ACT_NONE, ACT_RELU = 0, 1
 GATHER_CONCAT, GATHER_SUM = 0, 1
 
@@ -62,7 +62,8 @@ SIGNATURES = {
     "hoisdf_sdf_pad_input": (C.c_int, [vp, i64, vp, i64, vp]),
     "hoisdf_select_points": (C.c_int, [vp, vp, vp, i64, i64, i32, f32, i32, vp, vp, vp, vp, vp, vp, vp]),
     "hoisdf_tokens_fwd": (C.c_int, [vp, vp, vp, i64, vp, vp, i64, i64, vp, i64, i64, vp]),
-    "hoisdf_attention_fwd": (C.c_int, [vp, i64, vp, vp, i64, vp, i64, i64, i64, i64, i64, i64, vp, vp]),
+    "hoisdf_attention_workspace_bytes": (i64, [i64, i64, i64, i64]),
+    "hoisdf_attention_fwd": (C.c_int, [vp, i64, vp, vp, i64, vp, i64, i64, i64, i64, i64, i64, vp, vp, i64, vp]),
     "hoisdf_add_layernorm_fwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp]),
     "hoisdf_vote_joints_fwd": (C.c_int, [vp, vp, vp, i64, i64, i64, vp, vp]),
     "hoisdf_mano_fwd": (C.c_int, [C.POINTER(ManoModel), vp, vp, i64, vp, vp, vp]),

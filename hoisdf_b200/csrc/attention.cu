@@ -235,13 +235,24 @@ __global__ void __launch_bounds__(128) attention_small_kernel(const AttnParams p
   }
 }
 
+int64_t attention_tc_workspace_bytes(int64_t batch, int64_t heads, int64_t lq, int64_t lk);   // attention_tc.cu
+int launch_attention_tc(const float* q, int64_t ldq, const float* k, const float* v, int64_t ldk, float* out,
+                        int64_t ldo, int64_t batch, int64_t heads, int64_t lq, int64_t lk, int64_t kv_valid,
+                        void* workspace, cudaStream_t s);
+
 }  // namespace hoisdf
 
 using namespace hoisdf;
 
+HOISDF_API int64_t hoisdf_attention_workspace_bytes(int64_t batch, int64_t heads, int64_t lq, int64_t lk) {
+  if (batch <= 0 || heads <= 0 || lq <= 0 || lk <= 0) return 0;
+  return attention_tc_workspace_bytes(batch, heads, lq, lk);
+}
+
 HOISDF_API int hoisdf_attention_fwd(const float* q, int64_t ldq, const float* k, const float* v, int64_t ldk,
                                     float* out, int64_t ldo, int64_t batch, int64_t heads, int64_t lq, int64_t lk,
-                                    int64_t kv_valid, const uint8_t* mask, void* stream) {
+                                    int64_t kv_valid, const uint8_t* mask, void* workspace, int64_t workspace_bytes,
+                                    void* stream) {
   if (q == nullptr || k == nullptr || v == nullptr || out == nullptr) return HOISDF_E_NULL;
   if (batch <= 0 || batch > 65535 || heads <= 0 || heads > 65535 || lq <= 0 || lk <= 0 || kv_valid <= 0 ||
       lq > (1 << 24) || lk > (1 << 24))
@@ -255,6 +266,11 @@ HOISDF_API int hoisdf_attention_fwd(const float* q, int64_t ldq, const float* k,
   p.lq = static_cast<int>(lq); p.lk = static_cast<int>(lk);
   p.kv_valid = static_cast<int>(kv_valid < lk ? kv_valid : lk);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (workspace != nullptr && mask == nullptr) {
+    if (workspace_bytes < attention_tc_workspace_bytes(batch, heads, lq, lk)) return HOISDF_E_SHAPE;
+    if (!aligned16(workspace)) return HOISDF_E_ALIGN;
+    return launch_attention_tc(q, ldq, k, v, ldk, out, ldo, batch, heads, lq, lk, p.kv_valid, workspace, s);
+  }
   if (mask != nullptr || lq <= 32) {
     if (lq > 65535 * 32 || lk > 12000) return HOISDF_E_UNSUPPORTED;  // scores must fit in shared memory
     dim3 grid(static_cast<unsigned>(lq), static_cast<unsigned>(heads), static_cast<unsigned>(batch));

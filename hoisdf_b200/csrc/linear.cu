@@ -243,7 +243,7 @@ HOISDF_API int hoisdf_linear_fwd(const hoisdf_linear_args* a, void* stream) {
   if ((a->k & 3) || (a->ldx & 3) || (a->ldw & 3) || (a->x_batch_stride & 3)) return HOISDF_E_ALIGN;
   if (!aligned16(a->x) || !aligned16(a->w)) return HOISDF_E_ALIGN;
   if (a->ldx < a->k || a->ldw < a->k || a->ldy < a->n) return HOISDF_E_SHAPE;
-  if (a->w_lo != nullptr && a->x_rows_per_batch <= 0 && a->y_rows_per_batch <= 0) {
+  if (a->w_lo != nullptr && a->y_rows_per_batch <= 0) {
     if (!aligned16(a->w_lo)) return HOISDF_E_ALIGN;
     return launch_linear_tf32x3(a, static_cast<cudaStream_t>(stream));
   }

@@ -42,7 +42,8 @@ struct TcParams {
   const float* __restrict__ residual;
   float* __restrict__ y;
   int64_t ldy;
-  int64_t m;
+  int64_t rows_per_batch;   // X rows form groups of this many rows (plain GEMM: = M, one group)
+  int tiles_per_batch;      // ceil(rows_per_batch / 128)
   int n, k, act;
 };
 
@@ -70,6 +71,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (done) break;
     if (++spins > kSpinLimit) __trap();
   }
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
 }
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -136,7 +144,9 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (p.n + TC_BN - 1) / TC_BN;
-  const int m0 = static_cast<int>(blockIdx.x / n_tiles) * TC_BM;
+  const int m_tile = static_cast<int>(blockIdx.x / n_tiles);
+  const int grp = m_tile / p.tiles_per_batch;                       // row group (batched rows) of this tile
+  const int m0 = (m_tile - grp * p.tiles_per_batch) * TC_BM;         // first row inside the group
   const int n0 = static_cast<int>(blockIdx.x % n_tiles) * TC_BN;
   const int n_here = min(TC_BN, p.n - n0);
   const int n_inst = (n_here + 15) & ~15;                  // UMMA N (multiple of 16 for M = 128)
@@ -174,7 +184,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         mbar_wait(bar_empty(s), ph ^ 1u);
         const uint32_t st = base + s * TC_STAGE_BYTES;
         mbar_expect_tx(bar_full(s), TC_A_BYTES + 2 * TC_B_BYTES);
-        tma_load_2d(st, &map_x, bar_full(s), kb * TC_BK, m0);
+        tma_load_3d(st, &map_x, bar_full(s), kb * TC_BK, m0, grp);
         tma_load_2d(st + 2 * TC_A_BYTES, &map_whi, bar_full(s), kb * TC_BK, n0);
         tma_load_2d(st + 2 * TC_A_BYTES + TC_B_BYTES, &map_wlo, bar_full(s), kb * TC_BK, n0);
       }
@@ -235,8 +245,9 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     mbar_wait(bar_done, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int q = warp & 3;                        // TMEM lane quarter this warp may read
-    const int64_t row = static_cast<int64_t>(m0) + q * 32 + lane;
-    const bool row_ok = row < p.m;
+    const int64_t lrow = static_cast<int64_t>(m0) + q * 32 + lane;      // row inside the group
+    const bool row_ok = lrow < p.rows_per_batch;
+    const int64_t row = static_cast<int64_t>(grp) * p.rows_per_batch + lrow;   // output rows are dense
     float* yrow = p.y + (row_ok ? row * p.ldy : 0) + n0;
     const float* rrow = p.residual ? p.residual + (row_ok ? row * p.ldy : 0) + n0 : nullptr;
     const bool vec = ((p.ldy & 3) == 0) && aligned16(p.y) && (p.residual == nullptr || aligned16(p.residual));
@@ -324,16 +335,41 @@ static bool make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t c
   return r == CUDA_SUCCESS;
 }
 
-// called by hoisdf_linear_fwd when args->w_lo is set and the rows are not batched
+// X as (groups, rows_per_group, K): box = 1 x 128 rows x 16 floats
+static bool make_map_x(CUtensorMap* map, const float* ptr, int64_t groups, int64_t rows, int64_t cols, int64_t ld,
+                       int64_t group_stride) {
+  auto enc = encode_fn();
+  if (enc == nullptr) return false;
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(groups)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 4, static_cast<cuuint64_t>(group_stride) * 4};
+  cuuint32_t box[3] = {TC_BK, TC_BM, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// called by hoisdf_linear_fwd when args->w_lo is set and the OUTPUT rows are dense (input rows may be batched)
 int launch_linear_tf32x3(const hoisdf_linear_args* a, cudaStream_t s) {
   CUtensorMap mx, mhi, mlo;
-  if (!make_map(&mx, a->x, a->m, a->k, a->ldx, TC_BM)) return HOISDF_E_UNSUPPORTED;
+  int64_t groups = 1, rpb = a->m, gstride = a->m * a->ldx;
+  if (a->x_rows_per_batch > 0) {
+    if (a->m % a->x_rows_per_batch != 0) return HOISDF_E_SHAPE;
+    rpb = a->x_rows_per_batch;
+    groups = a->m / rpb;
+    gstride = a->x_batch_stride;
+  }
+  if (groups > 1 && ((gstride * 4) % 16 != 0)) return HOISDF_E_ALIGN;
+  if (groups == 1) gstride = rpb * a->ldx;   // unused by the hardware for a single group, but must be valid
+  if (!make_map_x(&mx, a->x, groups, rpb, a->k, a->ldx, gstride)) return HOISDF_E_UNSUPPORTED;
   if (!make_map(&mhi, a->w, a->n, a->k, a->ldw, TC_BN)) return HOISDF_E_UNSUPPORTED;
   if (!make_map(&mlo, a->w_lo, a->n, a->k, a->ldw, TC_BN)) return HOISDF_E_UNSUPPORTED;
   cudaError_t e = cudaFuncSetAttribute(linear_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   if (e != cudaSuccess) return static_cast<int>(e);
-  TcParams p{a->bias, a->residual, a->y, a->ldy, a->m, static_cast<int>(a->n), static_cast<int>(a->k), a->act};
-  const int64_t tiles = ceil_div(a->m, TC_BM) * ceil_div(a->n, TC_BN);
+  const int64_t tpb = ceil_div(rpb, TC_BM);
+  TcParams p{a->bias, a->residual, a->y, a->ldy, rpb, static_cast<int>(tpb), static_cast<int>(a->n),
+             static_cast<int>(a->k), a->act};
+  const int64_t tiles = groups * tpb * ceil_div(a->n, TC_BN);
   if (tiles > 0x7fffffffLL) return HOISDF_E_SHAPE;
   linear_tf32x3_kernel<<<static_cast<unsigned>(tiles), TC_THREADS, TC_SMEM_BYTES, s>>>(mx, mhi, mlo, p);
   return launch_status();

@@ -319,7 +319,7 @@ class Model(nn.Module):
         ops.tokens(hand_o_nt, hand_o_pe, hand_fea, hand_o_sdf, beta_o, obj_in, Po)
 
         tgt_mask = get_mano_tgt_mask().to(dev)
-        memory_mask = get_mano_memory_mask().to(dev)
+        memory_mask = get_mano_memory_mask()          # stays on the host: recognised as a key-range limit
         hs, memory, hand_enc = self.hand_transformer.forward_bm(hand_in, self.mano_query_embed.weight, None,
                                                                 tgt_mask, memory_mask)
         _, obj_enc = self.obj_transformer.forward_bm(obj_in, None)

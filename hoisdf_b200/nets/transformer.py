@@ -125,7 +125,8 @@ class TransformerDecoderLayer(_LayerBase):
         self.norm2 = nn.LayerNorm(d_model)
         self.norm3 = nn.LayerNorm(d_model)
 
-    def forward_bm(self, tgt, memory, pos, query_pos, tgt_mask, memory_mask, final_norm, final_out):
+    def forward_bm(self, tgt, memory, pos, query_pos, tgt_mask, memory_mask, final_norm, final_out,
+                   memory_kv_valid=None):
         """tgt (B, Lq, d), memory (B, S, d), query_pos (B, Lq, d) batch-major; masks uint8 (1 = blocked).
         upstream transformer.py:366-395 (forward_post)."""
         b, lq, d = tgt.shape
@@ -154,7 +155,13 @@ class TransformerDecoderLayer(_LayerBase):
             ops.linear((memory + pos).view(b * s, d), ca["k"], out=mkv[:, :d])
             ops.linear(m2d, ca["v"], out=mkv[:, d:])
         att2 = torch.empty(b * lq, d, device=dev, dtype=torch.float32)
-        ops.attention(q, d, mkv, mkv[:, d:], 2 * d, att2, d, b, self.nhead, lq, s, mask=memory_mask)
+        if memory_kv_valid is not None:
+            # memory_mask == "keys >= memory_kv_valid are blocked for every query" (common/utils/misc.py:42-47):
+            # expressed as a key-range limit, which the tensor-core kernel supports (a dense mask does not)
+            ops.attention(q, d, mkv, mkv[:, d:], 2 * d, att2, d, b, self.nhead, lq, s, kv_valid=memory_kv_valid,
+                          tensor_cores=True)
+        else:
+            ops.attention(q, d, mkv, mkv[:, d:], 2 * d, att2, d, b, self.nhead, lq, s, mask=memory_mask)
         y2 = ops.linear(att2, ca["out"], ops.ACT_NONE, residual=t1)
         t2 = ops.add_layernorm(y2, None, self.norm2.weight, self.norm2.bias)
         out = self._ffn_block(t2, self.norm3, final_norm, final_out)
@@ -196,13 +203,13 @@ class TransformerDecoder(nn.Module):
         self.norm = norm
         self.return_intermediate = return_intermediate
 
-    def forward_bm(self, tgt, memory, pos, query_pos, tgt_mask, memory_mask):
+    def forward_bm(self, tgt, memory, pos, query_pos, tgt_mask, memory_mask, memory_kv_valid=None):
         """-> hs (L, B, Lq, d) = norm(out_l) for every layer (upstream transformer.py:214-252)."""
         b, lq, d = tgt.shape
         hs = torch.empty(self.num_layers, b, lq, d, device=tgt.device, dtype=torch.float32)
         x = tgt
         for i, layer in enumerate(self.layers):
-            x = layer.forward_bm(x, memory, pos, query_pos, tgt_mask, memory_mask, self.norm, hs[i])
+            x = layer.forward_bm(x, memory, pos, query_pos, tgt_mask, memory_mask, self.norm, hs[i], memory_kv_valid)
         return hs
 
 
@@ -210,6 +217,20 @@ def _mask_u8(mask: Optional[torch.Tensor], device):
     if mask is None:
         return None
     return mask.to(device=device, dtype=torch.uint8).contiguous()
+
+
+def _suffix_mask_limit(mask: Optional[torch.Tensor]):
+    """If `mask` (Lq, S) bool blocks exactly the keys [n, S) for every query, return n; else None.  Only evaluated for
+    host tensors (the model builds its masks on the CPU, like upstream model.py:568-569), so no device sync."""
+    if mask is None or mask.is_cuda or mask.dtype != torch.bool or mask.dim() != 2:
+        return None
+    col = mask[0]
+    if not bool((mask == col).all()):
+        return None
+    n = int((~col).sum())
+    if n == 0 or bool(col[:n].any()) or not bool(col[n:].all()):
+        return None
+    return n
 
 
 def _xavier(module):
@@ -262,14 +283,18 @@ class Transformer(nn.Module):
         self.nhead = nhead
 
     def forward_bm(self, src_bm, query_embed, pos_bm, tgt_mask, memory_mask):
-        """src (B,S,d), query_embed (Lq,d) -> hs (L,B,Lq,d), memory (B,S,d), intermediate (Le,B,S,d)."""
+        """src (B,S,d), query_embed (Lq,d) -> hs (L,B,Lq,d), memory (B,S,d), intermediate (Le,B,S,d).
+        A memory_mask of the form "all queries blocked from keys >= n" (the only form upstream builds) is
+        recognised on the host and turned into a key-range limit."""
         b = src_bm.shape[0]
         x = src_bm if pos_bm is None else src_bm + pos_bm
         memory, inter = self.encoder.forward_bm(x.contiguous(), pos_bm)
         qpos = query_embed.detach().unsqueeze(0).expand(b, -1, -1).contiguous()
         tgt = torch.zeros_like(qpos)
         dev = src_bm.device
-        hs = self.decoder.forward_bm(tgt, memory, pos_bm, qpos, _mask_u8(tgt_mask, dev), _mask_u8(memory_mask, dev))
+        kv_valid = _suffix_mask_limit(memory_mask)
+        hs = self.decoder.forward_bm(tgt, memory, pos_bm, qpos, _mask_u8(tgt_mask, dev),
+                                     None if kv_valid is not None else _mask_u8(memory_mask, dev), kv_valid)
         return hs, memory, inter
 
     def forward(self, src, mask, query_embed, pos_embed, tgt_mask=None, src_mask=None, memory_mask=None):

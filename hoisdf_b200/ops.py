@@ -122,7 +122,8 @@ def linear_raw(x_ptr: int, ldx: int, m: int, pw: PackedLinear, y_ptr: int, ldy: 
                residual_ptr: Optional[int] = None, x_batch=(0, 0), y_batch=(0, 0)):
     if m == 0:
         return
-    tc = USE_TENSOR_CORES and pw.w_lo is not None and x_batch[0] <= 0 and y_batch[0] <= 0
+    tc = (USE_TENSOR_CORES and pw.w_lo is not None and y_batch[0] <= 0
+          and (x_batch[0] <= 0 or m % x_batch[0] == 0))
     a = _capi.LinearArgs(
         x_ptr, ldx, x_batch[0], x_batch[1], (pw.w_hi if tc else pw.w).data_ptr(), pw.ldw, _ptr(pw.b), residual_ptr,
         y_ptr, ldy, y_batch[0], y_batch[1], m, pw.n, pw.k, act, pw.w_lo.data_ptr() if tc else None)
@@ -361,11 +362,30 @@ def tokens(xyz, pe, fea, sdf, beta, out_tokens: torch.Tensor, t0: int):
 # ----------------------------------------------------------------------------------------------------
 # Transformer pieces
 # ----------------------------------------------------------------------------------------------------
-def attention(q, ldq, k, v, ldk, out, ldo, batch, heads, lq, lk, kv_valid=None, mask=None):
-    """q/k/v/out are tensors whose data_ptr is the first element of head 0 (may be column-offset views)."""
-    _count(1)
+_attn_ws = {}
+
+
+def _attention_workspace(device, nbytes: int) -> torch.Tensor:
+    """One grow-only scratch buffer per device for the bf16 hi/lo operand copies of the tensor-core attention."""
+    buf = _attn_ws.get(device)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(nbytes, device=device, dtype=torch.uint8)
+        _attn_ws[device] = buf
+    return buf
+
+
+def attention(q, ldq, k, v, ldk, out, ldo, batch, heads, lq, lk, kv_valid=None, mask=None, tensor_cores=None):
+    """q/k/v/out are tensors whose data_ptr is the first element of head 0 (may be column-offset views).
+    tensor_cores: None = automatic (long query sequences), True = also for short ones (decoder cross-attention)."""
+    ws, ws_bytes, n = None, 0, 1
+    if USE_TENSOR_CORES and mask is None and (lq > 32 or tensor_cores):
+        ws_bytes = lib.hoisdf_attention_workspace_bytes(batch, heads, lq, lk)
+        ws = _attention_workspace(out.device, ws_bytes)
+        n = 4
+    _count(n)
     check(lib.hoisdf_attention_fwd(q.data_ptr(), ldq, k.data_ptr(), v.data_ptr(), ldk, out.data_ptr(), ldo, batch,
-                                   heads, lq, lk, lk if kv_valid is None else kv_valid, _ptr(mask), _stream()),
+                                   heads, lq, lk, lk if kv_valid is None else kv_valid, _ptr(mask), _ptr(ws), ws_bytes,
+                                   _stream()),
           "hoisdf_attention_fwd")
     return out
 

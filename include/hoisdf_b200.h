@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 2
+#define HOISDF_ABI_VERSION 3
 
 enum {
   HOISDF_OK = 0,
@@ -51,7 +51,8 @@ const char* hoisdf_status_string(int status);
  *   w_lo == NULL : fp32 FMA kernel (bit-faithful fp32 products).
  *   w_lo != NULL : tcgen05 tensor-core kernel, 3xTF32 split (fp32-grade accuracy): `w` must then hold the
  *                  TF32-rounded weights and `w_lo` the residual W - w (both from hoisdf_split_tf32, same pitch).
- *                  Used only for un-batched rows; batched rows always take the FMA kernel.
+ *                  Input rows may be batched (m must then be a multiple of x_rows_per_batch); batched OUTPUT
+ *                  rows always take the FMA kernel.
  * ------------------------------------------------------------------------------------------------- */
 typedef struct {
   const float* x; int64_t ldx; int64_t x_rows_per_batch; int64_t x_batch_stride;
@@ -192,10 +193,16 @@ int hoisdf_tokens_fwd(const float* xyz, const float* posenc, const float* fea, i
  *   out (B, Lq, ldo).  scores = q.k^T / sqrt(64); keys >= kv_valid are masked (memory_mask of
  *   common/utils/misc.py:42-47); optional dense bool mask (Lq, Lk) uint8, 1 = blocked (misc.py:11-31).
  *   Streaming (flash-style) softmax: the Lq x Lk score matrix is never materialised.
+ * Three implementations behind one contract:
+ *   workspace != NULL and no dense mask       : tcgen05 tensor-core kernel (BF16x3 split, fp32 accumulate in TMEM);
+ *       `workspace` must hold hoisdf_attention_workspace_bytes(...) bytes (bf16 hi/lo copies of q, k, v^T);
+ *   dense mask, or lq <= 32 w/o workspace     : small kernel (decoder: 17 queries);
+ *   otherwise                                 : fp32 FMA streaming kernel.
  * ------------------------------------------------------------------------------------------------- */
+int64_t hoisdf_attention_workspace_bytes(int64_t batch, int64_t heads, int64_t lq, int64_t lk);
 int hoisdf_attention_fwd(const float* q, int64_t ldq, const float* k, const float* v, int64_t ldk, float* out,
                          int64_t ldo, int64_t batch, int64_t heads, int64_t lq, int64_t lk, int64_t kv_valid,
-                         const uint8_t* mask, void* stream);
+                         const uint8_t* mask, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* y = LayerNorm(x (+ res)) * gamma + beta, eps 1e-5, rows of 256 (transformer.py:296-301); optional second
  * output y2 = LayerNorm(y) with (gamma2, beta2) -- the shared `inter_norm` of transformer.py:196-197. */

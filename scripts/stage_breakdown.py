@@ -8,6 +8,7 @@ ap.add_argument("--ph", type=int, default=1536)
 ap.add_argument("--po", type=int, default=512)
 ap.add_argument("--arch", default="ho3d")
 ap.add_argument("--iters", type=int, default=3)
+ap.add_argument("--channels-last", action="store_true")
 a = ap.parse_args()
 from hoisdf_b200 import ops, synthetic as syn
 from hoisdf_b200.config import cfg
@@ -18,7 +19,8 @@ dev = torch.device("cuda:0")
 cfg.set_setting(a.arch); type(cfg).dataset = "ho3d"
 type(cfg).num_samp_hand, type(cfg).num_samp_obj = a.ph, a.po
 model = get_model("test", mano_buffers=syn.mano_buffers(0))
-model.load_state_dict(syn.full_state_dict(0, a.arch)); model = model.to(dev).eval().channels_last_()
+model.load_state_dict(syn.full_state_dict(0, a.arch)); model = model.to(dev).eval()
+if a.channels_last: model.channels_last_()
 B = a.batch
 inputs = {"img": syn.image_batch(100, B).to(dev)}; targets = {k: v.to(dev) for k, v in syn.eval_targets(B).items()}
 meta = {k: v.to(dev) for k, v in syn.camera_meta(100, B).items()}
