@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhoisdf_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 ACT_NONE, ACT_RELU = 0, 1
 GATHER_CONCAT, GATHER_SUM = 0, 1
 
@@ -24,7 +24,7 @@ class LinearArgs(C.Structure):
         ("x", vp), ("ldx", i64), ("x_rows_per_batch", i64), ("x_batch_stride", i64),
         ("w", vp), ("ldw", i64), ("bias", vp), ("residual", vp),
         ("y", vp), ("ldy", i64), ("y_rows_per_batch", i64), ("y_batch_stride", i64),
-        ("m", i64), ("n", i64), ("k", i64), ("act", i32), ("w_lo", vp),
+        ("m", i64), ("n", i64), ("k", i64), ("act", i32), ("w_lo", vp), ("tf32_passes", i32),
     ]
 
 
@@ -37,7 +37,7 @@ class Pyramid(C.Structure):
 
 class SdfWeights(C.Structure):
     _fields_ = [(n, vp) for n in ("w0", "b0", "w1", "b1", "w2", "b2", "w3", "b3", "w4", "b4",
-                                   "w0_lo", "w1_lo", "w2_lo", "w3_lo")]
+                                   "w0_lo", "w1_lo", "w2_lo", "w3_lo")] + [("tf32_passes", i32)]
 
 
 class ManoModel(C.Structure):

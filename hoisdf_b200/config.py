@@ -46,7 +46,14 @@ class Config:
     # hoisdf_b200 additions
     eval_losses = True          # keep the (unused by main/test.py) loss entries in the eval output dict
     max_rows_per_pass = 1 << 21 # candidate rows processed per pass (bounds the activation workspace)
-    screen_margin = 64          # extra rows kept by the tensor-core screening pass before the exact fp32 re-ranking
+    # Candidate screening before the exact fp32 re-ranking (Model.sdf_infer).  Default: 3xTF32 screening (error
+    # ~1.5e-7) with a margin of 64 rows (rank-P .. rank-(P+64) |sdf| gap ~2e-5: > 100x the error).  A single TF32 pass
+    # (screen_passes = 1) is 1.3x faster per GEMM but its ~6e-5 error needs a margin of >1000 rows at P = 1536, which
+    # costs more in fp32 re-ranking than it saves (measured), so it is opt-in; it is verified on the device and falls
+    # back to 3xTF32 when the gap is not > 3x the observed error.
+    screen_margin = 256         # margin used with screen_passes = 1
+    screen_margin_safe = 64     # margin used with 3xTF32 screening
+    screen_passes = 3
 
     def calc_mutliscale_dim(self, use_big_decoder_l, resnet_type_l):
         # upstream config.py:101-108 (sic: "mutliscale")

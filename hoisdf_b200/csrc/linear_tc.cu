@@ -45,6 +45,7 @@ struct TcParams {
   int64_t rows_per_batch;   // X rows form groups of this many rows (plain GEMM: = M, one group)
   int tiles_per_batch;      // ceil(rows_per_batch / 128)
   int n, k, act;
+  int passes;               // 3 = 3xTF32 (fp32-grade), 1 = single TF32 pass (screening only)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -183,10 +184,10 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         const uint32_t ph = (kb / TC_STAGES) & 1;
         mbar_wait(bar_empty(s), ph ^ 1u);
         const uint32_t st = base + s * TC_STAGE_BYTES;
-        mbar_expect_tx(bar_full(s), TC_A_BYTES + 2 * TC_B_BYTES);
+        mbar_expect_tx(bar_full(s), TC_A_BYTES + (p.passes == 3 ? 2 : 1) * TC_B_BYTES);
         tma_load_3d(st, &map_x, bar_full(s), kb * TC_BK, m0, grp);
         tma_load_2d(st + 2 * TC_A_BYTES, &map_whi, bar_full(s), kb * TC_BK, n0);
-        tma_load_2d(st + 2 * TC_A_BYTES + TC_B_BYTES, &map_wlo, bar_full(s), kb * TC_BK, n0);
+        if (p.passes == 3) tma_load_2d(st + 2 * TC_A_BYTES + TC_B_BYTES, &map_wlo, bar_full(s), kb * TC_BK, n0);
       }
     }
   } else if (warp == 1) {
@@ -199,7 +200,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         const int s = kb % TC_STAGES;
         const uint32_t ph = (kb / TC_STAGES) & 1;
         mbar_wait(bar_full(s), ph);
-        mbar_wait(bar_conv(s), ph);
+        if (p.passes == 3) mbar_wait(bar_conv(s), ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t st = base + s * TC_STAGE_BYTES;
         const uint64_t d_xhi = umma_desc_sw64(st), d_xlo = umma_desc_sw64(st + TC_A_BYTES);
@@ -209,9 +210,11 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         for (int kk = 0; kk < TC_BK / 8; ++kk) {
           const uint64_t adv = static_cast<uint64_t>(kk * 2);  // 8 tf32 = 32 bytes = 2 x 16-byte units
           const uint32_t acc = (kb | kk) != 0 ? 1u : 0u;
-          umma_tf32(tmem_acc, d_xhi + adv, d_whi + adv, idesc, acc);
-          umma_tf32(tmem_acc + TC_BN, d_xlo + adv, d_whi + adv, idesc, acc);
-          umma_tf32(tmem_acc + TC_BN, d_xhi + adv, d_wlo + adv, idesc, 1u);
+          umma_tf32(tmem_acc, d_xhi + adv, d_whi + adv, idesc, acc);   // single pass: the hardware truncates raw x
+          if (p.passes == 3) {
+            umma_tf32(tmem_acc + TC_BN, d_xlo + adv, d_whi + adv, idesc, acc);
+            umma_tf32(tmem_acc + TC_BN, d_xhi + adv, d_wlo + adv, idesc, 1u);
+          }
         }
         umma_commit(bar_empty(s));   // stage may be refilled once these MMAs have read it
       }
@@ -221,7 +224,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     // ------------------------------------------------ converter (mainloop), then epilogue
     const int t = threadIdx.x - 64;  // 0..127
     for (int c = t; c < TC_BN; c += 128) bias_s[c] = (p.bias != nullptr && c < n_here) ? __ldg(p.bias + n0 + c) : 0.f;
-    for (int kb = 0; kb < num_kb; ++kb) {
+    for (int kb = 0; kb < (p.passes == 3 ? num_kb : 0); ++kb) {
       const int s = kb % TC_STAGES;
       const uint32_t ph = (kb / TC_STAGES) & 1;
       mbar_wait(bar_full(s), ph);
@@ -255,7 +258,12 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
       uint32_t r[32], rc[32];
       const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0);
       tmem_ld32(taddr, r);
-      tmem_ld32(taddr + TC_BN, rc);
+      if (p.passes == 3) {
+        tmem_ld32(taddr + TC_BN, rc);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) rc[j] = 0u;
+      }
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       if (!row_ok) continue;
 #pragma unroll
@@ -368,7 +376,7 @@ int launch_linear_tf32x3(const hoisdf_linear_args* a, cudaStream_t s) {
   if (e != cudaSuccess) return static_cast<int>(e);
   const int64_t tpb = ceil_div(rpb, TC_BM);
   TcParams p{a->bias, a->residual, a->y, a->ldy, rpb, static_cast<int>(tpb), static_cast<int>(a->n),
-             static_cast<int>(a->k), a->act};
+             static_cast<int>(a->k), a->act, a->tf32_passes == 1 ? 1 : 3};
   const int64_t tiles = groups * tpb * ceil_div(a->n, TC_BN);
   if (tiles > 0x7fffffffLL) return HOISDF_E_SHAPE;
   linear_tf32x3_kernel<<<static_cast<unsigned>(tiles), TC_THREADS, TC_SMEM_BYTES, s>>>(mx, mhi, mlo, p);

@@ -141,16 +141,16 @@ HOISDF_API int hoisdf_sdf_decoder_fwd(const hoisdf_sdf_weights* w, float* x, int
   int st;
   const bool tc = w->w0_lo != nullptr && w->w1_lo != nullptr && w->w2_lo != nullptr && w->w3_lo != nullptr;
   // linh0: x[:, 0:292] -> h_a (512), ReLU
-  a = {x, ldx, 0, 0, w->w0, kDecInPad, w->b0, nullptr, h_a, 512, 0, 0, rows, 512, kDecInPad, HOISDF_ACT_RELU, tc ? w->w0_lo : nullptr};
+  a = {x, ldx, 0, 0, w->w0, kDecInPad, w->b0, nullptr, h_a, 512, 0, 0, rows, 512, kDecInPad, HOISDF_ACT_RELU, tc ? w->w0_lo : nullptr, w->tf32_passes};
   if ((st = hoisdf_linear_fwd(&a, stream)) != HOISDF_OK) return st;
   // linh1: h_a -> x[:, 292:515] (223), ReLU
-  a = {h_a, 512, 0, 0, w->w1, 512, w->b1, nullptr, x + kSkipOff, ldx, 0, 0, rows, kH1, 512, HOISDF_ACT_RELU, tc ? w->w1_lo : nullptr};
+  a = {h_a, 512, 0, 0, w->w1, 512, w->b1, nullptr, x + kSkipOff, ldx, 0, 0, rows, kH1, 512, HOISDF_ACT_RELU, tc ? w->w1_lo : nullptr, w->tf32_passes};
   if ((st = hoisdf_linear_fwd(&a, stream)) != HOISDF_OK) return st;
   // linh2: x[:, 0:516] (input | pad | h1 | pad, weight columns permuted to match) -> h_a, ReLU
-  a = {x, ldx, 0, 0, w->w2, kRowLd, w->b2, nullptr, h_a, 512, 0, 0, rows, 512, kRowLd, HOISDF_ACT_RELU, tc ? w->w2_lo : nullptr};
+  a = {x, ldx, 0, 0, w->w2, kRowLd, w->b2, nullptr, h_a, 512, 0, 0, rows, 512, kRowLd, HOISDF_ACT_RELU, tc ? w->w2_lo : nullptr, w->tf32_passes};
   if ((st = hoisdf_linear_fwd(&a, stream)) != HOISDF_OK) return st;
   // linh3: h_a -> h_b, ReLU
-  a = {h_a, 512, 0, 0, w->w3, 512, w->b3, nullptr, h_b, 512, 0, 0, rows, 512, 512, HOISDF_ACT_RELU, tc ? w->w3_lo : nullptr};
+  a = {h_a, 512, 0, 0, w->w3, 512, w->b3, nullptr, h_b, 512, 0, 0, rows, 512, 512, HOISDF_ACT_RELU, tc ? w->w3_lo : nullptr, w->tf32_passes};
   if ((st = hoisdf_linear_fwd(&a, stream)) != HOISDF_OK) return st;
   // linh4 + tanh
   sdf_head_kernel<<<static_cast<unsigned>(ceil_div(rows, 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(

@@ -10,7 +10,7 @@
 
 namespace hoisdf {
 
-constexpr int kMaxSel = 4096;
+constexpr int kMaxSel = 8192;
 constexpr int kSelThreads = 1024;
 
 __device__ __forceinline__ uint64_t composite_key(float sdf, uint32_t i) {
@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(kSelThreads) select_points_kernel(
     int num_points, int bins, float clamp, int order_by_row, int32_t* __restrict__ sel_index,
     int32_t* __restrict__ sel_row, float* __restrict__ points, float* __restrict__ out_sdf,
     float* __restrict__ posenc, int32_t* __restrict__ status_flag) {
-  __shared__ uint64_t keys[kMaxSel];
+  extern __shared__ __align__(16) uint64_t keys[];   // npad entries (next power of two >= num_points)
   __shared__ unsigned hist[256];
   __shared__ uint64_t s_prefix;
   __shared__ unsigned s_need;
@@ -158,7 +158,14 @@ HOISDF_API int hoisdf_select_points(const float* sdf, const int64_t* offsets, co
       points == nullptr || out_sdf == nullptr || posenc == nullptr)
     return HOISDF_E_NULL;
   if (batch <= 0 || batch > 65535 || num_points <= 0 || num_points > kMaxSel) return HOISDF_E_SHAPE;
-  select_points_kernel<<<static_cast<unsigned>(batch), kSelThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+  int npad = 1;
+  while (npad < num_points) npad <<= 1;
+  const size_t smem = static_cast<size_t>(npad) * sizeof(uint64_t);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(select_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+  select_points_kernel<<<static_cast<unsigned>(batch), kSelThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       sdf, offsets, cand_index, static_cast<int>(num_points), bins, clamp, order_by_row, sel_index, sel_row, points,
       out_sdf, posenc, status_flag);
   return launch_status();

@@ -119,14 +119,14 @@ class PackedLinear:
 
 
 def linear_raw(x_ptr: int, ldx: int, m: int, pw: PackedLinear, y_ptr: int, ldy: int, act: int = ACT_NONE,
-               residual_ptr: Optional[int] = None, x_batch=(0, 0), y_batch=(0, 0)):
+               residual_ptr: Optional[int] = None, x_batch=(0, 0), y_batch=(0, 0), passes: int = 3):
     if m == 0:
         return
     tc = (USE_TENSOR_CORES and pw.w_lo is not None and y_batch[0] <= 0
           and (x_batch[0] <= 0 or m % x_batch[0] == 0))
     a = _capi.LinearArgs(
         x_ptr, ldx, x_batch[0], x_batch[1], (pw.w_hi if tc else pw.w).data_ptr(), pw.ldw, _ptr(pw.b), residual_ptr,
-        y_ptr, ldy, y_batch[0], y_batch[1], m, pw.n, pw.k, act, pw.w_lo.data_ptr() if tc else None)
+        y_ptr, ldy, y_batch[0], y_batch[1], m, pw.n, pw.k, act, pw.w_lo.data_ptr() if tc else None, passes)
     _count()
     if PROFILE is None:
         check(lib.hoisdf_linear_fwd(C.byref(a), _stream()), "hoisdf_linear_fwd")
@@ -144,7 +144,7 @@ def fma_only(pw: PackedLinear) -> PackedLinear:
 
 
 def linear(x: torch.Tensor, pw: PackedLinear, act: int = ACT_NONE, out: Optional[torch.Tensor] = None,
-           residual: Optional[torch.Tensor] = None, out_ld: Optional[int] = None) -> torch.Tensor:
+           residual: Optional[torch.Tensor] = None, out_ld: Optional[int] = None, passes: int = 3) -> torch.Tensor:
     """x: (M, >=K) 2-D, unit inner stride.  Returns (M, N) (a view of a (M, out_ld) buffer if padded)."""
     assert x.dim() == 2 and x.stride(1) == 1 and x.shape[1] >= pw.k, (x.shape, x.stride(), pw.k)
     m = x.shape[0]
@@ -157,7 +157,7 @@ def linear(x: torch.Tensor, pw: PackedLinear, act: int = ACT_NONE, out: Optional
     assert out.stride(1) == 1
     if residual is not None:
         assert residual.shape == out.shape and residual.stride() == out.stride()
-    linear_raw(x.data_ptr(), x.stride(0), m, pw, out.data_ptr(), out.stride(0), act, _ptr(residual))
+    linear_raw(x.data_ptr(), x.stride(0), m, pw, out.data_ptr(), out.stride(0), act, _ptr(residual), passes=passes)
     return out
 
 
@@ -261,9 +261,12 @@ class PackedSdfDecoder:
     tensors: List[torch.Tensor]      # keeps the packed buffers alive
     struct_fma: _capi.SdfWeights     # fp32 FMA kernels
     struct_tc: Optional[_capi.SdfWeights]   # tcgen05 3xTF32 kernels (None when tensor cores are disabled)
+    struct_tc1: Optional[_capi.SdfWeights] = None   # tcgen05 single-pass TF32 (candidate screening only)
 
-    def struct(self, exact: bool = False):
-        return self.struct_fma if (exact or self.struct_tc is None or not USE_TENSOR_CORES) else self.struct_tc
+    def struct(self, exact: bool = False, screening: bool = False):
+        if exact or self.struct_tc is None or not USE_TENSOR_CORES:
+            return self.struct_fma
+        return self.struct_tc1 if screening else self.struct_tc
 
 
 def pack_sdf_decoder(dec_params: dict) -> PackedSdfDecoder:
@@ -286,13 +289,15 @@ def pack_sdf_decoder(dec_params: dict) -> PackedSdfDecoder:
     ws = (w0, w1, w2, w3)
     bp = [b.data_ptr() for b in bs]
     s_fma = _capi.SdfWeights(ws[0].data_ptr(), bp[0], ws[1].data_ptr(), bp[1], ws[2].data_ptr(), bp[2],
-                             ws[3].data_ptr(), bp[3], w4.data_ptr(), bp[4], None, None, None, None)
+                             ws[3].data_ptr(), bp[3], w4.data_ptr(), bp[4], None, None, None, None, 3)
     splits = [split_tf32(w) for w in ws]
     keep += [t for hl in splits for t in hl]
     his, los = [hl[0].data_ptr() for hl in splits], [hl[1].data_ptr() for hl in splits]
     s_tc = _capi.SdfWeights(his[0], bp[0], his[1], bp[1], his[2], bp[2], his[3], bp[3], w4.data_ptr(), bp[4],
-                            los[0], los[1], los[2], los[3])
-    return PackedSdfDecoder(keep, s_fma, s_tc)
+                            los[0], los[1], los[2], los[3], 3)
+    s_tc1 = _capi.SdfWeights(his[0], bp[0], his[1], bp[1], his[2], bp[2], his[3], bp[3], w4.data_ptr(), bp[4],
+                             los[0], los[1], los[2], los[3], 1)
+    return PackedSdfDecoder(keep, s_fma, s_tc, s_tc1)
 
 
 def posenc(rows_buf: torch.Tensor, *, lattice_index=None, points=None, bins: int = 64):
@@ -303,7 +308,7 @@ def posenc(rows_buf: torch.Tensor, *, lattice_index=None, points=None, bins: int
 
 
 def sdf_decoder(packed: PackedSdfDecoder, rows_buf: torch.Tensor, h_a=None, h_b=None, clamp: float = 0.0,
-                out: Optional[torch.Tensor] = None, exact: bool = False) -> torch.Tensor:
+                out: Optional[torch.Tensor] = None, exact: bool = False, screening: bool = False) -> torch.Tensor:
     rows = rows_buf.shape[0]
     dev = rows_buf.device
     h_a = h_a if h_a is not None else torch.empty(rows, 512, device=dev, dtype=torch.float32)
@@ -313,7 +318,7 @@ def sdf_decoder(packed: PackedSdfDecoder, rows_buf: torch.Tensor, h_a=None, h_b=
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    check(lib.hoisdf_sdf_decoder_fwd(C.byref(packed.struct(exact)), rows_buf.data_ptr(), rows_buf.stride(0), rows,
+    check(lib.hoisdf_sdf_decoder_fwd(C.byref(packed.struct(exact, screening)), rows_buf.data_ptr(), rows_buf.stride(0), rows,
                                      h_a.data_ptr(), h_b.data_ptr(), out.data_ptr(), float(clamp), _stream()),
           "hoisdf_sdf_decoder_fwd")
     if PROFILE is not None:

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 3
+#define HOISDF_ABI_VERSION 4
 
 enum {
   HOISDF_OK = 0,
@@ -63,6 +63,9 @@ typedef struct {
   int64_t m; int64_t n; int64_t k;
   int32_t act;
   const float* w_lo;                 /* may be NULL (see above) */
+  int32_t tf32_passes;               /* tensor-core kernel only: 0 or 3 = 3xTF32 (fp32-grade); 1 = one TF32 pass
+                                        (~5e-4 relative; used ONLY to pre-screen top-k candidates that an exact
+                                        pass re-ranks, never for a result that is returned) */
 } hoisdf_linear_args;
 
 int hoisdf_linear_fwd(const hoisdf_linear_args* args, void* stream);
@@ -153,6 +156,7 @@ typedef struct {
   const float* w4; const float* b4;
   /* optional TF32 residuals of w0..w3 (all four or none): selects the tensor-core Linear kernel */
   const float* w0_lo; const float* w1_lo; const float* w2_lo; const float* w3_lo;
+  int32_t tf32_passes;               /* as in hoisdf_linear_args */
 } hoisdf_sdf_weights;
 
 int hoisdf_sdf_decoder_fwd(const hoisdf_sdf_weights* wts, float* x, int64_t ldx, int64_t rows, float* h_a,

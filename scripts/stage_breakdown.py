@@ -62,3 +62,7 @@ for k, v in times.items():
     ms = sum(e0.elapsed_time(e1) for e0, e1 in v) / a.iters
     print("%-22s %9.3f ms  %5.1f%%  (%d calls/iter)" % (k, ms, 100 * ms / tot, len(v) // a.iters))
 print("samples/s", B * 1000 / tot)
+for kind in ("hand", "obj"):
+    t = model.last_taps[kind]
+    if "screen_gap" in t:
+        print(kind, "screen verified", t["screen_verified"], "gap min %.3e" % float(t["screen_gap"].min()), "err %.3e" % float(t["screen_err"]))
