@@ -17,6 +17,12 @@
 //               layout never has to be decoded), then the epilogue: tcgen05.ld 32 lanes x 32 columns per
 //               warp of both accumulators, fused bias (staged in smem) / residual / ReLU, 128-bit global stores.
 // Tails need no padding: TMA zero-fills rows >= M / >= N and columns >= K.
+//
+// Thread-block clusters: the kernel is bound by L2 -> SM traffic when every CTA streams the whole W tile (hi + lo =
+// 2 x 256 rows) next to its 128 X rows (25.6 FLOP per fetched byte).  CTAs are therefore launched as clusters of 2
+// that own two M tiles of the SAME N tile: each CTA fetches half of the W rows and TMA-multicasts them into both
+// CTAs' shared memory, so W crosses the L2 -> SM fabric once per pair (42.7 FLOP/B).  A stage is released to the
+// producers only when BOTH CTAs' tensor cores have consumed it (tcgen05.commit multicast to both `empty` barriers).
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -36,6 +42,9 @@ constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + TC_B
 constexpr int TC_THREADS = 192;
 constexpr uint32_t TC_TMEM_COLS = 512;          // main accumulator [0,256) + correction accumulator [256,512)
 constexpr uint32_t kSpinLimit = 1u << 27;       // watchdog: a protocol bug traps instead of hanging the GPU
+constexpr int TC_CLUSTER = 2;                   // CTAs per cluster (share the W tile through TMA multicast)
+constexpr int TC_W_SLICE_ROWS = TC_BN / TC_CLUSTER;          // W rows each CTA fetches (and multicasts)
+constexpr int TC_W_SLICE_BYTES = TC_W_SLICE_ROWS * TC_BK * 4;
 
 struct TcParams {
   const float* __restrict__ bias;
@@ -44,9 +53,20 @@ struct TcParams {
   int64_t ldy;
   int64_t rows_per_batch;   // X rows form groups of this many rows (plain GEMM: = M, one group)
   int tiles_per_batch;      // ceil(rows_per_batch / 128)
+  int m_tiles;              // groups * tiles_per_batch (CTAs beyond it are cluster padding)
   int n, k, act;
   int passes;               // 3 = 3xTF32 (fp32-grade), 1 = single TF32 pass (screening only)
+  unsigned long long* trace; // developer timeline (globaltimer ns) of CTA `trace_cta`; NULL in production
+  int trace_cta;
 };
+
+__device__ __forceinline__ void tc_trace(const TcParams& p, int slot) {
+  if (p.trace != nullptr && static_cast<int>(blockIdx.x) == p.trace_cta) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    p.trace[slot] = t;
+  }
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -81,6 +101,15 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -107,6 +136,17 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
 
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(cta_mask)
+      : "memory");
+}
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
@@ -145,14 +185,19 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (p.n + TC_BN - 1) / TC_BN;
-  const int m_tile = static_cast<int>(blockIdx.x / n_tiles);
-  const int grp = m_tile / p.tiles_per_batch;                       // row group (batched rows) of this tile
-  const int m0 = (m_tile - grp * p.tiles_per_batch) * TC_BM;         // first row inside the group
-  const int n0 = static_cast<int>(blockIdx.x % n_tiles) * TC_BN;
+  uint32_t cta_rank;
+  asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  const int cid = static_cast<int>(blockIdx.x) / TC_CLUSTER;          // cluster id: (M-tile pair, N tile), N fastest
+  const int m_tile = (cid / n_tiles) * TC_CLUSTER + static_cast<int>(cta_rank);
+  // cluster padding (odd number of M tiles): group index = #groups, every X row out of bounds -> zero-filled
+  const int grp = m_tile < p.m_tiles ? m_tile / p.tiles_per_batch : p.m_tiles / p.tiles_per_batch;
+  const int m0 = m_tile < p.m_tiles ? (m_tile - grp * p.tiles_per_batch) * TC_BM : 0;
+  const int n0 = (cid % n_tiles) * TC_BN;
   const int n_here = min(TC_BN, p.n - n0);
   const int n_inst = (n_here + 15) & ~15;                  // UMMA N (multiple of 16 for M = 128)
   const int num_kb = (p.k + TC_BK - 1) / TC_BK;
 
+  if (threadIdx.x == 0) tc_trace(p, 0);
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_whi) : "memory");
@@ -160,7 +205,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(bar_full(s), 1);
       mbar_init(bar_conv(s), 4);
-      mbar_init(bar_empty(s), 1);
+      mbar_init(bar_empty(s), TC_CLUSTER);   // both CTAs' tensor cores must have consumed the stage
     }
     mbar_init(bar_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -173,8 +218,11 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  cluster_sync_all();                        // the peer's barriers are initialised before any multicast lands there
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_acc = *tmem_slot;
+  constexpr uint16_t kAllCtas = (1u << TC_CLUSTER) - 1u;
+  if (threadIdx.x == 0) tc_trace(p, 1);
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer
@@ -183,11 +231,16 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         const int s = kb % TC_STAGES;
         const uint32_t ph = (kb / TC_STAGES) & 1;
         mbar_wait(bar_empty(s), ph ^ 1u);
+        if (kb < 40) tc_trace(p, 8 + kb);                       // producer: stage free
         const uint32_t st = base + s * TC_STAGE_BYTES;
         mbar_expect_tx(bar_full(s), TC_A_BYTES + (p.passes == 3 ? 2 : 1) * TC_B_BYTES);
         tma_load_3d(st, &map_x, bar_full(s), kb * TC_BK, m0, grp);
-        tma_load_2d(st + 2 * TC_A_BYTES, &map_whi, bar_full(s), kb * TC_BK, n0);
-        if (p.passes == 3) tma_load_2d(st + 2 * TC_A_BYTES + TC_B_BYTES, &map_wlo, bar_full(s), kb * TC_BK, n0);
+        // this CTA's slice of the W rows, multicast to every CTA of the cluster (same smem offset, same barrier)
+        const uint32_t wo = cta_rank * TC_W_SLICE_BYTES;
+        const int wrow = n0 + static_cast<int>(cta_rank) * TC_W_SLICE_ROWS;
+        tma_load_2d_mc(st + 2 * TC_A_BYTES + wo, &map_whi, bar_full(s), kb * TC_BK, wrow, kAllCtas);
+        if (p.passes == 3)
+          tma_load_2d_mc(st + 2 * TC_A_BYTES + TC_B_BYTES + wo, &map_wlo, bar_full(s), kb * TC_BK, wrow, kAllCtas);
       }
     }
   } else if (warp == 1) {
@@ -200,7 +253,9 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         const int s = kb % TC_STAGES;
         const uint32_t ph = (kb / TC_STAGES) & 1;
         mbar_wait(bar_full(s), ph);
+        if (kb < 40) tc_trace(p, 48 + kb);                      // MMA: TMA bytes landed
         if (p.passes == 3) mbar_wait(bar_conv(s), ph);
+        if (kb < 40) tc_trace(p, 88 + kb);                      // MMA: x split done
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t st = base + s * TC_STAGE_BYTES;
         const uint64_t d_xhi = umma_desc_sw64(st), d_xlo = umma_desc_sw64(st + TC_A_BYTES);
@@ -216,7 +271,8 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             umma_tf32(tmem_acc + TC_BN, d_xhi + adv, d_wlo + adv, idesc, 1u);
           }
         }
-        umma_commit(bar_empty(s));   // stage may be refilled once these MMAs have read it
+        umma_commit_mc(bar_empty(s), kAllCtas);   // stage may be refilled once BOTH CTAs' MMAs have read it
+        if (kb < 40) tc_trace(p, 128 + kb);                     // MMA: issued
       }
       umma_commit(bar_done);         // accumulator complete
     }
@@ -246,10 +302,11 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");   // bias_s visible to all four epilogue warps
     mbar_wait(bar_done, 0);
+    if (threadIdx.x == 64) tc_trace(p, 2);                       // accumulator complete
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int q = warp & 3;                        // TMEM lane quarter this warp may read
     const int64_t lrow = static_cast<int64_t>(m0) + q * 32 + lane;      // row inside the group
-    const bool row_ok = lrow < p.rows_per_batch;
+    const bool row_ok = lrow < p.rows_per_batch && m_tile < p.m_tiles;
     const int64_t row = static_cast<int64_t>(grp) * p.rows_per_batch + lrow;   // output rows are dense
     float* yrow = p.y + (row_ok ? row * p.ldy : 0) + n0;
     const float* rrow = p.residual ? p.residual + (row_ok ? row * p.ldy : 0) + n0 : nullptr;
@@ -299,8 +356,11 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
       }
     }
   }
+  if (threadIdx.x == 64) tc_trace(p, 3);                         // epilogue stores issued
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  cluster_sync_all();                        // no CTA exits while the peer may still signal its barriers
+  if (threadIdx.x == 0) tc_trace(p, 4);
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(TC_TMEM_COLS) : "memory");
   }
@@ -316,6 +376,10 @@ __global__ void split_tf32_kernel(const float* __restrict__ w, int64_t n, float*
   hi[i] = h;
   lo[i] = v - h;
 }
+
+// developer hook (not part of the public header): timeline of one CTA of the next launches
+static unsigned long long* g_tc_trace = nullptr;
+static int g_tc_trace_cta = 0;
 
 static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -370,22 +434,42 @@ int launch_linear_tf32x3(const hoisdf_linear_args* a, cudaStream_t s) {
   if (groups > 1 && ((gstride * 4) % 16 != 0)) return HOISDF_E_ALIGN;
   if (groups == 1) gstride = rpb * a->ldx;   // unused by the hardware for a single group, but must be valid
   if (!make_map_x(&mx, a->x, groups, rpb, a->k, a->ldx, gstride)) return HOISDF_E_UNSUPPORTED;
-  if (!make_map(&mhi, a->w, a->n, a->k, a->ldw, TC_BN)) return HOISDF_E_UNSUPPORTED;
-  if (!make_map(&mlo, a->w_lo, a->n, a->k, a->ldw, TC_BN)) return HOISDF_E_UNSUPPORTED;
+  if (!make_map(&mhi, a->w, a->n, a->k, a->ldw, TC_W_SLICE_ROWS)) return HOISDF_E_UNSUPPORTED;
+  if (!make_map(&mlo, a->w_lo, a->n, a->k, a->ldw, TC_W_SLICE_ROWS)) return HOISDF_E_UNSUPPORTED;
   cudaError_t e = cudaFuncSetAttribute(linear_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   if (e != cudaSuccess) return static_cast<int>(e);
   const int64_t tpb = ceil_div(rpb, TC_BM);
-  TcParams p{a->bias, a->residual, a->y, a->ldy, rpb, static_cast<int>(tpb), static_cast<int>(a->n),
-             static_cast<int>(a->k), a->act, a->tf32_passes == 1 ? 1 : 3};
-  const int64_t tiles = groups * tpb * ceil_div(a->n, TC_BN);
-  if (tiles > 0x7fffffffLL) return HOISDF_E_SHAPE;
-  linear_tf32x3_kernel<<<static_cast<unsigned>(tiles), TC_THREADS, TC_SMEM_BYTES, s>>>(mx, mhi, mlo, p);
+  const int64_t m_tiles = groups * tpb;
+  TcParams p{a->bias, a->residual, a->y, a->ldy, rpb, static_cast<int>(tpb), static_cast<int>(m_tiles),
+             static_cast<int>(a->n), static_cast<int>(a->k), a->act, a->tf32_passes == 1 ? 1 : 3, g_tc_trace,
+             g_tc_trace_cta};
+  const int64_t ctas = ceil_div(m_tiles, TC_CLUSTER) * TC_CLUSTER * ceil_div(a->n, TC_BN);
+  if (ctas > 0x7fffffffLL || m_tiles > 0x3fffffffLL) return HOISDF_E_SHAPE;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(ctas));
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = TC_SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = TC_CLUSTER;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, linear_tf32x3_kernel, mx, mhi, mlo, p);
+  if (e != cudaSuccess) return static_cast<int>(e);
   return launch_status();
 }
 
 }  // namespace hoisdf
 
 using namespace hoisdf;
+
+extern "C" __attribute__((visibility("default"))) void hoisdf_debug_tc_trace(unsigned long long* buf, int cta) {
+  g_tc_trace = buf;
+  g_tc_trace_cta = cta;
+}
 
 HOISDF_API int hoisdf_split_tf32(const float* w, int64_t count, float* w_hi, float* w_lo, void* stream) {
   if (w == nullptr || w_hi == nullptr || w_lo == nullptr) return HOISDF_E_NULL;
