@@ -282,8 +282,8 @@ def run_native(args):
         "launches_per_step": len(tc) / args.steps, "share_of_step": tc_ms / ms_total,
         "algorithmic_flops_per_step": tc_flops / args.steps,
         "tf32_mma_tflops_executed": 3.0 * achieved,
-        "note": "the kernel is bound by L2->SM operand delivery (26 FLOP per fetched byte at a 128x256 tile with hi+lo "
-                "weights; measured ~11.4 TB/s aggregate = the L2 fabric cap), see DESIGN.md section 4.1",
+        "note": "in the mainloop the TF32 pipe is ~75 % busy (CTA timeline trace, DESIGN.md 4.1); the rest is per-tile "
+                "prologue/epilogue that one-tile-per-CTA cannot overlap, and small-K shapes (K = 256 / 292)",
         "fp32_fma_linear": {"achieved_tflops": fma_flops / (fma_ms * 1e-3) / 1e12 if fma_ms > 0 else 0.0,
                             "share_of_step": fma_ms / ms_total, "launches_per_step": len(fma) / args.steps,
                             "fp32_fma_peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12},

@@ -9,6 +9,8 @@
 // 4-wide quads so every shared-memory read is one conflict-free LDS.128; operands are staged through
 // registers (global float4 along K -> transposed k-major smem), double buffered, one __syncthreads per
 // K step.  Both operands are K-contiguous ("NT" GEMM), so a warp reads 8 rows x 64 contiguous bytes.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace hoisdf {
@@ -230,7 +232,8 @@ __global__ void fold_weight_norm_kernel(const float* __restrict__ g, const float
   }
 }
 
-int launch_linear_tf32x3(const hoisdf_linear_args* a, cudaStream_t s);  // linear_tc.cu
+int launch_linear_tf32x3(const hoisdf_linear_args* a, cudaStream_t s);      // linear_tc.cu  (1-SM MMA)
+int launch_linear_tf32x3_2sm(const hoisdf_linear_args* a, cudaStream_t s);  // linear_tc2.cu (2-SM MMA)
 
 }  // namespace hoisdf
 
@@ -245,7 +248,11 @@ HOISDF_API int hoisdf_linear_fwd(const hoisdf_linear_args* a, void* stream) {
   if (a->ldx < a->k || a->ldw < a->k || a->ldy < a->n) return HOISDF_E_SHAPE;
   if (a->w_lo != nullptr && a->y_rows_per_batch <= 0) {
     if (!aligned16(a->w_lo)) return HOISDF_E_ALIGN;
-    return launch_linear_tf32x3(a, static_cast<cudaStream_t>(stream));
+    // the 2-SM (cta_group::2) variant is correct but measured slower (131 vs 200 TFLOP/s at K = 512): the 1-SM
+    // mainloop already runs at ~75 % of the TF32 pipe, so halving operand traffic buys nothing; opt-in for experiments
+    static const bool use_2sm = [] { const char* e = getenv("HOISDF_TC_2SM"); return e != nullptr && e[0] == '1'; }();
+    return use_2sm ? launch_linear_tf32x3_2sm(a, static_cast<cudaStream_t>(stream))
+                   : launch_linear_tf32x3(a, static_cast<cudaStream_t>(stream));
   }
   LinearParams p;
   p.x = a->x; p.w = a->w; p.bias = a->bias; p.residual = a->residual; p.y = a->y;
