@@ -56,6 +56,7 @@ struct TcParams {
   int m_tiles;              // groups * tiles_per_batch (CTAs beyond it are cluster padding)
   int n, k, act;
   int passes;               // 3 = 3xTF32 (fp32-grade), 1 = single TF32 pass (screening only)
+  int tma_store;            // 1: epilogue stages 32x32 boxes in smem and writes them with TMA (no residual, dense rows)
   unsigned long long* trace; // developer timeline (globaltimer ns) of CTA `trace_cta`; NULL in production
   int trace_cta;
 };
@@ -170,7 +171,8 @@ __device__ __forceinline__ float tf32_rna(float x) {
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
-                     const __grid_constant__ CUtensorMap map_wlo, const TcParams p) {
+                     const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_y,
+                     const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;           // swizzled tiles: keep every tile 1024-byte aligned
@@ -311,6 +313,49 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     float* yrow = p.y + (row_ok ? row * p.ldy : 0) + n0;
     const float* rrow = p.residual ? p.residual + (row_ok ? row * p.ldy : 0) + n0 : nullptr;
     const bool vec = ((p.ldy & 3) == 0) && aligned16(p.y) && (p.residual == nullptr || aligned16(p.residual));
+    if (p.tma_store) {
+      // Row-strided 16-byte stores cost one LSU sector operation per lane (the old epilogue spent ~4 us per tile in
+      // them).  Instead each warp stages its 32 rows x 32 columns as a 128B-swizzled box in the (now idle) operand
+      // ring and lets the TMA write it: full-line writes, rows >= M and columns >= N clipped by the tensor map.
+      uint8_t* stage_gen = gen + q * 32768;
+      const uint32_t stage_sh = base + q * 32768;
+      const int64_t row0 = static_cast<int64_t>(grp) * p.rows_per_batch + m0 + q * 32;
+      for (int c0 = 0; c0 < n_inst; c0 += 32) {
+        uint32_t r[32], rc[32];
+        const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0);
+        tmem_ld32(taddr, r);
+        if (p.passes == 3) {
+          tmem_ld32(taddr + TC_BN, rc);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) rc[j] = 0u;
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        uint8_t* box = stage_gen + (c0 >> 5) * 4096;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          float v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            v[j] = (__uint_as_float(r[g * 4 + j]) + __uint_as_float(rc[g * 4 + j])) + bias_s[c0 + g * 4 + j];
+            if (p.act == HOISDF_ACT_RELU) v[j] = fmaxf(v[j], 0.f);
+          }
+          *reinterpret_cast<float4*>(box + lane * 128 + ((g ^ (lane & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0 && m_tile < p.m_tiles && c0 < n_here) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                       ::"l"(&map_y), "r"(stage_sh + (c0 >> 5) * 4096), "r"(n0 + c0), "r"(static_cast<int>(row0))
+                       : "memory");
+        }
+      }
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem source consumed; kernel end flushes the writes
+      }
+      __syncwarp();
+    } else
     for (int c0 = 0; c0 < n_inst; c0 += 32) {
       uint32_t r[32], rc[32];
       const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0);
@@ -421,6 +466,18 @@ static bool make_map_x(CUtensorMap* map, const float* ptr, int64_t groups, int64
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Y as (rows, n) with pitch ldy: box = 32 rows x 32 floats, 128-byte swizzle (TMA-store epilogue)
+static bool make_map_y(CUtensorMap* map, float* ptr, int64_t rows, int64_t cols, int64_t ld) {
+  auto enc = encode_fn();
+  if (enc == nullptr) return false;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // called by hoisdf_linear_fwd when args->w_lo is set and the OUTPUT rows are dense (input rows may be batched)
 int launch_linear_tf32x3(const hoisdf_linear_args* a, cudaStream_t s) {
   CUtensorMap mx, mhi, mlo;
@@ -438,11 +495,16 @@ int launch_linear_tf32x3(const hoisdf_linear_args* a, cudaStream_t s) {
   if (!make_map(&mlo, a->w_lo, a->n, a->k, a->ldw, TC_W_SLICE_ROWS)) return HOISDF_E_UNSUPPORTED;
   cudaError_t e = cudaFuncSetAttribute(linear_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   if (e != cudaSuccess) return static_cast<int>(e);
+  // TMA-store epilogue: no residual, 16-byte aligned pitch, and tiles never straddle two row groups
+  const bool tma_store = a->residual == nullptr && (a->ldy % 4 == 0) && aligned16(a->y) &&
+                         (groups == 1 || rpb % TC_BM == 0) && a->m < 0x7fffffffLL;
+  CUtensorMap my = mx;   // placeholder when the TMA-store epilogue is not used
+  if (tma_store && !make_map_y(&my, a->y, a->m, a->n, a->ldy)) return HOISDF_E_UNSUPPORTED;
   const int64_t tpb = ceil_div(rpb, TC_BM);
   const int64_t m_tiles = groups * tpb;
   TcParams p{a->bias, a->residual, a->y, a->ldy, rpb, static_cast<int>(tpb), static_cast<int>(m_tiles),
-             static_cast<int>(a->n), static_cast<int>(a->k), a->act, a->tf32_passes == 1 ? 1 : 3, g_tc_trace,
-             g_tc_trace_cta};
+             static_cast<int>(a->n), static_cast<int>(a->k), a->act, a->tf32_passes == 1 ? 1 : 3, tma_store ? 1 : 0,
+             g_tc_trace, g_tc_trace_cta};
   const int64_t ctas = ceil_div(m_tiles, TC_CLUSTER) * TC_CLUSTER * ceil_div(a->n, TC_BN);
   if (ctas > 0x7fffffffLL || m_tiles > 0x3fffffffLL) return HOISDF_E_SHAPE;
   cudaLaunchConfig_t cfg{};
@@ -457,7 +519,7 @@ int launch_linear_tf32x3(const hoisdf_linear_args* a, cudaStream_t s) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, linear_tf32x3_kernel, mx, mhi, mlo, p);
+  e = cudaLaunchKernelEx(&cfg, linear_tf32x3_kernel, mx, mhi, mlo, my, p);
   if (e != cudaSuccess) return static_cast<int>(e);
   return launch_status();
 }
