@@ -43,6 +43,11 @@ class Config:
     point_sampling_epoch = 40
     random_ratio = [0.3, 0.7]
     random_move_dist = [0.03, 0.05, 0.07]
+    # loss weights read by the eval-mode MANO loss entries (upstream config.py:146-150)
+    lambda_verts3d = 1e4
+    lambda_joints3d = 1e4
+    lambda_manopose = 10
+    lambda_manoshape = 0.1
     # hoisdf_b200 additions
     eval_losses = True          # keep the (unused by main/test.py) loss entries in the eval output dict
     max_rows_per_pass = 1 << 21 # candidate rows processed per pass (bounds the activation workspace)

@@ -45,7 +45,8 @@ struct ManoParams {
   const float* __restrict__ j_regressor;
   const float* __restrict__ weights;
   const float* __restrict__ hands_mean;
-  const float* __restrict__ pose6d;
+  const float* __restrict__ pose6d;     // (N,16,6) rot6d, or NULL when pose_aa is given
+  const float* __restrict__ pose_aa;    // (N,48) axis-angle (ground-truth MANO parameters), or NULL
   const float* __restrict__ betas;
   float* __restrict__ verts;
   float* __restrict__ joints;
@@ -55,6 +56,8 @@ __device__ __forceinline__ void normalize3(float* a) {  // F.normalize: a / max(
   const float n = fmaxf(sqrtf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]), 1e-12f);
   a[0] = __fdiv_rn(a[0], n); a[1] = __fdiv_rn(a[1], n); a[2] = __fdiv_rn(a[2], n);
 }
+
+__device__ void rodrigues_rotation(const float* aa_in, const float* mean3, float* R);
 
 // upstream mano_head.py:185-217 then rodrigues_layer.py:43-56 for one joint
 __device__ void joint_rotation(const float* x6, const float* mean3, float* R) {
@@ -93,8 +96,14 @@ __device__ void joint_rotation(const float* x6, const float* mean3, float* R) {
   for (int i = 0; i < 3; ++i) {
     aa[i] = q[i + 1] * kk;
     if (isnan(aa[i])) aa[i] = 0.f;
-    aa[i] += mean3 ? mean3[i] : 0.f;  // manolayer.py:139-142 (th_hands_mean + pose, root excluded)
   }
+  rodrigues_rotation(aa, mean3, R);
+}
+
+// axis-angle (+ th_hands_mean for the 15 finger joints, manolayer.py:139-142) -> rotation matrix
+__device__ void rodrigues_rotation(const float* aa_in, const float* mean3, float* R) {
+  float aa[3];
+  for (int i = 0; i < 3; ++i) aa[i] = aa_in[i] + (mean3 ? mean3[i] : 0.f);
   // Rodrigues through a quaternion (rodrigues_layer.py:43-56, :16-40)
   const float e0 = aa[0] + 1e-8f, e1 = aa[1] + 1e-8f, e2 = aa[2] + 1e-8f;
   const float ang = sqrtf(e0 * e0 + e1 * e1 + e2 * e2);
@@ -135,7 +144,9 @@ __global__ void __launch_bounds__(256) mano_kernel(const ManoParams p) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
   if (tid < 16) {
-    joint_rotation(p.pose6d + (n * 16 + tid) * 6, tid > 0 ? p.hands_mean + (tid - 1) * 3 : nullptr, rot[tid]);
+    const float* mean3 = tid > 0 ? p.hands_mean + (tid - 1) * 3 : nullptr;
+    if (p.pose_aa != nullptr) rodrigues_rotation(p.pose_aa + n * 48 + tid * 3, mean3, rot[tid]);
+    else joint_rotation(p.pose6d + (n * 16 + tid) * 6, mean3, rot[tid]);
   }
   if (tid >= 32 && tid < 42) beta[tid - 32] = p.betas[n * 10 + tid - 32];
   __syncthreads();
@@ -258,7 +269,21 @@ HOISDF_API int hoisdf_mano_fwd(const hoisdf_mano_model* m, const float* pose6d, 
     return HOISDF_E_NULL;
   if (n <= 0 || n > 0x7fffffffLL) return HOISDF_E_SHAPE;
   ManoParams p{m->shapedirs, m->posedirs, m->v_template, m->j_regressor, m->weights, m->hands_mean,
-               pose6d, betas, verts, joints};
+               pose6d, nullptr, betas, verts, joints};
+  mano_kernel<<<static_cast<unsigned>(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return launch_status();
+}
+
+HOISDF_API int hoisdf_mano_aa_fwd(const hoisdf_mano_model* m, const float* pose_aa, const float* betas, int64_t n,
+                                  float* verts, float* joints, void* stream) {
+  if (m == nullptr || pose_aa == nullptr || betas == nullptr || verts == nullptr || joints == nullptr)
+    return HOISDF_E_NULL;
+  if (m->shapedirs == nullptr || m->posedirs == nullptr || m->v_template == nullptr || m->j_regressor == nullptr ||
+      m->weights == nullptr || m->hands_mean == nullptr)
+    return HOISDF_E_NULL;
+  if (n <= 0 || n > 0x7fffffffLL) return HOISDF_E_SHAPE;
+  ManoParams p{m->shapedirs, m->posedirs, m->v_template, m->j_regressor, m->weights, m->hands_mean,
+               nullptr, pose_aa, betas, verts, joints};
   mano_kernel<<<static_cast<unsigned>(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   return launch_status();
 }

@@ -23,7 +23,7 @@ import torch.nn as nn
 from . import ops
 from .config import cfg
 from .nets.layer import MLP, _require_inference
-from .nets.loss import eval_losses
+from .nets.loss import dexycb_losses, eval_losses
 from .nets.mano_head import ManoHead, ManoLayer
 from .nets.module import BackboneNet, DecoderNet, DecoderNet_big
 from .nets.sdf_net import SDFDecoder
@@ -289,19 +289,36 @@ class Model(nn.Module):
         if mode == "train":
             raise NotImplementedError("hoisdf_b200 builds the inference hot path; the training step "
                                       "(backward kernels, SURVEY.md section 8 f-2) is not built yet")
-        if cfg.dataset == "dexycb":
-            raise NotImplementedError("the dexycb eval extras (GT-point SDF supervision, GT MANO forward, "
-                                      "model.py:370-422,606-620) are not built yet; use hot_path() for the shared path")
         with torch.no_grad():
             img = inputs["img"]
             plans = self._plans(meta_info)
             if getattr(self, "_channels_last", False):
                 img = img.contiguous(memory_format=torch.channels_last)
             img_feat, skips = self.backbone_net(img)
-            feature_pyramid, _decoder_out = self.decoder_net(img_feat, skips)
-            out = self.hot_path(feature_pyramid, meta_info, plans)
+            feature_pyramid, decoder_out = self.decoder_net(img_feat, skips)
+            ctx = self._ctx(feature_pyramid)
+            dex = cfg.dataset == "dexycb"
+            mano_params = targets["mano_param"] if dex else None
+            out = self._hot_path(ctx, meta_info, plans, mano_params)
+            taps = self.last_taps
+            if dex:
+                # upstream model.py:370-422: SDF supervision points, heat-map / segmentation heads, GT MANO
+                root, objc, K = meta_info["mano_root"], meta_info["obj_center_cam"], meta_info["cam_intr"]
+                hand_s, _, _ = self.sdf_forward(ctx, inputs["hand_sdf_points"], root, K, cfg.hand_sdf_scale, "hand")
+                obj_s, _, _ = self.sdf_forward(ctx, inputs["obj_sdf_points"], objc, K, cfg.obj_sdf_scale, "obj")
+                out["joint_heatmap_out"] = decoder_out[:, 0]
+                out["hand_seg_gt_out"] = targets["hand_seg"]
+                out["hand_seg_pred_out"] = decoder_out[:, 1]
+                out["obj_seg_gt_out"] = targets["obj_seg"]
+                out["obj_seg_pred_out"] = decoder_out[:, 2]
+                out["mano_joints_gt_out"] = taps["gt_mano"]["joints3d"]
+                out["mano_mesh_gt_out"] = taps["gt_mano"]["verts3d"]
+                if cfg.eval_losses:
+                    out = {**dexycb_losses(out, taps, targets, decoder_out, hand_s, obj_s, taps["pred_mano"],
+                                           taps["gt_mano"]), **out}
             if cfg.eval_losses:
-                out = {**eval_losses(self.last_taps, targets, meta_info), **out}
+                joint_gt = targets["joint_cam_no_trans"][:, 1:] if dex else None
+                out = {**eval_losses(taps, targets, meta_info, joint_gt), **out}
         return out
 
     def _plans(self, meta_info):
@@ -309,13 +326,13 @@ class Model(nn.Module):
         return (self.plan_candidates(meta_info["mano_root"], K, meta_info["bbox_hand"], cfg.hand_sdf_scale),
                 self.plan_candidates(meta_info["obj_center_cam"], K, meta_info["bbox_obj"], cfg.obj_sdf_scale))
 
-    def hot_path(self, feature_pyramid, meta_info, plans=None):
+    def hot_path(self, feature_pyramid, meta_info, plans=None, mano_params=None):
         """Everything of upstream Model.forward(mode='eval') after the U-Net (model.py:424-638), on our kernels.
         Returns the `*_out` entries; intermediate tensors are left in `self.last_taps`."""
         with torch.no_grad():
-            return self._hot_path(feature_pyramid, meta_info, plans)
+            return self._hot_path(feature_pyramid, meta_info, plans, mano_params)
 
-    def _hot_path(self, feature_pyramid, meta_info, plans):
+    def _hot_path(self, feature_pyramid, meta_info, plans, mano_params=None):
         root = meta_info["mano_root"].to(torch.float32).contiguous()
         objc = meta_info["obj_center_cam"].to(torch.float32).contiguous()
         K = meta_info["cam_intr"].to(torch.float32).contiguous()
@@ -367,6 +384,12 @@ class Model(nn.Module):
         shape = self._head_rows(self.linear_shape, hs, Ld * b, 1, nq, first=cfg.mano_shape_indx).view(Ld, b, 10)
         verts, joints = self.mano_head.forward_bm(pose6d, shape)
         hand_joints = ops.vote_joints(hand_nt.contiguous(), hand_off, hand_cls)
+        pred_mano = gt_mano = None
+        if mano_params is not None:      # dexycb eval: ground-truth MANO forward + what the pose/shape losses need
+            from .nets.mano_head import rot6d2mat
+            pred_mano = {"verts3d": verts, "joints3d": joints, "mano_shape": shape,
+                         "mano_pose": rot6d2mat(pose6d.reshape(-1, 6)).view(Ld, b, cfg.mano_shape_indx, 3, 3)}
+            gt_mano = self.mano_head.forward_gt(mano_params)
 
         out = {
             "mano_mesh_out": verts[-1],
@@ -381,7 +404,7 @@ class Model(nn.Module):
             obj_h_sdf=obj_h_sdf, hand_transformer_in=hand_in, obj_transformer_in=obj_in, hs=hs, memory=memory,
             hand_encoder_out=hand_enc, obj_encoder_out=obj_enc, hand_off=hand_off, hand_cls=hand_cls, obj_rot=obj_rot,
             obj_trans=obj_trans, mano_pose6d=pose6d, mano_shape=shape, hand_joints=hand_joints, mano_verts=verts,
-            mano_joints=joints, hand_points_notrans=hand_nt)
+            mano_joints=joints, hand_points_notrans=hand_nt, pred_mano=pred_mano, gt_mano=gt_mano)
         return out
 
     @staticmethod

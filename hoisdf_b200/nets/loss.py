@@ -25,10 +25,40 @@ def joint_vote_losses(points, hand_off, hand_cls, hand_joints, joint_gt):
     return loss_joint_3d, loss_joint_cls, loss_all
 
 
-def eval_losses(taps, targets, meta_info):
+def render_gaussian_heatmap(joint_coord):
+    """upstream model.py:128-143: sum of 21 isotropic Gaussians on the 128x128 output grid, x255."""
+    h, w = cfg.output_hm_shape[1], cfg.output_hm_shape[2]
+    yy, xx = torch.meshgrid(torch.arange(h, device=joint_coord.device), torch.arange(w, device=joint_coord.device),
+                            indexing="ij")
+    xx, yy = xx[None, None].float(), yy[None, None].float()
+    x, y = joint_coord[:, :, 0, None, None], joint_coord[:, :, 1, None, None]
+    hm = torch.exp(-(((xx - x) / cfg.sigma) ** 2) / 2 - (((yy - y) / cfg.sigma) ** 2) / 2)
+    return hm.sum(1) * 255
+
+
+def dexycb_losses(out, taps, targets, decoder_out, hand_sdf_sample, obj_sdf_sample, pred_mano, gt_mano):
+    """The extra entries of the dexycb eval branch (upstream model.py:393-422,640-654)."""
+    c = cfg.ClampingDistance
+    loss = {
+        "sdfhand_loss": F.l1_loss(hand_sdf_sample, targets["hand_sdf"].clamp(-c, c).unsqueeze(-1)),
+        "sdfobj_loss": F.l1_loss(obj_sdf_sample, targets["obj_sdf"].clamp(-c, c).unsqueeze(-1)),
+        "joint_heatmap": (decoder_out[:, 0] - render_gaussian_heatmap(targets["joint_coord"])) ** 2,
+        "obj_seg": F.binary_cross_entropy(decoder_out[:, 2], targets["obj_seg"], reduction="none"),
+        "hand_seg": F.binary_cross_entropy(decoder_out[:, 1], targets["hand_seg"], reduction="none"),
+    }
+    exp = lambda k: gt_mano[k].unsqueeze(0).expand(pred_mano[k].shape)  # noqa: E731
+    loss["mano_mesh_loss"] = cfg.lambda_verts3d * F.mse_loss(pred_mano["verts3d"], exp("verts3d"))
+    loss["mano_joint_loss"] = cfg.lambda_joints3d * F.mse_loss(pred_mano["joints3d"], exp("joints3d"))
+    loss["pose_param_loss"] = cfg.lambda_manopose * F.mse_loss(pred_mano["mano_pose"], exp("mano_pose"))
+    loss["shape_param_loss"] = cfg.lambda_manoshape * F.mse_loss(pred_mano["mano_shape"], exp("mano_shape"))
+    return loss
+
+
+def eval_losses(taps, targets, meta_info, joint_gt=None):
     b = taps["hand_points_notrans"].shape[0]
     dev = taps["hand_points_notrans"].device
-    joint_gt = torch.zeros(b, 20, 3, device=dev)          # upstream model.py:629 (ho3d eval has no joint GT)
+    if joint_gt is None:
+        joint_gt = torch.zeros(b, 20, 3, device=dev)      # upstream model.py:629 (ho3d eval has no joint GT)
     l3d, lcls, lall = joint_vote_losses(taps["hand_points_notrans"], taps["hand_off"], taps["hand_cls"],
                                         taps["hand_joints"], joint_gt)
     obj_rot, obj_trans = taps["obj_rot"], taps["obj_trans"]

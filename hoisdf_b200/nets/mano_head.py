@@ -57,6 +57,10 @@ class ManoLayer(nn.Module):
         """pose6d (N,16,6), betas (N,10) -> verts (N,778,3), joints (N,21,3) in metres."""
         return ops.mano(self._struct(), pose6d.contiguous(), betas.contiguous())
 
+    def forward_aa(self, pose_aa: torch.Tensor, betas: torch.Tensor):
+        """axis-angle pose (N,48), betas (N,10) -> verts, joints in metres (ground-truth branch)."""
+        return ops.mano_aa(self._struct(), pose_aa.contiguous().float(), betas.contiguous().float())
+
 
 def _load_mano_pkl(path):
     try:
@@ -96,9 +100,41 @@ class ManoHead(nn.Module):
         v, j = self.mano_layer.forward_6d(pose6d_bm.reshape(l * b, 16, 6), shape_bm.reshape(l * b, 10))
         return v.view(l, b, 778, 3), j.view(l, b, 21, 3)
 
+    def forward_gt(self, mano_params: torch.Tensor):
+        """Ground-truth branch of upstream mano_head.py:258-276: mano_params (B,58) = axis-angle pose (48) | shape (10).
+        Upstream copies the pose slice (`.contiguous()` of a column slice, :260) before subtracting th_hands_mean,
+        so the caller's tensor is left untouched; same here."""
+        gt_shape = mano_params[:, self.mano_pose_size:].to(torch.float32)
+        gt_pose = mano_params[:, : self.mano_pose_size].to(torch.float32).clone()
+        gt_pose[:, 3:] = gt_pose[:, 3:] - self.mano_layer.th_hands_mean
+        verts, joints = self.mano_layer.forward_aa(gt_pose, gt_shape)
+        return {"verts3d": verts, "joints3d": joints, "mano_shape": gt_shape,
+                "mano_pose": batch_rodrigues(gt_pose.reshape(-1, 3)).view(-1, 16, 3, 3)}
+
     def forward(self, pose6d, shape, mano_params=None):
         """Upstream signature (mano_head.py:232): pose6d (L,16,B,6), shape (L,B,10)."""
-        if mano_params is not None:
-            raise NotImplementedError("ground-truth MANO forward (training / dexycb eval) is not built yet")
-        v, j = self.forward_bm(pose6d.permute(0, 2, 1, 3).contiguous(), shape.contiguous())
-        return {"verts3d": v, "joints3d": j, "mano_shape": shape}, None
+        p6 = pose6d.permute(0, 2, 1, 3).contiguous()
+        v, j = self.forward_bm(p6, shape.contiguous())
+        pred = {"verts3d": v, "joints3d": j, "mano_shape": shape, "mano_pose": rot6d2mat(p6.reshape(-1, 6)).view(
+            p6.shape[0], p6.shape[1], 16, 3, 3)}
+        return pred, (None if mano_params is None else self.forward_gt(mano_params))
+
+
+def rot6d2mat(x: torch.Tensor) -> torch.Tensor:
+    """(N,6) -> (N,3,3), columns b1 b2 b3 (upstream mano_head.py:185-194); only feeds the eval-mode pose loss."""
+    a1, a2 = x[:, 0:3], x[:, 3:6]
+    b1 = torch.nn.functional.normalize(a1)
+    b2 = torch.nn.functional.normalize(a2 - (b1 * a2).sum(-1, keepdim=True) * b1)
+    return torch.stack((b1, b2, torch.cross(b1, b2, dim=1)), dim=-1)
+
+
+def batch_rodrigues(theta: torch.Tensor) -> torch.Tensor:
+    """(N,3) axis-angle -> (N,3,3) through a quaternion (upstream mano_head.py:12-51); loss bookkeeping only."""
+    angle = torch.norm(theta + 1e-8, p=2, dim=1, keepdim=True)
+    n = theta / angle
+    q = torch.cat([torch.cos(angle * 0.5), torch.sin(angle * 0.5) * n], dim=1)
+    q = q / q.norm(p=2, dim=1, keepdim=True)
+    w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    return torch.stack([w * w + x * x - y * y - z * z, 2 * x * y - 2 * w * z, 2 * w * y + 2 * x * z,
+                        2 * w * z + 2 * x * y, w * w - x * x + y * y - z * z, 2 * y * z - 2 * w * x,
+                        2 * x * z - 2 * w * y, 2 * w * x + 2 * y * z, w * w - x * x - y * y + z * z], dim=1).view(-1, 3, 3)

@@ -425,3 +425,14 @@ def mano(model_struct, pose6d, betas):
     check(lib.hoisdf_mano_fwd(C.byref(model_struct), pose6d.data_ptr(), betas.data_ptr(), n, verts.data_ptr(),
                               joints.data_ptr(), _stream()), "hoisdf_mano_fwd")
     return verts, joints
+
+
+def mano_aa(model_struct, pose_aa, betas):
+    """pose_aa (N,48) axis-angle, betas (N,10) contiguous -> verts (N,778,3), joints (N,21,3) [m]."""
+    n = pose_aa.shape[0]
+    verts = torch.empty(n, 778, 3, device=pose_aa.device, dtype=torch.float32)
+    joints = torch.empty(n, 21, 3, device=pose_aa.device, dtype=torch.float32)
+    _count(1)
+    check(lib.hoisdf_mano_aa_fwd(C.byref(model_struct), pose_aa.data_ptr(), betas.data_ptr(), n, verts.data_ptr(),
+                                 joints.data_ptr(), _stream()), "hoisdf_mano_aa_fwd")
+    return verts, joints

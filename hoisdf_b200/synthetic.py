@@ -293,3 +293,26 @@ def feature_pyramid(seed: int, batch: int, arch: str = "ho3d", scale: float = 1.
 
 def eval_targets(batch: int):
     return {"obj_rot": torch.zeros(batch, 3), "rel_obj_trans": torch.zeros(batch, 3)}
+
+
+def dexycb_extras(seed: int, batch: int, ph: int, po: int):
+    """The extra `inputs` / `targets` the dexycb evaluation branch reads (upstream main/model.py:370-422,606-629;
+    dataset keys data/dexycb.py:627-655), shaped and distributed as SURVEY.md 8(d) states."""
+    g = _rng(seed, "dexycb.normal")
+    normal = lambda shape, std: torch.from_numpy((g.standard_normal(size=shape) * std).astype(np.float32))  # noqa
+    inputs = {
+        "hand_sdf_points": _uniform(seed, "dexycb.hand_sdf_points", (batch, ph, 3), -1.0, 1.0),
+        "obj_sdf_points": _uniform(seed, "dexycb.obj_sdf_points", (batch, po, 3), -1.0, 1.0),
+    }
+    targets = {
+        "hand_sdf": _uniform(seed, "dexycb.hand_sdf", (batch, ph), -0.1, 0.1),
+        "obj_sdf": _uniform(seed, "dexycb.obj_sdf", (batch, po), -0.1, 0.1),
+        "hand_seg": (_uniform(seed, "dexycb.hand_seg", (batch, 128, 128), 0.0, 1.0) > 0.5).float(),
+        "obj_seg": (_uniform(seed, "dexycb.obj_seg", (batch, 128, 128), 0.0, 1.0) > 0.5).float(),
+        "joint_coord": _uniform(seed, "dexycb.joint_coord", (batch, 21, 2), 0.0, 128.0),
+        "joint_cam_no_trans": normal((batch, 21, 3), 40.0),
+        "mano_param": normal((batch, 58), 0.1),
+        "obj_rot": torch.zeros(batch, 3),
+        "rel_obj_trans": torch.zeros(batch, 3),
+    }
+    return inputs, targets

@@ -238,6 +238,10 @@ typedef struct {
 
 int hoisdf_mano_fwd(const hoisdf_mano_model* model, const float* pose6d, const float* betas, int64_t n,
                     float* verts, float* joints, void* stream);
+/* Same MANO forward from axis-angle parameters (N,48) -- the ground-truth branch of ManoHead.forward
+ * (upstream common/nets/mano_head.py:258-276: training and the dexycb evaluation). */
+int hoisdf_mano_aa_fwd(const hoisdf_mano_model* model, const float* pose_aa, const float* betas, int64_t n,
+                       float* verts, float* joints, void* stream);
 
 #ifdef __cplusplus
 }

@@ -37,6 +37,8 @@ def default_cfg(**over):
         hand_sdf_scale=3.1, obj_sdf_scale=3.1, num_samp_hand=600, num_samp_obj=200,
         input_img_shape=(256, 256), hidden_dim=256, nheads=4, dim_feedforward=1024,
         enc_layers=6, dec_layers=4, mano_num_queries=17, mano_shape_indx=16,
+        output_hm_shape=(128, 128, 128), sigma=2.5 / 2, hand_cls_dist=0.04,
+        lambda_verts3d=1e4, lambda_joints3d=1e4, lambda_manopose=10, lambda_manoshape=0.1,
     )
     for k, v in over.items():
         setattr(c, k, v)
@@ -474,6 +476,18 @@ def mano_head(p, pose6d, shape):
     return verts.view(L, B, 778, 3) / 1000, joints.view(L, B, 21, 3) / 1000
 
 
+def mano_head_gt(p, mano_params):
+    """upstream common/nets/mano_head.py:258-276 (ground-truth branch: training and the dexycb evaluation).
+    mano_params (B,58) = axis-angle pose (48) | shape (10).  The pose slice is copied (`.contiguous()` of a
+    column slice, :260), so the caller's tensor is NOT modified."""
+    gt_shape = mano_params[:, 48:]
+    gt_pose = mano_params[:, :48].contiguous()
+    gt_pose[:, 3:] = gt_pose[:, 3:] - p["mano_head.mano_layer.th_hands_mean"]
+    rotmat = rodrigues(gt_pose.view(-1, 3)).view(-1, 16, 3, 3)      # batch_rodrigues, mano_head.py:12-51
+    verts, joints = mano_layer(p, "mano_head.mano_layer", gt_pose, gt_shape)
+    return {"verts3d": verts / 1000, "joints3d": joints / 1000, "mano_shape": gt_shape, "mano_pose": rotmat}
+
+
 def vote_joints(hand_points, hand_off, hand_cls):
     """upstream common/nets/loss.py:31-36,54-57: softmax over points of the class logits, weighted vote sum.
 
@@ -598,6 +612,8 @@ def hot_path_eval(p, pyramid, meta, cfg, taps=None):
     shape = mlp(p, "linear_shape", hs[:, cfg.mano_shape_indx], 3, False)
     verts, joints = mano_head(p, pose6d, shape)
     hand_joints = vote_joints(hand_nt, hand_off, hand_cls)
+    if taps is not None:
+        taps["hand_points_notrans"] = hand_nt
     out = {
         "mano_mesh_out": verts[-1],
         "mano_joints_out": joints[-1],
@@ -625,3 +641,77 @@ def model_eval(p, img, meta, cfg, arch="ho3d", taps=None):
         taps["pyramid"] = pyramid
         taps["decoder_out"] = decoder_out
     return hot_path_eval(p, pyramid, meta, cfg, taps)
+
+
+# ----------------------------------------------------------------------------------------------------
+# the dexycb evaluation branch (upstream main/model.py:370-422, 606-654) and the eval-mode loss entries
+# ----------------------------------------------------------------------------------------------------
+def render_gaussian_heatmap(joint_coord, cfg):
+    """upstream main/model.py:128-143."""
+    x = torch.arange(cfg.output_hm_shape[2])
+    y = torch.arange(cfg.output_hm_shape[1])
+    yy, xx = torch.meshgrid(y, x, indexing="ij")
+    xx, yy = xx[None, None].float(), yy[None, None].float()
+    x = joint_coord[:, :, 0, None, None]
+    y = joint_coord[:, :, 1, None, None]
+    heatmap = torch.exp(-(((xx - x) / cfg.sigma) ** 2) / 2 - (((yy - y) / cfg.sigma) ** 2) / 2)
+    return torch.sum(heatmap, 1) * 255
+
+
+def joint_vote_losses(hand_points, hand_off, hand_cls, hand_joints, joint_gt, cfg):
+    """upstream common/nets/loss.py:31-61 (the three loss values; `hand_joints` comes from vote_joints)."""
+    l, pn, b, j = hand_cls.shape
+    vote = hand_points.unsqueeze(2).unsqueeze(0) + hand_off.reshape(l, pn, b, j, 3).permute(0, 2, 1, 3, 4)
+    cls_gt = (torch.norm(hand_points.unsqueeze(2) - joint_gt.unsqueeze(1) / 1000, dim=-1) < cfg.hand_cls_dist).float()
+    l3d = F.smooth_l1_loss(vote * 1000, joint_gt.unsqueeze(1).unsqueeze(0).expand(l, b, pn, j, 3), reduction="none")
+    l3d = (l3d * cls_gt.unsqueeze(-1).unsqueeze(0).expand(l, b, pn, j, 3)).sum((1, 2, 3)) / cls_gt.sum()
+    lcls = F.binary_cross_entropy_with_logits(hand_cls.permute(0, 2, 1, 3).contiguous(),
+                                              cls_gt.unsqueeze(0).expand(l, b, pn, j))
+    lall = F.smooth_l1_loss(hand_joints * 1000, joint_gt.unsqueeze(0).expand(l, b, j, 3))
+    return l3d.mean(), lcls, lall
+
+
+def mano_losses(pred, gt, cfg):
+    """upstream common/nets/loss.py:99-153 with the lambdas of model.py:107-112."""
+    exp = lambda k: gt[k].unsqueeze(0).expand(pred[k].shape)  # noqa: E731
+    return {"mano_mesh_loss": cfg.lambda_verts3d * F.mse_loss(pred["verts3d"], exp("verts3d")),
+            "mano_joint_loss": cfg.lambda_joints3d * F.mse_loss(pred["joints3d"], exp("joints3d")),
+            "pose_param_loss": cfg.lambda_manopose * F.mse_loss(pred["mano_pose"], exp("mano_pose")),
+            "shape_param_loss": cfg.lambda_manoshape * F.mse_loss(pred["mano_shape"], exp("mano_shape"))}
+
+
+def model_eval_dexycb(p, img, inputs, targets, meta, cfg, arch="dexycb", taps=None, pyramid=None, decoder_out=None):
+    """upstream Model.forward(mode='eval') with cfg.dataset == 'dexycb' (model.py:357-665): the ho3d eval path
+    plus SDF supervision queries, heat-map / segmentation heads, the ground-truth MANO forward and every loss
+    entry.  Returns the flat dict upstream returns ({**loss, **out})."""
+    if pyramid is None:
+        feat, skips = backbone(p, img)
+        pyramid, decoder_out = unet_decoder(p, feat, skips, arch)
+    taps = {} if taps is None else taps
+    root, objc, K = meta["mano_root"], meta["obj_center_cam"], meta["cam_intr"]
+    c = cfg.ClampingDistance
+    loss = {}
+    hand_s, _, _ = sdf_forward(p, pyramid, inputs["hand_sdf_points"], root, K, cfg.hand_sdf_scale, "hand", cfg)
+    obj_s, _, _ = sdf_forward(p, pyramid, inputs["obj_sdf_points"], objc, K, cfg.obj_sdf_scale, "obj", cfg)
+    loss["sdfhand_loss"] = F.l1_loss(hand_s, targets["hand_sdf"].clamp(-c, c).unsqueeze(-1))
+    loss["sdfobj_loss"] = F.l1_loss(obj_s, targets["obj_sdf"].clamp(-c, c).unsqueeze(-1))
+    out = {"joint_heatmap_out": decoder_out[:, 0], "hand_seg_gt_out": targets["hand_seg"],
+           "hand_seg_pred_out": decoder_out[:, 1], "obj_seg_gt_out": targets["obj_seg"],
+           "obj_seg_pred_out": decoder_out[:, 2]}
+    loss["joint_heatmap"] = (decoder_out[:, 0] - render_gaussian_heatmap(targets["joint_coord"], cfg)) ** 2
+    loss["obj_seg"] = F.binary_cross_entropy(decoder_out[:, 2], targets["obj_seg"], reduction="none")
+    loss["hand_seg"] = F.binary_cross_entropy(decoder_out[:, 1], targets["hand_seg"], reduction="none")
+    out.update(hot_path_eval(p, pyramid, meta, cfg, taps))
+    pred = {"verts3d": taps["mano_verts"], "joints3d": taps["mano_joints"], "mano_shape": taps["mano_shape"]}
+    L, N, B, _ = taps["mano_pose6d"].shape
+    pred["mano_pose"] = rot6d_to_mat(taps["mano_pose6d"].permute(0, 2, 1, 3).reshape(L * B * N, 6)).view(L, B, N, 3, 3)
+    gt = mano_head_gt(p, targets["mano_param"])
+    out["mano_joints_gt_out"], out["mano_mesh_gt_out"] = gt["joints3d"], gt["verts3d"]
+    l3d, lcls, lall = joint_vote_losses(taps["hand_points_notrans"], taps["hand_off"], taps["hand_cls"],
+                                        taps["hand_joints"], targets["joint_cam_no_trans"][:, 1:], cfg)
+    loss.update(loss_joint_3d=l3d, loss_joint_cls=lcls, loss_all_joint_3d=lall)
+    loss.update(mano_losses(pred, gt, cfg))
+    obj_rot, obj_trans = taps["obj_rot"], taps["obj_trans"]
+    loss["obj_rot"] = F.smooth_l1_loss(obj_rot, targets["obj_rot"][None, None].expand_as(obj_rot))
+    loss["obj_trans"] = F.smooth_l1_loss(obj_trans, targets["rel_obj_trans"][None, None].expand_as(obj_trans))
+    return {**loss, **out}

@@ -32,13 +32,13 @@ def _np(d):
     return {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in d.items()}
 
 
-def build_reference(arch, seed, ph, po):
+def build_reference(arch, seed, ph, po, dataset="ho3d"):
     ns = rs.load(arch)
     cfg = ns["cfg"]
     type(cfg).num_samp_hand, type(cfg).num_samp_obj = ph, po
-    # the small ('dexycb') ARCHITECTURE is used for cheap fixtures, but with the ho3d eval branch: the dexycb
-    # DATASET branch (model.py:370-422) needs ground-truth SDF samples / MANO parameters that are not on this path
-    type(cfg).dataset = "ho3d"
+    # the small ('dexycb') ARCHITECTURE is used for cheap fixtures; most of them take the ho3d eval branch, the
+    # `dexycb_eval_case` fixture takes the dexycb DATASET branch (model.py:370-422: GT SDF samples, GT MANO, losses)
+    type(cfg).dataset = dataset
     model = rs.build_model(ns, syn.mano_buffers(seed))
     model.load_state_dict(syn.full_state_dict(seed, arch), strict=True)
     model.eval()
@@ -168,6 +168,19 @@ def image_case(name, arch, seed, batch, ph, po):
     print(name, {k: tuple(v.shape) for k, v in out.items() if k.endswith("_out")})
 
 
+def dexycb_eval_case(name, seed, batch, ph, po):
+    """The dexycb evaluation branch from the image: every `*_out` entry and every loss entry upstream returns."""
+    ns, model = build_reference("dexycb", seed, ph, po, dataset="dexycb")
+    img, meta = syn.image_batch(seed, batch), syn.camera_meta(seed, batch)
+    inputs, targets = syn.dexycb_extras(seed, batch, ph, po)
+    with torch.no_grad():
+        out = model({"img": img, **inputs}, {k: v.clone() for k, v in targets.items()}, meta, "eval")
+    fix = {"arch": "dexycb", "seed": seed, "batch": batch, "num_samp_hand": ph, "num_samp_obj": po}
+    fix.update({k: v for k, v in out.items() if not k.endswith("_gt_out") or "mano" in k})
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **_np(fix))
+    print(name, {k: tuple(v.shape) for k, v in out.items()})
+
+
 if __name__ == "__main__":
     assert rs.available(), "the upstream reference is not mounted; golden vectors can only be made in the build container"
     os.makedirs(OUT, exist_ok=True)
@@ -176,3 +189,4 @@ if __name__ == "__main__":
     hot_path_case("hot_path_dexycb_seed11", "dexycb", 11, 2, 64, 32)
     hot_path_case("hot_path_ho3d_seed12", "ho3d", 12, 1, 96, 40)
     image_case("image_dexycb_seed13", "dexycb", 13, 1, 48, 16)
+    dexycb_eval_case("dexycb_eval_seed14", 14, 2, 48, 16)

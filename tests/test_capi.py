@@ -34,7 +34,7 @@ def test_argument_validation_without_gpu(lib_built):
     a = _capi.LinearArgs()            # all NULL
     assert lib.hoisdf_linear_fwd(C.byref(a), None) == -1          # HOISDF_E_NULL
     assert lib.hoisdf_gather_fwd(None, None, 0, None, 0, 0, 0, None, 0, None, 0, None) == -1
-    assert lib.hoisdf_attention_fwd(None, 0, None, None, 0, None, 0, 1, 4, 1, 1, 1, None, None) == -1
+    assert lib.hoisdf_attention_fwd(None, 0, None, None, 0, None, 0, 1, 4, 1, 1, 1, None, None, 0, None) == -1
     assert lib.hoisdf_lattice_count(None, None, None, 3.1, 1, 64, None, None, None) == -1
     a.x, a.w, a.y = 16, 16, 16        # non-NULL, aligned dummies; bad K alignment must be rejected before launch
     a.m, a.n, a.k, a.ldx, a.ldw, a.ldy = 4, 4, 6, 8, 8, 4

@@ -324,3 +324,13 @@ def test_vote_and_mano(cuda):
     overts, ojoints = O.mano_head(sd, pose6d, shape)
     assert (res["verts3d"].cpu() - overts).abs().max() < 2e-6    # metres; hand extent ~0.2
     assert (res["joints3d"].cpu() - ojoints).abs().max() < 2e-6
+    # ground-truth branch (axis-angle parameters, upstream mano_head.py:258-276) through hoisdf_mano_aa_fwd
+    params = torch.cat([rnd(77, B, 48, lo=-0.6, hi=0.6), rnd(78, B, 10, lo=-2, hi=2)], 1)
+    keep = params.clone()
+    _, gt = head(pose6d.to(cuda), shape.to(cuda), mano_params=params.to(cuda))
+    ogt = O.mano_head_gt(sd, params)
+    assert torch.equal(params, keep)
+    for k in ("verts3d", "joints3d", "mano_pose", "mano_shape"):
+        assert gt[k].shape == ogt[k].shape, k
+        assert (gt[k].cpu() - ogt[k]).abs().max() < 2e-6, k
+    assert rel_err(res["mano_pose"], O.rot6d_to_mat(pose6d.permute(0, 2, 1, 3).reshape(-1, 6)).view(L, B, 16, 3, 3)) < 2e-6

@@ -208,3 +208,50 @@ def test_single_pass_screening_is_verified_or_falls_back(setup):
         align_selection(taps["index"], otaps["index"], torch.stack([torch.sort(c.abs())[0][:96] for c in otaps["cand_sdf"]]))
     finally:
         type(cfg).screen_passes = old
+
+
+def test_dexycb_eval_branch(setup):
+    """cfg.dataset == 'dexycb' (upstream model.py:370-422,606-654): GT-point SDF queries, heat-map / segmentation
+    outputs, ground-truth MANO forward and every loss entry, from the image, against the oracle AND against the
+    committed upstream fixture (tests/golden/dexycb_eval_seed14.npz)."""
+    import os
+    import numpy as np
+    from hoisdf_b200.config import cfg
+    from hoisdf_b200.model import get_model
+    if setup["arch"] != "dexycb":
+        pytest.skip("the dexycb dataset branch runs on the dexycb architecture")
+    dev = setup["dev"]
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "dexycb_eval_seed14.npz"))
+    seed, B, ph, po = int(g["seed"]), int(g["batch"]), int(g["num_samp_hand"]), int(g["num_samp_obj"])
+    old = (cfg.dataset, cfg.num_samp_hand, cfg.num_samp_obj)
+    type(cfg).dataset, type(cfg).num_samp_hand, type(cfg).num_samp_obj = "dexycb", ph, po
+    try:
+        sd = syn.full_state_dict(seed, "dexycb")
+        model = get_model("test", mano_buffers=syn.mano_buffers(seed))
+        model.load_state_dict(sd, strict=True)
+        model = model.to(dev).eval()
+        img, meta = syn.image_batch(seed, B), syn.camera_meta(seed, B)
+        inputs, targets = syn.dexycb_extras(seed, B, ph, po)
+        tdev = to_dev(targets, dev)
+        before = tdev["mano_param"].clone()
+        out = model({"img": img.to(dev), **to_dev(inputs, dev)}, tdev, to_dev(meta, dev), "eval")
+        assert torch.equal(before, tdev["mano_param"])
+        with torch.no_grad():
+            oout = O.model_eval_dexycb(sd, img, inputs, targets, meta,
+                                       O.default_cfg(dataset="dexycb", num_samp_hand=ph, num_samp_obj=po))
+        assert set(out) == set(oout), set(out) ^ set(oout)
+        # entries that do not pass through the top-k selection: tight
+        for k in ("sdfhand_loss", "sdfobj_loss", "joint_heatmap", "obj_seg", "hand_seg", "joint_heatmap_out",
+                  "hand_seg_pred_out", "obj_seg_pred_out", "mano_joints_gt_out", "mano_mesh_gt_out"):
+            assert out[k].shape == oout[k].shape, k
+            assert rel(out[k], oout[k]) < 1e-3, (k, rel(out[k], oout[k]))
+            assert rel(out[k], torch.from_numpy(g[k])) < 1e-3, (k, "vs upstream fixture")
+        for k in ("hand_seg_gt_out", "obj_seg_gt_out"):
+            assert torch.equal(out[k].cpu(), targets[k.replace("_gt_out", "")])
+        # entries behind the selection (cuDNN vs MKL-DNN pyramids can flip near-ties): same gate as the image test
+        for k in ("mano_mesh_out", "mano_joints_out", "hand_joints_out", "loss_all_joint_3d", "mano_mesh_loss",
+                  "mano_joint_loss", "pose_param_loss", "shape_param_loss", "loss_joint_cls", "obj_rot", "obj_trans"):
+            assert out[k].shape == oout[k].shape, k
+            assert rel(out[k], oout[k]) < 2e-2, (k, rel(out[k], oout[k]))
+    finally:
+        type(cfg).dataset, type(cfg).num_samp_hand, type(cfg).num_samp_obj = old

@@ -90,3 +90,28 @@ def test_image_fixture():
     close(taps["decoder_out"][:, :4, :4, :4], g["pyr_crop_decoder_out"], 1e-4)
     for k in ("mano_mesh_out", "mano_joints_out", "obj_rot_out", "obj_trans_out", "hand_joints_out"):
         close(out[k], g[k], 1e-3)      # through the conv stack and a top-k: looser across machines
+
+
+DEX_LOSS_KEYS = ("sdfhand_loss", "sdfobj_loss", "joint_heatmap", "obj_seg", "hand_seg", "loss_joint_3d",
+                 "loss_joint_cls", "loss_all_joint_3d", "mano_mesh_loss", "mano_joint_loss", "pose_param_loss",
+                 "shape_param_loss", "obj_rot", "obj_trans")
+DEX_OUT_KEYS = ("joint_heatmap_out", "hand_seg_pred_out", "obj_seg_pred_out", "mano_mesh_out", "mano_joints_out",
+                "mano_joints_gt_out", "mano_mesh_gt_out", "obj_rot_out", "obj_trans_out", "hand_joints_out")
+
+
+def test_dexycb_eval_fixture():
+    """The dexycb DATASET branch of the eval forward (upstream model.py:370-422,606-654): every output and loss."""
+    g = load("dexycb_eval_seed14")
+    seed, B = int(g["seed"]), int(g["batch"])
+    ph, po = int(g["num_samp_hand"]), int(g["num_samp_obj"])
+    sd = syn.full_state_dict(seed, "dexycb")
+    inputs, targets = syn.dexycb_extras(seed, B, ph, po)
+    before = targets["mano_param"].clone()
+    with torch.no_grad():
+        out = O.model_eval_dexycb(sd, syn.image_batch(seed, B), inputs, targets, syn.camera_meta(seed, B),
+                                  O.default_cfg(dataset="dexycb", num_samp_hand=ph, num_samp_obj=po))
+    assert torch.equal(before, targets["mano_param"])       # upstream works on a copy of the pose slice
+    assert set(DEX_LOSS_KEYS + DEX_OUT_KEYS) <= set(out) and set(g) >= set(DEX_LOSS_KEYS + DEX_OUT_KEYS)
+    for k in DEX_LOSS_KEYS + DEX_OUT_KEYS:
+        close(out[k], g[k], 1e-3 if k in ("obj_rot_out", "obj_trans_out", "hand_joints_out", "loss_joint_3d",
+                                            "loss_all_joint_3d", "loss_joint_cls", "obj_rot", "obj_trans") else 1e-4)
