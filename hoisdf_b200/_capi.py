@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhoisdf_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 ACT_NONE, ACT_RELU = 0, 1
 GATHER_CONCAT, GATHER_SUM = 0, 1
 
@@ -25,6 +25,15 @@ class LinearArgs(C.Structure):
         ("w", vp), ("ldw", i64), ("bias", vp), ("residual", vp),
         ("y", vp), ("ldy", i64), ("y_rows_per_batch", i64), ("y_batch_stride", i64),
         ("m", i64), ("n", i64), ("k", i64), ("act", i32), ("w_lo", vp), ("tf32_passes", i32),
+    ]
+
+
+class LinearH3Args(C.Structure):
+    _fields_ = [
+        ("x_hi", vp), ("x_lo", vp), ("ldx", i64), ("x_rows_per_batch", i64), ("x_batch_stride", i64),
+        ("w_a", vp), ("w_b", vp), ("w_c", vp), ("ldw", i64), ("bias", vp), ("residual", vp),
+        ("y", vp), ("ldy", i64), ("y_hi", vp), ("y_lo", vp), ("ldyh", i64),
+        ("m", i64), ("n", i64), ("k", i64), ("act", i32),
     ]
 
 
@@ -50,6 +59,10 @@ SIGNATURES = {
     "hoisdf_status_string": (C.c_char_p, [C.c_int]),
     "hoisdf_linear_fwd": (C.c_int, [C.POINTER(LinearArgs), vp]),
     "hoisdf_split_tf32": (C.c_int, [vp, i64, vp, vp, vp]),
+    "hoisdf_linear_h3_fwd": (C.c_int, [C.POINTER(LinearH3Args), vp]),
+    "hoisdf_pack_h3": (C.c_int, [vp, i64, i64, i64, vp, vp, vp, i64, vp]),
+    "hoisdf_split_rows": (C.c_int, [vp, i64, i64, i64, i64, vp, vp, i64, vp]),
+    "hoisdf_join_rows": (C.c_int, [vp, vp, i64, i64, i64, vp, i64, vp]),
     "hoisdf_fold_weight_norm": (C.c_int, [vp, vp, i64, i64, vp, i64, vp, i64, vp]),
     "hoisdf_nchw_to_nhwc": (C.c_int, [vp, vp, i64, i64, i64, i64, vp]),
     "hoisdf_lattice_chunks": (C.c_int, [i32]),

@@ -1,0 +1,552 @@
+// nn.Linear on the 5th-generation tensor cores at FP16 rate with fp32-grade accuracy ("FP16x3").
+//
+//   x = x_hi + x_lo,  w = w_hi + w_lo   (hi = fp16-rounded value, lo = exact residual; 11 + 11 significand bits,
+//                                        the same 22 bits a 3xTF32 split carries -- see tc_common.cuh)
+//   X.W^T ~= x_hi.w_hi + x_lo.w_hi + x_hi.w_lo      (dropped x_lo.w_lo < 2^-22 relative)
+// kind::f16 MMAs run at twice the kind::tf32 rate and their operands are half as wide, so the same fp32-grade product
+// costs half the tensor time and half the L2 -> SM bytes of the 3xTF32 kernel (linear_tc.cu).  To keep every term
+// in ONE fp32 accumulator (so that TMEM can hold two of them and the epilogue of tile i overlaps the main loop of
+// tile i+1) all three products are formed at a common scale of 2^11:
+//   activations (split-half format, produced by the previous kernel's epilogue):  x_hi, x_lo' = x_lo * 2^11
+//   weights (3 planes, packed once):  A = w_hi * 2^11,  B = w_hi,  C = w_lo * 2^11          (|w| < 32)
+//   acc = x_hi.A + x_lo'.B + x_hi.C = 2^11 * (x_hi.w_hi + x_lo.w_hi + x_hi.w_lo);   y = acc * 2^-11 + bias
+//
+// Persistent, warp-specialised, one CTA per SM (192 threads), clusters of CL CTAs that own CL consecutive M tiles of
+// the same N tile:
+//   warp 0      TMA producer: per 32-half K block the CTA's own x_hi / x_lo' tiles (128 rows) and ITS 1/CL slice of
+//               the three W planes, multicast to every CTA of the cluster -> 3-stage ring of 64 KB stages
+//   warp 1      tcgen05.mma issuer (one thread): 6 MMAs (M128 x N<=256 x K16) per stage into accumulator t & 1
+//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns, scale + bias + ReLU, then either fp32 or split-half output
+//               staged in swizzled smem boxes and written by TMA (double-buffered per warp), or direct stores when a
+//               residual is added.  TMEM buffer released as soon as the last tcgen05.ld of the tile has landed.
+#include "tc_common.cuh"
+
+namespace hoisdf {
+using namespace tc;
+
+constexpr int H3_BM = 128;
+constexpr int H3_BN = 256;
+constexpr int H3_BK = 32;                               // halfs per stage row = one 64-byte swizzle row
+constexpr int H3_STAGES = 3;
+constexpr int H3_X_BYTES = H3_BM * H3_BK * 2;           // 8 KB per plane
+constexpr int H3_W_BYTES = H3_BN * H3_BK * 2;           // 16 KB per plane
+constexpr int H3_STAGE_BYTES = 2 * H3_X_BYTES + 3 * H3_W_BYTES;   // 64 KB
+constexpr int H3_EPI_SLOT = 4096;                       // one 32 x 32 fp32 box (or hi + lo half boxes)
+constexpr int H3_EPI_BYTES = 4 * 2 * H3_EPI_SLOT;       // 4 warps x 2 slots
+constexpr int H3_BAR_BYTES = 256;
+constexpr int H3_SMEM_BYTES = H3_STAGES * H3_STAGE_BYTES + H3_EPI_BYTES + H3_BAR_BYTES + 1024 /*align*/;
+constexpr int H3_THREADS = 192;
+constexpr uint32_t H3_TMEM_COLS = 512;                  // two 256-column fp32 accumulators
+
+enum { H3_OUT_F32_TMA = 0, H3_OUT_SPLIT_TMA = 1, H3_OUT_F32_DIRECT = 2 };
+
+struct H3Params {
+  const float* __restrict__ bias;
+  const float* __restrict__ residual;
+  float* __restrict__ y;
+  int64_t ldy;
+  int64_t rows_per_batch;   // X rows form groups of this many rows (plain GEMM: = M, one group)
+  int tiles_per_batch;      // ceil(rows_per_batch / 128)
+  int m_tiles;              // groups * tiles_per_batch
+  int m_blocks;             // ceil(m_tiles / CL): work items along M
+  int n_tiles;
+  int n, k, act;
+  int out_mode;
+};
+
+template <int CL>
+__global__ void __launch_bounds__(H3_THREADS, 1)
+linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__ CUtensorMap map_xlo,
+                 const __grid_constant__ CUtensorMap map_wa, const __grid_constant__ CUtensorMap map_wb,
+                 const __grid_constant__ CUtensorMap map_wc, const __grid_constant__ CUtensorMap map_y0,
+                 const __grid_constant__ CUtensorMap map_y1, const H3Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw);
+  const uint32_t epi = base + H3_STAGES * H3_STAGE_BYTES;
+  const uint32_t bars = epi + H3_EPI_BYTES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + H3_STAGES * H3_STAGE_BYTES + H3_EPI_BYTES + 128);
+  auto bar_full = [&](int s) { return bars + 8u * s; };
+  auto bar_empty = [&](int s) { return bars + 8u * (H3_STAGES + s); };
+  auto bar_tfull = [&](int b) { return bars + 8u * (2 * H3_STAGES + b); };
+  auto bar_tempty = [&](int b) { return bars + 8u * (2 * H3_STAGES + 2 + b); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
+  const int cluster = static_cast<int>(blockIdx.x) / CL;
+  const int nclusters = static_cast<int>(gridDim.x) / CL;
+  const int items = p.m_blocks * p.n_tiles;
+  const int num_kb = (p.k + H3_BK - 1) / H3_BK;
+  constexpr uint16_t kAllCtas = static_cast<uint16_t>((1u << CL) - 1u);
+  constexpr int kSliceRows = H3_BN / CL;                 // W rows each CTA fetches (and multicasts)
+  constexpr int kSliceBytes = kSliceRows * H3_BK * 2;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_xhi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_xlo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wa) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wb) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wc) : "memory");
+    for (int s = 0; s < H3_STAGES; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), CL);          // every CTA's tensor core must have consumed the stage
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_tfull(b), 1);
+      mbar_init(bar_tempty(b), 4);          // the four epilogue warps
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(H3_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (CL > 1) cluster_sync_all();            // peers' barriers are initialised before any multicast lands there
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work item -> tile coordinates of THIS CTA
+  auto tile_of = [&](int item, int& m_tile, int& grp, int& m0, int& n0) {
+    const int mb = item / p.n_tiles;
+    m_tile = mb * CL + static_cast<int>(rank);
+    // cluster padding (M tiles beyond the last): group index = #groups, every X row out of bounds -> zero-filled
+    grp = m_tile < p.m_tiles ? m_tile / p.tiles_per_batch : p.m_tiles / p.tiles_per_batch;
+    m0 = m_tile < p.m_tiles ? (m_tile - grp * p.tiles_per_batch) * H3_BM : 0;
+    n0 = (item - mb * p.n_tiles) * H3_BN;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int item = cluster; item < items; item += nclusters) {
+        int m_tile, grp, m0, n0;
+        tile_of(item, m_tile, grp, m0, n0);
+        const int wrow = n0 + static_cast<int>(rank) * kSliceRows;
+        const uint32_t wo = rank * kSliceBytes;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % H3_STAGES;
+          const uint32_t ph = (it / H3_STAGES) & 1u;
+          mbar_wait(bar_empty(s), ph ^ 1u);
+          const uint32_t st = base + s * H3_STAGE_BYTES;
+          mbar_expect_tx(bar_full(s), H3_STAGE_BYTES);
+          tma_load_3d(st, &map_xhi, bar_full(s), kb * H3_BK, m0, grp);
+          tma_load_3d(st + H3_X_BYTES, &map_xlo, bar_full(s), kb * H3_BK, m0, grp);
+          const uint32_t w0 = st + 2 * H3_X_BYTES + wo;
+          if (CL > 1) {
+            tma_load_2d_mc(w0, &map_wa, bar_full(s), kb * H3_BK, wrow, kAllCtas);
+            tma_load_2d_mc(w0 + H3_W_BYTES, &map_wb, bar_full(s), kb * H3_BK, wrow, kAllCtas);
+            tma_load_2d_mc(w0 + 2 * H3_W_BYTES, &map_wc, bar_full(s), kb * H3_BK, wrow, kAllCtas);
+          } else {
+            tma_load_2d(w0, &map_wa, bar_full(s), kb * H3_BK, wrow);
+            tma_load_2d(w0 + H3_W_BYTES, &map_wb, bar_full(s), kb * H3_BK, wrow);
+            tma_load_2d(w0 + 2 * H3_W_BYTES, &map_wc, bar_full(s), kb * H3_BK, wrow);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      uint32_t it = 0, t = 0;
+      for (int item = cluster; item < items; item += nclusters, ++t) {
+        int m_tile, grp, m0, n0;
+        tile_of(item, m_tile, grp, m0, n0);
+        const int n_here = min(H3_BN, p.n - n0);
+        const int n_inst = (n_here + 15) & ~15;                 // UMMA N (multiple of 16 for M = 128)
+        const uint32_t idesc = umma_idesc_f16(H3_BM, n_inst);
+        const uint32_t buf = t & 1u;
+        mbar_wait(bar_tempty(buf), ((t >> 1) & 1u) ^ 1u);        // epilogue has drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t acc = tmem_base + buf * H3_BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % H3_STAGES;
+          const uint32_t ph = (it / H3_STAGES) & 1u;
+          mbar_wait(bar_full(s), ph);
+          tcgen05_fence_after();
+          const uint32_t st = base + s * H3_STAGE_BYTES;
+          const uint64_t d_xhi = umma_desc_sw64(st), d_xlo = umma_desc_sw64(st + H3_X_BYTES);
+          const uint64_t d_wa = umma_desc_sw64(st + 2 * H3_X_BYTES);
+          const uint64_t d_wb = umma_desc_sw64(st + 2 * H3_X_BYTES + H3_W_BYTES);
+          const uint64_t d_wc = umma_desc_sw64(st + 2 * H3_X_BYTES + 2 * H3_W_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < H3_BK / 16; ++kk) {
+            const uint64_t adv = static_cast<uint64_t>(kk * 2);    // 16 halfs = 32 bytes = 2 x 16-byte units
+            umma_f16(acc, d_xhi + adv, d_wa + adv, idesc, (kb | kk) != 0 ? 1u : 0u);
+            umma_f16(acc, d_xlo + adv, d_wb + adv, idesc, 1u);
+            umma_f16(acc, d_xhi + adv, d_wc + adv, idesc, 1u);
+          }
+          if (CL > 1) umma_commit_mc(bar_empty(s), kAllCtas);      // stage refillable once ALL CTAs' MMAs have read it
+          else umma_commit(bar_empty(s));
+        }
+        umma_commit(bar_tfull(buf));                               // accumulator complete
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;                                         // TMEM lane quarter this warp may read
+    const uint32_t slot0 = epi + static_cast<uint32_t>(q) * 2u * H3_EPI_SLOT;
+    uint8_t* slot0_gen = gen + H3_STAGES * H3_STAGE_BYTES + q * 2 * H3_EPI_SLOT;
+    uint32_t t = 0, chunk = 0;
+    for (int item = cluster; item < items; item += nclusters, ++t) {
+      int m_tile, grp, m0, n0;
+      tile_of(item, m_tile, grp, m0, n0);
+      const int n_here = min(H3_BN, p.n - n0);
+      const int n_inst = (n_here + 15) & ~15;
+      const uint32_t buf = t & 1u;
+      const bool tile_ok = m_tile < p.m_tiles;
+      const int64_t lrow = static_cast<int64_t>(m0) + q * 32 + lane;            // row inside the group
+      const bool row_ok = tile_ok && lrow < p.rows_per_batch;
+      const int64_t row = static_cast<int64_t>(grp) * p.rows_per_batch + lrow;   // output rows are dense
+      const int row0 = static_cast<int>(static_cast<int64_t>(grp) * p.rows_per_batch + m0 + q * 32);
+      mbar_wait(bar_tfull(buf), (t >> 1) & 1u);
+      tcgen05_fence_after();
+      for (int c0 = 0; c0 < n_inst; c0 += 32, ++chunk) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + buf * H3_BN + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0), r);
+        tmem_ld_wait();
+        if (c0 + 32 >= n_inst) {               // last read of this accumulator: hand it back to the MMA warp
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty(buf));
+        }
+        const float bl = (p.bias != nullptr && c0 + lane < n_here) ? __ldg(p.bias + n0 + c0 + lane) : 0.f;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          v[j] = fmaf(__uint_as_float(r[j]), kLoInv, __shfl_sync(0xffffffffu, bl, j));
+          if (p.out_mode != H3_OUT_F32_DIRECT && p.act == HOISDF_ACT_RELU) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (p.out_mode == H3_OUT_F32_DIRECT) {
+          if (!row_ok) continue;
+          float* yrow = p.y + row * p.ldy + n0;
+          const float* rrow = p.residual ? p.residual + row * p.ldy + n0 : nullptr;
+          const bool vec = ((p.ldy & 3) == 0) && aligned16(p.y) && (p.residual == nullptr || aligned16(p.residual));
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const int c = c0 + g * 4;
+            if (c >= n_here) break;
+            if (vec && c + 3 < n_here) {
+              float4 o = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+              if (rrow != nullptr) {
+                const float4 rr = *reinterpret_cast<const float4*>(rrow + c);
+                o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+              }
+              if (p.act == HOISDF_ACT_RELU) {
+                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+              }
+              *reinterpret_cast<float4*>(yrow + c) = o;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (c + j < n_here) {
+                  float o = v[g * 4 + j];
+                  if (rrow != nullptr) o += rrow[c + j];
+                  if (p.act == HOISDF_ACT_RELU) o = fmaxf(o, 0.f);
+                  yrow[c + j] = o;
+                }
+              }
+            }
+          }
+          continue;
+        }
+        // TMA-store paths: stage the 32 x 32 block in this warp's slot (chunk & 1); the store issued from the same
+        // slot two chunks ago must have finished READING it
+        const uint32_t sl = chunk & 1u;
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        uint8_t* box = slot0_gen + sl * H3_EPI_SLOT;
+        const uint32_t box_sh = slot0 + sl * H3_EPI_SLOT;
+        if (p.out_mode == H3_OUT_F32_TMA) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g)      // 128-byte rows, 128B swizzle
+            *reinterpret_cast<float4*>(box + lane * 128 + ((g ^ (lane & 7)) << 4)) =
+                make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+        } else {
+          // split-half output: hi box at +0, lo' box at +2048, 64-byte rows, 64B swizzle
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              __half h0, l0, h1, l1;
+              split_half(v[g * 8 + 2 * j], h0, l0);
+              split_half(v[g * 8 + 2 * j + 1], h1, l1);
+              hw[j] = static_cast<uint32_t>(__half_as_ushort(h0)) | (static_cast<uint32_t>(__half_as_ushort(h1)) << 16);
+              lw[j] = static_cast<uint32_t>(__half_as_ushort(l0)) | (static_cast<uint32_t>(__half_as_ushort(l1)) << 16);
+            }
+            const int off = lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4);
+            *reinterpret_cast<uint4*>(box + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(box + 2048 + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (tile_ok && c0 < n_here) {
+            tma_store_2d(&map_y0, box_sh, n0 + c0, row0);
+            if (p.out_mode == H3_OUT_SPLIT_TMA) tma_store_2d(&map_y1, box_sh + 2048, n0 + c0, row0);
+          }
+          tma_store_commit();
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_read<0>();     // smem sources consumed; kernel end flushes the global writes
+    __syncwarp();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (CL > 1) cluster_sync_all();              // no CTA exits while a peer may still multicast to it / signal its barriers
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(H3_TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// format conversion kernels
+// ---------------------------------------------------------------------------------------------------
+// W (n, ldw fp32, k valid columns) -> planes A = fp16(w * 2^11), B = fp16(A * 2^-11), C = fp16((w - A * 2^-11) * 2^11),
+// each (n, ldh halfs) with columns [k, ldh) zeroed
+__global__ void pack_h3_kernel(const float* __restrict__ w, int64_t n, int64_t k, int64_t ldw, __half* __restrict__ a,
+                               __half* __restrict__ b, __half* __restrict__ c, int64_t ldh) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n * ldh) return;
+  const int64_t r = i / ldh, col = i - r * ldh;
+  float v = col < k ? w[r * ldw + col] : 0.f;
+  const float vs = fminf(fmaxf(v * kLoScale, -65504.f), 65504.f);
+  const __half ha = __float2half_rn(vs);
+  const float whi = __half2float(ha) * kLoInv;           // exact (power-of-two scaling)
+  a[i] = ha;
+  b[i] = __float2half_rn(whi);
+  c[i] = __float2half_rn(fminf(fmaxf((v - whi) * kLoScale, -65504.f), 65504.f));
+}
+
+// X (m, ldx fp32, k valid columns) -> split-half planes (m, ldh halfs), columns [k, kpad) zeroed; 4 columns per thread
+__global__ void split_rows_kernel(const float* __restrict__ x, int64_t m, int64_t k, int64_t ldx, int64_t kpad,
+                                  __half* __restrict__ hi, __half* __restrict__ lo, int64_t ldh, int vec) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t per_row = kpad >> 2;
+  if (i >= m * per_row) return;
+  const int64_t r = i / per_row, c = (i - r * per_row) << 2;
+  float v[4];
+  if (vec && c + 3 < k) {
+    const float4 f = *reinterpret_cast<const float4*>(x + r * ldx + c);
+    v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = c + j < k ? x[r * ldx + c + j] : 0.f;
+  }
+  __half h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) split_half(v[j], h[j], l[j]);
+  uint2 ph, pl;
+  ph.x = static_cast<uint32_t>(__half_as_ushort(h[0])) | (static_cast<uint32_t>(__half_as_ushort(h[1])) << 16);
+  ph.y = static_cast<uint32_t>(__half_as_ushort(h[2])) | (static_cast<uint32_t>(__half_as_ushort(h[3])) << 16);
+  pl.x = static_cast<uint32_t>(__half_as_ushort(l[0])) | (static_cast<uint32_t>(__half_as_ushort(l[1])) << 16);
+  pl.y = static_cast<uint32_t>(__half_as_ushort(l[2])) | (static_cast<uint32_t>(__half_as_ushort(l[3])) << 16);
+  *reinterpret_cast<uint2*>(hi + r * ldh + c) = ph;
+  *reinterpret_cast<uint2*>(lo + r * ldh + c) = pl;
+}
+
+// split-half planes -> fp32 (m, k)
+__global__ void join_rows_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, int64_t ldh, int64_t m,
+                                 int64_t k, float* __restrict__ x, int64_t ldx) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= m * k) return;
+  const int64_t r = i / k, c = i - r * k;
+  x[r * ldx + c] = join_half(hi[r * ldh + c], lo[r * ldh + c]);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+static bool map_half_2d(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols,
+                        int box_rows, CUtensorMapSwizzle sw, CUtensorMapL2promotion l2) {
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  return make_tiled_map(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ptr, dims, strides, box, estr, sw, l2);
+}
+
+// X plane as (groups, rows_per_group, K): box = 1 x 128 rows x 32 halfs
+static bool map_x_3d(CUtensorMap* map, const void* ptr, int64_t groups, int64_t rows, int64_t cols, int64_t ld,
+                     int64_t group_stride) {
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(groups)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(group_stride) * 2};
+  cuuint32_t box[3] = {H3_BK, H3_BM, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return make_tiled_map(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, ptr, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_64B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+}
+
+template <int CL>
+static int max_clusters() {
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  cudaFuncSetAttribute(linear_h3_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, H3_SMEM_BYTES);
+  int n = 0;
+  if (CL == 1) {
+    cudaDeviceProp prop;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    n = cudaGetDeviceProperties(&prop, dev) == cudaSuccess ? prop.multiProcessorCount : kNumSMs;
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(kNumSMs / CL * CL);
+    cfg.blockDim = dim3(H3_THREADS);
+    cfg.dynamicSmemBytes = H3_SMEM_BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&n, linear_h3_kernel<CL>, &cfg) != cudaSuccess || n <= 0) n = kNumSMs / CL;
+    (void)cudaGetLastError();
+  }
+  cached = n;
+  return n;
+}
+
+static int g_h3_force_cluster = 0;   // developer hook: 0 = automatic
+
+template <int CL>
+static int launch_h3(const CUtensorMap* maps, const H3Params& p0, int64_t m_tiles, cudaStream_t s) {
+  H3Params p = p0;
+  p.m_blocks = static_cast<int>(ceil_div(m_tiles, CL));
+  const int64_t items = static_cast<int64_t>(p.m_blocks) * p.n_tiles;
+  const int64_t clusters = items < max_clusters<CL>() ? items : max_clusters<CL>();
+  cudaError_t e = cudaFuncSetAttribute(linear_h3_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, H3_SMEM_BYTES);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(clusters * CL));
+  cfg.blockDim = dim3(H3_THREADS);
+  cfg.dynamicSmemBytes = H3_SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, linear_h3_kernel<CL>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], p);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  return launch_status();
+}
+
+}  // namespace hoisdf
+
+using namespace hoisdf;
+
+extern "C" __attribute__((visibility("default"))) void hoisdf_debug_h3_cluster(int cl) { g_h3_force_cluster = cl; }
+
+HOISDF_API int hoisdf_linear_h3_fwd(const hoisdf_linear_h3_args* a, void* stream) {
+  if (a == nullptr || a->x_hi == nullptr || a->x_lo == nullptr || a->w_a == nullptr || a->w_b == nullptr ||
+      a->w_c == nullptr)
+    return HOISDF_E_NULL;
+  const bool split_out = a->y_hi != nullptr || a->y_lo != nullptr;
+  if (split_out ? (a->y_hi == nullptr || a->y_lo == nullptr || a->y != nullptr) : a->y == nullptr) return HOISDF_E_NULL;
+  if (a->m == 0) return HOISDF_OK;
+  if (a->m < 0 || a->n <= 0 || a->k <= 0 || a->m >= 0x7fffffffLL || a->n >= 0x7fffffffLL || a->k >= 0x7fffffffLL)
+    return HOISDF_E_SHAPE;
+  if ((a->ldx & 7) || (a->ldw & 7) || !aligned16(a->x_hi) || !aligned16(a->x_lo) || !aligned16(a->w_a) ||
+      !aligned16(a->w_b) || !aligned16(a->w_c) || a->ldx < a->k || a->ldw < a->k)
+    return HOISDF_E_ALIGN;
+  if (split_out && (a->residual != nullptr || (a->ldyh & 7) || !aligned16(a->y_hi) || !aligned16(a->y_lo)))
+    return a->residual != nullptr ? HOISDF_E_UNSUPPORTED : HOISDF_E_ALIGN;
+  int64_t groups = 1, rpb = a->m, gstride = a->m * a->ldx;
+  if (a->x_rows_per_batch > 0) {
+    if (a->m % a->x_rows_per_batch != 0) return HOISDF_E_SHAPE;
+    rpb = a->x_rows_per_batch;
+    groups = a->m / rpb;
+    gstride = a->x_batch_stride;
+    if (groups > 1 && (gstride & 7)) return HOISDF_E_ALIGN;
+  }
+  if (groups == 1) gstride = rpb * a->ldx;
+  const bool tile_safe = groups == 1 || rpb % H3_BM == 0;     // tiles never straddle two row groups
+  int out_mode;
+  if (split_out) {
+    if (!tile_safe) return HOISDF_E_UNSUPPORTED;
+    out_mode = H3_OUT_SPLIT_TMA;
+  } else {
+    out_mode = (a->residual == nullptr && (a->ldy & 3) == 0 && aligned16(a->y) && tile_safe) ? H3_OUT_F32_TMA
+                                                                                             : H3_OUT_F32_DIRECT;
+  }
+  const int64_t tpb = ceil_div(rpb, H3_BM);
+  const int64_t m_tiles = groups * tpb;
+  int cl = m_tiles >= 64 ? 4 : (m_tiles >= 2 ? 2 : 1);
+  if (g_h3_force_cluster == 1 || g_h3_force_cluster == 2 || g_h3_force_cluster == 4) cl = g_h3_force_cluster;
+  CUtensorMap maps[7];
+  if (!map_x_3d(&maps[0], a->x_hi, groups, rpb, a->k, a->ldx, gstride)) return HOISDF_E_UNSUPPORTED;
+  if (!map_x_3d(&maps[1], a->x_lo, groups, rpb, a->k, a->ldx, gstride)) return HOISDF_E_UNSUPPORTED;
+  const int slice = H3_BN / cl;
+  const void* wp[3] = {a->w_a, a->w_b, a->w_c};
+  for (int i = 0; i < 3; ++i)
+    if (!map_half_2d(&maps[2 + i], wp[i], a->n, a->k, a->ldw, H3_BK, slice, CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B))
+      return HOISDF_E_UNSUPPORTED;
+  maps[5] = maps[0];
+  maps[6] = maps[0];
+  if (out_mode == H3_OUT_F32_TMA) {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(a->n), static_cast<cuuint64_t>(a->m)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(a->ldy) * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    if (!make_tiled_map(&maps[5], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a->y, dims, strides, box, estr,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE))
+      return HOISDF_E_UNSUPPORTED;
+  } else if (out_mode == H3_OUT_SPLIT_TMA) {
+    if (!map_half_2d(&maps[5], a->y_hi, a->m, a->n, a->ldyh, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_NONE) ||
+        !map_half_2d(&maps[6], a->y_lo, a->m, a->n, a->ldyh, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_NONE))
+      return HOISDF_E_UNSUPPORTED;
+  }
+  H3Params p{a->bias, a->residual, a->y, a->ldy, rpb, static_cast<int>(tpb), static_cast<int>(m_tiles), 0,
+             static_cast<int>(ceil_div(a->n, H3_BN)), static_cast<int>(a->n), static_cast<int>(a->k), a->act, out_mode};
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (cl == 4) return launch_h3<4>(maps, p, m_tiles, s);
+  if (cl == 2) return launch_h3<2>(maps, p, m_tiles, s);
+  return launch_h3<1>(maps, p, m_tiles, s);
+}
+
+HOISDF_API int hoisdf_pack_h3(const float* w, int64_t n, int64_t k, int64_t ldw, uint16_t* w_a, uint16_t* w_b,
+                              uint16_t* w_c, int64_t ldh, void* stream) {
+  if (w == nullptr || w_a == nullptr || w_b == nullptr || w_c == nullptr) return HOISDF_E_NULL;
+  if (n <= 0 || k <= 0 || ldh < k || ldw < k) return HOISDF_E_SHAPE;
+  const int64_t total = n * ldh;
+  pack_h3_kernel<<<static_cast<unsigned>(ceil_div(total, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, n, k, ldw, reinterpret_cast<__half*>(w_a), reinterpret_cast<__half*>(w_b), reinterpret_cast<__half*>(w_c), ldh);
+  return launch_status();
+}
+
+HOISDF_API int hoisdf_split_rows(const float* x, int64_t m, int64_t k, int64_t ldx, int64_t kpad, uint16_t* hi,
+                                 uint16_t* lo, int64_t ldh, void* stream) {
+  if (x == nullptr || hi == nullptr || lo == nullptr) return HOISDF_E_NULL;
+  if (m == 0) return HOISDF_OK;
+  if (m < 0 || k <= 0 || kpad < k || (kpad & 3) || ldh < kpad || (ldh & 3) || ldx < k) return HOISDF_E_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(hi) & 7) || (reinterpret_cast<uintptr_t>(lo) & 7)) return HOISDF_E_ALIGN;
+  const int vec = ((ldx & 3) == 0 && aligned16(x)) ? 1 : 0;
+  const int64_t total = m * (kpad >> 2);
+  split_rows_kernel<<<static_cast<unsigned>(ceil_div(total, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, m, k, ldx, kpad, reinterpret_cast<__half*>(hi), reinterpret_cast<__half*>(lo), ldh, vec);
+  return launch_status();
+}
+
+HOISDF_API int hoisdf_join_rows(const uint16_t* hi, const uint16_t* lo, int64_t ldh, int64_t m, int64_t k, float* x,
+                                int64_t ldx, void* stream) {
+  if (x == nullptr || hi == nullptr || lo == nullptr) return HOISDF_E_NULL;
+  if (m == 0) return HOISDF_OK;
+  if (m < 0 || k <= 0 || ldh < k || ldx < k) return HOISDF_E_SHAPE;
+  join_rows_kernel<<<static_cast<unsigned>(ceil_div(m * k, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(hi), reinterpret_cast<const __half*>(lo), ldh, m, k, x, ldx);
+  return launch_status();
+}

@@ -161,6 +161,147 @@ def linear(x: torch.Tensor, pw: PackedLinear, act: int = ACT_NONE, out: Optional
     return out
 
 
+# ----------------------------------------------------------------------------------------------------
+# FP16x3 tensor-core Linear on split-half activations (csrc/linear_h3.cu)
+# ----------------------------------------------------------------------------------------------------
+class SplitRows:
+    """A (rows, cols) fp32-valued matrix in split-half format: `buf` is a (rows, 2, ld) fp16 tensor whose
+    [:, 0] plane holds hi = fp16(x) and [:, 1] plane lo = fp16((x - hi) * 2^11); `col0` selects a column window."""
+
+    def __init__(self, buf: torch.Tensor, cols: int, col0: int = 0):
+        assert buf.dtype == torch.float16 and buf.dim() == 3 and buf.shape[1] == 2 and buf.stride(2) == 1
+        assert buf.stride(1) % 8 == 0 and buf.stride(0) % 8 == 0 and col0 % 8 == 0 and buf.data_ptr() % 16 == 0
+        self.buf, self.cols, self.col0 = buf, cols, col0
+
+    @staticmethod
+    def empty(rows: int, cols: int, device, ld: Optional[int] = None) -> "SplitRows":
+        ld = ld or round_up(cols, 8)
+        return SplitRows(torch.empty(rows, 2, ld, device=device, dtype=torch.float16), cols)
+
+    @property
+    def rows(self) -> int:
+        return self.buf.shape[0]
+
+    @property
+    def ld(self) -> int:           # row pitch in halfs
+        return self.buf.stride(0)
+
+    @property
+    def hi_ptr(self) -> int:
+        return self.buf.data_ptr() + 2 * self.col0
+
+    @property
+    def lo_ptr(self) -> int:
+        return self.buf.data_ptr() + 2 * (self.buf.stride(1) + self.col0)
+
+    def window(self, col0: int, cols: int) -> "SplitRows":
+        return SplitRows(self.buf, cols, self.col0 + col0)
+
+    def head(self, rows: int) -> "SplitRows":
+        return SplitRows(self.buf[:rows], self.cols, self.col0)
+
+    def float(self) -> torch.Tensor:
+        """fp32 copy (tests / diagnostics)."""
+        out = torch.empty(self.rows, self.cols, device=self.buf.device, dtype=torch.float32)
+        _count(1)
+        check(lib.hoisdf_join_rows(self.hi_ptr, self.lo_ptr, self.ld, self.rows, self.cols, out.data_ptr(), self.cols,
+                                   _stream()), "hoisdf_join_rows")
+        return out
+
+
+def split_rows(x: torch.Tensor, out: Optional[SplitRows] = None, kpad: Optional[int] = None) -> SplitRows:
+    """fp32 (M, K) rows (unit inner stride) -> split-half; columns [K, kpad) are zeroed."""
+    assert x.dim() == 2 and x.stride(1) == 1 and x.dtype == torch.float32
+    m, k = x.shape
+    kpad = kpad or round_up(k, 4)
+    if out is None:
+        out = SplitRows.empty(m, k, x.device, round_up(kpad, 8))
+    _count(1)
+    check(lib.hoisdf_split_rows(x.data_ptr(), m, k, x.stride(0), kpad, out.hi_ptr, out.lo_ptr, out.ld, _stream()),
+          "hoisdf_split_rows")
+    return out
+
+
+@dataclass
+class PackedLinearH3:
+    """Three fp16 weight planes (A = w_hi * 2^11, B = w_hi, C = w_lo * 2^11), each (N, ld) halfs, + fp32 bias."""
+    planes: torch.Tensor          # (3, N, ld) fp16
+    b: Optional[torch.Tensor]
+    n: int
+    k: int
+    row0: int = 0                 # row window (N slice)
+    col0: int = 0                 # column window (K slice), multiple of 8
+
+    @staticmethod
+    def pack(weight: torch.Tensor, bias: Optional[torch.Tensor], k: Optional[int] = None) -> "PackedLinearH3":
+        w = weight.detach().to(torch.float32)
+        if w.stride(1) != 1:
+            w = w.contiguous()
+        n = w.shape[0]
+        k = k or w.shape[1]
+        if float(w.abs().max()) >= 31.9:
+            raise ValueError("FP16x3 Linear needs |w| < 32")
+        ld = round_up(k, 8)
+        planes = torch.empty(3, n, ld, device=w.device, dtype=torch.float16)
+        _count(1)
+        check(lib.hoisdf_pack_h3(w.data_ptr(), n, k, w.stride(0), planes[0].data_ptr(), planes[1].data_ptr(),
+                                 planes[2].data_ptr(), ld, _stream()), "hoisdf_pack_h3")
+        b = None if bias is None else bias.detach().to(torch.float32).contiguous()
+        return PackedLinearH3(planes, b, n, k)
+
+    @property
+    def ld(self) -> int:
+        return self.planes.stride(1)
+
+    def plane_ptr(self, i: int) -> int:
+        return self.planes[i].data_ptr() + 2 * (self.row0 * self.ld + self.col0)
+
+    def cols(self, start: int, stop: int) -> "PackedLinearH3":
+        assert start % 8 == 0
+        return PackedLinearH3(self.planes, None, self.n, stop - start, self.row0, self.col0 + start)
+
+    def rows(self, start: int, stop: int) -> "PackedLinearH3":
+        b = None if self.b is None else self.b[start:stop]
+        return PackedLinearH3(self.planes, b, stop - start, self.k, self.row0 + start, self.col0)
+
+
+def linear_h3(x: SplitRows, pw: PackedLinearH3, act: int = ACT_NONE, out=None, residual: Optional[torch.Tensor] = None,
+              split_out: bool = False, x_batch=(0, 0), m: Optional[int] = None):
+    """Y = act(X . W^T + b) (+ residual) on the FP16x3 tensor-core kernel.  `out` is an fp32 (M, N) tensor view (unit
+    inner stride) or a SplitRows window; allocated when None (fp32, or split-half if split_out).
+    x_batch = (rows_per_batch, batch_stride in halfs) walks strided row groups of `x` (m rows in total)."""
+    m = x.rows if m is None else m
+    assert x.cols >= pw.k, (x.cols, pw.k)
+    if out is None:
+        out = (SplitRows.empty(m, pw.n, x.buf.device) if split_out
+               else torch.empty(m, round_up(pw.n, 4), device=x.buf.device, dtype=torch.float32)[:, :pw.n])
+    if m == 0:
+        return out
+    a = _capi.LinearH3Args()
+    a.x_hi, a.x_lo, a.ldx, a.x_rows_per_batch, a.x_batch_stride = x.hi_ptr, x.lo_ptr, x.ld, x_batch[0], x_batch[1]
+    a.w_a, a.w_b, a.w_c, a.ldw = pw.plane_ptr(0), pw.plane_ptr(1), pw.plane_ptr(2), pw.ld
+    a.bias, a.residual = _ptr(pw.b), _ptr(residual)
+    if isinstance(out, SplitRows):
+        assert residual is None and out.cols >= pw.n
+        a.y, a.ldy, a.y_hi, a.y_lo, a.ldyh = None, 0, out.hi_ptr, out.lo_ptr, out.ld
+    else:
+        assert out.stride(1) == 1 and out.dtype == torch.float32
+        if residual is not None:
+            assert residual.stride() == out.stride()
+        a.y, a.ldy, a.y_hi, a.y_lo, a.ldyh = out.data_ptr(), out.stride(0), None, None, 0
+    a.m, a.n, a.k, a.act = m, pw.n, pw.k, act
+    _count()
+    if PROFILE is None:
+        check(lib.hoisdf_linear_h3_fwd(C.byref(a), _stream()), "hoisdf_linear_h3_fwd")
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(lib.hoisdf_linear_h3_fwd(C.byref(a), _stream()), "hoisdf_linear_h3_fwd")
+        e1.record()
+        PROFILE.append(("linear_h3", 2.0 * m * pw.n * pw.k, e0, e1))
+    return out
+
+
 def fold_weight_norm(g: Optional[torch.Tensor], v: torch.Tensor, cols_out: Optional[int] = None,
                      src_col: Optional[torch.Tensor] = None) -> torch.Tensor:
     v = _f32c(v.detach(), "weight_v")

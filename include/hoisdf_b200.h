@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 4
+#define HOISDF_ABI_VERSION 5
 
 enum {
   HOISDF_OK = 0,
@@ -72,6 +72,40 @@ int hoisdf_linear_fwd(const hoisdf_linear_args* args, void* stream);
 
 /* Elementwise split of `count` floats: w_hi = round-to-nearest TF32 of w, w_lo = w - w_hi (exact). */
 int hoisdf_split_tf32(const float* w, int64_t count, float* w_hi, float* w_lo, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * The same nn.Linear on the tensor cores at FP16 rate with fp32-grade accuracy ("FP16x3", csrc/linear_h3.cu).
+ * Activations travel in SPLIT-HALF format: an fp32 value x is two IEEE fp16 numbers
+ *     hi = fp16(x),   lo = fp16((x - hi) * 2^11)        x ~= hi + lo * 2^-11      (|x| <= 65504)
+ * stored as two planes (hi, lo) of uint16 with a common row pitch (in halfs, multiple of 8; bases 16-byte aligned).
+ * Weights are packed once by hoisdf_pack_h3 into three fp16 planes A = w_hi * 2^11, B = w_hi, C = w_lo * 2^11
+ * (|w| < 32).  Y = act(X . W^T + bias) (+ residual) is written EITHER as fp32 (`y`, pitch ldy floats) OR in
+ * split-half format (`y_hi`, `y_lo`, pitch ldyh halfs; no residual) for the next layer.  X rows may be batched
+ * like hoisdf_linear_fwd's (x_batch_stride in halfs); output rows are dense.  K is contracted over [0, k): columns
+ * beyond k of X and W are never read (no zero padding needed).
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const uint16_t* x_hi; const uint16_t* x_lo; int64_t ldx; int64_t x_rows_per_batch; int64_t x_batch_stride;
+  const uint16_t* w_a; const uint16_t* w_b; const uint16_t* w_c; int64_t ldw;
+  const float* bias;                 /* may be NULL */
+  const float* residual;             /* may be NULL; fp32, shares y's addressing */
+  float* y; int64_t ldy;             /* fp32 output, or NULL when y_hi / y_lo are given */
+  uint16_t* y_hi; uint16_t* y_lo; int64_t ldyh;
+  int64_t m; int64_t n; int64_t k;
+  int32_t act;
+} hoisdf_linear_h3_args;
+
+int hoisdf_linear_h3_fwd(const hoisdf_linear_h3_args* args, void* stream);
+
+/* W (n, ldw) fp32 with k valid columns -> planes A, B, C, each (n, ldh) halfs, columns [k, ldh) zeroed. */
+int hoisdf_pack_h3(const float* w, int64_t n, int64_t k, int64_t ldw, uint16_t* w_a, uint16_t* w_b, uint16_t* w_c,
+                   int64_t ldh, void* stream);
+/* fp32 rows (m, ldx), k valid columns -> split-half planes (m, ldh); columns [k, kpad) are zeroed (kpad % 4 == 0). */
+int hoisdf_split_rows(const float* x, int64_t m, int64_t k, int64_t ldx, int64_t kpad, uint16_t* hi, uint16_t* lo,
+                      int64_t ldh, void* stream);
+/* split-half planes -> fp32 rows. */
+int hoisdf_join_rows(const uint16_t* hi, const uint16_t* lo, int64_t ldh, int64_t m, int64_t k, float* x,
+                     int64_t ldx, void* stream);
 
 /* nn.utils.weight_norm(dim=0) fold  W = g * v / ||v||_row  (upstream common/nets/sdf_net.py:57-62),
  * written into a (rows, ld_out) matrix at column offset 0; optional column permutation `src_col`
