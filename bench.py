@@ -265,7 +265,8 @@ def run_native(args):
     # dominant kernel: the tcgen05 3xTF32 Linear kernel (stand-alone launches + the four inside every SDF-decoder
     # call); every such launch of the timed steps was bracketed by CUDA events on the launching stream
     torch.cuda.synchronize()
-    tc = [p for p in prof if p[0] in ("linear_tc", "sdf_decoder")]
+    tc = [p for p in prof if p[0] in ("linear_tc", "sdf_decoder", "linear_h3", "sdf_decoder_h3")]
+    h3 = any(p[0] in ("linear_h3", "sdf_decoder_h3") for p in tc)
     fma = [p for p in prof if p[0] == "linear"]
     tc_flops = sum(p[1] for p in tc)
     tc_ms = sum(p[2].elapsed_time(p[3]) for p in tc)
@@ -273,17 +274,22 @@ def run_native(args):
     fma_ms = sum(p[2].elapsed_time(p[3]) for p in fma)
     peaks = load_peaks()
     achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+    kernel_name = ("hoisdf::linear_h3_kernel (tcgen05.mma kind::f16 on split-half operands, 3 products per fp32-grade "
+                   "product; persistent, double-buffered TMEM; all launches of the step incl. the 4 GEMMs of every "
+                   "SDF-decoder call; FLOPs counted once per fp32 product, i.e. the tensor cores execute 3x this number "
+                   "of fp16 MACs)") if h3 else (
+        "hoisdf::linear_tf32x3_kernel (tcgen05.mma kind::tf32, 3-pass split = fp32-grade; all launches of the "
+        "step incl. the 4 GEMMs of every SDF-decoder call; FLOPs counted once per fp32 product, i.e. the "
+        "tensor cores execute 3x this number of TF32 MACs)")
     roofline = {
-        "kernel": "hoisdf::linear_tf32x3_kernel (tcgen05.mma kind::tf32, 3-pass split = fp32-grade; all launches of the "
-                  "step incl. the 4 GEMMs of every SDF-decoder call; FLOPs counted once per fp32 product, i.e. the "
-                  "tensor cores execute 3x this number of TF32 MACs)",
+        "kernel": kernel_name,
         "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
         "frac": achieved / peaks["tflops"], "traffic": None, "peak_source": peaks["source"],
         "launches_per_step": len(tc) / args.steps, "share_of_step": tc_ms / ms_total,
         "algorithmic_flops_per_step": tc_flops / args.steps,
-        "tf32_mma_tflops_executed": 3.0 * achieved,
-        "note": "in the mainloop the TF32 pipe is ~75 % busy (CTA timeline trace, DESIGN.md 4.1); the rest is per-tile "
-                "prologue/epilogue that one-tile-per-CTA cannot overlap, and small-K shapes (K = 256 / 292)",
+        "mma_tflops_executed": 3.0 * achieved,
+        "note": "fp32-grade accuracy costs 3 tensor-core products per algorithmic product, so frac tops out at 1/3; "
+                "mma_tflops_executed / peak is the tensor-pipe utilisation",
         "fp32_fma_linear": {"achieved_tflops": fma_flops / (fma_ms * 1e-3) / 1e12 if fma_ms > 0 else 0.0,
                             "share_of_step": fma_ms / ms_total, "launches_per_step": len(fma) / args.steps,
                             "fp32_fma_peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12},

@@ -49,6 +49,10 @@ class SdfWeights(C.Structure):
                                    "w0_lo", "w1_lo", "w2_lo", "w3_lo")] + [("tf32_passes", i32)]
 
 
+class SdfWeightsH3(C.Structure):
+    _fields_ = [("w", (vp * 3) * 4), ("ldw", i64 * 4), ("b", vp * 4), ("w4", vp), ("b4", vp)]
+
+
 class ManoModel(C.Structure):
     _fields_ = [(n, vp) for n in ("shapedirs", "posedirs", "v_template", "j_regressor", "weights", "hands_mean")]
 
@@ -70,6 +74,9 @@ SIGNATURES = {
     "hoisdf_lattice_compact": (C.c_int, [vp, vp, vp, f32, i64, i32, vp, vp, vp, vp, vp]),
     "hoisdf_project_points": (C.c_int, [vp, vp, vp, f32, i64, i64, vp, vp, vp]),
     "hoisdf_gather_fwd": (C.c_int, [C.POINTER(Pyramid), vp, i64, vp, i64, i64, i32, vp, i32, vp, i64, vp]),
+    "hoisdf_gather_split_fwd": (C.c_int, [C.POINTER(Pyramid), vp, i64, vp, i64, i64, i32, vp, i32, vp, vp, i64, vp]),
+    "hoisdf_posenc_split_fwd": (C.c_int, [vp, vp, i64, i32, vp, vp, i64, vp]),
+    "hoisdf_sdf_decoder_h3_fwd": (C.c_int, [C.POINTER(SdfWeightsH3), vp, vp, i64, i64, vp, vp, vp, vp, i64, vp, f32, vp]),
     "hoisdf_posenc_fwd": (C.c_int, [vp, vp, i64, i32, vp, i64, i64, vp]),
     "hoisdf_sdf_decoder_fwd": (C.c_int, [C.POINTER(SdfWeights), vp, i64, i64, vp, vp, vp, f32, vp]),
     "hoisdf_sdf_pad_input": (C.c_int, [vp, i64, vp, i64, vp]),

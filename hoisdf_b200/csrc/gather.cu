@@ -5,7 +5,7 @@
 // by one warp (lanes stride the channel quads), so all global traffic is fully coalesced.  Consecutive
 // rows of one sample are lattice neighbours along z and project to (almost) the same pixel, so the
 // 8 warps of a CTA hit the same lines in L1.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace hoisdf {
 
@@ -15,9 +15,29 @@ struct GatherParams {
   const int64_t* __restrict__ row_offsets;
   const float* __restrict__ bias;
   float* __restrict__ out;
+  __half* __restrict__ out_hi;   // split-half output planes (tc_common.cuh) instead of `out` when not NULL
+  __half* __restrict__ out_lo;
   int64_t rows, batch, rows_per_sample, ld_out;
   int act;
 };
+
+// store 4 consecutive columns of row `r` starting at column c, in the output format the caller asked for
+__device__ __forceinline__ void store4(const GatherParams& p, int64_t r, int c, float4 a) {
+  if (p.out_hi == nullptr) {
+    *reinterpret_cast<float4*>(p.out + r * p.ld_out + c) = a;
+    return;
+  }
+  __half h[4], l[4];
+  tc::split_half(a.x, h[0], l[0]); tc::split_half(a.y, h[1], l[1]);
+  tc::split_half(a.z, h[2], l[2]); tc::split_half(a.w, h[3], l[3]);
+  uint2 ph, pl;
+  ph.x = static_cast<uint32_t>(__half_as_ushort(h[0])) | (static_cast<uint32_t>(__half_as_ushort(h[1])) << 16);
+  ph.y = static_cast<uint32_t>(__half_as_ushort(h[2])) | (static_cast<uint32_t>(__half_as_ushort(h[3])) << 16);
+  pl.x = static_cast<uint32_t>(__half_as_ushort(l[0])) | (static_cast<uint32_t>(__half_as_ushort(l[1])) << 16);
+  pl.y = static_cast<uint32_t>(__half_as_ushort(l[2])) | (static_cast<uint32_t>(__half_as_ushort(l[3])) << 16);
+  *reinterpret_cast<uint2*>(p.out_hi + r * p.ld_out + c) = ph;
+  *reinterpret_cast<uint2*>(p.out_lo + r * p.ld_out + c) = pl;
+}
 
 struct Taps {
   int64_t o00, o01, o10, o11;  // element offsets of the 4 taps (channel 0)
@@ -87,16 +107,13 @@ __global__ void __launch_bounds__(256) gather_concat_kernel(const GatherParams p
   if (r >= p.rows) return;
   const int64_t b = sample_of_row(p, r);
   const float u = p.uv[r * 2 + 0], v = p.uv[r * 2 + 1];
-  float* o = p.out + r * p.ld_out;
   int off = 0;
 #pragma unroll 1
   for (int l = 0; l < p.pyr.levels; ++l) {
     const int C = p.pyr.c[l];
     const Taps t = make_taps(u, v, p.pyr.img_w, p.pyr.img_h, p.pyr.w[l], p.pyr.h[l], C, b);
     const float* m = p.pyr.map[l];
-    for (int c = lane * 4; c < C; c += 128) {
-      *reinterpret_cast<float4*>(o + off + c) = blend(m, t, c);
-    }
+    for (int c = lane * 4; c < C; c += 128) store4(p, r, off + c, blend(m, t, c));
     off += C;
   }
 }
@@ -126,14 +143,13 @@ __global__ void __launch_bounds__(256) gather_sum_kernel(const GatherParams p) {
       acc[q].x += s.x; acc[q].y += s.y; acc[q].z += s.z; acc[q].w += s.w;
     }
   }
-  float* o = p.out + r * p.ld_out;
 #pragma unroll
   for (int q = 0; q < CQ; ++q) {
     float4 a = acc[q];
     if (p.act == HOISDF_ACT_RELU) {
       a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
     }
-    *reinterpret_cast<float4*>(o + q * 128 + lane * 4) = a;
+    store4(p, r, q * 128 + lane * 4, a);
   }
 }
 
@@ -163,14 +179,21 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
 
 using namespace hoisdf;
 
-HOISDF_API int hoisdf_gather_fwd(const hoisdf_pyramid* pyr, const float* uv, int64_t rows,
-                                 const int64_t* row_offsets, int64_t batch, int64_t rows_per_sample, int32_t mode,
-                                 const float* bias, int32_t act, float* out, int64_t ld_out, void* stream) {
-  if (pyr == nullptr || uv == nullptr || out == nullptr) return HOISDF_E_NULL;
+static int gather_any(const hoisdf_pyramid* pyr, const float* uv, int64_t rows, const int64_t* row_offsets,
+                      int64_t batch, int64_t rows_per_sample, int32_t mode, const float* bias, int32_t act, float* out,
+                      uint16_t* out_hi, uint16_t* out_lo, int64_t ld_out, void* stream) {
+  const bool split = out_hi != nullptr || out_lo != nullptr;
+  if (pyr == nullptr || uv == nullptr) return HOISDF_E_NULL;
+  if (split ? (out_hi == nullptr || out_lo == nullptr) : out == nullptr) return HOISDF_E_NULL;
   if (rows == 0) return HOISDF_OK;
   if (rows < 0 || batch <= 0 || pyr->levels < 1 || pyr->levels > 5) return HOISDF_E_SHAPE;
   if (row_offsets == nullptr && rows_per_sample <= 0) return HOISDF_E_SHAPE;
-  if (!aligned16(out) || (ld_out & 3)) return HOISDF_E_ALIGN;
+  if (split) {
+    if ((reinterpret_cast<uintptr_t>(out_hi) & 7) || (reinterpret_cast<uintptr_t>(out_lo) & 7) || (ld_out & 3))
+      return HOISDF_E_ALIGN;
+  } else if (!aligned16(out) || (ld_out & 3)) {
+    return HOISDF_E_ALIGN;
+  }
   int ctot = 0;
   for (int l = 0; l < pyr->levels; ++l) {
     if (pyr->map[l] == nullptr) return HOISDF_E_NULL;
@@ -180,6 +203,7 @@ HOISDF_API int hoisdf_gather_fwd(const hoisdf_pyramid* pyr, const float* uv, int
   }
   GatherParams p;
   p.pyr = *pyr; p.uv = uv; p.row_offsets = row_offsets; p.bias = bias; p.out = out;
+  p.out_hi = reinterpret_cast<__half*>(out_hi); p.out_lo = reinterpret_cast<__half*>(out_lo);
   p.rows = rows; p.batch = batch; p.rows_per_sample = rows_per_sample; p.ld_out = ld_out; p.act = act;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const unsigned grid = static_cast<unsigned>(ceil_div(rows, 8));
@@ -200,6 +224,23 @@ HOISDF_API int hoisdf_gather_fwd(const hoisdf_pyramid* pyr, const float* uv, int
     return HOISDF_E_UNSUPPORTED;
   }
   return launch_status();
+}
+
+HOISDF_API int hoisdf_gather_fwd(const hoisdf_pyramid* pyr, const float* uv, int64_t rows,
+                                 const int64_t* row_offsets, int64_t batch, int64_t rows_per_sample, int32_t mode,
+                                 const float* bias, int32_t act, float* out, int64_t ld_out, void* stream) {
+  if (out == nullptr) return HOISDF_E_NULL;
+  return gather_any(pyr, uv, rows, row_offsets, batch, rows_per_sample, mode, bias, act, out, nullptr, nullptr, ld_out,
+                    stream);
+}
+
+HOISDF_API int hoisdf_gather_split_fwd(const hoisdf_pyramid* pyr, const float* uv, int64_t rows,
+                                       const int64_t* row_offsets, int64_t batch, int64_t rows_per_sample,
+                                       int32_t mode, const float* bias, int32_t act, uint16_t* out_hi,
+                                       uint16_t* out_lo, int64_t ld_out, void* stream) {
+  if (out_hi == nullptr || out_lo == nullptr) return HOISDF_E_NULL;
+  return gather_any(pyr, uv, rows, row_offsets, batch, rows_per_sample, mode, bias, act, nullptr, out_hi, out_lo,
+                    ld_out, stream);
 }
 
 HOISDF_API int hoisdf_nchw_to_nhwc(const float* src, float* dst, int64_t n, int64_t c, int64_t h, int64_t w,

@@ -482,7 +482,7 @@ HOISDF_API int hoisdf_linear_h3_fwd(const hoisdf_linear_h3_args* a, void* stream
   }
   const int64_t tpb = ceil_div(rpb, H3_BM);
   const int64_t m_tiles = groups * tpb;
-  int cl = m_tiles >= 64 ? 4 : (m_tiles >= 2 ? 2 : 1);
+  int cl = m_tiles >= 2 ? 2 : 1;   // measured: pairs beat quads (quads leave SMs idle and add lockstep stalls)
   if (g_h3_force_cluster == 1 || g_h3_force_cluster == 2 || g_h3_force_cluster == 4) cl = g_h3_force_cluster;
   CUtensorMap maps[7];
   if (!map_x_3d(&maps[0], a->x_hi, groups, rpb, a->k, a->ldx, gstride)) return HOISDF_E_UNSUPPORTED;

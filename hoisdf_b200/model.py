@@ -152,7 +152,10 @@ class Model(nn.Module):
         pts = sdf_points.detach().to(torch.float32).contiguous()
         b, p, _ = pts.shape
         cam, uv = ops.project_points(pts, center_joint.contiguous(), cam_intr.contiguous(), sdf_scale)
-        feats = torch.empty(b * p, ctx.channels, device=pts.device, dtype=torch.float32)
+        if ops.use_h3():    # the gather writes the (rows, C) matrix directly in the split-half format the MLP reads
+            feats = ops.SplitRows.empty(b * p, ctx.channels, pts.device)
+        else:
+            feats = torch.empty(b * p, ctx.channels, device=pts.device, dtype=torch.float32)
         ops.gather(ctx.maps, uv, b, mode=ops.GATHER_CONCAT, out=feats, rows_per_sample=p, img_hw=cfg.input_img_shape)
         latent = self.linear_transformerin.forward_rows(feats)
         return latent.view(b, p, -1) if latent.is_contiguous() else latent.unflatten(0, (b, p)), cam
@@ -166,16 +169,30 @@ class Model(nn.Module):
         dev = pts.device
         _, uv = ops.project_points(pts, center_joint.contiguous(), cam_intr.contiguous(), sdf_scale, want_cam=False)
         sdfin = self.linear_sdfin.packed()
+        dec = self.hand_sdf_decoder if type == "hand" else self.obj_sdf_decoder
+        if ops.use_h3():
+            h, rows = self._row_buffers(b * p, dev)
+            ops.gather(ctx.gmaps, uv, b, mode=ops.GATHER_SUM, out=h, rows_per_sample=p, bias=sdfin[0].b,
+                       act=ops.ACT_RELU, img_hw=cfg.input_img_shape)
+            ops.linear(h, sdfin[1], ops.ACT_RELU, out=rows.window(0, 256))
+            ops.posenc(rows, points=pts.view(b * p, 3), bins=cfg.bins_n)
+            sdf = ops.sdf_decoder(dec.packed(), rows, h_a=h, clamp=cfg.ClampingDistance)
+            pe = rows.window(256, 30).float().view(b, p, 30)
+            return sdf.view(b, p, 1), None, pe
         h = torch.empty(b * p, 512, device=dev, dtype=torch.float32)
         ops.gather(ctx.gmaps, uv, b, mode=ops.GATHER_SUM, out=h, rows_per_sample=p, bias=sdfin[0].b,
                    act=ops.ACT_RELU, img_hw=cfg.input_img_shape)
         rows = torch.empty(b * p, ops.ROW_LD, device=dev, dtype=torch.float32)
         ops.linear(h, sdfin[1], ops.ACT_RELU, out=rows[:, :256])
         ops.posenc(rows, points=pts.view(b * p, 3), bins=cfg.bins_n)
-        dec = self.hand_sdf_decoder if type == "hand" else self.obj_sdf_decoder
         sdf = ops.sdf_decoder(dec.packed(), rows, h_a=h, clamp=cfg.ClampingDistance)
         pe = rows[:, 256:286].contiguous().view(b, p, 30)
         return sdf.view(b, p, 1), (None if not cfg.ClassifierBranch else None), pe
+
+    @staticmethod
+    def _row_buffers(n, dev):
+        """Split-half scratch of the FP16x3 SDF chain: h (n, 512) and the decoder row buffer (n, 520)."""
+        return ops.SplitRows.empty(n, 512, dev), ops.SplitRows.empty(n, ops.ROWH_LD, dev)
 
     def plan_candidates(self, center_joint, cam_intr, bbox, sdf_scale) -> CandidatePlan:
         return CandidatePlan(center_joint, cam_intr, bbox, sdf_scale)
@@ -209,13 +226,31 @@ class Model(nn.Module):
         sdf = torch.empty(total, device=dev, dtype=torch.float32)
         step = int(cfg.max_rows_per_pass)
         cap = min(step, total)
-        h = torch.empty(cap, 512, device=dev, dtype=torch.float32)
-        h2 = torch.empty(cap, 512, device=dev, dtype=torch.float32)
-        rows = torch.empty(cap, ops.ROW_LD, device=dev, dtype=torch.float32)
+        bufs = {}
+
+        def fp32_buffers(n):
+            if "f32" not in bufs or bufs["f32"][0].shape[0] < n:
+                bufs["f32"] = (torch.empty(n, 512, device=dev, dtype=torch.float32),
+                               torch.empty(n, 512, device=dev, dtype=torch.float32),
+                               torch.empty(n, ops.ROW_LD, device=dev, dtype=torch.float32))
+            return bufs["f32"]
 
         def evaluate_all(passes):
-            """SDF of every candidate row on the tensor cores (passes = 3: 3xTF32, 1: single TF32 pass) or,
-            with tensor cores disabled, on the fp32 FMA kernels."""
+            """SDF of every candidate row on the tensor cores (FP16x3 on split-half rows by default; TC_MODE 'tf32':
+            passes = 3: 3xTF32, 1: single TF32 pass) or, with tensor cores disabled, on the fp32 FMA kernels."""
+            if ops.use_h3():
+                hs, rs = self._row_buffers(cap, dev)
+                hs2 = ops.SplitRows.empty(cap, 512, dev)
+                for r0 in range(0, total, step):
+                    n = min(step, total - r0)
+                    offs = plan.offsets if r0 == 0 else plan.offsets - r0
+                    ops.gather(gmaps, cand_uv[r0:r0 + n], b, mode=ops.GATHER_SUM, out=hs.head(n), row_offsets=offs,
+                               bias=sdfin[0].b, act=ops.ACT_RELU, img_hw=cfg.input_img_shape)
+                    ops.linear(hs.head(n), sdfin[1], ops.ACT_RELU, out=rs.head(n).window(0, 256))
+                    ops.posenc(rs.head(n), lattice_index=cand_index[r0:r0 + n], bins=cfg.bins_n)
+                    ops.sdf_decoder(packed, rs.head(n), h_a=hs.head(n), h_b=hs2.head(n), out=sdf[r0:r0 + n])
+                return
+            h, h2, rows = fp32_buffers(cap)
             for r0 in range(0, total, step):
                 n = min(step, total - r0)
                 offs = plan.offsets if r0 == 0 else plan.offsets - r0
@@ -235,7 +270,7 @@ class Model(nn.Module):
             s_index = cand_index.index_select(0, s_row)
             s_uv = cand_uv.index_select(0, s_row)
             m = b * pm
-            assert m <= cap
+            h, h2, rows = fp32_buffers(m)
             ops.gather(gmaps, s_uv, b, mode=ops.GATHER_SUM, out=h[:m], rows_per_sample=pm, bias=sdfin[0].b,
                        act=ops.ACT_RELU, img_hw=cfg.input_img_shape)
             ops.linear(h[:m], ops.fma_only(sdfin[1]), ops.ACT_RELU, out=rows[:m, :256])
@@ -263,7 +298,7 @@ class Model(nn.Module):
             # P + margin.  Equal to an all-fp32 pass whenever the screening error is smaller than the |sdf| gap
             # between rank P and rank P + margin -- verified on the device (observed error on the re-evaluated
             # rows x 3 against that gap); if the single-pass screening fails the check, redo it with 3xTF32.
-            passes = 1 if int(cfg.screen_passes) == 1 else 3
+            passes = 1 if (int(cfg.screen_passes) == 1 and not ops.use_h3()) else 3
             evaluate_all(passes)
             sdf_sel, cand_sel, offs_sel, screened = rerank(cfg.screen_margin if passes == 1 else cfg.screen_margin_safe)
             screened["verified"] = (screened["gap"] > 3.0 * screened["err"]).all()   # device tensor, read lazily
@@ -375,13 +410,17 @@ class Model(nn.Module):
         _, obj_enc = self.obj_transformer.forward_bm(obj_in, None)
 
         Le, Lo, Ld = hand_enc.shape[0], obj_enc.shape[0], hs.shape[0]
-        hand_off = self._head_rows(self.linear_handvote, hand_enc, Le * b, Ph, S).view(Le, b, Ph, 60)
-        hand_cls = self._head_rows(self.linear_handcls, hand_enc, Le * b, Ph, S).view(Le, b, Ph, 20)
-        obj_rot = self._head_rows(self.linear_obj_rot, obj_enc, Lo * b, Po, S).view(Lo, b, Po, 3)
-        obj_trans = self._head_rows(self.linear_obj_rel_trans, obj_enc, Lo * b, Po, S).view(Lo, b, Po, 3)
+        # FP16x3: every source tensor is split once and shared by the heads that read it
+        sp = (lambda t: ops.split_rows(t.view(-1, t.shape[-1]))) if ops.use_h3() else (lambda t: None)
+        hx, ox, qx = sp(hand_enc), sp(obj_enc), sp(hs)
+        hand_off = self._head_rows(self.linear_handvote, hand_enc, Le * b, Ph, S, xs=hx).view(Le, b, Ph, 60)
+        hand_cls = self._head_rows(self.linear_handcls, hand_enc, Le * b, Ph, S, xs=hx).view(Le, b, Ph, 20)
+        obj_rot = self._head_rows(self.linear_obj_rot, obj_enc, Lo * b, Po, S, xs=ox).view(Lo, b, Po, 3)
+        obj_trans = self._head_rows(self.linear_obj_rel_trans, obj_enc, Lo * b, Po, S, xs=ox).view(Lo, b, Po, 3)
         nq = hs.shape[2]
-        pose6d = self._head_rows(self.linear_pose, hs, Ld * b, cfg.mano_shape_indx, nq).view(Ld, b, cfg.mano_shape_indx, 6)
-        shape = self._head_rows(self.linear_shape, hs, Ld * b, 1, nq, first=cfg.mano_shape_indx).view(Ld, b, 10)
+        pose6d = self._head_rows(self.linear_pose, hs, Ld * b, cfg.mano_shape_indx, nq, xs=qx).view(
+            Ld, b, cfg.mano_shape_indx, 6)
+        shape = self._head_rows(self.linear_shape, hs, Ld * b, 1, nq, first=cfg.mano_shape_indx, xs=qx).view(Ld, b, 10)
         verts, joints = self.mano_head.forward_bm(pose6d, shape)
         hand_joints = ops.vote_joints(hand_nt.contiguous(), hand_off, hand_cls)
         pred_mano = gt_mano = None
@@ -408,12 +447,33 @@ class Model(nn.Module):
         return out
 
     @staticmethod
-    def _head_rows(mlp: MLP, x: torch.Tensor, groups: int, rows_per_group: int, group_len: int, first: int = 0):
+    def _head_rows(mlp: MLP, x: torch.Tensor, groups: int, rows_per_group: int, group_len: int, first: int = 0,
+                   xs=None):
         """Run `mlp` on tokens [first, first+rows_per_group) of every (layer, sample) group of a (L,B,T,256) tensor
         without gathering them first: the Linear kernel walks the strided row groups itself."""
         pk = mlp.packed()
         d = x.shape[-1]
         m = groups * rows_per_group
+        if ops.use_h3() and all(pw.h3 is not None for pw in pk):
+            # FP16x3: split the source tokens once (shared by the heads that read the same tensor), let the first
+            # layer walk the strided row groups, keep the hidden activations in split-half format
+            if xs is None:
+                xs = ops.split_rows(x.view(-1, d))
+            src = ops.SplitRows(xs.buf[first:], d)
+            h = None
+            for i, pw in enumerate(pk):
+                last = i == len(pk) - 1
+                act = ops.ACT_NONE if (last and not mlp.is_activation_last) else ops.ACT_RELU
+                if i == 0:
+                    # split-half output needs tiles that do not straddle two row groups; otherwise fp32 (re-split below)
+                    tile_safe = groups == 1 or rows_per_group % 128 == 0
+                    h = ops.linear_h3(src, pw.h3, act, split_out=(not last) and tile_safe,
+                                      x_batch=(rows_per_group, group_len * xs.ld), m=m)
+                    if not last and not tile_safe:
+                        h = ops.split_rows(h)
+                else:
+                    h = ops.linear_h3(h, pw.h3, act, split_out=not last)
+            return h if h.is_contiguous() else h.contiguous()
         base = x.data_ptr() + first * d * 4
         h_ptr, ld, batch = base, d, (rows_per_group, group_len * d)
         keep = []

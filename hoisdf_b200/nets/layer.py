@@ -46,17 +46,23 @@ class MLP(nn.Module):
         """x2d: (rows, >=K) unit inner stride -> (rows, N) view of a 4-padded buffer."""
         pk = self.packed()
         h = x2d
+        h3 = ops.use_h3() and all(pw.h3 is not None for pw in pk)
         for i, pw in enumerate(pk):
             last = i == len(pk) - 1
             act = ops.ACT_RELU if (not last or self.is_activation_last) else ops.ACT_NONE
-            h = ops.linear(_wide(h, pw.k), pw, act)
+            if h3:      # FP16x3: hidden activations stay in split-half format between the layers
+                h = ops.linear(h, pw, act, split_out=not last)
+            else:
+                h = ops.linear(_wide(h, pw.k), pw, act)
         return h
 
     def forward(self, x):
         _require_inference(self, x)
         lead = x.shape[:-1]
         x2d = x.reshape(-1, x.shape[-1])
-        if x2d.stride(-1) != 1 or x2d.data_ptr() % 16 or x2d.stride(0) % 4 or x2d.shape[1] % 4:
+        if ops.use_h3():
+            x2d = x2d if x2d.stride(-1) == 1 else x2d.contiguous()
+        elif x2d.stride(-1) != 1 or x2d.data_ptr() % 16 or x2d.stride(0) % 4 or x2d.shape[1] % 4:
             k4 = ops.round_up(x2d.shape[1], 4)
             buf = torch.zeros(x2d.shape[0], k4, device=x.device, dtype=torch.float32)
             buf[:, : x2d.shape[1]] = x2d

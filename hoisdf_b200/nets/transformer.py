@@ -72,7 +72,7 @@ class _LayerBase(nn.Module):
 
     def _ffn_block(self, x2d, norm, norm2=None, out2=None):
         l1, l2 = self.ffn_packed()
-        h = ops.linear(x2d, l1, ops.ACT_RELU)
+        h = ops.linear(x2d, l1, ops.ACT_RELU, split_out=ops.use_h3())
         y = ops.linear(h, l2, ops.ACT_NONE, residual=x2d)
         if norm2 is None:
             return ops.add_layernorm(y, None, norm.weight, norm.bias)

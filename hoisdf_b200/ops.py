@@ -16,6 +16,8 @@ from . import _capi
 from ._capi import ACT_NONE, ACT_RELU, GATHER_CONCAT, GATHER_SUM, check, lib
 
 ROW_LD = 516          # padded SDF row-buffer pitch (see csrc/sdf.cu)
+ROWH_LD = 520         # pitch (halfs per plane) of the split-half row buffer of the FP16x3 path
+SKIP_OFF_H = 296      # where relu(linh1) lands in it
 DEC_IN = 289
 DEC_IN_PAD = 292
 SKIP_OFF = 292
@@ -60,6 +62,13 @@ def round_up(x: int, m: int) -> int:
 # Linear implementation switch: True -> tcgen05 3xTF32 tensor-core kernel (fp32-grade accuracy) wherever the rows are
 # not batched; False -> fp32 FMA kernel everywhere.  HOISDF_TC=0 in the environment disables the tensor path.
 USE_TENSOR_CORES = os.environ.get("HOISDF_TC", "1") != "0"
+# Which tensor-core Linear: "h3" = FP16x3 on split-half activations (csrc/linear_h3.cu, default),
+# "tf32" = the 3xTF32 kernel on fp32 activations (csrc/linear_tc.cu).
+TC_MODE = os.environ.get("HOISDF_TC_MODE", "h3")
+
+
+def use_h3() -> bool:
+    return USE_TENSOR_CORES and TC_MODE == "h3"
 
 
 def split_tf32(w: torch.Tensor):
@@ -81,6 +90,7 @@ class PackedLinear:
     ldw: int
     w_hi: Optional[torch.Tensor] = None
     w_lo: Optional[torch.Tensor] = None
+    h3: Optional["PackedLinearH3"] = None      # FP16x3 planes of the same weights
 
     @staticmethod
     def pack(weight: torch.Tensor, bias: Optional[torch.Tensor], tensor_cores: bool = True) -> "PackedLinear":
@@ -93,10 +103,11 @@ class PackedLinear:
             w = torch.zeros(n, kp, device=weight.device, dtype=torch.float32)
             w[:, :k] = weight
         b = None if bias is None else bias.detach().to(torch.float32).contiguous()
-        hi = lo = None
+        hi = lo = h3 = None
         if tensor_cores and w.is_cuda:
             hi, lo = split_tf32(w)
-        return PackedLinear(w, b, n, kp, kp, hi, lo)
+            h3 = PackedLinearH3.pack(weight, b, k)
+        return PackedLinear(w, b, n, kp, kp, hi, lo, h3)
 
     @staticmethod
     def from_packed(w: torch.Tensor, bias: Optional[torch.Tensor], tensor_cores: bool = True) -> "PackedLinear":
@@ -110,12 +121,13 @@ class PackedLinear:
         """A K-slice W[:, start:stop] (no copy; start must be a multiple of 4). Bias dropped."""
         assert start % 4 == 0 and (stop - start) % 4 == 0
         w, hi, lo = self._sl(lambda t: t[:, start:stop])
-        return PackedLinear(w, None, self.n, stop - start, self.ldw, hi, lo)
+        h3 = self.h3.cols(start, min(stop, self.h3.k)) if (self.h3 is not None and start % 8 == 0) else None
+        return PackedLinear(w, None, self.n, stop - start, self.ldw, hi, lo, h3)
 
     def rows(self, start: int, stop: int) -> "PackedLinear":
         b = None if self.b is None else self.b[start:stop]
         w, hi, lo = self._sl(lambda t: t[start:stop])
-        return PackedLinear(w, b, stop - start, self.k, self.ldw, hi, lo)
+        return PackedLinear(w, b, stop - start, self.k, self.ldw, hi, lo, None if self.h3 is None else self.h3.rows(start, stop))
 
 
 def linear_raw(x_ptr: int, ldx: int, m: int, pw: PackedLinear, y_ptr: int, ldy: int, act: int = ACT_NONE,
@@ -140,12 +152,22 @@ def linear_raw(x_ptr: int, ldx: int, m: int, pw: PackedLinear, y_ptr: int, ldy: 
 
 def fma_only(pw: PackedLinear) -> PackedLinear:
     """The same weights, forced onto the fp32 FMA kernel."""
-    return PackedLinear(pw.w, pw.b, pw.n, pw.k, pw.ldw, None, None)
+    return PackedLinear(pw.w, pw.b, pw.n, pw.k, pw.ldw, None, None, None)
 
 
-def linear(x: torch.Tensor, pw: PackedLinear, act: int = ACT_NONE, out: Optional[torch.Tensor] = None,
-           residual: Optional[torch.Tensor] = None, out_ld: Optional[int] = None, passes: int = 3) -> torch.Tensor:
-    """x: (M, >=K) 2-D, unit inner stride.  Returns (M, N) (a view of a (M, out_ld) buffer if padded)."""
+def linear(x, pw: PackedLinear, act: int = ACT_NONE, out=None, residual: Optional[torch.Tensor] = None,
+           out_ld: Optional[int] = None, passes: int = 3, split_out: bool = False):
+    """x: (M, >=K) 2-D fp32 (unit inner stride) or SplitRows.  Returns (M, N) fp32 (a view of a (M, out_ld) buffer if
+    padded) -- or, on the FP16x3 path with split_out / a SplitRows `out`, the result in split-half format."""
+    if isinstance(x, SplitRows) or isinstance(out, SplitRows) or (use_h3() and pw.h3 is not None):
+        if pw.h3 is None or not use_h3():
+            raise RuntimeError("split-half activations need the FP16x3 Linear (tensor cores enabled, TC_MODE='h3')")
+        xs = x if isinstance(x, SplitRows) else split_rows(x[:, :pw.h3.k] if x.shape[1] > pw.h3.k else x)
+        if out is None and not split_out:
+            ld = out_ld or round_up(pw.n, 4)
+            alloc = torch.empty if ld == pw.n else torch.zeros
+            out = alloc(xs.rows, ld, device=xs.buf.device, dtype=torch.float32)[:, :pw.n]
+        return linear_h3(xs, pw.h3, act, out=out, residual=residual, split_out=split_out)
     assert x.dim() == 2 and x.stride(1) == 1 and x.shape[1] >= pw.k, (x.shape, x.stride(), pw.k)
     m = x.shape[0]
     if out is None:
@@ -351,9 +373,15 @@ def gather(maps: Sequence[torch.Tensor], uv: torch.Tensor, batch: int, *, mode: 
            row_offsets: Optional[torch.Tensor] = None, rows_per_sample: int = 0,
            bias: Optional[torch.Tensor] = None, act: int = ACT_NONE, img_hw=(256, 256)):
     rows = uv.shape[0]
-    assert uv.is_contiguous() and uv.shape[1] == 2 and out.stride(1) == 1
+    assert uv.is_contiguous() and uv.shape[1] == 2
     pyr = make_pyramid(maps, img_hw)
     _count(1)
+    if isinstance(out, SplitRows):
+        check(lib.hoisdf_gather_split_fwd(C.byref(pyr), uv.data_ptr(), rows, _ptr(row_offsets), batch, rows_per_sample,
+                                          mode, _ptr(bias), act, out.hi_ptr, out.lo_ptr, out.ld, _stream()),
+              "hoisdf_gather_split_fwd")
+        return out
+    assert out.stride(1) == 1
     check(lib.hoisdf_gather_fwd(C.byref(pyr), uv.data_ptr(), rows, _ptr(row_offsets), batch, rows_per_sample, mode,
                                 _ptr(bias), act, out.data_ptr(), out.stride(0), _stream()), "hoisdf_gather_fwd")
     return out
@@ -403,6 +431,7 @@ class PackedSdfDecoder:
     struct_fma: _capi.SdfWeights     # fp32 FMA kernels
     struct_tc: Optional[_capi.SdfWeights]   # tcgen05 3xTF32 kernels (None when tensor cores are disabled)
     struct_tc1: Optional[_capi.SdfWeights] = None   # tcgen05 single-pass TF32 (candidate screening only)
+    struct_h3: Optional[_capi.SdfWeightsH3] = None  # tcgen05 FP16x3 on split-half rows
 
     def struct(self, exact: bool = False, screening: bool = False):
         if exact or self.struct_tc is None or not USE_TENSOR_CORES:
@@ -438,18 +467,55 @@ def pack_sdf_decoder(dec_params: dict) -> PackedSdfDecoder:
                             los[0], los[1], los[2], los[3], 3)
     s_tc1 = _capi.SdfWeights(his[0], bp[0], his[1], bp[1], his[2], bp[2], his[3], bp[3], w4.data_ptr(), bp[4],
                              los[0], los[1], los[2], los[3], 1)
-    return PackedSdfDecoder(keep, s_fma, s_tc, s_tc1)
+    # FP16x3: the same folded weights as fp16 planes; linh2's columns follow the split-half row layout
+    # [input (289) | 0 x7 | h1 (223) | 0]
+    srch = torch.full((ROWH_LD,), -1, dtype=torch.int32)
+    srch[0:DEC_IN] = torch.arange(H1, H1 + DEC_IN, dtype=torch.int32)
+    srch[SKIP_OFF_H:SKIP_OFF_H + H1] = torch.arange(0, H1, dtype=torch.int32)
+    w2h = fold_weight_norm(dec_params["linh2.weight_g"], dec_params["linh2.weight_v"], ROWH_LD, srch.to(dev))
+    h3s = [PackedLinearH3.pack(w0, None, DEC_IN), PackedLinearH3.pack(w1, None, 512),
+           PackedLinearH3.pack(w2h, None, SKIP_OFF_H + H1), PackedLinearH3.pack(w3, None, 512)]
+    s_h3 = _capi.SdfWeightsH3()
+    for i, hp in enumerate(h3s):
+        for j in range(3):
+            s_h3.w[i][j] = hp.plane_ptr(j)
+        s_h3.ldw[i] = hp.ld
+        s_h3.b[i] = bp[i]
+    s_h3.w4, s_h3.b4 = w4.data_ptr(), bp[4]
+    keep += [hp.planes for hp in h3s]
+    return PackedSdfDecoder(keep, s_fma, s_tc, s_tc1, s_h3)
 
 
-def posenc(rows_buf: torch.Tensor, *, lattice_index=None, points=None, bins: int = 64):
-    rows = rows_buf.shape[0]
+def posenc(rows_buf, *, lattice_index=None, points=None, bins: int = 64):
     _count(1)
+    if isinstance(rows_buf, SplitRows):
+        check(lib.hoisdf_posenc_split_fwd(_ptr(lattice_index), _ptr(points), rows_buf.rows, bins, rows_buf.hi_ptr,
+                                          rows_buf.lo_ptr, rows_buf.ld, _stream()), "hoisdf_posenc_split_fwd")
+        return
+    rows = rows_buf.shape[0]
     check(lib.hoisdf_posenc_fwd(_ptr(lattice_index), _ptr(points), rows, bins, rows_buf.data_ptr(),
                                 rows_buf.stride(0), 256, _stream()), "hoisdf_posenc_fwd")
 
 
-def sdf_decoder(packed: PackedSdfDecoder, rows_buf: torch.Tensor, h_a=None, h_b=None, clamp: float = 0.0,
+def sdf_decoder(packed: PackedSdfDecoder, rows_buf, h_a=None, h_b=None, clamp: float = 0.0,
                 out: Optional[torch.Tensor] = None, exact: bool = False, screening: bool = False) -> torch.Tensor:
+    if isinstance(rows_buf, SplitRows):
+        rows, dev = rows_buf.rows, rows_buf.buf.device
+        h_a = h_a if h_a is not None else SplitRows.empty(rows, 512, dev)
+        h_b = h_b if h_b is not None else SplitRows.empty(rows, 512, dev)
+        out = out if out is not None else torch.empty(rows, device=dev, dtype=torch.float32)
+        assert h_a.ld == h_b.ld and rows_buf.col0 == 0 and h_a.col0 == 0 and h_b.col0 == 0
+        _count(5)
+        if PROFILE is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        check(lib.hoisdf_sdf_decoder_h3_fwd(C.byref(packed.struct_h3), rows_buf.hi_ptr, rows_buf.lo_ptr, rows_buf.ld,
+                                            rows, h_a.hi_ptr, h_a.lo_ptr, h_b.hi_ptr, h_b.lo_ptr, h_a.ld,
+                                            out.data_ptr(), float(clamp), _stream()), "hoisdf_sdf_decoder_h3_fwd")
+        if PROFILE is not None:
+            e1.record()
+            PROFILE.append(("sdf_decoder_h3", SDF_DECODER_FLOPS * rows, e0, e1))
+        return out
     rows = rows_buf.shape[0]
     dev = rows_buf.device
     h_a = h_a if h_a is not None else torch.empty(rows, 512, device=dev, dtype=torch.float32)
@@ -468,9 +534,13 @@ def sdf_decoder(packed: PackedSdfDecoder, rows_buf: torch.Tensor, h_a=None, h_b=
     return out
 
 
-def sdf_pad_input(x: torch.Tensor) -> torch.Tensor:
+def sdf_pad_input(x: torch.Tensor):
     x = _f32c(x, "SDFDecoder input")
     rows = x.shape[0]
+    if use_h3():
+        buf = SplitRows(torch.zeros(rows, 2, ROWH_LD, device=x.device, dtype=torch.float16), ROWH_LD)
+        split_rows(x, out=buf.window(0, DEC_IN), kpad=DEC_IN_PAD)
+        return buf
     buf = torch.empty(rows, ROW_LD, device=x.device, dtype=torch.float32)
     _count(1)
     check(lib.hoisdf_sdf_pad_input(x.data_ptr(), rows, buf.data_ptr(), ROW_LD, _stream()), "hoisdf_sdf_pad_input")

@@ -164,6 +164,11 @@ typedef struct {
 int hoisdf_gather_fwd(const hoisdf_pyramid* pyr, const float* uv, int64_t rows, const int64_t* row_offsets,
                       int64_t batch, int64_t rows_per_sample, int32_t mode, const float* bias, int32_t act,
                       float* out, int64_t ld_out, void* stream);
+/* Same gather with the output written in split-half format (planes out_hi / out_lo, pitch ld_out halfs, % 4 == 0)
+ * for the FP16x3 Linear that follows. */
+int hoisdf_gather_split_fwd(const hoisdf_pyramid* pyr, const float* uv, int64_t rows, const int64_t* row_offsets,
+                            int64_t batch, int64_t rows_per_sample, int32_t mode, const float* bias, int32_t act,
+                            uint16_t* out_hi, uint16_t* out_lo, int64_t ld_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * SDF decoder input tail: NeRF embedding (upstream common/utils/sdf_utils.py:96-141, 5 octaves, sin then
@@ -172,6 +177,10 @@ int hoisdf_gather_fwd(const hoisdf_pyramid* pyr, const float* uv, int64_t rows, 
  * ------------------------------------------------------------------------------------------------- */
 int hoisdf_posenc_fwd(const int32_t* lattice_index, const float* points, int64_t rows, int32_t bins,
                       float* out, int64_t ld_out, int64_t col0, void* stream);
+/* Same, written in split-half format into the FP16x3 row buffer (pitch >= 520 halfs per plane):
+ * columns [256,286) posenc, [286,289) xyz, [289,296) and [519] zero. */
+int hoisdf_posenc_split_fwd(const int32_t* lattice_index, const float* points, int64_t rows, int32_t bins,
+                            uint16_t* out_hi, uint16_t* out_lo, int64_t ld_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * SDFDecoder.forward -- upstream common/nets/sdf_net.py:87-122 (eval: dropout off):
@@ -195,6 +204,20 @@ typedef struct {
 
 int hoisdf_sdf_decoder_fwd(const hoisdf_sdf_weights* wts, float* x, int64_t ldx, int64_t rows, float* h_a,
                            float* h_b, float* out_sdf, float clamp, void* stream);
+
+/* The same decoder on the FP16x3 tensor-core Linear (hoisdf_linear_h3_fwd), activations in split-half format.
+ * x: row buffer, two planes with pitch ldx >= 520 halfs: cols [0,289) decoder input, [289,296) zero, [296,519)
+ * scratch for relu(linh1), col 519 zero.  Weights: hoisdf_pack_h3 planes (A, B, C) of w0 (512,289), w1 (223,512),
+ * w2 (512,519) [columns permuted to input | 0 | h1], w3 (512,512); fp32 biases; fp32 w4 (512), b4.
+ * h_a, h_b: split-half scratch (rows, ldh >= 512). */
+typedef struct {
+  const uint16_t* w[4][3]; int64_t ldw[4]; const float* b[4];
+  const float* w4; const float* b4;
+} hoisdf_sdf_weights_h3;
+
+int hoisdf_sdf_decoder_h3_fwd(const hoisdf_sdf_weights_h3* wts, uint16_t* x_hi, uint16_t* x_lo, int64_t ldx,
+                              int64_t rows, uint16_t* ha_hi, uint16_t* ha_lo, uint16_t* hb_hi, uint16_t* hb_lo,
+                              int64_t ldh, float* out_sdf, float clamp, void* stream);
 
 /* Expand a plain (rows, 289) decoder input (the upstream SDFDecoder.forward argument) into the padded
  * row buffer layout above. */

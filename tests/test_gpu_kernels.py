@@ -27,12 +27,13 @@ def rnd(seed, *shape, lo=-1.0, hi=1.0):
 @pytest.mark.parametrize("m,n,k", [(1, 1, 4), (127, 60, 256), (128, 128, 16), (333, 223, 512), (1000, 512, 292),
                                    (257, 1024, 3968), (64, 3, 256), (513, 768, 256), (300, 256, 1024)])
 @pytest.mark.parametrize("act", [0, 1])
-@pytest.mark.parametrize("impl", ["fma", "tf32x3"])
+@pytest.mark.parametrize("impl", ["fma", "tf32x3", "fp16x3"])
 def test_linear_matches_fp64(cuda, m, n, k, act, impl, monkeypatch):
-    """Both Linear kernels against fp64.  fp32 FMA: error ~ sqrt(K) * 2^-24.  tcgen05 3xTF32: the tensor core
-    truncates on every accumulate (K/8 of them), so its error grows ~linearly in K but stays fp32-grade."""
+    """The three Linear kernels against fp64.  fp32 FMA: error ~ sqrt(K) * 2^-24.  tcgen05 3xTF32 / FP16x3: the tensor
+    core truncates on every accumulate, so their error grows ~linearly in K but stays fp32-grade (22-bit operands)."""
     from hoisdf_b200 import ops
-    monkeypatch.setattr(ops, "USE_TENSOR_CORES", impl == "tf32x3")
+    monkeypatch.setattr(ops, "USE_TENSOR_CORES", impl != "fma")
+    monkeypatch.setattr(ops, "TC_MODE", "h3" if impl == "fp16x3" else "tf32")
     x, w, b = rnd(1, m, k), rnd(2, n, k, lo=-0.1, hi=0.1), rnd(3, n)
     res = rnd(4, m, ops.round_up(n, 4))[:, :n]
     pw = ops.PackedLinear.pack(w.to(cuda), b.to(cuda))
@@ -41,7 +42,7 @@ def test_linear_matches_fp64(cuda, m, n, k, act, impl, monkeypatch):
     ref = x.double() @ w.double().T + b.double()
     if act:
         ref = ref.relu()
-    tol = 2e-6 * max(1.0, math.sqrt(k / 256.0)) if impl == "fma" else 1.5e-6 + 3e-9 * k
+    tol = {"fma": 2e-6 * max(1.0, math.sqrt(k / 256.0)), "tf32x3": 1.5e-6 + 3e-9 * k, "fp16x3": 1.5e-6 + 4.5e-9 * k}[impl]
     assert rel_err(y, ref) < tol
     # with fused residual (same pitch as the output)
     out = torch.zeros(m, ops.round_up(n, 4), device=cuda)[:, :n]
@@ -159,7 +160,7 @@ def test_gather_sum_is_projected_linear(cuda):
     for m in maps:
         b, h, ww, c = m.shape
         g = torch.empty(b, h, ww, 512, device=cuda)
-        ops.linear(m.view(-1, c), pw.cols(off, off + c), 0, out=g.view(-1, 512))
+        ops.linear(m.view(-1, c), ops.fma_only(pw.cols(off, off + c)), 0, out=g.view(-1, 512))   # as Model does
         gm.append(g); off += c
     out = torch.empty(B * P, 512, device=cuda)
     uv2 = uv.view(-1, 2).to(cuda).contiguous()
@@ -174,11 +175,19 @@ def test_gather_sum_is_projected_linear(cuda):
     f1 = O.gather_pyramid(pyr, O.grid_from_uv(flat[:, n0:], cfg), sample=1)[0]
     ref2 = F.relu(torch.cat([f0, f1]).double() @ w.double().T + bias.double())
     assert rel_err(out, ref2) < 3e-6
+    # split-half output (what the FP16x3 Linear reads): same values to 2^-22
+    outs = ops.SplitRows.empty(B * P, 512, cuda)
+    ops.gather(gm, uv2, B, mode=ops.GATHER_SUM, out=outs, row_offsets=offsets, bias=pw.b, act=1)
+    assert rel_err(outs.float(), out) < 3e-7
 
 
 # ---------------------------------------------------------------- SDF decoder
-def test_sdf_decoder_matches_oracle(cuda):
+@pytest.mark.parametrize("impl", ["fma", "tf32x3", "fp16x3"])
+def test_sdf_decoder_matches_oracle(cuda, impl, monkeypatch):
+    from hoisdf_b200 import ops
     from hoisdf_b200.nets.sdf_net import SDFDecoder
+    monkeypatch.setattr(ops, "USE_TENSOR_CORES", impl != "fma")
+    monkeypatch.setattr(ops, "TC_MODE", "h3" if impl == "fp16x3" else "tf32")
     sd = syn.hot_path_state_dict(31, "dexycb")
     dec = SDFDecoder(256, 33).to(cuda).eval()
     dec.load_state_dict({k[len("hand_sdf_decoder."):]: v for k, v in sd.items() if k.startswith("hand_sdf_decoder.")})
@@ -187,7 +196,63 @@ def test_sdf_decoder_matches_oracle(cuda):
         got, _ = dec(x.to(cuda))
     ref = O.sdf_decoder(sd, "hand_sdf_decoder", x)
     assert got.shape == (1000, 1)
-    assert (got.cpu() - ref).abs().max() < 2e-6      # |sdf| < 1; fp32 accumulation-order differences only
+    # |sdf| < 1; fp32 accumulation-order differences only (FP16x3: one accumulator, 22-bit operands)
+    assert (got.cpu() - ref).abs().max() < (4e-6 if impl == "fp16x3" else 2e-6)
+
+
+# ---------------------------------------------------------------- split-half format / FP16x3 Linear
+def test_split_half_round_trip_and_posenc(cuda):
+    from hoisdf_b200 import ops
+    x = torch.cat([rnd(41, 300, 289, lo=-50, hi=50), rnd(42, 300, 289, lo=-1e-3, hi=1e-3)])
+    xs = ops.split_rows(x.to(cuda))
+    back = xs.float().cpu()
+    assert ((back - x).abs() <= x.abs() * 2.0 ** -21 + 1e-12).all()          # 22 significand bits
+    # zero-padded tail columns
+    xs2 = ops.SplitRows.empty(600, 296, cuda)
+    xs2.buf.fill_(float("nan"))
+    ops.split_rows(x.to(cuda), out=xs2.window(0, 289), kpad=292)
+    assert torch.equal(xs2.buf[:, :, 289:292].cpu(), torch.zeros(600, 2, 3, dtype=torch.float16))
+    # posenc written in split-half format == the fp32 kernel's columns
+    idx = torch.arange(0, 262144, 997, dtype=torch.int32, device=cuda)
+    rows32 = torch.zeros(idx.numel(), ops.ROW_LD, device=cuda)
+    ops.posenc(rows32, lattice_index=idx, bins=64)
+    rows16 = ops.SplitRows.empty(idx.numel(), ops.ROWH_LD, cuda)
+    rows16.buf.fill_(float("nan"))
+    ops.posenc(rows16, lattice_index=idx, bins=64)
+    got = rows16.window(256, 40).float()
+    assert rel_err(got[:, :33], rows32[:, 256:289]) < 3e-7 and float(got[:, 33:].abs().max()) == 0.0
+    assert float(rows16.window(512, 8).float()[:, 7].abs().max()) == 0.0     # column 519
+
+
+def test_linear_h3_modes(cuda):
+    """FP16x3 Linear: split-half output chaining, strided row groups, ragged M / N / K, residual path."""
+    from hoisdf_b200 import ops
+    m, k, n1, n2 = 777, 289, 512, 223
+    x, w1, b1 = rnd(51, m, k), rnd(52, n1, k, lo=-0.1, hi=0.1), rnd(53, n1)
+    w2, b2 = rnd(54, n2, n1, lo=-0.1, hi=0.1), rnd(55, n2)
+    p1, p2 = ops.PackedLinearH3.pack(w1.to(cuda), b1.to(cuda)), ops.PackedLinearH3.pack(w2.to(cuda), b2.to(cuda))
+    h = ops.linear_h3(ops.split_rows(x.to(cuda)), p1, ops.ACT_RELU, split_out=True)
+    y = ops.linear_h3(h, p2, ops.ACT_NONE)
+    href = (x.double() @ w1.double().T + b1.double()).relu()
+    assert rel_err(h.float(), href) < 3e-6
+    assert rel_err(y, href @ w2.double().T + b2.double()) < 5e-6
+    # output into a column window of a wider split-half buffer (the decoder's skip slot)
+    wide = ops.SplitRows.empty(m, ops.ROWH_LD, cuda)
+    wide.buf.zero_()
+    ops.linear_h3(h, p2, ops.ACT_RELU, out=wide.window(ops.SKIP_OFF_H, n2))
+    assert rel_err(wide.window(ops.SKIP_OFF_H, n2).float(), (href @ w2.double().T + b2.double()).relu()) < 5e-6
+    assert float(wide.window(0, ops.SKIP_OFF_H).float().abs().max()) == 0.0
+    # strided row groups: rows [2, 2+P) of every group of T rows
+    L, T, P, d = 5, 300, 128, 256
+    xb, w3, b3 = rnd(56, L * T, d), rnd(57, 60, d, lo=-0.1, hi=0.1), rnd(58, 60)
+    xs = ops.split_rows(xb.to(cuda))
+    p3 = ops.PackedLinearH3.pack(w3.to(cuda), b3.to(cuda))
+    for P in (128, 100):      # TMA-store epilogue / direct-store epilogue (groups not a multiple of the tile)
+        yb = ops.linear_h3(ops.SplitRows(xs.buf[2:], d), p3, 0, x_batch=(P, T * xs.ld), m=L * P)
+        ref = xb.view(L, T, d)[:, 2:2 + P].reshape(-1, d).double() @ w3.double().T + b3.double()
+        assert rel_err(yb, ref) < 3e-6
+    with pytest.raises(ValueError):
+        ops.PackedLinearH3.pack(torch.full((4, 8), 40.0, device=cuda), None)
 
 
 # ---------------------------------------------------------------- selection (bit-exact)
