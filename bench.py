@@ -265,7 +265,7 @@ def run_native(args):
     # dominant kernel: the tcgen05 3xTF32 Linear kernel (stand-alone launches + the four inside every SDF-decoder
     # call); every such launch of the timed steps was bracketed by CUDA events on the launching stream
     torch.cuda.synchronize()
-    tc = [p for p in prof if p[0] in ("linear_tc", "sdf_decoder", "linear_h3", "sdf_decoder_h3")]
+    tc = [p for p in prof if p[0] in ("linear_tc", "sdf_decoder", "linear_h3", "sdf_decoder_h3", "conv_h3")]
     h3 = any(p[0] in ("linear_h3", "sdf_decoder_h3") for p in tc)
     fma = [p for p in prof if p[0] == "linear"]
     tc_flops = sum(p[1] for p in tc)
@@ -276,7 +276,7 @@ def run_native(args):
     achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
     kernel_name = ("hoisdf::linear_h3_kernel (tcgen05.mma kind::f16 on split-half operands, 3 products per fp32-grade "
                    "product; persistent, double-buffered TMEM; all launches of the step incl. the 4 GEMMs of every "
-                   "SDF-decoder call; FLOPs counted once per fp32 product, i.e. the tensor cores execute 3x this number "
+                   "SDF-decoder call and the implicit-GEMM convolutions of the U-Net decoder; FLOPs counted once per fp32 product, i.e. the tensor cores execute 3x this number "
                    "of fp16 MACs)") if h3 else (
         "hoisdf::linear_tf32x3_kernel (tcgen05.mma kind::tf32, 3-pass split = fp32-grade; all launches of the "
         "step incl. the 4 GEMMs of every SDF-decoder call; FLOPs counted once per fp32 product, i.e. the "

@@ -33,7 +33,18 @@ class LinearH3Args(C.Structure):
         ("x_hi", vp), ("x_lo", vp), ("ldx", i64), ("x_rows_per_batch", i64), ("x_batch_stride", i64),
         ("w_a", vp), ("w_b", vp), ("w_c", vp), ("ldw", i64), ("bias", vp), ("residual", vp),
         ("y", vp), ("ldy", i64), ("y_hi", vp), ("y_lo", vp), ("ldyh", i64),
-        ("m", i64), ("n", i64), ("k", i64), ("act", i32),
+        ("m", i64), ("n", i64), ("k", i64), ("act", i32), ("two_acc", i32),
+    ]
+
+
+class ConvH3Args(C.Structure):
+    _fields_ = [
+        ("x_hi", vp), ("x_lo", vp), ("batch", i64), ("in_h", i64), ("in_w", i64), ("cin", i64), ("ldx", i64),
+        ("w_a", vp), ("w_b", vp), ("w_c", vp), ("ldw", i64), ("bias", vp),
+        ("taps", i32), ("tap_dy", i32 * 16), ("tap_dx", i32 * 16), ("stride", i32),
+        ("out_h", i64), ("out_w", i64), ("cout", i64),
+        ("y", vp), ("y_hi", vp), ("y_lo", vp), ("y_sx", i64), ("y_sy", i64), ("y_sb", i64),
+        ("act", i32), ("two_acc", i32),
     ]
 
 
@@ -64,11 +75,13 @@ SIGNATURES = {
     "hoisdf_linear_fwd": (C.c_int, [C.POINTER(LinearArgs), vp]),
     "hoisdf_split_tf32": (C.c_int, [vp, i64, vp, vp, vp]),
     "hoisdf_linear_h3_fwd": (C.c_int, [C.POINTER(LinearH3Args), vp]),
+    "hoisdf_conv_h3_fwd": (C.c_int, [C.POINTER(ConvH3Args), vp]),
     "hoisdf_pack_h3": (C.c_int, [vp, i64, i64, i64, vp, vp, vp, i64, vp]),
     "hoisdf_split_rows": (C.c_int, [vp, i64, i64, i64, i64, vp, vp, i64, vp]),
     "hoisdf_join_rows": (C.c_int, [vp, vp, i64, i64, i64, vp, i64, vp]),
     "hoisdf_fold_weight_norm": (C.c_int, [vp, vp, i64, i64, vp, i64, vp, i64, vp]),
     "hoisdf_nchw_to_nhwc": (C.c_int, [vp, vp, i64, i64, i64, i64, vp]),
+    "hoisdf_nchw_to_nhwc_split": (C.c_int, [vp, vp, vp, i64, i64, i64, i64, i64, vp]),
     "hoisdf_lattice_chunks": (C.c_int, [i32]),
     "hoisdf_lattice_count": (C.c_int, [vp, vp, vp, f32, i64, i32, vp, vp, vp]),
     "hoisdf_lattice_compact": (C.c_int, [vp, vp, vp, f32, i64, i32, vp, vp, vp, vp, vp]),

@@ -59,6 +59,9 @@ class Config:
     screen_margin = 256         # margin used with screen_passes = 1
     screen_margin_safe = 64     # margin used with 3xTF32 screening
     screen_passes = 3
+    # U-Net decoder (the step before the hot path) on the FP16x3 tensor-core convolution kernels
+    # instead of cuDNN's fp32 FMA convolutions (measured 3e-5 relative difference on the pyramid; 2.3x faster at B=4)
+    tc_unet = True
 
     def calc_mutliscale_dim(self, use_big_decoder_l, resnet_type_l):
         # upstream config.py:101-108 (sic: "mutliscale")

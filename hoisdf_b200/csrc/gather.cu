@@ -175,6 +175,33 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
   }
 }
 
+// (N, C, HW) fp32 -> split-half (N, HW, ld) planes at a channel offset, through a 32x33 shared tile
+__global__ void __launch_bounds__(256) nchw_to_nhwc_split_kernel(const float* __restrict__ src, __half* __restrict__ hi,
+                                                                 __half* __restrict__ lo, int C, int HW, int64_t ld) {
+  __shared__ float tile[32][33];
+  const int64_t n = blockIdx.z;
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const float* s = src + n * static_cast<int64_t>(C) * HW;
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int c = c0 + ty + j, pp = p0 + tx;
+    tile[ty + j][tx] = (c < C && pp < HW) ? s[static_cast<int64_t>(c) * HW + pp] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int pp = p0 + ty + j, c = c0 + tx;
+    if (c < C && pp < HW) {
+      __half h, l;
+      tc::split_half(tile[tx][ty + j], h, l);
+      const int64_t o = (n * HW + pp) * ld + c;
+      hi[o] = h;
+      lo[o] = l;
+    }
+  }
+}
+
 }  // namespace hoisdf
 
 using namespace hoisdf;
@@ -251,5 +278,18 @@ HOISDF_API int hoisdf_nchw_to_nhwc(const float* src, float* dst, int64_t n, int6
   dim3 grid(static_cast<unsigned>(ceil_div(HW, 32)), static_cast<unsigned>(ceil_div(c, 32)),
             static_cast<unsigned>(n));
   nchw_to_nhwc_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, static_cast<int>(c), HW);
+  return launch_status();
+}
+
+HOISDF_API int hoisdf_nchw_to_nhwc_split(const float* src, uint16_t* dst_hi, uint16_t* dst_lo, int64_t n, int64_t c,
+                                         int64_t h, int64_t w, int64_t ld, void* stream) {
+  if (src == nullptr || dst_hi == nullptr || dst_lo == nullptr) return HOISDF_E_NULL;
+  if (n <= 0 || c <= 0 || h <= 0 || w <= 0 || n > 65535 || c > (1 << 20) || h * w > (1 << 24) || ld < c)
+    return HOISDF_E_SHAPE;
+  const int HW = static_cast<int>(h * w);
+  dim3 grid(static_cast<unsigned>(ceil_div(HW, 32)), static_cast<unsigned>(ceil_div(c, 32)),
+            static_cast<unsigned>(n));
+  nchw_to_nhwc_split_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, reinterpret_cast<__half*>(dst_hi), reinterpret_cast<__half*>(dst_lo), static_cast<int>(c), HW, ld);
   return launch_status();
 }

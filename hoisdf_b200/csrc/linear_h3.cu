@@ -52,6 +52,13 @@ struct H3Params {
   int n_tiles;
   int n, k, act;
   int out_mode;
+  int two_acc;              // main / correction products in separate accumulators: the main sum sees 1/3 of the
+                            // accumulate-truncation events (3x smaller error at large K); no epilogue overlap
+  // implicit-GEMM convolution (taps > 0): X is an NHWC image batch (4-D tensor maps), M = output pixels in (b, y, x)
+  // order, K = taps x Cin; a 128-pixel M tile is a (tb x ty x tx) block of the output grid, a warp's 32 rows a
+  // (wy x wx) block
+  int taps, cin_blocks, out_w, out_h, stride, wx, wy;
+  int8_t dy[16], dx[16];
 };
 
 template <int CL>
@@ -77,7 +84,7 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
   const int cluster = static_cast<int>(blockIdx.x) / CL;
   const int nclusters = static_cast<int>(gridDim.x) / CL;
   const int items = p.m_blocks * p.n_tiles;
-  const int num_kb = (p.k + H3_BK - 1) / H3_BK;
+  const int num_kb = p.taps > 0 ? p.taps * p.cin_blocks : (p.k + H3_BK - 1) / H3_BK;
   constexpr uint16_t kAllCtas = static_cast<uint16_t>((1u << CL) - 1u);
   constexpr int kSliceRows = H3_BN / CL;                 // W rows each CTA fetches (and multicasts)
   constexpr int kSliceBytes = kSliceRows * H3_BK * 2;
@@ -129,14 +136,33 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
         tile_of(item, m_tile, grp, m0, n0);
         const int wrow = n0 + static_cast<int>(rank) * kSliceRows;
         const uint32_t wo = rank * kSliceBytes;
+        // convolution: first output pixel of the tile -> (image, row, column); tiles beyond the last land at b >= B
+        int cb0 = 0, cy0 = 0, cx0 = 0;
+        if (p.taps > 0) {
+          const int hw = p.out_h * p.out_w;
+          const int pix = m_tile * H3_BM;
+          cb0 = pix / hw;
+          const int rem = pix - cb0 * hw;
+          cy0 = (rem / p.out_w) * p.stride;
+          cx0 = (rem - (rem / p.out_w) * p.out_w) * p.stride;
+        }
+        int tap = 0, cblk = 0;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % H3_STAGES;
           const uint32_t ph = (it / H3_STAGES) & 1u;
           mbar_wait(bar_empty(s), ph ^ 1u);
           const uint32_t st = base + s * H3_STAGE_BYTES;
           mbar_expect_tx(bar_full(s), H3_STAGE_BYTES);
-          tma_load_3d(st, &map_xhi, bar_full(s), kb * H3_BK, m0, grp);
-          tma_load_3d(st + H3_X_BYTES, &map_xlo, bar_full(s), kb * H3_BK, m0, grp);
+          if (p.taps > 0) {
+            // shifted window of the input image for this tap; out-of-image pixels are zero-filled = zero padding
+            const int ix = cx0 + p.dx[tap], iy = cy0 + p.dy[tap];
+            tma_load_4d(st, &map_xhi, bar_full(s), cblk * H3_BK, ix, iy, cb0);
+            tma_load_4d(st + H3_X_BYTES, &map_xlo, bar_full(s), cblk * H3_BK, ix, iy, cb0);
+            if (++cblk == p.cin_blocks) { cblk = 0; ++tap; }
+          } else {
+            tma_load_3d(st, &map_xhi, bar_full(s), kb * H3_BK, m0, grp);
+            tma_load_3d(st + H3_X_BYTES, &map_xlo, bar_full(s), kb * H3_BK, m0, grp);
+          }
           const uint32_t w0 = st + 2 * H3_X_BYTES + wo;
           if (CL > 1) {
             tma_load_2d_mc(w0, &map_wa, bar_full(s), kb * H3_BK, wrow, kAllCtas);
@@ -160,10 +186,12 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
         const int n_here = min(H3_BN, p.n - n0);
         const int n_inst = (n_here + 15) & ~15;                 // UMMA N (multiple of 16 for M = 128)
         const uint32_t idesc = umma_idesc_f16(H3_BM, n_inst);
-        const uint32_t buf = t & 1u;
-        mbar_wait(bar_tempty(buf), ((t >> 1) & 1u) ^ 1u);        // epilogue has drained this accumulator
+        const uint32_t buf = p.two_acc ? 0u : (t & 1u);
+        const uint32_t par = p.two_acc ? (t & 1u) : ((t >> 1) & 1u);
+        mbar_wait(bar_tempty(buf), par ^ 1u);                    // epilogue has drained this accumulator
         tcgen05_fence_after();
         const uint32_t acc = tmem_base + buf * H3_BN;
+        const uint32_t acc2 = p.two_acc ? tmem_base + H3_BN : acc;   // where the two correction products go
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % H3_STAGES;
           const uint32_t ph = (it / H3_STAGES) & 1u;
@@ -177,9 +205,10 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
 #pragma unroll
           for (int kk = 0; kk < H3_BK / 16; ++kk) {
             const uint64_t adv = static_cast<uint64_t>(kk * 2);    // 16 halfs = 32 bytes = 2 x 16-byte units
-            umma_f16(acc, d_xhi + adv, d_wa + adv, idesc, (kb | kk) != 0 ? 1u : 0u);
-            umma_f16(acc, d_xlo + adv, d_wb + adv, idesc, 1u);
-            umma_f16(acc, d_xhi + adv, d_wc + adv, idesc, 1u);
+            const uint32_t later = (kb | kk) != 0 ? 1u : 0u;
+            umma_f16(acc, d_xhi + adv, d_wa + adv, idesc, later);
+            umma_f16(acc2, d_xlo + adv, d_wb + adv, idesc, p.two_acc ? later : 1u);
+            umma_f16(acc2, d_xhi + adv, d_wc + adv, idesc, 1u);
           }
           if (CL > 1) umma_commit_mc(bar_empty(s), kAllCtas);      // stage refillable once ALL CTAs' MMAs have read it
           else umma_commit(bar_empty(s));
@@ -198,18 +227,37 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
       tile_of(item, m_tile, grp, m0, n0);
       const int n_here = min(H3_BN, p.n - n0);
       const int n_inst = (n_here + 15) & ~15;
-      const uint32_t buf = t & 1u;
+      const uint32_t buf = p.two_acc ? 0u : (t & 1u);
+      const uint32_t par = p.two_acc ? (t & 1u) : ((t >> 1) & 1u);
       const bool tile_ok = m_tile < p.m_tiles;
+      int ob = 0, oy = 0, ox = 0;              // convolution: (image, row, column) of this warp's first output pixel
+      if (p.taps > 0) {
+        const int hw = p.out_h * p.out_w;
+        const int pix = m_tile * H3_BM + q * 32;
+        ob = pix / hw;
+        const int rem = pix - ob * hw;
+        oy = rem / p.out_w;
+        ox = rem - oy * p.out_w;
+      }
       const int64_t lrow = static_cast<int64_t>(m0) + q * 32 + lane;            // row inside the group
       const bool row_ok = tile_ok && lrow < p.rows_per_batch;
       const int64_t row = static_cast<int64_t>(grp) * p.rows_per_batch + lrow;   // output rows are dense
       const int row0 = static_cast<int>(static_cast<int64_t>(grp) * p.rows_per_batch + m0 + q * 32);
-      mbar_wait(bar_tfull(buf), (t >> 1) & 1u);
+      mbar_wait(bar_tfull(buf), par);
       tcgen05_fence_after();
       for (int c0 = 0; c0 < n_inst; c0 += 32, ++chunk) {
         uint32_t r[32];
-        tmem_ld32(tmem_base + buf * H3_BN + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0), r);
-        tmem_ld_wait();
+        const uint32_t taddr = tmem_base + buf * H3_BN + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0);
+        tmem_ld32(taddr, r);
+        if (p.two_acc) {
+          uint32_t r2[32];
+          tmem_ld32(taddr + H3_BN, r2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+        } else {
+          tmem_ld_wait();
+        }
         if (c0 + 32 >= n_inst) {               // last read of this accumulator: hand it back to the MMA warp
           tcgen05_fence_before();
           __syncwarp();
@@ -289,8 +337,13 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
         __syncwarp();
         if (lane == 0) {
           if (tile_ok && c0 < n_here) {
-            tma_store_2d(&map_y0, box_sh, n0 + c0, row0);
-            if (p.out_mode == H3_OUT_SPLIT_TMA) tma_store_2d(&map_y1, box_sh + 2048, n0 + c0, row0);
+            if (p.taps > 0) {
+              tma_store_4d(&map_y0, box_sh, n0 + c0, ox, oy, ob);
+              if (p.out_mode == H3_OUT_SPLIT_TMA) tma_store_4d(&map_y1, box_sh + 2048, n0 + c0, ox, oy, ob);
+            } else {
+              tma_store_2d(&map_y0, box_sh, n0 + c0, row0);
+              if (p.out_mode == H3_OUT_SPLIT_TMA) tma_store_2d(&map_y1, box_sh + 2048, n0 + c0, row0);
+            }
           }
           tma_store_commit();
         }
@@ -510,8 +563,102 @@ HOISDF_API int hoisdf_linear_h3_fwd(const hoisdf_linear_h3_args* a, void* stream
                      CU_TENSOR_MAP_L2_PROMOTION_NONE))
       return HOISDF_E_UNSUPPORTED;
   }
-  H3Params p{a->bias, a->residual, a->y, a->ldy, rpb, static_cast<int>(tpb), static_cast<int>(m_tiles), 0,
-             static_cast<int>(ceil_div(a->n, H3_BN)), static_cast<int>(a->n), static_cast<int>(a->k), a->act, out_mode};
+  H3Params p{};
+  p.bias = a->bias; p.residual = a->residual; p.y = a->y; p.ldy = a->ldy;
+  p.rows_per_batch = rpb; p.tiles_per_batch = static_cast<int>(tpb); p.m_tiles = static_cast<int>(m_tiles);
+  p.n_tiles = static_cast<int>(ceil_div(a->n, H3_BN));
+  p.n = static_cast<int>(a->n); p.k = static_cast<int>(a->k); p.act = a->act; p.out_mode = out_mode;
+  p.two_acc = a->two_acc ? 1 : 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (cl == 4) return launch_h3<4>(maps, p, m_tiles, s);
+  if (cl == 2) return launch_h3<2>(maps, p, m_tiles, s);
+  return launch_h3<1>(maps, p, m_tiles, s);
+}
+
+HOISDF_API int hoisdf_conv_h3_fwd(const hoisdf_conv_h3_args* a, void* stream) {
+  if (a == nullptr || a->x_hi == nullptr || a->x_lo == nullptr || a->w_a == nullptr || a->w_b == nullptr ||
+      a->w_c == nullptr)
+    return HOISDF_E_NULL;
+  const bool split_out = a->y_hi != nullptr || a->y_lo != nullptr;
+  if (split_out ? (a->y_hi == nullptr || a->y_lo == nullptr || a->y != nullptr) : a->y == nullptr) return HOISDF_E_NULL;
+  if (a->batch <= 0 || a->in_h <= 0 || a->in_w <= 0 || a->cin <= 0 || a->cout <= 0 || a->out_h <= 0 || a->out_w <= 0 ||
+      a->taps <= 0 || a->taps > 16 || a->stride < 1 || a->stride > 2)
+    return HOISDF_E_SHAPE;
+  if (a->cin % H3_BK != 0) return HOISDF_E_UNSUPPORTED;         // a K block never straddles two taps
+  const int64_t m = a->batch * a->out_h * a->out_w;
+  if (m >= 0x7fffffffLL || a->taps * a->cin >= 0x7fffffffLL) return HOISDF_E_SHAPE;
+  if ((a->ldx & 7) || (a->ldw & 7) || !aligned16(a->x_hi) || !aligned16(a->x_lo) || !aligned16(a->w_a) ||
+      !aligned16(a->w_b) || !aligned16(a->w_c) || a->ldx < a->cin || a->ldw < a->taps * a->cin)
+    return HOISDF_E_ALIGN;
+  const int esz = split_out ? 2 : 4;
+  if ((a->y_sx * esz) % 16 || (a->y_sy * esz) % 16 || (a->y_sb * esz) % 16) return HOISDF_E_ALIGN;
+  if (split_out ? (!aligned16(a->y_hi) || !aligned16(a->y_lo)) : !aligned16(a->y)) return HOISDF_E_ALIGN;
+  // tile geometry: 128 consecutive output pixels = tb images x ty rows x tx columns
+  const int tx = static_cast<int>(a->out_w < H3_BM ? a->out_w : H3_BM);
+  if (a->out_w % tx != 0 || H3_BM % tx != 0) return HOISDF_E_UNSUPPORTED;
+  const int ty_max = H3_BM / tx;
+  const int ty = static_cast<int>(a->out_h < ty_max ? a->out_h : ty_max);
+  if (a->out_h % ty != 0 || ty_max % ty != 0) return HOISDF_E_UNSUPPORTED;
+  const int tb = H3_BM / (tx * ty);
+  if (tx * ty < 32 || tx * a->stride > 256 || ty * a->stride > 256) return HOISDF_E_UNSUPPORTED;
+  const int wx = tx < 32 ? tx : 32, wy = 32 / wx;
+  CUtensorMap maps[7];
+  {
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(a->cin), static_cast<cuuint64_t>(a->in_w),
+                          static_cast<cuuint64_t>(a->in_h), static_cast<cuuint64_t>(a->batch)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(a->ldx) * 2, static_cast<cuuint64_t>(a->in_w * a->ldx) * 2,
+                             static_cast<cuuint64_t>(a->in_h * a->in_w * a->ldx) * 2};
+    cuuint32_t box[4] = {H3_BK, static_cast<cuuint32_t>(tx * a->stride), static_cast<cuuint32_t>(ty * a->stride),
+                         static_cast<cuuint32_t>(tb)};
+    cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(a->stride), static_cast<cuuint32_t>(a->stride), 1};
+    if (!make_tiled_map(&maps[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, a->x_hi, dims, strides, box, estr,
+                        CU_TENSOR_MAP_SWIZZLE_64B) ||
+        !make_tiled_map(&maps[1], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, a->x_lo, dims, strides, box, estr,
+                        CU_TENSOR_MAP_SWIZZLE_64B))
+      return HOISDF_E_UNSUPPORTED;
+  }
+  const int64_t m_tiles = ceil_div(m, H3_BM);
+  int cl = m_tiles >= 2 ? 2 : 1;
+  if (g_h3_force_cluster == 1 || g_h3_force_cluster == 2 || g_h3_force_cluster == 4) cl = g_h3_force_cluster;
+  const void* wp[3] = {a->w_a, a->w_b, a->w_c};
+  for (int i = 0; i < 3; ++i)
+    if (!map_half_2d(&maps[2 + i], wp[i], a->cout, a->taps * a->cin, a->ldw, H3_BK, H3_BN / cl,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B))
+      return HOISDF_E_UNSUPPORTED;
+  {
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(a->cout), static_cast<cuuint64_t>(a->out_w),
+                          static_cast<cuuint64_t>(a->out_h), static_cast<cuuint64_t>(a->batch)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(a->y_sx) * esz, static_cast<cuuint64_t>(a->y_sy) * esz,
+                             static_cast<cuuint64_t>(a->y_sb) * esz};
+    cuuint32_t box[4] = {32, static_cast<cuuint32_t>(wx), static_cast<cuuint32_t>(wy), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (split_out) {
+      if (!make_tiled_map(&maps[5], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, a->y_hi, dims, strides, box, estr,
+                          CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE) ||
+          !make_tiled_map(&maps[6], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, a->y_lo, dims, strides, box, estr,
+                          CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE))
+        return HOISDF_E_UNSUPPORTED;
+    } else {
+      if (!make_tiled_map(&maps[5], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a->y, dims, strides, box, estr,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE))
+        return HOISDF_E_UNSUPPORTED;
+      maps[6] = maps[5];
+    }
+  }
+  H3Params p{};
+  p.bias = a->bias; p.rows_per_batch = m; p.tiles_per_batch = static_cast<int>(m_tiles);
+  p.m_tiles = static_cast<int>(m_tiles); p.n_tiles = static_cast<int>(ceil_div(a->cout, H3_BN));
+  p.n = static_cast<int>(a->cout); p.k = static_cast<int>(a->taps * a->cin); p.act = a->act;
+  p.out_mode = split_out ? H3_OUT_SPLIT_TMA : H3_OUT_F32_TMA;
+  p.two_acc = a->two_acc ? 1 : 0;
+  p.taps = a->taps; p.cin_blocks = static_cast<int>(a->cin / H3_BK);
+  p.out_w = static_cast<int>(a->out_w); p.out_h = static_cast<int>(a->out_h); p.stride = a->stride;
+  p.wx = wx; p.wy = wy;
+  for (int t = 0; t < a->taps; ++t) {
+    if (a->tap_dy[t] < -64 || a->tap_dy[t] > 64 || a->tap_dx[t] < -64 || a->tap_dx[t] > 64) return HOISDF_E_SHAPE;
+    p.dy[t] = static_cast<int8_t>(a->tap_dy[t]);
+    p.dx[t] = static_cast<int8_t>(a->tap_dx[t]);
+  }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (cl == 4) return launch_h3<4>(maps, p, m_tiles, s);
   if (cl == 2) return launch_h3<2>(maps, p, m_tiles, s);

@@ -28,6 +28,7 @@ from .nets.mano_head import ManoHead, ManoLayer
 from .nets.module import BackboneNet, DecoderNet, DecoderNet_big
 from .nets.sdf_net import SDFDecoder
 from .nets.transformer import Transformer, VoteTransformer
+from .nets.unet_h3 import UNetH3
 from .utils.misc import get_mano_memory_mask, get_mano_tgt_mask
 
 
@@ -330,7 +331,7 @@ class Model(nn.Module):
             if getattr(self, "_channels_last", False):
                 img = img.contiguous(memory_format=torch.channels_last)
             img_feat, skips = self.backbone_net(img)
-            feature_pyramid, decoder_out = self.decoder_net(img_feat, skips)
+            feature_pyramid, decoder_out = self.run_decoder(img_feat, skips)
             ctx = self._ctx(feature_pyramid)
             dex = cfg.dataset == "dexycb"
             mano_params = targets["mano_param"] if dex else None
@@ -355,6 +356,14 @@ class Model(nn.Module):
                 joint_gt = targets["joint_cam_no_trans"][:, 1:] if dex else None
                 out = {**eval_losses(taps, targets, meta_info, joint_gt), **out}
         return out
+
+    def run_decoder(self, img_feat, skips):
+        """U-Net decoder: on the FP16x3 tensor-core kernels (nets/unet_h3.py) when enabled, else the cuDNN modules."""
+        if cfg.tc_unet and ops.use_h3():
+            if getattr(self, "_unet_h3", None) is None or self._unet_h3.dec is not self.decoder_net.resnet_decoder:
+                self._unet_h3 = UNetH3(self.decoder_net.resnet_decoder)
+            return self._unet_h3(img_feat, skips)
+        return self.decoder_net(img_feat, skips)
 
     def _plans(self, meta_info):
         K = meta_info["cam_intr"]

@@ -1,0 +1,169 @@
+"""U-Net decoder (upstream common/nets/module.py:98-218) on the FP16x3 tensor-core kernels.
+
+The decoder is 84 % of the convolution FLOPs in front of the hot path (55.8 of 66.5
+GFLOP/sample for the 'ho3d' setting) and cuDNN runs it on the fp32 FMA pipe.  Here every layer is an implicit GEMM
+on `hoisdf_conv_h3_fwd` / `hoisdf_linear_h3_fwd` (fp32-grade accuracy at fp16 tensor-core rate):
+
+  * BatchNorm (eval) is folded into the weights and bias, ReLU runs in the GEMM epilogue;
+  * activations are NHWC in split-half format; the skip concatenation costs no copy: the encoder feature map is
+    transposed into the left channel window of the concat buffer, the transposed convolution writes the right one;
+  * ConvTranspose2d(k=4, s=2, p=1) = four 2x2-tap convolutions, one per output-pixel parity class, each writing its
+    interleaved quarter of the output through a strided 4-D TMA store;
+  * each level's 3x3 convolution writes the pyramid level in fp32 NHWC (what the bilinear gather and the
+    `linear_sdfin` projection read) -- returned as logical-NCHW views, so callers see upstream's shapes.
+
+The parameters stay in the `Decoder` / `Decoder_big` modules (upstream names, strict checkpoint loading); this file
+only packs them (cached until a parameter changes) and launches kernels.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Tuple
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+TAPS_3X3 = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
+TAPS_1X1 = [(0, 0)]
+# ConvTranspose2d(k=4, s=2, p=1): output row 2y + py reads input rows y + d through kernel row ky
+_DECONV_TAPS = {0: [(1, 0), (3, -1)], 1: [(0, 1), (2, 0)]}     # parity -> [(k index, input offset)]
+
+
+def _fold_bn(weight: torch.Tensor, bias, bn: nn.BatchNorm2d, out_dim: int):
+    """conv/deconv weight with BatchNorm(eval) folded in: returns (scale-multiplied weight, bias)."""
+    w = weight.detach().double()
+    cout = w.shape[out_dim]
+    b = torch.zeros(cout, dtype=torch.float64, device=w.device) if bias is None else bias.detach().double()
+    if bn is not None:
+        scale = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+        shape = [1] * w.dim()
+        shape[out_dim] = cout
+        w = w * scale.view(shape)
+        b = (b - bn.running_mean.detach().double()) * scale + bn.bias.detach().double()
+    return w, b.float()
+
+
+def _pack_conv(conv: nn.Conv2d, bn) -> ops.PackedLinearH3:
+    """(Cout, Cin, kh, kw) -> planes of (Cout, kh*kw*Cin), K index = tap * Cin + channel."""
+    w, b = _fold_bn(conv.weight, conv.bias, bn, 0)
+    cout = w.shape[0]
+    mat = w.permute(0, 2, 3, 1).reshape(cout, -1).float().contiguous()
+    return ops.PackedLinearH3.pack(mat, b)
+
+
+def _pack_deconv(deconv: nn.ConvTranspose2d, bn) -> Dict[Tuple[int, int], Tuple[ops.PackedLinearH3, list]]:
+    """(Cin, Cout, 4, 4) -> one (Cout, 4*Cin) matrix + tap list per output parity class."""
+    w, b = _fold_bn(deconv.weight, deconv.bias, bn, 1)
+    out = {}
+    for py in (0, 1):
+        for px in (0, 1):
+            taps, mats = [], []
+            for ky, dy in _DECONV_TAPS[py]:
+                for kx, dx in _DECONV_TAPS[px]:
+                    taps.append((dy, dx))
+                    mats.append(w[:, :, ky, kx].t())            # (Cout, Cin)
+            mat = torch.stack(mats, 1).reshape(w.shape[1], -1).float().contiguous()
+            out[(py, px)] = (ops.PackedLinearH3.pack(mat, b), taps)
+    return out
+
+
+def _seq_conv_bn(seq: nn.Sequential) -> List[Tuple[nn.Conv2d, object, bool]]:
+    """[(conv, bn or None, relu?)] of a Conv(-BN-ReLU)* stack."""
+    mods, out, i = list(seq), [], 0
+    while i < len(mods):
+        conv = mods[i]
+        assert isinstance(conv, (nn.Conv2d, nn.ConvTranspose2d))
+        bn = mods[i + 1] if i + 1 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm2d) else None
+        relu = bn is not None and i + 2 < len(mods) and isinstance(mods[i + 2], nn.ReLU)
+        out.append((conv, bn, relu))
+        i += 3 if bn is not None else 1
+    return out
+
+
+class UNetH3:
+    """Runs a `Decoder` / `Decoder_big` module's forward on the FP16x3 kernels."""
+
+    def __init__(self, decoder: nn.Module):
+        self.dec = decoder
+        self.big = not hasattr(decoder, "conv0d")
+        self._packed = None
+        self._key = None
+
+    def _pack(self):
+        key = tuple((p.data_ptr(), p._version) for p in list(self.dec.parameters()) + list(self.dec.buffers()))
+        if self._packed is not None and self._key == key:
+            return self._packed
+        d, pk = self.dec, {}
+        for i in (1, 2, 3, 4):
+            (dc, dbn, _), = _seq_conv_bn(getattr(d, "deconv%d" % i))
+            pk["deconv%d" % i] = _pack_deconv(dc, dbn)
+            (cv, cbn, _), = _seq_conv_bn(getattr(d, "conv%d" % i))
+            pk["conv%d" % i] = _pack_conv(cv, cbn)
+            if not self.big:
+                (sv, sbn, _), = _seq_conv_bn(getattr(d, "conv%dd" % i))
+                pk["conv%dd" % i] = _pack_conv(sv, sbn)
+        if not self.big:
+            (sv, sbn, _), = _seq_conv_bn(d.conv0d)
+            pk["conv0d"] = _pack_conv(sv, sbn)
+        for name in ("convOut_hm", "convOut_hand_seg", "convOut_obj_seg"):
+            pk[name] = [(_pack_conv(cv, bn), relu) for cv, bn, relu in _seq_conv_bn(getattr(d, name))]
+        self._packed, self._key = pk, key
+        return pk
+
+    def __call__(self, img_feat: torch.Tensor, skips: Dict[str, torch.Tensor]):
+        """img_feat (B, 2048, 8, 8), skips {stride2..stride16} (logical NCHW fp32) -> (feature pyramid dict of
+        logical-NCHW fp32 tensors backed by NHWC memory, decoder_out (B, 3, 128, 128))."""
+        pk = self._pack()
+        dev = img_feat.device
+        b, c0, h, w = img_feat.shape
+        x = ops.nchw_to_split(img_feat, ops.SplitRows.empty(b * h * w, c0, dev))
+        cx = c0
+        pyr = {}
+        if self.big:
+            pyr["stride32"] = img_feat
+        else:
+            p0 = pk["conv0d"]
+            lvl = torch.empty(b, h, w, p0.n, device=dev, dtype=torch.float32)
+            ops.linear_h3(x, p0, ops.ACT_RELU, out=lvl.view(-1, p0.n))
+            pyr["stride32"] = lvl.permute(0, 3, 1, 2)
+        for i, name in ((1, "stride16"), (2, "stride8"), (3, "stride4"), (4, "stride2")):
+            skip = skips[name]
+            cs_in = skip.shape[1]
+            parts = pk["deconv%d" % i]
+            cu = parts[(0, 0)][0].n
+            ho, wo = 2 * h, 2 * w
+            assert skip.shape[2] == ho and skip.shape[3] == wo
+            if self.big:
+                cs = cs_in
+                cat = ops.SplitRows.empty(b * ho * wo, cs + cu, dev)
+                ops.nchw_to_split(skip, cat.window(0, cs))
+            else:       # 1x1 conv + BN + ReLU on the skip, written straight into the concat buffer
+                sp = pk["conv%dd" % i]
+                cs = sp.n
+                cat = ops.SplitRows.empty(b * ho * wo, cs + cu, dev)
+                sk = ops.nchw_to_split(skip, ops.SplitRows.empty(b * ho * wo, cs_in, dev))
+                ops.linear_h3(sk, sp, ops.ACT_RELU, out=cat.window(0, cs))
+            up = cat.window(cs, cu)
+            pitch = cat.ld
+            for (py, px), (pw, taps) in parts.items():
+                ops.conv_h3(x, b, h, w, cx, pw, taps, h, w, act=ops.ACT_RELU, out=up,
+                            out_strides=(2 * pitch, 2 * wo * pitch, ho * wo * pitch),
+                            out_offset=(py * wo + px) * pitch)
+            pc = pk["conv%d" % i]
+            lvl = torch.empty(b, ho, wo, pc.n, device=dev, dtype=torch.float32)
+            ops.conv_h3(cat, b, ho, wo, cs + cu, pc, TAPS_3X3, ho, wo, act=ops.ACT_RELU, out=lvl.view(-1, pc.n))
+            pyr[name] = lvl.permute(0, 3, 1, 2)
+            x = ops.split_rows(lvl.view(-1, pc.n))
+            h, w, cx = ho, wo, pc.n
+        # 1x1 heads on the stride-2 level: heat map, hand / object segmentation (sigmoid)
+        outs = []
+        for name in ("convOut_hm", "convOut_hand_seg", "convOut_obj_seg"):
+            hcur = x
+            layers = pk[name]
+            for j, (pw, relu) in enumerate(layers):
+                last = j == len(layers) - 1
+                hcur = ops.linear_h3(hcur, pw, ops.ACT_RELU if relu else ops.ACT_NONE, split_out=not last)
+            outs.append(hcur.reshape(b, 1, h, w))
+        out = torch.cat([outs[0], outs[1].sigmoid(), outs[2].sigmoid()], 1)
+        return pyr, out

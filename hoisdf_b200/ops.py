@@ -288,7 +288,7 @@ class PackedLinearH3:
 
 
 def linear_h3(x: SplitRows, pw: PackedLinearH3, act: int = ACT_NONE, out=None, residual: Optional[torch.Tensor] = None,
-              split_out: bool = False, x_batch=(0, 0), m: Optional[int] = None):
+              split_out: bool = False, x_batch=(0, 0), m: Optional[int] = None, two_acc: Optional[bool] = None):
     """Y = act(X . W^T + b) (+ residual) on the FP16x3 tensor-core kernel.  `out` is an fp32 (M, N) tensor view (unit
     inner stride) or a SplitRows window; allocated when None (fp32, or split-half if split_out).
     x_batch = (rows_per_batch, batch_stride in halfs) walks strided row groups of `x` (m rows in total)."""
@@ -312,6 +312,8 @@ def linear_h3(x: SplitRows, pw: PackedLinearH3, act: int = ACT_NONE, out=None, r
             assert residual.stride() == out.stride()
         a.y, a.ldy, a.y_hi, a.y_lo, a.ldyh = out.data_ptr(), out.stride(0), None, None, 0
     a.m, a.n, a.k, a.act = m, pw.n, pw.k, act
+    # long contractions: separate main / correction accumulators (3x smaller accumulate-truncation error)
+    a.two_acc = int(pw.k >= 2048 if two_acc is None else two_acc)
     _count()
     if PROFILE is None:
         check(lib.hoisdf_linear_h3_fwd(C.byref(a), _stream()), "hoisdf_linear_h3_fwd")
@@ -321,6 +323,60 @@ def linear_h3(x: SplitRows, pw: PackedLinearH3, act: int = ACT_NONE, out=None, r
         check(lib.hoisdf_linear_h3_fwd(C.byref(a), _stream()), "hoisdf_linear_h3_fwd")
         e1.record()
         PROFILE.append(("linear_h3", 2.0 * m * pw.n * pw.k, e0, e1))
+    return out
+
+
+def conv_h3(x: SplitRows, batch: int, in_h: int, in_w: int, cin: int, pw: PackedLinearH3, taps, out_h: int, out_w: int,
+            *, stride: int = 1, act: int = ACT_NONE, out=None, out_strides=None, out_offset: int = 0,
+            two_acc: Optional[bool] = None):
+    """Implicit-GEMM convolution on the FP16x3 kernel.  x: NHWC pixels (batch*in_h*in_w rows of >= cin columns) in
+    split-half format; pw: planes of the (cout, len(taps)*cin) weight matrix; taps: [(dy, dx), ...].
+    out: fp32 (rows, >= cout) tensor or SplitRows window; out_strides = (sx, sy, sb) in elements (default: dense
+    NHWC rows of `out`), out_offset = element offset of output pixel (0, 0, 0) from the start of `out`."""
+    assert x.rows == batch * in_h * in_w and x.cols >= cin and pw.k == len(taps) * cin
+    a = _capi.ConvH3Args()
+    a.x_hi, a.x_lo, a.batch, a.in_h, a.in_w, a.cin, a.ldx = x.hi_ptr, x.lo_ptr, batch, in_h, in_w, cin, x.ld
+    a.w_a, a.w_b, a.w_c, a.ldw, a.bias = pw.plane_ptr(0), pw.plane_ptr(1), pw.plane_ptr(2), pw.ld, _ptr(pw.b)
+    a.taps, a.stride = len(taps), stride
+    for i, (dy, dx) in enumerate(taps):
+        a.tap_dy[i], a.tap_dx[i] = dy, dx
+    a.out_h, a.out_w, a.cout = out_h, out_w, pw.n
+    if isinstance(out, SplitRows):
+        pitch = out.ld
+        a.y, a.y_hi, a.y_lo = None, out.hi_ptr + 2 * out_offset, out.lo_ptr + 2 * out_offset
+    else:
+        assert out.dtype == torch.float32 and out.stride(-1) == 1
+        pitch = out.stride(-2)
+        a.y, a.y_hi, a.y_lo = out.data_ptr() + 4 * out_offset, None, None
+    sx, sy, sb = out_strides if out_strides is not None else (pitch, out_w * pitch, out_h * out_w * pitch)
+    a.y_sx, a.y_sy, a.y_sb = sx, sy, sb
+    a.act = act
+    a.two_acc = int(pw.k >= 2048 if two_acc is None else two_acc)
+    _count()
+    flops = 2.0 * batch * out_h * out_w * pw.n * pw.k
+    if PROFILE is None:
+        check(lib.hoisdf_conv_h3_fwd(C.byref(a), _stream()), "hoisdf_conv_h3_fwd")
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(lib.hoisdf_conv_h3_fwd(C.byref(a), _stream()), "hoisdf_conv_h3_fwd")
+        e1.record()
+        PROFILE.append(("conv_h3", flops, e0, e1))
+    return out
+
+
+def nchw_to_split(x: torch.Tensor, out: SplitRows):
+    """(B, C, H, W) fp32 feature map -> NHWC pixels in split-half format, written at `out`'s column window."""
+    assert x.dim() == 4 and x.dtype == torch.float32 and x.is_cuda
+    b, c, h, w = x.shape
+    assert out.rows == b * h * w and out.cols >= c
+    nhwc = x.permute(0, 2, 3, 1)
+    if nhwc.is_contiguous():          # channels_last memory: a plain row-wise split
+        return split_rows(nhwc.reshape(b * h * w, c), out=out, kpad=c if c % 4 == 0 else None)
+    x = x.contiguous()
+    _count(1)
+    check(lib.hoisdf_nchw_to_nhwc_split(x.data_ptr(), out.hi_ptr, out.lo_ptr, b, c, h, w, out.ld, _stream()),
+          "hoisdf_nchw_to_nhwc_split")
     return out
 
 

@@ -93,9 +93,38 @@ typedef struct {
   uint16_t* y_hi; uint16_t* y_lo; int64_t ldyh;
   int64_t m; int64_t n; int64_t k;
   int32_t act;
+  int32_t two_acc;                   /* 1: main and correction products in separate TMEM accumulators -- 3x smaller
+                                        accumulate-truncation error (it grows ~linearly with K), no epilogue overlap;
+                                        meant for K >= ~2048 */
 } hoisdf_linear_h3_args;
 
 int hoisdf_linear_h3_fwd(const hoisdf_linear_h3_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Convolution as an implicit GEMM on the same FP16x3 kernel -- the U-Net decoder of upstream
+ * common/nets/module.py:147-218 (nn.Conv2d 3x3 / 1x1 and, one output-parity class at a time, nn.ConvTranspose2d
+ * k4 s2 p1), BatchNorm folded into weights and bias by the caller.
+ *   x: NHWC image batch in split-half format, (batch, in_h, in_w) pixels of ldx halfs each, cin % 32 == 0;
+ *   w: hoisdf_pack_h3 planes of a (cout, taps * cin) matrix, K index = tap * cin + channel;
+ *   output pixel (b, y, x) of the (out_h, out_w) grid reads input pixel (y * stride + tap_dy[t], x * stride +
+ *   tap_dx[t]) for tap t; pixels outside the image contribute zero (= zero padding);
+ *   element (b, y, x, c) of the result is written at  base + b * y_sb + y * y_sy + x * y_sx + c  (strides in
+ *   elements), fp32 (`y`) or split-half (`y_hi`, `y_lo`) -- strided placement lets a transposed convolution
+ *   interleave its four parity classes and lets a layer write into a channel window of a concat buffer.
+ * out_w must be a power of two <= 128 or a multiple of 128.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const uint16_t* x_hi; const uint16_t* x_lo;
+  int64_t batch; int64_t in_h; int64_t in_w; int64_t cin; int64_t ldx;
+  const uint16_t* w_a; const uint16_t* w_b; const uint16_t* w_c; int64_t ldw;
+  const float* bias;                 /* may be NULL */
+  int32_t taps; int32_t tap_dy[16]; int32_t tap_dx[16]; int32_t stride;
+  int64_t out_h; int64_t out_w; int64_t cout;
+  float* y; uint16_t* y_hi; uint16_t* y_lo; int64_t y_sx; int64_t y_sy; int64_t y_sb;
+  int32_t act; int32_t two_acc;
+} hoisdf_conv_h3_args;
+
+int hoisdf_conv_h3_fwd(const hoisdf_conv_h3_args* args, void* stream);
 
 /* W (n, ldw) fp32 with k valid columns -> planes A, B, C, each (n, ldh) halfs, columns [k, ldh) zeroed. */
 int hoisdf_pack_h3(const float* w, int64_t n, int64_t k, int64_t ldw, uint16_t* w_a, uint16_t* w_b, uint16_t* w_c,
@@ -118,6 +147,9 @@ int hoisdf_fold_weight_norm(const float* g, const float* v, int64_t rows, int64_
  * Layout: NCHW -> NHWC copy of one pyramid level (upstream keeps NCHW: common/nets/module.py:172-218).
  * ------------------------------------------------------------------------------------------------- */
 int hoisdf_nchw_to_nhwc(const float* src, float* dst, int64_t n, int64_t c, int64_t h, int64_t w, void* stream);
+/* Same transpose with the result in split-half format: planes (n, h*w, ld halfs), channels at columns [0, c). */
+int hoisdf_nchw_to_nhwc_split(const float* src, uint16_t* dst_hi, uint16_t* dst_lo, int64_t n, int64_t c, int64_t h,
+                              int64_t w, int64_t ld, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * sdf_infer candidate generation -- upstream main/model.py:257-302: the sheared 64^3 lattice,

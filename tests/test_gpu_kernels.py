@@ -399,3 +399,34 @@ def test_vote_and_mano(cuda):
         assert gt[k].shape == ogt[k].shape, k
         assert (gt[k].cpu() - ogt[k]).abs().max() < 2e-6, k
     assert rel_err(res["mano_pose"], O.rot6d_to_mat(pose6d.permute(0, 2, 1, 3).reshape(-1, 6)).view(L, B, 16, 3, 3)) < 2e-6
+
+
+# ---------------------------------------------------------------- U-Net decoder on the FP16x3 convolution kernels
+@pytest.mark.parametrize("arch", ["dexycb", "ho3d"])
+def test_unet_h3_matches_cudnn(cuda, arch):
+    """nets/unet_h3.py (implicit-GEMM 3x3 / 1x1 convolutions, 4-parity transposed convolutions, BN folded, NHWC
+    split-half activations) against the same modules on cuDNN fp32.  Tolerance: the tensor core truncates on every
+    accumulate, so the error grows with K (up to 9 x 2048 here): measured 1.4e-5 (dexycb) / 3.4e-5 (ho3d) of range."""
+    from hoisdf_b200.nets.module import Decoder, Decoder_big
+    from hoisdf_b200.nets.unet_h3 import UNetH3
+    B = 3           # odd: the 8x8 level packs two images per 128-pixel tile, the last tile is half empty
+    dec = (Decoder_big if arch == "ho3d" else Decoder)()
+    pre = "decoder_net.resnet_decoder."
+    dec.load_state_dict({k[len(pre):]: v for k, v in syn.full_state_dict(61, arch).items() if k.startswith(pre)})
+    dec = dec.to(cuda).eval()
+    feat = torch.relu(rnd(62, B, 2048, 8, 8)).to(cuda)
+    skips = {n: torch.relu(rnd(63 + i, B, c, s, s)).to(cuda)
+             for i, (n, c, s) in enumerate((("stride16", 1024, 16), ("stride8", 512, 32), ("stride4", 256, 64),
+                                            ("stride2", 64, 128)))}
+    with torch.no_grad():
+        ref_pyr, ref_out = dec(feat, skips)
+        pyr, out = UNetH3(dec)(feat, skips)
+        # channels_last inputs take the row-wise split instead of the transposing one
+        cl = lambda t: t.contiguous(memory_format=torch.channels_last)  # noqa: E731
+        pyr2, out2 = UNetH3(dec)(cl(feat), {k: cl(v) for k, v in skips.items()})
+    assert set(pyr) == set(ref_pyr)
+    for k in ref_pyr:
+        assert pyr[k].shape == ref_pyr[k].shape, k
+        assert rel_err(pyr[k], ref_pyr[k]) < 6e-5, (k, rel_err(pyr[k], ref_pyr[k]))
+        assert rel_err(pyr2[k], pyr[k]) < 1e-6, k
+    assert out.shape == ref_out.shape and rel_err(out, ref_out) < 6e-5 and rel_err(out2, out) < 1e-6
