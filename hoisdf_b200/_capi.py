@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhoisdf_b200.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 ACT_NONE, ACT_RELU = 0, 1
 GATHER_CONCAT, GATHER_SUM = 0, 1
 
@@ -34,6 +34,7 @@ class LinearH3Args(C.Structure):
         ("w_a", vp), ("w_b", vp), ("w_c", vp), ("ldw", i64), ("bias", vp), ("residual", vp),
         ("y", vp), ("ldy", i64), ("y_hi", vp), ("y_lo", vp), ("ldyh", i64),
         ("m", i64), ("n", i64), ("k", i64), ("act", i32), ("two_acc", i32),
+        ("res_hi", vp), ("res_lo", vp), ("ldr", i64),
     ]
 
 
@@ -45,6 +46,7 @@ class ConvH3Args(C.Structure):
         ("out_h", i64), ("out_w", i64), ("cout", i64),
         ("y", vp), ("y_hi", vp), ("y_lo", vp), ("y_sx", i64), ("y_sy", i64), ("y_sb", i64),
         ("act", i32), ("two_acc", i32),
+        ("res_hi", vp), ("res_lo", vp), ("ldr", i64),
     ]
 
 
@@ -76,6 +78,8 @@ SIGNATURES = {
     "hoisdf_split_tf32": (C.c_int, [vp, i64, vp, vp, vp]),
     "hoisdf_linear_h3_fwd": (C.c_int, [C.POINTER(LinearH3Args), vp]),
     "hoisdf_conv_h3_fwd": (C.c_int, [C.POINTER(ConvH3Args), vp]),
+    "hoisdf_stem_im2col_split": (C.c_int, [vp, i64, i64, i64, vp, vp, i64, vp]),
+    "hoisdf_maxpool3x3s2_split": (C.c_int, [vp, vp, i64, i64, i64, i64, i64, vp, vp, i64, vp]),
     "hoisdf_pack_h3": (C.c_int, [vp, i64, i64, i64, vp, vp, vp, i64, vp]),
     "hoisdf_split_rows": (C.c_int, [vp, i64, i64, i64, i64, vp, vp, i64, vp]),
     "hoisdf_join_rows": (C.c_int, [vp, vp, i64, i64, i64, vp, i64, vp]),
@@ -98,6 +102,7 @@ SIGNATURES = {
     "hoisdf_attention_workspace_bytes": (i64, [i64, i64, i64, i64]),
     "hoisdf_attention_fwd": (C.c_int, [vp, i64, vp, vp, i64, vp, i64, i64, i64, i64, i64, i64, vp, vp, i64, vp]),
     "hoisdf_add_layernorm_fwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp]),
+    "hoisdf_add_layernorm_split_fwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp, vp, i64, vp, vp, i64, vp]),
     "hoisdf_vote_joints_fwd": (C.c_int, [vp, vp, vp, i64, i64, i64, vp, vp]),
     "hoisdf_mano_fwd": (C.c_int, [C.POINTER(ManoModel), vp, vp, i64, vp, vp, vp]),
     "hoisdf_mano_aa_fwd": (C.c_int, [C.POINTER(ManoModel), vp, vp, i64, vp, vp, vp]),

@@ -62,6 +62,10 @@ class Config:
     # U-Net decoder (the step before the hot path) on the FP16x3 tensor-core convolution kernels
     # instead of cuDNN's fp32 FMA convolutions (measured 3e-5 relative difference on the pyramid; 2.3x faster at B=4)
     tc_unet = True
+    # ResNet-50 encoder on the same kernels (nets/resnet_h3.py): stem im2col + FP16x3 Linear, bottlenecks as 1x1 Linear /
+    # 3x3 implicit-GEMM convolution / 1x1 Linear with the shortcut added in the epilogue; needs tc_unet
+    tc_backbone = False       # off until the chunked-accumulation GEMM lands: the 16-block chain amplifies the
+                              # tensor core accumulate-truncation error to 4e-5 of range (cuDNN fp32: 2e-6)
 
     def calc_mutliscale_dim(self, use_big_decoder_l, resnet_type_l):
         # upstream config.py:101-108 (sic: "mutliscale")

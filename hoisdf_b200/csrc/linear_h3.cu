@@ -43,6 +43,9 @@ enum { H3_OUT_F32_TMA = 0, H3_OUT_SPLIT_TMA = 1, H3_OUT_F32_DIRECT = 2 };
 struct H3Params {
   const float* __restrict__ bias;
   const float* __restrict__ residual;
+  const __half* __restrict__ r_hi;   // residual in split-half format (TMA-store output modes), row pitch ldr halfs;
+  const __half* __restrict__ r_lo;   // row index = dense output row (Linear) / raster output pixel (convolution)
+  int64_t ldr;
   float* __restrict__ y;
   int64_t ldy;
   int64_t rows_per_batch;   // X rows form groups of this many rows (plain GEMM: = M, one group)
@@ -266,9 +269,30 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
         const float bl = (p.bias != nullptr && c0 + lane < n_here) ? __ldg(p.bias + n0 + c0 + lane) : 0.f;
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          v[j] = fmaf(__uint_as_float(r[j]), kLoInv, __shfl_sync(0xffffffffu, bl, j));
-          if (p.out_mode != H3_OUT_F32_DIRECT && p.act == HOISDF_ACT_RELU) v[j] = fmaxf(v[j], 0.f);
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), kLoInv, __shfl_sync(0xffffffffu, bl, j));
+        if (p.r_hi != nullptr) {
+          // split-half residual (ResNet bottleneck shortcut): this lane's row, 32 columns = 64 B per plane
+          const int64_t rr = p.taps > 0 ? static_cast<int64_t>(m_tile) * H3_BM + q * 32 + lane : row;
+          if (tile_ok && (p.taps > 0 ? rr < p.rows_per_batch : row_ok) && c0 < n_here) {
+            const uint4* ph = reinterpret_cast<const uint4*>(p.r_hi + rr * p.ldr + n0 + c0);
+            const uint4* pl = reinterpret_cast<const uint4*>(p.r_lo + rr * p.ldr + n0 + c0);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint4 a = __ldg(ph + g), b = __ldg(pl + g);
+              const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                v[g * 8 + 2 * j] += join_half(__ushort_as_half(static_cast<unsigned short>(aw[j] & 0xffffu)),
+                                              __ushort_as_half(static_cast<unsigned short>(bw[j] & 0xffffu)));
+                v[g * 8 + 2 * j + 1] += join_half(__ushort_as_half(static_cast<unsigned short>(aw[j] >> 16)),
+                                                  __ushort_as_half(static_cast<unsigned short>(bw[j] >> 16)));
+              }
+            }
+          }
+        }
+        if (p.out_mode != H3_OUT_F32_DIRECT && p.act == HOISDF_ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
         if (p.out_mode == H3_OUT_F32_DIRECT) {
           if (!row_ok) continue;
@@ -569,6 +593,14 @@ HOISDF_API int hoisdf_linear_h3_fwd(const hoisdf_linear_h3_args* a, void* stream
   p.n_tiles = static_cast<int>(ceil_div(a->n, H3_BN));
   p.n = static_cast<int>(a->n); p.k = static_cast<int>(a->k); p.act = a->act; p.out_mode = out_mode;
   p.two_acc = a->two_acc ? 1 : 0;
+  if (a->res_hi != nullptr || a->res_lo != nullptr) {
+    if (a->res_hi == nullptr || a->res_lo == nullptr) return HOISDF_E_NULL;
+    if (out_mode == H3_OUT_F32_DIRECT || a->residual != nullptr || (a->n & 31)) return HOISDF_E_UNSUPPORTED;
+    if ((a->ldr & 7) || a->ldr < a->n || !aligned16(a->res_hi) || !aligned16(a->res_lo)) return HOISDF_E_ALIGN;
+    p.r_hi = reinterpret_cast<const __half*>(a->res_hi);
+    p.r_lo = reinterpret_cast<const __half*>(a->res_lo);
+    p.ldr = a->ldr;
+  }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (cl == 4) return launch_h3<4>(maps, p, m_tiles, s);
   if (cl == 2) return launch_h3<2>(maps, p, m_tiles, s);
@@ -658,6 +690,14 @@ HOISDF_API int hoisdf_conv_h3_fwd(const hoisdf_conv_h3_args* a, void* stream) {
     if (a->tap_dy[t] < -64 || a->tap_dy[t] > 64 || a->tap_dx[t] < -64 || a->tap_dx[t] > 64) return HOISDF_E_SHAPE;
     p.dy[t] = static_cast<int8_t>(a->tap_dy[t]);
     p.dx[t] = static_cast<int8_t>(a->tap_dx[t]);
+  }
+  if (a->res_hi != nullptr || a->res_lo != nullptr) {
+    if (a->res_hi == nullptr || a->res_lo == nullptr) return HOISDF_E_NULL;
+    if (a->cout & 31) return HOISDF_E_UNSUPPORTED;
+    if ((a->ldr & 7) || a->ldr < a->cout || !aligned16(a->res_hi) || !aligned16(a->res_lo)) return HOISDF_E_ALIGN;
+    p.r_hi = reinterpret_cast<const __half*>(a->res_hi);
+    p.r_lo = reinterpret_cast<const __half*>(a->res_lo);
+    p.ldr = a->ldr;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (cl == 4) return launch_h3<4>(maps, p, m_tiles, s);

@@ -330,8 +330,7 @@ class Model(nn.Module):
             plans = self._plans(meta_info)
             if getattr(self, "_channels_last", False):
                 img = img.contiguous(memory_format=torch.channels_last)
-            img_feat, skips = self.backbone_net(img)
-            feature_pyramid, decoder_out = self.run_decoder(img_feat, skips)
+            feature_pyramid, decoder_out = self.run_image_encoder(img)
             ctx = self._ctx(feature_pyramid)
             dex = cfg.dataset == "dexycb"
             mano_params = targets["mano_param"] if dex else None
@@ -357,12 +356,30 @@ class Model(nn.Module):
                 out = {**eval_losses(taps, targets, meta_info, joint_gt), **out}
         return out
 
+    def run_image_encoder(self, img):
+        """ResNet-50 + U-Net -> (feature pyramid, decoder_out).  On the FP16x3 tensor-core kernels end to end when
+        enabled (activations never leave the NHWC split-half format between the two networks), else cuDNN."""
+        if cfg.tc_backbone and cfg.tc_unet and ops.use_h3():
+            from .nets.resnet_h3 import ResNetH3
+            if getattr(self, "_resnet_h3", None) is None or self._resnet_h3.net is not self.backbone_net.resnet:
+                self._resnet_h3 = ResNetH3(self.backbone_net.resnet)
+            unet = self._unet()
+            b, _, h, w = img.shape
+            cats, slots = unet.concat_slots(b, h // 32, w // 32, img.device)
+            feat, skips = self._resnet_h3(img, slots)
+            return unet.run(feat, skips, cats)
+        img_feat, skips = self.backbone_net(img)
+        return self.run_decoder(img_feat, skips)
+
+    def _unet(self):
+        if getattr(self, "_unet_h3", None) is None or self._unet_h3.dec is not self.decoder_net.resnet_decoder:
+            self._unet_h3 = UNetH3(self.decoder_net.resnet_decoder)
+        return self._unet_h3
+
     def run_decoder(self, img_feat, skips):
         """U-Net decoder: on the FP16x3 tensor-core kernels (nets/unet_h3.py) when enabled, else the cuDNN modules."""
         if cfg.tc_unet and ops.use_h3():
-            if getattr(self, "_unet_h3", None) is None or self._unet_h3.dec is not self.decoder_net.resnet_decoder:
-                self._unet_h3 = UNetH3(self.decoder_net.resnet_decoder)
-            return self._unet_h3(img_feat, skips)
+            return self._unet()(img_feat, skips)
         return self.decoder_net(img_feat, skips)
 
     def _plans(self, meta_info):
@@ -421,7 +438,10 @@ class Model(nn.Module):
         Le, Lo, Ld = hand_enc.shape[0], obj_enc.shape[0], hs.shape[0]
         # FP16x3: every source tensor is split once and shared by the heads that read it
         sp = (lambda t: ops.split_rows(t.view(-1, t.shape[-1]))) if ops.use_h3() else (lambda t: None)
-        hx, ox, qx = sp(hand_enc), sp(obj_enc), sp(hs)
+        # (the encoders' LayerNorm kernels already wrote split-half copies of their intermediate outputs)
+        hx = getattr(self.hand_transformer.encoder, "last_inter_split", None) or sp(hand_enc)
+        ox = getattr(self.obj_transformer.encoder, "last_inter_split", None) or sp(obj_enc)
+        qx = sp(hs)
         hand_off = self._head_rows(self.linear_handvote, hand_enc, Le * b, Ph, S, xs=hx).view(Le, b, Ph, 60)
         hand_cls = self._head_rows(self.linear_handcls, hand_enc, Le * b, Ph, S, xs=hx).view(Le, b, Ph, 20)
         obj_rot = self._head_rows(self.linear_obj_rot, obj_enc, Lo * b, Po, S, xs=ox).view(Lo, b, Po, 3)

@@ -70,13 +70,22 @@ class _LayerBase(nn.Module):
             self._ffn_key = key
         return self._ffn
 
-    def _ffn_block(self, x2d, norm, norm2=None, out2=None):
+    def _ffn_block(self, x2d, norm, norm2=None, out2=None, xs=None, out_split=None, out2_split=None):
+        """FFN + residual + LayerNorm (+ the shared second norm).  The residual is added by the LayerNorm kernel
+        (coalesced row reads) rather than in the GEMM epilogue; `xs` = split-half copy of x2d when the caller has
+        one, `out_split` / `out2_split` receive split-half copies of the results (FP16x3 path)."""
         l1, l2 = self.ffn_packed()
-        h = ops.linear(x2d, l1, ops.ACT_RELU, split_out=ops.use_h3())
-        y = ops.linear(h, l2, ops.ACT_NONE, residual=x2d)
+        h = ops.linear(xs if xs is not None else x2d, l1, ops.ACT_RELU, split_out=ops.use_h3())
+        y = ops.linear(h, l2, ops.ACT_NONE)
         if norm2 is None:
-            return ops.add_layernorm(y, None, norm.weight, norm.bias)
-        return ops.add_layernorm(y, None, norm.weight, norm.bias, gamma2=norm2.weight, beta2=norm2.bias, out2=out2)
+            return ops.add_layernorm(y, x2d, norm.weight, norm.bias, out_split=out_split)
+        return ops.add_layernorm(y, x2d, norm.weight, norm.bias, gamma2=norm2.weight, beta2=norm2.bias, out2=out2,
+                                 out_split=out_split, out2_split=out2_split)
+
+
+def _split_like(x2d):
+    """Split-half buffer for a (rows, d) activation on the FP16x3 path, else None."""
+    return ops.SplitRows.empty(x2d.shape[0], x2d.shape[1], x2d.device) if ops.use_h3() else None
 
 
 class TransformerEncoderLayer(_LayerBase):
@@ -88,19 +97,21 @@ class TransformerEncoderLayer(_LayerBase):
         self.norm1 = nn.LayerNorm(d_model)
         self.norm2 = nn.LayerNorm(d_model)
 
-    def forward_bm(self, x: torch.Tensor, pos: Optional[torch.Tensor], inter_norm=None, inter_out=None):
-        """x (B, S, d) batch-major contiguous -> same shape; upstream transformer.py:279-302 (forward_post)."""
+    def forward_bm(self, x: torch.Tensor, pos: Optional[torch.Tensor], inter_norm=None, inter_out=None, xs=None,
+                   out_split=None, inter_split=None):
+        """x (B, S, d) batch-major contiguous -> same shape; upstream transformer.py:279-302 (forward_post).
+        xs / out_split / inter_split: split-half copies of x / the result / the inter_norm output (FP16x3 path)."""
         b, s, d = x.shape
         x2d = x.view(b * s, d)
         pk = self.self_attn.packed()
         if pos is None:
-            qkv = ops.linear(x2d, pk["qkv"])                       # (rows, 3d): q | k | v
+            qkv = ops.linear(xs if xs is not None else x2d, pk["qkv"])   # (rows, 3d): q | k | v
             q, k, v, ld = qkv, qkv[:, d:], qkv[:, 2 * d:], 3 * d
             ldq = ld
         else:
             qk_in = (x + pos).view(b * s, d)
             qk = ops.linear(qk_in, pk["qk"])
-            vv = ops.linear(x2d, pk["v"])
+            vv = ops.linear(xs if xs is not None else x2d, pk["v"])
             # the attention entry point takes one pitch for k and v: copy v next to k
             kv = torch.empty(b * s, 2 * d, device=x.device, dtype=torch.float32)
             kv[:, :d] = qk[:, d:]
@@ -108,9 +119,10 @@ class TransformerEncoderLayer(_LayerBase):
             q, ldq, k, v, ld = qk, 2 * d, kv, kv[:, d:], 2 * d
         att = torch.empty(b * s, d, device=x.device, dtype=torch.float32)
         ops.attention(q, ldq, k, v, ld, att, d, b, self.nhead, s, s)
-        y = ops.linear(att, pk["out"], ops.ACT_NONE, residual=x2d)
-        x1 = ops.add_layernorm(y, None, self.norm1.weight, self.norm1.bias)
-        out = self._ffn_block(x1, self.norm2, inter_norm, inter_out)
+        y = ops.linear(att, pk["out"], ops.ACT_NONE)
+        x1s = _split_like(x2d)
+        x1 = ops.add_layernorm(y, x2d, self.norm1.weight, self.norm1.bias, out_split=x1s)
+        out = self._ffn_block(x1, self.norm2, inter_norm, inter_out, x1s, out_split, inter_split)
         return out.view(b, s, d)
 
 
@@ -126,7 +138,7 @@ class TransformerDecoderLayer(_LayerBase):
         self.norm3 = nn.LayerNorm(d_model)
 
     def forward_bm(self, tgt, memory, pos, query_pos, tgt_mask, memory_mask, final_norm, final_out,
-                   memory_kv_valid=None):
+                   memory_kv_valid=None, memory_split=None):
         """tgt (B, Lq, d), memory (B, S, d), query_pos (B, Lq, d) batch-major; masks uint8 (1 = blocked).
         upstream transformer.py:366-395 (forward_post)."""
         b, lq, d = tgt.shape
@@ -142,18 +154,18 @@ class TransformerDecoderLayer(_LayerBase):
         kv[:, :d] = qk[:, d:]
         att = torch.empty(b * lq, d, device=dev, dtype=torch.float32)
         ops.attention(qk, 2 * d, kv, kv[:, d:], 2 * d, att, d, b, self.nhead, lq, lq, mask=tgt_mask)
-        y = ops.linear(att, sa["out"], ops.ACT_NONE, residual=t2d)
-        t1 = ops.add_layernorm(y, None, self.norm1.weight, self.norm1.bias)
+        y = ops.linear(att, sa["out"], ops.ACT_NONE)
+        t1 = ops.add_layernorm(y, t2d, self.norm1.weight, self.norm1.bias)
         # cross-attention to the encoder memory
         ca = self.multihead_attn.packed()
         q = ops.linear((t1.view(b, lq, d) + query_pos).view(b * lq, d), ca["q"])
         m2d = memory.view(b * s, d)
         if pos is None:
-            mkv = ops.linear(m2d, ca["kv"])                       # (B*S, 2d): k | v
+            mkv = ops.linear(memory_split if memory_split is not None else m2d, ca["kv"])   # (B*S, 2d): k | v
         else:
             mkv = torch.empty(b * s, 2 * d, device=dev, dtype=torch.float32)
             ops.linear((memory + pos).view(b * s, d), ca["k"], out=mkv[:, :d])
-            ops.linear(m2d, ca["v"], out=mkv[:, d:])
+            ops.linear(memory_split if memory_split is not None else m2d, ca["v"], out=mkv[:, d:])
         att2 = torch.empty(b * lq, d, device=dev, dtype=torch.float32)
         if memory_kv_valid is not None:
             # memory_mask == "keys >= memory_kv_valid are blocked for every query" (common/utils/misc.py:42-47):
@@ -162,9 +174,10 @@ class TransformerDecoderLayer(_LayerBase):
                           tensor_cores=True)
         else:
             ops.attention(q, d, mkv, mkv[:, d:], 2 * d, att2, d, b, self.nhead, lq, s, mask=memory_mask)
-        y2 = ops.linear(att2, ca["out"], ops.ACT_NONE, residual=t1)
-        t2 = ops.add_layernorm(y2, None, self.norm2.weight, self.norm2.bias)
-        out = self._ffn_block(t2, self.norm3, final_norm, final_out)
+        y2 = ops.linear(att2, ca["out"], ops.ACT_NONE)
+        t2s = _split_like(t1)
+        t2 = ops.add_layernorm(y2, t1, self.norm2.weight, self.norm2.bias, out_split=t2s)
+        out = self._ffn_block(t2, self.norm3, final_norm, final_out, t2s)
         return out.view(b, lq, d)
 
 
@@ -185,13 +198,23 @@ class TransformerEncoder(nn.Module):
         """(B,S,d) -> (last (B,S,d), intermediate (L,B,S,d) = inter_norm of every layer output);
         upstream transformer.py:175-202."""
         b, s, d = x.shape
+        n = b * s
         inter = torch.empty(self.num_layers, b, s, d, device=x.device, dtype=torch.float32) \
             if self.return_intermediate else None
+        # FP16x3 path: every layer also emits its output (and the inter_norm output) in split-half format from the
+        # LayerNorm kernel, so neither the next layer's projections nor the heads need a separate split pass
+        h3 = ops.use_h3()
+        inter_split = ops.SplitRows.empty(self.num_layers * n, d, x.device) if (h3 and inter is not None) else None
+        xs = None
         for i, layer in enumerate(self.layers):
+            out_split = ops.SplitRows.empty(n, d, x.device) if h3 else None
             if inter is not None:
-                x = layer.forward_bm(x, pos, self.inter_norm, inter[i])
+                isp = ops.SplitRows(inter_split.buf[i * n:(i + 1) * n], d) if inter_split is not None else None
+                x = layer.forward_bm(x, pos, self.inter_norm, inter[i], xs, out_split, isp)
             else:
-                x = layer.forward_bm(x, pos)
+                x = layer.forward_bm(x, pos, None, None, xs, out_split)
+            xs = out_split
+        self.last_out_split, self.last_inter_split = xs, inter_split
         return x, inter
 
 
@@ -203,13 +226,15 @@ class TransformerDecoder(nn.Module):
         self.norm = norm
         self.return_intermediate = return_intermediate
 
-    def forward_bm(self, tgt, memory, pos, query_pos, tgt_mask, memory_mask, memory_kv_valid=None):
+    def forward_bm(self, tgt, memory, pos, query_pos, tgt_mask, memory_mask, memory_kv_valid=None,
+                   memory_split=None):
         """-> hs (L, B, Lq, d) = norm(out_l) for every layer (upstream transformer.py:214-252)."""
         b, lq, d = tgt.shape
         hs = torch.empty(self.num_layers, b, lq, d, device=tgt.device, dtype=torch.float32)
         x = tgt
         for i, layer in enumerate(self.layers):
-            x = layer.forward_bm(x, memory, pos, query_pos, tgt_mask, memory_mask, self.norm, hs[i], memory_kv_valid)
+            x = layer.forward_bm(x, memory, pos, query_pos, tgt_mask, memory_mask, self.norm, hs[i], memory_kv_valid,
+                                 memory_split)
         return hs
 
 
@@ -294,7 +319,8 @@ class Transformer(nn.Module):
         dev = src_bm.device
         kv_valid = _suffix_mask_limit(memory_mask)
         hs = self.decoder.forward_bm(tgt, memory, pos_bm, qpos, _mask_u8(tgt_mask, dev),
-                                     None if kv_valid is not None else _mask_u8(memory_mask, dev), kv_valid)
+                                     None if kv_valid is not None else _mask_u8(memory_mask, dev), kv_valid,
+                                     self.encoder.last_out_split)
         return hs, memory, inter
 
     def forward(self, src, mask, query_embed, pos_embed, tgt_mask=None, src_mask=None, memory_mask=None):

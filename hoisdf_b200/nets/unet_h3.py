@@ -30,6 +30,19 @@ TAPS_1X1 = [(0, 0)]
 _DECONV_TAPS = {0: [(1, 0), (3, -1)], 1: [(0, 1), (2, 0)]}     # parity -> [(k index, input offset)]
 
 
+class SplitMap:
+    """An NHWC feature map in split-half format: `rows` holds b*h*w pixel rows of (at least) c channels."""
+
+    def __init__(self, rows: "ops.SplitRows", b: int, h: int, w: int, c: int):
+        assert rows.rows == b * h * w and rows.cols >= c
+        self.rows, self.b, self.h, self.w, self.c = rows, b, h, w, c
+
+    def nchw(self) -> torch.Tensor:
+        """fp32 copy as a logical-NCHW view of NHWC memory."""
+        win = self.rows if self.rows.cols == self.c else ops.SplitRows(self.rows.buf, self.c, self.rows.col0)
+        return win.float().view(self.b, self.h, self.w, self.c).permute(0, 3, 1, 2)
+
+
 def _fold_bn(weight: torch.Tensor, bias, bn: nn.BatchNorm2d, out_dim: int):
     """conv/deconv weight with BatchNorm(eval) folded in: returns (scale-multiplied weight, bias)."""
     w = weight.detach().double()
@@ -111,39 +124,70 @@ class UNetH3:
         self._packed, self._key = pk, key
         return pk
 
+    LEVELS = ((1, "stride16"), (2, "stride8"), (3, "stride4"), (4, "stride2"))
+
+    def concat_slots(self, b: int, h: int, w: int, dev):
+        """'ho3d' decoder: allocate the four skip-concat buffers up front and return (cats, slots): the encoder writes
+        its stage outputs straight into `slots[name]` = the left channel window of `cats[name]`.  (h, w) = spatial
+        size of the stride-32 map.  The small decoder passes its skips through a 1x1 convolution first: no slots."""
+        if not self.big:
+            return {}, {}
+        pk = self._pack()
+        cats, slots = {}, {}
+        for i, name in self.LEVELS:
+            h, w = 2 * h, 2 * w
+            cu = pk["deconv%d" % i][(0, 0)][0].n
+            cs = pk["conv%d" % i].k // 9 - cu
+            cats[name] = ops.SplitRows.empty(b * h * w, cs + cu, dev)
+            slots[name] = cats[name].window(0, cs)
+        return cats, slots
+
     def __call__(self, img_feat: torch.Tensor, skips: Dict[str, torch.Tensor]):
         """img_feat (B, 2048, 8, 8), skips {stride2..stride16} (logical NCHW fp32) -> (feature pyramid dict of
         logical-NCHW fp32 tensors backed by NHWC memory, decoder_out (B, 3, 128, 128))."""
-        pk = self._pack()
         dev = img_feat.device
         b, c0, h, w = img_feat.shape
-        x = ops.nchw_to_split(img_feat, ops.SplitRows.empty(b * h * w, c0, dev))
-        cx = c0
+        x = SplitMap(ops.nchw_to_split(img_feat, ops.SplitRows.empty(b * h * w, c0, dev)), b, h, w, c0)
+        cats, slots = self.concat_slots(b, h, w, dev)
+        smaps = {}
+        for _, name in self.LEVELS:
+            skip = skips[name]
+            cs, ho, wo = skip.shape[1], skip.shape[2], skip.shape[3]
+            dst = slots[name] if self.big else ops.SplitRows.empty(b * ho * wo, cs, dev)
+            assert dst.rows == b * ho * wo and dst.cols == cs
+            smaps[name] = SplitMap(ops.nchw_to_split(skip, dst), b, ho, wo, cs)
+        return self.run(x, smaps, cats, img_feat)
+
+    def run(self, feat: SplitMap, skips: Dict[str, SplitMap], cats: Dict[str, "ops.SplitRows"],
+            img_feat: torch.Tensor = None):
+        """The decoder on split-half inputs (what nets/resnet_h3.py produces).  For the 'ho3d' decoder `cats` are
+        the buffers of `concat_slots`, whose left windows already hold the skips."""
+        pk = self._pack()
+        x, b, h, w, cx = feat.rows, feat.b, feat.h, feat.w, feat.c
+        dev = x.buf.device
         pyr = {}
         if self.big:
-            pyr["stride32"] = img_feat
+            pyr["stride32"] = img_feat if img_feat is not None else feat.nchw()
         else:
             p0 = pk["conv0d"]
             lvl = torch.empty(b, h, w, p0.n, device=dev, dtype=torch.float32)
             ops.linear_h3(x, p0, ops.ACT_RELU, out=lvl.view(-1, p0.n))
             pyr["stride32"] = lvl.permute(0, 3, 1, 2)
-        for i, name in ((1, "stride16"), (2, "stride8"), (3, "stride4"), (4, "stride2")):
+        for i, name in self.LEVELS:
             skip = skips[name]
-            cs_in = skip.shape[1]
             parts = pk["deconv%d" % i]
             cu = parts[(0, 0)][0].n
             ho, wo = 2 * h, 2 * w
-            assert skip.shape[2] == ho and skip.shape[3] == wo
+            assert skip.h == ho and skip.w == wo and skip.b == b
             if self.big:
-                cs = cs_in
-                cat = ops.SplitRows.empty(b * ho * wo, cs + cu, dev)
-                ops.nchw_to_split(skip, cat.window(0, cs))
+                cs = skip.c
+                cat = cats[name]
+                assert cat.rows == b * ho * wo and cat.cols == cs + cu
             else:       # 1x1 conv + BN + ReLU on the skip, written straight into the concat buffer
                 sp = pk["conv%dd" % i]
                 cs = sp.n
                 cat = ops.SplitRows.empty(b * ho * wo, cs + cu, dev)
-                sk = ops.nchw_to_split(skip, ops.SplitRows.empty(b * ho * wo, cs_in, dev))
-                ops.linear_h3(sk, sp, ops.ACT_RELU, out=cat.window(0, cs))
+                ops.linear_h3(skip.rows, sp, ops.ACT_RELU, out=cat.window(0, cs))
             up = cat.window(cs, cu)
             pitch = cat.ld
             for (py, px), (pw, taps) in parts.items():

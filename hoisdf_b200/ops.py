@@ -288,7 +288,8 @@ class PackedLinearH3:
 
 
 def linear_h3(x: SplitRows, pw: PackedLinearH3, act: int = ACT_NONE, out=None, residual: Optional[torch.Tensor] = None,
-              split_out: bool = False, x_batch=(0, 0), m: Optional[int] = None, two_acc: Optional[bool] = None):
+              split_out: bool = False, x_batch=(0, 0), m: Optional[int] = None, two_acc: Optional[bool] = None,
+              residual_split: Optional[SplitRows] = None):
     """Y = act(X . W^T + b) (+ residual) on the FP16x3 tensor-core kernel.  `out` is an fp32 (M, N) tensor view (unit
     inner stride) or a SplitRows window; allocated when None (fp32, or split-half if split_out).
     x_batch = (rows_per_batch, batch_stride in halfs) walks strided row groups of `x` (m rows in total)."""
@@ -314,6 +315,9 @@ def linear_h3(x: SplitRows, pw: PackedLinearH3, act: int = ACT_NONE, out=None, r
     a.m, a.n, a.k, a.act = m, pw.n, pw.k, act
     # long contractions: separate main / correction accumulators (3x smaller accumulate-truncation error)
     a.two_acc = int(pw.k >= 2048 if two_acc is None else two_acc)
+    if residual_split is not None:
+        assert residual_split.cols >= pw.n and residual_split.rows >= m
+        a.res_hi, a.res_lo, a.ldr = residual_split.hi_ptr, residual_split.lo_ptr, residual_split.ld
     _count()
     if PROFILE is None:
         check(lib.hoisdf_linear_h3_fwd(C.byref(a), _stream()), "hoisdf_linear_h3_fwd")
@@ -328,7 +332,7 @@ def linear_h3(x: SplitRows, pw: PackedLinearH3, act: int = ACT_NONE, out=None, r
 
 def conv_h3(x: SplitRows, batch: int, in_h: int, in_w: int, cin: int, pw: PackedLinearH3, taps, out_h: int, out_w: int,
             *, stride: int = 1, act: int = ACT_NONE, out=None, out_strides=None, out_offset: int = 0,
-            two_acc: Optional[bool] = None):
+            two_acc: Optional[bool] = None, residual_split: Optional[SplitRows] = None):
     """Implicit-GEMM convolution on the FP16x3 kernel.  x: NHWC pixels (batch*in_h*in_w rows of >= cin columns) in
     split-half format; pw: planes of the (cout, len(taps)*cin) weight matrix; taps: [(dy, dx), ...].
     out: fp32 (rows, >= cout) tensor or SplitRows window; out_strides = (sx, sy, sb) in elements (default: dense
@@ -352,6 +356,9 @@ def conv_h3(x: SplitRows, batch: int, in_h: int, in_w: int, cin: int, pw: Packed
     a.y_sx, a.y_sy, a.y_sb = sx, sy, sb
     a.act = act
     a.two_acc = int(pw.k >= 2048 if two_acc is None else two_acc)
+    if residual_split is not None:
+        assert residual_split.cols >= pw.n and residual_split.rows >= batch * out_h * out_w
+        a.res_hi, a.res_lo, a.ldr = residual_split.hi_ptr, residual_split.lo_ptr, residual_split.ld
     _count()
     flops = 2.0 * batch * out_h * out_w * pw.n * pw.k
     if PROFILE is None:
@@ -377,6 +384,35 @@ def nchw_to_split(x: torch.Tensor, out: SplitRows):
     _count(1)
     check(lib.hoisdf_nchw_to_nhwc_split(x.data_ptr(), out.hi_ptr, out.lo_ptr, b, c, h, w, out.ld, _stream()),
           "hoisdf_nchw_to_nhwc_split")
+    return out
+
+
+STEM_K = 147          # 7 x 7 x 3 im2col columns of the ResNet stem ...
+STEM_K_PAD = 160      # ... padded to 5 K blocks of 32 halfs
+
+
+def stem_im2col(img: torch.Tensor, out: Optional[SplitRows] = None) -> SplitRows:
+    """(B, 3, H, W) fp32 NCHW image -> (B*H/2*W/2, 160) split-half im2col rows of the 7x7 stride-2 pad-3 stem."""
+    assert img.dim() == 4 and img.shape[1] == 3 and img.dtype == torch.float32 and img.is_cuda
+    img = img.contiguous()
+    b, _, h, w = img.shape
+    if out is None:
+        out = SplitRows.empty(b * (h // 2) * (w // 2), STEM_K_PAD, img.device)
+    assert out.rows == b * (h // 2) * (w // 2) and out.cols >= STEM_K_PAD
+    _count(1)
+    check(lib.hoisdf_stem_im2col_split(img.data_ptr(), b, h, w, out.hi_ptr, out.lo_ptr, out.ld, _stream()),
+          "hoisdf_stem_im2col_split")
+    return out
+
+
+def maxpool3x3s2(x: SplitRows, batch: int, h: int, w: int, c: int, out: Optional[SplitRows] = None) -> SplitRows:
+    """NHWC split-half (batch, h, w, c) -> (batch, h/2, w/2, c): nn.MaxPool2d(3, 2, 1)."""
+    assert x.rows == batch * h * w and x.cols >= c
+    if out is None:
+        out = SplitRows.empty(batch * (h // 2) * (w // 2), c, x.buf.device)
+    _count(1)
+    check(lib.hoisdf_maxpool3x3s2_split(x.hi_ptr, x.lo_ptr, x.ld, batch, h, w, c, out.hi_ptr, out.lo_ptr, out.ld,
+                                        _stream()), "hoisdf_maxpool3x3s2_split")
     return out
 
 
@@ -662,14 +698,24 @@ def attention(q, ldq, k, v, ldk, out, ldo, batch, heads, lq, lk, kv_valid=None, 
     return out
 
 
-def add_layernorm(x, res, gamma, beta, out=None, gamma2=None, beta2=None, out2=None):
+def add_layernorm(x, res, gamma, beta, out=None, gamma2=None, beta2=None, out2=None,
+                  out_split: Optional[SplitRows] = None, out2_split: Optional[SplitRows] = None):
+    """LayerNorm(x (+ res)); `out_split` / `out2_split` additionally receive the result(s) in split-half format."""
     rows = x.numel() // x.shape[-1]
     d = x.shape[-1]
     out = out if out is not None else torch.empty_like(x)
     _count(1)
-    check(lib.hoisdf_add_layernorm_fwd(x.data_ptr(), _ptr(res), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
-                                       _ptr(gamma2), _ptr(beta2), _ptr(out2), rows, d, _stream()),
-          "hoisdf_add_layernorm_fwd")
+    if out_split is None and out2_split is None:
+        check(lib.hoisdf_add_layernorm_fwd(x.data_ptr(), _ptr(res), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
+                                           _ptr(gamma2), _ptr(beta2), _ptr(out2), rows, d, _stream()),
+              "hoisdf_add_layernorm_fwd")
+        return out
+    sp = lambda t: (None, None, 0) if t is None else (t.hi_ptr, t.lo_ptr, t.ld)  # noqa: E731
+    for t in (out_split, out2_split):
+        assert t is None or (t.rows >= rows and t.cols >= d)
+    check(lib.hoisdf_add_layernorm_split_fwd(x.data_ptr(), _ptr(res), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
+                                             _ptr(gamma2), _ptr(beta2), _ptr(out2), rows, d, *sp(out_split),
+                                             *sp(out2_split), _stream()), "hoisdf_add_layernorm_split_fwd")
     return out
 
 

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 5
+#define HOISDF_ABI_VERSION 6
 
 enum {
   HOISDF_OK = 0,
@@ -96,6 +96,11 @@ typedef struct {
   int32_t two_acc;                   /* 1: main and correction products in separate TMEM accumulators -- 3x smaller
                                         accumulate-truncation error (it grows ~linearly with K), no epilogue overlap;
                                         meant for K >= ~2048 */
+  const uint16_t* res_hi; const uint16_t* res_lo; int64_t ldr;
+                                     /* optional residual in split-half format, row r of the dense output reads row
+                                        r of these planes (pitch ldr halfs); added before the activation; needs the
+                                        TMA-store epilogue (no fp32 `residual`, n % 32 == 0) -- the shortcut of the
+                                        ResNet bottleneck, upstream common/nets/resnet.py (torchvision Bottleneck) */
 } hoisdf_linear_h3_args;
 
 int hoisdf_linear_h3_fwd(const hoisdf_linear_h3_args* args, void* stream);
@@ -122,9 +127,26 @@ typedef struct {
   int64_t out_h; int64_t out_w; int64_t cout;
   float* y; uint16_t* y_hi; uint16_t* y_lo; int64_t y_sx; int64_t y_sy; int64_t y_sb;
   int32_t act; int32_t two_acc;
+  const uint16_t* res_hi; const uint16_t* res_lo; int64_t ldr;
+                                     /* optional split-half residual: output pixel (b, y, x) reads row
+                                        (b * out_h + y) * out_w + x of these planes; cout % 32 == 0 */
 } hoisdf_conv_h3_args;
 
 int hoisdf_conv_h3_fwd(const hoisdf_conv_h3_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * ResNet-50 stem pieces (upstream common/nets/resnet.py:70-76 = torchvision conv1 7x7 s2 p3 + maxpool 3x3 s2 p1),
+ * the rest of the backbone being hoisdf_conv_h3_fwd / hoisdf_linear_h3_fwd calls.
+ *   hoisdf_stem_im2col_split: img (batch, 3, h, w) NCHW fp32 -> one row per output pixel of the (h/2, w/2) grid,
+ *     160 columns in split-half format: column (ky * 7 + kx) * 3 + c = img[b, c, 2y - 3 + ky, 2x - 3 + kx] (0 outside
+ *     the image), columns 147..159 zero.  The 7x7 convolution is then a Linear with K = 160.
+ *   hoisdf_maxpool3x3s2_split: NHWC split-half (batch, h, w, c) -> (batch, h/2, w/2, c), window 3x3 stride 2 pad 1
+ *     (padding never wins: max over the in-image taps), c % 8 == 0.
+ * ------------------------------------------------------------------------------------------------- */
+int hoisdf_stem_im2col_split(const float* img, int64_t batch, int64_t h, int64_t w, uint16_t* hi, uint16_t* lo,
+                             int64_t ldh, void* stream);
+int hoisdf_maxpool3x3s2_split(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx, int64_t batch, int64_t h,
+                              int64_t w, int64_t c, uint16_t* y_hi, uint16_t* y_lo, int64_t ldy, void* stream);
 
 /* W (n, ldw) fp32 with k valid columns -> planes A, B, C, each (n, ldh) halfs, columns [k, ldh) zeroed. */
 int hoisdf_pack_h3(const float* w, int64_t n, int64_t k, int64_t ldw, uint16_t* w_a, uint16_t* w_b, uint16_t* w_c,
@@ -302,6 +324,12 @@ int hoisdf_attention_fwd(const float* q, int64_t ldq, const float* k, const floa
 int hoisdf_add_layernorm_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* y,
                              const float* gamma2, const float* beta2, float* y2, int64_t rows, int64_t d,
                              void* stream);
+/* The same, additionally writing y (and y2) in split-half format (pitch in halfs, multiple of 4; NULL = skip) so the
+ * following FP16x3 Linear reads it without a separate hoisdf_split_rows pass. */
+int hoisdf_add_layernorm_split_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* y,
+                                   const float* gamma2, const float* beta2, float* y2, int64_t rows, int64_t d,
+                                   uint16_t* yh_hi, uint16_t* yh_lo, int64_t ldyh, uint16_t* y2h_hi, uint16_t* y2h_lo,
+                                   int64_t ldy2h, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Joint voting -- upstream common/nets/loss.py:31-36,54-57 (the part of JointvoteLoss that produces

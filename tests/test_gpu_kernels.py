@@ -430,3 +430,113 @@ def test_unet_h3_matches_cudnn(cuda, arch):
         assert rel_err(pyr[k], ref_pyr[k]) < 6e-5, (k, rel_err(pyr[k], ref_pyr[k]))
         assert rel_err(pyr2[k], pyr[k]) < 1e-6, k
     assert out.shape == ref_out.shape and rel_err(out, ref_out) < 6e-5 and rel_err(out2, out) < 1e-6
+
+
+# ---------------------------------------------------------------- ResNet-50 encoder on the FP16x3 kernels
+def _nhwc_rows(t):
+    """(B, C, H, W) -> (B*H*W, C) fp32 contiguous."""
+    b, c, h, w = t.shape
+    return t.permute(0, 2, 3, 1).reshape(b * h * w, c).contiguous()
+
+
+def test_stem_im2col_and_maxpool_split(cuda):
+    """hoisdf_stem_im2col_split + FP16x3 Linear == conv 7x7 s2 p3; hoisdf_maxpool3x3s2_split == MaxPool2d(3, 2, 1)."""
+    from hoisdf_b200 import ops
+    B, H, W = 3, 64, 32
+    img, w, b = rnd(81, B, 3, H, W), rnd(82, 64, 3, 7, 7, lo=-0.1, hi=0.1), rnd(83, 64)
+    cols = ops.stem_im2col(img.to(cuda))
+    assert cols.rows == B * (H // 2) * (W // 2) and cols.cols == ops.STEM_K_PAD
+    ref_cols = F.unfold(img.double(), 7, padding=3, stride=2)                       # (B, 3*49, L), index c*49 + tap
+    ref_cols = ref_cols.view(B, 3, 49, -1).permute(0, 3, 2, 1).reshape(-1, 147)     # -> tap*3 + c
+    got = cols.float().cpu()
+    assert torch.equal(got[:, 147:], torch.zeros(got.shape[0], 13))
+    assert ((got[:, :147].double() - ref_cols).abs() <= ref_cols.abs() * 2.0 ** -21 + 3e-11).all()
+    pw = ops.PackedLinearH3.pack(w.permute(0, 2, 3, 1).reshape(64, 147).contiguous().to(cuda), b.to(cuda))
+    y = ops.linear_h3(cols, pw, ops.ACT_RELU, split_out=True)
+    ref = F.conv2d(img.double(), w.double(), b.double(), stride=2, padding=3).relu()
+    assert rel_err(y.float(), _nhwc_rows(ref)) < 3e-6
+    # max-pool of the split-half map, input read through a column window of a wider buffer
+    wide = ops.SplitRows.empty(y.rows, 96, cuda)
+    wide.buf.fill_(float("nan"))
+    ops.split_rows(_nhwc_rows(ref).float().to(cuda), out=wide.window(0, 64))
+    pooled = ops.maxpool3x3s2(wide.window(0, 64), B, H // 2, W // 2, 64)
+    want = _nhwc_rows(F.max_pool2d(ref.float(), 3, 2, 1))
+    assert ((pooled.float().cpu() - want).abs() <= want.abs() * 2.0 ** -21 + 3e-11).all()
+
+
+@pytest.mark.parametrize("B", [1, 3])
+def test_conv_h3_stride2_and_split_residual(cuda, B):
+    """Implicit-GEMM convolution with stride 2 (3x3 pad 1 and 1x1) and the split-half residual epilogue of both the
+    convolution and the Linear entry -- the pieces the ResNet bottleneck adds to the U-Net's kernel -- against fp64."""
+    from hoisdf_b200 import ops
+    from hoisdf_b200.nets.unet_h3 import TAPS_1X1, TAPS_3X3
+    cin, cout, H = 64, 96, 16
+    x = rnd(91, B, cin, H, H)
+    xs = ops.split_rows(_nhwc_rows(x).to(cuda))
+    w3, b3 = rnd(92, cout, cin, 3, 3, lo=-0.1, hi=0.1), rnd(93, cout)
+    p3 = ops.PackedLinearH3.pack(w3.permute(0, 2, 3, 1).reshape(cout, -1).contiguous().to(cuda), b3.to(cuda))
+    res = rnd(94, B, cout, H // 2, H // 2)
+    rs = ops.split_rows(_nhwc_rows(res).to(cuda))
+    y = ops.conv_h3(xs, B, H, H, cin, p3, TAPS_3X3, H // 2, H // 2, stride=2, act=ops.ACT_RELU,
+                    out=ops.SplitRows.empty(B * (H // 2) ** 2, cout, cuda), residual_split=rs)
+    ref = (F.conv2d(x.double(), w3.double(), b3.double(), stride=2, padding=1) + res.double()).relu()
+    assert rel_err(y.float(), _nhwc_rows(ref)) < 4e-6
+    # stride-1 3x3 without residual, fp32 output
+    y1 = torch.empty(B * H * H, cout, device=cuda)
+    ops.conv_h3(xs, B, H, H, cin, p3, TAPS_3X3, H, H, act=ops.ACT_NONE, out=y1)
+    assert rel_err(y1, _nhwc_rows(F.conv2d(x.double(), w3.double(), b3.double(), padding=1))) < 4e-6
+    # 1x1 stride 2 (projection shortcut)
+    w1, b1 = rnd(95, cout, cin, 1, 1, lo=-0.1, hi=0.1), rnd(96, cout)
+    p1 = ops.PackedLinearH3.pack(w1.reshape(cout, cin).contiguous().to(cuda), b1.to(cuda))
+    yd = ops.conv_h3(xs, B, H, H, cin, p1, TAPS_1X1, H // 2, H // 2, stride=2,
+                     out=ops.SplitRows.empty(B * (H // 2) ** 2, cout, cuda))
+    assert rel_err(yd.float(), _nhwc_rows(F.conv2d(x.double(), w1.double(), b1.double(), stride=2))) < 3e-6
+    # Linear with a split-half residual read through a window of a wider buffer, ragged M
+    m = B * H * H - 5
+    wide = ops.SplitRows.empty(m, 160, cuda)
+    r2 = rnd(97, m, cout)
+    ops.split_rows(r2.to(cuda), out=wide.window(32, cout))
+    yl = ops.linear_h3(ops.SplitRows(xs.buf[:m], cin), p1, ops.ACT_RELU, split_out=True, residual_split=wide.window(32, cout))
+    refl = (_nhwc_rows(x)[:m].double() @ w1.reshape(cout, cin).double().T + b1.double() + r2.double()).relu()
+    assert rel_err(yl.float(), refl) < 3e-6
+    yf = ops.linear_h3(ops.SplitRows(xs.buf[:m], cin), p1, ops.ACT_NONE, residual_split=wide.window(32, cout))
+    assert rel_err(yf, _nhwc_rows(x)[:m].double() @ w1.reshape(cout, cin).double().T + b1.double() + r2.double()) < 3e-6
+
+
+def test_add_layernorm_split_outputs(cuda):
+    from hoisdf_b200 import ops
+    x, r = rnd(54, 333, 256), rnd(55, 333, 256)
+    g, b, g2, b2 = rnd(56, 256), rnd(57, 256), rnd(58, 256), rnd(59, 256)
+    y2 = torch.empty(333, 256, device=cuda)
+    s1, s2 = ops.SplitRows.empty(333, 256, cuda), ops.SplitRows.empty(333, 256, cuda)
+    y = ops.add_layernorm(x.to(cuda), r.to(cuda), g.to(cuda), b.to(cuda), gamma2=g2.to(cuda), beta2=b2.to(cuda), out2=y2,
+                          out_split=s1, out2_split=s2)
+    y_plain = ops.add_layernorm(x.to(cuda), r.to(cuda), g.to(cuda), b.to(cuda))
+    assert torch.equal(y, y_plain)
+    for s, f in ((s1, y), (s2, y2)):
+        # 22 significand bits; below fp16's normal range (|x| < 6e-5) the absolute floor is 2^-25 / 2^11 = 1.5e-11
+        assert ((s.float() - f).abs() <= f.abs() * 2.0 ** -21 + 3e-11).all()
+
+
+def test_resnet_h3_matches_cudnn(cuda):
+    """nets/resnet_h3.py (stem im2col + Linear, max-pool, 16 bottlenecks with the shortcut added in the GEMM epilogue,
+    BN folded) against the same module on cuDNN fp32, including writing the stage outputs into concat-buffer slots."""
+    from hoisdf_b200 import ops
+    from hoisdf_b200.nets.module import BackboneNet
+    from hoisdf_b200.nets.resnet_h3 import ResNetH3
+    B = 3
+    net = BackboneNet(50)
+    pre = "backbone_net."
+    net.load_state_dict({k[len(pre):]: v for k, v in syn.full_state_dict(61, "dexycb").items() if k.startswith(pre)})
+    net = net.to(cuda).eval()
+    img = syn.image_batch(5, B).to(cuda)
+    with torch.no_grad():
+        ref_feat, ref_skips = net(img)
+        feat, skips = ResNetH3(net.resnet)(img)
+        wide = ops.SplitRows.empty(B * 64 * 64, 512, cuda)
+        feat2, skips2 = ResNetH3(net.resnet)(img, {"stride4": wide.window(0, 256)})
+    assert (feat.b, feat.h, feat.w, feat.c) == tuple(ref_feat.shape[i] for i in (0, 2, 3, 1))
+    assert rel_err(feat.nchw(), ref_feat) < 1e-4, rel_err(feat.nchw(), ref_feat)
+    for k in ("stride2", "stride4", "stride8", "stride16"):
+        assert rel_err(skips[k].nchw(), ref_skips[k]) < 1e-4, (k, rel_err(skips[k].nchw(), ref_skips[k]))
+    assert torch.equal(skips2["stride4"].nchw(), skips["stride4"].nchw()) and torch.equal(feat2.nchw(), feat.nchw())
