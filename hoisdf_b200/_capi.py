@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhoisdf_b200.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 ACT_NONE, ACT_RELU = 0, 1
 GATHER_CONCAT, GATHER_SUM = 0, 1
 
@@ -33,7 +33,7 @@ class LinearH3Args(C.Structure):
         ("x_hi", vp), ("x_lo", vp), ("ldx", i64), ("x_rows_per_batch", i64), ("x_batch_stride", i64),
         ("w_a", vp), ("w_b", vp), ("w_c", vp), ("ldw", i64), ("bias", vp), ("residual", vp),
         ("y", vp), ("ldy", i64), ("y_hi", vp), ("y_lo", vp), ("ldyh", i64),
-        ("m", i64), ("n", i64), ("k", i64), ("act", i32), ("two_acc", i32),
+        ("m", i64), ("n", i64), ("k", i64), ("act", i32), ("chunk_kb", i32),
         ("res_hi", vp), ("res_lo", vp), ("ldr", i64),
     ]
 
@@ -45,7 +45,7 @@ class ConvH3Args(C.Structure):
         ("taps", i32), ("tap_dy", i32 * 16), ("tap_dx", i32 * 16), ("stride", i32),
         ("out_h", i64), ("out_w", i64), ("cout", i64),
         ("y", vp), ("y_hi", vp), ("y_lo", vp), ("y_sx", i64), ("y_sy", i64), ("y_sb", i64),
-        ("act", i32), ("two_acc", i32),
+        ("act", i32), ("chunk_kb", i32),
         ("res_hi", vp), ("res_lo", vp), ("ldr", i64),
     ]
 
@@ -63,7 +63,7 @@ class SdfWeights(C.Structure):
 
 
 class SdfWeightsH3(C.Structure):
-    _fields_ = [("w", (vp * 3) * 4), ("ldw", i64 * 4), ("b", vp * 4), ("w4", vp), ("b4", vp)]
+    _fields_ = [("w", (vp * 3) * 4), ("ldw", i64 * 4), ("b", vp * 4), ("w4", vp), ("b4", vp), ("chunk_kb", i32)]
 
 
 class ManoModel(C.Structure):

@@ -64,8 +64,11 @@ class Config:
     tc_unet = True
     # ResNet-50 encoder on the same kernels (nets/resnet_h3.py): stem im2col + FP16x3 Linear, bottlenecks as 1x1 Linear /
     # 3x3 implicit-GEMM convolution / 1x1 Linear with the shortcut added in the epilogue; needs tc_unet
-    tc_backbone = False       # off until the chunked-accumulation GEMM lands: the 16-block chain amplifies the
-                              # tensor core accumulate-truncation error to 4e-5 of range (cuDNN fp32: 2e-6)
+    tc_backbone = True
+    # TMEM accumulation chunk (K blocks of 32) of the encoder's GEMMs: the 53-convolution chain is where the tensor
+    # core's accumulate-truncation bias compounds, so it drains every K block (measured pyramid error vs fp64:
+    # 3.5e-6 at 1, 5.3e-6 at 2, 8.9e-6 at 4; cuDNN fp32: 2e-6 .. 3.7e-6)
+    backbone_chunk_kb = 1
 
     def calc_mutliscale_dim(self, use_big_decoder_l, resnet_type_l):
         # upstream config.py:101-108 (sic: "mutliscale")

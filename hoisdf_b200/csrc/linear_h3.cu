@@ -11,14 +11,16 @@
 //   weights (3 planes, packed once):  A = w_hi * 2^11,  B = w_hi,  C = w_lo * 2^11          (|w| < 32)
 //   acc = x_hi.A + x_lo'.B + x_hi.C = 2^11 * (x_hi.w_hi + x_lo.w_hi + x_hi.w_lo);   y = acc * 2^-11 + bias
 //
-// Persistent, warp-specialised, one CTA per SM (192 threads), clusters of CL CTAs that own CL consecutive M tiles of
+// Persistent, warp-specialised, one CTA per SM (320 threads), clusters of CL CTAs that own CL consecutive M tiles of
 // the same N tile:
 //   warp 0      TMA producer: per 32-half K block the CTA's own x_hi / x_lo' tiles (128 rows) and ITS 1/CL slice of
 //               the three W planes, multicast to every CTA of the cluster -> 3-stage ring of 64 KB stages
-//   warp 1      tcgen05.mma issuer (one thread): 6 MMAs (M128 x N<=256 x K16) per stage into accumulator t & 1
-//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns, scale + bias + ReLU, then either fp32 or split-half output
-//               staged in swizzled smem boxes and written by TMA (double-buffered per warp), or direct stores when a
-//               residual is added.  TMEM buffer released as soon as the last tcgen05.ld of the tile has landed.
+//   warp 1      tcgen05.mma issuer (one thread): 6 MMAs (M128 x N<=256 x K16) per stage; K is accumulated in TMEM one
+//               CHUNK (4 stages = 128 of K) at a time, alternating between two 256-column TMEM buffers
+//   warps 2..9  drain + epilogue: tcgen05.ld of every finished chunk, added round-to-nearest into 128 fp32 registers
+//               per thread (the tensor core truncates on accumulate -- see the note at the kernel); after the last
+//               chunk: scale + bias (+ split-half residual) + ReLU, then fp32 or split-half output staged in a
+//               swizzled smem box and written by TMA, or direct stores for the fp32-residual / ragged-group modes.
 #include "tc_common.cuh"
 
 namespace hoisdf {
@@ -31,12 +33,14 @@ constexpr int H3_STAGES = 3;
 constexpr int H3_X_BYTES = H3_BM * H3_BK * 2;           // 8 KB per plane
 constexpr int H3_W_BYTES = H3_BN * H3_BK * 2;           // 16 KB per plane
 constexpr int H3_STAGE_BYTES = 2 * H3_X_BYTES + 3 * H3_W_BYTES;   // 64 KB
-constexpr int H3_EPI_SLOT = 4096;                       // one 32 x 32 fp32 box (or hi + lo half boxes)
-constexpr int H3_EPI_BYTES = 4 * 2 * H3_EPI_SLOT;       // 4 warps x 2 slots
+constexpr int H3_EPI_WARPS = 8;                         // drain + epilogue warps (2 per TMEM lane quarter)
+constexpr int H3_EPI_SLOT = 4096;                       // one 32 x 32 fp32 box (or hi + lo half boxes) per warp
+constexpr int H3_EPI_BYTES = H3_EPI_WARPS * H3_EPI_SLOT;
 constexpr int H3_BAR_BYTES = 256;
 constexpr int H3_SMEM_BYTES = H3_STAGES * H3_STAGE_BYTES + H3_EPI_BYTES + H3_BAR_BYTES + 1024 /*align*/;
-constexpr int H3_THREADS = 192;
-constexpr uint32_t H3_TMEM_COLS = 512;                  // two 256-column fp32 accumulators
+constexpr int H3_THREADS = 64 + 32 * H3_EPI_WARPS;      // 320
+constexpr uint32_t H3_TMEM_COLS = 512;                  // two 256-column fp32 chunk accumulators
+constexpr int H3_CHUNK_KB = 4;                          // K blocks per accumulation chunk (4 x 32 = 128 of K)
 
 enum { H3_OUT_F32_TMA = 0, H3_OUT_SPLIT_TMA = 1, H3_OUT_F32_DIRECT = 2 };
 
@@ -55,8 +59,7 @@ struct H3Params {
   int n_tiles;
   int n, k, act;
   int out_mode;
-  int two_acc;              // main / correction products in separate accumulators: the main sum sees 1/3 of the
-                            // accumulate-truncation events (3x smaller error at large K); no epilogue overlap
+  int chunk_kb;             // K blocks accumulated in TMEM before the partial sum is drained into registers
   // implicit-GEMM convolution (taps > 0): X is an NHWC image batch (4-D tensor maps), M = output pixels in (b, y, x)
   // order, K = taps x Cin; a 128-pixel M tile is a (tb x ty x tx) block of the output grid, a warp's 32 rows a
   // (wy x wx) block
@@ -64,6 +67,13 @@ struct H3Params {
   int8_t dy[16], dx[16];
 };
 
+// Accuracy note (why the accumulator is drained in chunks).  The tensor core TRUNCATES when it adds a K=16 partial
+// product into the fp32 TMEM accumulator, so a long contraction accumulated entirely in TMEM picks up a bias that
+// grows linearly with K (measured 1.7e-5 relative at K = 4608 -- 10x the fp32 FMA pipe, and a chain of convolutions
+// amplifies it).  Here TMEM only ever holds the sum over one chunk of `chunk_kb` K blocks; the eight epilogue warps
+// pull every finished chunk out with tcgen05.ld and add it, round-to-nearest, into fp32 registers (128 per thread)
+// while the tensor core fills the other TMEM buffer with the next chunk.  24 truncating adds per chunk instead of
+// 3K/16 per tile: the result is as accurate as an fp32 FMA GEMM, at the same tensor-core rate.
 template <int CL>
 __global__ void __launch_bounds__(H3_THREADS, 1)
 linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__ CUtensorMap map_xlo,
@@ -79,8 +89,8 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + H3_STAGES * H3_STAGE_BYTES + H3_EPI_BYTES + 128);
   auto bar_full = [&](int s) { return bars + 8u * s; };
   auto bar_empty = [&](int s) { return bars + 8u * (H3_STAGES + s); };
-  auto bar_tfull = [&](int b) { return bars + 8u * (2 * H3_STAGES + b); };
-  auto bar_tempty = [&](int b) { return bars + 8u * (2 * H3_STAGES + 2 + b); };
+  auto bar_cfull = [&](uint32_t b) { return bars + 8u * (2 * H3_STAGES + b); };
+  auto bar_cempty = [&](uint32_t b) { return bars + 8u * (2 * H3_STAGES + 2 + b); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
@@ -88,6 +98,7 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
   const int nclusters = static_cast<int>(gridDim.x) / CL;
   const int items = p.m_blocks * p.n_tiles;
   const int num_kb = p.taps > 0 ? p.taps * p.cin_blocks : (p.k + H3_BK - 1) / H3_BK;
+  const int chb = p.chunk_kb;
   constexpr uint16_t kAllCtas = static_cast<uint16_t>((1u << CL) - 1u);
   constexpr int kSliceRows = H3_BN / CL;                 // W rows each CTA fetches (and multicasts)
   constexpr int kSliceBytes = kSliceRows * H3_BK * 2;
@@ -102,9 +113,9 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
       mbar_init(bar_full(s), 1);
       mbar_init(bar_empty(s), CL);          // every CTA's tensor core must have consumed the stage
     }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(bar_tfull(b), 1);
-      mbar_init(bar_tempty(b), 4);          // the four epilogue warps
+    for (uint32_t b = 0; b < 2; ++b) {
+      mbar_init(bar_cfull(b), 1);
+      mbar_init(bar_cempty(b), H3_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -182,20 +193,22 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      uint32_t it = 0, t = 0;
-      for (int item = cluster; item < items; item += nclusters, ++t) {
+      uint32_t it = 0, cc = 0;                                     // stage counter, chunk counter
+      for (int item = cluster; item < items; item += nclusters) {
         int m_tile, grp, m0, n0;
         tile_of(item, m_tile, grp, m0, n0);
         const int n_here = min(H3_BN, p.n - n0);
         const int n_inst = (n_here + 15) & ~15;                 // UMMA N (multiple of 16 for M = 128)
         const uint32_t idesc = umma_idesc_f16(H3_BM, n_inst);
-        const uint32_t buf = p.two_acc ? 0u : (t & 1u);
-        const uint32_t par = p.two_acc ? (t & 1u) : ((t >> 1) & 1u);
-        mbar_wait(bar_tempty(buf), par ^ 1u);                    // epilogue has drained this accumulator
-        tcgen05_fence_after();
-        const uint32_t acc = tmem_base + buf * H3_BN;
-        const uint32_t acc2 = p.two_acc ? tmem_base + H3_BN : acc;   // where the two correction products go
+        int in_chunk = 0;
+        uint32_t acc = tmem_base;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          if (in_chunk == 0) {                                     // new chunk: the drain of chunk cc - 2 has finished
+            const uint32_t buf = cc & 1u;
+            mbar_wait(bar_cempty(buf), ((cc >> 1) & 1u) ^ 1u);
+            tcgen05_fence_after();
+            acc = tmem_base + buf * H3_BN;
+          }
           const int s = it % H3_STAGES;
           const uint32_t ph = (it / H3_STAGES) & 1u;
           mbar_wait(bar_full(s), ph);
@@ -208,30 +221,33 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
 #pragma unroll
           for (int kk = 0; kk < H3_BK / 16; ++kk) {
             const uint64_t adv = static_cast<uint64_t>(kk * 2);    // 16 halfs = 32 bytes = 2 x 16-byte units
-            const uint32_t later = (kb | kk) != 0 ? 1u : 0u;
-            umma_f16(acc, d_xhi + adv, d_wa + adv, idesc, later);
-            umma_f16(acc2, d_xlo + adv, d_wb + adv, idesc, p.two_acc ? later : 1u);
-            umma_f16(acc2, d_xhi + adv, d_wc + adv, idesc, 1u);
+            umma_f16(acc, d_xhi + adv, d_wa + adv, idesc, (in_chunk | kk) != 0 ? 1u : 0u);
+            umma_f16(acc, d_xlo + adv, d_wb + adv, idesc, 1u);
+            umma_f16(acc, d_xhi + adv, d_wc + adv, idesc, 1u);
           }
           if (CL > 1) umma_commit_mc(bar_empty(s), kAllCtas);      // stage refillable once ALL CTAs' MMAs have read it
           else umma_commit(bar_empty(s));
+          if (++in_chunk == chb || kb == num_kb - 1) {
+            umma_commit(bar_cfull(cc & 1u));                       // chunk complete -> drain
+            ++cc;
+            in_chunk = 0;
+          }
         }
-        umma_commit(bar_tfull(buf));                               // accumulator complete
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue
+    // ------------------------------------------------------------------ drain + epilogue (8 warps)
+    const int ew = warp - 2;
     const int q = warp & 3;                                         // TMEM lane quarter this warp may read
-    const uint32_t slot0 = epi + static_cast<uint32_t>(q) * 2u * H3_EPI_SLOT;
-    uint8_t* slot0_gen = gen + H3_STAGES * H3_STAGE_BYTES + q * 2 * H3_EPI_SLOT;
-    uint32_t t = 0, chunk = 0;
-    for (int item = cluster; item < items; item += nclusters, ++t) {
+    const int hcol = ew >> 2;                                       // which 128-column half of the tile it owns
+    const uint32_t box_sh = epi + static_cast<uint32_t>(ew) * H3_EPI_SLOT;
+    uint8_t* box = gen + H3_STAGES * H3_STAGE_BYTES + ew * H3_EPI_SLOT;
+    uint32_t cc = 0;
+    for (int item = cluster; item < items; item += nclusters) {
       int m_tile, grp, m0, n0;
       tile_of(item, m_tile, grp, m0, n0);
       const int n_here = min(H3_BN, p.n - n0);
       const int n_inst = (n_here + 15) & ~15;
-      const uint32_t buf = p.two_acc ? 0u : (t & 1u);
-      const uint32_t par = p.two_acc ? (t & 1u) : ((t >> 1) & 1u);
       const bool tile_ok = m_tile < p.m_tiles;
       int ob = 0, oy = 0, ox = 0;              // convolution: (image, row, column) of this warp's first output pixel
       if (p.taps > 0) {
@@ -246,30 +262,42 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
       const bool row_ok = tile_ok && lrow < p.rows_per_batch;
       const int64_t row = static_cast<int64_t>(grp) * p.rows_per_batch + lrow;   // output rows are dense
       const int row0 = static_cast<int>(static_cast<int64_t>(grp) * p.rows_per_batch + m0 + q * 32);
-      mbar_wait(bar_tfull(buf), par);
-      tcgen05_fence_after();
-      for (int c0 = 0; c0 < n_inst; c0 += 32, ++chunk) {
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + buf * H3_BN + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0);
-        tmem_ld32(taddr, r);
-        if (p.two_acc) {
-          uint32_t r2[32];
-          tmem_ld32(taddr + H3_BN, r2);
-          tmem_ld_wait();
+
+      // ---- drain every chunk of this tile into registers
+      float acc[128];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
-        } else {
-          tmem_ld_wait();
+      for (int i = 0; i < 128; ++i) acc[i] = 0.f;
+      const int nchunks = (num_kb + chb - 1) / chb;
+      for (int c = 0; c < nchunks; ++c, ++cc) {
+        const uint32_t buf = cc & 1u;
+        mbar_wait(bar_cfull(buf), (cc >> 1) & 1u);
+        tcgen05_fence_after();
+        const uint32_t t0 = tmem_base + buf * H3_BN + (static_cast<uint32_t>(q * 32) << 16) +
+                            static_cast<uint32_t>(hcol * 128);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (hcol * 128 + j * 32 < n_inst) {                        // warp-uniform
+            uint32_t r[32];
+            tmem_ld32(t0 + j * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[j * 32 + i] += __uint_as_float(r[i]);
+          }
         }
-        if (c0 + 32 >= n_inst) {               // last read of this accumulator: hand it back to the MMA warp
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tempty(buf));
-        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_cempty(buf));                 // the tensor core may refill this buffer
+      }
+
+      // ---- epilogue: scale, bias, residual, activation, store
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c0 = hcol * 128 + j * 32;
+        if (c0 >= n_inst) continue;                                  // warp-uniform
         const float bl = (p.bias != nullptr && c0 + lane < n_here) ? __ldg(p.bias + n0 + c0 + lane) : 0.f;
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), kLoInv, __shfl_sync(0xffffffffu, bl, j));
+        for (int i = 0; i < 32; ++i) v[i] = fmaf(acc[j * 32 + i], kLoInv, __shfl_sync(0xffffffffu, bl, i));
         if (p.r_hi != nullptr) {
           // split-half residual (ResNet bottleneck shortcut): this lane's row, 32 columns = 64 B per plane
           const int64_t rr = p.taps > 0 ? static_cast<int64_t>(m_tile) * H3_BM + q * 32 + lane : row;
@@ -281,59 +309,57 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
               const uint4 a = __ldg(ph + g), b = __ldg(pl + g);
               const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                v[g * 8 + 2 * j] += join_half(__ushort_as_half(static_cast<unsigned short>(aw[j] & 0xffffu)),
-                                              __ushort_as_half(static_cast<unsigned short>(bw[j] & 0xffffu)));
-                v[g * 8 + 2 * j + 1] += join_half(__ushort_as_half(static_cast<unsigned short>(aw[j] >> 16)),
-                                                  __ushort_as_half(static_cast<unsigned short>(bw[j] >> 16)));
+              for (int i = 0; i < 4; ++i) {
+                v[g * 8 + 2 * i] += join_half(__ushort_as_half(static_cast<unsigned short>(aw[i] & 0xffffu)),
+                                              __ushort_as_half(static_cast<unsigned short>(bw[i] & 0xffffu)));
+                v[g * 8 + 2 * i + 1] += join_half(__ushort_as_half(static_cast<unsigned short>(aw[i] >> 16)),
+                                                  __ushort_as_half(static_cast<unsigned short>(bw[i] >> 16)));
               }
             }
           }
         }
-        if (p.out_mode != H3_OUT_F32_DIRECT && p.act == HOISDF_ACT_RELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
         if (p.out_mode == H3_OUT_F32_DIRECT) {
-          if (!row_ok) continue;
-          float* yrow = p.y + row * p.ldy + n0;
-          const float* rrow = p.residual ? p.residual + row * p.ldy + n0 : nullptr;
-          const bool vec = ((p.ldy & 3) == 0) && aligned16(p.y) && (p.residual == nullptr || aligned16(p.residual));
+          if (row_ok) {
+            float* yrow = p.y + row * p.ldy + n0;
+            const float* rrow = p.residual ? p.residual + row * p.ldy + n0 : nullptr;
+            const bool vec = ((p.ldy & 3) == 0) && aligned16(p.y) && (p.residual == nullptr || aligned16(p.residual));
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const int c = c0 + g * 4;
-            if (c >= n_here) break;
-            if (vec && c + 3 < n_here) {
-              float4 o = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-              if (rrow != nullptr) {
-                const float4 rr = *reinterpret_cast<const float4*>(rrow + c);
-                o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-              }
-              if (p.act == HOISDF_ACT_RELU) {
-                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-              }
-              *reinterpret_cast<float4*>(yrow + c) = o;
-            } else {
+            for (int g = 0; g < 8; ++g) {
+              const int c = c0 + g * 4;
+              if (c >= n_here) break;
+              if (vec && c + 3 < n_here) {
+                float4 o = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+                if (rrow != nullptr) {
+                  const float4 rr = *reinterpret_cast<const float4*>(rrow + c);
+                  o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+                }
+                if (p.act == HOISDF_ACT_RELU) {
+                  o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                }
+                *reinterpret_cast<float4*>(yrow + c) = o;
+              } else {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                if (c + j < n_here) {
-                  float o = v[g * 4 + j];
-                  if (rrow != nullptr) o += rrow[c + j];
-                  if (p.act == HOISDF_ACT_RELU) o = fmaxf(o, 0.f);
-                  yrow[c + j] = o;
+                for (int i = 0; i < 4; ++i) {
+                  if (c + i < n_here) {
+                    float o = v[g * 4 + i];
+                    if (rrow != nullptr) o += rrow[c + i];
+                    if (p.act == HOISDF_ACT_RELU) o = fmaxf(o, 0.f);
+                    yrow[c + i] = o;
+                  }
                 }
               }
             }
           }
           continue;
         }
-        // TMA-store paths: stage the 32 x 32 block in this warp's slot (chunk & 1); the store issued from the same
-        // slot two chunks ago must have finished READING it
-        const uint32_t sl = chunk & 1u;
-        if (lane == 0) tma_store_wait_read<1>();
+        if (p.act == HOISDF_ACT_RELU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        // TMA-store paths: stage the 32 x 32 block in this warp's slot; the previous store issued from it must have
+        // finished READING it
+        if (lane == 0) tma_store_wait_read<0>();
         __syncwarp();
-        uint8_t* box = slot0_gen + sl * H3_EPI_SLOT;
-        const uint32_t box_sh = slot0 + sl * H3_EPI_SLOT;
         if (p.out_mode == H3_OUT_F32_TMA) {
 #pragma unroll
           for (int g = 0; g < 8; ++g)      // 128-byte rows, 128B swizzle
@@ -345,12 +371,12 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
           for (int g = 0; g < 4; ++g) {
             uint32_t hw[4], lw[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int i = 0; i < 4; ++i) {
               __half h0, l0, h1, l1;
-              split_half(v[g * 8 + 2 * j], h0, l0);
-              split_half(v[g * 8 + 2 * j + 1], h1, l1);
-              hw[j] = static_cast<uint32_t>(__half_as_ushort(h0)) | (static_cast<uint32_t>(__half_as_ushort(h1)) << 16);
-              lw[j] = static_cast<uint32_t>(__half_as_ushort(l0)) | (static_cast<uint32_t>(__half_as_ushort(l1)) << 16);
+              split_half(v[g * 8 + 2 * i], h0, l0);
+              split_half(v[g * 8 + 2 * i + 1], h1, l1);
+              hw[i] = static_cast<uint32_t>(__half_as_ushort(h0)) | (static_cast<uint32_t>(__half_as_ushort(h1)) << 16);
+              lw[i] = static_cast<uint32_t>(__half_as_ushort(l0)) | (static_cast<uint32_t>(__half_as_ushort(l1)) << 16);
             }
             const int off = lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4);
             *reinterpret_cast<uint4*>(box + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
@@ -493,10 +519,12 @@ static int max_clusters() {
 }
 
 static int g_h3_force_cluster = 0;   // developer hook: 0 = automatic
+static int g_h3_chunk_kb = H3_CHUNK_KB;   // developer hook: K blocks per accumulation chunk
 
 template <int CL>
 static int launch_h3(const CUtensorMap* maps, const H3Params& p0, int64_t m_tiles, cudaStream_t s) {
   H3Params p = p0;
+  if (p.chunk_kb <= 0) p.chunk_kb = g_h3_chunk_kb > 0 ? g_h3_chunk_kb : H3_CHUNK_KB;
   p.m_blocks = static_cast<int>(ceil_div(m_tiles, CL));
   const int64_t items = static_cast<int64_t>(p.m_blocks) * p.n_tiles;
   const int64_t clusters = items < max_clusters<CL>() ? items : max_clusters<CL>();
@@ -524,6 +552,7 @@ static int launch_h3(const CUtensorMap* maps, const H3Params& p0, int64_t m_tile
 using namespace hoisdf;
 
 extern "C" __attribute__((visibility("default"))) void hoisdf_debug_h3_cluster(int cl) { g_h3_force_cluster = cl; }
+extern "C" __attribute__((visibility("default"))) void hoisdf_debug_h3_chunk(int kb) { g_h3_chunk_kb = kb; }
 
 HOISDF_API int hoisdf_linear_h3_fwd(const hoisdf_linear_h3_args* a, void* stream) {
   if (a == nullptr || a->x_hi == nullptr || a->x_lo == nullptr || a->w_a == nullptr || a->w_b == nullptr ||
@@ -592,7 +621,7 @@ HOISDF_API int hoisdf_linear_h3_fwd(const hoisdf_linear_h3_args* a, void* stream
   p.rows_per_batch = rpb; p.tiles_per_batch = static_cast<int>(tpb); p.m_tiles = static_cast<int>(m_tiles);
   p.n_tiles = static_cast<int>(ceil_div(a->n, H3_BN));
   p.n = static_cast<int>(a->n); p.k = static_cast<int>(a->k); p.act = a->act; p.out_mode = out_mode;
-  p.two_acc = a->two_acc ? 1 : 0;
+  p.chunk_kb = a->chunk_kb;
   if (a->res_hi != nullptr || a->res_lo != nullptr) {
     if (a->res_hi == nullptr || a->res_lo == nullptr) return HOISDF_E_NULL;
     if (out_mode == H3_OUT_F32_DIRECT || a->residual != nullptr || (a->n & 31)) return HOISDF_E_UNSUPPORTED;
@@ -682,7 +711,7 @@ HOISDF_API int hoisdf_conv_h3_fwd(const hoisdf_conv_h3_args* a, void* stream) {
   p.m_tiles = static_cast<int>(m_tiles); p.n_tiles = static_cast<int>(ceil_div(a->cout, H3_BN));
   p.n = static_cast<int>(a->cout); p.k = static_cast<int>(a->taps * a->cin); p.act = a->act;
   p.out_mode = split_out ? H3_OUT_SPLIT_TMA : H3_OUT_F32_TMA;
-  p.two_acc = a->two_acc ? 1 : 0;
+  p.chunk_kb = a->chunk_kb;
   p.taps = a->taps; p.cin_blocks = static_cast<int>(a->cin / H3_BK);
   p.out_w = static_cast<int>(a->out_w); p.out_h = static_cast<int>(a->out_h); p.stride = a->stride;
   p.wx = wx; p.wy = wy;

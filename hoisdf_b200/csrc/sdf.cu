@@ -273,7 +273,7 @@ HOISDF_API int hoisdf_sdf_decoder_h3_fwd(const hoisdf_sdf_weights_h3* w, uint16_
   auto layer = [&](int l, const uint16_t* xh, const uint16_t* xl, int64_t ld_in, int64_t k, uint16_t* yh, uint16_t* yl,
                    int64_t ld_out, int64_t n) {
     a = {xh, xl, ld_in, 0, 0, w->w[l][0], w->w[l][1], w->w[l][2], w->ldw[l], w->b[l], nullptr,
-         nullptr, 0, yh, yl, ld_out, rows, n, k, HOISDF_ACT_RELU};
+         nullptr, 0, yh, yl, ld_out, rows, n, k, HOISDF_ACT_RELU, w->chunk_kb};
     return hoisdf_linear_h3_fwd(&a, stream);
   };
   // linh0: x[:, 0:289] -> h_a (512);  linh1: h_a -> x[:, 296:519] (223);  linh2: x[:, 0:519] (weight columns

@@ -247,9 +247,11 @@ class Model(nn.Module):
                     offs = plan.offsets if r0 == 0 else plan.offsets - r0
                     ops.gather(gmaps, cand_uv[r0:r0 + n], b, mode=ops.GATHER_SUM, out=hs.head(n), row_offsets=offs,
                                bias=sdfin[0].b, act=ops.ACT_RELU, img_hw=cfg.input_img_shape)
-                    ops.linear(hs.head(n), sdfin[1], ops.ACT_RELU, out=rs.head(n).window(0, 256))
+                    ops.linear(hs.head(n), sdfin[1], ops.ACT_RELU, out=rs.head(n).window(0, 256),
+                               chunk_kb=ops.SCREEN_CHUNK_KB)
                     ops.posenc(rs.head(n), lattice_index=cand_index[r0:r0 + n], bins=cfg.bins_n)
-                    ops.sdf_decoder(packed, rs.head(n), h_a=hs.head(n), h_b=hs2.head(n), out=sdf[r0:r0 + n])
+                    ops.sdf_decoder(packed, rs.head(n), h_a=hs.head(n), h_b=hs2.head(n), out=sdf[r0:r0 + n],
+                                    chunk_kb=ops.SCREEN_CHUNK_KB)
                 return
             h, h2, rows = fp32_buffers(cap)
             for r0 in range(0, total, step):

@@ -21,6 +21,7 @@ from typing import Dict, Optional
 import torch
 
 from .. import ops
+from ..config import cfg
 from .unet_h3 import TAPS_1X1, TAPS_3X3, SplitMap, _fold_bn, _pack_conv
 
 
@@ -33,20 +34,23 @@ class ResNetH3:
         self._key = None
 
     def _pack(self):
-        key = tuple((p.data_ptr(), p._version) for p in list(self.net.parameters()) + list(self.net.buffers()))
+        key = tuple((p.data_ptr(), p._version) for p in list(self.net.parameters()) + list(self.net.buffers())) + \
+            (int(cfg.backbone_chunk_kb),)
         if self._packed is not None and self._key == key:
             return self._packed
         n, pk = self.net, {}
         w, b = _fold_bn(n.conv1.weight, None, n.bn1, 0)
         # K index = (ky * 7 + kx) * 3 + c -- the column order hoisdf_stem_im2col_split writes
-        pk["stem"] = ops.PackedLinearH3.pack(w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).float().contiguous(), b)
+        ck = int(cfg.backbone_chunk_kb)
+        pk["stem"] = ops.PackedLinearH3.pack(w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).float().contiguous(), b,
+                                             chunk_kb=ck)
         for lname, _ in self.STAGES:
             blocks = []
             for blk in getattr(n, lname):
-                d = {"conv1": _pack_conv(blk.conv1, blk.bn1), "conv2": _pack_conv(blk.conv2, blk.bn2),
-                     "conv3": _pack_conv(blk.conv3, blk.bn3), "stride": int(blk.conv2.stride[0]), "down": None}
+                d = {"conv1": _pack_conv(blk.conv1, blk.bn1, ck), "conv2": _pack_conv(blk.conv2, blk.bn2, ck),
+                     "conv3": _pack_conv(blk.conv3, blk.bn3, ck), "stride": int(blk.conv2.stride[0]), "down": None}
                 if blk.downsample is not None:
-                    d["down"] = _pack_conv(blk.downsample[0], blk.downsample[1])
+                    d["down"] = _pack_conv(blk.downsample[0], blk.downsample[1], ck)
                 blocks.append(d)
             pk[lname] = blocks
         self._packed, self._key = pk, key

@@ -57,12 +57,12 @@ def _fold_bn(weight: torch.Tensor, bias, bn: nn.BatchNorm2d, out_dim: int):
     return w, b.float()
 
 
-def _pack_conv(conv: nn.Conv2d, bn) -> ops.PackedLinearH3:
+def _pack_conv(conv: nn.Conv2d, bn, chunk_kb: int = 0) -> ops.PackedLinearH3:
     """(Cout, Cin, kh, kw) -> planes of (Cout, kh*kw*Cin), K index = tap * Cin + channel."""
     w, b = _fold_bn(conv.weight, conv.bias, bn, 0)
     cout = w.shape[0]
     mat = w.permute(0, 2, 3, 1).reshape(cout, -1).float().contiguous()
-    return ops.PackedLinearH3.pack(mat, b)
+    return ops.PackedLinearH3.pack(mat, b, chunk_kb=chunk_kb)
 
 
 def _pack_deconv(deconv: nn.ConvTranspose2d, bn) -> Dict[Tuple[int, int], Tuple[ops.PackedLinearH3, list]]:

@@ -22,6 +22,9 @@ DEC_IN = 289
 DEC_IN_PAD = 292
 SKIP_OFF = 292
 H1 = 223
+# TMEM accumulation chunk (K blocks of 32) of the FP16x3 GEMMs that only SCREEN candidates for the exact re-ranking:
+# one drain per tile, the fastest setting -- the re-ranking's device-side check covers its ~1e-6 error
+SCREEN_CHUNK_KB = 1 << 20
 # algorithmic FLOPs of one SDFDecoder row (2*(289*512+512*223+512*512+512*512+512))
 SDF_DECODER_FLOPS = 2.0 * (289 * 512 + 512 * 223 + 512 * 512 + 512 * 512 + 512)
 
@@ -65,6 +68,10 @@ USE_TENSOR_CORES = os.environ.get("HOISDF_TC", "1") != "0"
 # Which tensor-core Linear: "h3" = FP16x3 on split-half activations (csrc/linear_h3.cu, default),
 # "tf32" = the 3xTF32 kernel on fp32 activations (csrc/linear_tc.cu).
 TC_MODE = os.environ.get("HOISDF_TC_MODE", "h3")
+
+
+if os.environ.get("HOISDF_H3_CHUNK"):          # developer knob: K blocks (of 32) per TMEM accumulation chunk
+    lib.hoisdf_debug_h3_chunk(int(os.environ["HOISDF_H3_CHUNK"]))
 
 
 def use_h3() -> bool:
@@ -156,7 +163,7 @@ def fma_only(pw: PackedLinear) -> PackedLinear:
 
 
 def linear(x, pw: PackedLinear, act: int = ACT_NONE, out=None, residual: Optional[torch.Tensor] = None,
-           out_ld: Optional[int] = None, passes: int = 3, split_out: bool = False):
+           out_ld: Optional[int] = None, passes: int = 3, split_out: bool = False, chunk_kb: Optional[int] = None):
     """x: (M, >=K) 2-D fp32 (unit inner stride) or SplitRows.  Returns (M, N) fp32 (a view of a (M, out_ld) buffer if
     padded) -- or, on the FP16x3 path with split_out / a SplitRows `out`, the result in split-half format."""
     if isinstance(x, SplitRows) or isinstance(out, SplitRows) or (use_h3() and pw.h3 is not None):
@@ -167,7 +174,7 @@ def linear(x, pw: PackedLinear, act: int = ACT_NONE, out=None, residual: Optiona
             ld = out_ld or round_up(pw.n, 4)
             alloc = torch.empty if ld == pw.n else torch.zeros
             out = alloc(xs.rows, ld, device=xs.buf.device, dtype=torch.float32)[:, :pw.n]
-        return linear_h3(xs, pw.h3, act, out=out, residual=residual, split_out=split_out)
+        return linear_h3(xs, pw.h3, act, out=out, residual=residual, split_out=split_out, chunk_kb=chunk_kb)
     assert x.dim() == 2 and x.stride(1) == 1 and x.shape[1] >= pw.k, (x.shape, x.stride(), pw.k)
     m = x.shape[0]
     if out is None:
@@ -253,9 +260,11 @@ class PackedLinearH3:
     k: int
     row0: int = 0                 # row window (N slice)
     col0: int = 0                 # column window (K slice), multiple of 8
+    chunk_kb: int = 0             # TMEM accumulation chunk of the launches using these weights (0 = kernel default)
 
     @staticmethod
-    def pack(weight: torch.Tensor, bias: Optional[torch.Tensor], k: Optional[int] = None) -> "PackedLinearH3":
+    def pack(weight: torch.Tensor, bias: Optional[torch.Tensor], k: Optional[int] = None,
+             chunk_kb: int = 0) -> "PackedLinearH3":
         w = weight.detach().to(torch.float32)
         if w.stride(1) != 1:
             w = w.contiguous()
@@ -269,7 +278,7 @@ class PackedLinearH3:
         check(lib.hoisdf_pack_h3(w.data_ptr(), n, k, w.stride(0), planes[0].data_ptr(), planes[1].data_ptr(),
                                  planes[2].data_ptr(), ld, _stream()), "hoisdf_pack_h3")
         b = None if bias is None else bias.detach().to(torch.float32).contiguous()
-        return PackedLinearH3(planes, b, n, k)
+        return PackedLinearH3(planes, b, n, k, chunk_kb=chunk_kb)
 
     @property
     def ld(self) -> int:
@@ -280,15 +289,15 @@ class PackedLinearH3:
 
     def cols(self, start: int, stop: int) -> "PackedLinearH3":
         assert start % 8 == 0
-        return PackedLinearH3(self.planes, None, self.n, stop - start, self.row0, self.col0 + start)
+        return PackedLinearH3(self.planes, None, self.n, stop - start, self.row0, self.col0 + start, self.chunk_kb)
 
     def rows(self, start: int, stop: int) -> "PackedLinearH3":
         b = None if self.b is None else self.b[start:stop]
-        return PackedLinearH3(self.planes, b, stop - start, self.k, self.row0 + start, self.col0)
+        return PackedLinearH3(self.planes, b, stop - start, self.k, self.row0 + start, self.col0, self.chunk_kb)
 
 
 def linear_h3(x: SplitRows, pw: PackedLinearH3, act: int = ACT_NONE, out=None, residual: Optional[torch.Tensor] = None,
-              split_out: bool = False, x_batch=(0, 0), m: Optional[int] = None, two_acc: Optional[bool] = None,
+              split_out: bool = False, x_batch=(0, 0), m: Optional[int] = None, chunk_kb: Optional[int] = None,
               residual_split: Optional[SplitRows] = None):
     """Y = act(X . W^T + b) (+ residual) on the FP16x3 tensor-core kernel.  `out` is an fp32 (M, N) tensor view (unit
     inner stride) or a SplitRows window; allocated when None (fp32, or split-half if split_out).
@@ -313,8 +322,7 @@ def linear_h3(x: SplitRows, pw: PackedLinearH3, act: int = ACT_NONE, out=None, r
             assert residual.stride() == out.stride()
         a.y, a.ldy, a.y_hi, a.y_lo, a.ldyh = out.data_ptr(), out.stride(0), None, None, 0
     a.m, a.n, a.k, a.act = m, pw.n, pw.k, act
-    # long contractions: separate main / correction accumulators (3x smaller accumulate-truncation error)
-    a.two_acc = int(pw.k >= 2048 if two_acc is None else two_acc)
+    a.chunk_kb = int(pw.chunk_kb if chunk_kb is None else chunk_kb)
     if residual_split is not None:
         assert residual_split.cols >= pw.n and residual_split.rows >= m
         a.res_hi, a.res_lo, a.ldr = residual_split.hi_ptr, residual_split.lo_ptr, residual_split.ld
@@ -332,7 +340,7 @@ def linear_h3(x: SplitRows, pw: PackedLinearH3, act: int = ACT_NONE, out=None, r
 
 def conv_h3(x: SplitRows, batch: int, in_h: int, in_w: int, cin: int, pw: PackedLinearH3, taps, out_h: int, out_w: int,
             *, stride: int = 1, act: int = ACT_NONE, out=None, out_strides=None, out_offset: int = 0,
-            two_acc: Optional[bool] = None, residual_split: Optional[SplitRows] = None):
+            chunk_kb: Optional[int] = None, residual_split: Optional[SplitRows] = None):
     """Implicit-GEMM convolution on the FP16x3 kernel.  x: NHWC pixels (batch*in_h*in_w rows of >= cin columns) in
     split-half format; pw: planes of the (cout, len(taps)*cin) weight matrix; taps: [(dy, dx), ...].
     out: fp32 (rows, >= cout) tensor or SplitRows window; out_strides = (sx, sy, sb) in elements (default: dense
@@ -355,7 +363,7 @@ def conv_h3(x: SplitRows, batch: int, in_h: int, in_w: int, cin: int, pw: Packed
     sx, sy, sb = out_strides if out_strides is not None else (pitch, out_w * pitch, out_h * out_w * pitch)
     a.y_sx, a.y_sy, a.y_sb = sx, sy, sb
     a.act = act
-    a.two_acc = int(pw.k >= 2048 if two_acc is None else two_acc)
+    a.chunk_kb = int(pw.chunk_kb if chunk_kb is None else chunk_kb)
     if residual_split is not None:
         assert residual_split.cols >= pw.n and residual_split.rows >= batch * out_h * out_w
         a.res_hi, a.res_lo, a.ldr = residual_split.hi_ptr, residual_split.lo_ptr, residual_split.ld
@@ -590,7 +598,8 @@ def posenc(rows_buf, *, lattice_index=None, points=None, bins: int = 64):
 
 
 def sdf_decoder(packed: PackedSdfDecoder, rows_buf, h_a=None, h_b=None, clamp: float = 0.0,
-                out: Optional[torch.Tensor] = None, exact: bool = False, screening: bool = False) -> torch.Tensor:
+                out: Optional[torch.Tensor] = None, exact: bool = False, screening: bool = False,
+                chunk_kb: int = 0) -> torch.Tensor:
     if isinstance(rows_buf, SplitRows):
         rows, dev = rows_buf.rows, rows_buf.buf.device
         h_a = h_a if h_a is not None else SplitRows.empty(rows, 512, dev)
@@ -598,6 +607,7 @@ def sdf_decoder(packed: PackedSdfDecoder, rows_buf, h_a=None, h_b=None, clamp: f
         out = out if out is not None else torch.empty(rows, device=dev, dtype=torch.float32)
         assert h_a.ld == h_b.ld and rows_buf.col0 == 0 and h_a.col0 == 0 and h_b.col0 == 0
         _count(5)
+        packed.struct_h3.chunk_kb = int(chunk_kb)
         if PROFILE is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 6
+#define HOISDF_ABI_VERSION 7
 
 enum {
   HOISDF_OK = 0,
@@ -93,9 +93,12 @@ typedef struct {
   uint16_t* y_hi; uint16_t* y_lo; int64_t ldyh;
   int64_t m; int64_t n; int64_t k;
   int32_t act;
-  int32_t two_acc;                   /* 1: main and correction products in separate TMEM accumulators -- 3x smaller
-                                        accumulate-truncation error (it grows ~linearly with K), no epilogue overlap;
-                                        meant for K >= ~2048 */
+  int32_t chunk_kb;                  /* K blocks (of 32) accumulated in TMEM before the partial sum is drained into
+                                        fp32 registers (round-to-nearest adds).  The tensor core truncates on every
+                                        accumulate, so the error of a sum held in TMEM grows ~linearly with its
+                                        length: 0 = default (4 blocks = 128 of K: fp32-FMA-grade results); 1 = most
+                                        accurate (deep convolution chains); >= K/32 = one drain per tile (fastest;
+                                        only for values that an exact pass re-ranks) */
   const uint16_t* res_hi; const uint16_t* res_lo; int64_t ldr;
                                      /* optional residual in split-half format, row r of the dense output reads row
                                         r of these planes (pitch ldr halfs); added before the activation; needs the
@@ -126,7 +129,7 @@ typedef struct {
   int32_t taps; int32_t tap_dy[16]; int32_t tap_dx[16]; int32_t stride;
   int64_t out_h; int64_t out_w; int64_t cout;
   float* y; uint16_t* y_hi; uint16_t* y_lo; int64_t y_sx; int64_t y_sy; int64_t y_sb;
-  int32_t act; int32_t two_acc;
+  int32_t act; int32_t chunk_kb;     /* see hoisdf_linear_h3_args */
   const uint16_t* res_hi; const uint16_t* res_lo; int64_t ldr;
                                      /* optional split-half residual: output pixel (b, y, x) reads row
                                         (b * out_h + y) * out_w + x of these planes; cout % 32 == 0 */
@@ -267,6 +270,7 @@ int hoisdf_sdf_decoder_fwd(const hoisdf_sdf_weights* wts, float* x, int64_t ldx,
 typedef struct {
   const uint16_t* w[4][3]; int64_t ldw[4]; const float* b[4];
   const float* w4; const float* b4;
+  int32_t chunk_kb;                  /* passed to every hoisdf_linear_h3_fwd of the chain (0 = default) */
 } hoisdf_sdf_weights_h3;
 
 int hoisdf_sdf_decoder_h3_fwd(const hoisdf_sdf_weights_h3* wts, uint16_t* x_hi, uint16_t* x_lo, int64_t ldx,

@@ -38,7 +38,6 @@ def variants():
     yield "cudnn+cudnn", dict(tc_backbone=False, tc_unet=False), None
     yield "cudnn+h3", dict(tc_backbone=False, tc_unet=True), None
     yield "h3+h3", dict(tc_backbone=True, tc_unet=True), None
-    yield "h3+h3 two_acc", dict(tc_backbone=True, tc_unet=True), True
 
 
 def main():
@@ -63,10 +62,6 @@ def main():
     for name, flags, two in variants():
         for k, v in flags.items():
             setattr(type(cfg), k, v)
-        if two:
-            ops.linear_h3 = lambda *a, **kw: orig_lin(*a, **{**kw, "two_acc": True})
-            ops.conv_h3 = lambda *a, **kw: orig_conv(*a, **{**kw, "two_acc": True})
-            import hoisdf_b200.nets.unet_h3 as U, hoisdf_b200.nets.resnet_h3 as R  # noqa
         with torch.no_grad():
             pyr, _ = model.run_image_encoder(img.to(dev))
             errs = {k: rel(pyr[k], pyr64[k]) for k in pyr64}
