@@ -11,8 +11,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhoisdf_b200.so")
 
-ABI_VERSION = 7
-ACT_NONE, ACT_RELU = 0, 1
+ABI_VERSION = 9
+ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2      # ACT_SIGMOID: hoisdf_linear_narrow_split_fwd only
 GATHER_CONCAT, GATHER_SUM = 0, 1
 
 c_float_p = C.c_void_p  # device pointers are passed as integers (tensor.data_ptr())
@@ -34,7 +34,7 @@ class LinearH3Args(C.Structure):
         ("w_a", vp), ("w_b", vp), ("w_c", vp), ("ldw", i64), ("bias", vp), ("residual", vp),
         ("y", vp), ("ldy", i64), ("y_hi", vp), ("y_lo", vp), ("ldyh", i64),
         ("m", i64), ("n", i64), ("k", i64), ("act", i32), ("chunk_kb", i32),
-        ("res_hi", vp), ("res_lo", vp), ("ldr", i64),
+        ("res_hi", vp), ("res_lo", vp), ("ldr", i64), ("single_pass", i32),
     ]
 
 
@@ -46,7 +46,7 @@ class ConvH3Args(C.Structure):
         ("out_h", i64), ("out_w", i64), ("cout", i64),
         ("y", vp), ("y_hi", vp), ("y_lo", vp), ("y_sx", i64), ("y_sy", i64), ("y_sb", i64),
         ("act", i32), ("chunk_kb", i32),
-        ("res_hi", vp), ("res_lo", vp), ("ldr", i64),
+        ("res_hi", vp), ("res_lo", vp), ("ldr", i64), ("single_pass", i32),
     ]
 
 
@@ -63,7 +63,7 @@ class SdfWeights(C.Structure):
 
 
 class SdfWeightsH3(C.Structure):
-    _fields_ = [("w", (vp * 3) * 4), ("ldw", i64 * 4), ("b", vp * 4), ("w4", vp), ("b4", vp), ("chunk_kb", i32)]
+    _fields_ = [("w", (vp * 3) * 4), ("ldw", i64 * 4), ("b", vp * 4), ("w4", vp), ("b4", vp), ("chunk_kb", i32), ("single_pass", i32)]
 
 
 class ManoModel(C.Structure):
@@ -80,6 +80,7 @@ SIGNATURES = {
     "hoisdf_conv_h3_fwd": (C.c_int, [C.POINTER(ConvH3Args), vp]),
     "hoisdf_stem_im2col_split": (C.c_int, [vp, i64, i64, i64, vp, vp, i64, vp]),
     "hoisdf_maxpool3x3s2_split": (C.c_int, [vp, vp, i64, i64, i64, i64, i64, vp, vp, i64, vp]),
+    "hoisdf_linear_narrow_split_fwd": (C.c_int, [vp, vp, i64, i64, vp, i64, vp, i64, i64, i32, vp, i64, vp]),
     "hoisdf_pack_h3": (C.c_int, [vp, i64, i64, i64, vp, vp, vp, i64, vp]),
     "hoisdf_split_rows": (C.c_int, [vp, i64, i64, i64, i64, vp, vp, i64, vp]),
     "hoisdf_join_rows": (C.c_int, [vp, vp, i64, i64, i64, vp, i64, vp]),

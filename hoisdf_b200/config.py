@@ -59,6 +59,12 @@ class Config:
     screen_margin = 256         # margin used with screen_passes = 1
     screen_margin_safe = 64     # margin used with 3xTF32 screening
     screen_passes = 3
+    # FP16x3 path (default): stage A of the cascade evaluates ALL candidates with ONE fp16 tensor-core product per K
+    # step (error ~1e-4) and keeps P + screen_margin_single rows for the FP16x3 stage (which keeps P + screen_margin_safe
+    # for the exact stage).  Every stage is verified on the device (gap > 3 x observed error); a failed check re-runs
+    # the selection without stage A.
+    screen_single = True
+    screen_margin_single = 1024
     # U-Net decoder (the step before the hot path) on the FP16x3 tensor-core convolution kernels
     # instead of cuDNN's fp32 FMA convolutions (measured 3e-5 relative difference on the pyramid; 2.3x faster at B=4)
     tc_unet = True

@@ -29,10 +29,14 @@ using namespace tc;
 constexpr int H3_BM = 128;
 constexpr int H3_BN = 256;
 constexpr int H3_BK = 32;                               // halfs per stage row = one 64-byte swizzle row
-constexpr int H3_STAGES = 3;
+constexpr int H3_STAGES = 3;                            // three-product mode: 3 stages of 64 KB
+constexpr int H3_STAGES_1P = 8;                         // single-product mode: 8 stages of 24 KB (x_hi + w_hi only)
+constexpr int H3_MAX_STAGES = 8;
 constexpr int H3_X_BYTES = H3_BM * H3_BK * 2;           // 8 KB per plane
 constexpr int H3_W_BYTES = H3_BN * H3_BK * 2;           // 16 KB per plane
 constexpr int H3_STAGE_BYTES = 2 * H3_X_BYTES + 3 * H3_W_BYTES;   // 64 KB
+constexpr int H3_STAGE_BYTES_1P = H3_X_BYTES + H3_W_BYTES;         // 24 KB
+static_assert(H3_STAGES_1P * H3_STAGE_BYTES_1P <= H3_STAGES * H3_STAGE_BYTES, "single-product ring must fit");
 constexpr int H3_EPI_WARPS = 8;                         // drain + epilogue warps (2 per TMEM lane quarter)
 constexpr int H3_EPI_SLOT = 4096;                       // one 32 x 32 fp32 box (or hi + lo half boxes) per warp
 constexpr int H3_EPI_BYTES = H3_EPI_WARPS * H3_EPI_SLOT;
@@ -60,6 +64,8 @@ struct H3Params {
   int n, k, act;
   int out_mode;
   int chunk_kb;             // K blocks accumulated in TMEM before the partial sum is drained into registers
+  int single;               // 1: ONE product x_hi . w_hi per K step (11-bit operands, ~5e-4 relative): candidate
+                            // pre-screening only -- 1/3 of the tensor work, 3/8 of the operand bytes, deeper ring
   // implicit-GEMM convolution (taps > 0): X is an NHWC image batch (4-D tensor maps), M = output pixels in (b, y, x)
   // order, K = taps x Cin; a 128-pixel M tile is a (tb x ty x tx) block of the output grid, a warp's 32 rows a
   // (wy x wx) block
@@ -74,7 +80,7 @@ struct H3Params {
 // pull every finished chunk out with tcgen05.ld and add it, round-to-nearest, into fp32 registers (128 per thread)
 // while the tensor core fills the other TMEM buffer with the next chunk.  24 truncating adds per chunk instead of
 // 3K/16 per tile: the result is as accurate as an fp32 FMA GEMM, at the same tensor-core rate.
-template <int CL>
+template <int CL, bool DIRECT>
 __global__ void __launch_bounds__(H3_THREADS, 1)
 linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__ CUtensorMap map_xlo,
                  const __grid_constant__ CUtensorMap map_wa, const __grid_constant__ CUtensorMap map_wb,
@@ -86,11 +92,14 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
   uint8_t* gen = smem_raw + (base - raw);
   const uint32_t epi = base + H3_STAGES * H3_STAGE_BYTES;
   const uint32_t bars = epi + H3_EPI_BYTES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + H3_STAGES * H3_STAGE_BYTES + H3_EPI_BYTES + 128);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + H3_STAGES * H3_STAGE_BYTES + H3_EPI_BYTES + 192);
   auto bar_full = [&](int s) { return bars + 8u * s; };
-  auto bar_empty = [&](int s) { return bars + 8u * (H3_STAGES + s); };
-  auto bar_cfull = [&](uint32_t b) { return bars + 8u * (2 * H3_STAGES + b); };
-  auto bar_cempty = [&](uint32_t b) { return bars + 8u * (2 * H3_STAGES + 2 + b); };
+  auto bar_empty = [&](int s) { return bars + 8u * (H3_MAX_STAGES + s); };
+  auto bar_cfull = [&](uint32_t b) { return bars + 8u * (2 * H3_MAX_STAGES + b); };
+  auto bar_cempty = [&](uint32_t b) { return bars + 8u * (2 * H3_MAX_STAGES + 2 + b); };
+  const bool single = p.single != 0;
+  const int nstages = single ? H3_STAGES_1P : H3_STAGES;
+  const uint32_t stage_bytes = single ? H3_STAGE_BYTES_1P : H3_STAGE_BYTES;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
@@ -109,7 +118,7 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wa) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wb) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wc) : "memory");
-    for (int s = 0; s < H3_STAGES; ++s) {
+    for (int s = 0; s < H3_MAX_STAGES; ++s) {
       mbar_init(bar_full(s), 1);
       mbar_init(bar_empty(s), CL);          // every CTA's tensor core must have consumed the stage
     }
@@ -162,20 +171,26 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
         }
         int tap = 0, cblk = 0;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % H3_STAGES;
-          const uint32_t ph = (it / H3_STAGES) & 1u;
+          const int s = static_cast<int>(it % nstages);
+          const uint32_t ph = (it / nstages) & 1u;
           mbar_wait(bar_empty(s), ph ^ 1u);
-          const uint32_t st = base + s * H3_STAGE_BYTES;
-          mbar_expect_tx(bar_full(s), H3_STAGE_BYTES);
+          const uint32_t st = base + s * stage_bytes;
+          mbar_expect_tx(bar_full(s), stage_bytes);
           if (p.taps > 0) {
             // shifted window of the input image for this tap; out-of-image pixels are zero-filled = zero padding
             const int ix = cx0 + p.dx[tap], iy = cy0 + p.dy[tap];
             tma_load_4d(st, &map_xhi, bar_full(s), cblk * H3_BK, ix, iy, cb0);
-            tma_load_4d(st + H3_X_BYTES, &map_xlo, bar_full(s), cblk * H3_BK, ix, iy, cb0);
+            if (!single) tma_load_4d(st + H3_X_BYTES, &map_xlo, bar_full(s), cblk * H3_BK, ix, iy, cb0);
             if (++cblk == p.cin_blocks) { cblk = 0; ++tap; }
           } else {
             tma_load_3d(st, &map_xhi, bar_full(s), kb * H3_BK, m0, grp);
-            tma_load_3d(st + H3_X_BYTES, &map_xlo, bar_full(s), kb * H3_BK, m0, grp);
+            if (!single) tma_load_3d(st + H3_X_BYTES, &map_xlo, bar_full(s), kb * H3_BK, m0, grp);
+          }
+          if (single) {                       // stage = [x_hi 8 KB | w_hi 16 KB]
+            const uint32_t w0 = st + H3_X_BYTES + wo;
+            if (CL > 1) tma_load_2d_mc(w0, &map_wb, bar_full(s), kb * H3_BK, wrow, kAllCtas);
+            else tma_load_2d(w0, &map_wb, bar_full(s), kb * H3_BK, wrow);
+            continue;
           }
           const uint32_t w0 = st + 2 * H3_X_BYTES + wo;
           if (CL > 1) {
@@ -209,21 +224,30 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
             tcgen05_fence_after();
             acc = tmem_base + buf * H3_BN;
           }
-          const int s = it % H3_STAGES;
-          const uint32_t ph = (it / H3_STAGES) & 1u;
+          const int s = static_cast<int>(it % nstages);
+          const uint32_t ph = (it / nstages) & 1u;
           mbar_wait(bar_full(s), ph);
           tcgen05_fence_after();
-          const uint32_t st = base + s * H3_STAGE_BYTES;
-          const uint64_t d_xhi = umma_desc_sw64(st), d_xlo = umma_desc_sw64(st + H3_X_BYTES);
-          const uint64_t d_wa = umma_desc_sw64(st + 2 * H3_X_BYTES);
-          const uint64_t d_wb = umma_desc_sw64(st + 2 * H3_X_BYTES + H3_W_BYTES);
-          const uint64_t d_wc = umma_desc_sw64(st + 2 * H3_X_BYTES + 2 * H3_W_BYTES);
+          const uint32_t st = base + s * stage_bytes;
+          if (single) {
+            const uint64_t d_xhi = umma_desc_sw64(st), d_wb = umma_desc_sw64(st + H3_X_BYTES);
 #pragma unroll
-          for (int kk = 0; kk < H3_BK / 16; ++kk) {
-            const uint64_t adv = static_cast<uint64_t>(kk * 2);    // 16 halfs = 32 bytes = 2 x 16-byte units
-            umma_f16(acc, d_xhi + adv, d_wa + adv, idesc, (in_chunk | kk) != 0 ? 1u : 0u);
-            umma_f16(acc, d_xlo + adv, d_wb + adv, idesc, 1u);
-            umma_f16(acc, d_xhi + adv, d_wc + adv, idesc, 1u);
+            for (int kk = 0; kk < H3_BK / 16; ++kk) {
+              const uint64_t adv = static_cast<uint64_t>(kk * 2);
+              umma_f16(acc, d_xhi + adv, d_wb + adv, idesc, (in_chunk | kk) != 0 ? 1u : 0u);
+            }
+          } else {
+            const uint64_t d_xhi = umma_desc_sw64(st), d_xlo = umma_desc_sw64(st + H3_X_BYTES);
+            const uint64_t d_wa = umma_desc_sw64(st + 2 * H3_X_BYTES);
+            const uint64_t d_wb = umma_desc_sw64(st + 2 * H3_X_BYTES + H3_W_BYTES);
+            const uint64_t d_wc = umma_desc_sw64(st + 2 * H3_X_BYTES + 2 * H3_W_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < H3_BK / 16; ++kk) {
+              const uint64_t adv = static_cast<uint64_t>(kk * 2);    // 16 halfs = 32 bytes = 2 x 16-byte units
+              umma_f16(acc, d_xhi + adv, d_wa + adv, idesc, (in_chunk | kk) != 0 ? 1u : 0u);
+              umma_f16(acc, d_xlo + adv, d_wb + adv, idesc, 1u);
+              umma_f16(acc, d_xhi + adv, d_wc + adv, idesc, 1u);
+            }
           }
           if (CL > 1) umma_commit_mc(bar_empty(s), kAllCtas);      // stage refillable once ALL CTAs' MMAs have read it
           else umma_commit(bar_empty(s));
@@ -240,6 +264,7 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
     const int ew = warp - 2;
     const int q = warp & 3;                                         // TMEM lane quarter this warp may read
     const int hcol = ew >> 2;                                       // which 128-column half of the tile it owns
+    const float oscale = single ? 1.f : kLoInv;                     // single product: x_hi . w_hi is unscaled
     const uint32_t box_sh = epi + static_cast<uint32_t>(ew) * H3_EPI_SLOT;
     uint8_t* box = gen + H3_STAGES * H3_STAGE_BYTES + ew * H3_EPI_SLOT;
     uint32_t cc = 0;
@@ -263,136 +288,171 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
       const int64_t row = static_cast<int64_t>(grp) * p.rows_per_batch + lrow;   // output rows are dense
       const int row0 = static_cast<int>(static_cast<int64_t>(grp) * p.rows_per_batch + m0 + q * 32);
 
-      // ---- drain every chunk of this tile into registers
+      // ---- drain all chunks but the last into registers (the first one is loaded straight into them)
       float acc[128];
-#pragma unroll
-      for (int i = 0; i < 128; ++i) acc[i] = 0.f;
       const int nchunks = (num_kb + chb - 1) / chb;
-      for (int c = 0; c < nchunks; ++c, ++cc) {
+      for (int c = 0; c + 1 < nchunks; ++c, ++cc) {
         const uint32_t buf = cc & 1u;
         mbar_wait(bar_cfull(buf), (cc >> 1) & 1u);
         tcgen05_fence_after();
         const uint32_t t0 = tmem_base + buf * H3_BN + (static_cast<uint32_t>(q * 32) << 16) +
                             static_cast<uint32_t>(hcol * 128);
+        if (c == 0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (hcol * 128 + j * 32 < n_inst) {                        // warp-uniform
-            uint32_t r[32];
-            tmem_ld32(t0 + j * 32, r);
-            tmem_ld_wait();
+          for (int j = 0; j < 4; ++j)
+            if (hcol * 128 + j * 32 < n_inst) tmem_ld32(t0 + j * 32, reinterpret_cast<uint32_t*>(&acc[j * 32]));
+          tmem_ld_wait();
+        } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) acc[j * 32 + i] += __uint_as_float(r[i]);
+          for (int j = 0; j < 8; ++j) {                               // 16 columns at a time: registers are scarce here
+            if (hcol * 128 + j * 16 < n_inst) {                        // warp-uniform
+              uint32_t r[16];
+              tmem_ld16(t0 + j * 16, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) acc[j * 16 + i] += __uint_as_float(r[i]);
+            }
           }
         }
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_cempty(buf));                 // the tensor core may refill this buffer
       }
+      // ---- the last chunk is read 32 columns at a time, combined with the register sums and emitted right away
+      const uint32_t lbuf = cc & 1u;
+      mbar_wait(bar_cfull(lbuf), (cc >> 1) & 1u);
+      tcgen05_fence_after();
+      ++cc;
+      const uint32_t tl = tmem_base + lbuf * H3_BN + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(hcol * 128);
+      const int jlast = hcol * 128 < n_inst ? min(3, (n_inst - hcol * 128 - 1) >> 5) : -1;   // last 32-column pass of this warp
+      if (jlast < 0) {
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_cempty(lbuf));
+      }
 
-      // ---- epilogue: scale, bias, residual, activation, store
+      // ---- epilogue: scale, bias, residual, activation, store -- 32 columns per pass, 8 at a time in registers
+      const int64_t rrow = p.taps > 0 ? static_cast<int64_t>(m_tile) * H3_BM + q * 32 + lane : row;   // residual row
+      const bool res_ok = p.r_hi != nullptr && tile_ok && (p.taps > 0 ? rrow < p.rows_per_batch : row_ok);
+      const bool relu = p.act == HOISDF_ACT_RELU;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int c0 = hcol * 128 + j * 32;
         if (c0 >= n_inst) continue;                                  // warp-uniform
         const float bl = (p.bias != nullptr && c0 + lane < n_here) ? __ldg(p.bias + n0 + c0 + lane) : 0.f;
-        float v[32];
+        float* a = &acc[j * 32];                                    // (static indices: stays in registers)
+        if (nchunks == 1) {
+          tmem_ld32(tl + j * 32, reinterpret_cast<uint32_t*>(a));
+          tmem_ld_wait();
+        } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = fmaf(acc[j * 32 + i], kLoInv, __shfl_sync(0xffffffffu, bl, i));
-        if (p.r_hi != nullptr) {
-          // split-half residual (ResNet bottleneck shortcut): this lane's row, 32 columns = 64 B per plane
-          const int64_t rr = p.taps > 0 ? static_cast<int64_t>(m_tile) * H3_BM + q * 32 + lane : row;
-          if (tile_ok && (p.taps > 0 ? rr < p.rows_per_batch : row_ok) && c0 < n_here) {
-            const uint4* ph = reinterpret_cast<const uint4*>(p.r_hi + rr * p.ldr + n0 + c0);
-            const uint4* pl = reinterpret_cast<const uint4*>(p.r_lo + rr * p.ldr + n0 + c0);
+          for (int h = 0; h < 2; ++h) {
+            uint32_t r[16];
+            tmem_ld16(tl + j * 32 + h * 16, r);
+            tmem_ld_wait();
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const uint4 a = __ldg(ph + g), b = __ldg(pl + g);
-              const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                v[g * 8 + 2 * i] += join_half(__ushort_as_half(static_cast<unsigned short>(aw[i] & 0xffffu)),
-                                              __ushort_as_half(static_cast<unsigned short>(bw[i] & 0xffffu)));
-                v[g * 8 + 2 * i + 1] += join_half(__ushort_as_half(static_cast<unsigned short>(aw[i] >> 16)),
-                                                  __ushort_as_half(static_cast<unsigned short>(bw[i] >> 16)));
-              }
-            }
+            for (int i = 0; i < 16; ++i) a[h * 16 + i] += __uint_as_float(r[i]);
           }
         }
-        if (p.out_mode == H3_OUT_F32_DIRECT) {
-          if (row_ok) {
-            float* yrow = p.y + row * p.ldy + n0;
-            const float* rrow = p.residual ? p.residual + row * p.ldy + n0 : nullptr;
-            const bool vec = ((p.ldy & 3) == 0) && aligned16(p.y) && (p.residual == nullptr || aligned16(p.residual));
+        if (j == jlast) {                                            // TMEM buffer fully read: hand it back
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_cempty(lbuf));
+        }
+        if (!DIRECT) {
+          // TMA-store paths stage the 32 x 32 block in this warp's smem slot: the previous store issued from it must
+          // have finished READING it
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+        }
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const int c = c0 + g * 4;
-              if (c >= n_here) break;
-              if (vec && c + 3 < n_here) {
-                float4 o = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-                if (rrow != nullptr) {
-                  const float4 rr = *reinterpret_cast<const float4*>(rrow + c);
-                  o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-                }
-                if (p.act == HOISDF_ACT_RELU) {
-                  o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-                }
-                *reinterpret_cast<float4*>(yrow + c) = o;
-              } else {
+        for (int g = 0; g < 4; ++g) {                                  // 8 columns: c0 + 8g .. c0 + 8g + 7
+          float v[8];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  if (c + i < n_here) {
-                    float o = v[g * 4 + i];
-                    if (rrow != nullptr) o += rrow[c + i];
-                    if (p.act == HOISDF_ACT_RELU) o = fmaxf(o, 0.f);
-                    yrow[c + i] = o;
+          for (int i = 0; i < 8; ++i)
+            v[i] = fmaf(a[g * 8 + i], oscale, __shfl_sync(0xffffffffu, bl, g * 8 + i));
+          if (res_ok && c0 + g * 8 < n_here) {
+            // split-half residual (ResNet bottleneck shortcut): this lane's row, 8 columns = 16 B per plane
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.r_hi + rrow * p.ldr + n0 + c0 + g * 8));
+            const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.r_lo + rrow * p.ldr + n0 + c0 + g * 8));
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              v[2 * i] += join_half(__ushort_as_half(static_cast<unsigned short>(aw[i] & 0xffffu)),
+                                    __ushort_as_half(static_cast<unsigned short>(bw[i] & 0xffffu)));
+              v[2 * i + 1] += join_half(__ushort_as_half(static_cast<unsigned short>(aw[i] >> 16)),
+                                        __ushort_as_half(static_cast<unsigned short>(bw[i] >> 16)));
+            }
+          }
+          if (DIRECT) {
+            if (row_ok) {
+              float* yrow = p.y + row * p.ldy + n0;
+              const float* rr = p.residual ? p.residual + row * p.ldy + n0 : nullptr;
+              const bool vec = ((p.ldy & 3) == 0) && aligned16(p.y) && (p.residual == nullptr || aligned16(p.residual));
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int c = c0 + g * 8 + h * 4;
+                if (c >= n_here) break;
+                if (vec && c + 3 < n_here) {
+                  float4 o = make_float4(v[h * 4], v[h * 4 + 1], v[h * 4 + 2], v[h * 4 + 3]);
+                  if (rr != nullptr) {
+                    const float4 t = *reinterpret_cast<const float4*>(rr + c);
+                    o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+                  }
+                  if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                  *reinterpret_cast<float4*>(yrow + c) = o;
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    if (c + i < n_here) {
+                      float o = v[h * 4 + i];
+                      if (rr != nullptr) o += rr[c + i];
+                      if (relu) o = fmaxf(o, 0.f);
+                      yrow[c + i] = o;
+                    }
                   }
                 }
               }
             }
+            continue;
           }
-          continue;
-        }
-        if (p.act == HOISDF_ACT_RELU) {
+          if (relu) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-        }
-        // TMA-store paths: stage the 32 x 32 block in this warp's slot; the previous store issued from it must have
-        // finished READING it
-        if (lane == 0) tma_store_wait_read<0>();
-        __syncwarp();
-        if (p.out_mode == H3_OUT_F32_TMA) {
-#pragma unroll
-          for (int g = 0; g < 8; ++g)      // 128-byte rows, 128B swizzle
-            *reinterpret_cast<float4*>(box + lane * 128 + ((g ^ (lane & 7)) << 4)) =
-                make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-        } else {
-          // split-half output: hi box at +0, lo' box at +2048, 64-byte rows, 64B swizzle
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint32_t hw[4], lw[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              __half h0, l0, h1, l1;
-              split_half(v[g * 8 + 2 * i], h0, l0);
-              split_half(v[g * 8 + 2 * i + 1], h1, l1);
-              hw[i] = static_cast<uint32_t>(__half_as_ushort(h0)) | (static_cast<uint32_t>(__half_as_ushort(h1)) << 16);
-              lw[i] = static_cast<uint32_t>(__half_as_ushort(l0)) | (static_cast<uint32_t>(__half_as_ushort(l1)) << 16);
-            }
+            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (p.out_mode == H3_OUT_F32_TMA) {              // 128-byte rows, 128B swizzle: two 16-byte units
+            *reinterpret_cast<float4*>(box + lane * 128 + (((2 * g) ^ (lane & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(box + lane * 128 + (((2 * g + 1) ^ (lane & 7)) << 4)) =
+                make_float4(v[4], v[5], v[6], v[7]);
+          } else {
+            // split-half output: hi box at +0, lo' box at +2048, 64-byte rows, 64B swizzle.  The single-product mode
+            // writes the hi plane only (its consumers read nothing else).
             const int off = lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4);
-            *reinterpret_cast<uint4*>(box + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            *reinterpret_cast<uint4*>(box + 2048 + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            uint32_t hw[4], lw[4];
+            if (single) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) hw[i] = cvt_f16x2_sat(v[2 * i], v[2 * i + 1]);
+              *reinterpret_cast<uint4*>(box + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) split_half2(v[2 * i], v[2 * i + 1], hw[i], lw[i]);
+              *reinterpret_cast<uint4*>(box + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              *reinterpret_cast<uint4*>(box + 2048 + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
           }
         }
+        if (DIRECT) continue;
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
           if (tile_ok && c0 < n_here) {
+            const bool two = p.out_mode == H3_OUT_SPLIT_TMA && !single;
             if (p.taps > 0) {
               tma_store_4d(&map_y0, box_sh, n0 + c0, ox, oy, ob);
-              if (p.out_mode == H3_OUT_SPLIT_TMA) tma_store_4d(&map_y1, box_sh + 2048, n0 + c0, ox, oy, ob);
+              if (two) tma_store_4d(&map_y1, box_sh + 2048, n0 + c0, ox, oy, ob);
             } else {
               tma_store_2d(&map_y0, box_sh, n0 + c0, row0);
-              if (p.out_mode == H3_OUT_SPLIT_TMA) tma_store_2d(&map_y1, box_sh + 2048, n0 + c0, row0);
+              if (two) tma_store_2d(&map_y1, box_sh + 2048, n0 + c0, row0);
             }
           }
           tma_store_commit();
@@ -492,7 +552,8 @@ template <int CL>
 static int max_clusters() {
   static int cached = -1;
   if (cached >= 0) return cached;
-  cudaFuncSetAttribute(linear_h3_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, H3_SMEM_BYTES);
+  cudaFuncSetAttribute(linear_h3_kernel<CL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, H3_SMEM_BYTES);
+  cudaFuncSetAttribute(linear_h3_kernel<CL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, H3_SMEM_BYTES);
   int n = 0;
   if (CL == 1) {
     cudaDeviceProp prop;
@@ -511,7 +572,7 @@ static int max_clusters() {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (cudaOccupancyMaxActiveClusters(&n, linear_h3_kernel<CL>, &cfg) != cudaSuccess || n <= 0) n = kNumSMs / CL;
+    if (cudaOccupancyMaxActiveClusters(&n, linear_h3_kernel<CL, false>, &cfg) != cudaSuccess || n <= 0) n = kNumSMs / CL;
     (void)cudaGetLastError();
   }
   cached = n;
@@ -528,8 +589,8 @@ static int launch_h3(const CUtensorMap* maps, const H3Params& p0, int64_t m_tile
   p.m_blocks = static_cast<int>(ceil_div(m_tiles, CL));
   const int64_t items = static_cast<int64_t>(p.m_blocks) * p.n_tiles;
   const int64_t clusters = items < max_clusters<CL>() ? items : max_clusters<CL>();
-  cudaError_t e = cudaFuncSetAttribute(linear_h3_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, H3_SMEM_BYTES);
-  if (e != cudaSuccess) return static_cast<int>(e);
+  const bool direct = p.out_mode == H3_OUT_F32_DIRECT;
+  cudaError_t e = cudaSuccess;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(clusters * CL));
   cfg.blockDim = dim3(H3_THREADS);
@@ -542,7 +603,10 @@ static int launch_h3(const CUtensorMap* maps, const H3Params& p0, int64_t m_tile
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, linear_h3_kernel<CL>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], p);
+  e = direct ? cudaLaunchKernelEx(&cfg, linear_h3_kernel<CL, true>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5],
+                                  maps[6], p)
+             : cudaLaunchKernelEx(&cfg, linear_h3_kernel<CL, false>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5],
+                                  maps[6], p);
   if (e != cudaSuccess) return static_cast<int>(e);
   return launch_status();
 }
@@ -622,6 +686,7 @@ HOISDF_API int hoisdf_linear_h3_fwd(const hoisdf_linear_h3_args* a, void* stream
   p.n_tiles = static_cast<int>(ceil_div(a->n, H3_BN));
   p.n = static_cast<int>(a->n); p.k = static_cast<int>(a->k); p.act = a->act; p.out_mode = out_mode;
   p.chunk_kb = a->chunk_kb;
+  p.single = a->single_pass ? 1 : 0;
   if (a->res_hi != nullptr || a->res_lo != nullptr) {
     if (a->res_hi == nullptr || a->res_lo == nullptr) return HOISDF_E_NULL;
     if (out_mode == H3_OUT_F32_DIRECT || a->residual != nullptr || (a->n & 31)) return HOISDF_E_UNSUPPORTED;
@@ -712,6 +777,7 @@ HOISDF_API int hoisdf_conv_h3_fwd(const hoisdf_conv_h3_args* a, void* stream) {
   p.n = static_cast<int>(a->cout); p.k = static_cast<int>(a->taps * a->cin); p.act = a->act;
   p.out_mode = split_out ? H3_OUT_SPLIT_TMA : H3_OUT_F32_TMA;
   p.chunk_kb = a->chunk_kb;
+  p.single = a->single_pass ? 1 : 0;
   p.taps = a->taps; p.cin_blocks = static_cast<int>(a->cin / H3_BK);
   p.out_w = static_cast<int>(a->out_w); p.out_h = static_cast<int>(a->out_h); p.stride = a->stride;
   p.wx = wx; p.wy = wy;

@@ -82,7 +82,7 @@ __global__ void posenc_split_kernel(const int32_t* __restrict__ lattice_index, c
   lo[r * ld + col] = l;
 }
 
-// out[r] = tanh(h[r,:512] . w4 + b4) with h in split-half format; one warp per row
+// out[r] = tanh(h[r,:512] . w4 + b4) with h in split-half format (lo == nullptr: hi plane only); one warp per row
 __global__ void __launch_bounds__(256) sdf_head_split_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo,
                                                              int64_t ldh, int64_t rows, const float* __restrict__ w4,
                                                              const float* __restrict__ b4, float* __restrict__ out,
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256) sdf_head_split_kernel(const __half* __res
   for (int q = 0; q < 2; ++q) {
     const int c = q * 256 + lane * 8;
     const uint4 ph = __ldg(reinterpret_cast<const uint4*>(hi + r * ldh + c));
-    const uint4 pl = __ldg(reinterpret_cast<const uint4*>(lo + r * ldh + c));
+    const uint4 pl = lo != nullptr ? __ldg(reinterpret_cast<const uint4*>(lo + r * ldh + c)) : make_uint4(0, 0, 0, 0);
     const float4 wa = __ldg(reinterpret_cast<const float4*>(w4 + c));
     const float4 wb = __ldg(reinterpret_cast<const float4*>(w4 + c + 4));
     const uint32_t hw[4] = {ph.x, ph.y, ph.z, ph.w}, lw[4] = {pl.x, pl.y, pl.z, pl.w};
@@ -273,7 +273,7 @@ HOISDF_API int hoisdf_sdf_decoder_h3_fwd(const hoisdf_sdf_weights_h3* w, uint16_
   auto layer = [&](int l, const uint16_t* xh, const uint16_t* xl, int64_t ld_in, int64_t k, uint16_t* yh, uint16_t* yl,
                    int64_t ld_out, int64_t n) {
     a = {xh, xl, ld_in, 0, 0, w->w[l][0], w->w[l][1], w->w[l][2], w->ldw[l], w->b[l], nullptr,
-         nullptr, 0, yh, yl, ld_out, rows, n, k, HOISDF_ACT_RELU, w->chunk_kb};
+         nullptr, 0, yh, yl, ld_out, rows, n, k, HOISDF_ACT_RELU, w->chunk_kb, nullptr, nullptr, 0, w->single_pass};
     return hoisdf_linear_h3_fwd(&a, stream);
   };
   // linh0: x[:, 0:289] -> h_a (512);  linh1: h_a -> x[:, 296:519] (223);  linh2: x[:, 0:519] (weight columns
@@ -283,7 +283,7 @@ HOISDF_API int hoisdf_sdf_decoder_h3_fwd(const hoisdf_sdf_weights_h3* w, uint16_
   if ((st = layer(2, x_hi, x_lo, ldx, kSkipOffH + kH1, ha_hi, ha_lo, ldh, 512)) != HOISDF_OK) return st;
   if ((st = layer(3, ha_hi, ha_lo, ldh, 512, hb_hi, hb_lo, ldh, 512)) != HOISDF_OK) return st;
   sdf_head_split_kernel<<<static_cast<unsigned>(ceil_div(rows, 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __half*>(hb_hi), reinterpret_cast<const __half*>(hb_lo), ldh, rows, w->w4, w->b4, out_sdf,
-      clamp);
+      reinterpret_cast<const __half*>(hb_hi), w->single_pass ? nullptr : reinterpret_cast<const __half*>(hb_lo), ldh, rows,
+      w->w4, w->b4, out_sdf, clamp);      // single-product chain: only the hi planes were written
   return launch_status();
 }

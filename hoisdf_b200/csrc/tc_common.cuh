@@ -28,6 +28,17 @@ __device__ __forceinline__ void split_half(float x, __half& hi, __half& lo) {
   const float r = (x - __half2float(hi)) * kLoScale;
   lo = __float2half_rn(fminf(fmaxf(r, -65504.f), 65504.f));
 }
+// two values at once, packed (element 0 in the low half): one saturating f16x2 conversion per plane, no clamps
+__device__ __forceinline__ uint32_t cvt_f16x2_sat(float e0, float e1) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(e1), "f"(e0));
+  return r;
+}
+__device__ __forceinline__ void split_half2(float x0, float x1, uint32_t& hi2, uint32_t& lo2) {
+  hi2 = cvt_f16x2_sat(x0, x1);
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi2));
+  lo2 = cvt_f16x2_sat((x0 - hf.x) * kLoScale, (x1 - hf.y) * kLoScale);
+}
 __device__ __forceinline__ float join_half(__half hi, __half lo) {
   return fmaf(__half2float(lo), kLoInv, __half2float(hi));
 }
@@ -168,6 +179,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
 }

@@ -199,12 +199,17 @@ class Model(nn.Module):
         return CandidatePlan(center_joint, cam_intr, bbox, sdf_scale)
 
     def sdf_infer(self, feature_pyramid, center_joint, cam_intr, bbox, sdf_scale, num_points, type="hand",
-                  plan: Optional[CandidatePlan] = None, taps: Optional[dict] = None):
+                  plan: Optional[CandidatePlan] = None, taps: Optional[dict] = None, level: int = 0):
         """upstream model.py:246-355 -> (pose_points (B,P,3), pose_sdf (B,P,1), pose_posenc3d (B,P,30), None).
 
         Candidate lattice points of the whole batch are compacted into one row buffer (sample-major, ascending
         lattice index -- the order upstream's boolean-mask indexing yields), pushed through the projected-map
         gather + linear_sdfin + SDF decoder, and the `num_points` smallest |sdf| per sample are selected.
+
+        `level` picks the screening cascade: 0 = single-product FP16 -> FP16x3 -> exact fp32, 1 = FP16x3 -> exact,
+        2 = exact fp32 FMA on every candidate.  Each cascade step is verified on the device; a direct call (no
+        `taps`) reads the verdict and escalates the level itself, `Model.forward` reads it once after the whole
+        forward has been queued (`_hot_path`).
         """
         ctx = self._ctx(feature_pyramid)
         if plan is None:
@@ -228,6 +233,7 @@ class Model(nn.Module):
         step = int(cfg.max_rows_per_pass)
         cap = min(step, total)
         bufs = {}
+        nmin = int(n_f.min())
 
         def fp32_buffers(n):
             if "f32" not in bufs or bufs["f32"][0].shape[0] < n:
@@ -236,79 +242,115 @@ class Model(nn.Module):
                                torch.empty(n, ops.ROW_LD, device=dev, dtype=torch.float32))
             return bufs["f32"]
 
-        def evaluate_all(passes):
-            """SDF of every candidate row on the tensor cores (FP16x3 on split-half rows by default; TC_MODE 'tf32':
-            passes = 3: 3xTF32, 1: single TF32 pass) or, with tensor cores disabled, on the fp32 FMA kernels."""
-            if ops.use_h3():
-                hs, rs = self._row_buffers(cap, dev)
-                hs2 = ops.SplitRows.empty(cap, 512, dev)
-                for r0 in range(0, total, step):
-                    n = min(step, total - r0)
-                    offs = plan.offsets if r0 == 0 else plan.offsets - r0
-                    ops.gather(gmaps, cand_uv[r0:r0 + n], b, mode=ops.GATHER_SUM, out=hs.head(n), row_offsets=offs,
-                               bias=sdfin[0].b, act=ops.ACT_RELU, img_hw=cfg.input_img_shape)
-                    ops.linear(hs.head(n), sdfin[1], ops.ACT_RELU, out=rs.head(n).window(0, 256),
-                               chunk_kb=ops.SCREEN_CHUNK_KB)
-                    ops.posenc(rs.head(n), lattice_index=cand_index[r0:r0 + n], bins=cfg.bins_n)
-                    ops.sdf_decoder(packed, rs.head(n), h_a=hs.head(n), h_b=hs2.head(n), out=sdf[r0:r0 + n],
-                                    chunk_kb=ops.SCREEN_CHUNK_KB)
-                return
-            h, h2, rows = fp32_buffers(cap)
+        def h3_buffers(n):
+            if "h3" not in bufs or bufs["h3"][0].rows < n:
+                hs, rs = self._row_buffers(n, dev)
+                bufs["h3"] = (hs, rs, ops.SplitRows.empty(n, 512, dev))
+            return bufs["h3"]
+
+        def chain_h3(uv, index, out, single, row_offsets=None, rows_per_sample=0):
+            """gather -> linear_sdfin[1] -> posenc -> SDF decoder on the FP16x3 kernels (split-half rows).  These values
+            only RANK candidates for the next, more accurate stage: one TMEM drain per tile, and with `single` ONE
+            tensor-core product per K step instead of three."""
+            n = uv.shape[0]
+            hs, rs, hs2 = h3_buffers(n)
+            ops.gather(gmaps, uv, b, mode=ops.GATHER_SUM, out=hs.head(n), row_offsets=row_offsets,
+                       rows_per_sample=rows_per_sample, bias=sdfin[0].b, act=ops.ACT_RELU, img_hw=cfg.input_img_shape)
+            ops.linear(hs.head(n), sdfin[1], ops.ACT_RELU, out=rs.head(n).window(0, 256),
+                       chunk_kb=ops.SCREEN_CHUNK_KB, single=single)
+            ops.posenc(rs.head(n), lattice_index=index, bins=cfg.bins_n)
+            ops.sdf_decoder(packed, rs.head(n), h_a=hs.head(n), h_b=hs2.head(n), out=out,
+                            chunk_kb=ops.SCREEN_CHUNK_KB, single=single)
+
+        def chain_f32(uv, index, out, passes, exact, row_offsets=None, rows_per_sample=0):
+            """The same chain on fp32 rows: bit-faithful fp32 FMA kernels (exact), or the 3xTF32 / 1xTF32 tensor-core
+            kernels of TC_MODE 'tf32'."""
+            n = uv.shape[0]
+            h, h2, rows = fp32_buffers(n)
+            ops.gather(gmaps, uv, b, mode=ops.GATHER_SUM, out=h[:n], row_offsets=row_offsets,
+                       rows_per_sample=rows_per_sample, bias=sdfin[0].b, act=ops.ACT_RELU, img_hw=cfg.input_img_shape)
+            ops.linear(h[:n], ops.fma_only(sdfin[1]) if exact else sdfin[1], ops.ACT_RELU, out=rows[:n, :256],
+                       passes=passes)
+            ops.posenc(rows[:n], lattice_index=index, bins=cfg.bins_n)
+            ops.sdf_decoder(packed, rows[:n], h_a=h[:n], h_b=h2[:n], out=out, exact=exact,
+                            screening=(passes == 1 and not exact))
+
+        def evaluate_all(passes, single=False):
+            """SDF of every candidate row: FP16x3 / single-product FP16 on split-half rows by default; TC_MODE 'tf32':
+            passes = 3: 3xTF32, 1: single TF32 pass; with tensor cores disabled the fp32 FMA kernels."""
+            h3 = ops.use_h3()
+            if h3:
+                h3_buffers(cap)
+            else:
+                fp32_buffers(cap)
             for r0 in range(0, total, step):
                 n = min(step, total - r0)
                 offs = plan.offsets if r0 == 0 else plan.offsets - r0
-                ops.gather(gmaps, cand_uv[r0:r0 + n], b, mode=ops.GATHER_SUM, out=h[:n], row_offsets=offs,
-                           bias=sdfin[0].b, act=ops.ACT_RELU, img_hw=cfg.input_img_shape)
-                ops.linear(h[:n], sdfin[1], ops.ACT_RELU, out=rows[:n, :256], passes=passes)
-                ops.posenc(rows[:n], lattice_index=cand_index[r0:r0 + n], bins=cfg.bins_n)
-                ops.sdf_decoder(packed, rows[:n], h_a=h[:n], h_b=h2[:n], out=sdf[r0:r0 + n], screening=passes == 1)
+                if h3:
+                    chain_h3(cand_uv[r0:r0 + n], cand_index[r0:r0 + n], sdf[r0:r0 + n], single, row_offsets=offs)
+                else:
+                    chain_f32(cand_uv[r0:r0 + n], cand_index[r0:r0 + n], sdf[r0:r0 + n], passes,
+                              exact=not ops.USE_TENSOR_CORES, row_offsets=offs)
 
-        def rerank(margin):
-            """Keep the P + margin best rows of the tensor-core ranking (lattice order), re-evaluate them with the
-            bit-faithful fp32 FMA kernels.  Returns (exact sdf, lattice indices, offsets, diagnostics)."""
-            pm = int(min(num_points + margin, int(n_f.min()), 8192))
-            _, _, s_sdf, _, _, s_row = ops.select_points(sdf, plan.offsets, cand_index, b, pm, cfg.bins_n, 0.0,
+        def refine(src_sdf, src_offsets, src_index, src_uv, keep, target, evaluate):
+            """One cascade step: keep the `keep` best rows per sample of the current ranking (lattice order) and
+            re-evaluate them with the more accurate `evaluate`.  The step is loss-free for the `target` best rows
+            of the accurate ranking whenever the coarse error is smaller than the |sdf| gap between the accurate
+            rank-`target` value and the coarse rank-`keep` value; both are measured here on the device."""
+            _, _, s_sdf, _, _, s_row = ops.select_points(src_sdf, src_offsets, src_index, b, keep, cfg.bins_n, 0.0,
                                                          order_by_row=True)
             s_row = s_row.view(-1).long()
-            s_index = cand_index.index_select(0, s_row)
-            s_uv = cand_uv.index_select(0, s_row)
-            m = b * pm
-            h, h2, rows = fp32_buffers(m)
-            ops.gather(gmaps, s_uv, b, mode=ops.GATHER_SUM, out=h[:m], rows_per_sample=pm, bias=sdfin[0].b,
-                       act=ops.ACT_RELU, img_hw=cfg.input_img_shape)
-            ops.linear(h[:m], ops.fma_only(sdfin[1]), ops.ACT_RELU, out=rows[:m, :256])
-            ops.posenc(rows[:m], lattice_index=s_index, bins=cfg.bins_n)
-            exact = ops.sdf_decoder(packed, rows[:m], h_a=h[:m], h_b=h2[:m], exact=True)
-            s_offsets = torch.arange(0, (b + 1) * pm, pm, device=dev, dtype=torch.int64)
-            tc = s_sdf.view(b, pm)
-            ex = exact.view(b, pm)
-            err = (tc - ex).abs().max()                                   # observed screening error
-            kth = ex.abs().kthvalue(num_points, dim=1).values            # rank-P exact |sdf|
-            gap = tc.abs().max(dim=1).values - kth                        # rank-(P+margin) screening |sdf| - rank-P
-            return exact, s_index, s_offsets, dict(rows=s_row, err=err, gap=gap, pm=pm)
+            new_index = src_index.index_select(0, s_row)
+            new_uv = src_uv.index_select(0, s_row)
+            new_sdf = torch.empty(b * keep, device=dev, dtype=torch.float32)
+            evaluate(new_uv, new_index, new_sdf, rows_per_sample=keep)
+            new_offsets = torch.arange(0, (b + 1) * keep, keep, device=dev, dtype=torch.int64)
+            coarse, fine = s_sdf.view(b, keep), new_sdf.view(b, keep)
+            err = (coarse - fine).abs().max()                               # observed error of the coarse values
+            kth = fine.abs().kthvalue(target, dim=1).values                # accurate rank-`target` |sdf|
+            gap = coarse.abs().max(dim=1).values - kth                      # coarse rank-`keep` |sdf| - that
+            return new_sdf, new_offsets, new_index, new_uv, dict(rows=s_row, err=err, gap=gap, keep=keep,
+                                                                 verified=(gap > 3.0 * err).all())
 
-        screened = None
+        exact_eval = lambda uv, idx, out, rows_per_sample: chain_f32(uv, idx, out, 3, True,      # noqa: E731
+                                                                     rows_per_sample=rows_per_sample)
+        screened = pre = None
+        keep_exact = int(min(num_points + cfg.screen_margin_safe, nmin, 8192))
         if not ops.USE_TENSOR_CORES:
             evaluate_all(3)                                               # fp32 FMA everywhere: already exact
             sdf_sel, cand_sel, offs_sel = sdf, cand_index, plan.offsets
-        elif int(n_f.min()) <= num_points:
+        elif nmin <= num_points or level >= 2:
             # no room for a screening margin: every candidate is selected anyway, rank them all exactly
             with _tensor_cores(False):
                 evaluate_all(3)
             sdf_sel, cand_sel, offs_sel = sdf, cand_index, plan.offsets
+        elif ops.use_h3():
+            # Coarse-to-fine cascade.  (A) single-product FP16 on ALL candidates (1/3 of the tensor work) keeps the best
+            # P + screen_margin_single rows; (B) FP16x3 re-evaluates those and keeps P + screen_margin_safe;
+            # (C) the fp32 FMA kernels re-evaluate those and the final P are selected from the exact values.
+            # Equal to an all-fp32 pass whenever each stage's error is smaller than the |sdf| gap it leaves --
+            # verified on the device; `screen_ok` is read by the caller after the forward has been queued, and a
+            # failed check re-runs the query without stage A (or raises if the FP16x3 stage itself fails).
+            keep_a = int(min(num_points + cfg.screen_margin_single, 8192))
+            use_a = bool(cfg.screen_single) and level == 0 and nmin > keep_a and keep_a > keep_exact
+            evaluate_all(3, single=use_a)
+            cur = (sdf, plan.offsets, cand_index, cand_uv)
+            if use_a:
+                h3_eval = lambda uv, idx, out, rows_per_sample: chain_h3(uv, idx, out, False,    # noqa: E731
+                                                                         rows_per_sample=rows_per_sample)
+                *cur, pre = refine(*cur, keep_a, keep_exact, h3_eval)
+            sdf_sel, offs_sel, cand_sel, _, screened = refine(*cur, keep_exact, num_points, exact_eval)
         else:
-            # Coarse-to-fine selection: tensor cores rank ALL candidates, the fp32 FMA kernels re-rank the best
-            # P + margin.  Equal to an all-fp32 pass whenever the screening error is smaller than the |sdf| gap
-            # between rank P and rank P + margin -- verified on the device (observed error on the re-evaluated
-            # rows x 3 against that gap); if the single-pass screening fails the check, redo it with 3xTF32.
-            passes = 1 if (int(cfg.screen_passes) == 1 and not ops.use_h3()) else 3
+            # TC_MODE 'tf32': 3xTF32 (or opt-in single-pass TF32, verified with one tiny D2H read) screening + exact re-rank
+            passes = 1 if int(cfg.screen_passes) == 1 else 3
             evaluate_all(passes)
-            sdf_sel, cand_sel, offs_sel, screened = rerank(cfg.screen_margin if passes == 1 else cfg.screen_margin_safe)
-            screened["verified"] = (screened["gap"] > 3.0 * screened["err"]).all()   # device tensor, read lazily
-            if passes == 1 and not bool(screened["verified"]):                        # opt-in mode: one tiny D2H read
+            margin = cfg.screen_margin if passes == 1 else cfg.screen_margin_safe
+            cur = (sdf, plan.offsets, cand_index, cand_uv)
+            sdf_sel, offs_sel, cand_sel, _, screened = refine(*cur, int(min(num_points + margin, nmin, 8192)),
+                                                              num_points, exact_eval)
+            if passes == 1 and not bool(screened["verified"]):
                 evaluate_all(3)
-                sdf_sel, cand_sel, offs_sel, screened = rerank(cfg.screen_margin_safe)
-                screened["verified"] = (screened["gap"] > 3.0 * screened["err"]).all()
+                sdf_sel, offs_sel, cand_sel, _, screened = refine(*cur, keep_exact, num_points, exact_eval)
         sel, pts, out_sdf, pe, _flag, _ = ops.select_points(sdf_sel, offs_sel, cand_sel, b, num_points, cfg.bins_n,
                                                             cfg.ClampingDistance)
         if taps is not None:
@@ -316,8 +358,17 @@ class Model(nn.Module):
             if screened is not None:
                 taps["screen_gap"] = screened["gap"]
                 taps["screen_err"] = screened["err"]
-                taps["screen_rows"] = screened["rows"]
-                taps["screen_verified"] = screened.get("verified", True)
+                taps["screen_rows"] = screened["rows"] if pre is None else pre["rows"].index_select(0, screened["rows"])
+                taps["screen_verified"] = screened["verified"]
+            if pre is not None:
+                taps["pre_gap"], taps["pre_err"], taps["pre_verified"] = pre["gap"], pre["err"], pre["verified"]
+            taps["single_pass"] = pre is not None
+            taps["exact_sdf"], taps["exact_index"] = sdf_sel, cand_sel     # what the final selection ranked
+        elif ops.use_h3() and screened is not None:
+            ok = screened["verified"] if pre is None else (screened["verified"] & pre["verified"])
+            if not bool(ok):                                               # direct call: one tiny D2H read
+                return self.sdf_infer(ctx, center_joint, cam_intr, bbox, sdf_scale, num_points, type, plan, None,
+                                      level + 1)
         return pts, out_sdf, pe, None
 
     # ------------------------------------------------------------------------------------------------
@@ -395,7 +446,7 @@ class Model(nn.Module):
         with torch.no_grad():
             return self._hot_path(feature_pyramid, meta_info, plans, mano_params)
 
-    def _hot_path(self, feature_pyramid, meta_info, plans, mano_params=None):
+    def _hot_path(self, feature_pyramid, meta_info, plans, mano_params=None, level: int = 0):
         root = meta_info["mano_root"].to(torch.float32).contiguous()
         objc = meta_info["obj_center_cam"].to(torch.float32).contiguous()
         K = meta_info["cam_intr"].to(torch.float32).contiguous()
@@ -408,8 +459,18 @@ class Model(nn.Module):
         S = Ph + Po
         hs_scale, os_scale = cfg.hand_sdf_scale, cfg.obj_sdf_scale
         th, to = {}, {}
-        hand_points, hand_sdf, hand_pe, _ = self.sdf_infer(ctx, root, K, None, hs_scale, Ph, "hand", plans[0], th)
-        obj_points, obj_sdf, obj_pe, _ = self.sdf_infer(ctx, objc, K, None, os_scale, Po, "obj", plans[1], to)
+        hand_points, hand_sdf, hand_pe, _ = self.sdf_infer(ctx, root, K, None, hs_scale, Ph, "hand", plans[0], th, level)
+        obj_points, obj_sdf, obj_pe, _ = self.sdf_infer(ctx, objc, K, None, os_scale, Po, "obj", plans[1], to, level)
+        # verdict of the screening cascade (device-side checks): copied to pinned memory now, read after the rest of
+        # the forward has been queued -- the GPU never waits for the host
+        flags = [t[k] for t in (th, to) for k in ("pre_verified", "screen_verified") if k in t]
+        verdict = None
+        if flags:
+            if getattr(self, "_ok_host", None) is None:
+                self._ok_host = torch.empty(1, dtype=torch.bool, pin_memory=True)
+            self._ok_host.copy_(torch.stack(flags).all().view(1), non_blocking=True)
+            verdict = torch.cuda.Event()
+            verdict.record()
 
         self.hand_sigmoid_beta.data.clamp_(min=2e-3)   # upstream model.py:124 (side effect on the parameter)
         self.obj_sigmoid_beta.data.clamp_(min=2e-3)
@@ -468,6 +529,12 @@ class Model(nn.Module):
             "obj_trans_out": obj_trans[-1],
             "hand_joints_out": hand_joints[-1],
         }
+        if verdict is not None:
+            verdict.synchronize()
+            if not bool(self._ok_host[0]):
+                if level >= 2:
+                    raise RuntimeError("point-selection screening could not be verified")
+                return self._hot_path(ctx, meta_info, plans, mano_params, level + 1)   # rare: escalate the cascade
         self.last_taps = dict(
             hand=th, obj=to, hand_points=hand_points, hand_sdf=hand_sdf, hand_posenc=hand_pe, obj_points=obj_points,
             obj_sdf=obj_sdf, obj_posenc=obj_pe, hand_fea=hand_fea, obj_fea=obj_fea, hand_o_sdf=hand_o_sdf,
@@ -502,6 +569,9 @@ class Model(nn.Module):
                                       x_batch=(rows_per_group, group_len * xs.ld), m=m)
                     if not last and not tile_safe:
                         h = ops.split_rows(h)
+                elif last and pw.n <= ops.NARROW_MAX_N and isinstance(h, ops.SplitRows):
+                    # a handful of output columns: the HBM-bound narrow kernel beats a 128 x 256 tensor-core tile
+                    h = ops.linear_narrow(h, pw.w, pw.b, act, m=m)
                 else:
                     h = ops.linear_h3(h, pw.h3, act, split_out=not last)
             return h if h.is_contiguous() else h.contiguous()

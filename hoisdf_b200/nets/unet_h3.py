@@ -120,7 +120,11 @@ class UNetH3:
             (sv, sbn, _), = _seq_conv_bn(d.conv0d)
             pk["conv0d"] = _pack_conv(sv, sbn)
         for name in ("convOut_hm", "convOut_hand_seg", "convOut_obj_seg"):
-            pk[name] = [(_pack_conv(cv, bn), relu) for cv, bn, relu in _seq_conv_bn(getattr(d, name))]
+            layers = _seq_conv_bn(getattr(d, name))
+            pk[name] = [(_pack_conv(cv, bn), relu) for cv, bn, relu in layers[:-1]]
+            # the last 1x1 convolution has ONE output channel: fp32 weights for the narrow (HBM-bound) Linear kernel
+            w, b = _fold_bn(layers[-1][0].weight, layers[-1][0].bias, layers[-1][1], 0)
+            pk[name + ".last"] = (w.reshape(w.shape[0], -1).float().contiguous(), b)
         self._packed, self._key = pk, key
         return pk
 
@@ -204,10 +208,9 @@ class UNetH3:
         outs = []
         for name in ("convOut_hm", "convOut_hand_seg", "convOut_obj_seg"):
             hcur = x
-            layers = pk[name]
-            for j, (pw, relu) in enumerate(layers):
-                last = j == len(layers) - 1
-                hcur = ops.linear_h3(hcur, pw, ops.ACT_RELU if relu else ops.ACT_NONE, split_out=not last)
-            outs.append(hcur.reshape(b, 1, h, w))
-        out = torch.cat([outs[0], outs[1].sigmoid(), outs[2].sigmoid()], 1)
-        return pyr, out
+            for pw, relu in pk[name]:
+                hcur = ops.linear_h3(hcur, pw, ops.ACT_RELU if relu else ops.ACT_NONE, split_out=True)
+            wl, bl = pk[name + ".last"]
+            act = ops.ACT_NONE if name == "convOut_hm" else ops.ACT_SIGMOID      # upstream module.py:211,215
+            outs.append(ops.linear_narrow(hcur, wl, bl, act).reshape(b, 1, h, w))
+        return pyr, torch.cat(outs, 1)

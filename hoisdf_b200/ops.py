@@ -13,7 +13,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _capi
-from ._capi import ACT_NONE, ACT_RELU, GATHER_CONCAT, GATHER_SUM, check, lib
+from ._capi import ACT_NONE, ACT_RELU, ACT_SIGMOID, GATHER_CONCAT, GATHER_SUM, check, lib
 
 ROW_LD = 516          # padded SDF row-buffer pitch (see csrc/sdf.cu)
 ROWH_LD = 520         # pitch (halfs per plane) of the split-half row buffer of the FP16x3 path
@@ -163,7 +163,8 @@ def fma_only(pw: PackedLinear) -> PackedLinear:
 
 
 def linear(x, pw: PackedLinear, act: int = ACT_NONE, out=None, residual: Optional[torch.Tensor] = None,
-           out_ld: Optional[int] = None, passes: int = 3, split_out: bool = False, chunk_kb: Optional[int] = None):
+           out_ld: Optional[int] = None, passes: int = 3, split_out: bool = False, chunk_kb: Optional[int] = None,
+           single: bool = False):
     """x: (M, >=K) 2-D fp32 (unit inner stride) or SplitRows.  Returns (M, N) fp32 (a view of a (M, out_ld) buffer if
     padded) -- or, on the FP16x3 path with split_out / a SplitRows `out`, the result in split-half format."""
     if isinstance(x, SplitRows) or isinstance(out, SplitRows) or (use_h3() and pw.h3 is not None):
@@ -174,7 +175,8 @@ def linear(x, pw: PackedLinear, act: int = ACT_NONE, out=None, residual: Optiona
             ld = out_ld or round_up(pw.n, 4)
             alloc = torch.empty if ld == pw.n else torch.zeros
             out = alloc(xs.rows, ld, device=xs.buf.device, dtype=torch.float32)[:, :pw.n]
-        return linear_h3(xs, pw.h3, act, out=out, residual=residual, split_out=split_out, chunk_kb=chunk_kb)
+        return linear_h3(xs, pw.h3, act, out=out, residual=residual, split_out=split_out, chunk_kb=chunk_kb,
+                         single=single)
     assert x.dim() == 2 and x.stride(1) == 1 and x.shape[1] >= pw.k, (x.shape, x.stride(), pw.k)
     m = x.shape[0]
     if out is None:
@@ -298,7 +300,7 @@ class PackedLinearH3:
 
 def linear_h3(x: SplitRows, pw: PackedLinearH3, act: int = ACT_NONE, out=None, residual: Optional[torch.Tensor] = None,
               split_out: bool = False, x_batch=(0, 0), m: Optional[int] = None, chunk_kb: Optional[int] = None,
-              residual_split: Optional[SplitRows] = None):
+              residual_split: Optional[SplitRows] = None, single: bool = False):
     """Y = act(X . W^T + b) (+ residual) on the FP16x3 tensor-core kernel.  `out` is an fp32 (M, N) tensor view (unit
     inner stride) or a SplitRows window; allocated when None (fp32, or split-half if split_out).
     x_batch = (rows_per_batch, batch_stride in halfs) walks strided row groups of `x` (m rows in total)."""
@@ -323,6 +325,7 @@ def linear_h3(x: SplitRows, pw: PackedLinearH3, act: int = ACT_NONE, out=None, r
         a.y, a.ldy, a.y_hi, a.y_lo, a.ldyh = out.data_ptr(), out.stride(0), None, None, 0
     a.m, a.n, a.k, a.act = m, pw.n, pw.k, act
     a.chunk_kb = int(pw.chunk_kb if chunk_kb is None else chunk_kb)
+    a.single_pass = int(single)
     if residual_split is not None:
         assert residual_split.cols >= pw.n and residual_split.rows >= m
         a.res_hi, a.res_lo, a.ldr = residual_split.hi_ptr, residual_split.lo_ptr, residual_split.ld
@@ -334,7 +337,27 @@ def linear_h3(x: SplitRows, pw: PackedLinearH3, act: int = ACT_NONE, out=None, r
         e0.record()
         check(lib.hoisdf_linear_h3_fwd(C.byref(a), _stream()), "hoisdf_linear_h3_fwd")
         e1.record()
-        PROFILE.append(("linear_h3", 2.0 * m * pw.n * pw.k, e0, e1))
+        PROFILE.append(("linear_h3", 2.0 * m * pw.n * pw.k, e0, e1, "M=%d N=%d K=%d chunk=%d %s%s" % (
+            m, pw.n, pw.k, a.chunk_kb, "split" if isinstance(out, SplitRows) else "f32", " single" if single else "")))
+    return out
+
+
+NARROW_MAX_N = 24
+
+
+def linear_narrow(x: SplitRows, w: torch.Tensor, bias: Optional[torch.Tensor], act: int = ACT_NONE,
+                  out: Optional[torch.Tensor] = None, m: Optional[int] = None) -> torch.Tensor:
+    """Y (M, N <= 24) = act(X . W^T + b): split-half X, fp32 W (N, >= K, unit inner stride, K even) -> fp32."""
+    assert w.dim() == 2 and w.stride(1) == 1 and w.dtype == torch.float32 and w.is_cuda
+    n = w.shape[0]
+    k = w.shape[1] if w.shape[1] <= x.cols else x.cols
+    m = x.rows if m is None else m
+    if out is None:
+        out = torch.empty(m, n, device=w.device, dtype=torch.float32)
+    assert out.stride(1) == 1 and out.shape[0] >= m
+    _count(1)
+    check(lib.hoisdf_linear_narrow_split_fwd(x.hi_ptr, x.lo_ptr, x.ld, m, w.data_ptr(), w.stride(0), _ptr(bias), n, k, act,
+                                             out.data_ptr(), out.stride(0), _stream()), "hoisdf_linear_narrow_split_fwd")
     return out
 
 
@@ -376,7 +399,8 @@ def conv_h3(x: SplitRows, batch: int, in_h: int, in_w: int, cin: int, pw: Packed
         e0.record()
         check(lib.hoisdf_conv_h3_fwd(C.byref(a), _stream()), "hoisdf_conv_h3_fwd")
         e1.record()
-        PROFILE.append(("conv_h3", flops, e0, e1))
+        PROFILE.append(("conv_h3", flops, e0, e1, "conv B=%d %dx%d->%dx%d Cin=%d Cout=%d taps=%d s=%d chunk=%d" % (
+            batch, in_h, in_w, out_h, out_w, cin, pw.n, len(taps), stride, a.chunk_kb)))
     return out
 
 
@@ -599,7 +623,7 @@ def posenc(rows_buf, *, lattice_index=None, points=None, bins: int = 64):
 
 def sdf_decoder(packed: PackedSdfDecoder, rows_buf, h_a=None, h_b=None, clamp: float = 0.0,
                 out: Optional[torch.Tensor] = None, exact: bool = False, screening: bool = False,
-                chunk_kb: int = 0) -> torch.Tensor:
+                chunk_kb: int = 0, single: bool = False) -> torch.Tensor:
     if isinstance(rows_buf, SplitRows):
         rows, dev = rows_buf.rows, rows_buf.buf.device
         h_a = h_a if h_a is not None else SplitRows.empty(rows, 512, dev)
@@ -608,6 +632,7 @@ def sdf_decoder(packed: PackedSdfDecoder, rows_buf, h_a=None, h_b=None, clamp: f
         assert h_a.ld == h_b.ld and rows_buf.col0 == 0 and h_a.col0 == 0 and h_b.col0 == 0
         _count(5)
         packed.struct_h3.chunk_kb = int(chunk_kb)
+        packed.struct_h3.single_pass = int(single)
         if PROFILE is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -616,7 +641,8 @@ def sdf_decoder(packed: PackedSdfDecoder, rows_buf, h_a=None, h_b=None, clamp: f
                                             out.data_ptr(), float(clamp), _stream()), "hoisdf_sdf_decoder_h3_fwd")
         if PROFILE is not None:
             e1.record()
-            PROFILE.append(("sdf_decoder_h3", SDF_DECODER_FLOPS * rows, e0, e1))
+            PROFILE.append(("sdf_decoder_h3", SDF_DECODER_FLOPS * rows, e0, e1, "sdf_decoder rows=%d chunk=%d%s" % (
+                rows, chunk_kb, " single" if single else "")))
         return out
     rows = rows_buf.shape[0]
     dev = rows_buf.device

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 7
+#define HOISDF_ABI_VERSION 9
 
 enum {
   HOISDF_OK = 0,
@@ -104,6 +104,10 @@ typedef struct {
                                         r of these planes (pitch ldr halfs); added before the activation; needs the
                                         TMA-store epilogue (no fp32 `residual`, n % 32 == 0) -- the shortcut of the
                                         ResNet bottleneck, upstream common/nets/resnet.py (torchvision Bottleneck) */
+  int32_t single_pass;               /* 1: ONE tensor-core product x_hi . w_hi instead of three (11-bit operands,
+                                        ~5e-4 relative error, 3x less tensor work): ONLY for pre-screening top-k
+                                        candidates that an FP16x3 pass and then an exact pass re-rank, never for a
+                                        result that is returned */
 } hoisdf_linear_h3_args;
 
 int hoisdf_linear_h3_fwd(const hoisdf_linear_h3_args* args, void* stream);
@@ -133,6 +137,7 @@ typedef struct {
   const uint16_t* res_hi; const uint16_t* res_lo; int64_t ldr;
                                      /* optional split-half residual: output pixel (b, y, x) reads row
                                         (b * out_h + y) * out_w + x of these planes; cout % 32 == 0 */
+  int32_t single_pass;               /* see hoisdf_linear_h3_args */
 } hoisdf_conv_h3_args;
 
 int hoisdf_conv_h3_fwd(const hoisdf_conv_h3_args* args, void* stream);
@@ -150,6 +155,13 @@ int hoisdf_stem_im2col_split(const float* img, int64_t batch, int64_t h, int64_t
                              int64_t ldh, void* stream);
 int hoisdf_maxpool3x3s2_split(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx, int64_t batch, int64_t h,
                               int64_t w, int64_t c, uint16_t* y_hi, uint16_t* y_lo, int64_t ldy, void* stream);
+
+/* Narrow Linear for the last layer of the small heads (upstream main/model.py:81-90; convOut_* of
+ * common/nets/module.py): y (m, n <= 24) = act(x . w^T + bias), x in split-half format (k even), w fp32 (n, ldw),
+ * act: 0 none, 1 ReLU, 2 sigmoid.  fp32 FMA arithmetic on the joined values; HBM-bound (one warp per row). */
+int hoisdf_linear_narrow_split_fwd(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx, int64_t m, const float* w,
+                                   int64_t ldw, const float* bias, int64_t n, int64_t k, int32_t act, float* y,
+                                   int64_t ldy, void* stream);
 
 /* W (n, ldw) fp32 with k valid columns -> planes A, B, C, each (n, ldh) halfs, columns [k, ldh) zeroed. */
 int hoisdf_pack_h3(const float* w, int64_t n, int64_t k, int64_t ldw, uint16_t* w_a, uint16_t* w_b, uint16_t* w_c,
@@ -271,6 +283,7 @@ typedef struct {
   const uint16_t* w[4][3]; int64_t ldw[4]; const float* b[4];
   const float* w4; const float* b4;
   int32_t chunk_kb;                  /* passed to every hoisdf_linear_h3_fwd of the chain (0 = default) */
+  int32_t single_pass;               /* likewise (candidate pre-screening) */
 } hoisdf_sdf_weights_h3;
 
 int hoisdf_sdf_decoder_h3_fwd(const hoisdf_sdf_weights_h3* wts, uint16_t* x_hi, uint16_t* x_lo, int64_t ldx,

@@ -540,3 +540,36 @@ def test_resnet_h3_matches_cudnn(cuda):
     for k in ("stride2", "stride4", "stride8", "stride16"):
         assert rel_err(skips[k].nchw(), ref_skips[k]) < 1e-4, (k, rel_err(skips[k].nchw(), ref_skips[k]))
     assert torch.equal(skips2["stride4"].nchw(), skips["stride4"].nchw()) and torch.equal(feat2.nchw(), feat.nchw())
+
+
+@pytest.mark.parametrize("m,n,k,act", [(1000, 1, 64, 2), (333, 3, 256, 0), (4097, 20, 256, 1), (77, 24, 34, 0)])
+def test_linear_narrow_split(cuda, m, n, k, act):
+    """hoisdf_linear_narrow_split_fwd (last layer of the small heads) against fp64; x read through a column window."""
+    from hoisdf_b200 import ops
+    x, w, b = rnd(101, m, k), rnd(102, n, k, lo=-0.2, hi=0.2), rnd(103, n)
+    wide = ops.SplitRows.empty(m, ops.round_up(k, 8) + 16, cuda)
+    wide.buf.fill_(float("nan"))
+    xs = ops.split_rows(x.to(cuda), out=wide.window(8, k), kpad=k if k % 4 == 0 else None) if k % 4 == 0 else None
+    if xs is None:          # k not a multiple of 4: split into an exact-width buffer
+        xs = ops.split_rows(x.to(cuda))
+    y = ops.linear_narrow(ops.SplitRows(xs.buf, k, xs.col0), w.to(cuda), b.to(cuda), act)
+    ref = x.double() @ w.double().T + b.double()
+    ref = ref.relu() if act == 1 else (torch.sigmoid(ref) if act == 2 else ref)
+    assert y.shape == (m, n) and rel_err(y, ref) < 2e-6
+
+
+def test_linear_h3_single_product(cuda):
+    """single_pass = 1: ONE fp16 tensor-core product per K step (candidate pre-screening): 11-bit operands -> ~5e-4."""
+    from hoisdf_b200 import ops
+    m, k, n = 1000, 519, 512
+    x, w, b = rnd(111, m, k), rnd(112, n, k, lo=-0.1, hi=0.1), rnd(113, n)
+    pw = ops.PackedLinearH3.pack(w.to(cuda), b.to(cuda))
+    xs = ops.split_rows(x.to(cuda))
+    ref = (x.double() @ w.double().T + b.double()).relu()
+    y1 = ops.linear_h3(xs, pw, ops.ACT_RELU, split_out=True, single=True, chunk_kb=ops.SCREEN_CHUNK_KB)
+    y3 = ops.linear_h3(xs, pw, ops.ACT_RELU, split_out=True)
+    # the single-product mode writes the hi plane only (fp16 values)
+    e1, e3 = rel_err(y1.buf[:, 0, :n].float(), ref), rel_err(y3.float(), ref)
+    assert 1e-5 < e1 < 2e-3 and e3 < 3e-6, (e1, e3)
+    yf = ops.linear_h3(xs, pw, ops.ACT_NONE, single=True)                      # fp32 output, default chunking
+    assert rel_err(yf, x.double() @ w.double().T + b.double()) < 2e-3
