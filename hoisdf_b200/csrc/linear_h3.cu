@@ -80,7 +80,10 @@ struct H3Params {
 // pull every finished chunk out with tcgen05.ld and add it, round-to-nearest, into fp32 registers (128 per thread)
 // while the tensor core fills the other TMEM buffer with the next chunk.  24 truncating adds per chunk instead of
 // 3K/16 per tile: the result is as accurate as an fp32 FMA GEMM, at the same tensor-core rate.
-template <int CL, bool DIRECT>
+// Template parameters: CL = cluster size (CTAs sharing an N tile); OUT = H3_OUT_*; SINGLE = one tensor-core product per
+// K step (pre-screening); RES = split-half residual added in the epilogue.  Compile-time modes keep each
+// instantiation's epilogue small (instruction cache) and branch-free.
+template <int CL, int OUT, bool SINGLE, bool RES>
 __global__ void __launch_bounds__(H3_THREADS, 1)
 linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__ CUtensorMap map_xlo,
                  const __grid_constant__ CUtensorMap map_wa, const __grid_constant__ CUtensorMap map_wb,
@@ -97,7 +100,8 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
   auto bar_empty = [&](int s) { return bars + 8u * (H3_MAX_STAGES + s); };
   auto bar_cfull = [&](uint32_t b) { return bars + 8u * (2 * H3_MAX_STAGES + b); };
   auto bar_cempty = [&](uint32_t b) { return bars + 8u * (2 * H3_MAX_STAGES + 2 + b); };
-  const bool single = p.single != 0;
+  constexpr bool single = SINGLE;
+  constexpr bool DIRECT = OUT == H3_OUT_F32_DIRECT;
   const int nstages = single ? H3_STAGES_1P : H3_STAGES;
   const uint32_t stage_bytes = single ? H3_STAGE_BYTES_1P : H3_STAGE_BYTES;
 
@@ -333,7 +337,7 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
 
       // ---- epilogue: scale, bias, residual, activation, store -- 32 columns per pass, 8 at a time in registers
       const int64_t rrow = p.taps > 0 ? static_cast<int64_t>(m_tile) * H3_BM + q * 32 + lane : row;   // residual row
-      const bool res_ok = p.r_hi != nullptr && tile_ok && (p.taps > 0 ? rrow < p.rows_per_batch : row_ok);
+      const bool res_ok = RES && tile_ok && (p.taps > 0 ? rrow < p.rows_per_batch : row_ok);
       const bool relu = p.act == HOISDF_ACT_RELU;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -371,7 +375,7 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
 #pragma unroll
           for (int i = 0; i < 8; ++i)
             v[i] = fmaf(a[g * 8 + i], oscale, __shfl_sync(0xffffffffu, bl, g * 8 + i));
-          if (res_ok && c0 + g * 8 < n_here) {
+          if (RES && res_ok && c0 + g * 8 < n_here) {
             // split-half residual (ResNet bottleneck shortcut): this lane's row, 8 columns = 16 B per plane
             const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.r_hi + rrow * p.ldr + n0 + c0 + g * 8));
             const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.r_lo + rrow * p.ldr + n0 + c0 + g * 8));
@@ -420,7 +424,7 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
           }
-          if (p.out_mode == H3_OUT_F32_TMA) {              // 128-byte rows, 128B swizzle: two 16-byte units
+          if (OUT == H3_OUT_F32_TMA) {                     // 128-byte rows, 128B swizzle: two 16-byte units
             *reinterpret_cast<float4*>(box + lane * 128 + (((2 * g) ^ (lane & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
             *reinterpret_cast<float4*>(box + lane * 128 + (((2 * g + 1) ^ (lane & 7)) << 4)) =
                 make_float4(v[4], v[5], v[6], v[7]);
@@ -446,7 +450,7 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
         __syncwarp();
         if (lane == 0) {
           if (tile_ok && c0 < n_here) {
-            const bool two = p.out_mode == H3_OUT_SPLIT_TMA && !single;
+            constexpr bool two = OUT == H3_OUT_SPLIT_TMA && !single;
             if (p.taps > 0) {
               tma_store_4d(&map_y0, box_sh, n0 + c0, ox, oy, ob);
               if (two) tma_store_4d(&map_y1, box_sh + 2048, n0 + c0, ox, oy, ob);
@@ -552,8 +556,8 @@ template <int CL>
 static int max_clusters() {
   static int cached = -1;
   if (cached >= 0) return cached;
-  cudaFuncSetAttribute(linear_h3_kernel<CL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, H3_SMEM_BYTES);
-  cudaFuncSetAttribute(linear_h3_kernel<CL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, H3_SMEM_BYTES);
+  auto kern = linear_h3_kernel<CL, H3_OUT_SPLIT_TMA, false, false>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, H3_SMEM_BYTES);
   int n = 0;
   if (CL == 1) {
     cudaDeviceProp prop;
@@ -572,7 +576,7 @@ static int max_clusters() {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (cudaOccupancyMaxActiveClusters(&n, linear_h3_kernel<CL, false>, &cfg) != cudaSuccess || n <= 0) n = kNumSMs / CL;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) n = kNumSMs / CL;
     (void)cudaGetLastError();
   }
   cached = n;
@@ -582,15 +586,11 @@ static int max_clusters() {
 static int g_h3_force_cluster = 0;   // developer hook: 0 = automatic
 static int g_h3_chunk_kb = H3_CHUNK_KB;   // developer hook: K blocks per accumulation chunk
 
-template <int CL>
-static int launch_h3(const CUtensorMap* maps, const H3Params& p0, int64_t m_tiles, cudaStream_t s) {
-  H3Params p = p0;
-  if (p.chunk_kb <= 0) p.chunk_kb = g_h3_chunk_kb > 0 ? g_h3_chunk_kb : H3_CHUNK_KB;
-  p.m_blocks = static_cast<int>(ceil_div(m_tiles, CL));
-  const int64_t items = static_cast<int64_t>(p.m_blocks) * p.n_tiles;
-  const int64_t clusters = items < max_clusters<CL>() ? items : max_clusters<CL>();
-  const bool direct = p.out_mode == H3_OUT_F32_DIRECT;
-  cudaError_t e = cudaSuccess;
+template <int CL, int OUT, bool SINGLE, bool RES>
+static int launch_h3_inst(const CUtensorMap* maps, const H3Params& p, int64_t clusters, cudaStream_t s) {
+  auto kern = linear_h3_kernel<CL, OUT, SINGLE, RES>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, H3_SMEM_BYTES);
+  if (e != cudaSuccess) return static_cast<int>(e);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(clusters * CL));
   cfg.blockDim = dim3(H3_THREADS);
@@ -603,12 +603,33 @@ static int launch_h3(const CUtensorMap* maps, const H3Params& p0, int64_t m_tile
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = direct ? cudaLaunchKernelEx(&cfg, linear_h3_kernel<CL, true>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5],
-                                  maps[6], p)
-             : cudaLaunchKernelEx(&cfg, linear_h3_kernel<CL, false>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5],
-                                  maps[6], p);
+  e = cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], p);
   if (e != cudaSuccess) return static_cast<int>(e);
   return launch_status();
+}
+
+template <int CL>
+static int launch_h3(const CUtensorMap* maps, const H3Params& p0, int64_t m_tiles, cudaStream_t s) {
+  H3Params p = p0;
+  if (p.chunk_kb <= 0) p.chunk_kb = g_h3_chunk_kb > 0 ? g_h3_chunk_kb : H3_CHUNK_KB;
+  p.m_blocks = static_cast<int>(ceil_div(m_tiles, CL));
+  const int64_t items = static_cast<int64_t>(p.m_blocks) * p.n_tiles;
+  const int64_t clusters = items < max_clusters<CL>() ? items : max_clusters<CL>();
+  const bool res = p.r_hi != nullptr;
+  if (p.single && (res || p.out_mode == H3_OUT_F32_DIRECT)) return HOISDF_E_UNSUPPORTED;
+  switch (p.out_mode) {
+    case H3_OUT_F32_TMA:
+      if (p.single) return launch_h3_inst<CL, H3_OUT_F32_TMA, true, false>(maps, p, clusters, s);
+      return res ? launch_h3_inst<CL, H3_OUT_F32_TMA, false, true>(maps, p, clusters, s)
+                 : launch_h3_inst<CL, H3_OUT_F32_TMA, false, false>(maps, p, clusters, s);
+    case H3_OUT_SPLIT_TMA:
+      if (p.single) return launch_h3_inst<CL, H3_OUT_SPLIT_TMA, true, false>(maps, p, clusters, s);
+      return res ? launch_h3_inst<CL, H3_OUT_SPLIT_TMA, false, true>(maps, p, clusters, s)
+                 : launch_h3_inst<CL, H3_OUT_SPLIT_TMA, false, false>(maps, p, clusters, s);
+    default:
+      if (res) return HOISDF_E_UNSUPPORTED;
+      return launch_h3_inst<CL, H3_OUT_F32_DIRECT, false, false>(maps, p, clusters, s);
+  }
 }
 
 }  // namespace hoisdf
@@ -653,7 +674,7 @@ HOISDF_API int hoisdf_linear_h3_fwd(const hoisdf_linear_h3_args* a, void* stream
   const int64_t tpb = ceil_div(rpb, H3_BM);
   const int64_t m_tiles = groups * tpb;
   int cl = m_tiles >= 2 ? 2 : 1;   // measured: pairs beat quads (quads leave SMs idle and add lockstep stalls)
-  if (g_h3_force_cluster == 1 || g_h3_force_cluster == 2 || g_h3_force_cluster == 4) cl = g_h3_force_cluster;
+  if (g_h3_force_cluster == 1 || g_h3_force_cluster == 2) cl = g_h3_force_cluster;
   CUtensorMap maps[7];
   if (!map_x_3d(&maps[0], a->x_hi, groups, rpb, a->k, a->ldx, gstride)) return HOISDF_E_UNSUPPORTED;
   if (!map_x_3d(&maps[1], a->x_lo, groups, rpb, a->k, a->ldx, gstride)) return HOISDF_E_UNSUPPORTED;
@@ -696,7 +717,6 @@ HOISDF_API int hoisdf_linear_h3_fwd(const hoisdf_linear_h3_args* a, void* stream
     p.ldr = a->ldr;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (cl == 4) return launch_h3<4>(maps, p, m_tiles, s);
   if (cl == 2) return launch_h3<2>(maps, p, m_tiles, s);
   return launch_h3<1>(maps, p, m_tiles, s);
 }
@@ -745,7 +765,7 @@ HOISDF_API int hoisdf_conv_h3_fwd(const hoisdf_conv_h3_args* a, void* stream) {
   }
   const int64_t m_tiles = ceil_div(m, H3_BM);
   int cl = m_tiles >= 2 ? 2 : 1;
-  if (g_h3_force_cluster == 1 || g_h3_force_cluster == 2 || g_h3_force_cluster == 4) cl = g_h3_force_cluster;
+  if (g_h3_force_cluster == 1 || g_h3_force_cluster == 2) cl = g_h3_force_cluster;
   const void* wp[3] = {a->w_a, a->w_b, a->w_c};
   for (int i = 0; i < 3; ++i)
     if (!map_half_2d(&maps[2 + i], wp[i], a->cout, a->taps * a->cin, a->ldw, H3_BK, H3_BN / cl,
@@ -795,7 +815,6 @@ HOISDF_API int hoisdf_conv_h3_fwd(const hoisdf_conv_h3_args* a, void* stream) {
     p.ldr = a->ldr;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (cl == 4) return launch_h3<4>(maps, p, m_tiles, s);
   if (cl == 2) return launch_h3<2>(maps, p, m_tiles, s);
   return launch_h3<1>(maps, p, m_tiles, s);
 }

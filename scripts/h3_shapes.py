@@ -17,13 +17,14 @@ def rnd(*shape, s=1.0):
     return (torch.rand(*shape, generator=g) * 2 - 1).mul_(s).to(dev)
 
 
-def lin(m, n, k, split=True, residual=False, chunk=0, act=1):
+def lin(m, n, k, split=True, residual=False, chunk=0, act=1, single=False):
     x = ops.split_rows(rnd(m, k))
     pw = ops.PackedLinearH3.pack(rnd(n, k, s=0.1), rnd(n), chunk_kb=chunk)
     res = ops.split_rows(rnd(m, n)) if residual else None
     out = ops.SplitRows.empty(m, n, dev) if split else torch.empty(m, n, device=dev)
-    name = "lin M=%d N=%d K=%d %s%s chunk=%d" % (m, n, k, "split" if split else "f32", " +res" if residual else "", chunk)
-    return name, 2.0 * m * n * k, lambda: ops.linear_h3(x, pw, act, out=out, residual_split=res)
+    name = "lin M=%d N=%d K=%d %s%s chunk=%d%s" % (m, n, k, "split" if split else "f32", " +res" if residual else "", chunk,
+                                                  " single" if single else "")
+    return name, 2.0 * m * n * k, lambda: ops.linear_h3(x, pw, act, out=out, residual_split=res, single=single)
 
 
 def conv(b, h, cin, cout, stride=1, chunk=0):
@@ -37,6 +38,7 @@ def conv(b, h, cin, cout, stride=1, chunk=0):
 
 
 CASES = [
+    lin(628248, 512, 512, chunk=1 << 20, single=True),
     lin(131072, 256, 64, residual=True, chunk=1),
     lin(524288, 64, 128),
     lin(65536, 1024, 256),
