@@ -65,6 +65,10 @@ class Config:
     # the selection without stage A.
     screen_single = True
     screen_margin_single = 1024
+    # linear_sdfin layer 0 applied to the pyramid (Model: PyramidContext.gmaps) on the FP16x3 GEMM with a TMEM drain
+    # every `projection_chunk_kb` K blocks instead of the fp32 FMA kernel (3.2 ms -> 0.6 ms at batch 32)
+    tc_projection = True
+    projection_chunk_kb = 1
     # U-Net decoder (the step before the hot path) on the FP16x3 tensor-core convolution kernels
     # instead of cuDNN's fp32 FMA convolutions (measured 3e-5 relative difference on the pyramid; 2.3x faster at B=4)
     tc_unet = True

@@ -48,6 +48,7 @@ class PyramidContext:
 
     def __init__(self, feature_pyramid: Dict[str, torch.Tensor], model: "Model"):
         self.maps = [ops.to_nhwc(feature_pyramid[name]) for name in cfg.mutliscale_layers]
+        self.split = getattr(feature_pyramid, "split", {})        # split-half copies the U-Net already produced
         self.batch = self.maps[0].shape[0]
         self.channels = sum(m.shape[3] for m in self.maps)
         self._model = model
@@ -57,16 +58,28 @@ class PyramidContext:
     def gmaps(self):
         if self._gmaps is None:
             w0 = self._model.linear_sdfin.packed()[0]
-            # K up to 2048 here and the result feeds the top-k-critical candidate SDF: keep the fp32 FMA kernel
-            # (the tensor-core kernel's accumulate-truncation error grows with K; this stage is ~2% of a step)
-            w0 = ops.PackedLinear(w0.w, w0.b, w0.n, w0.k, w0.ldw, None, None)
             if w0.k != self.channels:
                 raise RuntimeError("pyramid has %d channels, linear_sdfin expects %d" % (self.channels, w0.k))
+            # K up to 2048 and the result feeds the top-k-critical candidate SDF.  Default: the FP16x3 GEMM draining
+            # its TMEM accumulator every K block (fp32-FMA-grade result, cfg.projection_chunk_kb); the projected maps
+            # are shared by every stage of the selection cascade, so their rounding cannot reorder it.
+            # cfg.tc_projection = False: the fp32 FMA kernel.
+            tc = bool(cfg.tc_projection) and ops.use_h3() and w0.h3 is not None
+            if not tc:
+                w0 = ops.PackedLinear(w0.w, w0.b, w0.n, w0.k, w0.ldw, None, None)
             g, off = [], 0
-            for m in self.maps:
+            for name, m in zip(cfg.mutliscale_layers, self.maps):
                 b, h, w, c = m.shape
                 out = torch.empty(b, h, w, w0.n, device=m.device, dtype=torch.float32)
-                ops.linear(m.view(b * h * w, c), w0.cols(off, off + c), ops.ACT_NONE, out=out.view(b * h * w, w0.n))
+                wl = w0.cols(off, off + c)
+                if tc and wl.h3 is not None:
+                    xs = self.split.get(name)
+                    if xs is None:
+                        xs = ops.split_rows(m.view(b * h * w, c))
+                    ops.linear_h3(xs, wl.h3, ops.ACT_NONE, out=out.view(b * h * w, w0.n),
+                                  chunk_kb=int(cfg.projection_chunk_kb))
+                else:
+                    ops.linear(m.view(b * h * w, c), ops.fma_only(wl), ops.ACT_NONE, out=out.view(b * h * w, w0.n))
                 g.append(out)
                 off += c
             self._gmaps = g

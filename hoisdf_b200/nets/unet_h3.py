@@ -30,6 +30,15 @@ TAPS_1X1 = [(0, 0)]
 _DECONV_TAPS = {0: [(1, 0), (3, -1)], 1: [(0, 1), (2, 0)]}     # parity -> [(k index, input offset)]
 
 
+class Pyramid(dict):
+    """Feature pyramid {name: logical-NCHW fp32 tensor}; `split[name]` holds the same level as NHWC rows in split-half
+    format when the producer had it anyway (saves the consumer a conversion pass)."""
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.split = {}
+
+
 class SplitMap:
     """An NHWC feature map in split-half format: `rows` holds b*h*w pixel rows of (at least) c channels."""
 
@@ -169,9 +178,10 @@ class UNetH3:
         pk = self._pack()
         x, b, h, w, cx = feat.rows, feat.b, feat.h, feat.w, feat.c
         dev = x.buf.device
-        pyr = {}
+        pyr = Pyramid()
         if self.big:
             pyr["stride32"] = img_feat if img_feat is not None else feat.nchw()
+            pyr.split["stride32"] = x if x.cols == cx else ops.SplitRows(x.buf, cx, x.col0)
         else:
             p0 = pk["conv0d"]
             lvl = torch.empty(b, h, w, p0.n, device=dev, dtype=torch.float32)
@@ -203,6 +213,7 @@ class UNetH3:
             ops.conv_h3(cat, b, ho, wo, cs + cu, pc, TAPS_3X3, ho, wo, act=ops.ACT_RELU, out=lvl.view(-1, pc.n))
             pyr[name] = lvl.permute(0, 3, 1, 2)
             x = ops.split_rows(lvl.view(-1, pc.n))
+            pyr.split[name] = x
             h, w, cx = ho, wo, pc.n
         # 1x1 heads on the stride-2 level: heat map, hand / object segmentation (sigmoid)
         outs = []
