@@ -64,6 +64,9 @@ class Config:
     # for the exact stage).  Every stage is verified on the device (gap > 3 x observed error); a failed check re-runs
     # the selection without stage A.
     screen_single = True
+    # kernels of the last cascade stage: "h3" = FP16x3 GEMM draining TMEM every K block (measured max |sdf - oracle|
+    # 2.4e-8 .. 3.4e-8, the fp32 FMA kernels: 2.8e-8 .. 5.2e-8; scripts/selection_error.py) | "fma" = fp32 FMA kernels
+    final_stage = "h3"
     screen_margin_single = 1024
     # linear_sdfin layer 0 applied to the pyramid (Model: PyramidContext.gmaps) on the FP16x3 GEMM with a TMEM drain
     # every `projection_chunk_kb` K blocks instead of the fp32 FMA kernel (3.2 ms -> 0.6 ms at batch 32)

@@ -261,7 +261,7 @@ class Model(nn.Module):
                 bufs["h3"] = (hs, rs, ops.SplitRows.empty(n, 512, dev))
             return bufs["h3"]
 
-        def chain_h3(uv, index, out, single, row_offsets=None, rows_per_sample=0):
+        def chain_h3(uv, index, out, single, row_offsets=None, rows_per_sample=0, chunk_kb=ops.SCREEN_CHUNK_KB):
             """gather -> linear_sdfin[1] -> posenc -> SDF decoder on the FP16x3 kernels (split-half rows).  These values
             only RANK candidates for the next, more accurate stage: one TMEM drain per tile, and with `single` ONE
             tensor-core product per K step instead of three."""
@@ -270,10 +270,10 @@ class Model(nn.Module):
             ops.gather(gmaps, uv, b, mode=ops.GATHER_SUM, out=hs.head(n), row_offsets=row_offsets,
                        rows_per_sample=rows_per_sample, bias=sdfin[0].b, act=ops.ACT_RELU, img_hw=cfg.input_img_shape)
             ops.linear(hs.head(n), sdfin[1], ops.ACT_RELU, out=rs.head(n).window(0, 256),
-                       chunk_kb=ops.SCREEN_CHUNK_KB, single=single)
+                       chunk_kb=chunk_kb, single=single)
             ops.posenc(rs.head(n), lattice_index=index, bins=cfg.bins_n)
             ops.sdf_decoder(packed, rs.head(n), h_a=hs.head(n), h_b=hs2.head(n), out=out,
-                            chunk_kb=ops.SCREEN_CHUNK_KB, single=single)
+                            chunk_kb=chunk_kb, single=single)
 
         def chain_f32(uv, index, out, passes, exact, row_offsets=None, rows_per_sample=0):
             """The same chain on fp32 rows: bit-faithful fp32 FMA kernels (exact), or the 3xTF32 / 1xTF32 tensor-core
@@ -325,9 +325,15 @@ class Model(nn.Module):
             return new_sdf, new_offsets, new_index, new_uv, dict(rows=s_row, err=err, gap=gap, keep=keep,
                                                                  verified=(gap > 3.0 * err).all())
 
-        exact_eval = lambda uv, idx, out, rows_per_sample: chain_f32(uv, idx, out, 3, True,      # noqa: E731
-                                                                     rows_per_sample=rows_per_sample)
+        if cfg.final_stage == "h3" and ops.use_h3():
+            # final ranking on the FP16x3 GEMM with a TMEM drain every K block (fp32-FMA-grade values)
+            exact_eval = lambda uv, idx, out, rows_per_sample: chain_h3(uv, idx, out, False,      # noqa: E731
+                                                                        rows_per_sample=rows_per_sample, chunk_kb=1)
+        else:
+            exact_eval = lambda uv, idx, out, rows_per_sample: chain_f32(uv, idx, out, 3, True,   # noqa: E731
+                                                                         rows_per_sample=rows_per_sample)
         screened = pre = None
+        single_used = False
         keep_exact = int(min(num_points + cfg.screen_margin_safe, nmin, 8192))
         if not ops.USE_TENSOR_CORES:
             evaluate_all(3)                                               # fp32 FMA everywhere: already exact
@@ -339,20 +345,28 @@ class Model(nn.Module):
             sdf_sel, cand_sel, offs_sel = sdf, cand_index, plan.offsets
         elif ops.use_h3():
             # Coarse-to-fine cascade.  (A) single-product FP16 on ALL candidates (1/3 of the tensor work) keeps the best
-            # P + screen_margin_single rows; (B) FP16x3 re-evaluates those and keeps P + screen_margin_safe;
-            # (C) the fp32 FMA kernels re-evaluate those and the final P are selected from the exact values.
-            # Equal to an all-fp32 pass whenever each stage's error is smaller than the |sdf| gap it leaves --
+            # P + screen_margin_single rows; final stage: FP16x3 with a TMEM drain every K block re-evaluates those
+            # and the final P are selected from its values (cfg.final_stage = "fma": (B) FP16x3 keeps
+            # P + screen_margin_safe, (C) the fp32 FMA kernels re-evaluate those).
+            # Equal to ranking ALL candidates with the final stage whenever each step's error is smaller than the |sdf| gap it leaves --
             # verified on the device; `screen_ok` is read by the caller after the forward has been queued, and a
             # failed check re-runs the query without stage A (or raises if the FP16x3 stage itself fails).
             keep_a = int(min(num_points + cfg.screen_margin_single, 8192))
             use_a = bool(cfg.screen_single) and level == 0 and nmin > keep_a and keep_a > keep_exact
             evaluate_all(3, single=use_a)
             cur = (sdf, plan.offsets, cand_index, cand_uv)
-            if use_a:
-                h3_eval = lambda uv, idx, out, rows_per_sample: chain_h3(uv, idx, out, False,    # noqa: E731
-                                                                         rows_per_sample=rows_per_sample)
-                *cur, pre = refine(*cur, keep_a, keep_exact, h3_eval)
-            sdf_sel, offs_sel, cand_sel, _, screened = refine(*cur, keep_exact, num_points, exact_eval)
+            single_used = use_a
+            if cfg.final_stage == "h3":
+                # the final stage is itself a tensor-core pass (FP16x3 draining TMEM every K block: measured as close
+                # to the oracle as the fp32 FMA kernels), cheap enough to take all of stage A's survivors at once
+                sdf_sel, offs_sel, cand_sel, _, screened = refine(*cur, keep_a if use_a else keep_exact, num_points,
+                                                                  exact_eval)
+            else:
+                if use_a:
+                    h3_eval = lambda uv, idx, out, rows_per_sample: chain_h3(uv, idx, out, False,    # noqa: E731
+                                                                             rows_per_sample=rows_per_sample)
+                    *cur, pre = refine(*cur, keep_a, keep_exact, h3_eval)
+                sdf_sel, offs_sel, cand_sel, _, screened = refine(*cur, keep_exact, num_points, exact_eval)
         else:
             # TC_MODE 'tf32': 3xTF32 (or opt-in single-pass TF32, verified with one tiny D2H read) screening + exact re-rank
             passes = 1 if int(cfg.screen_passes) == 1 else 3
@@ -375,7 +389,7 @@ class Model(nn.Module):
                 taps["screen_verified"] = screened["verified"]
             if pre is not None:
                 taps["pre_gap"], taps["pre_err"], taps["pre_verified"] = pre["gap"], pre["err"], pre["verified"]
-            taps["single_pass"] = pre is not None
+            taps["single_pass"] = single_used
             taps["exact_sdf"], taps["exact_index"] = sdf_sel, cand_sel     # what the final selection ranked
         elif ops.use_h3() and screened is not None:
             ok = screened["verified"] if pre is None else (screened["verified"] & pre["verified"])

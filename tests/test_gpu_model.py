@@ -76,7 +76,10 @@ def check_selection(taps_dev, taps_ref, P):
     return worst_all, worst
 
 
-def test_sdf_infer(setup):
+@pytest.mark.parametrize("final_stage", ["h3", "fma"])
+def test_sdf_infer(setup, final_stage, monkeypatch):
+    from hoisdf_b200.config import cfg
+    monkeypatch.setattr(type(cfg), "final_stage", final_stage)
     m, s = setup["model"], setup
     dev = s["dev"]
     pyr_d, meta_d = to_dev(s["pyr"], dev), to_dev(s["meta"], dev)
@@ -96,8 +99,10 @@ def test_sdf_infer(setup):
             assert bool(taps["screen_verified"])
             assert float(taps["screen_gap"].min()) > 3 * float(taps["screen_err"]) > 0
             if taps["single_pass"]:
-                assert bool(taps["pre_verified"]) and float(taps["pre_gap"].min()) > 3 * float(taps["pre_err"]) > 0
-                assert worst_all < 3e-3 and float(taps["pre_gap"].min()) > worst_all, (worst_all, taps["pre_gap"])
+                first = "pre" if "pre_gap" in taps else "screen"      # the step that follows the single-product stage
+                assert bool(taps[first + "_verified"])
+                assert float(taps[first + "_gap"].min()) > 3 * float(taps[first + "_err"]) > 0
+                assert worst_all < 3e-3 and float(taps[first + "_gap"].min()) > worst_all, (worst_all, taps[first + "_gap"])
             else:
                 assert worst_all < 5e-6 and float(taps["screen_gap"].min()) > 3 * worst_all
         else:
