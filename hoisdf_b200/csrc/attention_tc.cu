@@ -9,7 +9,7 @@
 //
 // Two kernels:
 //   attn_split_kernel   fp32 q|k|v rows -> bf16 hi/lo arrays laid out per (sample, head): Q, K as (B*H*L, 64),
-//                       V transposed as (B*H*64, Lk_pad) so that it is a K-major B operand.  q is pre-scaled by 1/8.
+//                       V transposed as (B*H*64, Lk_pad) so that it is a K-major B operand.  q is pre-scaled by log2(e)/8 (scores in log2 units).
 //   attention_tc_kernel one CTA per (128 queries, head, sample), 192 threads:
 //       warp 0      TMA producer (Q once; K / V^T tiles of 64 keys through a 3-stage ring, 128B swizzle)
 //       warp 1      tcgen05.mma issuer: S_t = Q.K_t^T (M128 N64 K16 x 12) into one of two TMEM score buffers,
@@ -117,6 +117,17 @@ __device__ __forceinline__ void at_tmem_st32(uint32_t taddr, const uint32_t* r) 
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+// two values at once, packed (element 0 in the low half): hi = bf16x2(x), lo = bf16x2(x - hi); 6 instructions per pair
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi2, uint32_t& lo2) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi2) : "f"(x1), "f"(x0));
+  const float h0 = __uint_as_float(hi2 << 16), h1 = __uint_as_float(hi2 & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(x1 - h1), "f"(x0 - h0));
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
   return static_cast<uint32_t>(__bfloat16_as_ushort(a)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
@@ -295,7 +306,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_co
     const int q = warp & 3;
     const int r = q * 32 + lane;                       // row in the tile == TMEM lane
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    const float kLog2e = 1.4426950408889634f;
     float m_run = -INFINITY, l_run = 0.f;
     for (int t = 0; t < T; ++t) {
       at_mbar_wait(bar_sf(t & 1), (t >> 1) & 1);
@@ -308,24 +318,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_co
       __syncwarp();
       if (lane == 0) at_mbar_arrive(bar_se(t & 1));
       const int valid = kend - t * AT_BK;              // keys of this tile that exist
-      float mx = -INFINITY;
+      if (valid < AT_BK) {                             // ragged last tile only (warp-uniform)
 #pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        float s = __uint_as_float(sr[j]);
-        if (j >= valid) s = -INFINITY;
-        sr[j] = __float_as_uint(s);
-        mx = fmaxf(mx, s);
+        for (int j = 0; j < 64; ++j)
+          if (j >= valid) sr[j] = __float_as_uint(-INFINITY);
       }
-      const float m_new = fmaxf(m_run, mx);
-      const float alpha = exp2f((m_run - m_new) * kLog2e);
-      float rs = 0.f;
+      // scores are in log2 units (q was pre-scaled by log2(e) / 8): p = 2^(s - m).  Four independent max / sum
+      // chains: one warp per scheduler cannot hide a 64-long dependent chain.
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int j = 0; j < 64; ++j) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(sr[j]));
+      const float m_new = fmaxf(m_run, fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])));
+      const float alpha = ex2_approx(m_run - m_new);
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int j = 0; j < 64; ++j) {
-        const float e = exp2f((__uint_as_float(sr[j]) - m_new) * kLog2e);
+        const float e = ex2_approx(__uint_as_float(sr[j]) - m_new);
         sr[j] = __float_as_uint(e);
-        rs += e;
+        rs4[j & 3] += e;
       }
-      l_run = l_run * alpha + rs;
+      l_run = l_run * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
       m_run = m_new;
       // previous P.V must have completed before P is overwritten / O rescaled
       at_mbar_wait(bar_pe, (t & 1) ^ 1u);
@@ -347,13 +359,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_co
       for (int j = 0; j < 8; ++j) {
         uint32_t hw[4], lw[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          __nv_bfloat16 h0, l0, h1, l1;
-          split_bf16(__uint_as_float(sr[j * 8 + 2 * e]), h0, l0);
-          split_bf16(__uint_as_float(sr[j * 8 + 2 * e + 1]), h1, l1);
-          hw[e] = pack2(h0, h1);
-          lw[e] = pack2(l0, l1);
-        }
+        for (int e = 0; e < 4; ++e)
+          split_bf16x2(__uint_as_float(sr[j * 8 + 2 * e]), __uint_as_float(sr[j * 8 + 2 * e + 1]), hw[e], lw[e]);
         const int off = r * 128 + ((j ^ (r & 7)) << 4);
         *reinterpret_cast<uint4*>(p_hi_gen + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
         *reinterpret_cast<uint4*>(p_lo_gen + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
@@ -440,7 +447,7 @@ int launch_attention_tc(const float* q, int64_t ldq, const float* k, const float
   {
     const int64_t nq = batch * lq * heads * 16, nk = batch * lk * heads * 16;
     attn_split_rows_kernel<<<static_cast<unsigned>(ceil_div(nq, 256)), 256, 0, s>>>(q, ldq, batch, static_cast<int>(heads),
-                                                                                  lq, 0.125f, qhi, qlo);
+                                                                                  lq, 0.125f * 1.4426950408889634f, qhi, qlo);   // scores in log2 units
     attn_split_rows_kernel<<<static_cast<unsigned>(ceil_div(nk, 256)), 256, 0, s>>>(k, ldk, batch, static_cast<int>(heads),
                                                                                   lk, 1.0f, khi, klo);
     dim3 g(static_cast<unsigned>(ceil_div(lk, 64)), static_cast<unsigned>(heads), static_cast<unsigned>(batch));
