@@ -275,21 +275,27 @@ def run_native(args):
     peaks = load_peaks()
     achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
     kernel_name = ("hoisdf::linear_h3_kernel (tcgen05.mma kind::f16 on split-half operands, 3 products per fp32-grade "
-                   "product; persistent, double-buffered TMEM; all launches of the step incl. the 4 GEMMs of every "
-                   "SDF-decoder call and the implicit-GEMM convolutions of the U-Net decoder; FLOPs counted once per fp32 product, i.e. the tensor cores execute 3x this number "
-                   "of fp16 MACs)") if h3 else (
+                   "product, 1 for the candidate pre-screening; persistent, chunked TMEM accumulation drained into fp32 "
+                   "registers; ALL its launches of the step: ResNet-50 + U-Net implicit-GEMM convolutions, pyramid "
+                   "projection, candidate / point MLPs incl. the 4 GEMMs of every SDF-decoder call, transformer and "
+                   "head linears; FLOPs counted once per product of the reference's fp32 arithmetic)") if h3 else (
         "hoisdf::linear_tf32x3_kernel (tcgen05.mma kind::tf32, 3-pass split = fp32-grade; all launches of the "
         "step incl. the 4 GEMMs of every SDF-decoder call; FLOPs counted once per fp32 product, i.e. the "
         "tensor cores execute 3x this number of TF32 MACs)")
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_h3_traffic.json")
+    if h3 and os.path.exists(tpath):            # from the committed ncu launch list of `bench.py --profile-step`
+        traffic = json.load(open(tpath))["dram_bytes_per_launch"]
+        traffic_src = "profiles/r01_h3_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, same command)"
     roofline = {
         "kernel": kernel_name,
         "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-        "frac": achieved / peaks["tflops"], "traffic": None, "peak_source": peaks["source"],
+        "frac": achieved / peaks["tflops"], "traffic": traffic, "traffic_unit": "bytes (dram read + write) per launch, "
+        "average over the kernel's launches of one step", "traffic_source": traffic_src, "peak_source": peaks["source"],
         "launches_per_step": len(tc) / args.steps, "share_of_step": tc_ms / ms_total,
         "algorithmic_flops_per_step": tc_flops / args.steps,
-        "mma_tflops_executed": 3.0 * achieved,
-        "note": "fp32-grade accuracy costs 3 tensor-core products per algorithmic product, so frac tops out at 1/3; "
-                "mma_tflops_executed / peak is the tensor-pipe utilisation",
+        "note": "fp32-grade accuracy costs 3 tensor-core products per algorithmic product (1 in the pre-screening "
+                "launches), so frac tops out near 1/3 of the fp16 peak for the three-product launches",
         "fp32_fma_linear": {"achieved_tflops": fma_flops / (fma_ms * 1e-3) / 1e12 if fma_ms > 0 else 0.0,
                             "share_of_step": fma_ms / ms_total, "launches_per_step": len(fma) / args.steps,
                             "fp32_fma_peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12},

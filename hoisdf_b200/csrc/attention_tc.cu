@@ -25,7 +25,8 @@
 
 namespace hoisdf {
 
-constexpr int AT_BQ = 128;                 // queries per CTA
+constexpr int AT_BQ = 128;                 // queries per softmax group (one MMA M tile)
+constexpr int AT_GROUPS = 2;               // query tiles per CTA: two softmax warpgroups ping-pong on the tensor core
 constexpr int AT_BK = 64;                  // keys per tile
 constexpr int AT_D = 64;                   // head dim
 constexpr int AT_STAGES = 3;
@@ -33,9 +34,9 @@ constexpr int AT_Q_BYTES = AT_BQ * AT_D * 2;      // 16 KB (one bf16 term)
 constexpr int AT_K_BYTES = AT_BK * AT_D * 2;      // 8 KB
 constexpr int AT_P_BYTES = AT_BQ * AT_BK * 2;     // 16 KB
 constexpr int AT_STAGE_BYTES = 4 * AT_K_BYTES;    // K_hi K_lo Vt_hi Vt_lo
-constexpr int AT_SMEM_BYTES = 2 * AT_Q_BYTES + AT_STAGES * AT_STAGE_BYTES + 2 * AT_P_BYTES + 1024 + 256;
-constexpr int AT_THREADS = 192;
-constexpr uint32_t AT_TMEM_COLS = 256;     // S0 [0,64) S1 [64,128) O [128,192)
+constexpr int AT_SMEM_BYTES = AT_GROUPS * 2 * AT_Q_BYTES + AT_STAGES * AT_STAGE_BYTES + AT_GROUPS * 2 * AT_P_BYTES + 1024 + 256;
+constexpr int AT_THREADS = 64 + AT_GROUPS * 128;
+constexpr uint32_t AT_TMEM_COLS = 512;     // group g: S0 [128g, +64) S1 [128g + 64, +64); O_g [256 + 64g, +64)
 constexpr uint32_t kAtSpinLimit = 1u << 27;
 
 struct AttnTcParams {
@@ -195,23 +196,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_co
   const uint32_t raw = at_smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - raw);
-  const uint32_t q_hi = base, q_lo = base + AT_Q_BYTES;
-  const uint32_t stages = base + 2 * AT_Q_BYTES;
-  const uint32_t p_hi = stages + AT_STAGES * AT_STAGE_BYTES, p_lo = p_hi + AT_P_BYTES;
-  const uint32_t bars = p_lo + AT_P_BYTES;
-  uint8_t* p_hi_gen = gen + 2 * AT_Q_BYTES + AT_STAGES * AT_STAGE_BYTES;
-  uint8_t* p_lo_gen = p_hi_gen + AT_P_BYTES;
-  // barriers: q_full | kv_full[3] | kv_empty[3] | s_full[2] | s_empty[2] | p_full | p_empty
+  // smem: Q_g hi | lo (g = 0, 1), K/V ring, P_g hi | lo, barriers
+  auto q_hi = [&](int g) { return base + static_cast<uint32_t>(g) * 2 * AT_Q_BYTES; };
+  auto q_lo = [&](int g) { return base + static_cast<uint32_t>(g) * 2 * AT_Q_BYTES + AT_Q_BYTES; };
+  const uint32_t stages = base + AT_GROUPS * 2 * AT_Q_BYTES;
+  const uint32_t p_base = stages + AT_STAGES * AT_STAGE_BYTES;
+  auto p_hi = [&](int g) { return p_base + static_cast<uint32_t>(g) * 2 * AT_P_BYTES; };
+  auto p_lo = [&](int g) { return p_base + static_cast<uint32_t>(g) * 2 * AT_P_BYTES + AT_P_BYTES; };
+  const uint32_t bars = p_base + AT_GROUPS * 2 * AT_P_BYTES;
+  uint8_t* p_gen = gen + (p_base - base);
+  // barriers: q_full | kv_full[3] | kv_empty[3] | s_full[g][2] | s_empty[g][2] | p_full[g] | p_empty[g]
   const uint32_t bar_q = bars;
   auto bar_kvf = [&](int s) { return bars + 8u * (1 + s); };
   auto bar_kve = [&](int s) { return bars + 8u * (4 + s); };
-  auto bar_sf = [&](int s) { return bars + 8u * (7 + s); };
-  auto bar_se = [&](int s) { return bars + 8u * (9 + s); };
-  const uint32_t bar_pf = bars + 8u * 11, bar_pe = bars + 8u * 12;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (bars - base) + 8 * 13);
+  auto bar_sf = [&](int g, int s) { return bars + 8u * (7 + 2 * g + s); };
+  auto bar_se = [&](int g, int s) { return bars + 8u * (11 + 2 * g + s); };
+  auto bar_pf = [&](int g) { return bars + 8u * (15 + g); };
+  auto bar_pe = [&](int g) { return bars + 8u * (17 + g); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (bars - base) + 8 * 20);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * AT_BQ;
+  const int q0 = blockIdx.x * AT_BQ * AT_GROUPS;
   const int h = blockIdx.y;
   const int64_t b = blockIdx.z;
   const int64_t bh = b * p.heads + h;
@@ -221,9 +226,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_co
   if (threadIdx.x == 0) {
     at_mbar_init(bar_q, 1);
     for (int s = 0; s < AT_STAGES; ++s) { at_mbar_init(bar_kvf(s), 1); at_mbar_init(bar_kve(s), 1); }
-    for (int s = 0; s < 2; ++s) { at_mbar_init(bar_sf(s), 1); at_mbar_init(bar_se(s), 4); }
-    at_mbar_init(bar_pf, 4);
-    at_mbar_init(bar_pe, 1);
+    for (int g = 0; g < AT_GROUPS; ++g) {
+      for (int s = 0; s < 2; ++s) { at_mbar_init(bar_sf(g, s), 1); at_mbar_init(bar_se(g, s), 4); }
+      at_mbar_init(bar_pf(g), 4);
+      at_mbar_init(bar_pe(g), 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -236,14 +243,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_co
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tmem_o = tmem + 128;
+  auto tmem_s = [&](int g, int buf) { return tmem + static_cast<uint32_t>(g * 128 + buf * AT_BK); };
+  auto tmem_o = [&](int g) { return tmem + static_cast<uint32_t>(256 + g * AT_D); };
 
   if (warp == 0) {
     if (lane == 0) {
-      at_mbar_expect_tx(bar_q, 2 * AT_Q_BYTES);
-      const int qrow = static_cast<int>(bh * p.lq + q0);
-      at_tma_2d(q_hi, &map_qhi, bar_q, 0, qrow);
-      at_tma_2d(q_lo, &map_qlo, bar_q, 0, qrow);
+      at_mbar_expect_tx(bar_q, AT_GROUPS * 2 * AT_Q_BYTES);
+      for (int g = 0; g < AT_GROUPS; ++g) {
+        // (a tile that starts beyond this (sample, head)'s queries reads the neighbour's rows or zeros: its
+        // results are never stored)
+        const int qrow = static_cast<int>(bh * p.lq + q0 + g * AT_BQ);
+        at_tma_2d(q_hi(g), &map_qhi, bar_q, 0, qrow);
+        at_tma_2d(q_lo(g), &map_qlo, bar_q, 0, qrow);
+      }
       for (int t = 0; t < T; ++t) {
         const int s = t % AT_STAGES;
         at_mbar_wait(bar_kve(s), ((t / AT_STAGES) & 1) ^ 1u);
@@ -262,16 +274,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_co
       // kind::f16: D = F32 (1<<4), A = B = BF16 (1<<7, 1<<10), K-major, N = 64 (8<<17), M = 128 (8<<24)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(AT_BK >> 3) << 17) |
                              (static_cast<uint32_t>(AT_BQ >> 4) << 24);
-      const uint64_t d_qhi = at_desc_sw128(q_hi), d_qlo = at_desc_sw128(q_lo);
-      const uint64_t d_phi = at_desc_sw128(p_hi), d_plo = at_desc_sw128(p_lo);
-      auto issue_qk = [&](int t) {
+      auto issue_qk = [&](int g, int t) {
         const int s = t % AT_STAGES;
         at_mbar_wait(bar_kvf(s), (t / AT_STAGES) & 1);
-        at_mbar_wait(bar_se(t & 1), ((t >> 1) & 1) ^ 1u);   // score buffer drained by the softmax warps
+        at_mbar_wait(bar_se(g, t & 1), ((t >> 1) & 1) ^ 1u);   // score buffer drained by the softmax warps
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t st = stages + s * AT_STAGE_BYTES;
+        const uint64_t d_qhi = at_desc_sw128(q_hi(g)), d_qlo = at_desc_sw128(q_lo(g));
         const uint64_t d_khi = at_desc_sw128(st), d_klo = at_desc_sw128(st + AT_K_BYTES);
-        const uint32_t d_s = tmem + (t & 1) * AT_BK;
+        const uint32_t d_s = tmem_s(g, t & 1);
 #pragma unroll
         for (int kk = 0; kk < AT_D / 16; ++kk) {
           const uint64_t adv = static_cast<uint64_t>(kk * 2);   // 16 bf16 = 32 bytes
@@ -279,44 +290,52 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_co
           at_umma_bf16(d_s, d_qhi + adv, d_klo + adv, idesc, 1u);
           at_umma_bf16(d_s, d_qhi + adv, d_khi + adv, idesc, 1u);
         }
-        at_commit(bar_sf(t & 1));
+        at_commit(bar_sf(g, t & 1));
       };
       at_mbar_wait(bar_q, 0);
-      issue_qk(0);
+      for (int g = 0; g < AT_GROUPS; ++g) issue_qk(g, 0);
       for (int t = 0; t < T; ++t) {
-        if (t + 1 < T) issue_qk(t + 1);
-        at_mbar_wait(bar_pf, t & 1);                         // P_t written, O rescaled
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (t + 1 < T)
+          for (int g = 0; g < AT_GROUPS; ++g) issue_qk(g, t + 1);
         const int s = t % AT_STAGES;
         const uint32_t st = stages + s * AT_STAGE_BYTES;
         const uint64_t d_vhi = at_desc_sw128(st + 2 * AT_K_BYTES), d_vlo = at_desc_sw128(st + 3 * AT_K_BYTES);
+        for (int g = 0; g < AT_GROUPS; ++g) {
+          at_mbar_wait(bar_pf(g), t & 1);                      // P_t of this group written, its O rescaled
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t d_phi = at_desc_sw128(p_hi(g)), d_plo = at_desc_sw128(p_lo(g));
+          const uint32_t d_o = tmem_o(g);
 #pragma unroll
-        for (int kk = 0; kk < AT_BK / 16; ++kk) {
-          const uint64_t adv = static_cast<uint64_t>(kk * 2);
-          at_umma_bf16(tmem_o, d_plo + adv, d_vhi + adv, idesc, (t | kk) != 0 ? 1u : 0u);
-          at_umma_bf16(tmem_o, d_phi + adv, d_vlo + adv, idesc, 1u);
-          at_umma_bf16(tmem_o, d_phi + adv, d_vhi + adv, idesc, 1u);
+          for (int kk = 0; kk < AT_BK / 16; ++kk) {
+            const uint64_t adv = static_cast<uint64_t>(kk * 2);
+            at_umma_bf16(d_o, d_plo + adv, d_vhi + adv, idesc, (t | kk) != 0 ? 1u : 0u);
+            at_umma_bf16(d_o, d_phi + adv, d_vlo + adv, idesc, 1u);
+            at_umma_bf16(d_o, d_phi + adv, d_vhi + adv, idesc, 1u);
+          }
+          at_commit(bar_pe(g));       // this group's P buffer free, its O updated
         }
-        at_commit(bar_pe);          // P buffer free, O updated
-        at_commit(bar_kve(s));      // K/V stage free
+        at_commit(bar_kve(s));        // K/V stage free (both groups' P.V have read it)
       }
     }
   } else {
     // ------------------------------------------------ softmax warps: thread <-> query row
+    const int g = (warp - 2) >> 2;                     // softmax group = query tile of this CTA
     const int q = warp & 3;
     const int r = q * 32 + lane;                       // row in the tile == TMEM lane
+    uint8_t* p_hi_gen = p_gen + g * 2 * AT_P_BYTES;
+    uint8_t* p_lo_gen = p_hi_gen + AT_P_BYTES;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     float m_run = -INFINITY, l_run = 0.f;
     for (int t = 0; t < T; ++t) {
-      at_mbar_wait(bar_sf(t & 1), (t >> 1) & 1);
+      at_mbar_wait(bar_sf(g, t & 1), (t >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       uint32_t sr[64];
-      at_tmem_ld32(tmem + lane_addr + (t & 1) * AT_BK, sr);
-      at_tmem_ld32(tmem + lane_addr + (t & 1) * AT_BK + 32, sr + 32);
+      at_tmem_ld32(tmem_s(g, t & 1) + lane_addr, sr);
+      at_tmem_ld32(tmem_s(g, t & 1) + lane_addr + 32, sr + 32);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) at_mbar_arrive(bar_se(t & 1));
+      if (lane == 0) at_mbar_arrive(bar_se(g, t & 1));
       const int valid = kend - t * AT_BK;              // keys of this tile that exist
       if (valid < AT_BK) {                             // ragged last tile only (warp-uniform)
 #pragma unroll
@@ -340,17 +359,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_co
       l_run = l_run * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
       m_run = m_new;
       // previous P.V must have completed before P is overwritten / O rescaled
-      at_mbar_wait(bar_pe, (t & 1) ^ 1u);
+      at_mbar_wait(bar_pe(g), (t & 1) ^ 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (t > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
         uint32_t o[32];
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-          at_tmem_ld32(tmem_o + lane_addr + half * 32, o);
+          at_tmem_ld32(tmem_o(g) + lane_addr + half * 32, o);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
           for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
-          at_tmem_st32(tmem_o + lane_addr + half * 32, o);
+          at_tmem_st32(tmem_o(g) + lane_addr + half * 32, o);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       }
@@ -368,18 +387,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_co
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) at_mbar_arrive(bar_pf);
+      if (lane == 0) at_mbar_arrive(bar_pf(g));
     }
     // epilogue: wait for the last P.V, then O / l
-    at_mbar_wait(bar_pe, (T & 1) ^ 1u);
+    at_mbar_wait(bar_pe(g), (T & 1) ^ 1u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int row = q0 + r;
+    const int row = q0 + g * AT_BQ + r;
     const float inv = __fdiv_rn(1.f, l_run);
     float* og = p.out + (b * p.lq + row) * p.ldo + h * AT_D;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       uint32_t o[32];
-      at_tmem_ld32(tmem_o + lane_addr + half * 32, o);
+      at_tmem_ld32(tmem_o(g) + lane_addr + half * 32, o);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       if (row < p.lq) {
 #pragma unroll
@@ -462,7 +481,7 @@ int launch_attention_tc(const float* q, int64_t ldq, const float* k, const float
   cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
   if (e != cudaSuccess) return static_cast<int>(e);
   AttnTcParams p{out, ldo, static_cast<int>(lq), static_cast<int>(lk), static_cast<int>(kv_valid), static_cast<int>(heads)};
-  dim3 grid(static_cast<unsigned>(ceil_div(lq, AT_BQ)), static_cast<unsigned>(heads), static_cast<unsigned>(batch));
+  dim3 grid(static_cast<unsigned>(ceil_div(lq, AT_BQ * AT_GROUPS)), static_cast<unsigned>(heads), static_cast<unsigned>(batch));
   attention_tc_kernel<<<grid, AT_THREADS, AT_SMEM_BYTES, s>>>(mqh, mql, mkh, mkl, mvh, mvl, p);
   return launch_status();
 }
