@@ -113,6 +113,52 @@ def test_sdf_infer(setup, final_stage, monkeypatch):
             assert (sdf.cpu() - osdf).abs().max() < 5e-6 and (pe.cpu() - ope).abs().max() < 2e-6
 
 
+@pytest.mark.parametrize("level", [1, 2])
+def test_sdf_infer_cascade_levels(setup, level):
+    """The fallback levels of the selection cascade (1: FP16x3 on every candidate -> final stage; 2: fp32 FMA kernels on
+    every candidate) select what the oracle selects."""
+    m, s = setup["model"], setup
+    dev = s["dev"]
+    pyr_d, meta_d = to_dev(s["pyr"], dev), to_dev(s["meta"], dev)
+    taps, otaps = {}, {}
+    with torch.no_grad():
+        m.sdf_infer(pyr_d, meta_d["mano_root"], meta_d["cam_intr"], meta_d["bbox_hand"], 3.1, 96, "hand", taps=taps,
+                    level=level)
+    O.sdf_infer(dict(s["sd"]), s["pyr"], s["meta"]["mano_root"], s["meta"]["cam_intr"], s["meta"]["bbox_hand"], 3.1, 96,
+                "hand", s["ocfg"], otaps)
+    worst_all, worst = check_selection(taps, otaps, 96)
+    assert not taps["single_pass"] and worst_all < 5e-6 and worst < 5e-6
+    assert ("screen_gap" in taps) == (level == 1)
+
+
+def test_unverified_cascade_escalates(setup, monkeypatch):
+    """Margins too small for the device-side check to pass: `hot_path` reads the verdict after queueing the forward and
+    re-runs it at the next cascade level until the selection is verified (level 1 if its own check happens to pass with
+    a margin of one row, else level 2: no screening at all); a direct
+    `sdf_infer` call escalates synchronously.  Either way the result is the oracle's selection."""
+    from hoisdf_b200.config import cfg
+    m, s = setup["model"], setup
+    dev = s["dev"]
+    monkeypatch.setattr(type(cfg), "screen_margin_single", 2)
+    monkeypatch.setattr(type(cfg), "screen_margin_safe", 1)
+    out = m.hot_path(to_dev(s["pyr"], dev), to_dev(s["meta"], dev))
+    taps = m.last_taps
+    for kind in ("hand", "obj"):
+        assert not taps[kind]["single_pass"]                                             # stage A was abandoned
+        assert "screen_gap" not in taps[kind] or bool(taps[kind]["screen_verified"])     # level 1 verified, or level 2
+    otaps = {}
+    with torch.no_grad():
+        oout = O.hot_path_eval(dict(s["sd"]), s["pyr"], s["meta"], s["ocfg"], otaps)
+    check_selection(taps["hand"], otaps["hand"], 96)
+    check_selection(taps["obj"], otaps["obj"], 40)
+    for k in ("mano_mesh_out", "mano_joints_out", "hand_joints_out"):
+        assert rel(out[k], oout[k]) < 1e-4, (k, rel(out[k], oout[k]))
+    pyr_d, meta_d = to_dev(s["pyr"], dev), to_dev(s["meta"], dev)
+    with torch.no_grad():
+        pts, _, _, _ = m.sdf_infer(pyr_d, meta_d["mano_root"], meta_d["cam_intr"], meta_d["bbox_hand"], 3.1, 96, "hand")
+    assert torch.equal(pts, taps["hand_points"])
+
+
 def test_sdf_infer_too_few_candidates(setup):
     m, s = setup["model"], setup
     dev = s["dev"]
