@@ -1,7 +1,7 @@
 """BASELINE config 5: SDF-MLP (SDFDecoder.forward) in isolation, point-count sweep 256/1024/4096/16384 at batch 32.
 Rows = 32 * points, input (rows, 289) ~ N(0,1).  Reports time, rows/s, algorithmic TFLOP/s (1 573 888 FLOP/row) and
-algorithmic HBM GB/s (1 160 B/row: 289 floats in, 1 out) against the measured peaks, for the tcgen05 3xTF32 path and
-the fp32 FMA path.  Developer tool: prints a markdown table (committed under profiles/)."""
+algorithmic HBM GB/s (1 160 B/row: 289 floats in, 1 out) against the measured peaks, for the tcgen05 FP16x3 path (default),
+the tcgen05 3xTF32 path and the fp32 FMA path.  Developer tool: prints a markdown table (committed under profiles/)."""
 import json, os, sys, torch, warnings
 warnings.filterwarnings("ignore")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -23,8 +23,9 @@ for pts in (256, 1024, 4096, 16384):
     x = torch.randn(rows, 289, generator=g)
     xd = x.to(dev)
     ref = O.sdf_decoder(sd, "hand_sdf_decoder", x[:4096])
-    for impl in ("tcgen05 3xTF32", "fp32 FMA"):
+    for impl in ("tcgen05 FP16x3", "tcgen05 3xTF32", "fp32 FMA"):
         ops.USE_TENSOR_CORES = impl.startswith("tc")
+        ops.TC_MODE = "h3" if "FP16" in impl else "tf32"
         dec._packed = None
         with torch.no_grad():
             for _ in range(3): out, _ = dec(xd)
