@@ -40,8 +40,10 @@ constexpr uint32_t AT_TMEM_COLS = 512;     // group g: S0 [128g, +64) S1 [128g +
 constexpr uint32_t kAtSpinLimit = 1u << 27;
 
 struct AttnTcParams {
-  float* __restrict__ out;
-  int64_t ldo;
+  float* __restrict__ out;           // fp32 output rows, or nullptr when the split-half planes are given
+  uint16_t* __restrict__ out_hi;     // split-half output (hi = fp16(x), lo = fp16((x - hi) * 2^11)): what the FP16x3
+  uint16_t* __restrict__ out_lo;     // out-projection GEMM reads, saving a conversion pass
+  int64_t ldo;                       // row pitch of whichever output is used (floats / halfs)
   int lq, lk, kv_valid, heads;
 };
 
@@ -394,18 +396,34 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_co
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int row = q0 + g * AT_BQ + r;
     const float inv = __fdiv_rn(1.f, l_run);
-    float* og = p.out + (b * p.lq + row) * p.ldo + h * AT_D;
+    const int64_t oo = (b * p.lq + row) * p.ldo + h * AT_D;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       uint32_t o[32];
       at_tmem_ld32(tmem_o(g) + lane_addr + half * 32, o);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       if (row < p.lq) {
+        if (p.out != nullptr) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          *reinterpret_cast<float4*>(og + half * 32 + j) =
-              make_float4(__uint_as_float(o[j]) * inv, __uint_as_float(o[j + 1]) * inv,
-                          __uint_as_float(o[j + 2]) * inv, __uint_as_float(o[j + 3]) * inv);
+          for (int j = 0; j < 32; j += 4) {
+            *reinterpret_cast<float4*>(p.out + oo + half * 32 + j) =
+                make_float4(__uint_as_float(o[j]) * inv, __uint_as_float(o[j + 1]) * inv,
+                            __uint_as_float(o[j + 2]) * inv, __uint_as_float(o[j + 3]) * inv);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float x0 = __uint_as_float(o[j + 2 * e]) * inv, x1 = __uint_as_float(o[j + 2 * e + 1]) * inv;
+              asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hw[e]) : "f"(x1), "f"(x0));
+              const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+              asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lw[e]) : "f"((x1 - hf.y) * 2048.f), "f"((x0 - hf.x) * 2048.f));
+            }
+            *reinterpret_cast<uint4*>(p.out_hi + oo + half * 32 + j) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(p.out_lo + oo + half * 32 + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
         }
       }
     }
@@ -452,7 +470,7 @@ int64_t attention_tc_workspace_bytes(int64_t batch, int64_t heads, int64_t lq, i
 
 int launch_attention_tc(const float* q, int64_t ldq, const float* k, const float* v, int64_t ldk, float* out,
                         int64_t ldo, int64_t batch, int64_t heads, int64_t lq, int64_t lk, int64_t kv_valid,
-                        void* workspace, cudaStream_t s) {
+                        void* workspace, cudaStream_t s, uint16_t* out_hi, uint16_t* out_lo) {
   if (batch * heads * (lq > lk ? lq : lk) > 0x7fffff00LL) return HOISDF_E_SHAPE;  // TMA row coordinates are int32
   const int64_t lk_pad = (lk + 7) / 8 * 8;
   auto up = [](int64_t x) { return (x + 255) / 256 * 256; };
@@ -480,7 +498,8 @@ int launch_attention_tc(const float* q, int64_t ldq, const float* k, const float
     return HOISDF_E_UNSUPPORTED;
   cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
   if (e != cudaSuccess) return static_cast<int>(e);
-  AttnTcParams p{out, ldo, static_cast<int>(lq), static_cast<int>(lk), static_cast<int>(kv_valid), static_cast<int>(heads)};
+  AttnTcParams p{out, out_hi, out_lo, ldo, static_cast<int>(lq), static_cast<int>(lk), static_cast<int>(kv_valid),
+                 static_cast<int>(heads)};
   dim3 grid(static_cast<unsigned>(ceil_div(lq, AT_BQ * AT_GROUPS)), static_cast<unsigned>(heads), static_cast<unsigned>(batch));
   attention_tc_kernel<<<grid, AT_THREADS, AT_SMEM_BYTES, s>>>(mqh, mql, mkh, mkl, mvh, mvl, p);
   return launch_status();

@@ -292,6 +292,24 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
       const int64_t row = static_cast<int64_t>(grp) * p.rows_per_batch + lrow;   // output rows are dense
       const int row0 = static_cast<int>(static_cast<int64_t>(grp) * p.rows_per_batch + m0 + q * 32);
 
+      if (RES && tile_ok) {
+        // pull this lane's residual row (128 columns x 2 planes = 4 x 128 B) into L2 now: the epilogue reads it 16 B
+        // at a time, and a DRAM miss per read would serialise ~1.5 us four times per tile
+        const int64_t pr = p.taps > 0 ? static_cast<int64_t>(m_tile) * H3_BM + q * 32 + lane : row;
+        if (p.taps > 0 ? pr < p.rows_per_batch : row_ok) {
+          const int cb = n0 + hcol * 128;
+          if (cb < p.n) {
+            const __half* ph = p.r_hi + pr * p.ldr + cb;
+            const __half* pl = p.r_lo + pr * p.ldr + cb;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ph));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pl));
+            if (cb + 64 < p.n) {
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(ph + 64));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(pl + 64));
+            }
+          }
+        }
+      }
       // ---- drain all chunks but the last into registers (the first one is loaded straight into them)
       float acc[128];
       const int nchunks = (num_kb + chb - 1) / chb;

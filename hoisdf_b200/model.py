@@ -105,6 +105,29 @@ class CandidatePlan:
         return self._host
 
 
+class GraphedForward:
+    """CUDA graphs of the two static-shape stages of one eval forward (same kernels, replayed without the ~400
+    Python / ctypes launches): G1 = image encoder + pyramid projection, G2 = everything after the point selection.
+    The selection itself stays eager: its row counts are data dependent (they size the candidate buffers)."""
+
+    def __init__(self, model: "Model", img, root, objc, K):
+        self.model = model
+        self.img, self.root, self.objc, self.K = img.clone(), root.clone(), objc.clone(), K.clone()
+        self.pool = torch.cuda.graph_pool_handle()
+        self.g1 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g1, pool=self.pool, capture_error_mode="relaxed"):
+            pyr, self.decoder_out = model.run_image_encoder(self.img)
+            self.ctx = PyramidContext(pyr, model)
+            self.ctx.gmaps                       # projection of the pyramid through linear_sdfin layer 0
+        self.g2 = self.sel = self.out = self.taps = None
+
+    def capture_pose(self, sel):
+        self.sel = {k: v.clone() for k, v in sel.items()}
+        self.g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g2, pool=self.pool, capture_error_mode="relaxed"):
+            self.out, self.taps = self.model._pose_from_points(self.ctx, self.sel, self.root, self.objc, self.K)
+
+
 class Model(nn.Module):
     def __init__(self, backbone_net, decoder_net, hand_sdf_decoder, obj_sdf_decoder, hand_transformer,
                  obj_transformer, mano_layer):
@@ -137,6 +160,7 @@ class Model(nn.Module):
         self.linear_obj_rel_trans = MLP(d, d, 3, 3)
         self.linear_obj_rot = MLP(d, d, 3, 3)
         self.last_taps = None      # diagnostics of the most recent forward (selected lattice indices, N_f, ...)
+        self._graphs = None        # CUDA-graph mode (enable_cuda_graphs): {shape key: GraphedForward}
 
     # ------------------------------------------------------------------------------------------------
     # layout helper
@@ -147,6 +171,17 @@ class Model(nn.Module):
         self.decoder_net.to(memory_format=torch.channels_last)
         self._channels_last = True
         return self
+
+    def enable_cuda_graphs(self, enabled: bool = True):
+        """Replay the static-shape stages of the eval forward (image encoder + projection; point features ->
+        transformers -> heads) from CUDA graphs.  Same kernels and results; removes ~400 host-side launches per
+        forward, so the step no longer depends on how fast the host can enqueue.  Graphs are captured per input shape on
+        first use and dropped whenever a parameter or buffer changes."""
+        self._graphs = {} if enabled else None
+        return self
+
+    def _weights_key(self):
+        return hash(tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers())))
 
     # ------------------------------------------------------------------------------------------------
     # upstream-signature operators
@@ -405,7 +440,14 @@ class Model(nn.Module):
         if mode == "train":
             raise NotImplementedError("hoisdf_b200 builds the inference hot path; the training step "
                                       "(backward kernels, SURVEY.md section 8 f-2) is not built yet")
+        graphed = (self._graphs is not None and cfg.dataset != "dexycb" and cfg.tc_backbone and cfg.tc_unet
+                   and ops.use_h3() and inputs["img"].is_cuda)
         with torch.no_grad():
+            if graphed:
+                out = self._forward_graphed(inputs["img"], meta_info)
+                if cfg.eval_losses:
+                    out = {**eval_losses(self.last_taps, targets, meta_info, None), **out}
+                return out
             img = inputs["img"]
             plans = self._plans(meta_info)
             if getattr(self, "_channels_last", False):
@@ -435,6 +477,46 @@ class Model(nn.Module):
                 joint_gt = targets["joint_cam_no_trans"][:, 1:] if dex else None
                 out = {**eval_losses(taps, targets, meta_info, joint_gt), **out}
         return out
+
+    def _forward_graphed(self, img, meta_info):
+        """The ho3d eval forward with its two static stages replayed from CUDA graphs (see GraphedForward)."""
+        root = meta_info["mano_root"].to(torch.float32).contiguous()
+        objc = meta_info["obj_center_cam"].to(torch.float32).contiguous()
+        K = meta_info["cam_intr"].to(torch.float32).contiguous()
+        img = img.to(torch.float32)
+        wkey = self._weights_key()
+        if self._graphs.get("weights") != wkey:
+            self._graphs = {"weights": wkey}         # parameters changed: packed weights were rebuilt, recapture
+        key = (tuple(img.shape), str(img.device), int(cfg.num_samp_hand), int(cfg.num_samp_obj), cfg.setting,
+               cfg.final_stage, bool(cfg.screen_single), bool(cfg.tc_projection), int(cfg.backbone_chunk_kb))
+        gs = self._graphs.get(key)
+        if gs is None:
+            # one eager forward first: packs the weights, sizes the workspaces, sets the kernel attributes
+            pyr, _ = self.run_image_encoder(img)
+            self._hot_path(PyramidContext(pyr, self), meta_info, None)
+            torch.cuda.synchronize()
+            gs = self._graphs[key] = GraphedForward(self, img, root, objc, K)
+        plans = self._plans(meta_info)               # eager: lattice counts + the async read-back of the row counts
+        gs.img.copy_(img)
+        gs.root.copy_(root)
+        gs.objc.copy_(objc)
+        gs.K.copy_(K)
+        gs.g1.replay()
+        level = 0
+        while True:
+            sel, th, to, verdict = self._select_points(gs.ctx, gs.root, gs.objc, gs.K, plans, level)
+            if gs.g2 is None:
+                gs.capture_pose(sel)
+            for k, v in sel.items():
+                gs.sel[k].copy_(v)
+            gs.g2.replay()
+            if self._verdict_ok(verdict):
+                break
+            if level >= 2:
+                raise RuntimeError("point-selection screening could not be verified")
+            level += 1                               # rare: escalate the cascade, replay the pose stage
+        self.last_taps = dict(gs.taps, hand=th, obj=to)
+        return {k: v.clone() for k, v in gs.out.items()}    # the graph's output buffers are reused by the next forward
 
     def run_image_encoder(self, img):
         """ResNet-50 + U-Net -> (feature pyramid, decoder_out).  On the FP16x3 tensor-core kernels end to end when
@@ -480,14 +562,22 @@ class Model(nn.Module):
         if plans is None:
             plans = self._plans(meta_info)
         ctx = self._ctx(feature_pyramid)
-        b = ctx.batch
-        dev = root.device
+        sel, th, to, verdict = self._select_points(ctx, root, objc, K, plans, level)
+        out, taps = self._pose_from_points(ctx, sel, root, objc, K, mano_params)
+        if not self._verdict_ok(verdict):
+            if level >= 2:
+                raise RuntimeError("point-selection screening could not be verified")
+            return self._hot_path(ctx, meta_info, plans, mano_params, level + 1)   # rare: escalate the cascade
+        self.last_taps = dict(taps, hand=th, obj=to)
+        return out
+
+    def _select_points(self, ctx, root, objc, K, plans, level):
+        """upstream model.py:424-481: the two `sdf_infer` calls.  Returns the selected points / SDF / positional
+        encodings, the per-field diagnostics and the (event, pinned flag) of the cascade's device-side verdict."""
         Ph, Po = int(cfg.num_samp_hand), int(cfg.num_samp_obj)
-        S = Ph + Po
-        hs_scale, os_scale = cfg.hand_sdf_scale, cfg.obj_sdf_scale
         th, to = {}, {}
-        hand_points, hand_sdf, hand_pe, _ = self.sdf_infer(ctx, root, K, None, hs_scale, Ph, "hand", plans[0], th, level)
-        obj_points, obj_sdf, obj_pe, _ = self.sdf_infer(ctx, objc, K, None, os_scale, Po, "obj", plans[1], to, level)
+        hp, hsdf, hpe, _ = self.sdf_infer(ctx, root, K, None, cfg.hand_sdf_scale, Ph, "hand", plans[0], th, level)
+        op, osdf, ope, _ = self.sdf_infer(ctx, objc, K, None, cfg.obj_sdf_scale, Po, "obj", plans[1], to, level)
         # verdict of the screening cascade (device-side checks): copied to pinned memory now, read after the rest of
         # the forward has been queued -- the GPU never waits for the host
         flags = [t[k] for t in (th, to) for k in ("pre_verified", "screen_verified") if k in t]
@@ -498,6 +588,33 @@ class Model(nn.Module):
             self._ok_host.copy_(torch.stack(flags).all().view(1), non_blocking=True)
             verdict = torch.cuda.Event()
             verdict.record()
+        sel = dict(hand_points=hp, hand_sdf=hsdf, hand_posenc=hpe, obj_points=op, obj_sdf=osdf, obj_posenc=ope)
+        return sel, th, to, verdict
+
+    def _verdict_ok(self, verdict) -> bool:
+        if verdict is None:
+            return True
+        verdict.synchronize()
+        return bool(self._ok_host[0])
+
+    def _masks(self, dev):
+        """(tgt_mask on the device, memory_mask on the host) -- constants, built once (upstream rebuilds them on the
+        CPU and copies them every forward, model.py:568-569)."""
+        key = (str(dev), int(cfg.num_samp_hand), int(cfg.num_samp_obj))
+        if getattr(self, "_mask_cache", None) is None or self._mask_cache[0] != key:
+            self._mask_cache = (key, get_mano_tgt_mask().to(dev), get_mano_memory_mask())
+        return self._mask_cache[1], self._mask_cache[2]
+
+    def _pose_from_points(self, ctx, sel, root, objc, K, mano_params=None):
+        """upstream model.py:483-638: point features, cross SDF queries, tokens, the two transformers, heads, MANO and
+        the joint vote, from the selected points.  Static shapes, no host round trip: capturable in a CUDA graph."""
+        b = ctx.batch
+        dev = root.device
+        Ph, Po = int(cfg.num_samp_hand), int(cfg.num_samp_obj)
+        S = Ph + Po
+        hs_scale, os_scale = cfg.hand_sdf_scale, cfg.obj_sdf_scale
+        hand_points, hand_sdf, hand_pe = sel["hand_points"], sel["hand_sdf"], sel["hand_posenc"]
+        obj_points, obj_sdf, obj_pe = sel["obj_points"], sel["obj_sdf"], sel["obj_posenc"]
 
         self.hand_sigmoid_beta.data.clamp_(min=2e-3)   # upstream model.py:124 (side effect on the parameter)
         self.obj_sigmoid_beta.data.clamp_(min=2e-3)
@@ -519,8 +636,7 @@ class Model(nn.Module):
         ops.tokens(obj_nt, obj_pe, obj_fea, obj_sdf, beta_o, obj_in, 0)
         ops.tokens(hand_o_nt, hand_o_pe, hand_fea, hand_o_sdf, beta_o, obj_in, Po)
 
-        tgt_mask = get_mano_tgt_mask().to(dev)
-        memory_mask = get_mano_memory_mask()          # stays on the host: recognised as a key-range limit
+        tgt_mask, memory_mask = self._masks(dev)      # memory_mask stays on the host: recognised as a key-range limit
         hs, memory, hand_enc = self.hand_transformer.forward_bm(hand_in, self.mano_query_embed.weight, None,
                                                                 tgt_mask, memory_mask)
         _, obj_enc = self.obj_transformer.forward_bm(obj_in, None)
@@ -556,20 +672,14 @@ class Model(nn.Module):
             "obj_trans_out": obj_trans[-1],
             "hand_joints_out": hand_joints[-1],
         }
-        if verdict is not None:
-            verdict.synchronize()
-            if not bool(self._ok_host[0]):
-                if level >= 2:
-                    raise RuntimeError("point-selection screening could not be verified")
-                return self._hot_path(ctx, meta_info, plans, mano_params, level + 1)   # rare: escalate the cascade
-        self.last_taps = dict(
-            hand=th, obj=to, hand_points=hand_points, hand_sdf=hand_sdf, hand_posenc=hand_pe, obj_points=obj_points,
+        taps = dict(
+            hand_points=hand_points, hand_sdf=hand_sdf, hand_posenc=hand_pe, obj_points=obj_points,
             obj_sdf=obj_sdf, obj_posenc=obj_pe, hand_fea=hand_fea, obj_fea=obj_fea, hand_o_sdf=hand_o_sdf,
             obj_h_sdf=obj_h_sdf, hand_transformer_in=hand_in, obj_transformer_in=obj_in, hs=hs, memory=memory,
             hand_encoder_out=hand_enc, obj_encoder_out=obj_enc, hand_off=hand_off, hand_cls=hand_cls, obj_rot=obj_rot,
             obj_trans=obj_trans, mano_pose6d=pose6d, mano_shape=shape, hand_joints=hand_joints, mano_verts=verts,
             mano_joints=joints, hand_points_notrans=hand_nt, pred_mano=pred_mano, gt_mano=gt_mano)
-        return out
+        return out, taps
 
     @staticmethod
     def _head_rows(mlp: MLP, x: torch.Tensor, groups: int, rows_per_group: int, group_len: int, first: int = 0,

@@ -117,7 +117,9 @@ class TransformerEncoderLayer(_LayerBase):
             kv[:, :d] = qk[:, d:]
             kv[:, d:] = vv
             q, ldq, k, v, ld = qk, 2 * d, kv, kv[:, d:], 2 * d
-        att = torch.empty(b * s, d, device=x.device, dtype=torch.float32)
+        # (tensor-core attention writes its result in the split-half format the out-projection GEMM reads)
+        att = ops.SplitRows.empty(b * s, d, x.device) if (ops.use_h3() and s > 32) else \
+            torch.empty(b * s, d, device=x.device, dtype=torch.float32)
         ops.attention(q, ldq, k, v, ld, att, d, b, self.nhead, s, s)
         y = ops.linear(att, pk["out"], ops.ACT_NONE)
         x1s = _split_like(x2d)

@@ -128,16 +128,25 @@ class UNetH3:
         if not self.big:
             (sv, sbn, _), = _seq_conv_bn(d.conv0d)
             pk["conv0d"] = _pack_conv(sv, sbn)
-        for name in ("convOut_hm", "convOut_hand_seg", "convOut_obj_seg"):
+        firsts = []
+        for name in self.HEADS:
             layers = _seq_conv_bn(getattr(d, name))
-            pk[name] = [(_pack_conv(cv, bn), relu) for cv, bn, relu in layers[:-1]]
+            assert len(layers) >= 2 and layers[0][2]
+            firsts.append(_fold_bn(layers[0][0].weight, layers[0][0].bias, layers[0][1], 0))
+            pk[name] = [(_pack_conv(cv, bn), relu) for cv, bn, relu in layers[1:-1]]
             # the last 1x1 convolution has ONE output channel: fp32 weights for the narrow (HBM-bound) Linear kernel
             w, b = _fold_bn(layers[-1][0].weight, layers[-1][0].bias, layers[-1][1], 0)
             pk[name + ".last"] = (w.reshape(w.shape[0], -1).float().contiguous(), b)
+        # the three heads' first 1x1 convolutions read the same 524 288-pixel map: ONE GEMM with their weights stacked
+        pk["heads.first"] = ops.PackedLinearH3.pack(
+            torch.cat([w.reshape(w.shape[0], -1).float() for w, _ in firsts], 0).contiguous(),
+            torch.cat([b for _, b in firsts], 0).contiguous())
+        pk["heads.width"] = firsts[0][0].shape[0]
         self._packed, self._key = pk, key
         return pk
 
     LEVELS = ((1, "stride16"), (2, "stride8"), (3, "stride4"), (4, "stride2"))
+    HEADS = ("convOut_hm", "convOut_hand_seg", "convOut_obj_seg")
 
     def concat_slots(self, b: int, h: int, w: int, dev):
         """'ho3d' decoder: allocate the four skip-concat buffers up front and return (cats, slots): the encoder writes
@@ -217,8 +226,10 @@ class UNetH3:
             h, w, cx = ho, wo, pc.n
         # 1x1 heads on the stride-2 level: heat map, hand / object segmentation (sigmoid)
         outs = []
-        for name in ("convOut_hm", "convOut_hand_seg", "convOut_obj_seg"):
-            hcur = x
+        h1 = ops.linear_h3(x, pk["heads.first"], ops.ACT_RELU, split_out=True)
+        n1 = pk["heads.width"]
+        for j, name in enumerate(self.HEADS):
+            hcur = h1.window(j * n1, n1)
             for pw, relu in pk[name]:
                 hcur = ops.linear_h3(hcur, pw, ops.ACT_RELU if relu else ops.ACT_NONE, split_out=True)
             wl, bl = pk[name + ".last"]

@@ -711,6 +711,10 @@ _attn_ws = {}
 
 def _attention_workspace(device, nbytes: int) -> torch.Tensor:
     """One grow-only scratch buffer per device for the bf16 hi/lo operand copies of the tensor-core attention."""
+    if torch.cuda.is_current_stream_capturing():
+        # CUDA-graph capture: the graph keeps using whatever address it captured, so it gets a buffer of its own from
+        # the graph's memory pool instead of the grow-only shared one (which a later, larger call would replace)
+        return torch.empty(nbytes, device=device, dtype=torch.uint8)
     buf = _attn_ws.get(device)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(nbytes, device=device, dtype=torch.uint8)
@@ -723,10 +727,18 @@ def attention(q, ldq, k, v, ldk, out, ldo, batch, heads, lq, lk, kv_valid=None, 
     tensor_cores: None = automatic (long query sequences), True = also for short ones (decoder cross-attention)."""
     ws, ws_bytes, n = None, 0, 1
     if USE_TENSOR_CORES and mask is None and (lq > 32 or tensor_cores):
+        dev = out.buf.device if isinstance(out, SplitRows) else out.device
         ws_bytes = lib.hoisdf_attention_workspace_bytes(batch, heads, lq, lk)
-        ws = _attention_workspace(out.device, ws_bytes)
+        ws = _attention_workspace(dev, ws_bytes)
         n = 4
     _count(n)
+    if isinstance(out, SplitRows):          # tensor-core path only: result straight in split-half format
+        if ws is None:
+            raise RuntimeError("split-half attention output needs the tensor-core attention kernel")
+        check(lib.hoisdf_attention_split_fwd(q.data_ptr(), ldq, k.data_ptr(), v.data_ptr(), ldk, out.hi_ptr, out.lo_ptr,
+                                             out.ld, batch, heads, lq, lk, lk if kv_valid is None else kv_valid,
+                                             _ptr(ws), ws_bytes, _stream()), "hoisdf_attention_split_fwd")
+        return out
     check(lib.hoisdf_attention_fwd(q.data_ptr(), ldq, k.data_ptr(), v.data_ptr(), ldk, out.data_ptr(), ldo, batch,
                                    heads, lq, lk, lk if kv_valid is None else kv_valid, _ptr(mask), _ptr(ws), ws_bytes,
                                    _stream()),

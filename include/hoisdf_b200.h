@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 9
+#define HOISDF_ABI_VERSION 10
 
 enum {
   HOISDF_OK = 0,
@@ -335,6 +335,12 @@ int64_t hoisdf_attention_workspace_bytes(int64_t batch, int64_t heads, int64_t l
 int hoisdf_attention_fwd(const float* q, int64_t ldq, const float* k, const float* v, int64_t ldk, float* out,
                          int64_t ldo, int64_t batch, int64_t heads, int64_t lq, int64_t lk, int64_t kv_valid,
                          const uint8_t* mask, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* The tensor-core path of hoisdf_attention_fwd (workspace required, no dense mask) writing its result in split-half
+ * format (two fp16 planes, pitch ldo halfs, multiple of 8) -- what the FP16x3 out-projection GEMM reads. */
+int hoisdf_attention_split_fwd(const float* q, int64_t ldq, const float* k, const float* v, int64_t ldk,
+                               uint16_t* out_hi, uint16_t* out_lo, int64_t ldo, int64_t batch, int64_t heads, int64_t lq,
+                               int64_t lk, int64_t kv_valid, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* y = LayerNorm(x (+ res)) * gamma + beta, eps 1e-5, rows of 256 (transformer.py:296-301); optional second
  * output y2 = LayerNorm(y) with (gamma2, beta2) -- the shared `inter_norm` of transformer.py:196-197. */

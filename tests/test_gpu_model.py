@@ -322,3 +322,37 @@ def test_dexycb_eval_branch(setup):
             assert rel(out[k], oout[k]) < 2e-2, (k, rel(out[k], oout[k]))
     finally:
         type(cfg).dataset, type(cfg).num_samp_hand, type(cfg).num_samp_obj = old
+
+
+def test_cuda_graph_forward_matches_eager(setup):
+    """`Model.enable_cuda_graphs()`: the static stages replayed from CUDA graphs give the eager forward's results bit for
+    bit, also when the graphs are replayed on new inputs, and are recaptured after a parameter changes."""
+    from hoisdf_b200.config import cfg
+    if setup["arch"] != "ho3d":
+        pytest.skip("one architecture is enough")
+    m, s = setup["model"], setup
+    dev = s["dev"]
+    batches = [({"img": syn.image_batch(sd_, s["B"]).to(dev)}, to_dev(syn.eval_targets(s["B"]), dev),
+                to_dev(syn.camera_meta(sd_, s["B"]), dev)) for sd_ in (s["seed"], s["seed"] + 1)]
+    eager = [m(*bt, "eval") for bt in batches]
+    m.enable_cuda_graphs()
+    try:
+        for rep in range(2):                     # second round: pure replays
+            for bt, ref in zip(batches, eager):
+                out = m(*bt, "eval")
+                assert set(out) == set(ref)
+                for k in ref:
+                    assert torch.equal(out[k], ref[k]), (rep, k)
+        assert len(m._graphs) == 2               # "weights" + one shape key
+        with torch.no_grad():
+            m.linear_pose.layers[0].bias.add_(0.01)          # parameter version changes -> graphs are rebuilt
+        out = m(*batches[0], "eval")
+        m.enable_cuda_graphs(False)
+        ref = m(*batches[0], "eval")
+        for k in ref:
+            assert torch.equal(out[k], ref[k]), k
+        assert not torch.equal(ref["mano_mesh_out"], eager[0]["mano_mesh_out"])
+    finally:
+        m.enable_cuda_graphs(False)
+        with torch.no_grad():
+            m.linear_pose.layers[0].bias.sub_(0.01)
