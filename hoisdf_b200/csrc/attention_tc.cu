@@ -14,9 +14,11 @@
 //       warp 0      TMA producer (Q once; K / V^T tiles of 64 keys through a 3-stage ring, 128B swizzle)
 //       warp 1      tcgen05.mma issuer: S_t = Q.K_t^T (M128 N64 K16 x 12) into one of two TMEM score buffers,
 //                   O += P_t.V_t (x 12) into the TMEM output accumulator
-//       warps 2..5  softmax: thread = query row (TMEM lane): tcgen05.ld the score row, online max / sum in
-//                   fp32 (exp2f), rescale O in TMEM (tcgen05.ld/st) only when the running max moved,
-//                   write P as bf16 hi/lo straight into the swizzled A-operand layout, epilogue O / l.
+//       warps 2..9  softmax (two groups of four, one 128-query tile each): thread = query row (TMEM lane):
+//                   tcgen05.ld the score row, online max / sum in fp32 (log2 domain), rescale O in TMEM
+//                   (tcgen05.ld/st) only when the running max moved, write P as packed bf16 hi / lo pairs back into
+//                   TMEM (tcgen05.st) where the P.V MMA reads it as its A operand -- P never touches shared memory,
+//                   whose bandwidth is what bounds this kernel; epilogue O / l.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_bf16.h>
@@ -29,14 +31,15 @@ constexpr int AT_BQ = 128;                 // queries per softmax group (one MMA
 constexpr int AT_GROUPS = 2;               // query tiles per CTA: two softmax warpgroups ping-pong on the tensor core
 constexpr int AT_BK = 64;                  // keys per tile
 constexpr int AT_D = 64;                   // head dim
-constexpr int AT_STAGES = 3;
+constexpr int AT_STAGES = 4;
 constexpr int AT_Q_BYTES = AT_BQ * AT_D * 2;      // 16 KB (one bf16 term)
 constexpr int AT_K_BYTES = AT_BK * AT_D * 2;      // 8 KB
 constexpr int AT_P_BYTES = AT_BQ * AT_BK * 2;     // 16 KB
 constexpr int AT_STAGE_BYTES = 4 * AT_K_BYTES;    // K_hi K_lo Vt_hi Vt_lo
-constexpr int AT_SMEM_BYTES = AT_GROUPS * 2 * AT_Q_BYTES + AT_STAGES * AT_STAGE_BYTES + AT_GROUPS * 2 * AT_P_BYTES + 1024 + 256;
+constexpr int AT_SMEM_BYTES = AT_GROUPS * 2 * AT_Q_BYTES + AT_STAGES * AT_STAGE_BYTES + 1024 + 256;
 constexpr int AT_THREADS = 64 + AT_GROUPS * 128;
-constexpr uint32_t AT_TMEM_COLS = 512;     // group g: S0 [128g, +64) S1 [128g + 64, +64); O_g [256 + 64g, +64)
+constexpr uint32_t AT_TMEM_COLS = 512;     // group g: S0 [128g, +64) S1 [128g + 64, +64); O_g [256 + 64g, +64);
+                                           // P_g (bf16 pairs, A operand of P.V): hi [384 + 64g, +32), lo [+32, +64)
 constexpr uint32_t kAtSpinLimit = 1u << 27;
 
 struct AttnTcParams {
@@ -88,6 +91,15 @@ __device__ __forceinline__ void at_umma_bf16(uint32_t tmem_d, uint64_t da, uint6
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// A operand in tensor memory (lane = row, each 32-bit column = two consecutive K elements), B from shared memory
+__device__ __forceinline__ void at_umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(acc)
       : "memory");
 }
 __device__ __forceinline__ void at_commit(uint32_t bar) {
@@ -202,20 +214,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_co
   auto q_hi = [&](int g) { return base + static_cast<uint32_t>(g) * 2 * AT_Q_BYTES; };
   auto q_lo = [&](int g) { return base + static_cast<uint32_t>(g) * 2 * AT_Q_BYTES + AT_Q_BYTES; };
   const uint32_t stages = base + AT_GROUPS * 2 * AT_Q_BYTES;
-  const uint32_t p_base = stages + AT_STAGES * AT_STAGE_BYTES;
-  auto p_hi = [&](int g) { return p_base + static_cast<uint32_t>(g) * 2 * AT_P_BYTES; };
-  auto p_lo = [&](int g) { return p_base + static_cast<uint32_t>(g) * 2 * AT_P_BYTES + AT_P_BYTES; };
-  const uint32_t bars = p_base + AT_GROUPS * 2 * AT_P_BYTES;
-  uint8_t* p_gen = gen + (p_base - base);
-  // barriers: q_full | kv_full[3] | kv_empty[3] | s_full[g][2] | s_empty[g][2] | p_full[g] | p_empty[g]
+  const uint32_t bars = stages + AT_STAGES * AT_STAGE_BYTES;
+  // barriers: q_full | kv_full[4] | kv_empty[4] | s_full[g][2] | s_empty[g][2] | p_full[g] | p_empty[g]
   const uint32_t bar_q = bars;
   auto bar_kvf = [&](int s) { return bars + 8u * (1 + s); };
-  auto bar_kve = [&](int s) { return bars + 8u * (4 + s); };
-  auto bar_sf = [&](int g, int s) { return bars + 8u * (7 + 2 * g + s); };
-  auto bar_se = [&](int g, int s) { return bars + 8u * (11 + 2 * g + s); };
-  auto bar_pf = [&](int g) { return bars + 8u * (15 + g); };
-  auto bar_pe = [&](int g) { return bars + 8u * (17 + g); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (bars - base) + 8 * 20);
+  auto bar_kve = [&](int s) { return bars + 8u * (1 + AT_STAGES + s); };
+  auto bar_sf = [&](int g, int s) { return bars + 8u * (1 + 2 * AT_STAGES + 2 * g + s); };
+  auto bar_se = [&](int g, int s) { return bars + 8u * (5 + 2 * AT_STAGES + 2 * g + s); };
+  auto bar_pf = [&](int g) { return bars + 8u * (9 + 2 * AT_STAGES + g); };
+  auto bar_pe = [&](int g) { return bars + 8u * (11 + 2 * AT_STAGES + g); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (bars - base) + 8 * (14 + 2 * AT_STAGES));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AT_BQ * AT_GROUPS;
@@ -247,6 +255,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_co
   const uint32_t tmem = *tmem_slot;
   auto tmem_s = [&](int g, int buf) { return tmem + static_cast<uint32_t>(g * 128 + buf * AT_BK); };
   auto tmem_o = [&](int g) { return tmem + static_cast<uint32_t>(256 + g * AT_D); };
+  auto tmem_p = [&](int g) { return tmem + static_cast<uint32_t>(384 + g * 64); };   // hi pairs; lo pairs at + 32
 
   if (warp == 0) {
     if (lane == 0) {
@@ -305,14 +314,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_co
         for (int g = 0; g < AT_GROUPS; ++g) {
           at_mbar_wait(bar_pf(g), t & 1);                      // P_t of this group written, its O rescaled
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint64_t d_phi = at_desc_sw128(p_hi(g)), d_plo = at_desc_sw128(p_lo(g));
+          const uint32_t a_hi = tmem_p(g), a_lo = tmem_p(g) + 32;
           const uint32_t d_o = tmem_o(g);
 #pragma unroll
           for (int kk = 0; kk < AT_BK / 16; ++kk) {
-            const uint64_t adv = static_cast<uint64_t>(kk * 2);
-            at_umma_bf16(d_o, d_plo + adv, d_vhi + adv, idesc, (t | kk) != 0 ? 1u : 0u);
-            at_umma_bf16(d_o, d_phi + adv, d_vlo + adv, idesc, 1u);
-            at_umma_bf16(d_o, d_phi + adv, d_vhi + adv, idesc, 1u);
+            const uint64_t adv = static_cast<uint64_t>(kk * 2);      // V^T: 16 keys = 32 bytes
+            const uint32_t ka = static_cast<uint32_t>(kk * 8);        // P in TMEM: 16 bf16 = 8 columns
+            at_umma_bf16_ts(d_o, a_lo + ka, d_vhi + adv, idesc, (t | kk) != 0 ? 1u : 0u);
+            at_umma_bf16_ts(d_o, a_hi + ka, d_vlo + adv, idesc, 1u);
+            at_umma_bf16_ts(d_o, a_hi + ka, d_vhi + adv, idesc, 1u);
           }
           at_commit(bar_pe(g));       // this group's P buffer free, its O updated
         }
@@ -324,8 +334,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_co
     const int g = (warp - 2) >> 2;                     // softmax group = query tile of this CTA
     const int q = warp & 3;
     const int r = q * 32 + lane;                       // row in the tile == TMEM lane
-    uint8_t* p_hi_gen = p_gen + g * 2 * AT_P_BYTES;
-    uint8_t* p_lo_gen = p_hi_gen + AT_P_BYTES;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     float m_run = -INFINITY, l_run = 0.f;
     for (int t = 0; t < T; ++t) {
@@ -375,18 +383,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_co
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       }
-      // P row -> bf16 hi/lo, 8 chunks of 16 bytes, chunk j lands at (j ^ (r & 7)) of the 128-byte row (128B swizzle)
+      // P row -> packed bf16 pairs (element 2e in the low half), hi and lo, written to this lane's TMEM row: the
+      // A operand of the P.V MMA
+      {
+        uint32_t ph[32], pl[32];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        uint32_t hw[4], lw[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          split_bf16x2(__uint_as_float(sr[j * 8 + 2 * e]), __uint_as_float(sr[j * 8 + 2 * e + 1]), hw[e], lw[e]);
-        const int off = r * 128 + ((j ^ (r & 7)) << 4);
-        *reinterpret_cast<uint4*>(p_hi_gen + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        *reinterpret_cast<uint4*>(p_lo_gen + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        for (int e = 0; e < 32; ++e)
+          split_bf16x2(__uint_as_float(sr[2 * e]), __uint_as_float(sr[2 * e + 1]), ph[e], pl[e]);
+        at_tmem_st32(tmem_p(g) + lane_addr, ph);
+        at_tmem_st32(tmem_p(g) + lane_addr + 32, pl);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) at_mbar_arrive(bar_pf(g));
