@@ -9,7 +9,11 @@ What is different by design (B200-first):
   * `linear_sdfin` layer 0 is applied to the pyramid once per image (a 1x1 projection of every level) and the
     bilinear gather then interpolates 512 projected channels instead of 3968 raw ones -- interpolation is
     linear, so  W.(sum_t w_t F_t) = sum_t w_t (W.F_t); 37x fewer FLOPs for that layer at N_f ~ 19k;
-  * the pyramid is read channels-last (NHWC), which cuDNN emits directly when the U-Net runs in channels_last.
+  * the image encoder (ResNet-50 + U-Net) runs on the same FP16x3 tensor-core GEMM as implicit-GEMM convolutions
+    (nets/resnet_h3.py, nets/unet_h3.py), NHWC split-half activations end to end; the cuDNN modules stay as the
+    reference path (cfg.tc_backbone / cfg.tc_unet = False);
+  * the near-surface selection is a verified coarse-to-fine cascade (single-product FP16 -> FP16x3), `sdf_infer`;
+  * the static-shape stages can be replayed from CUDA graphs (`enable_cuda_graphs`).
 Inference only for now (mode != "train"); training needs the backward kernels.
 """
 from __future__ import annotations

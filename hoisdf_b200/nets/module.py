@@ -1,10 +1,11 @@
 """ResNet-50 encoder + U-Net decoder: the step BEFORE the hot path.
 
-Not rewritten as hand kernels: these are plain library convolutions (cuDNN through PyTorch), kept with the
-upstream module / state-dict names (common/nets/module.py:18-218, common/nets/resnet.py:14-98) so released
-checkpoints load strictly.  The only B200-specific choice is the memory format: running them in
-`channels_last` makes cuDNN emit the pyramid directly in NHWC, which is the layout the fused gather reads, so no
-transpose pass is needed (`Model.channels_last_`).
+Parameter containers with the upstream module / state-dict names (common/nets/module.py:18-218,
+common/nets/resnet.py:14-98) so released checkpoints load strictly.  By default `Model.run_image_encoder` does NOT call
+their `forward`: it runs the same layers on the FP16x3 tensor-core convolution kernels (nets/resnet_h3.py,
+nets/unet_h3.py), which read these parameters.  The `forward`s below are the cuDNN reference path
+(cfg.tc_backbone / cfg.tc_unet = False; `Model.channels_last_` makes cuDNN emit the pyramid in NHWC) that the parity
+tests compare the tensor-core path against.
 """
 from __future__ import annotations
 
