@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhoisdf_b200.so")
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2      # ACT_SIGMOID: hoisdf_linear_narrow_split_fwd only
 GATHER_CONCAT, GATHER_SUM = 0, 1
 
@@ -108,6 +108,10 @@ SIGNATURES = {
     "hoisdf_vote_joints_fwd": (C.c_int, [vp, vp, vp, i64, i64, i64, vp, vp]),
     "hoisdf_mano_fwd": (C.c_int, [C.POINTER(ManoModel), vp, vp, i64, vp, vp, vp]),
     "hoisdf_mano_aa_fwd": (C.c_int, [C.POINTER(ManoModel), vp, vp, i64, vp, vp, vp]),
+    "hoisdf_obj_metrics_workspace_bytes": (i64, [i64, i64]),
+    "hoisdf_obj_metrics_fwd": (C.c_int, [vp, vp, i64, i64, vp, vp, i64, vp, vp, i64, vp, vp, vp, vp, vp, i64, vp]),
+    "hoisdf_mesh_metrics_fwd": (C.c_int, [vp, vp, i64, i64, vp, vp, vp, vp, i64, vp]),
+    "hoisdf_hand_joint_metrics_fwd": (C.c_int, [vp, vp, i64, i64, vp, vp, vp, vp]),
 }
 
 

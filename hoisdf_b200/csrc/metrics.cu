@@ -1,0 +1,414 @@
+// Test-time metrics of upstream common/metrics.py -- the consumer of the path's `obj_rot_out` / `obj_trans_out` /
+// `mano_joints_out` (main/test.py:126-195):
+//   * eval_batched_obj_direct (:110-185) with compute_obj_metrics_dexycb (:62-96) / compute_obj_metrics_ho3d (:99-108):
+//     mean of the per-point pose votes, batch_rodrigues (manopth/rodrigues_layer.py:15-56), posed template meshes,
+//     ADD-S (symmetric closest-point distance), MME (mean per-vertex error), MCE (mean bounding-box corner error),
+//     OCE (translation error) -- upstream materialises an (B, N, N, 3) difference tensor (N = 1000: 12 MB per sample,
+//     twice); here the target mesh is staged tile by tile in shared memory and nothing of size N x N exists;
+//   * eval_hand_joint / rigid_align / rigid_transform_3D (:188-228): MJE and Procrustes-aligned PA-MJE, upstream a
+//     per-sample numpy loop with a D2H copy per sample; here one CTA per sample, the 3x3 SVD by one-sided Jacobi in fp64.
+#include "common.cuh"
+
+namespace hoisdf {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kTile = 1024;      // target vertices staged per shared-memory tile (12 KB, SoA)
+constexpr int kPartial = 14;     // adds_sum, mme_sum, pred min xyz, pred max xyz, target min xyz, target max xyz
+
+// manopth/rodrigues_layer.py:44-56 (batch_rodrigues) followed by quat2mat (:15-41), row-major 3x3
+__device__ void rodrigues_quat(const float aa[3], float R[9]) {
+  const float ox = aa[0] + 1e-8f, oy = aa[1] + 1e-8f, oz = aa[2] + 1e-8f;
+  const float angle = sqrtf(ox * ox + oy * oy + oz * oz);
+  const float nx = aa[0] / angle, ny = aa[1] / angle, nz = aa[2] / angle;
+  const float half = angle * 0.5f;
+  const float vc = cosf(half), vs = sinf(half);
+  float w = vc, x = vs * nx, y = vs * ny, z = vs * nz;
+  const float qn = sqrtf(w * w + x * x + y * y + z * z);
+  w /= qn; x /= qn; y /= qn; z /= qn;
+  const float w2 = w * w, x2 = x * x, y2 = y * y, z2 = z * z;
+  const float wx = w * x, wy = w * y, wz = w * z, xy = x * y, xz = x * z, yz = y * z;
+  R[0] = w2 + x2 - y2 - z2; R[1] = 2 * xy - 2 * wz;    R[2] = 2 * wy + 2 * xz;
+  R[3] = 2 * wz + 2 * xy;    R[4] = w2 - x2 + y2 - z2; R[5] = 2 * yz - 2 * wx;
+  R[6] = 2 * xz - 2 * wy;    R[7] = 2 * wx + 2 * yz;    R[8] = w2 - x2 - y2 + z2;
+}
+
+__device__ __forceinline__ void apply_pose(const float* R, const float* t, float vx, float vy, float vz, float& ox,
+                                           float& oy, float& oz) {
+  // bmm(template, R^T) + t  (metrics.py:152-167): out[i] = sum_k v[k] * R[i][k] + t[i]
+  ox = vx * R[0] + vy * R[1] + vz * R[2] + t[0];
+  oy = vx * R[3] + vy * R[4] + vz * R[5] + t[1];
+  oz = vx * R[6] + vy * R[7] + vz * R[8] + t[2];
+}
+
+// Deterministic block reductions (fixed shuffle tree, fixed warp order): results never depend on scheduling.
+template <typename T, int NW>
+__device__ T block_reduce_sum(T v, T* scratch) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  T r = scratch[0];
+#pragma unroll
+  for (int i = 1; i < NW; ++i) r += scratch[i];
+  return r;
+}
+
+template <int NW, bool MAX>
+__device__ float block_reduce_minmax(float v, float* scratch) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float u = __shfl_xor_sync(0xffffffffu, v, o);
+    v = MAX ? fmaxf(v, u) : fminf(v, u);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  float r = scratch[0];
+#pragma unroll
+  for (int i = 1; i < NW; ++i) r = MAX ? fmaxf(r, scratch[i]) : fminf(r, scratch[i]);
+  return r;
+}
+
+// One CTA = kThreads predicted vertices of one sample against ALL target vertices of that sample.
+//   POSED = true : vertices come from a template mesh posed by (mean vote -> Rodrigues) prediction and ground truth
+//   POSED = false: vertices are read from the given predicted / target meshes (compute_obj_metrics_* called directly)
+template <bool POSED>
+__global__ void __launch_bounds__(kThreads)
+obj_metrics_partial_kernel(const float* __restrict__ templates, const int64_t* __restrict__ obj_ids, int64_t n_templates,
+                           int n_verts, const float* __restrict__ rot_pred, const float* __restrict__ trans_pred,
+                           int votes, const float* __restrict__ rot_gt, const float* __restrict__ trans_gt,
+                           const float* __restrict__ pred_meshes, const float* __restrict__ target_meshes,
+                           float* __restrict__ partial, float* __restrict__ oce) {
+  __shared__ float tile_x[kTile], tile_y[kTile], tile_z[kTile];
+  __shared__ float scratch[kThreads / 32];
+  __shared__ float pose[24];   // R_pred 9, t_pred 3, R_gt 9, t_gt 3
+  const int b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+  const float* src_pred;
+  const float* src_tgt;
+  if (POSED) {
+    // obj_rots = out["obj_rot"].mean(1), obj_trans = out["obj_trans"].mean(1)  (metrics.py:115-116)
+    float mean6[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      const float* src = (c < 3 ? rot_pred : trans_pred) + static_cast<int64_t>(b) * votes * 3 + (c % 3);
+      float acc = 0.f;
+      for (int i = tid; i < votes; i += kThreads) acc += src[static_cast<int64_t>(i) * 3];
+      mean6[c] = block_reduce_sum<float, kThreads / 32>(acc, scratch) / static_cast<float>(votes);
+    }
+    if (tid == 0) {
+      float R[9];
+      rodrigues_quat(mean6, R);
+      for (int i = 0; i < 9; ++i) pose[i] = R[i];
+      for (int i = 0; i < 3; ++i) pose[9 + i] = mean6[3 + i];
+      float g[3] = {rot_gt[b * 3 + 0], rot_gt[b * 3 + 1], rot_gt[b * 3 + 2]};
+      rodrigues_quat(g, R);
+      for (int i = 0; i < 9; ++i) pose[12 + i] = R[i];
+      float d2 = 0.f;
+      for (int i = 0; i < 3; ++i) {
+        pose[21 + i] = trans_gt[b * 3 + i];
+        const float d = mean6[3 + i] - pose[21 + i];
+        d2 += d * d;
+      }
+      if (chunk == 0 && oce != nullptr) oce[b] = sqrtf(d2);      // torch.norm(obj_trans - obj_trans_gt, dim=-1)
+    }
+    __syncthreads();
+    int64_t id = obj_ids != nullptr ? obj_ids[b] : b;
+    id = id < 0 ? 0 : (id >= n_templates ? n_templates - 1 : id);
+    src_pred = src_tgt = templates + id * static_cast<int64_t>(n_verts) * 3;
+  } else {
+    src_pred = pred_meshes + static_cast<int64_t>(b) * n_verts * 3;
+    src_tgt = target_meshes + static_cast<int64_t>(b) * n_verts * 3;
+  }
+
+  const int i = chunk * kThreads + tid;
+  const bool live = i < n_verts;
+  float px = 0.f, py = 0.f, pz = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
+  if (live) {
+    const float vx = src_pred[i * 3 + 0], vy = src_pred[i * 3 + 1], vz = src_pred[i * 3 + 2];
+    if (POSED) {
+      apply_pose(pose, pose + 9, vx, vy, vz, px, py, pz);
+      apply_pose(pose + 12, pose + 21, vx, vy, vz, gx, gy, gz);
+    } else {
+      px = vx; py = vy; pz = vz;
+      gx = src_tgt[i * 3 + 0]; gy = src_tgt[i * 3 + 1]; gz = src_tgt[i * 3 + 2];
+    }
+  }
+  // closest target vertex: min_j |g_j - p_i|  (torch.min(dis, dim=2), metrics.py:64-67,101-104)
+  float best = 3.402823466e+38f;
+  for (int j0 = 0; j0 < n_verts; j0 += kTile) {
+    const int cnt = min(kTile, n_verts - j0);
+    __syncthreads();
+    for (int j = tid; j < cnt; j += kThreads) {
+      const float vx = src_tgt[(j0 + j) * 3 + 0], vy = src_tgt[(j0 + j) * 3 + 1], vz = src_tgt[(j0 + j) * 3 + 2];
+      float tx, ty, tz;
+      if (POSED) apply_pose(pose + 12, pose + 21, vx, vy, vz, tx, ty, tz);
+      else { tx = vx; ty = vy; tz = vz; }
+      tile_x[j] = tx; tile_y[j] = ty; tile_z[j] = tz;
+    }
+    __syncthreads();
+    if (live) {
+#pragma unroll 4
+      for (int j = 0; j < cnt; ++j) {        // every thread reads the same shared word: broadcast, conflict-free
+        const float dx = tile_x[j] - px, dy = tile_y[j] - py, dz = tile_z[j] - pz;
+        best = fminf(best, dx * dx + dy * dy + dz * dz);
+      }
+    }
+  }
+  const float dx = gx - px, dy = gy - py, dz = gz - pz;
+  const float adds_i = live ? sqrtf(best) : 0.f;
+  const float mme_i = live ? sqrtf(dx * dx + dy * dy + dz * dz) : 0.f;
+  constexpr int NW = kThreads / 32;
+  constexpr float kBig = 3.402823466e+38f;
+  float out[kPartial];
+  out[0] = block_reduce_sum<float, NW>(adds_i, scratch);
+  out[1] = block_reduce_sum<float, NW>(mme_i, scratch);
+  out[2] = block_reduce_minmax<NW, false>(live ? px : kBig, scratch);
+  out[3] = block_reduce_minmax<NW, false>(live ? py : kBig, scratch);
+  out[4] = block_reduce_minmax<NW, false>(live ? pz : kBig, scratch);
+  out[5] = block_reduce_minmax<NW, true>(live ? px : -kBig, scratch);
+  out[6] = block_reduce_minmax<NW, true>(live ? py : -kBig, scratch);
+  out[7] = block_reduce_minmax<NW, true>(live ? pz : -kBig, scratch);
+  out[8] = block_reduce_minmax<NW, false>(live ? gx : kBig, scratch);
+  out[9] = block_reduce_minmax<NW, false>(live ? gy : kBig, scratch);
+  out[10] = block_reduce_minmax<NW, false>(live ? gz : kBig, scratch);
+  out[11] = block_reduce_minmax<NW, true>(live ? gx : -kBig, scratch);
+  out[12] = block_reduce_minmax<NW, true>(live ? gy : -kBig, scratch);
+  out[13] = block_reduce_minmax<NW, true>(live ? gz : -kBig, scratch);
+  if (tid == 0) {
+    float* dst = partial + (static_cast<int64_t>(b) * gridDim.x + chunk) * kPartial;
+#pragma unroll
+    for (int c = 0; c < kPartial; ++c) dst[c] = out[c];
+  }
+}
+
+// One warp per sample: fold the chunk partials in a fixed order, then the bounding-box corner error.
+__global__ void obj_metrics_finish_kernel(const float* __restrict__ partial, int chunks, int n_verts,
+                                          float* __restrict__ adds, float* __restrict__ mme, float* __restrict__ mce) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  constexpr float kBig = 3.402823466e+38f;
+  float v[kPartial];
+#pragma unroll
+  for (int c = 0; c < kPartial; ++c) v[c] = c < 2 ? 0.f : (((c - 2) / 3) % 2 == 0 ? kBig : -kBig);
+  for (int k = lane; k < chunks; k += 32) {
+    const float* src = partial + (static_cast<int64_t>(b) * chunks + k) * kPartial;
+#pragma unroll
+    for (int c = 0; c < kPartial; ++c) {
+      const float u = src[c];
+      v[c] = c < 2 ? v[c] + u : (((c - 2) / 3) % 2 == 0 ? fminf(v[c], u) : fmaxf(v[c], u));
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < kPartial; ++c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float u = __shfl_xor_sync(0xffffffffu, v[c], o);
+      v[c] = c < 2 ? v[c] + u : (((c - 2) / 3) % 2 == 0 ? fminf(v[c], u) : fmaxf(v[c], u));
+    }
+  }
+  if (lane == 0) {
+    if (adds != nullptr) adds[b] = v[0] / static_cast<float>(n_verts);
+    if (mme != nullptr) mme[b] = v[1] / static_cast<float>(n_verts);
+    if (mce != nullptr) {
+      // corner c takes min (0) or max (1) per axis, metrics.py:70-94
+      const int sel[3][8] = {{0, 1, 0, 0, 1, 0, 1, 1}, {0, 0, 1, 0, 1, 1, 0, 1}, {0, 0, 0, 1, 0, 1, 1, 1}};
+      float acc = 0.f;
+      for (int c = 0; c < 8; ++c) {
+        float d2 = 0.f;
+        for (int a = 0; a < 3; ++a) {
+          const float p = v[2 + 3 * sel[a][c] + a], g = v[8 + 3 * sel[a][c] + a];
+          d2 += (p - g) * (p - g);
+        }
+        acc += sqrtf(d2);
+      }
+      mce[b] = acc / 8.f;
+    }
+  }
+}
+
+// ---- hand joints: rigid_transform_3D / rigid_align / eval_hand_joint (metrics.py:188-248) ----
+
+__device__ void procrustes_from_moments(const double H[9], const double cA[3], const double cB[3], double varA,
+                                        double cR[9], double t[3]) {
+  // H = U S V^T by one-sided Jacobi (Hestenes): rotate column pairs of G = H until orthogonal; V accumulates.
+  double G[3][3], V[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) { G[i][j] = H[i * 3 + j]; V[i][j] = i == j ? 1.0 : 0.0; }
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    bool rotated = false;
+    for (int pq = 0; pq < 3; ++pq) {
+      const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;
+      double a = 0, bq = 0, g = 0;
+      for (int i = 0; i < 3; ++i) { a += G[i][p] * G[i][p]; bq += G[i][q] * G[i][q]; g += G[i][p] * G[i][q]; }
+      if (g == 0.0 || fabs(g) <= 1e-15 * sqrt(a * bq)) continue;
+      rotated = true;
+      const double zeta = (bq - a) / (2.0 * g);
+      const double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+      const double c = 1.0 / sqrt(1.0 + tt * tt), s = c * tt;
+      for (int i = 0; i < 3; ++i) {
+        const double x = G[i][p], y = G[i][q];
+        G[i][p] = c * x - s * y; G[i][q] = s * x + c * y;
+        const double vx = V[i][p], vy = V[i][q];
+        V[i][p] = c * vx - s * vy; V[i][q] = s * vx + c * vy;
+      }
+    }
+    if (!rotated) break;
+  }
+  double sig[3];
+  for (int j = 0; j < 3; ++j) sig[j] = sqrt(G[0][j] * G[0][j] + G[1][j] * G[1][j] + G[2][j] * G[2][j]);
+  int k0 = 0, k1 = 1, k2 = 2;      // singular values in descending order
+  if (sig[k0] < sig[k1]) { int s = k0; k0 = k1; k1 = s; }
+  if (sig[k1] < sig[k2]) { int s = k1; k1 = k2; k2 = s; }
+  if (sig[k0] < sig[k1]) { int s = k0; k0 = k1; k1 = s; }
+  // U: the two leading left vectors (completed when the spread is degenerate), third = right-handed completion
+  double u0[3], u1[3], u2[3];
+  if (sig[k0] > 0.0) { for (int i = 0; i < 3; ++i) u0[i] = G[i][k0] / sig[k0]; }
+  else { u0[0] = 1.0; u0[1] = 0.0; u0[2] = 0.0; }
+  if (sig[k1] > 1e-14 * sig[k0] && sig[k1] > 0.0) {
+    for (int i = 0; i < 3; ++i) u1[i] = G[i][k1] / sig[k1];
+  } else {
+    int m = fabs(u0[0]) <= fabs(u0[1]) ? (fabs(u0[0]) <= fabs(u0[2]) ? 0 : 2) : (fabs(u0[1]) <= fabs(u0[2]) ? 1 : 2);
+    double e[3] = {m == 0 ? 1.0 : 0.0, m == 1 ? 1.0 : 0.0, m == 2 ? 1.0 : 0.0};
+    u1[0] = u0[1] * e[2] - u0[2] * e[1]; u1[1] = u0[2] * e[0] - u0[0] * e[2]; u1[2] = u0[0] * e[1] - u0[1] * e[0];
+    const double n = sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+    for (int i = 0; i < 3; ++i) u1[i] /= n;
+  }
+  u2[0] = u0[1] * u1[2] - u0[2] * u1[1]; u2[1] = u0[2] * u1[0] - u0[0] * u1[2]; u2[2] = u0[0] * u1[1] - u0[1] * u1[0];
+  const double v0[3] = {V[0][k0], V[1][k0], V[2][k0]}, v1[3] = {V[0][k1], V[1][k1], V[2][k1]},
+               v2[3] = {V[0][k2], V[1][k2], V[2][k2]};
+  const double detV = v0[0] * (v1[1] * v2[2] - v1[2] * v2[1]) - v0[1] * (v1[0] * v2[2] - v1[2] * v2[0]) +
+                      v0[2] * (v1[0] * v2[1] - v1[1] * v2[0]);
+  // R = V diag(1, 1, d) U^T with det R = +1 (metrics.py:196-202: the det < 0 branch flips s[-1] and V[2]).  With the
+  // right-handed completion u2 this is R = v0 u0^T + v1 u1^T + sign(det V) v2 u2^T; the sign that multiplies the
+  // smallest singular value is d = sign(det V) * sign(<G[:,k2], u2>).
+  const double e = detV >= 0.0 ? 1.0 : -1.0;
+  const double dot2 = G[0][k2] * u2[0] + G[1][k2] * u2[1] + G[2][k2] * u2[2];
+  const double d = e * (dot2 >= 0.0 ? 1.0 : -1.0);
+  const double scale = (sig[k0] + sig[k1] + d * sig[k2]) / varA;      // c = 1 / varP * sum(s)   (:204-205)
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) cR[i * 3 + j] = scale * (v0[i] * u0[j] + v1[i] * u1[j] + e * v2[i] * u2[j]);
+  for (int i = 0; i < 3; ++i)
+    t[i] = -(cR[i * 3 + 0] * cA[0] + cR[i * 3 + 1] * cA[1] + cR[i * 3 + 2] * cA[2]) + cB[i];   // (:207)
+}
+
+constexpr int kJointThreads = 128;
+
+__global__ void __launch_bounds__(kJointThreads)
+hand_joint_metrics_kernel(const float* __restrict__ pred, const float* __restrict__ gt, int n, float* __restrict__ mje,
+                          float* __restrict__ pamje, float* __restrict__ aligned) {
+  __shared__ double scratch[kJointThreads / 32];
+  __shared__ double xf[12];       // c*R (9), t (3)
+  constexpr int NW = kJointThreads / 32;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* A = pred + static_cast<int64_t>(b) * n * 3;
+  const float* Bm = gt + static_cast<int64_t>(b) * n * 3;
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = tid; i < n; i += kJointThreads)
+    for (int c = 0; c < 3; ++c) { acc[c] += A[i * 3 + c]; acc[3 + c] += Bm[i * 3 + c]; }
+  double cen[6];
+  for (int c = 0; c < 6; ++c) cen[c] = block_reduce_sum<double, NW>(acc[c], scratch) / n;
+  double m[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};      // H (9) = (A - cA)^T (B - cB), sum |A - cA|^2
+  for (int i = tid; i < n; i += kJointThreads) {
+    double a[3], bb[3];
+    for (int c = 0; c < 3; ++c) { a[c] = A[i * 3 + c] - cen[c]; bb[c] = Bm[i * 3 + c] - cen[3 + c]; }
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) m[r * 3 + c] += a[r] * bb[c];
+    m[9] += a[0] * a[0] + a[1] * a[1] + a[2] * a[2];
+  }
+  for (int c = 0; c < 10; ++c) m[c] = block_reduce_sum<double, NW>(m[c], scratch) / n;
+  if (tid == 0) {
+    double cR[9], t[3];
+    procrustes_from_moments(m, cen, cen + 3, m[9], cR, t);
+    for (int i = 0; i < 9; ++i) xf[i] = cR[i];
+    for (int i = 0; i < 3; ++i) xf[9 + i] = t[i];
+  }
+  __syncthreads();
+  double e_raw = 0, e_pa = 0;
+  for (int i = tid; i < n; i += kJointThreads) {
+    const double a[3] = {A[i * 3 + 0], A[i * 3 + 1], A[i * 3 + 2]};
+    double dr = 0, dp = 0;
+    for (int r = 0; r < 3; ++r) {
+      const double al = xf[r * 3 + 0] * a[0] + xf[r * 3 + 1] * a[1] + xf[r * 3 + 2] * a[2] + xf[9 + r];
+      if (aligned != nullptr) aligned[(static_cast<int64_t>(b) * n + i) * 3 + r] = static_cast<float>(al);
+      const double g = Bm[i * 3 + r];
+      dr += (a[r] - g) * (a[r] - g);
+      dp += (al - g) * (al - g);
+    }
+    e_raw += sqrt(dr);
+    e_pa += sqrt(dp);
+  }
+  e_raw = block_reduce_sum<double, NW>(e_raw, scratch);
+  e_pa = block_reduce_sum<double, NW>(e_pa, scratch);
+  if (tid == 0) {
+    if (mje != nullptr) mje[b] = static_cast<float>(e_raw / n);
+    if (pamje != nullptr) pamje[b] = static_cast<float>(e_pa / n);
+  }
+}
+
+int check_metric_sizes(int64_t batch, int64_t n_verts) {
+  if (batch < 0 || batch > 65535 || n_verts < 1 || n_verts > (int64_t(1) << 24)) return HOISDF_E_SHAPE;
+  return HOISDF_OK;
+}
+
+}  // namespace
+}  // namespace hoisdf
+
+using namespace hoisdf;
+
+HOISDF_API int64_t hoisdf_obj_metrics_workspace_bytes(int64_t batch, int64_t n_verts) {
+  if (batch < 0 || n_verts < 1) return 0;
+  return batch * ceil_div(n_verts, kThreads) * kPartial * static_cast<int64_t>(sizeof(float));
+}
+
+HOISDF_API int hoisdf_obj_metrics_fwd(const float* templates, const int64_t* obj_ids, int64_t n_templates,
+                                      int64_t n_verts, const float* rot_pred, const float* trans_pred, int64_t votes,
+                                      const float* rot_gt, const float* trans_gt, int64_t batch, float* adds,
+                                      float* mme, float* mce, float* oce, void* workspace, int64_t workspace_bytes,
+                                      void* stream) {
+  if (!templates || !rot_pred || !trans_pred || !rot_gt || !trans_gt || !workspace) return HOISDF_E_NULL;
+  if (int s = check_metric_sizes(batch, n_verts)) return s;
+  if (n_templates < 1 || votes < 1 || votes > (int64_t(1) << 24)) return HOISDF_E_SHAPE;
+  if (obj_ids == nullptr && n_templates < batch) return HOISDF_E_SHAPE;
+  if (workspace_bytes < hoisdf_obj_metrics_workspace_bytes(batch, n_verts)) return HOISDF_E_SHAPE;
+  if (batch == 0) return HOISDF_OK;
+  const int chunks = static_cast<int>(ceil_div(n_verts, kThreads));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* partial = static_cast<float*>(workspace);
+  obj_metrics_partial_kernel<true><<<dim3(chunks, static_cast<unsigned>(batch)), kThreads, 0, st>>>(
+      templates, obj_ids, n_templates, static_cast<int>(n_verts), rot_pred, trans_pred, static_cast<int>(votes), rot_gt,
+      trans_gt, nullptr, nullptr, partial, oce);
+  obj_metrics_finish_kernel<<<static_cast<unsigned>(batch), 32, 0, st>>>(partial, chunks, static_cast<int>(n_verts), adds,
+                                                                        mme, mce);
+  return launch_status();
+}
+
+HOISDF_API int hoisdf_mesh_metrics_fwd(const float* pred_meshes, const float* target_meshes, int64_t batch,
+                                       int64_t n_verts, float* adds, float* mme, float* mce, void* workspace,
+                                       int64_t workspace_bytes, void* stream) {
+  if (!pred_meshes || !target_meshes || !workspace) return HOISDF_E_NULL;
+  if (int s = check_metric_sizes(batch, n_verts)) return s;
+  if (workspace_bytes < hoisdf_obj_metrics_workspace_bytes(batch, n_verts)) return HOISDF_E_SHAPE;
+  if (batch == 0) return HOISDF_OK;
+  const int chunks = static_cast<int>(ceil_div(n_verts, kThreads));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* partial = static_cast<float*>(workspace);
+  obj_metrics_partial_kernel<false><<<dim3(chunks, static_cast<unsigned>(batch)), kThreads, 0, st>>>(
+      nullptr, nullptr, 0, static_cast<int>(n_verts), nullptr, nullptr, 0, nullptr, nullptr, pred_meshes, target_meshes,
+      partial, nullptr);
+  obj_metrics_finish_kernel<<<static_cast<unsigned>(batch), 32, 0, st>>>(partial, chunks, static_cast<int>(n_verts), adds,
+                                                                        mme, mce);
+  return launch_status();
+}
+
+HOISDF_API int hoisdf_hand_joint_metrics_fwd(const float* pred, const float* gt, int64_t batch, int64_t n_points,
+                                             float* mje, float* pamje, float* aligned, void* stream) {
+  if (!pred || !gt) return HOISDF_E_NULL;
+  if (batch < 0 || n_points < 1 || n_points > (int64_t(1) << 24)) return HOISDF_E_SHAPE;
+  if (batch == 0) return HOISDF_OK;
+  hand_joint_metrics_kernel<<<static_cast<unsigned>(batch), kJointThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      pred, gt, static_cast<int>(n_points), mje, pamje, aligned);
+  return launch_status();
+}

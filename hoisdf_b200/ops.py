@@ -797,3 +797,67 @@ def mano_aa(model_struct, pose_aa, betas):
     check(lib.hoisdf_mano_aa_fwd(C.byref(model_struct), pose_aa.data_ptr(), betas.data_ptr(), n, verts.data_ptr(),
                                  joints.data_ptr(), _stream()), "hoisdf_mano_aa_fwd")
     return verts, joints
+
+
+# ----------------------------------------------------------------------------------------------------
+# Test-time metrics (upstream common/metrics.py)
+# ----------------------------------------------------------------------------------------------------
+def _metric_workspace(batch: int, n_verts: int, dev) -> torch.Tensor:
+    nbytes = int(lib.hoisdf_obj_metrics_workspace_bytes(batch, n_verts))
+    return torch.empty(max(nbytes // 4, 1), device=dev, dtype=torch.float32)
+
+
+def obj_pose_metrics(templates, obj_ids, rot_pred, trans_pred, rot_gt, trans_gt):
+    """templates (T,N,3), obj_ids (B) int64 or None, rot_pred / trans_pred (B,P,3) per-point votes, rot_gt / trans_gt
+    (B,3) -> (adds, mme, mce, oce), each (B).  upstream common/metrics.py:110-185."""
+    templates = _f32c(templates, "templates")
+    rot_pred, trans_pred = _f32c(rot_pred, "rot_pred"), _f32c(trans_pred, "trans_pred")
+    rot_gt, trans_gt = _f32c(rot_gt, "rot_gt"), _f32c(trans_gt, "trans_gt")
+    if rot_pred.dim() == 2:                                   # already one pose per sample
+        rot_pred, trans_pred = rot_pred[:, None], trans_pred[:, None]
+    b, votes = rot_pred.shape[0], rot_pred.shape[1]
+    t, n = templates.shape[0], templates.shape[1]
+    if rot_pred.shape != trans_pred.shape or rot_gt.shape != (b, 3) or trans_gt.shape != (b, 3) or \
+            templates.dim() != 3 or templates.shape[2] != 3 or rot_pred.shape[2] != 3:
+        raise ValueError("obj_pose_metrics: inconsistent shapes")
+    if obj_ids is not None:
+        if obj_ids.dtype != torch.int64 or not obj_ids.is_cuda or obj_ids.shape != (b,):
+            raise ValueError("obj_ids must be a CUDA int64 tensor of shape (B,)")
+        obj_ids = obj_ids.contiguous()
+    out = torch.empty(4, b, device=templates.device, dtype=torch.float32)
+    ws = _metric_workspace(b, n, templates.device)
+    _count(2)
+    check(lib.hoisdf_obj_metrics_fwd(templates.data_ptr(), _ptr(obj_ids), t, n, rot_pred.data_ptr(),
+                                     trans_pred.data_ptr(), votes, rot_gt.data_ptr(), trans_gt.data_ptr(), b,
+                                     out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(),
+                                     ws.data_ptr(), ws.numel() * 4, _stream()), "hoisdf_obj_metrics_fwd")
+    return out[0], out[1], out[2], out[3]
+
+
+def mesh_metrics(pred_meshes, target_meshes):
+    """(B,N,3) x2 -> (adds, mme, mce), each (B).  upstream common/metrics.py:62-108."""
+    pred_meshes, target_meshes = _f32c(pred_meshes, "pred_meshes"), _f32c(target_meshes, "target_meshes")
+    if pred_meshes.shape != target_meshes.shape or pred_meshes.dim() != 3 or pred_meshes.shape[2] != 3:
+        raise ValueError("mesh_metrics: meshes must both be (B, N, 3)")
+    b, n = pred_meshes.shape[0], pred_meshes.shape[1]
+    out = torch.empty(3, b, device=pred_meshes.device, dtype=torch.float32)
+    ws = _metric_workspace(b, n, pred_meshes.device)
+    _count(2)
+    check(lib.hoisdf_mesh_metrics_fwd(pred_meshes.data_ptr(), target_meshes.data_ptr(), b, n, out[0].data_ptr(),
+                                      out[1].data_ptr(), out[2].data_ptr(), ws.data_ptr(), ws.numel() * 4, _stream()),
+          "hoisdf_mesh_metrics_fwd")
+    return out[0], out[1], out[2]
+
+
+def hand_joint_metrics(pred, gt, want_aligned: bool = False):
+    """pred / gt (B,J,3) -> (mje (B), pamje (B)[, aligned (B,J,3)]).  upstream common/metrics.py:188-248."""
+    pred, gt = _f32c(pred, "pred"), _f32c(gt, "gt")
+    if pred.shape != gt.shape or pred.dim() != 3 or pred.shape[2] != 3:
+        raise ValueError("hand_joint_metrics: pred and gt must both be (B, J, 3)")
+    b, j = pred.shape[0], pred.shape[1]
+    out = torch.empty(2, b, device=pred.device, dtype=torch.float32)
+    aligned = torch.empty_like(pred) if want_aligned else None
+    _count(1)
+    check(lib.hoisdf_hand_joint_metrics_fwd(pred.data_ptr(), gt.data_ptr(), b, j, out[0].data_ptr(), out[1].data_ptr(),
+                                            _ptr(aligned), _stream()), "hoisdf_hand_joint_metrics_fwd")
+    return (out[0], out[1], aligned) if want_aligned else (out[0], out[1])

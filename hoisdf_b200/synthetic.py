@@ -316,3 +316,28 @@ def dexycb_extras(seed: int, batch: int, ph: int, po: int):
         "rel_obj_trans": torch.zeros(batch, 3),
     }
     return inputs, targets
+
+
+HO3D_OBJECT_NAMES = ("003_cracker_box", "006_mustard_bottle", "010_potted_meat_can", "019_pitcher_base", "021_bleach_cleanser")
+
+
+def metric_inputs(seed: int, batch: int, votes: int = 40, n_templates: int = 5, n_verts: int = 1000):
+    """Synthetic inputs of the test-time metrics (upstream common/metrics.py:110-248), shaped like main/test.py:85-135
+    feeds them: a list of object templates ({"verts": (n_verts, 3)} in metres, `prepare_model_template`), the id -> name
+    table, per-point pose votes `obj_rot` / `obj_trans` (B, votes, 3) around the ground truth, and joint sets (B, 21, 3)."""
+    templates = [{"verts": _uniform(seed, "metrics.template%d" % i, (n_verts, 3), -0.1, 0.1) *
+                  torch.tensor([1.0, 0.6 + 0.1 * i, 0.4])} for i in range(n_templates)]
+    obj_names = {i + 1: HO3D_OBJECT_NAMES[i % len(HO3D_OBJECT_NAMES)] + ("" if i < len(HO3D_OBJECT_NAMES) else "_%d" % i)
+                 for i in range(n_templates)}
+    rot_gt = _uniform(seed, "metrics.rot_gt", (batch, 3), -2.0, 2.0)
+    trans_gt = _uniform(seed, "metrics.trans_gt", (batch, 3), -0.2, 0.2)
+    out = {
+        "obj_rot": rot_gt[:, None] + _uniform(seed, "metrics.rot_noise", (batch, votes, 3), -0.3, 0.3),
+        "obj_trans": trans_gt[:, None] + _uniform(seed, "metrics.trans_noise", (batch, votes, 3), -0.03, 0.03),
+    }
+    targets = {"obj_rot": rot_gt, "rel_obj_trans": trans_gt}
+    ids = torch.from_numpy(_rng(seed, "metrics.obj_ids").integers(1, n_templates + 1, size=batch)).long()
+    joints_gt = _uniform(seed, "metrics.joints_gt", (batch, 21, 3), -0.1, 0.1)
+    joints_pred = joints_gt * 1.1 + _uniform(seed, "metrics.joints_noise", (batch, 21, 3), -0.02, 0.02) + 0.01
+    return dict(templates=templates, obj_names=obj_names, out=out, targets=targets, obj_cls_ids=ids,
+                obj_cls_names=[obj_names[int(i)] for i in ids], joints_pred=joints_pred, joints_gt=joints_gt)

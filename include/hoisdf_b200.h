@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 10
+#define HOISDF_ABI_VERSION 11
 
 enum {
   HOISDF_OK = 0,
@@ -382,6 +382,40 @@ int hoisdf_mano_fwd(const hoisdf_mano_model* model, const float* pose6d, const f
  * (upstream common/nets/mano_head.py:258-276: training and the dexycb evaluation). */
 int hoisdf_mano_aa_fwd(const hoisdf_mano_model* model, const float* pose_aa, const float* betas, int64_t n,
                        float* verts, float* joints, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Test-time metrics -- upstream common/metrics.py:62-185 (eval_batched_obj_direct with
+ * compute_obj_metrics_dexycb / compute_obj_metrics_ho3d; called from main/test.py:131-135) and :188-248
+ * (rigid_transform_3D / rigid_align / eval_hand_joint; main/test.py:186-193, main/train.py:241): the
+ * consumers of the path's obj_rot_out / obj_trans_out / mano_joints_out.
+ *
+ * hoisdf_obj_metrics_fwd: per sample b
+ *     rot = mean_p rot_pred[b,p,:], trans = mean_p trans_pred[b,p,:]            (metrics.py:115-116)
+ *     pred mesh = template . R(rot)^T + trans, target mesh = template . R(rot_gt[b])^T + trans_gt[b]
+ *                 with R = manopth batch_rodrigues (rodrigues_layer.py:15-56)     (metrics.py:152-167)
+ *     adds[b] = mean_i min_j |target_j - pred_i|      (ADD-S, :64-67)   mme[b] = mean_i |target_i - pred_i| (:106)
+ *     mce[b]  = mean over the 8 axis-aligned bounding-box corners of |corner_pred - corner_target| (:70-94)
+ *     oce[b]  = |trans - trans_gt[b]|                                              (:172,179)
+ *   templates (T, N, 3); obj_ids (B) int64 selects the template of each sample (NULL: T >= B, sample b uses
+ *   template b); rot_pred / trans_pred (B, votes, 3) axis-angle / metres; rot_gt / trans_gt (B, 3).
+ *   adds / mme / mce / oce: (B) each, any may be NULL.  The (N x N) distance tensor upstream materialises never
+ *   exists.  workspace: hoisdf_obj_metrics_workspace_bytes(batch, n_verts) bytes (per-CTA partials).
+ * hoisdf_mesh_metrics_fwd: the same three mesh metrics for given meshes (B, N, 3) -- compute_obj_metrics_dexycb /
+ *   compute_obj_metrics_ho3d called directly.
+ * hoisdf_hand_joint_metrics_fwd: per sample, mje = mean_i |pred_i - gt_i| and pamje = the same after the similarity
+ *   (scale, rotation, translation) alignment of rigid_transform_3D; `aligned` (B, n_points, 3), optional, receives
+ *   rigid_align(pred, gt).  pred / gt (B, n_points, 3); n_points = 21 joints or 778 vertices.
+ * ------------------------------------------------------------------------------------------------- */
+int64_t hoisdf_obj_metrics_workspace_bytes(int64_t batch, int64_t n_verts);
+int hoisdf_obj_metrics_fwd(const float* templates, const int64_t* obj_ids, int64_t n_templates, int64_t n_verts,
+                           const float* rot_pred, const float* trans_pred, int64_t votes, const float* rot_gt,
+                           const float* trans_gt, int64_t batch, float* adds, float* mme, float* mce, float* oce,
+                           void* workspace, int64_t workspace_bytes, void* stream);
+int hoisdf_mesh_metrics_fwd(const float* pred_meshes, const float* target_meshes, int64_t batch, int64_t n_verts,
+                            float* adds, float* mme, float* mce, void* workspace, int64_t workspace_bytes,
+                            void* stream);
+int hoisdf_hand_joint_metrics_fwd(const float* pred, const float* gt, int64_t batch, int64_t n_points, float* mje,
+                                  float* pamje, float* aligned, void* stream);
 
 #ifdef __cplusplus
 }

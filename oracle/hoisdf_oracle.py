@@ -715,3 +715,78 @@ def model_eval_dexycb(p, img, inputs, targets, meta, cfg, arch="dexycb", taps=No
     loss["obj_rot"] = F.smooth_l1_loss(obj_rot, targets["obj_rot"][None, None].expand_as(obj_rot))
     loss["obj_trans"] = F.smooth_l1_loss(obj_trans, targets["rel_obj_trans"][None, None].expand_as(obj_trans))
     return {**loss, **out}
+
+
+# ----------------------------------------------------------------------------------------------------
+# Test-time metrics (upstream common/metrics.py) -- the consumer of obj_rot_out / obj_trans_out / mano_joints_out
+# ----------------------------------------------------------------------------------------------------
+def batch_rodrigues(axisang):
+    """manopth/manopth/rodrigues_layer.py:15-56: axis-angle (N,3) -> quaternion -> rotation matrices (N,3,3)."""
+    angle = torch.norm(axisang + 1e-8, p=2, dim=1, keepdim=True)
+    normalized = axisang / angle
+    half = angle * 0.5
+    quat = torch.cat([torch.cos(half), torch.sin(half) * normalized], dim=1)
+    quat = quat / quat.norm(p=2, dim=1, keepdim=True)
+    w, x, y, z = quat[:, 0], quat[:, 1], quat[:, 2], quat[:, 3]
+    w2, x2, y2, z2 = w * w, x * x, y * y, z * z
+    wx, wy, wz, xy, xz, yz = w * x, w * y, w * z, x * y, x * z, y * z
+    return torch.stack([w2 + x2 - y2 - z2, 2 * xy - 2 * wz, 2 * wy + 2 * xz,
+                        2 * wz + 2 * xy, w2 - x2 + y2 - z2, 2 * yz - 2 * wx,
+                        2 * xz - 2 * wy, 2 * wx + 2 * yz, w2 - x2 - y2 + z2], dim=1).view(-1, 3, 3)
+
+
+def mesh_metrics(pred_meshes, target_meshes):
+    """common/metrics.py:62-108 (compute_obj_metrics_dexycb / _ho3d): per sample ADD-S (mean over predicted vertices of
+    the distance to the closest target vertex), MME (mean per-vertex distance) and MCE (mean distance between the 8
+    corners of the two axis-aligned bounding boxes).  (B,N,3) x2 -> three (B) tensors."""
+    dis = (target_meshes[:, None, :, :] - pred_meshes[:, :, None, :]).norm(dim=-1)          # [b, i(pred), j(target)]
+    adds = dis.min(dim=2)[0].mean(dim=1)
+    mme = (target_meshes - pred_meshes).norm(2, -1).mean(-1)
+    sel = torch.tensor([[0, 1, 0, 0, 1, 0, 1, 1], [0, 0, 1, 0, 1, 1, 0, 1], [0, 0, 0, 1, 0, 1, 1, 1]])
+
+    def corners(m):
+        mm = torch.stack([m.min(dim=1)[0], m.max(dim=1)[0]], dim=2)                          # (B, 3, 2)
+        return torch.stack([mm[:, 0, sel[0]], mm[:, 1, sel[1]], mm[:, 2, sel[2]]], dim=2)   # (B, 8, 3)
+
+    mce = (corners(pred_meshes) - corners(target_meshes)).norm(2, -1).mean(-1)
+    return adds, mme, mce
+
+
+def obj_pose_metrics(templates, obj_ids, rot_votes, trans_votes, rot_gt, trans_gt):
+    """common/metrics.py:110-185 (eval_batched_obj_direct) per sample, before the batch means: mean of the pose votes
+    (:115-116), posed template meshes (:147-167), then mesh_metrics and OCE = |trans - trans_gt| (:172,179).
+    templates (T,N,3), obj_ids (B) -> adds, mme, mce, oce, each (B)."""
+    rot, trans = rot_votes.mean(1), trans_votes.mean(1)
+    tm = templates[obj_ids]
+    target = torch.bmm(tm, batch_rodrigues(rot_gt).permute(0, 2, 1)) + trans_gt[:, None, :]
+    pred = torch.bmm(tm, batch_rodrigues(rot).permute(0, 2, 1)) + trans[:, None, :]
+    adds, mme, mce = mesh_metrics(pred, target)
+    return adds, mme, mce, torch.norm(trans - trans_gt, dim=-1)
+
+
+def rigid_align(A, B):
+    """common/metrics.py:188-213 (rigid_transform_3D + rigid_align), numpy like upstream: A (N,3) mapped onto B by the
+    best similarity transform (Umeyama: SVD of the cross-covariance, reflection fixed on the last singular vector)."""
+    import numpy as np
+    A, B = np.asarray(A), np.asarray(B)
+    n = A.shape[0]
+    ca, cb = A.mean(axis=0), B.mean(axis=0)
+    H = (A - ca).T @ (B - cb) / n
+    U, s, V = np.linalg.svd(H)
+    R = V.T @ U.T
+    if np.linalg.det(R) < 0:
+        s[-1] = -s[-1]
+        V[2] = -V[2]
+        R = V.T @ U.T
+    c = 1 / np.var(A, axis=0).sum() * s.sum()
+    t = -(c * R) @ ca + cb
+    return (c * R @ A.T).T + t
+
+
+def hand_joint_metrics(pred, gt):
+    """common/metrics.py:231-248 (eval_hand_joint) per sample, before the means: (B,J,3) x2 -> mje (B), pamje (B)."""
+    import numpy as np
+    pred, gt = np.asarray(pred), np.asarray(gt)
+    mje = [np.sqrt(((p - g) ** 2).sum(1)).mean() for p, g in zip(pred, gt)]
+    pamje = [np.sqrt(((rigid_align(p, g) - g) ** 2).sum(1)).mean() for p, g in zip(pred, gt)]
+    return torch.tensor(np.array(mje, dtype=np.float32)), torch.tensor(np.array(pamje, dtype=np.float32))

@@ -181,6 +181,38 @@ def dexycb_eval_case(name, seed, batch, ph, po):
     print(name, {k: tuple(v.shape) for k, v in out.items()})
 
 
+def metrics_case(name, seed, batch):
+    """Test-time metrics (upstream common/metrics.py) on seeded synthetic predictions: both dataset branches of
+    eval_batched_obj_direct, the two mesh-metric helpers, eval_hand_joint and rigid_align."""
+    rs.load("dexycb")
+    import common.metrics as UM
+    m = syn.metric_inputs(seed, batch)
+    fix = {"seed": seed, "batch": batch}
+    with torch.no_grad():
+        dex = UM.eval_batched_obj_direct(m["out"], m["targets"], {"obj_cls": m["obj_cls_ids"], "cam_intr": torch.eye(3)[None]},
+                                         m["templates"], None, m["obj_names"])
+        ho3d = UM.eval_batched_obj_direct(m["out"], m["targets"], {"obj_cls": m["obj_cls_names"], "cam_intr": torch.eye(3)[None]},
+                                          m["templates"], None, m["obj_names"])
+        fix["dexycb_result"] = np.array([dex[0], dex[1], dex[2], dex[4]], dtype=np.float64)      # ADDS, MCE, OCE, n
+        fix["ho3d_result"] = np.array([ho3d[0], ho3d[3], ho3d[4]], dtype=np.float64)              # ADDS, MME, n
+        assert dex[3] is None and ho3d[1] is None and ho3d[2] is None
+        # per-sample values of the helpers on the posed meshes of the dexycb branch
+        ids = m["obj_cls_ids"] - 1
+        tm = torch.stack([m["templates"][int(i)]["verts"] for i in ids])
+        rot, trans = m["out"]["obj_rot"].mean(1), m["out"]["obj_trans"].mean(1)
+        pred = torch.bmm(tm, UM.batch_rodrigues(rot).reshape(batch, 3, 3).permute(0, 2, 1)) + trans[:, None]
+        tgt = torch.bmm(tm, UM.batch_rodrigues(m["targets"]["obj_rot"]).reshape(batch, 3, 3).permute(0, 2, 1)) \
+            + m["targets"]["rel_obj_trans"][:, None]
+        fix["adds"], fix["mce"] = UM.compute_obj_metrics_dexycb(pred, tgt)
+        adds2, fix["mme"] = UM.compute_obj_metrics_ho3d(pred, tgt)
+        assert torch.equal(adds2, fix["adds"])
+        fix["hand_joint_result"] = np.array(UM.eval_hand_joint(m["joints_pred"], m["joints_gt"]), dtype=np.float64)
+        fix["aligned0"] = UM.rigid_align(m["joints_pred"][0].numpy(), m["joints_gt"][0].numpy())
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **_np(fix))
+    print(name, {k: np.asarray(v).shape for k, v in fix.items()}, fix["dexycb_result"], fix["ho3d_result"],
+          fix["hand_joint_result"])
+
+
 if __name__ == "__main__":
     assert rs.available(), "the upstream reference is not mounted; golden vectors can only be made in the build container"
     os.makedirs(OUT, exist_ok=True)
@@ -190,3 +222,4 @@ if __name__ == "__main__":
     hot_path_case("hot_path_ho3d_seed12", "ho3d", 12, 1, 96, 40)
     image_case("image_dexycb_seed13", "dexycb", 13, 1, 48, 16)
     dexycb_eval_case("dexycb_eval_seed14", 14, 2, 48, 16)
+    metrics_case("metrics_seed15", 15, 6)

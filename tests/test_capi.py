@@ -48,6 +48,16 @@ def test_argument_validation_without_gpu(lib_built):
     assert lib.hoisdf_lattice_chunks(64) == 256
 
 
+def test_metric_argument_validation(lib_built):
+    from hoisdf_b200 import _capi
+    lib = _capi.lib
+    assert lib.hoisdf_obj_metrics_fwd(None, None, 1, 1, None, None, 1, None, None, 1, None, None, None, None, None, 0, None) == -1
+    assert lib.hoisdf_mesh_metrics_fwd(16, 16, 1, 0, None, None, None, 16, 1 << 20, None) == -2
+    assert lib.hoisdf_mesh_metrics_fwd(16, 16, 1, 1000, None, None, None, 16, 8, None) == -2      # workspace too small
+    assert lib.hoisdf_hand_joint_metrics_fwd(None, None, 1, 21, None, None, None, None) == -1
+    assert lib.hoisdf_obj_metrics_workspace_bytes(32, 1000) == 32 * 4 * 14 * 4
+
+
 def test_no_cpu_fallback(lib_built):
     """The product path refuses CPU tensors instead of silently computing elsewhere."""
     import torch

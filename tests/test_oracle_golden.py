@@ -115,3 +115,23 @@ def test_dexycb_eval_fixture():
     for k in DEX_LOSS_KEYS + DEX_OUT_KEYS:
         close(out[k], g[k], 1e-3 if k in ("obj_rot_out", "obj_trans_out", "hand_joints_out", "loss_joint_3d",
                                             "loss_all_joint_3d", "loss_joint_cls", "obj_rot", "obj_trans") else 1e-4)
+
+
+def test_metrics_fixture():
+    """Test-time metrics (upstream common/metrics.py:62-248): the oracle's per-sample restatement reproduces the batch
+    results of the upstream functions on both dataset branches, and its helpers per sample."""
+    g = load("metrics_seed15")
+    seed, B = int(g["seed"]), int(g["batch"])
+    m = syn.metric_inputs(seed, B)
+    templates = torch.stack([t["verts"] for t in m["templates"]])
+    ids = m["obj_cls_ids"] - 1
+    adds, mme, mce, oce = O.obj_pose_metrics(templates, ids, m["out"]["obj_rot"], m["out"]["obj_trans"],
+                                             m["targets"]["obj_rot"], m["targets"]["rel_obj_trans"])
+    close(adds, g["adds"]); close(mce, g["mce"]); close(mme, g["mme"])
+    close([adds.mean(), mce.mean(), oce.mean(), B], g["dexycb_result"])
+    used = [i for i, n in enumerate(m["obj_cls_names"]) if n != "019_pitcher_base"]
+    assert 0 < len(used) < B                      # the fixture exercises the HO3D exclusion (metrics.py:129-141)
+    close([adds[used].mean(), mme[used].mean(), len(used)], g["ho3d_result"])
+    mje, pamje = O.hand_joint_metrics(m["joints_pred"], m["joints_gt"])
+    close([mje.mean(), pamje.mean()], g["hand_joint_result"])
+    close(O.rigid_align(m["joints_pred"][0].numpy(), m["joints_gt"][0].numpy()), g["aligned0"])
