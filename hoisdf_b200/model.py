@@ -752,3 +752,21 @@ def get_model(mode, mano_buffers=None, mano_root="tool/mano_models"):
                            use_pca=False, buffers=mano_buffers)
     return Model(backbone_net, decoder_net, hand_sdf_decoder, obj_sdf_decoder, hand_transformer, obj_transformer,
                  mano_layer)
+
+
+def load_checkpoint(model: nn.Module, checkpoint, strict: bool = True):
+    """Load a released / trainer-written snapshot (upstream common/base.py:137-145 writes {"epoch", "network",
+    "optimizer", ...} with the state dict of the `DataParallel` wrapper, i.e. every key prefixed `module.`;
+    `Tester._make_model`, base.py:179-193, loads it into the wrapper with strict=True).  `checkpoint` is a path, the
+    loaded dict, or a bare state dict; the `module.` prefix is stripped when `model` is not itself wrapped.
+    Returns the checkpoint dict (epoch etc.) for the caller."""
+    ckpt = torch.load(checkpoint, map_location="cpu", weights_only=False) if isinstance(checkpoint, (str, bytes)) \
+        or hasattr(checkpoint, "__fspath__") else checkpoint
+    state = ckpt["network"] if isinstance(ckpt, dict) and "network" in ckpt else ckpt
+    wrapped = isinstance(model, (nn.DataParallel, nn.parallel.DistributedDataParallel))
+    if not wrapped and state and all(k.startswith("module.") for k in state):
+        state = {k[len("module."):]: v for k, v in state.items()}
+    elif wrapped and state and not any(k.startswith("module.") for k in state):
+        state = {"module." + k: v for k, v in state.items()}
+    model.load_state_dict(state, strict=strict)
+    return ckpt

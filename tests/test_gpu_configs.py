@@ -41,8 +41,18 @@ def sized(request, cuda):
     type(cfg).dataset, type(cfg).num_samp_hand, type(cfg).num_samp_obj = old[1], old[2], old[3]
 
 
+def _record(name, measured):
+    """Leave the measured errors where a gpurun call brings them back (gpurun_out/), if that directory exists."""
+    import json
+    import os
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "config_parity_%s.json" % name), "w") as fh:
+            json.dump(measured, fh, indent=1)
+
+
 def test_hot_path_at_config_size(sized):
-    """Selected index sets identical to the oracle's, every `*_out` within the north star's 1e-3 (1e-4 measured bar)."""
+    """Selected index sets identical to the oracle's, every `*_out` within the north star's 1e-3."""
     s, m, dev = sized, sized["model"], sized["dev"]
     B, ph, po = 2, s["ph"], s["po"]
     meta, pyr = syn.camera_meta(s["seed"], B), syn.feature_pyramid(s["seed"], B, s["arch"])
@@ -55,11 +65,14 @@ def test_hot_path_at_config_size(sized):
     check_selection(taps["obj"], otaps["obj"], po)
     align_selection(taps["hand"]["index"], otaps["hand"]["index"], otaps["hand_sdf"])
     op = align_selection(taps["obj"]["index"], otaps["obj"]["index"], otaps["obj_sdf"])
-    assert rel(taps["hs"], otaps["hs"].transpose(1, 2)) < 1e-4
+    measured = {"hs": rel(taps["hs"], otaps["hs"].transpose(1, 2))}
     for k in oout:
         got = aligned(out[k], op) if k in ("obj_rot_out", "obj_trans_out") else out[k]
         assert got.shape == oout[k].shape, k
-        assert rel(got, oout[k]) < 1e-4, (k, rel(got, oout[k]))        # north star: 1e-3
+        measured[k] = rel(got, oout[k])
+    _record(s["name"], measured)
+    for k, v in measured.items():
+        assert v < 1e-3, (k, v)                                         # the north star's bar (measured: ~1e-5)
 
 
 def test_full_batch_properties(sized):

@@ -48,9 +48,21 @@ def test_state_dict_contract(lib_built, arch, C):
         assert msd["mano_query_embed.weight"].shape == (17, 256) and msd["norm1.weight"].shape == (C,)
         assert msd["mano_head.mano_layer.th_faces"].dtype == torch.int64
         # checkpoints written under DataParallel carry a "module." prefix (upstream common/base.py:188-191)
-        wrapped = torch.nn.DataParallel(model) if False else None
+        import os
+        import tempfile
+        from hoisdf_b200.model import load_checkpoint
         pref = {"module." + k: v for k, v in sd.items()}
-        model.load_state_dict({k[len("module."):]: v for k, v in pref.items()}, strict=True)
+        with tempfile.TemporaryDirectory() as d:
+            path = os.path.join(d, "snapshot_0.pth.tar")         # the trainer's file layout (base.py:137-145)
+            torch.save({"epoch": 7, "network": pref, "optimizer": {}}, path)
+            fresh = get_model("test", mano_buffers=syn.mano_buffers(1))
+            assert load_checkpoint(fresh, path)["epoch"] == 7
+        got = fresh.state_dict()
+        assert all(torch.equal(got[k], sd[k]) for k in sd)
+        load_checkpoint(torch.nn.DataParallel(fresh), {"network": pref})      # the wrapper keeps the prefix
+        load_checkpoint(fresh, sd)                                            # bare state dict
+        with pytest.raises(RuntimeError):                                     # strict: a missing key is an error
+            load_checkpoint(fresh, {"network": {k: v for k, v in pref.items() if "linear_pose" not in k}})
     finally:
         cfg.set_setting(old)
 

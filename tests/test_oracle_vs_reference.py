@@ -36,3 +36,24 @@ def test_masks_and_lattice_match_upstream():
     ocfg = O.default_cfg()
     assert torch.equal(get_mano_tgt_mask(), O.mano_tgt_mask(ocfg))
     assert torch.equal(get_mano_memory_mask(), O.mano_memory_mask(ocfg))
+
+
+def test_metrics_match_upstream():
+    """common/metrics.py on a second seed and other sizes than the committed fixture."""
+    rs.load("dexycb")
+    import common.metrics as UM
+    B = 5
+    m = syn.metric_inputs(33, B, votes=17, n_templates=4, n_verts=300)
+    templates = torch.stack([t["verts"] for t in m["templates"]])
+    adds, mme, mce, oce = O.obj_pose_metrics(templates, m["obj_cls_ids"] - 1, m["out"]["obj_rot"], m["out"]["obj_trans"],
+                                             m["targets"]["obj_rot"], m["targets"]["rel_obj_trans"])
+    dex = UM.eval_batched_obj_direct(m["out"], m["targets"], {"obj_cls": m["obj_cls_ids"], "cam_intr": torch.eye(3)[None]},
+                                     m["templates"], None, m["obj_names"])
+    for got, want in zip((adds.mean(), mce.mean(), oce.mean()), dex[:3]):
+        assert abs(float(got) - want) <= 1e-5 * abs(want)
+    assert dex[3] is None and dex[4] == B
+    mje, pamje = O.hand_joint_metrics(m["joints_pred"], m["joints_gt"])
+    want = UM.eval_hand_joint(m["joints_pred"], m["joints_gt"])
+    assert abs(float(mje.mean()) - want[0]) <= 1e-5 * want[0] and abs(float(pamje.mean()) - want[1]) <= 1e-5 * want[1]
+    assert torch.allclose(O.batch_rodrigues(m["targets"]["obj_rot"]).reshape(B, 9),
+                          UM.batch_rodrigues(m["targets"]["obj_rot"]), atol=1e-6)
