@@ -322,10 +322,10 @@ def run_native(args):
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, sec, threads = time_cpu(2, 3, 1)
+        v, sec, threads = time_cpu(4, 4, 1)                 # ~10-15 s of host work on the box's cores
         cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": "oracle port of the upstream eval forward, 2 samples/step of the same workload, "
-                                  "1 warm-up + 3 timed steps (%.1f s/step)" % sec}
+                        "sample": "oracle port of the upstream eval forward, 4 samples/step of the same workload, "
+                                  "1 warm-up + 4 timed steps (%.1f s/step)" % sec}
     if rank == 0:
         conf = workload_config(world, B)
         if n_f is not None:
