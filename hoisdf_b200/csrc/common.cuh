@@ -6,6 +6,8 @@
 #include "../../include/hoisdf_b200.h"
 
 #define HOISDF_API extern "C" __attribute__((visibility("default")))
+// kernel launch on `stream` with no dynamic shared memory; tests/emu/cuda_emu.h redefines it to run the kernel on CPU threads
+#define HOISDF_LAUNCH(kernel, grid, block, stream, ...) kernel<<<grid, block, 0, stream>>>(__VA_ARGS__)
 
 namespace hoisdf {
 

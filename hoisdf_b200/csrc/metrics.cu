@@ -7,7 +7,11 @@
 //     twice); here the target mesh is staged tile by tile in shared memory and nothing of size N x N exists;
 //   * eval_hand_joint / rigid_align / rigid_transform_3D (:188-228): MJE and Procrustes-aligned PA-MJE, upstream a
 //     per-sample numpy loop with a D2H copy per sample; here one CTA per sample, the 3x3 SVD by one-sided Jacobi in fp64.
+#ifdef HOISDF_EMULATE
+#include "cuda_emu.h"      // tests/emu: the CPU thread emulator that runs this file's kernels in the "not gpu" test suite
+#else
 #include "common.cuh"
+#endif
 
 namespace hoisdf {
 namespace {
@@ -377,11 +381,11 @@ HOISDF_API int hoisdf_obj_metrics_fwd(const float* templates, const int64_t* obj
   const int chunks = static_cast<int>(ceil_div(n_verts, kThreads));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* partial = static_cast<float*>(workspace);
-  obj_metrics_partial_kernel<true><<<dim3(chunks, static_cast<unsigned>(batch)), kThreads, 0, st>>>(
-      templates, obj_ids, n_templates, static_cast<int>(n_verts), rot_pred, trans_pred, static_cast<int>(votes), rot_gt,
-      trans_gt, nullptr, nullptr, partial, oce);
-  obj_metrics_finish_kernel<<<static_cast<unsigned>(batch), 32, 0, st>>>(partial, chunks, static_cast<int>(n_verts), adds,
-                                                                        mme, mce);
+  HOISDF_LAUNCH(obj_metrics_partial_kernel<true>, dim3(chunks, static_cast<unsigned>(batch)), kThreads, st, templates,
+                obj_ids, n_templates, static_cast<int>(n_verts), rot_pred, trans_pred, static_cast<int>(votes), rot_gt,
+                trans_gt, static_cast<const float*>(nullptr), static_cast<const float*>(nullptr), partial, oce);
+  HOISDF_LAUNCH(obj_metrics_finish_kernel, static_cast<unsigned>(batch), 32, st, static_cast<const float*>(partial),
+                chunks, static_cast<int>(n_verts), adds, mme, mce);
   return launch_status();
 }
 
@@ -395,11 +399,12 @@ HOISDF_API int hoisdf_mesh_metrics_fwd(const float* pred_meshes, const float* ta
   const int chunks = static_cast<int>(ceil_div(n_verts, kThreads));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* partial = static_cast<float*>(workspace);
-  obj_metrics_partial_kernel<false><<<dim3(chunks, static_cast<unsigned>(batch)), kThreads, 0, st>>>(
-      nullptr, nullptr, 0, static_cast<int>(n_verts), nullptr, nullptr, 0, nullptr, nullptr, pred_meshes, target_meshes,
-      partial, nullptr);
-  obj_metrics_finish_kernel<<<static_cast<unsigned>(batch), 32, 0, st>>>(partial, chunks, static_cast<int>(n_verts), adds,
-                                                                        mme, mce);
+  const float* none = nullptr;
+  HOISDF_LAUNCH(obj_metrics_partial_kernel<false>, dim3(chunks, static_cast<unsigned>(batch)), kThreads, st, none,
+                static_cast<const int64_t*>(nullptr), int64_t(0), static_cast<int>(n_verts), none, none, 0, none, none,
+                pred_meshes, target_meshes, partial, static_cast<float*>(nullptr));
+  HOISDF_LAUNCH(obj_metrics_finish_kernel, static_cast<unsigned>(batch), 32, st, static_cast<const float*>(partial),
+                chunks, static_cast<int>(n_verts), adds, mme, mce);
   return launch_status();
 }
 
@@ -408,7 +413,7 @@ HOISDF_API int hoisdf_hand_joint_metrics_fwd(const float* pred, const float* gt,
   if (!pred || !gt) return HOISDF_E_NULL;
   if (batch < 0 || n_points < 1 || n_points > (int64_t(1) << 24)) return HOISDF_E_SHAPE;
   if (batch == 0) return HOISDF_OK;
-  hand_joint_metrics_kernel<<<static_cast<unsigned>(batch), kJointThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      pred, gt, static_cast<int>(n_points), mje, pamje, aligned);
+  HOISDF_LAUNCH(hand_joint_metrics_kernel, static_cast<unsigned>(batch), kJointThreads, static_cast<cudaStream_t>(stream),
+                pred, gt, static_cast<int>(n_points), mje, pamje, aligned);
   return launch_status();
 }

@@ -1,0 +1,89 @@
+// TEST INFRASTRUCTURE: a minimal CPU emulation of the CUDA execution model, enough to run the simple (non-tensor-core)
+// kernels of hoisdf_b200/csrc/*.cu unchanged on a host without a GPU: one OS thread per CUDA thread, blocks executed
+// one after another, `__shared__` = function-local static storage, `__syncthreads()` = a std::barrier over the block,
+// warp shuffles = an exchange buffer between two block barriers (valid for block-uniform shuffles, which is how these
+// kernels use them).  Built by tests/test_kernel_emulation.py with `g++ -std=c++20 -DHOISDF_EMULATE`; never part of
+// libhoisdf_b200.so.
+#pragma once
+#include <stdint.h>
+
+#include <algorithm>
+#include <barrier>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#include "../../include/hoisdf_b200.h"
+
+#define HOISDF_API extern "C" __attribute__((visibility("default")))
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __shared__ static
+
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+using cudaStream_t = void*;
+
+namespace emu {
+inline thread_local dim3 thread_idx, block_idx;
+inline dim3 block_dim, grid_dim;
+inline std::unique_ptr<std::barrier<>> block_barrier;
+inline unsigned char exchange[1024][16];
+
+template <typename K, typename... Args>
+void launch(K kernel, dim3 grid, dim3 block, Args... args) {
+  grid_dim = grid;
+  block_dim = block;
+  const unsigned n = block.x * block.y * block.z;
+  for (unsigned bz = 0; bz < grid.z; ++bz)
+    for (unsigned by = 0; by < grid.y; ++by)
+      for (unsigned bx = 0; bx < grid.x; ++bx) {
+        block_barrier = std::make_unique<std::barrier<>>(n);
+        std::vector<std::thread> threads;
+        threads.reserve(n);
+        for (unsigned t = 0; t < n; ++t)
+          threads.emplace_back([=]() {
+            thread_idx = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+            block_idx = dim3(bx, by, bz);
+            kernel(args...);
+          });
+        for (auto& th : threads) th.join();
+      }
+}
+}  // namespace emu
+
+#define threadIdx emu::thread_idx
+#define blockIdx emu::block_idx
+#define blockDim emu::block_dim
+#define gridDim emu::grid_dim
+#define HOISDF_LAUNCH(kernel, grid, block, stream, ...) emu::launch(kernel, dim3(grid), dim3(block), __VA_ARGS__)
+
+inline void __syncthreads() { emu::block_barrier->arrive_and_wait(); }
+
+template <typename T>
+inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
+  static_assert(sizeof(T) <= 16, "exchange slot too small");
+  const unsigned tid = threadIdx.x + threadIdx.y * blockDim.x + threadIdx.z * blockDim.x * blockDim.y;
+  std::memcpy(emu::exchange[tid], &v, sizeof(T));
+  __syncthreads();
+  T r;
+  std::memcpy(&r, emu::exchange[(tid & ~31u) | ((tid ^ static_cast<unsigned>(lane_mask)) & 31u)], sizeof(T));
+  __syncthreads();
+  return r;
+}
+
+using std::max;
+using std::min;
+
+namespace hoisdf {
+static inline int launch_status() { return HOISDF_OK; }
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+}  // namespace hoisdf

@@ -1,0 +1,108 @@
+"""The simple (non-tensor-core) CUDA kernels of csrc/metrics.cu executed UNCHANGED on the host by a CPU thread emulator
+(tests/emu/cuda_emu.h: one OS thread per CUDA thread, std::barrier for __syncthreads, an exchange buffer for warp
+shuffles) and compared with the oracle -- so that the kernel source, its launch geometry and its C-ABI argument
+handling are checked in the GPU-less suite too.  Test infrastructure: the emulated library is built from the same
+.cu file with `g++ -DHOISDF_EMULATE` into tests/emu/_build/ and is never loaded by the product."""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from hoisdf_b200 import synthetic as syn
+from oracle import hoisdf_oracle as O
+from util import rel
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU = os.path.join(ROOT, "tests", "emu")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    out = os.path.join(EMU, "_build")
+    os.makedirs(out, exist_ok=True)
+    lib = os.path.join(out, "libmetrics_emu.so")
+    src = os.path.join(ROOT, "hoisdf_b200", "csrc", "metrics.cu")
+    deps = [src, os.path.join(EMU, "cuda_emu.h"), os.path.join(ROOT, "include", "hoisdf_b200.h")]
+    if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(d) for d in deps):
+        subprocess.run([gxx, "-std=c++20", "-O1", "-pthread", "-fPIC", "-shared", "-DHOISDF_EMULATE", "-I" + EMU,
+                        "-x", "c++", src, "-o", lib], check=True)
+    lib = C.CDLL(lib)
+    lib.hoisdf_obj_metrics_workspace_bytes.restype = C.c_int64
+    lib.hoisdf_obj_metrics_workspace_bytes.argtypes = [C.c_int64, C.c_int64]
+    vp, i64 = C.c_void_p, C.c_int64
+    lib.hoisdf_obj_metrics_fwd.argtypes = [vp, vp, i64, i64, vp, vp, i64, vp, vp, i64, vp, vp, vp, vp, vp, i64, vp]
+    lib.hoisdf_mesh_metrics_fwd.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp, i64, vp]
+    lib.hoisdf_hand_joint_metrics_fwd.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp]
+    return lib
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def f32(t):
+    return np.ascontiguousarray(torch.as_tensor(t).numpy(), dtype=np.float32)
+
+
+@pytest.mark.parametrize("B,N,votes,by_id", [(2, 300, 17, True), (1, 1, 1, True), (2, 1100, 300, False)])
+def test_obj_metrics_kernels_on_the_emulator(emu, B, N, votes, by_id):
+    m = syn.metric_inputs(40 + N, B, votes=votes, n_templates=3, n_verts=N)
+    templates = torch.stack([t["verts"] for t in m["templates"]])
+    ids = m["obj_cls_ids"] - 1
+    args = (m["out"]["obj_rot"], m["out"]["obj_trans"], m["targets"]["obj_rot"], m["targets"]["rel_obj_trans"])
+    want = O.obj_pose_metrics(templates, ids, *args)
+    tm = f32(templates if by_id else templates[ids])
+    idn = np.ascontiguousarray(ids.numpy(), dtype=np.int64) if by_id else None
+    rp, tp, rg, tg = (f32(a) for a in args)
+    out = np.full((4, B), np.nan, np.float32)
+    nbytes = emu.hoisdf_obj_metrics_workspace_bytes(B, N)
+    ws = np.zeros(nbytes // 4, np.float32)
+    rc = emu.hoisdf_obj_metrics_fwd(ptr(tm), ptr(idn), tm.shape[0], N, ptr(rp), ptr(tp), votes, ptr(rg), ptr(tg), B,
+                                    out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data, out[3].ctypes.data,
+                                    ptr(ws), nbytes, None)
+    assert rc == 0
+    for name, got, ref in zip(("adds", "mme", "mce", "oce"), out, want):
+        assert rel(got, ref) < 1e-5 or float(np.abs(got - ref.numpy()).max()) < 1e-9, (name, got, ref)
+    # the same meshes given directly (compute_obj_metrics_* entry)
+    tsel = templates[ids]
+    pred = torch.bmm(tsel, O.batch_rodrigues(args[0].mean(1)).permute(0, 2, 1)) + args[1].mean(1)[:, None]
+    tgt = torch.bmm(tsel, O.batch_rodrigues(args[2]).permute(0, 2, 1)) + args[3][:, None]
+    out2 = np.full((3, B), np.nan, np.float32)
+    pm, tmesh = f32(pred), f32(tgt)
+    rc = emu.hoisdf_mesh_metrics_fwd(ptr(pm), ptr(tmesh), B, N, out2[0].ctypes.data, out2[1].ctypes.data,
+                                     out2[2].ctypes.data, ptr(ws), nbytes, None)
+    assert rc == 0
+    for name, got, ref in zip(("adds", "mme", "mce"), out2, O.mesh_metrics(pred, tgt)):
+        assert rel(got, ref) < 1e-5 or float(np.abs(got - ref.numpy()).max()) < 1e-9, (name, got, ref)
+    assert emu.hoisdf_mesh_metrics_fwd(ptr(pm), ptr(tmesh), B, N, None, None, None, ptr(ws), 4, None) == -2
+
+
+@pytest.mark.parametrize("J", [21, 300, 3])
+def test_hand_joint_kernel_on_the_emulator(emu, J):
+    gen = torch.Generator().manual_seed(J)
+    B = 5
+    gt = torch.randn(B, J, 3, generator=gen) * 0.08
+    pred = gt * 1.2 + torch.randn(B, J, 3, generator=gen) * 0.01 + 0.02
+    q, _ = torch.linalg.qr(torch.randn(3, 3, generator=gen))
+    pred[1] = gt[1] @ q.T * 0.7 + 0.3
+    pred[2] = gt[2] * torch.tensor([1.0, 1.0, -1.0])        # mirror image: the det < 0 branch (metrics.py:197-202)
+    if J > 3:
+        pred[3, :, 2] = 0.0
+        gt[3, :, 2] = 0.0                                   # planar: rank-deficient cross-covariance
+    p, g = f32(pred), f32(gt)
+    mje, pamje, aligned = np.zeros(B, np.float32), np.zeros(B, np.float32), np.zeros((B, J, 3), np.float32)
+    assert emu.hoisdf_hand_joint_metrics_fwd(ptr(p), ptr(g), B, J, ptr(mje), ptr(pamje), ptr(aligned), None) == 0
+    omje, opamje = O.hand_joint_metrics(pred, gt)
+    scale = float(gt.abs().max())
+    assert rel(mje, omje) < 1e-5
+    assert float(np.abs(pamje - opamje.numpy()).max()) < 1e-5 * scale
+    for b in range(B):
+        assert float(np.abs(aligned[b] - O.rigid_align(p[b], g[b])).max()) < 2e-5 * scale, b
+    assert emu.hoisdf_hand_joint_metrics_fwd(None, None, B, J, None, None, None, None) == -1
