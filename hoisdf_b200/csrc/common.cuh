@@ -1,5 +1,9 @@
 // Shared helpers for the hoisdf_b200 kernels (sm_100a only).
 #pragma once
+#ifdef HOISDF_EMULATE
+// tests/emu: the CPU thread emulator that runs the simple (non-tensor-core) kernels in the "not gpu" test suite
+#include "cuda_emu.h"
+#else
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -8,14 +12,19 @@
 #define HOISDF_API extern "C" __attribute__((visibility("default")))
 // kernel launch on `stream` with no dynamic shared memory; tests/emu/cuda_emu.h redefines it to run the kernel on CPU threads
 #define HOISDF_LAUNCH(kernel, grid, block, stream, ...) kernel<<<grid, block, 0, stream>>>(__VA_ARGS__)
+#endif
 
 namespace hoisdf {
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
 static inline int launch_status() {
+#ifdef HOISDF_EMULATE
+  return HOISDF_OK;
+#else
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? HOISDF_OK : static_cast<int>(e);
+#endif
 }
 
 __host__ __device__ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

@@ -186,9 +186,9 @@ HOISDF_API int hoisdf_lattice_count(const float* center, const float* cam_intr, 
   const int total = bins * bins * bins;
   const int chunks = hoisdf_lattice_chunks(bins);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  lattice_count_kernel<<<dim3(chunks, static_cast<unsigned>(batch)), 32, 0, s>>>(center, cam_intr, bbox, sdf_scale,
-                                                                                 bins, total, chunks, chunk_counts);
-  lattice_scan_kernel<<<1, 1024, 0, s>>>(chunk_counts, batch, chunks, offsets);
+  HOISDF_LAUNCH(lattice_count_kernel, dim3(chunks, static_cast<unsigned>(batch)), 32, s, center, cam_intr, bbox,
+                sdf_scale, bins, total, chunks, chunk_counts);
+  HOISDF_LAUNCH(lattice_scan_kernel, 1, 1024, s, chunk_counts, batch, chunks, offsets);
   return launch_status();
 }
 
@@ -202,8 +202,8 @@ HOISDF_API int hoisdf_lattice_compact(const float* center, const float* cam_intr
   if (reinterpret_cast<uintptr_t>(cand_uv) & 7u) return HOISDF_E_ALIGN;
   const int total = bins * bins * bins;
   const int chunks = hoisdf_lattice_chunks(bins);
-  lattice_compact_kernel<<<dim3(chunks, static_cast<unsigned>(batch)), 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      center, cam_intr, bbox, sdf_scale, bins, total, chunks, chunk_counts, cand_index, cand_uv);
+  HOISDF_LAUNCH(lattice_compact_kernel, dim3(chunks, static_cast<unsigned>(batch)), 32, static_cast<cudaStream_t>(stream),
+                center, cam_intr, bbox, sdf_scale, bins, total, chunks, chunk_counts, cand_index, cand_uv);
   return launch_status();
 }
 
@@ -213,7 +213,7 @@ HOISDF_API int hoisdf_project_points(const float* points, const float* center, c
   if (points == nullptr || center == nullptr || cam_intr == nullptr || uv == nullptr) return HOISDF_E_NULL;
   if (batch <= 0 || p <= 0) return HOISDF_E_SHAPE;
   const int64_t n = batch * p;
-  project_points_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      points, center, cam_intr, sdf_scale, batch, p, cam, uv);
+  HOISDF_LAUNCH(project_points_kernel, static_cast<unsigned>(ceil_div(n, 256)), 256, static_cast<cudaStream_t>(stream),
+                points, center, cam_intr, sdf_scale, batch, p, cam, uv);
   return launch_status();
 }

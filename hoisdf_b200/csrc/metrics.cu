@@ -7,11 +7,7 @@
 //     twice); here the target mesh is staged tile by tile in shared memory and nothing of size N x N exists;
 //   * eval_hand_joint / rigid_align / rigid_transform_3D (:188-228): MJE and Procrustes-aligned PA-MJE, upstream a
 //     per-sample numpy loop with a D2H copy per sample; here one CTA per sample, the 3x3 SVD by one-sided Jacobi in fp64.
-#ifdef HOISDF_EMULATE
-#include "cuda_emu.h"      // tests/emu: the CPU thread emulator that runs this file's kernels in the "not gpu" test suite
-#else
 #include "common.cuh"
-#endif
 
 namespace hoisdf {
 namespace {

@@ -36,6 +36,7 @@ namespace emu {
 inline thread_local dim3 thread_idx, block_idx;
 inline dim3 block_dim, grid_dim;
 inline std::unique_ptr<std::barrier<>> block_barrier;
+inline std::vector<std::unique_ptr<std::barrier<>>> warp_barrier;
 inline unsigned char exchange[1024][16];
 
 template <typename K, typename... Args>
@@ -47,6 +48,9 @@ void launch(K kernel, dim3 grid, dim3 block, Args... args) {
     for (unsigned by = 0; by < grid.y; ++by)
       for (unsigned bx = 0; bx < grid.x; ++bx) {
         block_barrier = std::make_unique<std::barrier<>>(n);
+        warp_barrier.clear();
+        for (unsigned w = 0; w * 32 < n; ++w)
+          warp_barrier.push_back(std::make_unique<std::barrier<>>(std::min(32u, n - w * 32)));
         std::vector<std::thread> threads;
         threads.reserve(n);
         for (unsigned t = 0; t < n; ++t)
@@ -67,23 +71,57 @@ void launch(K kernel, dim3 grid, dim3 block, Args... args) {
 #define HOISDF_LAUNCH(kernel, grid, block, stream, ...) emu::launch(kernel, dim3(grid), dim3(block), __VA_ARGS__)
 
 inline void __syncthreads() { emu::block_barrier->arrive_and_wait(); }
+inline unsigned emu_tid() { return threadIdx.x + threadIdx.y * blockDim.x + threadIdx.z * blockDim.x * blockDim.y; }
+inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_barrier[emu_tid() >> 5]->arrive_and_wait(); }
 
 template <typename T>
 inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
   static_assert(sizeof(T) <= 16, "exchange slot too small");
-  const unsigned tid = threadIdx.x + threadIdx.y * blockDim.x + threadIdx.z * blockDim.x * blockDim.y;
+  const unsigned tid = emu_tid();
   std::memcpy(emu::exchange[tid], &v, sizeof(T));
-  __syncthreads();
+  __syncwarp();
   T r;
   std::memcpy(&r, emu::exchange[(tid & ~31u) | ((tid ^ static_cast<unsigned>(lane_mask)) & 31u)], sizeof(T));
-  __syncthreads();
+  __syncwarp();
   return r;
 }
 
+template <typename T>
+inline T __shfl_up_sync(unsigned, T v, unsigned delta) {
+  const unsigned tid = emu_tid();
+  std::memcpy(emu::exchange[tid], &v, sizeof(T));
+  __syncwarp();
+  T r = v;                                                   // lanes below `delta` keep their own value
+  if ((tid & 31u) >= delta) std::memcpy(&r, emu::exchange[tid - delta], sizeof(T));
+  __syncwarp();
+  return r;
+}
+
+inline unsigned __ballot_sync(unsigned, bool pred) {
+  const unsigned tid = emu_tid();
+  const unsigned n = blockDim.x * blockDim.y * blockDim.z;
+  emu::exchange[tid][0] = pred ? 1 : 0;
+  __syncwarp();
+  unsigned m = 0;
+  for (unsigned l = 0; l < 32; ++l) {
+    const unsigned t = (tid & ~31u) | l;
+    if (t < n && emu::exchange[t][0]) m |= 1u << l;
+  }
+  __syncwarp();
+  return m;
+}
+
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+
+// separately rounded IEEE single-precision operations (x86-64 SSE arithmetic is IEEE; `volatile` keeps the compiler from
+// contracting or reassociating them)
+inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
+
+struct float2 { float x, y; };
+inline float2 make_float2(float x, float y) { return float2{x, y}; }
+
 using std::max;
 using std::min;
-
-namespace hoisdf {
-static inline int launch_status() { return HOISDF_OK; }
-static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
-}  // namespace hoisdf

@@ -51,7 +51,8 @@ def test_obj_pose_metrics_shapes(cuda, B, N, votes):
     again = ops.obj_pose_metrics(templates.to(cuda), ids.to(cuda), *[a.to(cuda) for a in args])
     for name, a, a2, b in zip(("adds", "mme", "mce", "oce"), got, again, want):
         assert torch.equal(a, a2), name                              # deterministic reductions
-        assert rel(a, b) < TOL or float((a.cpu() - b).abs().max()) < 1e-9, (name, rel(a, b))
+        # 1e-5 relative, or the fp32 rounding of the posed coordinates (|x| ~ 0.3 m -> 3e-8 m) for the few-mm values
+        assert rel(a, b) < TOL or float((a.cpu() - b).abs().max()) < 2e-7, (name, rel(a, b))
     # obj_ids = None: sample b poses template b
     per_sample = templates[ids].contiguous()
     got2 = ops.obj_pose_metrics(per_sample.to(cuda), None, *[a.to(cuda) for a in args])

@@ -1,4 +1,4 @@
-"""The simple (non-tensor-core) CUDA kernels of csrc/metrics.cu executed UNCHANGED on the host by a CPU thread emulator
+"""The simple (non-tensor-core) CUDA kernels of csrc/metrics.cu and csrc/lattice.cu executed UNCHANGED on the host by a CPU thread emulator
 (tests/emu/cuda_emu.h: one OS thread per CUDA thread, std::barrier for __syncthreads, an exchange buffer for warp
 shuffles) and compared with the oracle -- so that the kernel source, its launch geometry and its C-ABI argument
 handling are checked in the GPU-less suite too.  Test infrastructure: the emulated library is built from the same
@@ -20,20 +20,26 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU = os.path.join(ROOT, "tests", "emu")
 
 
-@pytest.fixture(scope="module")
-def emu():
+def build_emulated(name):
+    """g++ build of hoisdf_b200/csrc/<name>.cu against the emulator header -> tests/emu/_build/lib<name>_emu.so"""
     gxx = shutil.which("g++")
     if gxx is None:
         pytest.skip("g++ not available")
     out = os.path.join(EMU, "_build")
     os.makedirs(out, exist_ok=True)
-    lib = os.path.join(out, "libmetrics_emu.so")
-    src = os.path.join(ROOT, "hoisdf_b200", "csrc", "metrics.cu")
-    deps = [src, os.path.join(EMU, "cuda_emu.h"), os.path.join(ROOT, "include", "hoisdf_b200.h")]
+    lib = os.path.join(out, "lib%s_emu.so" % name)
+    src = os.path.join(ROOT, "hoisdf_b200", "csrc", name + ".cu")
+    deps = [src, os.path.join(EMU, "cuda_emu.h"), os.path.join(ROOT, "include", "hoisdf_b200.h"),
+            os.path.join(ROOT, "hoisdf_b200", "csrc", "common.cuh")]
     if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(d) for d in deps):
         subprocess.run([gxx, "-std=c++20", "-O1", "-pthread", "-fPIC", "-shared", "-DHOISDF_EMULATE", "-I" + EMU,
                         "-x", "c++", src, "-o", lib], check=True)
-    lib = C.CDLL(lib)
+    return C.CDLL(lib)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    lib = build_emulated("metrics")
     lib.hoisdf_obj_metrics_workspace_bytes.restype = C.c_int64
     lib.hoisdf_obj_metrics_workspace_bytes.argtypes = [C.c_int64, C.c_int64]
     vp, i64 = C.c_void_p, C.c_int64
@@ -106,3 +112,38 @@ def test_hand_joint_kernel_on_the_emulator(emu, J):
     for b in range(B):
         assert float(np.abs(aligned[b] - O.rigid_align(p[b], g[b])).max()) < 2e-5 * scale, b
     assert emu.hoisdf_hand_joint_metrics_fwd(None, None, B, J, None, None, None, None) == -1
+
+
+def test_lattice_kernels_on_the_emulator():
+    """Candidate generation (upstream main/model.py:257-302): the sheared lattice, projection, strict bbox test and the
+    stable compaction of csrc/lattice.cu give the oracle's boolean mask and pixel coordinates BIT FOR BIT."""
+    lib = build_emulated("lattice")
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
+    lib.hoisdf_lattice_count.argtypes = [vp, vp, vp, C.c_float, i64, i32, vp, vp, vp]
+    lib.hoisdf_lattice_compact.argtypes = [vp, vp, vp, C.c_float, i64, i32, vp, vp, vp, vp, vp]
+    lib.hoisdf_project_points.argtypes = [vp, vp, vp, C.c_float, i64, i64, vp, vp, vp]
+    B, bins = 2, 64
+    meta = syn.camera_meta(9, B)
+    center, K, bbox = f32(meta["obj_center_cam"]), f32(meta["cam_intr"]), f32(meta["bbox_obj"])
+    chunks = lib.hoisdf_lattice_chunks(bins)
+    counts, offsets = np.zeros(B * chunks, np.int32), np.zeros(B + 1, np.int64)
+    assert lib.hoisdf_lattice_count(ptr(center), ptr(K), ptr(bbox), 3.1, B, bins, ptr(counts), ptr(offsets), None) == 0
+    total = int(offsets[-1])
+    cand, uv = np.full(total, -1, np.int32), np.full((total, 2), np.nan, np.float32)
+    assert lib.hoisdf_lattice_compact(ptr(center), ptr(K), ptr(bbox), 3.1, B, bins, ptr(counts), ptr(offsets), ptr(cand),
+                                      ptr(uv), None) == 0
+    lat = O.lattice(bins)
+    for b in range(B):
+        mask, ouv = O.candidate_mask(lat, meta["obj_center_cam"][b], meta["cam_intr"][b], meta["bbox_obj"][b], 3.1)
+        want = mask.nonzero().flatten().numpy()
+        got = cand[offsets[b]:offsets[b + 1]]
+        assert 3000 < len(want) < bins ** 3 and np.array_equal(got, want)                 # the index mask, exactly
+        assert np.array_equal(uv[offsets[b]:offsets[b + 1]], ouv[mask].numpy())          # projected pixels, bit for bit
+    # explicit points (model.py:148-150,190-192)
+    P = 77
+    pts = f32(torch.rand(B, P, 3, generator=torch.Generator().manual_seed(1)) * 2 - 1)
+    cam, puv = np.zeros((B, P, 3), np.float32), np.zeros((B, P, 2), np.float32)
+    assert lib.hoisdf_project_points(ptr(pts), ptr(center), ptr(K), 3.1, B, P, ptr(cam), ptr(puv), None) == 0
+    ocam = torch.from_numpy(pts) / 3.1 + meta["obj_center_cam"][:, None]
+    assert np.array_equal(cam, ocam.numpy())
+    assert np.abs(puv - O.project(ocam, meta["cam_intr"]).numpy()).max() < 1e-4
