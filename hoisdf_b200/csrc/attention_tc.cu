@@ -32,6 +32,7 @@ constexpr int AT_GROUPS = 2;               // query tiles per CTA: two softmax w
 constexpr int AT_BK = 64;                  // keys per tile
 constexpr int AT_D = 64;                   // head dim
 constexpr int AT_STAGES = 4;
+constexpr float AT_RESCALE_LOG2 = 8.f;     // lazy softmax rescaling threshold (log2 units), see the softmax warps
 constexpr int AT_Q_BYTES = AT_BQ * AT_D * 2;      // 16 KB (one bf16 term)
 constexpr int AT_K_BYTES = AT_BK * AT_D * 2;      // 8 KB
 constexpr int AT_P_BYTES = AT_BQ * AT_BK * 2;     // 16 KB
@@ -357,8 +358,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_co
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int j = 0; j < 64; ++j) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(sr[j]));
-      const float m_new = fmaxf(m_run, fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])));
-      const float alpha = ex2_approx(m_run - m_new);
+      // Lazy rescaling: the running reference m_run only moves when the tile maximum exceeds it by more than 2^8
+      // (scores are in log2 units), so p = 2^(s - m_run) stays below 256 -- harmless in the fp32 sums and in the
+      // bf16 hi/lo split (relative precision) -- and O / l need rescaling only in the first few K/V tiles instead of
+      // in most of them.  The O rescale is a 32 KB TMEM read + write per tile (TMEM reads run at 64 B/clk: 512 cycles
+      // against 768 cycles of MMAs) and sits on the P.V critical path.  The final O / l is unchanged mathematically.
+      const float m_tile = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      const float m_new = (m_tile - m_run > AT_RESCALE_LOG2) ? m_tile : m_run;      // first tile: m_run = -inf -> taken
+      const float alpha = (m_new == m_run) ? 1.f : ex2_approx(m_run - m_new);
       float rs4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int j = 0; j < 64; ++j) {
