@@ -12,6 +12,8 @@
 #define HOISDF_API extern "C" __attribute__((visibility("default")))
 // kernel launch on `stream` with no dynamic shared memory; tests/emu/cuda_emu.h redefines it to run the kernel on CPU threads
 #define HOISDF_LAUNCH(kernel, grid, block, stream, ...) kernel<<<grid, block, 0, stream>>>(__VA_ARGS__)
+#define HOISDF_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#define HOISDF_DYNAMIC_SMEM(type, name) extern __shared__ __align__(16) type name[]
 #endif
 
 namespace hoisdf {

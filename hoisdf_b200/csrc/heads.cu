@@ -255,8 +255,8 @@ HOISDF_API int hoisdf_vote_joints_fwd(const float* points, const float* off, con
                                       int64_t batch, int64_t p, float* joints, void* stream) {
   if (points == nullptr || off == nullptr || cls == nullptr || joints == nullptr) return HOISDF_E_NULL;
   if (layers <= 0 || batch <= 0 || p <= 0 || layers * batch > 0x7fffffffLL) return HOISDF_E_SHAPE;
-  vote_joints_kernel<<<static_cast<unsigned>(layers * batch), 640, 0, static_cast<cudaStream_t>(stream)>>>(
-      points, off, cls, batch, p, joints);
+  HOISDF_LAUNCH(vote_joints_kernel, static_cast<unsigned>(layers * batch), 640, static_cast<cudaStream_t>(stream), points,
+                off, cls, batch, p, joints);
   return launch_status();
 }
 
@@ -270,7 +270,7 @@ HOISDF_API int hoisdf_mano_fwd(const hoisdf_mano_model* m, const float* pose6d, 
   if (n <= 0 || n > 0x7fffffffLL) return HOISDF_E_SHAPE;
   ManoParams p{m->shapedirs, m->posedirs, m->v_template, m->j_regressor, m->weights, m->hands_mean,
                pose6d, nullptr, betas, verts, joints};
-  mano_kernel<<<static_cast<unsigned>(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  HOISDF_LAUNCH(mano_kernel, static_cast<unsigned>(n), 256, static_cast<cudaStream_t>(stream), p);
   return launch_status();
 }
 
@@ -284,6 +284,6 @@ HOISDF_API int hoisdf_mano_aa_fwd(const hoisdf_mano_model* m, const float* pose_
   if (n <= 0 || n > 0x7fffffffLL) return HOISDF_E_SHAPE;
   ManoParams p{m->shapedirs, m->posedirs, m->v_template, m->j_regressor, m->weights, m->hands_mean,
                nullptr, pose_aa, betas, verts, joints};
-  mano_kernel<<<static_cast<unsigned>(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  HOISDF_LAUNCH(mano_kernel, static_cast<unsigned>(n), 256, static_cast<cudaStream_t>(stream), p);
   return launch_status();
 }

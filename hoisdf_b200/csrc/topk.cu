@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(kSelThreads) select_points_kernel(
     int num_points, int bins, float clamp, int order_by_row, int32_t* __restrict__ sel_index,
     int32_t* __restrict__ sel_row, float* __restrict__ points, float* __restrict__ out_sdf,
     float* __restrict__ posenc, int32_t* __restrict__ status_flag) {
-  extern __shared__ __align__(16) uint64_t keys[];   // npad entries (next power of two >= num_points)
+  HOISDF_DYNAMIC_SMEM(uint64_t, keys);               // npad entries (next power of two >= num_points)
   __shared__ unsigned hist[256];
   __shared__ uint64_t s_prefix;
   __shared__ unsigned s_need;
@@ -161,12 +161,14 @@ HOISDF_API int hoisdf_select_points(const float* sdf, const int64_t* offsets, co
   int npad = 1;
   while (npad < num_points) npad <<= 1;
   const size_t smem = static_cast<size_t>(npad) * sizeof(uint64_t);
+#ifndef HOISDF_EMULATE
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(select_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     if (e != cudaSuccess) return static_cast<int>(e);
   }
-  select_points_kernel<<<static_cast<unsigned>(batch), kSelThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      sdf, offsets, cand_index, static_cast<int>(num_points), bins, clamp, order_by_row, sel_index, sel_row, points,
-      out_sdf, posenc, status_flag);
+#endif
+  HOISDF_LAUNCH_SMEM(select_points_kernel, static_cast<unsigned>(batch), kSelThreads, smem,
+                     static_cast<cudaStream_t>(stream), sdf, offsets, cand_index, static_cast<int>(num_points), bins,
+                     clamp, order_by_row, sel_index, sel_row, points, out_sdf, posenc, status_flag);
   return launch_status();
 }

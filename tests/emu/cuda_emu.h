@@ -38,6 +38,7 @@ inline dim3 block_dim, grid_dim;
 inline std::unique_ptr<std::barrier<>> block_barrier;
 inline std::vector<std::unique_ptr<std::barrier<>>> warp_barrier;
 inline unsigned char exchange[1024][16];
+alignas(16) inline unsigned char dynamic_smem[228 * 1024];      // `extern __shared__` storage of the running block
 
 template <typename K, typename... Args>
 void launch(K kernel, dim3 grid, dim3 block, Args... args) {
@@ -69,6 +70,8 @@ void launch(K kernel, dim3 grid, dim3 block, Args... args) {
 #define blockDim emu::block_dim
 #define gridDim emu::grid_dim
 #define HOISDF_LAUNCH(kernel, grid, block, stream, ...) emu::launch(kernel, dim3(grid), dim3(block), __VA_ARGS__)
+#define HOISDF_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) emu::launch(kernel, dim3(grid), dim3(block), __VA_ARGS__)
+#define HOISDF_DYNAMIC_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::dynamic_smem)
 
 inline void __syncthreads() { emu::block_barrier->arrive_and_wait(); }
 inline unsigned emu_tid() { return threadIdx.x + threadIdx.y * blockDim.x + threadIdx.z * blockDim.x * blockDim.y; }
@@ -112,6 +115,11 @@ inline unsigned __ballot_sync(unsigned, bool pred) {
 }
 
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+template <typename T> inline T __ldg(const T* p) { return *p; }
+template <typename T> inline T atomicAdd(T* p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+template <typename T> inline T atomicExch(T* p, T v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
 
 // separately rounded IEEE single-precision operations (x86-64 SSE arithmetic is IEEE; `volatile` keeps the compiler from
 // contracting or reassociating them)
@@ -123,5 +131,6 @@ inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 struct float2 { float x, y; };
 inline float2 make_float2(float x, float y) { return float2{x, y}; }
 
+using std::isnan;
 using std::max;
 using std::min;

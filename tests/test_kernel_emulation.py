@@ -1,4 +1,4 @@
-"""The simple (non-tensor-core) CUDA kernels of csrc/metrics.cu and csrc/lattice.cu executed UNCHANGED on the host by a CPU thread emulator
+"""The simple (non-tensor-core) CUDA kernels of csrc/metrics.cu, lattice.cu, topk.cu and heads.cu executed UNCHANGED on the host by a CPU thread emulator
 (tests/emu/cuda_emu.h: one OS thread per CUDA thread, std::barrier for __syncthreads, an exchange buffer for warp
 shuffles) and compared with the oracle -- so that the kernel source, its launch geometry and its C-ABI argument
 handling are checked in the GPU-less suite too.  Test infrastructure: the emulated library is built from the same
@@ -147,3 +147,92 @@ def test_lattice_kernels_on_the_emulator():
     ocam = torch.from_numpy(pts) / 3.1 + meta["obj_center_cam"][:, None]
     assert np.array_equal(cam, ocam.numpy())
     assert np.abs(puv - O.project(ocam, meta["cam_intr"]).numpy()).max() < 1e-4
+
+
+def rnd(seed, *shape, lo=-1.0, hi=1.0):
+    g = np.random.Generator(np.random.PCG64(seed))
+    return (g.random(size=shape, dtype=np.float32) * (hi - lo) + lo).astype(np.float32)
+
+
+@pytest.mark.parametrize("P", [1, 37, 600])
+def test_select_points_kernel_on_the_emulator(P):
+    """Near-surface selection (upstream main/model.py:345-354): radix select + bitonic sort on the composite key give the
+    stable |sdf| order BIT FOR BIT (ties -> lower row), lattice coordinates exactly, the clamp after the selection."""
+    lib = build_emulated("topk")
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
+    lib.hoisdf_select_points.argtypes = [vp, vp, vp, i64, i64, i32, C.c_float, i32, vp, vp, vp, vp, vp, vp, vp]
+    B, n_f = 2, [max(P, 700), 3000]
+    g = np.random.Generator(np.random.PCG64(41 + P))
+    sdf = np.tanh(g.standard_normal(sum(n_f)).astype(np.float32) * 0.4).astype(np.float32)
+    sdf[10] = sdf[20] = np.float32(1e-4)               # a tie among the selected: the lower row must win
+    sdf[n_f[0] + 5] = -sdf[n_f[0] + 9]                 # |sdf| tie across signs
+    offsets = np.concatenate([[0], np.cumsum(n_f)]).astype(np.int64)
+    cand = np.concatenate([np.sort(g.choice(64 ** 3, n, replace=False)) for n in n_f]).astype(np.int32)
+    lat = O.lattice(64)
+
+    def run(p, by_row):
+        sel, row = np.full((B, p), -7, np.int32), np.full((B, p), -7, np.int32)
+        pts, osdf, pe = np.zeros((B, p, 3), np.float32), np.zeros((B, p), np.float32), np.zeros((B, p, 30), np.float32)
+        flag = np.zeros(1, np.int32)
+        assert lib.hoisdf_select_points(ptr(sdf), ptr(offsets), ptr(cand), B, p, 64, 0.15, int(by_row), ptr(sel), ptr(row),
+                                        ptr(pts), ptr(osdf), ptr(pe), ptr(flag), None) == 0
+        return sel, row, pts, osdf, pe, int(flag[0])
+
+    sel, row, pts, osdf, pe, flag = run(P, False)
+    assert flag == 0
+    sel_r, row_r, *_ = run(P, True)
+    assert np.array_equal(np.sort(row, axis=1), row_r) and np.array_equal(cand[row_r], sel_r)
+    for b in range(B):
+        s = torch.from_numpy(sdf[offsets[b]:offsets[b + 1]])
+        order = torch.sort(s.abs(), stable=True)[1][:P]
+        want = torch.from_numpy(cand[offsets[b]:offsets[b + 1]])[order].long()
+        assert np.array_equal(sel[b], want.numpy())
+        assert np.array_equal(pts[b], lat[want].numpy())
+        assert np.array_equal(osdf[b], s[order].clamp(-0.15, 0.15).numpy())
+        assert np.abs(pe[b] - O.nerf_embed(lat[want]).numpy()).max() < 2e-6
+    if P > 1:
+        assert run(n_f[0] + 1, False)[5] == 1          # too few candidates -> flag (upstream model.py:348 fails there)
+    assert lib.hoisdf_select_points(ptr(sdf), ptr(offsets), ptr(cand), B, 8193, 64, 0.15, 0, ptr(sel), ptr(row), ptr(pts),
+                                    ptr(osdf), ptr(pe), None, None) == -2
+
+
+def test_vote_and_mano_kernels_on_the_emulator():
+    """Joint voting (upstream common/nets/loss.py:31-36,54-57) and ManoHead + ManoLayer (mano_head.py:185-256,
+    manolayer.py:111-276) of csrc/heads.cu against the oracle."""
+    lib = build_emulated("heads")
+    vp, i64 = C.c_void_p, C.c_int64
+
+    class ManoModel(C.Structure):
+        _fields_ = [(n, vp) for n in ("shapedirs", "posedirs", "v_template", "j_regressor", "weights", "hands_mean")]
+
+    lib.hoisdf_vote_joints_fwd.argtypes = [vp, vp, vp, i64, i64, i64, vp, vp]
+    lib.hoisdf_mano_fwd.argtypes = [C.POINTER(ManoModel), vp, vp, i64, vp, vp, vp]
+    lib.hoisdf_mano_aa_fwd.argtypes = [C.POINTER(ManoModel), vp, vp, i64, vp, vp, vp]
+    L, B, P = 2, 2, 133
+    pts, off, cls = rnd(71, B, P, 3, lo=-0.1, hi=0.1), rnd(72, L, B, P, 60, lo=-0.05, hi=0.05), rnd(73, L, B, P, 20, lo=-3, hi=3)
+    joints = np.zeros((L, B, 20, 3), np.float32)
+    assert lib.hoisdf_vote_joints_fwd(ptr(pts), ptr(off), ptr(cls), L, B, P, ptr(joints), None) == 0
+    ref = O.vote_joints(torch.from_numpy(pts), torch.from_numpy(off).permute(0, 2, 1, 3), torch.from_numpy(cls).permute(0, 2, 1, 3))
+    assert rel(joints, ref) < 2e-6
+
+    sd = syn.hot_path_state_dict(74, "dexycb")
+    bufs = {k: f32(v.reshape(-1)) for k, v in syn.mano_buffers(74).items() if v.dtype == torch.float32}
+    model = ManoModel(*[ptr(bufs[k]) for k in ("th_shapedirs", "th_posedirs", "th_v_template", "th_J_regressor",
+                                               "th_weights", "th_hands_mean")])
+    pose6d, shape = torch.from_numpy(rnd(75, L, 16, B, 6)), torch.from_numpy(rnd(76, L, B, 10, lo=-2, hi=2))
+    pose6d[0, 3, 0] = torch.tensor([1.0, 0, 0, 0, 1.0, 0])       # identity rotation -> the NaN->0 branch
+    p6 = f32(pose6d.permute(0, 2, 1, 3).reshape(L * B, 16, 6))
+    sh = f32(shape.reshape(L * B, 10))
+    verts, jts = np.zeros((L * B, 778, 3), np.float32), np.zeros((L * B, 21, 3), np.float32)
+    assert lib.hoisdf_mano_fwd(C.byref(model), ptr(p6), ptr(sh), L * B, ptr(verts), ptr(jts), None) == 0
+    overts, ojoints = O.mano_head(sd, pose6d, shape)
+    assert np.abs(verts - overts.reshape(L * B, 778, 3).numpy()).max() < 2e-6     # metres; hand extent ~0.2
+    assert np.abs(jts - ojoints.reshape(L * B, 21, 3).numpy()).max() < 2e-6
+    params = torch.cat([torch.from_numpy(rnd(77, B, 48, lo=-0.6, hi=0.6)), torch.from_numpy(rnd(78, B, 10, lo=-2, hi=2))], 1)
+    ogt = O.mano_head_gt(sd, params.clone())
+    pose = params[:, :48].clone()
+    pose[:, 3:] -= syn.mano_buffers(74)["th_hands_mean"].reshape(-1)
+    pa, be = f32(pose), f32(params[:, 48:])
+    verts, jts = np.zeros((B, 778, 3), np.float32), np.zeros((B, 21, 3), np.float32)
+    assert lib.hoisdf_mano_aa_fwd(C.byref(model), ptr(pa), ptr(be), B, ptr(verts), ptr(jts), None) == 0
+    assert np.abs(verts - ogt["verts3d"].numpy()).max() < 2e-6 and np.abs(jts - ogt["joints3d"].numpy()).max() < 2e-6
