@@ -236,16 +236,16 @@ static int gather_any(const hoisdf_pyramid* pyr, const float* uv, int64_t rows, 
   const unsigned grid = static_cast<unsigned>(ceil_div(rows, 8));
   if (mode == HOISDF_GATHER_CONCAT) {
     if (ld_out < ctot) return HOISDF_E_SHAPE;
-    gather_concat_kernel<<<grid, 256, 0, s>>>(p);
+    HOISDF_LAUNCH(gather_concat_kernel, grid, 256, s, p);
   } else if (mode == HOISDF_GATHER_SUM) {
     const int C = pyr->c[0];
     for (int l = 1; l < pyr->levels; ++l)
       if (pyr->c[l] != C) return HOISDF_E_SHAPE;
     if (ld_out < C) return HOISDF_E_SHAPE;
     if (bias != nullptr && !aligned16(bias)) return HOISDF_E_ALIGN;
-    if (C == 512) gather_sum_kernel<4><<<grid, 256, 0, s>>>(p);
-    else if (C == 256) gather_sum_kernel<2><<<grid, 256, 0, s>>>(p);
-    else if (C == 128) gather_sum_kernel<1><<<grid, 256, 0, s>>>(p);
+    if (C == 512) HOISDF_LAUNCH(gather_sum_kernel<4>, grid, 256, s, p);
+    else if (C == 256) HOISDF_LAUNCH(gather_sum_kernel<2>, grid, 256, s, p);
+    else if (C == 128) HOISDF_LAUNCH(gather_sum_kernel<1>, grid, 256, s, p);
     else return HOISDF_E_UNSUPPORTED;
   } else {
     return HOISDF_E_UNSUPPORTED;
@@ -277,7 +277,7 @@ HOISDF_API int hoisdf_nchw_to_nhwc(const float* src, float* dst, int64_t n, int6
   const int HW = static_cast<int>(h * w);
   dim3 grid(static_cast<unsigned>(ceil_div(HW, 32)), static_cast<unsigned>(ceil_div(c, 32)),
             static_cast<unsigned>(n));
-  nchw_to_nhwc_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, static_cast<int>(c), HW);
+  HOISDF_LAUNCH(nchw_to_nhwc_kernel, grid, 256, static_cast<cudaStream_t>(stream), src, dst, static_cast<int>(c), HW);
   return launch_status();
 }
 
@@ -289,7 +289,7 @@ HOISDF_API int hoisdf_nchw_to_nhwc_split(const float* src, uint16_t* dst_hi, uin
   const int HW = static_cast<int>(h * w);
   dim3 grid(static_cast<unsigned>(ceil_div(HW, 32)), static_cast<unsigned>(ceil_div(c, 32)),
             static_cast<unsigned>(n));
-  nchw_to_nhwc_split_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      src, reinterpret_cast<__half*>(dst_hi), reinterpret_cast<__half*>(dst_lo), static_cast<int>(c), HW, ld);
+  HOISDF_LAUNCH(nchw_to_nhwc_split_kernel, grid, 256, static_cast<cudaStream_t>(stream), src,
+                reinterpret_cast<__half*>(dst_hi), reinterpret_cast<__half*>(dst_lo), static_cast<int>(c), HW, ld);
   return launch_status();
 }

@@ -86,9 +86,10 @@ static int add_layernorm_launch(const float* x, const float* res, const float* g
   if (!aligned16(x) || !aligned16(y) || !aligned16(gamma) || !aligned16(beta) || (res && !aligned16(res)) ||
       (y2 && (!aligned16(y2) || !aligned16(gamma2) || !aligned16(beta2))))
     return HOISDF_E_ALIGN;
-  add_layernorm_kernel<256><<<static_cast<unsigned>(ceil_div(rows, 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, res, gamma, beta, y, gamma2, beta2, y2, rows, reinterpret_cast<__half*>(yh_hi), reinterpret_cast<__half*>(yh_lo),
-      ldyh, reinterpret_cast<__half*>(y2h_hi), reinterpret_cast<__half*>(y2h_lo), ldy2h);
+  HOISDF_LAUNCH(add_layernorm_kernel<256>, static_cast<unsigned>(ceil_div(rows, 8)), 256,
+                static_cast<cudaStream_t>(stream), x, res, gamma, beta, y, gamma2, beta2, y2, rows,
+                reinterpret_cast<__half*>(yh_hi), reinterpret_cast<__half*>(yh_lo), ldyh, reinterpret_cast<__half*>(y2h_hi),
+                reinterpret_cast<__half*>(y2h_lo), ldy2h);
   return launch_status();
 }
 

@@ -185,8 +185,8 @@ HOISDF_API int hoisdf_posenc_fwd(const int32_t* lattice_index, const float* poin
   if (rows == 0) return HOISDF_OK;
   if (rows < 0 || ld_out < kRowLd || col0 != kFea) return HOISDF_E_SHAPE;
   const int64_t n = rows * 37;
-  posenc_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      lattice_index, points, rows, bins, out, ld_out, col0);
+  HOISDF_LAUNCH(posenc_kernel, static_cast<unsigned>(ceil_div(n, 256)), 256, static_cast<cudaStream_t>(stream),
+                lattice_index, points, rows, bins, out, ld_out, col0);
   return launch_status();
 }
 
@@ -195,8 +195,8 @@ HOISDF_API int hoisdf_sdf_pad_input(const float* in, int64_t rows, float* x, int
   if (rows == 0) return HOISDF_OK;
   if (rows < 0 || ldx < kRowLd) return HOISDF_E_SHAPE;
   const int64_t n = rows * 293;
-  sdf_pad_input_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      in, rows, x, ldx);
+  HOISDF_LAUNCH(sdf_pad_input_kernel, static_cast<unsigned>(ceil_div(n, 256)), 256, static_cast<cudaStream_t>(stream), in,
+                rows, x, ldx);
   return launch_status();
 }
 
@@ -225,8 +225,8 @@ HOISDF_API int hoisdf_sdf_decoder_fwd(const hoisdf_sdf_weights* w, float* x, int
   a = {h_a, 512, 0, 0, w->w3, 512, w->b3, nullptr, h_b, 512, 0, 0, rows, 512, 512, HOISDF_ACT_RELU, tc ? w->w3_lo : nullptr, w->tf32_passes};
   if ((st = hoisdf_linear_fwd(&a, stream)) != HOISDF_OK) return st;
   // linh4 + tanh
-  sdf_head_kernel<<<static_cast<unsigned>(ceil_div(rows, 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      h_b, 512, rows, w->w4, w->b4, out_sdf, clamp);
+  HOISDF_LAUNCH(sdf_head_kernel, static_cast<unsigned>(ceil_div(rows, 8)), 256, static_cast<cudaStream_t>(stream), h_b,
+                int64_t(512), rows, w->w4, w->b4, out_sdf, clamp);
   return launch_status();
 }
 
@@ -238,8 +238,8 @@ HOISDF_API int hoisdf_tokens_fwd(const float* xyz, const float* posenc, const fl
     return HOISDF_E_NULL;
   if (batch <= 0 || p <= 0 || t0 < 0 || t0 + p > s_total || ld_fea < 223) return HOISDF_E_SHAPE;
   const int64_t n = batch * p * 256;
-  tokens_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      xyz, posenc, fea, ld_fea, sdf, beta, batch, p, tokens, s_total, t0);
+  HOISDF_LAUNCH(tokens_kernel, static_cast<unsigned>(ceil_div(n, 256)), 256, static_cast<cudaStream_t>(stream), xyz, posenc,
+                fea, ld_fea, sdf, beta, batch, p, tokens, s_total, t0);
   return launch_status();
 }
 
@@ -249,8 +249,9 @@ HOISDF_API int hoisdf_posenc_split_fwd(const int32_t* lattice_index, const float
   if (rows == 0) return HOISDF_OK;
   if (rows < 0 || ld_out < kRowLdH) return HOISDF_E_SHAPE;
   const int64_t n = rows * 41;
-  posenc_split_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      lattice_index, points, rows, bins, reinterpret_cast<__half*>(out_hi), reinterpret_cast<__half*>(out_lo), ld_out);
+  HOISDF_LAUNCH(posenc_split_kernel, static_cast<unsigned>(ceil_div(n, 256)), 256, static_cast<cudaStream_t>(stream),
+                lattice_index, points, rows, bins, reinterpret_cast<__half*>(out_hi), reinterpret_cast<__half*>(out_lo),
+                ld_out);
   return launch_status();
 }
 
@@ -282,8 +283,9 @@ HOISDF_API int hoisdf_sdf_decoder_h3_fwd(const hoisdf_sdf_weights_h3* w, uint16_
   if ((st = layer(1, ha_hi, ha_lo, ldh, 512, x_hi + kSkipOffH, x_lo + kSkipOffH, ldx, kH1)) != HOISDF_OK) return st;
   if ((st = layer(2, x_hi, x_lo, ldx, kSkipOffH + kH1, ha_hi, ha_lo, ldh, 512)) != HOISDF_OK) return st;
   if ((st = layer(3, ha_hi, ha_lo, ldh, 512, hb_hi, hb_lo, ldh, 512)) != HOISDF_OK) return st;
-  sdf_head_split_kernel<<<static_cast<unsigned>(ceil_div(rows, 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __half*>(hb_hi), w->single_pass ? nullptr : reinterpret_cast<const __half*>(hb_lo), ldh, rows,
-      w->w4, w->b4, out_sdf, clamp);      // single-product chain: only the hi planes were written
+  HOISDF_LAUNCH(sdf_head_split_kernel, static_cast<unsigned>(ceil_div(rows, 8)), 256, static_cast<cudaStream_t>(stream),
+                reinterpret_cast<const __half*>(hb_hi),
+                w->single_pass ? nullptr : reinterpret_cast<const __half*>(hb_lo),      // single-product chain: only
+                ldh, rows, w->w4, w->b4, out_sdf, clamp);                               // the hi planes were written
   return launch_status();
 }

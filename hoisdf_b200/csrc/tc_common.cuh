@@ -1,11 +1,13 @@
 // sm_100a building blocks shared by the FP16x3 tensor-core kernels (linear_h3.cu, conv_h3.cu): mbarrier, TMA,
 // tcgen05 (UMMA / TMEM) wrappers and the "split-half" number format.
 #pragma once
+#ifndef HOISDF_EMULATE
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_fp16.h>
+#endif
 
-#include "common.cuh"
+#include "common.cuh"      // under HOISDF_EMULATE: tests/emu/cuda_emu.h (CPU thread emulator, software __half)
 
 namespace hoisdf {
 namespace tc {
@@ -30,9 +32,15 @@ __device__ __forceinline__ void split_half(float x, __half& hi, __half& lo) {
 }
 // two values at once, packed (element 0 in the low half): one saturating f16x2 conversion per plane, no clamps
 __device__ __forceinline__ uint32_t cvt_f16x2_sat(float e0, float e1) {
+#ifdef HOISDF_EMULATE
+  const __half h0 = __float2half_rn(fminf(fmaxf(e0, -65504.f), 65504.f));
+  const __half h1 = __float2half_rn(fminf(fmaxf(e1, -65504.f), 65504.f));
+  return static_cast<uint32_t>(__half_as_ushort(h0)) | (static_cast<uint32_t>(__half_as_ushort(h1)) << 16);
+#else
   uint32_t r;
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(e1), "f"(e0));
   return r;
+#endif
 }
 __device__ __forceinline__ void split_half2(float x0, float x1, uint32_t& hi2, uint32_t& lo2) {
   hi2 = cvt_f16x2_sat(x0, x1);
@@ -43,6 +51,7 @@ __device__ __forceinline__ float join_half(__half hi, __half lo) {
   return fmaf(__half2float(lo), kLoInv, __half2float(hi));
 }
 
+#ifndef HOISDF_EMULATE      // everything below is PTX (mbarrier, TMA, tcgen05): tensor-core kernels only
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -214,6 +223,7 @@ inline bool make_tiled_map(CUtensorMap* map, CUtensorMapDataType dt, int rank, c
   return enc(map, dt, static_cast<cuuint32_t>(rank), const_cast<void*>(ptr), dims, strides, box, elem_strides,
              CU_TENSOR_MAP_INTERLEAVE_NONE, sw, l2, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+#endif  // HOISDF_EMULATE
 
 }  // namespace tc
 }  // namespace hoisdf

@@ -124,12 +124,29 @@ template <typename T> inline T atomicExch(T* p, T v) { return __atomic_exchange_
 // separately rounded IEEE single-precision operations (x86-64 SSE arithmetic is IEEE; `volatile` keeps the compiler from
 // contracting or reassociating them)
 inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 
 struct float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(8) uint2 { unsigned x, y; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
 inline float2 make_float2(float x, float y) { return float2{x, y}; }
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
+inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
+
+// software fp16 (IEEE binary16 through the compiler's _Float16: conversions round to nearest even like cvt.rn)
+struct __half { _Float16 v; };
+struct __half2 { __half x, y; };
+inline __half __float2half_rn(float f) { return __half{static_cast<_Float16>(f)}; }
+inline float __half2float(__half h) { return static_cast<float>(h.v); }
+inline unsigned short __half_as_ushort(__half h) { unsigned short u; std::memcpy(&u, &h.v, 2); return u; }
+inline __half __ushort_as_half(unsigned short u) { __half h; std::memcpy(&h.v, &u, 2); return h; }
+inline float2 __half22float2(__half2 h) { return float2{__half2float(h.x), __half2float(h.y)}; }
 
 using std::isnan;
 using std::max;

@@ -1,4 +1,4 @@
-"""The simple (non-tensor-core) CUDA kernels of csrc/metrics.cu, lattice.cu, topk.cu and heads.cu executed UNCHANGED on the host by a CPU thread emulator
+"""The simple (non-tensor-core) CUDA kernels of csrc/metrics.cu, lattice.cu, topk.cu, heads.cu, gather.cu, layernorm.cu and sdf.cu executed UNCHANGED on the host by a CPU thread emulator
 (tests/emu/cuda_emu.h: one OS thread per CUDA thread, std::barrier for __syncthreads, an exchange buffer for warp
 shuffles) and compared with the oracle -- so that the kernel source, its launch geometry and its C-ABI argument
 handling are checked in the GPU-less suite too.  Test infrastructure: the emulated library is built from the same
@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU = os.path.join(ROOT, "tests", "emu")
 
 
-def build_emulated(name):
+def build_emulated(name, extra=()):
     """g++ build of hoisdf_b200/csrc/<name>.cu against the emulator header -> tests/emu/_build/lib<name>_emu.so"""
     gxx = shutil.which("g++")
     if gxx is None:
@@ -33,7 +33,7 @@ def build_emulated(name):
             os.path.join(ROOT, "hoisdf_b200", "csrc", "common.cuh")]
     if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(d) for d in deps):
         subprocess.run([gxx, "-std=c++20", "-O1", "-pthread", "-fPIC", "-shared", "-DHOISDF_EMULATE", "-I" + EMU,
-                        "-x", "c++", src, "-o", lib], check=True)
+                        "-x", "c++", src] + [os.path.join(EMU, e) for e in extra] + ["-o", lib], check=True)
     return C.CDLL(lib)
 
 
@@ -236,3 +236,139 @@ def test_vote_and_mano_kernels_on_the_emulator():
     verts, jts = np.zeros((B, 778, 3), np.float32), np.zeros((B, 21, 3), np.float32)
     assert lib.hoisdf_mano_aa_fwd(C.byref(model), ptr(pa), ptr(be), B, ptr(verts), ptr(jts), None) == 0
     assert np.abs(verts - ogt["verts3d"].numpy()).max() < 2e-6 and np.abs(jts - ogt["joints3d"].numpy()).max() < 2e-6
+
+
+class Pyramid(C.Structure):
+    _fields_ = [("map", C.c_void_p * 5), ("c", C.c_int32 * 5), ("h", C.c_int32 * 5), ("w", C.c_int32 * 5),
+                ("levels", C.c_int32), ("img_h", C.c_int32), ("img_w", C.c_int32)]
+
+
+def make_pyramid(maps_nhwc):
+    p = Pyramid()
+    for i, m in enumerate(maps_nhwc):
+        p.map[i], p.c[i], p.h[i], p.w[i] = m.ctypes.data, m.shape[3], m.shape[1], m.shape[2]
+    p.levels, p.img_h, p.img_w = len(maps_nhwc), 256, 256
+    return p
+
+
+def join_split(hi, lo):
+    return hi.view(np.float16).astype(np.float32) + lo.view(np.float16).astype(np.float32) / 2048.0
+
+
+def test_gather_kernels_on_the_emulator():
+    """Fused bilinear gather (upstream F.grid_sample x5, bilinear / border / align_corners=True, main/model.py:164-175):
+    CONCAT mode against ATen's grid_sample incl. out-of-image projections and the image corners; SUM mode (+bias, ReLU)
+    with ragged row offsets; split-half output."""
+    import torch.nn.functional as F
+    lib = build_emulated("gather")
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
+    lib.hoisdf_gather_fwd.argtypes = [C.POINTER(Pyramid), vp, i64, vp, i64, i64, i32, vp, i32, vp, i64, vp]
+    lib.hoisdf_gather_split_fwd.argtypes = [C.POINTER(Pyramid), vp, i64, vp, i64, i64, i32, vp, i32, vp, vp, i64, vp]
+    lib.hoisdf_nchw_to_nhwc.argtypes = [vp, vp, i64, i64, i64, i64, vp]
+    B, P = 2, 21
+    pyr = syn.feature_pyramid(21, B, "dexycb")
+    uv = torch.from_numpy(rnd(22, B, P, 2, lo=-20.0, hi=275.0))
+    uv[0, 0] = torch.tensor([0.0, 255.0]); uv[0, 1] = torch.tensor([255.0, 0.0]); uv[0, 2] = torch.tensor([127.5, 127.5])
+    cfg = O.default_cfg()
+    ref = O.gather_pyramid(pyr, O.grid_from_uv(uv, cfg))
+    maps = []
+    for n in O.LEVELS:                                   # NCHW -> NHWC through the kernel itself
+        src = f32(pyr[n])
+        dst = np.zeros((B, src.shape[2], src.shape[3], src.shape[1]), np.float32)
+        assert lib.hoisdf_nchw_to_nhwc(ptr(src), ptr(dst), B, src.shape[1], src.shape[2], src.shape[3], None) == 0
+        assert np.array_equal(dst, src.transpose(0, 2, 3, 1))
+        maps.append(dst)
+    Ctot = sum(m.shape[3] for m in maps)
+    pstruct = make_pyramid(maps)
+    uvf = f32(uv.reshape(-1, 2))
+    out = np.zeros((B * P, Ctot), np.float32)
+    assert lib.hoisdf_gather_fwd(C.byref(pstruct), ptr(uvf), B * P, None, B, P, 0, None, 0, ptr(out), Ctot, None) == 0
+    assert np.abs(out.reshape(B, P, Ctot) - ref.numpy()).max() < 5e-6
+    # SUM mode over equal-width maps, ragged rows
+    gen = torch.Generator().manual_seed(3)
+    gm = [torch.randn(B, 128, h, h, generator=gen) for h in (16, 8, 4)]
+    bias = torch.randn(128, generator=gen)
+    n0 = 9
+    flat = uv.reshape(1, -1, 2)
+    parts = []
+    for s, sl in ((0, slice(0, n0)), (1, slice(n0, B * P))):
+        g = O.grid_from_uv(flat[:, sl], cfg).unsqueeze(1)
+        parts.append(sum(F.grid_sample(m[s:s + 1], g, padding_mode="border", align_corners=True) for m in gm)[0, :, 0].T)
+    ref2 = torch.relu(torch.cat(parts) + bias)
+    gmn = [np.ascontiguousarray(f32(m).transpose(0, 2, 3, 1)) for m in gm]
+    ps = make_pyramid(gmn)
+    offsets = np.array([0, n0, B * P], np.int64)
+    bz = f32(bias)
+    out2 = np.zeros((B * P, 128), np.float32)
+    assert lib.hoisdf_gather_fwd(C.byref(ps), ptr(uvf), B * P, ptr(offsets), B, 0, 1, ptr(bz), 1, ptr(out2), 128, None) == 0
+    assert np.abs(out2 - ref2.numpy()).max() < 5e-6 * max(1.0, float(ref2.abs().max()))
+    hi, lo = np.zeros((B * P, 128), np.uint16), np.zeros((B * P, 128), np.uint16)
+    assert lib.hoisdf_gather_split_fwd(C.byref(ps), ptr(uvf), B * P, ptr(offsets), B, 0, 1, ptr(bz), 1, ptr(hi), ptr(lo), 128,
+                                       None) == 0
+    assert np.abs(join_split(hi, lo) - out2).max() < 3e-7 * float(np.abs(out2).max())
+    assert lib.hoisdf_gather_fwd(C.byref(ps), ptr(uvf), B * P, None, B, 0, 1, None, 0, ptr(out2), 128, None) == -2
+
+
+def test_add_layernorm_kernel_on_the_emulator():
+    """Residual + LayerNorm (+ the shared inter_norm) of upstream common/nets/transformer.py:296-301,196-197."""
+    import torch.nn.functional as F
+    lib = build_emulated("layernorm")
+    vp, i64 = C.c_void_p, C.c_int64
+    lib.hoisdf_add_layernorm_split_fwd.argtypes = [vp] * 8 + [i64, i64, vp, vp, i64, vp, vp, i64, vp]
+    rows, d = 19, 256
+    x, res = rnd(1, rows, d, lo=-2, hi=2), rnd(2, rows, d)
+    g1, b1, g2, b2 = rnd(3, d, lo=0.5, hi=1.5), rnd(4, d), rnd(5, d, lo=0.5, hi=1.5), rnd(6, d)
+    y, y2 = np.zeros((rows, d), np.float32), np.zeros((rows, d), np.float32)
+    hi, lo = np.zeros((rows, d), np.uint16), np.zeros((rows, d), np.uint16)
+    hi2, lo2 = np.zeros((rows, d), np.uint16), np.zeros((rows, d), np.uint16)
+    assert lib.hoisdf_add_layernorm_split_fwd(ptr(x), ptr(res), ptr(g1), ptr(b1), ptr(y), ptr(g2), ptr(b2), ptr(y2), rows, d,
+                                              ptr(hi), ptr(lo), d, ptr(hi2), ptr(lo2), d, None) == 0
+    t = torch.from_numpy
+    r1 = F.layer_norm(t(x) + t(res), (d,), t(g1), t(b1), 1e-5)
+    r2 = F.layer_norm(r1, (d,), t(g2), t(b2), 1e-5)
+    assert np.abs(y - r1.numpy()).max() < 3e-6 and np.abs(y2 - r2.numpy()).max() < 3e-6
+    assert np.abs(join_split(hi, lo) - y).max() < 3e-7 * float(np.abs(y).max())
+    assert np.abs(join_split(hi2, lo2) - y2).max() < 3e-7 * float(np.abs(y2).max())
+    assert lib.hoisdf_add_layernorm_split_fwd(ptr(x), None, ptr(g1), ptr(b1), ptr(y), None, None, None, rows, 128,
+                                              None, None, 0, None, None, 0, None) == -4
+
+
+def test_posenc_and_token_kernels_on_the_emulator():
+    """NeRF embedding + row-buffer tail (upstream common/utils/sdf_utils.py:96-141, main/model.py:218-219,332-333), the
+    SDFDecoder input padding and the token assembly with the SDF activation (model.py:123-126,520-531) of csrc/sdf.cu."""
+    lib = build_emulated("sdf", extra=("tensor_core_stubs.cpp",))
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
+    lib.hoisdf_posenc_fwd.argtypes = [vp, vp, i64, i32, vp, i64, i64, vp]
+    lib.hoisdf_posenc_split_fwd.argtypes = [vp, vp, i64, i32, vp, vp, i64, vp]
+    lib.hoisdf_sdf_pad_input.argtypes = [vp, i64, vp, i64, vp]
+    lib.hoisdf_tokens_fwd.argtypes = [vp, vp, vp, i64, vp, vp, i64, i64, vp, i64, i64, vp]
+    rows = 29
+    lat = O.lattice(64)
+    idx = np.random.Generator(np.random.PCG64(5)).choice(64 ** 3, rows, replace=False).astype(np.int32)
+    want = torch.cat([O.nerf_embed(lat[idx.astype(np.int64)]), lat[idx.astype(np.int64)]], 1).numpy()      # posenc | xyz
+    buf = np.full((rows, 516), 7.0, np.float32)
+    assert lib.hoisdf_posenc_fwd(ptr(idx), None, rows, 64, ptr(buf), 516, 256, None) == 0
+    assert np.abs(buf[:, 256:286] - want[:, :30]).max() < 2e-6 and np.array_equal(buf[:, 286:289], want[:, 30:])
+    assert not buf[:, 289:292].any() and not buf[:, 515].any() and (buf[:, :256] == 7.0).all() and (buf[:, 292:515] == 7.0).all()
+    pts = rnd(6, rows, 3)
+    assert lib.hoisdf_posenc_fwd(None, ptr(pts), rows, 64, ptr(buf), 516, 256, None) == 0
+    assert np.abs(buf[:, 256:286] - O.nerf_embed(torch.from_numpy(pts)).numpy()).max() < 2e-6
+    hi, lo = np.zeros((rows, 520), np.uint16), np.zeros((rows, 520), np.uint16)
+    assert lib.hoisdf_posenc_split_fwd(ptr(idx), None, rows, 64, ptr(hi), ptr(lo), 520, None) == 0
+    assert np.abs(join_split(hi, lo)[:, 256:289] - want).max() < 3e-7 * 1.1 + 2e-6
+    assert not hi[:, 289:296].any() and not hi[:, 519].any()
+    x = rnd(7, rows, 289)
+    padded = np.full((rows, 516), 7.0, np.float32)
+    assert lib.hoisdf_sdf_pad_input(ptr(x), rows, ptr(padded), 516, None) == 0
+    assert np.array_equal(padded[:, :289], x) and not padded[:, 289:292].any() and not padded[:, 515].any()
+    # tokens = cat[xyz (3), posenc (30), fea (223) * sigmoid(sdf / beta) / beta] at token offset t0 of an S-token sequence
+    B, P, S, t0 = 2, 5, 9, 3
+    xyz, pe, fea, sdf = rnd(8, B, P, 3), rnd(9, B, P, 30), rnd(10, B, P, 223), rnd(11, B, P, lo=-0.15, hi=0.15)
+    beta = np.array([0.1], np.float32)
+    tokens = np.zeros((B, S, 256), np.float32)
+    assert lib.hoisdf_tokens_fwd(ptr(xyz), ptr(pe), ptr(fea), 223, ptr(sdf), ptr(beta), B, P, ptr(tokens), S, t0, None) == 0
+    sig = O.sdf_activation({"hand_sigmoid_beta": torch.tensor([0.1])}, "hand_sigmoid_beta", torch.from_numpy(sdf)[..., None])
+    ref = torch.cat([torch.from_numpy(xyz), torch.from_numpy(pe), torch.from_numpy(fea) * sig], 2).numpy()
+    assert np.abs(tokens[:, t0:t0 + P] - ref).max() < 2e-6 * float(np.abs(ref).max())
+    assert not tokens[:, :t0].any() and not tokens[:, t0 + P:].any()
+    assert lib.hoisdf_tokens_fwd(ptr(xyz), ptr(pe), ptr(fea), 223, ptr(sdf), ptr(beta), B, P, ptr(tokens), S, S - 2, None) == -2
