@@ -22,6 +22,9 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -449,6 +452,286 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_co
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// attention kernel, 128-key tiles (the default for lk >= 128)
+// ---------------------------------------------------------------------------------------------------
+// Measured on B200 (scripts/umma_rate.cu, profiles/r01_umma_rate.txt): a tcgen05.mma M128 x N x K16 costs N/2 cycles only
+// down to N = 128; below that there is a ~46-cycle floor (N = 64: 48 cycles), so the 64-key kernel above runs the
+// tensor core at 2/3 rate at best and pays one softmax <-> tensor hand-over per 64 keys.  Here a K/V tile has 128 keys:
+//   * S_t = Q.K_t^T is M128 x N128 (full rate); P_t.V_t stays N = 64 (the head dimension) with K = 128;
+//   * TMEM per query tile g: one 128-column region that holds S_t (fp32) and is then OVERWRITTEN in place by P_t
+//     (packed bf16 pairs: hi in columns [0, 64), lo in [64, 128)) + the 64-column O accumulator = 192 columns, 384 for
+//     the two query tiles of a CTA.  tcgen05.mma instructions of one thread execute in order, so Q.K_{t+1}^T, issued
+//     right after P_t.V_t, cannot overwrite P_t early, and "S_{t+1} complete" implies "P_t.V_t complete": the softmax
+//     warps need no separate barrier before rescaling O or writing P_{t+1};
+//   * K and V^T tiles travel through separate 2-deep rings (K_{t+2} is fetched as soon as both Q.K_t^T have
+//     been issued and completed, V_{t+2} after both P_t.V_t), 32 KB per tile each.
+constexpr int A2_BK = 128;
+constexpr int A2_STAGES = 2;
+constexpr int A2_K_BYTES = A2_BK * AT_D * 2;       // 16 KB per bf16 term
+constexpr int A2_V_HALF = AT_D * 64 * 2;           // one 64-key box of V^T: 8 KB
+constexpr int A2_KSTAGE = 2 * A2_K_BYTES;          // K_hi | K_lo
+constexpr int A2_VSTAGE = 4 * A2_V_HALF;           // Vt_hi (2 boxes) | Vt_lo (2 boxes)
+constexpr int A2_SMEM_BYTES = AT_GROUPS * 2 * AT_Q_BYTES + A2_STAGES * (A2_KSTAGE + A2_VSTAGE) + 1024 + 256;
+constexpr uint32_t A2_GROUP_COLS = 192;            // S/P 128 + O 64
+
+__device__ __forceinline__ void at_tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15};"
+      ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(taddr)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attention_tc128_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant__ CUtensorMap map_qlo,
+                       const __grid_constant__ CUtensorMap map_khi, const __grid_constant__ CUtensorMap map_klo,
+                       const __grid_constant__ CUtensorMap map_vhi, const __grid_constant__ CUtensorMap map_vlo,
+                       const AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = at_smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw);
+  auto q_hi = [&](int g) { return base + static_cast<uint32_t>(g) * 2 * AT_Q_BYTES; };
+  auto q_lo = [&](int g) { return base + static_cast<uint32_t>(g) * 2 * AT_Q_BYTES + AT_Q_BYTES; };
+  const uint32_t kring = base + AT_GROUPS * 2 * AT_Q_BYTES;
+  const uint32_t vring = kring + A2_STAGES * A2_KSTAGE;
+  const uint32_t bars = vring + A2_STAGES * A2_VSTAGE;
+  // barriers: q | k_full[2] k_empty[2] v_full[2] v_empty[2] | s_full[g] p_full[g] o_full[g]
+  const uint32_t bar_q = bars;
+  auto bar_kf = [&](int s) { return bars + 8u * (1 + s); };
+  auto bar_ke = [&](int s) { return bars + 8u * (3 + s); };
+  auto bar_vf = [&](int s) { return bars + 8u * (5 + s); };
+  auto bar_ve = [&](int s) { return bars + 8u * (7 + s); };
+  auto bar_sf = [&](int g) { return bars + 8u * (9 + g); };
+  auto bar_pf = [&](int g) { return bars + 8u * (11 + g); };
+  auto bar_of = [&](int g) { return bars + 8u * (13 + g); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (bars - base) + 8 * 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * AT_BQ * AT_GROUPS;
+  const int h = blockIdx.y;
+  const int64_t b = blockIdx.z;
+  const int64_t bh = b * p.heads + h;
+  const int kend = min(p.lk, p.kv_valid);
+  const int T = (kend + A2_BK - 1) / A2_BK;
+
+  if (threadIdx.x == 0) {
+    at_mbar_init(bar_q, 1);
+    for (int s = 0; s < A2_STAGES; ++s) {
+      at_mbar_init(bar_kf(s), 1); at_mbar_init(bar_ke(s), 1);
+      at_mbar_init(bar_vf(s), 1); at_mbar_init(bar_ve(s), 1);
+    }
+    for (int g = 0; g < AT_GROUPS; ++g) {
+      at_mbar_init(bar_sf(g), 1);
+      at_mbar_init(bar_pf(g), 4);
+      at_mbar_init(bar_of(g), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(at_smem_u32(tmem_slot)),
+                 "r"(AT_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+  auto tmem_sp = [&](int g) { return tmem + static_cast<uint32_t>(g) * A2_GROUP_COLS; };          // S, then P in place
+  auto tmem_o = [&](int g) { return tmem + static_cast<uint32_t>(g) * A2_GROUP_COLS + 128u; };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      at_mbar_expect_tx(bar_q, AT_GROUPS * 2 * AT_Q_BYTES);
+      for (int g = 0; g < AT_GROUPS; ++g) {
+        const int qrow = static_cast<int>(bh * p.lq + q0 + g * AT_BQ);
+        at_tma_2d(q_hi(g), &map_qhi, bar_q, 0, qrow);
+        at_tma_2d(q_lo(g), &map_qlo, bar_q, 0, qrow);
+      }
+      const int vrow = static_cast<int>(bh * AT_D);
+      for (int t = 0; t < T; ++t) {
+        const int s = t % A2_STAGES;
+        const uint32_t ph = ((t / A2_STAGES) & 1) ^ 1u;
+        at_mbar_wait(bar_ke(s), ph);
+        const uint32_t ks = kring + s * A2_KSTAGE;
+        at_mbar_expect_tx(bar_kf(s), A2_KSTAGE);
+        const int krow = static_cast<int>(bh * p.lk + t * A2_BK);
+        at_tma_2d(ks, &map_khi, bar_kf(s), 0, krow);
+        at_tma_2d(ks + A2_K_BYTES, &map_klo, bar_kf(s), 0, krow);
+        at_mbar_wait(bar_ve(s), ph);
+        const uint32_t vs = vring + s * A2_VSTAGE;
+        at_mbar_expect_tx(bar_vf(s), A2_VSTAGE);
+        at_tma_2d(vs, &map_vhi, bar_vf(s), t * A2_BK, vrow);
+        at_tma_2d(vs + A2_V_HALF, &map_vhi, bar_vf(s), t * A2_BK + 64, vrow);
+        at_tma_2d(vs + 2 * A2_V_HALF, &map_vlo, bar_vf(s), t * A2_BK, vrow);
+        at_tma_2d(vs + 3 * A2_V_HALF, &map_vlo, bar_vf(s), t * A2_BK + 64, vrow);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // kind::f16: D = F32 (1<<4), A = B = BF16 (1<<7, 1<<10), K-major, N >> 3 at bit 17, M = 128 (8<<24)
+      const uint32_t idesc_common = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(AT_BQ >> 4) << 24);
+      const uint32_t idesc_qk = idesc_common | (static_cast<uint32_t>(A2_BK >> 3) << 17);
+      const uint32_t idesc_pv = idesc_common | (static_cast<uint32_t>(AT_D >> 3) << 17);
+      auto issue_qk = [&](int g, int t) {
+        const int s = t % A2_STAGES;
+        const uint32_t ks = kring + s * A2_KSTAGE;
+        const uint64_t d_qhi = at_desc_sw128(q_hi(g)), d_qlo = at_desc_sw128(q_lo(g));
+        const uint64_t d_khi = at_desc_sw128(ks), d_klo = at_desc_sw128(ks + A2_K_BYTES);
+        const uint32_t d_s = tmem_sp(g);
+#pragma unroll
+        for (int kk = 0; kk < AT_D / 16; ++kk) {
+          const uint64_t adv = static_cast<uint64_t>(kk * 2);   // 16 bf16 = 32 bytes
+          at_umma_bf16(d_s, d_qlo + adv, d_khi + adv, idesc_qk, kk != 0 ? 1u : 0u);
+          at_umma_bf16(d_s, d_qhi + adv, d_klo + adv, idesc_qk, 1u);
+          at_umma_bf16(d_s, d_qhi + adv, d_khi + adv, idesc_qk, 1u);
+        }
+        at_commit(bar_sf(g));
+      };
+      at_mbar_wait(bar_q, 0);
+      at_mbar_wait(bar_kf(0), 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int g = 0; g < AT_GROUPS; ++g) issue_qk(g, 0);
+      at_commit(bar_ke(0));
+      for (int t = 0; t < T; ++t) {
+        const int s = t % A2_STAGES;
+        const uint32_t vs = vring + s * A2_VSTAGE;
+        at_mbar_wait(bar_vf(s), (t / A2_STAGES) & 1);
+        for (int g = 0; g < AT_GROUPS; ++g) {
+          at_mbar_wait(bar_pf(g), t & 1);                        // P_t of this group written, its O rescaled
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_hi = tmem_sp(g), a_lo = tmem_sp(g) + 64;
+          const uint32_t d_o = tmem_o(g);
+#pragma unroll
+          for (int kk = 0; kk < A2_BK / 16; ++kk) {
+            const uint32_t box = static_cast<uint32_t>(kk >> 2) * A2_V_HALF;          // which 64-key box of V^T
+            const uint64_t adv = static_cast<uint64_t>((kk & 3) * 2);                 // 16 keys = 32 bytes inside the box
+            const uint64_t d_vhi = at_desc_sw128(vs + box) + adv, d_vlo = at_desc_sw128(vs + 2 * A2_V_HALF + box) + adv;
+            const uint32_t ka = static_cast<uint32_t>(kk * 8);                         // P in TMEM: 16 bf16 = 8 columns
+            at_umma_bf16_ts(d_o, a_lo + ka, d_vhi, idesc_pv, (t | kk) != 0 ? 1u : 0u);
+            at_umma_bf16_ts(d_o, a_hi + ka, d_vlo, idesc_pv, 1u);
+            at_umma_bf16_ts(d_o, a_hi + ka, d_vhi, idesc_pv, 1u);
+          }
+          if (t + 1 < T) {
+            if (g == 0) {
+              at_mbar_wait(bar_kf((t + 1) % A2_STAGES), ((t + 1) / A2_STAGES) & 1);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            issue_qk(g, t + 1);                                   // executes after P_t.V_t: S_{t+1} overwrites P_t
+          } else {
+            at_commit(bar_of(g));                                 // last P.V of this group done: O final
+          }
+        }
+        at_commit(bar_ve(s));                                     // V_t consumed by both groups
+        if (t + 1 < T) at_commit(bar_ke((t + 1) % A2_STAGES));    // K_{t+1} consumed by both groups
+      }
+    }
+  } else {
+    // ------------------------------------------------ softmax warps: thread <-> query row
+    const int g = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int t = 0; t < T; ++t) {
+      at_mbar_wait(bar_sf(g), t & 1);          // S_t complete (and with it P_{t-1}.V_{t-1}: same issuing thread, in order)
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t sr[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) at_tmem_ld32(tmem_sp(g) + lane_addr + c * 32, sr + c * 32);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const int valid = kend - t * A2_BK;
+      if (valid < A2_BK) {                               // ragged last tile only (warp-uniform)
+#pragma unroll
+        for (int j = 0; j < 128; ++j)
+          if (j >= valid) sr[j] = __float_as_uint(-INFINITY);
+      }
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int j = 0; j < 128; ++j) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(sr[j]));
+      const float m_tile = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      const float m_new = (m_tile - m_run > AT_RESCALE_LOG2) ? m_tile : m_run;      // lazy rescaling, see above
+      const float alpha = (m_new == m_run) ? 1.f : ex2_approx(m_run - m_new);
+      if (t > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+        uint32_t o[32];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          at_tmem_ld32(tmem_o(g) + lane_addr + half * 32, o);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+          at_tmem_st32(tmem_o(g) + lane_addr + half * 32, o);
+        }
+      }
+      // p = 2^(s - m), row sum, and P as packed bf16 pairs (hi, lo) written over S, 32 keys at a time
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t ph[16], pl[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float e0 = ex2_approx(__uint_as_float(sr[c * 32 + 2 * e]) - m_new);
+          const float e1 = ex2_approx(__uint_as_float(sr[c * 32 + 2 * e + 1]) - m_new);
+          rs4[e & 3] += e0 + e1;
+          split_bf16x2(e0, e1, ph[e], pl[e]);
+        }
+        at_tmem_st16(tmem_sp(g) + lane_addr + c * 16, ph);
+        at_tmem_st16(tmem_sp(g) + lane_addr + 64 + c * 16, pl);
+      }
+      l_run = l_run * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
+      m_run = m_new;
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) at_mbar_arrive(bar_pf(g));
+    }
+    at_mbar_wait(bar_of(g), 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int row = q0 + g * AT_BQ + r;
+    const float inv = __fdiv_rn(1.f, l_run);
+    const int64_t oo = (b * p.lq + row) * p.ldo + h * AT_D;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t o[32];
+      at_tmem_ld32(tmem_o(g) + lane_addr + half * 32, o);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row < p.lq) {
+        if (p.out != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            *reinterpret_cast<float4*>(p.out + oo + half * 32 + j) =
+                make_float4(__uint_as_float(o[j]) * inv, __uint_as_float(o[j + 1]) * inv,
+                            __uint_as_float(o[j + 2]) * inv, __uint_as_float(o[j + 3]) * inv);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float x0 = __uint_as_float(o[j + 2 * e]) * inv, x1 = __uint_as_float(o[j + 2 * e + 1]) * inv;
+              asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hw[e]) : "f"(x1), "f"(x0));
+              const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+              asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lw[e]) : "f"((x1 - hf.y) * 2048.f), "f"((x0 - hf.x) * 2048.f));
+            }
+            *reinterpret_cast<uint4*>(p.out_hi + oo + half * 32 + j) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(p.out_lo + oo + half * 32 + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(AT_TMEM_COLS) : "memory");
+  }
+}
+
 static PFN_cuTensorMapEncodeTiled_v12000 at_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   if (fn == nullptr) {
@@ -506,15 +789,25 @@ int launch_attention_tc(const float* q, int64_t ldq, const float* k, const float
   }
   CUtensorMap mqh, mql, mkh, mkl, mvh, mvl;
   const int64_t bh = batch * heads;
+  // 128-key tiles (attention_tc128_kernel) for the long sequences; HOISDF_ATTN_BK=64 keeps the 64-key kernel
+  static const bool allow_wide = [] { const char* e = getenv("HOISDF_ATTN_BK"); return e == nullptr || atoi(e) != 64; }();
+  const bool wide = allow_wide && (kv_valid < lk ? kv_valid : lk) >= A2_BK;
+  const int kbox = wide ? A2_BK : AT_BK;
   if (!at_make_map(&mqh, qhi, bh * lq, AT_D, AT_D, AT_BQ) || !at_make_map(&mql, qlo, bh * lq, AT_D, AT_D, AT_BQ) ||
-      !at_make_map(&mkh, khi, bh * lk, AT_D, AT_D, AT_BK) || !at_make_map(&mkl, klo, bh * lk, AT_D, AT_D, AT_BK) ||
+      !at_make_map(&mkh, khi, bh * lk, AT_D, AT_D, kbox) || !at_make_map(&mkl, klo, bh * lk, AT_D, AT_D, kbox) ||
       !at_make_map(&mvh, vhi, bh * AT_D, lk_pad, lk_pad, AT_D) || !at_make_map(&mvl, vlo, bh * AT_D, lk_pad, lk_pad, AT_D))
     return HOISDF_E_UNSUPPORTED;
-  cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
-  if (e != cudaSuccess) return static_cast<int>(e);
   AttnTcParams p{out, out_hi, out_lo, ldo, static_cast<int>(lq), static_cast<int>(lk), static_cast<int>(kv_valid),
                  static_cast<int>(heads)};
   dim3 grid(static_cast<unsigned>(ceil_div(lq, AT_BQ * AT_GROUPS)), static_cast<unsigned>(heads), static_cast<unsigned>(batch));
+  if (wide) {
+    cudaError_t e = cudaFuncSetAttribute(attention_tc128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM_BYTES);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attention_tc128_kernel<<<grid, AT_THREADS, A2_SMEM_BYTES, s>>>(mqh, mql, mkh, mkl, mvh, mvl, p);
+    return launch_status();
+  }
+  cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
+  if (e != cudaSuccess) return static_cast<int>(e);
   attention_tc_kernel<<<grid, AT_THREADS, AT_SMEM_BYTES, s>>>(mqh, mql, mkh, mkl, mvh, mvl, p);
   return launch_status();
 }
