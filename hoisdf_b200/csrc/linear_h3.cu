@@ -21,6 +21,8 @@
 //               per thread (the tensor core truncates on accumulate -- see the note at the kernel); after the last
 //               chunk: scale + bias (+ split-half residual) + ReLU, then fp32 or split-half output staged in a
 //               swizzled smem box and written by TMA, or direct stores for the fp32-residual / ragged-group modes.
+#include <cstdlib>
+
 #include "tc_common.cuh"
 
 namespace hoisdf {
@@ -66,6 +68,10 @@ struct H3Params {
   int chunk_kb;             // K blocks accumulated in TMEM before the partial sum is drained into registers
   int single;               // 1: ONE product x_hi . w_hi per K step (11-bit operands, ~5e-4 relative): candidate
                             // pre-screening only -- 1/3 of the tensor work, 3/8 of the operand bytes, deeper ring
+  int w_rows;               // three-product mode: rows of W kept per plane in a stage (64 / 128 / 256 >= N of one N tile).
+  int nstages;              // A narrow layer does not pay for 256 rows of (mostly zero-filled) W per K block: its stages
+                            // shrink from 64 KB to 40 / 28 KB and the ring deepens from 3 to 4 / 6 stages -- the thin
+                            // shapes are bound by load latency, not by tensor work (N <= 64 MMAs sit on the issue floor)
   // implicit-GEMM convolution (taps > 0): X is an NHWC image batch (4-D tensor maps), M = output pixels in (b, y, x)
   // order, K = taps x Cin; a 128-pixel M tile is a (tb x ty x tx) block of the output grid, a warp's 32 rows a
   // (wy x wx) block
@@ -102,8 +108,9 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
   auto bar_cempty = [&](uint32_t b) { return bars + 8u * (2 * H3_MAX_STAGES + 2 + b); };
   constexpr bool single = SINGLE;
   constexpr bool DIRECT = OUT == H3_OUT_F32_DIRECT;
-  const int nstages = single ? H3_STAGES_1P : H3_STAGES;
-  const uint32_t stage_bytes = single ? H3_STAGE_BYTES_1P : H3_STAGE_BYTES;
+  const int nstages = single ? H3_STAGES_1P : p.nstages;
+  const uint32_t w_bytes = single ? H3_W_BYTES : static_cast<uint32_t>(p.w_rows) * H3_BK * 2;     // one W plane of a stage
+  const uint32_t stage_bytes = single ? H3_STAGE_BYTES_1P : 2 * H3_X_BYTES + 3 * w_bytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
@@ -113,8 +120,8 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
   const int num_kb = p.taps > 0 ? p.taps * p.cin_blocks : (p.k + H3_BK - 1) / H3_BK;
   const int chb = p.chunk_kb;
   constexpr uint16_t kAllCtas = static_cast<uint16_t>((1u << CL) - 1u);
-  constexpr int kSliceRows = H3_BN / CL;                 // W rows each CTA fetches (and multicasts)
-  constexpr int kSliceBytes = kSliceRows * H3_BK * 2;
+  const int kSliceRows = (single ? H3_BN : p.w_rows) / CL;   // W rows each CTA fetches (and multicasts)
+  const uint32_t kSliceBytes = static_cast<uint32_t>(kSliceRows) * H3_BK * 2;
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_xhi) : "memory");
@@ -199,12 +206,12 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
           const uint32_t w0 = st + 2 * H3_X_BYTES + wo;
           if (CL > 1) {
             tma_load_2d_mc(w0, &map_wa, bar_full(s), kb * H3_BK, wrow, kAllCtas);
-            tma_load_2d_mc(w0 + H3_W_BYTES, &map_wb, bar_full(s), kb * H3_BK, wrow, kAllCtas);
-            tma_load_2d_mc(w0 + 2 * H3_W_BYTES, &map_wc, bar_full(s), kb * H3_BK, wrow, kAllCtas);
+            tma_load_2d_mc(w0 + w_bytes, &map_wb, bar_full(s), kb * H3_BK, wrow, kAllCtas);
+            tma_load_2d_mc(w0 + 2 * w_bytes, &map_wc, bar_full(s), kb * H3_BK, wrow, kAllCtas);
           } else {
             tma_load_2d(w0, &map_wa, bar_full(s), kb * H3_BK, wrow);
-            tma_load_2d(w0 + H3_W_BYTES, &map_wb, bar_full(s), kb * H3_BK, wrow);
-            tma_load_2d(w0 + 2 * H3_W_BYTES, &map_wc, bar_full(s), kb * H3_BK, wrow);
+            tma_load_2d(w0 + w_bytes, &map_wb, bar_full(s), kb * H3_BK, wrow);
+            tma_load_2d(w0 + 2 * w_bytes, &map_wc, bar_full(s), kb * H3_BK, wrow);
           }
         }
       }
@@ -243,8 +250,8 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
           } else {
             const uint64_t d_xhi = umma_desc_sw64(st), d_xlo = umma_desc_sw64(st + H3_X_BYTES);
             const uint64_t d_wa = umma_desc_sw64(st + 2 * H3_X_BYTES);
-            const uint64_t d_wb = umma_desc_sw64(st + 2 * H3_X_BYTES + H3_W_BYTES);
-            const uint64_t d_wc = umma_desc_sw64(st + 2 * H3_X_BYTES + 2 * H3_W_BYTES);
+            const uint64_t d_wb = umma_desc_sw64(st + 2 * H3_X_BYTES + w_bytes);
+            const uint64_t d_wc = umma_desc_sw64(st + 2 * H3_X_BYTES + 2 * w_bytes);
 #pragma unroll
             for (int kk = 0; kk < H3_BK / 16; ++kk) {
               const uint64_t adv = static_cast<uint64_t>(kk * 2);    // 16 halfs = 32 bytes = 2 x 16-byte units
@@ -602,6 +609,18 @@ static int max_clusters() {
 }
 
 static int g_h3_force_cluster = 0;   // developer hook: 0 = automatic
+
+// W rows per stage plane for a layer with `n` outputs (see H3Params::w_rows); HOISDF_H3_WIDE_STAGES=1 keeps 256 always
+static int h3_w_rows(int64_t n, bool single) {
+  static const bool wide_only = [] { const char* e = getenv("HOISDF_H3_WIDE_STAGES"); return e != nullptr && atoi(e) != 0; }();
+  if (single || wide_only || n > 128) return H3_BN;
+  return n > 64 ? 128 : 64;
+}
+static int h3_stage_count(int w_rows) {
+  const int stage = 2 * H3_X_BYTES + 3 * w_rows * H3_BK * 2;
+  const int n = H3_STAGES * H3_STAGE_BYTES / stage;
+  return n < H3_MAX_STAGES ? n : H3_MAX_STAGES;
+}
 static int g_h3_chunk_kb = H3_CHUNK_KB;   // developer hook: K blocks per accumulation chunk
 
 template <int CL, int OUT, bool SINGLE, bool RES>
@@ -696,7 +715,8 @@ HOISDF_API int hoisdf_linear_h3_fwd(const hoisdf_linear_h3_args* a, void* stream
   CUtensorMap maps[7];
   if (!map_x_3d(&maps[0], a->x_hi, groups, rpb, a->k, a->ldx, gstride)) return HOISDF_E_UNSUPPORTED;
   if (!map_x_3d(&maps[1], a->x_lo, groups, rpb, a->k, a->ldx, gstride)) return HOISDF_E_UNSUPPORTED;
-  const int slice = H3_BN / cl;
+  const int w_rows = h3_w_rows(a->n, a->single_pass != 0);
+  const int slice = w_rows / cl;
   const void* wp[3] = {a->w_a, a->w_b, a->w_c};
   for (int i = 0; i < 3; ++i)
     if (!map_half_2d(&maps[2 + i], wp[i], a->n, a->k, a->ldw, H3_BK, slice, CU_TENSOR_MAP_SWIZZLE_64B,
@@ -726,6 +746,7 @@ HOISDF_API int hoisdf_linear_h3_fwd(const hoisdf_linear_h3_args* a, void* stream
   p.n = static_cast<int>(a->n); p.k = static_cast<int>(a->k); p.act = a->act; p.out_mode = out_mode;
   p.chunk_kb = a->chunk_kb;
   p.single = a->single_pass ? 1 : 0;
+  p.w_rows = w_rows; p.nstages = h3_stage_count(w_rows);
   if (a->res_hi != nullptr || a->res_lo != nullptr) {
     if (a->res_hi == nullptr || a->res_lo == nullptr) return HOISDF_E_NULL;
     if (out_mode == H3_OUT_F32_DIRECT || a->residual != nullptr || (a->n & 31)) return HOISDF_E_UNSUPPORTED;
@@ -785,8 +806,9 @@ HOISDF_API int hoisdf_conv_h3_fwd(const hoisdf_conv_h3_args* a, void* stream) {
   int cl = m_tiles >= 2 ? 2 : 1;
   if (g_h3_force_cluster == 1 || g_h3_force_cluster == 2) cl = g_h3_force_cluster;
   const void* wp[3] = {a->w_a, a->w_b, a->w_c};
+  const int w_rows = h3_w_rows(a->cout, a->single_pass != 0);
   for (int i = 0; i < 3; ++i)
-    if (!map_half_2d(&maps[2 + i], wp[i], a->cout, a->taps * a->cin, a->ldw, H3_BK, H3_BN / cl,
+    if (!map_half_2d(&maps[2 + i], wp[i], a->cout, a->taps * a->cin, a->ldw, H3_BK, w_rows / cl,
                      CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B))
       return HOISDF_E_UNSUPPORTED;
   {
@@ -816,6 +838,7 @@ HOISDF_API int hoisdf_conv_h3_fwd(const hoisdf_conv_h3_args* a, void* stream) {
   p.out_mode = split_out ? H3_OUT_SPLIT_TMA : H3_OUT_F32_TMA;
   p.chunk_kb = a->chunk_kb;
   p.single = a->single_pass ? 1 : 0;
+  p.w_rows = w_rows; p.nstages = h3_stage_count(w_rows);
   p.taps = a->taps; p.cin_blocks = static_cast<int>(a->cin / H3_BK);
   p.out_w = static_cast<int>(a->out_w); p.out_h = static_cast<int>(a->out_h); p.stride = a->stride;
   p.wx = wx; p.wy = wy;
