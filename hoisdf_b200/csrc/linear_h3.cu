@@ -69,6 +69,8 @@ struct H3Params {
   int single;               // 1: ONE product x_hi . w_hi per K step (11-bit operands, ~5e-4 relative): candidate
                             // pre-screening only -- 1/3 of the tensor work, 3/8 of the operand bytes, deeper ring
   int w_rows;               // three-product mode: rows of W kept per plane in a stage (64 / 128 / 256 >= N of one N tile).
+  int bn;                   // columns of one N tile (256; 64 / 128 when the whole layer is narrower, or -- for launches that
+                            // would occupy only a few SMs -- to split N into more, narrower tiles with deeper rings)
   int nstages;              // A narrow layer does not pay for 256 rows of (mostly zero-filled) W per K block: its stages
                             // shrink from 64 KB to 40 / 28 KB and the ring deepens from 3 to 4 / 6 stages -- the thin
                             // shapes are bound by load latency, not by tensor work (N <= 64 MMAs sit on the issue floor)
@@ -158,7 +160,7 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
     // cluster padding (M tiles beyond the last): group index = #groups, every X row out of bounds -> zero-filled
     grp = m_tile < p.m_tiles ? m_tile / p.tiles_per_batch : p.m_tiles / p.tiles_per_batch;
     m0 = m_tile < p.m_tiles ? (m_tile - grp * p.tiles_per_batch) * H3_BM : 0;
-    n0 = (item - mb * p.n_tiles) * H3_BN;
+    n0 = (item - mb * p.n_tiles) * p.bn;
   };
 
   if (warp == 0) {
@@ -223,7 +225,7 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
       for (int item = cluster; item < items; item += nclusters) {
         int m_tile, grp, m0, n0;
         tile_of(item, m_tile, grp, m0, n0);
-        const int n_here = min(H3_BN, p.n - n0);
+        const int n_here = min(p.bn, p.n - n0);
         const int n_inst = (n_here + 15) & ~15;                 // UMMA N (multiple of 16 for M = 128)
         const uint32_t idesc = umma_idesc_f16(H3_BM, n_inst);
         int in_chunk = 0;
@@ -282,7 +284,7 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
     for (int item = cluster; item < items; item += nclusters) {
       int m_tile, grp, m0, n0;
       tile_of(item, m_tile, grp, m0, n0);
-      const int n_here = min(H3_BN, p.n - n0);
+      const int n_here = min(p.bn, p.n - n0);
       const int n_inst = (n_here + 15) & ~15;
       const bool tile_ok = m_tile < p.m_tiles;
       int ob = 0, oy = 0, ox = 0;              // convolution: (image, row, column) of this warp's first output pixel
@@ -715,7 +717,11 @@ HOISDF_API int hoisdf_linear_h3_fwd(const hoisdf_linear_h3_args* a, void* stream
   CUtensorMap maps[7];
   if (!map_x_3d(&maps[0], a->x_hi, groups, rpb, a->k, a->ldx, gstride)) return HOISDF_E_UNSUPPORTED;
   if (!map_x_3d(&maps[1], a->x_lo, groups, rpb, a->k, a->ldx, gstride)) return HOISDF_E_UNSUPPORTED;
-  const int w_rows = h3_w_rows(a->n, a->single_pass != 0);
+  // launches with very few tiles (the 17-query decoder layers, M = 544): N tiles of 64 columns instead of 256 -> 4x the
+  // CTAs and a 6-stage ring, the K loop is pure load latency there
+  const bool few = a->single_pass == 0 && a->n > 64 && m_tiles * ceil_div(a->n, H3_BN) <= kNumSMs / 4;
+  const int w_rows = few ? 64 : h3_w_rows(a->n, a->single_pass != 0);
+  const int bn = w_rows;                                 // three-product mode: one N tile = the W rows of a stage
   const int slice = w_rows / cl;
   const void* wp[3] = {a->w_a, a->w_b, a->w_c};
   for (int i = 0; i < 3; ++i)
@@ -742,7 +748,8 @@ HOISDF_API int hoisdf_linear_h3_fwd(const hoisdf_linear_h3_args* a, void* stream
   H3Params p{};
   p.bias = a->bias; p.residual = a->residual; p.y = a->y; p.ldy = a->ldy;
   p.rows_per_batch = rpb; p.tiles_per_batch = static_cast<int>(tpb); p.m_tiles = static_cast<int>(m_tiles);
-  p.n_tiles = static_cast<int>(ceil_div(a->n, H3_BN));
+  p.bn = a->single_pass ? H3_BN : bn;
+  p.n_tiles = static_cast<int>(ceil_div(a->n, p.bn));
   p.n = static_cast<int>(a->n); p.k = static_cast<int>(a->k); p.act = a->act; p.out_mode = out_mode;
   p.chunk_kb = a->chunk_kb;
   p.single = a->single_pass ? 1 : 0;
@@ -833,7 +840,8 @@ HOISDF_API int hoisdf_conv_h3_fwd(const hoisdf_conv_h3_args* a, void* stream) {
   }
   H3Params p{};
   p.bias = a->bias; p.rows_per_batch = m; p.tiles_per_batch = static_cast<int>(m_tiles);
-  p.m_tiles = static_cast<int>(m_tiles); p.n_tiles = static_cast<int>(ceil_div(a->cout, H3_BN));
+  p.bn = a->single_pass ? H3_BN : w_rows;
+  p.m_tiles = static_cast<int>(m_tiles); p.n_tiles = static_cast<int>(ceil_div(a->cout, p.bn));
   p.n = static_cast<int>(a->cout); p.k = static_cast<int>(a->taps * a->cin); p.act = a->act;
   p.out_mode = split_out ? H3_OUT_SPLIT_TMA : H3_OUT_F32_TMA;
   p.chunk_kb = a->chunk_kb;
