@@ -301,10 +301,10 @@ def run_native(args):
         "step incl. the 4 GEMMs of every SDF-decoder call; FLOPs counted once per fp32 product, i.e. the "
         "tensor cores execute 3x this number of TF32 MACs)")
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_h3_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r01n_h3_traffic.json")
     if h3 and os.path.exists(tpath):            # from the committed ncu launch list of `bench.py --profile-step`
         traffic = json.load(open(tpath))["dram_bytes_per_launch"]
-        traffic_src = "profiles/r01_h3_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, same command)"
+        traffic_src = "profiles/r01n_h3_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, same command)"
     roofline = {
         "kernel": kernel_name,
         "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
