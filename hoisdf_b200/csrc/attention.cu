@@ -32,7 +32,7 @@ struct AttnParams {
 };
 
 __global__ void __launch_bounds__(256, 2) attention_flash_kernel(const AttnParams p) {
-  extern __shared__ __align__(16) float smem[];
+  HOISDF_DYNAMIC_SMEM(float, smem);
   float* Qs = smem;                    // [BQ][PITCH]
   float* Ps = Qs + BQ * PITCH;         // [BQ][PITCH]
   float* Ks = Ps + BQ * PITCH;         // [BKV][PITCH]
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256, 2) attention_flash_kernel(const AttnParam
 
 // one CTA (128 threads) per (query, head, sample); scores in dynamic smem (lk floats)
 __global__ void __launch_bounds__(128) attention_small_kernel(const AttnParams p) {
-  extern __shared__ __align__(16) float sc[];
+  HOISDF_DYNAMIC_SMEM(float, sc);
   __shared__ float qs[HD];
   __shared__ float red[4];
   __shared__ float part[2][HD];
@@ -274,8 +274,9 @@ HOISDF_API int hoisdf_attention_fwd(const float* q, int64_t ldq, const float* k,
   if (mask != nullptr || lq <= 32) {
     if (lq > 65535 * 32 || lk > 12000) return HOISDF_E_UNSUPPORTED;  // scores must fit in shared memory
     dim3 grid(static_cast<unsigned>(lq), static_cast<unsigned>(heads), static_cast<unsigned>(batch));
-    attention_small_kernel<<<grid, 128, static_cast<size_t>(lk) * sizeof(float), s>>>(p);
+    HOISDF_LAUNCH_SMEM(attention_small_kernel, grid, 128, static_cast<size_t>(lk) * sizeof(float), s, p);
   } else {
+#ifndef HOISDF_EMULATE
     static bool configured = false;
     if (!configured) {
       cudaError_t e = cudaFuncSetAttribute(attention_flash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -283,8 +284,9 @@ HOISDF_API int hoisdf_attention_fwd(const float* q, int64_t ldq, const float* k,
       if (e != cudaSuccess) return static_cast<int>(e);
       configured = true;
     }
+#endif
     dim3 grid(static_cast<unsigned>(ceil_div(lq, BQ)), static_cast<unsigned>(heads), static_cast<unsigned>(batch));
-    attention_flash_kernel<<<grid, 256, kFlashSmem, s>>>(p);
+    HOISDF_LAUNCH_SMEM(attention_flash_kernel, grid, 256, kFlashSmem, s, p);
   }
   return launch_status();
 }

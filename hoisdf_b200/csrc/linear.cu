@@ -264,9 +264,9 @@ HOISDF_API int hoisdf_linear_fwd(const hoisdf_linear_args* a, void* stream) {
   const int64_t nt = a->n > 64 ? ceil_div(a->n, 128) : 1;
   if (mt * nt > 0x7fffffffLL) return HOISDF_E_SHAPE;
   if (a->n > 64) {
-    linear_fp32_kernel<128, 128><<<static_cast<unsigned>(mt * nt), 256, 0, s>>>(p);
+    HOISDF_LAUNCH((linear_fp32_kernel<128, 128>), static_cast<unsigned>(mt * nt), 256, s, p);
   } else {
-    linear_fp32_kernel<128, 64><<<static_cast<unsigned>(mt * nt), 256, 0, s>>>(p);
+    HOISDF_LAUNCH((linear_fp32_kernel<128, 64>), static_cast<unsigned>(mt * nt), 256, s, p);
   }
   return launch_status();
 }
@@ -275,7 +275,7 @@ HOISDF_API int hoisdf_fold_weight_norm(const float* g, const float* v, int64_t r
                                        int64_t ld_out, const int32_t* src_col, int64_t cols_out, void* stream) {
   if (v == nullptr || out == nullptr) return HOISDF_E_NULL;
   if (rows <= 0 || cols <= 0 || cols_out <= 0 || ld_out < cols_out) return HOISDF_E_SHAPE;
-  fold_weight_norm_kernel<<<static_cast<unsigned>(rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      g, v, rows, cols, out, ld_out, src_col, cols_out);
+  HOISDF_LAUNCH(fold_weight_norm_kernel, static_cast<unsigned>(rows), 256, static_cast<cudaStream_t>(stream), g, v, rows,
+                cols, out, ld_out, src_col, cols_out);
   return launch_status();
 }

@@ -76,8 +76,8 @@ HOISDF_API int hoisdf_linear_narrow_split_fwd(const uint16_t* x_hi, const uint16
   const __half* xh = reinterpret_cast<const __half*>(x_hi);
   const __half* xl = reinterpret_cast<const __half*>(x_lo);
   const int ni = static_cast<int>(n), ki = static_cast<int>(k);
-  if (n <= 4) linear_narrow_kernel<4><<<blocks, 256, 0, s>>>(xh, xl, ldx, m, w, ldw, bias, ni, ki, act, y, ldy);
-  else if (n <= 12) linear_narrow_kernel<12><<<blocks, 256, 0, s>>>(xh, xl, ldx, m, w, ldw, bias, ni, ki, act, y, ldy);
-  else linear_narrow_kernel<24><<<blocks, 256, 0, s>>>(xh, xl, ldx, m, w, ldw, bias, ni, ki, act, y, ldy);
+  if (n <= 4) HOISDF_LAUNCH(linear_narrow_kernel<4>, blocks, 256, s, xh, xl, ldx, m, w, ldw, bias, ni, ki, act, y, ldy);
+  else if (n <= 12) HOISDF_LAUNCH(linear_narrow_kernel<12>, blocks, 256, s, xh, xl, ldx, m, w, ldw, bias, ni, ki, act, y, ldy);
+  else HOISDF_LAUNCH(linear_narrow_kernel<24>, blocks, 256, s, xh, xl, ldx, m, w, ldw, bias, ni, ki, act, y, ldy);
   return launch_status();
 }

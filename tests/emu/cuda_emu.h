@@ -25,6 +25,7 @@
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
 
 struct dim3 {
   unsigned x, y, z;
@@ -45,23 +46,29 @@ void launch(K kernel, dim3 grid, dim3 block, Args... args) {
   grid_dim = grid;
   block_dim = block;
   const unsigned n = block.x * block.y * block.z;
-  for (unsigned bz = 0; bz < grid.z; ++bz)
-    for (unsigned by = 0; by < grid.y; ++by)
-      for (unsigned bx = 0; bx < grid.x; ++bx) {
-        block_barrier = std::make_unique<std::barrier<>>(n);
-        warp_barrier.clear();
-        for (unsigned w = 0; w * 32 < n; ++w)
-          warp_barrier.push_back(std::make_unique<std::barrier<>>(std::min(32u, n - w * 32)));
-        std::vector<std::thread> threads;
-        threads.reserve(n);
-        for (unsigned t = 0; t < n; ++t)
-          threads.emplace_back([=]() {
-            thread_idx = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+  block_barrier = std::make_unique<std::barrier<>>(n);
+  warp_barrier.clear();
+  for (unsigned w = 0; w * 32 < n; ++w)
+    warp_barrier.push_back(std::make_unique<std::barrier<>>(std::min(32u, n - w * 32)));
+  // one OS thread per CUDA thread of a block, reused for every block of the grid (blocks run one after another; the
+  // end-of-block barrier keeps a block's `__shared__` storage alive until all of its threads have left the kernel).
+  // Limitation, as in any such emulation: threads that leave a kernel early must not be waited for by a later
+  // __syncthreads() of the others (none of the emulated kernels does that).
+  std::barrier<> end_of_block(n);
+  std::vector<std::thread> threads;
+  threads.reserve(n);
+  for (unsigned t = 0; t < n; ++t)
+    threads.emplace_back([&, t]() {
+      thread_idx = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+      for (unsigned bz = 0; bz < grid.z; ++bz)
+        for (unsigned by = 0; by < grid.y; ++by)
+          for (unsigned bx = 0; bx < grid.x; ++bx) {
             block_idx = dim3(bx, by, bz);
             kernel(args...);
-          });
-        for (auto& th : threads) th.join();
-      }
+            end_of_block.arrive_and_wait();
+          }
+    });
+  for (auto& th : threads) th.join();
 }
 }  // namespace emu
 
