@@ -1,0 +1,290 @@
+// Backward kernels of the SDF branch (groundwork for the training step; upstream
+// main/train.py:106-140 back-propagates loss["sdfhand_loss"] / ["sdfobj_loss"] -- main/model.py:370-401 -- through
+// SDFDecoder, linear_sdfin and the bilinear gather into the U-Net pyramid).  fp32 SIMT arithmetic throughout: these are
+// the reference-grade kernels the tensor-core backward will be checked against.  STATUS: verified against PyTorch
+// autograd on the CPU thread emulator (tests/test_kernel_emulation.py) and compiled for sm_100a; not yet wired into
+// Model.forward(mode="train") and not yet run on a GPU.
+//   hoisdf_gemm_f32          C (M,N) = op(A) . op(B) (+ C): the three contractions of a Linear's backward
+//                            (dX = dZ . W, dW = dZ^T . X) and its forward (Y = X . W^T) on one tiled fp32 FMA kernel
+//   hoisdf_act_bias_bwd      dZ = dY * relu'(Y) in place, db = column sums of dZ
+//   hoisdf_weight_norm_bwd   gradients of nn.utils.weight_norm (dim 0): W = g * v / |v|  ->  dg, dv
+//   hoisdf_gather_bwd        bilinear gather backward: scatter-add of row gradients into the NHWC pyramid gradient
+//                            (the sampling grid is detached upstream, main/model.py:158,199: no gradient to the points)
+//   hoisdf_sdf_loss_bwd      clamp + L1 mean of SepSDFLoss (common/nets/loss.py:64-78) and tanh': dLoss / d(pre-tanh)
+#include "common.cuh"
+
+namespace hoisdf {
+namespace {
+
+constexpr int GB = 64;      // C tile edge
+constexpr int GK = 16;      // K step
+
+// C[m, n] = sum_k a(m, k) * b(k, n); TA: A is stored (K, M) (a(m,k) = A[k*lda + m]), else (M, K);
+//                                    TB: B is stored (N, K) (b(k,n) = B[n*ldb + k]), else (K, N).  256 threads, 4 x 4 each.
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256)
+gemm_f32_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb, float* __restrict__ Cm,
+                int64_t ldc, int64_t M, int64_t N, int64_t K, int accumulate) {
+  __shared__ float As[GK][GB + 4];
+  __shared__ float Bs[GK][GB + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t m0 = static_cast<int64_t>(blockIdx.y) * GB, n0 = static_cast<int64_t>(blockIdx.x) * GB;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int64_t k0 = 0; k0 < K; k0 += GK) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int f = tid + 256 * e;                    // 1024 elements per operand tile
+      // pick the fast-running index along the operand's contiguous dimension
+      const int ka = TA ? f / GB : f % GK, ma = TA ? f % GB : f / GK;
+      const int64_t m = m0 + ma, k = k0 + ka;
+      As[ka][ma] = (m < M && k < K) ? (TA ? A[k * lda + m] : A[m * lda + k]) : 0.f;
+      const int kb = TB ? f % GK : f / GB, nb = TB ? f / GK : f % GB;
+      const int64_t n = n0 + nb, kk = k0 + kb;
+      Bs[kb][nb] = (n < N && kk < K) ? (TB ? B[n * ldb + kk] : B[kk * ldb + n]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t n = n0 + tx * 4 + j;
+      if (n < N) Cm[m * ldc + n] = accumulate ? Cm[m * ldc + n] + acc[i][j] : acc[i][j];
+    }
+  }
+}
+
+// dZ = dY * (Y > 0) in place (act == ReLU; the forward stored Y = relu(Z)), then db[n] = sum_m dZ[m, n].
+// grid = ceil(N / 32) blocks of 256 threads: 32 columns x 8 row lanes, fixed-order tree -> deterministic sums
+__global__ void __launch_bounds__(256)
+act_bias_bwd_kernel(float* __restrict__ dy, int64_t lddy, const float* __restrict__ y, int64_t ldy, int64_t M, int64_t N,
+                    int act, float* __restrict__ db, int accumulate) {
+  __shared__ float part[8][33];
+  const int c = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int64_t n = static_cast<int64_t>(blockIdx.x) * 32 + c;
+  float s = 0.f;
+  if (n < N) {
+    for (int64_t m = rl; m < M; m += 8) {
+      float g = dy[m * lddy + n];
+      if (act == HOISDF_ACT_RELU && !(y[m * ldy + n] > 0.f)) {
+        g = 0.f;
+        dy[m * lddy + n] = 0.f;
+      }
+      s += g;
+    }
+  }
+  part[rl][c] = s;
+  __syncthreads();
+  if (rl == 0 && n < N && db != nullptr) {
+    float t = part[0][c];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) t += part[i][c];
+    db[n] = accumulate ? db[n] + t : t;
+  }
+}
+
+// W[r, :] = g[r] * v[r, :] / |v[r, :]|:  dg[r] = <dW[r], v[r]> / |v[r]|,  dv[r] = g[r] / |v[r]| * (dW[r] - dg[r] * v[r] / |v[r]|)
+__global__ void __launch_bounds__(256)
+weight_norm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ v, const float* __restrict__ dw,
+                       int64_t lddw, int64_t cols, float* __restrict__ dg, float* __restrict__ dv, int accumulate) {
+  __shared__ float red[2][8];
+  const int64_t r = blockIdx.x;
+  const float* vr = v + r * cols;
+  const float* dr = dw + r * lddw;
+  float ss = 0.f, dot = 0.f;
+  for (int64_t c = threadIdx.x; c < cols; c += 256) {
+    ss = fmaf(vr[c], vr[c], ss);
+    dot = fmaf(dr[c], vr[c], dot);
+  }
+  ss = warp_sum(ss);
+  dot = warp_sum(dot);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = ss; red[1][threadIdx.x >> 5] = dot; }
+  __syncthreads();
+  float tss = 0.f, tdot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { tss += red[0][i]; tdot += red[1][i]; }
+  const float norm = sqrtf(tss);
+  const float dgr = tdot / norm;
+  const float scale = g[r] / norm;
+  if (threadIdx.x == 0) dg[r] = accumulate ? dg[r] + dgr : dgr;
+  for (int64_t c = threadIdx.x; c < cols; c += 256) {
+    const float val = scale * (dr[c] - dgr * vr[c] / norm);
+    dv[r * cols + c] = accumulate ? dv[r * cols + c] + val : val;
+  }
+}
+
+struct GatherBwdParams {
+  hoisdf_pyramid grad;            // NHWC gradient maps (zero-initialised or accumulating), same geometry as the forward
+  const float* __restrict__ uv;
+  const int64_t* __restrict__ row_offsets;
+  const float* __restrict__ dout; // (rows, ld) gradient of the CONCAT output
+  int64_t rows, batch, rows_per_sample, ld;
+};
+
+__device__ __forceinline__ void atomic_add_f32(float* p, float v) {
+#ifdef HOISDF_EMULATE
+  unsigned old = __atomic_load_n(reinterpret_cast<unsigned*>(p), __ATOMIC_RELAXED), neu;
+  do {
+    neu = __float_as_uint(__uint_as_float(old) + v);
+  } while (!__atomic_compare_exchange_n(reinterpret_cast<unsigned*>(p), &old, neu, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+#else
+  atomicAdd(p, v);
+#endif
+}
+
+// one warp per row, the forward's tap arithmetic (ATen grid_sampler_2d, align_corners=True, border padding)
+__global__ void __launch_bounds__(256) gather_concat_bwd_kernel(const GatherBwdParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (r >= p.rows) return;
+  int64_t b;
+  if (p.row_offsets == nullptr) {
+    b = r / p.rows_per_sample;
+  } else {
+    int64_t lo = 0, hi = p.batch;
+    while (hi - lo > 1) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (p.row_offsets[mid] <= r) lo = mid; else hi = mid;
+    }
+    b = lo;
+  }
+  const float u = p.uv[r * 2 + 0], v = p.uv[r * 2 + 1];
+  int off = 0;
+  for (int l = 0; l < p.grad.levels; ++l) {
+    const int C = p.grad.c[l], W = p.grad.w[l], H = p.grad.h[l];
+    const float nx = static_cast<float>(p.grad.img_w - 1) / 2.0f, ny = static_cast<float>(p.grad.img_h - 1) / 2.0f;
+    const float gx = __fdiv_rn(__fsub_rn(u, nx), nx), gy = __fdiv_rn(__fsub_rn(v, ny), ny);
+    float x = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.f), 2.f), static_cast<float>(W - 1));
+    float y = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.f), 2.f), static_cast<float>(H - 1));
+    x = fminf(static_cast<float>(W - 1), fmaxf(x, 0.f));
+    y = fminf(static_cast<float>(H - 1), fmaxf(y, 0.f));
+    const float x0f = floorf(x), y0f = floorf(y);
+    const float tx = x - x0f, ty = y - y0f;
+    const int x0 = static_cast<int>(x0f), y0 = static_cast<int>(y0f);
+    const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+    const float ax = __fsub_rn(x0f + 1.f, x), ay = __fsub_rn(y0f + 1.f, y);
+    float w00 = ax * ay, w01 = tx * ay, w10 = ax * ty, w11 = tx * ty;
+    if (x0 + 1 > W - 1) { w01 = 0.f; w11 = 0.f; }
+    if (y0 + 1 > H - 1) { w10 = 0.f; w11 = 0.f; }
+    const int64_t base = b * static_cast<int64_t>(H) * W;
+    float* m = const_cast<float*>(p.grad.map[l]);
+    float* t00 = m + (base + static_cast<int64_t>(y0) * W + x0) * C;
+    float* t01 = m + (base + static_cast<int64_t>(y0) * W + x1) * C;
+    float* t10 = m + (base + static_cast<int64_t>(y1) * W + x0) * C;
+    float* t11 = m + (base + static_cast<int64_t>(y1) * W + x1) * C;
+    const float* d = p.dout + r * p.ld + off;
+    for (int c = lane; c < C; c += 32) {
+      const float gval = d[c];
+      if (w00 != 0.f) atomic_add_f32(t00 + c, gval * w00);
+      if (w01 != 0.f) atomic_add_f32(t01 + c, gval * w01);
+      if (w10 != 0.f) atomic_add_f32(t10 + c, gval * w10);
+      if (w11 != 0.f) atomic_add_f32(t11 + c, gval * w11);
+    }
+    off += C;
+  }
+}
+
+// SDFLoss on the decoder's pre-activation z (sdf = tanh(z)):
+//   loss = mean_i | clamp(tanh(z_i), -c, c) - clamp(gt_i, -c, c) |   (upstream common/nets/loss.py:64-78 SepSDFLoss = L1,
+//   reduction mean; the clamps to ClampingDistance are main/model.py:241 and :388-395)
+//   dz_i = scale / n * sign(pred_i - gt_i) * [|tanh(z_i)| < c] * (1 - tanh(z_i)^2)
+__global__ void sdf_loss_bwd_kernel(const float* __restrict__ z, const float* __restrict__ gt, int64_t n, float clamp,
+                                    float scale, float* __restrict__ dz) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float t = tanhf(z[i]);
+  const float pred = fminf(fmaxf(t, -clamp), clamp), tgt = fminf(fmaxf(gt[i], -clamp), clamp);
+  const float diff = pred - tgt;
+  const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+  const bool pass = t >= -clamp && t <= clamp;        // torch.clamp passes the gradient inside (and at) the bounds
+  dz[i] = pass ? scale / static_cast<float>(n) * sgn * (1.f - t * t) : 0.f;
+}
+
+}  // namespace
+}  // namespace hoisdf
+
+using namespace hoisdf;
+
+HOISDF_API int hoisdf_gemm_f32(const float* a, int64_t lda, int32_t trans_a, const float* b, int64_t ldb, int32_t trans_b,
+                               float* c, int64_t ldc, int64_t m, int64_t n, int64_t k, int32_t accumulate, void* stream) {
+  if (a == nullptr || b == nullptr || c == nullptr) return HOISDF_E_NULL;
+  if (m <= 0 || n <= 0 || k <= 0 || ldc < n) return HOISDF_E_SHAPE;
+  if (lda < (trans_a ? m : k) || ldb < (trans_b ? k : n)) return HOISDF_E_SHAPE;
+  const int64_t gx = ceil_div(n, GB), gy = ceil_div(m, GB);
+  if (gy > 65535 || gx > 0x7fffffffLL) return HOISDF_E_SHAPE;
+  const dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(gy));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int acc = accumulate ? 1 : 0;
+  if (trans_a && trans_b) HOISDF_LAUNCH((gemm_f32_kernel<true, true>), grid, 256, s, a, lda, b, ldb, c, ldc, m, n, k, acc);
+  else if (trans_a) HOISDF_LAUNCH((gemm_f32_kernel<true, false>), grid, 256, s, a, lda, b, ldb, c, ldc, m, n, k, acc);
+  else if (trans_b) HOISDF_LAUNCH((gemm_f32_kernel<false, true>), grid, 256, s, a, lda, b, ldb, c, ldc, m, n, k, acc);
+  else HOISDF_LAUNCH((gemm_f32_kernel<false, false>), grid, 256, s, a, lda, b, ldb, c, ldc, m, n, k, acc);
+  return launch_status();
+}
+
+HOISDF_API int hoisdf_act_bias_bwd(float* dy, int64_t lddy, const float* y, int64_t ldy, int64_t m, int64_t n, int32_t act,
+                                   float* db, int32_t accumulate, void* stream) {
+  if (dy == nullptr || (act == HOISDF_ACT_RELU && y == nullptr)) return HOISDF_E_NULL;
+  if (m <= 0 || n <= 0 || lddy < n || (y != nullptr && ldy < n)) return HOISDF_E_SHAPE;
+  if (act != HOISDF_ACT_NONE && act != HOISDF_ACT_RELU) return HOISDF_E_UNSUPPORTED;
+  HOISDF_LAUNCH(act_bias_bwd_kernel, static_cast<unsigned>(ceil_div(n, 32)), 256, static_cast<cudaStream_t>(stream), dy, lddy,
+                y, ldy, m, n, act, db, accumulate ? 1 : 0);
+  return launch_status();
+}
+
+HOISDF_API int hoisdf_weight_norm_bwd(const float* g, const float* v, const float* dw, int64_t lddw, int64_t rows,
+                                      int64_t cols, float* dg, float* dv, int32_t accumulate, void* stream) {
+  if (g == nullptr || v == nullptr || dw == nullptr || dg == nullptr || dv == nullptr) return HOISDF_E_NULL;
+  if (rows <= 0 || rows > 0x7fffffffLL || cols <= 0 || lddw < cols) return HOISDF_E_SHAPE;
+  HOISDF_LAUNCH(weight_norm_bwd_kernel, static_cast<unsigned>(rows), 256, static_cast<cudaStream_t>(stream), g, v, dw, lddw,
+                cols, dg, dv, accumulate ? 1 : 0);
+  return launch_status();
+}
+
+HOISDF_API int hoisdf_gather_bwd(const hoisdf_pyramid* grad, const float* uv, int64_t rows, const int64_t* row_offsets,
+                                 int64_t batch, int64_t rows_per_sample, const float* dout, int64_t ld_dout, void* stream) {
+  if (grad == nullptr || uv == nullptr || dout == nullptr) return HOISDF_E_NULL;
+  if (rows == 0) return HOISDF_OK;
+  if (rows < 0 || batch <= 0 || grad->levels < 1 || grad->levels > 5) return HOISDF_E_SHAPE;
+  if (row_offsets == nullptr && rows_per_sample <= 0) return HOISDF_E_SHAPE;
+  int ctot = 0;
+  for (int l = 0; l < grad->levels; ++l) {
+    if (grad->map[l] == nullptr) return HOISDF_E_NULL;
+    if (grad->c[l] <= 0 || grad->h[l] <= 0 || grad->w[l] <= 0) return HOISDF_E_SHAPE;
+    ctot += grad->c[l];
+  }
+  if (ld_dout < ctot) return HOISDF_E_SHAPE;
+  GatherBwdParams p;
+  p.grad = *grad; p.uv = uv; p.row_offsets = row_offsets; p.dout = dout;
+  p.rows = rows; p.batch = batch; p.rows_per_sample = rows_per_sample; p.ld = ld_dout;
+  HOISDF_LAUNCH(gather_concat_bwd_kernel, static_cast<unsigned>(ceil_div(rows, 8)), 256, static_cast<cudaStream_t>(stream), p);
+  return launch_status();
+}
+
+HOISDF_API int hoisdf_sdf_loss_bwd(const float* z, const float* sdf_gt, int64_t n, float clamp, float scale, float* dz,
+                                   void* stream) {
+  if (z == nullptr || sdf_gt == nullptr || dz == nullptr) return HOISDF_E_NULL;
+  if (n <= 0 || !(clamp > 0.f)) return HOISDF_E_SHAPE;
+  HOISDF_LAUNCH(sdf_loss_bwd_kernel, static_cast<unsigned>(ceil_div(n, 256)), 256, static_cast<cudaStream_t>(stream), z, sdf_gt,
+                n, clamp, scale, dz);
+  return launch_status();
+}

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 11
+#define HOISDF_ABI_VERSION 12
 
 enum {
   HOISDF_OK = 0,
@@ -416,6 +416,34 @@ int hoisdf_mesh_metrics_fwd(const float* pred_meshes, const float* target_meshes
                             void* stream);
 int hoisdf_hand_joint_metrics_fwd(const float* pred, const float* gt, int64_t batch, int64_t n_points, float* mje,
                                   float* pamje, float* aligned, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Backward kernels of the SDF branch -- groundwork for the training step (upstream main/train.py:106-140
+ * back-propagates loss["sdfhand_loss"] / ["sdfobj_loss"], main/model.py:370-401, through SDFDecoder, linear_sdfin and
+ * the bilinear gather into the U-Net pyramid).  fp32 SIMT arithmetic (csrc/backward.cu).  STATUS: checked against
+ * PyTorch autograd on the CPU thread emulator; not yet called by Model.forward (mode="train" is not built).
+ *   hoisdf_gemm_f32: C (m, n; pitch ldc) = op(A) . op(B) (+ C when accumulate): trans_a: A is stored (k, m), else (m, k);
+ *     trans_b: B is stored (n, k), else (k, n).  A Linear Y = X . W^T has dX = dZ . W (no transposes), dW = dZ^T . X
+ *     (trans_a) and Y itself (trans_b).
+ *   hoisdf_act_bias_bwd: dZ = dY * [Y > 0] in place when act == HOISDF_ACT_RELU (Y = the forward's output), and
+ *     db[n] = sum_m dZ[m, n] (db may be NULL; deterministic fixed-order sums).
+ *   hoisdf_weight_norm_bwd: W = g * v / |v| per row (nn.utils.weight_norm, dim 0; upstream sdf_net.py:57-62):
+ *     dg (rows), dv (rows, cols) from dW (rows, cols; pitch lddw).
+ *   hoisdf_gather_bwd: CONCAT-mode bilinear gather backward: grad->map[l] (NHWC, same geometry as the forward's
+ *     pyramid) += scatter of dout (rows, ld_dout) with the forward's tap weights (atomic adds; the sampling grid is
+ *     detached upstream, main/model.py:158,199, so the points receive no gradient).
+ *   hoisdf_sdf_loss_bwd: dz_i = d/dz_i [ scale * mean_i | clamp(tanh(z_i), +-clamp) - clamp(gt_i, +-clamp) | ]
+ *     (upstream SepSDFLoss, common/nets/loss.py:64-78, with the clamps of main/model.py:241,388-395).
+ * ------------------------------------------------------------------------------------------------- */
+int hoisdf_gemm_f32(const float* a, int64_t lda, int32_t trans_a, const float* b, int64_t ldb, int32_t trans_b, float* c,
+                    int64_t ldc, int64_t m, int64_t n, int64_t k, int32_t accumulate, void* stream);
+int hoisdf_act_bias_bwd(float* dy, int64_t lddy, const float* y, int64_t ldy, int64_t m, int64_t n, int32_t act, float* db,
+                        int32_t accumulate, void* stream);
+int hoisdf_weight_norm_bwd(const float* g, const float* v, const float* dw, int64_t lddw, int64_t rows, int64_t cols,
+                           float* dg, float* dv, int32_t accumulate, void* stream);
+int hoisdf_gather_bwd(const hoisdf_pyramid* grad, const float* uv, int64_t rows, const int64_t* row_offsets, int64_t batch,
+                      int64_t rows_per_sample, const float* dout, int64_t ld_dout, void* stream);
+int hoisdf_sdf_loss_bwd(const float* z, const float* sdf_gt, int64_t n, float clamp, float scale, float* dz, void* stream);
 
 #ifdef __cplusplus
 }

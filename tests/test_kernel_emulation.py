@@ -21,7 +21,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU = os.path.join(ROOT, "tests", "emu")
 
 
-EMULATED = ("metrics", "lattice", "topk", "heads", "gather", "layernorm", "sdf", "linear", "attention", "narrow")
+EMULATED = ("metrics", "lattice", "topk", "heads", "gather", "layernorm", "sdf", "linear", "attention", "narrow", "backward")
 STUBS = ("stubs_linear.cpp", "stubs_attention.cpp", "stubs_h3.cpp")
 _LIB = {}
 
@@ -542,3 +542,170 @@ def test_narrow_linear_kernel_on_the_emulator(n, act):
     ref = np.maximum(ref, 0) if act == 1 else (1 / (1 + np.exp(-ref)) if act == 2 else ref)
     assert np.abs(y - ref).max() < 2e-6 * max(1.0, float(np.abs(ref).max()))
     assert np.abs(join_split(xh, xl) - x).max() < 3e-7 * 2
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# backward kernels of the SDF branch (csrc/backward.cu) against PyTorch autograd
+# ---------------------------------------------------------------------------------------------------------------------
+def backward_lib():
+    lib = build_emulated("backward")
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
+    lib.hoisdf_gemm_f32.argtypes = [vp, i64, i32, vp, i64, i32, vp, i64, i64, i64, i64, i32, vp]
+    lib.hoisdf_act_bias_bwd.argtypes = [vp, i64, vp, i64, i64, i64, i32, vp, i32, vp]
+    lib.hoisdf_weight_norm_bwd.argtypes = [vp, vp, vp, i64, i64, i64, vp, vp, i32, vp]
+    lib.hoisdf_gather_bwd.argtypes = [C.POINTER(Pyramid), vp, i64, vp, i64, i64, vp, i64, vp]
+    lib.hoisdf_sdf_loss_bwd.argtypes = [vp, vp, i64, C.c_float, C.c_float, vp, vp]
+    return lib
+
+
+def gemm(lib, a, ta, b, tb, accumulate_into=None):
+    """C = op(A) . op(B) through hoisdf_gemm_f32 (a, b: 2-D float32 arrays as STORED)."""
+    a, b = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(b, np.float32)
+    m, k = (a.shape[1], a.shape[0]) if ta else a.shape
+    n = b.shape[0] if tb else b.shape[1]
+    c = np.zeros((m, n), np.float32) if accumulate_into is None else accumulate_into
+    assert lib.hoisdf_gemm_f32(ptr(a), a.shape[1], int(ta), ptr(b), b.shape[1], int(tb), ptr(c), n, m, n, k,
+                               int(accumulate_into is not None), None) == 0
+    return c
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
+def test_gemm_f32_kernel_on_the_emulator(ta, tb):
+    lib = backward_lib()
+    m, n, k = 70, 45, 37                                         # ragged in every dimension
+    a = rnd(1, *((k, m) if ta else (m, k)))
+    b = rnd(2, *((n, k) if tb else (k, n)))
+    ref = (a.T if ta else a).astype(np.float64) @ (b.T if tb else b).astype(np.float64)
+    c = gemm(lib, a, ta, b, tb)
+    assert np.abs(c - ref).max() < 2e-6 * float(np.abs(ref).max())
+    c2 = gemm(lib, a, ta, b, tb, accumulate_into=c.copy())
+    assert np.abs(c2 - 2 * ref).max() < 4e-6 * float(np.abs(ref).max())
+    assert lib.hoisdf_gemm_f32(ptr(a), 1, int(ta), ptr(b), b.shape[1], int(tb), ptr(c), n, m, n, k, 0, None) == -2
+
+
+def test_elementwise_backward_kernels_on_the_emulator():
+    """ReLU mask + bias gradient, weight-norm gradient, clamp / L1 / tanh gradient against autograd."""
+    lib = backward_lib()
+    t = torch.from_numpy
+    m, n = 53, 70
+    y = np.maximum(rnd(1, m, n), 0).astype(np.float32)           # a ReLU output: zeros where the unit was off
+    dy = rnd(2, m, n)
+    want_dz = dy * (y > 0)
+    dz, db = dy.copy(), np.zeros(n, np.float32)
+    assert lib.hoisdf_act_bias_bwd(ptr(dz), n, ptr(y), n, m, n, 1, ptr(db), 0, None) == 0
+    assert np.array_equal(dz, want_dz) and np.abs(db - want_dz.sum(0)).max() < 1e-5
+    dz2, db2 = dy.copy(), db.copy()
+    assert lib.hoisdf_act_bias_bwd(ptr(dz2), n, None, 0, m, n, 0, ptr(db2), 1, None) == 0        # no activation, accumulate
+    assert np.array_equal(dz2, dy) and np.abs(db2 - (want_dz.sum(0) + dy.sum(0))).max() < 1e-5
+    # weight norm (nn.utils.weight_norm, dim 0): W = g * v / |v|
+    rows, cols = 23, 289
+    g, v, dw = t(rnd(3, rows, 1, lo=0.5, hi=1.5)).requires_grad_(), t(rnd(4, rows, cols)).requires_grad_(), rnd(5, rows, cols)
+    (O.fold_weight_norm(g, v) * t(dw)).sum().backward()
+    dg, dv = np.zeros(rows, np.float32), np.zeros((rows, cols), np.float32)
+    assert lib.hoisdf_weight_norm_bwd(ptr(f32(g.detach()).reshape(-1)), ptr(f32(v.detach())), ptr(dw), cols, rows, cols,
+                                      ptr(dg), ptr(dv), 0, None) == 0
+    assert np.abs(dg - g.grad.numpy().reshape(-1)).max() < 1e-5 and np.abs(dv - v.grad.numpy()).max() < 1e-6
+    # SepSDFLoss on the pre-tanh value, with the clamps of sdf_forward / Model.forward
+    nrow, clamp = 200, 0.05
+    z = t(rnd(6, nrow, lo=-0.2, hi=0.2)).requires_grad_()
+    gt = rnd(7, nrow, lo=-0.1, hi=0.1)
+    loss = torch.nn.functional.l1_loss(torch.clamp(torch.tanh(z), -clamp, clamp), torch.clamp(t(gt), -clamp, clamp))
+    (3.0 * loss).backward()
+    dzl = np.zeros(nrow, np.float32)
+    assert lib.hoisdf_sdf_loss_bwd(ptr(f32(z.detach())), ptr(gt), nrow, clamp, 3.0, ptr(dzl), None) == 0
+    assert (z.grad == 0).any() and (z.grad != 0).any()           # both sides of the clamp are exercised
+    assert np.abs(dzl - z.grad.numpy()).max() < 1e-7
+
+
+def test_gather_backward_kernel_on_the_emulator():
+    """Scatter-add of the bilinear gather (F.grid_sample backward w.r.t. the feature maps; the grid is detached upstream)."""
+    lib = backward_lib()
+    B, P = 2, 19
+    gen = torch.Generator().manual_seed(4)
+    maps = [torch.randn(B, c, h, h, generator=gen).requires_grad_() for c, h in ((12, 16), (20, 8), (8, 4))]
+    uv = torch.from_numpy(rnd(22, B, P, 2, lo=-20.0, hi=275.0))
+    uv[0, 0] = torch.tensor([0.0, 255.0]); uv[0, 1] = torch.tensor([255.0, 0.0]); uv[1, 2] = torch.tensor([127.5, 127.5])
+    cfg = O.default_cfg()
+    g = O.grid_from_uv(uv, cfg).unsqueeze(1)
+    feats = torch.cat([torch.nn.functional.grid_sample(m, g, padding_mode="border", align_corners=True) for m in maps], 1)
+    feats = feats.squeeze(2).permute(0, 2, 1)                    # (B, P, C) as O.gather_pyramid
+    dout = rnd(23, B, P, feats.shape[2])
+    (feats * torch.from_numpy(dout)).sum().backward()
+    grads = [np.zeros((B, m.shape[2], m.shape[3], m.shape[1]), np.float32) for m in maps]
+    ps = make_pyramid(grads)
+    uvf = f32(uv.reshape(-1, 2))
+    do = np.ascontiguousarray(dout.reshape(B * P, -1))
+    assert lib.hoisdf_gather_bwd(C.byref(ps), ptr(uvf), B * P, None, B, P, ptr(do), do.shape[1], None) == 0
+    for got, m in zip(grads, maps):
+        want = m.grad.permute(0, 2, 3, 1).numpy()
+        assert np.abs(got - want).max() < 2e-6 * max(1.0, float(np.abs(want).max()))
+    # ragged rows: sample 0 owns the first 7 rows only
+    grads2 = [np.zeros_like(x) for x in grads]
+    ps2 = make_pyramid(grads2)
+    offsets = np.array([0, 7, B * P], np.int64)
+    assert lib.hoisdf_gather_bwd(C.byref(ps2), ptr(uvf), B * P, ptr(offsets), B, 0, ptr(do), do.shape[1], None) == 0
+    assert not np.array_equal(grads2[0], grads[0]) and abs(float(grads2[0].sum() - grads[0].sum())) < 1e-3
+
+
+def test_sdf_decoder_backward_chain_on_the_emulator():
+    """The whole SDFDecoder backward (upstream common/nets/sdf_net.py:87-122 under the SDF L1 loss) composed from the
+    entry points of csrc/backward.cu -- GEMMs, ReLU masks / bias sums, the skip concat, weight-norm gradients, the loss
+    head -- against autograd of the oracle: gradients of every parameter and of the decoder input."""
+    lib = backward_lib()
+    sd = {k: v.clone() for k, v in syn.hot_path_state_dict(7, "dexycb").items() if k.startswith("hand_sdf_decoder.")}
+    pre = "hand_sdf_decoder."
+    rows, clamp = 37, 0.15
+    x_t = torch.from_numpy(rnd(9, rows, 289)).requires_grad_()
+    gt = rnd(10, rows, lo=-0.2, hi=0.2)
+    params = {k: v.requires_grad_() for k, v in sd.items()}
+    pred = O.sdf_decoder(params, "hand_sdf_decoder", x_t)
+    loss = torch.nn.functional.l1_loss(torch.clamp(pred, -clamp, clamp), torch.clamp(torch.from_numpy(gt), -clamp, clamp)[:, None])
+    loss.backward()
+
+    # ---- forward on the kernels (activations kept, as a training forward must)
+    W = [O.fold_weight_norm(sd[pre + "linh%d.weight_g" % i].detach(), sd[pre + "linh%d.weight_v" % i].detach()).numpy()
+         for i in range(4)] + [f32(sd[pre + "linh4.weight"].detach())]
+    bias = [f32(sd[pre + "linh%d.bias" % i].detach()) for i in range(5)]
+    x = f32(x_t.detach())
+    h0 = np.maximum(gemm(lib, x, False, W[0], True) + bias[0], 0)
+    h1 = np.maximum(gemm(lib, h0, False, W[1], True) + bias[1], 0)
+    cat = np.ascontiguousarray(np.concatenate([h1, x], 1))       # torch.cat([xh, input], 1), sdf_net.py:97-98
+    h2 = np.maximum(gemm(lib, cat, False, W[2], True) + bias[2], 0)
+    h3 = np.maximum(gemm(lib, h2, False, W[3], True) + bias[3], 0)
+    z4 = (gemm(lib, h3, False, W[4], True) + bias[4]).reshape(-1)
+    assert np.abs(np.tanh(z4) - pred.detach().numpy()[:, 0]).max() < 2e-6
+
+    # ---- backward on the kernels
+    dz4 = np.zeros(rows, np.float32)
+    assert lib.hoisdf_sdf_loss_bwd(ptr(np.ascontiguousarray(z4)), ptr(gt), rows, clamp, 1.0, ptr(dz4), None) == 0
+    dW, dB = [None] * 5, [None] * 5
+
+    def layer_bwd(i, dout, out, inp, relu):
+        d = np.ascontiguousarray(dout, np.float32)
+        dB[i] = np.zeros(d.shape[1], np.float32)
+        assert lib.hoisdf_act_bias_bwd(ptr(d), d.shape[1], ptr(out) if relu else None, out.shape[1] if relu else 0,
+                                       d.shape[0], d.shape[1], 1 if relu else 0, ptr(dB[i]), 0, None) == 0
+        dW[i] = gemm(lib, d, True, inp, False)                   # dW = dZ^T . X
+        return gemm(lib, d, False, W[i], False)                  # dX = dZ . W
+
+    dh3 = layer_bwd(4, dz4[:, None], None, h3, False)
+    dh2 = layer_bwd(3, dh3, h3, h2, True)
+    dcat = layer_bwd(2, dh2, h2, cat, True)
+    dh0 = layer_bwd(1, dcat[:, :223], h1, h0, True)
+    dx = layer_bwd(0, dh0, h0, x, True) + dcat[:, 223:]
+
+    def close(got, want, what):
+        want = want.numpy()
+        assert np.abs(got.reshape(want.shape) - want).max() < 1e-5 * max(float(np.abs(want).max()), 1e-3), what
+
+    close(dx, x_t.grad, "input")
+    close(dW[4], params[pre + "linh4.weight"].grad, "linh4.weight")
+    for i in range(5):
+        close(dB[i], params[pre + "linh%d.bias" % i].grad, "linh%d.bias" % i)
+    for i in range(4):
+        g, v = f32(sd[pre + "linh%d.weight_g" % i].detach()).reshape(-1), f32(sd[pre + "linh%d.weight_v" % i].detach())
+        dg, dv = np.zeros(g.shape[0], np.float32), np.zeros_like(v)
+        assert lib.hoisdf_weight_norm_bwd(ptr(g), ptr(v), ptr(dW[i]), v.shape[1], v.shape[0], v.shape[1], ptr(dg), ptr(dv), 0,
+                                          None) == 0
+        close(dg, params[pre + "linh%d.weight_g" % i].grad, "linh%d.weight_g" % i)
+        close(dv, params[pre + "linh%d.weight_v" % i].grad, "linh%d.weight_v" % i)
