@@ -2,8 +2,8 @@
 // main/train.py:106-140 back-propagates loss["sdfhand_loss"] / ["sdfobj_loss"] -- main/model.py:370-401 -- through
 // SDFDecoder, linear_sdfin and the bilinear gather into the U-Net pyramid).  fp32 SIMT arithmetic throughout: these are
 // the reference-grade kernels the tensor-core backward will be checked against.  STATUS: verified against PyTorch
-// autograd on the CPU thread emulator (tests/test_kernel_emulation.py) and compiled for sm_100a; not yet wired into
-// Model.forward(mode="train") and not yet run on a GPU.
+// autograd on the CPU thread emulator (tests/test_kernel_emulation.py) and on the B200 (tests/test_gpu_zz_backward.py);
+// not yet wired into Model.forward(mode="train").
 //   hoisdf_gemm_f32          C (M,N) = op(A) . op(B) (+ C): the three contractions of a Linear's backward
 //                            (dX = dZ . W, dW = dZ^T . X) and its forward (Y = X . W^T) on one tiled fp32 FMA kernel
 //   hoisdf_act_bias_bwd      dZ = dY * relu'(Y) in place, db = column sums of dZ

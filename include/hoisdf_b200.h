@@ -421,7 +421,7 @@ int hoisdf_hand_joint_metrics_fwd(const float* pred, const float* gt, int64_t ba
  * Backward kernels of the SDF branch -- groundwork for the training step (upstream main/train.py:106-140
  * back-propagates loss["sdfhand_loss"] / ["sdfobj_loss"], main/model.py:370-401, through SDFDecoder, linear_sdfin and
  * the bilinear gather into the U-Net pyramid).  fp32 SIMT arithmetic (csrc/backward.cu).  STATUS: checked against
- * PyTorch autograd on the CPU thread emulator; not yet called by Model.forward (mode="train" is not built).
+ * PyTorch autograd on the CPU thread emulator and on the B200; not yet called by Model.forward (mode="train" is not built).
  *   hoisdf_gemm_f32: C (m, n; pitch ldc) = op(A) . op(B) (+ C when accumulate): trans_a: A is stored (k, m), else (m, k);
  *     trans_b: B is stored (n, k), else (k, n).  A Linear Y = X . W^T has dX = dZ . W (no transposes), dW = dZ^T . X
  *     (trans_a) and Y itself (trans_b).
