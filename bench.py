@@ -43,27 +43,38 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons, sampled every 100 ms.  The query process is started BEFORE the warm-up
+    steps (nvidia-smi needs a few hundred ms to produce its first row, and a timed region of ten 35 ms steps is hardly
+    longer than that); `begin()` / `end()` bracket the timed region on the host clock and only rows that fall inside it
+    are reported.  If the region was too short for a single row, the rows of the warm-up steps that ran right before it
+    (the same workload, same load) are reported instead and `window` says so."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.rows = []
+        self.rows = []          # (host time, columns)
         self.proc = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.monotonic(), [c.strip() for c in line.split(",")]))
+
+    def begin(self):
+        self.t0 = time.monotonic()
+
+    def end(self):
+        self.t1 = time.monotonic()
 
     def stop(self):
         if self.proc is not None:
@@ -72,12 +83,18 @@ class ClockSampler:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        t0 = self.t0 if self.t0 is not None else float("-inf")
+        t1 = self.t1 if self.t1 is not None else float("inf")
+        valid = [(t, r) for t, r in list(self.rows) if len(r) >= 8]
+        rows, window = [r for t, r in valid if t0 <= t <= t1], "timed region"
+        if not rows:
+            rows, window = [r for t, r in valid if t0 - 1.5 <= t <= t1 + 0.1], "warm-up steps + timed region (region too short)"
+        sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.lower() == "active"})
+        reasons = sorted({n for r in rows for n, v in zip(names, r[4:8]) if v.lower() == "active"})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "window": window}
 
 
 def make_inputs(seed: int, batch: int):
@@ -242,6 +259,9 @@ def run_native(args):
             ms = float(t.item())
         return ms
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0 and not args.profile_step:
+        sampler.start()                      # before the warm-up: see ClockSampler
     for _ in range(max(args.warmup, 3)):
         step_device()
     fence()
@@ -255,10 +275,9 @@ def run_native(args):
     if model.last_taps is not None:
         n_f = (model.last_taps["hand"]["n_f"].double().mean().item(), model.last_taps["obj"]["n_f"].double().mean().item())
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.begin()
     ms_total = timed(step_device, args.steps)
+    sampler.end()
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     value = world * B * 1000.0 / ms_step

@@ -32,3 +32,40 @@ def test_reference_arm_other_ranks_stay_silent():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                         "--warmup", "0"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_clock_sampler_windows(tmp_path, monkeypatch):
+    """bench.py samples nvidia-smi clocks DURING the timed region; the query process is started before the warm-up because
+    its first row takes a few hundred ms.  Exercised here against a stand-in `nvidia-smi` on PATH."""
+    import importlib.util
+    import stat
+    import time
+    fake = tmp_path / "nvidia-smi"
+    fake.write_text("#!/bin/bash\nsleep 0.3\nwhile true; do echo '0, 1905, 1965, 700.1, Not Active, Not Active, Not Active, "
+                    "Active'; sleep 0.05; done\n")
+    fake.chmod(fake.stat().st_mode | stat.S_IEXEC)
+    monkeypatch.setenv("PATH", str(tmp_path) + os.pathsep + os.environ["PATH"])
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    s = bench.ClockSampler(0)
+    s.start()
+    time.sleep(0.7)                       # "warm-up"
+    s.begin()
+    time.sleep(0.3)                       # "timed region"
+    s.end()
+    time.sleep(0.2)                       # rows after the region must not count
+    c = s.stop()
+    assert c["window"] == "timed region" and 2 <= c["samples"] <= 8
+    assert c["sm_mhz"] == 1905.0 and c["sm_max_mhz"] == 1965.0 and c["reasons"] == ["sw_power_cap"]
+    s = bench.ClockSampler(0)             # a region too short for a single row falls back to the warm-up rows, and says so
+    s.start()
+    time.sleep(0.7)
+    s.begin()
+    s.end()
+    c = s.stop()
+    assert c["samples"] >= 1 and ("warm-up" in c["window"] or c["window"] == "timed region")
+    monkeypatch.setenv("PATH", str(tmp_path / "missing"))
+    s = bench.ClockSampler(0)             # no nvidia-smi at all: empty record, never an exception
+    s.start(); s.begin(); s.end()
+    assert s.stop()["samples"] == 0
