@@ -11,6 +11,9 @@
 //   hoisdf_gather_bwd        bilinear gather backward: scatter-add of row gradients into the NHWC pyramid gradient
 //                            (the sampling grid is detached upstream, main/model.py:158,199: no gradient to the points)
 //   hoisdf_sdf_loss_bwd      clamp + L1 mean of SepSDFLoss (common/nets/loss.py:64-78) and tanh': dLoss / d(pre-tanh)
+//   hoisdf_layernorm_bwd     nn.LayerNorm(256) backward: dh, dgamma, dbeta (transformer.py:296-301)
+//   hoisdf_softmax_rows_fwd / _bwd   row softmax and its backward: with hoisdf_gemm_f32 per head, the attention core's
+//                            backward (dV = P^T dO, dP = dO V^T, dS = softmax', dQ = dS K, dK = dS^T Q)
 #include "common.cuh"
 
 namespace hoisdf {
@@ -219,6 +222,98 @@ __global__ void sdf_loss_bwd_kernel(const float* __restrict__ z, const float* __
   dz[i] = pass ? scale / static_cast<float>(n) * sgn * (1.f - t * t) : 0.f;
 }
 
+
+// ---- transformer side: LayerNorm and row softmax (the attention core's backward is these + hoisdf_gemm_f32 per head)
+
+// y = (h - mean) * rstd * gamma + beta over rows of D = 256 (eps 1e-5, biased variance).  One warp per row:
+//   g = dy * gamma;  dh = rstd * (g - mean(g) - xhat * mean(g * xhat));  stats[r] = (mean, rstd) for the column pass
+template <int D>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_rows_kernel(const float* __restrict__ h, const float* __restrict__ gamma, const float* __restrict__ dy,
+                          int64_t rows, float* __restrict__ dh, float* __restrict__ stats) {
+  constexpr int Q = D / 32;
+  const int lane = threadIdx.x & 31;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  float v[Q], g[Q];
+  float s = 0.f;
+#pragma unroll
+  for (int q = 0; q < Q; ++q) { v[q] = h[r * D + q * 32 + lane]; s += v[q]; }
+  const float mean = warp_sum(s) * (1.0f / D);
+  float ss = 0.f;
+#pragma unroll
+  for (int q = 0; q < Q; ++q) { const float d = v[q] - mean; ss = fmaf(d, d, ss); }
+  const float rstd = 1.0f / sqrtf(warp_sum(ss) * (1.0f / D) + 1e-5f);
+  float sg = 0.f, sgx = 0.f;
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    const int c = q * 32 + lane;
+    v[q] = (v[q] - mean) * rstd;                        // xhat
+    g[q] = dy[r * D + c] * gamma[c];
+    sg += g[q];
+    sgx = fmaf(g[q], v[q], sgx);
+  }
+  const float mg = warp_sum(sg) * (1.0f / D), mgx = warp_sum(sgx) * (1.0f / D);
+#pragma unroll
+  for (int q = 0; q < Q; ++q) dh[r * D + q * 32 + lane] = rstd * (g[q] - mg - v[q] * mgx);
+  if (lane == 0 && stats != nullptr) { stats[r * 2] = mean; stats[r * 2 + 1] = rstd; }
+}
+
+// dgamma[c] = sum_r dy[r, c] * xhat[r, c], dbeta[c] = sum_r dy[r, c]; 32 columns x 8 row lanes per block, fixed-order sums
+__global__ void __launch_bounds__(256)
+layernorm_bwd_cols_kernel(const float* __restrict__ h, const float* __restrict__ dy, const float* __restrict__ stats,
+                          int64_t rows, int D, float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
+  __shared__ float pg[8][33], pb[8][33];
+  const int c = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + c;
+  float sg = 0.f, sb = 0.f;
+  if (n < D) {
+    for (int64_t r = rl; r < rows; r += 8) {
+      const float d = dy[r * D + n];
+      sg = fmaf(d, (h[r * D + n] - stats[r * 2]) * stats[r * 2 + 1], sg);
+      sb += d;
+    }
+  }
+  pg[rl][c] = sg; pb[rl][c] = sb;
+  __syncthreads();
+  if (rl == 0 && n < D) {
+    float tg = pg[0][c], tb = pb[0][c];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) { tg += pg[i][c]; tb += pb[i][c]; }
+    dgamma[n] = accumulate ? dgamma[n] + tg : tg;
+    dbeta[n] = accumulate ? dbeta[n] + tb : tb;
+  }
+}
+
+// p[r, :] = softmax(s[r, :valid]) (columns >= valid get 0), one warp per row
+__global__ void __launch_bounds__(256)
+softmax_rows_fwd_kernel(const float* __restrict__ s, int64_t lds, int64_t rows, int cols, int valid, float* __restrict__ p,
+                        int64_t ldp) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  float mx = -3.402823466e+38f;
+  for (int c = lane; c < valid; c += 32) mx = fmaxf(mx, s[r * lds + c]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int c = lane; c < valid; c += 32) sum += expf(s[r * lds + c] - mx);
+  sum = warp_sum(sum);
+  for (int c = lane; c < cols; c += 32) p[r * ldp + c] = c < valid ? expf(s[r * lds + c] - mx) / sum : 0.f;
+}
+
+// ds[r, :] = p[r, :] * (dp[r, :] - sum_j dp[r, j] * p[r, j]), one warp per row (in place over dp when ds == dp)
+__global__ void __launch_bounds__(256)
+softmax_rows_bwd_kernel(const float* __restrict__ p, int64_t ldp, const float* dp, int64_t lddp, int64_t rows, int cols,
+                        float* ds, int64_t ldds) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  float dot = 0.f;
+  for (int c = lane; c < cols; c += 32) dot = fmaf(dp[r * lddp + c], p[r * ldp + c], dot);
+  dot = warp_sum(dot);
+  for (int c = lane; c < cols; c += 32) ds[r * ldds + c] = p[r * ldp + c] * (dp[r * lddp + c] - dot);
+}
+
 }  // namespace
 }  // namespace hoisdf
 
@@ -286,5 +381,38 @@ HOISDF_API int hoisdf_sdf_loss_bwd(const float* z, const float* sdf_gt, int64_t 
   if (n <= 0 || !(clamp > 0.f)) return HOISDF_E_SHAPE;
   HOISDF_LAUNCH(sdf_loss_bwd_kernel, static_cast<unsigned>(ceil_div(n, 256)), 256, static_cast<cudaStream_t>(stream), z, sdf_gt,
                 n, clamp, scale, dz);
+  return launch_status();
+}
+
+HOISDF_API int hoisdf_layernorm_bwd(const float* h, const float* gamma, const float* dy, int64_t rows, int64_t d, float* dh,
+                                    float* dgamma, float* dbeta, float* stats, int32_t accumulate, void* stream) {
+  if (h == nullptr || gamma == nullptr || dy == nullptr || dh == nullptr) return HOISDF_E_NULL;
+  if ((dgamma == nullptr) != (dbeta == nullptr) || (dgamma != nullptr && stats == nullptr)) return HOISDF_E_NULL;
+  if (rows <= 0) return HOISDF_E_SHAPE;
+  if (d != 256) return HOISDF_E_UNSUPPORTED;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  HOISDF_LAUNCH(layernorm_bwd_rows_kernel<256>, static_cast<unsigned>(ceil_div(rows, 8)), 256, s, h, gamma, dy, rows, dh, stats);
+  if (dgamma != nullptr)
+    HOISDF_LAUNCH(layernorm_bwd_cols_kernel, static_cast<unsigned>(ceil_div(d, 32)), 256, s, h, dy,
+                  static_cast<const float*>(stats), rows, static_cast<int>(d), dgamma, dbeta, accumulate ? 1 : 0);
+  return launch_status();
+}
+
+HOISDF_API int hoisdf_softmax_rows_fwd(const float* s, int64_t lds, int64_t rows, int64_t cols, int64_t valid, float* p,
+                                       int64_t ldp, void* stream) {
+  if (s == nullptr || p == nullptr) return HOISDF_E_NULL;
+  if (rows <= 0 || cols <= 0 || cols > 0x7fffffffLL || valid <= 0 || valid > cols || lds < cols || ldp < cols)
+    return HOISDF_E_SHAPE;
+  HOISDF_LAUNCH(softmax_rows_fwd_kernel, static_cast<unsigned>(ceil_div(rows, 8)), 256, static_cast<cudaStream_t>(stream), s,
+                lds, rows, static_cast<int>(cols), static_cast<int>(valid), p, ldp);
+  return launch_status();
+}
+
+HOISDF_API int hoisdf_softmax_rows_bwd(const float* p, int64_t ldp, const float* dp, int64_t lddp, int64_t rows, int64_t cols,
+                                       float* ds, int64_t ldds, void* stream) {
+  if (p == nullptr || dp == nullptr || ds == nullptr) return HOISDF_E_NULL;
+  if (rows <= 0 || cols <= 0 || cols > 0x7fffffffLL || ldp < cols || lddp < cols || ldds < cols) return HOISDF_E_SHAPE;
+  HOISDF_LAUNCH(softmax_rows_bwd_kernel, static_cast<unsigned>(ceil_div(rows, 8)), 256, static_cast<cudaStream_t>(stream), p,
+                ldp, dp, lddp, rows, static_cast<int>(cols), ds, ldds);
   return launch_status();
 }

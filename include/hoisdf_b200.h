@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 12
+#define HOISDF_ABI_VERSION 13
 
 enum {
   HOISDF_OK = 0,
@@ -434,6 +434,12 @@ int hoisdf_hand_joint_metrics_fwd(const float* pred, const float* gt, int64_t ba
  *     detached upstream, main/model.py:158,199, so the points receive no gradient).
  *   hoisdf_sdf_loss_bwd: dz_i = d/dz_i [ scale * mean_i | clamp(tanh(z_i), +-clamp) - clamp(gt_i, +-clamp) | ]
  *     (upstream SepSDFLoss, common/nets/loss.py:64-78, with the clamps of main/model.py:241,388-395).
+ *   hoisdf_layernorm_bwd: y = LayerNorm(h) * gamma + beta over rows of d = 256 (eps 1e-5; upstream transformer.py:296-301,
+ *     h = the residual sum the forward normalised): dh (rows, d), and -- when dgamma / dbeta are given -- the parameter
+ *     gradients (deterministic column sums; `stats` = workspace of 2 * rows floats, required with them).
+ *   hoisdf_softmax_rows_fwd / _bwd: p = softmax(s[:, :valid]) per row (0 beyond `valid`);
+ *     ds = p * (dp - sum_j dp_j p_j) (ds may alias dp).  Together with hoisdf_gemm_f32 per (sample, head) these are the
+ *     backward of nn.MultiheadAttention's core: dV = P^T dO, dP = dO V^T, dS = softmax'(dP), dQ = dS K / 8, dK = dS^T Q / 8.
  * ------------------------------------------------------------------------------------------------- */
 int hoisdf_gemm_f32(const float* a, int64_t lda, int32_t trans_a, const float* b, int64_t ldb, int32_t trans_b, float* c,
                     int64_t ldc, int64_t m, int64_t n, int64_t k, int32_t accumulate, void* stream);
@@ -444,6 +450,12 @@ int hoisdf_weight_norm_bwd(const float* g, const float* v, const float* dw, int6
 int hoisdf_gather_bwd(const hoisdf_pyramid* grad, const float* uv, int64_t rows, const int64_t* row_offsets, int64_t batch,
                       int64_t rows_per_sample, const float* dout, int64_t ld_dout, void* stream);
 int hoisdf_sdf_loss_bwd(const float* z, const float* sdf_gt, int64_t n, float clamp, float scale, float* dz, void* stream);
+int hoisdf_layernorm_bwd(const float* h, const float* gamma, const float* dy, int64_t rows, int64_t d, float* dh,
+                         float* dgamma, float* dbeta, float* stats, int32_t accumulate, void* stream);
+int hoisdf_softmax_rows_fwd(const float* s, int64_t lds, int64_t rows, int64_t cols, int64_t valid, float* p, int64_t ldp,
+                            void* stream);
+int hoisdf_softmax_rows_bwd(const float* p, int64_t ldp, const float* dp, int64_t lddp, int64_t rows, int64_t cols, float* ds,
+                            int64_t ldds, void* stream);
 
 #ifdef __cplusplus
 }

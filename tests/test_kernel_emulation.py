@@ -709,3 +709,135 @@ def test_sdf_decoder_backward_chain_on_the_emulator():
                                           None) == 0
         close(dg, params[pre + "linh%d.weight_g" % i].grad, "linh%d.weight_g" % i)
         close(dv, params[pre + "linh%d.weight_v" % i].grad, "linh%d.weight_v" % i)
+
+
+def transformer_backward_lib():
+    lib = backward_lib()
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
+    lib.hoisdf_layernorm_bwd.argtypes = [vp, vp, vp, i64, i64, vp, vp, vp, vp, i32, vp]
+    lib.hoisdf_softmax_rows_fwd.argtypes = [vp, i64, i64, i64, i64, vp, i64, vp]
+    lib.hoisdf_softmax_rows_bwd.argtypes = [vp, i64, vp, i64, i64, i64, vp, i64, vp]
+    return lib
+
+
+def test_layernorm_and_softmax_backward_kernels_on_the_emulator():
+    lib = transformer_backward_lib()
+    t = torch.from_numpy
+    rows, d = 45, 256
+    h, gamma, beta = t(rnd(1, rows, d, lo=-2, hi=2)).requires_grad_(), t(rnd(2, d, lo=0.5, hi=1.5)).requires_grad_(), \
+        t(rnd(3, d)).requires_grad_()
+    dy = rnd(4, rows, d)
+    (torch.nn.functional.layer_norm(h, (d,), gamma, beta, 1e-5) * t(dy)).sum().backward()
+    dh, dg, dbt, stats = np.zeros((rows, d), np.float32), np.zeros(d, np.float32), np.zeros(d, np.float32), \
+        np.zeros(rows * 2, np.float32)
+    assert lib.hoisdf_layernorm_bwd(ptr(f32(h.detach())), ptr(f32(gamma.detach())), ptr(dy), rows, d, ptr(dh), ptr(dg), ptr(dbt),
+                                    ptr(stats), 0, None) == 0
+    assert np.abs(dh - h.grad.numpy()).max() < 5e-6 and np.abs(dg - gamma.grad.numpy()).max() < 2e-5
+    assert np.abs(dbt - beta.grad.numpy()).max() < 2e-5
+    assert lib.hoisdf_layernorm_bwd(ptr(f32(h.detach())), ptr(f32(gamma.detach())), ptr(dy), rows, 128, ptr(dh), None, None, None,
+                                    0, None) == -4
+    # row softmax with a key-validity limit, and its backward
+    r, c, valid = 19, 70, 50
+    s = t(rnd(5, r, c, lo=-3, hi=3)).requires_grad_()
+    dp = rnd(6, r, c)
+    p_ref = torch.softmax(s[:, :valid], -1)
+    (p_ref * t(dp[:, :valid])).sum().backward()
+    p = np.full((r, c), 7.0, np.float32)
+    assert lib.hoisdf_softmax_rows_fwd(ptr(f32(s.detach())), c, r, c, valid, ptr(p), c, None) == 0
+    assert np.abs(p[:, :valid] - p_ref.detach().numpy()).max() < 1e-6 and not p[:, valid:].any()
+    ds = dp.copy()
+    assert lib.hoisdf_softmax_rows_bwd(ptr(p), c, ptr(ds), c, r, c, ptr(ds), c, None) == 0          # in place
+    assert np.abs(ds[:, :valid] - s.grad.numpy()[:, :valid]).max() < 1e-6 and not ds[:, valid:].any()
+
+
+def test_encoder_layer_backward_chain_on_the_emulator():
+    """One post-norm transformer encoder layer (upstream common/nets/transformer.py:286-302: MHA with 4 heads of 64, residual,
+    LayerNorm, FFN with ReLU, residual, LayerNorm) differentiated with the entry points of csrc/backward.cu -- per-head
+    GEMMs + row softmax for the attention core, GEMMs + ReLU masks for the projections and the FFN, LayerNorm backward --
+    against autograd of the oracle's encoder layer: gradients of the layer input and of all 12 parameter tensors."""
+    lib = transformer_backward_lib()
+    t = torch.from_numpy
+    S, d, H, ffn = 23, 256, 4, 1024
+    full = syn.hot_path_state_dict(7, "dexycb")
+    pre = "hand_transformer.encoder.layers.0."
+    P = {k: v.clone().requires_grad_() for k, v in full.items() if k.startswith(pre)}
+    src = t(rnd(1, S, 1, d)).requires_grad_()                      # (S, B = 1, d) as upstream
+    out = O.encoder_layer(P, pre[:-1], src, torch.zeros_like(src), H)
+    dout = rnd(2, S, d)
+    (out[:, 0] * t(dout)).sum().backward()
+
+    W = {k[len(pre):]: f32(v.detach()) for k, v in P.items()}
+    x = f32(src.detach())[:, 0]
+
+    def lin(a, w, b):
+        return gemm(lib, a, False, w, True) + b
+
+    def lin_bwd(dz, a, w):
+        """-> dX, dW, db of Z = A . W^T + b given dZ (no activation)."""
+        dz = np.ascontiguousarray(dz, np.float32)
+        db = np.zeros(dz.shape[1], np.float32)
+        assert lib.hoisdf_act_bias_bwd(ptr(dz), dz.shape[1], None, 0, dz.shape[0], dz.shape[1], 0, ptr(db), 0, None) == 0
+        return gemm(lib, dz, False, w, False), gemm(lib, dz, True, a, False), db
+
+    def ln(hh, g, b):
+        return torch.nn.functional.layer_norm(t(hh), (d,), t(g), t(b), 1e-5).numpy()
+
+    def ln_bwd(hh, g, dy):
+        dh, dg, dbt, stats = np.zeros_like(hh), np.zeros(d, np.float32), np.zeros(d, np.float32), np.zeros(2 * len(hh), np.float32)
+        assert lib.hoisdf_layernorm_bwd(ptr(hh), ptr(g), ptr(np.ascontiguousarray(dy)), len(hh), d, ptr(dh), ptr(dg), ptr(dbt),
+                                        ptr(stats), 0, None) == 0
+        return dh, dg, dbt
+
+    # ---- forward (activations kept); pos = 0, so q = k = v input = src
+    qkv = lin(x, W["self_attn.in_proj_weight"], W["self_attn.in_proj_bias"])
+    heads, probs = [], []
+    for hd in range(H):
+        q, k, v = (np.ascontiguousarray(qkv[:, i * d + hd * 64:i * d + hd * 64 + 64]) for i in range(3))
+        sc = gemm(lib, q * np.float32(0.125), False, k, True)
+        p = np.zeros_like(sc)
+        assert lib.hoisdf_softmax_rows_fwd(ptr(sc), S, S, S, S, ptr(p), S, None) == 0
+        probs.append(p)
+        heads.append(gemm(lib, p, False, v, False))
+    attn = np.ascontiguousarray(np.concatenate(heads, 1))
+    proj = lin(attn, W["self_attn.out_proj.weight"], W["self_attn.out_proj.bias"])
+    h1 = np.ascontiguousarray(x + proj)
+    y1 = ln(h1, W["norm1.weight"], W["norm1.bias"])
+    f1 = np.maximum(lin(y1, W["linear1.weight"], W["linear1.bias"]), 0)
+    f2 = lin(f1, W["linear2.weight"], W["linear2.bias"])
+    h2 = np.ascontiguousarray(y1 + f2)
+    y2 = ln(h2, W["norm2.weight"], W["norm2.bias"])
+    assert np.abs(y2 - out.detach().numpy()[:, 0]).max() < 5e-6
+
+    # ---- backward
+    G = {}
+    dh2, G["norm2.weight"], G["norm2.bias"] = ln_bwd(h2, W["norm2.weight"], dout)
+    df1, G["linear2.weight"], G["linear2.bias"] = lin_bwd(dh2, f1, W["linear2.weight"])
+    dz1 = np.ascontiguousarray(df1)
+    G["linear1.bias"] = np.zeros(ffn, np.float32)
+    assert lib.hoisdf_act_bias_bwd(ptr(dz1), ffn, ptr(f1), ffn, S, ffn, 1, ptr(G["linear1.bias"]), 0, None) == 0
+    G["linear1.weight"] = gemm(lib, dz1, True, y1, False)
+    dy1 = gemm(lib, dz1, False, W["linear1.weight"], False) + dh2
+    dh1, G["norm1.weight"], G["norm1.bias"] = ln_bwd(h1, W["norm1.weight"], dy1)
+    dattn, G["self_attn.out_proj.weight"], G["self_attn.out_proj.bias"] = lin_bwd(dh1, attn, W["self_attn.out_proj.weight"])
+    dqkv = np.zeros_like(qkv)
+    for hd in range(H):
+        q, k, v = (np.ascontiguousarray(qkv[:, i * d + hd * 64:i * d + hd * 64 + 64]) for i in range(3))
+        do = np.ascontiguousarray(dattn[:, hd * 64:hd * 64 + 64])
+        dv = gemm(lib, probs[hd], True, do, False)               # dV = P^T dO
+        dp = gemm(lib, do, False, v, True)                       # dP = dO V^T
+        assert lib.hoisdf_softmax_rows_bwd(ptr(probs[hd]), S, ptr(dp), S, S, S, ptr(dp), S, None) == 0
+        dq = gemm(lib, dp, False, k, False) * np.float32(0.125)  # dQ = dS K / 8
+        dk = gemm(lib, dp, True, q, False) * np.float32(0.125)   # dK = dS^T Q / 8
+        for i, blk in enumerate((dq, dk, dv)):
+            dqkv[:, i * d + hd * 64:i * d + hd * 64 + 64] = blk
+    dx_attn, G["self_attn.in_proj_weight"], G["self_attn.in_proj_bias"] = lin_bwd(dqkv, x, W["self_attn.in_proj_weight"])
+    dx = dx_attn + dh1
+
+    def close(got, want, what):
+        want = want.numpy().reshape(got.shape)
+        assert np.abs(got - want).max() < 2e-5 * max(float(np.abs(want).max()), 1e-3), (what, np.abs(got - want).max())
+
+    close(dx, src.grad[:, 0], "src")
+    assert set(G) == set(W)
+    for k in G:
+        close(G[k], P[pre + k].grad, k)
