@@ -6,7 +6,8 @@ Every function cites the upstream file:line it follows.  It takes a flat paramet
 state-dict key names, so the same dict drives the reference, the oracle and the B200 path.
 
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` legs may import
-this module; the product (`hoisdf_b200/`) never does and fails loudly without its CUDA library.
+this module (plus the developer measurement tools under `scripts/`, which use it as the checker next to a timing);
+the product (`hoisdf_b200/`) never does and fails loudly without its CUDA library.
 
 Pinning: the upstream repository has no tests or golden vectors for this path, so the
 oracle is pinned against outputs of the upstream code itself, run in the build container through
