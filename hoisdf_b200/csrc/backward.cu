@@ -14,6 +14,9 @@
 //   hoisdf_layernorm_bwd     nn.LayerNorm(256) backward: dh, dgamma, dbeta (transformer.py:296-301)
 //   hoisdf_softmax_rows_fwd / _bwd   row softmax and its backward: with hoisdf_gemm_f32 per head, the attention core's
 //                            backward (dV = P^T dO, dP = dO V^T, dS = softmax', dQ = dS K, dK = dS^T Q)
+//   hoisdf_adamw_step        torch.optim.AdamW over a flat parameter buffer (upstream common/base.py:68)
+#include <cmath>
+
 #include "common.cuh"
 
 namespace hoisdf {
@@ -314,6 +317,23 @@ softmax_rows_bwd_kernel(const float* __restrict__ p, int64_t ldp, const float* d
   for (int c = lane; c < cols; c += 32) ds[r * ldds + c] = p[r * ldp + c] * (dp[r * lddp + c] - dot);
 }
 
+
+// torch.optim.AdamW (upstream common/base.py:68: lr 1e-4, default betas / eps / weight_decay 0.01), one fused pass over a
+// flat parameter buffer, the arithmetic in the order PyTorch's single-tensor implementation applies it
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                             int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, float step_size,
+                             float bias2_sqrt) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float grad = g[i];
+  float w = p[i] * (1.f - lr * weight_decay);                  // param.mul_(1 - lr * weight_decay)
+  const float mi = m[i] + (grad - m[i]) * (1.f - beta1);       // exp_avg.lerp_(grad, 1 - beta1)
+  const float vi = fmaf(grad * grad, 1.f - beta2, v[i] * beta2);   // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+  const float denom = sqrtf(vi) / bias2_sqrt + eps;
+  w -= step_size * (mi / denom);                               // param.addcdiv_(exp_avg, denom, value=-step_size)
+  p[i] = w; m[i] = mi; v[i] = vi;
+}
+
 }  // namespace
 }  // namespace hoisdf
 
@@ -414,5 +434,17 @@ HOISDF_API int hoisdf_softmax_rows_bwd(const float* p, int64_t ldp, const float*
   if (rows <= 0 || cols <= 0 || cols > 0x7fffffffLL || ldp < cols || lddp < cols || ldds < cols) return HOISDF_E_SHAPE;
   HOISDF_LAUNCH(softmax_rows_bwd_kernel, static_cast<unsigned>(ceil_div(rows, 8)), 256, static_cast<cudaStream_t>(stream), p,
                 ldp, dp, lddp, rows, static_cast<int>(cols), ds, ldds);
+  return launch_status();
+}
+
+HOISDF_API int hoisdf_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                                 float beta1, float beta2, float eps, float weight_decay, int64_t step, void* stream) {
+  if (param == nullptr || grad == nullptr || exp_avg == nullptr || exp_avg_sq == nullptr) return HOISDF_E_NULL;
+  if (n <= 0 || step < 1 || !(beta1 >= 0.f && beta1 < 1.f) || !(beta2 >= 0.f && beta2 < 1.f)) return HOISDF_E_SHAPE;
+  const double b1 = 1.0 - pow(static_cast<double>(beta1), static_cast<double>(step));
+  const double b2 = 1.0 - pow(static_cast<double>(beta2), static_cast<double>(step));
+  HOISDF_LAUNCH(adamw_kernel, static_cast<unsigned>(ceil_div(n, 256)), 256, static_cast<cudaStream_t>(stream), param, grad,
+                exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, static_cast<float>(lr / b1),
+                static_cast<float>(sqrt(b2)));
   return launch_status();
 }

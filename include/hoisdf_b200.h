@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 13
+#define HOISDF_ABI_VERSION 14
 
 enum {
   HOISDF_OK = 0,
@@ -440,6 +440,8 @@ int hoisdf_hand_joint_metrics_fwd(const float* pred, const float* gt, int64_t ba
  *   hoisdf_softmax_rows_fwd / _bwd: p = softmax(s[:, :valid]) per row (0 beyond `valid`);
  *     ds = p * (dp - sum_j dp_j p_j) (ds may alias dp).  Together with hoisdf_gemm_f32 per (sample, head) these are the
  *     backward of nn.MultiheadAttention's core: dV = P^T dO, dP = dO V^T, dS = softmax'(dP), dQ = dS K / 8, dK = dS^T Q / 8.
+ *   hoisdf_adamw_step: one torch.optim.AdamW update (upstream common/base.py:68) of a flat buffer of n parameters,
+ *     `step` = 1-based update count (bias correction); decoupled weight decay, PyTorch's operation order.
  * ------------------------------------------------------------------------------------------------- */
 int hoisdf_gemm_f32(const float* a, int64_t lda, int32_t trans_a, const float* b, int64_t ldb, int32_t trans_b, float* c,
                     int64_t ldc, int64_t m, int64_t n, int64_t k, int32_t accumulate, void* stream);
@@ -456,6 +458,8 @@ int hoisdf_softmax_rows_fwd(const float* s, int64_t lds, int64_t rows, int64_t c
                             void* stream);
 int hoisdf_softmax_rows_bwd(const float* p, int64_t ldp, const float* dp, int64_t lddp, int64_t rows, int64_t cols, float* ds,
                             int64_t ldds, void* stream);
+int hoisdf_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                      float beta2, float eps, float weight_decay, int64_t step, void* stream);
 
 #ifdef __cplusplus
 }

@@ -841,3 +841,23 @@ def test_encoder_layer_backward_chain_on_the_emulator():
     assert set(G) == set(W)
     for k in G:
         close(G[k], P[pre + k].grad, k)
+
+
+def test_adamw_kernel_on_the_emulator():
+    """torch.optim.AdamW (upstream common/base.py:68: lr 1e-4, PyTorch defaults otherwise) over three updates."""
+    lib = backward_lib()
+    vp, f = C.c_void_p, C.c_float
+    lib.hoisdf_adamw_step.argtypes = [vp, vp, vp, vp, C.c_int64, f, f, f, f, f, C.c_int64, vp]
+    n = 1000
+    w = torch.from_numpy(rnd(1, n)).requires_grad_()
+    opt = torch.optim.AdamW([w], lr=1e-4)
+    p, m, v = f32(w.detach()).copy(), np.zeros(n, np.float32), np.zeros(n, np.float32)
+    for step in range(1, 4):
+        g = rnd(10 + step, n, lo=-3, hi=3)
+        w.grad = torch.from_numpy(g.copy())
+        opt.step()
+        assert lib.hoisdf_adamw_step(ptr(p), ptr(g), ptr(m), ptr(v), n, 1e-4, 0.9, 0.999, 1e-8, 0.01, step, None) == 0
+        assert np.abs(p - w.detach().numpy()).max() < 2e-7
+    st = opt.state[w]
+    assert np.abs(m - st["exp_avg"].numpy()).max() < 1e-6 and np.abs(v - st["exp_avg_sq"].numpy()).max() < 1e-6
+    assert lib.hoisdf_adamw_step(ptr(p), ptr(g), ptr(m), ptr(v), n, 1e-4, 0.9, 0.999, 1e-8, 0.01, 0, None) == -2
