@@ -22,7 +22,7 @@ from . import ops
 
 HO3D_SKIPPED_OBJECT = "019_pitcher_base"        # upstream metrics.py:129: excluded from the HO3D object metrics
 
-_TEMPLATE_CACHE: Dict[Tuple[int, str], torch.Tensor] = {}
+_TEMPLATE_CACHE: Dict[tuple, torch.Tensor] = {}
 
 
 def _dev(t, device) -> torch.Tensor:
@@ -41,13 +41,16 @@ def _cuda_device(*tensors) -> torch.device:
 def stack_templates(templates: Sequence[dict], device) -> torch.Tensor:
     """`prepare_model_template` (upstream data/dataset_util.py:353-379) returns a list of {"verts": (1000, 3), "face"};
     the kernels read them as one (T, N, 3) device tensor, stacked once per template list and device."""
-    key = (id(templates), str(device))
+    # keyed by the identity of every vertex tensor (an `id()` of the list alone could be recycled by another list)
+    verts = [torch.as_tensor(t["verts"]) for t in templates]
+    key = (str(device),) + tuple((v.data_ptr(), tuple(v.shape), v._version) for v in verts)
     hit = _TEMPLATE_CACHE.get(key)
-    if hit is None or hit.shape[0] != len(templates):
-        n = {int(t["verts"].shape[0]) for t in templates}
+    if hit is None:
+        n = {int(v.shape[0]) for v in verts}
         if len(n) != 1:
             raise ValueError("object templates must share one vertex count, got %s" % sorted(n))
-        hit = torch.stack([_dev(t["verts"], device) for t in templates]).contiguous()
+        hit = torch.stack([_dev(v, device) for v in verts]).contiguous()
+        _TEMPLATE_CACHE.clear()                      # one template set at a time (main/test.py builds it once)
         _TEMPLATE_CACHE[key] = hit
     return hit
 
