@@ -288,20 +288,27 @@ layernorm_bwd_cols_kernel(const float* __restrict__ h, const float* __restrict__
   }
 }
 
-// p[r, :] = softmax(s[r, :valid]) (columns >= valid get 0), one warp per row
+// p[r, :] = softmax over the columns c < valid that are not blocked by mask[r % mask_rows, c] (bool attn_mask of
+// nn.MultiheadAttention: non-zero = blocked); blocked / invalid columns get exactly 0.  One warp per row.
 __global__ void __launch_bounds__(256)
-softmax_rows_fwd_kernel(const float* __restrict__ s, int64_t lds, int64_t rows, int cols, int valid, float* __restrict__ p,
-                        int64_t ldp) {
+softmax_rows_fwd_kernel(const float* __restrict__ s, int64_t lds, int64_t rows, int cols, int valid,
+                        const uint8_t* __restrict__ mask, int64_t mask_rows, float* __restrict__ p, int64_t ldp) {
   const int lane = threadIdx.x & 31;
   const int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (r >= rows) return;
+  const uint8_t* mrow = mask != nullptr ? mask + (r % mask_rows) * cols : nullptr;
   float mx = -3.402823466e+38f;
-  for (int c = lane; c < valid; c += 32) mx = fmaxf(mx, s[r * lds + c]);
+  for (int c = lane; c < valid; c += 32)
+    if (mrow == nullptr || mrow[c] == 0) mx = fmaxf(mx, s[r * lds + c]);
   mx = warp_max(mx);
   float sum = 0.f;
-  for (int c = lane; c < valid; c += 32) sum += expf(s[r * lds + c] - mx);
+  for (int c = lane; c < valid; c += 32)
+    if (mrow == nullptr || mrow[c] == 0) sum += expf(s[r * lds + c] - mx);
   sum = warp_sum(sum);
-  for (int c = lane; c < cols; c += 32) p[r * ldp + c] = c < valid ? expf(s[r * lds + c] - mx) / sum : 0.f;
+  for (int c = lane; c < cols; c += 32) {
+    const bool on = c < valid && (mrow == nullptr || mrow[c] == 0);
+    p[r * ldp + c] = on ? expf(s[r * lds + c] - mx) / sum : 0.f;
+  }
 }
 
 // ds[r, :] = p[r, :] * (dp[r, :] - sum_j dp[r, j] * p[r, j]), one warp per row (in place over dp when ds == dp)
@@ -418,13 +425,14 @@ HOISDF_API int hoisdf_layernorm_bwd(const float* h, const float* gamma, const fl
   return launch_status();
 }
 
-HOISDF_API int hoisdf_softmax_rows_fwd(const float* s, int64_t lds, int64_t rows, int64_t cols, int64_t valid, float* p,
-                                       int64_t ldp, void* stream) {
+HOISDF_API int hoisdf_softmax_rows_fwd(const float* s, int64_t lds, int64_t rows, int64_t cols, int64_t valid,
+                                       const uint8_t* mask, int64_t mask_rows, float* p, int64_t ldp, void* stream) {
   if (s == nullptr || p == nullptr) return HOISDF_E_NULL;
   if (rows <= 0 || cols <= 0 || cols > 0x7fffffffLL || valid <= 0 || valid > cols || lds < cols || ldp < cols)
     return HOISDF_E_SHAPE;
+  if (mask != nullptr && mask_rows <= 0) return HOISDF_E_SHAPE;
   HOISDF_LAUNCH(softmax_rows_fwd_kernel, static_cast<unsigned>(ceil_div(rows, 8)), 256, static_cast<cudaStream_t>(stream), s,
-                lds, rows, static_cast<int>(cols), static_cast<int>(valid), p, ldp);
+                lds, rows, static_cast<int>(cols), static_cast<int>(valid), mask, mask_rows, p, ldp);
   return launch_status();
 }
 

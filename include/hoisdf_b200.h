@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 14
+#define HOISDF_ABI_VERSION 15
 
 enum {
   HOISDF_OK = 0,
@@ -437,7 +437,8 @@ int hoisdf_hand_joint_metrics_fwd(const float* pred, const float* gt, int64_t ba
  *   hoisdf_layernorm_bwd: y = LayerNorm(h) * gamma + beta over rows of d = 256 (eps 1e-5; upstream transformer.py:296-301,
  *     h = the residual sum the forward normalised): dh (rows, d), and -- when dgamma / dbeta are given -- the parameter
  *     gradients (deterministic column sums; `stats` = workspace of 2 * rows floats, required with them).
- *   hoisdf_softmax_rows_fwd / _bwd: p = softmax(s[:, :valid]) per row (0 beyond `valid`);
+ *   hoisdf_softmax_rows_fwd / _bwd: p = softmax(s[:, :valid]) per row (0 beyond `valid`, and 0 where the optional bool
+ *     attn_mask (mask_rows, cols) -- row r uses mask row r % mask_rows, non-zero = blocked -- blocks a column);
  *     ds = p * (dp - sum_j dp_j p_j) (ds may alias dp).  Together with hoisdf_gemm_f32 per (sample, head) these are the
  *     backward of nn.MultiheadAttention's core: dV = P^T dO, dP = dO V^T, dS = softmax'(dP), dQ = dS K / 8, dK = dS^T Q / 8.
  *   hoisdf_adamw_step: one torch.optim.AdamW update (upstream common/base.py:68) of a flat buffer of n parameters,
@@ -454,8 +455,8 @@ int hoisdf_gather_bwd(const hoisdf_pyramid* grad, const float* uv, int64_t rows,
 int hoisdf_sdf_loss_bwd(const float* z, const float* sdf_gt, int64_t n, float clamp, float scale, float* dz, void* stream);
 int hoisdf_layernorm_bwd(const float* h, const float* gamma, const float* dy, int64_t rows, int64_t d, float* dh,
                          float* dgamma, float* dbeta, float* stats, int32_t accumulate, void* stream);
-int hoisdf_softmax_rows_fwd(const float* s, int64_t lds, int64_t rows, int64_t cols, int64_t valid, float* p, int64_t ldp,
-                            void* stream);
+int hoisdf_softmax_rows_fwd(const float* s, int64_t lds, int64_t rows, int64_t cols, int64_t valid, const uint8_t* mask,
+                            int64_t mask_rows, float* p, int64_t ldp, void* stream);
 int hoisdf_softmax_rows_bwd(const float* p, int64_t ldp, const float* dp, int64_t lddp, int64_t rows, int64_t cols, float* ds,
                             int64_t ldds, void* stream);
 int hoisdf_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,

@@ -715,7 +715,7 @@ def transformer_backward_lib():
     lib = backward_lib()
     vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
     lib.hoisdf_layernorm_bwd.argtypes = [vp, vp, vp, i64, i64, vp, vp, vp, vp, i32, vp]
-    lib.hoisdf_softmax_rows_fwd.argtypes = [vp, i64, i64, i64, i64, vp, i64, vp]
+    lib.hoisdf_softmax_rows_fwd.argtypes = [vp, i64, i64, i64, i64, vp, i64, vp, i64, vp]
     lib.hoisdf_softmax_rows_bwd.argtypes = [vp, i64, vp, i64, i64, i64, vp, i64, vp]
     return lib
 
@@ -743,7 +743,7 @@ def test_layernorm_and_softmax_backward_kernels_on_the_emulator():
     p_ref = torch.softmax(s[:, :valid], -1)
     (p_ref * t(dp[:, :valid])).sum().backward()
     p = np.full((r, c), 7.0, np.float32)
-    assert lib.hoisdf_softmax_rows_fwd(ptr(f32(s.detach())), c, r, c, valid, ptr(p), c, None) == 0
+    assert lib.hoisdf_softmax_rows_fwd(ptr(f32(s.detach())), c, r, c, valid, None, 0, ptr(p), c, None) == 0
     assert np.abs(p[:, :valid] - p_ref.detach().numpy()).max() < 1e-6 and not p[:, valid:].any()
     ds = dp.copy()
     assert lib.hoisdf_softmax_rows_bwd(ptr(p), c, ptr(ds), c, r, c, ptr(ds), c, None) == 0          # in place
@@ -795,7 +795,7 @@ def test_encoder_layer_backward_chain_on_the_emulator():
         q, k, v = (np.ascontiguousarray(qkv[:, i * d + hd * 64:i * d + hd * 64 + 64]) for i in range(3))
         sc = gemm(lib, q * np.float32(0.125), False, k, True)
         p = np.zeros_like(sc)
-        assert lib.hoisdf_softmax_rows_fwd(ptr(sc), S, S, S, S, ptr(p), S, None) == 0
+        assert lib.hoisdf_softmax_rows_fwd(ptr(sc), S, S, S, S, None, 0, ptr(p), S, None) == 0
         probs.append(p)
         heads.append(gemm(lib, p, False, v, False))
     attn = np.ascontiguousarray(np.concatenate(heads, 1))
@@ -861,3 +861,128 @@ def test_adamw_kernel_on_the_emulator():
     st = opt.state[w]
     assert np.abs(m - st["exp_avg"].numpy()).max() < 1e-6 and np.abs(v - st["exp_avg_sq"].numpy()).max() < 1e-6
     assert lib.hoisdf_adamw_step(ptr(p), ptr(g), ptr(m), ptr(v), n, 1e-4, 0.9, 0.999, 1e-8, 0.01, 0, None) == -2
+
+
+def test_decoder_layer_backward_chain_on_the_emulator():
+    """One post-norm transformer decoder layer (upstream common/nets/transformer.py:366-395): masked self-attention over
+    the 17 MANO queries (block-diagonal tgt_mask, common/utils/misc.py:11-36), cross-attention to the encoder memory under
+    the memory mask (object tokens blocked, misc.py:39-47), FFN, three LayerNorms -- differentiated with csrc/backward.cu
+    against autograd of the oracle: gradients of tgt, memory, query_pos and of all 18 parameter tensors."""
+    lib = transformer_backward_lib()
+    t = torch.from_numpy
+    Lq, S, d, H, ffn, Ph = 17, 23, 256, 4, 1024, 15
+    full = syn.hot_path_state_dict(7, "dexycb")
+    pre = "hand_transformer.decoder.layers.1."
+    P = {k: v.clone().requires_grad_() for k, v in full.items() if k.startswith(pre)}
+    cfg = O.default_cfg(num_samp_hand=Ph, num_samp_obj=S - Ph)
+    tgt_mask, mem_mask = O.mano_tgt_mask(cfg), O.mano_memory_mask(cfg)
+    tgt, memory, qpos = (t(rnd(i, n, 1, d)).requires_grad_() for i, n in ((1, Lq), (2, S), (3, Lq)))
+    out = O.decoder_layer(P, pre[:-1], tgt, memory, torch.zeros_like(memory), qpos, tgt_mask, mem_mask, H)
+    dout = rnd(4, Lq, d)
+    (out[:, 0] * t(dout)).sum().backward()
+    W = {k[len(pre):]: f32(v.detach()) for k, v in P.items()}
+    x, mem, qp = f32(tgt.detach())[:, 0], f32(memory.detach())[:, 0], f32(qpos.detach())[:, 0]
+    masks = {"self_attn": np.ascontiguousarray(tgt_mask.numpy().astype(np.uint8)),
+             "multihead_attn": np.ascontiguousarray(mem_mask.numpy().astype(np.uint8))}
+
+    def lin(a, w, b):
+        return gemm(lib, a, False, w, True) + b
+
+    def lin_bwd(dz, a, w):
+        dz = np.ascontiguousarray(dz, np.float32)
+        db = np.zeros(dz.shape[1], np.float32)
+        assert lib.hoisdf_act_bias_bwd(ptr(dz), dz.shape[1], None, 0, dz.shape[0], dz.shape[1], 0, ptr(db), 0, None) == 0
+        return gemm(lib, dz, False, w, False), gemm(lib, dz, True, a, False), db
+
+    def ln(hh, name):
+        return torch.nn.functional.layer_norm(t(hh), (d,), t(W[name + ".weight"]), t(W[name + ".bias"]), 1e-5).numpy()
+
+    def ln_bwd(hh, name, dy, G):
+        dh, dg, dbt, st = np.zeros_like(hh), np.zeros(d, np.float32), np.zeros(d, np.float32), np.zeros(2 * len(hh), np.float32)
+        assert lib.hoisdf_layernorm_bwd(ptr(hh), ptr(W[name + ".weight"]), ptr(np.ascontiguousarray(dy)), len(hh), d, ptr(dh),
+                                        ptr(dg), ptr(dbt), ptr(st), 0, None) == 0
+        G[name + ".weight"], G[name + ".bias"] = dg, dbt
+        return dh
+
+    def mha_fwd(name, qin, kin, vin):
+        """-> (output, saved activations) of nn.MultiheadAttention with the bool mask of this attention."""
+        Wi, bi = W[name + ".in_proj_weight"], W[name + ".in_proj_bias"]
+        q, k, v = lin(qin, Wi[:d], bi[:d]), lin(kin, Wi[d:2 * d], bi[d:2 * d]), lin(vin, Wi[2 * d:], bi[2 * d:])
+        m = masks[name]
+        probs, heads = [], []
+        for hd in range(H):
+            sl = slice(hd * 64, hd * 64 + 64)
+            sc = gemm(lib, np.ascontiguousarray(q[:, sl]) * np.float32(0.125), False, np.ascontiguousarray(k[:, sl]), True)
+            p = np.zeros_like(sc)
+            assert lib.hoisdf_softmax_rows_fwd(ptr(sc), sc.shape[1], sc.shape[0], sc.shape[1], sc.shape[1], ptr(m), m.shape[0],
+                                               ptr(p), sc.shape[1], None) == 0
+            probs.append(p)
+            heads.append(gemm(lib, p, False, np.ascontiguousarray(v[:, sl]), False))
+        cat = np.ascontiguousarray(np.concatenate(heads, 1))
+        return lin(cat, W[name + ".out_proj.weight"], W[name + ".out_proj.bias"]), (qin, kin, vin, q, k, v, probs, cat)
+
+    def mha_bwd(name, dy, saved, G):
+        """-> gradients of the three inputs (query side, key side, value side)."""
+        qin, kin, vin, q, k, v, probs, cat = saved
+        dcat, G[name + ".out_proj.weight"], G[name + ".out_proj.bias"] = lin_bwd(dy, cat, W[name + ".out_proj.weight"])
+        dq, dk, dv = np.zeros_like(q), np.zeros_like(k), np.zeros_like(v)
+        for hd in range(H):
+            sl = slice(hd * 64, hd * 64 + 64)
+            do = np.ascontiguousarray(dcat[:, sl])
+            dv[:, sl] = gemm(lib, probs[hd], True, do, False)
+            dp = gemm(lib, do, False, np.ascontiguousarray(v[:, sl]), True)
+            n = dp.shape[1]
+            assert lib.hoisdf_softmax_rows_bwd(ptr(probs[hd]), n, ptr(dp), n, dp.shape[0], n, ptr(dp), n, None) == 0
+            dq[:, sl] = gemm(lib, dp, False, np.ascontiguousarray(k[:, sl]), False) * np.float32(0.125)
+            dk[:, sl] = gemm(lib, dp, True, np.ascontiguousarray(q[:, sl]), False) * np.float32(0.125)
+        Wi = W[name + ".in_proj_weight"]
+        dqin, gq, bq = lin_bwd(dq, qin, Wi[:d])
+        dkin, gk, bk = lin_bwd(dk, kin, Wi[d:2 * d])
+        dvin, gv, bv = lin_bwd(dv, vin, Wi[2 * d:])
+        G[name + ".in_proj_weight"], G[name + ".in_proj_bias"] = np.concatenate([gq, gk, gv]), np.concatenate([bq, bk, bv])
+        return dqin, dkin, dvin
+
+    # ---- forward
+    qk = np.ascontiguousarray(x + qp)
+    a1, s1 = mha_fwd("self_attn", qk, qk, x)
+    h1 = np.ascontiguousarray(x + a1)
+    y1 = ln(h1, "norm1")
+    q2 = np.ascontiguousarray(y1 + qp)
+    a2, s2 = mha_fwd("multihead_attn", q2, mem, mem)
+    h2 = np.ascontiguousarray(y1 + a2)
+    y2 = ln(h2, "norm2")
+    f1 = np.maximum(lin(y2, W["linear1.weight"], W["linear1.bias"]), 0)
+    h3 = np.ascontiguousarray(y2 + lin(f1, W["linear2.weight"], W["linear2.bias"]))
+    y3 = ln(h3, "norm3")
+    assert np.abs(y3 - out.detach().numpy()[:, 0]).max() < 5e-6
+    # the memory mask gives the blocked (object-side) keys exactly zero weight
+    assert all(not p[:, Ph:].any() for p in s2[6])
+
+    # ---- backward
+    G = {}
+    dh3 = ln_bwd(h3, "norm3", dout, G)
+    df1, G["linear2.weight"], G["linear2.bias"] = lin_bwd(dh3, f1, W["linear2.weight"])
+    dz1 = np.ascontiguousarray(df1)
+    G["linear1.bias"] = np.zeros(ffn, np.float32)
+    assert lib.hoisdf_act_bias_bwd(ptr(dz1), ffn, ptr(f1), ffn, Lq, ffn, 1, ptr(G["linear1.bias"]), 0, None) == 0
+    G["linear1.weight"] = gemm(lib, dz1, True, y2, False)
+    dy2 = gemm(lib, dz1, False, W["linear1.weight"], False) + dh3
+    dh2 = ln_bwd(h2, "norm2", dy2, G)
+    dq2, dmem_k, dmem_v = mha_bwd("multihead_attn", dh2, s2, G)
+    dy1 = dh2 + dq2
+    dh1 = ln_bwd(h1, "norm1", dy1, G)
+    dqk_q, dqk_k, dx_v = mha_bwd("self_attn", dh1, s1, G)
+    dx = dh1 + dqk_q + dqk_k + dx_v
+    dqp = dq2 + dqk_q + dqk_k
+    dmem = dmem_k + dmem_v
+
+    def close(got, want, what):
+        want = want.numpy().reshape(got.shape)
+        assert np.abs(got - want).max() < 2e-5 * max(float(np.abs(want).max()), 1e-3), (what, np.abs(got - want).max())
+
+    close(dx, tgt.grad[:, 0], "tgt")
+    close(dmem, memory.grad[:, 0], "memory")
+    close(dqp, qpos.grad[:, 0], "query_pos")
+    assert set(G) == set(W)
+    for k in G:
+        close(G[k], P[pre + k].grad, k)
