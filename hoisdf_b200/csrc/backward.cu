@@ -15,6 +15,8 @@
 //   hoisdf_softmax_rows_fwd / _bwd   row softmax and its backward: with hoisdf_gemm_f32 per head, the attention core's
 //                            backward (dV = P^T dO, dP = dO V^T, dS = softmax', dQ = dS K, dK = dS^T Q)
 //   hoisdf_adamw_step        torch.optim.AdamW over a flat parameter buffer (upstream common/base.py:68)
+//   hoisdf_vote_loss_bwd     JointvoteLoss (common/nets/loss.py:22-61): gradients of the three losses w.r.t. the vote
+//                            offsets and the class logits
 #include <cmath>
 
 #include "common.cuh"
@@ -341,6 +343,108 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
   p[i] = w; m[i] = mi; v[i] = vi;
 }
 
+
+// ---- JointvoteLoss backward (upstream common/nets/loss.py:22-61), batch-major like the forward vote kernel:
+//   points (B,P,3) [m], off (L,B,P,60), cls (L,B,P,20), joint_gt (B,20,3) [mm]
+//   vote = point + off;  mask[b,p,j] = |point - gt_j / 1000| < cls_dist;  n_pos = sum(mask)
+//   loss_joint_3d     = sum_{l,b,p,j,c} smooth_l1(1000 vote - gt) * mask / (3 L n_pos)
+//   loss_joint_cls    = mean_{l,b,p,j} BCEWithLogits(cls, mask)
+//   loss_all_joint_3d = mean_{l,b,j,c} smooth_l1(1000 * sum_p softmax_p(cls) vote - gt)
+// given the three upstream gradients g1, g2, g3 (the training loop sums the losses: all 1).  The points carry no gradient
+// (selected lattice points / jittered pre-points).
+constexpr int kVoteJ = 20;
+
+__global__ void __launch_bounds__(256)
+vote_count_pos_kernel(const float* __restrict__ points, const float* __restrict__ gt, int64_t batch, int64_t p, float dist,
+                      float* __restrict__ npos) {
+  __shared__ float red[8];
+  float n = 0.f;
+  const int64_t total = batch * p * kVoteJ;
+  for (int64_t i = threadIdx.x; i < total; i += 256) {
+    const int j = static_cast<int>(i % kVoteJ);
+    const int64_t bp = i / kVoteJ, b = bp / p;
+    float d2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float d = points[bp * 3 + c] - gt[(b * kVoteJ + j) * 3 + c] / 1000.f;
+      d2 += d * d;
+    }
+    n += sqrtf(d2) < dist ? 1.f : 0.f;
+  }
+  n = warp_sum(n);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = n;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i];
+    npos[0] = t;
+  }
+}
+
+__device__ __forceinline__ float smooth_l1_grad(float x) { return fminf(fmaxf(x, -1.f), 1.f); }   // beta = 1
+
+// one CTA per (layer, sample): warps 0..7 own joints j = w, w + 8, w + 16 for the softmax statistics, then all threads
+// walk the (point, joint) pairs
+__global__ void __launch_bounds__(256)
+vote_loss_bwd_kernel(const float* __restrict__ points, const float* __restrict__ off, const float* __restrict__ cls,
+                     const float* __restrict__ gt, int64_t layers, int64_t batch, int64_t p, float dist, float g1, float g2,
+                     float g3, const float* __restrict__ npos, float* __restrict__ d_off, float* __restrict__ d_cls) {
+  __shared__ float s_max[kVoteJ], s_sum[kVoteJ], s_joint[kVoteJ][3];
+  const int64_t lb = blockIdx.x, b = lb % batch;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* pts = points + b * p * 3;
+  const float* o = off + lb * p * 60;
+  const float* c = cls + lb * p * kVoteJ;
+  const float* g = gt + b * kVoteJ * 3;
+  for (int j = warp; j < kVoteJ; j += 8) {
+    float mx = -3.402823466e+38f;
+    for (int64_t i = lane; i < p; i += 32) mx = fmaxf(mx, c[i * kVoteJ + j]);
+    mx = warp_max(mx);
+    float se = 0.f, sv[3] = {0.f, 0.f, 0.f};
+    for (int64_t i = lane; i < p; i += 32) {
+      const float e = expf(c[i * kVoteJ + j] - mx);
+      se += e;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) sv[k] = fmaf(e, pts[i * 3 + k] + o[i * 60 + j * 3 + k], sv[k]);
+    }
+    se = warp_sum(se);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) sv[k] = warp_sum(sv[k]);
+    if (lane == 0) {
+      s_max[j] = mx; s_sum[j] = se;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) s_joint[j][k] = sv[k] / se;
+    }
+  }
+  __syncthreads();
+  const float k1 = g1 * 1000.f / (3.f * static_cast<float>(layers) * npos[0]);
+  const float k2 = g2 / static_cast<float>(layers * batch * p * kVoteJ);
+  const float k3 = g3 * 1000.f / static_cast<float>(layers * batch * kVoteJ * 3);
+  for (int64_t e = threadIdx.x; e < p * kVoteJ; e += 256) {
+    const int64_t i = e / kVoteJ;
+    const int j = static_cast<int>(e - i * kVoteJ);
+    float d2 = 0.f, vote[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float d = pts[i * 3 + k] - g[j * 3 + k] / 1000.f;
+      d2 += d * d;
+      vote[k] = pts[i * 3 + k] + o[i * 60 + j * 3 + k];
+    }
+    const float mask = sqrtf(d2) < dist ? 1.f : 0.f;
+    const float logit = c[i * kVoteJ + j];
+    const float w = expf(logit - s_max[j]) / s_sum[j];
+    float dc = k2 * (1.f / (1.f + expf(-logit)) - mask);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float dj = k3 * smooth_l1_grad(1000.f * s_joint[j][k] - g[j * 3 + k]);      // d loss / d joints[j][k]
+      d_off[lb * p * 60 + i * 60 + j * 3 + k] = k1 * mask * smooth_l1_grad(1000.f * vote[k] - g[j * 3 + k]) + dj * w;
+      dc = fmaf(dj * w, vote[k] - s_joint[j][k], dc);
+    }
+    d_cls[lb * p * kVoteJ + e] = dc;
+  }
+}
+
 }  // namespace
 }  // namespace hoisdf
 
@@ -454,5 +558,19 @@ HOISDF_API int hoisdf_adamw_step(float* param, const float* grad, float* exp_avg
   HOISDF_LAUNCH(adamw_kernel, static_cast<unsigned>(ceil_div(n, 256)), 256, static_cast<cudaStream_t>(stream), param, grad,
                 exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, static_cast<float>(lr / b1),
                 static_cast<float>(sqrt(b2)));
+  return launch_status();
+}
+
+HOISDF_API int hoisdf_vote_loss_bwd(const float* points, const float* off, const float* cls, const float* joint_gt,
+                                    int64_t layers, int64_t batch, int64_t p, float cls_dist, float g_joint_3d, float g_cls,
+                                    float g_all_joint_3d, float* d_off, float* d_cls, float* npos_ws, void* stream) {
+  if (points == nullptr || off == nullptr || cls == nullptr || joint_gt == nullptr || d_off == nullptr || d_cls == nullptr ||
+      npos_ws == nullptr)
+    return HOISDF_E_NULL;
+  if (layers <= 0 || batch <= 0 || p <= 0 || layers * batch > 0x7fffffffLL) return HOISDF_E_SHAPE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  HOISDF_LAUNCH(vote_count_pos_kernel, 1, 256, s, points, joint_gt, batch, p, cls_dist, npos_ws);
+  HOISDF_LAUNCH(vote_loss_bwd_kernel, static_cast<unsigned>(layers * batch), 256, s, points, off, cls, joint_gt, layers, batch,
+                p, cls_dist, g_joint_3d, g_cls, g_all_joint_3d, static_cast<const float*>(npos_ws), d_off, d_cls);
   return launch_status();
 }

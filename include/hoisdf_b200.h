@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 15
+#define HOISDF_ABI_VERSION 16
 
 enum {
   HOISDF_OK = 0,
@@ -441,6 +441,10 @@ int hoisdf_hand_joint_metrics_fwd(const float* pred, const float* gt, int64_t ba
  *     attn_mask (mask_rows, cols) -- row r uses mask row r % mask_rows, non-zero = blocked -- blocks a column);
  *     ds = p * (dp - sum_j dp_j p_j) (ds may alias dp).  Together with hoisdf_gemm_f32 per (sample, head) these are the
  *     backward of nn.MultiheadAttention's core: dV = P^T dO, dP = dO V^T, dS = softmax'(dP), dQ = dS K / 8, dK = dS^T Q / 8.
+ *   hoisdf_vote_loss_bwd: JointvoteLoss (upstream common/nets/loss.py:22-61), batch-major like hoisdf_vote_joints_fwd:
+ *     points (B,P,3) [m], off (L,B,P,60), cls (L,B,P,20), joint_gt (B,20,3) [mm]; d_off / d_cls = gradients of
+ *     g_joint_3d * loss_joint_3d + g_cls * loss_joint_cls + g_all_joint_3d * loss_all_joint_3d (the points carry no
+ *     gradient); npos_ws: one float of workspace (the number of positive point / joint pairs).
  *   hoisdf_adamw_step: one torch.optim.AdamW update (upstream common/base.py:68) of a flat buffer of n parameters,
  *     `step` = 1-based update count (bias correction); decoupled weight decay, PyTorch's operation order.
  * ------------------------------------------------------------------------------------------------- */
@@ -459,6 +463,9 @@ int hoisdf_softmax_rows_fwd(const float* s, int64_t lds, int64_t rows, int64_t c
                             int64_t mask_rows, float* p, int64_t ldp, void* stream);
 int hoisdf_softmax_rows_bwd(const float* p, int64_t ldp, const float* dp, int64_t lddp, int64_t rows, int64_t cols, float* ds,
                             int64_t ldds, void* stream);
+int hoisdf_vote_loss_bwd(const float* points, const float* off, const float* cls, const float* joint_gt, int64_t layers,
+                         int64_t batch, int64_t p, float cls_dist, float g_joint_3d, float g_cls, float g_all_joint_3d,
+                         float* d_off, float* d_cls, float* npos_ws, void* stream);
 int hoisdf_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                       float beta2, float eps, float weight_decay, int64_t step, void* stream);
 

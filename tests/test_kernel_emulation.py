@@ -986,3 +986,30 @@ def test_decoder_layer_backward_chain_on_the_emulator():
     assert set(G) == set(W)
     for k in G:
         close(G[k], P[pre + k].grad, k)
+
+
+def test_vote_loss_backward_kernel_on_the_emulator():
+    """JointvoteLoss (upstream common/nets/loss.py:22-61): gradients of loss_joint_3d + loss_joint_cls + loss_all_joint_3d
+    w.r.t. the vote offsets and class logits against autograd of the oracle's restatement."""
+    lib = backward_lib()
+    vp, i64, f = C.c_void_p, C.c_int64, C.c_float
+    lib.hoisdf_vote_loss_bwd.argtypes = [vp, vp, vp, vp, i64, i64, i64, f, f, f, f, vp, vp, vp, vp]
+    t = torch.from_numpy
+    L, B, Pn = 2, 2, 70
+    pts = rnd(1, B, Pn, 3, lo=-0.1, hi=0.1)
+    gt = rnd(2, B, 20, 3, lo=-100, hi=100)                        # millimetres
+    off, cls = rnd(3, L, B, Pn, 60, lo=-0.05, hi=0.05), rnd(4, L, B, Pn, 20, lo=-3, hi=3)
+    cfg = O.default_cfg(hand_cls_dist=0.06)
+    off_t, cls_t = t(off).requires_grad_(), t(cls).requires_grad_()
+    off_u, cls_u = off_t.permute(0, 2, 1, 3), cls_t.permute(0, 2, 1, 3)          # upstream layout (L, P, B, .)
+    joints = O.vote_joints(t(pts), off_u, cls_u)
+    l1, l2, l3 = O.joint_vote_losses(t(pts), off_u, cls_u, joints, t(gt), cfg)
+    gw = (1.0, 0.5, 2.0)
+    (gw[0] * l1 + gw[1] * l2 + gw[2] * l3).backward()
+    d_off, d_cls, npos = np.zeros_like(off), np.zeros_like(cls), np.zeros(1, np.float32)
+    assert lib.hoisdf_vote_loss_bwd(ptr(pts), ptr(off), ptr(cls), ptr(gt), L, B, Pn, cfg.hand_cls_dist, gw[0], gw[1], gw[2],
+                                    ptr(d_off), ptr(d_cls), ptr(npos), None) == 0
+    mask = (torch.norm(t(pts).unsqueeze(2) - t(gt).unsqueeze(1) / 1000, dim=-1) < cfg.hand_cls_dist)
+    assert 0 < int(mask.sum()) < mask.numel() and float(npos[0]) == float(mask.sum())
+    assert np.abs(d_off - off_t.grad.numpy()).max() < 2e-5 * float(off_t.grad.abs().max())
+    assert np.abs(d_cls - cls_t.grad.numpy()).max() < 2e-5 * float(cls_t.grad.abs().max())
