@@ -1,18 +1,21 @@
 // TEST INFRASTRUCTURE: a minimal CPU emulation of the CUDA execution model, enough to run the simple (non-tensor-core)
-// kernels of hoisdf_b200/csrc/*.cu unchanged on a host without a GPU: one OS thread per CUDA thread, blocks executed
-// one after another, `__shared__` = function-local static storage, `__syncthreads()` = a std::barrier over the block,
-// warp shuffles = an exchange buffer between two block barriers (valid for block-uniform shuffles, which is how these
-// kernels use them).  Built by tests/test_kernel_emulation.py with `g++ -std=c++20 -DHOISDF_EMULATE`; never part of
-// libhoisdf_b200.so.
+// kernels of hoisdf_b200/csrc/*.cu unchanged on a host without a GPU.  Every CUDA thread of a block is a FIBER (ucontext)
+// on one OS thread; blocks run one after another; `__shared__` = function-local static storage; `__syncthreads()` and
+// the warp collectives (shuffles, ballots, __syncwarp) are cooperative barriers: a fiber that arrives yields to the next
+// one until the barrier's generation advances.  As on the GPU, threads that have left the kernel are not waited for.
+// Deterministic (round-robin schedule) and free of kernel-level thread switches.  Built by
+// tests/test_kernel_emulation.py with `g++ -std=c++20 -DHOISDF_EMULATE`; never part of libhoisdf_b200.so.
 #pragma once
 #include <stdint.h>
 
+#include <ucontext.h>
+
 #include <algorithm>
-#include <barrier>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <memory>
-#include <thread>
 #include <vector>
 
 #include "../../include/hoisdf_b200.h"
@@ -34,41 +37,97 @@ struct dim3 {
 using cudaStream_t = void*;
 
 namespace emu {
-inline thread_local dim3 thread_idx, block_idx;
+inline dim3 thread_idx, block_idx;          // of the running fiber (one OS thread: plain globals)
 inline dim3 block_dim, grid_dim;
-inline std::unique_ptr<std::barrier<>> block_barrier;
-inline std::vector<std::unique_ptr<std::barrier<>>> warp_barrier;
 inline unsigned char exchange[1024][16];
 alignas(16) inline unsigned char dynamic_smem[228 * 1024];      // `extern __shared__` storage of the running block
+
+struct Barrier {
+  unsigned alive = 0, count = 0, generation = 0;
+  void release_if_complete() {
+    if (alive > 0 && count >= alive) {
+      count = 0;
+      ++generation;
+    }
+  }
+};
+
+struct Fiber {
+  ucontext_t ctx;
+  std::unique_ptr<unsigned char[]> stack;
+  dim3 tid;
+  bool done = false;
+};
+
+constexpr size_t kStackBytes = 256 * 1024;
+inline ucontext_t scheduler_ctx;
+inline std::vector<Fiber> fibers;
+inline unsigned current = 0;
+inline Barrier block_barrier;
+inline std::vector<Barrier> warp_barrier;
+inline std::function<void()> block_body;
+
+inline void yield() { swapcontext(&fibers[current].ctx, &scheduler_ctx); }
+
+inline void wait(Barrier& b) {
+  const unsigned gen = b.generation;
+  ++b.count;
+  b.release_if_complete();
+  while (b.generation == gen) yield();
+}
+
+inline void fiber_entry() {
+  block_body();
+  Fiber& f = fibers[current];
+  f.done = true;                              // a thread that has left the kernel is no longer waited for
+  --block_barrier.alive;
+  block_barrier.release_if_complete();
+  Barrier& w = warp_barrier[current >> 5];
+  --w.alive;
+  w.release_if_complete();
+  swapcontext(&f.ctx, &scheduler_ctx);        // never resumed
+}
 
 template <typename K, typename... Args>
 void launch(K kernel, dim3 grid, dim3 block, Args... args) {
   grid_dim = grid;
   block_dim = block;
   const unsigned n = block.x * block.y * block.z;
-  block_barrier = std::make_unique<std::barrier<>>(n);
-  warp_barrier.clear();
-  for (unsigned w = 0; w * 32 < n; ++w)
-    warp_barrier.push_back(std::make_unique<std::barrier<>>(std::min(32u, n - w * 32)));
-  // one OS thread per CUDA thread of a block, reused for every block of the grid (blocks run one after another; the
-  // end-of-block barrier keeps a block's `__shared__` storage alive until all of its threads have left the kernel).
-  // Limitation, as in any such emulation: threads that leave a kernel early must not be waited for by a later
-  // __syncthreads() of the others (none of the emulated kernels does that).
-  std::barrier<> end_of_block(n);
-  std::vector<std::thread> threads;
-  threads.reserve(n);
-  for (unsigned t = 0; t < n; ++t)
-    threads.emplace_back([&, t]() {
-      thread_idx = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
-      for (unsigned bz = 0; bz < grid.z; ++bz)
-        for (unsigned by = 0; by < grid.y; ++by)
-          for (unsigned bx = 0; bx < grid.x; ++bx) {
-            block_idx = dim3(bx, by, bz);
-            kernel(args...);
-            end_of_block.arrive_and_wait();
+  if (fibers.size() < n) {
+    const size_t old = fibers.size();
+    fibers.resize(n);
+    for (size_t i = old; i < n; ++i) fibers[i].stack.reset(new unsigned char[kStackBytes]);
+  }
+  block_body = [&]() { kernel(args...); };
+  for (unsigned bz = 0; bz < grid.z; ++bz)
+    for (unsigned by = 0; by < grid.y; ++by)
+      for (unsigned bx = 0; bx < grid.x; ++bx) {
+        block_idx = dim3(bx, by, bz);
+        block_barrier = Barrier{n, 0, 0};
+        warp_barrier.assign((n + 31) / 32, Barrier{});
+        for (unsigned w = 0; w * 32 < n; ++w) warp_barrier[w].alive = std::min(32u, n - w * 32);
+        for (unsigned t = 0; t < n; ++t) {
+          Fiber& f = fibers[t];
+          f.done = false;
+          f.tid = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+          getcontext(&f.ctx);
+          f.ctx.uc_stack.ss_sp = f.stack.get();
+          f.ctx.uc_stack.ss_size = kStackBytes;
+          f.ctx.uc_link = nullptr;
+          makecontext(&f.ctx, fiber_entry, 0);
+        }
+        unsigned remaining = n;
+        while (remaining > 0) {               // round-robin until every thread of the block has left the kernel
+          remaining = 0;
+          for (unsigned t = 0; t < n; ++t) {
+            if (fibers[t].done) continue;
+            current = t;
+            thread_idx = fibers[t].tid;
+            swapcontext(&scheduler_ctx, &fibers[t].ctx);
+            if (!fibers[t].done) ++remaining;
           }
-    });
-  for (auto& th : threads) th.join();
+        }
+      }
 }
 }  // namespace emu
 
@@ -80,9 +139,9 @@ void launch(K kernel, dim3 grid, dim3 block, Args... args) {
 #define HOISDF_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) emu::launch(kernel, dim3(grid), dim3(block), __VA_ARGS__)
 #define HOISDF_DYNAMIC_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::dynamic_smem)
 
-inline void __syncthreads() { emu::block_barrier->arrive_and_wait(); }
-inline unsigned emu_tid() { return threadIdx.x + threadIdx.y * blockDim.x + threadIdx.z * blockDim.x * blockDim.y; }
-inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_barrier[emu_tid() >> 5]->arrive_and_wait(); }
+inline void __syncthreads() { emu::wait(emu::block_barrier); }
+inline unsigned emu_tid() { return emu::current; }
+inline void __syncwarp(unsigned = 0xffffffffu) { emu::wait(emu::warp_barrier[emu::current >> 5]); }
 
 template <typename T>
 inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {

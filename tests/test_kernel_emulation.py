@@ -1,9 +1,10 @@
-"""The simple (non-tensor-core) CUDA kernels of csrc/metrics.cu, lattice.cu, topk.cu, heads.cu, gather.cu, layernorm.cu, sdf.cu, linear.cu (fp32 FMA GEMM),
-attention.cu (SIMT attention) and narrow.cu executed UNCHANGED on the host by a CPU thread emulator
-(tests/emu/cuda_emu.h: one OS thread per CUDA thread, std::barrier for __syncthreads, an exchange buffer for warp
-shuffles) and compared with the oracle -- so that the kernel source, its launch geometry and its C-ABI argument
-handling are checked in the GPU-less suite too.  Test infrastructure: the emulated library is built from the same
-.cu file with `g++ -DHOISDF_EMULATE` into tests/emu/_build/ and is never loaded by the product."""
+"""The simple (non-tensor-core) CUDA kernels of csrc/metrics.cu, lattice.cu, topk.cu, heads.cu, gather.cu, layernorm.cu,
+sdf.cu, linear.cu (fp32 FMA GEMM), attention.cu (SIMT attention), narrow.cu and backward.cu executed UNCHANGED on the host
+by a CPU emulator (tests/emu/cuda_emu.h: every CUDA thread of a block is a fiber, __syncthreads / shuffles / ballots are
+cooperative barriers, `_Float16` stands in for `__half`) and compared with the oracle or with PyTorch autograd -- so that
+the kernel sources, their launch geometry and their C-ABI argument handling are checked in the GPU-less suite too.  Test
+infrastructure: the emulated library is built from the same .cu files with `g++ -DHOISDF_EMULATE` into tests/emu/_build/
+and is never loaded by the product."""
 import ctypes as C
 import os
 import shutil
