@@ -15,6 +15,8 @@
 //   hoisdf_softmax_rows_fwd / _bwd   row softmax and its backward: with hoisdf_gemm_f32 per head, the attention core's
 //                            backward (dV = P^T dO, dP = dO V^T, dS = softmax', dQ = dS K, dK = dS^T Q)
 //   hoisdf_adamw_step        torch.optim.AdamW over a flat parameter buffer (upstream common/base.py:68)
+//   hoisdf_tokens_bwd        token assembly with the SDF activation sigmoid(sdf / beta) / beta (model.py:123-126,520-531):
+//                            gradients of the point features, the SDF values and beta
 //   hoisdf_vote_loss_bwd     JointvoteLoss (common/nets/loss.py:22-61): gradients of the three losses w.r.t. the vote
 //                            offsets and the class logits
 #include <cmath>
@@ -445,6 +447,63 @@ vote_loss_bwd_kernel(const float* __restrict__ points, const float* __restrict__
   }
 }
 
+
+// ---- token assembly backward (upstream main/model.py:123-126,520-531): tokens[.., 33 + c] = fea[c] * sig,
+// sig = sigmoid(sdf / beta) / beta.  d_fea = d_tok * sig;  d_sdf = <d_tok, fea> * s (1 - s) / beta^2;
+// d_beta = sum over points of <d_tok, fea> * (-s / beta^2 - s (1 - s) sdf / beta^3)   (s = sigmoid(sdf / beta)).
+// One warp per point; d_beta partials per block (fixed order), folded by the second kernel.
+__global__ void __launch_bounds__(256)
+tokens_bwd_kernel(const float* __restrict__ d_tok, int64_t s_total, int64_t t0, const float* __restrict__ fea, int64_t ld_fea,
+                  const float* __restrict__ sdf, const float* __restrict__ beta, int64_t batch, int64_t p,
+                  float* __restrict__ d_fea, int64_t ld_dfea, float* __restrict__ d_sdf, float* __restrict__ partial) {
+  __shared__ float red[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t bt = static_cast<int64_t>(blockIdx.x) * 8 + warp;
+  float db = 0.f;
+  if (bt < batch * p) {
+    const int64_t b = bt / p, t = bt - b * p;
+    const float be = beta[0];
+    const float z = __fdiv_rn(sdf[bt], be);
+    const float sg = __fdiv_rn(1.f, 1.f + expf(-z));
+    const float sig = __fdiv_rn(sg, be);
+    const float* dt = d_tok + (b * s_total + t0 + t) * 256 + 33;
+    float dot = 0.f;
+    for (int c = lane; c < 223; c += 32) {
+      const float g = dt[c];
+      d_fea[bt * ld_dfea + c] = g * sig;
+      dot = fmaf(g, fea[bt * ld_fea + c], dot);
+    }
+    dot = warp_sum(dot);
+    const float ds = sg * (1.f - sg);
+    if (lane == 0 && d_sdf != nullptr) d_sdf[bt] = dot * ds / (be * be);
+    db = dot * (-sg / (be * be) - ds * sdf[bt] / (be * be * be));
+  }
+  if (lane == 0) red[warp] = db;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tsum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tsum += red[i];
+    partial[blockIdx.x] = tsum;
+  }
+}
+
+__global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ partial, int64_t n, float* __restrict__ out,
+                                                           int accumulate) {
+  __shared__ float red[8];
+  float sacc = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += 256) sacc += partial[i];
+  sacc = warp_sum(sacc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sacc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tsum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tsum += red[i];
+    out[0] = accumulate ? out[0] + tsum : tsum;
+  }
+}
+
 }  // namespace
 }  // namespace hoisdf
 
@@ -572,5 +631,29 @@ HOISDF_API int hoisdf_vote_loss_bwd(const float* points, const float* off, const
   HOISDF_LAUNCH(vote_count_pos_kernel, 1, 256, s, points, joint_gt, batch, p, cls_dist, npos_ws);
   HOISDF_LAUNCH(vote_loss_bwd_kernel, static_cast<unsigned>(layers * batch), 256, s, points, off, cls, joint_gt, layers, batch,
                 p, cls_dist, g_joint_3d, g_cls, g_all_joint_3d, static_cast<const float*>(npos_ws), d_off, d_cls);
+  return launch_status();
+}
+
+HOISDF_API int64_t hoisdf_tokens_bwd_workspace_bytes(int64_t batch, int64_t p) {
+  if (batch <= 0 || p <= 0) return 0;
+  return ceil_div(batch * p, 8) * static_cast<int64_t>(sizeof(float));
+}
+
+HOISDF_API int hoisdf_tokens_bwd(const float* d_tokens, int64_t s_total, int64_t t0, const float* fea, int64_t ld_fea,
+                                 const float* sdf, const float* beta, int64_t batch, int64_t p, float* d_fea, int64_t ld_dfea,
+                                 float* d_sdf, float* d_beta, int32_t accumulate_beta, void* workspace, int64_t workspace_bytes,
+                                 void* stream) {
+  if (d_tokens == nullptr || fea == nullptr || sdf == nullptr || beta == nullptr || d_fea == nullptr || d_beta == nullptr ||
+      workspace == nullptr)
+    return HOISDF_E_NULL;
+  if (batch <= 0 || p <= 0 || t0 < 0 || t0 + p > s_total || ld_fea < 223 || ld_dfea < 223) return HOISDF_E_SHAPE;
+  if (workspace_bytes < hoisdf_tokens_bwd_workspace_bytes(batch, p)) return HOISDF_E_SHAPE;
+  const int64_t blocks = ceil_div(batch * p, 8);
+  if (blocks > 0x7fffffffLL) return HOISDF_E_SHAPE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* partial = static_cast<float*>(workspace);
+  HOISDF_LAUNCH(tokens_bwd_kernel, static_cast<unsigned>(blocks), 256, s, d_tokens, s_total, t0, fea, ld_fea, sdf, beta, batch, p,
+                d_fea, ld_dfea, d_sdf, partial);
+  HOISDF_LAUNCH(sum_partials_kernel, 1, 256, s, static_cast<const float*>(partial), blocks, d_beta, accumulate_beta ? 1 : 0);
   return launch_status();
 }

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 16
+#define HOISDF_ABI_VERSION 17
 
 enum {
   HOISDF_OK = 0,
@@ -441,6 +441,10 @@ int hoisdf_hand_joint_metrics_fwd(const float* pred, const float* gt, int64_t ba
  *     attn_mask (mask_rows, cols) -- row r uses mask row r % mask_rows, non-zero = blocked -- blocks a column);
  *     ds = p * (dp - sum_j dp_j p_j) (ds may alias dp).  Together with hoisdf_gemm_f32 per (sample, head) these are the
  *     backward of nn.MultiheadAttention's core: dV = P^T dO, dP = dO V^T, dS = softmax'(dP), dQ = dS K / 8, dK = dS^T Q / 8.
+ *   hoisdf_tokens_bwd: backward of hoisdf_tokens_fwd (upstream main/model.py:123-126,520-531) for one token group:
+ *     d_tokens (B, s_total, 256) -> d_fea (B*P, ld_dfea >= 223) = d_tok[.., 33:] * sigmoid(sdf / beta) / beta, d_sdf (B*P,
+ *     may be NULL: the selected points' SDF is detached upstream), d_beta (1 float; the learnable hand / obj_sigmoid_beta);
+ *     workspace: hoisdf_tokens_bwd_workspace_bytes(batch, p) (per-block partials of d_beta, folded in a fixed order).
  *   hoisdf_vote_loss_bwd: JointvoteLoss (upstream common/nets/loss.py:22-61), batch-major like hoisdf_vote_joints_fwd:
  *     points (B,P,3) [m], off (L,B,P,60), cls (L,B,P,20), joint_gt (B,20,3) [mm]; d_off / d_cls = gradients of
  *     g_joint_3d * loss_joint_3d + g_cls * loss_joint_cls + g_all_joint_3d * loss_all_joint_3d (the points carry no
@@ -463,6 +467,10 @@ int hoisdf_softmax_rows_fwd(const float* s, int64_t lds, int64_t rows, int64_t c
                             int64_t mask_rows, float* p, int64_t ldp, void* stream);
 int hoisdf_softmax_rows_bwd(const float* p, int64_t ldp, const float* dp, int64_t lddp, int64_t rows, int64_t cols, float* ds,
                             int64_t ldds, void* stream);
+int64_t hoisdf_tokens_bwd_workspace_bytes(int64_t batch, int64_t p);
+int hoisdf_tokens_bwd(const float* d_tokens, int64_t s_total, int64_t t0, const float* fea, int64_t ld_fea, const float* sdf,
+                      const float* beta, int64_t batch, int64_t p, float* d_fea, int64_t ld_dfea, float* d_sdf, float* d_beta,
+                      int32_t accumulate_beta, void* workspace, int64_t workspace_bytes, void* stream);
 int hoisdf_vote_loss_bwd(const float* points, const float* off, const float* cls, const float* joint_gt, int64_t layers,
                          int64_t batch, int64_t p, float cls_dist, float g_joint_3d, float g_cls, float g_all_joint_3d,
                          float* d_off, float* d_cls, float* npos_ws, void* stream);

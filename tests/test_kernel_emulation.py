@@ -1014,3 +1014,33 @@ def test_vote_loss_backward_kernel_on_the_emulator():
     assert 0 < int(mask.sum()) < mask.numel() and float(npos[0]) == float(mask.sum())
     assert np.abs(d_off - off_t.grad.numpy()).max() < 2e-5 * float(off_t.grad.abs().max())
     assert np.abs(d_cls - cls_t.grad.numpy()).max() < 2e-5 * float(cls_t.grad.abs().max())
+
+
+def test_tokens_backward_kernel_on_the_emulator():
+    """Token assembly with the SDF activation (upstream main/model.py:123-126,520-531): gradients of the point features,
+    the SDF values and the learnable beta against autograd of the oracle's sdf_activation."""
+    lib = backward_lib()
+    vp, i64 = C.c_void_p, C.c_int64
+    lib.hoisdf_tokens_bwd_workspace_bytes.restype = i64
+    lib.hoisdf_tokens_bwd_workspace_bytes.argtypes = [i64, i64]
+    lib.hoisdf_tokens_bwd.argtypes = [vp, i64, i64, vp, i64, vp, vp, i64, i64, vp, i64, vp, vp, C.c_int32, vp, i64, vp]
+    t = torch.from_numpy
+    B, Pn, S, t0 = 2, 13, 20, 4
+    fea, sdf = t(rnd(1, B, Pn, 223)).requires_grad_(), t(rnd(2, B, Pn, lo=-0.15, hi=0.15)).requires_grad_()
+    beta = torch.tensor([0.1], requires_grad=True)
+    d_tok = rnd(3, B, S, 256)
+    sig = O.sdf_activation({"b": beta.detach().clone()}, "b", sdf.detach()[..., None])       # value check of the oracle path
+    tok_fea = fea * (torch.sigmoid(sdf[..., None] / beta) / beta)
+    assert torch.allclose(tok_fea.detach(), fea.detach() * sig, atol=1e-6)
+    (tok_fea * t(d_tok[:, t0:t0 + Pn, 33:])).sum().backward()
+    d_fea, d_sdf, d_beta = np.zeros((B * Pn, 223), np.float32), np.zeros(B * Pn, np.float32), np.zeros(1, np.float32)
+    nbytes = lib.hoisdf_tokens_bwd_workspace_bytes(B, Pn)
+    ws = np.zeros(nbytes // 4, np.float32)
+    assert lib.hoisdf_tokens_bwd(ptr(d_tok), S, t0, ptr(f32(fea.detach()).reshape(B * Pn, 223)), 223,
+                                 ptr(f32(sdf.detach()).reshape(-1)), ptr(f32(beta.detach())), B, Pn, ptr(d_fea), 223, ptr(d_sdf),
+                                 ptr(d_beta), 0, ptr(ws), nbytes, None) == 0
+    assert np.abs(d_fea - fea.grad.numpy().reshape(B * Pn, 223)).max() < 1e-5 * float(fea.grad.abs().max())
+    assert np.abs(d_sdf - sdf.grad.numpy().reshape(-1)).max() < 1e-5 * float(sdf.grad.abs().max())
+    assert abs(float(d_beta[0]) - float(beta.grad)) < 1e-4 * abs(float(beta.grad))
+    assert lib.hoisdf_tokens_bwd(ptr(d_tok), S, S - 2, ptr(d_fea), 223, ptr(d_sdf), ptr(d_beta), B, Pn, ptr(d_fea), 223, None,
+                                 ptr(d_beta), 0, ptr(ws), nbytes, None) == -2
