@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhoisdf_b200.so")
 
-ABI_VERSION = 17
+ABI_VERSION = 18
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2      # ACT_SIGMOID: hoisdf_linear_narrow_split_fwd only
 GATHER_CONCAT, GATHER_SUM = 0, 1
 
@@ -66,6 +66,16 @@ class SdfWeightsH3(C.Structure):
     _fields_ = [("w", (vp * 3) * 4), ("ldw", i64 * 4), ("b", vp * 4), ("w4", vp), ("b4", vp), ("chunk_kb", i32), ("single_pass", i32)]
 
 
+class SdfChainArgs(C.Structure):
+    _fields_ = [
+        ("a0", vp), ("lda0", i64), ("x", vp), ("ldx", i64),
+        ("lattice_index", vp), ("points", vp), ("bins", i32),
+        ("w_s1", vp), ("ldw_s1", i64), ("b_s1", vp),
+        ("w", vp * 4), ("ldw", i64 * 4), ("b", vp * 4), ("w4", vp), ("b4", vp),
+        ("rows", i64), ("clamp", f32), ("out_sdf", vp),
+    ]
+
+
 class ManoModel(C.Structure):
     _fields_ = [(n, vp) for n in ("shapedirs", "posedirs", "v_template", "j_regressor", "weights", "hands_mean")]
 
@@ -95,6 +105,7 @@ SIGNATURES = {
     "hoisdf_gather_split_fwd": (C.c_int, [C.POINTER(Pyramid), vp, i64, vp, i64, i64, i32, vp, i32, vp, vp, i64, vp]),
     "hoisdf_posenc_split_fwd": (C.c_int, [vp, vp, i64, i32, vp, vp, i64, vp]),
     "hoisdf_sdf_decoder_h3_fwd": (C.c_int, [C.POINTER(SdfWeightsH3), vp, vp, i64, i64, vp, vp, vp, vp, i64, vp, f32, vp]),
+    "hoisdf_sdf_chain_fwd": (C.c_int, [C.POINTER(SdfChainArgs), vp]),
     "hoisdf_posenc_fwd": (C.c_int, [vp, vp, i64, i32, vp, i64, i64, vp]),
     "hoisdf_sdf_decoder_fwd": (C.c_int, [C.POINTER(SdfWeights), vp, i64, i64, vp, vp, vp, f32, vp]),
     "hoisdf_sdf_pad_input": (C.c_int, [vp, i64, vp, i64, vp]),

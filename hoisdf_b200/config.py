@@ -67,6 +67,9 @@ class Config:
     # kernels of the last cascade stage: "h3" = FP16x3 GEMM draining TMEM every K block (measured max |sdf - oracle|
     # 2.4e-8 .. 3.4e-8, the fp32 FMA kernels: 2.8e-8 .. 5.2e-8; scripts/selection_error.py) | "fma" = fp32 FMA kernels
     final_stage = "h3"
+    # stage A (all candidates, single-product fp16) as ONE persistent tcgen05 kernel with the activation tile kept in
+    # shared / tensor memory (csrc/sdf_chain.cu) instead of 5 GEMM launches + posenc + head with split-half round trips
+    fused_chain = True
     screen_margin_single = 1024
     # linear_sdfin layer 0 applied to the pyramid (Model: PyramidContext.gmaps) on the FP16x3 GEMM with a TMEM drain
     # every `projection_chunk_kb` K blocks instead of the fp32 FMA kernel (3.2 ms -> 0.6 ms at batch 32)

@@ -1,0 +1,630 @@
+// The candidate chain of `sdf_infer` (upstream main/model.py:316-346 + common/nets/sdf_net.py:87-122) as ONE persistent
+// tcgen05 kernel: for a tile of 128 candidate rows
+//
+//   A0 (128 x 512)  relu(linear_sdfin.layers.0 of the gathered features)       [TMA from HBM, or gathered in-kernel]
+//   s1   linear_sdfin.layers.1   512 -> 256, ReLU        -> SKIP[:, 0:256]      (shared memory)
+//        NeRF embedding (30) + xyz (3) of the lattice point -> SKIP[:, 256:289]  (shared memory)
+//   l0   linh0   289 -> 512, ReLU                        -> ACT (128 x 512 fp16, packed pairs, TENSOR MEMORY)
+//   l1   linh1   512 -> 223, ReLU   (A operand read from TMEM)      -> H1 (shared memory)
+//   l2   linh2   [input 289 | h1 223] -> 512, ReLU       -> ACT (tensor memory)
+//   l3   linh3   512 -> 512, ReLU, fused with linh4 (512 -> 1) + tanh           -> out_sdf[row]  (4 bytes per row)
+//
+// Nothing but the 4-byte result ever goes back to HBM: the activation tile lives in shared memory (the 289-wide decoder
+// input, which the skip connection needs twice, and the 223-wide linh1 output) and in tensor memory (the two 512-wide
+// hidden activations, consumed as the A operand of the next MMA straight from TMEM, like P in the attention kernel).
+// ONE tensor-core product per K step on fp16-rounded operands (fp32 accumulation in TMEM): this is the candidate
+// SCREENING arithmetic of the verified coarse-to-fine cascade -- ~5e-5 absolute on the SDF;
+// the survivors are re-ranked by the FP16x3 chain.
+//
+// Persistent, warp-specialised, one CTA per SM, clusters of CL CTAs that walk consecutive row tiles in lock step and
+// share every weight stage (each CTA fetches 1/CL of it and multicasts it):
+//   warp 0       weight producer: [128 rows of W x 64 of K] fp16 stages (16 KB, 128-byte swizzle) through a 5-deep ring;
+//                1.9 MB of weights per tile stream from L2 (they are shared by every SM, hence always L2 hits)
+//   warp 1       tcgen05.mma issuer (one thread), M128 x N128 x K16, N processed in 128-column "quarters" that alternate
+//                between two TMEM accumulators D0 / D1, so the epilogue of one quarter overlaps the MMAs of the next
+//   warps 2..9   epilogue: tcgen05.ld of a finished quarter (2 warps per TMEM lane quarter, 64 columns each), bias, ReLU,
+//                fp16 -> shared memory (swizzled K-major operand layout) / tensor memory (tcgen05.st) / the linh4 dot
+//   warp 10      row producer: TMA of the A0 K blocks (a 4-slot ring that re-uses the H1 region, dead during s1), or of
+//                the decoder input rows in decoder-only mode
+// TMEM: D0 [0,128) D1 [128,256) ACT [256,512) -- all 512 columns.
+// SMEM: SKIP 5 x 16 KB | H1 / A0 ring 4 x 16 KB | W ring 5 x 16 KB | barriers = 226 KB.
+#include <cstdlib>
+
+#include "tc_common.cuh"
+
+namespace hoisdf {
+using namespace tc;
+
+constexpr int CH_BM = 128;
+constexpr int CH_BLK = CH_BM * 64 * 2;              // one 128 x 64 fp16 K block: 16 KB
+constexpr int CH_SKIP_BLKS = 5;                     // decoder input: 256 fea + 33 (+ padding) = 5 K blocks
+constexpr int CH_H1_BLKS = 4;                       // relu(linh1): 223 (+ padding); the A0 ring during s1
+constexpr int CH_W_STAGES = 5;
+constexpr int CH_OFF_H1 = CH_SKIP_BLKS * CH_BLK;
+constexpr int CH_OFF_W = CH_OFF_H1 + CH_H1_BLKS * CH_BLK;
+constexpr int CH_OFF_BAR = CH_OFF_W + CH_W_STAGES * CH_BLK;
+constexpr int CH_BAR_BYTES = 1024;                  // 44 mbarriers + TMEM slot + the 128-float linh4 reduction scratch
+constexpr int CH_SMEM_BYTES = CH_OFF_BAR + CH_BAR_BYTES + 1024 /*align*/;
+static_assert(CH_SMEM_BYTES <= 232448, "shared memory budget of one CTA");
+constexpr int CH_EPI_WARPS = 8;
+constexpr int CH_THREADS = 32 * (2 + CH_EPI_WARPS + 1);   // 352
+constexpr uint32_t CH_TMEM_COLS = 512;
+constexpr uint32_t CH_TM_ACT = 256;                 // first TMEM column of the packed fp16 activation tile
+
+enum { CH_MODE_ROWS = 0 /* A0 rows by TMA */, CH_MODE_DECODER = 1 /* decoder input rows by TMA, no s1 */ };
+
+struct ChainParams {
+  const float* __restrict__ b_s1;
+  const float* __restrict__ b[4];
+  const float* __restrict__ w4;
+  const float* __restrict__ b4;
+  const int32_t* __restrict__ lattice_index;
+  const float* __restrict__ points;
+  float* __restrict__ out;
+  int64_t rows;
+  int tiles;          // ceil(rows / 128)
+  int bins;
+  int mode;
+  float clamp;
+};
+
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31};"
+      ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]), "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// byte offset of 16-byte chunk `c` (8 halfs) of row `r` inside a 128 x 64 fp16 K block with 128-byte swizzle
+__device__ __forceinline__ uint32_t sw128_off(int r, int c) {
+  return static_cast<uint32_t>((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+}
+
+template <int CL>
+__global__ void __launch_bounds__(CH_THREADS, 1)
+sdf_chain_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__ CUtensorMap map_ws1,
+                 const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_w1,
+                 const __grid_constant__ CUtensorMap map_w2a, const __grid_constant__ CUtensorMap map_w2b,
+                 const __grid_constant__ CUtensorMap map_w3, const ChainParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw);
+  const uint32_t bars = base + CH_OFF_BAR;
+  // barrier map (8 bytes each)
+  auto bar_wfull = [&](int s) { return bars + 8u * s; };                       // 0..4
+  auto bar_wempty = [&](int s) { return bars + 8u * (5 + s); };                // 5..9
+  auto bar_afull = [&](int s) { return bars + 8u * (10 + s); };                // 10..13
+  auto bar_aempty = [&](int s) { return bars + 8u * (14 + s); };               // 14..17
+  auto bar_dfull = [&](int b) { return bars + 8u * (18 + b); };                // 18..19
+  auto bar_dempty = [&](int b) { return bars + 8u * (20 + b); };               // 20..21
+  auto bar_skip = [&](int kb) { return bars + 8u * (22 + kb); };               // 22..26  SKIP K block written
+  auto bar_act = [&](int kb) { return bars + 8u * (27 + kb); };                // 27..34  ACT K block (64 columns) written
+  auto bar_h1 = [&](int kb) { return bars + 8u * (35 + kb); };                 // 35..38  H1 K block written
+  const uint32_t bar_rfree = bars + 8u * 39;                                   // SKIP / H1 region reusable (linh2 done)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + CH_OFF_BAR + 8 * 44);
+  float* red = reinterpret_cast<float*>(gen + CH_OFF_BAR + 512);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
+  const int cluster = static_cast<int>(blockIdx.x) / CL;
+  const int nclusters = static_cast<int>(gridDim.x) / CL;
+  const int npairs = (p.tiles + CL - 1) / CL;
+  constexpr uint16_t kAllCtas = static_cast<uint16_t>((1u << CL) - 1u);
+  const bool decoder_only = p.mode == CH_MODE_DECODER;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_rows) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ws1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w2a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w2b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w3) : "memory");
+    for (int s = 0; s < CH_W_STAGES; ++s) {
+      mbar_init(bar_wfull(s), 1);
+      mbar_init(bar_wempty(s), CL);          // every CTA's tensor core must have consumed the stage
+    }
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(bar_afull(s), 1);
+      mbar_init(bar_aempty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_dfull(b), 1);
+      mbar_init(bar_dempty(b), CH_EPI_WARPS);
+    }
+    // SKIP blocks: written by 4 epilogue warps each (block 4, the embedding: by all 8) -- or by one TMA in decoder mode
+    for (int kb = 0; kb < 5; ++kb) mbar_init(bar_skip(kb), decoder_only ? 1 : (kb < 4 ? 4 : CH_EPI_WARPS));
+    for (int kb = 0; kb < 8; ++kb) mbar_init(bar_act(kb), 4);
+    for (int kb = 0; kb < 4; ++kb) mbar_init(bar_h1(kb), 4);
+    mbar_init(bar_rfree, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(CH_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (CL > 1) cluster_sync_all();            // peers' barriers are initialised before any multicast lands there
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ weight producer
+    if (lane == 0) {
+      uint32_t wi = 0;
+      auto put = [&](const CUtensorMap* m, int row0, int col0) {
+        const int s = static_cast<int>(wi % CH_W_STAGES);
+        const uint32_t ph = (wi / CH_W_STAGES) & 1u;
+        mbar_wait(bar_wempty(s), ph ^ 1u);
+        mbar_expect_tx(bar_wfull(s), CH_BLK);
+        const uint32_t dst = base + CH_OFF_W + s * CH_BLK + rank * (CH_BLK / CL);
+        if (CL > 1) tma_load_2d_mc(dst, m, bar_wfull(s), col0, row0 + static_cast<int>(rank) * (128 / CL), kAllCtas);
+        else tma_load_2d(dst, m, bar_wfull(s), col0, row0);
+        ++wi;
+      };
+      for (int pair = cluster; pair < npairs; pair += nclusters) {
+        if (!decoder_only)
+          for (int kb = 0; kb < 8; ++kb)
+            for (int h = 0; h < 2; ++h) put(&map_ws1, 128 * h, 64 * kb);
+        for (int q = 0; q < 4; ++q)
+          for (int kb = 0; kb < 5; ++kb) put(&map_w0, 128 * q, 64 * kb);
+        for (int q = 0; q < 2; ++q)
+          for (int kb = 0; kb < 8; ++kb) put(&map_w1, 128 * q, 64 * kb);
+        for (int q = 0; q < 4; ++q)
+          for (int kb = 0; kb < 9; ++kb) {
+            if (kb < 5) put(&map_w2a, 128 * q, 64 * kb);
+            else put(&map_w2b, 128 * q, 64 * (kb - 5));
+          }
+        for (int q = 0; q < 4; ++q)
+          for (int kb = 0; kb < 8; ++kb) put(&map_w3, 128 * q, 64 * kb);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      uint32_t wi = 0, ai = 0, du[2] = {0u, 0u}, it = 0;
+      const uint32_t idesc128 = umma_idesc_f16(CH_BM, 128), idesc96 = umma_idesc_f16(CH_BM, 96);
+      auto d_acquire = [&](int b) {
+        mbar_wait(bar_dempty(b), (du[b] & 1u) ^ 1u);
+        tcgen05_fence_after();
+      };
+      auto d_publish = [&](int b) {
+        umma_commit(bar_dfull(b));
+        ++du[b];
+      };
+      // one weight stage: nk MMAs of K = 16; A from shared memory (a_smem != 0) or from TMEM
+      auto stage = [&](uint32_t d, uint32_t a_smem, uint32_t a_tmem, uint32_t idesc, int nk, bool first) {
+        const int s = static_cast<int>(wi % CH_W_STAGES);
+        mbar_wait(bar_wfull(s), (wi / CH_W_STAGES) & 1u);
+        tcgen05_fence_after();
+        const uint64_t db = umma_desc_sw128(base + CH_OFF_W + s * CH_BLK);
+        if (a_smem != 0u) {
+          const uint64_t da = umma_desc_sw128(a_smem);
+#pragma unroll 4
+          for (int kk = 0; kk < nk; ++kk)
+            umma_f16(d, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc,
+                     (first && kk == 0) ? 0u : 1u);
+        } else {
+#pragma unroll 4
+          for (int kk = 0; kk < nk; ++kk)
+            umma_f16_ts(d, a_tmem + static_cast<uint32_t>(kk * 8), db + static_cast<uint64_t>(kk * 2), idesc,
+                        (first && kk == 0) ? 0u : 1u);
+        }
+        if (CL > 1) umma_commit_mc(bar_wempty(s), kAllCtas);
+        else umma_commit(bar_wempty(s));
+        ++wi;
+      };
+      const uint32_t d0 = tmem_base, d1 = tmem_base + 128u, act = tmem_base + CH_TM_ACT;
+      for (int pair = cluster; pair < npairs; pair += nclusters, ++it) {
+        const uint32_t tp = it & 1u;
+        // ---- s1: A0 K blocks from the row ring, both 128-column halves of the 256 outputs per K block
+        if (!decoder_only) {
+          d_acquire(0);
+          d_acquire(1);
+          for (int kb = 0; kb < 8; ++kb, ++ai) {
+            const int s = static_cast<int>(ai & 3u);
+            mbar_wait(bar_afull(s), (ai >> 2) & 1u);
+            tcgen05_fence_after();
+            const uint32_t a0 = base + CH_OFF_H1 + s * CH_BLK;
+            stage(d0, a0, 0u, idesc128, 4, kb == 0);
+            stage(d1, a0, 0u, idesc128, 4, kb == 0);
+            umma_commit(bar_aempty(s));
+          }
+          d_publish(0);
+          d_publish(1);
+        }
+        // ---- l0: SKIP (shared memory) -> 512
+        for (int q = 0; q < 4; ++q) {
+          const int b = q & 1;
+          d_acquire(b);
+          for (int kb = 0; kb < 5; ++kb) {
+            if (q == 0) {
+              mbar_wait(bar_skip(kb), tp);
+              tcgen05_fence_after();
+            }
+            stage(b ? d1 : d0, base + kb * CH_BLK, 0u, idesc128, kb == 4 ? 3 : 4, kb == 0);
+          }
+          d_publish(b);
+        }
+        // ---- l1: ACT (TMEM) -> 223  (quarters of 128 and 96 columns)
+        for (int q = 0; q < 2; ++q) {
+          d_acquire(q);
+          for (int kb = 0; kb < 8; ++kb) {
+            if (q == 0) {
+              mbar_wait(bar_act(kb), 0u);                 // first completion of this barrier in the tile
+              tcgen05_fence_after();
+            }
+            stage(q ? d1 : d0, 0u, act + static_cast<uint32_t>(kb * 32), q ? idesc96 : idesc128, 4, kb == 0);
+          }
+          d_publish(q);
+        }
+        // ---- l2: [SKIP | H1] (shared memory) -> 512
+        for (int q = 0; q < 4; ++q) {
+          const int b = q & 1;
+          d_acquire(b);
+          for (int kb = 0; kb < 9; ++kb) {
+            if (q == 0 && kb >= 5) {
+              mbar_wait(bar_h1(kb - 5), tp);
+              tcgen05_fence_after();
+            }
+            stage(b ? d1 : d0, base + kb * CH_BLK, 0u, idesc128, kb == 8 ? 2 : (kb == 4 ? 3 : 4), kb == 0);
+          }
+          d_publish(b);
+        }
+        umma_commit(bar_rfree);                            // SKIP / H1 no longer read: the next tile's rows may land
+        // ---- l3: ACT (TMEM) -> 512 (the epilogue folds linh4 + tanh)
+        for (int q = 0; q < 4; ++q) {
+          const int b = q & 1;
+          d_acquire(b);
+          for (int kb = 0; kb < 8; ++kb) {
+            if (q == 0) {
+              mbar_wait(bar_act(kb), 1u);                 // second completion in the tile
+              tcgen05_fence_after();
+            }
+            stage(b ? d1 : d0, 0u, act + static_cast<uint32_t>(kb * 32), idesc128, 4, kb == 0);
+          }
+          d_publish(b);
+        }
+      }
+    }
+  } else if (warp == 2 + CH_EPI_WARPS) {
+    // ------------------------------------------------------------------ row producer (TMA)
+    if (lane == 0) {
+      uint32_t ai = 0, it = 0;
+      for (int pair = cluster; pair < npairs; pair += nclusters, ++it) {
+        const int row0 = (pair * CL + static_cast<int>(rank)) * CH_BM;   // beyond the last row: zero-filled tile
+        if (it > 0) mbar_wait(bar_rfree, (it - 1) & 1u);
+        if (decoder_only) {
+          for (int kb = 0; kb < 5; ++kb) {
+            mbar_expect_tx(bar_skip(kb), CH_BLK);
+            tma_load_2d(base + kb * CH_BLK, &map_rows, bar_skip(kb), 64 * kb, row0);
+          }
+        } else {
+          for (int kb = 0; kb < 8; ++kb, ++ai) {
+            const int s = static_cast<int>(ai & 3u);
+            mbar_wait(bar_aempty(s), ((ai >> 2) & 1u) ^ 1u);
+            mbar_expect_tx(bar_afull(s), CH_BLK);
+            tma_load_2d(base + CH_OFF_H1 + s * CH_BLK, &map_rows, bar_afull(s), 64 * kb, row0);
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (8 warps)
+    const int ew = warp - 2;
+    const int lq = warp & 3;                    // TMEM lane quarter this warp may read
+    const int h = ew >> 2;                      // which 64-column half of a 128-column quarter it owns
+    const int r = lq * 32 + lane;               // row inside the tile
+    const uint32_t lane_addr = static_cast<uint32_t>(lq * 32) << 16;
+    uint32_t eu[2] = {0u, 0u};
+    auto d_wait = [&](int b) {
+      mbar_wait(bar_dfull(b), eu[b] & 1u);
+      tcgen05_fence_after();
+    };
+    auto d_release = [&](int b) {               // after tcgen05.wait::ld of everything this warp reads from D_b
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_dempty(b));
+      ++eu[b];
+    };
+    // 64 accumulator columns of this warp -> v = relu(acc + bias[c0 + j]) packed as 32 fp16 pairs
+    auto load_pack = [&](int b, const float* bias, int c0, int nvalid, uint32_t* pk) {
+      uint32_t a[64];
+      const uint32_t t0 = tmem_base + static_cast<uint32_t>(b * 128 + h * 64) + lane_addr;
+      tmem_ld32(t0, a);
+      tmem_ld32(t0 + 32, a + 32);
+      tmem_ld_wait();
+      if (nvalid >= 64) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
+          pk[2 * j] = cvt_f16x2_sat(fmaxf(__uint_as_float(a[4 * j]) + bb.x, 0.f),
+                                    fmaxf(__uint_as_float(a[4 * j + 1]) + bb.y, 0.f));
+          pk[2 * j + 1] = cvt_f16x2_sat(fmaxf(__uint_as_float(a[4 * j + 2]) + bb.z, 0.f),
+                                        fmaxf(__uint_as_float(a[4 * j + 3]) + bb.w, 0.f));
+        }
+      } else {                                  // ragged tail (linh1's last 31 outputs): guarded scalar loads
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int c = 2 * j;
+          const float b0 = c < nvalid ? __ldg(bias + c0 + c) : 0.f;
+          const float b1 = c + 1 < nvalid ? __ldg(bias + c0 + c + 1) : 0.f;
+          const float v0 = c < nvalid ? fmaxf(__uint_as_float(a[c]) + b0, 0.f) : 0.f;
+          const float v1 = c + 1 < nvalid ? fmaxf(__uint_as_float(a[c + 1]) + b1, 0.f) : 0.f;
+          pk[j] = cvt_f16x2_sat(v0, v1);
+        }
+      }
+    };
+    auto store_block = [&](uint32_t blk_off, const uint32_t* pk) {      // this lane's 128-byte row of a K block
+      uint8_t* blk = gen + blk_off;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(blk + sw128_off(r, c)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+    };
+    auto publish_smem = [&](uint32_t bar) {
+      fence_async_smem();                       // generic-proxy stores -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar);
+    };
+    // quarter -> ACT (TMEM): columns [128 q + 64 h, +64) = packed columns [64 q + 32 h, +32)
+    auto quarter_to_act = [&](int q, const float* bias) {
+      const int b = q & 1;
+      d_wait(b);
+      uint32_t pk[32];
+      load_pack(b, bias, 128 * q + 64 * h, 64, pk);
+      d_release(b);
+      tmem_st32(tmem_base + CH_TM_ACT + static_cast<uint32_t>(64 * q + 32 * h) + lane_addr, pk);
+      tmem_st_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_act(2 * q + h));
+    };
+
+    for (int pair = cluster; pair < npairs; pair += nclusters) {
+      const int64_t row = static_cast<int64_t>(pair * CL + static_cast<int>(rank)) * CH_BM + r;
+      const bool row_ok = row < p.rows;
+      if (!decoder_only) {
+        // ---- NeRF embedding + xyz -> SKIP block 4 (columns 256..319).  Every MMA that read the previous tile's SKIP
+        // has completed: this warp has already seen that tile's linh3 accumulators.
+        uint32_t pk[32];
+        if (h == 0) {
+          float x[3] = {0.f, 0.f, 0.f};
+          if (row_ok) {
+            if (p.lattice_index != nullptr) lattice_point(p.lattice_index[row], p.bins, x[0], x[1], x[2]);
+            else { x[0] = p.points[row * 3 + 0]; x[1] = p.points[row * 3 + 1]; x[2] = p.points[row * 3 + 2]; }
+          }
+          float e[32];
+#pragma unroll
+          for (int oct = 0; oct < 5; ++oct) {
+#pragma unroll
+            for (int w = 0; w < 3; ++w) {
+              const float a = x[w] * static_cast<float>(1 << oct);     // exact scaling by 2^k
+              e[oct * 6 + w] = sinf(a);
+              e[oct * 6 + 3 + w] = cosf(a);
+            }
+          }
+          e[30] = x[0];
+          e[31] = x[1];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = cvt_f16x2_sat(e[2 * j], e[2 * j + 1]);
+          uint8_t* blk = gen + 4 * CH_BLK;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<uint4*>(blk + sw128_off(r, c)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        } else {
+          float z = 0.f;
+          if (row_ok) {
+            if (p.lattice_index != nullptr) {
+              float x0, x1;
+              lattice_point(p.lattice_index[row], p.bins, x0, x1, z);
+            } else {
+              z = p.points[row * 3 + 2];
+            }
+          }
+          uint8_t* blk = gen + 4 * CH_BLK;
+          *reinterpret_cast<uint4*>(blk + sw128_off(r, 4)) = make_uint4(cvt_f16x2_sat(z, 0.f), 0u, 0u, 0u);
+#pragma unroll
+          for (int c = 5; c < 8; ++c) *reinterpret_cast<uint4*>(blk + sw128_off(r, c)) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        publish_smem(bar_skip(4));
+        // ---- s1 epilogue: D0 -> SKIP blocks 0 / 1, D1 -> SKIP blocks 2 / 3
+        for (int b = 0; b < 2; ++b) {
+          d_wait(b);
+          load_pack(b, p.b_s1, 128 * b + 64 * h, 64, pk);
+          d_release(b);
+          store_block(static_cast<uint32_t>(2 * b + h) * CH_BLK, pk);
+          publish_smem(bar_skip(2 * b + h));
+        }
+      }
+      // ---- l0 -> ACT
+      for (int q = 0; q < 4; ++q) quarter_to_act(q, p.b[0]);
+      // ---- l1 -> H1 blocks (223 valid outputs: quarter 1 has 96 accumulator columns, 95 of them real)
+      for (int q = 0; q < 2; ++q) {
+        d_wait(q);
+        uint32_t pk[32];
+        const int c0 = 128 * q + 64 * h;
+        const int nvalid = min(64, 223 - c0);
+        load_pack(q, p.b[1], c0, nvalid, pk);
+        d_release(q);
+        store_block(CH_OFF_H1 + static_cast<uint32_t>(2 * q + h) * CH_BLK, pk);
+        publish_smem(bar_h1(2 * q + h));
+      }
+      // ---- l2 -> ACT
+      for (int q = 0; q < 4; ++q) quarter_to_act(q, p.b[2]);
+      // ---- l3 + linh4: partial dot product of relu(acc + b3) with w4 over this warp's 4 x 64 columns
+      float part = 0.f;
+      for (int q = 0; q < 4; ++q) {
+        const int b = q & 1;
+        d_wait(b);
+        uint32_t a[64];
+        const uint32_t t0 = tmem_base + static_cast<uint32_t>(b * 128 + h * 64) + lane_addr;
+        tmem_ld32(t0, a);
+        tmem_ld32(t0 + 32, a + 32);
+        tmem_ld_wait();
+        d_release(b);
+        const int c0 = 128 * q + 64 * h;
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b[3] + c0) + j);
+          const float4 ww = __ldg(reinterpret_cast<const float4*>(p.w4 + c0) + j);
+          s4[0] = fmaf(fmaxf(__uint_as_float(a[4 * j]) + bb.x, 0.f), ww.x, s4[0]);
+          s4[1] = fmaf(fmaxf(__uint_as_float(a[4 * j + 1]) + bb.y, 0.f), ww.y, s4[1]);
+          s4[2] = fmaf(fmaxf(__uint_as_float(a[4 * j + 2]) + bb.z, 0.f), ww.z, s4[2]);
+          s4[3] = fmaf(fmaxf(__uint_as_float(a[4 * j + 3]) + bb.w, 0.f), ww.w, s4[3]);
+        }
+        part += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+      }
+      if (h == 1) red[r] = part;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + lq) : "memory");     // the two warps of this lane quarter
+      if (h == 0 && row_ok) {
+        float t = tanhf(part + red[r] + __ldg(p.b4));
+        if (p.clamp > 0.f) t = fminf(fmaxf(t, -p.clamp), p.clamp);
+        p.out[row] = t;
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (CL > 1) cluster_sync_all();              // no CTA exits while a peer may still multicast to it / signal its barriers
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(CH_TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+static bool chain_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  return make_tiled_map(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+}
+
+template <int CL>
+static int chain_max_clusters() {
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  auto kern = sdf_chain_kernel<CL>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_BYTES);
+  int n = 0;
+  if (CL == 1) {
+    cudaDeviceProp prop;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    n = cudaGetDeviceProperties(&prop, dev) == cudaSuccess ? prop.multiProcessorCount : kNumSMs;
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(kNumSMs / CL * CL);
+    cfg.blockDim = dim3(CH_THREADS);
+    cfg.dynamicSmemBytes = CH_SMEM_BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) n = kNumSMs / CL;
+    (void)cudaGetLastError();
+  }
+  cached = n;
+  return n;
+}
+
+template <int CL>
+static int chain_launch(const CUtensorMap* maps, const ChainParams& p, cudaStream_t s) {
+  auto kern = sdf_chain_kernel<CL>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_BYTES);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  const int64_t npairs = ceil_div(p.tiles, CL);
+  const int64_t clusters = npairs < chain_max_clusters<CL>() ? npairs : chain_max_clusters<CL>();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(clusters * CL));
+  cfg.blockDim = dim3(CH_THREADS);
+  cfg.dynamicSmemBytes = CH_SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], p);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  return launch_status();
+}
+
+}  // namespace hoisdf
+
+using namespace hoisdf;
+
+HOISDF_API int hoisdf_sdf_chain_fwd(const hoisdf_sdf_chain_args* a, void* stream) {
+  if (a == nullptr || a->out_sdf == nullptr || a->w4 == nullptr || a->b4 == nullptr) return HOISDF_E_NULL;
+  const bool decoder_only = a->x != nullptr;
+  if (decoder_only ? a->a0 != nullptr : a->a0 == nullptr) return HOISDF_E_NULL;
+  if (!decoder_only && (a->w_s1 == nullptr || a->b_s1 == nullptr || (a->lattice_index == nullptr && a->points == nullptr)))
+    return HOISDF_E_NULL;
+  for (int l = 0; l < 4; ++l)
+    if (a->w[l] == nullptr || a->b[l] == nullptr) return HOISDF_E_NULL;
+  if (a->rows == 0) return HOISDF_OK;
+  if (a->rows < 0 || a->rows >= (int64_t(1) << 30)) return HOISDF_E_SHAPE;
+  // weight pitches: linh0 (512, >= 296) zero beyond column 289; linh1 (223, >= 512); linh2 (512, >= 520) in the
+  // [input 289 | 0 x7 | h1 223 | 0] column layout; linh3 (512, >= 512)
+  if (a->ldw[0] < 296 || a->ldw[1] < 512 || a->ldw[2] < 520 || a->ldw[3] < 512) return HOISDF_E_SHAPE;
+  if (!decoder_only && (a->ldw_s1 < 512 || a->lda0 < 512)) return HOISDF_E_SHAPE;
+  if (decoder_only && a->ldx < 296) return HOISDF_E_SHAPE;
+  for (int l = 0; l < 4; ++l)
+    if ((a->ldw[l] & 7) || !aligned16(a->w[l])) return HOISDF_E_ALIGN;
+  if (decoder_only ? ((a->ldx & 7) || !aligned16(a->x))
+                   : ((a->lda0 & 7) || !aligned16(a->a0) || (a->ldw_s1 & 7) || !aligned16(a->w_s1)))
+    return HOISDF_E_ALIGN;
+  const int64_t tiles = ceil_div(a->rows, CH_BM);
+  const int cl = tiles >= 2 ? 2 : 1;
+  CUtensorMap maps[7];
+  const int wbox = 128 / cl;
+  bool ok = decoder_only ? chain_map(&maps[0], a->x, a->rows, 296, a->ldx, CH_BM)
+                         : chain_map(&maps[0], a->a0, a->rows, 512, a->lda0, CH_BM);
+  ok = ok && (decoder_only ? chain_map(&maps[1], a->w[0], 512, 296, a->ldw[0], wbox)      // unused in this mode
+                           : chain_map(&maps[1], a->w_s1, 256, 512, a->ldw_s1, wbox));
+  ok = ok && chain_map(&maps[2], a->w[0], 512, 296, a->ldw[0], wbox);
+  ok = ok && chain_map(&maps[3], a->w[1], 223, 512, a->ldw[1], wbox);
+  ok = ok && chain_map(&maps[4], a->w[2], 512, 296, a->ldw[2], wbox);
+  ok = ok && chain_map(&maps[5], a->w[2] + 296, 512, 224, a->ldw[2], wbox);
+  ok = ok && chain_map(&maps[6], a->w[3], 512, 512, a->ldw[3], wbox);
+  if (!ok) return HOISDF_E_UNSUPPORTED;
+  ChainParams p{};
+  p.b_s1 = a->b_s1;
+  for (int l = 0; l < 4; ++l) p.b[l] = a->b[l];
+  p.w4 = a->w4; p.b4 = a->b4;
+  p.lattice_index = a->lattice_index; p.points = a->points; p.bins = a->bins;
+  p.out = a->out_sdf; p.rows = a->rows; p.tiles = static_cast<int>(tiles);
+  p.mode = decoder_only ? CH_MODE_DECODER : CH_MODE_ROWS;
+  p.clamp = a->clamp;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (cl == 2) return chain_launch<2>(maps, p, s);
+  return chain_launch<1>(maps, p, s);
+}

@@ -308,6 +308,9 @@ class Model(nn.Module):
             hs, rs, hs2 = h3_buffers(n)
             ops.gather(gmaps, uv, b, mode=ops.GATHER_SUM, out=hs.head(n), row_offsets=row_offsets,
                        rows_per_sample=rows_per_sample, bias=sdfin[0].b, act=ops.ACT_RELU, img_hw=cfg.input_img_shape)
+            if single and cfg.fused_chain:
+                ops.sdf_chain(packed, out, sdfin1=sdfin[1], a0=hs.head(n), lattice_index=index, bins=cfg.bins_n)
+                return
             ops.linear(hs.head(n), sdfin[1], ops.ACT_RELU, out=rs.head(n).window(0, 256),
                        chunk_kb=chunk_kb, single=single)
             ops.posenc(rs.head(n), lattice_index=index, bins=cfg.bins_n)

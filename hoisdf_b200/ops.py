@@ -662,6 +662,43 @@ def sdf_decoder(packed: PackedSdfDecoder, rows_buf, h_a=None, h_b=None, clamp: f
     return out
 
 
+def sdf_chain(packed: PackedSdfDecoder, out: torch.Tensor, *, sdfin1: Optional[PackedLinear] = None,
+              a0: Optional[SplitRows] = None, x: Optional[SplitRows] = None, lattice_index=None, points=None,
+              bins: int = 64, clamp: float = 0.0) -> torch.Tensor:
+    """The fused candidate chain (csrc/sdf_chain.cu): linear_sdfin.layers.1 -> posenc/xyz -> linh0..linh4 -> tanh in ONE
+    persistent tcgen05 kernel, single-product fp16 (screening arithmetic).  `a0` = hi plane of relu(linear_sdfin.layers.0)
+    rows (rows mode) or `x` = hi plane of the decoder input rows (decoder-only mode)."""
+    assert packed.struct_h3 is not None and (a0 is None) != (x is None)
+    src = a0 if a0 is not None else x
+    rows = src.rows
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() >= rows
+    a = _capi.SdfChainArgs()
+    if a0 is not None:
+        assert a0.cols >= 512 and sdfin1 is not None and sdfin1.h3 is not None and sdfin1.n == 256
+        a.a0, a.lda0 = a0.hi_ptr, a0.ld
+        a.w_s1, a.ldw_s1, a.b_s1 = sdfin1.h3.plane_ptr(1), sdfin1.h3.ld, _ptr(sdfin1.b)
+        a.lattice_index, a.points, a.bins = _ptr(lattice_index), _ptr(points), int(bins)
+    else:
+        assert x.cols >= DEC_IN and x.ld >= SKIP_OFF_H
+        a.x, a.ldx = x.hi_ptr, x.ld
+    h3 = packed.struct_h3
+    for l in range(4):
+        a.w[l], a.ldw[l], a.b[l] = h3.w[l][1], h3.ldw[l], h3.b[l]
+    a.w4, a.b4 = h3.w4, h3.b4
+    a.rows, a.clamp, a.out_sdf = rows, float(clamp), out.data_ptr()
+    _count(1)
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    check(lib.hoisdf_sdf_chain_fwd(C.byref(a), _stream()), "hoisdf_sdf_chain_fwd")
+    if PROFILE is not None:
+        e1.record()
+        flops = SDF_DECODER_FLOPS + (2.0 * 512 * 256 if a0 is not None else 0.0)
+        PROFILE.append(("sdf_chain", flops * rows, e0, e1, "sdf_chain rows=%d %s single" % (
+            rows, "rows" if a0 is not None else "decoder")))
+    return out
+
+
 def sdf_pad_input(x: torch.Tensor):
     x = _f32c(x, "SDFDecoder input")
     rows = x.shape[0]

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 17
+#define HOISDF_ABI_VERSION 18
 
 enum {
   HOISDF_OK = 0,
@@ -289,6 +289,29 @@ typedef struct {
 int hoisdf_sdf_decoder_h3_fwd(const hoisdf_sdf_weights_h3* wts, uint16_t* x_hi, uint16_t* x_lo, int64_t ldx,
                               int64_t rows, uint16_t* ha_hi, uint16_t* ha_lo, uint16_t* hb_hi, uint16_t* hb_lo,
                               int64_t ldh, float* out_sdf, float clamp, void* stream);
+
+/* The candidate chain of sdf_infer as ONE persistent tcgen05 kernel (csrc/sdf_chain.cu) -- upstream
+ * main/model.py:330-346 (linear_sdfin.layers.1 -> NeRF embedding + xyz -> SDFDecoder, common/nets/sdf_net.py:87-122)
+ * on single-product fp16 tensor-core arithmetic (the SCREENING stage of the selection cascade; ~5e-5 absolute).
+ * Activations never leave the SM: 4 bytes per row (the SDF value) are written.
+ *   rows mode     a0 != NULL: (rows, 512) fp16 = relu(bias + gathered projected maps), i.e. the output of
+ *                 linear_sdfin.layers.0; posenc / xyz are computed in the kernel from lattice_index (or points).
+ *   decoder mode  x != NULL: (rows, >= 296) fp16 decoder input rows [fea 256 | posenc 30 | xyz 3 | 0 x 7];
+ *                 w_s1 / lattice_index / points unused (SDFDecoder.forward in isolation, BASELINE configs[4]).
+ * Weights are the fp16 "B" planes (w_hi) that hoisdf_pack_h3 writes: w_s1 (256, >= 512); w[0] linh0 (512, >= 296,
+ * zero beyond column 289); w[1] linh1 (223, >= 512); w[2] linh2 (512, >= 520) in the column layout
+ * [input 289 | 0 x 7 | h1 223 | 0]; w[3] linh3 (512, >= 512); w4 (512) / b4 (1) fp32 (linh4). */
+typedef struct {
+  const uint16_t* a0; int64_t lda0;
+  const uint16_t* x; int64_t ldx;
+  const int32_t* lattice_index; const float* points; int32_t bins;
+  const uint16_t* w_s1; int64_t ldw_s1; const float* b_s1;
+  const uint16_t* w[4]; int64_t ldw[4]; const float* b[4];
+  const float* w4; const float* b4;
+  int64_t rows; float clamp; float* out_sdf;
+} hoisdf_sdf_chain_args;
+
+int hoisdf_sdf_chain_fwd(const hoisdf_sdf_chain_args* args, void* stream);
 
 /* Expand a plain (rows, 289) decoder input (the upstream SDFDecoder.forward argument) into the padded
  * row buffer layout above. */
