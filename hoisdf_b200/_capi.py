@@ -34,7 +34,7 @@ class LinearH3Args(C.Structure):
         ("w_a", vp), ("w_b", vp), ("w_c", vp), ("ldw", i64), ("bias", vp), ("residual", vp),
         ("y", vp), ("ldy", i64), ("y_hi", vp), ("y_lo", vp), ("ldyh", i64),
         ("m", i64), ("n", i64), ("k", i64), ("act", i32), ("chunk_kb", i32),
-        ("res_hi", vp), ("res_lo", vp), ("ldr", i64), ("single_pass", i32),
+        ("res_hi", vp), ("res_lo", vp), ("ldr", i64), ("single_pass", i32), ("w_scale", f32),
     ]
 
 
@@ -46,7 +46,7 @@ class ConvH3Args(C.Structure):
         ("out_h", i64), ("out_w", i64), ("cout", i64),
         ("y", vp), ("y_hi", vp), ("y_lo", vp), ("y_sx", i64), ("y_sy", i64), ("y_sb", i64),
         ("act", i32), ("chunk_kb", i32),
-        ("res_hi", vp), ("res_lo", vp), ("ldr", i64), ("single_pass", i32),
+        ("res_hi", vp), ("res_lo", vp), ("ldr", i64), ("single_pass", i32), ("w_scale", f32),
     ]
 
 

@@ -79,6 +79,7 @@ struct H3Params {
   // (wy x wx) block
   int taps, cin_blocks, out_w, out_h, stride, wx, wy;
   int8_t dy[16], dx[16];
+  float w_scale;            // power-of-two scale the packed weights were divided by (|w| >= 32 layers); 1 normally
 };
 
 // Accuracy note (why the accumulator is drained in chunks).  The tensor core TRUNCATES when it adds a K=16 partial
@@ -277,7 +278,7 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
     const int ew = warp - 2;
     const int q = warp & 3;                                         // TMEM lane quarter this warp may read
     const int hcol = ew >> 2;                                       // which 128-column half of the tile it owns
-    const float oscale = single ? 1.f : kLoInv;                     // single product: x_hi . w_hi is unscaled
+    const float oscale = (single ? 1.f : kLoInv) * p.w_scale;       // single product: x_hi . w_hi is unscaled
     const uint32_t box_sh = epi + static_cast<uint32_t>(ew) * H3_EPI_SLOT;
     uint8_t* box = gen + H3_STAGES * H3_STAGE_BYTES + ew * H3_EPI_SLOT;
     uint32_t cc = 0;
@@ -754,6 +755,7 @@ HOISDF_API int hoisdf_linear_h3_fwd(const hoisdf_linear_h3_args* a, void* stream
   p.chunk_kb = a->chunk_kb;
   p.single = a->single_pass ? 1 : 0;
   p.w_rows = w_rows; p.nstages = h3_stage_count(w_rows);
+  p.w_scale = a->w_scale > 0.f ? a->w_scale : 1.f;
   if (a->res_hi != nullptr || a->res_lo != nullptr) {
     if (a->res_hi == nullptr || a->res_lo == nullptr) return HOISDF_E_NULL;
     if (out_mode == H3_OUT_F32_DIRECT || a->residual != nullptr || (a->n & 31)) return HOISDF_E_UNSUPPORTED;
@@ -847,6 +849,7 @@ HOISDF_API int hoisdf_conv_h3_fwd(const hoisdf_conv_h3_args* a, void* stream) {
   p.chunk_kb = a->chunk_kb;
   p.single = a->single_pass ? 1 : 0;
   p.w_rows = w_rows; p.nstages = h3_stage_count(w_rows);
+  p.w_scale = a->w_scale > 0.f ? a->w_scale : 1.f;
   p.taps = a->taps; p.cin_blocks = static_cast<int>(a->cin / H3_BK);
   p.out_w = static_cast<int>(a->out_w); p.out_h = static_cast<int>(a->out_h); p.stride = a->stride;
   p.wx = wx; p.wy = wy;

@@ -65,6 +65,7 @@ struct ChainParams {
   int tiles;          // ceil(rows / 128)
   int bins;
   int mode;
+  int wstages;        // depth of the weight ring actually used (<= CH_W_STAGES; developer knob)
   float clamp;
 };
 
@@ -127,6 +128,7 @@ sdf_chain_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_cons
   const int npairs = (p.tiles + CL - 1) / CL;
   constexpr uint16_t kAllCtas = static_cast<uint16_t>((1u << CL) - 1u);
   const bool decoder_only = p.mode == CH_MODE_DECODER;
+  const uint32_t nst = static_cast<uint32_t>(p.wstages);
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_rows) : "memory");
@@ -172,8 +174,8 @@ sdf_chain_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_cons
     if (lane == 0) {
       uint32_t wi = 0;
       auto put = [&](const CUtensorMap* m, int row0, int col0) {
-        const int s = static_cast<int>(wi % CH_W_STAGES);
-        const uint32_t ph = (wi / CH_W_STAGES) & 1u;
+        const int s = static_cast<int>(wi % nst);
+        const uint32_t ph = (wi / nst) & 1u;
         mbar_wait(bar_wempty(s), ph ^ 1u);
         mbar_expect_tx(bar_wfull(s), CH_BLK);
         const uint32_t dst = base + CH_OFF_W + s * CH_BLK + rank * (CH_BLK / CL);
@@ -213,8 +215,8 @@ sdf_chain_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_cons
       };
       // one weight stage: nk MMAs of K = 16; A from shared memory (a_smem != 0) or from TMEM
       auto stage = [&](uint32_t d, uint32_t a_smem, uint32_t a_tmem, uint32_t idesc, int nk, bool first) {
-        const int s = static_cast<int>(wi % CH_W_STAGES);
-        mbar_wait(bar_wfull(s), (wi / CH_W_STAGES) & 1u);
+        const int s = static_cast<int>(wi % nst);
+        mbar_wait(bar_wfull(s), (wi / nst) & 1u);
         tcgen05_fence_after();
         const uint64_t db = umma_desc_sw128(base + CH_OFF_W + s * CH_BLK);
         if (a_smem != 0u) {
@@ -603,7 +605,9 @@ HOISDF_API int hoisdf_sdf_chain_fwd(const hoisdf_sdf_chain_args* a, void* stream
                    : ((a->lda0 & 7) || !aligned16(a->a0) || (a->ldw_s1 & 7) || !aligned16(a->w_s1)))
     return HOISDF_E_ALIGN;
   const int64_t tiles = ceil_div(a->rows, CH_BM);
-  const int cl = tiles >= 2 ? 2 : 1;
+  static const int force_cl = [] { const char* e = getenv("HOISDF_CHAIN_CL"); return e ? atoi(e) : 0; }();
+  static const int force_st = [] { const char* e = getenv("HOISDF_CHAIN_STAGES"); return e ? atoi(e) : 0; }();
+  const int cl = force_cl == 1 ? 1 : (tiles >= 2 ? 2 : 1);
   CUtensorMap maps[7];
   const int wbox = 128 / cl;
   bool ok = decoder_only ? chain_map(&maps[0], a->x, a->rows, 296, a->ldx, CH_BM)
@@ -624,6 +628,7 @@ HOISDF_API int hoisdf_sdf_chain_fwd(const hoisdf_sdf_chain_args* a, void* stream
   p.out = a->out_sdf; p.rows = a->rows; p.tiles = static_cast<int>(tiles);
   p.mode = decoder_only ? CH_MODE_DECODER : CH_MODE_ROWS;
   p.clamp = a->clamp;
+  p.wstages = (force_st >= 1 && force_st <= CH_W_STAGES) ? force_st : CH_W_STAGES;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (cl == 2) return chain_launch<2>(maps, p, s);
   return chain_launch<1>(maps, p, s);

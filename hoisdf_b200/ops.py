@@ -6,6 +6,7 @@ ours, launched through `libhoisdf_b200.so`.  Nothing in this file computes with 
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
@@ -263,6 +264,7 @@ class PackedLinearH3:
     row0: int = 0                 # row window (N slice)
     col0: int = 0                 # column window (K slice), multiple of 8
     chunk_kb: int = 0             # TMEM accumulation chunk of the launches using these weights (0 = kernel default)
+    scale: float = 1.0            # power of two the weights were divided by before packing (multiplied back in the epilogue)
 
     @staticmethod
     def pack(weight: torch.Tensor, bias: Optional[torch.Tensor], k: Optional[int] = None,
@@ -272,15 +274,22 @@ class PackedLinearH3:
             w = w.contiguous()
         n = w.shape[0]
         k = k or w.shape[1]
-        if float(w.abs().max()) >= 31.9:
-            raise ValueError("FP16x3 Linear needs |w| < 32")
+        # plane A = w_hi * 2^11 must fit fp16: layers with |w| >= 16 (a BatchNorm fold with a tiny running variance can do
+        # that) are divided by a power of two -- exact -- which the GEMM epilogue multiplies back (`w_scale`)
+        wmax = float(w.abs().max()) if w.numel() else 0.0
+        if not math.isfinite(wmax):
+            raise ValueError("FP16x3 Linear: non-finite weight")
+        scale = 1.0
+        if wmax >= 16.0:
+            scale = float(2.0 ** math.ceil(math.log2(wmax / 8.0)))
+            w = w * (1.0 / scale)
         ld = round_up(k, 8)
         planes = torch.empty(3, n, ld, device=w.device, dtype=torch.float16)
         _count(1)
         check(lib.hoisdf_pack_h3(w.data_ptr(), n, k, w.stride(0), planes[0].data_ptr(), planes[1].data_ptr(),
                                  planes[2].data_ptr(), ld, _stream()), "hoisdf_pack_h3")
         b = None if bias is None else bias.detach().to(torch.float32).contiguous()
-        return PackedLinearH3(planes, b, n, k, chunk_kb=chunk_kb)
+        return PackedLinearH3(planes, b, n, k, chunk_kb=chunk_kb, scale=scale)
 
     @property
     def ld(self) -> int:
@@ -291,11 +300,13 @@ class PackedLinearH3:
 
     def cols(self, start: int, stop: int) -> "PackedLinearH3":
         assert start % 8 == 0
-        return PackedLinearH3(self.planes, None, self.n, stop - start, self.row0, self.col0 + start, self.chunk_kb)
+        return PackedLinearH3(self.planes, None, self.n, stop - start, self.row0, self.col0 + start, self.chunk_kb,
+                              self.scale)
 
     def rows(self, start: int, stop: int) -> "PackedLinearH3":
         b = None if self.b is None else self.b[start:stop]
-        return PackedLinearH3(self.planes, b, stop - start, self.k, self.row0 + start, self.col0, self.chunk_kb)
+        return PackedLinearH3(self.planes, b, stop - start, self.k, self.row0 + start, self.col0, self.chunk_kb,
+                              self.scale)
 
 
 def linear_h3(x: SplitRows, pw: PackedLinearH3, act: int = ACT_NONE, out=None, residual: Optional[torch.Tensor] = None,
@@ -326,6 +337,7 @@ def linear_h3(x: SplitRows, pw: PackedLinearH3, act: int = ACT_NONE, out=None, r
     a.m, a.n, a.k, a.act = m, pw.n, pw.k, act
     a.chunk_kb = int(pw.chunk_kb if chunk_kb is None else chunk_kb)
     a.single_pass = int(single)
+    a.w_scale = float(pw.scale)
     if residual_split is not None:
         assert residual_split.cols >= pw.n and residual_split.rows >= m
         a.res_hi, a.res_lo, a.ldr = residual_split.hi_ptr, residual_split.lo_ptr, residual_split.ld
@@ -387,6 +399,7 @@ def conv_h3(x: SplitRows, batch: int, in_h: int, in_w: int, cin: int, pw: Packed
     a.y_sx, a.y_sy, a.y_sb = sx, sy, sb
     a.act = act
     a.chunk_kb = int(pw.chunk_kb if chunk_kb is None else chunk_kb)
+    a.w_scale = float(pw.scale)
     if residual_split is not None:
         assert residual_split.cols >= pw.n and residual_split.rows >= batch * out_h * out_w
         a.res_hi, a.res_lo, a.ldr = residual_split.hi_ptr, residual_split.lo_ptr, residual_split.ld
@@ -599,6 +612,8 @@ def pack_sdf_decoder(dec_params: dict) -> PackedSdfDecoder:
     w2h = fold_weight_norm(dec_params["linh2.weight_g"], dec_params["linh2.weight_v"], ROWH_LD, srch.to(dev))
     h3s = [PackedLinearH3.pack(w0, None, DEC_IN), PackedLinearH3.pack(w1, None, 512),
            PackedLinearH3.pack(w2h, None, SKIP_OFF_H + H1), PackedLinearH3.pack(w3, None, 512)]
+    if any(hp.scale != 1.0 for hp in h3s):
+        raise ValueError("SDF decoder weights >= 16 in magnitude are not supported by the FP16x3 decoder chain")
     s_h3 = _capi.SdfWeightsH3()
     for i, hp in enumerate(h3s):
         for j in range(3):
@@ -675,6 +690,7 @@ def sdf_chain(packed: PackedSdfDecoder, out: torch.Tensor, *, sdfin1: Optional[P
     a = _capi.SdfChainArgs()
     if a0 is not None:
         assert a0.cols >= 512 and sdfin1 is not None and sdfin1.h3 is not None and sdfin1.n == 256
+        assert sdfin1.h3.scale == 1.0, "linear_sdfin.layers.1 weights >= 16 in magnitude: use the unfused chain"
         a.a0, a.lda0 = a0.hi_ptr, a0.ld
         a.w_s1, a.ldw_s1, a.b_s1 = sdfin1.h3.plane_ptr(1), sdfin1.h3.ld, _ptr(sdfin1.b)
         a.lattice_index, a.points, a.bins = _ptr(lattice_index), _ptr(points), int(bins)

@@ -108,6 +108,9 @@ typedef struct {
                                         ~5e-4 relative error, 3x less tensor work): ONLY for pre-screening top-k
                                         candidates that an FP16x3 pass and then an exact pass re-rank, never for a
                                         result that is returned */
+  float w_scale;                     /* power-of-two factor the packed weights were divided by before packing (layers
+                                        with |w| >= 32, e.g. BatchNorm folds with a tiny running variance); the
+                                        epilogue multiplies it back.  0 = 1 */
 } hoisdf_linear_h3_args;
 
 int hoisdf_linear_h3_fwd(const hoisdf_linear_h3_args* args, void* stream);
@@ -138,6 +141,7 @@ typedef struct {
                                      /* optional split-half residual: output pixel (b, y, x) reads row
                                         (b * out_h + y) * out_w + x of these planes; cout % 32 == 0 */
   int32_t single_pass;               /* see hoisdf_linear_h3_args */
+  float w_scale;                     /* see hoisdf_linear_h3_args */
 } hoisdf_conv_h3_args;
 
 int hoisdf_conv_h3_fwd(const hoisdf_conv_h3_args* args, void* stream);

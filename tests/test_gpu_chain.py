@@ -45,7 +45,7 @@ def test_decoder_mode_matches_oracle(cuda, rows):
     assert err < SCREEN_TOL, float(err)
     # the unfused single-product chain computes the same thing (same operands; accumulation order may differ)
     unf = ops.sdf_decoder(dec.packed(), buf, chunk_kb=ops.SCREEN_CHUNK_KB, single=True)
-    assert (out - unf).abs().max() < 2e-5
+    assert (out - unf).abs().max() < 1e-4      # the unfused chain rounds relu(linh3) to fp16 before the head
 
 
 @pytest.mark.parametrize("rows", [64, 128 * 3, 2500])
@@ -76,7 +76,7 @@ def test_rows_mode_matches_oracle(cuda, rows):
     ops.linear(hs, pw, ops.ACT_RELU, out=rs.window(0, 256), chunk_kb=ops.SCREEN_CHUNK_KB, single=True)
     ops.posenc(rs, lattice_index=idx.to(cuda), bins=64)
     unf = ops.sdf_decoder(dec.packed(), rs, chunk_kb=ops.SCREEN_CHUNK_KB, single=True)
-    assert (out - unf).abs().max() < 2e-5
+    assert (out - unf).abs().max() < 1e-4      # the unfused chain rounds relu(linh3) to fp16 before the head
 
 
 def test_rows_mode_with_points_and_clamp(cuda):

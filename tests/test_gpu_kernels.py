@@ -53,6 +53,30 @@ def test_linear_matches_fp64(cuda, m, n, k, act, impl, monkeypatch):
     assert rel_err(y2, ref2) < tol
 
 
+@pytest.mark.parametrize("wmax", [15.0, 40.0, 700.0, 3.0e4])
+def test_linear_h3_large_weights(cuda, wmax):
+    """a BatchNorm fold with a tiny running variance can push |w| beyond the fp16 range of the packed planes
+    (w_hi * 2^11 < 65504).  PackedLinearH3.pack divides such a layer by a power of two and the epilogue multiplies it
+    back; the result stays fp32-grade."""
+    from hoisdf_b200 import ops
+    m, n, k = 300, 96, 256
+    x, w, b = rnd(1, m, k), rnd(2, n, k, lo=-0.1, hi=0.1), rnd(3, n)
+    w[5] *= wmax / 0.1                      # one output channel with a huge folded scale
+    w[17, 3] = wmax
+    pw = ops.PackedLinearH3.pack(w.to(cuda), b.to(cuda))
+    assert (pw.scale > 1.0) == (wmax >= 16.0)
+    assert torch.isfinite(pw.planes.float()).all()
+    y = ops.linear_h3(ops.split_rows(x.to(cuda)), pw, 1)
+    ref = (x.double() @ w.double().T + b.double()).relu()
+    assert rel_err(y, ref) < 4e-6
+    # and the implicit-GEMM convolution path (1x1 convolution = the same GEMM)
+    xs = ops.split_rows(rnd(4, 2 * 8 * 8, k).to(cuda))
+    yc = torch.empty(2 * 8 * 8, n, device=cuda)
+    ops.conv_h3(xs, 2, 8, 8, k, pw, [(0, 0)], 8, 8, out=yc)
+    refc = rnd(4, 2 * 8 * 8, k).double() @ w.double().T + b.double()
+    assert rel_err(yc, refc) < 4e-6
+
+
 def test_linear_batched_rows_and_errors(cuda):
     from hoisdf_b200 import ops, _capi
     L, T, P, d = 3, 10, 7, 256
