@@ -65,7 +65,6 @@ struct ChainParams {
   int tiles;          // ceil(rows / 128)
   int bins;
   int mode;
-  int wstages;        // depth of the weight ring actually used (<= CH_W_STAGES; developer knob)
   float clamp;
 };
 
@@ -96,7 +95,12 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int c) {
   return static_cast<uint32_t>((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
 }
 
-template <int CL>
+// developer profile of CTA 0 (HOISDF_CHAIN_PROF=1): cycles the MMA issuer spent waiting for [0] weights, [1] a free
+// accumulator, [2] its A operand, [3] its total; [4] epilogue warp 2: waiting for accumulators, [5] its total;
+// [6] weight producer: waiting for a free stage, [7] its total
+__device__ long long g_chain_prof[16];   // [8..12] MMA issuer: cycles from 'stage ready' to 'commit issued', per layer
+
+template <int CL, bool PROF>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 sdf_chain_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__ CUtensorMap map_ws1,
                  const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_w1,
@@ -110,8 +114,7 @@ sdf_chain_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_cons
   // barrier map (8 bytes each)
   auto bar_wfull = [&](int s) { return bars + 8u * s; };                       // 0..4
   auto bar_wempty = [&](int s) { return bars + 8u * (5 + s); };                // 5..9
-  auto bar_afull = [&](int s) { return bars + 8u * (10 + s); };                // 10..13
-  auto bar_aempty = [&](int s) { return bars + 8u * (14 + s); };               // 14..17
+  auto bar_afull = [&](int kb) { return bars + 8u * (10 + kb); };              // 10..17  A0 K block landed
   auto bar_dfull = [&](int b) { return bars + 8u * (18 + b); };                // 18..19
   auto bar_dempty = [&](int b) { return bars + 8u * (20 + b); };               // 20..21
   auto bar_skip = [&](int kb) { return bars + 8u * (22 + kb); };               // 22..26  SKIP K block written
@@ -121,14 +124,14 @@ sdf_chain_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + CH_OFF_BAR + 8 * 44);
   float* red = reinterpret_cast<float*>(gen + CH_OFF_BAR + 512);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // provably warp-uniform
+  const int lane = threadIdx.x & 31;
   const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
   const int cluster = static_cast<int>(blockIdx.x) / CL;
   const int nclusters = static_cast<int>(gridDim.x) / CL;
   const int npairs = (p.tiles + CL - 1) / CL;
   constexpr uint16_t kAllCtas = static_cast<uint16_t>((1u << CL) - 1u);
   const bool decoder_only = p.mode == CH_MODE_DECODER;
-  const uint32_t nst = static_cast<uint32_t>(p.wstages);
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_rows) : "memory");
@@ -142,10 +145,7 @@ sdf_chain_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_cons
       mbar_init(bar_wfull(s), 1);
       mbar_init(bar_wempty(s), CL);          // every CTA's tensor core must have consumed the stage
     }
-    for (int s = 0; s < 4; ++s) {
-      mbar_init(bar_afull(s), 1);
-      mbar_init(bar_aempty(s), 1);
-    }
+    for (int kb = 0; kb < 8; ++kb) mbar_init(bar_afull(kb), 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_dfull(b), 1);
       mbar_init(bar_dempty(b), CH_EPI_WARPS);
@@ -167,166 +167,182 @@ sdf_chain_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_cons
   __syncthreads();
   if (CL > 1) cluster_sync_all();            // peers' barriers are initialised before any multicast lands there
   tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  // The per-tile program is a list of "quarters" (layer, q): layer 0 = s1 (rows mode only), 1..4 = linh0..linh3.  Every
+  // role walks the same list with compact, NON-unrolled loops: the MMA issuer is one thread executing ~500 instructions
+  // per quarter, and an unrolled per-layer code path (17 k SASS instructions in the first version) made it stall on
+  // instruction fetch for half of its time (ncu: stall_no_inst at every reconvergence point, tensor pipe 25 % active).
+  const int layer0 = decoder_only ? 1 : 0;
+  auto quarters_of = [](int layer) { return (layer == 0 || layer == 2) ? 2 : 4; };
+  auto kblocks_of = [](int layer) { return layer == 1 ? 5 : (layer == 3 ? 9 : 8); };
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ weight producer
-    if (lane == 0) {
-      uint32_t wi = 0;
-      auto put = [&](const CUtensorMap* m, int row0, int col0) {
-        const int s = static_cast<int>(wi % nst);
-        const uint32_t ph = (wi / nst) & 1u;
-        mbar_wait(bar_wempty(s), ph ^ 1u);
-        mbar_expect_tx(bar_wfull(s), CH_BLK);
-        const uint32_t dst = base + CH_OFF_W + s * CH_BLK + rank * (CH_BLK / CL);
-        if (CL > 1) tma_load_2d_mc(dst, m, bar_wfull(s), col0, row0 + static_cast<int>(rank) * (128 / CL), kAllCtas);
-        else tma_load_2d(dst, m, bar_wfull(s), col0, row0);
-        ++wi;
-      };
+    // ------------------------------------------------------------------ weight producer (whole warp, one lane issues)
+    {
+      uint32_t ws = 0, wph = 1;           // stage, parity of the "stage free" phase to wait for
+      const bool prof = PROF && blockIdx.x == 0;
+      long long tw = 0;
+      const long long tstart = PROF ? clock64() : 0;
       for (int pair = cluster; pair < npairs; pair += nclusters) {
-        if (!decoder_only)
-          for (int kb = 0; kb < 8; ++kb)
-            for (int h = 0; h < 2; ++h) put(&map_ws1, 128 * h, 64 * kb);
-        for (int q = 0; q < 4; ++q)
-          for (int kb = 0; kb < 5; ++kb) put(&map_w0, 128 * q, 64 * kb);
-        for (int q = 0; q < 2; ++q)
-          for (int kb = 0; kb < 8; ++kb) put(&map_w1, 128 * q, 64 * kb);
-        for (int q = 0; q < 4; ++q)
-          for (int kb = 0; kb < 9; ++kb) {
-            if (kb < 5) put(&map_w2a, 128 * q, 64 * kb);
-            else put(&map_w2b, 128 * q, 64 * (kb - 5));
+#pragma unroll 1
+        for (int layer = layer0; layer < 5; ++layer) {
+          const CUtensorMap* m = layer == 0 ? &map_ws1 : layer == 1 ? &map_w0 : layer == 2 ? &map_w1 : layer == 3 ? &map_w2a : &map_w3;
+          const int nq = quarters_of(layer), nkb = kblocks_of(layer);
+#pragma unroll 1
+          for (int q = 0; q < nq; ++q) {
+#pragma unroll 1
+            for (int kb = 0; kb < nkb; ++kb) {
+              const uint32_t s = ws;
+              const long long c0 = prof ? clock64() : 0;
+              mbar_wait(bar_wempty(s), wph);
+              if (prof) tw += clock64() - c0;
+              if (++ws == CH_W_STAGES) { ws = 0; wph ^= 1u; }
+              const uint32_t dst = base + CH_OFF_W + s * CH_BLK + rank * (CH_BLK / CL);
+              const CUtensorMap* mm = (layer == 3 && kb >= 5) ? &map_w2b : m;
+              const int col0 = 64 * ((layer == 3 && kb >= 5) ? kb - 5 : kb);
+              const int row0 = 128 * q + static_cast<int>(rank) * (128 / CL);
+              if (elect_one()) {
+                mbar_expect_tx(bar_wfull(s), CH_BLK);
+                if (CL > 1) tma_load_2d_mc(dst, mm, bar_wfull(s), col0, row0, kAllCtas);
+                else tma_load_2d(dst, mm, bar_wfull(s), col0, row0);
+              }
+              __syncwarp();
+            }
           }
-        for (int q = 0; q < 4; ++q)
-          for (int kb = 0; kb < 8; ++kb) put(&map_w3, 128 * q, 64 * kb);
+        }
+      }
+      if (prof && lane == 0) {
+        g_chain_prof[6] += tw;
+        g_chain_prof[7] += clock64() - tstart;
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      uint32_t wi = 0, ai = 0, du[2] = {0u, 0u}, it = 0;
+    // ------------------------------------------------------------------ MMA issuer: the whole warp walks the program
+    // (uniform control flow); one elected lane issues the tcgen05 instructions.  tcgen05.mma issue BLOCKS while the tensor
+    // core is busy (measured: 64 cycles per M128 x N128 x K16 MMA in the issuing thread), so every instruction of this
+    // loop that is not an MMA is tensor-core idle time: stage / phase / descriptor bookkeeping is incremental.
+    {
+      uint32_t ws = 0, wph = 0, du0 = 0u, du1 = 0u, it = 0;    // weight stage + phase; uses of accumulator D0 / D1 so far
       const uint32_t idesc128 = umma_idesc_f16(CH_BM, 128), idesc96 = umma_idesc_f16(CH_BM, 96);
-      auto d_acquire = [&](int b) {
-        mbar_wait(bar_dempty(b), (du[b] & 1u) ^ 1u);
-        tcgen05_fence_after();
-      };
-      auto d_publish = [&](int b) {
-        umma_commit(bar_dfull(b));
-        ++du[b];
-      };
-      // one weight stage: nk MMAs of K = 16; A from shared memory (a_smem != 0) or from TMEM
-      auto stage = [&](uint32_t d, uint32_t a_smem, uint32_t a_tmem, uint32_t idesc, int nk, bool first) {
-        const int s = static_cast<int>(wi % nst);
-        mbar_wait(bar_wfull(s), (wi / nst) & 1u);
-        tcgen05_fence_after();
-        const uint64_t db = umma_desc_sw128(base + CH_OFF_W + s * CH_BLK);
-        if (a_smem != 0u) {
-          const uint64_t da = umma_desc_sw128(a_smem);
-#pragma unroll 4
-          for (int kk = 0; kk < nk; ++kk)
-            umma_f16(d, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc,
-                     (first && kk == 0) ? 0u : 1u);
-        } else {
-#pragma unroll 4
-          for (int kk = 0; kk < nk; ++kk)
-            umma_f16_ts(d, a_tmem + static_cast<uint32_t>(kk * 8), db + static_cast<uint64_t>(kk * 2), idesc,
-                        (first && kk == 0) ? 0u : 1u);
-        }
-        if (CL > 1) umma_commit_mc(bar_wempty(s), kAllCtas);
-        else umma_commit(bar_wempty(s));
-        ++wi;
-      };
-      const uint32_t d0 = tmem_base, d1 = tmem_base + 128u, act = tmem_base + CH_TM_ACT;
+      const uint32_t act = tmem_base + CH_TM_ACT;
+      const uint64_t desc_w0 = umma_desc_sw128(base + CH_OFF_W), desc_a0 = umma_desc_sw128(base);
+      constexpr uint64_t kBlkDesc = CH_BLK >> 4;               // one 16 KB block in descriptor address units
+      const bool prof = PROF && blockIdx.x == 0;
+      long long t_w = 0, t_d = 0, t_a = 0, t_l[5] = {0, 0, 0, 0, 0};
+      const long long tstart = PROF ? clock64() : 0;
       for (int pair = cluster; pair < npairs; pair += nclusters, ++it) {
         const uint32_t tp = it & 1u;
-        // ---- s1: A0 K blocks from the row ring, both 128-column halves of the 256 outputs per K block
-        if (!decoder_only) {
-          d_acquire(0);
-          d_acquire(1);
-          for (int kb = 0; kb < 8; ++kb, ++ai) {
-            const int s = static_cast<int>(ai & 3u);
-            mbar_wait(bar_afull(s), (ai >> 2) & 1u);
+#pragma unroll 1
+        for (int layer = layer0; layer < 5; ++layer) {
+          const int nq = quarters_of(layer), nkb = kblocks_of(layer);
+          const bool a_tmem = layer == 2 || layer == 4;
+          // "A operand K block kb is in place" barriers of this layer: bar(kb) = abar + 8 kb for kb >= akb0
+          //   s1: A0 blocks; linh0: SKIP blocks; linh1 / linh3: ACT blocks (completed twice per tile: linh0 writes phase 0,
+          //   linh2 phase 1); linh2: only the H1 blocks (K blocks 5..8) are new, SKIP was already waited for by linh0
+          const uint32_t abar = layer == 0 ? bar_afull(0) : layer == 1 ? bar_skip(0) : layer == 3 ? bar_h1(0) - 40u : bar_act(0);
+          const int akb0 = layer == 3 ? 5 : 0;
+          const uint32_t apar = layer == 2 ? 0u : layer == 4 ? 1u : tp;
+#pragma unroll 1
+          for (int q = 0; q < nq; ++q) {
+            const int b = q & 1;
+            long long c0 = prof ? clock64() : 0;
+            mbar_wait(bar_dempty(b), ((b ? du1 : du0) & 1u) ^ 1u);     // the epilogue has drained this accumulator
+            if (prof) t_d += clock64() - c0;
             tcgen05_fence_after();
-            const uint32_t a0 = base + CH_OFF_H1 + s * CH_BLK;
-            stage(d0, a0, 0u, idesc128, 4, kb == 0);
-            stage(d1, a0, 0u, idesc128, 4, kb == 0);
-            umma_commit(bar_aempty(s));
-          }
-          d_publish(0);
-          d_publish(1);
-        }
-        // ---- l0: SKIP (shared memory) -> 512
-        for (int q = 0; q < 4; ++q) {
-          const int b = q & 1;
-          d_acquire(b);
-          for (int kb = 0; kb < 5; ++kb) {
-            if (q == 0) {
-              mbar_wait(bar_skip(kb), tp);
+            const uint32_t d = tmem_base + static_cast<uint32_t>(b) * 128u;
+            const uint32_t idesc = (layer == 2 && q == 1) ? idesc96 : idesc128;
+#pragma unroll 1
+            for (int kb = 0; kb < nkb; ++kb) {
+              if (q == 0 && kb >= akb0) {                                // the A operand of this K block is in place
+                if (prof) c0 = clock64();
+                mbar_wait(abar + 8u * kb, apar);
+                if (prof) t_a += clock64() - c0;
+              }
+              if (prof) c0 = clock64();
+              mbar_wait(bar_wfull(ws), wph);
+              if (prof) { const long long c1 = clock64(); t_w += c1 - c0; c0 = c1; }
               tcgen05_fence_after();
+              const uint64_t db = desc_w0 + ws * kBlkDesc;
+              const int nk = (layer == 3 && kb == 8) ? 2 : (((layer == 1 || layer == 3) && kb == 4) ? 3 : 4);
+              // s1 reads the A0 blocks (K blocks 0..3 in the H1 region, 4..7 in SKIP blocks 0..3), linh0 / linh2 SKIP | H1
+              const int blk = layer == 0 ? (kb < 4 ? CH_SKIP_BLKS + kb : kb - 4) : kb;
+              const uint64_t da = desc_a0 + blk * kBlkDesc;
+              const uint32_t at = act + static_cast<uint32_t>(kb * 32);
+              if (elect_one()) {
+                if (a_tmem) {
+#pragma unroll
+                  for (int kk = 0; kk < 4; ++kk)
+                    if (kk < nk)
+                      umma_f16_ts(d, at + static_cast<uint32_t>(kk * 8), db + static_cast<uint64_t>(kk * 2), idesc,
+                                  (kb | kk) != 0 ? 1u : 0u);
+                } else {
+#pragma unroll
+                  for (int kk = 0; kk < 4; ++kk)
+                    if (kk < nk)
+                      umma_f16(d, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc,
+                               (kb | kk) != 0 ? 1u : 0u);
+                }
+                if (CL > 1) umma_commit_mc(bar_wempty(ws), kAllCtas);
+                else umma_commit(bar_wempty(ws));
+              }
+              __syncwarp();
+              if (++ws == CH_W_STAGES) { ws = 0; wph ^= 1u; }
+              if (prof) t_l[layer] += clock64() - c0;
             }
-            stage(b ? d1 : d0, base + kb * CH_BLK, 0u, idesc128, kb == 4 ? 3 : 4, kb == 0);
-          }
-          d_publish(b);
-        }
-        // ---- l1: ACT (TMEM) -> 223  (quarters of 128 and 96 columns)
-        for (int q = 0; q < 2; ++q) {
-          d_acquire(q);
-          for (int kb = 0; kb < 8; ++kb) {
-            if (q == 0) {
-              mbar_wait(bar_act(kb), 0u);                 // first completion of this barrier in the tile
-              tcgen05_fence_after();
+            // publish the accumulator.  s1: both halves together -- its epilogue overwrites SKIP blocks that still hold
+            // A0 K blocks until the second half has been computed
+            if (layer == 0) {
+              if (q == 1) {
+                if (elect_one()) {
+                  umma_commit(bar_dfull(0));
+                  umma_commit(bar_dfull(1));
+                }
+                ++du0;
+                ++du1;
+              }
+            } else {
+              if (elect_one()) umma_commit(bar_dfull(b));
+              if (b) ++du1; else ++du0;
             }
-            stage(q ? d1 : d0, 0u, act + static_cast<uint32_t>(kb * 32), q ? idesc96 : idesc128, 4, kb == 0);
+            __syncwarp();
           }
-          d_publish(q);
+          if (layer == 3 && elect_one()) umma_commit(bar_rfree);   // SKIP / H1 no longer read: the next tile's rows may land
+          __syncwarp();
         }
-        // ---- l2: [SKIP | H1] (shared memory) -> 512
-        for (int q = 0; q < 4; ++q) {
-          const int b = q & 1;
-          d_acquire(b);
-          for (int kb = 0; kb < 9; ++kb) {
-            if (q == 0 && kb >= 5) {
-              mbar_wait(bar_h1(kb - 5), tp);
-              tcgen05_fence_after();
-            }
-            stage(b ? d1 : d0, base + kb * CH_BLK, 0u, idesc128, kb == 8 ? 2 : (kb == 4 ? 3 : 4), kb == 0);
-          }
-          d_publish(b);
-        }
-        umma_commit(bar_rfree);                            // SKIP / H1 no longer read: the next tile's rows may land
-        // ---- l3: ACT (TMEM) -> 512 (the epilogue folds linh4 + tanh)
-        for (int q = 0; q < 4; ++q) {
-          const int b = q & 1;
-          d_acquire(b);
-          for (int kb = 0; kb < 8; ++kb) {
-            if (q == 0) {
-              mbar_wait(bar_act(kb), 1u);                 // second completion in the tile
-              tcgen05_fence_after();
-            }
-            stage(b ? d1 : d0, 0u, act + static_cast<uint32_t>(kb * 32), idesc128, 4, kb == 0);
-          }
-          d_publish(b);
-        }
+      }
+      if (prof && lane == 0) {
+        g_chain_prof[0] += t_w;
+        g_chain_prof[1] += t_d;
+        g_chain_prof[2] += t_a;
+        g_chain_prof[3] += clock64() - tstart;
+        for (int l = 0; l < 5; ++l) g_chain_prof[8 + l] += t_l[l];
       }
     }
   } else if (warp == 2 + CH_EPI_WARPS) {
-    // ------------------------------------------------------------------ row producer (TMA)
-    if (lane == 0) {
-      uint32_t ai = 0, it = 0;
+    // ------------------------------------------------------------------ row producer (TMA; whole warp, one lane issues)
+    {
+      uint32_t it = 0;
       for (int pair = cluster; pair < npairs; pair += nclusters, ++it) {
         const int row0 = (pair * CL + static_cast<int>(rank)) * CH_BM;   // beyond the last row: zero-filled tile
         if (it > 0) mbar_wait(bar_rfree, (it - 1) & 1u);
         if (decoder_only) {
-          for (int kb = 0; kb < 5; ++kb) {
-            mbar_expect_tx(bar_skip(kb), CH_BLK);
-            tma_load_2d(base + kb * CH_BLK, &map_rows, bar_skip(kb), 64 * kb, row0);
+          if (elect_one()) {
+            for (int kb = 0; kb < 5; ++kb) {
+              mbar_expect_tx(bar_skip(kb), CH_BLK);
+              tma_load_2d(base + kb * CH_BLK, &map_rows, bar_skip(kb), 64 * kb, row0);
+            }
           }
+          __syncwarp();
         } else {
-          for (int kb = 0; kb < 8; ++kb, ++ai) {
-            const int s = static_cast<int>(ai & 3u);
-            mbar_wait(bar_aempty(s), ((ai >> 2) & 1u) ^ 1u);
-            mbar_expect_tx(bar_afull(s), CH_BLK);
-            tma_load_2d(base + CH_OFF_H1 + s * CH_BLK, &map_rows, bar_afull(s), 64 * kb, row0);
+          if (elect_one()) {
+            for (int kb = 0; kb < 8; ++kb) {
+              const int blk = kb < 4 ? CH_SKIP_BLKS + kb : kb - 4;
+              mbar_expect_tx(bar_afull(kb), CH_BLK);
+              tma_load_2d(base + blk * CH_BLK, &map_rows, bar_afull(kb), 64 * kb, row0);
+            }
           }
+          __syncwarp();
         }
       }
     }
@@ -337,69 +353,10 @@ sdf_chain_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_cons
     const int h = ew >> 2;                      // which 64-column half of a 128-column quarter it owns
     const int r = lq * 32 + lane;               // row inside the tile
     const uint32_t lane_addr = static_cast<uint32_t>(lq * 32) << 16;
-    uint32_t eu[2] = {0u, 0u};
-    auto d_wait = [&](int b) {
-      mbar_wait(bar_dfull(b), eu[b] & 1u);
-      tcgen05_fence_after();
-    };
-    auto d_release = [&](int b) {               // after tcgen05.wait::ld of everything this warp reads from D_b
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_dempty(b));
-      ++eu[b];
-    };
-    // 64 accumulator columns of this warp -> v = relu(acc + bias[c0 + j]) packed as 32 fp16 pairs
-    auto load_pack = [&](int b, const float* bias, int c0, int nvalid, uint32_t* pk) {
-      uint32_t a[64];
-      const uint32_t t0 = tmem_base + static_cast<uint32_t>(b * 128 + h * 64) + lane_addr;
-      tmem_ld32(t0, a);
-      tmem_ld32(t0 + 32, a + 32);
-      tmem_ld_wait();
-      if (nvalid >= 64) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
-          pk[2 * j] = cvt_f16x2_sat(fmaxf(__uint_as_float(a[4 * j]) + bb.x, 0.f),
-                                    fmaxf(__uint_as_float(a[4 * j + 1]) + bb.y, 0.f));
-          pk[2 * j + 1] = cvt_f16x2_sat(fmaxf(__uint_as_float(a[4 * j + 2]) + bb.z, 0.f),
-                                        fmaxf(__uint_as_float(a[4 * j + 3]) + bb.w, 0.f));
-        }
-      } else {                                  // ragged tail (linh1's last 31 outputs): guarded scalar loads
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int c = 2 * j;
-          const float b0 = c < nvalid ? __ldg(bias + c0 + c) : 0.f;
-          const float b1 = c + 1 < nvalid ? __ldg(bias + c0 + c + 1) : 0.f;
-          const float v0 = c < nvalid ? fmaxf(__uint_as_float(a[c]) + b0, 0.f) : 0.f;
-          const float v1 = c + 1 < nvalid ? fmaxf(__uint_as_float(a[c + 1]) + b1, 0.f) : 0.f;
-          pk[j] = cvt_f16x2_sat(v0, v1);
-        }
-      }
-    };
-    auto store_block = [&](uint32_t blk_off, const uint32_t* pk) {      // this lane's 128-byte row of a K block
-      uint8_t* blk = gen + blk_off;
-#pragma unroll
-      for (int c = 0; c < 8; ++c)
-        *reinterpret_cast<uint4*>(blk + sw128_off(r, c)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-    };
-    auto publish_smem = [&](uint32_t bar) {
-      fence_async_smem();                       // generic-proxy stores -> visible to the tensor core (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar);
-    };
-    // quarter -> ACT (TMEM): columns [128 q + 64 h, +64) = packed columns [64 q + 32 h, +32)
-    auto quarter_to_act = [&](int q, const float* bias) {
-      const int b = q & 1;
-      d_wait(b);
-      uint32_t pk[32];
-      load_pack(b, bias, 128 * q + 64 * h, 64, pk);
-      d_release(b);
-      tmem_st32(tmem_base + CH_TM_ACT + static_cast<uint32_t>(64 * q + 32 * h) + lane_addr, pk);
-      tmem_st_wait();
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_act(2 * q + h));
-    };
+    uint32_t eu0 = 0u, eu1 = 0u;
+    const bool prof = PROF && blockIdx.x == 0 && warp == 2 && lane == 0;
+    long long t_e = 0;
+    const long long tstart = PROF ? clock64() : 0;
 
     for (int pair = cluster; pair < npairs; pair += nclusters) {
       const int64_t row = static_cast<int64_t>(pair * CL + static_cast<int>(rank)) * CH_BM + r;
@@ -407,94 +364,116 @@ sdf_chain_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_cons
       if (!decoder_only) {
         // ---- NeRF embedding + xyz -> SKIP block 4 (columns 256..319).  Every MMA that read the previous tile's SKIP
         // has completed: this warp has already seen that tile's linh3 accumulators.
-        uint32_t pk[32];
+        uint8_t* blk = gen + 4 * CH_BLK;
+        float x[3] = {0.f, 0.f, 0.f};
+        if (row_ok) {
+          if (p.lattice_index != nullptr) lattice_point(p.lattice_index[row], p.bins, x[0], x[1], x[2]);
+          else { x[0] = p.points[row * 3 + 0]; x[1] = p.points[row * 3 + 1]; x[2] = p.points[row * 3 + 2]; }
+        }
         if (h == 0) {
-          float x[3] = {0.f, 0.f, 0.f};
-          if (row_ok) {
-            if (p.lattice_index != nullptr) lattice_point(p.lattice_index[row], p.bins, x[0], x[1], x[2]);
-            else { x[0] = p.points[row * 3 + 0]; x[1] = p.points[row * 3 + 1]; x[2] = p.points[row * 3 + 2]; }
-          }
-          float e[32];
+          // columns 0..31 of the block: 30 embedding values (octave-major: sin xyz, cos xyz) + x, y
+          uint32_t pk[16];
 #pragma unroll
           for (int oct = 0; oct < 5; ++oct) {
+            float sn[3], cs[3];
 #pragma unroll
             for (int w = 0; w < 3; ++w) {
               const float a = x[w] * static_cast<float>(1 << oct);     // exact scaling by 2^k
-              e[oct * 6 + w] = sinf(a);
-              e[oct * 6 + 3 + w] = cosf(a);
+              sn[w] = sinf(a);
+              cs[w] = cosf(a);
             }
+            pk[oct * 3 + 0] = cvt_f16x2_sat(sn[0], sn[1]);
+            pk[oct * 3 + 1] = cvt_f16x2_sat(sn[2], cs[0]);
+            pk[oct * 3 + 2] = cvt_f16x2_sat(cs[1], cs[2]);
           }
-          e[30] = x[0];
-          e[31] = x[1];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) pk[j] = cvt_f16x2_sat(e[2 * j], e[2 * j + 1]);
-          uint8_t* blk = gen + 4 * CH_BLK;
+          pk[15] = cvt_f16x2_sat(x[0], x[1]);
 #pragma unroll
           for (int c = 0; c < 4; ++c)
             *reinterpret_cast<uint4*>(blk + sw128_off(r, c)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
         } else {
-          float z = 0.f;
-          if (row_ok) {
-            if (p.lattice_index != nullptr) {
-              float x0, x1;
-              lattice_point(p.lattice_index[row], p.bins, x0, x1, z);
-            } else {
-              z = p.points[row * 3 + 2];
-            }
-          }
-          uint8_t* blk = gen + 4 * CH_BLK;
-          *reinterpret_cast<uint4*>(blk + sw128_off(r, 4)) = make_uint4(cvt_f16x2_sat(z, 0.f), 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(blk + sw128_off(r, 4)) = make_uint4(cvt_f16x2_sat(x[2], 0.f), 0u, 0u, 0u);
 #pragma unroll
           for (int c = 5; c < 8; ++c) *reinterpret_cast<uint4*>(blk + sw128_off(r, c)) = make_uint4(0u, 0u, 0u, 0u);
         }
-        publish_smem(bar_skip(4));
-        // ---- s1 epilogue: D0 -> SKIP blocks 0 / 1, D1 -> SKIP blocks 2 / 3
-        for (int b = 0; b < 2; ++b) {
-          d_wait(b);
-          load_pack(b, p.b_s1, 128 * b + 64 * h, 64, pk);
-          d_release(b);
-          store_block(static_cast<uint32_t>(2 * b + h) * CH_BLK, pk);
-          publish_smem(bar_skip(2 * b + h));
-        }
+        fence_async_smem();                     // generic-proxy stores -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_skip(4));
       }
-      // ---- l0 -> ACT
-      for (int q = 0; q < 4; ++q) quarter_to_act(q, p.b[0]);
-      // ---- l1 -> H1 blocks (223 valid outputs: quarter 1 has 96 accumulator columns, 95 of them real)
-      for (int q = 0; q < 2; ++q) {
-        d_wait(q);
-        uint32_t pk[32];
-        const int c0 = 128 * q + 64 * h;
-        const int nvalid = min(64, 223 - c0);
-        load_pack(q, p.b[1], c0, nvalid, pk);
-        d_release(q);
-        store_block(CH_OFF_H1 + static_cast<uint32_t>(2 * q + h) * CH_BLK, pk);
-        publish_smem(bar_h1(2 * q + h));
-      }
-      // ---- l2 -> ACT
-      for (int q = 0; q < 4; ++q) quarter_to_act(q, p.b[2]);
-      // ---- l3 + linh4: partial dot product of relu(acc + b3) with w4 over this warp's 4 x 64 columns
-      float part = 0.f;
-      for (int q = 0; q < 4; ++q) {
-        const int b = q & 1;
-        d_wait(b);
-        uint32_t a[64];
-        const uint32_t t0 = tmem_base + static_cast<uint32_t>(b * 128 + h * 64) + lane_addr;
-        tmem_ld32(t0, a);
-        tmem_ld32(t0 + 32, a + 32);
-        tmem_ld_wait();
-        d_release(b);
-        const int c0 = 128 * q + 64 * h;
-        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+      float part = 0.f;                         // linh4 partial dot product of this thread's row
+#pragma unroll 1
+      for (int layer = layer0; layer < 5; ++layer) {
+        const int nq = quarters_of(layer);
+        const float* bias = layer == 0 ? p.b_s1 : layer == 1 ? p.b[0] : layer == 2 ? p.b[1] : layer == 3 ? p.b[2] : p.b[3];
+#pragma unroll 1
+        for (int q = 0; q < nq; ++q) {
+          const int b = q & 1;
+          const int c0 = 128 * q + 64 * h;       // first output column of this warp's 64
+          const long long tc0 = prof ? clock64() : 0;
+          mbar_wait(bar_dfull(b), (b ? eu1 : eu0) & 1u);
+          if (prof) t_e += clock64() - tc0;
+          tcgen05_fence_after();
+          uint32_t a[64];
+          const uint32_t t0 = tmem_base + static_cast<uint32_t>(b * 128 + h * 64) + lane_addr;
+          tmem_ld32(t0, a);
+          tmem_ld32(t0 + 32, a + 32);
+          tmem_ld_wait();
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_dempty(b));       // the accumulator is in registers: hand the buffer back
+          if (b) ++eu1; else ++eu0;
+          if (layer == 4) {
+            // linh3 + linh4: relu(acc + b3) . w4 over this warp's columns
+            float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b[3] + c0) + j);
-          const float4 ww = __ldg(reinterpret_cast<const float4*>(p.w4 + c0) + j);
-          s4[0] = fmaf(fmaxf(__uint_as_float(a[4 * j]) + bb.x, 0.f), ww.x, s4[0]);
-          s4[1] = fmaf(fmaxf(__uint_as_float(a[4 * j + 1]) + bb.y, 0.f), ww.y, s4[1]);
-          s4[2] = fmaf(fmaxf(__uint_as_float(a[4 * j + 2]) + bb.z, 0.f), ww.z, s4[2]);
-          s4[3] = fmaf(fmaxf(__uint_as_float(a[4 * j + 3]) + bb.w, 0.f), ww.w, s4[3]);
+            for (int j = 0; j < 16; ++j) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
+              const float4 ww = __ldg(reinterpret_cast<const float4*>(p.w4 + c0) + j);
+              s4[0] = fmaf(fmaxf(__uint_as_float(a[4 * j]) + bb.x, 0.f), ww.x, s4[0]);
+              s4[1] = fmaf(fmaxf(__uint_as_float(a[4 * j + 1]) + bb.y, 0.f), ww.y, s4[1]);
+              s4[2] = fmaf(fmaxf(__uint_as_float(a[4 * j + 2]) + bb.z, 0.f), ww.z, s4[2]);
+              s4[3] = fmaf(fmaxf(__uint_as_float(a[4 * j + 3]) + bb.w, 0.f), ww.w, s4[3]);
+            }
+            part += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+            continue;
+          }
+          // bias + ReLU + fp16: 64 columns -> 32 packed pairs.  linh1 has 223 outputs: the tail is zero-filled.
+          const int nvalid = layer == 2 ? min(64, 223 - c0) : 64;
+          uint32_t pk[32];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (4 * j + 3 < nvalid) {
+              bb = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
+            } else {
+              if (4 * j < nvalid) bb.x = __ldg(bias + c0 + 4 * j);
+              if (4 * j + 1 < nvalid) bb.y = __ldg(bias + c0 + 4 * j + 1);
+              if (4 * j + 2 < nvalid) bb.z = __ldg(bias + c0 + 4 * j + 2);
+            }
+            const float v0 = 4 * j < nvalid ? fmaxf(__uint_as_float(a[4 * j]) + bb.x, 0.f) : 0.f;
+            const float v1 = 4 * j + 1 < nvalid ? fmaxf(__uint_as_float(a[4 * j + 1]) + bb.y, 0.f) : 0.f;
+            const float v2 = 4 * j + 2 < nvalid ? fmaxf(__uint_as_float(a[4 * j + 2]) + bb.z, 0.f) : 0.f;
+            const float v3 = 4 * j + 3 < nvalid ? fmaxf(__uint_as_float(a[4 * j + 3]) + bb.w, 0.f) : 0.f;
+            pk[2 * j] = cvt_f16x2_sat(v0, v1);
+            pk[2 * j + 1] = cvt_f16x2_sat(v2, v3);
+          }
+          if (layer == 1 || layer == 3) {
+            // -> ACT (TMEM): columns [128 q + 64 h, +64) = packed columns [64 q + 32 h, +32)
+            tmem_st32(tmem_base + CH_TM_ACT + static_cast<uint32_t>(64 * q + 32 * h) + lane_addr, pk);
+            tmem_st_wait();
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_act(2 * q + h));
+          } else {
+            // -> this lane's 128-byte row of a shared-memory K block: s1 -> SKIP block 2q+h, linh1 -> H1 block 2q+h
+            uint8_t* blk = gen + static_cast<uint32_t>((layer == 0 ? 0 : CH_SKIP_BLKS) + 2 * q + h) * CH_BLK;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              *reinterpret_cast<uint4*>(blk + sw128_off(r, c)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(layer == 0 ? bar_skip(2 * q + h) : bar_h1(2 * q + h));
+          }
         }
-        part += (s4[0] + s4[1]) + (s4[2] + s4[3]);
       }
       if (h == 1) red[r] = part;
       asm volatile("bar.sync %0, 64;" ::"r"(1 + lq) : "memory");     // the two warps of this lane quarter
@@ -503,6 +482,10 @@ sdf_chain_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_cons
         if (p.clamp > 0.f) t = fminf(fmaxf(t, -p.clamp), p.clamp);
         p.out[row] = t;
       }
+    }
+    if (prof) {
+      g_chain_prof[4] += t_e;
+      g_chain_prof[5] += clock64() - tstart;
     }
   }
   tcgen05_fence_before();
@@ -529,7 +512,7 @@ template <int CL>
 static int chain_max_clusters() {
   static int cached = -1;
   if (cached >= 0) return cached;
-  auto kern = sdf_chain_kernel<CL>;
+  auto kern = sdf_chain_kernel<CL, false>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_BYTES);
   int n = 0;
   if (CL == 1) {
@@ -556,9 +539,9 @@ static int chain_max_clusters() {
   return n;
 }
 
-template <int CL>
+template <int CL, bool PROF>
 static int chain_launch(const CUtensorMap* maps, const ChainParams& p, cudaStream_t s) {
-  auto kern = sdf_chain_kernel<CL>;
+  auto kern = sdf_chain_kernel<CL, PROF>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_BYTES);
   if (e != cudaSuccess) return static_cast<int>(e);
   const int64_t npairs = ceil_div(p.tiles, CL);
@@ -584,6 +567,13 @@ static int chain_launch(const CUtensorMap* maps, const ChainParams& p, cudaStrea
 
 using namespace hoisdf;
 
+// developer hook: read and reset the CTA-0 wait-cycle profile (see g_chain_prof)
+extern "C" __attribute__((visibility("default"))) int hoisdf_debug_chain_profile(long long* out16) {
+  long long zero[16] = {0};
+  if (cudaMemcpyFromSymbol(out16, g_chain_prof, sizeof(zero)) != cudaSuccess) return -1;
+  return cudaMemcpyToSymbol(g_chain_prof, zero, sizeof(zero)) == cudaSuccess ? 0 : -1;
+}
+
 HOISDF_API int hoisdf_sdf_chain_fwd(const hoisdf_sdf_chain_args* a, void* stream) {
   if (a == nullptr || a->out_sdf == nullptr || a->w4 == nullptr || a->b4 == nullptr) return HOISDF_E_NULL;
   const bool decoder_only = a->x != nullptr;
@@ -606,7 +596,6 @@ HOISDF_API int hoisdf_sdf_chain_fwd(const hoisdf_sdf_chain_args* a, void* stream
     return HOISDF_E_ALIGN;
   const int64_t tiles = ceil_div(a->rows, CH_BM);
   static const int force_cl = [] { const char* e = getenv("HOISDF_CHAIN_CL"); return e ? atoi(e) : 0; }();
-  static const int force_st = [] { const char* e = getenv("HOISDF_CHAIN_STAGES"); return e ? atoi(e) : 0; }();
   const int cl = force_cl == 1 ? 1 : (tiles >= 2 ? 2 : 1);
   CUtensorMap maps[7];
   const int wbox = 128 / cl;
@@ -628,8 +617,8 @@ HOISDF_API int hoisdf_sdf_chain_fwd(const hoisdf_sdf_chain_args* a, void* stream
   p.out = a->out_sdf; p.rows = a->rows; p.tiles = static_cast<int>(tiles);
   p.mode = decoder_only ? CH_MODE_DECODER : CH_MODE_ROWS;
   p.clamp = a->clamp;
-  p.wstages = (force_st >= 1 && force_st <= CH_W_STAGES) ? force_st : CH_W_STAGES;
+  static const int prof = [] { const char* e = getenv("HOISDF_CHAIN_PROF"); return e ? atoi(e) : 0; }();
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (cl == 2) return chain_launch<2>(maps, p, s);
-  return chain_launch<1>(maps, p, s);
+  if (prof) return cl == 2 ? chain_launch<2, true>(maps, p, s) : chain_launch<1, true>(maps, p, s);
+  return cl == 2 ? chain_launch<2, false>(maps, p, s) : chain_launch<1, false>(maps, p, s);
 }

@@ -176,6 +176,15 @@ __device__ __forceinline__ uint32_t cluster_nctaid_x() {   // number of clusters
   asm("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
   return r;
 }
+// One lane of a fully converged warp.  The MMA / TMA issuing roles run their loops on ALL 32 lanes (uniform control flow,
+// operands provably warp-uniform -> the compiler keeps descriptors in uniform registers) and predicate only the issuing
+// instruction with this; a role body under `if (lane == 0)` instead makes the compiler wrap every tcgen05.mma in a
+// vector -> uniform register "waterfall" loop (ELECT + 6 x R2UR + branch), ~200 cycles per MMA issued.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\t@p mov.u32 %0, 1;\n\t}" : "+r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 

@@ -256,6 +256,47 @@ def test_full_forward_from_image(setup):
     compare(m({"img": img.to(dev)}, to_dev(syn.eval_targets(s["B"]), dev), to_dev(s["meta"], dev), "eval"))
 
 
+def test_image_encoder_matches_oracle(setup):
+    """ResNet-50 + U-Net on the FP16x3 tensor-core convolution kernels against the ORACLE's encoder
+    (oracle backbone / unet_decoder, pinned to upstream by tests/golden/image_*.npz), every pyramid level and the
+    heat-map / segmentation head, <= 1e-4 of the level's range, both architectures."""
+    m, s = setup["model"], setup
+    img = syn.image_batch(s["seed"] + 20, s["B"])
+    with torch.no_grad():
+        feat, skips = O.backbone(dict(s["sd"]), img)
+        opyr, odec = O.unet_decoder(dict(s["sd"]), feat, skips, s["arch"])
+        pyr, dec = m.run_image_encoder(img.to(s["dev"]))
+    for name, want in opyr.items():
+        got = pyr[name]
+        assert tuple(got.shape) == tuple(want.shape), name
+        assert rel(got, want) < 1e-4, (name, rel(got, want))
+    assert tuple(dec.shape) == tuple(odec.shape) and rel(dec, odec) < 1e-4, rel(dec, odec)
+
+
+def test_image_to_pose_tight(setup):
+    """the exact path bench.py times (image -> pose), gated tightly.  The oracle is fed the pyramid the
+    GPU encoder produced (its own encoder differs from ours at ~1e-6, which may flip near-tied selections), so the
+    selected index SETS must be identical and every `*_out` within the north star's 1e-3 (measured ~1e-5)."""
+    m, s = setup["model"], setup
+    dev = s["dev"]
+    img = syn.image_batch(s["seed"] + 21, s["B"])
+    out = m({"img": img.to(dev)}, to_dev(syn.eval_targets(s["B"]), dev), to_dev(s["meta"], dev), "eval")
+    taps = m.last_taps
+    with torch.no_grad():
+        pyr, _ = m.run_image_encoder(img.to(dev))
+        cpu_pyr = {k: v.float().cpu().contiguous() for k, v in pyr.items()}
+        otaps = {}
+        oout = O.hot_path_eval(dict(s["sd"]), cpu_pyr, s["meta"], s["ocfg"], otaps)
+    perms = {}
+    for kind in ("hand", "obj"):
+        want_sdf = torch.stack([torch.sort(c.abs())[0][:otaps[kind]["index"].shape[1]] for c in otaps[kind]["cand_sdf"]])
+        perms[kind] = align_selection(taps[kind]["index"], otaps[kind]["index"], want_sdf)
+    for k, want in oout.items():
+        got = aligned(out[k], perms["obj"]) if k in ("obj_rot_out", "obj_trans_out") else out[k]
+        assert got.shape == want.shape, k
+        assert rel(got, want) < 1e-3, (k, rel(got, want))
+
+
 def test_single_pass_screening_is_verified_or_falls_back(setup):
     """Opt-in single-pass TF32 screening: ~6e-5 error, so the device-side check (gap > 3 x observed error) decides
     between accepting it and redoing the screening with 3xTF32; either way the selection equals the oracle's."""
