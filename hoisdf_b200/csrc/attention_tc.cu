@@ -89,6 +89,13 @@ __device__ __forceinline__ uint64_t at_desc_sw128(uint32_t smem_addr) {
   return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) |
          (1ull << 46) | (2ull << 61);
 }
+// One lane of a converged warp: the TMA / MMA issuing roles run on all 32 lanes and predicate only the issuing instructions
+// with this, so that their operands stay in uniform registers (see tc::elect_one in tc_common.cuh)
+__device__ __forceinline__ bool at_elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\t@p mov.u32 %0, 1;\n\t}" : "+r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void at_umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -229,7 +236,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_co
   auto bar_pe = [&](int g) { return bars + 8u * (11 + 2 * AT_STAGES + g); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (bars - base) + 8 * (14 + 2 * AT_STAGES));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // provably warp-uniform
+  const int lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AT_BQ * AT_GROUPS;
   const int h = blockIdx.y;
   const int64_t b = blockIdx.z;
@@ -256,36 +264,38 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_co
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   auto tmem_s = [&](int g, int buf) { return tmem + static_cast<uint32_t>(g * 128 + buf * AT_BK); };
   auto tmem_o = [&](int g) { return tmem + static_cast<uint32_t>(256 + g * AT_D); };
   auto tmem_p = [&](int g) { return tmem + static_cast<uint32_t>(384 + g * 64); };   // hi pairs; lo pairs at + 32
 
   if (warp == 0) {
-    if (lane == 0) {
-      at_mbar_expect_tx(bar_q, AT_GROUPS * 2 * AT_Q_BYTES);
+    {
+      const bool leader = at_elect_one();        // all 32 lanes walk the loops; this one issues
+      if (leader) at_mbar_expect_tx(bar_q, AT_GROUPS * 2 * AT_Q_BYTES);
       for (int g = 0; g < AT_GROUPS; ++g) {
         // (a tile that starts beyond this (sample, head)'s queries reads the neighbour's rows or zeros: its
         // results are never stored)
         const int qrow = static_cast<int>(bh * p.lq + q0 + g * AT_BQ);
-        at_tma_2d(q_hi(g), &map_qhi, bar_q, 0, qrow);
-        at_tma_2d(q_lo(g), &map_qlo, bar_q, 0, qrow);
+        if (leader) at_tma_2d(q_hi(g), &map_qhi, bar_q, 0, qrow);
+        if (leader) at_tma_2d(q_lo(g), &map_qlo, bar_q, 0, qrow);
       }
       for (int t = 0; t < T; ++t) {
         const int s = t % AT_STAGES;
         at_mbar_wait(bar_kve(s), ((t / AT_STAGES) & 1) ^ 1u);
         const uint32_t st = stages + s * AT_STAGE_BYTES;
-        at_mbar_expect_tx(bar_kvf(s), AT_STAGE_BYTES);
+        if (leader) at_mbar_expect_tx(bar_kvf(s), AT_STAGE_BYTES);
         const int krow = static_cast<int>(bh * p.lk + t * AT_BK);
-        at_tma_2d(st, &map_khi, bar_kvf(s), 0, krow);
-        at_tma_2d(st + AT_K_BYTES, &map_klo, bar_kvf(s), 0, krow);
+        if (leader) at_tma_2d(st, &map_khi, bar_kvf(s), 0, krow);
+        if (leader) at_tma_2d(st + AT_K_BYTES, &map_klo, bar_kvf(s), 0, krow);
         const int vrow = static_cast<int>(bh * AT_D);
-        at_tma_2d(st + 2 * AT_K_BYTES, &map_vhi, bar_kvf(s), t * AT_BK, vrow);
-        at_tma_2d(st + 3 * AT_K_BYTES, &map_vlo, bar_kvf(s), t * AT_BK, vrow);
+        if (leader) at_tma_2d(st + 2 * AT_K_BYTES, &map_vhi, bar_kvf(s), t * AT_BK, vrow);
+        if (leader) at_tma_2d(st + 3 * AT_K_BYTES, &map_vlo, bar_kvf(s), t * AT_BK, vrow);
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      const bool leader = at_elect_one();        // all 32 lanes walk the loops; this one issues
       // kind::f16: D = F32 (1<<4), A = B = BF16 (1<<7, 1<<10), K-major, N = 64 (8<<17), M = 128 (8<<24)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(AT_BK >> 3) << 17) |
                              (static_cast<uint32_t>(AT_BQ >> 4) << 24);
@@ -301,11 +311,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_co
 #pragma unroll
         for (int kk = 0; kk < AT_D / 16; ++kk) {
           const uint64_t adv = static_cast<uint64_t>(kk * 2);   // 16 bf16 = 32 bytes
-          at_umma_bf16(d_s, d_qlo + adv, d_khi + adv, idesc, kk != 0 ? 1u : 0u);
-          at_umma_bf16(d_s, d_qhi + adv, d_klo + adv, idesc, 1u);
-          at_umma_bf16(d_s, d_qhi + adv, d_khi + adv, idesc, 1u);
+          if (leader) at_umma_bf16(d_s, d_qlo + adv, d_khi + adv, idesc, kk != 0 ? 1u : 0u);
+          if (leader) at_umma_bf16(d_s, d_qhi + adv, d_klo + adv, idesc, 1u);
+          if (leader) at_umma_bf16(d_s, d_qhi + adv, d_khi + adv, idesc, 1u);
         }
-        at_commit(bar_sf(g, t & 1));
+        if (leader) at_commit(bar_sf(g, t & 1));
       };
       at_mbar_wait(bar_q, 0);
       for (int g = 0; g < AT_GROUPS; ++g) issue_qk(g, 0);
@@ -324,13 +334,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_co
           for (int kk = 0; kk < AT_BK / 16; ++kk) {
             const uint64_t adv = static_cast<uint64_t>(kk * 2);      // V^T: 16 keys = 32 bytes
             const uint32_t ka = static_cast<uint32_t>(kk * 8);        // P in TMEM: 16 bf16 = 8 columns
-            at_umma_bf16_ts(d_o, a_lo + ka, d_vhi + adv, idesc, (t | kk) != 0 ? 1u : 0u);
-            at_umma_bf16_ts(d_o, a_hi + ka, d_vlo + adv, idesc, 1u);
-            at_umma_bf16_ts(d_o, a_hi + ka, d_vhi + adv, idesc, 1u);
+            if (leader) at_umma_bf16_ts(d_o, a_lo + ka, d_vhi + adv, idesc, (t | kk) != 0 ? 1u : 0u);
+            if (leader) at_umma_bf16_ts(d_o, a_hi + ka, d_vlo + adv, idesc, 1u);
+            if (leader) at_umma_bf16_ts(d_o, a_hi + ka, d_vhi + adv, idesc, 1u);
           }
-          at_commit(bar_pe(g));       // this group's P buffer free, its O updated
+          if (leader) at_commit(bar_pe(g));       // this group's P buffer free, its O updated
         }
-        at_commit(bar_kve(s));        // K/V stage free (both groups' P.V have read it)
+        if (leader) at_commit(bar_kve(s));        // K/V stage free (both groups' P.V have read it)
       }
     }
   } else {
@@ -510,7 +520,8 @@ attention_tc128_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid
   auto bar_of = [&](int g) { return bars + 8u * (13 + g); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (bars - base) + 8 * 16);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // provably warp-uniform
+  const int lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AT_BQ * AT_GROUPS;
   const int h = blockIdx.y;
   const int64_t b = blockIdx.z;
@@ -540,17 +551,18 @@ attention_tc128_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   auto tmem_sp = [&](int g) { return tmem + static_cast<uint32_t>(g) * A2_GROUP_COLS; };          // S, then P in place
   auto tmem_o = [&](int g) { return tmem + static_cast<uint32_t>(g) * A2_GROUP_COLS + 128u; };
 
   if (warp == 0) {
-    if (lane == 0) {
-      at_mbar_expect_tx(bar_q, AT_GROUPS * 2 * AT_Q_BYTES);
+    {
+      const bool leader = at_elect_one();        // all 32 lanes walk the loops; this one issues
+      if (leader) at_mbar_expect_tx(bar_q, AT_GROUPS * 2 * AT_Q_BYTES);
       for (int g = 0; g < AT_GROUPS; ++g) {
         const int qrow = static_cast<int>(bh * p.lq + q0 + g * AT_BQ);
-        at_tma_2d(q_hi(g), &map_qhi, bar_q, 0, qrow);
-        at_tma_2d(q_lo(g), &map_qlo, bar_q, 0, qrow);
+        if (leader) at_tma_2d(q_hi(g), &map_qhi, bar_q, 0, qrow);
+        if (leader) at_tma_2d(q_lo(g), &map_qlo, bar_q, 0, qrow);
       }
       const int vrow = static_cast<int>(bh * AT_D);
       for (int t = 0; t < T; ++t) {
@@ -558,21 +570,22 @@ attention_tc128_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid
         const uint32_t ph = ((t / A2_STAGES) & 1) ^ 1u;
         at_mbar_wait(bar_ke(s), ph);
         const uint32_t ks = kring + s * A2_KSTAGE;
-        at_mbar_expect_tx(bar_kf(s), A2_KSTAGE);
+        if (leader) at_mbar_expect_tx(bar_kf(s), A2_KSTAGE);
         const int krow = static_cast<int>(bh * p.lk + t * A2_BK);
-        at_tma_2d(ks, &map_khi, bar_kf(s), 0, krow);
-        at_tma_2d(ks + A2_K_BYTES, &map_klo, bar_kf(s), 0, krow);
+        if (leader) at_tma_2d(ks, &map_khi, bar_kf(s), 0, krow);
+        if (leader) at_tma_2d(ks + A2_K_BYTES, &map_klo, bar_kf(s), 0, krow);
         at_mbar_wait(bar_ve(s), ph);
         const uint32_t vs = vring + s * A2_VSTAGE;
-        at_mbar_expect_tx(bar_vf(s), A2_VSTAGE);
-        at_tma_2d(vs, &map_vhi, bar_vf(s), t * A2_BK, vrow);
-        at_tma_2d(vs + A2_V_HALF, &map_vhi, bar_vf(s), t * A2_BK + 64, vrow);
-        at_tma_2d(vs + 2 * A2_V_HALF, &map_vlo, bar_vf(s), t * A2_BK, vrow);
-        at_tma_2d(vs + 3 * A2_V_HALF, &map_vlo, bar_vf(s), t * A2_BK + 64, vrow);
+        if (leader) at_mbar_expect_tx(bar_vf(s), A2_VSTAGE);
+        if (leader) at_tma_2d(vs, &map_vhi, bar_vf(s), t * A2_BK, vrow);
+        if (leader) at_tma_2d(vs + A2_V_HALF, &map_vhi, bar_vf(s), t * A2_BK + 64, vrow);
+        if (leader) at_tma_2d(vs + 2 * A2_V_HALF, &map_vlo, bar_vf(s), t * A2_BK, vrow);
+        if (leader) at_tma_2d(vs + 3 * A2_V_HALF, &map_vlo, bar_vf(s), t * A2_BK + 64, vrow);
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      const bool leader = at_elect_one();        // all 32 lanes walk the loops; this one issues
       // kind::f16: D = F32 (1<<4), A = B = BF16 (1<<7, 1<<10), K-major, N >> 3 at bit 17, M = 128 (8<<24)
       const uint32_t idesc_common = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(AT_BQ >> 4) << 24);
       const uint32_t idesc_qk = idesc_common | (static_cast<uint32_t>(A2_BK >> 3) << 17);
@@ -586,17 +599,17 @@ attention_tc128_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid
 #pragma unroll
         for (int kk = 0; kk < AT_D / 16; ++kk) {
           const uint64_t adv = static_cast<uint64_t>(kk * 2);   // 16 bf16 = 32 bytes
-          at_umma_bf16(d_s, d_qlo + adv, d_khi + adv, idesc_qk, kk != 0 ? 1u : 0u);
-          at_umma_bf16(d_s, d_qhi + adv, d_klo + adv, idesc_qk, 1u);
-          at_umma_bf16(d_s, d_qhi + adv, d_khi + adv, idesc_qk, 1u);
+          if (leader) at_umma_bf16(d_s, d_qlo + adv, d_khi + adv, idesc_qk, kk != 0 ? 1u : 0u);
+          if (leader) at_umma_bf16(d_s, d_qhi + adv, d_klo + adv, idesc_qk, 1u);
+          if (leader) at_umma_bf16(d_s, d_qhi + adv, d_khi + adv, idesc_qk, 1u);
         }
-        at_commit(bar_sf(g));
+        if (leader) at_commit(bar_sf(g));
       };
       at_mbar_wait(bar_q, 0);
       at_mbar_wait(bar_kf(0), 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       for (int g = 0; g < AT_GROUPS; ++g) issue_qk(g, 0);
-      at_commit(bar_ke(0));
+      if (leader) at_commit(bar_ke(0));
       for (int t = 0; t < T; ++t) {
         const int s = t % A2_STAGES;
         const uint32_t vs = vring + s * A2_VSTAGE;
@@ -612,9 +625,9 @@ attention_tc128_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid
             const uint64_t adv = static_cast<uint64_t>((kk & 3) * 2);                 // 16 keys = 32 bytes inside the box
             const uint64_t d_vhi = at_desc_sw128(vs + box) + adv, d_vlo = at_desc_sw128(vs + 2 * A2_V_HALF + box) + adv;
             const uint32_t ka = static_cast<uint32_t>(kk * 8);                         // P in TMEM: 16 bf16 = 8 columns
-            at_umma_bf16_ts(d_o, a_lo + ka, d_vhi, idesc_pv, (t | kk) != 0 ? 1u : 0u);
-            at_umma_bf16_ts(d_o, a_hi + ka, d_vlo, idesc_pv, 1u);
-            at_umma_bf16_ts(d_o, a_hi + ka, d_vhi, idesc_pv, 1u);
+            if (leader) at_umma_bf16_ts(d_o, a_lo + ka, d_vhi, idesc_pv, (t | kk) != 0 ? 1u : 0u);
+            if (leader) at_umma_bf16_ts(d_o, a_hi + ka, d_vlo, idesc_pv, 1u);
+            if (leader) at_umma_bf16_ts(d_o, a_hi + ka, d_vhi, idesc_pv, 1u);
           }
           if (t + 1 < T) {
             if (g == 0) {
@@ -623,10 +636,10 @@ attention_tc128_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid
             }
             issue_qk(g, t + 1);                                   // executes after P_t.V_t: S_{t+1} overwrites P_t
           } else {
-            at_commit(bar_of(g));                                 // last P.V of this group done: O final
+            if (leader) at_commit(bar_of(g));                                 // last P.V of this group done: O final
           }
         }
-        at_commit(bar_ve(s));                                     // V_t consumed by both groups
+        if (leader) at_commit(bar_ve(s));                                     // V_t consumed by both groups
         if (t + 1 < T) at_commit(bar_ke((t + 1) % A2_STAGES));    // K_{t+1} consumed by both groups
       }
     }

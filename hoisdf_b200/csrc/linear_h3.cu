@@ -115,7 +115,10 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
   const uint32_t w_bytes = single ? H3_W_BYTES : static_cast<uint32_t>(p.w_rows) * H3_BK * 2;     // one W plane of a stage
   const uint32_t stage_bytes = single ? H3_STAGE_BYTES_1P : 2 * H3_X_BYTES + 3 * w_bytes;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index made provably warp-uniform: the producer and MMA roles run their loops on all 32 lanes and predicate
+  // only the issuing instructions (tc::elect_one), so that the compiler keeps TMA / UMMA operands in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
   const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
   const int cluster = static_cast<int>(blockIdx.x) / CL;
   const int nclusters = static_cast<int>(gridDim.x) / CL;
@@ -152,7 +155,7 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
   __syncthreads();
   if (CL > 1) cluster_sync_all();            // peers' barriers are initialised before any multicast lands there
   tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   // work item -> tile coordinates of THIS CTA
   auto tile_of = [&](int item, int& m_tile, int& grp, int& m0, int& n0) {
@@ -165,9 +168,10 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
   };
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      uint32_t it = 0;
+    // ------------------------------------------------------------------ TMA producer (whole warp; one lane issues)
+    {
+      int s = 0;                                                   // ring stage and the parity of its "free" phase
+      uint32_t ph = 1u;
       for (int item = cluster; item < items; item += nclusters) {
         int m_tile, grp, m0, n0;
         tile_of(item, m_tile, grp, m0, n0);
@@ -184,45 +188,52 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
           cx0 = (rem - (rem / p.out_w) * p.out_w) * p.stride;
         }
         int tap = 0, cblk = 0;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = static_cast<int>(it % nstages);
-          const uint32_t ph = (it / nstages) & 1u;
-          mbar_wait(bar_empty(s), ph ^ 1u);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_empty(s), ph);
           const uint32_t st = base + s * stage_bytes;
-          mbar_expect_tx(bar_full(s), stage_bytes);
+          const bool issue = elect_one();
+          if (issue) mbar_expect_tx(bar_full(s), stage_bytes);
           if (p.taps > 0) {
             // shifted window of the input image for this tap; out-of-image pixels are zero-filled = zero padding
             const int ix = cx0 + p.dx[tap], iy = cy0 + p.dy[tap];
-            tma_load_4d(st, &map_xhi, bar_full(s), cblk * H3_BK, ix, iy, cb0);
-            if (!single) tma_load_4d(st + H3_X_BYTES, &map_xlo, bar_full(s), cblk * H3_BK, ix, iy, cb0);
+            if (issue) {
+              tma_load_4d(st, &map_xhi, bar_full(s), cblk * H3_BK, ix, iy, cb0);
+              if (!single) tma_load_4d(st + H3_X_BYTES, &map_xlo, bar_full(s), cblk * H3_BK, ix, iy, cb0);
+            }
             if (++cblk == p.cin_blocks) { cblk = 0; ++tap; }
-          } else {
+          } else if (issue) {
             tma_load_3d(st, &map_xhi, bar_full(s), kb * H3_BK, m0, grp);
             if (!single) tma_load_3d(st + H3_X_BYTES, &map_xlo, bar_full(s), kb * H3_BK, m0, grp);
           }
-          if (single) {                       // stage = [x_hi 8 KB | w_hi 16 KB]
-            const uint32_t w0 = st + H3_X_BYTES + wo;
-            if (CL > 1) tma_load_2d_mc(w0, &map_wb, bar_full(s), kb * H3_BK, wrow, kAllCtas);
-            else tma_load_2d(w0, &map_wb, bar_full(s), kb * H3_BK, wrow);
-            continue;
+          if (issue) {
+            if (single) {                       // stage = [x_hi 8 KB | w_hi 16 KB]
+              const uint32_t w0 = st + H3_X_BYTES + wo;
+              if (CL > 1) tma_load_2d_mc(w0, &map_wb, bar_full(s), kb * H3_BK, wrow, kAllCtas);
+              else tma_load_2d(w0, &map_wb, bar_full(s), kb * H3_BK, wrow);
+            } else {
+              const uint32_t w0 = st + 2 * H3_X_BYTES + wo;
+              if (CL > 1) {
+                tma_load_2d_mc(w0, &map_wa, bar_full(s), kb * H3_BK, wrow, kAllCtas);
+                tma_load_2d_mc(w0 + w_bytes, &map_wb, bar_full(s), kb * H3_BK, wrow, kAllCtas);
+                tma_load_2d_mc(w0 + 2 * w_bytes, &map_wc, bar_full(s), kb * H3_BK, wrow, kAllCtas);
+              } else {
+                tma_load_2d(w0, &map_wa, bar_full(s), kb * H3_BK, wrow);
+                tma_load_2d(w0 + w_bytes, &map_wb, bar_full(s), kb * H3_BK, wrow);
+                tma_load_2d(w0 + 2 * w_bytes, &map_wc, bar_full(s), kb * H3_BK, wrow);
+              }
+            }
           }
-          const uint32_t w0 = st + 2 * H3_X_BYTES + wo;
-          if (CL > 1) {
-            tma_load_2d_mc(w0, &map_wa, bar_full(s), kb * H3_BK, wrow, kAllCtas);
-            tma_load_2d_mc(w0 + w_bytes, &map_wb, bar_full(s), kb * H3_BK, wrow, kAllCtas);
-            tma_load_2d_mc(w0 + 2 * w_bytes, &map_wc, bar_full(s), kb * H3_BK, wrow, kAllCtas);
-          } else {
-            tma_load_2d(w0, &map_wa, bar_full(s), kb * H3_BK, wrow);
-            tma_load_2d(w0 + w_bytes, &map_wb, bar_full(s), kb * H3_BK, wrow);
-            tma_load_2d(w0 + 2 * w_bytes, &map_wc, bar_full(s), kb * H3_BK, wrow);
-          }
+          __syncwarp();
+          if (++s == nstages) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      uint32_t it = 0, cc = 0;                                     // stage counter, chunk counter
+    // ------------------------------------------------------------------ MMA issuer (whole warp; one lane issues: tcgen05.mma
+    // issue blocks while the tensor core is busy, so everything else in this loop is kept to a minimum)
+    {
+      uint32_t cc = 0, ph = 0u;                                    // chunk counter; parity of the stage's "full" phase
+      int s = 0;                                                   // ring stage
       for (int item = cluster; item < items; item += nclusters) {
         int m_tile, grp, m0, n0;
         tile_of(item, m_tile, grp, m0, n0);
@@ -231,18 +242,17 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
         const uint32_t idesc = umma_idesc_f16(H3_BM, n_inst);
         int in_chunk = 0;
         uint32_t acc = tmem_base;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb = 0; kb < num_kb; ++kb) {
           if (in_chunk == 0) {                                     // new chunk: the drain of chunk cc - 2 has finished
             const uint32_t buf = cc & 1u;
             mbar_wait(bar_cempty(buf), ((cc >> 1) & 1u) ^ 1u);
             tcgen05_fence_after();
             acc = tmem_base + buf * H3_BN;
           }
-          const int s = static_cast<int>(it % nstages);
-          const uint32_t ph = (it / nstages) & 1u;
           mbar_wait(bar_full(s), ph);
           tcgen05_fence_after();
           const uint32_t st = base + s * stage_bytes;
+          if (elect_one()) {
           if (single) {
             const uint64_t d_xhi = umma_desc_sw64(st), d_wb = umma_desc_sw64(st + H3_X_BYTES);
 #pragma unroll
@@ -265,8 +275,11 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
           }
           if (CL > 1) umma_commit_mc(bar_empty(s), kAllCtas);      // stage refillable once ALL CTAs' MMAs have read it
           else umma_commit(bar_empty(s));
+          if (in_chunk + 1 == chb || kb == num_kb - 1) umma_commit(bar_cfull(cc & 1u));   // chunk complete -> drain
+          }
+          __syncwarp();
+          if (++s == nstages) { s = 0; ph ^= 1u; }
           if (++in_chunk == chb || kb == num_kb - 1) {
-            umma_commit(bar_cfull(cc & 1u));                       // chunk complete -> drain
             ++cc;
             in_chunk = 0;
           }

@@ -275,8 +275,10 @@ def test_linear_h3_modes(cuda):
         yb = ops.linear_h3(ops.SplitRows(xs.buf[2:], d), p3, 0, x_batch=(P, T * xs.ld), m=L * P)
         ref = xb.view(L, T, d)[:, 2:2 + P].reshape(-1, d).double() @ w3.double().T + b3.double()
         assert rel_err(yb, ref) < 3e-6
+    # |w| >= 16: packed with a power-of-two scale (test_linear_h3_large_weights); non-finite weights are refused
+    assert ops.PackedLinearH3.pack(torch.full((4, 8), 40.0, device=cuda), None).scale == 8.0
     with pytest.raises(ValueError):
-        ops.PackedLinearH3.pack(torch.full((4, 8), 40.0, device=cuda), None)
+        ops.PackedLinearH3.pack(torch.full((4, 8), float("inf"), device=cuda), None)
 
 
 # ---------------------------------------------------------------- selection (bit-exact)
