@@ -31,6 +31,9 @@ UNIT = "samples/s"
 P_HAND, P_OBJ = 1536, 512
 ARCH = "ho3d"
 WEIGHT_SEED = 0
+# --config 3 = BASELINE.json configs[2] (SURVEY.md 8(d) "config 3"): global batch 128, DexYCB-shaped inputs (dexycb arch,
+# C = 992, the dataset's eval branch with its SDF supervision points), 4096 points, STRONG scaling over the ranks
+CONFIG3 = {"arch": "dexycb", "p_hand": 3072, "p_obj": 1024, "global_batch": 128}
 
 
 def load_peaks():
@@ -38,7 +41,7 @@ def load_peaks():
     if os.path.exists(p):
         d = json.load(open(p))
         return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
-                "source": "measured (MEASURED_PEAKS.json, sustained bf16)"}
+                "burst": d["bf16_tflops"], "source": "measured (MEASURED_PEAKS.json, sustained bf16)"}
     return {"hbm_gbs": 6650.0, "tflops": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
@@ -97,8 +100,11 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm), "window": window}
 
 
-def make_inputs(seed: int, batch: int):
+def make_inputs(seed: int, batch: int, config: int = 2):
     from hoisdf_b200 import synthetic as syn
+    if config == 3:
+        extra_in, targets = syn.dexycb_extras(seed, batch, CONFIG3["p_hand"], CONFIG3["p_obj"])
+        return {"img": syn.image_batch(seed, batch), **extra_in}, targets, syn.camera_meta(seed, batch)
     return {"img": syn.image_batch(seed, batch)}, syn.eval_targets(batch), syn.camera_meta(seed, batch)
 
 
@@ -134,6 +140,38 @@ def time_cpu(sample_batch: int, steps: int, warmup: int):
     return sample_batch * steps / dt, dt / steps, threads
 
 
+def time_gpu_eager(dev, sample_batch: int, steps: int, warmup: int):
+    """The oracle port (= upstream's algorithm, op for op) with every tensor on the GPU: stock PyTorch eager kernels
+    (cuDNN convolutions, cuBLAS sgemm, ATen grid_sampler / sort), per-sample Python loop and CPU bbox mask as upstream."""
+    import torch
+
+    from hoisdf_b200 import synthetic as syn
+    from oracle import hoisdf_oracle as O
+
+    sd = {k: v.to(dev) for k, v in syn.full_state_dict(WEIGHT_SEED, ARCH).items()}
+    ocfg = O.default_cfg(num_samp_hand=P_HAND, num_samp_obj=P_OBJ)
+    inputs, _, meta = make_inputs(1000, sample_batch)
+    img, meta = inputs["img"].to(dev), {k: v.to(dev) for k, v in meta.items()}
+
+    def step():
+        with torch.no_grad():
+            return O.model_eval(sd, img, meta, ocfg, ARCH)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": sample_batch * 1000.0 / ms, "unit": UNIT, "ms_per_step": ms, "samples_per_step": sample_batch,
+            "kind": "oracle port on the same GPU through stock PyTorch eager (cuDNN / cuBLAS fp32, TF32 off)",
+            "sample": "%d samples/step of the configs[1] workload, %d warm-up + %d timed steps" % (sample_batch, warmup, steps)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -154,7 +192,19 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n_gpus, batch=32, sample_batch_note=None):
+def workload_config(n_gpus, batch=32, sample_batch_note=None, config=2):
+    if config == 3:
+        return {
+            "workload": "BASELINE configs[2]: global batch 128 DexYCB-shaped synthetic inputs (256x256 crops, dexycb arch "
+                        "C=992, dataset eval branch incl. SDF supervision points + GT MANO), 4096 SDF points/sample "
+                        "(3072 hand + 1024 object), sharded by sample over the ranks (strong scaling)",
+            "global_batch": batch * n_gpus, "per_gpu_batch": batch, "points_hand": CONFIG3["p_hand"],
+            "points_obj": CONFIG3["p_obj"],
+            "parallelism": "sample-sharded x%d, one all-gather of packed results per step" % n_gpus,
+            "l2": "no explicit flush: each step streams several GB of activations/weights (>> 126 MB L2)",
+            "image_encoder": "ResNet-50 + U-Net on the FP16x3 tensor-core convolution kernels (no cuDNN)",
+            "cuda_graphs": "static stages replayed from CUDA graphs (--no-graphs: eager launches)",
+        }
     cfg = {
         "workload": "BASELINE configs[1]: batch=32 per GPU, synthetic 256x256 images, 2048 SDF points/sample "
                     "(1536 hand + 512 object), ho3d arch (C=3968), full backbone+U-Net+SDF+decoder eval forward",
@@ -198,11 +248,18 @@ def run_native(args):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.benchmark = True
-    cfg.set_setting(ARCH)
-    type(cfg).num_samp_hand, type(cfg).num_samp_obj = P_HAND, P_OBJ
-    B = args.batch
+    c3 = args.config == 3
+    arch, p_hand, p_obj = (CONFIG3["arch"], CONFIG3["p_hand"], CONFIG3["p_obj"]) if c3 else (ARCH, P_HAND, P_OBJ)
+    cfg.set_setting(arch)                       # config 3: also cfg.dataset = "dexycb" (the dataset's eval branch)
+    type(cfg).num_samp_hand, type(cfg).num_samp_obj = p_hand, p_obj
+    if c3:
+        if CONFIG3["global_batch"] % world:
+            raise SystemExit("bench.py --config 3: the global batch of 128 must divide by the number of ranks")
+        B = CONFIG3["global_batch"] // world    # strong scaling: the global batch is fixed
+    else:
+        B = args.batch
     model = get_model("test", mano_buffers=syn.mano_buffers(WEIGHT_SEED))
-    model.load_state_dict(syn.full_state_dict(WEIGHT_SEED, ARCH), strict=True)
+    model.load_state_dict(syn.full_state_dict(WEIGHT_SEED, arch), strict=True)
     # fp32 cuDNN is ~1.6x faster in NCHW than in channels_last on B200 (36 ms vs 58 ms for this batch), and the
     # NCHW->NHWC transposes the gather needs cost 0.3 ms, so the backbone stays NCHW here
     model = model.to(dev).eval()
@@ -211,12 +268,12 @@ def run_native(args):
         # CUDA graphs: same kernels, ~400 fewer host launches per step
         model.enable_cuda_graphs()
 
-    inputs, targets, meta = make_inputs(100 + rank, B)
+    inputs, targets, meta = make_inputs(100 + rank, B, args.config)
     pin = lambda d: {k: v.pin_memory() for k, v in d.items()}  # noqa
     h_inputs, h_targets, h_meta = pin(inputs), pin(targets), pin(meta)
     to_dev = lambda d: {k: v.to(dev, non_blocking=True) for k, v in d.items()}  # noqa
     d_inputs, d_targets, d_meta = to_dev(h_inputs), to_dev(h_targets), to_dev(h_meta)
-    width = packed_width(P_OBJ)
+    width = packed_width(p_obj)
     gathered = torch.empty(world * B, width, device=dev) if world > 1 else None
     h_result = torch.empty(B, width).pin_memory()
     h2d_bytes = sum(v.numel() * v.element_size() for d in (h_inputs, h_targets, h_meta) for v in d.values())
@@ -224,7 +281,7 @@ def run_native(args):
 
     def step_device():
         out = model(d_inputs, d_targets, d_meta, "eval")
-        packed = pack_outputs(out, P_OBJ)
+        packed = pack_outputs(out, p_obj)
         if world > 1:
             dist.all_gather_into_tensor(gathered, packed)
         return packed
@@ -232,7 +289,7 @@ def run_native(args):
     def step_e2e():
         di, dt, dm = to_dev(h_inputs), to_dev(h_targets), to_dev(h_meta)
         out = model(di, dt, dm, "eval")
-        packed = pack_outputs(out, P_OBJ)
+        packed = pack_outputs(out, p_obj)
         if world > 1:
             dist.all_gather_into_tensor(gathered, packed)
         h_result.copy_(packed, non_blocking=True)
@@ -288,6 +345,24 @@ def run_native(args):
     e2e = {"value": world * B * 1000.0 / ms_e2e, "unit": UNIT, "ms_per_step": ms_e2e,
            "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes}
 
+    # the hot path alone (SURVEY.md 8(d) "Metric" (ii): sdf_infer x2 ... hand_joints, i.e. everything after the U-Net),
+    # on the pyramid the image encoder produced for these inputs; eager launches
+    hot_path_only = None
+    if not c3:
+        with torch.no_grad():
+            pyr, _ = model.run_image_encoder(d_inputs["img"])
+        for _ in range(2):
+            model.hot_path(pyr, d_meta)
+        ms_hot = timed(lambda: model.hot_path(pyr, d_meta), args.steps) / args.steps
+        hot_path_only = {"value": world * B * 1000.0 / ms_hot, "unit": UNIT, "ms_per_step": ms_hot,
+                         "note": "Model.hot_path (everything after the U-Net) on a resident pyramid, eager launches"}
+    allgather_ms = None
+    if world > 1:                               # the collective alone (one packed block per rank)
+        blk = torch.zeros(B, width, device=dev)
+        for _ in range(3):
+            dist.all_gather_into_tensor(gathered, blk)
+        allgather_ms = timed(lambda: dist.all_gather_into_tensor(gathered, blk), 20) / 20
+
     # roofline pass: the same steps once more, launched eagerly (no graph replay) with a CUDA-event pair on the launching
     # stream around every launch of the dominant kernel; `share_of_step` is relative to this pass's own step time
     model.enable_cuda_graphs(False)
@@ -303,6 +378,7 @@ def run_native(args):
     # call); every such launch of the timed steps was bracketed by CUDA events on the launching stream
     torch.cuda.synchronize()
     tc = [p for p in prof if p[0] in ("linear_tc", "sdf_decoder", "linear_h3", "sdf_decoder_h3", "conv_h3")]
+    chain = [p for p in prof if p[0] == "sdf_chain"]
     h3 = any(p[0] in ("linear_h3", "sdf_decoder_h3") for p in tc)
     fma = [p for p in prof if p[0] == "linear"]
     tc_flops = sum(p[1] for p in tc)
@@ -324,6 +400,24 @@ def run_native(args):
     if h3 and os.path.exists(tpath):            # from the committed ncu launch list of `bench.py --profile-step`
         traffic = json.load(open(tpath))["dram_bytes_per_launch"]
         traffic_src = "profiles/r01n_h3_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, same command)"
+    chain_ms = sum(p[2].elapsed_time(p[3]) for p in chain)
+    chain_flops = sum(p[1] for p in chain)
+    chain_rows = sum(int(p[4].split("rows=")[1].split()[0]) for p in chain)
+    burst = peaks.get("burst", peaks["tflops"])
+    chain_stats = None
+    if chain_ms > 0:
+        chain_stats = {
+            "kernel": "hoisdf::sdf_chain_kernel (ONE persistent tcgen05 kernel per field for the candidate chain: "
+                      "linear_sdfin.1 -> NeRF embedding -> linh0..linh4 -> tanh; single-product fp16 screening "
+                      "arithmetic, activations in shared / tensor memory, 4 B per row written)",
+            "bound": "tensor", "achieved": chain_flops / (chain_ms * 1e-3) / 1e12, "peak": peaks["tflops"],
+            "unit": "TFLOP/s", "frac": chain_flops / (chain_ms * 1e-3) / 1e12 / peaks["tflops"],
+            "launches_per_step": len(chain) / args.steps, "share_of_step": chain_ms / ms_total,
+            "rows_per_step": chain_rows / args.steps, "ms_per_step": chain_ms / args.steps,
+            "algorithmic_bytes_per_row": 1028,
+            "note": "FLOPs = executed tensor-core FLOPs (one product per K step); algorithmic HBM bytes per row: "
+                    "1024 in (512 fp16) + 4 out",
+        }
     roofline = {
         "kernel": kernel_name,
         "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
@@ -337,16 +431,21 @@ def run_native(args):
         "fp32_fma_linear": {"achieved_tflops": fma_flops / (fma_ms * 1e-3) / 1e12 if fma_ms > 0 else 0.0,
                             "share_of_step": fma_ms / ms_total, "launches_per_step": len(fma) / args.steps,
                             "fp32_fma_peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12},
+        "candidate_chain": chain_stats,
     }
 
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    cpu_baseline = gpu_eager = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not c3:
         v, sec, threads = time_cpu(4, 4, 1)                 # ~10-15 s of host work on the box's cores
         cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                         "sample": "oracle port of the upstream eval forward, 4 samples/step of the same workload, "
                                   "1 warm-up + 4 timed steps (%.1f s/step)" % sec}
+        # "the existing GPU implementation" (BASELINE.md section 4): the same reference algorithm through stock PyTorch
+        # eager on this B200 (cuDNN / cuBLAS fp32, TF32 off) -- upstream ships no CUDA of its own
+        torch.cuda.empty_cache()
+        gpu_eager = time_gpu_eager(dev, 8, 3, 1)
     if rank == 0:
-        conf = workload_config(world, B)
+        conf = workload_config(world, B, config=args.config)
         if n_f is not None:
             conf["mean_candidates_per_sample"] = {"hand": n_f[0], "obj": n_f[1]}
         line = {
@@ -354,7 +453,12 @@ def run_native(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": conf, "clocks": clocks, "e2e": e2e,
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "gpu_eager_baseline": gpu_eager, "hot_path_only": hot_path_only,
         }
+        if c3:
+            line["scaling"] = "strong"
+        if allgather_ms is not None:
+            line["allgather_ms"] = allgather_ms
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -367,6 +471,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="samples per GPU per step (configs[1]: 32)")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3],
+                    help="2 = BASELINE configs[1] (default, the metric's config); 3 = configs[2]: global batch 128, dexycb, "
+                         "4096 points, strong scaling")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly (no CUDA-graph replay)")
     ap.add_argument("--profile-step", action="store_true",

@@ -111,25 +111,33 @@ class CandidatePlan:
 
 class GraphedForward:
     """CUDA graphs of the two static-shape stages of one eval forward (same kernels, replayed without the ~400
-    Python / ctypes launches): G1 = image encoder + pyramid projection, G2 = everything after the point selection.
+    Python / ctypes launches): G1 = image encoder + pyramid projection, G2 = everything after the point selection
+    (for the dexycb dataset branch also the two SDF queries at the supervision points and the ground-truth MANO forward).
     The selection itself stays eager: its row counts are data dependent (they size the candidate buffers)."""
 
-    def __init__(self, model: "Model", img, root, objc, K):
+    def __init__(self, model: "Model", img, root, objc, K, extras=None):
         self.model = model
         self.img, self.root, self.objc, self.K = img.clone(), root.clone(), objc.clone(), K.clone()
+        self.extras = None if extras is None else {k: v.clone() for k, v in extras.items()}
         self.pool = torch.cuda.graph_pool_handle()
         self.g1 = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.g1, pool=self.pool, capture_error_mode="relaxed"):
             pyr, self.decoder_out = model.run_image_encoder(self.img)
             self.ctx = PyramidContext(pyr, model)
             self.ctx.gmaps                       # projection of the pyramid through linear_sdfin layer 0
-        self.g2 = self.sel = self.out = self.taps = None
+        self.g2 = self.sel = self.out = self.taps = self.dex_sdf = None
 
     def capture_pose(self, sel):
         self.sel = {k: v.clone() for k, v in sel.items()}
         self.g2 = torch.cuda.CUDAGraph()
+        m, ex = self.model, self.extras
         with torch.cuda.graph(self.g2, pool=self.pool, capture_error_mode="relaxed"):
-            self.out, self.taps = self.model._pose_from_points(self.ctx, self.sel, self.root, self.objc, self.K)
+            self.out, self.taps = m._pose_from_points(self.ctx, self.sel, self.root, self.objc, self.K,
+                                                      None if ex is None else ex["mano_param"])
+            if ex is not None:                   # upstream model.py:376-391: SDF at the supervision points
+                hand_s, _, _ = m.sdf_forward(self.ctx, ex["hand_sdf_points"], self.root, self.K, cfg.hand_sdf_scale, "hand")
+                obj_s, _, _ = m.sdf_forward(self.ctx, ex["obj_sdf_points"], self.objc, self.K, cfg.obj_sdf_scale, "obj")
+                self.dex_sdf = (hand_s, obj_s)
 
 
 class Model(nn.Module):
@@ -447,67 +455,84 @@ class Model(nn.Module):
         if mode == "train":
             raise NotImplementedError("hoisdf_b200 builds the inference hot path; the training step "
                                       "(backward kernels, SURVEY.md section 8 f-2) is not built yet")
-        graphed = (self._graphs is not None and cfg.dataset != "dexycb" and cfg.tc_backbone and cfg.tc_unet
-                   and ops.use_h3() and inputs["img"].is_cuda)
+        graphed = (self._graphs is not None and cfg.tc_backbone and cfg.tc_unet and ops.use_h3()
+                   and inputs["img"].is_cuda)
+        dex = cfg.dataset == "dexycb"
         with torch.no_grad():
             if graphed:
-                out = self._forward_graphed(inputs["img"], meta_info)
-                if cfg.eval_losses:
-                    out = {**eval_losses(self.last_taps, targets, meta_info, None), **out}
-                return out
-            img = inputs["img"]
-            plans = self._plans(meta_info)
-            if getattr(self, "_channels_last", False):
-                img = img.contiguous(memory_format=torch.channels_last)
-            feature_pyramid, decoder_out = self.run_image_encoder(img)
-            ctx = self._ctx(feature_pyramid)
-            dex = cfg.dataset == "dexycb"
-            mano_params = targets["mano_param"] if dex else None
-            out = self._hot_path(ctx, meta_info, plans, mano_params)
+                out, decoder_out, dex_sdf = self._forward_graphed(inputs, targets, meta_info)
+            else:
+                img = inputs["img"]
+                plans = self._plans(meta_info)
+                if getattr(self, "_channels_last", False):
+                    img = img.contiguous(memory_format=torch.channels_last)
+                feature_pyramid, decoder_out = self.run_image_encoder(img)
+                ctx = self._ctx(feature_pyramid)
+                out = self._hot_path(ctx, meta_info, plans, targets["mano_param"] if dex else None)
+                dex_sdf = None
+                if dex:
+                    # upstream model.py:370-391: SDF at the supervision points
+                    root, objc, K = meta_info["mano_root"], meta_info["obj_center_cam"], meta_info["cam_intr"]
+                    hand_s, _, _ = self.sdf_forward(ctx, inputs["hand_sdf_points"], root, K, cfg.hand_sdf_scale, "hand")
+                    obj_s, _, _ = self.sdf_forward(ctx, inputs["obj_sdf_points"], objc, K, cfg.obj_sdf_scale, "obj")
+                    dex_sdf = (hand_s, obj_s)
             taps = self.last_taps
             if dex:
-                # upstream model.py:370-422: SDF supervision points, heat-map / segmentation heads, GT MANO
-                root, objc, K = meta_info["mano_root"], meta_info["obj_center_cam"], meta_info["cam_intr"]
-                hand_s, _, _ = self.sdf_forward(ctx, inputs["hand_sdf_points"], root, K, cfg.hand_sdf_scale, "hand")
-                obj_s, _, _ = self.sdf_forward(ctx, inputs["obj_sdf_points"], objc, K, cfg.obj_sdf_scale, "obj")
+                # upstream model.py:393-422,606-620: heat-map / segmentation heads, GT MANO, the extra loss entries
                 out["joint_heatmap_out"] = decoder_out[:, 0]
                 out["hand_seg_gt_out"] = targets["hand_seg"]
                 out["hand_seg_pred_out"] = decoder_out[:, 1]
                 out["obj_seg_gt_out"] = targets["obj_seg"]
                 out["obj_seg_pred_out"] = decoder_out[:, 2]
-                out["mano_joints_gt_out"] = taps["gt_mano"]["joints3d"]
-                out["mano_mesh_gt_out"] = taps["gt_mano"]["verts3d"]
+                out["mano_joints_gt_out"] = taps["gt_mano"]["joints3d"].clone() if graphed else taps["gt_mano"]["joints3d"]
+                out["mano_mesh_gt_out"] = taps["gt_mano"]["verts3d"].clone() if graphed else taps["gt_mano"]["verts3d"]
                 if cfg.eval_losses:
-                    out = {**dexycb_losses(out, taps, targets, decoder_out, hand_s, obj_s, taps["pred_mano"],
+                    out = {**dexycb_losses(out, taps, targets, decoder_out, dex_sdf[0], dex_sdf[1], taps["pred_mano"],
                                            taps["gt_mano"]), **out}
             if cfg.eval_losses:
                 joint_gt = targets["joint_cam_no_trans"][:, 1:] if dex else None
                 out = {**eval_losses(taps, targets, meta_info, joint_gt), **out}
         return out
 
-    def _forward_graphed(self, img, meta_info):
-        """The ho3d eval forward with its two static stages replayed from CUDA graphs (see GraphedForward)."""
+    def _forward_graphed(self, inputs, targets, meta_info):
+        """The eval forward with its two static stages replayed from CUDA graphs (see GraphedForward).  Returns
+        (`*_out` dict, decoder_out, (hand, obj) SDF at the dexycb supervision points or None): copies, the graphs'
+        output buffers are reused by the next forward."""
         root = meta_info["mano_root"].to(torch.float32).contiguous()
         objc = meta_info["obj_center_cam"].to(torch.float32).contiguous()
         K = meta_info["cam_intr"].to(torch.float32).contiguous()
-        img = img.to(torch.float32)
+        img = inputs["img"].to(torch.float32)
+        dex = cfg.dataset == "dexycb"
+        extras = None
+        if dex:
+            extras = {"hand_sdf_points": inputs["hand_sdf_points"].to(torch.float32).contiguous(),
+                      "obj_sdf_points": inputs["obj_sdf_points"].to(torch.float32).contiguous(),
+                      "mano_param": targets["mano_param"].to(torch.float32).contiguous()}
         wkey = self._weights_key()
         if self._graphs.get("weights") != wkey:
             self._graphs = {"weights": wkey}         # parameters changed: packed weights were rebuilt, recapture
-        key = (tuple(img.shape), str(img.device), int(cfg.num_samp_hand), int(cfg.num_samp_obj), cfg.setting,
-               cfg.final_stage, bool(cfg.screen_single), bool(cfg.tc_projection), int(cfg.backbone_chunk_kb))
+        key = (tuple(img.shape), str(img.device), int(cfg.num_samp_hand), int(cfg.num_samp_obj), cfg.setting, cfg.dataset,
+               cfg.final_stage, bool(cfg.screen_single), bool(cfg.tc_projection), int(cfg.backbone_chunk_kb),
+               bool(cfg.fused_chain), None if extras is None else tuple(tuple(v.shape) for v in extras.values()))
         gs = self._graphs.get(key)
         if gs is None:
             # one eager forward first: packs the weights, sizes the workspaces, sets the kernel attributes
             pyr, _ = self.run_image_encoder(img)
-            self._hot_path(PyramidContext(pyr, self), meta_info, None)
+            ctx = PyramidContext(pyr, self)
+            self._hot_path(ctx, meta_info, None, None if extras is None else extras["mano_param"])
+            if dex:
+                self.sdf_forward(ctx, extras["hand_sdf_points"], root, K, cfg.hand_sdf_scale, "hand")
+                self.sdf_forward(ctx, extras["obj_sdf_points"], objc, K, cfg.obj_sdf_scale, "obj")
             torch.cuda.synchronize()
-            gs = self._graphs[key] = GraphedForward(self, img, root, objc, K)
+            gs = self._graphs[key] = GraphedForward(self, img, root, objc, K, extras)
         plans = self._plans(meta_info)               # eager: lattice counts + the async read-back of the row counts
         gs.img.copy_(img)
         gs.root.copy_(root)
         gs.objc.copy_(objc)
         gs.K.copy_(K)
+        if dex:
+            for k, v in extras.items():
+                gs.extras[k].copy_(v)
         gs.g1.replay()
         level = 0
         while True:
@@ -523,7 +548,10 @@ class Model(nn.Module):
                 raise RuntimeError("point-selection screening could not be verified")
             level += 1                               # rare: escalate the cascade, replay the pose stage
         self.last_taps = dict(gs.taps, hand=th, obj=to)
-        return {k: v.clone() for k, v in gs.out.items()}    # the graph's output buffers are reused by the next forward
+        out = {k: v.clone() for k, v in gs.out.items()}
+        if not dex:
+            return out, None, None
+        return out, gs.decoder_out.clone(), tuple(t.clone() for t in gs.dex_sdf)
 
     def run_image_encoder(self, img):
         """ResNet-50 + U-Net -> (feature pyramid, decoder_out).  On the FP16x3 tensor-core kernels end to end when

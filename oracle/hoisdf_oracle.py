@@ -117,7 +117,7 @@ def lattice(bins_n=64):
 
 def grid_from_uv(uv, cfg):
     """upstream main/model.py:152-157 / :194-198 / :304-310."""
-    normalizer = torch.tensor([cfg.input_img_shape[1] - 1, cfg.input_img_shape[0] - 1]) / 2
+    normalizer = (torch.tensor([cfg.input_img_shape[1] - 1, cfg.input_img_shape[0] - 1]) / 2).to(uv.device)
     return (uv - normalizer) / normalizer
 
 
@@ -169,20 +169,23 @@ def sdf_infer(p, pyramid, center, K, bbox, sdf_scale, num_points, kind, cfg, tap
     `cand_index` / `cand_sdf` lists (per sample: lattice indices that passed the bbox, raw SDF values).
     """
     B = center.shape[0]
+    dev = center.device               # cuda only in bench.py's "stock PyTorch eager on the same GPU" baseline leg
     samples = lattice(cfg.bins_n)
     all_idx = torch.arange(cfg.bins_n ** 3)
-    pts = torch.zeros(B, num_points, 3)
-    sdf = torch.zeros(B, num_points, 1)
-    pe = torch.zeros(B, num_points, cfg.PointFeatSize - 3)
-    sel_index = torch.zeros(B, num_points, dtype=torch.long)
+    pts = torch.zeros(B, num_points, 3, device=dev)
+    sdf = torch.zeros(B, num_points, 1, device=dev)
+    pe = torch.zeros(B, num_points, cfg.PointFeatSize - 3, device=dev)
+    sel_index = torch.zeros(B, num_points, dtype=torch.long, device=dev)
     n_f = torch.zeros(B, dtype=torch.long)
     cand_index, cand_sdf = [], []
     dec = "%s_sdf_decoder" % kind
     for b in range(B):
-        m, uv = candidate_mask(samples, center[b], K[b], bbox[b], sdf_scale)
-        b_uv = uv[m].unsqueeze(0)
-        b_samples = samples[m].clone()
-        b_index = all_idx[m]
+        # upstream does the projection and the bbox test on the CPU whatever the model's device (model.py:286-302:
+        # three .cpu() copies, then the surviving points go back with .cuda())
+        m, uv = candidate_mask(samples, center[b].cpu(), K[b].cpu(), bbox[b].cpu(), sdf_scale)
+        b_uv = uv[m].unsqueeze(0).to(dev)
+        b_samples = samples[m].clone().to(dev)
+        b_index = all_idx[m].to(dev)
         feats = gather_pyramid(pyramid, grid_from_uv(b_uv, cfg), sample=b)
         fea = mlp(p, "linear_sdfin", feats, 2, True)
         b_pe = nerf_embed(b_samples, (cfg.PointFeatSize - 3) // 6)
@@ -428,7 +431,7 @@ def mano_layer(p, prefix, pose_aa, betas):
     weights, hands_mean = p[prefix + ".th_weights"], p[prefix + ".th_hands_mean"]
     full_pose = torch.cat([pose_aa[:, :3], hands_mean + pose_aa[:, 3:48]], 1)
     rot_map = rodrigues(full_pose.contiguous().view(-1, 3)).view(N, 16 * 9)
-    eye = torch.eye(3).view(1, 9).repeat(N, 16)
+    eye = torch.eye(3, device=pose_aa.device).view(1, 9).repeat(N, 16)
     pose_map = (rot_map - eye)[:, 9:]
     root_rot = rot_map[:, :9].view(N, 3, 3)
     rot_map = rot_map[:, 9:]
@@ -458,7 +461,7 @@ def mano_layer(p, prefix, pose_aa, betas):
     tmp2 = torch.matmul(results, joint_js.unsqueeze(3))
     results2 = (results - torch.cat([tmp2.new_zeros(N, 16, 4, 3), tmp2], 3)).permute(0, 2, 3, 1)
     T = torch.matmul(results2, weights.transpose(0, 1))
-    rest_h = torch.cat([v_posed.transpose(2, 1), torch.ones(N, 1, v_posed.shape[1])], 1)
+    rest_h = torch.cat([v_posed.transpose(2, 1), torch.ones(N, 1, v_posed.shape[1], device=v_posed.device)], 1)
     verts = (T * rest_h.unsqueeze(1)).sum(2).transpose(2, 1)[:, :, :3]
     jtr = results[:, :, :3, 3]
     tips = verts[:, [745, 317, 444, 556, 673]]
@@ -602,7 +605,8 @@ def hot_path_eval(p, pyramid, meta, cfg, taps=None):
     obj_in = torch.cat([tok(obj_nt, obj_pe, obj_fea * sigma_obj),
                         tok(hand_o_nt, hand_o_pe, hand_fea * sigma_hand_o)], dim=0)
     hs, memory, hand_enc = transformer(p, "hand_transformer", hand_in, p["mano_query_embed.weight"],
-                                       torch.zeros_like(hand_in), mano_tgt_mask(cfg), mano_memory_mask(cfg), cfg)
+                                       torch.zeros_like(hand_in), mano_tgt_mask(cfg).to(hand_in.device),
+                                       mano_memory_mask(cfg).to(hand_in.device), cfg)
     _, obj_enc = vote_transformer(p, "obj_transformer", obj_in, torch.zeros_like(obj_in), cfg)
     Ph, Po = cfg.num_samp_hand, cfg.num_samp_obj
     hand_off = mlp(p, "linear_handvote", hand_enc[:, :Ph], 4, False)

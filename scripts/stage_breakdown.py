@@ -32,7 +32,7 @@ def wrap(obj, name, label):
         e0.record(); r = fn(*args, **kw); e1.record()
         times.setdefault(label, []).append((e0, e1)); return r
     setattr(obj, name, w)
-wrap(model.backbone_net, "forward", "backbone(cudnn)"); wrap(model.decoder_net, "forward", "unet(cudnn)")
+wrap(model, "run_image_encoder", "image_encoder(resnet+unet)")
 wrap(model, "sdf_infer", "sdf_infer"); wrap(model, "get_input_transformer", "point_features"); wrap(model, "sdf_forward", "sdf_forward(cross)")
 wrap(model.hand_transformer, "forward_bm", "hand_transformer"); wrap(model.obj_transformer, "forward_bm", "obj_transformer")
 wrap(model.mano_head, "forward_bm", "mano"); wrap(ops, "vote_joints", "vote")

@@ -356,6 +356,14 @@ def test_dexycb_eval_branch(setup):
             assert rel(out[k], torch.from_numpy(g[k])) < 1e-3, (k, "vs upstream fixture")
         for k in ("hand_seg_gt_out", "obj_seg_gt_out"):
             assert torch.equal(out[k].cpu(), targets[k.replace("_gt_out", "")])
+        # the same branch with its static stages replayed from CUDA graphs (bench.py --config 3): bit-identical, twice
+        model.enable_cuda_graphs()
+        for _ in range(2):
+            gout = model({"img": img.to(dev), **to_dev(inputs, dev)}, tdev, to_dev(meta, dev), "eval")
+            assert set(gout) == set(out)
+            for k in out:
+                assert torch.equal(gout[k], out[k]), k
+        model.enable_cuda_graphs(False)
         # entries behind the selection (cuDNN vs MKL-DNN pyramids can flip near-ties): same gate as the image test
         for k in ("mano_mesh_out", "mano_joints_out", "hand_joints_out", "loss_all_joint_3d", "mano_mesh_loss",
                   "mano_joint_loss", "pose_param_loss", "shape_param_loss", "loss_joint_cls", "obj_rot", "obj_trans"):
