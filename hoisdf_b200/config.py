@@ -86,6 +86,36 @@ class Config:
     # 3.5e-6 at 1, 5.3e-6 at 2, 8.9e-6 at 4; cuDNN fp32: 2e-6 .. 3.7e-6)
     backbone_chunk_kb = 1
 
+    # ---- read-through to the upstream singleton -------------------------------------------------------------------
+    # When hoisdf_b200 runs under the upstream harness (main/test.py patched as INTEGRATION.md shows), the caller edits
+    # `main.config.cfg` (e.g. cfg.num_samp_hand, the dataset `setting`); after `link_upstream()` every attribute that
+    # upstream's Config also defines is READ from that object at call time, so those edits reach the kernels.
+    _upstream = None
+
+    def link_upstream(self, upstream_cfg=None):
+        """Read the attributes upstream also defines from `upstream_cfg` (default: `main.config.cfg` if that module has
+        been imported).  Returns True when linked.  `link_upstream(False)` unlinks."""
+        import sys
+        cls = type(self)
+        if upstream_cfg is False:
+            cls._upstream = None
+            return False
+        if upstream_cfg is None:
+            mod = sys.modules.get("main.config") or sys.modules.get("config")
+            upstream_cfg = getattr(mod, "cfg", None) if mod is not None else None
+        if upstream_cfg is None or upstream_cfg is self:
+            return False
+        cls._upstream = upstream_cfg
+        return True
+
+    def __getattribute__(self, name):
+        if not name.startswith("_"):
+            up = type(self)._upstream
+            if up is not None and name in type(self).__dict__ and not callable(type(self).__dict__[name]) \
+                    and hasattr(up, name):
+                return getattr(up, name)
+        return object.__getattribute__(self, name)
+
     def calc_mutliscale_dim(self, use_big_decoder_l, resnet_type_l):
         # upstream config.py:101-108 (sic: "mutliscale")
         self.mutliscale_dim = 128 + 256 + 512 + 1024 + 2048 if use_big_decoder_l else 32 + 64 + 128 + 256 + 512

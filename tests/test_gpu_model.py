@@ -405,3 +405,33 @@ def test_cuda_graph_forward_matches_eager(setup):
         m.enable_cuda_graphs(False)
         with torch.no_grad():
             m.linear_pose.layers[0].bias.sub_(0.01)
+
+
+def test_drop_in_under_the_upstream_harness(setup, tmp_path):
+    """drive the drop-in exactly like upstream's Tester (common/base.py:179-193) and test loop
+    (main/test.py:119-129): get_model("test") -> .cuda() -> DataParallel -> torch.load(snapshot) ->
+    load_state_dict(ckpt["network"], strict=True) with `module.`-prefixed keys -> .eval() -> model(inputs, targets,
+    meta_info, "eval") on CPU batch tensors (DataParallel scatters them) -> split into `*_out` / losses, `.mean()`."""
+    from torch.nn import DataParallel
+    from hoisdf_b200.model import get_model
+    s = setup
+    snap = tmp_path / "snapshot_0_0.pth.tar"
+    torch.save({"epoch": 0, "network": {"module." + k: v for k, v in s["sd"].items()}}, snap)   # common/base.py:113-118
+    model = get_model("test", mano_buffers=syn.mano_buffers(s["seed"]))
+    model = model.cuda()
+    model = DataParallel(model, device_ids=[0])
+    ckpt = torch.load(snap)
+    model.load_state_dict(ckpt["network"], strict=True)
+    model.eval()
+    img = syn.image_batch(s["seed"] + 30, s["B"])
+    inputs, targets, meta = {"img": img}, syn.eval_targets(s["B"]), s["meta"]
+    with torch.no_grad():
+        model_out = model(inputs, targets, meta, "eval")
+    out = {k[:-4]: model_out[k] for k in model_out.keys() if "_out" in k}
+    loss = {k: model_out[k] for k in model_out.keys() if "_out" not in k}
+    loss = {k: loss[k].mean() for k in loss}
+    assert set(out) == {"hand_joints", "mano_joints", "mano_mesh", "obj_rot", "obj_trans"}
+    assert all(v.is_cuda and v.shape[0] == s["B"] for v in out.values()) and all(v.dim() == 0 for v in loss.values())
+    direct = s["model"]({"img": img.to(s["dev"])}, to_dev(targets, s["dev"]), to_dev(meta, s["dev"]), "eval")
+    for k in out:
+        assert torch.equal(out[k], direct[k + "_out"]), k

@@ -111,3 +111,19 @@ def test_shard_and_pack():
     assert packed.shape == (b, packed_width(po)) and packed_width(200) == 3657 and packed_width(1024) == 8601
     back = unpack_outputs(packed, po)
     assert all(torch.equal(back[k], out[k]) for k in out)
+
+
+def test_config_reads_through_to_upstream_singleton():
+    """edits of upstream's `main.config.cfg` reach hoisdf_b200 once the two are linked."""
+    from types import SimpleNamespace
+    from hoisdf_b200.config import cfg
+    up = SimpleNamespace(num_samp_hand=123, num_samp_obj=45, hand_sdf_scale=6.2, unrelated=1)
+    try:
+        assert cfg.link_upstream(up)
+        assert (cfg.num_samp_hand, cfg.num_samp_obj, cfg.hand_sdf_scale) == (123, 45, 6.2)
+        assert cfg.bins_n == 64 and cfg.fused_chain in (True, False)     # not defined upstream: our own value
+        up.num_samp_hand = 77                                            # read at call time, like upstream's cfg
+        assert cfg.num_samp_hand == 77
+    finally:
+        cfg.link_upstream(False)
+    assert cfg.num_samp_hand != 77
