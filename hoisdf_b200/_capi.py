@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhoisdf_b200.so")
 
-ABI_VERSION = 18
+ABI_VERSION = 20
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2      # ACT_SIGMOID: hoisdf_linear_narrow_split_fwd only
 GATHER_CONCAT, GATHER_SUM = 0, 1
 
@@ -73,7 +73,12 @@ class SdfChainArgs(C.Structure):
         ("w_s1", vp), ("ldw_s1", i64), ("b_s1", vp),
         ("w", vp * 4), ("ldw", i64 * 4), ("b", vp * 4), ("w4", vp), ("b4", vp),
         ("rows", i64), ("clamp", f32), ("out_sdf", vp),
+        ("gmaps", vp), ("uv", vp), ("row_offsets", vp), ("batch", i64), ("rows_per_sample", i64), ("b_s0", vp),
     ]
+
+
+class PyramidH(C.Structure):
+    _fields_ = [("map", vp * 5), ("h", i32 * 5), ("w", i32 * 5), ("levels", i32), ("c", i32), ("img_h", i32), ("img_w", i32)]
 
 
 class ManoModel(C.Structure):
@@ -106,6 +111,8 @@ SIGNATURES = {
     "hoisdf_posenc_split_fwd": (C.c_int, [vp, vp, i64, i32, vp, vp, i64, vp]),
     "hoisdf_sdf_decoder_h3_fwd": (C.c_int, [C.POINTER(SdfWeightsH3), vp, vp, i64, i64, vp, vp, vp, vp, i64, vp, f32, vp]),
     "hoisdf_sdf_chain_fwd": (C.c_int, [C.POINTER(SdfChainArgs), vp]),
+    "hoisdf_f32_to_f16": (C.c_int, [vp, vp, i64, vp]),
+    "hoisdf_gather_sum_h16_fwd": (C.c_int, [C.POINTER(PyramidH), vp, i64, vp, i64, i64, vp, i32, vp, i64, vp]),
     "hoisdf_posenc_fwd": (C.c_int, [vp, vp, i64, i32, vp, i64, i64, vp]),
     "hoisdf_sdf_decoder_fwd": (C.c_int, [C.POINTER(SdfWeights), vp, i64, i64, vp, vp, vp, f32, vp]),
     "hoisdf_sdf_pad_input": (C.c_int, [vp, i64, vp, i64, vp]),

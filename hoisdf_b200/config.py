@@ -70,6 +70,14 @@ class Config:
     # stage A (all candidates, single-product fp16) as ONE persistent tcgen05 kernel with the activation tile kept in
     # shared / tensor memory (csrc/sdf_chain.cu) instead of 5 GEMM launches + posenc + head with split-half round trips
     fused_chain = True
+    # fp16 copy of the projected maps for stage A: the screening gather reads half the bytes per tap and writes only the
+    # fp16 hi plane the chain kernel consumes (csrc/gather.cu gather_sum_h16_kernel)
+    gather_h16 = True
+    # the bilinear gather done by 8 gather warps INSIDE the chain kernel (hoisdf_sdf_chain_fwd gather mode): the gathered
+    # (N, 512) rows never exist in HBM, but the kernel's 226 KB of shared memory leave ~24 KB of L1, so its 20 taps x 1 KB
+    # per row come from L2 instead of L1 (the stand-alone gather runs with the full 256 KB L1: 73 % hit rate).  Measured:
+    # 5.9 ms per step against 2.4 + 1.6 for chain + stand-alone fp16 gather -- correct, tested, but off by default
+    fused_gather = False
     screen_margin_single = 1024
     # linear_sdfin layer 0 applied to the pyramid (Model: PyramidContext.gmaps) on the FP16x3 GEMM with a TMEM drain
     # every `projection_chunk_kb` K blocks instead of the fp32 FMA kernel (3.2 ms -> 0.6 ms at batch 32)

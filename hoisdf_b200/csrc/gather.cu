@@ -153,6 +153,76 @@ __global__ void __launch_bounds__(256) gather_sum_kernel(const GatherParams p) {
   }
 }
 
+// SUM mode on fp16 maps with an fp16 (hi plane only) result: the candidate SCREENING path (single-product chain kernel,
+// csrc/sdf_chain.cu, which reads nothing but the hi plane).  Half the L1 / L2 bytes per tap of the fp32 kernel above and a
+// quarter of its output bytes.  One warp per row, C = 512: every lane owns 16 channels (2 x 16 bytes per tap).
+struct GatherH16Params {
+  const uint4* __restrict__ map[5];     // (B, H_l, W_l, 512) halfs
+  int h[5], w[5];
+  int levels, img_w, img_h;
+  const float* __restrict__ uv;
+  const int64_t* __restrict__ row_offsets;
+  const float* __restrict__ bias;
+  __half* __restrict__ out_hi;
+  int64_t rows, batch, rows_per_sample, ld_out;
+  int act;
+};
+
+__global__ void __launch_bounds__(256) gather_sum_h16_kernel(const GatherH16Params p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (r >= p.rows) return;
+  int64_t b;
+  if (p.row_offsets == nullptr) {
+    b = r / p.rows_per_sample;
+  } else {
+    int64_t lo = 0, hi = p.batch;
+    while (hi - lo > 1) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (p.row_offsets[mid] <= r) lo = mid; else hi = mid;
+    }
+    b = lo;
+  }
+  const float u = p.uv[r * 2 + 0], v = p.uv[r * 2 + 1];
+  float acc[16];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 bb = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + lane * 16) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    acc[4 * q] = bb.x; acc[4 * q + 1] = bb.y; acc[4 * q + 2] = bb.z; acc[4 * q + 3] = bb.w;
+  }
+#pragma unroll
+  for (int l = 0; l < 5; ++l) {
+    if (l >= p.levels) break;
+    const Taps t = make_taps(u, v, p.img_w, p.img_h, p.w[l], p.h[l], 64, b);     // offsets in uint4 units (64 per pixel)
+    const uint4* m = p.map[l] + lane * 2;
+#pragma unroll
+    for (int hseg = 0; hseg < 2; ++hseg) {
+      const uint4 a = __ldg(m + t.o00 + hseg), c = __ldg(m + t.o01 + hseg), d = __ldg(m + t.o10 + hseg), e = __ldg(m + t.o11 + hseg);
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, cw[4] = {c.x, c.y, c.z, c.w}, dw[4] = {d.x, d.y, d.z, d.w},
+                     ew[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&aw[j]));
+        const float2 fc = __half22float2(*reinterpret_cast<const __half2*>(&cw[j]));
+        const float2 fd = __half22float2(*reinterpret_cast<const __half2*>(&dw[j]));
+        const float2 fe = __half22float2(*reinterpret_cast<const __half2*>(&ew[j]));
+        acc[hseg * 8 + 2 * j] += fmaf(fe.x, t.w11, fmaf(fd.x, t.w10, fmaf(fc.x, t.w01, fa.x * t.w00)));
+        acc[hseg * 8 + 2 * j + 1] += fmaf(fe.y, t.w11, fmaf(fd.y, t.w10, fmaf(fc.y, t.w01, fa.y * t.w00)));
+      }
+    }
+  }
+  uint32_t o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float x0 = acc[2 * j], x1 = acc[2 * j + 1];
+    if (p.act == HOISDF_ACT_RELU) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+    o[j] = tc::cvt_f16x2_sat(x0, x1);
+  }
+  uint4* dst = reinterpret_cast<uint4*>(p.out_hi + r * p.ld_out + lane * 16);
+  dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+  dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
 // (N, C, HW) -> (N, HW, C) through a 32x33 shared tile
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                                            int C, int HW) {
@@ -291,5 +361,30 @@ HOISDF_API int hoisdf_nchw_to_nhwc_split(const float* src, uint16_t* dst_hi, uin
             static_cast<unsigned>(n));
   HOISDF_LAUNCH(nchw_to_nhwc_split_kernel, grid, 256, static_cast<cudaStream_t>(stream), src,
                 reinterpret_cast<__half*>(dst_hi), reinterpret_cast<__half*>(dst_lo), static_cast<int>(c), HW, ld);
+  return launch_status();
+}
+
+HOISDF_API int hoisdf_gather_sum_h16_fwd(const hoisdf_pyramid_h* pyr, const float* uv, int64_t rows, const int64_t* row_offsets,
+                                         int64_t batch, int64_t rows_per_sample, const float* bias, int32_t act,
+                                         uint16_t* out_hi, int64_t ld_out, void* stream) {
+  if (pyr == nullptr || uv == nullptr || out_hi == nullptr) return HOISDF_E_NULL;
+  if (rows == 0) return HOISDF_OK;
+  if (rows < 0 || batch <= 0 || pyr->levels < 1 || pyr->levels > 5 || pyr->c != 512 || ld_out < 512) return HOISDF_E_SHAPE;
+  if (row_offsets == nullptr && rows_per_sample <= 0) return HOISDF_E_SHAPE;
+  if (!aligned16(out_hi) || (ld_out & 7) || (bias != nullptr && !aligned16(bias))) return HOISDF_E_ALIGN;
+  GatherH16Params p;
+  for (int l = 0; l < 5; ++l) {
+    const int ll = l < pyr->levels ? l : 0;
+    if (pyr->map[ll] == nullptr) return HOISDF_E_NULL;
+    if (!aligned16(pyr->map[ll])) return HOISDF_E_ALIGN;
+    if (pyr->h[ll] <= 0 || pyr->w[ll] <= 0) return HOISDF_E_SHAPE;
+    p.map[l] = reinterpret_cast<const uint4*>(pyr->map[ll]);
+    p.h[l] = pyr->h[ll];
+    p.w[l] = pyr->w[ll];
+  }
+  p.levels = pyr->levels; p.img_w = pyr->img_w; p.img_h = pyr->img_h;
+  p.uv = uv; p.row_offsets = row_offsets; p.bias = bias; p.out_hi = reinterpret_cast<__half*>(out_hi);
+  p.rows = rows; p.batch = batch; p.rows_per_sample = rows_per_sample; p.ld_out = ld_out; p.act = act;
+  HOISDF_LAUNCH(gather_sum_h16_kernel, static_cast<unsigned>(ceil_div(rows, 8)), 256, static_cast<cudaStream_t>(stream), p);
   return launch_status();
 }

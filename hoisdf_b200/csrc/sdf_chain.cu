@@ -47,11 +47,26 @@ constexpr int CH_BAR_BYTES = 1024;                  // 44 mbarriers + TMEM slot 
 constexpr int CH_SMEM_BYTES = CH_OFF_BAR + CH_BAR_BYTES + 1024 /*align*/;
 static_assert(CH_SMEM_BYTES <= 232448, "shared memory budget of one CTA");
 constexpr int CH_EPI_WARPS = 8;
-constexpr int CH_THREADS = 32 * (2 + CH_EPI_WARPS + 1);   // 352
+constexpr int CH_THREADS = 32 * (2 + CH_EPI_WARPS + 1);   // 352: weights, MMA, 8 epilogue, 1 row producer (TMA)
+constexpr int CH_GATHER_WARPS = 8;
+constexpr int CH_THREADS_G = 32 * (2 + CH_EPI_WARPS + CH_GATHER_WARPS);   // 576: ... 8 gather warps instead (96 registers each)
 constexpr uint32_t CH_TMEM_COLS = 512;
 constexpr uint32_t CH_TM_ACT = 256;                 // first TMEM column of the packed fp16 activation tile
 
-enum { CH_MODE_ROWS = 0 /* A0 rows by TMA */, CH_MODE_DECODER = 1 /* decoder input rows by TMA, no s1 */ };
+enum { CH_MODE_ROWS = 0 /* A0 rows by TMA */, CH_MODE_DECODER = 1 /* decoder input rows by TMA, no s1 */,
+       CH_MODE_GATHER = 2 /* A0 rows gathered in the kernel from the fp16 projected maps */ };
+
+// gather mode: the projected pyramid G_l = F_l . W0_l^T (linear_sdfin layer 0 applied per level) as NHWC fp16
+struct ChainGather {
+  const uint4* __restrict__ map[5];      // (B, H_l, W_l, 512) halfs, 8 per uint4
+  int h[5], w[5];
+  int levels;
+  float nx, ny;                          // (img_w - 1) / 2, (img_h - 1) / 2
+  const float* __restrict__ uv;          // (rows, 2) projected pixel of every candidate
+  const int64_t* __restrict__ row_offsets;   // (batch + 1) or NULL
+  const float* __restrict__ b0;          // linear_sdfin.layers.0.bias (512)
+  int64_t batch, rows_per_sample;
+};
 
 struct ChainParams {
   const float* __restrict__ b_s1;
@@ -66,6 +81,7 @@ struct ChainParams {
   int bins;
   int mode;
   float clamp;
+  ChainGather g;
 };
 
 __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
@@ -88,6 +104,14 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
         "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]), "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15};"
+      ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // byte offset of 16-byte chunk `c` (8 halfs) of row `r` inside a 128 x 64 fp16 K block with 128-byte swizzle
@@ -100,8 +124,8 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int c) {
 // [6] weight producer: waiting for a free stage, [7] its total
 __device__ long long g_chain_prof[16];   // [8..12] MMA issuer: cycles from 'stage ready' to 'commit issued', per layer
 
-template <int CL, bool PROF>
-__global__ void __launch_bounds__(CH_THREADS, 1)
+template <int CL, bool PROF, bool GATHER>
+__global__ void __launch_bounds__(GATHER ? CH_THREADS_G : CH_THREADS, 1)
 sdf_chain_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__ CUtensorMap map_ws1,
                  const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_w1,
                  const __grid_constant__ CUtensorMap map_w2a, const __grid_constant__ CUtensorMap map_w2b,
@@ -145,7 +169,7 @@ sdf_chain_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_cons
       mbar_init(bar_wfull(s), 1);
       mbar_init(bar_wempty(s), CL);          // every CTA's tensor core must have consumed the stage
     }
-    for (int kb = 0; kb < 8; ++kb) mbar_init(bar_afull(kb), 1);
+    for (int kb = 0; kb < 8; ++kb) mbar_init(bar_afull(kb), GATHER ? CH_GATHER_WARPS : 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_dfull(b), 1);
       mbar_init(bar_dempty(b), CH_EPI_WARPS);
@@ -319,7 +343,7 @@ sdf_chain_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_cons
         for (int l = 0; l < 5; ++l) g_chain_prof[8 + l] += t_l[l];
       }
     }
-  } else if (warp == 2 + CH_EPI_WARPS) {
+  } else if (!GATHER && warp == 2 + CH_EPI_WARPS) {
     // ------------------------------------------------------------------ row producer (TMA; whole warp, one lane issues)
     {
       uint32_t it = 0;
@@ -346,7 +370,7 @@ sdf_chain_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_cons
         }
       }
     }
-  } else {
+  } else if (warp < 2 + CH_EPI_WARPS) {
     // ------------------------------------------------------------------ epilogue (8 warps)
     const int ew = warp - 2;
     const int lq = warp & 3;                    // TMEM lane quarter this warp may read
@@ -407,68 +431,78 @@ sdf_chain_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_cons
 #pragma unroll 1
         for (int q = 0; q < nq; ++q) {
           const int b = q & 1;
-          const int c0 = 128 * q + 64 * h;       // first output column of this warp's 64
           const long long tc0 = prof ? clock64() : 0;
           mbar_wait(bar_dfull(b), (b ? eu1 : eu0) & 1u);
           if (prof) t_e += clock64() - tc0;
           tcgen05_fence_after();
-          uint32_t a[64];
           const uint32_t t0 = tmem_base + static_cast<uint32_t>(b * 128 + h * 64) + lane_addr;
-          tmem_ld32(t0, a);
-          tmem_ld32(t0 + 32, a + 32);
-          tmem_ld_wait();
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_dempty(b));       // the accumulator is in registers: hand the buffer back
-          if (b) ++eu1; else ++eu0;
-          if (layer == 4) {
-            // linh3 + linh4: relu(acc + b3) . w4 over this warp's columns
-            float s4[4] = {0.f, 0.f, 0.f, 0.f};
+          // this warp's 64 columns in two passes of 32 (the kernel runs 18 warps in gather mode: 96 registers per thread)
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
-              const float4 ww = __ldg(reinterpret_cast<const float4*>(p.w4 + c0) + j);
-              s4[0] = fmaf(fmaxf(__uint_as_float(a[4 * j]) + bb.x, 0.f), ww.x, s4[0]);
-              s4[1] = fmaf(fmaxf(__uint_as_float(a[4 * j + 1]) + bb.y, 0.f), ww.y, s4[1]);
-              s4[2] = fmaf(fmaxf(__uint_as_float(a[4 * j + 2]) + bb.z, 0.f), ww.z, s4[2]);
-              s4[3] = fmaf(fmaxf(__uint_as_float(a[4 * j + 3]) + bb.w, 0.f), ww.w, s4[3]);
+          for (int half = 0; half < 2; ++half) {
+            const int c0 = 128 * q + 64 * h + 32 * half;     // first output column of this pass
+            uint32_t a[32];
+            tmem_ld32(t0 + 32 * half, a);
+            tmem_ld_wait();
+            if (half == 1) {                                   // the accumulator is in registers: hand the buffer back
+              tcgen05_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_dempty(b));
+              if (b) ++eu1; else ++eu0;
             }
-            part += (s4[0] + s4[1]) + (s4[2] + s4[3]);
-            continue;
-          }
-          // bias + ReLU + fp16: 64 columns -> 32 packed pairs.  linh1 has 223 outputs: the tail is zero-filled.
-          const int nvalid = layer == 2 ? min(64, 223 - c0) : 64;
-          uint32_t pk[32];
+            if (layer == 4) {
+              // linh3 + linh4: relu(acc + b3) . w4 over this warp's columns
+              float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (4 * j + 3 < nvalid) {
-              bb = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
+              for (int j = 0; j < 8; ++j) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
+                const float4 ww = __ldg(reinterpret_cast<const float4*>(p.w4 + c0) + j);
+                s4[0] = fmaf(fmaxf(__uint_as_float(a[4 * j]) + bb.x, 0.f), ww.x, s4[0]);
+                s4[1] = fmaf(fmaxf(__uint_as_float(a[4 * j + 1]) + bb.y, 0.f), ww.y, s4[1]);
+                s4[2] = fmaf(fmaxf(__uint_as_float(a[4 * j + 2]) + bb.z, 0.f), ww.z, s4[2]);
+                s4[3] = fmaf(fmaxf(__uint_as_float(a[4 * j + 3]) + bb.w, 0.f), ww.w, s4[3]);
+              }
+              part += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+              continue;
+            }
+            // bias + ReLU + fp16: 32 columns -> 16 packed pairs.  linh1 has 223 outputs: the tail is zero-filled.
+            const int nvalid = layer == 2 ? min(32, 223 - c0) : 32;
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (4 * j + 3 < nvalid) {
+                bb = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
+              } else {
+                if (4 * j < nvalid) bb.x = __ldg(bias + c0 + 4 * j);
+                if (4 * j + 1 < nvalid) bb.y = __ldg(bias + c0 + 4 * j + 1);
+                if (4 * j + 2 < nvalid) bb.z = __ldg(bias + c0 + 4 * j + 2);
+              }
+              const float v0 = 4 * j < nvalid ? fmaxf(__uint_as_float(a[4 * j]) + bb.x, 0.f) : 0.f;
+              const float v1 = 4 * j + 1 < nvalid ? fmaxf(__uint_as_float(a[4 * j + 1]) + bb.y, 0.f) : 0.f;
+              const float v2 = 4 * j + 2 < nvalid ? fmaxf(__uint_as_float(a[4 * j + 2]) + bb.z, 0.f) : 0.f;
+              const float v3 = 4 * j + 3 < nvalid ? fmaxf(__uint_as_float(a[4 * j + 3]) + bb.w, 0.f) : 0.f;
+              pk[2 * j] = cvt_f16x2_sat(v0, v1);
+              pk[2 * j + 1] = cvt_f16x2_sat(v2, v3);
+            }
+            if (layer == 1 || layer == 3) {
+              // -> ACT (TMEM): columns [c0, c0 + 32) = packed columns [c0 / 2, + 16)
+              tmem_st16(tmem_base + CH_TM_ACT + static_cast<uint32_t>(c0 >> 1) + lane_addr, pk);
             } else {
-              if (4 * j < nvalid) bb.x = __ldg(bias + c0 + 4 * j);
-              if (4 * j + 1 < nvalid) bb.y = __ldg(bias + c0 + 4 * j + 1);
-              if (4 * j + 2 < nvalid) bb.z = __ldg(bias + c0 + 4 * j + 2);
+              // -> this lane's row of a shared-memory K block (s1 -> SKIP block 2q+h, linh1 -> H1 block 2q+h): 64 bytes
+              uint8_t* blk = gen + static_cast<uint32_t>((layer == 0 ? 0 : CH_SKIP_BLKS) + 2 * q + h) * CH_BLK;
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<uint4*>(blk + sw128_off(r, 4 * half + c)) =
+                    make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
             }
-            const float v0 = 4 * j < nvalid ? fmaxf(__uint_as_float(a[4 * j]) + bb.x, 0.f) : 0.f;
-            const float v1 = 4 * j + 1 < nvalid ? fmaxf(__uint_as_float(a[4 * j + 1]) + bb.y, 0.f) : 0.f;
-            const float v2 = 4 * j + 2 < nvalid ? fmaxf(__uint_as_float(a[4 * j + 2]) + bb.z, 0.f) : 0.f;
-            const float v3 = 4 * j + 3 < nvalid ? fmaxf(__uint_as_float(a[4 * j + 3]) + bb.w, 0.f) : 0.f;
-            pk[2 * j] = cvt_f16x2_sat(v0, v1);
-            pk[2 * j + 1] = cvt_f16x2_sat(v2, v3);
           }
+          if (layer == 4) continue;
           if (layer == 1 || layer == 3) {
-            // -> ACT (TMEM): columns [128 q + 64 h, +64) = packed columns [64 q + 32 h, +32)
-            tmem_st32(tmem_base + CH_TM_ACT + static_cast<uint32_t>(64 * q + 32 * h) + lane_addr, pk);
             tmem_st_wait();
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_act(2 * q + h));
           } else {
-            // -> this lane's 128-byte row of a shared-memory K block: s1 -> SKIP block 2q+h, linh1 -> H1 block 2q+h
-            uint8_t* blk = gen + static_cast<uint32_t>((layer == 0 ? 0 : CH_SKIP_BLKS) + 2 * q + h) * CH_BLK;
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-              *reinterpret_cast<uint4*>(blk + sw128_off(r, c)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(layer == 0 ? bar_skip(2 * q + h) : bar_h1(2 * q + h));
@@ -486,6 +520,100 @@ sdf_chain_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_cons
     if (prof) {
       g_chain_prof[4] += t_e;
       g_chain_prof[5] += clock64() - tstart;
+    }
+  } else if (GATHER) {
+    // ------------------------------------------------------------------ gather warps (8): A0 = relu(b0 + sum over the 5
+    // levels of the bilinear sample of the projected fp16 map) written straight into the swizzled A-operand blocks.
+    // Warp gw owns rows [16 gw, 16 gw + 16) of the tile; per K block (64 channels) it makes 4 passes of 4 rows: lanes
+    // 8 i .. 8 i + 7 hold the 8 channel octets of one row, so every tap is one 128-byte line read by 8 lanes.
+    // The tap parameters of a row (pixel index, edge flags, fractions for 5 levels) are computed once per tile by lane
+    // (row & 15) and broadcast with shuffles.
+    const int gw = warp - (2 + CH_EPI_WARPS);
+    const int oct = lane & 7, rsub = lane >> 3;
+    uint32_t it = 0;
+    for (int pair = cluster; pair < npairs; pair += nclusters, ++it) {
+      const int64_t row = static_cast<int64_t>(pair * CL + static_cast<int>(rank)) * CH_BM + gw * 16 + (lane & 15);
+      float u = 0.f, v = 0.f;
+      int64_t sample = 0;
+      if (row < p.rows) {
+        u = __ldg(p.g.uv + 2 * row);
+        v = __ldg(p.g.uv + 2 * row + 1);
+        if (p.g.row_offsets == nullptr) {
+          sample = row / p.g.rows_per_sample;
+        } else {
+          int64_t lo = 0, hi = p.g.batch;                      // largest b with offsets[b] <= row
+          while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (__ldg(p.g.row_offsets + mid) <= row) lo = mid; else hi = mid;
+          }
+          sample = lo;
+        }
+      }
+      // ATen grid_sampler_2d arithmetic (align_corners = True, border padding), as csrc/gather.cu make_taps
+      const float gx = __fdiv_rn(__fsub_rn(u, p.g.nx), p.g.nx), gy = __fdiv_rn(__fsub_rn(v, p.g.ny), p.g.ny);
+      uint32_t tp_o[5];
+      float tp_x[5], tp_y[5];
+#pragma unroll
+      for (int l = 0; l < 5; ++l) {
+        const int W = p.g.w[l], H = p.g.h[l];
+        float x = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.f), 2.f), static_cast<float>(W - 1));
+        float y = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.f), 2.f), static_cast<float>(H - 1));
+        x = fminf(static_cast<float>(W - 1), fmaxf(x, 0.f));
+        y = fminf(static_cast<float>(H - 1), fmaxf(y, 0.f));
+        const float x0f = floorf(x), y0f = floorf(y);
+        const int x0 = static_cast<int>(x0f), y0 = static_cast<int>(y0f);
+        tp_x[l] = x - x0f;
+        tp_y[l] = y - y0f;
+        const uint32_t pix = static_cast<uint32_t>((static_cast<int>(sample) * H + y0) * W + x0);
+        tp_o[l] = pix | (x0 + 1 <= W - 1 ? 1u << 30 : 0u) | (y0 + 1 <= H - 1 ? 1u << 31 : 0u);
+      }
+      if (it > 0) mbar_wait(bar_rfree, (it - 1) & 1u);          // linh2 of the previous tile has read SKIP / H1
+#pragma unroll 1
+      for (int kb = 0; kb < 8; ++kb) {
+        uint8_t* blk = gen + static_cast<uint32_t>(kb < 4 ? CH_SKIP_BLKS + kb : kb - 4) * CH_BLK;
+        const float4 ba = __ldg(reinterpret_cast<const float4*>(p.g.b0 + kb * 64 + oct * 8));
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.g.b0 + kb * 64 + oct * 8 + 4));
+        const uint32_t coff = static_cast<uint32_t>(kb * 8 + oct);     // uint4 index of this lane's 8 channels inside a pixel
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) {
+          const int src = i * 4 + rsub;                                 // row inside this warp's 16 = the lane that holds its taps
+          float acc[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+          for (int l = 0; l < 5; ++l) {
+            if (l < p.g.levels) {
+              const uint32_t o = __shfl_sync(0xffffffffu, tp_o[l], src);
+              const float tx = __shfl_sync(0xffffffffu, tp_x[l], src), ty = __shfl_sync(0xffffffffu, tp_y[l], src);
+              const uint32_t pix = o & 0x3fffffffu, dx = (o >> 30) & 1u, dy = o >> 31;
+              const uint4* m = p.g.map[l] + coff;
+              const uint32_t p00 = pix * 64u, p01 = (pix + dx) * 64u;
+              const uint32_t down = dy * static_cast<uint32_t>(p.g.w[l]) * 64u;
+              const uint4 q00 = __ldg(m + p00), q01 = __ldg(m + p01), q10 = __ldg(m + p00 + down), q11 = __ldg(m + p01 + down);
+              const float ax = 1.f - tx, ay = 1.f - ty;               // == ATen's (x0 + 1) - x, see DESIGN.md
+              const float w00 = ax * ay, w01 = dx ? tx * ay : 0.f, w10 = dy ? ax * ty : 0.f, w11 = (dx & dy) ? tx * ty : 0.f;
+              const uint32_t a00[4] = {q00.x, q00.y, q00.z, q00.w}, a01[4] = {q01.x, q01.y, q01.z, q01.w};
+              const uint32_t a10[4] = {q10.x, q10.y, q10.z, q10.w}, a11[4] = {q11.x, q11.y, q11.z, q11.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f00 = __half22float2(*reinterpret_cast<const __half2*>(&a00[j]));
+                const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&a01[j]));
+                const float2 f10 = __half22float2(*reinterpret_cast<const __half2*>(&a10[j]));
+                const float2 f11 = __half22float2(*reinterpret_cast<const __half2*>(&a11[j]));
+                acc[2 * j] += fmaf(f11.x, w11, fmaf(f10.x, w10, fmaf(f01.x, w01, f00.x * w00)));
+                acc[2 * j + 1] += fmaf(f11.y, w11, fmaf(f10.y, w10, fmaf(f01.y, w01, f00.y * w00)));
+              }
+            }
+          }
+          uint4 o4;
+          o4.x = cvt_f16x2_sat(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f));
+          o4.y = cvt_f16x2_sat(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
+          o4.z = cvt_f16x2_sat(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f));
+          o4.w = cvt_f16x2_sat(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
+          *reinterpret_cast<uint4*>(blk + sw128_off(gw * 16 + src, oct)) = o4;
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_afull(kb));
+      }
     }
   }
   tcgen05_fence_before();
@@ -508,11 +636,11 @@ static bool chain_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t c
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
 }
 
-template <int CL>
+template <int CL, bool GATHER>
 static int chain_max_clusters() {
   static int cached = -1;
   if (cached >= 0) return cached;
-  auto kern = sdf_chain_kernel<CL, false>;
+  auto kern = sdf_chain_kernel<CL, false, GATHER>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_BYTES);
   int n = 0;
   if (CL == 1) {
@@ -523,7 +651,7 @@ static int chain_max_clusters() {
   } else {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(kNumSMs / CL * CL);
-    cfg.blockDim = dim3(CH_THREADS);
+    cfg.blockDim = dim3(GATHER ? CH_THREADS_G : CH_THREADS);
     cfg.dynamicSmemBytes = CH_SMEM_BYTES;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -539,16 +667,17 @@ static int chain_max_clusters() {
   return n;
 }
 
-template <int CL, bool PROF>
+template <int CL, bool PROF, bool GATHER>
 static int chain_launch(const CUtensorMap* maps, const ChainParams& p, cudaStream_t s) {
-  auto kern = sdf_chain_kernel<CL, PROF>;
+  auto kern = sdf_chain_kernel<CL, PROF, GATHER>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_BYTES);
   if (e != cudaSuccess) return static_cast<int>(e);
   const int64_t npairs = ceil_div(p.tiles, CL);
-  const int64_t clusters = npairs < chain_max_clusters<CL>() ? npairs : chain_max_clusters<CL>();
+  const int64_t cap = chain_max_clusters<CL, GATHER>();
+  const int64_t clusters = npairs < cap ? npairs : cap;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(clusters * CL));
-  cfg.blockDim = dim3(CH_THREADS);
+  cfg.blockDim = dim3(GATHER ? CH_THREADS_G : CH_THREADS);
   cfg.dynamicSmemBytes = CH_SMEM_BYTES;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -563,6 +692,21 @@ static int chain_launch(const CUtensorMap* maps, const ChainParams& p, cudaStrea
   return launch_status();
 }
 
+template <int CL>
+static int chain_dispatch(const CUtensorMap* maps, const ChainParams& p, bool prof, cudaStream_t s) {
+  if (p.mode == CH_MODE_GATHER)
+    return prof ? chain_launch<CL, true, true>(maps, p, s) : chain_launch<CL, false, true>(maps, p, s);
+  return prof ? chain_launch<CL, true, false>(maps, p, s) : chain_launch<CL, false, false>(maps, p, s);
+}
+
+// fp32 -> fp16 (round to nearest, saturating), 8 values per thread: the fp16 copy of the projected maps that gather mode reads
+__global__ void f32_to_f16_kernel(const float4* __restrict__ x, uint4* __restrict__ y, int64_t n8) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const float4 a = __ldg(x + 2 * i), b = __ldg(x + 2 * i + 1);
+  y[i] = make_uint4(cvt_f16x2_sat(a.x, a.y), cvt_f16x2_sat(a.z, a.w), cvt_f16x2_sat(b.x, b.y), cvt_f16x2_sat(b.z, b.w));
+}
+
 }  // namespace hoisdf
 
 using namespace hoisdf;
@@ -574,12 +718,24 @@ extern "C" __attribute__((visibility("default"))) int hoisdf_debug_chain_profile
   return cudaMemcpyToSymbol(g_chain_prof, zero, sizeof(zero)) == cudaSuccess ? 0 : -1;
 }
 
+HOISDF_API int hoisdf_f32_to_f16(const float* x, uint16_t* y, int64_t n, void* stream) {
+  if (x == nullptr || y == nullptr) return HOISDF_E_NULL;
+  if (n == 0) return HOISDF_OK;
+  if (n < 0 || (n & 7)) return HOISDF_E_SHAPE;
+  if (!aligned16(x) || !aligned16(y)) return HOISDF_E_ALIGN;
+  f32_to_f16_kernel<<<static_cast<unsigned>(ceil_div(n >> 3, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(x), reinterpret_cast<uint4*>(y), n >> 3);
+  return launch_status();
+}
+
 HOISDF_API int hoisdf_sdf_chain_fwd(const hoisdf_sdf_chain_args* a, void* stream) {
   if (a == nullptr || a->out_sdf == nullptr || a->w4 == nullptr || a->b4 == nullptr) return HOISDF_E_NULL;
   const bool decoder_only = a->x != nullptr;
-  if (decoder_only ? a->a0 != nullptr : a->a0 == nullptr) return HOISDF_E_NULL;
+  const bool gather = a->gmaps != nullptr;
+  if ((decoder_only ? 1 : 0) + (gather ? 1 : 0) + (a->a0 != nullptr ? 1 : 0) != 1) return HOISDF_E_NULL;   // exactly one source
   if (!decoder_only && (a->w_s1 == nullptr || a->b_s1 == nullptr || (a->lattice_index == nullptr && a->points == nullptr)))
     return HOISDF_E_NULL;
+  if (gather && (a->uv == nullptr || a->b_s0 == nullptr)) return HOISDF_E_NULL;
   for (int l = 0; l < 4; ++l)
     if (a->w[l] == nullptr || a->b[l] == nullptr) return HOISDF_E_NULL;
   if (a->rows == 0) return HOISDF_OK;
@@ -587,19 +743,42 @@ HOISDF_API int hoisdf_sdf_chain_fwd(const hoisdf_sdf_chain_args* a, void* stream
   // weight pitches: linh0 (512, >= 296) zero beyond column 289; linh1 (223, >= 512); linh2 (512, >= 520) in the
   // [input 289 | 0 x7 | h1 223 | 0] column layout; linh3 (512, >= 512)
   if (a->ldw[0] < 296 || a->ldw[1] < 512 || a->ldw[2] < 520 || a->ldw[3] < 512) return HOISDF_E_SHAPE;
-  if (!decoder_only && (a->ldw_s1 < 512 || a->lda0 < 512)) return HOISDF_E_SHAPE;
+  if (!decoder_only && a->ldw_s1 < 512) return HOISDF_E_SHAPE;
+  if (a->a0 != nullptr && a->lda0 < 512) return HOISDF_E_SHAPE;
   if (decoder_only && a->ldx < 296) return HOISDF_E_SHAPE;
   for (int l = 0; l < 4; ++l)
     if ((a->ldw[l] & 7) || !aligned16(a->w[l])) return HOISDF_E_ALIGN;
-  if (decoder_only ? ((a->ldx & 7) || !aligned16(a->x))
-                   : ((a->lda0 & 7) || !aligned16(a->a0) || (a->ldw_s1 & 7) || !aligned16(a->w_s1)))
-    return HOISDF_E_ALIGN;
+  if (decoder_only && ((a->ldx & 7) || !aligned16(a->x))) return HOISDF_E_ALIGN;
+  if (a->a0 != nullptr && ((a->lda0 & 7) || !aligned16(a->a0))) return HOISDF_E_ALIGN;
+  if (!decoder_only && ((a->ldw_s1 & 7) || !aligned16(a->w_s1))) return HOISDF_E_ALIGN;
+  ChainParams p{};
+  if (gather) {
+    const hoisdf_pyramid_h* g = a->gmaps;
+    if (g->levels < 1 || g->levels > 5 || g->c != 512 || a->batch <= 0) return HOISDF_E_SHAPE;
+    if (a->row_offsets == nullptr && a->rows_per_sample <= 0) return HOISDF_E_SHAPE;
+    if (!aligned16(a->b_s0)) return HOISDF_E_ALIGN;
+    for (int l = 0; l < 5; ++l) {
+      const int ll = l < g->levels ? l : 0;                    // unused levels alias level 0 (never read)
+      if (g->map[ll] == nullptr) return HOISDF_E_NULL;
+      if (!aligned16(g->map[ll])) return HOISDF_E_ALIGN;
+      if (g->h[ll] <= 0 || g->w[ll] <= 0 || a->batch * g->h[ll] * g->w[ll] >= (int64_t(1) << 30)) return HOISDF_E_SHAPE;
+      p.g.map[l] = reinterpret_cast<const uint4*>(g->map[ll]);
+      p.g.h[l] = g->h[ll];
+      p.g.w[l] = g->w[ll];
+    }
+    p.g.levels = g->levels;
+    p.g.nx = static_cast<float>(g->img_w - 1) / 2.0f;
+    p.g.ny = static_cast<float>(g->img_h - 1) / 2.0f;
+    p.g.uv = a->uv; p.g.row_offsets = a->row_offsets; p.g.b0 = a->b_s0;
+    p.g.batch = a->batch; p.g.rows_per_sample = a->rows_per_sample;
+  }
   const int64_t tiles = ceil_div(a->rows, CH_BM);
   static const int force_cl = [] { const char* e = getenv("HOISDF_CHAIN_CL"); return e ? atoi(e) : 0; }();
   const int cl = force_cl == 1 ? 1 : (tiles >= 2 ? 2 : 1);
   CUtensorMap maps[7];
   const int wbox = 128 / cl;
   bool ok = decoder_only ? chain_map(&maps[0], a->x, a->rows, 296, a->ldx, CH_BM)
+            : gather     ? chain_map(&maps[0], a->w[0], 512, 296, a->ldw[0], wbox)      // unused in this mode
                          : chain_map(&maps[0], a->a0, a->rows, 512, a->lda0, CH_BM);
   ok = ok && (decoder_only ? chain_map(&maps[1], a->w[0], 512, 296, a->ldw[0], wbox)      // unused in this mode
                            : chain_map(&maps[1], a->w_s1, 256, 512, a->ldw_s1, wbox));
@@ -609,16 +788,14 @@ HOISDF_API int hoisdf_sdf_chain_fwd(const hoisdf_sdf_chain_args* a, void* stream
   ok = ok && chain_map(&maps[5], a->w[2] + 296, 512, 224, a->ldw[2], wbox);
   ok = ok && chain_map(&maps[6], a->w[3], 512, 512, a->ldw[3], wbox);
   if (!ok) return HOISDF_E_UNSUPPORTED;
-  ChainParams p{};
   p.b_s1 = a->b_s1;
   for (int l = 0; l < 4; ++l) p.b[l] = a->b[l];
   p.w4 = a->w4; p.b4 = a->b4;
   p.lattice_index = a->lattice_index; p.points = a->points; p.bins = a->bins;
   p.out = a->out_sdf; p.rows = a->rows; p.tiles = static_cast<int>(tiles);
-  p.mode = decoder_only ? CH_MODE_DECODER : CH_MODE_ROWS;
+  p.mode = decoder_only ? CH_MODE_DECODER : (gather ? CH_MODE_GATHER : CH_MODE_ROWS);
   p.clamp = a->clamp;
   static const int prof = [] { const char* e = getenv("HOISDF_CHAIN_PROF"); return e ? atoi(e) : 0; }();
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (prof) return cl == 2 ? chain_launch<2, true>(maps, p, s) : chain_launch<1, true>(maps, p, s);
-  return cl == 2 ? chain_launch<2, false>(maps, p, s) : chain_launch<1, false>(maps, p, s);
+  return cl == 2 ? chain_dispatch<2>(maps, p, prof != 0, s) : chain_dispatch<1>(maps, p, prof != 0, s);
 }

@@ -57,6 +57,14 @@ class PyramidContext:
         self.channels = sum(m.shape[3] for m in self.maps)
         self._model = model
         self._gmaps = None
+        self._gmaps16 = None
+
+    @property
+    def gmaps16(self):
+        """fp16 copy of the projected maps: what the fused candidate chain's gather warps interpolate."""
+        if self._gmaps16 is None:
+            self._gmaps16 = ops.maps_to_half(self.gmaps)
+        return self._gmaps16
 
     @property
     def gmaps(self):
@@ -125,6 +133,8 @@ class GraphedForward:
             pyr, self.decoder_out = model.run_image_encoder(self.img)
             self.ctx = PyramidContext(pyr, model)
             self.ctx.gmaps                       # projection of the pyramid through linear_sdfin layer 0
+            if cfg.fused_chain and (cfg.fused_gather or cfg.gather_h16) and cfg.screen_single:
+                self.ctx.gmaps16                 # + its fp16 copy for the candidate screening stage
         self.g2 = self.sel = self.out = self.taps = self.dex_sdf = None
 
     def capture_pose(self, sel):
@@ -313,12 +323,25 @@ class Model(nn.Module):
             only RANK candidates for the next, more accurate stage: one TMEM drain per tile, and with `single` ONE
             tensor-core product per K step instead of three."""
             n = uv.shape[0]
+            if single and cfg.fused_chain and cfg.fused_gather:
+                # ONE kernel: gather -> linear_sdfin.1 -> embedding -> SDF decoder; 4 bytes per row written
+                ops.sdf_chain(packed, out, sdfin1=sdfin[1], gmaps16=ctx.gmaps16, uv=uv, row_offsets=row_offsets, batch=b,
+                              rows_per_sample=rows_per_sample, bias0=sdfin[0].b, lattice_index=index, bins=cfg.bins_n,
+                              img_hw=cfg.input_img_shape)
+                return
             hs, rs, hs2 = h3_buffers(n)
-            ops.gather(gmaps, uv, b, mode=ops.GATHER_SUM, out=hs.head(n), row_offsets=row_offsets,
-                       rows_per_sample=rows_per_sample, bias=sdfin[0].b, act=ops.ACT_RELU, img_hw=cfg.input_img_shape)
             if single and cfg.fused_chain:
+                if cfg.gather_h16:      # fp16 maps in, fp16 hi plane out: all the single-product chain kernel reads
+                    ops.gather_h16(ctx.gmaps16, uv, b, hs.head(n), row_offsets=row_offsets, rows_per_sample=rows_per_sample,
+                                   bias=sdfin[0].b, act=ops.ACT_RELU, img_hw=cfg.input_img_shape)
+                else:
+                    ops.gather(gmaps, uv, b, mode=ops.GATHER_SUM, out=hs.head(n), row_offsets=row_offsets,
+                               rows_per_sample=rows_per_sample, bias=sdfin[0].b, act=ops.ACT_RELU,
+                               img_hw=cfg.input_img_shape)
                 ops.sdf_chain(packed, out, sdfin1=sdfin[1], a0=hs.head(n), lattice_index=index, bins=cfg.bins_n)
                 return
+            ops.gather(gmaps, uv, b, mode=ops.GATHER_SUM, out=hs.head(n), row_offsets=row_offsets,
+                       rows_per_sample=rows_per_sample, bias=sdfin[0].b, act=ops.ACT_RELU, img_hw=cfg.input_img_shape)
             ops.linear(hs.head(n), sdfin[1], ops.ACT_RELU, out=rs.head(n).window(0, 256),
                        chunk_kb=chunk_kb, single=single)
             ops.posenc(rs.head(n), lattice_index=index, bins=cfg.bins_n)
@@ -343,7 +366,8 @@ class Model(nn.Module):
             passes = 3: 3xTF32, 1: single TF32 pass; with tensor cores disabled the fp32 FMA kernels."""
             h3 = ops.use_h3()
             if h3:
-                h3_buffers(cap)
+                if not (single and cfg.fused_chain and cfg.fused_gather):      # the fused kernel needs no row buffers
+                    h3_buffers(cap)
             else:
                 fp32_buffers(cap)
             for r0 in range(0, total, step):
@@ -513,7 +537,7 @@ class Model(nn.Module):
             self._graphs = {"weights": wkey}         # parameters changed: packed weights were rebuilt, recapture
         key = (tuple(img.shape), str(img.device), int(cfg.num_samp_hand), int(cfg.num_samp_obj), cfg.setting, cfg.dataset,
                cfg.final_stage, bool(cfg.screen_single), bool(cfg.tc_projection), int(cfg.backbone_chunk_kb),
-               bool(cfg.fused_chain), None if extras is None else tuple(tuple(v.shape) for v in extras.values()))
+               bool(cfg.fused_chain), bool(cfg.fused_gather), bool(cfg.gather_h16), None if extras is None else tuple(tuple(v.shape) for v in extras.values()))
         gs = self._graphs.get(key)
         if gs is None:
             # one eager forward first: packs the weights, sizes the workspaces, sets the kernel attributes

@@ -677,26 +677,71 @@ def sdf_decoder(packed: PackedSdfDecoder, rows_buf, h_a=None, h_b=None, clamp: f
     return out
 
 
+def maps_to_half(maps: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    """fp16 copies of NHWC fp32 maps (the projected pyramid the chain kernel's gather mode reads)."""
+    out = []
+    for m in maps:
+        assert m.is_contiguous() and m.dtype == torch.float32 and m.numel() % 8 == 0
+        h = torch.empty(m.shape, device=m.device, dtype=torch.float16)
+        _count(1)
+        check(lib.hoisdf_f32_to_f16(m.data_ptr(), h.data_ptr(), m.numel(), _stream()), "hoisdf_f32_to_f16")
+        out.append(h)
+    return out
+
+
+def _pyramid_h(gmaps16: Sequence[torch.Tensor], img_hw) -> _capi.PyramidH:
+    pyr = _capi.PyramidH()
+    pyr.levels, pyr.c, pyr.img_h, pyr.img_w = len(gmaps16), 512, int(img_hw[0]), int(img_hw[1])
+    for i, m in enumerate(gmaps16):
+        assert m.is_contiguous() and m.dtype == torch.float16 and m.shape[3] == 512 and m.is_cuda
+        pyr.map[i], pyr.h[i], pyr.w[i] = m.data_ptr(), m.shape[1], m.shape[2]
+    return pyr
+
+
+def gather_h16(gmaps16: Sequence[torch.Tensor], uv: torch.Tensor, batch: int, out: SplitRows, *, row_offsets=None,
+               rows_per_sample: int = 0, bias=None, act: int = ACT_NONE, img_hw=(256, 256)) -> SplitRows:
+    """SUM-mode gather of fp16 maps into the HI plane of `out` (the lo plane is left untouched): the screening path."""
+    rows = uv.shape[0]
+    assert uv.is_contiguous() and uv.shape[1] == 2 and out.cols >= 512 and out.rows >= rows
+    pyr = _pyramid_h(gmaps16, img_hw)
+    _count(1)
+    check(lib.hoisdf_gather_sum_h16_fwd(C.byref(pyr), uv.data_ptr(), rows, _ptr(row_offsets), batch, rows_per_sample,
+                                        _ptr(bias), act, out.hi_ptr, out.ld, _stream()), "hoisdf_gather_sum_h16_fwd")
+    return out
+
+
 def sdf_chain(packed: PackedSdfDecoder, out: torch.Tensor, *, sdfin1: Optional[PackedLinear] = None,
               a0: Optional[SplitRows] = None, x: Optional[SplitRows] = None, lattice_index=None, points=None,
-              bins: int = 64, clamp: float = 0.0) -> torch.Tensor:
-    """The fused candidate chain (csrc/sdf_chain.cu): linear_sdfin.layers.1 -> posenc/xyz -> linh0..linh4 -> tanh in ONE
-    persistent tcgen05 kernel, single-product fp16 (screening arithmetic).  `a0` = hi plane of relu(linear_sdfin.layers.0)
-    rows (rows mode) or `x` = hi plane of the decoder input rows (decoder-only mode)."""
-    assert packed.struct_h3 is not None and (a0 is None) != (x is None)
-    src = a0 if a0 is not None else x
-    rows = src.rows
-    assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() >= rows
+              bins: int = 64, clamp: float = 0.0, gmaps16: Optional[Sequence[torch.Tensor]] = None, uv=None,
+              row_offsets=None, batch: int = 0, rows_per_sample: int = 0, bias0=None, img_hw=(256, 256)) -> torch.Tensor:
+    """The fused candidate chain (csrc/sdf_chain.cu): [gather ->] linear_sdfin.layers.1 -> posenc/xyz -> linh0..linh4 ->
+    tanh in ONE persistent tcgen05 kernel, single-product fp16 (screening arithmetic).  Row source, exactly one of:
+    `gmaps16` + `uv` (gather mode: fp16 projected maps (B,H,W,512), projected pixels (rows, 2)), `a0` = hi plane of
+    relu(linear_sdfin.layers.0) rows (rows mode), `x` = hi plane of the decoder input rows (decoder-only mode)."""
+    assert packed.struct_h3 is not None and sum(v is not None for v in (a0, x, gmaps16)) == 1
     a = _capi.SdfChainArgs()
-    if a0 is not None:
-        assert a0.cols >= 512 and sdfin1 is not None and sdfin1.h3 is not None and sdfin1.n == 256
-        assert sdfin1.h3.scale == 1.0, "linear_sdfin.layers.1 weights >= 16 in magnitude: use the unfused chain"
-        a.a0, a.lda0 = a0.hi_ptr, a0.ld
-        a.w_s1, a.ldw_s1, a.b_s1 = sdfin1.h3.plane_ptr(1), sdfin1.h3.ld, _ptr(sdfin1.b)
-        a.lattice_index, a.points, a.bins = _ptr(lattice_index), _ptr(points), int(bins)
-    else:
+    keep = None
+    if x is not None:
+        rows = x.rows
         assert x.cols >= DEC_IN and x.ld >= SKIP_OFF_H
         a.x, a.ldx = x.hi_ptr, x.ld
+    else:
+        assert sdfin1 is not None and sdfin1.h3 is not None and sdfin1.n == 256
+        assert sdfin1.h3.scale == 1.0, "linear_sdfin.layers.1 weights >= 16 in magnitude: use the unfused chain"
+        a.w_s1, a.ldw_s1, a.b_s1 = sdfin1.h3.plane_ptr(1), sdfin1.h3.ld, _ptr(sdfin1.b)
+        a.lattice_index, a.points, a.bins = _ptr(lattice_index), _ptr(points), int(bins)
+        if a0 is not None:
+            rows = a0.rows
+            assert a0.cols >= 512
+            a.a0, a.lda0 = a0.hi_ptr, a0.ld
+        else:
+            rows = uv.shape[0]
+            assert uv.is_contiguous() and uv.shape[1] == 2 and uv.dtype == torch.float32 and bias0 is not None
+            pyr = _pyramid_h(gmaps16, img_hw)
+            keep = pyr
+            a.gmaps, a.uv, a.row_offsets = C.addressof(pyr), uv.data_ptr(), _ptr(row_offsets)
+            a.batch, a.rows_per_sample, a.b_s0 = int(batch), int(rows_per_sample), bias0.data_ptr()
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() >= rows
     h3 = packed.struct_h3
     for l in range(4):
         a.w[l], a.ldw[l], a.b[l] = h3.w[l][1], h3.ldw[l], h3.b[l]
@@ -707,11 +752,12 @@ def sdf_chain(packed: PackedSdfDecoder, out: torch.Tensor, *, sdfin1: Optional[P
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     check(lib.hoisdf_sdf_chain_fwd(C.byref(a), _stream()), "hoisdf_sdf_chain_fwd")
+    del keep
     if PROFILE is not None:
         e1.record()
-        flops = SDF_DECODER_FLOPS + (2.0 * 512 * 256 if a0 is not None else 0.0)
+        flops = SDF_DECODER_FLOPS + (2.0 * 512 * 256 if x is None else 0.0)
         PROFILE.append(("sdf_chain", flops * rows, e0, e1, "sdf_chain rows=%d %s single" % (
-            rows, "rows" if a0 is not None else "decoder")))
+            rows, "decoder" if x is not None else ("rows" if a0 is not None else "gather"))))
     return out
 
 

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 18
+#define HOISDF_ABI_VERSION 20
 
 enum {
   HOISDF_OK = 0,
@@ -305,6 +305,15 @@ int hoisdf_sdf_decoder_h3_fwd(const hoisdf_sdf_weights_h3* wts, uint16_t* x_hi, 
  * Weights are the fp16 "B" planes (w_hi) that hoisdf_pack_h3 writes: w_s1 (256, >= 512); w[0] linh0 (512, >= 296,
  * zero beyond column 289); w[1] linh1 (223, >= 512); w[2] linh2 (512, >= 520) in the column layout
  * [input 289 | 0 x 7 | h1 223 | 0]; w[3] linh3 (512, >= 512); w4 (512) / b4 (1) fp32 (linh4). */
+/* The projected pyramid G_l = F_l . W0_l^T (linear_sdfin.layers.0 applied to every level once per image) as NHWC fp16
+ * maps (B, H_l, W_l, c = 512): what the chain kernel's gather mode interpolates. */
+typedef struct {
+  const uint16_t* map[5];
+  int32_t h[5]; int32_t w[5];
+  int32_t levels; int32_t c;
+  int32_t img_h, img_w;
+} hoisdf_pyramid_h;
+
 typedef struct {
   const uint16_t* a0; int64_t lda0;
   const uint16_t* x; int64_t ldx;
@@ -313,9 +322,21 @@ typedef struct {
   const uint16_t* w[4]; int64_t ldw[4]; const float* b[4];
   const float* w4; const float* b4;
   int64_t rows; float clamp; float* out_sdf;
+  /* gather mode (a0 == NULL and x == NULL): the kernel itself computes relu(b_s0 + sum_l bilinear sample of gmaps level l)
+   * -- upstream's 5 x F.grid_sample + cat + linear_sdfin.layers.0 (main/model.py:316-330) -- for every row from its
+   * projected pixel uv (rows, 2); row r belongs to sample upper_bound(row_offsets, r) - 1, or r / rows_per_sample. */
+  const hoisdf_pyramid_h* gmaps; const float* uv; const int64_t* row_offsets; int64_t batch; int64_t rows_per_sample;
+  const float* b_s0;
 } hoisdf_sdf_chain_args;
 
 int hoisdf_sdf_chain_fwd(const hoisdf_sdf_chain_args* args, void* stream);
+/* SUM-mode gather (see hoisdf_gather_fwd) on fp16 maps with an fp16 result: out_hi[r, 0:512] = fp16(act(bias + sum_l sample_l)),
+ * row pitch ld_out halfs.  The candidate-screening form of upstream main/model.py:316-330 feeding hoisdf_sdf_chain_fwd (rows mode). */
+int hoisdf_gather_sum_h16_fwd(const hoisdf_pyramid_h* pyr, const float* uv, int64_t rows, const int64_t* row_offsets,
+                              int64_t batch, int64_t rows_per_sample, const float* bias, int32_t act, uint16_t* out_hi,
+                              int64_t ld_out, void* stream);
+/* fp32 -> fp16 (round to nearest, saturating); n % 8 == 0.  Produces the fp16 copy of the projected maps. */
+int hoisdf_f32_to_f16(const float* x, uint16_t* y, int64_t n, void* stream);
 
 /* Expand a plain (rows, 289) decoder input (the upstream SDFDecoder.forward argument) into the padded
  * row buffer layout above. */

@@ -100,3 +100,52 @@ def test_chain_argument_errors(cuda):
     import ctypes as C
     a = _capi.SdfChainArgs()
     assert _capi.lib.hoisdf_sdf_chain_fwd(C.byref(a), None) == -1      # HOISDF_E_NULL
+
+
+@pytest.mark.parametrize("rows,offsets", [(700, True), (128 * 5, False), (3000, True)])
+def test_gather_mode_matches_unfused_gather(cuda, rows, offsets):
+    """Gather mode: the kernel's own 8 gather warps interpolate the fp16 projected maps (upstream's 5 x F.grid_sample + cat +
+    linear_sdfin.layers.0, main/model.py:316-330, in the commuted form of DESIGN.md 2.2).  Against (a) the stand-alone
+    gather kernel on the SAME fp16-rounded maps followed by the rows-mode chain (only the fp32 summation order inside a
+    level differs: fp16 round-off flips), (b) the gather on the fp32 maps (adds the fp16 rounding of the maps)."""
+    from hoisdf_b200 import ops
+    sd = syn.hot_path_state_dict(37, "dexycb")
+    dec = _decoder(cuda, sd)
+    pw = ops.PackedLinear.pack(sd["linear_sdfin.layers.1.weight"].to(cuda), sd["linear_sdfin.layers.1.bias"].to(cuda))
+    B = 3
+    sizes = [(24, 24), (12, 12), (6, 6), (3, 3), (2, 2)]
+    maps = [rnd(50 + i, B, h, w, 512, lo=-0.2, hi=0.2).to(cuda) for i, (h, w) in enumerate(sizes)]
+    maps16 = ops.maps_to_half(maps)
+    bias0 = rnd(60, 512, lo=-0.05, hi=0.05).to(cuda)
+    uv = rnd(61 + rows, rows, 2, lo=-20.0, hi=275.0).to(cuda).contiguous()          # incl. pixels outside the image (border)
+    idx = torch.from_numpy(np.random.Generator(np.random.PCG64(rows)).integers(0, 64 ** 3, size=rows).astype(np.int32)).to(cuda)
+    if offsets:
+        cuts = sorted(np.random.Generator(np.random.PCG64(7)).integers(1, rows, size=B - 1).tolist())
+        row_offsets = torch.tensor([0] + cuts + [rows], dtype=torch.int64, device=cuda)
+        rps = 0
+    else:
+        row_offsets, rps = None, rows // B if rows % B == 0 else None
+        if rps is None:
+            row_offsets, rps = torch.tensor([0, rows // 3, 2 * rows // 3, rows], dtype=torch.int64, device=cuda), 0
+    out = torch.full((rows,), float("nan"), device=cuda)
+    ops.sdf_chain(dec.packed(), out, sdfin1=pw, gmaps16=maps16, uv=uv, row_offsets=row_offsets, batch=B,
+                  rows_per_sample=rps, bias0=bias0, lattice_index=idx, bins=64)
+    assert torch.isfinite(out).all()
+
+    def unfused(ms):
+        hs = ops.SplitRows.empty(rows, 512, cuda)
+        ops.gather(ms, uv, B, mode=ops.GATHER_SUM, out=hs, row_offsets=row_offsets, rows_per_sample=rps, bias=bias0,
+                   act=ops.ACT_RELU)
+        ref = torch.empty(rows, device=cuda)
+        ops.sdf_chain(dec.packed(), ref, sdfin1=pw, a0=hs, lattice_index=idx, bins=64)
+        return ref
+
+    same_maps = unfused([m.float() for m in maps16])
+    assert (out - same_maps).abs().max() < 5e-5, float((out - same_maps).abs().max())
+    assert (out - unfused(maps)).abs().max() < SCREEN_TOL
+    # the stand-alone fp16 gather (hoisdf_gather_sum_h16_fwd: fp16 maps in, fp16 hi plane out) + rows-mode chain: same values
+    hs = ops.SplitRows.empty(rows, 512, cuda)
+    ops.gather_h16(maps16, uv, B, hs, row_offsets=row_offsets, rows_per_sample=rps, bias=bias0, act=ops.ACT_RELU)
+    ref = torch.empty(rows, device=cuda)
+    ops.sdf_chain(dec.packed(), ref, sdfin1=pw, a0=hs, lattice_index=idx, bins=64)
+    assert (ref - same_maps).abs().max() < 5e-5, float((ref - same_maps).abs().max())
