@@ -17,21 +17,30 @@ dec.load_state_dict({k[len("hand_sdf_decoder."):]: v for k, v in sd.items() if k
 FLOP, BYTES = ops.SDF_DECODER_FLOPS, 1160.0
 print("| points/sample | rows | impl | ms | M rows/s | TFLOP/s (algorithmic) | % of bf16 burst peak | GB/s (algorithmic) | % of HBM peak | max abs err vs oracle |")
 print("|---|---|---|---|---|---|---|---|---|---|")
-for pts in (256, 1024, 4096, 16384):
+for pts in ((int(sys.argv[1]),) if len(sys.argv) > 1 else (256, 1024, 4096, 16384)):
     rows = 32 * pts
     g = torch.Generator().manual_seed(pts)
     x = torch.randn(rows, 289, generator=g)
     xd = x.to(dev)
     ref = O.sdf_decoder(sd, "hand_sdf_decoder", x[:4096])
-    for impl in ("tcgen05 FP16x3", "tcgen05 3xTF32", "fp32 FMA"):
-        ops.USE_TENSOR_CORES = impl.startswith("tc")
-        ops.TC_MODE = "h3" if "FP16" in impl else "tf32"
+    for impl in ("fused tcgen05 kernel, 1 fp16 product (screening)", "tcgen05 FP16x3", "tcgen05 3xTF32", "fp32 FMA"):
+        fused = impl.startswith("fused")
+        ops.USE_TENSOR_CORES = impl.startswith("tc") or fused
+        ops.TC_MODE = "tf32" if "TF32" in impl else "h3"
         dec._packed = None
+        if fused:
+            # the ONE persistent kernel (csrc/sdf_chain.cu, decoder mode): input rows already in the fp16 row format, like
+            # inside sdf_infer where the previous kernel's epilogue writes them; 4 bytes per row come back
+            buf = ops.sdf_pad_input(xd)
+            o1 = torch.empty(rows, device=dev)
+            run = lambda: (ops.sdf_chain(dec.packed(), o1, x=buf).view(-1, 1), None)
+        else:
+            run = lambda: dec(xd)
         with torch.no_grad():
-            for _ in range(3): out, _ = dec(xd)
+            for _ in range(3): out, _ = run()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for _ in range(10): out, _ = dec(xd)
+            for _ in range(10): out, _ = run()
             e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
         err = float((out[:4096].cpu() - ref).abs().max())
