@@ -396,10 +396,13 @@ def run_native(args):
         "step incl. the 4 GEMMs of every SDF-decoder call; FLOPs counted once per fp32 product, i.e. the "
         "tensor cores execute 3x this number of TF32 MACs)")
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01n_h3_traffic.json")
-    if h3 and os.path.exists(tpath):            # from the committed ncu launch list of `bench.py --profile-step`
+    import glob
+    tpaths = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_h3_traffic.json")))
+    if h3 and tpaths:            # newest committed ncu launch list of `bench.py --profile-step` (ncu cannot run inside a timed run)
+        tpath = tpaths[-1]
         traffic = json.load(open(tpath))["dram_bytes_per_launch"]
-        traffic_src = "profiles/r01n_h3_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, same command)"
+        traffic_src = ("profiles/%s (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch of `bench.py "
+                       "--profile-step`, the same workload)" % os.path.basename(tpath))
     chain_ms = sum(p[2].elapsed_time(p[3]) for p in chain)
     chain_flops = sum(p[1] for p in chain)
     chain_rows = sum(int(p[4].split("rows=")[1].split()[0]) for p in chain)
