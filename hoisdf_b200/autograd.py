@@ -1,0 +1,297 @@
+"""torch.autograd wrappers of the hoisdf_b200 kernels -- what `Model.forward(mode="train")` is assembled from
+(upstream main/train.py:104-140 back-propagates through main/model.py:357-665).
+
+Every Function calls the C ABI for the forward AND the backward; PyTorch only provides the tape.
+
+  LinearFn        Y = act(X W^T + b)            forward : FP16x3 tcgen05 GEMM (hoisdf_linear_h3_fwd)
+                                                 backward: dZ = dY * relu' + db (hoisdf_act_bias_bwd), then the SAME tensor-core
+                                                 GEMM on transposed operands: dX = dZ . W  = linear_h3(dZ, pack(W^T)),
+                                                 dW^T = X^T . dZ = linear_h3(X^T, pack(dZ^T)).  Gradients are brought into the fp16
+                                                 planes' range by a power-of-two scale computed ON THE DEVICE (exact, undone
+                                                 after the product), so no host read-back is involved
+  WeightNormFn    W = g v / |v|                 hoisdf_fold_weight_norm / hoisdf_weight_norm_bwd
+  GatherFn        5-level bilinear gather       hoisdf_gather_fwd (CONCAT) / hoisdf_gather_bwd (scatter-add into the pyramid grad)
+  AddLayerNormFn  LayerNorm(x + res)            hoisdf_add_layernorm_fwd / hoisdf_layernorm_bwd
+  AttentionFn     softmax(q k^T / 8 [mask]) v   forward: tcgen05 flash kernel (hoisdf_attention_fwd) when there is no dropout on the
+                                                 probabilities, else the materialised form; backward: hoisdf_gemm_f32_batched +
+                                                 hoisdf_softmax_rows_fwd / _bwd per (sample, head) -- fp32 SIMT, the S x S
+                                                 probabilities are recomputed, not stored
+  TokensFn        token assembly + sdf_activation  hoisdf_tokens_fwd / hoisdf_tokens_bwd (own-field blocks only: upstream detaches
+                                                 the SDF values and the cross-field tokens, model.py:483-484,536,555)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+from torch.autograd import Function
+
+from . import _capi, ops
+from ._capi import check, lib
+from .ops import _count, _ptr, _stream
+
+ACT_NONE, ACT_RELU = ops.ACT_NONE, ops.ACT_RELU
+TRAIN_CHUNK_KB = 4          # TMEM accumulation chunk of the training GEMMs (K blocks of 32 per drain)
+
+
+# ----------------------------------------------------------------------------------------------------
+# tensor-core A . B^T with on-device power-of-two scaling
+# ----------------------------------------------------------------------------------------------------
+def _pow2_scale(t: torch.Tensor, log2_target: int) -> torch.Tensor:
+    """0-dim device tensor s = 2^e with max|t| / s in (2^(log2_target-1), 2^log2_target]; 1 for an all-zero tensor."""
+    amax = t.abs().amax()
+    e = torch.ceil(torch.log2(amax.clamp_min(1e-30))) - log2_target
+    return torch.where(amax > 0, torch.exp2(e), torch.ones_like(e))
+
+
+def _c2d(t: torch.Tensor) -> torch.Tensor:
+    return t if (t.stride(-1) == 1 and t.dim() == 2) else t.contiguous()
+
+
+def matmul_nt(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+              chunk_kb: int = TRAIN_CHUNK_KB) -> torch.Tensor:
+    """act(a (M,K) . b (N,K)^T + bias) -> (M,N) fp32 on the FP16x3 kernel.  `b` is the "weight" operand: |b| < 16 (its hi
+    plane is stored times 2^11 in fp16); `a` any fp16-range values.  No host synchronisation.  Products with a handful of
+    output columns or a tiny contraction (the N = 1 / 3 / 6 / 10 head layers and their gradients) are not tensor-core
+    shapes: they take the fp32 FMA GEMM."""
+    a, b = _c2d(a), _c2d(b)
+    m, k = a.shape
+    n = b.shape[0]
+    if n <= 16 or k <= 16:
+        y = torch.empty(m, n, device=a.device, dtype=torch.float32)
+        _count(1)
+        check(lib.hoisdf_gemm_f32(a.data_ptr(), a.stride(0), 0, b.data_ptr(), b.stride(0), 1, y.data_ptr(), n, m, n, k, 0,
+                                  _stream()), "hoisdf_gemm_f32")
+        if bias is not None:
+            y += bias
+        return torch.relu_(y) if act == ACT_RELU else y
+    xs = ops.split_rows(a)
+    pw = ops.PackedLinearH3.pack(b, None if bias is None else bias.detach(), assume_max=1.0)
+    return ops.linear_h3(xs, pw, act, chunk_kb=chunk_kb)
+
+
+class LinearFn(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, act):
+        x = _c2d(x)
+        y = matmul_nt(x, weight, bias, act)
+        ctx.act = act
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, weight, y if act == ACT_RELU else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        m, n = dy.shape
+        dz = dy.contiguous().clone() if ctx.act == ACT_RELU else dy.contiguous()
+        db = torch.empty(n, device=dy.device, dtype=torch.float32) if ctx.has_bias else None
+        if ctx.act == ACT_RELU or db is not None:
+            _count(1)
+            check(lib.hoisdf_act_bias_bwd(dz.data_ptr(), dz.stride(0), _ptr(y), 0 if y is None else y.stride(0), m, n,
+                                          ctx.act, _ptr(db), 0, _stream()), "hoisdf_act_bias_bwd")
+        s = _pow2_scale(dz, 3)                       # |dz / s| <= 8: fits both operand formats
+        dzs = dz * (1.0 / s)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = matmul_nt(dzs, weight.detach().t().contiguous())            # (M,N) . (K,N)^T
+            dx = dx.mul_(s) if dx.is_contiguous() else dx * s
+        if ctx.needs_input_grad[1]:
+            dwt = matmul_nt(x.t().contiguous(), dzs.t().contiguous())        # (K,M) . (N,M)^T = dW^T / s
+            dw = dwt.t() * s
+        return dx, dw, db, None
+
+
+def linear(x2d: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], act: int = ACT_NONE) -> torch.Tensor:
+    return LinearFn.apply(x2d, weight, bias, act)
+
+
+class WeightNormFn(Function):
+    """nn.utils.weight_norm (dim 0): W[r] = g[r] * v[r] / |v[r]| (upstream common/nets/sdf_net.py:57-62)."""
+
+    @staticmethod
+    def forward(ctx, g, v):
+        w = ops.fold_weight_norm(g, v)[:, : v.shape[1]]
+        ctx.save_for_backward(g, v)
+        return w
+
+    @staticmethod
+    def backward(ctx, dw):
+        g, v = ctx.saved_tensors
+        dw = _c2d(dw)
+        rows, cols = v.shape
+        dg = torch.empty(rows, device=v.device, dtype=torch.float32)
+        dv = torch.empty(rows, cols, device=v.device, dtype=torch.float32)
+        vc, gc = v.detach().contiguous(), g.detach().reshape(-1).contiguous()
+        _count(1)
+        check(lib.hoisdf_weight_norm_bwd(gc.data_ptr(), vc.data_ptr(), dw.data_ptr(), dw.stride(0), rows, cols,
+                                         dg.data_ptr(), dv.data_ptr(), 0, _stream()), "hoisdf_weight_norm_bwd")
+        return dg.view_as(g), dv
+
+
+class GatherFn(Function):
+    """CONCAT-mode bilinear gather of the 5 NHWC pyramid levels at `uv` (rows, 2) pixels (upstream F.grid_sample calls,
+    main/model.py:166-171,206-211; the grid is detached there, so `uv` gets no gradient)."""
+
+    @staticmethod
+    def forward(ctx, uv, batch, rows_per_sample, img_hw, *maps):
+        maps = [m.contiguous() for m in maps]
+        rows = uv.shape[0]
+        out = torch.empty(rows, sum(m.shape[3] for m in maps), device=uv.device, dtype=torch.float32)
+        ops.gather(maps, uv, batch, mode=ops.GATHER_CONCAT, out=out, rows_per_sample=rows_per_sample, img_hw=img_hw)
+        ctx.save_for_backward(uv)
+        ctx.geom = (batch, rows_per_sample, img_hw, [tuple(m.shape) for m in maps])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (uv,) = ctx.saved_tensors
+        batch, rps, img_hw, shapes = ctx.geom
+        dout = _c2d(dout)
+        grads = [torch.zeros(s, device=dout.device, dtype=torch.float32) for s in shapes]
+        pyr = ops.make_pyramid(grads, img_hw)
+        _count(1)
+        check(lib.hoisdf_gather_bwd(C.byref(pyr), uv.data_ptr(), uv.shape[0], None, batch, rps, dout.data_ptr(),
+                                    dout.stride(0), _stream()), "hoisdf_gather_bwd")
+        return (None, None, None, None, *grads)
+
+
+class AddLayerNormFn(Function):
+    """LayerNorm(x + res) over the last dim (256), eps 1e-5 (upstream transformer.py:296-301)."""
+
+    @staticmethod
+    def forward(ctx, x, res, gamma, beta):
+        h = x if res is None else x + res
+        h = h.contiguous()
+        y = ops.add_layernorm(h, None, gamma.detach(), beta.detach())
+        ctx.save_for_backward(h, gamma)
+        ctx.has_res = res is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        h, gamma = ctx.saved_tensors
+        d = h.shape[-1]
+        rows = h.numel() // d
+        dy = dy.contiguous()
+        dh = torch.empty_like(h)
+        dg = torch.empty(d, device=h.device, dtype=torch.float32)
+        db = torch.empty(d, device=h.device, dtype=torch.float32)
+        stats = torch.empty(rows * 2, device=h.device, dtype=torch.float32)
+        gc = gamma.detach().contiguous()
+        _count(2)
+        check(lib.hoisdf_layernorm_bwd(h.data_ptr(), gc.data_ptr(), dy.data_ptr(), rows, d, dh.data_ptr(), dg.data_ptr(),
+                                       db.data_ptr(), stats.data_ptr(), 0, _stream()), "hoisdf_layernorm_bwd")
+        return dh, (dh if ctx.has_res else None), dg, db
+
+
+def _gemm_batched(a, lda, ta, a_o, a_i, b, ldb, tb, b_o, b_i, c, ldc, c_o, c_i, m, n, k, alpha, bo, bi):
+    _count(1)
+    check(lib.hoisdf_gemm_f32_batched(a, lda, ta, a_o, a_i, b, ldb, tb, b_o, b_i, c, ldc, c_o, c_i, m, n, k, alpha, 0,
+                                      bo, bi, _stream()), "hoisdf_gemm_f32_batched")
+
+
+class AttentionFn(Function):
+    """Multi-head attention core on (B*L, d) row matrices (head h = columns [64h, 64h+64)): softmax(q k^T / 8 + mask) v.
+    q: (B*Lq, d) view with pitch ldq, k / v: (B*Lk, d) views; `mask` uint8 (Lq, Lk), non-zero = blocked; keys >= kv_valid are
+    blocked for every query; `p_drop` = dropout on the probabilities (nn.MultiheadAttention's), applied with a torch mask."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, batch, heads, lq, lk, mask, kv_valid, p_drop):
+        d = heads * 64
+        for t in (q, k, v):
+            assert t.stride(1) == 1 and t.shape[1] == d
+        dev = q.device
+        out = torch.empty(batch * lq, d, device=dev, dtype=torch.float32)
+        keep = None
+        if p_drop > 0.0:
+            # materialised form: P (B, H, Lq, Lk) is needed for the dropout mask
+            p = AttentionFn._probs(q, k, batch, heads, lq, lk, mask, kv_valid)
+            keep = (torch.rand_like(p) >= p_drop)
+            p = p * keep * (1.0 / (1.0 - p_drop))
+            _gemm_batched(p.data_ptr(), lk, 0, heads * lq * lk, lq * lk, v.data_ptr(), v.stride(0), 0, lk * v.stride(0), 64,
+                          out.data_ptr(), d, lq * d, 64, lq, 64, lk, 1.0, batch, heads)
+        else:
+            vv = v
+            if k.stride(0) != v.stride(0):
+                raise ValueError("attention: k and v must share their row pitch")
+            ops.attention(q, q.stride(0), k, vv, k.stride(0), out, d, batch, heads, lq, lk, kv_valid=kv_valid, mask=mask,
+                          tensor_cores=(mask is None))
+        ctx.save_for_backward(q, k, v, mask, keep)
+        ctx.geom = (batch, heads, lq, lk, kv_valid, p_drop)
+        return out
+
+    @staticmethod
+    def _probs(q, k, batch, heads, lq, lk, mask, kv_valid):
+        s = torch.empty(batch, heads, lq, lk, device=q.device, dtype=torch.float32)
+        _gemm_batched(q.data_ptr(), q.stride(0), 0, lq * q.stride(0), 64, k.data_ptr(), k.stride(0), 1, lk * k.stride(0), 64,
+                      s.data_ptr(), lk, heads * lq * lk, lq * lk, lq, lk, 64, 0.125, batch, heads)
+        _count(1)
+        check(lib.hoisdf_softmax_rows_fwd(s.data_ptr(), lk, batch * heads * lq, lk, lk if kv_valid is None else kv_valid,
+                                          _ptr(mask), 0 if mask is None else lq, s.data_ptr(), lk, _stream()),
+              "hoisdf_softmax_rows_fwd")
+        return s
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, mask, keep = ctx.saved_tensors
+        batch, heads, lq, lk, kv_valid, p_drop = ctx.geom
+        d = heads * 64
+        dev = q.device
+        dout = dout.contiguous()
+        p = AttentionFn._probs(q, k, batch, heads, lq, lk, mask, kv_valid)
+        pd = p if keep is None else p * keep * (1.0 / (1.0 - p_drop))        # what multiplied V in the forward
+        dq = torch.empty(batch * lq, d, device=dev, dtype=torch.float32)
+        dk = torch.empty(batch * lk, d, device=dev, dtype=torch.float32)
+        dv = torch.empty(batch * lk, d, device=dev, dtype=torch.float32)
+        hh = heads * lq * lk
+        # dV = Pd^T dO
+        _gemm_batched(pd.data_ptr(), lk, 1, hh, lq * lk, dout.data_ptr(), d, 0, lq * d, 64, dv.data_ptr(), d, lk * d, 64,
+                      lk, 64, lq, 1.0, batch, heads)
+        # dPd = dO V^T
+        dp = torch.empty(batch, heads, lq, lk, device=dev, dtype=torch.float32)
+        _gemm_batched(dout.data_ptr(), d, 0, lq * d, 64, v.data_ptr(), v.stride(0), 1, lk * v.stride(0), 64, dp.data_ptr(),
+                      lk, hh, lq * lk, lq, lk, 64, 1.0, batch, heads)
+        if keep is not None:
+            dp = dp * keep * (1.0 / (1.0 - p_drop))
+        # dS = P * (dP - sum_j dP_j P_j)
+        _count(1)
+        check(lib.hoisdf_softmax_rows_bwd(p.data_ptr(), lk, dp.data_ptr(), lk, batch * heads * lq, lk, dp.data_ptr(), lk,
+                                          _stream()), "hoisdf_softmax_rows_bwd")
+        # dQ = dS K / 8, dK = dS^T Q / 8
+        _gemm_batched(dp.data_ptr(), lk, 0, hh, lq * lk, k.data_ptr(), k.stride(0), 0, lk * k.stride(0), 64, dq.data_ptr(),
+                      d, lq * d, 64, lq, 64, lk, 0.125, batch, heads)
+        _gemm_batched(dp.data_ptr(), lk, 1, hh, lq * lk, q.data_ptr(), q.stride(0), 0, lq * q.stride(0), 64, dk.data_ptr(),
+                      d, lk * d, 64, lk, 64, lq, 0.125, batch, heads)
+        return dq, dk, dv, None, None, None, None, None, None, None
+
+
+class TokensFn(Function):
+    """One own-field token block (upstream main/model.py:520-531 with sdf_activation :123-126):
+    tokens (B, P, 256) = [xyz (3) | posenc (30) | fea (223) * sigmoid(sdf / beta) / beta].  Gradients: fea and beta (the SDF
+    values are detached upstream, :483-484)."""
+
+    @staticmethod
+    def forward(ctx, fea, beta, xyz, pe, sdf):
+        b, p, _ = xyz.shape
+        fea = fea.contiguous()
+        out = torch.empty(b, p, 256, device=fea.device, dtype=torch.float32)
+        ops.tokens(xyz.contiguous(), pe.contiguous(), fea, sdf.contiguous(), beta.detach(), out, 0)
+        ctx.save_for_backward(fea, beta, sdf.contiguous())
+        return out
+
+    @staticmethod
+    def backward(ctx, dtok):
+        fea, beta, sdf = ctx.saved_tensors
+        b, p, f = fea.shape
+        dtok = dtok.contiguous()
+        dfea = torch.empty(b * p, f, device=fea.device, dtype=torch.float32)
+        dbeta = torch.empty(1, device=fea.device, dtype=torch.float32)
+        nbytes = lib.hoisdf_tokens_bwd_workspace_bytes(b, p)
+        ws = torch.empty(max(int(nbytes), 4), device=fea.device, dtype=torch.uint8)
+        _count(2)
+        check(lib.hoisdf_tokens_bwd(dtok.data_ptr(), p, 0, fea.data_ptr(), f, sdf.data_ptr(), beta.detach().data_ptr(), b, p,
+                                    dfea.data_ptr(), f, None, dbeta.data_ptr(), 0, ws.data_ptr(), nbytes, _stream()),
+              "hoisdf_tokens_bwd")
+        return dfea.view(b, p, f), dbeta.view_as(beta), None, None, None

@@ -29,15 +29,27 @@ namespace {
 constexpr int GB = 64;      // C tile edge
 constexpr int GK = 16;      // K step
 
+struct GemmBatch {          // strides (in floats) of the two batch levels of hoisdf_gemm_f32_batched; all 0 / inner 1 = one matrix
+  int64_t a_outer, a_inner, b_outer, b_inner, c_outer, c_inner;
+  int inner;
+  float alpha;
+};
+
 // C[m, n] = sum_k a(m, k) * b(k, n); TA: A is stored (K, M) (a(m,k) = A[k*lda + m]), else (M, K);
 //                                    TB: B is stored (N, K) (b(k,n) = B[n*ldb + k]), else (K, N).  256 threads, 4 x 4 each.
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(256)
 gemm_f32_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb, float* __restrict__ Cm,
-                int64_t ldc, int64_t M, int64_t N, int64_t K, int accumulate) {
+                int64_t ldc, int64_t M, int64_t N, int64_t K, int accumulate, GemmBatch gb) {
   __shared__ float As[GK][GB + 4];
   __shared__ float Bs[GK][GB + 4];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  {   // batched form: blockIdx.z = outer * inner_count + inner (e.g. sample x head), per-operand strides in floats
+    const int64_t zo = blockIdx.z / gb.inner, zi = blockIdx.z % gb.inner;
+    A += zo * gb.a_outer + zi * gb.a_inner;
+    B += zo * gb.b_outer + zi * gb.b_inner;
+    Cm += zo * gb.c_outer + zi * gb.c_inner;
+  }
   const int64_t m0 = static_cast<int64_t>(blockIdx.y) * GB, n0 = static_cast<int64_t>(blockIdx.x) * GB;
   float acc[4][4];
 #pragma unroll
@@ -78,22 +90,27 @@ gemm_f32_kernel(const float* __restrict__ A, int64_t lda, const float* __restric
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int64_t n = n0 + tx * 4 + j;
-      if (n < N) Cm[m * ldc + n] = accumulate ? Cm[m * ldc + n] + acc[i][j] : acc[i][j];
+      if (n < N) Cm[m * ldc + n] = accumulate ? Cm[m * ldc + n] + gb.alpha * acc[i][j] : gb.alpha * acc[i][j];
     }
   }
 }
 
 // dZ = dY * (Y > 0) in place (act == ReLU; the forward stored Y = relu(Z)), then db[n] = sum_m dZ[m, n].
-// grid = ceil(N / 32) blocks of 256 threads: 32 columns x 8 row lanes, fixed-order tree -> deterministic sums
+// grid = (ceil(N / 32), row chunks) blocks of 256 threads: 32 columns x 8 row lanes, fixed-order tree.  One row chunk
+// (M <= ACT_BWD_CHUNK): deterministic sums; more: the chunks' partial sums meet in db through atomicAdd (db zeroed by the
+// host entry unless accumulating), so large-M launches fill the GPU instead of ceil(N / 32) SMs.
+constexpr int64_t ACT_BWD_CHUNK = 2048;
 __global__ void __launch_bounds__(256)
 act_bias_bwd_kernel(float* __restrict__ dy, int64_t lddy, const float* __restrict__ y, int64_t ldy, int64_t M, int64_t N,
                     int act, float* __restrict__ db, int accumulate) {
   __shared__ float part[8][33];
   const int c = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int64_t n = static_cast<int64_t>(blockIdx.x) * 32 + c;
+  const int64_t m_lo = gridDim.y > 1 ? static_cast<int64_t>(blockIdx.y) * ACT_BWD_CHUNK : 0;
+  const int64_t m_hi = gridDim.y > 1 ? (m_lo + ACT_BWD_CHUNK < M ? m_lo + ACT_BWD_CHUNK : M) : M;
   float s = 0.f;
   if (n < N) {
-    for (int64_t m = rl; m < M; m += 8) {
+    for (int64_t m = m_lo + rl; m < m_hi; m += 8) {
       float g = dy[m * lddy + n];
       if (act == HOISDF_ACT_RELU && !(y[m * ldy + n] > 0.f)) {
         g = 0.f;
@@ -108,7 +125,8 @@ act_bias_bwd_kernel(float* __restrict__ dy, int64_t lddy, const float* __restric
     float t = part[0][c];
 #pragma unroll
     for (int i = 1; i < 8; ++i) t += part[i][c];
-    db[n] = accumulate ? db[n] + t : t;
+    if (gridDim.y > 1) atomicAdd(db + n, t);
+    else db[n] = accumulate ? db[n] + t : t;
   }
 }
 
@@ -509,21 +527,37 @@ __global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restri
 
 using namespace hoisdf;
 
-HOISDF_API int hoisdf_gemm_f32(const float* a, int64_t lda, int32_t trans_a, const float* b, int64_t ldb, int32_t trans_b,
-                               float* c, int64_t ldc, int64_t m, int64_t n, int64_t k, int32_t accumulate, void* stream) {
+static int gemm_f32_launch(const float* a, int64_t lda, int32_t trans_a, const float* b, int64_t ldb, int32_t trans_b, float* c,
+                           int64_t ldc, int64_t m, int64_t n, int64_t k, int32_t accumulate, const GemmBatch& gb, int64_t batches,
+                           void* stream) {
   if (a == nullptr || b == nullptr || c == nullptr) return HOISDF_E_NULL;
-  if (m <= 0 || n <= 0 || k <= 0 || ldc < n) return HOISDF_E_SHAPE;
+  if (m <= 0 || n <= 0 || k <= 0 || ldc < n || batches <= 0 || batches > 65535) return HOISDF_E_SHAPE;
   if (lda < (trans_a ? m : k) || ldb < (trans_b ? k : n)) return HOISDF_E_SHAPE;
   const int64_t gx = ceil_div(n, GB), gy = ceil_div(m, GB);
   if (gy > 65535 || gx > 0x7fffffffLL) return HOISDF_E_SHAPE;
-  const dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(gy));
+  const dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(gy), static_cast<unsigned>(batches));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int acc = accumulate ? 1 : 0;
-  if (trans_a && trans_b) HOISDF_LAUNCH((gemm_f32_kernel<true, true>), grid, 256, s, a, lda, b, ldb, c, ldc, m, n, k, acc);
-  else if (trans_a) HOISDF_LAUNCH((gemm_f32_kernel<true, false>), grid, 256, s, a, lda, b, ldb, c, ldc, m, n, k, acc);
-  else if (trans_b) HOISDF_LAUNCH((gemm_f32_kernel<false, true>), grid, 256, s, a, lda, b, ldb, c, ldc, m, n, k, acc);
-  else HOISDF_LAUNCH((gemm_f32_kernel<false, false>), grid, 256, s, a, lda, b, ldb, c, ldc, m, n, k, acc);
+  if (trans_a && trans_b) HOISDF_LAUNCH((gemm_f32_kernel<true, true>), grid, 256, s, a, lda, b, ldb, c, ldc, m, n, k, acc, gb);
+  else if (trans_a) HOISDF_LAUNCH((gemm_f32_kernel<true, false>), grid, 256, s, a, lda, b, ldb, c, ldc, m, n, k, acc, gb);
+  else if (trans_b) HOISDF_LAUNCH((gemm_f32_kernel<false, true>), grid, 256, s, a, lda, b, ldb, c, ldc, m, n, k, acc, gb);
+  else HOISDF_LAUNCH((gemm_f32_kernel<false, false>), grid, 256, s, a, lda, b, ldb, c, ldc, m, n, k, acc, gb);
   return launch_status();
+}
+
+HOISDF_API int hoisdf_gemm_f32(const float* a, int64_t lda, int32_t trans_a, const float* b, int64_t ldb, int32_t trans_b,
+                               float* c, int64_t ldc, int64_t m, int64_t n, int64_t k, int32_t accumulate, void* stream) {
+  GemmBatch gb{0, 0, 0, 0, 0, 0, 1, 1.0f};
+  return gemm_f32_launch(a, lda, trans_a, b, ldb, trans_b, c, ldc, m, n, k, accumulate, gb, 1, stream);
+}
+
+HOISDF_API int hoisdf_gemm_f32_batched(const float* a, int64_t lda, int32_t trans_a, int64_t a_outer, int64_t a_inner,
+                                       const float* b, int64_t ldb, int32_t trans_b, int64_t b_outer, int64_t b_inner, float* c,
+                                       int64_t ldc, int64_t c_outer, int64_t c_inner, int64_t m, int64_t n, int64_t k, float alpha,
+                                       int32_t accumulate, int64_t batch_outer, int64_t batch_inner, void* stream) {
+  if (batch_outer <= 0 || batch_inner <= 0 || batch_inner > 65535) return HOISDF_E_SHAPE;
+  GemmBatch gb{a_outer, a_inner, b_outer, b_inner, c_outer, c_inner, static_cast<int>(batch_inner), alpha};
+  return gemm_f32_launch(a, lda, trans_a, b, ldb, trans_b, c, ldc, m, n, k, accumulate, gb, batch_outer * batch_inner, stream);
 }
 
 HOISDF_API int hoisdf_act_bias_bwd(float* dy, int64_t lddy, const float* y, int64_t ldy, int64_t m, int64_t n, int32_t act,
@@ -531,8 +565,15 @@ HOISDF_API int hoisdf_act_bias_bwd(float* dy, int64_t lddy, const float* y, int6
   if (dy == nullptr || (act == HOISDF_ACT_RELU && y == nullptr)) return HOISDF_E_NULL;
   if (m <= 0 || n <= 0 || lddy < n || (y != nullptr && ldy < n)) return HOISDF_E_SHAPE;
   if (act != HOISDF_ACT_NONE && act != HOISDF_ACT_RELU) return HOISDF_E_UNSUPPORTED;
-  HOISDF_LAUNCH(act_bias_bwd_kernel, static_cast<unsigned>(ceil_div(n, 32)), 256, static_cast<cudaStream_t>(stream), dy, lddy,
-                y, ldy, m, n, act, db, accumulate ? 1 : 0);
+  const int64_t chunks = m > 4 * ACT_BWD_CHUNK ? ceil_div(m, ACT_BWD_CHUNK) : 1;
+  if (chunks > 65535) return HOISDF_E_SHAPE;
+  if (chunks > 1 && db != nullptr && !accumulate) {
+    const cudaError_t e = cudaMemsetAsync(db, 0, sizeof(float) * n, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+  const dim3 grid(static_cast<unsigned>(ceil_div(n, 32)), static_cast<unsigned>(chunks));
+  HOISDF_LAUNCH(act_bias_bwd_kernel, grid, 256, static_cast<cudaStream_t>(stream), dy, lddy, y, ldy, m, n, act, db,
+                accumulate ? 1 : 0);
   return launch_status();
 }
 

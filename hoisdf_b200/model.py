@@ -14,7 +14,7 @@ What is different by design (B200-first):
     reference path (cfg.tc_backbone / cfg.tc_unet = False);
   * the near-surface selection is a verified coarse-to-fine cascade (single-product FP16 -> FP16x3), `sdf_infer`;
   * the static-shape stages can be replayed from CUDA graphs (`enable_cuda_graphs`).
-Inference only for now (mode != "train"); training needs the backward kernels.
+`mode="train"` (forward with the autograd tape of hoisdf_b200/autograd.py) lives in hoisdf_b200/train.py.
 """
 from __future__ import annotations
 
@@ -181,8 +181,15 @@ class Model(nn.Module):
         self.linear_objcls = MLP(d, d, 8, 3)
         self.linear_obj_rel_trans = MLP(d, d, 3, 3)
         self.linear_obj_rot = MLP(d, d, 3, 3)
+        self.freeze_stages()
         self.last_taps = None      # diagnostics of the most recent forward (selected lattice indices, N_f, ...)
         self._graphs = None        # CUDA-graph mode (enable_cuda_graphs): {shape key: GraphedForward}
+
+    def freeze_stages(self):
+        """upstream model.py:114-121: the backbone's BatchNorm affine parameters are not trained."""
+        for name, param in self.backbone_net.named_parameters():
+            if "bn" in name:
+                param.requires_grad = False
 
     # ------------------------------------------------------------------------------------------------
     # layout helper
@@ -477,8 +484,8 @@ class Model(nn.Module):
     # ------------------------------------------------------------------------------------------------
     def forward(self, inputs, targets, meta_info, mode, epoch_cnt=1e8, batch_ratio=0):
         if mode == "train":
-            raise NotImplementedError("hoisdf_b200 builds the inference hot path; the training step "
-                                      "(backward kernels, SURVEY.md section 8 f-2) is not built yet")
+            from .train import forward_train          # upstream model.py:357-665, train branch (hoisdf_b200/train.py)
+            return forward_train(self, inputs, targets, meta_info, epoch_cnt, batch_ratio)
         graphed = (self._graphs is not None and cfg.tc_backbone and cfg.tc_unet and ops.use_h3()
                    and inputs["img"].is_cuda)
         dex = cfg.dataset == "dexycb"

@@ -268,7 +268,9 @@ class PackedLinearH3:
 
     @staticmethod
     def pack(weight: torch.Tensor, bias: Optional[torch.Tensor], k: Optional[int] = None,
-             chunk_kb: int = 0) -> "PackedLinearH3":
+             chunk_kb: int = 0, assume_max: Optional[float] = None) -> "PackedLinearH3":
+        """`assume_max`: the caller's bound on max |w| -- skips the host read-back of the real maximum (the training
+        path packs operands every step and scales them on the device, hoisdf_b200/autograd.py)."""
         w = weight.detach().to(torch.float32)
         if w.stride(1) != 1:
             w = w.contiguous()
@@ -276,7 +278,7 @@ class PackedLinearH3:
         k = k or w.shape[1]
         # plane A = w_hi * 2^11 must fit fp16: layers with |w| >= 16 (a BatchNorm fold with a tiny running variance can do
         # that) are divided by a power of two -- exact -- which the GEMM epilogue multiplies back (`w_scale`)
-        wmax = float(w.abs().max()) if w.numel() else 0.0
+        wmax = float(assume_max) if assume_max is not None else (float(w.abs().max()) if w.numel() else 0.0)
         if not math.isfinite(wmax):
             raise ValueError("FP16x3 Linear: non-finite weight")
         scale = 1.0

@@ -318,6 +318,15 @@ def dexycb_extras(seed: int, batch: int, ph: int, po: int):
     return inputs, targets
 
 
+def train_extras(seed: int, batch: int, ph: int, po: int):
+    """`inputs` / `targets` of a training step (upstream data/ho3d.py:527-589: P_h + P_o SDF supervision points and as many
+    `*_pre_points` per sample, all in normalised coordinates)."""
+    inputs, targets = dexycb_extras(seed, batch, ph, po)
+    inputs["hand_pre_points"] = _uniform(seed, "train.hand_pre_points", (batch, ph, 3), -0.3, 0.3)
+    inputs["obj_pre_points"] = _uniform(seed, "train.obj_pre_points", (batch, po, 3), -0.3, 0.3)
+    return inputs, targets
+
+
 HO3D_OBJECT_NAMES = ("003_cracker_box", "006_mustard_bottle", "010_potted_meat_can", "019_pitcher_base", "021_bleach_cleanser")
 
 

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 20
+#define HOISDF_ABI_VERSION 21
 
 enum {
   HOISDF_OK = 0,
@@ -502,6 +502,13 @@ int hoisdf_hand_joint_metrics_fwd(const float* pred, const float* gt, int64_t ba
  * ------------------------------------------------------------------------------------------------- */
 int hoisdf_gemm_f32(const float* a, int64_t lda, int32_t trans_a, const float* b, int64_t ldb, int32_t trans_b, float* c,
                     int64_t ldc, int64_t m, int64_t n, int64_t k, int32_t accumulate, void* stream);
+/* batched form: batch_outer x batch_inner matrices (e.g. sample x head), per-operand strides in floats for both levels;
+ * C = alpha * op(A) . op(B) (+ C).  The attention core's backward on the (B, S, 3 d) projections: head h of sample b
+ * lives at b * S * ld + h * 64. */
+int hoisdf_gemm_f32_batched(const float* a, int64_t lda, int32_t trans_a, int64_t a_outer, int64_t a_inner, const float* b,
+                            int64_t ldb, int32_t trans_b, int64_t b_outer, int64_t b_inner, float* c, int64_t ldc,
+                            int64_t c_outer, int64_t c_inner, int64_t m, int64_t n, int64_t k, float alpha, int32_t accumulate,
+                            int64_t batch_outer, int64_t batch_inner, void* stream);
 int hoisdf_act_bias_bwd(float* dy, int64_t lddy, const float* y, int64_t ldy, int64_t m, int64_t n, int32_t act, float* db,
                         int32_t accumulate, void* stream);
 int hoisdf_weight_norm_bwd(const float* g, const float* v, const float* dw, int64_t lddw, int64_t rows, int64_t cols,

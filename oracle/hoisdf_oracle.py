@@ -231,7 +231,8 @@ def get_input_transformer(p, pyramid, sdf_points, center, K, sdf_scale, cfg):
 def sdf_activation(p, name, sdf):
     """upstream main/model.py:123-126 (in-place floor of beta at 2e-3, then sigmoid(sdf/beta)/beta)."""
     beta = p[name]
-    beta.copy_(torch.maximum(torch.zeros_like(beta) + 2e-3, beta))
+    # upstream clamps `beta.data` (no tape, no version bump), so a leaf that requires grad stays usable under autograd
+    beta.data.copy_(torch.maximum(torch.zeros_like(beta) + 2e-3, beta.data))
     return torch.sigmoid(sdf / beta) / beta
 
 
@@ -506,65 +507,72 @@ def vote_joints(hand_points, hand_off, hand_cls):
 # ----------------------------------------------------------------------------------------------------
 # ResNet-50 + U-Net (the step BEFORE the hot path; needed for the full-forward CPU baseline)
 # ----------------------------------------------------------------------------------------------------
-def _bn(p, prefix, x):
+def _bn(p, prefix, x, training=False):
+    """nn.BatchNorm2d: running statistics in eval mode; in training mode the batch statistics (upstream trains with
+    model.train(), main/train.py:89 -- also for the backbone, whose BN affine parameters alone are frozen,
+    main/model.py:117-121).  The running-statistics update of training mode does not touch outputs or gradients and is
+    left out."""
+    if training:
+        return F.batch_norm(x, None, None, p[prefix + ".weight"], p[prefix + ".bias"], True, 0.1, 1e-5)
     return F.batch_norm(x, p[prefix + ".running_mean"], p[prefix + ".running_var"],
                         p[prefix + ".weight"], p[prefix + ".bias"], False, 0.0, 1e-5)
 
 
-def _bottleneck(p, prefix, x, stride):
+def _bottleneck(p, prefix, x, stride, training=False):
     """torchvision Bottleneck (v1.5: stride on the 3x3) as instantiated by upstream resnet.py:19,49-68."""
-    out = F.relu(_bn(p, prefix + ".bn1", F.conv2d(x, p[prefix + ".conv1.weight"])))
-    out = F.relu(_bn(p, prefix + ".bn2", F.conv2d(out, p[prefix + ".conv2.weight"], stride=stride, padding=1)))
-    out = _bn(p, prefix + ".bn3", F.conv2d(out, p[prefix + ".conv3.weight"]))
+    out = F.relu(_bn(p, prefix + ".bn1", F.conv2d(x, p[prefix + ".conv1.weight"]), training))
+    out = F.relu(_bn(p, prefix + ".bn2", F.conv2d(out, p[prefix + ".conv2.weight"], stride=stride, padding=1), training))
+    out = _bn(p, prefix + ".bn3", F.conv2d(out, p[prefix + ".conv3.weight"]), training)
     if prefix + ".downsample.0.weight" in p:
-        x = _bn(p, prefix + ".downsample.1", F.conv2d(x, p[prefix + ".downsample.0.weight"], stride=stride))
+        x = _bn(p, prefix + ".downsample.1", F.conv2d(x, p[prefix + ".downsample.0.weight"], stride=stride), training)
     return F.relu(out + x)
 
 
-def backbone(p, img, prefix="backbone_net.resnet"):
+def backbone(p, img, prefix="backbone_net.resnet", training=False):
     """upstream common/nets/resnet.py:70-87."""
     skips = {}
-    x = F.relu(_bn(p, prefix + ".bn1", F.conv2d(img, p[prefix + ".conv1.weight"], stride=2, padding=3)))
+    x = F.relu(_bn(p, prefix + ".bn1", F.conv2d(img, p[prefix + ".conv1.weight"], stride=2, padding=3), training))
     skips["stride2"] = x
     x = F.max_pool2d(x, 3, 2, 1)
     for li, (blocks, name) in enumerate(((3, "stride4"), (4, "stride8"), (6, "stride16"), (3, "stride32")), 1):
         for bi in range(blocks):
-            x = _bottleneck(p, "%s.layer%d.%d" % (prefix, li, bi), x, 2 if (bi == 0 and li > 1) else 1)
+            x = _bottleneck(p, "%s.layer%d.%d" % (prefix, li, bi), x, 2 if (bi == 0 and li > 1) else 1, training)
         skips[name] = x
     return x, skips
 
 
-def _conv_stack(p, prefix, x, n, k, final_bn=True):
+def _conv_stack(p, prefix, x, n, k, final_bn=True, training=False):
     idx = 0
     for i in range(n):
         x = F.conv2d(x, p["%s.%d.weight" % (prefix, idx)], p["%s.%d.bias" % (prefix, idx)], padding=k // 2)
         idx += 1
         if i < n - 1 or final_bn:
-            x = F.relu(_bn(p, "%s.%d" % (prefix, idx), x))
+            x = F.relu(_bn(p, "%s.%d" % (prefix, idx), x, training))
             idx += 2
     return x
 
 
-def _deconv(p, prefix, x):
+def _deconv(p, prefix, x, training=False):
     x = F.conv_transpose2d(x, p[prefix + ".0.weight"], stride=2, padding=1)
-    return F.relu(_bn(p, prefix + ".1", x))
+    return F.relu(_bn(p, prefix + ".1", x, training))
 
 
-def unet_decoder(p, feat, skips, arch, prefix="decoder_net.resnet_decoder"):
+def unet_decoder(p, feat, skips, arch, prefix="decoder_net.resnet_decoder", training=False):
     """upstream common/nets/module.py:172-218 (Decoder_big, 'ho3d') / :98-144 (Decoder, resnet50)."""
     pyr = {}
     big = arch == "ho3d"
-    pyr["stride32"] = feat if big else _conv_stack(p, prefix + ".conv0d", feat, 1, 1)
+    t = training
+    pyr["stride32"] = feat if big else _conv_stack(p, prefix + ".conv0d", feat, 1, 1, training=t)
     x = feat
     for i, name in ((1, "stride16"), (2, "stride8"), (3, "stride4"), (4, "stride2")):
-        skip = skips[name] if big else _conv_stack(p, "%s.conv%dd" % (prefix, i), skips[name], 1, 1)
-        up = _deconv(p, "%s.deconv%d" % (prefix, i), x)
-        x = _conv_stack(p, "%s.conv%d" % (prefix, i), torch.cat((skip, up), 1), 1, 3)
+        skip = skips[name] if big else _conv_stack(p, "%s.conv%dd" % (prefix, i), skips[name], 1, 1, training=t)
+        up = _deconv(p, "%s.deconv%d" % (prefix, i), x, t)
+        x = _conv_stack(p, "%s.conv%d" % (prefix, i), torch.cat((skip, up), 1), 1, 3, training=t)
         pyr[name] = x
     n_out = 3 if big else 2
-    hm = _conv_stack(p, prefix + ".convOut_hm", x, n_out, 1, final_bn=False)
-    hs = _conv_stack(p, prefix + ".convOut_hand_seg", x, n_out, 1, final_bn=False).sigmoid()
-    os_ = _conv_stack(p, prefix + ".convOut_obj_seg", x, n_out, 1, final_bn=False).sigmoid()
+    hm = _conv_stack(p, prefix + ".convOut_hm", x, n_out, 1, final_bn=False, training=t)
+    hs = _conv_stack(p, prefix + ".convOut_hand_seg", x, n_out, 1, final_bn=False, training=t).sigmoid()
+    os_ = _conv_stack(p, prefix + ".convOut_obj_seg", x, n_out, 1, final_bn=False, training=t).sigmoid()
     return pyr, torch.cat([hm, hs, os_], dim=1)
 
 
@@ -582,8 +590,18 @@ def hot_path_eval(p, pyramid, meta, cfg, taps=None):
                                                   cfg.num_samp_hand, "hand", cfg, th)
     obj_points, obj_sdf, obj_pe, _ = sdf_infer(p, pyramid, objc, K, meta["bbox_obj"], cfg.obj_sdf_scale,
                                                cfg.num_samp_obj, "obj", cfg, to)
-    sigma_hand = sdf_activation(p, "hand_sigmoid_beta", hand_sdf)
-    sigma_obj = sdf_activation(p, "obj_sigmoid_beta", obj_sdf)
+    if taps is not None:
+        taps.update(hand=th, obj=to)
+    return pose_from_points(p, pyramid, meta, cfg, hand_points, hand_sdf, hand_pe, obj_points, obj_sdf, obj_pe, taps)
+
+
+def pose_from_points(p, pyramid, meta, cfg, hand_points, hand_sdf, hand_pe, obj_points, obj_sdf, obj_pe, taps=None):
+    """upstream main/model.py:483-638: from the points the pose branch works on (selected by sdf_infer in eval mode,
+    jittered `*_pre_points` in the first training epochs) to the `*_out` dict.  The `.detach()` calls are upstream's
+    (:483-484,518-519,536,555): they only matter under autograd (`model_train`)."""
+    root, objc, K = meta["mano_root"], meta["obj_center_cam"], meta["cam_intr"]
+    sigma_hand = sdf_activation(p, "hand_sigmoid_beta", hand_sdf.detach())
+    sigma_obj = sdf_activation(p, "obj_sigmoid_beta", obj_sdf.detach())
     hand_fea, hand_cam = get_input_transformer(p, pyramid, hand_points, root, K, cfg.hand_sdf_scale, cfg)
     hand_nt = hand_cam - root[:, None, :]
     obj_fea, obj_cam = get_input_transformer(p, pyramid, obj_points, objc, K, cfg.obj_sdf_scale, cfg)
@@ -594,16 +612,16 @@ def hot_path_eval(p, pyramid, meta, cfg, taps=None):
     obj_h_points = (obj_cam - root[:, None, :]) * cfg.hand_sdf_scale
     obj_h_nt = obj_cam - root[:, None, :]                         # upstream model.py:508 ("bug", kept)
     obj_h_sdf, _, obj_h_pe = sdf_forward(p, pyramid, obj_h_points, root, K, cfg.hand_sdf_scale, "hand", cfg)
-    sigma_hand_o = sdf_activation(p, "obj_sigmoid_beta", hand_o_sdf)
-    sigma_obj_h = sdf_activation(p, "hand_sigmoid_beta", obj_h_sdf)
+    sigma_hand_o = sdf_activation(p, "obj_sigmoid_beta", hand_o_sdf.detach())
+    sigma_obj_h = sdf_activation(p, "hand_sigmoid_beta", obj_h_sdf.detach())
 
     def tok(nt, pe, fea):
         return torch.cat([nt, pe, fea], dim=2).permute(1, 0, 2).contiguous()
 
     hand_in = torch.cat([tok(hand_nt, hand_pe, hand_fea * sigma_hand),
-                         tok(obj_h_nt, obj_h_pe, obj_fea * sigma_obj_h)], dim=0)
+                         tok(obj_h_nt, obj_h_pe, obj_fea * sigma_obj_h).detach()], dim=0)
     obj_in = torch.cat([tok(obj_nt, obj_pe, obj_fea * sigma_obj),
-                        tok(hand_o_nt, hand_o_pe, hand_fea * sigma_hand_o)], dim=0)
+                        tok(hand_o_nt, hand_o_pe, hand_fea * sigma_hand_o).detach()], dim=0)
     hs, memory, hand_enc = transformer(p, "hand_transformer", hand_in, p["mano_query_embed.weight"],
                                        torch.zeros_like(hand_in), mano_tgt_mask(cfg).to(hand_in.device),
                                        mano_memory_mask(cfg).to(hand_in.device), cfg)
@@ -628,7 +646,7 @@ def hot_path_eval(p, pyramid, meta, cfg, taps=None):
     }
     if taps is not None:
         taps.update(
-            hand=th, obj=to, hand_points=hand_points, hand_sdf=hand_sdf, hand_posenc=hand_pe,
+            hand_points=hand_points, hand_sdf=hand_sdf, hand_posenc=hand_pe,
             obj_points=obj_points, obj_sdf=obj_sdf, obj_posenc=obj_pe, hand_fea=hand_fea, obj_fea=obj_fea,
             hand_o_sdf=hand_o_sdf, obj_h_sdf=obj_h_sdf, hand_transformer_in=hand_in,
             obj_transformer_in=obj_in, hs=hs, memory=memory, hand_encoder_out=hand_enc,
@@ -720,6 +738,61 @@ def model_eval_dexycb(p, img, inputs, targets, meta, cfg, arch="dexycb", taps=No
     loss["obj_rot"] = F.smooth_l1_loss(obj_rot, targets["obj_rot"][None, None].expand_as(obj_rot))
     loss["obj_trans"] = F.smooth_l1_loss(obj_trans, targets["rel_obj_trans"][None, None].expand_as(obj_trans))
     return {**loss, **out}
+
+
+def model_train(p, img, inputs, targets, meta, cfg, arch="ho3d", noise=None, taps=None):
+    """upstream Model.forward(mode='train') (main/model.py:357-665) in the branch the first `cfg.point_sampling_epoch`
+    epochs take (:426-466: the pose branch works on `*_pre_points` + uniform jitter; `noise` = (hand, obj) jitter tensors
+    or None for zero jitter), with BatchNorm on batch statistics (model.train()) and every dropout at p = 0 (the parity
+    configuration; dropout masks are not reproducible across implementations).  Plain differentiable torch ops: when the
+    tensors of `p` require grad, `sum(weighted means).backward()` gives the reference gradients (main/train.py:111-131).
+    Returns {**loss, **out} like upstream."""
+    feat, skips = backbone(p, img, training=True)
+    pyramid, decoder_out = unet_decoder(p, feat, skips, arch, training=True)
+    taps = {} if taps is None else taps
+    root, objc, K = meta["mano_root"], meta["obj_center_cam"], meta["cam_intr"]
+    c = cfg.ClampingDistance
+    loss = {}
+    hand_s, _, _ = sdf_forward(p, pyramid, inputs["hand_sdf_points"], root, K, cfg.hand_sdf_scale, "hand", cfg)
+    obj_s, _, _ = sdf_forward(p, pyramid, inputs["obj_sdf_points"], objc, K, cfg.obj_sdf_scale, "obj", cfg)
+    loss["sdfhand_loss"] = F.l1_loss(hand_s, targets["hand_sdf"].clamp(-c, c).unsqueeze(-1))
+    loss["sdfobj_loss"] = F.l1_loss(obj_s, targets["obj_sdf"].clamp(-c, c).unsqueeze(-1))
+    out = {"joint_heatmap_out": decoder_out[:, 0], "hand_seg_gt_out": targets["hand_seg"],
+           "hand_seg_pred_out": decoder_out[:, 1], "obj_seg_gt_out": targets["obj_seg"],
+           "obj_seg_pred_out": decoder_out[:, 2]}
+    loss["joint_heatmap"] = (decoder_out[:, 0] - render_gaussian_heatmap(targets["joint_coord"], cfg)) ** 2
+    loss["obj_seg"] = F.binary_cross_entropy(decoder_out[:, 2], targets["obj_seg"], reduction="none")
+    loss["hand_seg"] = F.binary_cross_entropy(decoder_out[:, 1], targets["hand_seg"], reduction="none")
+    hand_points = inputs["hand_pre_points"] + (0.0 if noise is None else noise[0])
+    obj_points = inputs["obj_pre_points"] + (0.0 if noise is None else noise[1])
+    hand_sdf, _, hand_pe = sdf_forward(p, pyramid, hand_points, root, K, cfg.hand_sdf_scale, "hand", cfg)
+    obj_sdf, _, obj_pe = sdf_forward(p, pyramid, obj_points, objc, K, cfg.obj_sdf_scale, "obj", cfg)
+    pose = pose_from_points(p, pyramid, meta, cfg, hand_points, hand_sdf, hand_pe, obj_points, obj_sdf, obj_pe, taps)
+    out.update({k: v for k, v in pose.items() if k not in ("obj_rot_out", "obj_trans_out")})     # model.py:618-620
+    pred = {"verts3d": taps["mano_verts"], "joints3d": taps["mano_joints"], "mano_shape": taps["mano_shape"]}
+    L, N, B, _ = taps["mano_pose6d"].shape
+    pred["mano_pose"] = rot6d_to_mat(taps["mano_pose6d"].permute(0, 2, 1, 3).reshape(L * B * N, 6)).view(L, B, N, 3, 3)
+    gt = mano_head_gt(p, targets["mano_param"])
+    l3d, lcls, lall = joint_vote_losses(taps["hand_points_notrans"], taps["hand_off"], taps["hand_cls"],
+                                        taps["hand_joints"], targets["joint_cam_no_trans"][:, 1:], cfg)
+    loss.update(loss_joint_3d=l3d, loss_joint_cls=lcls, loss_all_joint_3d=lall)
+    loss.update(mano_losses(pred, gt, cfg))
+    obj_rot, obj_trans = taps["obj_rot"], taps["obj_trans"]
+    loss["obj_rot"] = F.smooth_l1_loss(obj_rot, targets["obj_rot"][None, None].expand_as(obj_rot))
+    loss["obj_trans"] = F.smooth_l1_loss(obj_trans, targets["rel_obj_trans"][None, None].expand_as(obj_trans))
+    return {**loss, **out}
+
+
+# loss weights of upstream main/train.py:115-128 with the values of main/config.py:136-145
+TRAIN_LOSS_WEIGHTS = {"sdfhand_loss": 50.0, "sdfobj_loss": 25.0, "joint_heatmap": 100.0 / 100000, "obj_seg": 1.0,
+                      "hand_seg": 1.0, "obj_rot": 0.7, "obj_trans": 100.0, "loss_joint_3d": 0.1, "loss_joint_cls": 1.0,
+                      "loss_all_joint_3d": 0.1}
+
+
+def train_total_loss(model_out):
+    """upstream main/train.py:111-131: mean of every non-`_out` entry, weighted, summed (the scalar `.backward()` runs on)."""
+    loss = {k: v.mean() * TRAIN_LOSS_WEIGHTS.get(k, 1.0) for k, v in model_out.items() if "_out" not in k}
+    return sum(loss.values()), loss
 
 
 # ----------------------------------------------------------------------------------------------------

@@ -181,6 +181,50 @@ def dexycb_eval_case(name, seed, batch, ph, po):
     print(name, {k: tuple(v.shape) for k, v in out.items()})
 
 
+GRAD_PROBES = 24      # gradient entries stored per parameter tensor (evenly strided) next to its abs-max and L2 norm
+
+
+def grad_summary(g):
+    """What the training fixture keeps of one parameter's gradient (full gradients of a 52 M-parameter model do not
+    belong in git): abs-max, L2 norm and GRAD_PROBES evenly strided entries."""
+    f = g.detach().reshape(-1).double()
+    idx = torch.linspace(0, f.numel() - 1, min(GRAD_PROBES, f.numel())).long()
+    return np.concatenate([[float(f.abs().max()), float(f.norm())], f[idx].numpy()])
+
+
+def train_case(name, seed, batch, ph, po):
+    """One training step's forward + backward (upstream Model.forward(mode="train") in the `*_pre_points` branch,
+    main/model.py:426-466, then main/train.py:111-131): every loss entry, the `*_out` tensors, the summed weighted loss and
+    a summary of every parameter's gradient.  Dropout 0 everywhere and zero jitter: the parity configuration."""
+    ns, model = build_reference("dexycb", seed, ph, po, dataset="ho3d")
+    cfg = ns["cfg"]
+    old = (cfg.dropout, cfg.random_move_dist)
+    type(cfg).random_move_dist = [0.0, 0.0, 0.0]
+    model.train()
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+        if isinstance(m, torch.nn.MultiheadAttention):
+            m.dropout = 0.0
+    model.hand_sdf_decoder.dropout_prob = 0.0
+    model.obj_sdf_decoder.dropout_prob = 0.0
+    img, meta = syn.image_batch(seed, batch), syn.camera_meta(seed, batch)
+    inputs, targets = syn.train_extras(seed, batch, ph, po)
+    out = model({"img": img, **inputs}, {k: v.clone() for k, v in targets.items()}, meta, "train", 0, 0.0)
+    total, parts = O.train_total_loss(out)
+    total.backward()
+    type(cfg).random_move_dist = old[1]
+    fix = {"arch": "dexycb", "seed": seed, "batch": batch, "num_samp_hand": ph, "num_samp_obj": po,
+           "total": float(total)}
+    fix.update({"loss." + k: float(v) for k, v in parts.items()})
+    fix.update({k: v for k, v in out.items() if k.endswith("_out") and "_gt_" not in k})
+    for n, p in model.named_parameters():
+        if p.grad is not None:
+            fix["grad." + n] = grad_summary(p.grad)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **_np(fix))
+    print(name, "total", float(total), "params with grad", sum(1 for k in fix if k.startswith("grad.")))
+
+
 def metrics_case(name, seed, batch):
     """Test-time metrics (upstream common/metrics.py) on seeded synthetic predictions: both dataset branches of
     eval_batched_obj_direct, the two mesh-metric helpers, eval_hand_joint and rigid_align."""
@@ -223,3 +267,4 @@ if __name__ == "__main__":
     image_case("image_dexycb_seed13", "dexycb", 13, 1, 48, 16)
     dexycb_eval_case("dexycb_eval_seed14", 14, 2, 48, 16)
     metrics_case("metrics_seed15", 15, 6)
+    train_case("train_dexycb_seed21", 21, 2, 24, 8)

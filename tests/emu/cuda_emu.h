@@ -35,6 +35,9 @@ struct dim3 {
   dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
 };
 using cudaStream_t = void*;
+using cudaError_t = int;
+constexpr cudaError_t cudaSuccess = 0;
+inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
 
 namespace emu {
 inline dim3 thread_idx, block_idx;          // of the running fiber (one OS thread: plain globals)

@@ -1,0 +1,213 @@
+"""The training step on the B200 (BASELINE configs[3]): every autograd Function of hoisdf_b200/autograd.py
+against PyTorch autograd of the same formula, then `Model.forward(mode="train")` + backward against the oracle's autograd
+(which tests/test_oracle_golden.py pins to the unmodified upstream model): every loss entry and the gradient of every
+parameter tensor, relative to the largest gradient of its sub-network.  Finally the optimiser step against
+torch.optim.AdamW."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from hoisdf_b200 import synthetic as syn
+from util import group_scales, oracle_train_step, param_group
+
+pytestmark = pytest.mark.gpu
+
+
+def _rnd(seed, *shape, lo=-1.0, hi=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(*shape, generator=g) * (hi - lo) + lo
+
+
+def _close(a, b, tol, what=""):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    err = float((a - b).abs().max()) / max(float(b.abs().max()), 1e-30)
+    assert err <= tol, (what, err)
+    return err
+
+
+@pytest.mark.parametrize("m,k,n,act", [(1000, 289, 512, 1), (777, 512, 223, 1), (2048, 256, 768, 0), (300, 512, 1, 0),
+                                       (513, 256, 3, 0), (34, 256, 256, 1), (4096, 992, 512, 1), (640, 256, 60, 0)])
+def test_linear_fn(cuda, m, k, n, act):
+    """Y = act(X W^T + b): forward, dX, dW, db on the tensor-core GEMM (tiny N / K: the fp32 FMA GEMM) vs fp64 autograd."""
+    from hoisdf_b200 import autograd as A
+    x, w, b, dy = _rnd(1, m, k), _rnd(2, n, k, lo=-0.1, hi=0.1), _rnd(3, n), _rnd(4, m, n) * 1e-3
+    xr, wr, br = x.double().requires_grad_(), w.double().requires_grad_(), b.double().requires_grad_()
+    yr = F.linear(xr, wr, br)
+    yr = F.relu(yr) if act else yr
+    (yr * dy.double()).sum().backward()
+    xd, wd, bd = x.to(cuda).requires_grad_(), w.to(cuda).requires_grad_(), b.to(cuda).requires_grad_()
+    y = A.linear(xd, wd, bd, act)
+    (y * dy.to(cuda)).sum().backward()
+    _close(y, yr, 2e-6, "y")
+    _close(xd.grad, xr.grad, 5e-6, "dx")
+    _close(wd.grad, wr.grad, 5e-6, "dw")
+    _close(bd.grad, br.grad, 5e-6, "db")
+
+
+def test_weight_norm_gather_layernorm_tokens_fns(cuda):
+    from hoisdf_b200 import autograd as A
+    # weight norm
+    g, v, dw = _rnd(1, 223, 1, lo=0.5, hi=1.5), _rnd(2, 223, 512), _rnd(3, 223, 512)
+    gr, vr = g.double().requires_grad_(), v.double().requires_grad_()
+    ((gr * vr / vr.norm(dim=1, keepdim=True)) * dw.double()).sum().backward()
+    gd, vd = g.to(cuda).requires_grad_(), v.to(cuda).requires_grad_()
+    w = A.WeightNormFn.apply(gd, vd)
+    (w * dw.to(cuda)).sum().backward()
+    _close(gd.grad, gr.grad, 1e-5, "dg")
+    _close(vd.grad, vr.grad, 1e-5, "dv")
+    # gather (vs ATen grid_sample, the upstream op)
+    B, P = 2, 700
+    maps = [_rnd(10 + i, B, c, h, h) for i, (c, h) in enumerate(((32, 128), (64, 64), (128, 32), (256, 16), (512, 8)))]
+    uv = torch.cat([_rnd(20, B * P, 1, lo=-20, hi=275), _rnd(21, B * P, 1, lo=-20, hi=275)], 1)
+    dout = _rnd(22, B * P, 992)
+    mr = [m.clone().requires_grad_() for m in maps]
+    grid = ((uv.view(B, 1, P, 2) - 127.5) / 127.5)
+    ref = torch.cat([F.grid_sample(m, grid, mode="bilinear", padding_mode="border", align_corners=True)[:, :, 0]
+                     for m in mr], 1).permute(0, 2, 1).reshape(B * P, -1)
+    (ref * dout).sum().backward()
+    md = [m.to(cuda).permute(0, 2, 3, 1).contiguous().requires_grad_() for m in maps]
+    out = A.GatherFn.apply(uv.to(cuda), B, P, (256, 256), *md)
+    (out * dout.to(cuda)).sum().backward()
+    _close(out, ref, 1e-5, "gather")
+    for a, b in zip(md, mr):
+        _close(a.grad.permute(0, 3, 1, 2), b.grad, 1e-5, "gather grad")
+    # residual + LayerNorm
+    x, r, gm, bt, dy = _rnd(30, 1045, 256), _rnd(31, 1045, 256), _rnd(32, 256, lo=0.5, hi=1.5), _rnd(33, 256), _rnd(34, 1045, 256)
+    ts = [t.double().requires_grad_() for t in (x, r, gm, bt)]
+    (F.layer_norm(ts[0] + ts[1], (256,), ts[2], ts[3], 1e-5) * dy.double()).sum().backward()
+    td = [t.to(cuda).requires_grad_() for t in (x, r, gm, bt)]
+    y = A.AddLayerNormFn.apply(*td)
+    (y * dy.to(cuda)).sum().backward()
+    for a, b, n in zip(td, ts, ("dx", "dres", "dgamma", "dbeta")):
+        _close(a.grad, b.grad, 2e-5, n)
+    # tokens + sdf_activation
+    B, P = 3, 50
+    fea, beta, xyz, pe, sdf = _rnd(40, B, P, 223), torch.tensor([0.1]), _rnd(41, B, P, 3), _rnd(42, B, P, 30), \
+        _rnd(43, B, P, 1, lo=-0.15, hi=0.15)
+    dt = _rnd(44, B, P, 256)
+    fr, br = fea.double().requires_grad_(), beta.double().requires_grad_()
+    tok = torch.cat([xyz.double(), pe.double(), fr * (torch.sigmoid(sdf.double() / br) / br)], 2)
+    (tok * dt.double()).sum().backward()
+    fd, bd = fea.to(cuda).requires_grad_(), beta.to(cuda).requires_grad_()
+    t = A.TokensFn.apply(fd, bd, xyz.to(cuda), pe.to(cuda), sdf.to(cuda))
+    (t * dt.to(cuda)).sum().backward()
+    _close(t, tok, 1e-5, "tokens")
+    _close(fd.grad, fr.grad, 1e-5, "dfea")
+    _close(bd.grad, br.grad, 1e-4, "dbeta")
+
+
+@pytest.mark.parametrize("lq,lk,masked,kv_valid", [(128, 128, False, None), (17, 17, True, None), (17, 200, False, 150)])
+def test_attention_fn(cuda, lq, lk, masked, kv_valid):
+    """softmax(q k^T / 8 [+ mask]) v over 4 heads of 64: tcgen05 flash forward (SIMT with a dense mask), batched fp32
+    backward, vs fp64 autograd."""
+    from hoisdf_b200 import autograd as A
+    B, H, d = 3, 4, 256
+    q, k, v, do = _rnd(1, B * lq, d), _rnd(2, B * lk, d), _rnd(3, B * lk, d), _rnd(4, B * lq, d)
+    mask = None
+    if masked:
+        mask = (_rnd(5, lq, lk) > 0.3)
+        mask[:, 0] = False
+    ts = [t.double().requires_grad_() for t in (q, k, v)]
+    qh, kh, vh = (t.view(B, -1, H, 64).transpose(1, 2) for t in ts)
+    s = qh @ kh.transpose(-1, -2) / 8.0
+    if mask is not None:
+        s = s.masked_fill(mask, float("-inf"))
+    if kv_valid is not None:
+        s[..., kv_valid:] = float("-inf")
+    ref = (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(B * lq, d)
+    (ref * do.double()).sum().backward()
+    td = [t.to(cuda).requires_grad_() for t in (q, k, v)]
+    out = A.AttentionFn.apply(td[0], td[1], td[2], B, H, lq, lk,
+                              None if mask is None else mask.to(cuda).to(torch.uint8).contiguous(), kv_valid, 0.0)
+    (out * do.to(cuda)).sum().backward()
+    _close(out, ref, 2e-5, "attention")
+    for a, b, n in zip(td, ts, ("dq", "dk", "dv")):
+        _close(a.grad, b.grad, 2e-5, n)
+
+
+@pytest.fixture(scope="module")
+def train_setup(cuda):
+    from hoisdf_b200.config import cfg
+    from hoisdf_b200.model import get_model
+    arch, seed, B, ph, po = "dexycb", 31, 2, 48, 16
+    old = (cfg.setting, cfg.num_samp_hand, cfg.num_samp_obj, cfg.dropout, list(cfg.random_move_dist))
+    cfg.set_setting(arch)
+    type(cfg).dataset = "ho3d"
+    type(cfg).num_samp_hand, type(cfg).num_samp_obj = ph, po
+    type(cfg).dropout = 0.0
+    type(cfg).random_move_dist = [0.0, 0.0, 0.0]
+    model = get_model("train", mano_buffers=syn.mano_buffers(seed))
+    model.load_state_dict(syn.full_state_dict(seed, arch), strict=True)
+    model = model.to(cuda)
+    model.hand_sdf_decoder.dropout_prob = model.obj_sdf_decoder.dropout_prob = 0.0
+    mv = lambda d: {k: v.to(cuda) for k, v in d.items()}  # noqa: E731
+    inputs, targets = syn.train_extras(seed, B, ph, po)
+    batch = ({"img": syn.image_batch(seed, B).to(cuda), **mv(inputs)}, mv(targets), mv(syn.camera_meta(seed, B)))
+    yield dict(arch=arch, seed=seed, B=B, ph=ph, po=po, model=model, batch=batch, dev=cuda)
+    cfg.set_setting(old[0])
+    type(cfg).num_samp_hand, type(cfg).num_samp_obj, type(cfg).dropout, type(cfg).random_move_dist = old[1:]
+
+
+def test_train_forward_backward_matches_oracle(train_setup):
+    """Model.forward(mode="train") -> weighted loss sum -> backward on the B200 vs the oracle's autograd on the CPU."""
+    from hoisdf_b200.train import total_loss
+    s = train_setup
+    model = s["model"].train()
+    for p in model.parameters():
+        p.grad = None
+    out = model(*s["batch"], "train", 0, 0.0)
+    total, parts = total_loss(out)
+    total.backward()
+    oout, oparts, ototal, ograds = oracle_train_step(s["seed"], s["arch"], s["B"], s["ph"], s["po"])
+    assert set(parts) == set(oparts)
+    for k, v in oparts.items():
+        assert abs(float(parts[k]) - float(v)) <= 1e-3 * max(abs(float(v)), 1e-3), (k, float(parts[k]), float(v))
+    assert abs(float(total) - float(ototal)) <= 1e-4 * abs(float(ototal))
+    for k in ("joint_heatmap_out", "hand_seg_pred_out", "obj_seg_pred_out", "mano_mesh_out", "mano_joints_out",
+              "hand_joints_out"):
+        _close(out[k], oout[k], 1e-3, k)
+    assert "obj_rot_out" not in out and "obj_trans_out" not in out          # upstream model.py:618-620
+    got = {n: p.grad for n, p in model.named_parameters() if p.grad is not None}
+    # same set of trained tensors as upstream: everything except the frozen backbone BN affine and the dead modules
+    # (upstream's rule is `"bn" in name`, model.py:119-121: the shortcut BatchNorms, named downsample.1, stay trainable)
+    frozen = {n for n in ograds if n.startswith("backbone_net.") and "bn" in n[len("backbone_net."):]}
+    assert set(got) == set(ograds) - frozen, sorted(set(got) ^ (set(ograds) - frozen))[:10]
+    scales = group_scales(ograds)
+    worst = {}
+    for n, g in got.items():
+        e = float((g.cpu() - ograds[n]).abs().max()) / scales[param_group(n)]
+        worst[param_group(n)] = max(worst.get(param_group(n), 0.0), e)
+    print("worst gradient error per sub-network (relative to its largest gradient):", worst)
+    for grp, e in worst.items():
+        assert e <= 1e-3, (grp, e)
+
+
+def test_trainer_step_matches_adamw(train_setup):
+    """Trainer.step: flat-buffer AdamW (hoisdf_adamw_step) vs torch.optim.AdamW fed the SAME gradients; parameters the graph
+    never reaches stay untouched like upstream's (grad None -> skipped)."""
+    from hoisdf_b200.train import Trainer
+    s = train_setup
+    model = s["model"]
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    tr = Trainer(model, lr=1e-4)
+    total, parts, _ = tr.step(*s["batch"], epoch_cnt=0, batch_ratio=0.0)
+    assert torch.isfinite(total)
+    grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.requires_grad}
+    ref = {n: torch.nn.Parameter(before[n].clone()) for n in grads}
+    used = [n for n in ref if float(grads[n].abs().max()) > 0]
+    for n in used:
+        ref[n].grad = grads[n].clone()
+    opt = torch.optim.AdamW([ref[n] for n in used], lr=1e-4)
+    opt.step()
+    for n, p in model.named_parameters():
+        if not p.requires_grad:
+            assert torch.equal(p.detach(), before[n]), n
+        elif n in used:
+            assert float((p.detach() - ref[n].detach()).abs().max()) <= 1e-6 * max(float(before[n].abs().max()), 1e-3) + 2e-7, n
+        else:
+            assert torch.equal(p.detach(), before[n]), n                        # e.g. norm1, linear_objvote, linear_objcls
+    assert any(n.startswith("linear_objvote") for n in grads if n not in used)
+    # a second step runs (packed-weight caches see the new values) and changes the loss
+    total2, _, _ = tr.step(*s["batch"], epoch_cnt=0, batch_ratio=0.0)
+    assert torch.isfinite(total2) and float(total2) != float(total)
+    model.eval()

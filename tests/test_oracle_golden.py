@@ -135,3 +135,34 @@ def test_metrics_fixture():
     mje, pamje = O.hand_joint_metrics(m["joints_pred"], m["joints_gt"])
     close([mje.mean(), pamje.mean()], g["hand_joint_result"])
     close(O.rigid_align(m["joints_pred"][0].numpy(), m["joints_gt"][0].numpy()), g["aligned0"])
+
+
+def test_train_step_fixture():
+    """One training step (upstream Model.forward(mode="train") + the weighted loss sum of main/train.py:111-131 +
+    backward): the oracle's autograd reproduces every loss entry, the outputs and the gradient of EVERY parameter tensor
+    of the unmodified upstream model (fixture: abs-max, norm and 24 entries per tensor; tolerance relative to the largest
+    gradient of the tensor's sub-network)."""
+    from util import grad_summary, group_scales, oracle_train_step, param_group
+    g = load("train_dexycb_seed21")
+    seed, B = int(g["seed"]), int(g["batch"])
+    ph, po = int(g["num_samp_hand"]), int(g["num_samp_obj"])
+    out, parts, total, grads = oracle_train_step(seed, "dexycb", B, ph, po)
+    total, parts = total.detach(), {k: v.detach() for k, v in parts.items()}
+    assert abs(float(total) - float(g["total"])) <= 1e-5 * abs(float(g["total"]))
+    for k, v in parts.items():
+        assert abs(float(v) - float(g["loss." + k])) <= 1e-4 * max(abs(float(g["loss." + k])), 1e-3), k
+    for k in ("joint_heatmap_out", "hand_seg_pred_out", "obj_seg_pred_out", "mano_mesh_out", "mano_joints_out",
+              "hand_joints_out"):
+        close(out[k].detach(), g[k], 1e-4)
+    ref = {k[len("grad."):]: torch.from_numpy(g[k]) for k in g if k.startswith("grad.")}
+    # upstream leaves the parameters its graph never reaches without a gradient (norm1, linear_objvote, linear_objcls) and
+    # freezes the backbone's BatchNorm affine parameters (model.py:117-121): none of them is in the fixture
+    assert not any(n.startswith(("norm1.", "linear_objvote.", "linear_objcls.")) or ("backbone" in n and ".bn" in n)
+                   for n in ref)
+    scales = group_scales(ref)
+    assert set(ref) <= set(grads)
+    for n, r in ref.items():
+        s = grad_summary(grads[n])
+        tol = 2e-4 * scales[param_group(n)]
+        assert float((s[2:] - r[2:]).abs().max()) <= tol, (n, float((s[2:] - r[2:]).abs().max()), tol)
+        assert abs(float(s[0] - r[0])) <= tol and abs(float(s[1] - r[1])) <= 2e-4 * max(float(r[1]), scales[param_group(n)]), n

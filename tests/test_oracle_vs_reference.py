@@ -57,3 +57,41 @@ def test_metrics_match_upstream():
     assert abs(float(mje.mean()) - want[0]) <= 1e-5 * want[0] and abs(float(pamje.mean()) - want[1]) <= 1e-5 * want[1]
     assert torch.allclose(O.batch_rodrigues(m["targets"]["obj_rot"]).reshape(B, 9),
                           UM.batch_rodrigues(m["targets"]["obj_rot"]), atol=1e-6)
+
+
+def test_train_step_matches_upstream():
+    """Forward + backward of one training step against the unmodified upstream model, live: every loss entry and the
+    gradient of every parameter (relative to its sub-network's largest gradient)."""
+    from util import group_scales, oracle_train_step, param_group
+    arch, seed, B, ph, po = "dexycb", 23, 2, 16, 8
+    ns = rs.load(arch)
+    cfg = ns["cfg"]
+    type(cfg).num_samp_hand, type(cfg).num_samp_obj, type(cfg).dataset = ph, po, "ho3d"
+    old_move = cfg.random_move_dist
+    type(cfg).random_move_dist = [0.0, 0.0, 0.0]
+    try:
+        model = rs.build_model(ns, syn.mano_buffers(seed))
+        model.load_state_dict(syn.full_state_dict(seed, arch), strict=True)
+        model.train()
+        for m in model.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+            if isinstance(m, torch.nn.MultiheadAttention):
+                m.dropout = 0.0
+        model.hand_sdf_decoder.dropout_prob = model.obj_sdf_decoder.dropout_prob = 0.0
+        inputs, targets = syn.train_extras(seed, B, ph, po)
+        out = model({"img": syn.image_batch(seed, B), **inputs}, {k: v.clone() for k, v in targets.items()},
+                    syn.camera_meta(seed, B), "train", 0, 0.0)
+        total, parts = O.train_total_loss(out)
+        total.backward()
+    finally:
+        type(cfg).random_move_dist = old_move
+    _, oparts, ototal, grads = oracle_train_step(seed, arch, B, ph, po)
+    assert abs(float(ototal) - float(total)) <= 1e-5 * abs(float(total))
+    for k, v in parts.items():
+        assert abs(float(oparts[k]) - float(v)) <= 1e-4 * max(abs(float(v)), 1e-3), k
+    ref = {n: p.grad for n, p in model.named_parameters() if p.grad is not None}
+    scales = group_scales(ref)
+    assert set(ref) <= set(grads)
+    for n, r in ref.items():
+        assert float((grads[n] - r).abs().max()) <= 2e-4 * scales[param_group(n)], n
