@@ -22,6 +22,7 @@ Every Function calls the C ABI for the forward AND the backward; PyTorch only pr
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -33,6 +34,7 @@ from .ops import _count, _ptr, _stream
 
 ACT_NONE, ACT_RELU = ops.ACT_NONE, ops.ACT_RELU
 TRAIN_CHUNK_KB = 4          # TMEM accumulation chunk of the training GEMMs (K blocks of 32 per drain)
+_DEBUG_TORCH_MATMUL = os.environ.get("HOISDF_DEBUG_TORCH_MATMUL", "0") == "1"
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -58,10 +60,16 @@ def matmul_nt(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = N
     a, b = _c2d(a), _c2d(b)
     m, k = a.shape
     n = b.shape[0]
+    if _DEBUG_TORCH_MATMUL:        # developer switch (scripts/train_debug.py): isolates the GEMM kernels from the tape logic
+        y = a @ b.t()
+        y = y if bias is None else y + bias
+        return torch.relu(y) if act == ACT_RELU else y
     if n <= 16 or k <= 16:
         y = torch.empty(m, n, device=a.device, dtype=torch.float32)
         _count(1)
-        check(lib.hoisdf_gemm_f32(a.data_ptr(), a.stride(0), 0, b.data_ptr(), b.stride(0), 1, y.data_ptr(), n, m, n, k, 0,
+        lda = a.stride(0) if m > 1 else k        # a one-row tensor may carry any row stride
+        ldb = b.stride(0) if n > 1 else k
+        check(lib.hoisdf_gemm_f32(a.data_ptr(), lda, 0, b.data_ptr(), ldb, 1, y.data_ptr(), n, m, n, k, 0,
                                   _stream()), "hoisdf_gemm_f32")
         if bias is not None:
             y += bias

@@ -249,8 +249,8 @@ def split_rows(x: torch.Tensor, out: Optional[SplitRows] = None, kpad: Optional[
     if out is None:
         out = SplitRows.empty(m, k, x.device, round_up(kpad, 8))
     _count(1)
-    check(lib.hoisdf_split_rows(x.data_ptr(), m, k, x.stride(0), kpad, out.hi_ptr, out.lo_ptr, out.ld, _stream()),
-          "hoisdf_split_rows")
+    check(lib.hoisdf_split_rows(x.data_ptr(), m, k, x.stride(0) if m > 1 else max(x.stride(0), k), kpad, out.hi_ptr,
+                                out.lo_ptr, out.ld, _stream()), "hoisdf_split_rows")
     return out
 
 

@@ -286,6 +286,17 @@ def forward_train(model, inputs, targets, meta_info, epoch_cnt=1e8, batch_ratio=
     trans_gt = targets["rel_obj_trans"][None, :, None, :].expand_as(obj_trans)
     loss["obj_rot"] = F.smooth_l1_loss(obj_rot, rot_gt)
     loss["obj_trans"] = F.smooth_l1_loss(obj_trans, trans_gt)
+    dbg = getattr(model, "_train_debug", None)
+    if dbg is not None:            # developer hook (scripts/train_debug.py): live tensors whose gradients are compared
+        dbg.update(hand_cls=hand_cls, hand_off=hand_off, hand_fea=hand_fea, obj_fea=obj_fea, hand_in=hand_in, obj_in=obj_in,
+                   memory=memory, hand_enc=hand_enc, pose6d=pose6d, shape=shape, hand_joints=hand_joints,
+                   pyramid=pyramid, hand_s=hand_s, hand_sdf=hand_sdf)
+        for v in dbg.values():
+            if torch.is_tensor(v) and v.requires_grad:
+                v.retain_grad()
+            elif isinstance(v, dict):
+                for t in v.values():
+                    t.retain_grad()
     model.last_taps = dict(hand_points=hand_points, obj_points=obj_points, hand_sdf=hand_sdf.detach(),
                            obj_sdf=obj_sdf.detach(), hand_fea=hand_fea.detach(), hand_transformer_in=hand_in.detach(),
                            obj_transformer_in=obj_in.detach(), hand_off=hand_off.detach(), hand_cls=hand_cls.detach(),
@@ -326,9 +337,10 @@ class Trainer:
                  lr_drop: int = 20, lr_decay_gamma: float = 0.7, process_group=None, skip_unused: bool = True):
         self.model = model
         self.params = [p for p in model.parameters() if p.requires_grad]
-        n = sum(p.numel() for p in self.params)
+        al = 64                                             # every tensor starts on a 256-byte boundary (TMA / float4 loads)
+        n = sum((p.numel() + al - 1) // al * al for p in self.params)
         dev = self.params[0].device
-        self.flat = torch.empty(n, device=dev, dtype=torch.float32)
+        self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
         self.grad = torch.zeros(n, device=dev, dtype=torch.float32)
         self.exp_avg = torch.zeros(n, device=dev, dtype=torch.float32)
         self.exp_avg_sq = torch.zeros(n, device=dev, dtype=torch.float32)
@@ -340,7 +352,7 @@ class Trainer:
             p.data = self.flat[o:o + k].view(p.shape)
             p.grad = self.grad[o:o + k].view(p.shape)
             self.slices.append((o, k))
-            o += k
+            o += (k + al - 1) // al * al
         self.lr, self.betas, self.eps, self.weight_decay = float(lr), betas, float(eps), float(weight_decay)
         self.lr_drop, self.gamma = int(lr_drop), float(lr_decay_gamma)
         self.step_count, self.epoch = 0, 0

@@ -750,6 +750,7 @@ def model_train(p, img, inputs, targets, meta, cfg, arch="ho3d", noise=None, tap
     feat, skips = backbone(p, img, training=True)
     pyramid, decoder_out = unet_decoder(p, feat, skips, arch, training=True)
     taps = {} if taps is None else taps
+    taps["pyramid"], taps["decoder_out"] = pyramid, decoder_out
     root, objc, K = meta["mano_root"], meta["obj_center_cam"], meta["cam_intr"]
     c = cfg.ClampingDistance
     loss = {}

@@ -158,7 +158,12 @@ def test_train_forward_backward_matches_oracle(train_setup):
     out = model(*s["batch"], "train", 0, 0.0)
     total, parts = total_loss(out)
     total.backward()
-    oout, oparts, ototal, ograds = oracle_train_step(s["seed"], s["arch"], s["B"], s["ph"], s["po"])
+    # Yardstick: the oracle's formulas (pinned to upstream in fp32 by tests/test_oracle_golden.py) evaluated in float64.
+    # Two fp32 evaluations cannot be compared with each other directly: the vote losses are smooth-L1 on MILLIMETRE
+    # residuals (x1000) and the graph is full of ReLU / threshold decisions, so a 1e-6 forward difference moves
+    # individual gradient entries by 1e-3 and more -- at this seed upstream's own fp32 CPU gradients sit 7.6e-2
+    # (decoder_net) / 6.3e-3 (linear_handcls) of the sub-network's largest gradient away from the float64 ones.
+    oout, oparts, ototal, ograds = oracle_train_step(s["seed"], s["arch"], s["B"], s["ph"], s["po"], dtype=torch.float64)
     assert set(parts) == set(oparts)
     for k, v in oparts.items():
         assert abs(float(parts[k]) - float(v)) <= 1e-3 * max(abs(float(v)), 1e-3), (k, float(parts[k]), float(v))
@@ -172,14 +177,33 @@ def test_train_forward_backward_matches_oracle(train_setup):
     # (upstream's rule is `"bn" in name`, model.py:119-121: the shortcut BatchNorms, named downsample.1, stay trainable)
     frozen = {n for n in ograds if n.startswith("backbone_net.") and "bn" in n[len("backbone_net."):]}
     assert set(got) == set(ograds) - frozen, sorted(set(got) ^ (set(ograds) - frozen))[:10]
+    # Metric: relative L2 error of each sub-network's gradient.  The per-kernel tests above hold every autograd Function to
+    # 5e-6 .. 2e-5 of fp64; end to end the graph is piecewise linear (ReLU, clamps, smooth-L1 on millimetre residuals), so
+    # ONE pre-activation that is +8e-7 here and 0 in the reference switches a whole unit's gradient on or off (measured at
+    # this seed: 1 of 21 408 `hand_fea` entries, carrying 0.126 of a largest |d fea| of 0.33 -- scripts/train_debug.py),
+    # which moves linear_transformerin by 3e-3 and, through the pyramid, the encoder's gradients by 2-4e-2.  Upstream's own
+    # fp32 CPU evaluation differs from the float64 one by the same amounts (decoder_net 7.6e-2, linear_handcls 6.3e-3 in
+    # max-norm: a flip elsewhere).  Hence: 1e-2 for the hot-path sub-networks, 1e-1 for the image encoder (whose backward is
+    # cuDNN's, not ours), and 3e-4 for the sub-networks no such decision feeds at this seed.
+    num, den, worst = {}, {}, {}
     scales = group_scales(ograds)
-    worst = {}
     for n, g in got.items():
-        e = float((g.cpu() - ograds[n]).abs().max()) / scales[param_group(n)]
-        worst[param_group(n)] = max(worst.get(param_group(n), 0.0), e)
-    print("worst gradient error per sub-network (relative to its largest gradient):", worst)
-    for grp, e in worst.items():
-        assert e <= 1e-3, (grp, e)
+        grp = param_group(n)
+        d = g.cpu().double() - ograds[n]
+        num[grp] = num.get(grp, 0.0) + float(d.pow(2).sum())
+        den[grp] = den.get(grp, 0.0) + float(ograds[n].pow(2).sum())
+        worst[grp] = max(worst.get(grp, 0.0), float(d.abs().max()) / scales[grp])
+    l2 = {grp: (num[grp] / den[grp]) ** 0.5 for grp in num}
+    print("relative L2 gradient error per sub-network:", {k: "%.1e" % v for k, v in l2.items()})
+    print("max-norm error per sub-network (of its largest gradient):", {k: "%.1e" % v for k, v in worst.items()})
+    for grp, e in l2.items():
+        tol = 1e-1 if grp in ("backbone_net", "decoder_net") else 1e-2
+        assert e <= tol, (grp, e)
+    tight = [g for g in l2 if g.startswith(("linear_hand", "linear_obj", "linear_pose", "linear_shape", "mano_query",
+                                            "hand_transformer.decoder", "obj_transformer"))]
+    assert len(tight) >= 8
+    for grp in tight:
+        assert l2[grp] <= 3e-4, (grp, l2[grp])
 
 
 def test_trainer_step_matches_adamw(train_setup):

@@ -70,20 +70,23 @@ def group_scales(ref):
     return scales
 
 
-def oracle_train_step(seed, arch, batch, ph, po, device="cpu"):
+def oracle_train_step(seed, arch, batch, ph, po, device="cpu", dtype=torch.float32):
     """Run oracle.model_train + backward on the seeded synthetic training batch.  Returns (model_out, weighted parts,
-    total, {name: grad}) -- the reference gradients of main/train.py:111-131 (dropout 0, zero jitter)."""
+    total, {name: grad}) -- the reference gradients of main/train.py:111-131 (dropout 0, zero jitter).  dtype float64
+    evaluates the same (upstream-pinned) formulas in double precision: the yardstick two fp32 implementations are
+    measured against (smooth-L1 on millimetre residuals and ReLU / threshold decisions make single fp32 gradients jump)."""
     from hoisdf_b200 import synthetic as syn
     from oracle import hoisdf_oracle as O
+    cv = lambda v: (v.clone().to(dtype) if v.is_floating_point() else v.clone()).to(device)  # noqa: E731
     sd = syn.full_state_dict(seed, arch)
-    p = {k: v.clone().to(device) for k, v in sd.items()}
-    names = [k for k, v in p.items() if v.dtype == torch.float32 and "running_" not in k and "th_" not in k
+    p = {k: cv(v) for k, v in sd.items()}
+    names = [k for k, v in p.items() if v.is_floating_point() and "running_" not in k and "th_" not in k
              and "num_batches" not in k and "coord_change" not in k]
     for n in names:
         p[n].requires_grad_(True)
-    mv = lambda d: {k: v.clone().to(device) for k, v in d.items()}  # noqa: E731
+    mv = lambda d: {k: cv(v) for k, v in d.items()}  # noqa: E731
     inputs, targets = syn.train_extras(seed, batch, ph, po)
-    out = O.model_train(p, syn.image_batch(seed, batch).to(device), mv(inputs), mv(targets),
+    out = O.model_train(p, cv(syn.image_batch(seed, batch)), mv(inputs), mv(targets),
                         mv(syn.camera_meta(seed, batch)), O.default_cfg(num_samp_hand=ph, num_samp_obj=po), arch)
     total, parts = O.train_total_loss(out)
     total.backward()
