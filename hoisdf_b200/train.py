@@ -323,6 +323,17 @@ def total_loss(model_out: Dict[str, torch.Tensor]):
     return sum(loss.values()), loss
 
 
+def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:
+    """Data parallel over samples (upstream: DataParallel, common/base.py:103): every rank holds the gradient of ITS
+    batch-mean loss; the global-batch gradient is their average -- ONE all-reduce of the flat gradient buffer per step.
+    No-op without an initialised process group / with a single rank."""
+    dist = torch.distributed
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, group=group)
+        flat.mul_(1.0 / dist.get_world_size(group))
+    return flat
+
+
 class Trainer:
     """zero_grad -> forward("train") -> weighted loss sum -> backward -> AdamW step (upstream main/train.py:104-140 with
     common/base.py:64-70: AdamW(lr=cfg.lr) over all parameters, StepLR(cfg.lr_drop, cfg.lr_decay_gamma) per epoch).
@@ -379,12 +390,7 @@ class Trainer:
         out = model(inputs, targets, meta_info, "train", epoch_cnt, batch_ratio)
         total, parts = total_loss(out)
         total.backward()
-        dist = torch.distributed
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
-            # data parallel over samples (upstream: DataParallel, common/base.py:103): every rank holds the gradient of ITS
-            # batch-mean loss; the global-batch gradient is their average -- one all-reduce of the flat buffer
-            dist.all_reduce(self.grad, group=self.group)
-            self.grad.mul_(1.0 / dist.get_world_size(self.group))
+        allreduce_mean_(self.grad, self.group)
         self.step_count += 1
         if self.skip_unused and self._unused is None:
             # parameters the graph never reaches (upstream: norm1, linear_objvote, linear_objcls -- model.py:55,86-87) have

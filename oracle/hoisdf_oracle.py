@@ -671,8 +671,8 @@ def model_eval(p, img, meta, cfg, arch="ho3d", taps=None):
 # ----------------------------------------------------------------------------------------------------
 def render_gaussian_heatmap(joint_coord, cfg):
     """upstream main/model.py:128-143."""
-    x = torch.arange(cfg.output_hm_shape[2])
-    y = torch.arange(cfg.output_hm_shape[1])
+    x = torch.arange(cfg.output_hm_shape[2], device=joint_coord.device)
+    y = torch.arange(cfg.output_hm_shape[1], device=joint_coord.device)
     yy, xx = torch.meshgrid(y, x, indexing="ij")
     xx, yy = xx[None, None].float(), yy[None, None].float()
     x = joint_coord[:, :, 0, None, None]

@@ -188,6 +188,7 @@ inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); r
 inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
 template <typename T> inline T __ldg(const T* p) { return *p; }
 template <typename T> inline T atomicAdd(T* p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline float atomicAdd(float* p, float v) { const float old = *p; *p = old + v; return old; }   // fibers on ONE OS thread
 template <typename T> inline T atomicExch(T* p, T v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
 
 // separately rounded IEEE single-precision operations (x86-64 SSE arithmetic is IEEE; `volatile` keeps the compiler from

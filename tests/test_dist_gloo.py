@@ -63,3 +63,30 @@ def test_sharded_forward_ragged_batch():
 
 def test_sharded_forward_fewer_samples_than_ranks():
     _run(1)
+
+
+def _grad_worker(rank, world, port, ok):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from hoisdf_b200.train import allreduce_mean_
+        flat = torch.arange(1000, dtype=torch.float32) * (rank + 1)          # rank r holds (r + 1) * [0, 1, 2, ...]
+        allreduce_mean_(flat)
+        ok[rank] = int(torch.equal(flat, torch.arange(1000, dtype=torch.float32) * (sum(range(1, world + 1)) / world)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_allreduce_mean_two_ranks():
+    """The training step's only collective (hoisdf_b200.train.allreduce_mean_): one all-reduce of the flat gradient buffer,
+    then the mean -- the global-batch gradient of per-rank batch-mean losses."""
+    world = 2
+    ok = mp.get_context("spawn").Array("i", [0] * world)
+    mp.spawn(_grad_worker, args=(world, _free_port(), ok), nprocs=world, join=True)
+    assert list(ok) == [1] * world
+
+
+def test_gradient_allreduce_single_process_is_a_noop():
+    from hoisdf_b200.train import allreduce_mean_
+    flat = torch.arange(8, dtype=torch.float32)
+    assert torch.equal(allreduce_mean_(flat.clone()), flat)

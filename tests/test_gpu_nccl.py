@@ -57,3 +57,64 @@ def test_sharded_forward_two_nccl_ranks(cuda):
     ok = mp.get_context("spawn").Array("i", [0] * world)
     mp.spawn(_worker, args=(world, _free_port(), ok), nprocs=world, join=True)
     assert list(ok) == [1] * world
+
+
+def _train_worker(rank, world, port, ok):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from hoisdf_b200 import synthetic as syn
+        from hoisdf_b200.config import cfg
+        from hoisdf_b200.model import get_model
+        from hoisdf_b200.train import Trainer, total_loss
+        dev = torch.device("cuda", rank)
+        cfg.set_setting("dexycb")
+        type(cfg).dataset = "ho3d"
+        type(cfg).num_samp_hand, type(cfg).num_samp_obj, type(cfg).dropout = 48, 16, 0.0
+        seed, B = 9, 2
+        model = get_model("train", mano_buffers=syn.mano_buffers(seed))
+        model.load_state_dict(syn.full_state_dict(seed, "dexycb"), strict=True)
+        model = model.to(dev)
+        model.hand_sdf_decoder.dropout_prob = model.obj_sdf_decoder.dropout_prob = 0.0
+        to = lambda d: {k: v.to(dev) for k, v in d.items()}    # noqa: E731
+        ins, tgt = syn.train_extras(seed + rank, B, 48, 16)     # every rank trains on its OWN samples
+        batch = (to({"img": syn.image_batch(seed + rank, B), **ins}), to(tgt), to(syn.camera_meta(seed + rank, B)))
+        # this rank's local gradient, without the exchange
+        model.train()
+        total, _ = total_loss(model(*batch, "train", 0, 0.0))
+        total.backward()
+        local = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.requires_grad and p.grad is not None])
+        used = [p.grad is not None for p in model.parameters() if p.requires_grad]
+        for p in model.parameters():
+            p.grad = None
+        both = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(both, local)
+        want = sum(both) / world
+        tr = Trainer(model, lr=1e-4)
+        tr.step(*batch, epoch_cnt=0, batch_ratio=0.0)
+        got = torch.cat([tr.grad[o:o + k] for (o, k), u in zip(tr.slices, used) if u])
+        good = float((got - want).abs().max()) <= 1e-5 * float(want.abs().max())
+        # and the replicas stay identical after the update
+        mine = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+        theirs = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(theirs, mine)
+        good = good and all(torch.equal(t, mine) for t in theirs)
+        flag = torch.tensor([int(good)], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok[rank] = int(flag.item())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_training_step_two_nccl_ranks(cuda):
+    """Data-parallel training step: the flat gradient buffer after Trainer.step is the mean of the two ranks' local gradients
+    (one NCCL all-reduce) and the replicas' parameters stay bit-identical."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    world = 2
+    ok = mp.get_context("spawn").Array("i", [0] * world)
+    mp.spawn(_train_worker, args=(world, _free_port(), ok), nprocs=world, join=True)
+    assert list(ok) == [1] * world
