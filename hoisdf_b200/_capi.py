@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhoisdf_b200.so")
 
-ABI_VERSION = 21
+ABI_VERSION = 22
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2      # ACT_SIGMOID: hoisdf_linear_narrow_split_fwd only
 GATHER_CONCAT, GATHER_SUM = 0, 1
 
@@ -81,6 +81,21 @@ class PyramidH(C.Structure):
     _fields_ = [("map", vp * 5), ("h", i32 * 5), ("w", i32 * 5), ("levels", i32), ("c", i32), ("img_h", i32), ("img_w", i32)]
 
 
+class SdfInferArgs(C.Structure):
+    _fields_ = [
+        ("center", vp), ("cam_intr", vp), ("bbox", vp),
+        ("sdf_scale", f32), ("bins", i32), ("batch", i64), ("num_points", i64), ("margin", i64), ("clamp", f32),
+        ("gmaps", vp), ("gmaps16", vp), ("bias0", vp),
+        ("s1_a", vp), ("s1_b", vp), ("s1_c", vp), ("ld_s1", i64), ("b_s1", vp), ("s1_scale", f32),
+        ("dec", vp),
+        ("workspace", vp), ("workspace_bytes", i64), ("max_rows", i64),
+        ("planned", i32), ("chunk_counts", vp), ("offsets", vp), ("host_offsets", vp), ("n_f", vp),
+        ("points", vp), ("sdf", vp), ("posenc", vp), ("sel_index", vp), ("status_flag", vp),
+        ("screen_err", vp), ("screen_gap", vp), ("verified", vp),
+        ("cand_sdf", vp), ("cand_index", vp), ("exact_sdf", vp), ("exact_index", vp), ("screen_rows", vp),
+    ]
+
+
 class ManoModel(C.Structure):
     _fields_ = [(n, vp) for n in ("shapedirs", "posedirs", "v_template", "j_regressor", "weights", "hands_mean")]
 
@@ -117,6 +132,10 @@ SIGNATURES = {
     "hoisdf_sdf_decoder_fwd": (C.c_int, [C.POINTER(SdfWeights), vp, i64, i64, vp, vp, vp, f32, vp]),
     "hoisdf_sdf_pad_input": (C.c_int, [vp, i64, vp, i64, vp]),
     "hoisdf_select_points": (C.c_int, [vp, vp, vp, i64, i64, i32, f32, i32, vp, vp, vp, vp, vp, vp, vp]),
+    "hoisdf_sdf_infer_keep": (i64, [i64, i64]),
+    "hoisdf_sdf_infer_workspace_bytes": (i64, [i64, i64, i64, i64, i32]),
+    "hoisdf_sdf_infer_plan": (C.c_int, [vp, vp, vp, f32, i64, i32, vp, vp, vp, vp]),
+    "hoisdf_sdf_infer_fwd": (C.c_int, [C.POINTER(SdfInferArgs), vp]),
     "hoisdf_tokens_fwd": (C.c_int, [vp, vp, vp, i64, vp, vp, i64, i64, vp, i64, i64, vp]),
     "hoisdf_attention_workspace_bytes": (i64, [i64, i64, i64, i64]),
     "hoisdf_attention_fwd": (C.c_int, [vp, i64, vp, vp, i64, vp, i64, i64, i64, i64, i64, i64, vp, vp, i64, vp]),
@@ -163,6 +182,9 @@ def _load():
 
 
 lib = _load()
+
+
+E_UNSUPPORTED, E_WORKSPACE, E_TOO_FEW_POINTS = -4, -5, -6      # include/hoisdf_b200.h
 
 
 class HoisdfError(RuntimeError):

@@ -79,6 +79,9 @@ class Config:
     # 5.9 ms per step against 2.4 + 1.6 for chain + stand-alone fp16 gather -- correct, tested, but off by default
     fused_gather = False
     screen_margin_single = 1024
+    # the default cascade (fused chain + fp16 gather + FP16x3 final stage) run by ONE C entry point, hoisdf_sdf_infer_fwd
+    # (csrc/sdf_infer.cu), instead of ~30 Python-level launches with ATen glue; False = the Python orchestration
+    native_sdf_infer = True
     # linear_sdfin layer 0 applied to the pyramid (Model: PyramidContext.gmaps) on the FP16x3 GEMM with a TMEM drain
     # every `projection_chunk_kb` K blocks instead of the fp32 FMA kernel (3.2 ms -> 0.6 ms at batch 32)
     tc_projection = True

@@ -293,6 +293,15 @@ class Model(nn.Module):
             plan = self.plan_candidates(center_joint, cam_intr, bbox, sdf_scale)
         b = plan.center.shape[0]
         dev = plan.center.device
+        if (level == 0 and cfg.native_sdf_infer and ops.use_h3() and cfg.fused_chain and cfg.gather_h16
+                and not cfg.fused_gather and cfg.final_stage == "h3" and cfg.screen_single):
+            # the default cascade behind ONE C entry point (csrc/sdf_infer.cu: hoisdf_sdf_infer_fwd); None = a sample has
+            # no room for the screening margin -> the general path below ranks every row exactly
+            res = self._sdf_infer_native(ctx, plan, int(num_points), type, taps)
+            if res is not None:
+                if taps is None and not bool(res[1]):              # direct call: one tiny D2H read of the verdict
+                    return self.sdf_infer(ctx, center_joint, cam_intr, bbox, sdf_scale, num_points, type, plan, None, 1)
+                return res[0]
         host = plan.host_offsets()
         total = int(host[-1])
         n_f = host[1:] - host[:-1]
@@ -478,6 +487,78 @@ class Model(nn.Module):
                 return self.sdf_infer(ctx, center_joint, cam_intr, bbox, sdf_scale, num_points, type, plan, None,
                                       level + 1)
         return pts, out_sdf, pe, None
+
+    def _sdf_infer_native(self, ctx, plan, num_points, type, taps):
+        """`hoisdf_sdf_infer_fwd`: candidate compaction, the screening cascade, its device-side verdict and the final
+        top-P in one C call with a caller-owned workspace.  Returns ((points, sdf, posenc, None), verified flag tensor) or
+        None when the C side asks for the general path."""
+        import ctypes as C
+        from . import _capi
+        b, dev = plan.center.shape[0], plan.center.device
+        sdfin = self.linear_sdfin.packed()
+        s1 = sdfin[1].h3
+        if s1 is None or s1.scale != 1.0 or sdfin[1].n != 256 or sdfin[1].k != 512:
+            return None
+        dec = self.hand_sdf_decoder if type == "hand" else self.obj_sdf_decoder
+        packed = dec.packed()
+        if packed.struct_h3 is None:
+            return None
+        host = plan.host_offsets()                  # the plan's event: the B + 1 row offsets have landed in pinned memory
+        total = int(host[-1])
+        n_f = host[1:] - host[:-1]
+        margin = int(cfg.screen_margin_single)
+        keep = int(_capi.lib.hoisdf_sdf_infer_keep(num_points, margin))
+        max_rows = max(ops.round_up(total, 1 << 16), 1 << 16)
+        nbytes = int(_capi.lib.hoisdf_sdf_infer_workspace_bytes(b, max_rows, num_points, margin, int(cfg.bins_n)))
+        ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        pts = torch.empty(b, num_points, 3, device=dev, dtype=torch.float32)
+        sdf = torch.empty(b, num_points, 1, device=dev, dtype=torch.float32)
+        pe = torch.empty(b, num_points, 30, device=dev, dtype=torch.float32)
+        sel = torch.empty(b, num_points, device=dev, dtype=torch.int32)
+        flag = torch.zeros(1, device=dev, dtype=torch.int32)
+        err = torch.empty(1, device=dev, dtype=torch.float32)
+        gap = torch.empty(b, device=dev, dtype=torch.float32)
+        ok = torch.empty(1, device=dev, dtype=torch.int32)
+        gm, gm16 = ops.make_pyramid(ctx.gmaps, cfg.input_img_shape), ops._pyramid_h(ctx.gmaps16, cfg.input_img_shape)
+        a = _capi.SdfInferArgs()
+        a.center, a.cam_intr, a.bbox = plan.center.data_ptr(), plan.cam_intr.data_ptr(), plan.bbox.data_ptr()
+        a.sdf_scale, a.bins, a.batch, a.num_points, a.margin = plan.sdf_scale, int(cfg.bins_n), b, num_points, margin
+        a.clamp = float(cfg.ClampingDistance)
+        a.gmaps, a.gmaps16, a.bias0 = C.addressof(gm), C.addressof(gm16), sdfin[0].b.data_ptr()
+        a.s1_a, a.s1_b, a.s1_c, a.ld_s1 = s1.plane_ptr(0), s1.plane_ptr(1), s1.plane_ptr(2), s1.ld
+        a.b_s1, a.s1_scale = sdfin[1].b.data_ptr(), float(s1.scale)
+        a.dec = C.addressof(packed.struct_h3)
+        a.workspace, a.workspace_bytes, a.max_rows = ws.data_ptr(), nbytes, max_rows
+        a.planned, a.chunk_counts, a.offsets, a.host_offsets = 1, plan.counts.data_ptr(), plan.offsets.data_ptr(), host.data_ptr()
+        a.points, a.sdf, a.posenc, a.sel_index, a.status_flag = pts.data_ptr(), sdf.data_ptr(), pe.data_ptr(), \
+            sel.data_ptr(), flag.data_ptr()
+        a.screen_err, a.screen_gap, a.verified = err.data_ptr(), gap.data_ptr(), ok.data_ptr()
+        diag = {}
+        if taps is not None:                        # diagnostics the parity tests read
+            diag = dict(cand_sdf=torch.empty(max(total, 1), device=dev, dtype=torch.float32),
+                        cand_index=torch.empty(max(total, 1), device=dev, dtype=torch.int32),
+                        exact_sdf=torch.empty(b * keep, device=dev, dtype=torch.float32),
+                        exact_index=torch.empty(b * keep, device=dev, dtype=torch.int32),
+                        screen_rows=torch.empty(b * keep, device=dev, dtype=torch.int32))
+            a.cand_sdf, a.cand_index = diag["cand_sdf"].data_ptr(), diag["cand_index"].data_ptr()
+            a.exact_sdf, a.exact_index = diag["exact_sdf"].data_ptr(), diag["exact_index"].data_ptr()
+            a.screen_rows = diag["screen_rows"].data_ptr()
+        ops._count(14)
+        st = _capi.lib.hoisdf_sdf_infer_fwd(C.byref(a), ops._stream())
+        if st == _capi.E_UNSUPPORTED:
+            return None
+        if st == _capi.E_TOO_FEW_POINTS:
+            # upstream fails here too (model.py:348: shape mismatch when N_f < num_points)
+            raise RuntimeError("sdf_infer: sample %d has %d lattice points inside its bbox, fewer than num_points=%d"
+                               % (int(n_f.argmin()), int(n_f.min()), num_points))
+        _capi.check(st, "hoisdf_sdf_infer_fwd")
+        verified = ok.view(()) != 0
+        if taps is not None:
+            taps.update(index=sel, n_f=n_f.clone(), cand_index=diag["cand_index"][:total], cand_sdf=diag["cand_sdf"][:total],
+                        offsets=host.clone(), screen_gap=gap, screen_err=err.view(()), screen_rows=diag["screen_rows"].long(),
+                        screen_verified=verified, single_pass=True, exact_sdf=diag["exact_sdf"],
+                        exact_index=diag["exact_index"], native=True)
+        return (pts, sdf, pe, None), verified
 
     # ------------------------------------------------------------------------------------------------
     # forward

@@ -24,14 +24,16 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 21
+#define HOISDF_ABI_VERSION 22
 
 enum {
   HOISDF_OK = 0,
   HOISDF_E_NULL = -1,      /* required pointer is NULL */
   HOISDF_E_SHAPE = -2,     /* size out of the supported range */
   HOISDF_E_ALIGN = -3,     /* pointer or leading dimension not 16-byte aligned */
-  HOISDF_E_UNSUPPORTED = -4
+  HOISDF_E_UNSUPPORTED = -4,
+  HOISDF_E_WORKSPACE = -5,        /* caller-owned workspace too small for this input */
+  HOISDF_E_TOO_FEW_POINTS = -6    /* a sample has fewer lattice points inside its bbox than num_points (upstream raises too) */
 };
 
 enum { HOISDF_ACT_NONE = 0, HOISDF_ACT_RELU = 1 };
@@ -357,6 +359,47 @@ int hoisdf_select_points(const float* sdf, const int64_t* offsets, const int32_t
                          int64_t batch, int64_t num_points, int32_t bins, float clamp, int32_t order_by_row,
                          int32_t* sel_index, int32_t* sel_row, float* points, float* out_sdf, float* posenc,
                          int32_t* status_flag, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Model.sdf_infer for the whole batch behind ONE entry point -- upstream main/model.py:246-355 (csrc/sdf_infer.cu):
+ * candidate generation, the verified coarse-to-fine selection cascade (stage A: fp16 gather + the fused single-product
+ * chain kernel on every candidate; final stage: FP16x3 draining TMEM every K block on the P + margin survivors), the
+ * device-side verdict of the screening step and the final top-P by |sdf|.
+ *   gmaps / gmaps16: the pyramid projected through linear_sdfin.layers.0 (fp32 NHWC (B,H,W,512) and its fp16 copy),
+ *     bias0 that layer's bias; s1_*: hoisdf_pack_h3 planes (256, ld_s1) + bias of linear_sdfin.layers.1; dec: the SDF
+ *     decoder's planes.
+ *   Outputs (device): points (B,P,3) lattice coordinates in selection order, sdf (B,P) clamped to +-clamp, posenc (B,P,30),
+ *     sel_index (B,P) lattice indices; screen_err (1) = max |coarse - fine|, screen_gap (B) = coarse rank-(P+margin)
+ *     |sdf| minus fine rank-P |sdf|, verified (1) = all(gap > 3 err): when 0 the caller re-runs the general path;
+ *     status_flag: as hoisdf_select_points.  n_f (HOST, B, may be NULL): candidate count per sample.
+ *   Optional diagnostics (device, may be NULL): cand_sdf / cand_index (total rows), exact_sdf / exact_index / screen_rows
+ *     (B * hoisdf_sdf_infer_keep(P, margin)).
+ *   Workspace: hoisdf_sdf_infer_workspace_bytes(batch, max_rows, ...) bytes, max_rows >= the total candidate count.
+ *   Host interaction: the B + 1 row offsets (they size the launches) are read from `host_offsets` (pinned, caller-owned).
+ *     planned = 1: the caller ran hoisdf_sdf_infer_plan earlier on this stream with the same chunk_counts / offsets /
+ *     host_offsets and has waited for that copy (e.g. an event recorded right after it, before queueing the image
+ *     encoder: nothing stalls); planned = 0: this call plans and synchronises the stream itself.
+ *   Returns HOISDF_E_TOO_FEW_POINTS like upstream's shape error (model.py:348), HOISDF_E_UNSUPPORTED when a sample has no
+ *   room for the screening margin (the caller then ranks every row exactly), HOISDF_E_WORKSPACE when max_rows is too small.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* center; const float* cam_intr; const float* bbox;
+  float sdf_scale; int32_t bins; int64_t batch; int64_t num_points; int64_t margin; float clamp;
+  const hoisdf_pyramid* gmaps; const hoisdf_pyramid_h* gmaps16; const float* bias0;
+  const uint16_t* s1_a; const uint16_t* s1_b; const uint16_t* s1_c; int64_t ld_s1; const float* b_s1; float s1_scale;
+  const hoisdf_sdf_weights_h3* dec;
+  void* workspace; int64_t workspace_bytes; int64_t max_rows;
+  int32_t planned; int32_t* chunk_counts; int64_t* offsets; int64_t* host_offsets; int64_t* n_f;
+  float* points; float* sdf; float* posenc; int32_t* sel_index; int32_t* status_flag;
+  float* screen_err; float* screen_gap; int32_t* verified;
+  float* cand_sdf; int32_t* cand_index; float* exact_sdf; int32_t* exact_index; int32_t* screen_rows;
+} hoisdf_sdf_infer_args;
+
+int64_t hoisdf_sdf_infer_keep(int64_t num_points, int64_t margin);
+int64_t hoisdf_sdf_infer_workspace_bytes(int64_t batch, int64_t max_rows, int64_t num_points, int64_t margin, int32_t bins);
+int hoisdf_sdf_infer_plan(const float* center, const float* cam_intr, const float* bbox, float sdf_scale, int64_t batch,
+                          int32_t bins, int32_t* chunk_counts, int64_t* offsets, int64_t* host_offsets, void* stream);
+int hoisdf_sdf_infer_fwd(const hoisdf_sdf_infer_args* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Token assembly -- upstream main/model.py:123-126 (sdf_activation) + :520-562:

@@ -76,6 +76,42 @@ def check_selection(taps_dev, taps_ref, P):
     return worst_all, worst
 
 
+def test_sdf_infer_c_entry_equals_python_orchestration(setup, monkeypatch):
+    """hoisdf_sdf_infer_fwd (ONE C call: compaction, stage A, screening, final stage, device-side verdict, top-P) against
+    the Python orchestration of the same kernels: identical to the bit, including the verdict's gap / error values."""
+    from hoisdf_b200.config import cfg
+    from hoisdf_b200 import _capi
+    s = setup
+    model, dev = s["model"], s["dev"]
+    meta = to_dev(s["meta"], dev)
+    pyr = to_dev(s["pyr"], dev)
+    for kind, ck, bk, P in (("hand", "mano_root", "bbox_hand", 96), ("obj", "obj_center_cam", "bbox_obj", 40)):
+        res = {}
+        for native in (True, False):
+            monkeypatch.setattr(type(cfg), "native_sdf_infer", native)
+            taps = {}
+            with torch.no_grad():
+                ctx = model._ctx(pyr)
+                out = model.sdf_infer(ctx, meta[ck], meta["cam_intr"], meta[bk], 3.1, P, kind, taps=taps)
+            assert bool(taps.get("native", False)) == native and taps["single_pass"]
+            res[native] = (out, taps)
+        (a, ta), (b, tb) = res[True], res[False]
+        for x, y in zip(a[:3], b[:3]):
+            assert torch.equal(x, y)
+        for k in ("index", "cand_index", "cand_sdf", "exact_sdf", "exact_index", "screen_gap", "screen_rows"):
+            assert torch.equal(ta[k].reshape(-1).to(tb[k].dtype), tb[k].reshape(-1)), k
+        assert float(ta["screen_err"]) == float(tb["screen_err"]) and bool(ta["screen_verified"]) == bool(tb["screen_verified"])
+    # error contract: fewer lattice points inside the bbox than num_points -> the upstream-like exception
+    tiny = meta["bbox_hand"].clone()
+    tiny[:, 2:] = tiny[:, :2] + 2.0
+    monkeypatch.setattr(type(cfg), "native_sdf_infer", True)
+    with pytest.raises(RuntimeError, match="fewer than num_points"), torch.no_grad():
+        model.sdf_infer(model._ctx(pyr), meta["mano_root"], meta["cam_intr"], tiny, 3.1, 96, "hand")
+    # workspace contract of the C entry
+    assert _capi.lib.hoisdf_sdf_infer_workspace_bytes(2, 1 << 16, 96, 1024, 64) > 0
+    assert _capi.lib.hoisdf_sdf_infer_keep(96, 1024) == 1120 and _capi.lib.hoisdf_sdf_infer_keep(8000, 1024) == 8192
+
+
 @pytest.mark.parametrize("final_stage", ["h3", "fma"])
 def test_sdf_infer(setup, final_stage, monkeypatch):
     from hoisdf_b200.config import cfg
