@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhoisdf_b200.so")
 
-ABI_VERSION = 22
+ABI_VERSION = 23
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2      # ACT_SIGMOID: hoisdf_linear_narrow_split_fwd only
 GATHER_CONCAT, GATHER_SUM = 0, 1
 
@@ -96,6 +96,23 @@ class SdfInferArgs(C.Structure):
     ]
 
 
+class H3Linear(C.Structure):
+    _fields_ = [("a", vp), ("b", vp), ("c", vp), ("ld", i64), ("bias", vp), ("scale", f32)]
+
+
+class EncoderLayer(C.Structure):
+    _fields_ = [("qkv", H3Linear), ("out", H3Linear), ("lin1", H3Linear), ("lin2", H3Linear),
+                ("norm1_g", vp), ("norm1_b", vp), ("norm2_g", vp), ("norm2_b", vp)]
+
+
+class EncoderArgs(C.Structure):
+    _fields_ = [("layers", C.POINTER(EncoderLayer)), ("num_layers", i32), ("heads", i32), ("d_ff", i64),
+                ("inter_g", vp), ("inter_b", vp), ("batch", i64), ("seq", i64), ("x", vp),
+                ("out", vp), ("out_hi", vp), ("out_lo", vp), ("ld_out", i64),
+                ("inter", vp), ("inter_hi", vp), ("inter_lo", vp), ("ld_inter", i64),
+                ("workspace", vp), ("workspace_bytes", i64)]
+
+
 class ManoModel(C.Structure):
     _fields_ = [(n, vp) for n in ("shapedirs", "posedirs", "v_template", "j_regressor", "weights", "hands_mean")]
 
@@ -142,6 +159,8 @@ SIGNATURES = {
     "hoisdf_attention_split_fwd": (C.c_int, [vp, i64, vp, vp, i64, vp, vp, i64, i64, i64, i64, i64, i64, vp, i64, vp]),
     "hoisdf_add_layernorm_fwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp]),
     "hoisdf_add_layernorm_split_fwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp, vp, i64, vp, vp, i64, vp]),
+    "hoisdf_encoder_workspace_bytes": (i64, [i64, i64, i64, i32]),
+    "hoisdf_encoder_fwd": (C.c_int, [C.POINTER(EncoderArgs), vp]),
     "hoisdf_vote_joints_fwd": (C.c_int, [vp, vp, vp, i64, i64, i64, vp, vp]),
     "hoisdf_mano_fwd": (C.c_int, [C.POINTER(ManoModel), vp, vp, i64, vp, vp, vp]),
     "hoisdf_mano_aa_fwd": (C.c_int, [C.POINTER(ManoModel), vp, vp, i64, vp, vp, vp]),

@@ -82,6 +82,8 @@ class Config:
     # the default cascade (fused chain + fp16 gather + FP16x3 final stage) run by ONE C entry point, hoisdf_sdf_infer_fwd
     # (csrc/sdf_infer.cu), instead of ~30 Python-level launches with ATen glue; False = the Python orchestration
     native_sdf_infer = True
+    # likewise the transformer encoder stacks: hoisdf_encoder_fwd (csrc/transformer.cu) runs all layers in one C call
+    native_encoder = True
     # linear_sdfin layer 0 applied to the pyramid (Model: PyramidContext.gmaps) on the FP16x3 GEMM with a TMEM drain
     # every `projection_chunk_kb` K blocks instead of the fp32 FMA kernel (3.2 ms -> 0.6 ms at batch 32)
     tc_projection = True

@@ -293,7 +293,7 @@ class Model(nn.Module):
             plan = self.plan_candidates(center_joint, cam_intr, bbox, sdf_scale)
         b = plan.center.shape[0]
         dev = plan.center.device
-        if (level == 0 and cfg.native_sdf_infer and ops.use_h3() and cfg.fused_chain and cfg.gather_h16
+        if (level == 0 and cfg.native_sdf_infer and ops.PROFILE is None and ops.use_h3() and cfg.fused_chain and cfg.gather_h16
                 and not cfg.fused_gather and cfg.final_stage == "h3" and cfg.screen_single):
             # the default cascade behind ONE C entry point (csrc/sdf_infer.cu: hoisdf_sdf_infer_fwd); None = a sample has
             # no room for the screening margin -> the general path below ranks every row exactly

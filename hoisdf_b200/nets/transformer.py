@@ -201,6 +201,12 @@ class TransformerEncoder(nn.Module):
         upstream transformer.py:175-202."""
         b, s, d = x.shape
         n = b * s
+        from ..config import cfg
+        if (pos is None and ops.use_h3() and s > 32 and cfg.native_encoder and self.norm is None and ops.PROFILE is None
+                and (not self.return_intermediate or self.inter_norm is not None)):
+            res = self._forward_native(x)
+            if res is not None:
+                return res
         inter = torch.empty(self.num_layers, b, s, d, device=x.device, dtype=torch.float32) \
             if self.return_intermediate else None
         # FP16x3 path: every layer also emits its output (and the inter_norm output) in split-half format from the
@@ -218,6 +224,65 @@ class TransformerEncoder(nn.Module):
             xs = out_split
         self.last_out_split, self.last_inter_split = xs, inter_split
         return x, inter
+
+
+    def _forward_native(self, x):
+        """The whole stack through ONE C call (csrc/transformer.cu: hoisdf_encoder_fwd) with a caller-owned workspace;
+        same kernels, same order as the per-layer Python path below (bit-identical).  None = not applicable."""
+        import ctypes as C
+        from .. import _capi
+        b, s, d = x.shape
+        n, dev = b * s, x.device
+        L = self.num_layers
+        layers = (_capi.EncoderLayer * L)()
+        keep = []
+        d_ff = None
+
+        def fill(dst, pw):
+            h3 = pw.h3
+            if h3 is None:
+                return False
+            dst.a, dst.b, dst.c, dst.ld = h3.plane_ptr(0), h3.plane_ptr(1), h3.plane_ptr(2), h3.ld
+            dst.bias, dst.scale = ops._ptr(h3.b), float(h3.scale)
+            keep.append(h3)
+            return True
+
+        for i, layer in enumerate(self.layers):
+            pk = layer.self_attn.packed()
+            l1, l2 = layer.ffn_packed()
+            if not (fill(layers[i].qkv, pk["qkv"]) and fill(layers[i].out, pk["out"]) and fill(layers[i].lin1, l1)
+                    and fill(layers[i].lin2, l2)):
+                return None
+            d_ff = l1.n if d_ff is None else d_ff
+            if l1.n != d_ff or layer.nhead * 64 != d:
+                return None
+            layers[i].norm1_g, layers[i].norm1_b = layer.norm1.weight.data_ptr(), layer.norm1.bias.data_ptr()
+            layers[i].norm2_g, layers[i].norm2_b = layer.norm2.weight.data_ptr(), layer.norm2.bias.data_ptr()
+        heads = self.layers[0].nhead
+        nbytes = int(_capi.lib.hoisdf_encoder_workspace_bytes(b, s, d_ff, heads))
+        ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        out = torch.empty(b, s, d, device=dev, dtype=torch.float32)
+        out_split = ops.SplitRows.empty(n, d, dev)
+        inter = inter_split = None
+        a = _capi.EncoderArgs()
+        a.layers, a.num_layers, a.heads, a.d_ff = layers, L, heads, d_ff
+        a.batch, a.seq, a.x = b, s, x.data_ptr()
+        a.out, a.out_hi, a.out_lo, a.ld_out = out.data_ptr(), out_split.hi_ptr, out_split.lo_ptr, out_split.ld
+        if self.return_intermediate:
+            inter = torch.empty(L, b, s, d, device=dev, dtype=torch.float32)
+            inter_split = ops.SplitRows.empty(L * n, d, dev)
+            a.inter_g, a.inter_b = self.inter_norm.weight.data_ptr(), self.inter_norm.bias.data_ptr()
+            a.inter, a.inter_hi, a.inter_lo, a.ld_inter = inter.data_ptr(), inter_split.hi_ptr, inter_split.lo_ptr, \
+                inter_split.ld
+        a.workspace, a.workspace_bytes = ws.data_ptr(), nbytes
+        ops._count(L * 12 + 1)
+        st = _capi.lib.hoisdf_encoder_fwd(C.byref(a), ops._stream())
+        if st == _capi.E_UNSUPPORTED:
+            return None
+        _capi.check(st, "hoisdf_encoder_fwd")
+        del keep
+        self.last_out_split, self.last_inter_split = out_split, inter_split
+        return out, inter
 
 
 class TransformerDecoder(nn.Module):

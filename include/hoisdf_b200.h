@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 22
+#define HOISDF_ABI_VERSION 23
 
 enum {
   HOISDF_OK = 0,
@@ -444,6 +444,36 @@ int hoisdf_add_layernorm_split_fwd(const float* x, const float* res, const float
                                    const float* gamma2, const float* beta2, float* y2, int64_t rows, int64_t d,
                                    uint16_t* yh_hi, uint16_t* yh_lo, int64_t ldyh, uint16_t* y2h_hi, uint16_t* y2h_lo,
                                    int64_t ldy2h, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * A whole transformer ENCODER stack behind one entry point (csrc/transformer.cu) -- upstream
+ * common/nets/transformer.py:175-202 (TransformerEncoder.forward) over :279-302 (forward_post), pos_embed == 0
+ * (main/model.py:541-543), d_model 256, heads of 64, ReLU feed-forward of width d_ff, eval mode.
+ *   x (B*S, 256) fp32 batch-major tokens -> out (B*S, 256) = last layer's output (+ its split-half copy when out_hi is
+ *   given: what the decoder's key / value projection reads) and, when `inter` is given, inter (L, B*S, 256) =
+ *   inter_norm(out_l) for every layer (+ split-half copies: what the vote heads read).
+ *   Weights: hoisdf_pack_h3 planes (a, b, c; pitch ld) + fp32 bias per Linear; `scale` as hoisdf_linear_h3_args.w_scale.
+ *   seq <= 32 returns HOISDF_E_UNSUPPORTED (short sequences use the SIMT attention kernel through hoisdf_attention_fwd).
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct { const uint16_t* a; const uint16_t* b; const uint16_t* c; int64_t ld; const float* bias; float scale; } hoisdf_h3_linear;
+typedef struct {
+  hoisdf_h3_linear qkv;   /* in_proj (768, 256): rows [q; k; v] */
+  hoisdf_h3_linear out;   /* out_proj (256, 256) */
+  hoisdf_h3_linear lin1;  /* linear1 (d_ff, 256) */
+  hoisdf_h3_linear lin2;  /* linear2 (256, d_ff) */
+  const float* norm1_g; const float* norm1_b; const float* norm2_g; const float* norm2_b;
+} hoisdf_encoder_layer;
+typedef struct {
+  const hoisdf_encoder_layer* layers; int32_t num_layers; int32_t heads; int64_t d_ff;
+  const float* inter_g; const float* inter_b;
+  int64_t batch; int64_t seq;
+  const float* x;
+  float* out; uint16_t* out_hi; uint16_t* out_lo; int64_t ld_out;
+  float* inter; uint16_t* inter_hi; uint16_t* inter_lo; int64_t ld_inter;
+  void* workspace; int64_t workspace_bytes;
+} hoisdf_encoder_args;
+int64_t hoisdf_encoder_workspace_bytes(int64_t batch, int64_t seq, int64_t d_ff, int32_t heads);
+int hoisdf_encoder_fwd(const hoisdf_encoder_args* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Joint voting -- upstream common/nets/loss.py:31-36,54-57 (the part of JointvoteLoss that produces

@@ -398,6 +398,27 @@ def test_transformer_matches_oracle(cuda):
         type(cfg).num_samp_hand, type(cfg).num_samp_obj = old
 
 
+def test_encoder_c_entry_equals_python_layers(cuda, monkeypatch):
+    """hoisdf_encoder_fwd (the whole encoder stack in ONE C call, caller-owned workspace) against the per-layer Python path
+    over the same kernels: last output, every inter_norm output and their split-half copies, identical to the bit."""
+    from hoisdf_b200.config import cfg
+    from hoisdf_b200.nets.transformer import Transformer
+    sd = syn.hot_path_state_dict(61, "dexycb")
+    tr = Transformer(256, 4, 6, 4, 1024, 0.1, "relu", False, True).to(cuda).eval()
+    _load_prefix(tr, sd, "hand_transformer.")
+    x = rnd(64, 3, 200, 256).to(cuda)
+    res = {}
+    for native in (True, False):
+        monkeypatch.setattr(type(cfg), "native_encoder", native)
+        with torch.no_grad():
+            out, inter = tr.encoder.forward_bm(x, None)
+        res[native] = (out.clone(), inter.clone(), tr.encoder.last_out_split.float(), tr.encoder.last_inter_split.float())
+    for a, b in zip(res[True], res[False]):
+        assert a.shape == b.shape and torch.equal(a, b)
+    from hoisdf_b200 import _capi
+    assert _capi.lib.hoisdf_encoder_workspace_bytes(3, 200, 1024, 4) > 0 and _capi.lib.hoisdf_encoder_workspace_bytes(3, 20, 1024, 4) == 0
+
+
 # ---------------------------------------------------------------- heads
 def test_vote_and_mano(cuda):
     from hoisdf_b200 import ops
