@@ -277,12 +277,10 @@ HOISDF_API int hoisdf_attention_fwd(const float* q, int64_t ldq, const float* k,
     HOISDF_LAUNCH_SMEM(attention_small_kernel, grid, 128, static_cast<size_t>(lk) * sizeof(float), s, p);
   } else {
 #ifndef HOISDF_EMULATE
-    static bool configured = false;
-    if (!configured) {
+    {   // per call: the attribute belongs to the CURRENT device's instance of the kernel (a process may drive several GPUs)
       cudaError_t e = cudaFuncSetAttribute(attention_flash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            kFlashSmem);
       if (e != cudaSuccess) return static_cast<int>(e);
-      configured = true;
     }
 #endif
     dim3 grid(static_cast<unsigned>(ceil_div(lq, BQ)), static_cast<unsigned>(heads), static_cast<unsigned>(batch));

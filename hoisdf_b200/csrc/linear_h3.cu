@@ -111,6 +111,7 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
   auto bar_cempty = [&](uint32_t b) { return bars + 8u * (2 * H3_MAX_STAGES + 2 + b); };
   constexpr bool single = SINGLE;
   constexpr bool DIRECT = OUT == H3_OUT_F32_DIRECT;
+  constexpr bool RES_STAGED = RES && OUT == H3_OUT_SPLIT_TMA;     // residual tile staged through the epilogue's smem slot
   const int nstages = single ? H3_STAGES_1P : p.nstages;
   const uint32_t w_bytes = single ? H3_W_BYTES : static_cast<uint32_t>(p.w_rows) * H3_BK * 2;     // one W plane of a stage
   const uint32_t stage_bytes = single ? H3_STAGE_BYTES_1P : 2 * H3_X_BYTES + 3 * w_bytes;
@@ -410,6 +411,28 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
           if (lane == 0) tma_store_wait_read<0>();
           __syncwarp();
         }
+        if (RES_STAGED) {
+          // split-half residual of this warp's 32 rows x 32 columns, both planes, pulled into the staging slot with
+          // COALESCED loads (4 lanes cover one row's 64 B per plane: 8 rows per instruction) in the layout the output will
+          // take (64-byte rows, 16-byte chunks XOR-swizzled).  The per-lane form -- every lane reading 16 B of its own row
+          // -- costs 32 L1 wavefronts per instruction and made conv3 + shortcut 3x slower than the same GEMM without it.
+          const int64_t wrow0 = p.taps > 0 ? static_cast<int64_t>(m_tile) * H3_BM + q * 32 : row - lane;
+          const int64_t wlim = p.taps > 0 ? static_cast<int64_t>(p.rows_per_batch)
+                                          : static_cast<int64_t>(grp + 1) * p.rows_per_batch;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = (lane >> 2) + 8 * i, ch = lane & 3;
+            uint4 vh = make_uint4(0u, 0u, 0u, 0u), vl = vh;
+            if (tile_ok && wrow0 + r < wlim && c0 + ch * 8 < n_here) {
+              vh = __ldg(reinterpret_cast<const uint4*>(p.r_hi + (wrow0 + r) * p.ldr + n0 + c0 + ch * 8));
+              vl = __ldg(reinterpret_cast<const uint4*>(p.r_lo + (wrow0 + r) * p.ldr + n0 + c0 + ch * 8));
+            }
+            const int roff = r * 64 + ((ch ^ ((r >> 1) & 3)) << 4);
+            *reinterpret_cast<uint4*>(box + roff) = vh;
+            *reinterpret_cast<uint4*>(box + 2048 + roff) = vl;
+          }
+          __syncwarp();
+        }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {                                  // 8 columns: c0 + 8g .. c0 + 8g + 7
           float v[8];
@@ -418,8 +441,15 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
             v[i] = fmaf(a[g * 8 + i], oscale, __shfl_sync(0xffffffffu, bl, g * 8 + i));
           if (RES && res_ok && c0 + g * 8 < n_here) {
             // split-half residual (ResNet bottleneck shortcut): this lane's row, 8 columns = 16 B per plane
-            const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.r_hi + rrow * p.ldr + n0 + c0 + g * 8));
-            const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.r_lo + rrow * p.ldr + n0 + c0 + g * 8));
+            uint4 a, b;
+            if (RES_STAGED) {       // this lane's row from the staging slot (the output chunk g then overwrites exactly these bytes)
+              const int roff = lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4);
+              a = *reinterpret_cast<const uint4*>(box + roff);
+              b = *reinterpret_cast<const uint4*>(box + 2048 + roff);
+            } else {
+              a = __ldg(reinterpret_cast<const uint4*>(p.r_hi + rrow * p.ldr + n0 + c0 + g * 8));
+              b = __ldg(reinterpret_cast<const uint4*>(p.r_lo + rrow * p.ldr + n0 + c0 + g * 8));
+            }
             const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {

@@ -564,6 +564,12 @@ class Model(nn.Module):
     # forward
     # ------------------------------------------------------------------------------------------------
     def forward(self, inputs, targets, meta_info, mode, epoch_cnt=1e8, batch_ratio=0):
+        dev = inputs["img"].device
+        if dev.type == "cuda" and dev.index is not None and dev.index != torch.cuda.current_device():
+            # every launch below goes to the CURRENT device's stream: make the tensors' device current (a process driving
+            # several GPUs, e.g. a DataParallel replica thread that was handed cuda:1 tensors)
+            with torch.cuda.device(dev):
+                return self.forward(inputs, targets, meta_info, mode, epoch_cnt, batch_ratio)
         if mode == "train":
             from .train import forward_train          # upstream model.py:357-665, train branch (hoisdf_b200/train.py)
             return forward_train(self, inputs, targets, meta_info, epoch_cnt, batch_ratio)
@@ -897,14 +903,17 @@ def get_model(mode, mano_buffers=None, mano_root="tool/mano_models"):
                  mano_layer)
 
 
-def load_checkpoint(model: nn.Module, checkpoint, strict: bool = True):
+def load_checkpoint(model: nn.Module, checkpoint, strict: bool = True, trusted_pickle: bool = False):
     """Load a released / trainer-written snapshot (upstream common/base.py:137-145 writes {"epoch", "network",
     "optimizer", ...} with the state dict of the `DataParallel` wrapper, i.e. every key prefixed `module.`;
     `Tester._make_model`, base.py:179-193, loads it into the wrapper with strict=True).  `checkpoint` is a path, the
     loaded dict, or a bare state dict; the `module.` prefix is stripped when `model` is not itself wrapped.
-    Returns the checkpoint dict (epoch etc.) for the caller."""
-    ckpt = torch.load(checkpoint, map_location="cpu", weights_only=False) if isinstance(checkpoint, (str, bytes)) \
-        or hasattr(checkpoint, "__fspath__") else checkpoint
+    Returns the checkpoint dict (epoch etc.) for the caller."""  # noqa: D401
+    # weights_only=True: tensors, containers and primitives only -- a snapshot file cannot execute code on load.  Upstream's
+    # trainer pickles nothing else ({"epoch", "network", "optimizer"}); `trusted_pickle=True` restores torch.load's legacy
+    # behaviour for files that do carry arbitrary Python objects and come from a trusted source
+    ckpt = torch.load(checkpoint, map_location="cpu", weights_only=not trusted_pickle) \
+        if isinstance(checkpoint, (str, bytes)) or hasattr(checkpoint, "__fspath__") else checkpoint
     state = ckpt["network"] if isinstance(ckpt, dict) and "network" in ckpt else ckpt
     wrapped = isinstance(model, (nn.DataParallel, nn.parallel.DistributedDataParallel))
     if not wrapped and state and all(k.startswith("module.") for k in state):

@@ -1,5 +1,6 @@
 """`MLP` with the upstream constructor / state-dict contract (common/nets/layer.py:168-201), running on the
-hoisdf_b200 Linear kernel.  Inference only: the backward kernels are a later milestone.
+hoisdf_b200 Linear kernel.  `forward` is the inference operator; the training step differentiates the same layers
+through hoisdf_b200/autograd.py (hoisdf_b200/train.py:mlp_rows).
 """
 from __future__ import annotations
 
@@ -10,11 +11,15 @@ from .. import ops
 
 
 def _require_inference(module: nn.Module, x: torch.Tensor):
+    """The module-level forwards (`MLP.forward`, `SDFDecoder.forward`, `Transformer.forward`, ...) are the INFERENCE
+    operators: their results carry no autograd graph.  Calling them with gradients enabled on tensors / parameters that
+    require grad would silently hand fine-tuning code `None` gradients, so that is an error -- in train() AND in
+    eval() mode.  Training goes through `Model.forward(mode="train")` (hoisdf_b200/train.py), which differentiates the same
+    kernels through hoisdf_b200/autograd.py."""
     if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in module.parameters())):
-        if module.training:
-            raise NotImplementedError(
-                "hoisdf_b200 implements the inference hot path; call under torch.no_grad() / model.eval() "
-                "(backward kernels: SURVEY.md section 8 f-2, not built yet)")
+        raise RuntimeError(
+            "hoisdf_b200: %s.forward is an inference operator (no autograd graph); call it under torch.no_grad(), or "
+            "train through Model.forward(..., mode='train')" % type(module).__name__)
 
 
 class MLP(nn.Module):

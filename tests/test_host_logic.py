@@ -88,11 +88,22 @@ def test_masks_and_config(lib_built):
     assert cfg.mutliscale_dim == 3968 and cfg.use_big_decoder
 
 
-def test_training_mode_is_refused(lib_built):
+def test_inference_operators_refuse_autograd_and_training_needs_the_gpu(lib_built):
+    """The module forwards are inference operators: with gradients enabled on parameters that require grad they raise instead
+    of returning graph-less tensors -- training goes through Model.forward(mode="train"), which fails loudly
+    without the CUDA path (no CPU fallback)."""
     from hoisdf_b200.model import get_model
+    from hoisdf_b200.nets.layer import MLP
     model = get_model("test", mano_buffers=syn.mano_buffers(0))
-    with pytest.raises(NotImplementedError):
-        model({}, {}, {}, "train")
+    assert all(not p.requires_grad for n, p in model.backbone_net.named_parameters() if "bn" in n)      # freeze_stages
+    assert any(p.requires_grad for n, p in model.backbone_net.named_parameters() if "downsample.1" in n)
+    mlp = MLP(8, 8, 4, 2).eval()
+    with pytest.raises(RuntimeError, match="inference operator"):
+        mlp(torch.zeros(3, 8))
+    inputs = {"img": torch.zeros(1, 3, 256, 256)}
+    with pytest.raises(Exception):
+        model(inputs, {}, {"mano_root": torch.zeros(1, 3), "obj_center_cam": torch.zeros(1, 3),
+                           "cam_intr": torch.eye(3)[None]}, "train")
 
 
 def test_shard_and_pack():
