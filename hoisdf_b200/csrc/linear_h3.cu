@@ -92,7 +92,7 @@ struct H3Params {
 // Template parameters: CL = cluster size (CTAs sharing an N tile); OUT = H3_OUT_*; SINGLE = one tensor-core product per
 // K step (pre-screening); RES = split-half residual added in the epilogue.  Compile-time modes keep each
 // instantiation's epilogue small (instruction cache) and branch-free.
-template <int CL, int OUT, bool SINGLE, bool RES>
+template <int CL, int OUT, bool SINGLE, bool RES, bool PAIR>
 __global__ void __launch_bounds__(H3_THREADS, 1)
 linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__ CUtensorMap map_xlo,
                  const __grid_constant__ CUtensorMap map_wa, const __grid_constant__ CUtensorMap map_wb,
@@ -112,8 +112,14 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
   constexpr bool single = SINGLE;
   constexpr bool DIRECT = OUT == H3_OUT_F32_DIRECT;
   constexpr bool RES_STAGED = RES && OUT == H3_OUT_SPLIT_TMA;     // residual tile staged through the epilogue's smem slot
+  static_assert(!PAIR || (CL == 2 && !SINGLE), "cta_group::2 mode: a pair of CTAs, three-product arithmetic");
+  // PAIR (tcgen05.mma.cta_group::2): the two CTAs of a cluster compute their two M tiles with ONE M = 256 instruction stream
+  // issued by the leader (rank 0).  Each CTA stages its own X tiles and only HALF of the W rows (the tensor cores of both
+  // SMs read both halves), so a K block costs 40 KB of TMA writes + 48 KB of operand reads per SM instead of 64 + 72:
+  // the shared-memory bandwidth that capped the fat shapes at 72 % tensor activity is no longer the limit.
   const int nstages = single ? H3_STAGES_1P : p.nstages;
-  const uint32_t w_bytes = single ? H3_W_BYTES : static_cast<uint32_t>(p.w_rows) * H3_BK * 2;     // one W plane of a stage
+  const uint32_t w_bytes = single ? H3_W_BYTES                                                   // one W plane of a stage,
+                                  : static_cast<uint32_t>(PAIR ? p.w_rows / 2 : p.w_rows) * H3_BK * 2;   // as THIS CTA stores it
   const uint32_t stage_bytes = single ? H3_STAGE_BYTES_1P : 2 * H3_X_BYTES + 3 * w_bytes;
 
   // warp index made provably warp-uniform: the producer and MMA roles run their loops on all 32 lanes and predicate
@@ -138,19 +144,26 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wc) : "memory");
     for (int s = 0; s < H3_MAX_STAGES; ++s) {
       mbar_init(bar_full(s), 1);
-      mbar_init(bar_empty(s), CL);          // every CTA's tensor core must have consumed the stage
+      mbar_init(bar_empty(s), PAIR ? 1 : CL);   // every CTA's tensor core must have consumed the stage (PAIR: one commit)
     }
     for (uint32_t b = 0; b < 2; ++b) {
       mbar_init(bar_cfull(b), 1);
-      mbar_init(bar_cempty(b), H3_EPI_WARPS);
+      mbar_init(bar_cempty(b), PAIR ? 2 * H3_EPI_WARPS : H3_EPI_WARPS);   // PAIR: both CTAs' drain warps free the leader's buffer
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(H3_TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(H3_TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(H3_TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -176,8 +189,10 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
       for (int item = cluster; item < items; item += nclusters) {
         int m_tile, grp, m0, n0;
         tile_of(item, m_tile, grp, m0, n0);
-        const int wrow = n0 + static_cast<int>(rank) * kSliceRows;
-        const uint32_t wo = rank * kSliceBytes;
+        const int p_n_inst = (min(p.bn, p.n - n0) + 15) & ~15;
+        // PAIR: the M = 256 instruction reads W rows [0, N/2) from the leader and [N/2, N) from its peer
+        const int wrow = n0 + static_cast<int>(rank) * (PAIR ? p_n_inst / 2 : kSliceRows);
+        const uint32_t wo = PAIR ? 0u : rank * kSliceBytes;
         // convolution: first output pixel of the tile -> (image, row, column); tiles beyond the last land at b >= B
         int cb0 = 0, cy0 = 0, cx0 = 0;
         if (p.taps > 0) {
@@ -193,21 +208,38 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
           mbar_wait(bar_empty(s), ph);
           const uint32_t st = base + s * stage_bytes;
           const bool issue = elect_one();
-          if (issue) mbar_expect_tx(bar_full(s), stage_bytes);
+          // PAIR: both CTAs' loads complete on the LEADER's barrier, which expects the bytes of both stages
+          const uint32_t fbar = PAIR ? map_to_rank(bar_full(s), 0u) : bar_full(s);
+          if (issue && (!PAIR || rank == 0)) mbar_expect_tx(bar_full(s), PAIR ? 2 * stage_bytes : stage_bytes);
           if (p.taps > 0) {
             // shifted window of the input image for this tap; out-of-image pixels are zero-filled = zero padding
             const int ix = cx0 + p.dx[tap], iy = cy0 + p.dy[tap];
             if (issue) {
-              tma_load_4d(st, &map_xhi, bar_full(s), cblk * H3_BK, ix, iy, cb0);
-              if (!single) tma_load_4d(st + H3_X_BYTES, &map_xlo, bar_full(s), cblk * H3_BK, ix, iy, cb0);
+              if (PAIR) {
+                tma_load_4d_pair(st, &map_xhi, fbar, cblk * H3_BK, ix, iy, cb0);
+                tma_load_4d_pair(st + H3_X_BYTES, &map_xlo, fbar, cblk * H3_BK, ix, iy, cb0);
+              } else {
+                tma_load_4d(st, &map_xhi, bar_full(s), cblk * H3_BK, ix, iy, cb0);
+                if (!single) tma_load_4d(st + H3_X_BYTES, &map_xlo, bar_full(s), cblk * H3_BK, ix, iy, cb0);
+              }
             }
             if (++cblk == p.cin_blocks) { cblk = 0; ++tap; }
           } else if (issue) {
-            tma_load_3d(st, &map_xhi, bar_full(s), kb * H3_BK, m0, grp);
-            if (!single) tma_load_3d(st + H3_X_BYTES, &map_xlo, bar_full(s), kb * H3_BK, m0, grp);
+            if (PAIR) {
+              tma_load_3d_pair(st, &map_xhi, fbar, kb * H3_BK, m0, grp);
+              tma_load_3d_pair(st + H3_X_BYTES, &map_xlo, fbar, kb * H3_BK, m0, grp);
+            } else {
+              tma_load_3d(st, &map_xhi, bar_full(s), kb * H3_BK, m0, grp);
+              if (!single) tma_load_3d(st + H3_X_BYTES, &map_xlo, bar_full(s), kb * H3_BK, m0, grp);
+            }
           }
           if (issue) {
-            if (single) {                       // stage = [x_hi 8 KB | w_hi 16 KB]
+            if (PAIR) {                         // stage = [x_hi | x_lo | this CTA's half of A | of B | of C]
+              const uint32_t w0 = st + 2 * H3_X_BYTES;
+              tma_load_2d_pair(w0, &map_wa, fbar, kb * H3_BK, wrow);
+              tma_load_2d_pair(w0 + w_bytes, &map_wb, fbar, kb * H3_BK, wrow);
+              tma_load_2d_pair(w0 + 2 * w_bytes, &map_wc, fbar, kb * H3_BK, wrow);
+            } else if (single) {                // stage = [x_hi 8 KB | w_hi 16 KB]
               const uint32_t w0 = st + H3_X_BYTES + wo;
               if (CL > 1) tma_load_2d_mc(w0, &map_wb, bar_full(s), kb * H3_BK, wrow, kAllCtas);
               else tma_load_2d(w0, &map_wb, bar_full(s), kb * H3_BK, wrow);
@@ -235,12 +267,12 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
     {
       uint32_t cc = 0, ph = 0u;                                    // chunk counter; parity of the stage's "full" phase
       int s = 0;                                                   // ring stage
-      for (int item = cluster; item < items; item += nclusters) {
+      for (int item = (PAIR && rank != 0) ? items : cluster; item < items; item += nclusters) {   // PAIR: the leader issues
         int m_tile, grp, m0, n0;
         tile_of(item, m_tile, grp, m0, n0);
         const int n_here = min(p.bn, p.n - n0);
         const int n_inst = (n_here + 15) & ~15;                 // UMMA N (multiple of 16 for M = 128)
-        const uint32_t idesc = umma_idesc_f16(H3_BM, n_inst);
+        const uint32_t idesc = umma_idesc_f16(PAIR ? 2 * H3_BM : H3_BM, n_inst);
         int in_chunk = 0;
         uint32_t acc = tmem_base;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -269,14 +301,25 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
 #pragma unroll
             for (int kk = 0; kk < H3_BK / 16; ++kk) {
               const uint64_t adv = static_cast<uint64_t>(kk * 2);    // 16 halfs = 32 bytes = 2 x 16-byte units
-              umma_f16(acc, d_xhi + adv, d_wa + adv, idesc, (in_chunk | kk) != 0 ? 1u : 0u);
-              umma_f16(acc, d_xlo + adv, d_wb + adv, idesc, 1u);
-              umma_f16(acc, d_xhi + adv, d_wc + adv, idesc, 1u);
+              if (PAIR) {
+                umma2_f16(acc, d_xhi + adv, d_wa + adv, idesc, (in_chunk | kk) != 0 ? 1u : 0u);
+                umma2_f16(acc, d_xlo + adv, d_wb + adv, idesc, 1u);
+                umma2_f16(acc, d_xhi + adv, d_wc + adv, idesc, 1u);
+              } else {
+                umma_f16(acc, d_xhi + adv, d_wa + adv, idesc, (in_chunk | kk) != 0 ? 1u : 0u);
+                umma_f16(acc, d_xlo + adv, d_wb + adv, idesc, 1u);
+                umma_f16(acc, d_xhi + adv, d_wc + adv, idesc, 1u);
+              }
             }
           }
+          if (PAIR) {
+            umma2_commit_mc(bar_empty(s), kAllCtas);               // both CTAs' producers may refill the stage
+            if (in_chunk + 1 == chb || kb == num_kb - 1) umma2_commit_mc(bar_cfull(cc & 1u), kAllCtas);   // both drain
+          } else {
           if (CL > 1) umma_commit_mc(bar_empty(s), kAllCtas);      // stage refillable once ALL CTAs' MMAs have read it
           else umma_commit(bar_empty(s));
           if (in_chunk + 1 == chb || kb == num_kb - 1) umma_commit(bar_cfull(cc & 1u));   // chunk complete -> drain
+          }
           }
           __syncwarp();
           if (++s == nstages) { s = 0; ph ^= 1u; }
@@ -293,6 +336,11 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
     const int q = warp & 3;                                         // TMEM lane quarter this warp may read
     const int hcol = ew >> 2;                                       // which 128-column half of the tile it owns
     const float oscale = (single ? 1.f : kLoInv) * p.w_scale;       // single product: x_hi . w_hi is unscaled
+    // PAIR: the accumulator buffers of both CTAs are refilled by the leader's MMA warp -> free them on ITS barrier
+    auto cempty_arrive = [&](uint32_t b) {
+      if (PAIR) mbar_arrive_cluster(map_to_rank(bar_cempty(b), 0u));
+      else mbar_arrive(bar_cempty(b));
+    };
     const uint32_t box_sh = epi + static_cast<uint32_t>(ew) * H3_EPI_SLOT;
     uint8_t* box = gen + H3_STAGES * H3_STAGE_BYTES + ew * H3_EPI_SLOT;
     uint32_t cc = 0;
@@ -362,7 +410,7 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
         }
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_cempty(buf));                 // the tensor core may refill this buffer
+        if (lane == 0) cempty_arrive(buf);                 // the tensor core may refill this buffer
       }
       // ---- the last chunk is read 32 columns at a time, combined with the register sums and emitted right away
       const uint32_t lbuf = cc & 1u;
@@ -374,7 +422,7 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
       if (jlast < 0) {
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_cempty(lbuf));
+        if (lane == 0) cempty_arrive(lbuf);
       }
 
       // ---- epilogue: scale, bias, residual, activation, store -- 32 columns per pass, 8 at a time in registers
@@ -403,7 +451,7 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
         if (j == jlast) {                                            // TMEM buffer fully read: hand it back
           tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_cempty(lbuf));
+          if (lane == 0) cempty_arrive(lbuf);
         }
         if (!DIRECT) {
           // TMA-store paths stage the 32 x 32 block in this warp's smem slot: the previous store issued from it must
@@ -541,7 +589,8 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
   __syncthreads();
   if (CL > 1) cluster_sync_all();              // no CTA exits while a peer may still multicast to it / signal its barriers
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(H3_TMEM_COLS) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(H3_TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(H3_TMEM_COLS) : "memory");
   }
 }
 
@@ -627,7 +676,7 @@ template <int CL>
 static int max_clusters() {
   static int cached = -1;
   if (cached >= 0) return cached;
-  auto kern = linear_h3_kernel<CL, H3_OUT_SPLIT_TMA, false, false>;
+  auto kern = linear_h3_kernel<CL, H3_OUT_SPLIT_TMA, false, false, false>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, H3_SMEM_BYTES);
   int n = 0;
   if (CL == 1) {
@@ -667,11 +716,18 @@ static int h3_stage_count(int w_rows) {
   const int n = H3_STAGES * H3_STAGE_BYTES / stage;
   return n < H3_MAX_STAGES ? n : H3_MAX_STAGES;
 }
+static int h3_stage_count_pair(int w_rows) {        // cta_group::2: each CTA stages half of the W rows
+  const int stage = 2 * H3_X_BYTES + 3 * (w_rows / 2) * H3_BK * 2;
+  const int n = H3_STAGES * H3_STAGE_BYTES / stage;
+  return n < H3_MAX_STAGES ? n : H3_MAX_STAGES;
+}
 static int g_h3_chunk_kb = H3_CHUNK_KB;   // developer hook: K blocks per accumulation chunk
+// tcgen05.mma.cta_group::2 for launches that run as clusters of two CTAs: 0 never, 1 where it pays (launch_h3), 2 always
+static int g_h3_pair = [] { const char* e = getenv("HOISDF_H3_PAIR"); return e == nullptr ? 1 : atoi(e); }();
 
-template <int CL, int OUT, bool SINGLE, bool RES>
+template <int CL, int OUT, bool SINGLE, bool RES, bool PAIR = false>
 static int launch_h3_inst(const CUtensorMap* maps, const H3Params& p, int64_t clusters, cudaStream_t s) {
-  auto kern = linear_h3_kernel<CL, OUT, SINGLE, RES>;
+  auto kern = linear_h3_kernel<CL, OUT, SINGLE, RES, PAIR>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, H3_SMEM_BYTES);
   if (e != cudaSuccess) return static_cast<int>(e);
   cudaLaunchConfig_t cfg{};
@@ -700,6 +756,28 @@ static int launch_h3(const CUtensorMap* maps, const H3Params& p0, int64_t m_tile
   const int64_t clusters = items < max_clusters<CL>() ? items : max_clusters<CL>();
   const bool res = p.r_hi != nullptr;
   if (p.single && (res || p.out_mode == H3_OUT_F32_DIRECT)) return HOISDF_E_UNSUPPORTED;
+  if constexpr (CL == 2) {
+    // tcgen05.mma.cta_group::2 (half of W per CTA, deeper ring) pays where the K loop is long and wide enough to be bound by
+    // shared-memory bandwidth: measured +8 .. +20 % for N >= 256, K >= 1024 (U-Net 3x3 / transposed convolutions, the point
+    // MLP, FFN2), but the cross-CTA hand-overs cost 10 .. 80 % on thin / short-K / drain-every-K-block launches
+    // (profiles/r02s_h3_pair_vs_single.txt).  HOISDF_H3_PAIR: 0 never, 1 automatic (default), 2 always.
+    const int64_t kk = p.taps > 0 ? static_cast<int64_t>(p.taps) * p.cin_blocks * H3_BK : p.k;
+    const bool pays = p.n >= 256 && p.bn == H3_BN && kk >= 1024 && p.chunk_kb != 1;
+    if ((g_h3_pair == 2 || (g_h3_pair == 1 && pays)) && !p.single) {
+      p.nstages = h3_stage_count_pair(p.w_rows);
+      switch (p.out_mode) {
+        case H3_OUT_F32_TMA:
+          return res ? launch_h3_inst<CL, H3_OUT_F32_TMA, false, true, true>(maps, p, clusters, s)
+                     : launch_h3_inst<CL, H3_OUT_F32_TMA, false, false, true>(maps, p, clusters, s);
+        case H3_OUT_SPLIT_TMA:
+          return res ? launch_h3_inst<CL, H3_OUT_SPLIT_TMA, false, true, true>(maps, p, clusters, s)
+                     : launch_h3_inst<CL, H3_OUT_SPLIT_TMA, false, false, true>(maps, p, clusters, s);
+        default:
+          if (res) return HOISDF_E_UNSUPPORTED;
+          return launch_h3_inst<CL, H3_OUT_F32_DIRECT, false, false, true>(maps, p, clusters, s);
+      }
+    }
+  }
   switch (p.out_mode) {
     case H3_OUT_F32_TMA:
       if (p.single) return launch_h3_inst<CL, H3_OUT_F32_TMA, true, false>(maps, p, clusters, s);
@@ -721,6 +799,7 @@ using namespace hoisdf;
 
 extern "C" __attribute__((visibility("default"))) void hoisdf_debug_h3_cluster(int cl) { g_h3_force_cluster = cl; }
 extern "C" __attribute__((visibility("default"))) void hoisdf_debug_h3_chunk(int kb) { g_h3_chunk_kb = kb; }
+extern "C" __attribute__((visibility("default"))) void hoisdf_debug_h3_pair(int mode) { g_h3_pair = mode; }
 
 HOISDF_API int hoisdf_linear_h3_fwd(const hoisdf_linear_h3_args* a, void* stream) {
   if (a == nullptr || a->x_hi == nullptr || a->x_lo == nullptr || a->w_a == nullptr || a->w_b == nullptr ||

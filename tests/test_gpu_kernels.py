@@ -605,6 +605,63 @@ def test_linear_narrow_split(cuda, m, n, k, act):
     assert y.shape == (m, n) and rel_err(y, ref) < 2e-6
 
 
+@pytest.fixture
+def h3_pair_forced(cuda):
+    """Force tcgen05.mma.cta_group::2 for every 2-CTA launch of the FP16x3 GEMM (default: only where it pays)."""
+    from hoisdf_b200 import _capi
+    _capi.lib.hoisdf_debug_h3_pair(2)
+    yield
+    _capi.lib.hoisdf_debug_h3_pair(1)
+
+
+def test_linear_h3_cta_pair(cuda, h3_pair_forced):
+    """The cta_group::2 form of the FP16x3 GEMM (a PAIR of CTAs computes an M = 256 tile, each staging half of W): every
+    output mode and shape class -- ragged M / N / K, odd tile counts, N tiles of 64 / 128 / 256 rows, chunk 1 and 4,
+    split-half chaining, residual, strided row groups, implicit-GEMM convolution -- against fp64; and the automatic mode
+    picks it for the fat shapes (same results)."""
+    from hoisdf_b200 import ops, _capi
+    for (m, k, n, chunk) in ((777, 289, 512, 4), (129, 147, 64, 1), (1000, 1024, 223, 4), (4096, 3968, 1024, 4),
+                             (300, 256, 60, 1), (2048, 2048, 512, 1), (128 * 5, 512, 384, 4)):
+        x, w, b = rnd(201, m, k), rnd(202, n, k, lo=-0.1, hi=0.1), rnd(203, n)
+        pw = ops.PackedLinearH3.pack(w.to(cuda), b.to(cuda))
+        ref = (x.double() @ w.double().T + b.double()).relu()
+        y = ops.linear_h3(ops.split_rows(x.to(cuda)), pw, ops.ACT_RELU, chunk_kb=chunk)
+        ys = ops.linear_h3(ops.split_rows(x.to(cuda)), pw, ops.ACT_RELU, split_out=True, chunk_kb=chunk)
+        assert rel_err(y, ref) < 4e-6 and rel_err(ys.float(), ref) < 4e-6, (m, k, n, chunk)
+    # split-half residual (ResNet shortcut) and the direct-store epilogue (strided row groups)
+    m, k, n = 1000, 256, 256
+    x, w, b, r = rnd(204, m, k), rnd(205, n, k, lo=-0.1, hi=0.1), rnd(206, n), rnd(207, m, n)
+    pw = ops.PackedLinearH3.pack(w.to(cuda), b.to(cuda))
+    y = ops.linear_h3(ops.split_rows(x.to(cuda)), pw, ops.ACT_RELU, split_out=True, residual_split=ops.split_rows(r.to(cuda)))
+    assert rel_err(y.float(), (x.double() @ w.double().T + b.double() + r.double()).relu()) < 4e-6
+    L, T, P, d = 5, 300, 100, 256
+    xb, w3, b3 = rnd(208, L * T, d), rnd(209, 60, d, lo=-0.1, hi=0.1), rnd(210, 60)
+    xs = ops.split_rows(xb.to(cuda))
+    yb = ops.linear_h3(ops.SplitRows(xs.buf[2:], d), ops.PackedLinearH3.pack(w3.to(cuda), b3.to(cuda)), 0,
+                       x_batch=(P, T * xs.ld), m=L * P)
+    assert rel_err(yb, xb.view(L, T, d)[:, 2:2 + P].reshape(-1, d).double() @ w3.double().T + b3.double()) < 4e-6
+    # 3x3 convolution, zero padding, into fp32 (vs ATen conv2d in fp64)
+    B, H, W, cin, cout = 2, 16, 16, 64, 256
+    xi, wc, bc = rnd(211, B, cin, H, W), rnd(212, cout, cin, 3, 3, lo=-0.05, hi=0.05), rnd(213, cout)
+    xs = ops.split_rows(xi.permute(0, 2, 3, 1).reshape(B * H * W, cin).contiguous().to(cuda))
+    wk = wc.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous()
+    taps = [(dy, dx) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+    yc = torch.empty(B * H * W, cout, device=cuda)
+    ops.conv_h3(xs, B, H, W, cin, ops.PackedLinearH3.pack(wk.to(cuda), bc.to(cuda)), taps, H, W, out=yc)
+    refc = F.conv2d(xi.double(), wc.double(), bc.double(), padding=1).permute(0, 2, 3, 1).reshape(B * H * W, cout)
+    assert rel_err(yc, refc) < 4e-6
+    # automatic mode: the fat shape takes the pair form, bit-identical to the forced run
+    m, k, n = 4096, 3968, 1024
+    x, w = rnd(214, m, k).to(cuda), rnd(215, n, k, lo=-0.1, hi=0.1).to(cuda)
+    pw, xs = ops.PackedLinearH3.pack(w, None), ops.split_rows(x)
+    forced = ops.linear_h3(xs, pw, 0).clone()
+    _capi.lib.hoisdf_debug_h3_pair(1)
+    auto = ops.linear_h3(xs, pw, 0).clone()
+    _capi.lib.hoisdf_debug_h3_pair(0)
+    single = ops.linear_h3(xs, pw, 0).clone()
+    assert torch.equal(forced, auto) and rel_err(single, forced.double()) < 2e-6
+
+
 def test_linear_h3_single_product(cuda):
     """single_pass = 1: ONE fp16 tensor-core product per K step (candidate pre-screening): 11-bit operands -> ~5e-4."""
     from hoisdf_b200 import ops
