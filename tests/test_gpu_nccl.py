@@ -68,11 +68,12 @@ def _train_worker(rank, world, port, ok):
         from hoisdf_b200 import synthetic as syn
         from hoisdf_b200.config import cfg
         from hoisdf_b200.model import get_model
-        from hoisdf_b200.train import Trainer, total_loss
+        from hoisdf_b200.train import Trainer
         dev = torch.device("cuda", rank)
         cfg.set_setting("dexycb")
         type(cfg).dataset = "ho3d"
         type(cfg).num_samp_hand, type(cfg).num_samp_obj, type(cfg).dropout = 48, 16, 0.0
+        type(cfg).random_move_dist = [0.0, 0.0, 0.0]           # no jitter: the two passes below must see the same points
         seed, B = 9, 2
         model = get_model("train", mano_buffers=syn.mano_buffers(seed))
         model.load_state_dict(syn.full_state_dict(seed, "dexycb"), strict=True)
@@ -81,26 +82,36 @@ def _train_worker(rank, world, port, ok):
         to = lambda d: {k: v.to(dev) for k, v in d.items()}    # noqa: E731
         ins, tgt = syn.train_extras(seed + rank, B, 48, 16)     # every rank trains on its OWN samples
         batch = (to({"img": syn.image_batch(seed + rank, B), **ins}), to(tgt), to(syn.camera_meta(seed + rank, B)))
-        # this rank's local gradient, without the exchange
-        model.train()
-        total, _ = total_loss(model(*batch, "train", 0, 0.0))
-        total.backward()
-        local = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.requires_grad and p.grad is not None])
-        used = [p.grad is not None for p in model.parameters() if p.requires_grad]
-        for p in model.parameters():
-            p.grad = None
+        # capture this rank's LOCAL flat gradient right before the exchange (recomputing it in a second pass would differ
+        # by the run-to-run noise of atomics / cuDNN in the backward, measured 2e-4 of the largest gradient)
+        import hoisdf_b200.train as T
+        captured = {}
+        real = T.allreduce_mean_
+
+        def spy(flat, group=None):
+            captured["local"] = flat.clone()
+            return real(flat, group)
+
+        T.allreduce_mean_ = spy
+        tr = Trainer(model, lr=1e-4)
+        tr.step(*batch, epoch_cnt=0, batch_ratio=0.0)
+        T.allreduce_mean_ = real
+        local = captured["local"]
         both = [torch.empty_like(local) for _ in range(world)]
         dist.all_gather(both, local)
         want = sum(both) / world
-        tr = Trainer(model, lr=1e-4)
-        tr.step(*batch, epoch_cnt=0, batch_ratio=0.0)
-        got = torch.cat([tr.grad[o:o + k] for (o, k), u in zip(tr.slices, used) if u])
-        good = float((got - want).abs().max()) <= 1e-5 * float(want.abs().max())
+        got = tr.grad
+        assert float((both[0] - both[1]).abs().max()) > 0          # the ranks really trained on different samples
+        gerr = float((got - want).abs().max()) / float(want.abs().max())
+        good = gerr <= 1e-6
+        print("rank %d: flat gradient vs mean of local gradients: rel err %.3e (%d values)" % (rank, gerr, got.numel()), flush=True)
         # and the replicas stay identical after the update
         mine = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
         theirs = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(theirs, mine)
-        good = good and all(torch.equal(t, mine) for t in theirs)
+        same = all(torch.equal(t, mine) for t in theirs)
+        print("rank %d: replicas identical after the step: %s" % (rank, same), flush=True)
+        good = good and same
         flag = torch.tensor([int(good)], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         ok[rank] = int(flag.item())
