@@ -93,6 +93,43 @@ class LinearFn(Function):
     def backward(ctx, dy):
         x, weight, y = ctx.saved_tensors
         m, n = dy.shape
+        k = x.shape[1]
+        if min(m, n, k) <= 16 or _DEBUG_TORCH_MATMUL:
+            return LinearFn._backward_small(ctx, dy, x, weight, y)
+        # tensor-core backward: operands prepared in two passes over dY (csrc/train_prep.cu), no host read-back
+        dy = _c2d(dy)
+        dev = dy.device
+        amax = torch.empty(1, device=dev, dtype=torch.float32)
+        scale = torch.empty(1, device=dev, dtype=torch.float32)
+        dz = ops.SplitRows.empty(m, n, dev)
+        ldt = ops.round_up(m, 8)
+        dzt = torch.empty(3, n, ldt, device=dev, dtype=torch.float16)
+        db = torch.empty(n, device=dev, dtype=torch.float32) if ctx.has_bias else None
+        _count(2)
+        check(lib.hoisdf_absmax(dy.data_ptr(), m, n, dy.stride(0), amax.data_ptr(), _stream()), "hoisdf_absmax")
+        check(lib.hoisdf_linear_bwd_prep(dy.data_ptr(), dy.stride(0), _ptr(y), 0 if y is None else y.stride(0), m, n, ctx.act,
+                                         amax.data_ptr(), dz.hi_ptr, dz.lo_ptr, dz.ld, dzt[0].data_ptr(), dzt[1].data_ptr(),
+                                         dzt[2].data_ptr(), ldt, _ptr(db), scale.data_ptr(), _stream()),
+              "hoisdf_linear_bwd_prep")
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            pwt = ops.PackedLinearH3.pack(weight.detach().t().contiguous(), None, assume_max=1.0)      # W^T (K, N)
+            dx = ops.linear_h3(dz, pwt, ACT_NONE, chunk_kb=TRAIN_CHUNK_KB)                               # dZ/s . W
+            dx = dx.mul_(scale) if dx.is_contiguous() else dx * scale
+        if ctx.needs_input_grad[1]:
+            xt = ops.SplitRows.empty(k, m, dev)
+            _count(1)
+            check(lib.hoisdf_split_rows_t(x.data_ptr(), m, k, x.stride(0) if m > 1 else max(x.stride(0), k), xt.hi_ptr,
+                                          xt.lo_ptr, xt.ld, _stream()), "hoisdf_split_rows_t")
+            pdz = ops.PackedLinearH3(dzt, None, n, m)
+            dwt = ops.linear_h3(xt, pdz, ACT_NONE, chunk_kb=TRAIN_CHUNK_KB)                             # X^T . dZ/s = dW^T / s
+            dw = dwt.t() * scale
+        return dx, dw, db, None
+
+    @staticmethod
+    def _backward_small(ctx, dy, x, weight, y):
+        """Heads with a handful of outputs (N = 1 / 3 / 6 / 10), tiny batches: torch glue + the fp32 FMA GEMM."""
+        m, n = dy.shape
         dz = dy.contiguous().clone() if ctx.act == ACT_RELU else dy.contiguous()
         db = torch.empty(n, device=dy.device, dtype=torch.float32) if ctx.has_bias else None
         if ctx.act == ACT_RELU or db is not None:

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 23
+#define HOISDF_ABI_VERSION 24
 
 enum {
   HOISDF_OK = 0,
@@ -595,6 +595,19 @@ int hoisdf_softmax_rows_fwd(const float* s, int64_t lds, int64_t rows, int64_t c
                             int64_t mask_rows, float* p, int64_t ldp, void* stream);
 int hoisdf_softmax_rows_bwd(const float* p, int64_t ldp, const float* dp, int64_t lddp, int64_t rows, int64_t cols, float* ds,
                             int64_t ldds, void* stream);
+/* Operand preparation for the tensor-core backward of a Linear (csrc/train_prep.cu): dX = dZ . W and dW^T = X^T . dZ run on
+ * hoisdf_linear_h3_fwd with
+ *   hoisdf_absmax: out[0] = max |x| over a (rows, cols; pitch ld) matrix (device scalar);
+ *   hoisdf_linear_bwd_prep: dZ = dY * [Y > 0] (act == HOISDF_ACT_RELU), s = 2^(ceil(log2(amax)) - 3) computed on the device
+ *     (written to scale_out), then in ONE pass dZ / s in split-half format (dz_hi / dz_lo, pitch ld_dz: the x operand of the dX
+ *     GEMM), (dZ / s)^T as the three hoisdf_pack_h3 planes (dzt_*, (n, ld_dzt >= m): the w operand of the dW GEMM) and
+ *     db[c] = sum_r dZ[r, c] (may be NULL; atomic adds);
+ *   hoisdf_split_rows_t: X (m, k) fp32 -> X^T in split-half format, planes (k, ldh >= m). */
+int hoisdf_absmax(const float* x, int64_t rows, int64_t cols, int64_t ld, float* out, void* stream);
+int hoisdf_linear_bwd_prep(const float* dy, int64_t lddy, const float* y, int64_t ldy, int64_t m, int64_t n, int32_t act,
+                           const float* amax, uint16_t* dz_hi, uint16_t* dz_lo, int64_t ld_dz, uint16_t* dzt_a, uint16_t* dzt_b,
+                           uint16_t* dzt_c, int64_t ld_dzt, float* db, float* scale_out, void* stream);
+int hoisdf_split_rows_t(const float* x, int64_t m, int64_t k, int64_t ldx, uint16_t* hi, uint16_t* lo, int64_t ldh, void* stream);
 int64_t hoisdf_tokens_bwd_workspace_bytes(int64_t batch, int64_t p);
 int hoisdf_tokens_bwd(const float* d_tokens, int64_t s_total, int64_t t0, const float* fea, int64_t ld_fea, const float* sdf,
                       const float* beta, int64_t batch, int64_t p, float* d_fea, int64_t ld_dfea, float* d_sdf, float* d_beta,
