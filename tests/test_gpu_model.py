@@ -107,7 +107,35 @@ def test_sdf_infer_c_entry_equals_python_orchestration(setup, monkeypatch):
     monkeypatch.setattr(type(cfg), "native_sdf_infer", True)
     with pytest.raises(RuntimeError, match="fewer than num_points"), torch.no_grad():
         model.sdf_infer(model._ctx(pyr), meta["mano_root"], meta["cam_intr"], tiny, 3.1, 96, "hand")
-    # workspace contract of the C entry
+    # workspace contract of the C entry: a too-small row budget is refused before anything is launched
+    import ctypes as C
+    from hoisdf_b200 import ops
+    plan = model.plan_candidates(meta["mano_root"], meta["cam_intr"], meta["bbox_hand"], 3.1)
+    host = plan.host_offsets()
+    a = _capi.SdfInferArgs()
+    ctx = model._ctx(pyr)
+    sdfin, packed = model.linear_sdfin.packed(), model.hand_sdf_decoder.packed()
+    gm, gm16 = ops.make_pyramid(ctx.gmaps, cfg.input_img_shape), ops._pyramid_h(ctx.gmaps16, cfg.input_img_shape)
+    small = 1024
+    nbytes = int(_capi.lib.hoisdf_sdf_infer_workspace_bytes(2, small, 96, 1024, 64))
+    ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    outs = [torch.empty(2 * 96 * 30, device=dev) for _ in range(8)]
+    a.center, a.cam_intr, a.bbox = plan.center.data_ptr(), plan.cam_intr.data_ptr(), plan.bbox.data_ptr()
+    a.sdf_scale, a.bins, a.batch, a.num_points, a.margin, a.clamp = 3.1, 64, 2, 96, 1024, 0.15
+    a.gmaps, a.gmaps16, a.bias0 = C.addressof(gm), C.addressof(gm16), sdfin[0].b.data_ptr()
+    s1 = sdfin[1].h3
+    a.s1_a, a.s1_b, a.s1_c, a.ld_s1, a.b_s1, a.s1_scale = s1.plane_ptr(0), s1.plane_ptr(1), s1.plane_ptr(2), s1.ld, \
+        sdfin[1].b.data_ptr(), 1.0
+    a.dec, a.workspace, a.workspace_bytes, a.max_rows = C.addressof(packed.struct_h3), ws.data_ptr(), nbytes, small
+    a.planned, a.chunk_counts, a.offsets, a.host_offsets = 1, plan.counts.data_ptr(), plan.offsets.data_ptr(), host.data_ptr()
+    a.points, a.sdf, a.posenc, a.sel_index, a.status_flag, a.screen_err, a.screen_gap, a.verified = \
+        (t.data_ptr() for t in outs)
+    assert int(host[-1]) > small
+    assert _capi.lib.hoisdf_sdf_infer_fwd(C.byref(a), ops._stream()) == _capi.E_WORKSPACE
+    a.workspace_bytes = 1024
+    assert _capi.lib.hoisdf_sdf_infer_fwd(C.byref(a), ops._stream()) == _capi.E_WORKSPACE
+    a.workspace = None
+    assert _capi.lib.hoisdf_sdf_infer_fwd(C.byref(a), ops._stream()) == -1
     assert _capi.lib.hoisdf_sdf_infer_workspace_bytes(2, 1 << 16, 96, 1024, 64) > 0
     assert _capi.lib.hoisdf_sdf_infer_keep(96, 1024) == 1120 and _capi.lib.hoisdf_sdf_infer_keep(8000, 1024) == 8192
 

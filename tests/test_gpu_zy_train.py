@@ -96,6 +96,45 @@ def test_weight_norm_gather_layernorm_tokens_fns(cuda):
     _close(bd.grad, br.grad, 1e-4, "dbeta")
 
 
+def test_backward_prep_kernels(cuda):
+    """csrc/train_prep.cu: hoisdf_absmax, hoisdf_linear_bwd_prep (ReLU mask, device-side power-of-two scale, split-half dZ,
+    transposed weight planes of dZ, bias sums) and hoisdf_split_rows_t, each against its definition -- incl. ragged sizes,
+    pitched inputs, an all-zero gradient and a gradient 1e-12 in magnitude (the scale keeps it out of fp16's subnormals)."""
+    from hoisdf_b200 import _capi, ops
+    lib = _capi.lib
+    st = torch.cuda.current_stream().cuda_stream
+    for m, n, mag in ((1000, 223, 1e-3), (33, 512, 1e-12), (4097, 60, 7.0), (64, 64, 0.0)):
+        dy = (_rnd(1, m, n + 5) * mag).to(cuda)[:, :n]                  # pitched view
+        y = _rnd(2, m, n).to(cuda)
+        amax, scale = torch.empty(1, device=cuda), torch.empty(1, device=cuda)
+        assert lib.hoisdf_absmax(dy.data_ptr(), m, n, dy.stride(0), amax.data_ptr(), st) == 0
+        assert float(amax) == float(dy.abs().max())
+        dz = ops.SplitRows.empty(m, n, cuda)
+        ldt = ops.round_up(m, 8)
+        dzt = torch.zeros(3, n, ldt, device=cuda, dtype=torch.float16)
+        db = torch.empty(n, device=cuda)
+        assert lib.hoisdf_linear_bwd_prep(dy.data_ptr(), dy.stride(0), y.data_ptr(), y.stride(0), m, n, 1, amax.data_ptr(),
+                                          dz.hi_ptr, dz.lo_ptr, dz.ld, dzt[0].data_ptr(), dzt[1].data_ptr(), dzt[2].data_ptr(),
+                                          ldt, db.data_ptr(), scale.data_ptr(), st) == 0
+        ref = (dy * (y > 0)).double().cpu()
+        s = float(scale)
+        assert s > 0 and (mag == 0.0 or 4.0 < float(dy.abs().max()) / s <= 8.0) and float(torch.tensor(s).log2()) % 1 == 0
+        tol = 2.0 ** -21 * max(float(ref.abs().max()), 1e-300)
+        assert float((dz.float().cpu().double() * s - ref).abs().max()) <= tol
+        a, b, c = (dzt[i, :, :m].float().cpu().double() for i in range(3))
+        # planes in hoisdf_pack_h3's format: B + C / 2^11 reproduces the value, A = B * 2^11 (B rounds only where A / 2^11
+        # falls into fp16's subnormal range: below 2^-24 absolute)
+        assert float(((b + c / 2048.0) * s - ref.t()).abs().max()) <= tol
+        assert float((a / 2048.0 - b).abs().max()) <= 2.0 ** -24
+        assert float((db.cpu().double() - ref.sum(0)).abs().max()) <= 1e-5 * max(float(ref.abs().sum(0).max()), 1e-300)
+    x = _rnd(3, 777, 300).to(cuda)
+    xt = ops.SplitRows.empty(300, 777, cuda)
+    assert lib.hoisdf_split_rows_t(x.data_ptr(), 777, 300, x.stride(0), xt.hi_ptr, xt.lo_ptr, xt.ld, st) == 0
+    assert float((xt.float() - x.t()).abs().max()) <= 2.0 ** -21 * float(x.abs().max())
+    assert lib.hoisdf_split_rows_t(x.data_ptr(), 777, 300, 100, xt.hi_ptr, xt.lo_ptr, xt.ld, st) == -2      # ldx < k
+    assert lib.hoisdf_absmax(None, 1, 1, 1, amax.data_ptr(), st) == -1
+
+
 @pytest.mark.parametrize("lq,lk,masked,kv_valid", [(128, 128, False, None), (17, 17, True, None), (17, 200, False, 150)])
 def test_attention_fn(cuda, lq, lk, masked, kv_valid):
     """softmax(q k^T / 8 [+ mask]) v over 4 heads of 64: tcgen05 flash forward (SIMT with a dense mask), batched fp32
