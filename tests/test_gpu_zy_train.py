@@ -135,7 +135,8 @@ def test_backward_prep_kernels(cuda):
     assert lib.hoisdf_absmax(None, 1, 1, 1, amax.data_ptr(), st) == -1
 
 
-@pytest.mark.parametrize("lq,lk,masked,kv_valid", [(128, 128, False, None), (17, 17, True, None), (17, 200, False, 150)])
+@pytest.mark.parametrize("lq,lk,masked,kv_valid", [(128, 128, False, None), (17, 17, True, None), (17, 200, False, 150),
+                                                     (300, 333, False, None), (257, 800, False, 700)])
 def test_attention_fn(cuda, lq, lk, masked, kv_valid):
     """softmax(q k^T / 8 [+ mask]) v over 4 heads of 64: tcgen05 flash forward (SIMT with a dense mask), batched fp32
     backward, vs fp64 autograd."""
