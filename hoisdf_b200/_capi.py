@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhoisdf_b200.so")
 
-ABI_VERSION = 24
+ABI_VERSION = 25
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2      # ACT_SIGMOID: hoisdf_linear_narrow_split_fwd only
 GATHER_CONCAT, GATHER_SUM = 0, 1
 
@@ -181,6 +181,8 @@ SIGNATURES = {
     "hoisdf_absmax": (C.c_int, [vp, i64, i64, i64, vp, vp]),
     "hoisdf_linear_bwd_prep": (C.c_int, [vp, i64, vp, i64, i64, i64, i32, vp, vp, vp, i64, vp, vp, vp, i64, vp, vp, vp]),
     "hoisdf_split_rows_t": (C.c_int, [vp, i64, i64, i64, vp, vp, i64, vp]),
+    "hoisdf_softmax_dropout_rows_fwd": (C.c_int, [vp, i64, i64, i64, i64, vp, i64, vp, i64, vp, i64, f32, C.c_uint64, vp]),
+    "hoisdf_softmax_dropout_rows_bwd": (C.c_int, [vp, i64, vp, i64, i64, i64, vp, i64, f32, C.c_uint64, vp]),
     "hoisdf_tokens_bwd_workspace_bytes": (i64, [i64, i64]),
     "hoisdf_tokens_bwd": (C.c_int, [vp, i64, i64, vp, i64, vp, vp, i64, i64, vp, i64, vp, vp, i32, vp, i64, vp]),
     "hoisdf_vote_loss_bwd": (C.c_int, [vp, vp, vp, vp, i64, i64, i64, f32, f32, f32, f32, vp, vp, vp, vp]),

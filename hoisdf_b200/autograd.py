@@ -15,7 +15,8 @@ Every Function calls the C ABI for the forward AND the backward; PyTorch only pr
   AttentionFn     softmax(q k^T / 8 [mask]) v   forward: tcgen05 flash kernel (hoisdf_attention_fwd) when there is no dropout on the
                                                  probabilities, else the materialised form; backward: hoisdf_gemm_f32_batched +
                                                  hoisdf_softmax_rows_fwd / _bwd per (sample, head) -- fp32 SIMT, the S x S
-                                                 probabilities are recomputed, not stored
+                                                 probabilities are recomputed, not stored; dropout on the probabilities through
+                                                 hoisdf_softmax_dropout_rows_fwd / _bwd (hashed keep decisions: only a seed is kept)
   TokensFn        token assembly + sdf_activation  hoisdf_tokens_fwd / hoisdf_tokens_bwd (own-field blocks only: upstream detaches
                                                  the SDF values and the cross-field tokens, model.py:483-484,536,555)
 """
@@ -249,13 +250,14 @@ class AttentionFn(Function):
             assert t.stride(1) == 1 and t.shape[1] == d
         dev = q.device
         out = torch.empty(batch * lq, d, device=dev, dtype=torch.float32)
-        keep = None
+        seed = 0
         if p_drop > 0.0:
-            # materialised form: P (B, H, Lq, Lk) is needed for the dropout mask
-            p = AttentionFn._probs(q, k, batch, heads, lq, lk, mask, kv_valid)
-            keep = (torch.rand_like(p) >= p_drop)
-            p = p * keep * (1.0 / (1.0 - p_drop))
-            _gemm_batched(p.data_ptr(), lk, 0, heads * lq * lk, lq * lk, v.data_ptr(), v.stride(0), 0, lk * v.stride(0), 64,
+            # materialised form: the dropped probabilities Pd (B, H, Lq, Lk) multiply V.  The keep decisions are a hash of
+            # (seed, position): nothing but the seed is kept for the backward (CPU generator: no device sync, reproducible
+            # under torch.manual_seed)
+            seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64))
+            pd = AttentionFn._probs(q, k, batch, heads, lq, lk, mask, kv_valid, p_drop, seed)[1]
+            _gemm_batched(pd.data_ptr(), lk, 0, heads * lq * lk, lq * lk, v.data_ptr(), v.stride(0), 0, lk * v.stride(0), 64,
                           out.data_ptr(), d, lq * d, 64, lq, 64, lk, 1.0, batch, heads)
         else:
             vv = v
@@ -263,30 +265,37 @@ class AttentionFn(Function):
                 raise ValueError("attention: k and v must share their row pitch")
             ops.attention(q, q.stride(0), k, vv, k.stride(0), out, d, batch, heads, lq, lk, kv_valid=kv_valid, mask=mask,
                           tensor_cores=(mask is None))
-        ctx.save_for_backward(q, k, v, mask, keep)
-        ctx.geom = (batch, heads, lq, lk, kv_valid, p_drop)
+        ctx.save_for_backward(q, k, v, mask)
+        ctx.geom = (batch, heads, lq, lk, kv_valid, p_drop, seed)
         return out
 
     @staticmethod
-    def _probs(q, k, batch, heads, lq, lk, mask, kv_valid):
+    def _probs(q, k, batch, heads, lq, lk, mask, kv_valid, p_drop=0.0, seed=0, want_p=False):
+        """-> (P or None, Pd): softmax(q k^T / 8 [mask]) per (sample, head) and, with dropout, its dropped / rescaled copy.
+        Without dropout Pd is P.  The scores are overwritten in place."""
         s = torch.empty(batch, heads, lq, lk, device=q.device, dtype=torch.float32)
         _gemm_batched(q.data_ptr(), q.stride(0), 0, lq * q.stride(0), 64, k.data_ptr(), k.stride(0), 1, lk * k.stride(0), 64,
                       s.data_ptr(), lk, heads * lq * lk, lq * lk, lq, lk, 64, 0.125, batch, heads)
+        rows, valid = batch * heads * lq, lk if kv_valid is None else kv_valid
         _count(1)
-        check(lib.hoisdf_softmax_rows_fwd(s.data_ptr(), lk, batch * heads * lq, lk, lk if kv_valid is None else kv_valid,
-                                          _ptr(mask), 0 if mask is None else lq, s.data_ptr(), lk, _stream()),
-              "hoisdf_softmax_rows_fwd")
-        return s
+        if p_drop <= 0.0:
+            check(lib.hoisdf_softmax_rows_fwd(s.data_ptr(), lk, rows, lk, valid, _ptr(mask), 0 if mask is None else lq,
+                                              s.data_ptr(), lk, _stream()), "hoisdf_softmax_rows_fwd")
+            return s, s
+        pd = torch.empty_like(s) if want_p else s
+        check(lib.hoisdf_softmax_dropout_rows_fwd(s.data_ptr(), lk, rows, lk, valid, _ptr(mask), 0 if mask is None else lq,
+                                                  s.data_ptr() if want_p else None, lk, pd.data_ptr(), lk, float(p_drop),
+                                                  int(seed), _stream()), "hoisdf_softmax_dropout_rows_fwd")
+        return (s if want_p else None), pd
 
     @staticmethod
     def backward(ctx, dout):
-        q, k, v, mask, keep = ctx.saved_tensors
-        batch, heads, lq, lk, kv_valid, p_drop = ctx.geom
+        q, k, v, mask = ctx.saved_tensors
+        batch, heads, lq, lk, kv_valid, p_drop, seed = ctx.geom
         d = heads * 64
         dev = q.device
         dout = dout.contiguous()
-        p = AttentionFn._probs(q, k, batch, heads, lq, lk, mask, kv_valid)
-        pd = p if keep is None else p * keep * (1.0 / (1.0 - p_drop))        # what multiplied V in the forward
+        p, pd = AttentionFn._probs(q, k, batch, heads, lq, lk, mask, kv_valid, p_drop, seed, want_p=True)
         dq = torch.empty(batch * lq, d, device=dev, dtype=torch.float32)
         dk = torch.empty(batch * lk, d, device=dev, dtype=torch.float32)
         dv = torch.empty(batch * lk, d, device=dev, dtype=torch.float32)
@@ -294,16 +303,18 @@ class AttentionFn(Function):
         # dV = Pd^T dO
         _gemm_batched(pd.data_ptr(), lk, 1, hh, lq * lk, dout.data_ptr(), d, 0, lq * d, 64, dv.data_ptr(), d, lk * d, 64,
                       lk, 64, lq, 1.0, batch, heads)
-        # dPd = dO V^T
-        dp = torch.empty(batch, heads, lq, lk, device=dev, dtype=torch.float32)
+        # dPd = dO V^T (over the Pd buffer when it is a separate one)
+        dp = pd if pd is not p else torch.empty(batch, heads, lq, lk, device=dev, dtype=torch.float32)
         _gemm_batched(dout.data_ptr(), d, 0, lq * d, 64, v.data_ptr(), v.stride(0), 1, lk * v.stride(0), 64, dp.data_ptr(),
                       lk, hh, lq * lk, lq, lk, 64, 1.0, batch, heads)
-        if keep is not None:
-            dp = dp * keep * (1.0 / (1.0 - p_drop))
-        # dS = P * (dP - sum_j dP_j P_j)
+        # dS = P * (g - sum_j g_j P_j), g = dPd with the dropout mask folded in
         _count(1)
-        check(lib.hoisdf_softmax_rows_bwd(p.data_ptr(), lk, dp.data_ptr(), lk, batch * heads * lq, lk, dp.data_ptr(), lk,
-                                          _stream()), "hoisdf_softmax_rows_bwd")
+        if p_drop > 0.0:
+            check(lib.hoisdf_softmax_dropout_rows_bwd(p.data_ptr(), lk, dp.data_ptr(), lk, batch * heads * lq, lk, dp.data_ptr(),
+                                                      lk, float(p_drop), int(seed), _stream()), "hoisdf_softmax_dropout_rows_bwd")
+        else:
+            check(lib.hoisdf_softmax_rows_bwd(p.data_ptr(), lk, dp.data_ptr(), lk, batch * heads * lq, lk, dp.data_ptr(), lk,
+                                              _stream()), "hoisdf_softmax_rows_bwd")
         # dQ = dS K / 8, dK = dS^T Q / 8
         _gemm_batched(dp.data_ptr(), lk, 0, hh, lq * lk, k.data_ptr(), k.stride(0), 0, lk * k.stride(0), 64, dq.data_ptr(),
                       d, lq * d, 64, lq, 64, lk, 0.125, batch, heads)

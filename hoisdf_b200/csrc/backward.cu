@@ -358,6 +358,64 @@ softmax_rows_bwd_kernel(const float* __restrict__ p, int64_t ldp, const float* d
 }
 
 
+// ---- nn.MultiheadAttention's dropout on the attention probabilities (upstream cfg.dropout = 0.1, transformer.py layers)
+// without materialising a mask: keep(r, c) is a counter-based hash of (seed, r * cols + c), so the backward regenerates the
+// very same decisions from the seed.  The forward emits the dropped, rescaled probabilities pd = keep ? p / (1 - q) : 0 (and
+// optionally p itself); the backward folds the mask into the softmax derivative:
+//   g = keep ? dpd / (1 - q) : 0;   ds = p * (g - sum_j g_j p_j).
+__host__ __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t idx, float p_drop) {
+  uint64_t z = seed + (idx + 1) * 0x9E3779B97F4A7C15ull;          // splitmix64 finaliser
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return static_cast<float>(z >> 40) * (1.0f / 16777216.0f) >= p_drop;     // 24 uniform bits
+}
+
+__global__ void __launch_bounds__(256)
+softmax_dropout_rows_fwd_kernel(const float* s, int64_t lds, int64_t rows, int cols, int valid,
+                                const uint8_t* __restrict__ mask, int64_t mask_rows, float* p, int64_t ldp, float* pd,
+                                int64_t ldpd, float p_drop, uint64_t seed) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const uint8_t* mrow = mask != nullptr ? mask + (r % mask_rows) * cols : nullptr;
+  float mx = -3.402823466e+38f;
+  for (int c = lane; c < valid; c += 32)
+    if (mrow == nullptr || mrow[c] == 0) mx = fmaxf(mx, s[r * lds + c]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int c = lane; c < valid; c += 32)
+    if (mrow == nullptr || mrow[c] == 0) sum += expf(s[r * lds + c] - mx);
+  sum = warp_sum(sum);
+  const float keep_scale = 1.0f / (1.0f - p_drop);
+  for (int c = lane; c < cols; c += 32) {
+    const bool on = c < valid && (mrow == nullptr || mrow[c] == 0);
+    const float pv = on ? expf(s[r * lds + c] - mx) / sum : 0.f;      // (s may alias p or pd: read before either write)
+    const bool keep = dropout_keep(seed, static_cast<uint64_t>(r) * cols + c, p_drop);
+    if (p != nullptr) p[r * ldp + c] = pv;
+    pd[r * ldpd + c] = keep ? pv * keep_scale : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+softmax_dropout_rows_bwd_kernel(const float* __restrict__ p, int64_t ldp, const float* dpd, int64_t lddp, int64_t rows, int cols,
+                                float* ds, int64_t ldds, float p_drop, uint64_t seed) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float keep_scale = 1.0f / (1.0f - p_drop);
+  float dot = 0.f;
+  for (int c = lane; c < cols; c += 32) {
+    const float g = dropout_keep(seed, static_cast<uint64_t>(r) * cols + c, p_drop) ? dpd[r * lddp + c] * keep_scale : 0.f;
+    dot = fmaf(g, p[r * ldp + c], dot);
+  }
+  dot = warp_sum(dot);
+  for (int c = lane; c < cols; c += 32) {
+    const float g = dropout_keep(seed, static_cast<uint64_t>(r) * cols + c, p_drop) ? dpd[r * lddp + c] * keep_scale : 0.f;
+    ds[r * ldds + c] = p[r * ldp + c] * (g - dot);
+  }
+}
+
 // torch.optim.AdamW (upstream common/base.py:68: lr 1e-4, default betas / eps / weight_decay 0.01), one fused pass over a
 // flat parameter buffer, the arithmetic in the order PyTorch's single-tensor implementation applies it
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
@@ -665,6 +723,29 @@ HOISDF_API int hoisdf_softmax_rows_bwd(const float* p, int64_t ldp, const float*
   if (rows <= 0 || cols <= 0 || cols > 0x7fffffffLL || ldp < cols || lddp < cols || ldds < cols) return HOISDF_E_SHAPE;
   HOISDF_LAUNCH(softmax_rows_bwd_kernel, static_cast<unsigned>(ceil_div(rows, 8)), 256, static_cast<cudaStream_t>(stream), p,
                 ldp, dp, lddp, rows, static_cast<int>(cols), ds, ldds);
+  return launch_status();
+}
+
+HOISDF_API int hoisdf_softmax_dropout_rows_fwd(const float* s, int64_t lds, int64_t rows, int64_t cols, int64_t valid,
+                                               const uint8_t* mask, int64_t mask_rows, float* p, int64_t ldp, float* pd,
+                                               int64_t ldpd, float p_drop, uint64_t seed, void* stream) {
+  if (s == nullptr || pd == nullptr) return HOISDF_E_NULL;
+  if (rows <= 0 || cols <= 0 || cols > 0x7fffffffLL || valid <= 0 || valid > cols || lds < cols || ldpd < cols ||
+      (p != nullptr && ldp < cols) || !(p_drop >= 0.f && p_drop < 1.f))
+    return HOISDF_E_SHAPE;
+  if (mask != nullptr && mask_rows <= 0) return HOISDF_E_SHAPE;
+  HOISDF_LAUNCH(softmax_dropout_rows_fwd_kernel, static_cast<unsigned>(ceil_div(rows, 8)), 256, static_cast<cudaStream_t>(stream),
+                s, lds, rows, static_cast<int>(cols), static_cast<int>(valid), mask, mask_rows, p, ldp, pd, ldpd, p_drop, seed);
+  return launch_status();
+}
+
+HOISDF_API int hoisdf_softmax_dropout_rows_bwd(const float* p, int64_t ldp, const float* dpd, int64_t lddp, int64_t rows,
+                                               int64_t cols, float* ds, int64_t ldds, float p_drop, uint64_t seed, void* stream) {
+  if (p == nullptr || dpd == nullptr || ds == nullptr) return HOISDF_E_NULL;
+  if (rows <= 0 || cols <= 0 || cols > 0x7fffffffLL || ldp < cols || lddp < cols || ldds < cols || !(p_drop >= 0.f && p_drop < 1.f))
+    return HOISDF_E_SHAPE;
+  HOISDF_LAUNCH(softmax_dropout_rows_bwd_kernel, static_cast<unsigned>(ceil_div(rows, 8)), 256, static_cast<cudaStream_t>(stream),
+                p, ldp, dpd, lddp, rows, static_cast<int>(cols), ds, ldds, p_drop, seed);
   return launch_status();
 }
 

@@ -16,6 +16,7 @@ What runs where:
 """
 from __future__ import annotations
 
+import os
 import random
 from typing import Dict, Optional
 
@@ -30,6 +31,10 @@ from .nets.loss import joint_vote_losses, render_gaussian_heatmap
 from .nets.mano_torch import mano_head_train
 
 ACT_NONE, ACT_RELU = ops.ACT_NONE, ops.ACT_RELU
+# encoder layout in training: channels_last activations let cuDNN's tensor-op convolutions skip their NCHW <-> NHWC
+# conversion kernels and make the pyramid's NHWC view free: measured 280 -> 247 ms per step (HOISDF_TRAIN_CL=0: NCHW).
+# (PyTorch's native BatchNorm kernels instead of cuDNN's were measured too: 7-15 ms slower.)
+_ENC_CHANNELS_LAST = os.environ.get("HOISDF_TRAIN_CL", "1") != "0"
 
 
 def _drop(x, p):
@@ -188,6 +193,8 @@ def forward_train(model, inputs, targets, meta_info, epoch_cnt=1e8, batch_ratio=
     c = cfg.ClampingDistance
     loss, out = {}, {}
 
+    if _ENC_CHANNELS_LAST:
+        img = img.contiguous(memory_format=torch.channels_last)
     img_feat, skips = model.backbone_net(img)
     pyramid, decoder_out = model.decoder_net(img_feat, skips)
     maps = [pyramid[name].permute(0, 2, 3, 1).contiguous() for name in cfg.mutliscale_layers]     # NHWC, once

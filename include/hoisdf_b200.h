@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 24
+#define HOISDF_ABI_VERSION 25
 
 enum {
   HOISDF_OK = 0,
@@ -608,6 +608,15 @@ int hoisdf_linear_bwd_prep(const float* dy, int64_t lddy, const float* y, int64_
                            const float* amax, uint16_t* dz_hi, uint16_t* dz_lo, int64_t ld_dz, uint16_t* dzt_a, uint16_t* dzt_b,
                            uint16_t* dzt_c, int64_t ld_dzt, float* db, float* scale_out, void* stream);
 int hoisdf_split_rows_t(const float* x, int64_t m, int64_t k, int64_t ldx, uint16_t* hi, uint16_t* lo, int64_t ldh, void* stream);
+/* Row softmax with nn.MultiheadAttention's dropout on the probabilities (p_drop in [0, 1)) and its backward, without a stored
+ * mask: keep(r, c) is a counter-based hash of (seed, r * cols + c).  Forward: p (may be NULL) as hoisdf_softmax_rows_fwd,
+ * pd = keep ? p / (1 - p_drop) : 0 (s may alias p or pd).  Backward: ds = p * (g - sum_j g_j p_j) with
+ * g = keep ? dpd / (1 - p_drop) : 0 (ds may alias dpd). */
+int hoisdf_softmax_dropout_rows_fwd(const float* s, int64_t lds, int64_t rows, int64_t cols, int64_t valid, const uint8_t* mask,
+                                    int64_t mask_rows, float* p, int64_t ldp, float* pd, int64_t ldpd, float p_drop, uint64_t seed,
+                                    void* stream);
+int hoisdf_softmax_dropout_rows_bwd(const float* p, int64_t ldp, const float* dpd, int64_t lddp, int64_t rows, int64_t cols,
+                                    float* ds, int64_t ldds, float p_drop, uint64_t seed, void* stream);
 int64_t hoisdf_tokens_bwd_workspace_bytes(int64_t batch, int64_t p);
 int hoisdf_tokens_bwd(const float* d_tokens, int64_t s_total, int64_t t0, const float* fea, int64_t ld_fea, const float* sdf,
                       const float* beta, int64_t batch, int64_t p, float* d_fea, int64_t ld_dfea, float* d_sdf, float* d_beta,

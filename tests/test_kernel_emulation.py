@@ -718,6 +718,8 @@ def transformer_backward_lib():
     lib.hoisdf_layernorm_bwd.argtypes = [vp, vp, vp, i64, i64, vp, vp, vp, vp, i32, vp]
     lib.hoisdf_softmax_rows_fwd.argtypes = [vp, i64, i64, i64, i64, vp, i64, vp, i64, vp]
     lib.hoisdf_softmax_rows_bwd.argtypes = [vp, i64, vp, i64, i64, i64, vp, i64, vp]
+    lib.hoisdf_softmax_dropout_rows_fwd.argtypes = [vp, i64, i64, i64, i64, vp, i64, vp, i64, vp, i64, C.c_float, C.c_uint64, vp]
+    lib.hoisdf_softmax_dropout_rows_bwd.argtypes = [vp, i64, vp, i64, i64, i64, vp, i64, C.c_float, C.c_uint64, vp]
     return lib
 
 
@@ -749,6 +751,32 @@ def test_layernorm_and_softmax_backward_kernels_on_the_emulator():
     ds = dp.copy()
     assert lib.hoisdf_softmax_rows_bwd(ptr(p), c, ptr(ds), c, r, c, ptr(ds), c, None) == 0          # in place
     assert np.abs(ds[:, :valid] - s.grad.numpy()[:, :valid]).max() < 1e-6 and not ds[:, valid:].any()
+
+
+def test_softmax_dropout_kernels_on_the_emulator():
+    """hoisdf_softmax_dropout_rows_fwd / _bwd: nn.MultiheadAttention's dropout on the probabilities with hashed keep decisions.
+    The forward's pd is p * keep / (1 - q) with a keep rate of 1 - q, reproducible from the seed and different for another
+    seed; the backward equals autograd of softmax -> mask -> scale for exactly that mask."""
+    lib = transformer_backward_lib()
+    t = torch.from_numpy
+    r, c, valid, q = 64, 200, 180, 0.1
+    s = t(rnd(7, r, c, lo=-3, hi=3)).requires_grad_()
+    p, pd, pd2, pd3 = (np.zeros((r, c), np.float32) for _ in range(4))
+    args = (ptr(f32(s.detach())), c, r, c, valid, None, 0)
+    assert lib.hoisdf_softmax_dropout_rows_fwd(*args, ptr(p), c, ptr(pd), c, q, 1234, None) == 0
+    assert lib.hoisdf_softmax_dropout_rows_fwd(*args, None, 0, ptr(pd2), c, q, 1234, None) == 0
+    assert lib.hoisdf_softmax_dropout_rows_fwd(*args, None, 0, ptr(pd3), c, q, 1235, None) == 0
+    p_ref = torch.softmax(s[:, :valid], -1).detach().numpy()
+    assert np.abs(p[:, :valid] - p_ref).max() < 1e-6 and not p[:, valid:].any() and not pd[:, valid:].any()
+    keep = pd[:, :valid] != 0
+    assert abs(keep.mean() - (1 - q)) < 0.02 and np.array_equal(pd, pd2) and (pd3 != pd).any()
+    assert np.abs(pd[:, :valid] - p_ref * keep / (1 - q)).max() < 1e-6
+    dpd = rnd(8, r, c)
+    (torch.softmax(s[:, :valid], -1) * t(keep.astype(np.float32)) / (1 - q) * t(dpd[:, :valid])).sum().backward()
+    ds = dpd.copy()
+    assert lib.hoisdf_softmax_dropout_rows_bwd(ptr(p), c, ptr(ds), c, r, c, ptr(ds), c, q, 1234, None) == 0      # in place
+    assert np.abs(ds[:, :valid] - s.grad.numpy()[:, :valid]).max() < 1e-6 and not ds[:, valid:].any()
+    assert lib.hoisdf_softmax_dropout_rows_fwd(*args, None, 0, ptr(pd), c, 1.0, 1, None) == -2                    # p_drop < 1
 
 
 def test_encoder_layer_backward_chain_on_the_emulator():
