@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhoisdf_b200.so")
 
-ABI_VERSION = 25
+ABI_VERSION = 26
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2      # ACT_SIGMOID: hoisdf_linear_narrow_split_fwd only
 GATHER_CONCAT, GATHER_SUM = 0, 1
 
@@ -113,6 +113,18 @@ class EncoderArgs(C.Structure):
                 ("workspace", vp), ("workspace_bytes", i64)]
 
 
+class DecoderLayer(C.Structure):
+    _fields_ = [(n, H3Linear) for n in ("sa_qk", "sa_v", "sa_out", "ca_q", "ca_kv", "ca_out", "lin1", "lin2")] + \
+               [(n, vp) for n in ("norm1_g", "norm1_b", "norm2_g", "norm2_b", "norm3_g", "norm3_b")]
+
+
+class DecoderArgs(C.Structure):
+    _fields_ = [("layers", C.POINTER(DecoderLayer)), ("num_layers", i32), ("heads", i32), ("d_ff", i64),
+                ("norm_g", vp), ("norm_b", vp), ("batch", i64), ("queries", i64), ("seq", i64), ("kv_valid", i64),
+                ("query_pos", vp), ("tgt_mask", vp), ("memory_hi", vp), ("memory_lo", vp), ("ld_memory", i64),
+                ("hs", vp), ("workspace", vp), ("workspace_bytes", i64)]
+
+
 class ManoModel(C.Structure):
     _fields_ = [(n, vp) for n in ("shapedirs", "posedirs", "v_template", "j_regressor", "weights", "hands_mean")]
 
@@ -161,6 +173,8 @@ SIGNATURES = {
     "hoisdf_add_layernorm_split_fwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp, vp, i64, vp, vp, i64, vp]),
     "hoisdf_encoder_workspace_bytes": (i64, [i64, i64, i64, i32]),
     "hoisdf_encoder_fwd": (C.c_int, [C.POINTER(EncoderArgs), vp]),
+    "hoisdf_decoder_workspace_bytes": (i64, [i64, i64, i64, i64, i32]),
+    "hoisdf_decoder_fwd": (C.c_int, [C.POINTER(DecoderArgs), vp]),
     "hoisdf_vote_joints_fwd": (C.c_int, [vp, vp, vp, i64, i64, i64, vp, vp]),
     "hoisdf_mano_fwd": (C.c_int, [C.POINTER(ManoModel), vp, vp, i64, vp, vp, vp]),
     "hoisdf_mano_aa_fwd": (C.c_int, [C.POINTER(ManoModel), vp, vp, i64, vp, vp, vp]),

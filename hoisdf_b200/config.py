@@ -84,6 +84,7 @@ class Config:
     native_sdf_infer = True
     # likewise the transformer encoder stacks: hoisdf_encoder_fwd (csrc/transformer.cu) runs all layers in one C call
     native_encoder = True
+    native_decoder = True       # and the 17-query decoder stack: hoisdf_decoder_fwd
     # linear_sdfin layer 0 applied to the pyramid (Model: PyramidContext.gmaps) on the FP16x3 GEMM with a TMEM drain
     # every `projection_chunk_kb` K blocks instead of the fp32 FMA kernel (3.2 ms -> 0.6 ms at batch 32)
     tc_projection = True

@@ -39,6 +39,38 @@ EncLayout enc_layout(int64_t batch, int64_t seq, int64_t d_ff, int64_t heads) {
   return L;
 }
 
+__global__ void add_rows_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = a[i] + b[i];
+}
+
+struct DecLayout { int64_t tin[2], add, xs, qk, kv, att, y, t1, q, mkv, att2, t2, t2s, h, attn_ws, attn_bytes, total; };
+
+DecLayout dec_layout(int64_t batch, int64_t lq, int64_t seq, int64_t d_ff, int64_t heads) {
+  DecLayout L{};
+  int64_t o = 0;
+  auto take = [&](int64_t bytes) { const int64_t at = o; o += upT(bytes); return at; };
+  const int64_t n = batch * lq, d = heads * 64;
+  for (int i = 0; i < 2; ++i) L.tin[i] = take(n * d * 4);      // layer input / output (fp32), ping-pong
+  L.add = take(n * d * 4);
+  L.xs = take(n * 2 * d * 2);                                   // split-half scratch for the (rows, d) operands
+  L.qk = take(n * 2 * d * 4);
+  L.kv = take(n * 2 * d * 4);
+  L.att = take(n * d * 4);
+  L.y = take(n * d * 4);
+  L.t1 = take(n * d * 4);
+  L.q = take(n * d * 4);
+  L.mkv = take(batch * seq * 2 * d * 4);
+  L.att2 = take(n * d * 4);
+  L.t2 = take(n * d * 4);
+  L.t2s = take(n * 2 * d * 2);
+  L.h = take(n * 2 * d_ff * 2);
+  L.attn_bytes = hoisdf_attention_workspace_bytes(batch, heads, lq, seq);
+  L.attn_ws = take(L.attn_bytes);
+  L.total = o;
+  return L;
+}
+
 int h3_linear(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx, const hoisdf_h3_linear& w, int64_t m, int64_t n,
               int64_t k, int act, float* y, int64_t ldy, uint16_t* y_hi, uint16_t* y_lo, int64_t ldyh, void* stream) {
   hoisdf_linear_h3_args l;
@@ -121,6 +153,97 @@ HOISDF_API int hoisdf_encoder_fwd(const hoisdf_encoder_args* a, void* stream) {
     x = xo;
     xs = xo_hi;
     if (!(last && a->out_hi != nullptr) && xo_lo != xs + d) return HOISDF_E_SHAPE;
+  }
+  return launch_status();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// hoisdf_decoder_fwd -- the post-norm transformer DECODER stack over a handful of learned queries (upstream
+// common/nets/transformer.py:214-252 over TransformerDecoderLayer.forward_post :366-395; tgt = 0, query_pos = the query
+// embedding, pos = 0): masked self-attention among the queries, cross-attention to the encoder memory with the keys
+// >= kv_valid blocked (the only memory_mask upstream builds, common/utils/misc.py:42-47), ReLU feed-forward, three residual
+// LayerNorms, and `norm(out_l)` of every layer as the result.  Same launches, same order as
+// hoisdf_b200/nets/transformer.py:TransformerDecoderLayer.forward_bm (bit-identical).
+HOISDF_API int64_t hoisdf_decoder_workspace_bytes(int64_t batch, int64_t queries, int64_t seq, int64_t d_ff, int32_t heads) {
+  if (batch <= 0 || queries <= 0 || seq <= 0 || d_ff <= 0 || heads <= 0) return 0;
+  return dec_layout(batch, queries, seq, d_ff, heads).total;
+}
+
+HOISDF_API int hoisdf_decoder_fwd(const hoisdf_decoder_args* a, void* stream) {
+  if (a == nullptr || a->layers == nullptr || a->query_pos == nullptr || a->memory_hi == nullptr || a->memory_lo == nullptr ||
+      a->norm_g == nullptr || a->norm_b == nullptr || a->hs == nullptr || a->workspace == nullptr)
+    return HOISDF_E_NULL;
+  if (a->num_layers <= 0 || a->batch <= 0 || a->queries <= 0 || a->seq <= 0 || a->heads * 64 != 256 || a->d_ff <= 0 ||
+      (a->d_ff & 31) || a->kv_valid <= 0 || a->kv_valid > a->seq)
+    return HOISDF_E_SHAPE;
+  if (!aligned16(a->workspace)) return HOISDF_E_ALIGN;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t B = a->batch, Lq = a->queries, S = a->seq, n = B * Lq, d = 256, H = a->heads;
+  const DecLayout L = dec_layout(B, Lq, S, a->d_ff, H);
+  if (L.total > a->workspace_bytes) return HOISDF_E_WORKSPACE;
+  char* ws = static_cast<char*>(a->workspace);
+  auto h16 = [&](int64_t off) { return reinterpret_cast<uint16_t*>(ws + off); };
+  auto f32 = [&](int64_t off) { return reinterpret_cast<float*>(ws + off); };
+  const int64_t lds = 2 * d, ldh = 2 * a->d_ff;
+  const unsigned add_blocks = static_cast<unsigned>(ceil_div(n * d, 256));
+  int st;
+  // fp32 (rows, d) -> split-half scratch -> GEMM
+  auto lin = [&](const float* x, const hoisdf_h3_linear& w, int64_t nn, int act, float* y, int64_t ldy) -> int {
+    uint16_t* xs = h16(L.xs);
+    int e = hoisdf_split_rows(x, n, d, d, d, xs, xs + d, lds, stream);
+    if (e != HOISDF_OK) return e;
+    return h3_linear(xs, xs + d, lds, w, n, nn, d, act, y, ldy, nullptr, nullptr, 0, stream);
+  };
+  float* t = f32(L.tin[0]);
+  if (cudaMemsetAsync(t, 0, n * d * 4, s) != cudaSuccess) return HOISDF_E_SHAPE;        // tgt = zeros (transformer.py:150)
+  for (int li = 0; li < a->num_layers; ++li) {
+    const hoisdf_decoder_layer& ly = a->layers[li];
+    float* add = f32(L.add);
+    // ---- masked self-attention among the queries: q = k = tgt + query_pos, v = tgt
+    add_rows_kernel<<<add_blocks, 256, 0, s>>>(t, a->query_pos, add, n * d);
+    float* qk = f32(L.qk);
+    if ((st = lin(add, ly.sa_qk, 2 * d, HOISDF_ACT_NONE, qk, 2 * d)) != HOISDF_OK) return st;
+    float* kv = f32(L.kv);
+    if ((st = lin(t, ly.sa_v, d, HOISDF_ACT_NONE, kv + d, 2 * d)) != HOISDF_OK) return st;
+    if (cudaMemcpy2DAsync(kv, 2 * d * 4, qk + d, 2 * d * 4, d * 4, n, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+      return HOISDF_E_SHAPE;
+    float* att = f32(L.att);
+    st = hoisdf_attention_fwd(qk, 2 * d, kv, kv + d, 2 * d, att, d, B, H, Lq, Lq, Lq, a->tgt_mask, nullptr, 0, stream);
+    if (st != HOISDF_OK) return st;
+    float* y = f32(L.y);
+    if ((st = lin(att, ly.sa_out, d, HOISDF_ACT_NONE, y, d)) != HOISDF_OK) return st;
+    float* t1 = f32(L.t1);
+    st = hoisdf_add_layernorm_fwd(y, t, ly.norm1_g, ly.norm1_b, t1, nullptr, nullptr, nullptr, n, d, stream);
+    if (st != HOISDF_OK) return st;
+    // ---- cross-attention to the memory (keys >= kv_valid blocked)
+    add_rows_kernel<<<add_blocks, 256, 0, s>>>(t1, a->query_pos, add, n * d);
+    float* q = f32(L.q);
+    if ((st = lin(add, ly.ca_q, d, HOISDF_ACT_NONE, q, d)) != HOISDF_OK) return st;
+    float* mkv = f32(L.mkv);
+    st = h3_linear(a->memory_hi, a->memory_lo, a->ld_memory, ly.ca_kv, B * S, 2 * d, d, HOISDF_ACT_NONE, mkv, 2 * d, nullptr,
+                   nullptr, 0, stream);
+    if (st != HOISDF_OK) return st;
+    float* att2 = f32(L.att2);
+    st = hoisdf_attention_fwd(q, d, mkv, mkv + d, 2 * d, att2, d, B, H, Lq, S, a->kv_valid, nullptr, ws + L.attn_ws, L.attn_bytes,
+                              stream);
+    if (st != HOISDF_OK) return st;
+    if ((st = lin(att2, ly.ca_out, d, HOISDF_ACT_NONE, y, d)) != HOISDF_OK) return st;
+    float* t2 = f32(L.t2);
+    uint16_t* t2s = h16(L.t2s);
+    st = hoisdf_add_layernorm_split_fwd(y, t1, ly.norm2_g, ly.norm2_b, t2, nullptr, nullptr, nullptr, n, d, t2s, t2s + d, lds,
+                                        nullptr, nullptr, 0, stream);
+    if (st != HOISDF_OK) return st;
+    // ---- feed-forward, third LayerNorm, and the stack's norm of the layer output
+    uint16_t* hh = h16(L.h);
+    st = h3_linear(t2s, t2s + d, lds, ly.lin1, n, a->d_ff, d, HOISDF_ACT_RELU, nullptr, 0, hh, hh + a->d_ff, ldh, stream);
+    if (st != HOISDF_OK) return st;
+    st = h3_linear(hh, hh + a->d_ff, ldh, ly.lin2, n, d, a->d_ff, HOISDF_ACT_NONE, y, d, nullptr, nullptr, 0, stream);
+    if (st != HOISDF_OK) return st;
+    float* out = f32(L.tin[(li + 1) & 1]);
+    st = hoisdf_add_layernorm_fwd(y, t2, ly.norm3_g, ly.norm3_b, out, a->norm_g, a->norm_b, a->hs + static_cast<int64_t>(li) * n * d,
+                                  n, d, stream);
+    if (st != HOISDF_OK) return st;
+    t = out;
   }
   return launch_status();
 }

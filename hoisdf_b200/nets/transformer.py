@@ -292,17 +292,76 @@ class TransformerDecoder(nn.Module):
         self.num_layers = num_layers
         self.norm = norm
         self.return_intermediate = return_intermediate
+        self._tgt_is_zero = False          # set by Transformer.forward_bm, which builds tgt = zeros itself
 
     def forward_bm(self, tgt, memory, pos, query_pos, tgt_mask, memory_mask, memory_kv_valid=None,
                    memory_split=None):
         """-> hs (L, B, Lq, d) = norm(out_l) for every layer (upstream transformer.py:214-252)."""
         b, lq, d = tgt.shape
         hs = torch.empty(self.num_layers, b, lq, d, device=tgt.device, dtype=torch.float32)
+        from ..config import cfg
+        if (pos is None and memory_kv_valid is not None and memory_split is not None and ops.use_h3() and cfg.native_decoder
+                and ops.PROFILE is None and self.norm is not None):
+            # (the C entry starts from tgt = 0, which is what Transformer.forward_bm passes -- upstream transformer.py:150)
+            if self._tgt_is_zero and self._forward_native(hs, memory, query_pos, tgt_mask, memory_kv_valid, memory_split):
+                return hs
         x = tgt
         for i, layer in enumerate(self.layers):
             x = layer.forward_bm(x, memory, pos, query_pos, tgt_mask, memory_mask, self.norm, hs[i], memory_kv_valid,
                                  memory_split)
         return hs
+
+
+def _fill_h3(dst, pw, keep):
+    h3 = pw.h3
+    if h3 is None:
+        return False
+    dst.a, dst.b, dst.c, dst.ld = h3.plane_ptr(0), h3.plane_ptr(1), h3.plane_ptr(2), h3.ld
+    dst.bias, dst.scale = ops._ptr(h3.b), float(h3.scale)
+    keep.append(h3)
+    return True
+
+
+def _decoder_forward_native(self, hs, memory, query_pos, tgt_mask, kv_valid, memory_split):
+    """The whole decoder stack through ONE C call (csrc/transformer.cu: hoisdf_decoder_fwd; tgt = 0 as upstream
+    transformer.py:150): same kernels, same order as the per-layer Python path (bit-identical).  False = not applicable."""
+    import ctypes as C
+    from .. import _capi
+    L, b, lq, d = hs.shape
+    s = memory.shape[1]
+    layers = (_capi.DecoderLayer * L)()
+    keep, d_ff = [], None
+    for i, layer in enumerate(self.layers):
+        sa, ca = layer.self_attn.packed(), layer.multihead_attn.packed()
+        l1, l2 = layer.ffn_packed()
+        ok = (_fill_h3(layers[i].sa_qk, sa["qk"], keep) and _fill_h3(layers[i].sa_v, sa["v"], keep)
+              and _fill_h3(layers[i].sa_out, sa["out"], keep) and _fill_h3(layers[i].ca_q, ca["q"], keep)
+              and _fill_h3(layers[i].ca_kv, ca["kv"], keep) and _fill_h3(layers[i].ca_out, ca["out"], keep)
+              and _fill_h3(layers[i].lin1, l1, keep) and _fill_h3(layers[i].lin2, l2, keep))
+        d_ff = l1.n if d_ff is None else d_ff
+        if not ok or l1.n != d_ff or layer.nhead * 64 != d:
+            return False
+        for j, nm in enumerate((layer.norm1, layer.norm2, layer.norm3), 1):
+            setattr(layers[i], "norm%d_g" % j, nm.weight.data_ptr())
+            setattr(layers[i], "norm%d_b" % j, nm.bias.data_ptr())
+    heads = self.layers[0].nhead
+    nbytes = int(_capi.lib.hoisdf_decoder_workspace_bytes(b, lq, s, d_ff, heads))
+    ws = torch.empty(nbytes, device=hs.device, dtype=torch.uint8)
+    qp = query_pos.contiguous()
+    a = _capi.DecoderArgs()
+    a.layers, a.num_layers, a.heads, a.d_ff = layers, L, heads, d_ff
+    a.norm_g, a.norm_b = self.norm.weight.data_ptr(), self.norm.bias.data_ptr()
+    a.batch, a.queries, a.seq, a.kv_valid = b, lq, s, int(kv_valid)
+    a.query_pos, a.tgt_mask = qp.data_ptr(), ops._ptr(tgt_mask)
+    a.memory_hi, a.memory_lo, a.ld_memory = memory_split.hi_ptr, memory_split.lo_ptr, memory_split.ld
+    a.hs, a.workspace, a.workspace_bytes = hs.data_ptr(), ws.data_ptr(), nbytes
+    ops._count(L * 22)
+    _capi.check(_capi.lib.hoisdf_decoder_fwd(C.byref(a), ops._stream()), "hoisdf_decoder_fwd")
+    del keep
+    return True
+
+
+TransformerDecoder._forward_native = _decoder_forward_native
 
 
 def _mask_u8(mask: Optional[torch.Tensor], device):
@@ -385,9 +444,13 @@ class Transformer(nn.Module):
         tgt = torch.zeros_like(qpos)
         dev = src_bm.device
         kv_valid = _suffix_mask_limit(memory_mask)
-        hs = self.decoder.forward_bm(tgt, memory, pos_bm, qpos, _mask_u8(tgt_mask, dev),
-                                     None if kv_valid is not None else _mask_u8(memory_mask, dev), kv_valid,
-                                     self.encoder.last_out_split)
+        self.decoder._tgt_is_zero = True       # tgt was built as zeros right above: the C entry may start from its own zeros
+        try:
+            hs = self.decoder.forward_bm(tgt, memory, pos_bm, qpos, _mask_u8(tgt_mask, dev),
+                                         None if kv_valid is not None else _mask_u8(memory_mask, dev), kv_valid,
+                                         self.encoder.last_out_split)
+        finally:
+            self.decoder._tgt_is_zero = False
         return hs, memory, inter
 
     def forward(self, src, mask, query_embed, pos_embed, tgt_mask=None, src_mask=None, memory_mask=None):

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 25
+#define HOISDF_ABI_VERSION 26
 
 enum {
   HOISDF_OK = 0,
@@ -474,6 +474,32 @@ typedef struct {
 } hoisdf_encoder_args;
 int64_t hoisdf_encoder_workspace_bytes(int64_t batch, int64_t seq, int64_t d_ff, int32_t heads);
 int hoisdf_encoder_fwd(const hoisdf_encoder_args* args, void* stream);
+
+/* The transformer DECODER stack over `queries` learned queries (csrc/transformer.cu) -- upstream
+ * common/nets/transformer.py:214-252 (TransformerDecoder.forward) over :366-395 (forward_post) with tgt = 0,
+ * query_pos = the query embedding expanded over the batch ((B * queries, 256) fp32), pos = 0:
+ *   hs (L, B * queries, 256) = norm(out_l) for every layer.
+ * memory: the encoder's last output in split-half format (hoisdf_encoder_fwd's out_hi / out_lo; row pitch ld_memory),
+ * B * seq rows; tgt_mask uint8 (queries, queries), non-zero = blocked (may be NULL); keys >= kv_valid of the memory are
+ * blocked for every query.  Weights as in hoisdf_encoder_layer: in_proj row windows [q; k] / [v] of the self-attention,
+ * [q] / [k; v] of the cross-attention. */
+typedef struct {
+  hoisdf_h3_linear sa_qk; hoisdf_h3_linear sa_v; hoisdf_h3_linear sa_out;
+  hoisdf_h3_linear ca_q; hoisdf_h3_linear ca_kv; hoisdf_h3_linear ca_out;
+  hoisdf_h3_linear lin1; hoisdf_h3_linear lin2;
+  const float* norm1_g; const float* norm1_b; const float* norm2_g; const float* norm2_b; const float* norm3_g; const float* norm3_b;
+} hoisdf_decoder_layer;
+typedef struct {
+  const hoisdf_decoder_layer* layers; int32_t num_layers; int32_t heads; int64_t d_ff;
+  const float* norm_g; const float* norm_b;
+  int64_t batch; int64_t queries; int64_t seq; int64_t kv_valid;
+  const float* query_pos; const uint8_t* tgt_mask;
+  const uint16_t* memory_hi; const uint16_t* memory_lo; int64_t ld_memory;
+  float* hs;
+  void* workspace; int64_t workspace_bytes;
+} hoisdf_decoder_args;
+int64_t hoisdf_decoder_workspace_bytes(int64_t batch, int64_t queries, int64_t seq, int64_t d_ff, int32_t heads);
+int hoisdf_decoder_fwd(const hoisdf_decoder_args* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Joint voting -- upstream common/nets/loss.py:31-36,54-57 (the part of JointvoteLoss that produces

@@ -417,6 +417,24 @@ def test_encoder_c_entry_equals_python_layers(cuda, monkeypatch):
         assert a.shape == b.shape and torch.equal(a, b)
     from hoisdf_b200 import _capi
     assert _capi.lib.hoisdf_encoder_workspace_bytes(3, 200, 1024, 4) > 0 and _capi.lib.hoisdf_encoder_workspace_bytes(3, 20, 1024, 4) == 0
+    # the decoder stack (hoisdf_decoder_fwd) the same way: hs of all 4 layers identical to the bit, through the whole
+    # Transformer.forward_bm (encoder + decoder, masked self-attention, key-range-limited cross-attention)
+    from hoisdf_b200.utils.misc import get_mano_memory_mask, get_mano_tgt_mask
+    old = (cfg.num_samp_hand, cfg.num_samp_obj)
+    type(cfg).num_samp_hand, type(cfg).num_samp_obj = 150, 50
+    try:
+        outs = {}
+        for native in (True, False):
+            monkeypatch.setattr(type(cfg), "native_decoder", native)
+            with torch.no_grad():
+                hs, mem, inter = tr.forward_bm(x, sd["mano_query_embed.weight"].to(cuda), None, get_mano_tgt_mask().to(cuda),
+                                               get_mano_memory_mask())
+            outs[native] = hs.clone()
+        assert outs[True].shape == (4, 3, 17, 256) and torch.equal(outs[True], outs[False])
+        assert float(outs[True].abs().max()) > 0
+        assert _capi.lib.hoisdf_decoder_workspace_bytes(3, 17, 200, 1024, 4) > 0
+    finally:
+        type(cfg).num_samp_hand, type(cfg).num_samp_obj = old
 
 
 # ---------------------------------------------------------------- heads
