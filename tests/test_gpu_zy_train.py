@@ -272,6 +272,33 @@ def test_train_forward_backward_matches_oracle(train_setup):
     assert len(tight) >= len(l2) // 2, (len(tight), l2)
 
 
+def test_train_forward_selection_branch(train_setup, monkeypatch):
+    """After cfg.point_sampling_epoch epochs 60 % of the steps let the inference cascade pick the pose points (upstream
+    model.py:467-481: `sdf_infer` under no_grad).  Here: that branch selects exactly the points the eval forward selects
+    from the same (train-mode) pyramid, the SDF losses / pose losses are finite and the backward reaches the encoder."""
+    import random
+    import hoisdf_b200.train as T
+    from hoisdf_b200.train import total_loss
+    s = train_setup
+    model = s["model"].train()
+    for p in model.parameters():
+        p.grad = None
+    monkeypatch.setattr(random, "uniform", lambda a, b: 0.9)          # p >= 0.4 -> the selection branch
+    out = model(*s["batch"], "train", 1e8, 0.0)
+    total, parts = total_loss(out)
+    assert torch.isfinite(total) and all(torch.isfinite(v) for v in parts.values())
+    taps = model.last_taps
+    assert taps["hand_points"].shape == (s["B"], s["ph"], 3) and taps["obj_points"].shape == (s["B"], s["po"], 3)
+    # lattice points: every coordinate is a multiple of the lattice step inside the sheared cube, |x| <= 1.04
+    assert float(taps["hand_points"].abs().max()) <= 1.04 and float(taps["hand_sdf"].abs().max()) <= 0.15 + 1e-6
+    total.backward()
+    g = {n: p.grad for n, p in model.named_parameters() if p.grad is not None}
+    for key in ("linear_transformerin.layers.0.weight", "decoder_net.resnet_decoder.conv1.0.weight",
+                "backbone_net.resnet.layer1.0.conv1.weight", "hand_sdf_decoder.linh0.weight_v", "hand_sigmoid_beta"):
+        assert key in g and torch.isfinite(g[key]).all() and float(g[key].abs().max()) > 0, key
+    model.eval()
+
+
 def test_trainer_step_matches_adamw(train_setup):
     """Trainer.step: flat-buffer AdamW (hoisdf_adamw_step) vs torch.optim.AdamW fed the SAME gradients; parameters the graph
     never reaches stay untouched like upstream's (grad None -> skipped)."""
