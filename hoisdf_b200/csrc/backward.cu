@@ -1,9 +1,9 @@
-// Backward kernels of the SDF branch (groundwork for the training step; upstream
-// main/train.py:106-140 back-propagates loss["sdfhand_loss"] / ["sdfobj_loss"] -- main/model.py:370-401 -- through
-// SDFDecoder, linear_sdfin and the bilinear gather into the U-Net pyramid).  fp32 SIMT arithmetic throughout: these are
-// the reference-grade kernels the tensor-core backward will be checked against.  STATUS: verified against PyTorch
-// autograd on the CPU thread emulator (tests/test_kernel_emulation.py) and on the B200 (tests/test_gpu_zz_backward.py);
-// not yet wired into Model.forward(mode="train").
+// Backward kernels of the training step (upstream main/train.py:104-140 back-propagates the weighted
+// loss sum through main/model.py:357-665).  fp32 SIMT arithmetic: the element-wise / reduction / scatter pieces of the
+// backward and the small or batched products that are not tensor-core shapes; the large Linear gradients (dX, dW) run on the
+// FP16x3 tcgen05 GEMM with operands prepared by csrc/train_prep.cu.  Called through hoisdf_b200/autograd.py; every kernel is
+// checked against PyTorch autograd on the CPU thread emulator (tests/test_kernel_emulation.py) and on the B200
+// (tests/test_gpu_zz_backward.py, tests/test_gpu_zy_train.py).
 //   hoisdf_gemm_f32          C (M,N) = op(A) . op(B) (+ C): the three contractions of a Linear's backward
 //                            (dX = dZ . W, dW = dZ^T . X) and its forward (Y = X . W^T) on one tiled fp32 FMA kernel
 //   hoisdf_act_bias_bwd      dZ = dY * relu'(Y) in place, db = column sums of dZ

@@ -565,10 +565,11 @@ int hoisdf_hand_joint_metrics_fwd(const float* pred, const float* gt, int64_t ba
                                   float* pamje, float* aligned, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
- * Backward kernels of the SDF branch -- groundwork for the training step (upstream main/train.py:106-140
- * back-propagates loss["sdfhand_loss"] / ["sdfobj_loss"], main/model.py:370-401, through SDFDecoder, linear_sdfin and
- * the bilinear gather into the U-Net pyramid).  fp32 SIMT arithmetic (csrc/backward.cu).  STATUS: checked against
- * PyTorch autograd on the CPU thread emulator and on the B200; not yet called by Model.forward (mode="train" is not built).
+ * Backward kernels of the training step (upstream main/train.py:104-140: `loss.backward()` through main/model.py:357-665
+ * and `optimizer.step()`, common/base.py:64-70).  fp32 SIMT arithmetic (csrc/backward.cu); the large Linear gradients run on
+ * hoisdf_linear_h3_fwd with operands from hoisdf_linear_bwd_prep (csrc/train_prep.cu).  Called by hoisdf_b200/autograd.py
+ * (Model.forward(mode="train"), hoisdf_b200/train.py); checked against PyTorch autograd on the CPU thread emulator and on the
+ * B200.
  *   hoisdf_gemm_f32: C (m, n; pitch ldc) = op(A) . op(B) (+ C when accumulate): trans_a: A is stored (k, m), else (m, k);
  *     trans_b: B is stored (n, k), else (k, n).  A Linear Y = X . W^T has dX = dZ . W (no transposes), dW = dZ^T . X
  *     (trans_a) and Y itself (trans_b).
