@@ -75,6 +75,33 @@ def test_hot_path_at_config_size(sized):
         assert v < 1e-3, (k, v)                                         # the north star's bar (measured: ~1e-5)
 
 
+def test_hot_path_full_batch_values(sized):
+    """VALUES at the full batch: configs[1] at batch 32, configs[2] at its per-GPU shard of 16 -- the
+    oracle on every sample (about half a minute of host time): identical selected index sets, every `*_out` within 1e-3."""
+    s, m, dev = sized, sized["model"], sized["dev"]
+    B = 32 if s["name"] == "config2" else 16
+    ph, po = s["ph"], s["po"]
+    meta, pyr = syn.camera_meta(s["seed"] + 2, B), syn.feature_pyramid(s["seed"] + 2, B, s["arch"])
+    out = m.hot_path(to_dev(pyr, dev), to_dev(meta, dev))
+    otaps = {}
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    with torch.no_grad():
+        oout = O.hot_path_eval(dict(s["sd"]), pyr, meta, O.default_cfg(num_samp_hand=ph, num_samp_obj=po), otaps)
+    taps = m.last_taps
+    check_selection(taps["hand"], otaps["hand"], ph)
+    check_selection(taps["obj"], otaps["obj"], po)
+    align_selection(taps["hand"]["index"], otaps["hand"]["index"], otaps["hand_sdf"])
+    op = align_selection(taps["obj"]["index"], otaps["obj"]["index"], otaps["obj_sdf"])
+    measured = {}
+    for k in oout:
+        got = aligned(out[k], op) if k in ("obj_rot_out", "obj_trans_out") else out[k]
+        assert got.shape == oout[k].shape and got.shape[0] == B, k
+        measured[k] = rel(got, oout[k])
+    _record(s["name"] + "_full_batch", measured)
+    for k, v in measured.items():
+        assert v < 1e-3, (k, v)
+
+
 def test_full_batch_properties(sized):
     """configs[1] at its full batch of 32 (configs[2] at its per-GPU shard of 16)."""
     s, m, dev = sized, sized["model"], sized["dev"]
