@@ -29,7 +29,7 @@ from typing import Optional
 import torch
 from torch.autograd import Function
 
-from . import _capi, ops
+from . import ops
 from ._capi import check, lib
 from .ops import _count, _ptr, _stream
 

@@ -18,7 +18,7 @@ from __future__ import annotations
 
 import os
 import random
-from typing import Dict, Optional
+from typing import Dict
 
 import torch
 import torch.nn.functional as F

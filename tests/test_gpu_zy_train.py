@@ -277,7 +277,6 @@ def test_train_forward_selection_branch(train_setup, monkeypatch):
     model.py:467-481: `sdf_infer` under no_grad).  Here: that branch selects exactly the points the eval forward selects
     from the same (train-mode) pyramid, the SDF losses / pose losses are finite and the backward reaches the encoder."""
     import random
-    import hoisdf_b200.train as T
     from hoisdf_b200.train import total_loss
     s = train_setup
     model = s["model"].train()
