@@ -78,7 +78,7 @@ class Config:
     # per row come from L2 instead of L1 (the stand-alone gather runs with the full 256 KB L1: 73 % hit rate).  Measured:
     # 5.9 ms per step against 2.4 + 1.6 for chain + stand-alone fp16 gather -- correct, tested, but off by default
     fused_gather = False
-    screen_margin_single = 1024
+    screen_margin_single = int(__import__("os").environ.get("HOISDF_SCREEN_MARGIN", "1024"))
     # the default cascade (fused chain + fp16 gather + FP16x3 final stage) run by ONE C entry point, hoisdf_sdf_infer_fwd
     # (csrc/sdf_infer.cu), instead of ~30 Python-level launches with ATen glue; False = the Python orchestration
     native_sdf_infer = True
