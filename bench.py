@@ -578,7 +578,12 @@ def run_train(args):
     phases = {"forward_ms": ev[0].elapsed_time(ev[1]), "backward_ms": ev[1].elapsed_time(ev[2])}
     eager = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        eager = time_train_eager(dev, arch, 8, ph, po)
+        torch.cuda.empty_cache()
+        try:                                   # the same batch as ours; a smaller one if the eager graph does not fit
+            eager = time_train_eager(dev, arch, B, ph, po)
+        except RuntimeError:
+            torch.cuda.empty_cache()
+            eager = time_train_eager(dev, arch, 8, ph, po)
     if rank == 0:
         value = world * B * args.steps * 1000.0 / ms
         line = {
