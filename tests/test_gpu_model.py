@@ -132,6 +132,37 @@ def test_sdf_infer_c_entry_equals_python_orchestration(setup, monkeypatch):
         (t.data_ptr() for t in outs)
     assert int(host[-1]) > small
     assert _capi.lib.hoisdf_sdf_infer_fwd(C.byref(a), ops._stream()) == _capi.E_WORKSPACE
+    # planned = 0: the entry plans, waits for the B + 1 offsets itself (its own counts / offsets / pinned buffer) and must
+    # give exactly what the planned call gives
+    rows = ops.round_up(int(host[-1]), 1 << 16)
+    nb = int(_capi.lib.hoisdf_sdf_infer_workspace_bytes(2, rows, 96, 1024, 64))
+    ws2 = torch.empty(nb, device=dev, dtype=torch.uint8)
+    res = {}
+    for planned in (1, 0):
+        o = dict(points=torch.empty(2, 96, 3, device=dev), sdf=torch.empty(2, 96, 1, device=dev),
+                 posenc=torch.empty(2, 96, 30, device=dev), sel=torch.empty(2, 96, device=dev, dtype=torch.int32),
+                 flag=torch.zeros(1, device=dev, dtype=torch.int32), err=torch.empty(1, device=dev),
+                 gap=torch.empty(2, device=dev), ok=torch.empty(1, device=dev, dtype=torch.int32))
+        pinned = torch.empty(3, dtype=torch.int64).pin_memory()
+        nf = torch.zeros(2, dtype=torch.int64)
+        a.workspace, a.workspace_bytes, a.max_rows, a.planned = ws2.data_ptr(), nb, rows, planned
+        if planned:
+            a.chunk_counts, a.offsets, a.host_offsets = plan.counts.data_ptr(), plan.offsets.data_ptr(), host.data_ptr()
+        else:
+            a.chunk_counts, a.offsets, a.host_offsets = None, None, pinned.data_ptr()
+        a.n_f = nf.data_ptr()
+        a.points, a.sdf, a.posenc, a.sel_index, a.status_flag = (o[k].data_ptr() for k in ("points", "sdf", "posenc", "sel", "flag"))
+        a.screen_err, a.screen_gap, a.verified = o["err"].data_ptr(), o["gap"].data_ptr(), o["ok"].data_ptr()
+        assert _capi.lib.hoisdf_sdf_infer_fwd(C.byref(a), ops._stream()) == 0
+        torch.cuda.synchronize()
+        assert torch.equal(nf, host[1:] - host[:-1]) and int(o["ok"]) == 1
+        if not planned:
+            assert torch.equal(pinned, host)
+        res[planned] = o
+    for k in res[1]:
+        assert torch.equal(res[1][k], res[0][k]), k
+    a.workspace, a.workspace_bytes, a.max_rows, a.planned = ws.data_ptr(), nbytes, small, 1
+    a.chunk_counts, a.offsets, a.host_offsets, a.n_f = plan.counts.data_ptr(), plan.offsets.data_ptr(), host.data_ptr(), None
     a.workspace_bytes = 1024
     assert _capi.lib.hoisdf_sdf_infer_fwd(C.byref(a), ops._stream()) == _capi.E_WORKSPACE
     a.workspace = None
