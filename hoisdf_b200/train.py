@@ -218,8 +218,11 @@ def forward_train(model, inputs, targets, meta_info, epoch_cnt=1e8, batch_ratio=
         dist = cfg.random_move_dist[len([a for a in cfg.random_ratio if batch_ratio > a])]
         hand_points = inputs["hand_pre_points"] + torch.empty_like(inputs["hand_pre_points"]).uniform_(-dist, dist)
         obj_points = inputs["obj_pre_points"] + torch.empty_like(inputs["obj_pre_points"]).uniform_(-dist, dist)
-        hand_sdf, hand_pe = sdf_forward(model, maps, hand_points, root, K, hs_scale, "hand")
-        obj_sdf, obj_pe = sdf_forward(model, maps, obj_points, objc, K, os_scale, "obj")
+        # upstream runs these two queries with the tape on, but consumes their results only detached (`hand_sdf.detach()`,
+        # model.py:483-484) or as constants (the positional encoding): no gradient ever flows through them
+        with torch.no_grad():
+            hand_sdf, hand_pe = sdf_forward(model, maps, hand_points, root, K, hs_scale, "hand")
+            obj_sdf, obj_pe = sdf_forward(model, maps, obj_points, objc, K, os_scale, "obj")
     else:
         with torch.no_grad():       # the inference selection on the tensor-core cascade, from a detached pyramid
             dpyr = {k: v.detach() for k, v in pyramid.items()}
