@@ -4,11 +4,13 @@
 Every Function calls the C ABI for the forward AND the backward; PyTorch only provides the tape.
 
   LinearFn        Y = act(X W^T + b)            forward : FP16x3 tcgen05 GEMM (hoisdf_linear_h3_fwd)
-                                                 backward: dZ = dY * relu' + db (hoisdf_act_bias_bwd), then the SAME tensor-core
-                                                 GEMM on transposed operands: dX = dZ . W  = linear_h3(dZ, pack(W^T)),
-                                                 dW^T = X^T . dZ = linear_h3(X^T, pack(dZ^T)).  Gradients are brought into the fp16
-                                                 planes' range by a power-of-two scale computed ON THE DEVICE (exact, undone
-                                                 after the product), so no host read-back is involved
+                                                 backward: hoisdf_absmax + hoisdf_linear_bwd_prep (one pass over dY: dZ = dY *
+                                                 relu', db, and both GEMM operands in their tensor-core formats), then the
+                                                 SAME tensor-core GEMM on transposed operands: dX = dZ . W = linear_h3(dZ,
+                                                 pack(W^T)), dW^T = X^T . dZ = linear_h3(X^T, pack(dZ^T)).  Gradients are brought
+                                                 into the fp16 planes' range by a power-of-two scale computed ON THE DEVICE
+                                                 (exact, undone after the product): no host read-back.  Layers with <= 16 rows,
+                                                 inputs or outputs take hoisdf_act_bias_bwd + the fp32 FMA GEMM
   WeightNormFn    W = g v / |v|                 hoisdf_fold_weight_norm / hoisdf_weight_norm_bwd
   GatherFn        5-level bilinear gather       hoisdf_gather_fwd (CONCAT) / hoisdf_gather_bwd (scatter-add into the pyramid grad)
   AddLayerNormFn  LayerNorm(x + res)            hoisdf_add_layernorm_fwd / hoisdf_layernorm_bwd
@@ -241,7 +243,7 @@ def _gemm_batched(a, lda, ta, a_o, a_i, b, ldb, tb, b_o, b_i, c, ldc, c_o, c_i, 
 class AttentionFn(Function):
     """Multi-head attention core on (B*L, d) row matrices (head h = columns [64h, 64h+64)): softmax(q k^T / 8 + mask) v.
     q: (B*Lq, d) view with pitch ldq, k / v: (B*Lk, d) views; `mask` uint8 (Lq, Lk), non-zero = blocked; keys >= kv_valid are
-    blocked for every query; `p_drop` = dropout on the probabilities (nn.MultiheadAttention's), applied with a torch mask."""
+    blocked for every query; `p_drop` = dropout on the probabilities (nn.MultiheadAttention's), fused into the softmax kernels."""
 
     @staticmethod
     def forward(ctx, q, k, v, batch, heads, lq, lk, mask, kv_valid, p_drop):

@@ -399,15 +399,23 @@ class Trainer:
         self.zero_grad()
         out = model(inputs, targets, meta_info, "train", epoch_cnt, batch_ratio)
         total, parts = total_loss(out)
-        total.backward()
+        if self.skip_unused and self._unused is None:
+            # parameters the graph never reaches (upstream: norm1, linear_objvote, linear_objcls -- model.py:55,86-87) keep
+            # grad None there and torch.optim.AdamW skips them.  Found once, from the tape itself (not from gradient VALUES:
+            # a reached parameter may well have an all-zero gradient): the first backward runs with unset .grad fields
+            for p in self.params:
+                p.grad = None
+            total.backward()
+            self._unused = [i for i, p in enumerate(self.params) if p.grad is None]
+            for p, (o, k) in zip(self.params, self.slices):
+                if p.grad is not None:
+                    self.grad[o:o + k].copy_(p.grad.reshape(-1))
+                p.grad = self.grad[o:o + k].view(p.shape)
+        else:
+            total.backward()
         allreduce_mean_(self.grad, self.group)
         self.step_count += 1
-        if self.skip_unused and self._unused is None:
-            # parameters the graph never reaches (upstream: norm1, linear_objvote, linear_objcls -- model.py:55,86-87) have
-            # grad None there and torch.optim.AdamW skips them; here their slice stays exactly zero.  Found once (one
-            # host read-back at the first step), then their values are restored after every step (undoes the weight decay)
-            amax = torch.stack([self.grad[o:o + k].abs().amax() for o, k in self.slices])
-            self._unused = [i for i, z in enumerate((amax == 0).tolist()) if z]
+        # their slices stay exactly zero; their values are restored after the step (undoes the decoupled weight decay)
         saved = [(o, k, self.flat[o:o + k].clone()) for o, k in (self.slices[i] for i in (self._unused or []))]
         check(lib.hoisdf_adamw_step(self.flat.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
                                     self.exp_avg_sq.data_ptr(), self.flat.numel(), self.lr, self.betas[0], self.betas[1],
