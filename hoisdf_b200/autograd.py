@@ -14,8 +14,9 @@ Every Function calls the C ABI for the forward AND the backward; PyTorch only pr
   WeightNormFn    W = g v / |v|                 hoisdf_fold_weight_norm / hoisdf_weight_norm_bwd
   GatherFn        5-level bilinear gather       hoisdf_gather_fwd (CONCAT) / hoisdf_gather_bwd (scatter-add into the pyramid grad)
   AddLayerNormFn  LayerNorm(x + res)            hoisdf_add_layernorm_fwd / hoisdf_layernorm_bwd
-  AttentionFn     softmax(q k^T / 8 [mask]) v   forward: tcgen05 flash kernel (hoisdf_attention_fwd) when there is no dropout on the
-                                                 probabilities, else the materialised form; backward: hoisdf_gemm_f32_batched +
+  AttentionFn     softmax(q k^T / 8 [mask]) v   forward: tcgen05 flash kernel (hoisdf_attention_fwd; hoisdf_attention_dropout_fwd with
+                                                 dropout on the probabilities), the materialised form for masked / short
+                                                 sequences with dropout; backward: hoisdf_gemm_f32_batched +
                                                  hoisdf_softmax_rows_fwd / _bwd per (sample, head) -- fp32 SIMT, the S x S
                                                  probabilities are recomputed, not stored; dropout on the probabilities through
                                                  hoisdf_softmax_dropout_rows_fwd / _bwd (hashed keep decisions: only a seed is kept)
@@ -254,13 +255,23 @@ class AttentionFn(Function):
         out = torch.empty(batch * lq, d, device=dev, dtype=torch.float32)
         seed = 0
         if p_drop > 0.0:
-            # materialised form: the dropped probabilities Pd (B, H, Lq, Lk) multiply V.  The keep decisions are a hash of
-            # (seed, position): nothing but the seed is kept for the backward (CPU generator: no device sync, reproducible
-            # under torch.manual_seed)
+            # The keep decisions are a hash of (seed, position): nothing but the seed is kept for the backward (CPU
+            # generator: no device sync, reproducible under torch.manual_seed)
             seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64))
-            pd = AttentionFn._probs(q, k, batch, heads, lq, lk, mask, kv_valid, p_drop, seed)[1]
-            _gemm_batched(pd.data_ptr(), lk, 0, heads * lq * lk, lq * lk, v.data_ptr(), v.stride(0), 0, lk * v.stride(0), 64,
-                          out.data_ptr(), d, lq * d, 64, lq, 64, lk, 1.0, batch, heads)
+            kend = lk if kv_valid is None else min(lk, kv_valid)
+            if ops.USE_TENSOR_CORES and mask is None and lq > 32 and kend >= 128 and k.stride(0) == v.stride(0):
+                # encoder self-attention: the tensor-core flash kernel applies the dropout to P on its way to P.V
+                nbytes = lib.hoisdf_attention_workspace_bytes(batch, heads, lq, lk)
+                ws = ops._attention_workspace(dev, nbytes)
+                _count(4)
+                check(lib.hoisdf_attention_dropout_fwd(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0),
+                                                       out.data_ptr(), d, batch, heads, lq, lk, kend, float(p_drop), seed,
+                                                       _ptr(ws), nbytes, _stream()), "hoisdf_attention_dropout_fwd")
+            else:
+                # materialised form (masked / short decoder attention): the dropped probabilities Pd (B, H, Lq, Lk) times V
+                pd = AttentionFn._probs(q, k, batch, heads, lq, lk, mask, kv_valid, p_drop, seed)[1]
+                _gemm_batched(pd.data_ptr(), lk, 0, heads * lq * lk, lq * lk, v.data_ptr(), v.stride(0), 0, lk * v.stride(0),
+                              64, out.data_ptr(), d, lq * d, 64, lq, 64, lk, 1.0, batch, heads)
         else:
             vv = v
             if k.stride(0) != v.stride(0):

@@ -52,6 +52,10 @@ struct AttnTcParams {
   uint16_t* __restrict__ out_lo;     // out-projection GEMM reads, saving a conversion pass
   int64_t ldo;                       // row pitch of whichever output is used (floats / halfs)
   int lq, lk, kv_valid, heads;
+  // training only (attention_tc128_kernel<true>): dropout on the probabilities, decisions hashed from (seed, row, key)
+  uint64_t seed;
+  uint32_t drop_threshold;
+  float keep_scale;                  // 1 / (1 - p_drop)
 };
 
 __device__ __forceinline__ uint32_t at_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -495,6 +499,11 @@ __device__ __forceinline__ void at_tmem_st16(uint32_t taddr, const uint32_t* r) 
       : "memory");
 }
 
+// DROP: nn.MultiheadAttention's dropout on the probabilities (training, upstream cfg.dropout = 0.1): the row sum l keeps
+// every p, the P operand of P.V carries keep ? p / (1 - q) : 0 -- O / l is then dropout(softmax(S)) . V.  keep() is
+// common.cuh's counter hash with row = (sample * heads + head) * lq + query and col = key, the indexing of
+// hoisdf_softmax_dropout_rows_fwd / _bwd on the (B, H, Lq, Lk) probabilities, so the backward regenerates the decisions.
+template <bool DROP>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attention_tc128_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant__ CUtensorMap map_qlo,
                        const __grid_constant__ CUtensorMap map_khi, const __grid_constant__ CUtensorMap map_klo,
@@ -650,6 +659,8 @@ attention_tc128_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid
     const int r = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     float m_run = -INFINITY, l_run = 0.f;
+    uint32_t drop_key = 0;
+    if (DROP) drop_key = dropout_row_key(p.seed, static_cast<uint64_t>(bh) * p.lq + static_cast<uint64_t>(q0 + g * AT_BQ + r));
     for (int t = 0; t < T; ++t) {
       at_mbar_wait(bar_sf(g), t & 1);          // S_t complete (and with it P_{t-1}.V_{t-1}: same issuing thread, in order)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -687,9 +698,14 @@ attention_tc128_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid
         uint32_t ph[16], pl[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-          const float e0 = ex2_approx(__uint_as_float(sr[c * 32 + 2 * e]) - m_new);
-          const float e1 = ex2_approx(__uint_as_float(sr[c * 32 + 2 * e + 1]) - m_new);
+          float e0 = ex2_approx(__uint_as_float(sr[c * 32 + 2 * e]) - m_new);
+          float e1 = ex2_approx(__uint_as_float(sr[c * 32 + 2 * e + 1]) - m_new);
           rs4[e & 3] += e0 + e1;
+          if (DROP) {
+            const uint32_t key0 = static_cast<uint32_t>(t * A2_BK + c * 32 + 2 * e);
+            e0 = dropout_keep(drop_key, key0, p.drop_threshold) ? e0 * p.keep_scale : 0.f;
+            e1 = dropout_keep(drop_key, key0 + 1, p.drop_threshold) ? e1 * p.keep_scale : 0.f;
+          }
           split_bf16x2(e0, e1, ph[e], pl[e]);
         }
         at_tmem_st16(tmem_sp(g) + lane_addr + c * 16, ph);
@@ -780,7 +796,7 @@ int64_t attention_tc_workspace_bytes(int64_t batch, int64_t heads, int64_t lq, i
 
 int launch_attention_tc(const float* q, int64_t ldq, const float* k, const float* v, int64_t ldk, float* out,
                         int64_t ldo, int64_t batch, int64_t heads, int64_t lq, int64_t lk, int64_t kv_valid,
-                        void* workspace, cudaStream_t s, uint16_t* out_hi, uint16_t* out_lo) {
+                        void* workspace, cudaStream_t s, uint16_t* out_hi, uint16_t* out_lo, float p_drop, uint64_t seed) {
   if (batch * heads * (lq > lk ? lq : lk) > 0x7fffff00LL) return HOISDF_E_SHAPE;  // TMA row coordinates are int32
   const int64_t lk_pad = (lk + 7) / 8 * 8;
   auto up = [](int64_t x) { return (x + 255) / 256 * 256; };
@@ -810,13 +826,15 @@ int launch_attention_tc(const float* q, int64_t ldq, const float* k, const float
       !at_make_map(&mkh, khi, bh * lk, AT_D, AT_D, kbox) || !at_make_map(&mkl, klo, bh * lk, AT_D, AT_D, kbox) ||
       !at_make_map(&mvh, vhi, bh * AT_D, lk_pad, lk_pad, AT_D) || !at_make_map(&mvl, vlo, bh * AT_D, lk_pad, lk_pad, AT_D))
     return HOISDF_E_UNSUPPORTED;
+  if (p_drop > 0.f && !wide) return HOISDF_E_UNSUPPORTED;      // dropout lives in the 128-key kernel only
   AttnTcParams p{out, out_hi, out_lo, ldo, static_cast<int>(lq), static_cast<int>(lk), static_cast<int>(kv_valid),
-                 static_cast<int>(heads)};
+                 static_cast<int>(heads), seed, dropout_threshold(p_drop), 1.0f / (1.0f - p_drop)};
   dim3 grid(static_cast<unsigned>(ceil_div(lq, AT_BQ * AT_GROUPS)), static_cast<unsigned>(heads), static_cast<unsigned>(batch));
   if (wide) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM_BYTES);
+    auto kernel = p_drop > 0.f ? attention_tc128_kernel<true> : attention_tc128_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM_BYTES);
     if (e != cudaSuccess) return static_cast<int>(e);
-    attention_tc128_kernel<<<grid, AT_THREADS, A2_SMEM_BYTES, s>>>(mqh, mql, mkh, mkl, mvh, mvl, p);
+    kernel<<<grid, AT_THREADS, A2_SMEM_BYTES, s>>>(mqh, mql, mkh, mkl, mvh, mvl, p);
     return launch_status();
   }
   cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);

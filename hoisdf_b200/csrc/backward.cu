@@ -359,18 +359,10 @@ softmax_rows_bwd_kernel(const float* __restrict__ p, int64_t ldp, const float* d
 
 
 // ---- nn.MultiheadAttention's dropout on the attention probabilities (upstream cfg.dropout = 0.1, transformer.py layers)
-// without materialising a mask: keep(r, c) is a counter-based hash of (seed, r * cols + c), so the backward regenerates the
-// very same decisions from the seed.  The forward emits the dropped, rescaled probabilities pd = keep ? p / (1 - q) : 0 (and
+// without materialising a mask: keep(r, c) is a counter-based hash of (seed, r, c) (common.cuh), so the backward regenerates
+// the very same decisions from the seed.  The forward emits the dropped, rescaled probabilities pd = keep ? p / (1 - q) : 0 (and
 // optionally p itself); the backward folds the mask into the softmax derivative:
 //   g = keep ? dpd / (1 - q) : 0;   ds = p * (g - sum_j g_j p_j).
-__host__ __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t idx, float p_drop) {
-  uint64_t z = seed + (idx + 1) * 0x9E3779B97F4A7C15ull;          // splitmix64 finaliser
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  return static_cast<float>(z >> 40) * (1.0f / 16777216.0f) >= p_drop;     // 24 uniform bits
-}
-
 __global__ void __launch_bounds__(256)
 softmax_dropout_rows_fwd_kernel(const float* s, int64_t lds, int64_t rows, int cols, int valid,
                                 const uint8_t* __restrict__ mask, int64_t mask_rows, float* p, int64_t ldp, float* pd,
@@ -388,10 +380,11 @@ softmax_dropout_rows_fwd_kernel(const float* s, int64_t lds, int64_t rows, int c
     if (mrow == nullptr || mrow[c] == 0) sum += expf(s[r * lds + c] - mx);
   sum = warp_sum(sum);
   const float keep_scale = 1.0f / (1.0f - p_drop);
+  const uint32_t key = dropout_row_key(seed, static_cast<uint64_t>(r)), thr = dropout_threshold(p_drop);
   for (int c = lane; c < cols; c += 32) {
     const bool on = c < valid && (mrow == nullptr || mrow[c] == 0);
     const float pv = on ? expf(s[r * lds + c] - mx) / sum : 0.f;      // (s may alias p or pd: read before either write)
-    const bool keep = dropout_keep(seed, static_cast<uint64_t>(r) * cols + c, p_drop);
+    const bool keep = dropout_keep(key, static_cast<uint32_t>(c), thr);
     if (p != nullptr) p[r * ldp + c] = pv;
     pd[r * ldpd + c] = keep ? pv * keep_scale : 0.f;
   }
@@ -404,14 +397,15 @@ softmax_dropout_rows_bwd_kernel(const float* __restrict__ p, int64_t ldp, const 
   const int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (r >= rows) return;
   const float keep_scale = 1.0f / (1.0f - p_drop);
+  const uint32_t key = dropout_row_key(seed, static_cast<uint64_t>(r)), thr = dropout_threshold(p_drop);
   float dot = 0.f;
   for (int c = lane; c < cols; c += 32) {
-    const float g = dropout_keep(seed, static_cast<uint64_t>(r) * cols + c, p_drop) ? dpd[r * lddp + c] * keep_scale : 0.f;
+    const float g = dropout_keep(key, static_cast<uint32_t>(c), thr) ? dpd[r * lddp + c] * keep_scale : 0.f;
     dot = fmaf(g, p[r * ldp + c], dot);
   }
   dot = warp_sum(dot);
   for (int c = lane; c < cols; c += 32) {
-    const float g = dropout_keep(seed, static_cast<uint64_t>(r) * cols + c, p_drop) ? dpd[r * lddp + c] * keep_scale : 0.f;
+    const float g = dropout_keep(key, static_cast<uint32_t>(c), thr) ? dpd[r * lddp + c] * keep_scale : 0.f;
     ds[r * ldds + c] = p[r * ldp + c] * (g - dot);
   }
 }

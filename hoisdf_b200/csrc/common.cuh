@@ -61,4 +61,27 @@ __device__ __forceinline__ void lattice_point(int idx, int bins, float& s0, floa
   s2 = __fadd_rn(__fmul_rn(c2, vs), -1.0f);
 }
 
+// ---- counter-based dropout decisions (nn.MultiheadAttention's dropout on the attention probabilities, upstream cfg.dropout):
+// keep(row, col) is a pure function of (seed, row, col), so the backward regenerates the forward's decisions from the seed
+// alone.  Two levels: a 32-bit key per probability ROW (splitmix64 finaliser of (seed, row), computed once per row) and a
+// 32-bit avalanche hash of (key, col) per element -- ~10 integer instructions, cheap enough for the softmax warps of the
+// tensor-core attention kernel.  An element is dropped when its top 24 hash bits fall below p_drop * 2^24.
+__host__ __device__ __forceinline__ uint32_t dropout_row_key(uint64_t seed, uint64_t row) {
+  uint64_t z = seed + (row + 1) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return static_cast<uint32_t>(z ^ (z >> 32));
+}
+__host__ __device__ __forceinline__ uint32_t dropout_threshold(float p_drop) {       // p_drop in [0, 1)
+  return static_cast<uint32_t>(p_drop * 16777216.0f + 0.5f);
+}
+__host__ __device__ __forceinline__ bool dropout_keep(uint32_t row_key, uint32_t col, uint32_t threshold) {
+  uint32_t x = row_key + col * 0x9E3779B1u;
+  x ^= x >> 16; x *= 0x7FEB352Du;
+  x ^= x >> 15; x *= 0x846CA68Bu;
+  x ^= x >> 16;
+  return (x >> 8) >= threshold;
+}
+
 }  // namespace hoisdf

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 26
+#define HOISDF_ABI_VERSION 27
 
 enum {
   HOISDF_OK = 0,
@@ -426,6 +426,16 @@ int64_t hoisdf_attention_workspace_bytes(int64_t batch, int64_t heads, int64_t l
 int hoisdf_attention_fwd(const float* q, int64_t ldq, const float* k, const float* v, int64_t ldk, float* out,
                          int64_t ldo, int64_t batch, int64_t heads, int64_t lq, int64_t lk, int64_t kv_valid,
                          const uint8_t* mask, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Training forward of the same operator with nn.MultiheadAttention's dropout on the probabilities (upstream
+ * common/nets/transformer.py:294 with cfg.dropout, main/config.py): out = dropout(softmax(q k^T / 8), p_drop) . v on the
+ * tensor-core kernel, the S x S probabilities never leave the SM.  The keep decisions are a counter hash of
+ * (seed, (sample * heads + head) * lq + query, key) -- the ones hoisdf_softmax_dropout_rows_fwd / _bwd (below) regenerate
+ * on the (B, H, Lq, Lk) probabilities in the backward.  No dense mask; min(lk, kv_valid) >= 128 (HOISDF_E_UNSUPPORTED
+ * otherwise: use the materialised form); 0 <= p_drop < 1; workspace as for hoisdf_attention_fwd (required). */
+int hoisdf_attention_dropout_fwd(const float* q, int64_t ldq, const float* k, const float* v, int64_t ldk, float* out,
+                                 int64_t ldo, int64_t batch, int64_t heads, int64_t lq, int64_t lk, int64_t kv_valid,
+                                 float p_drop, uint64_t seed, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* The tensor-core path of hoisdf_attention_fwd (workspace required, no dense mask) writing its result in split-half
  * format (two fp16 planes, pitch ldo halfs, multiple of 8) -- what the FP16x3 out-projection GEMM reads. */

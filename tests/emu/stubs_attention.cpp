@@ -5,7 +5,7 @@
 namespace hoisdf {
 int64_t attention_tc_workspace_bytes(int64_t, int64_t, int64_t, int64_t) { return 0; }
 int launch_attention_tc(const float*, int64_t, const float*, const float*, int64_t, float*, int64_t, int64_t, int64_t,
-                        int64_t, int64_t, int64_t, void*, cudaStream_t, uint16_t*, uint16_t*) {
+                        int64_t, int64_t, int64_t, void*, cudaStream_t, uint16_t*, uint16_t*, float, uint64_t) {
   return HOISDF_E_UNSUPPORTED;
 }
 }  // namespace hoisdf

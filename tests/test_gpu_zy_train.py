@@ -165,25 +165,45 @@ def test_attention_fn(cuda, lq, lk, masked, kv_valid):
         _close(a.grad, b.grad, 2e-5, n)
 
 
-def test_attention_fn_with_dropout(cuda):
+@pytest.mark.parametrize("lq,lk,kv_valid,masked,tc", [(150, 170, None, False, True), (300, 800, 700, False, True),
+                                                        (257, 128, None, False, True), (150, 100, None, False, False),
+                                                        (17, 170, None, False, False), (40, 170, None, True, False)])
+def test_attention_fn_with_dropout(cuda, lq, lk, kv_valid, masked, tc, monkeypatch):
     """Dropout on the attention probabilities (nn.MultiheadAttention's; upstream cfg.dropout = 0.1): forward and backward
     against fp64 autograd of softmax -> mask / (1 - q) -> P.V with the SAME keep decisions (regenerated from the seed the
-    Function drew), no mask tensor stored."""
+    Function drew), no mask tensor stored.  Long unmasked sequences run the forward on the tensor-core flash kernel
+    (hoisdf_attention_dropout_fwd), which must make the very decisions the materialised kernels of the backward regenerate."""
     from hoisdf_b200 import autograd as A
-    B, H, d, lq, lk, pdrop = 2, 4, 256, 150, 170, 0.1
+    from hoisdf_b200._capi import lib
+    B, H, d, pdrop = 2, 4, 256, 0.1
+    calls = []
+    real = lib.hoisdf_attention_dropout_fwd
+    monkeypatch.setattr(lib, "hoisdf_attention_dropout_fwd", lambda *a: (calls.append(1), real(*a))[1])
+    mask = None
+    if masked:
+        mask = (_rnd(5, lq, lk) > 0.3)
+        mask[:, 0] = False
     q, k, v, do = _rnd(1, B * lq, d), _rnd(2, B * lk, d), _rnd(3, B * lk, d), _rnd(4, B * lq, d)
     td = [t.to(cuda).requires_grad_() for t in (q, k, v)]
     torch.manual_seed(5)
-    out = A.AttentionFn.apply(td[0], td[1], td[2], B, H, lq, lk, None, None, pdrop)
+    dmask = None if mask is None else mask.to(cuda).to(torch.uint8).contiguous()
+    out = A.AttentionFn.apply(td[0], td[1], td[2], B, H, lq, lk, dmask, kv_valid, pdrop)
+    assert len(calls) == (1 if tc else 0)
     (out * do.to(cuda)).sum().backward()
     torch.manual_seed(5)
     seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64))
-    P, Pd = A.AttentionFn._probs(td[0].detach(), td[1].detach(), B, H, lq, lk, None, None, pdrop, seed, want_p=True)
-    keep = (Pd != 0).cpu()
-    assert abs(float(keep.double().mean()) - (1 - pdrop)) < 0.01
+    P, Pd = A.AttentionFn._probs(td[0].detach(), td[1].detach(), B, H, lq, lk, dmask, kv_valid, pdrop, seed, want_p=True)
+    keep = ((Pd != 0) | (P == 0)).cpu()                       # (blocked keys carry p = 0 whatever their decision)
+    live = (P != 0).cpu()
+    assert abs(float(keep[live].double().mean()) - (1 - pdrop)) < 0.01
     ts = [t.double().requires_grad_() for t in (q, k, v)]
     qh, kh, vh = (t.view(B, -1, H, 64).transpose(1, 2) for t in ts)
-    pr = torch.softmax(qh @ kh.transpose(-1, -2) / 8.0, -1) * keep / (1 - pdrop)
+    sc = qh @ kh.transpose(-1, -2) / 8.0
+    if mask is not None:
+        sc = sc.masked_fill(mask, float("-inf"))
+    if kv_valid is not None:
+        sc[..., kv_valid:] = float("-inf")
+    pr = torch.softmax(sc, -1) * keep / (1 - pdrop)
     ref = (pr @ vh).transpose(1, 2).reshape(B * lq, d)
     (ref * do.double()).sum().backward()
     _close(out, ref, 2e-5, "attention+dropout")
