@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhoisdf_b200.so")
 
-ABI_VERSION = 27
+ABI_VERSION = 28
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2      # ACT_SIGMOID: hoisdf_linear_narrow_split_fwd only
 GATHER_CONCAT, GATHER_SUM = 0, 1
 
@@ -168,7 +168,10 @@ SIGNATURES = {
     "hoisdf_tokens_fwd": (C.c_int, [vp, vp, vp, i64, vp, vp, i64, i64, vp, i64, i64, vp]),
     "hoisdf_attention_workspace_bytes": (i64, [i64, i64, i64, i64]),
     "hoisdf_attention_fwd": (C.c_int, [vp, i64, vp, vp, i64, vp, i64, i64, i64, i64, i64, i64, vp, vp, i64, vp]),
-    "hoisdf_attention_dropout_fwd": (C.c_int, [vp, i64, vp, vp, i64, vp, i64, i64, i64, i64, i64, i64, f32, C.c_uint64, vp, i64, vp]),
+    "hoisdf_attention_train_fwd": (C.c_int, [vp, i64, vp, vp, i64, vp, i64, vp, i64, i64, i64, i64, i64, f32, C.c_uint64, vp, i64, vp]),
+    "hoisdf_attention_bwd_workspace_bytes": (i64, [i64, i64, i64, i64]),
+    "hoisdf_attention_bwd": (C.c_int, [vp, i64, vp, vp, i64, vp, vp, i64, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, f32,
+                                       C.c_uint64, vp, i64, vp]),
     "hoisdf_attention_split_fwd": (C.c_int, [vp, i64, vp, vp, i64, vp, vp, i64, i64, i64, i64, i64, i64, vp, i64, vp]),
     "hoisdf_add_layernorm_fwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp]),
     "hoisdf_add_layernorm_split_fwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp, vp, i64, vp, vp, i64, vp]),

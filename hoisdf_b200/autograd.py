@@ -39,6 +39,7 @@ from .ops import _count, _ptr, _stream
 ACT_NONE, ACT_RELU = ops.ACT_NONE, ops.ACT_RELU
 TRAIN_CHUNK_KB = 4          # TMEM accumulation chunk of the training GEMMs (K blocks of 32 per drain)
 _DEBUG_TORCH_MATMUL = os.environ.get("HOISDF_DEBUG_TORCH_MATMUL", "0") == "1"
+_ATTN_BWD_TC = os.environ.get("HOISDF_ATTN_BWD_TC", "1") != "0"     # 0: batched fp32 FMA attention backward everywhere
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -253,32 +254,33 @@ class AttentionFn(Function):
             assert t.stride(1) == 1 and t.shape[1] == d
         dev = q.device
         out = torch.empty(batch * lq, d, device=dev, dtype=torch.float32)
-        seed = 0
+        seed, lse = 0, None
         if p_drop > 0.0:
             # The keep decisions are a hash of (seed, position): nothing but the seed is kept for the backward (CPU
             # generator: no device sync, reproducible under torch.manual_seed)
             seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64))
-            kend = lk if kv_valid is None else min(lk, kv_valid)
-            if ops.USE_TENSOR_CORES and mask is None and lq > 32 and kend >= 128 and k.stride(0) == v.stride(0):
-                # encoder self-attention: the tensor-core flash kernel applies the dropout to P on its way to P.V
-                nbytes = lib.hoisdf_attention_workspace_bytes(batch, heads, lq, lk)
-                ws = ops._attention_workspace(dev, nbytes)
-                _count(4)
-                check(lib.hoisdf_attention_dropout_fwd(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0),
-                                                       out.data_ptr(), d, batch, heads, lq, lk, kend, float(p_drop), seed,
-                                                       _ptr(ws), nbytes, _stream()), "hoisdf_attention_dropout_fwd")
-            else:
-                # materialised form (masked / short decoder attention): the dropped probabilities Pd (B, H, Lq, Lk) times V
-                pd = AttentionFn._probs(q, k, batch, heads, lq, lk, mask, kv_valid, p_drop, seed)[1]
-                _gemm_batched(pd.data_ptr(), lk, 0, heads * lq * lk, lq * lk, v.data_ptr(), v.stride(0), 0, lk * v.stride(0),
-                              64, out.data_ptr(), d, lq * d, 64, lq, 64, lk, 1.0, batch, heads)
+        kend = lk if kv_valid is None else min(lk, kv_valid)
+        if ops.USE_TENSOR_CORES and mask is None and lq > 32 and kend >= 128 and k.stride(0) == v.stride(0):
+            # encoder self-attention: tensor-core flash kernel (dropout applied to P on its way to P.V); it also leaves the
+            # log-sum-exp rows the tensor-core backward recomputes the probabilities from
+            nbytes = lib.hoisdf_attention_workspace_bytes(batch, heads, lq, lk)
+            ws = ops._attention_workspace(dev, nbytes)
+            lse = torch.empty(batch * heads * lq, device=dev, dtype=torch.float32) if _ATTN_BWD_TC else None
+            _count(4)
+            check(lib.hoisdf_attention_train_fwd(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0),
+                                                 out.data_ptr(), d, _ptr(lse), batch, heads, lq, lk, kend, float(p_drop), seed,
+                                                 _ptr(ws), nbytes, _stream()), "hoisdf_attention_train_fwd")
+        elif p_drop > 0.0:
+            # materialised form (masked / short decoder attention): the dropped probabilities Pd (B, H, Lq, Lk) times V
+            pd = AttentionFn._probs(q, k, batch, heads, lq, lk, mask, kv_valid, p_drop, seed)[1]
+            _gemm_batched(pd.data_ptr(), lk, 0, heads * lq * lk, lq * lk, v.data_ptr(), v.stride(0), 0, lk * v.stride(0),
+                          64, out.data_ptr(), d, lq * d, 64, lq, 64, lk, 1.0, batch, heads)
         else:
-            vv = v
             if k.stride(0) != v.stride(0):
                 raise ValueError("attention: k and v must share their row pitch")
-            ops.attention(q, q.stride(0), k, vv, k.stride(0), out, d, batch, heads, lq, lk, kv_valid=kv_valid, mask=mask,
+            ops.attention(q, q.stride(0), k, v, k.stride(0), out, d, batch, heads, lq, lk, kv_valid=kv_valid, mask=mask,
                           tensor_cores=(mask is None))
-        ctx.save_for_backward(q, k, v, mask)
+        ctx.save_for_backward(q, k, v, mask, lse, out if lse is not None else None)
         ctx.geom = (batch, heads, lq, lk, kv_valid, p_drop, seed)
         return out
 
@@ -303,11 +305,24 @@ class AttentionFn(Function):
 
     @staticmethod
     def backward(ctx, dout):
-        q, k, v, mask = ctx.saved_tensors
+        q, k, v, mask, lse, out = ctx.saved_tensors
         batch, heads, lq, lk, kv_valid, p_drop, seed = ctx.geom
         d = heads * 64
         dev = q.device
         dout = dout.contiguous()
+        if lse is not None:
+            # tensor-core backward: P recomputed tile by tile from the forward's log-sum-exp rows, never materialised
+            dq = torch.empty(batch * lq, d, device=dev, dtype=torch.float32)
+            dk = torch.empty(batch * lk, d, device=dev, dtype=torch.float32)
+            dv = torch.empty(batch * lk, d, device=dev, dtype=torch.float32)
+            nbytes = lib.hoisdf_attention_bwd_workspace_bytes(batch, heads, lq, lk)
+            ws = ops._attention_workspace(dev, nbytes)
+            _count(10)
+            check(lib.hoisdf_attention_bwd(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0), out.data_ptr(),
+                                           dout.data_ptr(), d, lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), d,
+                                           batch, heads, lq, lk, lk if kv_valid is None else min(lk, kv_valid),
+                                           float(p_drop), seed, _ptr(ws), nbytes, _stream()), "hoisdf_attention_bwd")
+            return dq, dk, dv, None, None, None, None, None, None, None
         p, pd = AttentionFn._probs(q, k, batch, heads, lq, lk, mask, kv_valid, p_drop, seed, want_p=True)
         dq = torch.empty(batch * lq, d, device=dev, dtype=torch.float32)
         dk = torch.empty(batch * lk, d, device=dev, dtype=torch.float32)

@@ -239,7 +239,13 @@ int64_t attention_tc_workspace_bytes(int64_t batch, int64_t heads, int64_t lq, i
 int launch_attention_tc(const float* q, int64_t ldq, const float* k, const float* v, int64_t ldk, float* out,
                         int64_t ldo, int64_t batch, int64_t heads, int64_t lq, int64_t lk, int64_t kv_valid,
                         void* workspace, cudaStream_t s, uint16_t* out_hi = nullptr, uint16_t* out_lo = nullptr,
-                        float p_drop = 0.f, uint64_t seed = 0);
+                        float p_drop = 0.f, uint64_t seed = 0, float* lse = nullptr);
+
+int64_t attention_bwd_tc_workspace_bytes(int64_t batch, int64_t heads, int64_t lq, int64_t lk);
+int launch_attention_bwd_tc(const float* q, int64_t ldq, const float* k, const float* v, int64_t ldk, const float* out,
+                            const float* dout, int64_t ldo, const float* lse, float* dq, float* dk, float* dv, int64_t ldg,
+                            int64_t batch, int64_t heads, int64_t lq, int64_t lk, int64_t kv_valid, float p_drop,
+                            uint64_t seed, void* workspace, cudaStream_t s);
 
 }  // namespace hoisdf
 
@@ -290,10 +296,10 @@ HOISDF_API int hoisdf_attention_fwd(const float* q, int64_t ldq, const float* k,
   return launch_status();
 }
 
-HOISDF_API int hoisdf_attention_dropout_fwd(const float* q, int64_t ldq, const float* k, const float* v, int64_t ldk,
-                                            float* out, int64_t ldo, int64_t batch, int64_t heads, int64_t lq, int64_t lk,
-                                            int64_t kv_valid, float p_drop, uint64_t seed, void* workspace,
-                                            int64_t workspace_bytes, void* stream) {
+HOISDF_API int hoisdf_attention_train_fwd(const float* q, int64_t ldq, const float* k, const float* v, int64_t ldk,
+                                          float* out, int64_t ldo, float* lse, int64_t batch, int64_t heads, int64_t lq,
+                                          int64_t lk, int64_t kv_valid, float p_drop, uint64_t seed, void* workspace,
+                                          int64_t workspace_bytes, void* stream) {
   if (q == nullptr || k == nullptr || v == nullptr || out == nullptr || workspace == nullptr) return HOISDF_E_NULL;
   if (batch <= 0 || batch > 65535 || heads <= 0 || heads > 65535 || lq <= 0 || lk <= 0 || kv_valid <= 0 ||
       lq > (1 << 24) || lk > (1 << 24) || !(p_drop >= 0.f && p_drop < 1.f))
@@ -305,7 +311,31 @@ HOISDF_API int hoisdf_attention_dropout_fwd(const float* q, int64_t ldq, const f
   if (workspace_bytes < attention_tc_workspace_bytes(batch, heads, lq, lk)) return HOISDF_E_SHAPE;
   if ((kv_valid < lk ? kv_valid : lk) < 128) return HOISDF_E_UNSUPPORTED;       // the 128-key tensor-core kernel only
   return launch_attention_tc(q, ldq, k, v, ldk, out, ldo, batch, heads, lq, lk, kv_valid < lk ? kv_valid : lk, workspace,
-                             static_cast<cudaStream_t>(stream), nullptr, nullptr, p_drop, seed);
+                             static_cast<cudaStream_t>(stream), nullptr, nullptr, p_drop, seed, lse);
+}
+
+HOISDF_API int64_t hoisdf_attention_bwd_workspace_bytes(int64_t batch, int64_t heads, int64_t lq, int64_t lk) {
+  if (batch <= 0 || heads <= 0 || lq <= 0 || lk <= 0) return 0;
+  return attention_bwd_tc_workspace_bytes(batch, heads, lq, lk);
+}
+
+HOISDF_API int hoisdf_attention_bwd(const float* q, int64_t ldq, const float* k, const float* v, int64_t ldk, const float* out,
+                                    const float* dout, int64_t ldo, const float* lse, float* dq, float* dk, float* dv,
+                                    int64_t ldg, int64_t batch, int64_t heads, int64_t lq, int64_t lk, int64_t kv_valid,
+                                    float p_drop, uint64_t seed, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (q == nullptr || k == nullptr || v == nullptr || out == nullptr || dout == nullptr || lse == nullptr || dq == nullptr ||
+      dk == nullptr || dv == nullptr || workspace == nullptr)
+    return HOISDF_E_NULL;
+  if (batch <= 0 || batch > 65535 || heads <= 0 || heads > 65535 || lq <= 0 || lk <= 0 || kv_valid <= 0 ||
+      lq > (1 << 24) || lk > (1 << 24) || !(p_drop >= 0.f && p_drop < 1.f))
+    return HOISDF_E_SHAPE;
+  if (ldq < heads * HD || ldk < heads * HD || ldo < heads * HD || ldg < heads * HD) return HOISDF_E_SHAPE;
+  if ((ldq & 3) || (ldk & 3) || (ldo & 3) || (ldg & 3) || !aligned16(q) || !aligned16(k) || !aligned16(v) ||
+      !aligned16(out) || !aligned16(dout) || !aligned16(dq) || !aligned16(dk) || !aligned16(dv) || !aligned16(workspace))
+    return HOISDF_E_ALIGN;
+  if (workspace_bytes < attention_bwd_tc_workspace_bytes(batch, heads, lq, lk)) return HOISDF_E_SHAPE;
+  return launch_attention_bwd_tc(q, ldq, k, v, ldk, out, dout, ldo, lse, dq, dk, dv, ldg, batch, heads, lq, lk,
+                                 kv_valid < lk ? kv_valid : lk, p_drop, seed, workspace, static_cast<cudaStream_t>(stream));
 }
 
 HOISDF_API int hoisdf_attention_split_fwd(const float* q, int64_t ldq, const float* k, const float* v, int64_t ldk,

@@ -56,6 +56,8 @@ struct AttnTcParams {
   uint64_t seed;
   uint32_t drop_threshold;
   float keep_scale;                  // 1 / (1 - p_drop)
+  float* __restrict__ lse;           // (B*H*lq) log2-sum-exp of the scaled score rows (log2 units), or nullptr: what the
+                                     // tensor-core backward recomputes P = 2^(s - lse) from
 };
 
 __device__ __forceinline__ uint32_t at_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -722,6 +724,7 @@ attention_tc128_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int row = q0 + g * AT_BQ + r;
     const float inv = __fdiv_rn(1.f, l_run);
+    if (p.lse != nullptr && row < p.lq) p.lse[bh * p.lq + row] = m_run + log2f(l_run);
     const int64_t oo = (b * p.lq + row) * p.ldo + h * AT_D;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -751,6 +754,474 @@ attention_tc128_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid
             *reinterpret_cast<uint4*>(p.out_lo + oo + half * 32 + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
           }
         }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(AT_TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// backward of the encoder self-attention on the tensor cores (training step)
+// ---------------------------------------------------------------------------------------------------
+// With the forward's log-sum-exp rows (lse, log2 units) and delta_i = sum_d dO_id O_id the probabilities are recomputed tile
+// by tile, P_ij = 2^(s_ij - lse_i), and never stored:
+//      g_ij  = keep_ij ? (dO V^T)_ij / (1 - q) : 0            (keep == 1 without dropout)
+//      dS_ij = P_ij (g_ij - delta_i)
+//      dQ = dS K / 8         dK = dS^T Q / 8         dV = Pd^T dO,   Pd_ij = keep_ij ? P_ij / (1 - q) : 0
+// Two kernels, both built from the forward's pieces (BF16x3 products, S in TMEM, the softmax warps rewrite it in place as
+// the bf16 hi / lo A operand of the next MMA, every shared-memory operand K-major through TMA with the 128-byte swizzle):
+//   attention_bwd_dq_kernel   CTA = 128 queries of one (sample, head); TMEM lanes = queries.  Per 128-key tile:
+//                             S = Q K_t^T and dP = dO V_t^T (M128 N128 K64), dS in place of S, dQ += dS K_t (B = K^T copy)
+//   attention_bwd_dkv_kernel  CTA = 128 keys; TMEM lanes = keys.  Per 128-query tile: S^T = K Q_t^T, dP^T = V dO_t^T,
+//                             Pd^T in place of S^T, dS^T in place of dP^T, dV += Pd^T dO_t (B = dO^T copy),
+//                             dK += dS^T Q_t (B = Q^T copy)
+// so every product has its contraction axis contiguous in both operands and no accumulator is shared between CTAs (no
+// atomics; the price is that S and dP are formed twice, 2 x 24 of the 120 MMAs per tile pair).
+// 320 threads: warp 0 TMA, warp 1 MMA issue, warps 2..9 the element-wise stage -- TMEM lane quarter = warp % 4, the two
+// warps of a quarter split the 128 columns.  In-place operand layout, per chunk c of 32 columns: fp32 columns [32c, 32c+32)
+// become bf16 pairs hi [32c, 32c+16) | lo [32c+16, 32c+32), so a warp only overwrites columns it has read itself.
+constexpr int AB_THREADS = 64 + 256;
+constexpr int AB_TILE = 128 * AT_D * 2;            // one bf16 term of a 128 x 64 row tile: 16 KB
+constexpr int AB_TBOX = AT_D * 64 * 2;             // one 64-column box of a transposed (64 x L) operand: 8 KB
+constexpr int AB_DQ_SMEM = 8 * AB_TILE + 4 * AB_TBOX + 1024 + 256;          // Q dO | K V | K^T
+constexpr int AB_DKV_SMEM = 8 * AB_TILE + 8 * AB_TBOX + 1024 + 256;         // K V | Q dO | Q^T dO^T
+
+struct AttnBwdParams {
+  const float* __restrict__ lse;      // (B*H*lq), log2 units (attention_tc128_kernel)
+  const float* __restrict__ delta;    // (B*H*lq)
+  float* __restrict__ dq;             // (B*lq, ldg)
+  float* __restrict__ dk;             // (B*lk, ldg)
+  float* __restrict__ dv;
+  int64_t ldg;
+  int lq, lk, kv_valid, heads;
+  uint64_t seed;
+  uint32_t drop_threshold;
+  float keep_scale;
+};
+
+// delta[(b*H + h)*lq + i] = sum_d dO[b*lq + i][64h + d] * O[...]: one warp per (row, head)
+__global__ void attn_bwd_delta_kernel(const float* __restrict__ dout, const float* __restrict__ out, int64_t ldo, int64_t batch,
+                                      int heads, int64_t lq, float* __restrict__ delta) {
+  const int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= batch * lq * heads) return;
+  const int64_t row = w / heads;
+  const int h = static_cast<int>(w - row * heads);
+  const int64_t b = row / lq, i = row - b * lq;
+  const float2 a = __ldg(reinterpret_cast<const float2*>(dout + row * ldo + h * 64 + lane * 2));
+  const float2 o = __ldg(reinterpret_cast<const float2*>(out + row * ldo + h * 64 + lane * 2));
+  const float s = warp_sum(fmaf(a.x, o.x, a.y * o.y));
+  if (lane == 0) delta[(b * heads + h) * lq + i] = s;
+}
+
+__device__ __forceinline__ void at_named_barrier(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+template <bool DROP>
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant__ CUtensorMap map_qlo,
+                        const __grid_constant__ CUtensorMap map_dohi, const __grid_constant__ CUtensorMap map_dolo,
+                        const __grid_constant__ CUtensorMap map_khi, const __grid_constant__ CUtensorMap map_klo,
+                        const __grid_constant__ CUtensorMap map_vhi, const __grid_constant__ CUtensorMap map_vlo,
+                        const __grid_constant__ CUtensorMap map_kthi, const __grid_constant__ CUtensorMap map_ktlo,
+                        const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = at_smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw);
+  const uint32_t s_q = base;                        // Q hi | Q lo | dO hi | dO lo   (resident)
+  const uint32_t s_kv = base + 4 * AB_TILE;         // K hi | K lo | V hi | V lo     (key tile t)
+  const uint32_t s_kt = base + 8 * AB_TILE;         // K^T hi (2 boxes) | K^T lo (2 boxes)
+  const uint32_t bars = s_kt + 4 * AB_TBOX;
+  const uint32_t bar_q = bars, bar_kvf = bars + 8, bar_kve = bars + 16, bar_ktf = bars + 24, bar_kte = bars + 32,
+                 bar_sf = bars + 40, bar_pf = bars + 48, bar_of = bars + 56;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (bars - base) + 64);
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128;
+  const int h = blockIdx.y;
+  const int64_t b = blockIdx.z;
+  const int64_t bh = b * p.heads + h;
+  const int kend = min(p.lk, p.kv_valid);
+  const int T = (kend + 127) / 128;
+
+  if (threadIdx.x == 0) {
+    at_mbar_init(bar_q, 1);
+    at_mbar_init(bar_kvf, 1); at_mbar_init(bar_kve, 1);
+    at_mbar_init(bar_ktf, 1); at_mbar_init(bar_kte, 1);
+    at_mbar_init(bar_sf, 1); at_mbar_init(bar_pf, 8); at_mbar_init(bar_of, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(at_smem_u32(tmem_slot)),
+                 "r"(AT_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const uint32_t tmem_s = tmem, tmem_dp = tmem + 128u, tmem_acc = tmem + 256u;
+
+  if (warp == 0) {
+    const bool leader = at_elect_one();
+    const int qrow = static_cast<int>(bh * p.lq + q0);
+    if (leader) at_mbar_expect_tx(bar_q, 4 * AB_TILE);
+    if (leader) at_tma_2d(s_q, &map_qhi, bar_q, 0, qrow);
+    if (leader) at_tma_2d(s_q + AB_TILE, &map_qlo, bar_q, 0, qrow);
+    if (leader) at_tma_2d(s_q + 2 * AB_TILE, &map_dohi, bar_q, 0, qrow);
+    if (leader) at_tma_2d(s_q + 3 * AB_TILE, &map_dolo, bar_q, 0, qrow);
+    const int trow = static_cast<int>(bh * AT_D);
+    for (int t = 0; t < T; ++t) {
+      const uint32_t ph = (t & 1) ^ 1u;
+      const int krow = static_cast<int>(bh * p.lk + t * 128);
+      at_mbar_wait(bar_kve, ph);
+      if (leader) at_mbar_expect_tx(bar_kvf, 4 * AB_TILE);
+      if (leader) at_tma_2d(s_kv, &map_khi, bar_kvf, 0, krow);
+      if (leader) at_tma_2d(s_kv + AB_TILE, &map_klo, bar_kvf, 0, krow);
+      if (leader) at_tma_2d(s_kv + 2 * AB_TILE, &map_vhi, bar_kvf, 0, krow);
+      if (leader) at_tma_2d(s_kv + 3 * AB_TILE, &map_vlo, bar_kvf, 0, krow);
+      at_mbar_wait(bar_kte, ph);
+      if (leader) at_mbar_expect_tx(bar_ktf, 4 * AB_TBOX);
+      if (leader) at_tma_2d(s_kt, &map_kthi, bar_ktf, t * 128, trow);
+      if (leader) at_tma_2d(s_kt + AB_TBOX, &map_kthi, bar_ktf, t * 128 + 64, trow);
+      if (leader) at_tma_2d(s_kt + 2 * AB_TBOX, &map_ktlo, bar_ktf, t * 128, trow);
+      if (leader) at_tma_2d(s_kt + 3 * AB_TBOX, &map_ktlo, bar_ktf, t * 128 + 64, trow);
+    }
+  } else if (warp == 1) {
+    const bool leader = at_elect_one();
+    const uint32_t idesc_common = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(128 >> 4) << 24);
+    const uint32_t idesc_n128 = idesc_common | (static_cast<uint32_t>(128 >> 3) << 17);
+    const uint32_t idesc_n64 = idesc_common | (static_cast<uint32_t>(64 >> 3) << 17);
+    const uint64_t d_qhi = at_desc_sw128(s_q), d_qlo = at_desc_sw128(s_q + AB_TILE);
+    const uint64_t d_dohi = at_desc_sw128(s_q + 2 * AB_TILE), d_dolo = at_desc_sw128(s_q + 3 * AB_TILE);
+    const uint64_t d_khi = at_desc_sw128(s_kv), d_klo = at_desc_sw128(s_kv + AB_TILE);
+    const uint64_t d_vhi = at_desc_sw128(s_kv + 2 * AB_TILE), d_vlo = at_desc_sw128(s_kv + 3 * AB_TILE);
+    at_mbar_wait(bar_q, 0);
+    for (int t = 0; t < T; ++t) {
+      at_mbar_wait(bar_kvf, t & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int kk = 0; kk < AT_D / 16; ++kk) {                   // S = Q K_t^T
+        const uint64_t adv = static_cast<uint64_t>(kk * 2);
+        if (leader) at_umma_bf16(tmem_s, d_qlo + adv, d_khi + adv, idesc_n128, kk != 0 ? 1u : 0u);
+        if (leader) at_umma_bf16(tmem_s, d_qhi + adv, d_klo + adv, idesc_n128, 1u);
+        if (leader) at_umma_bf16(tmem_s, d_qhi + adv, d_khi + adv, idesc_n128, 1u);
+      }
+#pragma unroll
+      for (int kk = 0; kk < AT_D / 16; ++kk) {                   // dP = dO V_t^T
+        const uint64_t adv = static_cast<uint64_t>(kk * 2);
+        if (leader) at_umma_bf16(tmem_dp, d_dolo + adv, d_vhi + adv, idesc_n128, kk != 0 ? 1u : 0u);
+        if (leader) at_umma_bf16(tmem_dp, d_dohi + adv, d_vlo + adv, idesc_n128, 1u);
+        if (leader) at_umma_bf16(tmem_dp, d_dohi + adv, d_vhi + adv, idesc_n128, 1u);
+      }
+      if (leader) at_commit(bar_sf);
+      if (leader) at_commit(bar_kve);                            // K / V row tiles consumed
+      at_mbar_wait(bar_pf, t & 1);                               // dS_t written over S_t
+      at_mbar_wait(bar_ktf, t & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {                           // dQ += dS K_t: 16 keys per step
+        const uint32_t a_hi = tmem_s + static_cast<uint32_t>((kk >> 1) * 32 + (kk & 1) * 8), a_lo = a_hi + 16;
+        const uint32_t box = static_cast<uint32_t>(kk >> 2) * AB_TBOX;
+        const uint64_t adv = static_cast<uint64_t>((kk & 3) * 2);
+        const uint64_t d_hi = at_desc_sw128(s_kt + box) + adv, d_lo = at_desc_sw128(s_kt + 2 * AB_TBOX + box) + adv;
+        if (leader) at_umma_bf16_ts(tmem_acc, a_lo, d_hi, idesc_n64, (t | kk) != 0 ? 1u : 0u);
+        if (leader) at_umma_bf16_ts(tmem_acc, a_hi, d_lo, idesc_n64, 1u);
+        if (leader) at_umma_bf16_ts(tmem_acc, a_hi, d_hi, idesc_n64, 1u);
+      }
+      if (leader) at_commit(bar_kte);
+      if (t + 1 == T && leader) at_commit(bar_of);
+    }
+  } else {
+    const int qd = warp & 3;                           // TMEM lane quarter of this warp
+    const int half = (warp - 2) >> 2;                  // which 64 of the 128 columns
+    const int r = qd * 32 + lane;                      // query row of the tile == TMEM lane
+    const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
+    const int qi = q0 + r;
+    const bool row_ok = qi < p.lq;
+    // an absent row: lse = +inf makes every p exactly 0
+    const float lse = row_ok ? __ldg(p.lse + bh * p.lq + qi) : INFINITY;
+    const float delta = row_ok ? __ldg(p.delta + bh * p.lq + qi) : 0.f;
+    uint32_t drop_key = 0;
+    if (DROP) drop_key = dropout_row_key(p.seed, static_cast<uint64_t>(bh) * p.lq + static_cast<uint64_t>(qi));
+    for (int t = 0; t < T; ++t) {
+      at_mbar_wait(bar_sf, t & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int valid = kend - t * 128;                // keys of this tile that exist
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;
+        uint32_t sv[32], dp[32], hi[16], lo[16];
+        at_tmem_ld32(tmem_s + lane_addr + c * 32, sv);
+        at_tmem_ld32(tmem_dp + lane_addr + c * 32, dp);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          float ds[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int col = c * 32 + 2 * e + u;
+            const float pv = ex2_approx(__uint_as_float(sv[2 * e + u]) - lse);
+            float g = __uint_as_float(dp[2 * e + u]);
+            if (DROP) g = dropout_keep(drop_key, static_cast<uint32_t>(t * 128 + col), p.drop_threshold) ? g * p.keep_scale : 0.f;
+            ds[u] = col < valid ? pv * (g - delta) : 0.f;
+          }
+          split_bf16x2(ds[0], ds[1], hi[e], lo[e]);
+        }
+        at_tmem_st16(tmem_s + lane_addr + c * 32, hi);
+        at_tmem_st16(tmem_s + lane_addr + c * 32 + 16, lo);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) at_mbar_arrive(bar_pf);
+    }
+    at_mbar_wait(bar_of, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t o[32];
+    at_tmem_ld32(tmem_acc + lane_addr + half * 32, o);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (row_ok) {
+      float* dst = p.dq + (b * p.lq + qi) * p.ldg + h * AT_D + half * 32;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(dst + j) =
+            make_float4(__uint_as_float(o[j]) * 0.125f, __uint_as_float(o[j + 1]) * 0.125f,
+                        __uint_as_float(o[j + 2]) * 0.125f, __uint_as_float(o[j + 3]) * 0.125f);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(AT_TMEM_COLS) : "memory");
+  }
+}
+
+template <bool DROP>
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_khi, const __grid_constant__ CUtensorMap map_klo,
+                         const __grid_constant__ CUtensorMap map_vhi, const __grid_constant__ CUtensorMap map_vlo,
+                         const __grid_constant__ CUtensorMap map_qhi, const __grid_constant__ CUtensorMap map_qlo,
+                         const __grid_constant__ CUtensorMap map_dohi, const __grid_constant__ CUtensorMap map_dolo,
+                         const __grid_constant__ CUtensorMap map_qthi, const __grid_constant__ CUtensorMap map_qtlo,
+                         const __grid_constant__ CUtensorMap map_dothi, const __grid_constant__ CUtensorMap map_dotlo,
+                         const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ float lse_s[2][128];
+  __shared__ float delta_s[2][128];
+  __shared__ uint32_t key_s[2][128];
+  const uint32_t raw = at_smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw);
+  const uint32_t s_kv = base;                       // K hi | K lo | V hi | V lo      (resident)
+  const uint32_t s_qd = base + 4 * AB_TILE;         // Q hi | Q lo | dO hi | dO lo    (query tile t)
+  const uint32_t s_t = base + 8 * AB_TILE;          // Q^T hi (2 boxes) | Q^T lo | dO^T hi | dO^T lo
+  const uint32_t bars = s_t + 8 * AB_TBOX;
+  const uint32_t bar_kv = bars, bar_rf = bars + 8, bar_re = bars + 16, bar_tf = bars + 24, bar_te = bars + 32,
+                 bar_sf = bars + 40, bar_pf = bars + 48, bar_of = bars + 56;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (bars - base) + 64);
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * 128;
+  const int h = blockIdx.y;
+  const int64_t b = blockIdx.z;
+  const int64_t bh = b * p.heads + h;
+  const int kend = min(p.lk, p.kv_valid);
+  const int T = (p.lq + 127) / 128;
+
+  if (k0 >= kend) {                                  // keys no query attends to: zero gradients
+    for (int e = threadIdx.x; e < 128 * 16; e += AB_THREADS) {
+      const int r = e >> 4, c4 = (e & 15) * 4;
+      if (k0 + r < p.lk) {
+        const int64_t o = (b * p.lk + k0 + r) * p.ldg + h * AT_D + c4;
+        *reinterpret_cast<float4*>(p.dk + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(p.dv + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    return;
+  }
+
+  if (threadIdx.x == 0) {
+    at_mbar_init(bar_kv, 1);
+    at_mbar_init(bar_rf, 1); at_mbar_init(bar_re, 1);
+    at_mbar_init(bar_tf, 1); at_mbar_init(bar_te, 1);
+    at_mbar_init(bar_sf, 1); at_mbar_init(bar_pf, 8); at_mbar_init(bar_of, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(at_smem_u32(tmem_slot)),
+                 "r"(AT_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const uint32_t tmem_s = tmem, tmem_dp = tmem + 128u, tmem_dv = tmem + 256u, tmem_dk = tmem + 320u;
+
+  if (warp == 0) {
+    const bool leader = at_elect_one();
+    const int krow = static_cast<int>(bh * p.lk + k0);
+    if (leader) at_mbar_expect_tx(bar_kv, 4 * AB_TILE);
+    if (leader) at_tma_2d(s_kv, &map_khi, bar_kv, 0, krow);
+    if (leader) at_tma_2d(s_kv + AB_TILE, &map_klo, bar_kv, 0, krow);
+    if (leader) at_tma_2d(s_kv + 2 * AB_TILE, &map_vhi, bar_kv, 0, krow);
+    if (leader) at_tma_2d(s_kv + 3 * AB_TILE, &map_vlo, bar_kv, 0, krow);
+    const int trow = static_cast<int>(bh * AT_D);
+    for (int t = 0; t < T; ++t) {
+      const uint32_t ph = (t & 1) ^ 1u;
+      const int qrow = static_cast<int>(bh * p.lq + t * 128);
+      at_mbar_wait(bar_re, ph);
+      if (leader) at_mbar_expect_tx(bar_rf, 4 * AB_TILE);
+      if (leader) at_tma_2d(s_qd, &map_qhi, bar_rf, 0, qrow);
+      if (leader) at_tma_2d(s_qd + AB_TILE, &map_qlo, bar_rf, 0, qrow);
+      if (leader) at_tma_2d(s_qd + 2 * AB_TILE, &map_dohi, bar_rf, 0, qrow);
+      if (leader) at_tma_2d(s_qd + 3 * AB_TILE, &map_dolo, bar_rf, 0, qrow);
+      at_mbar_wait(bar_te, ph);
+      if (leader) at_mbar_expect_tx(bar_tf, 8 * AB_TBOX);
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        if (leader) at_tma_2d(s_t + x * AB_TBOX, &map_qthi, bar_tf, t * 128 + 64 * x, trow);
+        if (leader) at_tma_2d(s_t + (2 + x) * AB_TBOX, &map_qtlo, bar_tf, t * 128 + 64 * x, trow);
+        if (leader) at_tma_2d(s_t + (4 + x) * AB_TBOX, &map_dothi, bar_tf, t * 128 + 64 * x, trow);
+        if (leader) at_tma_2d(s_t + (6 + x) * AB_TBOX, &map_dotlo, bar_tf, t * 128 + 64 * x, trow);
+      }
+    }
+  } else if (warp == 1) {
+    const bool leader = at_elect_one();
+    const uint32_t idesc_common = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(128 >> 4) << 24);
+    const uint32_t idesc_n128 = idesc_common | (static_cast<uint32_t>(128 >> 3) << 17);
+    const uint32_t idesc_n64 = idesc_common | (static_cast<uint32_t>(64 >> 3) << 17);
+    const uint64_t d_khi = at_desc_sw128(s_kv), d_klo = at_desc_sw128(s_kv + AB_TILE);
+    const uint64_t d_vhi = at_desc_sw128(s_kv + 2 * AB_TILE), d_vlo = at_desc_sw128(s_kv + 3 * AB_TILE);
+    const uint64_t d_qhi = at_desc_sw128(s_qd), d_qlo = at_desc_sw128(s_qd + AB_TILE);
+    const uint64_t d_dohi = at_desc_sw128(s_qd + 2 * AB_TILE), d_dolo = at_desc_sw128(s_qd + 3 * AB_TILE);
+    at_mbar_wait(bar_kv, 0);
+    for (int t = 0; t < T; ++t) {
+      at_mbar_wait(bar_rf, t & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int kk = 0; kk < AT_D / 16; ++kk) {                   // S^T = K Q_t^T
+        const uint64_t adv = static_cast<uint64_t>(kk * 2);
+        if (leader) at_umma_bf16(tmem_s, d_klo + adv, d_qhi + adv, idesc_n128, kk != 0 ? 1u : 0u);
+        if (leader) at_umma_bf16(tmem_s, d_khi + adv, d_qlo + adv, idesc_n128, 1u);
+        if (leader) at_umma_bf16(tmem_s, d_khi + adv, d_qhi + adv, idesc_n128, 1u);
+      }
+#pragma unroll
+      for (int kk = 0; kk < AT_D / 16; ++kk) {                   // dP^T = V dO_t^T
+        const uint64_t adv = static_cast<uint64_t>(kk * 2);
+        if (leader) at_umma_bf16(tmem_dp, d_vlo + adv, d_dohi + adv, idesc_n128, kk != 0 ? 1u : 0u);
+        if (leader) at_umma_bf16(tmem_dp, d_vhi + adv, d_dolo + adv, idesc_n128, 1u);
+        if (leader) at_umma_bf16(tmem_dp, d_vhi + adv, d_dohi + adv, idesc_n128, 1u);
+      }
+      if (leader) at_commit(bar_sf);
+      if (leader) at_commit(bar_re);                             // Q / dO row tiles consumed
+      at_mbar_wait(bar_pf, t & 1);                               // Pd^T, dS^T written
+      at_mbar_wait(bar_tf, t & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {                           // 16 queries per step
+        const uint32_t off = static_cast<uint32_t>((kk >> 1) * 32 + (kk & 1) * 8);
+        const uint32_t box = static_cast<uint32_t>(kk >> 2) * AB_TBOX;
+        const uint64_t adv = static_cast<uint64_t>((kk & 3) * 2);
+        const uint64_t d_qthi = at_desc_sw128(s_t + box) + adv, d_qtlo = at_desc_sw128(s_t + 2 * AB_TBOX + box) + adv;
+        const uint64_t d_dthi = at_desc_sw128(s_t + 4 * AB_TBOX + box) + adv,
+                       d_dtlo = at_desc_sw128(s_t + 6 * AB_TBOX + box) + adv;
+        const uint32_t acc = (t | kk) != 0 ? 1u : 0u;
+        // dV += Pd^T dO_t
+        if (leader) at_umma_bf16_ts(tmem_dv, tmem_s + off + 16, d_dthi, idesc_n64, acc);
+        if (leader) at_umma_bf16_ts(tmem_dv, tmem_s + off, d_dtlo, idesc_n64, 1u);
+        if (leader) at_umma_bf16_ts(tmem_dv, tmem_s + off, d_dthi, idesc_n64, 1u);
+        // dK += dS^T Q_t
+        if (leader) at_umma_bf16_ts(tmem_dk, tmem_dp + off + 16, d_qthi, idesc_n64, acc);
+        if (leader) at_umma_bf16_ts(tmem_dk, tmem_dp + off, d_qtlo, idesc_n64, 1u);
+        if (leader) at_umma_bf16_ts(tmem_dk, tmem_dp + off, d_qthi, idesc_n64, 1u);
+      }
+      if (leader) at_commit(bar_te);
+      if (t + 1 == T && leader) at_commit(bar_of);
+    }
+  } else {
+    const int qd = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int r = qd * 32 + lane;                      // key row of the tile == TMEM lane
+    const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
+    const int kj = k0 + r;
+    const bool key_ok = kj < kend;
+    const int st = static_cast<int>(threadIdx.x) - 64;           // 0..255 among the element-wise warps
+    for (int t = 0; t < T; ++t) {
+      // per-query (column) terms of this tile; double-buffered: a warp is at most one tile ahead of the slowest one
+      if (st < 128) {
+        const int qi = t * 128 + st;
+        const bool ok = qi < p.lq;
+        lse_s[t & 1][st] = ok ? __ldg(p.lse + bh * p.lq + qi) : INFINITY;      // absent query: p = 0
+        delta_s[t & 1][st] = ok ? __ldg(p.delta + bh * p.lq + qi) : 0.f;
+        if (DROP) key_s[t & 1][st] = dropout_row_key(p.seed, static_cast<uint64_t>(bh) * p.lq + static_cast<uint64_t>(qi));
+      }
+      at_named_barrier(1, 256);
+      at_mbar_wait(bar_sf, t & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;
+        uint32_t sv[32], dp[32], phi[16], plo[16], dhi[16], dlo[16];
+        at_tmem_ld32(tmem_s + lane_addr + c * 32, sv);
+        at_tmem_ld32(tmem_dp + lane_addr + c * 32, dp);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          float pd[2], ds[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int col = c * 32 + 2 * e + u;
+            float pv = ex2_approx(__uint_as_float(sv[2 * e + u]) - lse_s[t & 1][col]);
+            float g = __uint_as_float(dp[2 * e + u]);
+            pd[u] = pv;
+            if (DROP) {
+              const bool keep = dropout_keep(key_s[t & 1][col], static_cast<uint32_t>(kj), p.drop_threshold);
+              g = keep ? g * p.keep_scale : 0.f;
+              pd[u] = keep ? pv * p.keep_scale : 0.f;
+            }
+            ds[u] = pv * (g - delta_s[t & 1][col]);
+            if (!key_ok) { pd[u] = 0.f; ds[u] = 0.f; }
+          }
+          split_bf16x2(pd[0], pd[1], phi[e], plo[e]);
+          split_bf16x2(ds[0], ds[1], dhi[e], dlo[e]);
+        }
+        at_tmem_st16(tmem_s + lane_addr + c * 32, phi);
+        at_tmem_st16(tmem_s + lane_addr + c * 32 + 16, plo);
+        at_tmem_st16(tmem_dp + lane_addr + c * 32, dhi);
+        at_tmem_st16(tmem_dp + lane_addr + c * 32 + 16, dlo);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) at_mbar_arrive(bar_pf);
+    }
+    at_mbar_wait(bar_of, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t ov[32], ok_[32];
+    at_tmem_ld32(tmem_dv + lane_addr + half * 32, ov);
+    at_tmem_ld32(tmem_dk + lane_addr + half * 32, ok_);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (kj < p.lk) {
+      const int64_t o = (b * p.lk + kj) * p.ldg + h * AT_D + half * 32;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        *reinterpret_cast<float4*>(p.dv + o + j) = make_float4(__uint_as_float(ov[j]), __uint_as_float(ov[j + 1]),
+                                                               __uint_as_float(ov[j + 2]), __uint_as_float(ov[j + 3]));
+        *reinterpret_cast<float4*>(p.dk + o + j) =
+            make_float4(__uint_as_float(ok_[j]) * 0.125f, __uint_as_float(ok_[j + 1]) * 0.125f,
+                        __uint_as_float(ok_[j + 2]) * 0.125f, __uint_as_float(ok_[j + 3]) * 0.125f);
       }
     }
   }
@@ -796,7 +1267,7 @@ int64_t attention_tc_workspace_bytes(int64_t batch, int64_t heads, int64_t lq, i
 
 int launch_attention_tc(const float* q, int64_t ldq, const float* k, const float* v, int64_t ldk, float* out,
                         int64_t ldo, int64_t batch, int64_t heads, int64_t lq, int64_t lk, int64_t kv_valid,
-                        void* workspace, cudaStream_t s, uint16_t* out_hi, uint16_t* out_lo, float p_drop, uint64_t seed) {
+                        void* workspace, cudaStream_t s, uint16_t* out_hi, uint16_t* out_lo, float p_drop, uint64_t seed, float* lse) {
   if (batch * heads * (lq > lk ? lq : lk) > 0x7fffff00LL) return HOISDF_E_SHAPE;  // TMA row coordinates are int32
   const int64_t lk_pad = (lk + 7) / 8 * 8;
   auto up = [](int64_t x) { return (x + 255) / 256 * 256; };
@@ -826,9 +1297,9 @@ int launch_attention_tc(const float* q, int64_t ldq, const float* k, const float
       !at_make_map(&mkh, khi, bh * lk, AT_D, AT_D, kbox) || !at_make_map(&mkl, klo, bh * lk, AT_D, AT_D, kbox) ||
       !at_make_map(&mvh, vhi, bh * AT_D, lk_pad, lk_pad, AT_D) || !at_make_map(&mvl, vlo, bh * AT_D, lk_pad, lk_pad, AT_D))
     return HOISDF_E_UNSUPPORTED;
-  if (p_drop > 0.f && !wide) return HOISDF_E_UNSUPPORTED;      // dropout lives in the 128-key kernel only
+  if ((p_drop > 0.f || lse != nullptr) && !wide) return HOISDF_E_UNSUPPORTED;      // training: the 128-key kernel only
   AttnTcParams p{out, out_hi, out_lo, ldo, static_cast<int>(lq), static_cast<int>(lk), static_cast<int>(kv_valid),
-                 static_cast<int>(heads), seed, dropout_threshold(p_drop), 1.0f / (1.0f - p_drop)};
+                 static_cast<int>(heads), seed, dropout_threshold(p_drop), 1.0f / (1.0f - p_drop), lse};
   dim3 grid(static_cast<unsigned>(ceil_div(lq, AT_BQ * AT_GROUPS)), static_cast<unsigned>(heads), static_cast<unsigned>(batch));
   if (wide) {
     auto kernel = p_drop > 0.f ? attention_tc128_kernel<true> : attention_tc128_kernel<false>;
@@ -840,6 +1311,77 @@ int launch_attention_tc(const float* q, int64_t ldq, const float* k, const float
   cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
   if (e != cudaSuccess) return static_cast<int>(e);
   attention_tc_kernel<<<grid, AT_THREADS, AT_SMEM_BYTES, s>>>(mqh, mql, mkh, mkl, mvh, mvl, p);
+  return launch_status();
+}
+
+
+int64_t attention_bwd_tc_workspace_bytes(int64_t batch, int64_t heads, int64_t lq, int64_t lk) {
+  const int64_t lq_pad = (lq + 7) / 8 * 8, lk_pad = (lk + 7) / 8 * 8, bh = batch * heads;
+  auto up = [](int64_t x) { return (x + 255) / 256 * 256; };
+  const int64_t qb = up(bh * lq * AT_D * 2), kb = up(bh * lk * AT_D * 2), qtb = up(bh * AT_D * lq_pad * 2),
+                ktb = up(bh * AT_D * lk_pad * 2);
+  return 4 * qb + 4 * kb + 4 * qtb + 2 * ktb + up(bh * lq * 4);
+}
+
+int launch_attention_bwd_tc(const float* q, int64_t ldq, const float* k, const float* v, int64_t ldk, const float* out,
+                            const float* dout, int64_t ldo, const float* lse, float* dq, float* dk, float* dv, int64_t ldg,
+                            int64_t batch, int64_t heads, int64_t lq, int64_t lk, int64_t kv_valid, float p_drop,
+                            uint64_t seed, void* workspace, cudaStream_t s) {
+  if (batch * heads * (lq > lk ? lq : lk) > 0x7fffff00LL) return HOISDF_E_SHAPE;  // TMA row coordinates are int32
+  const int64_t lq_pad = (lq + 7) / 8 * 8, lk_pad = (lk + 7) / 8 * 8, bh = batch * heads;
+  auto up = [](int64_t x) { return (x + 255) / 256 * 256; };
+  const int64_t qb = up(bh * lq * AT_D * 2), kb = up(bh * lk * AT_D * 2), qtb = up(bh * AT_D * lq_pad * 2),
+                ktb = up(bh * AT_D * lk_pad * 2);
+  uint8_t* w = static_cast<uint8_t*>(workspace);
+  auto take = [&](int64_t bytes) { auto* r = reinterpret_cast<__nv_bfloat16*>(w); w += bytes; return r; };
+  __nv_bfloat16 *qhi = take(qb), *qlo = take(qb), *dohi = take(qb), *dolo = take(qb);
+  __nv_bfloat16 *khi = take(kb), *klo = take(kb), *vhi = take(kb), *vlo = take(kb);
+  __nv_bfloat16 *qthi = take(qtb), *qtlo = take(qtb), *dothi = take(qtb), *dotlo = take(qtb);
+  __nv_bfloat16 *kthi = take(ktb), *ktlo = take(ktb);
+  float* delta = reinterpret_cast<float*>(w);
+  const int H = static_cast<int>(heads);
+  {
+    const int64_t nw = batch * lq * heads;                               // one warp each
+    attn_bwd_delta_kernel<<<static_cast<unsigned>(ceil_div(nw * 32, 256)), 256, 0, s>>>(dout, out, ldo, batch, H, lq, delta);
+    const int64_t nq = batch * lq * heads * 16, nk = batch * lk * heads * 16;
+    const unsigned gq = static_cast<unsigned>(ceil_div(nq, 256)), gk = static_cast<unsigned>(ceil_div(nk, 256));
+    attn_split_rows_kernel<<<gq, 256, 0, s>>>(q, ldq, batch, H, lq, 0.125f * 1.4426950408889634f, qhi, qlo);   // as the forward
+    attn_split_rows_kernel<<<gq, 256, 0, s>>>(dout, ldo, batch, H, lq, 1.0f, dohi, dolo);
+    attn_split_rows_kernel<<<gk, 256, 0, s>>>(k, ldk, batch, H, lk, 1.0f, khi, klo);
+    attn_split_rows_kernel<<<gk, 256, 0, s>>>(v, ldk, batch, H, lk, 1.0f, vhi, vlo);
+    const dim3 tq(static_cast<unsigned>(ceil_div(lq, 64)), static_cast<unsigned>(heads), static_cast<unsigned>(batch));
+    const dim3 tk(static_cast<unsigned>(ceil_div(lk, 64)), static_cast<unsigned>(heads), static_cast<unsigned>(batch));
+    attn_split_vt_kernel<<<tq, 256, 0, s>>>(q, ldq, H, lq, lq_pad, qthi, qtlo);
+    attn_split_vt_kernel<<<tq, 256, 0, s>>>(dout, ldo, H, lq, lq_pad, dothi, dotlo);
+    attn_split_vt_kernel<<<tk, 256, 0, s>>>(k, ldk, H, lk, lk_pad, kthi, ktlo);
+  }
+  CUtensorMap mqh, mql, mdh, mdl, mkh, mkl, mvh, mvl, mqth, mqtl, mdth, mdtl, mkth, mktl;
+  if (!at_make_map(&mqh, qhi, bh * lq, AT_D, AT_D, 128) || !at_make_map(&mql, qlo, bh * lq, AT_D, AT_D, 128) ||
+      !at_make_map(&mdh, dohi, bh * lq, AT_D, AT_D, 128) || !at_make_map(&mdl, dolo, bh * lq, AT_D, AT_D, 128) ||
+      !at_make_map(&mkh, khi, bh * lk, AT_D, AT_D, 128) || !at_make_map(&mkl, klo, bh * lk, AT_D, AT_D, 128) ||
+      !at_make_map(&mvh, vhi, bh * lk, AT_D, AT_D, 128) || !at_make_map(&mvl, vlo, bh * lk, AT_D, AT_D, 128) ||
+      !at_make_map(&mqth, qthi, bh * AT_D, lq_pad, lq_pad, AT_D) || !at_make_map(&mqtl, qtlo, bh * AT_D, lq_pad, lq_pad, AT_D) ||
+      !at_make_map(&mdth, dothi, bh * AT_D, lq_pad, lq_pad, AT_D) ||
+      !at_make_map(&mdtl, dotlo, bh * AT_D, lq_pad, lq_pad, AT_D) ||
+      !at_make_map(&mkth, kthi, bh * AT_D, lk_pad, lk_pad, AT_D) || !at_make_map(&mktl, ktlo, bh * AT_D, lk_pad, lk_pad, AT_D))
+    return HOISDF_E_UNSUPPORTED;
+  AttnBwdParams p{lse, delta, dq, dk, dv, ldg, static_cast<int>(lq), static_cast<int>(lk), static_cast<int>(kv_valid),
+                  H, seed, dropout_threshold(p_drop), 1.0f / (1.0f - p_drop)};
+  const bool drop = p_drop > 0.f;
+  {
+    auto kernel = drop ? attention_bwd_dq_kernel<true> : attention_bwd_dq_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_DQ_SMEM);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    const dim3 grid(static_cast<unsigned>(ceil_div(lq, 128)), static_cast<unsigned>(heads), static_cast<unsigned>(batch));
+    kernel<<<grid, AB_THREADS, AB_DQ_SMEM, s>>>(mqh, mql, mdh, mdl, mkh, mkl, mvh, mvl, mkth, mktl, p);
+  }
+  {
+    auto kernel = drop ? attention_bwd_dkv_kernel<true> : attention_bwd_dkv_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_DKV_SMEM);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    const dim3 grid(static_cast<unsigned>(ceil_div(lk, 128)), static_cast<unsigned>(heads), static_cast<unsigned>(batch));
+    kernel<<<grid, AB_THREADS, AB_DKV_SMEM, s>>>(mkh, mkl, mvh, mvl, mqh, mql, mdh, mdl, mqth, mqtl, mdth, mdtl, p);
+  }
   return launch_status();
 }
 

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 27
+#define HOISDF_ABI_VERSION 28
 
 enum {
   HOISDF_OK = 0,
@@ -427,15 +427,27 @@ int hoisdf_attention_fwd(const float* q, int64_t ldq, const float* k, const floa
                          int64_t ldo, int64_t batch, int64_t heads, int64_t lq, int64_t lk, int64_t kv_valid,
                          const uint8_t* mask, void* workspace, int64_t workspace_bytes, void* stream);
 
-/* Training forward of the same operator with nn.MultiheadAttention's dropout on the probabilities (upstream
- * common/nets/transformer.py:294 with cfg.dropout, main/config.py): out = dropout(softmax(q k^T / 8), p_drop) . v on the
- * tensor-core kernel, the S x S probabilities never leave the SM.  The keep decisions are a counter hash of
- * (seed, (sample * heads + head) * lq + query, key) -- the ones hoisdf_softmax_dropout_rows_fwd / _bwd (below) regenerate
- * on the (B, H, Lq, Lk) probabilities in the backward.  No dense mask; min(lk, kv_valid) >= 128 (HOISDF_E_UNSUPPORTED
- * otherwise: use the materialised form); 0 <= p_drop < 1; workspace as for hoisdf_attention_fwd (required). */
-int hoisdf_attention_dropout_fwd(const float* q, int64_t ldq, const float* k, const float* v, int64_t ldk, float* out,
-                                 int64_t ldo, int64_t batch, int64_t heads, int64_t lq, int64_t lk, int64_t kv_valid,
-                                 float p_drop, uint64_t seed, void* workspace, int64_t workspace_bytes, void* stream);
+/* Training forward / backward of the same operator on the tensor cores (upstream main/train.py:131 `loss.backward()`
+ * through common/nets/transformer.py:294, with nn.MultiheadAttention's dropout on the probabilities, cfg.dropout):
+ *   out = dropout(softmax(q k^T / 8), p_drop) . v
+ * The S x S probabilities never leave the SM in either direction.  The keep decisions are a counter hash of
+ * (seed, (sample * heads + head) * lq + query, key) -- also what hoisdf_softmax_dropout_rows_fwd / _bwd (below) regenerate
+ * on materialised (B, H, Lq, Lk) probabilities.  No dense mask; 0 <= p_drop < 1 (0: no dropout).
+ *   _train_fwd : also writes lse (B*H*lq floats, may be NULL): log2-sum-exp of each scaled score row, from which the
+ *                backward recomputes P.  min(lk, kv_valid) >= 128 (HOISDF_E_UNSUPPORTED otherwise: use the materialised
+ *                form); workspace = hoisdf_attention_workspace_bytes(...) (required).
+ *   _bwd       : dq (B*lq, ldg), dk, dv (B*lk, ldg) from q, k, v, out, dout (pitch ldo) and lse, same p_drop / seed as
+ *                the forward; two tcgen05 kernels (dQ per query tile, dK / dV per key tile; no atomics), BF16x3 products.
+ *                workspace = hoisdf_attention_bwd_workspace_bytes(...) (required). */
+int hoisdf_attention_train_fwd(const float* q, int64_t ldq, const float* k, const float* v, int64_t ldk, float* out,
+                               int64_t ldo, float* lse, int64_t batch, int64_t heads, int64_t lq, int64_t lk,
+                               int64_t kv_valid, float p_drop, uint64_t seed, void* workspace, int64_t workspace_bytes,
+                               void* stream);
+int64_t hoisdf_attention_bwd_workspace_bytes(int64_t batch, int64_t heads, int64_t lq, int64_t lk);
+int hoisdf_attention_bwd(const float* q, int64_t ldq, const float* k, const float* v, int64_t ldk, const float* out,
+                         const float* dout, int64_t ldo, const float* lse, float* dq, float* dk, float* dv, int64_t ldg,
+                         int64_t batch, int64_t heads, int64_t lq, int64_t lk, int64_t kv_valid, float p_drop,
+                         uint64_t seed, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* The tensor-core path of hoisdf_attention_fwd (workspace required, no dense mask) writing its result in split-half
  * format (two fp16 planes, pitch ldo halfs, multiple of 8) -- what the FP16x3 out-projection GEMM reads. */

@@ -135,12 +135,15 @@ def test_backward_prep_kernels(cuda):
     assert lib.hoisdf_absmax(None, 1, 1, 1, amax.data_ptr(), st) == -1
 
 
-@pytest.mark.parametrize("lq,lk,masked,kv_valid", [(128, 128, False, None), (17, 17, True, None), (17, 200, False, 150),
-                                                     (300, 333, False, None), (257, 800, False, 700)])
-def test_attention_fn(cuda, lq, lk, masked, kv_valid):
-    """softmax(q k^T / 8 [+ mask]) v over 4 heads of 64: tcgen05 flash forward (SIMT with a dense mask), batched fp32
-    backward, vs fp64 autograd."""
+@pytest.mark.parametrize("lq,lk,masked,kv_valid,bwd_tc", [(128, 128, False, None, True), (17, 17, True, None, True),
+                                                            (17, 200, False, 150, True), (300, 333, False, None, True),
+                                                            (257, 800, False, 700, True), (300, 333, False, None, False),
+                                                            (800, 800, False, None, True), (130, 129, False, 128, True)])
+def test_attention_fn(cuda, lq, lk, masked, kv_valid, bwd_tc, monkeypatch):
+    """softmax(q k^T / 8 [+ mask]) v over 4 heads of 64 vs fp64 autograd: tcgen05 flash forward (SIMT with a dense mask);
+    backward on the two tensor-core kernels for the long unmasked sequences (bwd_tc), batched fp32 FMA GEMMs otherwise."""
     from hoisdf_b200 import autograd as A
+    monkeypatch.setattr(A, "_ATTN_BWD_TC", bwd_tc)
     B, H, d = 3, 4, 256
     q, k, v, do = _rnd(1, B * lq, d), _rnd(2, B * lk, d), _rnd(3, B * lk, d), _rnd(4, B * lq, d)
     mask = None
@@ -172,13 +175,15 @@ def test_attention_fn_with_dropout(cuda, lq, lk, kv_valid, masked, tc, monkeypat
     """Dropout on the attention probabilities (nn.MultiheadAttention's; upstream cfg.dropout = 0.1): forward and backward
     against fp64 autograd of softmax -> mask / (1 - q) -> P.V with the SAME keep decisions (regenerated from the seed the
     Function drew), no mask tensor stored.  Long unmasked sequences run the forward on the tensor-core flash kernel
-    (hoisdf_attention_dropout_fwd), which must make the very decisions the materialised kernels of the backward regenerate."""
+    and the backward on its two tensor-core kernels (hoisdf_attention_train_fwd / hoisdf_attention_bwd), which must make the
+    very decisions the materialised kernels (here: `_probs`, the reference's mask) regenerate from the seed."""
     from hoisdf_b200 import autograd as A
     from hoisdf_b200._capi import lib
     B, H, d, pdrop = 2, 4, 256, 0.1
     calls = []
-    real = lib.hoisdf_attention_dropout_fwd
-    monkeypatch.setattr(lib, "hoisdf_attention_dropout_fwd", lambda *a: (calls.append(1), real(*a))[1])
+    real, real_bwd = lib.hoisdf_attention_train_fwd, lib.hoisdf_attention_bwd
+    monkeypatch.setattr(lib, "hoisdf_attention_train_fwd", lambda *a: (calls.append(1), real(*a))[1])
+    monkeypatch.setattr(lib, "hoisdf_attention_bwd", lambda *a: (calls.append(2), real_bwd(*a))[1])
     mask = None
     if masked:
         mask = (_rnd(5, lq, lk) > 0.3)
@@ -188,8 +193,8 @@ def test_attention_fn_with_dropout(cuda, lq, lk, kv_valid, masked, tc, monkeypat
     torch.manual_seed(5)
     dmask = None if mask is None else mask.to(cuda).to(torch.uint8).contiguous()
     out = A.AttentionFn.apply(td[0], td[1], td[2], B, H, lq, lk, dmask, kv_valid, pdrop)
-    assert len(calls) == (1 if tc else 0)
     (out * do.to(cuda)).sum().backward()
+    assert calls == ([1, 2] if tc else [])
     torch.manual_seed(5)
     seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64))
     P, Pd = A.AttentionFn._probs(td[0].detach(), td[1].detach(), B, H, lq, lk, dmask, kv_valid, pdrop, seed, want_p=True)
