@@ -69,6 +69,13 @@ def matmul_nt(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = N
         y = a @ b.t()
         y = y if bias is None else y + bias
         return torch.relu(y) if act == ACT_RELU else y
+    if n <= 16 and m > 16:
+        # a handful of output features over many rows: one streaming pass over `a` (csrc/backward.cu: thin_linear_fwd)
+        y = torch.empty(m, n, device=a.device, dtype=torch.float32)
+        _count(1)
+        check(lib.hoisdf_thin_linear_fwd(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0) if n > 1 else k, _ptr(bias), m, k,
+                                         n, act, y.data_ptr(), n, _stream()), "hoisdf_thin_linear_fwd")
+        return y
     if n <= 16 or k <= 16:
         y = torch.empty(m, n, device=a.device, dtype=torch.float32)
         _count(1)
@@ -148,8 +155,15 @@ class LinearFn(Function):
             dx = matmul_nt(dzs, weight.detach().t().contiguous())            # (M,N) . (K,N)^T
             dx = dx.mul_(s) if dx.is_contiguous() else dx * s
         if ctx.needs_input_grad[1]:
-            dwt = matmul_nt(x.t().contiguous(), dzs.t().contiguous())        # (K,M) . (N,M)^T = dW^T / s
-            dw = dwt.t() * s
+            if n <= 16 and m > 16:
+                # dW = dZ^T X as one pass over X: no transposed copies, no 64-wide tiles for 1 / 3 / 6 / 10 output features
+                dw = torch.empty(n, x.shape[1], device=dy.device, dtype=torch.float32)
+                _count(2)
+                check(lib.hoisdf_thin_linear_dw(x.data_ptr(), x.stride(0), dz.data_ptr(), dz.stride(0), m, x.shape[1], n,
+                                                dw.data_ptr(), dw.stride(0), 0, _stream()), "hoisdf_thin_linear_dw")
+            else:
+                dwt = matmul_nt(x.t().contiguous(), dzs.t().contiguous())    # (K,M) . (N,M)^T = dW^T / s
+                dw = dwt.t() * s
         return dx, dw, db, None
 
 

@@ -410,6 +410,78 @@ softmax_dropout_rows_bwd_kernel(const float* __restrict__ p, int64_t ldp, const 
   }
 }
 
+// ---- Linear layers with a handful of output features (n <= 16: the SDF value, class and offset heads; upstream
+// common/nets/sdf_net.py:53-64 `linh4`, main/model.py:82-91) over tens of thousands of rows.  A 64-wide GEMM tile wastes most of
+// its work there and the weight gradient is a tall reduction (k = rows): both are one streaming pass over X instead.
+//   thin_linear_fwd   y (m, n) = act(x (m, k) . w (n, k)^T + b): one warp per row, lanes stride over k
+//   thin_linear_dw    dw (n, k) = dz (m, n)^T . x (m, k): CTA = 256 columns of x times a chunk of rows, dz rows staged in
+//                     shared memory, per-thread partial sums, one atomicAdd per (output feature, column) and CTA
+constexpr int THIN_MAX_N = 16;
+
+__global__ void __launch_bounds__(256)
+thin_linear_fwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w, int64_t ldw,
+                       const float* __restrict__ bias, int64_t m, int k, int n, int act, float* __restrict__ y, int64_t ldy) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t r = warp; r < m; r += nwarps) {
+    float acc[THIN_MAX_N];
+#pragma unroll
+    for (int j = 0; j < THIN_MAX_N; ++j) acc[j] = 0.f;
+    for (int c = lane; c < k; c += 32) {
+      const float xv = x[r * ldx + c];
+#pragma unroll
+      for (int j = 0; j < THIN_MAX_N; ++j)
+        if (j < n) acc[j] = fmaf(xv, w[j * ldw + c], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < THIN_MAX_N; ++j) {
+      if (j < n) {                                     // (n is warp-uniform)
+        float v = warp_sum(acc[j]);
+        if (lane == 0) {
+          if (bias != nullptr) v += bias[j];
+          if (act == HOISDF_ACT_RELU) v = fmaxf(v, 0.f);
+          y[r * ldy + j] = v;
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+thin_linear_dw_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ dz, int64_t lddz, int64_t m, int k,
+                      int n, int64_t rows_per_cta, float* __restrict__ dw, int64_t lddw) {
+  __shared__ float dzs[64][THIN_MAX_N];
+  const int c = static_cast<int>(blockIdx.x) * 256 + static_cast<int>(threadIdx.x);
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_cta;
+  const int64_t r1 = r0 + rows_per_cta < m ? r0 + rows_per_cta : m;
+  float acc[THIN_MAX_N];
+#pragma unroll
+  for (int j = 0; j < THIN_MAX_N; ++j) acc[j] = 0.f;
+  for (int64_t rb = r0; rb < r1; rb += 64) {
+    const int cnt = static_cast<int>(r1 - rb < 64 ? r1 - rb : 64);
+    __syncthreads();
+    for (int e = threadIdx.x; e < cnt * n; e += 256) {
+      const int rr = e / n, j = e - rr * n;
+      dzs[rr][j] = dz[(rb + rr) * lddz + j];
+    }
+    __syncthreads();
+    if (c < k) {
+      for (int rr = 0; rr < cnt; ++rr) {
+        const float xv = x[(rb + rr) * ldx + c];
+#pragma unroll
+        for (int j = 0; j < THIN_MAX_N; ++j)
+          if (j < n) acc[j] = fmaf(xv, dzs[rr][j], acc[j]);
+      }
+    }
+  }
+  if (c < k) {
+#pragma unroll
+    for (int j = 0; j < THIN_MAX_N; ++j)
+      if (j < n) atomicAdd(dw + j * lddw + c, acc[j]);
+  }
+}
+
 // torch.optim.AdamW (upstream common/base.py:68: lr 1e-4, default betas / eps / weight_decay 0.01), one fused pass over a
 // flat parameter buffer, the arithmetic in the order PyTorch's single-tensor implementation applies it
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
@@ -637,6 +709,42 @@ HOISDF_API int hoisdf_act_bias_bwd(float* dy, int64_t lddy, const float* y, int6
   const dim3 grid(static_cast<unsigned>(ceil_div(n, 32)), static_cast<unsigned>(chunks));
   HOISDF_LAUNCH(act_bias_bwd_kernel, grid, 256, static_cast<cudaStream_t>(stream), dy, lddy, y, ldy, m, n, act, db,
                 accumulate ? 1 : 0);
+  return launch_status();
+}
+
+HOISDF_API int hoisdf_thin_linear_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, int64_t m,
+                                      int64_t k, int64_t n, int32_t act, float* y, int64_t ldy, void* stream) {
+  if (x == nullptr || w == nullptr || y == nullptr) return HOISDF_E_NULL;
+  if (m <= 0 || k <= 0 || k > 0x7fffffffLL || n <= 0 || ldx < k || ldw < k || ldy < n) return HOISDF_E_SHAPE;
+  if (n > THIN_MAX_N || (act != HOISDF_ACT_NONE && act != HOISDF_ACT_RELU)) return HOISDF_E_UNSUPPORTED;
+  const int64_t want = ceil_div(m, 8);
+  const unsigned blocks = static_cast<unsigned>(want < kNumSMs * 16 ? want : kNumSMs * 16);
+  HOISDF_LAUNCH(thin_linear_fwd_kernel, blocks, 256, static_cast<cudaStream_t>(stream), x, ldx, w, ldw, bias, m,
+                static_cast<int>(k), static_cast<int>(n), act, y, ldy);
+  return launch_status();
+}
+
+HOISDF_API int hoisdf_thin_linear_dw(const float* x, int64_t ldx, const float* dz, int64_t lddz, int64_t m, int64_t k,
+                                     int64_t n, float* dw, int64_t lddw, int32_t accumulate, void* stream) {
+  if (x == nullptr || dz == nullptr || dw == nullptr) return HOISDF_E_NULL;
+  if (m <= 0 || k <= 0 || k > 0x7fffffffLL || n <= 0 || ldx < k || lddz < n || lddw < k) return HOISDF_E_SHAPE;
+  if (n > THIN_MAX_N) return HOISDF_E_UNSUPPORTED;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!accumulate) {
+    for (int64_t j = 0; j < (lddw == k ? 1 : n); ++j) {
+      const cudaError_t e = cudaMemsetAsync(dw + j * lddw, 0, sizeof(float) * (lddw == k ? n * k : k), s);
+      if (e != cudaSuccess) return static_cast<int>(e);
+    }
+  }
+  const int64_t gx = ceil_div(k, 256);
+  int64_t chunks = (kNumSMs * 4) / gx;                       // ~4 CTAs per SM in total
+  if (chunks < 1) chunks = 1;
+  int64_t rows_per_cta = ceil_div(ceil_div(m, chunks), 64) * 64;
+  chunks = ceil_div(m, rows_per_cta);
+  if (chunks > 65535) return HOISDF_E_SHAPE;
+  const dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(chunks));
+  HOISDF_LAUNCH(thin_linear_dw_kernel, grid, 256, s, x, ldx, dz, lddz, m, static_cast<int>(k), static_cast<int>(n),
+                rows_per_cta, dw, lddw);
   return launch_status();
 }
 

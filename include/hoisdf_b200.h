@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 28
+#define HOISDF_ABI_VERSION 29
 
 enum {
   HOISDF_OK = 0,
@@ -631,6 +631,16 @@ int hoisdf_gemm_f32_batched(const float* a, int64_t lda, int32_t trans_a, int64_
                             int64_t ldb, int32_t trans_b, int64_t b_outer, int64_t b_inner, float* c, int64_t ldc,
                             int64_t c_outer, int64_t c_inner, int64_t m, int64_t n, int64_t k, float alpha, int32_t accumulate,
                             int64_t batch_outer, int64_t batch_inner, void* stream);
+/* Linear layers with n <= 16 output features over many rows (the SDF value / class / offset heads: upstream
+ * common/nets/sdf_net.py:53-64, main/model.py:82-91), fp32 FMA, one streaming pass over x:
+ *   hoisdf_thin_linear_fwd: y (m, n; pitch ldy) = act(x (m, k) . w (n, k)^T + bias) (bias may be NULL);
+ *   hoisdf_thin_linear_dw : dw (n, k; pitch lddw) = dz (m, n)^T . x (m, k) (+ dw when accumulate) -- the weight gradient,
+ *                           without transposed copies of x or dz; partial sums meet in atomicAdd.
+ * n > 16: HOISDF_E_UNSUPPORTED (use the GEMMs). */
+int hoisdf_thin_linear_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, int64_t m, int64_t k,
+                           int64_t n, int32_t act, float* y, int64_t ldy, void* stream);
+int hoisdf_thin_linear_dw(const float* x, int64_t ldx, const float* dz, int64_t lddz, int64_t m, int64_t k, int64_t n,
+                          float* dw, int64_t lddw, int32_t accumulate, void* stream);
 int hoisdf_act_bias_bwd(float* dy, int64_t lddy, const float* y, int64_t ldy, int64_t m, int64_t n, int32_t act, float* db,
                         int32_t accumulate, void* stream);
 int hoisdf_weight_norm_bwd(const float* g, const float* v, const float* dw, int64_t lddw, int64_t rows, int64_t cols,

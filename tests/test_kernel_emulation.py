@@ -1072,3 +1072,39 @@ def test_tokens_backward_kernel_on_the_emulator():
     assert abs(float(d_beta[0]) - float(beta.grad)) < 1e-4 * abs(float(beta.grad))
     assert lib.hoisdf_tokens_bwd(ptr(d_tok), S, S - 2, ptr(d_fea), 223, ptr(d_sdf), ptr(d_beta), B, Pn, ptr(d_fea), 223, None,
                                  ptr(d_beta), 0, ptr(ws), nbytes, None) == -2
+
+
+@pytest.mark.parametrize("m,k,n,relu", [(300, 512, 1, False), (77, 256, 3, True), (1000, 100, 10, False), (65, 33, 16, True)])
+def test_thin_linear_kernels_on_the_emulator(m, k, n, relu):
+    """hoisdf_thin_linear_fwd / _dw: the n <= 16 heads (upstream sdf_net.py:53-64 `linh4`, model.py:82-91) as streaming passes
+    over x; pitched x / dz views, the accumulate flag and the error contract."""
+    lib = backward_lib()
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
+    lib.hoisdf_thin_linear_fwd.argtypes = [vp, i64, vp, i64, vp, i64, i64, i64, i32, vp, i64, vp]
+    lib.hoisdf_thin_linear_dw.argtypes = [vp, i64, vp, i64, i64, i64, i64, vp, i64, i32, vp]
+    rng = np.random.default_rng(m + n)
+    ldx, lddz = k + 5, n + 3
+    xb = rng.standard_normal((m, ldx)).astype(np.float32)
+    w = rng.standard_normal((n, k)).astype(np.float32)
+    b = rng.standard_normal(n).astype(np.float32)
+    dzb = rng.standard_normal((m, lddz)).astype(np.float32)
+    x, dz = xb[:, :k], dzb[:, :n]
+    y = np.empty((m, n), np.float32)
+    assert lib.hoisdf_thin_linear_fwd(ptr(xb), ldx, ptr(w), k, ptr(b), m, k, n, 1 if relu else 0, ptr(y), n, None) == 0
+    ref = x.astype(np.float64) @ w.astype(np.float64).T + b
+    ref = np.maximum(ref, 0) if relu else ref
+    assert np.abs(y - ref).max() <= 1e-5 * max(np.abs(ref).max(), 1.0)
+    assert lib.hoisdf_thin_linear_fwd(ptr(xb), ldx, ptr(w), k, None, m, k, n, 0, ptr(y), n, None) == 0          # no bias
+    assert np.abs(y - x.astype(np.float64) @ w.astype(np.float64).T).max() <= 1e-5 * max(np.abs(ref).max(), 1.0)
+    dw = np.full((n, k), 7.0, np.float32)
+    assert lib.hoisdf_thin_linear_dw(ptr(xb), ldx, ptr(dzb), lddz, m, k, n, ptr(dw), k, 0, None) == 0
+    dref = dz.astype(np.float64).T @ x.astype(np.float64)
+    assert np.abs(dw - dref).max() <= 1e-5 * np.abs(dref).max()
+    assert lib.hoisdf_thin_linear_dw(ptr(xb), ldx, ptr(dzb), lddz, m, k, n, ptr(dw), k, 1, None) == 0           # accumulate
+    assert np.abs(dw - 2 * dref).max() <= 2e-5 * np.abs(dref).max()
+    dwp = np.full((n, k + 4), 7.0, np.float32)                                                                    # pitched dw
+    assert lib.hoisdf_thin_linear_dw(ptr(xb), ldx, ptr(dzb), lddz, m, k, n, ptr(dwp), k + 4, 0, None) == 0
+    assert np.abs(dwp[:, :k] - dref).max() <= 1e-5 * np.abs(dref).max() and (dwp[:, k:] == 7.0).all()
+    assert lib.hoisdf_thin_linear_fwd(ptr(xb), ldx, ptr(w), k, None, m, k, 17, 0, ptr(y), 17, None) == -4          # n > 16
+    assert lib.hoisdf_thin_linear_dw(ptr(xb), k - 1, ptr(dzb), lddz, m, k, n, ptr(dw), k, 0, None) == -2           # ldx < k
+    assert lib.hoisdf_thin_linear_dw(None, ldx, ptr(dzb), lddz, m, k, n, ptr(dw), k, 0, None) == -1
