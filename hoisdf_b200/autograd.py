@@ -126,16 +126,14 @@ class LinearFn(Function):
         dx = dw = None
         if ctx.needs_input_grad[0]:
             pwt = ops.PackedLinearH3.pack(weight.detach().t().contiguous(), None, assume_max=1.0)      # W^T (K, N)
-            dx = ops.linear_h3(dz, pwt, ACT_NONE, chunk_kb=TRAIN_CHUNK_KB)                               # dZ/s . W
-            dx = dx.mul_(scale) if dx.is_contiguous() else dx * scale
+            dx = ops.linear_h3(dz, pwt, ACT_NONE, chunk_kb=TRAIN_CHUNK_KB, y_scale=scale)                # (dZ/s . W) * s
         if ctx.needs_input_grad[1]:
             xt = ops.SplitRows.empty(k, m, dev)
             _count(1)
             check(lib.hoisdf_split_rows_t(x.data_ptr(), m, k, x.stride(0) if m > 1 else max(x.stride(0), k), xt.hi_ptr,
                                           xt.lo_ptr, xt.ld, _stream()), "hoisdf_split_rows_t")
             pdz = ops.PackedLinearH3(dzt, None, n, m)
-            dwt = ops.linear_h3(xt, pdz, ACT_NONE, chunk_kb=TRAIN_CHUNK_KB)                             # X^T . dZ/s = dW^T / s
-            dw = dwt.t() * scale
+            dw = ops.linear_h3(xt, pdz, ACT_NONE, chunk_kb=TRAIN_CHUNK_KB, y_scale=scale).t()          # (X^T . dZ/s) * s = dW^T
         return dx, dw, db, None
 
     @staticmethod

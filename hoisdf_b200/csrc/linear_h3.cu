@@ -80,6 +80,7 @@ struct H3Params {
   int taps, cin_blocks, out_w, out_h, stride, wx, wy;
   int8_t dy[16], dx[16];
   float w_scale;            // power-of-two scale the packed weights were divided by (|w| >= 32 layers); 1 normally
+  const float* __restrict__ y_scale;   // optional device scalar multiplied into the product (training backward); may be null
 };
 
 // Accuracy note (why the accumulator is drained in chunks).  The tensor core TRUNCATES when it adds a K=16 partial
@@ -335,7 +336,8 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
     const int ew = warp - 2;
     const int q = warp & 3;                                         // TMEM lane quarter this warp may read
     const int hcol = ew >> 2;                                       // which 128-column half of the tile it owns
-    const float oscale = (single ? 1.f : kLoInv) * p.w_scale;       // single product: x_hi . w_hi is unscaled
+    const float oscale = (single ? 1.f : kLoInv) * p.w_scale *      // single product: x_hi . w_hi is unscaled
+                         (p.y_scale != nullptr ? __ldg(p.y_scale) : 1.f);
     // PAIR: the accumulator buffers of both CTAs are refilled by the leader's MMA warp -> free them on ITS barrier
     auto cempty_arrive = [&](uint32_t b) {
       if (PAIR) mbar_arrive_cluster(map_to_rank(bar_cempty(b), 0u));
@@ -878,6 +880,7 @@ HOISDF_API int hoisdf_linear_h3_fwd(const hoisdf_linear_h3_args* a, void* stream
   p.single = a->single_pass ? 1 : 0;
   p.w_rows = w_rows; p.nstages = h3_stage_count(w_rows);
   p.w_scale = a->w_scale > 0.f ? a->w_scale : 1.f;
+  p.y_scale = a->y_scale;
   if (a->res_hi != nullptr || a->res_lo != nullptr) {
     if (a->res_hi == nullptr || a->res_lo == nullptr) return HOISDF_E_NULL;
     if (out_mode == H3_OUT_F32_DIRECT || a->residual != nullptr || (a->n & 31)) return HOISDF_E_UNSUPPORTED;

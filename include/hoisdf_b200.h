@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 29
+#define HOISDF_ABI_VERSION 30
 
 enum {
   HOISDF_OK = 0,
@@ -113,6 +113,9 @@ typedef struct {
   float w_scale;                     /* power-of-two factor the packed weights were divided by before packing (layers
                                         with |w| >= 32, e.g. BatchNorm folds with a tiny running variance); the
                                         epilogue multiplies it back.  0 = 1 */
+  const float* y_scale;              /* optional: ONE float in device memory the product x . w^T is multiplied by in the
+                                        epilogue (before the bias) -- the power-of-two factor hoisdf_linear_bwd_prep took
+                                        out of a gradient, put back without a host read-back or an extra pass */
 } hoisdf_linear_h3_args;
 
 int hoisdf_linear_h3_fwd(const hoisdf_linear_h3_args* args, void* stream);
