@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhoisdf_b200.so")
 
-ABI_VERSION = 30
+ABI_VERSION = 31
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2      # ACT_SIGMOID: hoisdf_linear_narrow_split_fwd only
 GATHER_CONCAT, GATHER_SUM = 0, 1
 
@@ -35,6 +35,7 @@ class LinearH3Args(C.Structure):
         ("y", vp), ("ldy", i64), ("y_hi", vp), ("y_lo", vp), ("ldyh", i64),
         ("m", i64), ("n", i64), ("k", i64), ("act", i32), ("chunk_kb", i32),
         ("res_hi", vp), ("res_lo", vp), ("ldr", i64), ("single_pass", i32), ("w_scale", f32), ("y_scale", vp),
+        ("split_k", i32),
     ]
 
 

@@ -133,7 +133,8 @@ class LinearFn(Function):
             check(lib.hoisdf_split_rows_t(x.data_ptr(), m, k, x.stride(0) if m > 1 else max(x.stride(0), k), xt.hi_ptr,
                                           xt.lo_ptr, xt.ld, _stream()), "hoisdf_split_rows_t")
             pdz = ops.PackedLinearH3(dzt, None, n, m)
-            dw = ops.linear_h3(xt, pdz, ACT_NONE, chunk_kb=TRAIN_CHUNK_KB, y_scale=scale).t()          # (X^T . dZ/s) * s = dW^T
+            dw = ops.linear_h3(xt, pdz, ACT_NONE, chunk_kb=TRAIN_CHUNK_KB, y_scale=scale,
+                               split_k=True).t()                                              # (X^T . dZ/s) * s = dW^T
         return dx, dw, db, None
 
     @staticmethod

@@ -81,6 +81,11 @@ struct H3Params {
   int8_t dy[16], dx[16];
   float w_scale;            // power-of-two scale the packed weights were divided by (|w| >= 32 layers); 1 normally
   const float* __restrict__ y_scale;   // optional device scalar multiplied into the product (training backward); may be null
+  // split-K (plain GEMM, fp32 TMA output, no activation): a work item is (M block, N tile, K range); every item ADDS its
+  // partial product into the zero-initialised output with a TMA reduction.  For the weight gradients of the training step
+  // (a 256 x 256 output over a 51 200-long contraction is ONE tile pair otherwise: 2 of 148 SMs busy)
+  int splits;               // <= 1: off
+  int kb_per_split;         // K blocks per item
 };
 
 // Accuracy note (why the accumulator is drained in chunks).  The tensor core TRUNCATES when it adds a K=16 partial
@@ -130,7 +135,8 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
   const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
   const int cluster = static_cast<int>(blockIdx.x) / CL;
   const int nclusters = static_cast<int>(gridDim.x) / CL;
-  const int items = p.m_blocks * p.n_tiles;
+  const int splits = p.splits > 1 ? p.splits : 1;
+  const int items = p.m_blocks * p.n_tiles * splits;
   const int num_kb = p.taps > 0 ? p.taps * p.cin_blocks : (p.k + H3_BK - 1) / H3_BK;
   const int chb = p.chunk_kb;
   constexpr uint16_t kAllCtas = static_cast<uint16_t>((1u << CL) - 1u);
@@ -173,7 +179,14 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   // work item -> tile coordinates of THIS CTA
+  auto k_range = [&](int item, int& kb0, int& kb1) {           // K blocks [kb0, kb1) of a work item (split-K)
+    const int sp = item % splits;
+    kb0 = splits > 1 ? sp * p.kb_per_split : 0;
+    kb1 = splits > 1 ? min(num_kb, kb0 + p.kb_per_split) : num_kb;
+    return sp;
+  };
   auto tile_of = [&](int item, int& m_tile, int& grp, int& m0, int& n0) {
+    item /= splits;
     const int mb = item / p.n_tiles;
     m_tile = mb * CL + static_cast<int>(rank);
     // cluster padding (M tiles beyond the last): group index = #groups, every X row out of bounds -> zero-filled
@@ -205,7 +218,9 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
           cx0 = (rem - (rem / p.out_w) * p.out_w) * p.stride;
         }
         int tap = 0, cblk = 0;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        int kb0, kb1;
+        k_range(item, kb0, kb1);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_empty(s), ph);
           const uint32_t st = base + s * stage_bytes;
           const bool issue = elect_one();
@@ -276,7 +291,9 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
         const uint32_t idesc = umma_idesc_f16(PAIR ? 2 * H3_BM : H3_BM, n_inst);
         int in_chunk = 0;
         uint32_t acc = tmem_base;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        int kb0, kb1;
+        k_range(item, kb0, kb1);
+        for (int kb = kb0; kb < kb1; ++kb) {
           if (in_chunk == 0) {                                     // new chunk: the drain of chunk cc - 2 has finished
             const uint32_t buf = cc & 1u;
             mbar_wait(bar_cempty(buf), ((cc >> 1) & 1u) ^ 1u);
@@ -315,16 +332,16 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
           }
           if (PAIR) {
             umma2_commit_mc(bar_empty(s), kAllCtas);               // both CTAs' producers may refill the stage
-            if (in_chunk + 1 == chb || kb == num_kb - 1) umma2_commit_mc(bar_cfull(cc & 1u), kAllCtas);   // both drain
+            if (in_chunk + 1 == chb || kb == kb1 - 1) umma2_commit_mc(bar_cfull(cc & 1u), kAllCtas);   // both drain
           } else {
           if (CL > 1) umma_commit_mc(bar_empty(s), kAllCtas);      // stage refillable once ALL CTAs' MMAs have read it
           else umma_commit(bar_empty(s));
-          if (in_chunk + 1 == chb || kb == num_kb - 1) umma_commit(bar_cfull(cc & 1u));   // chunk complete -> drain
+          if (in_chunk + 1 == chb || kb == kb1 - 1) umma_commit(bar_cfull(cc & 1u));   // chunk complete -> drain
           }
           }
           __syncwarp();
           if (++s == nstages) { s = 0; ph ^= 1u; }
-          if (++in_chunk == chb || kb == num_kb - 1) {
+          if (++in_chunk == chb || kb == kb1 - 1) {
             ++cc;
             in_chunk = 0;
           }
@@ -386,7 +403,9 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
       }
       // ---- drain all chunks but the last into registers (the first one is loaded straight into them)
       float acc[128];
-      const int nchunks = (num_kb + chb - 1) / chb;
+      int kb0, kb1;
+      const int sp = k_range(item, kb0, kb1);
+      const int nchunks = (kb1 - kb0 + chb - 1) / chb;
       for (int c = 0; c + 1 < nchunks; ++c, ++cc) {
         const uint32_t buf = cc & 1u;
         mbar_wait(bar_cfull(buf), (cc >> 1) & 1u);
@@ -435,7 +454,7 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
       for (int j = 0; j < 4; ++j) {
         const int c0 = hcol * 128 + j * 32;
         if (c0 >= n_inst) continue;                                  // warp-uniform
-        const float bl = (p.bias != nullptr && c0 + lane < n_here) ? __ldg(p.bias + n0 + c0 + lane) : 0.f;
+        const float bl = (p.bias != nullptr && sp == 0 && c0 + lane < n_here) ? __ldg(p.bias + n0 + c0 + lane) : 0.f;
         float* a = &acc[j * 32];                                    // (static indices: stays in registers)
         if (nchunks == 1) {
           tmem_ld32(tl + j * 32, reinterpret_cast<uint32_t*>(a));
@@ -576,7 +595,8 @@ linear_h3_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_const
               tma_store_4d(&map_y0, box_sh, n0 + c0, ox, oy, ob);
               if (two) tma_store_4d(&map_y1, box_sh + 2048, n0 + c0, ox, oy, ob);
             } else {
-              tma_store_2d(&map_y0, box_sh, n0 + c0, row0);
+              if (OUT == H3_OUT_F32_TMA && splits > 1) tma_reduce_add_2d(&map_y0, box_sh, n0 + c0, row0);
+              else tma_store_2d(&map_y0, box_sh, n0 + c0, row0);
               if (two) tma_store_2d(&map_y1, box_sh + 2048, n0 + c0, row0);
             }
           }
@@ -725,6 +745,8 @@ static int h3_stage_count_pair(int w_rows) {        // cta_group::2: each CTA st
 }
 static int g_h3_chunk_kb = H3_CHUNK_KB;   // developer hook: K blocks per accumulation chunk
 // tcgen05.mma.cta_group::2 for launches that run as clusters of two CTAs: 0 never, 1 where it pays (launch_h3), 2 always
+// split-K for few-tile / long-contraction GEMMs (hoisdf_linear_h3_fwd): HOISDF_H3_SPLITK=0 turns it off
+static int g_h3_splitk = [] { const char* e = getenv("HOISDF_H3_SPLITK"); return e == nullptr ? 1 : atoi(e); }();
 static int g_h3_pair = [] { const char* e = getenv("HOISDF_H3_PAIR"); return e == nullptr ? 1 : atoi(e); }();
 
 template <int CL, int OUT, bool SINGLE, bool RES, bool PAIR = false>
@@ -754,7 +776,7 @@ static int launch_h3(const CUtensorMap* maps, const H3Params& p0, int64_t m_tile
   H3Params p = p0;
   if (p.chunk_kb <= 0) p.chunk_kb = g_h3_chunk_kb > 0 ? g_h3_chunk_kb : H3_CHUNK_KB;
   p.m_blocks = static_cast<int>(ceil_div(m_tiles, CL));
-  const int64_t items = static_cast<int64_t>(p.m_blocks) * p.n_tiles;
+  const int64_t items = static_cast<int64_t>(p.m_blocks) * p.n_tiles * (p.splits > 1 ? p.splits : 1);
   const int64_t clusters = items < max_clusters<CL>() ? items : max_clusters<CL>();
   const bool res = p.r_hi != nullptr;
   if (p.single && (res || p.out_mode == H3_OUT_F32_DIRECT)) return HOISDF_E_UNSUPPORTED;
@@ -844,7 +866,22 @@ HOISDF_API int hoisdf_linear_h3_fwd(const hoisdf_linear_h3_args* a, void* stream
   if (!map_x_3d(&maps[1], a->x_lo, groups, rpb, a->k, a->ldx, gstride)) return HOISDF_E_UNSUPPORTED;
   // launches with very few tiles (the 17-query decoder layers, M = 544): N tiles of 64 columns instead of 256 -> 4x the
   // CTAs and a 6-stage ring, the K loop is pure load latency there
-  const bool few = a->single_pass == 0 && a->n > 64 && m_tiles * ceil_div(a->n, H3_BN) <= kNumSMs / 4;
+  // split-K: a handful of output tiles over a long contraction (the weight gradients of the training step)
+  int splits = 1, kb_per_split = 0;
+  {
+    const int64_t num_kb = ceil_div(a->k, H3_BK);
+    const int64_t items0 = ceil_div(m_tiles, cl) * ceil_div(a->n, h3_w_rows(a->n, false));
+    const int64_t room = (kNumSMs / cl) / items0;
+    if (g_h3_splitk && a->split_k != 0 && out_mode == H3_OUT_F32_TMA && a->single_pass == 0 && a->act == HOISDF_ACT_NONE &&
+        a->res_hi == nullptr && a->res_lo == nullptr && groups == 1 && room >= 2 && num_kb >= 64) {
+      const int64_t want = room < num_kb / 8 ? room : num_kb / 8;          // >= 8 K blocks (256 of K) per item
+      const int64_t per = ceil_div(ceil_div(num_kb, want), 4) * 4;         // whole TMEM chunks
+      splits = static_cast<int>(ceil_div(num_kb, per));
+      kb_per_split = static_cast<int>(per);
+      if (splits < 2) splits = 1;
+    }
+  }
+  const bool few = splits == 1 && a->single_pass == 0 && a->n > 64 && m_tiles * ceil_div(a->n, H3_BN) <= kNumSMs / 4;
   const int w_rows = few ? 64 : h3_w_rows(a->n, a->single_pass != 0);
   const int bn = w_rows;                                 // three-product mode: one N tile = the W rows of a stage
   const int slice = w_rows / cl;
@@ -881,6 +918,7 @@ HOISDF_API int hoisdf_linear_h3_fwd(const hoisdf_linear_h3_args* a, void* stream
   p.w_rows = w_rows; p.nstages = h3_stage_count(w_rows);
   p.w_scale = a->w_scale > 0.f ? a->w_scale : 1.f;
   p.y_scale = a->y_scale;
+  p.splits = splits; p.kb_per_split = kb_per_split;
   if (a->res_hi != nullptr || a->res_lo != nullptr) {
     if (a->res_hi == nullptr || a->res_lo == nullptr) return HOISDF_E_NULL;
     if (out_mode == H3_OUT_F32_DIRECT || a->residual != nullptr || (a->n & 31)) return HOISDF_E_UNSUPPORTED;
@@ -890,6 +928,11 @@ HOISDF_API int hoisdf_linear_h3_fwd(const hoisdf_linear_h3_args* a, void* stream
     p.ldr = a->ldr;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (splits > 1) {                            // the items add into the output
+    const cudaError_t e = cudaMemset2DAsync(a->y, static_cast<size_t>(a->ldy) * 4, 0, static_cast<size_t>(a->n) * 4,
+                                            static_cast<size_t>(a->m), s);
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
   if (cl == 2) return launch_h3<2>(maps, p, m_tiles, s);
   return launch_h3<1>(maps, p, m_tiles, s);
 }

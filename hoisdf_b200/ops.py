@@ -313,11 +313,13 @@ class PackedLinearH3:
 
 def linear_h3(x: SplitRows, pw: PackedLinearH3, act: int = ACT_NONE, out=None, residual: Optional[torch.Tensor] = None,
               split_out: bool = False, x_batch=(0, 0), m: Optional[int] = None, chunk_kb: Optional[int] = None,
-              residual_split: Optional[SplitRows] = None, single: bool = False, y_scale: Optional[torch.Tensor] = None):
+              residual_split: Optional[SplitRows] = None, single: bool = False, y_scale: Optional[torch.Tensor] = None,
+              split_k: bool = False):
     """Y = act(X . W^T + b) (+ residual) on the FP16x3 tensor-core kernel.  `out` is an fp32 (M, N) tensor view (unit
     inner stride) or a SplitRows window; allocated when None (fp32, or split-half if split_out).
     x_batch = (rows_per_batch, batch_stride in halfs) walks strided row groups of `x` (m rows in total).
-    y_scale: one fp32 value ON THE DEVICE the product is multiplied by in the epilogue (training backward)."""
+    y_scale: one fp32 value ON THE DEVICE the product is multiplied by in the epilogue (training backward).
+    split_k: allow the few-tile / long-contraction launches to split K over the SMs (summation order then varies)."""
     m = x.rows if m is None else m
     assert x.cols >= pw.k, (x.cols, pw.k)
     if out is None:
@@ -342,6 +344,7 @@ def linear_h3(x: SplitRows, pw: PackedLinearH3, act: int = ACT_NONE, out=None, r
     a.single_pass = int(single)
     a.w_scale = float(pw.scale)
     a.y_scale = _ptr(y_scale)
+    a.split_k = int(split_k)
     if residual_split is not None:
         assert residual_split.cols >= pw.n and residual_split.rows >= m
         a.res_hi, a.res_lo, a.ldr = residual_split.hi_ptr, residual_split.lo_ptr, residual_split.ld

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 30
+#define HOISDF_ABI_VERSION 31
 
 enum {
   HOISDF_OK = 0,
@@ -116,6 +116,12 @@ typedef struct {
   const float* y_scale;              /* optional: ONE float in device memory the product x . w^T is multiplied by in the
                                         epilogue (before the bias) -- the power-of-two factor hoisdf_linear_bwd_prep took
                                         out of a gradient, put back without a host read-back or an extra pass */
+  int32_t split_k;                   /* 1: a launch with only a handful of output tiles over a long contraction (K >= 2048;
+                                        the weight gradients of the training step: 256 x 256 outputs over K = rows) is
+                                        split along K over the idle SMs; the partial products are ADDED into the
+                                        zero-initialised output by TMA reductions, so the fp32 summation order -- not the
+                                        value up to rounding -- varies from run to run.  fp32 `y` output, act == NONE,
+                                        no residual; ignored otherwise.  0 (default): never, results are reproducible */
 } hoisdf_linear_h3_args;
 
 int hoisdf_linear_h3_fwd(const hoisdf_linear_h3_args* args, void* stream);

@@ -695,3 +695,26 @@ def test_linear_h3_single_product(cuda):
     assert 1e-5 < e1 < 2e-3 and e3 < 3e-6, (e1, e3)
     yf = ops.linear_h3(xs, pw, ops.ACT_NONE, single=True)                      # fp32 output, default chunking
     assert rel_err(yf, x.double() @ w.double().T + b.double()) < 2e-3
+
+
+def test_linear_h3_split_k(cuda):
+    """Split-K form of the FP16x3 GEMM (hoisdf_linear_h3_args.split_k: the weight gradients of the training step -- a
+    handful of output tiles over a contraction as long as the batch has rows): partial products added into the output by TMA
+    reductions, vs fp64; bias added once, the device-scalar y_scale applied, ragged M / N / K; shapes that do not qualify
+    (activation, many tiles, short K) ignore the flag and stay bit-identical to the plain launch."""
+    from hoisdf_b200 import ops
+    for i, (m, k, n) in enumerate(((256, 51200, 256), (289, 38400, 223), (1024, 12800, 256), (256, 230400, 60),
+                                   (3968, 12800, 512), (100, 2048, 20), (512, 5000, 1024))):
+        x, w, b = rnd(301 + i, m, k), rnd(311 + i, n, k, lo=-0.1, hi=0.1), rnd(321 + i, n)
+        pw = ops.PackedLinearH3.pack(w.to(cuda), b.to(cuda))
+        xs = ops.split_rows(x.to(cuda))
+        sc = torch.tensor([0.25], device=cuda)
+        ref = (x.double() @ w.double().T) * 0.25 + b.double()
+        plain = ops.linear_h3(xs, pw, ops.ACT_NONE, y_scale=sc)
+        split = ops.linear_h3(xs, pw, ops.ACT_NONE, y_scale=sc, split_k=True)
+        assert rel_err(plain, ref) < 4e-6 and rel_err(split, ref) < 4e-6, (m, k, n, rel_err(split, ref))
+    # not eligible: ReLU epilogue / enough tiles / short contraction -> the flag changes nothing
+    for (m, k, n, act) in ((256, 51200, 256, ops.ACT_RELU), (20000, 4096, 512, ops.ACT_NONE), (256, 1024, 256, ops.ACT_NONE)):
+        x, w = rnd(331, m, k), rnd(332, n, k, lo=-0.1, hi=0.1)
+        pw, xs = ops.PackedLinearH3.pack(w.to(cuda), None), ops.split_rows(x.to(cuda))
+        assert torch.equal(ops.linear_h3(xs, pw, act), ops.linear_h3(xs, pw, act, split_k=True)), (m, k, n)
