@@ -18,7 +18,7 @@ from __future__ import annotations
 
 import os
 import random
-from typing import Dict
+from typing import Dict, Optional
 
 import torch
 import torch.nn.functional as F
@@ -392,6 +392,69 @@ class Trainer:
         self.epoch += 1
         if self.epoch % self.lr_drop == 0:
             self.lr *= self.gamma
+
+    # ------------------------------------------------------------------ checkpoints
+    def _torch_optimizer(self):
+        """A stock torch.optim.AdamW / StepLR pair over ALL named parameters, as upstream builds them (common/base.py:64-
+        75): used only to read and write optimizer state in torch's own format, never to step."""
+        opt = torch.optim.AdamW([{"params": [p for _, p in self.model.named_parameters()]}], lr=self.lr, betas=self.betas,
+                                eps=self.eps, weight_decay=self.weight_decay)
+        sched = torch.optim.lr_scheduler.StepLR(opt, self.lr_drop, gamma=self.gamma)
+        return opt, sched
+
+    def state_dict(self, epoch: Optional[int] = None) -> Dict[str, object]:
+        """The snapshot upstream's trainer writes (main/train.py:559-568 -> common/base.py:111-116): {"epoch", "network",
+        "optimizer", "lr_scheduler"}, the network keys prefixed `module.` like the DataParallel wrapper's, the optimizer /
+        scheduler entries in torch.optim's own state-dict format (per-parameter `step`, `exp_avg`, `exp_avg_sq`; parameters
+        that never received a gradient have no entry, as with torch.optim) -- loadable by upstream's `load_model`
+        (base.py:145-150) and by `Trainer.load_state_dict`."""
+        opt, sched = self._torch_optimizer()
+        unused = set(self._unused or [])
+        with torch.no_grad():
+            for i, (p, (o, k)) in enumerate(zip(self.params, self.slices)):
+                if self.step_count == 0 or i in unused:
+                    continue
+                opt.state[p] = {"step": torch.tensor(float(self.step_count)),
+                                "exp_avg": self.exp_avg[o:o + k].view(p.shape).clone(),
+                                "exp_avg_sq": self.exp_avg_sq[o:o + k].view(p.shape).clone()}
+        base_lr = self.lr / (self.gamma ** (self.epoch // self.lr_drop)) if self.lr_drop > 0 else self.lr
+        sd_s = sched.state_dict()
+        sd_s.update({"last_epoch": self.epoch, "_step_count": self.epoch + 1, "base_lrs": [base_lr], "_last_lr": [self.lr]})
+        sd_o = opt.state_dict()
+        for g in sd_o["param_groups"]:
+            g["lr"], g["initial_lr"] = self.lr, base_lr
+        net = {"module." + k: v.detach().clone() for k, v in self.model.state_dict().items()}
+        return {"epoch": self.epoch - 1 if epoch is None else int(epoch), "network": net, "optimizer": sd_o,
+                "lr_scheduler": sd_s}
+
+    def load_state_dict(self, ckpt: Dict[str, object]) -> int:
+        """Resume from a snapshot in upstream's layout (see state_dict); returns the epoch to continue with
+        (upstream: `start_epoch = ckpt["epoch"] + 1`, base.py:146)."""
+        from .model import load_checkpoint
+        load_checkpoint(self.model, {"network": ckpt["network"]})          # strict, `module.` prefix handled; writes into
+        opt, _ = self._torch_optimizer()                                      # the flat buffer (p.data are views of it)
+        opt.load_state_dict(ckpt["optimizer"])                               # torch validates the layout
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        steps = [0]
+        with torch.no_grad():
+            for p, (o, k) in zip(self.params, self.slices):
+                st = opt.state.get(p)
+                if not st:
+                    continue
+                self.exp_avg[o:o + k].copy_(st["exp_avg"].reshape(-1))
+                self.exp_avg_sq[o:o + k].copy_(st["exp_avg_sq"].reshape(-1))
+                steps.append(int(st["step"]))
+        self.step_count = max(steps)
+        g = opt.param_groups[0]
+        self.lr, self.betas, self.eps, self.weight_decay = float(g["lr"]), tuple(g["betas"]), float(g["eps"]), \
+            float(g["weight_decay"])
+        sd_s = ckpt.get("lr_scheduler")
+        self.epoch = int(sd_s["last_epoch"]) if sd_s else int(ckpt["epoch"]) + 1
+        if sd_s:
+            self.lr_drop, self.gamma = int(sd_s.get("step_size", self.lr_drop)), float(sd_s.get("gamma", self.gamma))
+        torch.autograd.graph.increment_version(self.params)
+        return int(ckpt["epoch"]) + 1
 
     def step(self, inputs, targets, meta_info, epoch_cnt=0, batch_ratio=0.0):
         model = self.model

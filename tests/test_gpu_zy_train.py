@@ -335,7 +335,10 @@ def test_trainer_step_matches_adamw(train_setup):
     assert torch.isfinite(total)
     grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.requires_grad}
     ref = {n: torch.nn.Parameter(before[n].clone()) for n in grads}
-    used = [n for n in ref if float(grads[n].abs().max()) > 0]
+    names = [n for n, p in model.named_parameters() if p.requires_grad]
+    unreached = {names[i] for i in tr._unused}                                   # found from the tape at the first step
+    used = [n for n in ref if n not in unreached]
+    assert all(float(grads[n].abs().max()) == 0 for n in unreached)
     for n in used:
         ref[n].grad = grads[n].clone()
     opt = torch.optim.AdamW([ref[n] for n in used], lr=1e-4)
@@ -351,4 +354,20 @@ def test_trainer_step_matches_adamw(train_setup):
     # a second step runs (packed-weight caches see the new values) and changes the loss
     total2, _, _ = tr.step(*s["batch"], epoch_cnt=0, batch_ratio=0.0)
     assert torch.isfinite(total2) and float(total2) != float(total)
+    # snapshot in upstream's layout -> a fresh trainer on a fresh model resumes and takes the same third step
+    import copy
+    snap = copy.deepcopy(tr.state_dict(epoch=0))
+    from hoisdf_b200.model import get_model
+    from hoisdf_b200 import synthetic as syn
+    fresh_model = get_model("train", mano_buffers=syn.mano_buffers(s["seed"])).to(s["batch"][0]["img"].device)
+    fresh = Trainer(fresh_model, lr=1.0)
+    assert fresh.load_state_dict(snap) == 1 and fresh.step_count == 2 and fresh.lr == 1e-4
+    for m in (model, fresh_model):
+        m.hand_sdf_decoder.dropout_prob = m.obj_sdf_decoder.dropout_prob = 0.0
+    t3, _, _ = tr.step(*s["batch"], epoch_cnt=0, batch_ratio=0.0)
+    f3, _, _ = fresh.step(*s["batch"], epoch_cnt=0, batch_ratio=0.0)
+    assert abs(float(t3) - float(f3)) <= 1e-5 * abs(float(t3))
+    fp = dict(fresh_model.named_parameters())
+    for n, p in model.named_parameters():
+        assert float((p.detach() - fp[n].detach()).abs().max()) <= 2e-6 * max(float(p.detach().abs().max()), 1e-3), n
     model.eval()

@@ -138,3 +138,59 @@ def test_config_reads_through_to_upstream_singleton():
     finally:
         cfg.link_upstream(False)
     assert cfg.num_samp_hand != 77
+
+
+def test_trainer_snapshot_is_upstreams_layout(lib_built):
+    """`Trainer.state_dict()` is the snapshot upstream writes (main/train.py:559-568): `module.`-prefixed
+    network keys, optimizer / scheduler entries that stock torch.optim.AdamW / StepLR over ALL named parameters (upstream
+    common/base.py:64-75) load as they are; a fresh Trainer resumes from it bit for bit.  (Host logic only: no kernel runs.)"""
+    from hoisdf_b200.config import cfg
+    from hoisdf_b200.model import get_model
+    from hoisdf_b200.train import Trainer
+    old = cfg.setting
+    cfg.set_setting("dexycb")
+    try:
+        model = get_model("train", mano_buffers=syn.mano_buffers(0))
+        model.load_state_dict(syn.full_state_dict(0, "dexycb"), strict=True)
+        tr = Trainer(model, lr=1e-4, lr_drop=2, lr_decay_gamma=0.5)
+        g = torch.Generator().manual_seed(1)
+        tr.exp_avg.copy_(torch.randn(tr.exp_avg.shape, generator=g))
+        tr.exp_avg_sq.copy_(torch.rand(tr.exp_avg_sq.shape, generator=g))
+        tr.step_count, tr._unused = 7, [3, 10]
+        for _ in range(3):
+            tr.epoch_end()                                    # epochs 0, 1, 2 done: one lr drop (at epoch 2)
+        assert tr.lr == 5e-5 and tr.epoch == 3
+        snap = tr.state_dict()
+        assert snap["epoch"] == 2 and set(snap) == {"epoch", "network", "optimizer", "lr_scheduler"}
+        assert all(k.startswith("module.") for k in snap["network"])
+        # upstream's side: DataParallel-style strict load + stock optimizer / scheduler
+        ref = get_model("train", mano_buffers=syn.mano_buffers(1))
+        ref.load_state_dict({k[len("module."):]: v for k, v in snap["network"].items()}, strict=True)
+        opt = torch.optim.AdamW([{"params": [p for _, p in ref.named_parameters()]}], lr=1e-4)
+        sched = torch.optim.lr_scheduler.StepLR(opt, 2, gamma=0.5)
+        opt.load_state_dict(snap["optimizer"])
+        sched.load_state_dict(snap["lr_scheduler"])
+        assert opt.param_groups[0]["lr"] == 5e-5 and sched.last_epoch == 3 and sched.get_last_lr() == [5e-5]
+        sched.step()                                          # epoch 3 done -> epoch 4: second drop
+        assert abs(opt.param_groups[0]["lr"] - 2.5e-5) < 1e-12
+        named = dict(ref.named_parameters())
+        trained = [n for n, p in model.named_parameters() if p.requires_grad]
+        assert len(opt.state) == len(trained) - 2             # the two graph-unreached tensors carry no state, like torch's
+        n0 = trained[0]
+        o, k = tr.slices[0]
+        assert torch.equal(opt.state[named[n0]]["exp_avg"].reshape(-1), tr.exp_avg[o:o + k]) and \
+            float(opt.state[named[n0]]["step"]) == 7.0
+        assert named[trained[3]] not in opt.state
+        # our side: a fresh trainer resumes from the snapshot
+        fresh = Trainer(get_model("train", mano_buffers=syn.mano_buffers(2)), lr=1.0)
+        assert fresh.load_state_dict(snap) == 3
+        assert (fresh.lr, fresh.epoch, fresh.step_count, fresh.lr_drop, fresh.gamma) == (5e-5, 3, 7, 2, 0.5)
+        assert torch.equal(fresh.flat, tr.flat)
+        for i, (o, k) in enumerate(tr.slices):                # (the alignment gaps between the slices carry nothing)
+            if i in (3, 10):
+                assert not fresh.exp_avg[o:o + k].any() and not fresh.exp_avg_sq[o:o + k].any()
+            else:
+                assert torch.equal(fresh.exp_avg[o:o + k], tr.exp_avg[o:o + k])
+                assert torch.equal(fresh.exp_avg_sq[o:o + k], tr.exp_avg_sq[o:o + k])
+    finally:
+        cfg.set_setting(old)
