@@ -364,10 +364,17 @@ def test_trainer_step_matches_adamw(train_setup):
     assert fresh.load_state_dict(snap) == 1 and fresh.step_count == 2 and fresh.lr == 1e-4
     for m in (model, fresh_model):
         m.hand_sdf_decoder.dropout_prob = m.obj_sdf_decoder.dropout_prob = 0.0
+    # restored exactly: parameters, both moment buffers of every trained tensor, step count, learning rate
+    assert torch.equal(fresh.flat, tr.flat)
+    for i, (o, k) in enumerate(tr.slices):
+        if i not in tr._unused:
+            assert torch.equal(fresh.exp_avg[o:o + k], tr.exp_avg[o:o + k]) and \
+                torch.equal(fresh.exp_avg_sq[o:o + k], tr.exp_avg_sq[o:o + k]), i
+    # ... and the third step starts from the same loss.  (The parameters AFTER it are not compared: AdamW moves every entry
+    # by ~lr whatever its gradient's size, so entries whose true gradient is zero -- a convolution bias in front of a
+    # BatchNorm -- follow the run-to-run rounding noise of the gradient kernels, here as upstream.)
     t3, _, _ = tr.step(*s["batch"], epoch_cnt=0, batch_ratio=0.0)
     f3, _, _ = fresh.step(*s["batch"], epoch_cnt=0, batch_ratio=0.0)
     assert abs(float(t3) - float(f3)) <= 1e-5 * abs(float(t3))
-    fp = dict(fresh_model.named_parameters())
-    for n, p in model.named_parameters():
-        assert float((p.detach() - fp[n].detach()).abs().max()) <= 2e-6 * max(float(p.detach().abs().max()), 1e-3), n
+    assert fresh.step_count == tr.step_count == 3
     model.eval()
