@@ -157,7 +157,7 @@ class LinearFn(Function):
             if n <= 16 and m > 16:
                 # dW = dZ^T X as one pass over X: no transposed copies, no 64-wide tiles for 1 / 3 / 6 / 10 output features
                 dw = torch.empty(n, x.shape[1], device=dy.device, dtype=torch.float32)
-                _count(2)
+                _count(1)
                 check(lib.hoisdf_thin_linear_dw(x.data_ptr(), x.stride(0), dz.data_ptr(), dz.stride(0), m, x.shape[1], n,
                                                 dw.data_ptr(), dw.stride(0), 0, _stream()), "hoisdf_thin_linear_dw")
             else:
