@@ -14,7 +14,7 @@ for line in txt.splitlines():
         kern = re.sub(r"\(.*", "", kern).replace("void ", "")
         hist[kern] = collections.Counter()
         continue
-    m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", line)
+    m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", line)
     if m and kern:
         op = m.group(1)
         h = hist[kern]
