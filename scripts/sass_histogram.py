@@ -1,11 +1,11 @@
 """Per-kernel histogram of the Blackwell-specific SASS opcodes of the built library (cuobjdump -sass), the evidence that
 the hot kernels are tcgen05 / TMEM / TMA code:  UTCHMMA (tcgen05.mma), UTCBAR (tcgen05.commit), LDTM / STTM (tcgen05.ld /
-st), UTMALDG / UTMASTG (TMA load / store), SYNCS (mbarrier), plus HMMA / FFMA counts for contrast.
+st), UTMALDG / UTMASTG / UTMAREDG (TMA load / store / reduce-add), SYNCS (mbarrier), plus HMMA / FFMA counts for contrast.
     python scripts/sass_histogram.py [lib.so] > profiles/rNN_sass_histogram.txt"""
 import collections, re, subprocess, sys
 lib = sys.argv[1] if len(sys.argv) > 1 else "hoisdf_b200/libhoisdf_b200.so"
 txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
-OPS = ["UTCHMMA", "UTCHMMA.2CTA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMALDG.MULTICAST", "UTMASTG", "SYNCS", "HMMA", "FFMA", "total"]
+OPS = ["UTCHMMA", "UTCHMMA.2CTA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMALDG.MULTICAST", "UTMASTG", "UTMAREDG", "SYNCS", "HMMA", "FFMA", "total"]
 kern, hist = None, collections.OrderedDict()
 for line in txt.splitlines():
     m = re.search(r"Function : (\S+)", line)
@@ -20,7 +20,7 @@ for line in txt.splitlines():
         h = hist[kern]
         h["total"] += 1
         base = op.split(".")[0]
-        if base in ("UTCHMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "SYNCS", "HMMA", "FFMA"):
+        if base in ("UTCHMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAREDG", "SYNCS", "HMMA", "FFMA"):
             h[base] += 1
         if base == "UTCHMMA" and ".2CTA" in op: h["UTCHMMA.2CTA"] += 1
         if base == "UTMALDG" and "MULTICAST" in op: h["UTMALDG.MULTICAST"] += 1
