@@ -91,11 +91,42 @@ def matmul_nt(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = N
     return ops.linear_h3(xs, pw, act, chunk_kb=chunk_kb)
 
 
+_lin_ws = {}
+
+
+def _linear_workspace(device, nbytes: int) -> torch.Tensor:
+    """Grow-only scratch buffer per device for hoisdf_linear_train_fwd / _bwd (operand copies in the tensor-core formats; used
+    inside one call only, calls are ordered on the stream)."""
+    buf = _lin_ws.get(device)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes), device=device, dtype=torch.uint8)
+        _lin_ws[device] = buf
+    return buf
+
+
+def _fused_linear(m: int, n: int, k: int) -> bool:
+    """One C call per direction (hoisdf_linear_train_fwd / _bwd) for the tensor-core shapes; the per-kernel Python path stays
+    for bench.py's per-launch profile and the developer switch."""
+    return min(m, n, k) > 16 and not _DEBUG_TORCH_MATMUL and ops.PROFILE is None
+
+
 class LinearFn(Function):
     @staticmethod
     def forward(ctx, x, weight, bias, act):
         x = _c2d(x)
-        y = matmul_nt(x, weight, bias, act)
+        m, k = x.shape
+        n = weight.shape[0]
+        if _fused_linear(m, n, k):
+            w = _c2d(weight.detach())
+            y = torch.empty(m, ops.round_up(n, 4), device=x.device, dtype=torch.float32)[:, :n]
+            nbytes = lib.hoisdf_linear_train_workspace_bytes(m, n, k)
+            ws = _linear_workspace(x.device, nbytes)
+            _count(3)
+            check(lib.hoisdf_linear_train_fwd(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0),
+                                              _ptr(None if bias is None else bias.detach()), m, n, k, act, y.data_ptr(),
+                                              y.stride(0), ws.data_ptr(), nbytes, _stream()), "hoisdf_linear_train_fwd")
+        else:
+            y = matmul_nt(x, weight, bias, act)
         ctx.act = act
         ctx.has_bias = bias is not None
         ctx.save_for_backward(x, weight, y if act == ACT_RELU else None)
@@ -108,6 +139,23 @@ class LinearFn(Function):
         k = x.shape[1]
         if min(m, n, k) <= 16 or _DEBUG_TORCH_MATMUL:
             return LinearFn._backward_small(ctx, dy, x, weight, y)
+        if _fused_linear(m, n, k):
+            dy = _c2d(dy)
+            dev = dy.device
+            w = _c2d(weight.detach())
+            want_dx, want_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+            dx = torch.empty(m, ops.round_up(k, 4), device=dev, dtype=torch.float32)[:, :k] if want_dx else None
+            dwt = torch.empty(k, ops.round_up(n, 4), device=dev, dtype=torch.float32)[:, :n] if want_dw else None
+            db = torch.empty(n, device=dev, dtype=torch.float32) if ctx.has_bias else None
+            nbytes = lib.hoisdf_linear_train_workspace_bytes(m, n, k)
+            ws = _linear_workspace(dev, nbytes)
+            _count(2 + 2 * int(want_dx) + 2 * int(want_dw))
+            check(lib.hoisdf_linear_train_bwd(dy.data_ptr(), dy.stride(0), _ptr(y), 0 if y is None else y.stride(0),
+                                              x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), m, n, k, ctx.act,
+                                              _ptr(dx), 0 if dx is None else dx.stride(0), _ptr(dwt),
+                                              0 if dwt is None else dwt.stride(0), _ptr(db), ws.data_ptr(), nbytes, _stream()),
+                  "hoisdf_linear_train_bwd")
+            return dx, (None if dwt is None else dwt.t()), db, None
         # tensor-core backward: operands prepared in two passes over dY (csrc/train_prep.cu), no host read-back
         dy = _c2d(dy)
         dev = dy.device

@@ -11,6 +11,13 @@
 //                            (w operand of the dW GEMM, tile transpose through shared memory) and adds the column sums
 //                            into db                                                        (1 read of dY and Y)
 //   hoisdf_split_rows_t      X (M, K) fp32 -> X^T in split-half format (K rows of M)        (1 read)
+// and, so that a layer costs the host ONE call per direction instead of 3 / 7 (the 17-query decoder layers and the small heads
+// are bound by the host's launch rate, not by the GPU):
+//   hoisdf_linear_train_fwd  split(X), pack(W), GEMM                        -> Y
+//   hoisdf_linear_train_bwd  absmax, prep, pack(W^T) + GEMM -> dX, X^T + split-K GEMM -> dW^T, db
+// on a caller-owned workspace (hoisdf_linear_train_workspace_bytes).
+#include <cstring>
+
 #include "tc_common.cuh"
 
 namespace hoisdf {
@@ -122,6 +129,58 @@ split_rows_t_kernel(const float* __restrict__ x, int64_t m, int64_t k, int64_t l
   }
 }
 
+
+// W (n, k) fp32 -> hoisdf_pack_h3 planes of W^T: (k rows, ldh >= n halfs); 32 x 32 tile per block (32 x 8 threads)
+__global__ void __launch_bounds__(256)
+pack_h3_t_kernel(const float* __restrict__ w, int64_t n, int64_t k, int64_t ldw, __half* __restrict__ a, __half* __restrict__ b,
+                 __half* __restrict__ c, int64_t ldh) {
+  __shared__ float tile[32][33];
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * 32, c0 = static_cast<int64_t>(blockIdx.x) * 32;   // rows of w, cols of w
+  const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rl = ty + 8 * i;
+    const int64_t r = r0 + rl, cc = c0 + tx;
+    tile[rl][tx] = (r < n && cc < k) ? w[r * ldw + cc] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int cl = ty + 8 * i;
+    const int64_t orow = c0 + cl, ocol = r0 + tx;              // element (orow, ocol) of W^T
+    if (orow < k && ocol < n) {
+      const float v = tile[tx][cl];
+      const __half ha = __float2half_rn(fminf(fmaxf(v * kLoScale, -65504.f), 65504.f));
+      const float whi = __half2float(ha) * kLoInv;
+      a[orow * ldh + ocol] = ha;
+      b[orow * ldh + ocol] = __float2half_rn(whi);
+      c[orow * ldh + ocol] = __float2half_rn(fminf(fmaxf((v - whi) * kLoScale, -65504.f), 65504.f));
+    }
+  }
+}
+
+inline int64_t up8(int64_t v) { return (v + 7) / 8 * 8; }
+inline int64_t up256(int64_t v) { return (v + 255) / 256 * 256; }
+
+struct TrainWs {                       // byte offsets into the workspace
+  int64_t scal, xs, wp, dz, dzt, wt, xt, total;
+};
+inline TrainWs train_ws(int64_t m, int64_t n, int64_t k) {
+  TrainWs w;
+  int64_t o = 0;
+  w.scal = o; o += 256;                                   // amax | scale
+  w.xs = o;   o += up256(2 * m * up8(k) * 2);             // forward: X split-half (hi plane | lo plane)
+  w.wp = o;   o += up256(3 * n * up8(k) * 2);             // forward: W planes
+  const int64_t fwd_end = o;
+  o = 256;                                                // the backward reuses the same bytes
+  w.dz = o;   o += up256(2 * m * up8(n) * 2);             // dZ / s split-half
+  w.dzt = o;  o += up256(3 * n * up8(m) * 2);             // (dZ / s)^T planes
+  w.wt = o;   o += up256(3 * k * up8(n) * 2);             // W^T planes
+  w.xt = o;   o += up256(2 * k * up8(m) * 2);             // X^T split-half
+  w.total = o > fwd_end ? o : fwd_end;
+  return w;
+}
+
 }  // namespace
 }  // namespace hoisdf
 
@@ -172,4 +231,93 @@ HOISDF_API int hoisdf_split_rows_t(const float* x, int64_t m, int64_t k, int64_t
                         static_cast<cudaStream_t>(stream)>>>(x, m, k, ldx, reinterpret_cast<__half*>(hi),
                                                              reinterpret_cast<__half*>(lo), ldh);
   return launch_status();
+}
+
+HOISDF_API int64_t hoisdf_linear_train_workspace_bytes(int64_t m, int64_t n, int64_t k) {
+  if (m <= 0 || n <= 0 || k <= 0) return 0;
+  return train_ws(m, n, k).total;
+}
+
+HOISDF_API int hoisdf_linear_train_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, int64_t m,
+                                       int64_t n, int64_t k, int32_t act, float* y, int64_t ldy, void* workspace,
+                                       int64_t workspace_bytes, void* stream) {
+  if (x == nullptr || w == nullptr || y == nullptr || workspace == nullptr) return HOISDF_E_NULL;
+  if (m <= 0 || n <= 0 || k <= 0 || ldx < k || ldw < k || ldy < n) return HOISDF_E_SHAPE;
+  const TrainWs o = train_ws(m, n, k);
+  if (workspace_bytes < o.total) return HOISDF_E_WORKSPACE;
+  if (!aligned16(workspace)) return HOISDF_E_ALIGN;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const int64_t ldh = up8(k);
+  uint16_t* xh = reinterpret_cast<uint16_t*>(ws + o.xs);
+  uint16_t* xl = xh + m * ldh;
+  uint16_t* wa = reinterpret_cast<uint16_t*>(ws + o.wp);
+  int st = hoisdf_split_rows(x, m, k, ldx, (k + 3) / 4 * 4, xh, xl, ldh, stream);
+  if (st != HOISDF_OK) return st;
+  st = hoisdf_pack_h3(w, n, k, ldw, wa, wa + n * ldh, wa + 2 * n * ldh, ldh, stream);
+  if (st != HOISDF_OK) return st;
+  hoisdf_linear_h3_args a;
+  memset(&a, 0, sizeof(a));
+  a.x_hi = xh; a.x_lo = xl; a.ldx = ldh;
+  a.w_a = wa; a.w_b = wa + n * ldh; a.w_c = wa + 2 * n * ldh; a.ldw = ldh; a.bias = bias;
+  a.y = y; a.ldy = ldy; a.m = m; a.n = n; a.k = k; a.act = act; a.chunk_kb = 4;
+  return hoisdf_linear_h3_fwd(&a, stream);
+}
+
+HOISDF_API int hoisdf_linear_train_bwd(const float* dy, int64_t lddy, const float* y, int64_t ldy, const float* x, int64_t ldx,
+                                       const float* w, int64_t ldw, int64_t m, int64_t n, int64_t k, int32_t act, float* dx,
+                                       int64_t lddx, float* dwt, int64_t lddwt, float* db, void* workspace,
+                                       int64_t workspace_bytes, void* stream) {
+  if (dy == nullptr || workspace == nullptr || (dx != nullptr && w == nullptr) || (dwt != nullptr && x == nullptr) ||
+      (act == HOISDF_ACT_RELU && y == nullptr))
+    return HOISDF_E_NULL;
+  if (m <= 0 || n <= 0 || k <= 0 || lddy < n || (dx != nullptr && (lddx < k || ldw < k)) ||
+      (dwt != nullptr && (lddwt < n || ldx < k)))
+    return HOISDF_E_SHAPE;
+  const TrainWs o = train_ws(m, n, k);
+  if (workspace_bytes < o.total) return HOISDF_E_WORKSPACE;
+  if (!aligned16(workspace)) return HOISDF_E_ALIGN;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  float* amax = reinterpret_cast<float*>(ws + o.scal);
+  float* scale = amax + 1;
+  const int64_t ld_dz = up8(n), ld_t = up8(m);
+  uint16_t* dzh = reinterpret_cast<uint16_t*>(ws + o.dz);
+  uint16_t* dzl = dzh + m * ld_dz;
+  uint16_t* ta = reinterpret_cast<uint16_t*>(ws + o.dzt);
+  int st = hoisdf_absmax(dy, m, n, lddy, amax, stream);
+  if (st != HOISDF_OK) return st;
+  st = hoisdf_linear_bwd_prep(dy, lddy, y, ldy, m, n, act, amax, dzh, dzl, ld_dz, ta, ta + n * ld_t, ta + 2 * n * ld_t, ld_t, db,
+                              scale, stream);
+  if (st != HOISDF_OK) return st;
+  hoisdf_linear_h3_args a;
+  if (dx != nullptr) {                                     // dX = (dZ / s . W) * s: weight operand = W^T (k rows of n)
+    uint16_t* wt = reinterpret_cast<uint16_t*>(ws + o.wt);
+    const int64_t gy = ceil_div(n, 32), gx = ceil_div(k, 32);
+    if (gy > 65535) return HOISDF_E_SHAPE;
+    pack_h3_t_kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(gy)), dim3(32, 8), 0,
+                       static_cast<cudaStream_t>(stream)>>>(w, n, k, ldw, reinterpret_cast<__half*>(wt),
+                                                            reinterpret_cast<__half*>(wt + k * ld_dz),
+                                                            reinterpret_cast<__half*>(wt + 2 * k * ld_dz), ld_dz);
+    st = launch_status();
+    if (st != HOISDF_OK) return st;
+    memset(&a, 0, sizeof(a));
+    a.x_hi = dzh; a.x_lo = dzl; a.ldx = ld_dz;
+    a.w_a = wt; a.w_b = wt + k * ld_dz; a.w_c = wt + 2 * k * ld_dz; a.ldw = ld_dz;
+    a.y = dx; a.ldy = lddx; a.m = m; a.n = k; a.k = n; a.act = HOISDF_ACT_NONE; a.chunk_kb = 4; a.y_scale = scale;
+    st = hoisdf_linear_h3_fwd(&a, stream);
+    if (st != HOISDF_OK) return st;
+  }
+  if (dwt != nullptr) {                                    // dW^T = (X^T . dZ / s) * s, split over the long contraction
+    uint16_t* xth = reinterpret_cast<uint16_t*>(ws + o.xt);
+    uint16_t* xtl = xth + k * ld_t;
+    st = hoisdf_split_rows_t(x, m, k, ldx, xth, xtl, ld_t, stream);
+    if (st != HOISDF_OK) return st;
+    memset(&a, 0, sizeof(a));
+    a.x_hi = xth; a.x_lo = xtl; a.ldx = ld_t;
+    a.w_a = ta; a.w_b = ta + n * ld_t; a.w_c = ta + 2 * n * ld_t; a.ldw = ld_t;
+    a.y = dwt; a.ldy = lddwt; a.m = k; a.n = n; a.k = m; a.act = HOISDF_ACT_NONE; a.chunk_kb = 4; a.y_scale = scale;
+    a.split_k = 1;
+    st = hoisdf_linear_h3_fwd(&a, stream);
+    if (st != HOISDF_OK) return st;
+  }
+  return HOISDF_OK;
 }

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 31
+#define HOISDF_ABI_VERSION 32
 
 enum {
   HOISDF_OK = 0,
@@ -640,6 +640,21 @@ int hoisdf_gemm_f32_batched(const float* a, int64_t lda, int32_t trans_a, int64_
                             int64_t ldb, int32_t trans_b, int64_t b_outer, int64_t b_inner, float* c, int64_t ldc,
                             int64_t c_outer, int64_t c_inner, int64_t m, int64_t n, int64_t k, float alpha, int32_t accumulate,
                             int64_t batch_outer, int64_t batch_inner, void* stream);
+/* One Linear of the training step per call (what hoisdf_b200/autograd.py:LinearFn runs; upstream main/train.py:108-131 through
+ * every nn.Linear of the hot path), fp32 in / fp32 out on the FP16x3 tensor-core GEMM, caller-owned workspace of
+ * hoisdf_linear_train_workspace_bytes(m, n, k) bytes (16-byte aligned; HOISDF_E_WORKSPACE when too small):
+ *   _fwd: y (m, n) = act(x (m, k) . w (n, k)^T + bias)              = hoisdf_split_rows + hoisdf_pack_h3 + hoisdf_linear_h3_fwd
+ *   _bwd: dZ = dy * [y > 0] (act == RELU), db (n) = column sums of dZ (may be NULL),
+ *         dx (m, k) = dZ . w (may be NULL), dwt (k, n) = x^T . dZ = dW TRANSPOSED (may be NULL; split-K, see
+ *         hoisdf_linear_h3_args.split_k)                           = hoisdf_absmax + hoisdf_linear_bwd_prep + two GEMMs
+ * Pitches ldy / lddx / lddwt that are multiples of 4 floats (and 16-byte aligned bases) take the TMA-store epilogue. */
+int64_t hoisdf_linear_train_workspace_bytes(int64_t m, int64_t n, int64_t k);
+int hoisdf_linear_train_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, int64_t m, int64_t n,
+                            int64_t k, int32_t act, float* y, int64_t ldy, void* workspace, int64_t workspace_bytes,
+                            void* stream);
+int hoisdf_linear_train_bwd(const float* dy, int64_t lddy, const float* y, int64_t ldy, const float* x, int64_t ldx,
+                            const float* w, int64_t ldw, int64_t m, int64_t n, int64_t k, int32_t act, float* dx, int64_t lddx,
+                            float* dwt, int64_t lddwt, float* db, void* workspace, int64_t workspace_bytes, void* stream);
 /* Linear layers with n <= 16 output features over many rows (the SDF value / class / offset heads: upstream
  * common/nets/sdf_net.py:53-64, main/model.py:82-91), fp32 FMA, one streaming pass over x:
  *   hoisdf_thin_linear_fwd: y (m, n; pitch ldy) = act(x (m, k) . w (n, k)^T + bias) (bias may be NULL);

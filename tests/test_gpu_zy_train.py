@@ -27,9 +27,14 @@ def _close(a, b, tol, what=""):
 
 @pytest.mark.parametrize("m,k,n,act", [(1000, 289, 512, 1), (777, 512, 223, 1), (2048, 256, 768, 0), (300, 512, 1, 0),
                                        (513, 256, 3, 0), (34, 256, 256, 1), (4096, 992, 512, 1), (640, 256, 60, 0)])
-def test_linear_fn(cuda, m, k, n, act):
-    """Y = act(X W^T + b): forward, dX, dW, db on the tensor-core GEMM (tiny N / K: the fp32 FMA GEMM) vs fp64 autograd."""
+@pytest.mark.parametrize("fused", [True, False])
+def test_linear_fn(cuda, m, k, n, act, fused, monkeypatch):
+    """Y = act(X W^T + b): forward, dX, dW, db on the tensor-core GEMM (<= 16 outputs: the streaming fp32 kernels) vs fp64
+    autograd -- through the one-call-per-direction C entries (hoisdf_linear_train_fwd / _bwd) and through the per-kernel
+    Python orchestration that bench.py's per-launch profile uses."""
     from hoisdf_b200 import autograd as A
+    if not fused:
+        monkeypatch.setattr(A, "_fused_linear", lambda *a: False)
     x, w, b, dy = _rnd(1, m, k), _rnd(2, n, k, lo=-0.1, hi=0.1), _rnd(3, n), _rnd(4, m, n) * 1e-3
     xr, wr, br = x.double().requires_grad_(), w.double().requires_grad_(), b.double().requires_grad_()
     yr = F.linear(xr, wr, br)
@@ -42,6 +47,26 @@ def test_linear_fn(cuda, m, k, n, act):
     _close(xd.grad, xr.grad, 5e-6, "dx")
     _close(wd.grad, wr.grad, 5e-6, "dw")
     _close(bd.grad, br.grad, 5e-6, "db")
+
+
+def test_linear_train_entries_error_contract(cuda):
+    from hoisdf_b200._capi import lib
+    m, n, k = 64, 32, 48
+    x, w, y = torch.zeros(m, k, device=cuda), torch.zeros(n, k, device=cuda), torch.zeros(m, n, device=cuda)
+    need = lib.hoisdf_linear_train_workspace_bytes(m, n, k)
+    assert need > 0 and lib.hoisdf_linear_train_workspace_bytes(0, n, k) == 0
+    ws = torch.zeros(need, device=cuda, dtype=torch.uint8)
+    st = torch.cuda.current_stream().cuda_stream
+    args = (x.data_ptr(), k, w.data_ptr(), k, None, m, n, k, 0, y.data_ptr(), n)
+    assert lib.hoisdf_linear_train_fwd(*args, ws.data_ptr(), need, st) == 0
+    assert lib.hoisdf_linear_train_fwd(*args, ws.data_ptr(), need - 1, st) == -5          # HOISDF_E_WORKSPACE
+    assert lib.hoisdf_linear_train_fwd(*args, None, need, st) == -1
+    assert lib.hoisdf_linear_train_fwd(x.data_ptr(), k - 1, w.data_ptr(), k, None, m, n, k, 0, y.data_ptr(), n, ws.data_ptr(),
+                                       need, st) == -2
+    bw = (y.data_ptr(), n, None, 0, x.data_ptr(), k, w.data_ptr(), k, m, n, k)
+    assert lib.hoisdf_linear_train_bwd(*bw, 1, None, 0, None, 0, None, ws.data_ptr(), need, st) == -1      # ReLU needs y
+    assert lib.hoisdf_linear_train_bwd(*bw, 0, None, 0, None, 0, None, ws.data_ptr(), need, st) == 0       # nothing asked: ok
+    torch.cuda.synchronize()
 
 
 def test_weight_norm_gather_layernorm_tokens_fns(cuda):
