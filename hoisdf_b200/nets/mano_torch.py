@@ -74,6 +74,18 @@ def axis_angle_to_matrix(aa: torch.Tensor) -> torch.Tensor:
         2 * x * z - 2 * w * y, 2 * w * x + 2 * y * z, w * w - x * x - y * y + z * z], 1).view(-1, 3, 3)
 
 
+_index_cache = {}
+
+
+def _index(device, which: str) -> torch.Tensor:
+    key = (str(device), which)
+    t = _index_cache.get(key)
+    if t is None:
+        t = torch.tensor(_TIPS if which == "tips" else _ORDER21, device=device, dtype=torch.int64)
+        _index_cache[key] = t
+    return t
+
+
 def mano_forward(layer, rot: torch.Tensor, betas: torch.Tensor):
     """`layer`: the ManoLayer module (buffers th_*); rot (N, 16, 3, 3) joint rotations, betas (N, 10)
     -> verts (N, 778, 3), joints (N, 21, 3) in metres, wrist-centred."""
@@ -92,7 +104,9 @@ def mano_forward(layer, rot: torch.Tensor, betas: torch.Tensor):
     Rv = torch.einsum("vj,njab->nvab", layer.th_weights, Rg)
     tv = torch.einsum("vj,nja->nva", layer.th_weights, off)
     verts = (Rv @ v_posed.unsqueeze(-1)).squeeze(-1) + tv
-    joints = torch.cat([tg, verts[:, _TIPS]], 1)[:, _ORDER21]
+    # (index tensors cached per device: indexing with a Python list builds one with a host copy on every call, which also
+    # cannot be captured into a CUDA graph)
+    joints = torch.cat([tg, verts.index_select(1, _index(rot.device, "tips"))], 1).index_select(1, _index(rot.device, "order"))
     centre = joints[:, :1]
     # upstream scales to millimetres inside ManoLayer and back to metres in ManoHead
     return (verts - centre) * 1000 / 1000, (joints - centre) * 1000 / 1000

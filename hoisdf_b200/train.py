@@ -175,6 +175,53 @@ def vote_joints(points, off, cls):
     return (vote * w).sum(2)
 
 
+_TAIL_LOSSES = ("loss_joint_3d", "loss_joint_cls", "loss_all_joint_3d", "mano_mesh_loss", "mano_joint_loss", "pose_param_loss",
+                "shape_param_loss", "obj_rot", "obj_trans")
+_GRAPH_TAIL = os.environ.get("HOISDF_TRAIN_GRAPH_TAIL", "1") != "0"
+_tail_graphs = {}
+
+
+def _tail_fn(mano_head, consts):
+    """MANO head on the predicted parameters, joint votes and every pose loss (upstream main/model.py:572-665): plain torch ops
+    on bookkeeping-sized tensors.  -> (mano_mesh_out, mano_joints_out, hand_joints of all layers, the 9 loss entries of
+    _TAIL_LOSSES)."""
+    l_verts, l_joints, l_pose, l_shape = consts
+
+    def fn(pose6d, shape, hand_off, hand_cls, obj_rot, obj_trans, hand_nt, joint_gt, gt_verts, gt_joints, gt_pose, gt_shape,
+           rot_gt, trans_gt):
+        pred = mano_head_train(mano_head, pose6d, shape)
+        hand_joints = vote_joints(hand_nt, hand_off, hand_cls)
+        l3d, lcls, lall = joint_vote_losses(hand_nt, hand_off, hand_cls, hand_joints, joint_gt)
+        exp = lambda t, like: t.unsqueeze(0).expand(like.shape)     # noqa: E731
+        return (pred["verts3d"][-1], pred["joints3d"][-1], hand_joints, l3d, lcls, lall,
+                l_verts * F.mse_loss(pred["verts3d"], exp(gt_verts, pred["verts3d"])),
+                l_joints * F.mse_loss(pred["joints3d"], exp(gt_joints, pred["joints3d"])),
+                l_pose * F.mse_loss(pred["mano_pose"], exp(gt_pose, pred["mano_pose"])),
+                l_shape * F.mse_loss(pred["mano_shape"], exp(gt_shape, pred["mano_shape"])),
+                F.smooth_l1_loss(obj_rot, rot_gt[None, :, None, :].expand_as(obj_rot)),
+                F.smooth_l1_loss(obj_trans, trans_gt[None, :, None, :].expand_as(obj_trans)))
+    return fn
+
+
+def _graphed_tail(model, args):
+    """The tail of the training forward, eagerly or -- default on CUDA -- as a pair of CUDA graphs (forward and backward) made
+    by torch.cuda.make_graphed_callables, one pair per (shapes, loss constants): static shapes, no host read-back, no random
+    numbers in there.  HOISDF_TRAIN_GRAPH_TAIL=0, or any input without gradient (a frozen head), takes the eager form."""
+    consts = (float(cfg.lambda_verts3d), float(cfg.lambda_joints3d), float(cfg.lambda_manopose), float(cfg.lambda_manoshape))
+    fn = _tail_fn(model.mano_head, consts)
+    grads = tuple(a.requires_grad for a in args)
+    if not (_GRAPH_TAIL and args[0].is_cuda and torch.is_grad_enabled() and all(grads[:6])
+            and not torch.cuda.is_current_stream_capturing()):
+        return fn(*args)
+    key = (id(model.mano_head), consts, float(cfg.hand_cls_dist), args[0].device, tuple(tuple(a.shape) for a in args))
+    graphed = _tail_graphs.get(key)
+    if graphed is None:
+        sample = tuple(a.detach().clone().requires_grad_(g) for a, g in zip(args, grads))
+        graphed = torch.cuda.make_graphed_callables(fn, sample)
+        _tail_graphs[key] = graphed
+    return graphed(*[a.contiguous() for a in args])
+
+
 # ----------------------------------------------------------------------------------------------------
 # the training forward
 # ----------------------------------------------------------------------------------------------------
@@ -276,26 +323,21 @@ def forward_train(model, inputs, targets, meta_info, epoch_cnt=1e8, batch_ratio=
         Ld, b, cfg.mano_shape_indx, 6)
     shape = mlp_rows(model.linear_shape, hs_all[:, :, cfg.mano_shape_indx].reshape(-1, 256)).view(Ld, b, 10)
 
-    pred_mano = mano_head_train(model.mano_head, pose6d, shape)
     with torch.no_grad():
         gt_mano = model.mano_head.forward_gt(targets["mano_param"])
-    out["mano_mesh_out"] = pred_mano["verts3d"][-1]
-    out["mano_joints_out"] = pred_mano["joints3d"][-1]
-
     joint_gt = targets["joint_cam_no_trans"][:, 1:]
-    hand_joints = vote_joints(hand_nt, hand_off, hand_cls)
-    loss["loss_joint_3d"], loss["loss_joint_cls"], loss["loss_all_joint_3d"] = joint_vote_losses(
-        hand_nt, hand_off, hand_cls, hand_joints, joint_gt)
-    out["hand_joints_out"] = hand_joints[-1]
-    exp = lambda k: gt_mano[k].unsqueeze(0).expand(pred_mano[k].shape)     # noqa: E731
-    loss["mano_mesh_loss"] = cfg.lambda_verts3d * F.mse_loss(pred_mano["verts3d"], exp("verts3d"))
-    loss["mano_joint_loss"] = cfg.lambda_joints3d * F.mse_loss(pred_mano["joints3d"], exp("joints3d"))
-    loss["pose_param_loss"] = cfg.lambda_manopose * F.mse_loss(pred_mano["mano_pose"], exp("mano_pose"))
-    loss["shape_param_loss"] = cfg.lambda_manoshape * F.mse_loss(pred_mano["mano_shape"], exp("mano_shape"))
-    rot_gt = targets["obj_rot"][None, :, None, :].expand_as(obj_rot)
-    trans_gt = targets["rel_obj_trans"][None, :, None, :].expand_as(obj_trans)
-    loss["obj_rot"] = F.smooth_l1_loss(obj_rot, rot_gt)
-    loss["obj_trans"] = F.smooth_l1_loss(obj_trans, trans_gt)
+    # MANO + vote aggregation + the scalar loss formulas: ~700 bookkeeping-sized torch kernels forward and as many backward,
+    # bound by the host's launch rate -> replayed as two CUDA graphs (_graphed_tail)
+    tail = _graphed_tail(model, (pose6d, shape, hand_off, hand_cls, obj_rot, obj_trans, hand_nt.detach(),
+                                 joint_gt.contiguous(), gt_mano["verts3d"], gt_mano["joints3d"], gt_mano["mano_pose"],
+                                 gt_mano["mano_shape"], targets["obj_rot"].contiguous(),
+                                 targets["rel_obj_trans"].contiguous()))
+    # (graph outputs live in the graph's static buffers, which the next step overwrites: the returned tensors are copies)
+    hand_joints = tail[2]
+    out["mano_mesh_out"], out["mano_joints_out"], out["hand_joints_out"] = tail[0].clone(), tail[1].clone(), \
+        hand_joints[-1].clone()
+    for key, v in zip(_TAIL_LOSSES, tail[3:12]):
+        loss[key] = v
     dbg = getattr(model, "_train_debug", None)
     if dbg is not None:            # developer hook (scripts/train_debug.py): live tensors whose gradients are compared
         dbg.update(hand_cls=hand_cls, hand_off=hand_off, hand_fea=hand_fea, obj_fea=obj_fea, hand_in=hand_in, obj_in=obj_in,
