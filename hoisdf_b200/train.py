@@ -217,7 +217,11 @@ def _graphed_tail(model, args):
     graphed = _tail_graphs.get(key)
     if graphed is None:
         sample = tuple(a.detach().clone().requires_grad_(g) for a, g in zip(args, grads))
-        graphed = torch.cuda.make_graphed_callables(fn, sample)
+        import warnings
+        with warnings.catch_warnings():
+            # (the capture's warm-up runs on a side stream: autograd notes that the sample leaves were made on another one)
+            warnings.simplefilter("ignore")
+            graphed = torch.cuda.make_graphed_callables(fn, sample)
         _tail_graphs[key] = graphed
     return graphed(*[a.contiguous() for a in args])
 
