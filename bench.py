@@ -579,11 +579,11 @@ def run_train(args):
     # roofline of the dominant kernel of OURS in the step: every FP16x3 GEMM launch (forward, dX, split-K dW) timed with an
     # event pair on the launching stream during one extra step; FLOPs = 2 M N K of the fp32 product each one stands for
     roofline = None
+    ops.PROFILE = []
+    step_device()                       # EVERY rank takes this step: it contains the gradient all-reduce
+    torch.cuda.synchronize()
+    rec, ops.PROFILE = ops.PROFILE, None
     if rank == 0:
-        ops.PROFILE = []
-        step_device()
-        torch.cuda.synchronize()
-        rec, ops.PROFILE = ops.PROFILE, None
         gemm = [r for r in rec if r[0] == "linear_h3"]
         if gemm:
             g_ms = sum(r[2].elapsed_time(r[3]) for r in gemm)
