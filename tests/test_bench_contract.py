@@ -69,3 +69,35 @@ def test_clock_sampler_windows(tmp_path, monkeypatch):
     s = bench.ClockSampler(0)             # no nvidia-smi at all: empty record, never an exception
     s.start(); s.begin(); s.end()
     assert s.stop()["samples"] == 0
+
+
+def test_no_rank_conditional_collectives_in_bench():
+    """Under torchrun every rank must make the same collective calls.  Static guard for the bench functions: nothing that
+    contains a collective -- a trainer / sharded step, a barrier, an all-reduce / all-gather -- may sit under an
+    `if rank == 0` (or `world == 1`-free rank test).  (A rank-0-only extra training step, with its gradient all-reduce
+    inside, once hung a 2-GPU `--config 4` run.)"""
+    import ast
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    tree = ast.parse(src)
+    collective = {"step_device", "step_e2e", "fence", "timed", "barrier", "all_reduce", "all_gather_into_tensor",
+                  "sharded_forward", "run_steps", "step"}
+
+    def calls(node):
+        for n in ast.walk(node):
+            if isinstance(n, ast.Call):
+                f = n.func
+                name = f.id if isinstance(f, ast.Name) else f.attr if isinstance(f, ast.Attribute) else None
+                if name in collective:
+                    yield name, n.lineno
+
+    def mentions_rank_only(test):
+        names = {n.id for n in ast.walk(test) if isinstance(n, ast.Name)}
+        return "rank" in names and "world" not in names           # `rank == 0 and world == 1` legs run on a single process
+
+    bad = []
+    for fn in (n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name in ("run_train", "main", "run", "run_native")):
+        for node in ast.walk(fn):
+            if isinstance(node, ast.If) and mentions_rank_only(node.test):
+                for stmt in node.body:
+                    bad += ["%s:%d under `if %s`" % (name, line, ast.unparse(node.test)) for name, line in calls(stmt)]
+    assert not bad, bad
