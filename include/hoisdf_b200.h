@@ -692,7 +692,8 @@ int hoisdf_linear_bwd_prep(const float* dy, int64_t lddy, const float* y, int64_
                            uint16_t* dzt_c, int64_t ld_dzt, float* db, float* scale_out, void* stream);
 int hoisdf_split_rows_t(const float* x, int64_t m, int64_t k, int64_t ldx, uint16_t* hi, uint16_t* lo, int64_t ldh, void* stream);
 /* Row softmax with nn.MultiheadAttention's dropout on the probabilities (p_drop in [0, 1)) and its backward, without a stored
- * mask: keep(r, c) is a counter-based hash of (seed, r * cols + c).  Forward: p (may be NULL) as hoisdf_softmax_rows_fwd,
+ * mask: keep(r, c) is a counter-based hash of (seed, row r, column c) -- the decisions of hoisdf_attention_train_fwd / _bwd for
+ * row = (sample * heads + head) * lq + query.  Forward: p (may be NULL) as hoisdf_softmax_rows_fwd,
  * pd = keep ? p / (1 - p_drop) : 0 (s may alias p or pd).  Backward: ds = p * (g - sum_j g_j p_j) with
  * g = keep ? dpd / (1 - p_drop) : 0 (ds may alias dpd). */
 int hoisdf_softmax_dropout_rows_fwd(const float* s, int64_t lds, int64_t rows, int64_t cols, int64_t valid, const uint8_t* mask,
