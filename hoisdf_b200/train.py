@@ -206,12 +206,15 @@ def _tail_fn(mano_head, consts):
 def _graphed_tail(model, args):
     """The tail of the training forward, eagerly or -- default on CUDA -- as a pair of CUDA graphs (forward and backward) made
     by torch.cuda.make_graphed_callables, one pair per (shapes, loss constants): static shapes, no host read-back, no random
-    numbers in there.  HOISDF_TRAIN_GRAPH_TAIL=0, or any input without gradient (a frozen head), takes the eager form."""
+    numbers in there.  HOISDF_TRAIN_GRAPH_TAIL=0, any input without gradient (a frozen head) or a DataParallel replica takes the
+    eager form."""
     consts = (float(cfg.lambda_verts3d), float(cfg.lambda_joints3d), float(cfg.lambda_manopose), float(cfg.lambda_manoshape))
     fn = _tail_fn(model.mano_head, consts)
     grads = tuple(a.requires_grad for a in args)
+    # (nn.DataParallel rebuilds its replicas -- new module objects, new buffer copies -- on every forward: nothing to key a
+    # captured graph on, so replicas take the eager form)
     if not (_GRAPH_TAIL and args[0].is_cuda and torch.is_grad_enabled() and all(grads[:6])
-            and not torch.cuda.is_current_stream_capturing()):
+            and not torch.cuda.is_current_stream_capturing() and not getattr(model, "_is_replica", False)):
         return fn(*args)
     key = (id(model.mano_head), consts, float(cfg.hand_cls_dist), args[0].device, tuple(tuple(a.shape) for a in args))
     graphed = _tail_graphs.get(key)
