@@ -1,0 +1,185 @@
+"""Data feed, image path: the crop / warp that upstream's dataset runs per frame on a DataLoader
+worker -- `data_crop` (data/ho3d.py:399-427, evaluation) and the image / mask part of `data_aug` (:351-381, training);
+data/dexycb.py likewise -- for a whole batch of frames that are already in device memory.
+
+Upstream warps every frame with PIL (`dataset_util.transform_img`, data/dataset_util.py:44-51: an affine `Image.transform` with
+PIL's default NEAREST resampling), shrinks the two segmentation masks with `Image.resize((64, 64), NEAREST)` and ships float
+tensors; here the raw 8-bit frames are uploaded once (3 bytes per pixel instead of 12) and `hoisdf_image_crop_fwd` produces the
+`(B, 3, res, res)` network input and the `(B, 64, 64)` masks, bit-exact with Pillow.  The geometry that comes with the crop --
+bounding boxes, the fused crop window, the affine matrix, the updated camera intrinsics -- is a few dozen floating-point
+operations per frame and stays on the host in numpy, with the arithmetic (float64 intermediates, `int()` truncations, float32
+casts) of data/dataset_util.py so that `cam_intr`, `bbox_hand`, `bbox_obj` and the crop coefficients are the numbers upstream's
+dataset returns.
+
+Not covered: decoding the image files, the random draws of the augmentation (the caller passes centre, scale and angle), the
+training-only filters after the warp (PIL GaussianBlur, colour jitter), the MANO / object pose rotation (cv2.Rodrigues) and
+the random SDF point sampling (`np.random.choice`, ho3d.py:462-478), whose outcome is defined by numpy's generator state.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import ops
+from ._capi import check, lib
+
+__all__ = ["bbox_from_points", "fuse_boxes", "crop_affine", "apply_affine", "pil_coefficients", "resize_coefficients",
+           "crop_geometry", "crop_images", "crop_masks", "data_crop"]
+
+
+def bbox_from_points(points2d: np.ndarray, factor: float = 1.1) -> np.ndarray:
+    """`dataset_util.get_bbox_joints` (data/dataset_util.py:106-116): box around 2-D points, centre truncated to an integer,
+    half extents scaled by `factor`; float32 [x0, y0, x1, y1]."""
+    pts = np.asarray(points2d)
+    lo, hi = pts.min(0), pts.max(0)
+    centre = np.asarray([int((hi[0] + lo[0]) / 2), int((hi[1] + lo[1]) / 2)])
+    half = np.asarray([(hi[0] - lo[0]) * factor / 2, (hi[1] - lo[1]) * factor / 2])
+    return np.array([*(centre - half), *(centre + half)], dtype=np.float32)
+
+
+def fuse_boxes(box_a: np.ndarray, box_b: np.ndarray, img_size: Sequence[int], scale_factor: float = 1.0):
+    """`dataset_util.fuse_bbox` (:319-332): the square window (integer centre, side) covering both boxes, clipped to the image
+    (`img_size` = PIL's (width, height))."""
+    both = np.concatenate((np.asarray(box_a).reshape(2, 2), np.asarray(box_b).reshape(2, 2)), axis=0)
+    lo, hi = both.min(0), both.max(0)
+    x0, y0 = max(0, lo[0]), max(0, lo[1])
+    x1, y1 = min(hi[0], img_size[0]), min(hi[1], img_size[1])
+    centre = np.asarray([int((x1 + x0) / 2), int((y1 + y0) / 2)])
+    return centre, max(x1 - x0, y1 - y0) * scale_factor
+
+
+def crop_affine(centre: np.ndarray, scale: float, res: int, rot: float = 0.0) -> np.ndarray:
+    """`dataset_util.get_affine_transform(center, scale, [res, res], rot)[0]` (:54-66,96-103): rotation by `rot` radians about
+    the image origin, then scale / translate the rotated centre to the middle of the crop; source pixel -> crop pixel, float32
+    (3, 3).  `rot` = 0 is the evaluation crop, a drawn angle the training augmentation (ho3d.py:318-321)."""
+    sn, cs = np.sin(rot), np.cos(rot)
+    turn = np.zeros((3, 3))
+    turn[0, :2] = [cs, -sn]
+    turn[1, :2] = [sn, cs]
+    turn[2, 2] = 1
+    c = turn.dot(np.asarray(centre).tolist() + [1])[:2]
+    m = np.zeros((3, 3))
+    m[0, 0] = float(res) / scale
+    m[1, 1] = float(res) / scale
+    m[0, 2] = res * (-float(c[0]) / scale + 0.5)
+    m[1, 2] = res * (-float(c[1]) / scale + 0.5)
+    m[2, 2] = 1
+    return m.dot(turn).astype(np.float32)
+
+
+def apply_affine(points2d: np.ndarray, affine: np.ndarray) -> np.ndarray:
+    """`dataset_util.transform_coords` (:37-41)."""
+    pts = np.asarray(points2d)
+    hom = np.concatenate([pts, np.ones([pts.shape[0], 1])], 1)
+    return affine.dot(hom.transpose()).transpose()[:, :2]
+
+
+def pil_coefficients(affine: np.ndarray) -> np.ndarray:
+    """`dataset_util.transform_img` (:44-51): PIL's AFFINE `data` = the first two rows of the inverse (crop pixel -> source
+    pixel), inverted in the matrix's own precision (float32 for upstream's matrices) and handed to C as doubles."""
+    inv = np.linalg.inv(affine)
+    return np.array([inv[0, 0], inv[0, 1], inv[0, 2], inv[1, 0], inv[1, 1], inv[1, 2]], dtype=np.float64)
+
+
+def resize_coefficients(src_size: int, dst_size: int) -> np.ndarray:
+    """What `Image.resize((dst, dst), Image.NEAREST)` of a (src, src) image hands to the same C routine (Pillow
+    src/_imaging.c `_resize`: a = (src / dst, 0, 0, 0, src / dst, 0)) -- the masks' shrink, ho3d.py:369-371,377-379."""
+    return np.array([src_size / dst_size, 0.0, 0.0, 0.0, src_size / dst_size, 0.0], dtype=np.float64)
+
+
+def _fixed_point_ok(a: np.ndarray, size: int) -> bool:
+    """Pillow takes its 16.16 fixed-point loop iff all four output corners map to |coordinate| < 32768."""
+    for x, y in ((0, 0), (size, size), (0, size), (size, 0)):
+        if not (abs(x * a[0] + y * a[1] + a[2]) < 32768.0 and abs(x * a[3] + y * a[4] + a[5]) < 32768.0):
+            return False
+    return True
+
+
+def _warp(frames: torch.Tensor, coefficients: np.ndarray, res: int, divisor: float, as_bytes: bool) -> torch.Tensor:
+    if not frames.is_cuda:
+        raise RuntimeError("hoisdf_b200.feed runs on the GPU; got a %s tensor (no CPU fallback)" % frames.device)
+    if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[3] not in (1, 3) or frames.stride(3) != 1 or \
+            frames.stride(2) != frames.shape[3]:
+        raise ValueError("frames must be (B, H, W, C) uint8 with packed pixels, C = 1 or 3")
+    b, h, w, ch = frames.shape
+    coef = np.ascontiguousarray(np.asarray(coefficients, dtype=np.float64).reshape(b, 6))
+    if not np.isfinite(coef).all():
+        raise ValueError("non-finite crop coefficients")
+    for a in coef:
+        if (a[1] != 0.0 or a[3] != 0.0) and not _fixed_point_ok(a, res):
+            raise ValueError("crop transform outside Pillow's fixed-point range (|source coordinate| >= 32768)")
+    dev = frames.device
+    with torch.cuda.device(dev):
+        coef_d = torch.from_numpy(coef).to(dev)
+        tables = torch.empty(b, 2, res, device=dev, dtype=torch.int32)
+        if as_bytes:
+            out = torch.empty(b, res, res, ch, device=dev, dtype=torch.uint8)
+            args = (None, out.data_ptr())
+        else:
+            out = torch.empty(b, ch, res, res, device=dev, dtype=torch.float32)
+            args = (out.data_ptr(), None)
+        ops._count(2)
+        check(lib.hoisdf_image_crop_fwd(frames.data_ptr(), b, h, w, ch, frames.stride(1), frames.stride(0), coef_d.data_ptr(),
+                                        res, float(divisor), args[0], args[1], tables.data_ptr(), ops._stream()),
+              "hoisdf_image_crop_fwd")
+    return out
+
+
+def crop_images(frames: torch.Tensor, coefficients: np.ndarray, res: int, as_bytes: bool = False) -> torch.Tensor:
+    """frames: (B, H, W, 3) uint8 CUDA tensor (row-contiguous); coefficients: (B, 6) PIL AFFINE data (`pil_coefficients`).
+    -> (B, 3, res, res) float32 in [0, 1] = `ToTensor()(np.asarray(img.transform(...)).astype(np.float32)) / 255.0`
+    (ho3d.py:550,624), or with `as_bytes` the (B, res, res, 3) uint8 PIL images themselves (what the training feed hands to
+    its blur / colour-jitter filters)."""
+    if frames.dim() != 4 or frames.shape[3] != 3:
+        raise ValueError("frames must be (B, H, W, 3) uint8")
+    return _warp(frames, coefficients, res, 255.0, as_bytes)
+
+
+def crop_masks(masks: torch.Tensor, coefficients: np.ndarray, res: int, out_res: int) -> torch.Tensor:
+    """The segmentation masks of the training feed (ho3d.py:366-381, :551-552): masks (B, H, W) uint8 (mode "L") on the GPU ->
+    `transform_img` to (res, res) with the frame's coefficients, `.resize((out_res, out_res), Image.NEAREST)`,
+    `.astype(np.float32)` -> (B, out_res, out_res) float32."""
+    if masks.dim() != 3:
+        raise ValueError("masks must be (B, H, W) uint8")
+    b = masks.shape[0]
+    warped = _warp(masks.unsqueeze(3), coefficients, res, 1.0, True)
+    shrink = np.tile(resize_coefficients(res, out_res), (b, 1))
+    return _warp(warped, shrink, out_res, 1.0, False).squeeze(1)
+
+
+def crop_geometry(cam_intr: np.ndarray, bbox_hand: np.ndarray, obj_p2d: np.ndarray, img_size: Sequence[int], res: int = 256
+                  ) -> Tuple[np.ndarray, Dict[str, np.ndarray]]:
+    """The host half of `data_crop` (data/ho3d.py:399-427) for a batch: -> ((B, 6) PIL coefficients, {"cam_intr" (B, 3, 3),
+    "bbox_hand" (B, 4), "bbox_obj" (B, 4)} float32).  `img_size` = PIL's (width, height)."""
+    b = len(cam_intr)
+    coef = np.empty((b, 6), np.float64)
+    K_out = np.empty((b, 3, 3), np.float32)
+    hand_out = np.empty((b, 4), np.float32)
+    obj_out = np.empty((b, 4), np.float32)
+    for i in range(b):
+        hand = np.asarray(bbox_hand[i]).copy().reshape(2, 2)
+        p2d = np.asarray(obj_p2d[i])
+        window_hand = bbox_from_points(hand, 1.5)
+        window_obj = bbox_from_points(p2d, 1.5)
+        box_hand = bbox_from_points(hand, 1.2)
+        box_obj = bbox_from_points(p2d, 1.0)
+        centre, scale = fuse_boxes(window_hand, window_obj, img_size)
+        affine = crop_affine(centre, scale, res)
+        hand_out[i] = apply_affine(box_hand.reshape(2, 2), affine).flatten()
+        obj_out[i] = apply_affine(box_obj.reshape(2, 2), affine).flatten()
+        K_out[i] = affine.dot(np.asarray(cam_intr[i]))
+        coef[i] = pil_coefficients(affine)
+    return coef, {"cam_intr": K_out, "bbox_hand": hand_out, "bbox_obj": obj_out}
+
+
+def data_crop(frames: torch.Tensor, cam_intr: np.ndarray, bbox_hand: np.ndarray, obj_p2d: np.ndarray, res: int = 256
+              ) -> Tuple[torch.Tensor, Dict[str, np.ndarray]]:
+    """Batched `data_crop` (data/ho3d.py:399-427) + the tensor conversion of `__getitem__` (:624).
+    frames (B, H, W, 3) uint8 on the GPU; cam_intr (B, 3, 3); bbox_hand (B, 4) = the annotation's hand box; obj_p2d (B, N, 2) =
+    projected object box corners.  -> (img (B, 3, res, res) float32, {"cam_intr" (B, 3, 3), "bbox_hand" (B, 4), "bbox_obj" (B, 4)}
+    float32) -- the `inputs["img"]` and the geometric `meta_info` entries of upstream's evaluation sample."""
+    _, h, w, _ = frames.shape
+    coef, meta = crop_geometry(cam_intr, bbox_hand, obj_p2d, (w, h), res)
+    return crop_images(frames, coef, res), meta

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 32
+#define HOISDF_ABI_VERSION 33
 
 enum {
   HOISDF_OK = 0,
@@ -640,6 +640,26 @@ int hoisdf_gemm_f32_batched(const float* a, int64_t lda, int32_t trans_a, int64_
                             int64_t ldb, int32_t trans_b, int64_t b_outer, int64_t b_inner, float* c, int64_t ldc,
                             int64_t c_outer, int64_t c_inner, int64_t m, int64_t n, int64_t k, float alpha, int32_t accumulate,
                             int64_t batch_outer, int64_t batch_inner, void* stream);
+/* ---------------------------------------------------------------------------------------------------
+ * Data feed, image warp (upstream data/ho3d.py:399-427 `data_crop`, :351-381 in `data_aug`,
+ * data/dexycb.py likewise; data/dataset_util.py:44-51 `transform_img`): PIL `Image.transform((size, size), AFFINE, coef)` with
+ * its default NEAREST resampling on a batch of 8-bit frames in device memory, bit-exact with Pillow 12.2.0 (both of its 8-bit
+ * code paths: the scale-only table walk of the evaluation crop -- also what `Image.resize(..., NEAREST)` of the segmentation
+ * masks runs -- and the 16.16 fixed-point affine of the rotation augmentation).
+ *   src: (batch, src_h, src_w, channels) bytes, channels = 3 (RGB) or 1 (mode "L" masks), row pitch src_pitch bytes, frame
+ *        pitch src_stride bytes;
+ *   coef: 6 doubles per sample, PIL's `data` = the first two rows of the INVERSE affine (output pixel -> source pixel);
+ *   out_f32 (batch, channels, size, size) = pixel / divisor in fp32 (divisor 255: upstream's ToTensor(...) / 255.0,
+ *        ho3d.py:550,624; divisor 1: the masks' astype(float32), :551-552) and / or
+ *   out_u8 (batch, size, size, channels) = the PIL image; pixels that map outside the source are 0;
+ *   tables: 2 * size int32 per sample of scratch.
+ * Transforms that Pillow evaluates with its floating-point loop (an output corner mapping to |coordinate| >= 32768) are not
+ * restated: the caller checks (hoisdf_b200/feed.py raises).
+ * ------------------------------------------------------------------------------------------------- */
+int hoisdf_image_crop_fwd(const uint8_t* src, int64_t batch, int64_t src_h, int64_t src_w, int64_t channels, int64_t src_pitch,
+                          int64_t src_stride, const double* coef, int64_t size, float divisor, float* out_f32, uint8_t* out_u8,
+                          int32_t* tables, void* stream);
+
 /* One Linear of the training step per call (what hoisdf_b200/autograd.py:LinearFn runs; upstream main/train.py:108-131 through
  * every nn.Linear of the hot path), fp32 in / fp32 out on the FP16x3 tensor-core GEMM, caller-owned workspace of
  * hoisdf_linear_train_workspace_bytes(m, n, k) bytes (16-byte aligned; HOISDF_E_WORKSPACE when too small):

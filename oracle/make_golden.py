@@ -257,6 +257,49 @@ def metrics_case(name, seed, batch):
           fix["hand_joint_result"])
 
 
+def feed_case(name, seed, n_eval, n_aug):
+    """Data feed: the UNMODIFIED upstream `Dataset.data_crop` (data/ho3d.py:399-427) + the tensor conversion of
+    :624 on seeded synthetic frames, and the frame / mask warp of `data_aug` (:318-321,351-353,366-381) for seeded
+    augmentation draws, both through upstream's data/dataset_util.py helpers and this image's Pillow."""
+    import PIL
+    import torchvision.transforms as T
+    from PIL import Image
+    from oracle import feed_oracle as FO
+    mods = rs.load_data_modules()
+    DU, H = mods["dataset_util"], mods["ho3d"]
+
+    class Self:
+        inp_res = 256
+
+    fix = {"seed": seed, "n_eval": n_eval, "n_aug": n_aug, "pillow": np.array(PIL.__version__)}
+    # the float image is stored as the PIL bytes + upstream's byte -> float conversion of all 256 values (noise frames do not
+    # compress; 4x smaller than the float tensor and exactly as informative)
+    ramp = np.arange(256, dtype=np.uint8).reshape(1, 256, 1)
+    fix["u8_to_f32"] = (T.ToTensor()(ramp.astype(np.float32)) / 255.0).numpy().reshape(256)
+    ev = {"eval_bytes": [], "eval_K": [], "eval_bbox_hand": [], "eval_bbox_obj": []}
+    for i in range(n_eval):
+        img, K, bh, p2d = FO.synthetic_frame(seed + i)
+        im, K2, hand, obj = H.Dataset.data_crop(Self(), Image.fromarray(img), K, bh, p2d)
+        ev["eval_bytes"].append(np.asarray(im))
+        ev["eval_K"].append(K2)
+        ev["eval_bbox_hand"].append(hand.astype(np.float32))          # ho3d.py:649-650
+        ev["eval_bbox_obj"].append(obj.astype(np.float32))
+    au = {"aug_bytes": [], "aug_affine": [], "aug_hand_seg": [], "aug_obj_seg": []}
+    for i in range(n_aug):
+        img, hs, os_, center, scale, rot = FO.synthetic_aug(seed + i)
+        affine, _ = DU.get_affine_transform(center, scale, [256, 256], rot=rot)
+        au["aug_affine"].append(affine)
+        au["aug_bytes"].append(np.asarray(DU.transform_img(Image.fromarray(img), affine, [256, 256]).crop((0, 0, 256, 256))))
+        for key, seg in (("aug_hand_seg", hs), ("aug_obj_seg", os_)):
+            w = DU.transform_img(Image.fromarray(seg), affine, [256, 256]).crop((0, 0, 256, 256))
+            au[key].append(np.asarray(w.resize((64, 64), Image.NEAREST)).astype(np.float32))
+    for d in (ev, au):
+        for k, v in d.items():
+            fix[k] = np.stack(v)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **fix)
+    print(name, {k: np.asarray(v).shape for k, v in fix.items()})
+
+
 if __name__ == "__main__":
     assert rs.available(), "the upstream reference is not mounted; golden vectors can only be made in the build container"
     os.makedirs(OUT, exist_ok=True)
@@ -268,3 +311,4 @@ if __name__ == "__main__":
     dexycb_eval_case("dexycb_eval_seed14", 14, 2, 48, 16)
     metrics_case("metrics_seed15", 15, 6)
     train_case("train_dexycb_seed21", 21, 2, 24, 8)
+    feed_case("feed_seed31", 31, 2, 1)

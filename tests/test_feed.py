@@ -1,0 +1,184 @@
+"""Data feed, GPU-less half:
+  * oracle/feed_oracle.py against the UNMODIFIED upstream functions where /root/reference is mounted, and against the committed
+    fixture tests/golden/feed_seed31.npz (generated from the upstream functions by oracle/make_golden.py:feed_case) everywhere;
+  * the host geometry of hoisdf_b200/feed.py against the oracle (bit-equal float32 / float64 results);
+  * csrc/feed.cu executed unchanged on the CPU emulator against Pillow itself: evaluation crops (scale-only path), rotated
+    training warps (16.16 fixed-point path), mode-"L" masks with the NEAREST shrink, ragged sizes and windows that leave the
+    frame (zero fill) -- every comparison bit-exact."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+from PIL import Image
+
+from hoisdf_b200 import feed
+from oracle import feed_oracle as FO
+from oracle import reference_shim as rs
+from test_kernel_emulation import build_emulated
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "feed_seed31.npz")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    lib = build_emulated("feed")
+    vp, i64 = C.c_void_p, C.c_int64
+    lib.hoisdf_image_crop_fwd.argtypes = [vp, i64, i64, i64, i64, i64, i64, vp, i64, C.c_float, vp, vp, vp, vp]
+    lib.hoisdf_image_crop_fwd.restype = C.c_int
+    return lib
+
+
+def emu_warp(lib, frames, coef, size, divisor=255.0):
+    """frames (B, H, W, C) uint8 -> (out_f32 (B, C, size, size), out_u8 (B, size, size, C)) from ONE call with both outputs."""
+    frames = np.ascontiguousarray(frames)
+    b, h, w, ch = frames.shape
+    coef = np.ascontiguousarray(coef, dtype=np.float64).reshape(b, 6)
+    of = np.full((b, ch, size, size), np.nan, np.float32)
+    ou = np.full((b, size, size, ch), 7, np.uint8)
+    tables = np.zeros((b, 2, size), np.int32)
+    rc = lib.hoisdf_image_crop_fwd(frames.ctypes.data, b, h, w, ch, w * ch, h * w * ch, coef.ctypes.data, size, divisor,
+                                   of.ctypes.data, ou.ctypes.data, tables.ctypes.data, None)
+    assert rc == 0
+    return of, ou
+
+
+def pil_warp(frame, coef, size):
+    img = Image.fromarray(frame if frame.shape[2] == 3 else frame[:, :, 0])
+    out = np.asarray(img.transform((size, size), Image.AFFINE, tuple(float(c) for c in coef)))
+    return out.reshape(size, size, -1)
+
+
+# ---------------------------------------------------------------------------------------------- oracle pinning
+@pytest.mark.skipif(not rs.available(), reason="upstream reference not mounted")
+def test_feed_oracle_matches_upstream_live():
+    import torchvision.transforms as T
+    mods = rs.load_data_modules()
+    DU, H = mods["dataset_util"], mods["ho3d"]
+
+    class Self:
+        inp_res = 256
+
+    for seed in range(12):
+        img, K, bh, p2d = FO.synthetic_frame(seed)
+        im, K_ref, hand_ref, obj_ref = H.Dataset.data_crop(Self(), Image.fromarray(img), K, bh, p2d)
+        ref = (T.ToTensor()(np.asarray(im).astype(np.float32)) / 255.0).numpy()           # ho3d.py:624
+        got, K_got, hand_got, obj_got = FO.data_crop(img, K, bh, p2d)
+        assert np.array_equal(ref, got) and got.dtype == np.float32
+        assert np.array_equal(K_ref, K_got) and K_ref.dtype == K_got.dtype
+        assert np.array_equal(hand_ref.astype(np.float32), hand_got) and np.array_equal(obj_ref.astype(np.float32), obj_got)
+    for seed in range(6):
+        img, hs, os_, center, scale, rot = FO.synthetic_aug(seed)
+        affine, _ = DU.get_affine_transform(center, scale, [256, 256], rot=rot)
+        ref_img = DU.transform_img(Image.fromarray(img), affine, [256, 256]).crop((0, 0, 256, 256))
+        ref_seg = DU.transform_img(Image.fromarray(hs), affine, [256, 256]).crop((0, 0, 256, 256))
+        ref_seg = np.asarray(ref_seg.resize((64, 64), Image.NEAREST)).astype(np.float32)
+        pil_bytes, tensor, hand_seg, _, aff = FO.aug_warp(img, hs, os_, center, scale, rot)
+        assert np.array_equal(affine, aff)
+        assert np.array_equal(np.asarray(ref_img), pil_bytes) and np.array_equal(ref_seg, hand_seg)
+
+
+def test_feed_oracle_matches_golden():
+    g = np.load(GOLDEN)
+    n_eval, n_aug = int(g["n_eval"]), int(g["n_aug"])
+    for i in range(n_eval):
+        img, K, bh, p2d = FO.synthetic_frame(int(g["seed"]) + i)
+        got = FO.data_crop(img, K, bh, p2d)
+        assert np.array_equal(g["u8_to_f32"][g["eval_bytes"][i]].transpose(2, 0, 1), got[0])
+        for name, val in zip(("eval_K", "eval_bbox_hand", "eval_bbox_obj"), got[1:]):
+            assert np.array_equal(g[name][i], val), (name, i)
+    for i in range(n_aug):
+        img, hs, os_, center, scale, rot = FO.synthetic_aug(int(g["seed"]) + i)
+        pil_bytes, _, hand_seg, obj_seg, aff = FO.aug_warp(img, hs, os_, center, scale, rot)
+        assert np.array_equal(g["aug_bytes"][i], pil_bytes) and np.array_equal(g["aug_affine"][i], aff)
+        assert np.array_equal(g["aug_hand_seg"][i], hand_seg) and np.array_equal(g["aug_obj_seg"][i], obj_seg)
+
+
+# ---------------------------------------------------------------------------------------------- host geometry
+def test_host_geometry_is_bit_equal_to_the_oracle():
+    frames = [FO.synthetic_frame(s) for s in range(40, 56)]
+    K = np.stack([f[1] for f in frames])
+    bh = np.stack([f[2] for f in frames])
+    p2d = np.stack([f[3] for f in frames])
+    coef, meta = feed.crop_geometry(K, bh, p2d, (640, 480), 256)
+    for i, (img, k, b, p) in enumerate(frames):
+        _, K_ref, hand_ref, obj_ref = FO.data_crop(img, k, b, p)
+        assert np.array_equal(meta["cam_intr"][i], K_ref)
+        assert np.array_equal(meta["bbox_hand"][i], hand_ref) and np.array_equal(meta["bbox_obj"][i], obj_ref)
+        centre, scale = FO.fuse_bbox(FO.get_bbox_joints(b.reshape(2, 2), 1.5), FO.get_bbox_joints(p, 1.5), (640, 480))
+        aff, _ = FO.get_affine_transform(centre, scale, [256, 256])
+        inv = np.linalg.inv(aff)
+        assert np.array_equal(coef[i], np.array([inv[0, 0], inv[0, 1], inv[0, 2], inv[1, 0], inv[1, 1], inv[1, 2]], np.float64))
+        assert coef[i, 1] == 0.0 and coef[i, 3] == 0.0                 # the evaluation crop takes Pillow's scale-only path
+    for s in range(6):
+        _, _, _, center, scale, rot = FO.synthetic_aug(s)
+        want, _ = FO.get_affine_transform(center, scale, [256, 256], rot=rot)
+        assert np.array_equal(feed.crop_affine(center, scale, 256, rot), want)
+    assert np.array_equal(feed.resize_coefficients(256, 64), [4.0, 0, 0, 0, 4.0, 0])
+
+
+def test_crop_refuses_host_tensors_and_bad_layouts():
+    import torch
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        feed.crop_images(torch.zeros(1, 8, 8, 3, dtype=torch.uint8), np.array([[1.0, 0, 0, 0, 1, 0]]), 4)
+    with pytest.raises(ValueError):
+        feed.crop_images(torch.zeros(1, 8, 8, dtype=torch.uint8), np.array([[1.0, 0, 0, 0, 1, 0]]), 4)
+    assert not feed._fixed_point_ok(np.array([300.0, 0.1, 0, 0, 1, 0]), 256)
+    assert feed._fixed_point_ok(np.array([2.0, 0.1, -50, 0.1, 2.0, 30]), 256)
+
+
+# ---------------------------------------------------------------------------------------------- kernel on the emulator
+def test_evaluation_crop_kernel_is_bit_exact_with_pillow(emu):
+    frames = [FO.synthetic_frame(s) for s in range(60, 64)]
+    K = np.stack([f[1] for f in frames])
+    bh = np.stack([f[2] for f in frames])
+    p2d = np.stack([f[3] for f in frames])
+    coef, _ = feed.crop_geometry(K, bh, p2d, (640, 480), 256)
+    imgs = np.stack([f[0] for f in frames])
+    of, ou = emu_warp(emu, imgs, coef, 256)
+    for i, (img, k, b, p) in enumerate(frames):
+        want = FO.data_crop(img, k, b, p)[0]
+        assert np.array_equal(of[i], want)
+        assert np.array_equal(ou[i], pil_warp(img, coef[i], 256))
+    assert (ou == 0).all(axis=3).any()                      # some window leaves the frame: the zero fill was exercised
+
+
+def test_rotated_warp_and_masks_are_bit_exact_with_pillow(emu):
+    for s in range(4):
+        img, hs, os_, center, scale, rot = FO.synthetic_aug(s)
+        pil_bytes, tensor, hand_seg, obj_seg, aff = FO.aug_warp(img, hs, os_, center, scale, rot)
+        coef = feed.pil_coefficients(feed.crop_affine(center, scale, 256, rot))[None]
+        assert coef[0, 1] != 0.0 and feed._fixed_point_ok(coef[0], 256)
+        of, ou = emu_warp(emu, img[None], coef, 256)
+        assert np.array_equal(ou[0], pil_bytes) and np.array_equal(of[0], tensor)
+        masks = np.stack([hs, os_])[:, :, :, None]
+        _, warped = emu_warp(emu, masks, np.tile(coef, (2, 1)), 256, divisor=1.0)
+        small, _ = emu_warp(emu, warped, np.tile(feed.resize_coefficients(256, 64), (2, 1)), 64, divisor=1.0)
+        assert np.array_equal(small[0, 0], hand_seg) and np.array_equal(small[1, 0], obj_seg)
+
+
+@pytest.mark.parametrize("h,w,size", [(37, 53, 19), (5, 7, 33), (480, 640, 1), (64, 64, 64)])
+def test_ragged_sizes_and_out_of_frame_windows(emu, h, w, size):
+    rng = np.random.default_rng(h * 1000 + w)
+    img = rng.integers(1, 256, (3, h, w, 3), dtype=np.uint8)
+    coef = np.array([[w / size * 1.37, 0, -0.31 * w, 0, h / size * 0.83, 0.4 * h],              # scale-only, partly outside
+                     [0.91, -0.43, 0.2 * w, 0.43, 0.91, -0.3 * h],                              # rotation, partly outside
+                     [1e-3, 0, w + 5.0, 0, 1e-3, 2.0]])                                         # entirely outside
+    of, ou = emu_warp(emu, img, coef, size)
+    for i in range(3):
+        want = pil_warp(img[i], coef[i], size)
+        assert np.array_equal(ou[i], want)
+        assert np.array_equal(of[i], want.astype(np.float32).transpose(2, 0, 1) / np.float32(255.0))
+    assert not ou[2].any()
+
+
+def test_argument_checks(emu):
+    buf = np.zeros(64, np.uint8)
+    coef = np.array([1.0, 0, 0, 0, 1, 0])
+    t = np.zeros(8, np.int32)
+    call = emu.hoisdf_image_crop_fwd
+    assert call(None, 1, 2, 2, 3, 6, 12, coef.ctypes.data, 2, 255.0, buf.ctypes.data, None, t.ctypes.data, None) == -1
+    assert call(buf.ctypes.data, 1, 2, 2, 3, 6, 12, coef.ctypes.data, 2, 255.0, None, None, t.ctypes.data, None) == -1
+    assert call(buf.ctypes.data, 1, 2, 2, 2, 6, 12, coef.ctypes.data, 2, 255.0, buf.ctypes.data, None, t.ctypes.data, None) == -2
+    assert call(buf.ctypes.data, 1, 2, 2, 3, 5, 12, coef.ctypes.data, 2, 255.0, buf.ctypes.data, None, t.ctypes.data, None) == -2
+    assert call(buf.ctypes.data, 1, 2, 2, 3, 6, 12, coef.ctypes.data, 2, 0.0, buf.ctypes.data, None, t.ctypes.data, None) == -2

@@ -1,0 +1,90 @@
+"""Data feed on the GPU (csrc/feed.cu through the C ABI via hoisdf_b200/feed.py): bit-exact against
+Pillow (the library upstream's dataset warps frames with, data/dataset_util.py:44-51) through the oracle's restatement of
+`data_crop` / `data_aug` (oracle/feed_oracle.py) and against the committed upstream fixture tests/golden/feed_seed31.npz.
+The same kernel source passes the same comparisons on the CPU emulator (tests/test_feed.py); this file sorts last so that it is
+the final thing the -x run reaches."""
+import os
+
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+from oracle import feed_oracle as FO
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "feed_seed31.npz")
+
+
+def _batch(seeds):
+    frames = [FO.synthetic_frame(s) for s in seeds]
+    return frames, np.stack([f[0] for f in frames]), np.stack([f[1] for f in frames]), np.stack([f[2] for f in frames]), \
+        np.stack([f[3] for f in frames])
+
+
+def test_evaluation_crop_batch_vs_oracle_and_fixture(cuda):
+    from hoisdf_b200 import feed
+    g = np.load(GOLDEN)
+    seeds = list(range(int(g["seed"]), int(g["seed"]) + 32))            # BASELINE configs[1] batch
+    frames, imgs, K, bh, p2d = _batch(seeds)
+    img, meta = feed.data_crop(torch.from_numpy(imgs).to(cuda), K, bh, p2d, 256)
+    assert img.shape == (32, 3, 256, 256) and img.dtype == torch.float32
+    got = img.cpu().numpy()
+    for i, (f, k, b, p) in enumerate(frames):
+        want, K_ref, hand_ref, obj_ref = FO.data_crop(f, k, b, p)
+        assert np.array_equal(got[i], want), i
+        assert np.array_equal(meta["cam_intr"][i], K_ref) and np.array_equal(meta["bbox_hand"][i], hand_ref)
+        assert np.array_equal(meta["bbox_obj"][i], obj_ref)
+    for i in range(int(g["n_eval"])):
+        assert np.array_equal(got[i], g["u8_to_f32"][g["eval_bytes"][i]].transpose(2, 0, 1))
+        assert np.array_equal(meta["cam_intr"][i], g["eval_K"][i])
+
+
+def test_rotated_warp_and_masks_vs_oracle_and_fixture(cuda):
+    from hoisdf_b200 import feed
+    g = np.load(GOLDEN)
+    seeds = list(range(int(g["seed"]), int(g["seed"]) + 8))
+    draws = [FO.synthetic_aug(s) for s in seeds]
+    coef = np.stack([feed.pil_coefficients(feed.crop_affine(c, sc, 256, r)) for _, _, _, c, sc, r in draws])
+    frames = torch.from_numpy(np.stack([d[0] for d in draws])).to(cuda)
+    as_bytes = feed.crop_images(frames, coef, 256, as_bytes=True).cpu().numpy()
+    as_float = feed.crop_images(frames, coef, 256).cpu().numpy()
+    hand = feed.crop_masks(torch.from_numpy(np.stack([d[1] for d in draws])).to(cuda), coef, 256, 64).cpu().numpy()
+    obj = feed.crop_masks(torch.from_numpy(np.stack([d[2] for d in draws])).to(cuda), coef, 256, 64).cpu().numpy()
+    for i, (img, hs, os_, c, sc, r) in enumerate(draws):
+        pil_bytes, tensor, hand_seg, obj_seg, _ = FO.aug_warp(img, hs, os_, c, sc, r)
+        assert np.array_equal(as_bytes[i], pil_bytes) and np.array_equal(as_float[i], tensor), i
+        assert np.array_equal(hand[i], hand_seg) and np.array_equal(obj[i], obj_seg), i
+    assert np.array_equal(as_bytes[0], g["aug_bytes"][0]) and np.array_equal(hand[0], g["aug_hand_seg"][0])
+    assert np.array_equal(obj[0], g["aug_obj_seg"][0])
+
+
+@pytest.mark.parametrize("h,w,size", [(37, 53, 19), (5, 7, 33), (480, 640, 1), (1080, 1920, 512)])
+def test_ragged_sizes_and_out_of_frame_windows(cuda, h, w, size):
+    from hoisdf_b200 import feed
+    rng = np.random.default_rng(h * 1000 + w)
+    img = rng.integers(1, 256, (3, h, w, 3), dtype=np.uint8)
+    coef = np.array([[w / size * 1.37, 0, -0.31 * w, 0, h / size * 0.83, 0.4 * h],
+                     [0.91, -0.43, 0.2 * w, 0.43, 0.91, -0.3 * h],
+                     [1e-3, 0, w + 5.0, 0, 1e-3, 2.0]])
+    got = feed.crop_images(torch.from_numpy(img).to(cuda), coef, size, as_bytes=True).cpu().numpy()
+    for i in range(3):
+        want = np.asarray(Image.fromarray(img[i]).transform((size, size), Image.AFFINE, tuple(float(c) for c in coef[i])))
+        assert np.array_equal(got[i], want), i
+    assert not got[2].any()
+
+
+def test_whole_feed_properties_at_full_batch(cuda):
+    """Size-independent properties at BASELINE configs[2]'s batch (128 frames): the identity transform returns the frame, a
+    pure integer shift moves it, and the byte and float outputs agree."""
+    from hoisdf_b200 import feed
+    gen = torch.Generator().manual_seed(5)
+    frames = torch.randint(0, 256, (128, 256, 256, 3), dtype=torch.uint8, generator=gen).to(cuda)
+    ident = np.tile(np.array([1.0, 0, 0, 0, 1.0, 0]), (128, 1))
+    assert torch.equal(feed.crop_images(frames, ident, 256, as_bytes=True), frames)
+    shift = np.tile(np.array([1.0, 0, 3.0, 0, 1.0, -2.0]), (128, 1))
+    moved = feed.crop_images(frames, shift, 256, as_bytes=True)
+    assert torch.equal(moved[:, 2:, :253], frames[:, :254, 3:]) and not moved[:, :2].any() and not moved[:, :, 253:].any()
+    as_float = feed.crop_images(frames, shift, 256)
+    # (on the host: torch's CUDA division by a scalar multiplies by the reciprocal, which is not the IEEE quotient)
+    assert torch.equal(as_float.cpu(), moved.cpu().permute(0, 3, 1, 2).float() / 255.0)

@@ -22,7 +22,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU = os.path.join(ROOT, "tests", "emu")
 
 
-EMULATED = ("metrics", "lattice", "topk", "heads", "gather", "layernorm", "sdf", "linear", "attention", "narrow", "backward")
+EMULATED = ("metrics", "lattice", "topk", "heads", "gather", "layernorm", "sdf", "linear", "attention", "narrow", "backward",
+            "feed")
 STUBS = ("stubs_linear.cpp", "stubs_attention.cpp", "stubs_h3.cpp")
 _LIB = {}
 
