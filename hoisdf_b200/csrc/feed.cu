@@ -88,6 +88,58 @@ affine_crop_kernel(const uint8_t* __restrict__ src, int64_t src_pitch, int64_t s
   }
 }
 
+// ---- SDF point sets of a training / evaluation sample (upstream data/ho3d.py:484-486 row gather `sdf_data[all_idx]`, :333
+// rotation of the augmentation, :524-548 normalisation, :561-579 the `inputs` / `targets` entries; data/dexycb.py:515-548 with
+// its mirror flip :547-548) from the packed rows `[x, y, z, sdf_hand, sdf_obj, label]` (tool/pre_process_sdf.py:140-147) of a
+// batch of frames resident in device memory.  One thread per selected row: 24 bytes in, 12-16 bytes out.
+// The indices are the caller's (`np.random.choice` draws: their values are defined by numpy's generator state); groups along
+// the index axis, in upstream's order: [hand (n_hand) | object (n_obj) | hand_pre (n_hand) | obj_pre (n_obj)], the last two
+// only when n_sel = 2 * (n_hand + n_obj).  Arithmetic as numpy's float32: rotation = the sgemm accumulation order
+// x * r0 -> fma(y, r1, .) -> fma(z, r2, .), subtraction and scaling as separately rounded float32 operations.
+struct SdfRowsArgs {
+  const float* rows; const int64_t* row_offsets; const int64_t* index; int64_t n_sel; int n_hand, n_obj;
+  const float* rot; const int32_t* flip; const float* hand_root; const float* obj_centre; float hand_scale, obj_scale;
+  float* hand_points; float* obj_points; float* hand_pre; float* obj_pre; float* hand_sdf; float* obj_sdf; int* status;
+};
+
+__global__ void __launch_bounds__(256) sdf_rows_kernel(SdfRowsArgs a) {
+  const int b = blockIdx.y;
+  const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (j >= a.n_sel) return;
+  const int64_t first = a.row_offsets[b], count = a.row_offsets[b + 1] - first;
+  const int64_t idx = a.index[b * a.n_sel + j];
+  if (idx < 0 || idx >= count) {            // an index outside the frame's rows: flagged, nothing written for it
+    atomicExch(a.status, 1);
+    return;
+  }
+  const float2* r2 = reinterpret_cast<const float2*>(a.rows + (first + idx) * 6);       // rows are 24 bytes: 8-byte aligned
+  const float2 p01 = __ldg(r2), p23 = __ldg(r2 + 1), p45 = __ldg(r2 + 2);
+  float x = p01.x, y = p01.y, z = p23.x;
+  if (a.flip != nullptr && a.flip[b] != 0) x = -x;                                        // dexycb.py:547-548
+  if (a.rot != nullptr) {                                                                 // ho3d.py:333 `.dot(rot_mat.T)`
+    const float* r = a.rot + static_cast<int64_t>(b) * 9;
+    const float nx = __fmaf_rn(z, r[2], __fmaf_rn(y, r[1], __fmul_rn(x, r[0])));
+    const float ny = __fmaf_rn(z, r[5], __fmaf_rn(y, r[4], __fmul_rn(x, r[3])));
+    const float nz = __fmaf_rn(z, r[8], __fmaf_rn(y, r[7], __fmul_rn(x, r[6])));
+    x = nx; y = ny; z = nz;
+  }
+  const int per = a.n_hand + a.n_obj;
+  const int g = j >= per ? 2 : 0, k = static_cast<int>(j - (g ? per : 0));
+  const bool hand = k < a.n_hand;
+  const int slot = hand ? k : k - a.n_hand, n = hand ? a.n_hand : a.n_obj;
+  const float* c = (hand ? a.hand_root : a.obj_centre) + static_cast<int64_t>(b) * 3;
+  const float sc = hand ? a.hand_scale : a.obj_scale;
+  float* dst = g ? (hand ? a.hand_pre : a.obj_pre) : (hand ? a.hand_points : a.obj_points);
+  float* o = dst + (static_cast<int64_t>(b) * n + slot) * 3;
+  o[0] = __fmul_rn(__fsub_rn(x, c[0]), sc);
+  o[1] = __fmul_rn(__fsub_rn(y, c[1]), sc);
+  o[2] = __fmul_rn(__fsub_rn(z, c[2]), sc);
+  if (g == 0) {                                                                           // ho3d.py:575-576
+    if (hand) a.hand_sdf[static_cast<int64_t>(b) * n + slot] = __fmul_rn(p23.y, sc);
+    else a.obj_sdf[static_cast<int64_t>(b) * n + slot] = __fmul_rn(p45.x, sc);
+  }
+}
+
 }  // namespace
 }  // namespace hoisdf
 
@@ -106,5 +158,25 @@ HOISDF_API int hoisdf_image_crop_fwd(const uint8_t* src, int64_t batch, int64_t 
   const dim3 grid(static_cast<unsigned>(ceil_div(size * size, 256)), static_cast<unsigned>(batch));
   HOISDF_LAUNCH(affine_crop_kernel, grid, 256, s, src, src_pitch, src_stride, static_cast<int>(src_w), static_cast<int>(src_h),
                 static_cast<int>(channels), coef, tables, static_cast<int>(size), divisor, out_f32, out_u8);
+  return launch_status();
+}
+
+HOISDF_API int hoisdf_sdf_rows_fwd(const float* rows, const int64_t* row_offsets, const int64_t* index, int64_t batch,
+                                   int64_t n_sel, int64_t n_hand, int64_t n_obj, const float* rot, const int32_t* flip,
+                                   const float* hand_root, const float* obj_centre, float hand_scale, float obj_scale,
+                                   float* hand_points, float* obj_points, float* hand_pre, float* obj_pre, float* hand_sdf,
+                                   float* obj_sdf, int32_t* status, void* stream) {
+  if (rows == nullptr || row_offsets == nullptr || index == nullptr || hand_root == nullptr || obj_centre == nullptr ||
+      hand_points == nullptr || obj_points == nullptr || hand_sdf == nullptr || obj_sdf == nullptr || status == nullptr)
+    return HOISDF_E_NULL;
+  if (batch <= 0 || batch > 65535 || n_hand <= 0 || n_obj <= 0 || n_hand + n_obj > (1 << 28) ||
+      (n_sel != n_hand + n_obj && n_sel != 2 * (n_hand + n_obj)))
+    return HOISDF_E_SHAPE;
+  if (n_sel == 2 * (n_hand + n_obj) && (hand_pre == nullptr || obj_pre == nullptr)) return HOISDF_E_NULL;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  SdfRowsArgs a{rows, row_offsets, index, n_sel, static_cast<int>(n_hand), static_cast<int>(n_obj), rot, flip, hand_root,
+                obj_centre, hand_scale, obj_scale, hand_points, obj_points, hand_pre, obj_pre, hand_sdf, obj_sdf, status};
+  const dim3 grid(static_cast<unsigned>(ceil_div(n_sel, 256)), static_cast<unsigned>(batch));
+  HOISDF_LAUNCH(sdf_rows_kernel, grid, 256, s, a);
   return launch_status();
 }

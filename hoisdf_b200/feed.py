@@ -26,7 +26,7 @@ from . import ops
 from ._capi import check, lib
 
 __all__ = ["bbox_from_points", "fuse_boxes", "crop_affine", "apply_affine", "pil_coefficients", "resize_coefficients",
-           "crop_geometry", "crop_images", "crop_masks", "data_crop"]
+           "crop_geometry", "crop_images", "crop_masks", "data_crop", "sdf_point_sets"]
 
 
 def bbox_from_points(points2d: np.ndarray, factor: float = 1.1) -> np.ndarray:
@@ -183,3 +183,61 @@ def data_crop(frames: torch.Tensor, cam_intr: np.ndarray, bbox_hand: np.ndarray,
     _, h, w, _ = frames.shape
     coef, meta = crop_geometry(cam_intr, bbox_hand, obj_p2d, (w, h), res)
     return crop_images(frames, coef, res), meta
+
+
+def sdf_point_sets(rows: torch.Tensor, row_offsets: torch.Tensor, index: torch.Tensor, n_hand: int, n_obj: int,
+                   hand_root: torch.Tensor, obj_centre: torch.Tensor, hand_scale: float, obj_scale: float,
+                   rot: Optional[torch.Tensor] = None, flip: Optional[torch.Tensor] = None
+                   ) -> Tuple[Dict[str, torch.Tensor], Dict[str, torch.Tensor]]:
+    """The SDF point sets of a batch of samples (data/ho3d.py:484-486,333,524-548,561-579; data/dexycb.py:515-548) from the
+    packed `.npy` rows of the frames, resident on the GPU.
+    rows (total, 6) float32 = the frames' `[x, y, z, sdf_hand, sdf_obj, label]` rows back to back, row_offsets (B + 1,) int64;
+    index (B, n_sel) int64 = upstream's `all_idx` per frame (the caller's `np.random.choice` draws), n_sel = n_hand + n_obj
+    (evaluation) or twice that (training: + the near-surface `*_pre` draws); hand_root / obj_centre (B, 3) float32 (`mano_root`,
+    `obj_center_cam`); rot (B, 3, 3) float32 = the augmentation's `rot_mat` or None; flip (B,) = dexycb's `do_flip` or None.
+    -> (inputs, targets) with upstream's keys: `hand_sdf_points`, `obj_sdf_points` (, `hand_pre_points`, `obj_pre_points`)
+    (B, n, 3); `hand_sdf`, `obj_sdf` (B, n)."""
+    if not rows.is_cuda:
+        raise RuntimeError("hoisdf_b200.feed runs on the GPU; got a %s tensor (no CPU fallback)" % rows.device)
+    dev = rows.device
+    if rows.dtype != torch.float32 or rows.dim() != 2 or rows.shape[1] != 6 or not rows.is_contiguous():
+        raise ValueError("rows must be a contiguous (total, 6) float32 tensor")
+    b, n_sel = index.shape
+    per = n_hand + n_obj
+    if n_sel not in (per, 2 * per):
+        raise ValueError("index must hold n_hand + n_obj draws per frame, or twice that with the *_pre draws")
+    if row_offsets.shape != (b + 1,):
+        raise ValueError("row_offsets must hold batch + 1 entries")
+
+    def prep(t, dtype, shape, what):
+        if t is None:
+            return None
+        t = t.to(device=dev, dtype=dtype).contiguous()
+        if tuple(t.shape) != shape:
+            raise ValueError("%s must have shape %s" % (what, shape))
+        return t
+
+    row_offsets = prep(row_offsets, torch.int64, (b + 1,), "row_offsets")
+    index = prep(index, torch.int64, (b, n_sel), "index")
+    hand_root = prep(hand_root, torch.float32, (b, 3), "hand_root")
+    obj_centre = prep(obj_centre, torch.float32, (b, 3), "obj_centre")
+    rot = prep(rot, torch.float32, (b, 3, 3), "rot")
+    flip = prep(flip, torch.int32, (b,), "flip")
+    with torch.cuda.device(dev):
+        new = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float32)      # noqa: E731
+        hp, op_, hs, os_ = new(b, n_hand, 3), new(b, n_obj, 3), new(b, n_hand), new(b, n_obj)
+        pre = n_sel == 2 * per
+        hpre, opre = (new(b, n_hand, 3), new(b, n_obj, 3)) if pre else (None, None)
+        status = torch.zeros(1, device=dev, dtype=torch.int32)
+        ops._count(1)
+        check(lib.hoisdf_sdf_rows_fwd(rows.data_ptr(), row_offsets.data_ptr(), index.data_ptr(), b, n_sel, n_hand, n_obj,
+                                      ops._ptr(rot), ops._ptr(flip), hand_root.data_ptr(), obj_centre.data_ptr(),
+                                      float(hand_scale), float(obj_scale), hp.data_ptr(), op_.data_ptr(), ops._ptr(hpre),
+                                      ops._ptr(opre), hs.data_ptr(), os_.data_ptr(), status.data_ptr(), ops._stream()),
+              "hoisdf_sdf_rows_fwd")
+        if int(status.item()) != 0:
+            raise IndexError("sdf_point_sets: an index lies outside its frame's rows")
+    inputs = {"hand_sdf_points": hp, "obj_sdf_points": op_}
+    if pre:
+        inputs.update(hand_pre_points=hpre, obj_pre_points=opre)
+    return inputs, {"hand_sdf": hs, "obj_sdf": os_}

@@ -399,7 +399,11 @@ class Model(nn.Module):
             """One cascade step: keep the `keep` best rows per sample of the current ranking (lattice order) and
             re-evaluate them with the more accurate `evaluate`.  The step is loss-free for the `target` best rows
             of the accurate ranking whenever the coarse error is smaller than the |sdf| gap between the accurate
-            rank-`target` value and the coarse rank-`keep` value; both are measured here on the device."""
+            rank-`target` value and the coarse rank-`keep` value; both are measured here on the device.  The error is
+            observed on the KEPT rows only (the discarded rows are never re-evaluated), so the verdict is an estimate
+            with a 3x margin, not a proof: a discarded row whose coarse error exceeded 3x the largest kept-row error
+            would go unnoticed.  The configs[1] / configs[2] parity runs (profiles/r03c_parity_*.json: identical selected
+            sets at full batch) are the evidence that the margin holds on this path's activations."""
             _, _, s_sdf, _, _, s_row = ops.select_points(src_sdf, src_offsets, src_index, b, keep, cfg.bins_n, 0.0,
                                                          order_by_row=True)
             s_row = s_row.view(-1).long()

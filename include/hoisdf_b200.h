@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 33
+#define HOISDF_ABI_VERSION 34
 
 enum {
   HOISDF_OK = 0,
@@ -659,6 +659,23 @@ int hoisdf_gemm_f32_batched(const float* a, int64_t lda, int32_t trans_a, int64_
 int hoisdf_image_crop_fwd(const uint8_t* src, int64_t batch, int64_t src_h, int64_t src_w, int64_t channels, int64_t src_pitch,
                           int64_t src_stride, const double* coef, int64_t size, float divisor, float* out_f32, uint8_t* out_u8,
                           int32_t* tables, void* stream);
+
+/* Data feed, SDF point sets (upstream data/ho3d.py:484-486 `sdf_data[all_idx]`, :333 the augmentation's
+ * rotation, :524-548 normalisation, :561-579 the `inputs` / `targets` entries; data/dexycb.py:515-548 incl. the mirror flip):
+ * from the packed rows [x, y, z, sdf_hand, sdf_obj, label] (tool/pre_process_sdf.py:140-147) of `batch` frames in device
+ * memory -- rows (total, 6) float32, frame b = rows[row_offsets[b] .. row_offsets[b + 1]) -- and the caller's draws
+ * index (batch, n_sel) int64 (frame-local, upstream's `all_idx`: [hand n_hand | object n_obj | hand_pre n_hand | obj_pre n_obj],
+ * the last two only when n_sel = 2 * (n_hand + n_obj)) to
+ *   hand_points / hand_pre (batch, n_hand, 3) = (R xyz - hand_root) * hand_scale,  hand_sdf (batch, n_hand) = row[3] * hand_scale,
+ *   obj_points / obj_pre (batch, n_obj, 3) = (R xyz - obj_centre) * obj_scale,     obj_sdf (batch, n_obj) = row[4] * obj_scale
+ * in numpy's float32 arithmetic (xyz . rot^T accumulated x, y, z with fused multiply-adds as sgemm does).
+ *   rot (batch, 3, 3) or NULL (evaluation: no rotation); flip (batch) int32 or NULL (dexycb mirror: x -> -x before the rotation);
+ *   status: one int32 the kernel sets to 1 when an index lies outside its frame's rows (the caller clears and reads it).
+ * ------------------------------------------------------------------------------------------------- */
+int hoisdf_sdf_rows_fwd(const float* rows, const int64_t* row_offsets, const int64_t* index, int64_t batch, int64_t n_sel,
+                        int64_t n_hand, int64_t n_obj, const float* rot, const int32_t* flip, const float* hand_root,
+                        const float* obj_centre, float hand_scale, float obj_scale, float* hand_points, float* obj_points,
+                        float* hand_pre, float* obj_pre, float* hand_sdf, float* obj_sdf, int32_t* status, void* stream);
 
 /* One Linear of the training step per call (what hoisdf_b200/autograd.py:LinearFn runs; upstream main/train.py:108-131 through
  * every nn.Linear of the hot path), fp32 in / fp32 out on the FP16x3 tensor-core GEMM, caller-owned workspace of

@@ -119,3 +119,52 @@ def synthetic_aug(seed, h=480, w=640):
     scale = scale * float(np.clip(0.2 * rng.standard_normal() + 1, 0.8, 1.2))
     rot = float(rng.uniform(-np.pi, np.pi))
     return img, masks[0], masks[1], center, scale, rot
+
+
+def sdf_point_sets(sdf_data, all_idx, n_hand, n_obj, hand_root, obj_center_cam, hand_sdf_scale, obj_sdf_scale, rot_mat=None,
+                   do_flip=False):
+    """The SDF part of `__getitem__`: data/ho3d.py:484-486 (row gather), :333 (rotation inside data_aug), :524-548
+    (normalisation), :561-579 (dict entries); data/dexycb.py:544-548 (mirror flip before the augmentation).
+    sdf_data (N, 6) float32 = the frame's .npy; all_idx = concatenated draws.  -> (inputs, targets) dicts of numpy arrays."""
+    sdf_data = sdf_data[all_idx]
+    sdf_points = sdf_data[:, :5]
+    if do_flip:
+        sdf_points[:, 0] *= -1
+    if rot_mat is not None:
+        sdf_points = sdf_points.copy()
+        sdf_points[:, :3] = sdf_points[:, :3].dot(rot_mat.T)
+    hand_sdf_points = sdf_points[:int(n_hand)]
+    obj_sdf_points = sdf_points[int(n_hand):int(n_hand + n_obj)]
+    hand_sdf_points[:, :3] = hand_sdf_points[:, :3] - hand_root[None]
+    hand_sdf_points = hand_sdf_points * hand_sdf_scale
+    obj_sdf_points[:, :3] = obj_sdf_points[:, :3] - obj_center_cam[None]
+    obj_sdf_points = obj_sdf_points * obj_sdf_scale
+    inputs = {"hand_sdf_points": hand_sdf_points[:, :3], "obj_sdf_points": obj_sdf_points[:, :3]}
+    if len(all_idx) == 2 * (n_hand + n_obj):
+        hand_pre_points = sdf_points[int(n_hand + n_obj):int(n_hand * 2 + n_obj)]
+        obj_pre_points = sdf_points[int(n_hand * 2 + n_obj):]
+        hand_pre_points[:, :3] = hand_pre_points[:, :3] - hand_root[None]
+        hand_pre_points = hand_pre_points * hand_sdf_scale
+        obj_pre_points[:, :3] = obj_pre_points[:, :3] - obj_center_cam[None]
+        obj_pre_points = obj_pre_points * obj_sdf_scale
+        inputs.update(hand_pre_points=hand_pre_points[:, :3], obj_pre_points=obj_pre_points[:, :3])
+    return inputs, {"hand_sdf": hand_sdf_points[:, 3], "obj_sdf": obj_sdf_points[:, 4]}
+
+
+def synthetic_sdf_frame(seed, n_hand, n_obj, train=True, dist=0.02):
+    """A packed SDF file in upstream's layout (tool/pre_process_sdf.py:140-147: hand rows then object rows,
+    [x, y, z, sdf_hand, sdf_obj, label] float32) + the draws of ho3d.py:462-482 from a seeded generator + a rotation.
+    -> (rows, number of hand rows, all_idx, rot_mat, hand_root, obj_center_cam)"""
+    rng = np.random.default_rng(2000 + seed)
+    nh, no = int(rng.integers(3 * n_hand, 5 * n_hand)), int(rng.integers(3 * n_obj, 5 * n_obj))
+    data = np.concatenate([rng.uniform(-0.15, 0.15, (nh + no, 3)), rng.normal(0, 0.03, (nh + no, 2)),
+                           rng.integers(0, 6, (nh + no, 1))], axis=1).astype(np.float32)
+    draws = [rng.choice(nh, n_hand, replace=False), nh + rng.choice(no, n_obj, replace=False)]
+    if train:
+        draws.append(rng.choice(np.where(np.abs(data[:nh, 3]) < dist)[0], n_hand, replace=False))
+        draws.append(rng.choice(np.where(np.abs(data[nh:, 4]) < dist)[0] + nh, n_obj, replace=False))
+    th = rng.uniform(-np.pi, np.pi)
+    rot = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]]).astype(np.float32)
+    root = rng.uniform(-0.1, 0.1, 3).astype(np.float32)
+    centre = rng.uniform(-0.1, 0.1, 3).astype(np.float32)
+    return data, nh, np.concatenate(draws).astype(np.int64), rot, root, centre

@@ -296,6 +296,19 @@ def feed_case(name, seed, n_eval, n_aug):
     for d in (ev, au):
         for k, v in d.items():
             fix[k] = np.stack(v)
+    # one whole training sample through the unmodified `Dataset.__getitem__` (oracle/reference_shim.py:ho3d_train_item): the
+    # SDF point sets + masks it returns and the draws / augmentation arguments needed to reproduce them
+    inputs, targets, meta, taps = rs.ho3d_train_item(seed)
+    a = taps["affine"][0]
+    fix.update(item_draws=np.concatenate(taps["draws"]).astype(np.int64), item_center=a["center"], item_scale=a["scale"],
+               item_rot=a["rot"], item_rot_mat=a["rot_mat"], item_mano_root=meta["mano_root"],
+               item_obj_center_cam=meta["obj_center_cam"], item_hand_sdf_scale=taps["hand_sdf_scale"],
+               item_obj_sdf_scale=taps["obj_sdf_scale"], item_hand_seg=targets["hand_seg"].numpy(),
+               item_obj_seg=targets["obj_seg"].numpy(), item_hand_sdf=targets["hand_sdf"], item_obj_sdf=targets["obj_sdf"],
+               item_img_bytes=np.round(inputs["img"].numpy().transpose(1, 2, 0) * 255.0).astype(np.uint8))
+    assert np.array_equal(fix["u8_to_f32"][fix["item_img_bytes"]].transpose(2, 0, 1), inputs["img"].numpy())
+    for k in ("hand_sdf_points", "obj_sdf_points", "hand_pre_points", "obj_pre_points"):
+        fix["item_" + k] = inputs[k]
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **fix)
     print(name, {k: np.asarray(v).shape for k, v in fix.items()})
 
@@ -311,4 +324,4 @@ if __name__ == "__main__":
     dexycb_eval_case("dexycb_eval_seed14", 14, 2, 48, 16)
     metrics_case("metrics_seed15", 15, 6)
     train_case("train_dexycb_seed21", 21, 2, 24, 8)
-    feed_case("feed_seed31", 31, 2, 1)
+    feed_case("feed_seed31", 31, 1, 1)

@@ -156,3 +156,84 @@ def load_data_modules():
 
     _loaded["data"] = {"dataset_util": DU, "ho3d": H}
     return _loaded["data"]
+
+
+def ho3d_train_item(seed, n_hand=24, n_obj=8):
+    """ONE training sample through the UNMODIFIED upstream `data.ho3d.Dataset.__getitem__` (data/ho3d.py:432-589, mode "train"),
+    on a synthetic frame written to a scratch directory (PNG + packed SDF .npy in upstream's layouts).  The dataset object is
+    made with `__new__` (its constructor reads the HO3D tree, absent here) and given exactly the attributes `__getitem__` /
+    `data_aug` read; blur and colour jitter are switched off through upstream's own parameters (radius / ranges 0: PIL's
+    GaussianBlur(0) and the empty jitter list are identities), every other random draw is upstream's, from seeded generators.
+    Returns (inputs, targets, meta_info, taps): taps = the draws (`np.random.choice` results, affine arguments) and the raw
+    arrays a restatement needs to reproduce the item."""
+    import random
+
+    import numpy as np
+    from PIL import Image
+    import torchvision.transforms as transforms
+
+    from oracle import feed_oracle as FO
+
+    mods = load_data_modules()
+    DU, H = mods["dataset_util"], mods["ho3d"]
+    scratch = tempfile.mkdtemp(prefix="hoisdf_feed_")
+    img, hand_mask, obj_mask, _, _, _ = FO.synthetic_aug(seed)
+    _, K, _, p2d = FO.synthetic_frame(seed)
+    sdf, nh, _, _, _, _ = FO.synthetic_sdf_frame(seed, n_hand, n_obj)
+    no = len(sdf) - nh
+    rng = np.random.default_rng(3000 + seed)
+    Image.fromarray(img).save(os.path.join(scratch, "frame.png"))
+    np.save(os.path.join(scratch, "sdf.npy"), sdf)
+    joints_3d = rng.uniform(-0.1, 0.1, (21, 3)).astype(np.float32) + np.array([0, 0, 0.6], np.float32)
+    uvw = joints_3d.dot(K.T)
+    ds = H.Dataset.__new__(H.Dataset)
+    ds.mode = "train"
+    ds.image_paths = [os.path.join(scratch, "frame.png")]
+    ds.K = [K]
+    ds.joints_uv = [(uvw[:, :2] / uvw[:, 2:]).astype(np.float32)]
+    ds.mano_params = [rng.uniform(-0.5, 0.5, 61).astype(np.float32)]
+    ds.joints_3d = [joints_3d]
+    ds.hand_segs = [np.packbits(hand_mask)]
+    ds.obj_segs = [np.packbits(obj_mask)]
+    ds.obj_p2ds = [p2d]
+    ds.obj_p3ds = [rng.uniform(-0.1, 0.1, (21, 3)).astype(np.float32) + np.array([0, 0, 0.6], np.float32)]
+    ds.obj_rot_list = [rng.uniform(-1, 1, 3).astype(np.float32)]
+    ds.obj_trans_list = [np.array([0.02, -0.03, 0.6], np.float32)]
+    ds.obj_cls_list = ["003_cracker_box"]
+    ds.sdf_paths = [os.path.join(scratch, "sdf.npy")]
+    ds.sdf_indexes = [np.array([nh, no])]
+    ds.num_samp_hand, ds.num_samp_obj = n_hand, n_obj
+    ds.dist = 0.02
+    ds.hand_sdf_scale, ds.obj_sdf_scale = 6.2, 5.8
+    ds.obj_depth_mean_value = 0.7
+    ds.inp_res, ds.heatmap_res = 256, 64
+    ds.transform = transforms.ToTensor()
+    ds.coord_change_mat = np.array([[1.0, 0.0, 0.0], [0, -1.0, 0.0], [0.0, 0.0, -1.0]], dtype=np.float32)
+    ds.hue = ds.contrast = ds.brightness = ds.saturation = 0
+    ds.blur_radius = 0
+    ds.scale_jittering, ds.center_jittering, ds.max_rot = 0.2, 0.1, np.pi
+    taps = {"draws": [], "affine": [], "sdf": sdf, "n_hand_rows": nh, "frame": img, "hand_mask": hand_mask,
+            "obj_mask": obj_mask, "hand_sdf_scale": ds.hand_sdf_scale, "obj_sdf_scale": ds.obj_sdf_scale}
+    real_choice, real_affine = np.random.choice, DU.get_affine_transform
+
+    def tap_choice(*a, **k):
+        out = real_choice(*a, **k)
+        taps["draws"].append(np.asarray(out).copy())
+        return out
+
+    def tap_affine(center, scale, res, rot=0, K=None):
+        out = real_affine(center, scale, res, rot=rot, K=K)
+        taps["affine"].append({"center": np.asarray(center).copy(), "scale": float(scale), "rot": float(rot),
+                               "affinetrans": out[0].copy(), "rot_mat": out[-1].copy()})
+        return out
+
+    np.random.seed(seed)
+    random.seed(seed)
+    np.random.choice, DU.get_affine_transform = tap_choice, tap_affine
+    try:
+        inputs, targets, meta = ds[0]
+    finally:
+        np.random.choice, DU.get_affine_transform = real_choice, real_affine
+        import shutil
+        shutil.rmtree(scratch, ignore_errors=True)
+    return inputs, targets, meta, taps

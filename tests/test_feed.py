@@ -182,3 +182,134 @@ def test_argument_checks(emu):
     assert call(buf.ctypes.data, 1, 2, 2, 2, 6, 12, coef.ctypes.data, 2, 255.0, buf.ctypes.data, None, t.ctypes.data, None) == -2
     assert call(buf.ctypes.data, 1, 2, 2, 3, 5, 12, coef.ctypes.data, 2, 255.0, buf.ctypes.data, None, t.ctypes.data, None) == -2
     assert call(buf.ctypes.data, 1, 2, 2, 3, 6, 12, coef.ctypes.data, 2, 0.0, buf.ctypes.data, None, t.ctypes.data, None) == -2
+
+
+# ---------------------------------------------------------------------------------------------- SDF point sets
+N_HAND, N_OBJ = 24, 8
+
+
+def _item_from_fixture(g):
+    """The oracle's restatement of the fixture's training item (frame / masks / SDF file regenerated from the seed)."""
+    seed = int(g["seed"])
+    sdf = FO.synthetic_sdf_frame(seed, N_HAND, N_OBJ)[0]
+    frame, hand_mask, obj_mask = FO.synthetic_aug(seed)[:3]
+    return sdf, frame, hand_mask, obj_mask
+
+
+@pytest.mark.skipif(not rs.available(), reason="upstream reference not mounted")
+def test_feed_oracle_matches_upstream_training_item_live():
+    """The UNMODIFIED upstream `Dataset.__getitem__` (mode "train") on synthetic files against the oracle: image, both
+    masks, the four point sets and the two SDF targets, bit for bit."""
+    for seed in (1, 2, 6):
+        inputs, targets, meta, taps = rs.ho3d_train_item(seed, N_HAND, N_OBJ)
+        a = taps["affine"][0]
+        got_in, got_t = FO.sdf_point_sets(taps["sdf"], np.concatenate(taps["draws"]), N_HAND, N_OBJ, meta["mano_root"],
+                                          meta["obj_center_cam"], taps["hand_sdf_scale"], taps["obj_sdf_scale"],
+                                          rot_mat=a["rot_mat"])
+        for k, v in got_in.items():
+            assert np.array_equal(v, inputs[k]), k
+        for k, v in got_t.items():
+            assert np.array_equal(v, targets[k]), k
+        _, tensor, hs, os_, aff = FO.aug_warp(taps["frame"], taps["hand_mask"], taps["obj_mask"], a["center"], a["scale"],
+                                              a["rot"])
+        assert np.array_equal(aff, a["affinetrans"]) and np.array_equal(tensor, inputs["img"].numpy())
+        assert np.array_equal(hs, targets["hand_seg"].numpy()) and np.array_equal(os_, targets["obj_seg"].numpy())
+
+
+def test_feed_oracle_matches_golden_training_item():
+    g = np.load(GOLDEN)
+    sdf, frame, hand_mask, obj_mask = _item_from_fixture(g)
+    got_in, got_t = FO.sdf_point_sets(sdf, g["item_draws"], N_HAND, N_OBJ, g["item_mano_root"], g["item_obj_center_cam"],
+                                      float(g["item_hand_sdf_scale"]), float(g["item_obj_sdf_scale"]),
+                                      rot_mat=g["item_rot_mat"])
+    for k, v in got_in.items():
+        assert np.array_equal(v, g["item_" + k]), k
+    assert np.array_equal(got_t["hand_sdf"], g["item_hand_sdf"]) and np.array_equal(got_t["obj_sdf"], g["item_obj_sdf"])
+    pil_bytes, _, hs, os_, _ = FO.aug_warp(frame, hand_mask, obj_mask, g["item_center"], float(g["item_scale"]),
+                                           float(g["item_rot"]))
+    assert np.array_equal(pil_bytes, g["item_img_bytes"])
+    assert np.array_equal(hs, g["item_hand_seg"]) and np.array_equal(os_, g["item_obj_seg"])
+
+
+@pytest.fixture(scope="module")
+def emu_rows(emu):
+    vp, i64, f = C.c_void_p, C.c_int64, C.c_float
+    emu.hoisdf_sdf_rows_fwd.argtypes = [vp, vp, vp, i64, i64, i64, i64, vp, vp, vp, vp, f, f, vp, vp, vp, vp, vp, vp, vp, vp]
+    emu.hoisdf_sdf_rows_fwd.restype = C.c_int
+    return emu
+
+
+def emu_point_sets(lib, frames, n_hand, n_obj, hand_scale, obj_scale, use_rot=True, flip=None):
+    """frames: list of (rows, all_idx, rot, root, centre) -> dict of outputs + status, one call for the batch."""
+    b = len(frames)
+    rows = np.ascontiguousarray(np.concatenate([f[0] for f in frames]))
+    offsets = np.cumsum([0] + [len(f[0]) for f in frames]).astype(np.int64)
+    index = np.ascontiguousarray(np.stack([f[1] for f in frames]).astype(np.int64))
+    rot = np.ascontiguousarray(np.stack([f[2] for f in frames]).astype(np.float32)) if use_rot else None
+    root = np.ascontiguousarray(np.stack([f[3] for f in frames]).astype(np.float32))
+    centre = np.ascontiguousarray(np.stack([f[4] for f in frames]).astype(np.float32))
+    n_sel = index.shape[1]
+    pre = n_sel == 2 * (n_hand + n_obj)
+    out = {"hand_sdf_points": np.full((b, n_hand, 3), np.nan, np.float32), "obj_sdf_points": np.full((b, n_obj, 3), np.nan, np.float32),
+           "hand_pre_points": np.full((b, n_hand, 3), np.nan, np.float32) if pre else None,
+           "obj_pre_points": np.full((b, n_obj, 3), np.nan, np.float32) if pre else None,
+           "hand_sdf": np.full((b, n_hand), np.nan, np.float32), "obj_sdf": np.full((b, n_obj), np.nan, np.float32)}
+    status = np.zeros(1, np.int32)
+    p = lambda a: None if a is None else a.ctypes.data                   # noqa: E731
+    fl = None if flip is None else np.ascontiguousarray(flip, dtype=np.int32)
+    rc = lib.hoisdf_sdf_rows_fwd(p(rows), p(offsets), p(index), b, n_sel, n_hand, n_obj, p(rot), p(fl), p(root), p(centre),
+                                 hand_scale, obj_scale, p(out["hand_sdf_points"]), p(out["obj_sdf_points"]),
+                                 p(out["hand_pre_points"]), p(out["obj_pre_points"]), p(out["hand_sdf"]), p(out["obj_sdf"]),
+                                 p(status), None)
+    return rc, out, int(status[0])
+
+
+def close32(got, want):
+    """float32 results of at most three fused operations: equal to numpy's up to the last bit of the largest operand
+    (bit-equal on the build container's OpenBLAS; another sgemm kernel may order the three products differently)."""
+    return float(np.abs(got - want).max()) <= 4 * np.finfo(np.float32).eps * max(1.0, float(np.abs(want).max()))
+
+
+@pytest.mark.parametrize("train,use_rot,flip", [(True, True, False), (False, False, False), (False, False, True), (True, True, True)])
+def test_sdf_rows_kernel_vs_oracle(emu_rows, train, use_rot, flip):
+    n_hand, n_obj, hs, os_ = 37, 11, 6.2, 5.8
+    frames = []
+    for s in range(5):
+        rows, _, idx, rot, root, centre = FO.synthetic_sdf_frame(s, n_hand, n_obj, train=train)
+        frames.append((rows, idx, rot, root, centre))
+    flips = np.array([1, 0, 1, 1, 0], np.int32) if flip else None
+    rc, out, status = emu_point_sets(emu_rows, frames, n_hand, n_obj, hs, os_, use_rot, flips)
+    assert rc == 0 and status == 0
+    exact = True
+    for i, (rows, idx, rot, root, centre) in enumerate(frames):
+        want_in, want_t = FO.sdf_point_sets(rows, idx, n_hand, n_obj, root, centre, hs, os_, rot_mat=rot if use_rot else None,
+                                            do_flip=bool(flip and flips[i]))
+        for k, v in {**want_in, **want_t}.items():
+            assert close32(out[k][i], v), (k, i)
+            exact &= np.array_equal(out[k][i], v)
+    if not train:
+        assert out["hand_pre_points"] is None
+    if not use_rot:
+        assert exact                           # without the sgemm the arithmetic is two separately rounded operations
+
+
+def test_sdf_rows_kernel_reproduces_upstream_item(emu_rows):
+    g = np.load(GOLDEN)
+    sdf = _item_from_fixture(g)[0]
+    frame = (sdf, g["item_draws"], g["item_rot_mat"], g["item_mano_root"], g["item_obj_center_cam"])
+    rc, out, status = emu_point_sets(emu_rows, [frame], N_HAND, N_OBJ, float(g["item_hand_sdf_scale"]),
+                                     float(g["item_obj_sdf_scale"]))
+    assert rc == 0 and status == 0
+    for k in ("hand_sdf_points", "obj_sdf_points", "hand_pre_points", "obj_pre_points", "hand_sdf", "obj_sdf"):
+        assert close32(out[k][0], g["item_" + k]), k
+
+
+def test_sdf_rows_kernel_flags_bad_indices_and_arguments(emu_rows):
+    rows, _, idx, rot, root, centre = FO.synthetic_sdf_frame(0, 8, 4, train=False)
+    bad = idx.copy()
+    bad[3] = len(rows)
+    rc, out, status = emu_point_sets(emu_rows, [(rows, bad, rot, root, centre)], 8, 4, 1.0, 1.0, False)
+    assert rc == 0 and status == 1 and np.isnan(out["hand_sdf_points"][0, 3]).all()
+    assert not np.isnan(out["hand_sdf_points"][0, :3]).any()
+    rc, _, _ = emu_point_sets(emu_rows, [(rows, idx[:-1], rot, root, centre)], 8, 4, 1.0, 1.0, False)
+    assert rc == -2

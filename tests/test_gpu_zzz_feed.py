@@ -88,3 +88,58 @@ def test_whole_feed_properties_at_full_batch(cuda):
     as_float = feed.crop_images(frames, shift, 256)
     # (on the host: torch's CUDA division by a scalar multiplies by the reciprocal, which is not the IEEE quotient)
     assert torch.equal(as_float.cpu(), moved.cpu().permute(0, 3, 1, 2).float() / 255.0)
+
+
+def _close32(got, want):
+    return float(np.abs(got - want).max()) <= 4 * np.finfo(np.float32).eps * max(1.0, float(np.abs(want).max()))
+
+
+@pytest.mark.parametrize("train,use_rot,flip", [(True, True, False), (False, False, True)])
+def test_sdf_point_sets_vs_oracle(cuda, train, use_rot, flip):
+    """`hoisdf_sdf_rows_fwd` at the training configuration's set sizes (cfg.num_samp_hand / num_samp_obj = 600 / 200, batch 64)."""
+    from hoisdf_b200 import feed
+    n_hand, n_obj, hs, os_, B = 600, 200, 6.2, 5.8, 64
+    frames = [FO.synthetic_sdf_frame(s, n_hand, n_obj, train=train) for s in range(B)]
+    rows = torch.from_numpy(np.concatenate([f[0] for f in frames])).to(cuda)
+    offsets = torch.from_numpy(np.cumsum([0] + [len(f[0]) for f in frames]).astype(np.int64))
+    index = torch.from_numpy(np.stack([f[2] for f in frames]))
+    rot = torch.from_numpy(np.stack([f[3] for f in frames])) if use_rot else None
+    flips = torch.from_numpy((np.arange(B) % 3 == 0).astype(np.int32)) if flip else None
+    root = torch.from_numpy(np.stack([f[4] for f in frames]))
+    centre = torch.from_numpy(np.stack([f[5] for f in frames]))
+    inputs, targets = feed.sdf_point_sets(rows, offsets, index, n_hand, n_obj, root, centre, hs, os_, rot=rot, flip=flips)
+    got = {k: v.cpu().numpy() for k, v in {**inputs, **targets}.items()}
+    assert ("hand_pre_points" in got) == train
+    for i, (data, _, idx, r, ro, ce) in enumerate(frames):
+        want_in, want_t = FO.sdf_point_sets(data, idx, n_hand, n_obj, ro, ce, hs, os_, rot_mat=r if use_rot else None,
+                                            do_flip=bool(flip and i % 3 == 0))
+        for k, v in {**want_in, **want_t}.items():
+            assert _close32(got[k][i], v), (k, i)
+            if not use_rot:
+                assert np.array_equal(got[k][i], v), (k, i)
+    bad = index.clone()
+    bad[5, 7] = 10 ** 9
+    with pytest.raises(IndexError):
+        feed.sdf_point_sets(rows, offsets, bad, n_hand, n_obj, root, centre, hs, os_, rot=rot, flip=flips)
+
+
+def test_training_item_reproduces_the_upstream_fixture(cuda):
+    """The three feed calls together against ONE sample of the unmodified upstream `Dataset.__getitem__` (mode "train";
+    fixture made by oracle/make_golden.py:feed_case through oracle/reference_shim.py:ho3d_train_item)."""
+    from hoisdf_b200 import feed
+    g = np.load(GOLDEN)
+    seed = int(g["seed"])
+    sdf = FO.synthetic_sdf_frame(seed, 24, 8)[0]
+    frame, hand_mask, obj_mask = FO.synthetic_aug(seed)[:3]
+    coef = feed.pil_coefficients(feed.crop_affine(g["item_center"], float(g["item_scale"]), 256, float(g["item_rot"])))[None]
+    img = feed.crop_images(torch.from_numpy(frame[None]).to(cuda), coef, 256)
+    assert np.array_equal(img[0].cpu().numpy(), g["u8_to_f32"][g["item_img_bytes"]].transpose(2, 0, 1))
+    masks = feed.crop_masks(torch.from_numpy(np.stack([hand_mask, obj_mask])).to(cuda), np.tile(coef, (2, 1)), 256, 64)
+    assert np.array_equal(masks[0].cpu().numpy(), g["item_hand_seg"]) and np.array_equal(masks[1].cpu().numpy(), g["item_obj_seg"])
+    inputs, targets = feed.sdf_point_sets(torch.from_numpy(sdf).to(cuda), torch.tensor([0, len(sdf)]),
+                                          torch.from_numpy(g["item_draws"])[None], 24, 8,
+                                          torch.from_numpy(g["item_mano_root"])[None],
+                                          torch.from_numpy(g["item_obj_center_cam"])[None], float(g["item_hand_sdf_scale"]),
+                                          float(g["item_obj_sdf_scale"]), rot=torch.from_numpy(g["item_rot_mat"])[None])
+    for k, v in {**inputs, **targets}.items():
+        assert _close32(v[0].cpu().numpy(), g["item_" + k]), k
