@@ -26,7 +26,7 @@ from . import ops
 from ._capi import check, lib
 
 __all__ = ["bbox_from_points", "fuse_boxes", "crop_affine", "apply_affine", "pil_coefficients", "resize_coefficients",
-           "crop_geometry", "crop_images", "crop_masks", "data_crop", "sdf_point_sets"]
+           "crop_geometry", "crop_images", "crop_masks", "data_crop", "draw_sdf_indices", "sdf_point_sets"]
 
 
 def bbox_from_points(points2d: np.ndarray, factor: float = 1.1) -> np.ndarray:
@@ -183,6 +183,24 @@ def data_crop(frames: torch.Tensor, cam_intr: np.ndarray, bbox_hand: np.ndarray,
     _, h, w, _ = frames.shape
     coef, meta = crop_geometry(cam_intr, bbox_hand, obj_p2d, (w, h), res)
     return crop_images(frames, coef, res), meta
+
+
+def draw_sdf_indices(sdf_rows: np.ndarray, n_hand_rows: int, n_hand: int, n_obj: int, dist: Optional[float] = None
+                     ) -> np.ndarray:
+    """Upstream's draws of one sample (data/ho3d.py:462-482, data/dexycb.py:519-541) from numpy's GLOBAL legacy generator, in
+    upstream's order, so that after the same `np.random.seed` the indices ARE upstream's: `np.random.choice(n, ...)` consumes
+    the generator exactly as upstream's `np.random.choice(list(range(n)), ...)` does (both reduce to `permutation(n)[:size]`)
+    without building a Python list of every row number per sample -- the cost SURVEY section 8 f-4 names.
+    sdf_rows: the frame's (N, 6) `.npy` rows on the host, hand rows first; `dist` = cfg.points_filter_dist for the training
+    sample's near-surface `*_pre` draws, None for an evaluation sample.  -> `all_idx` int64."""
+    n_rows = sdf_rows.shape[0]
+    draws = [np.random.choice(n_hand_rows, size=int(n_hand), replace=False),
+             n_hand_rows + np.random.choice(n_rows - n_hand_rows, size=int(n_obj), replace=False)]
+    if dist is not None:
+        draws.append(np.random.choice(np.where(np.abs(sdf_rows[:n_hand_rows, 3]) < dist)[0], size=n_hand, replace=False))
+        draws.append(np.random.choice(np.where(np.abs(sdf_rows[n_hand_rows:, 4]) < dist)[0] + n_hand_rows, size=n_obj,
+                                      replace=False))
+    return np.concatenate(draws).astype(np.int64)
 
 
 def sdf_point_sets(rows: torch.Tensor, row_offsets: torch.Tensor, index: torch.Tensor, n_hand: int, n_obj: int,

@@ -203,6 +203,9 @@ def test_feed_oracle_matches_upstream_training_item_live():
     for seed in (1, 2, 6):
         inputs, targets, meta, taps = rs.ho3d_train_item(seed, N_HAND, N_OBJ)
         a = taps["affine"][0]
+        np.random.seed(seed)                       # the product's draws after the same seed are upstream's draws
+        assert np.array_equal(feed.draw_sdf_indices(taps["sdf"], taps["n_hand_rows"], N_HAND, N_OBJ, 0.02),
+                              np.concatenate(taps["draws"]))
         got_in, got_t = FO.sdf_point_sets(taps["sdf"], np.concatenate(taps["draws"]), N_HAND, N_OBJ, meta["mano_root"],
                                           meta["obj_center_cam"], taps["hand_sdf_scale"], taps["obj_sdf_scale"],
                                           rot_mat=a["rot_mat"])
@@ -219,6 +222,11 @@ def test_feed_oracle_matches_upstream_training_item_live():
 def test_feed_oracle_matches_golden_training_item():
     g = np.load(GOLDEN)
     sdf, frame, hand_mask, obj_mask = _item_from_fixture(g)
+    state = np.random.get_state()
+    np.random.seed(int(g["seed"]))                 # numpy's legacy generator is a frozen stream: upstream's draws, from the fixture
+    assert np.array_equal(feed.draw_sdf_indices(sdf, FO.synthetic_sdf_frame(int(g["seed"]), N_HAND, N_OBJ)[1], N_HAND, N_OBJ, 0.02),
+                          g["item_draws"])
+    np.random.set_state(state)
     got_in, got_t = FO.sdf_point_sets(sdf, g["item_draws"], N_HAND, N_OBJ, g["item_mano_root"], g["item_obj_center_cam"],
                                       float(g["item_hand_sdf_scale"]), float(g["item_obj_sdf_scale"]),
                                       rot_mat=g["item_rot_mat"])
