@@ -17,6 +17,8 @@
 // `channels` = 3 (RGB frames) or 1 (mode "L": the hand / object segmentation masks of the training feed, ho3d.py:366-381,
 // which upstream warps with the same call and then shrinks with `resize((64, 64), Image.NEAREST)` = the scale-only path again
 // with coefficients (w_in / w_out, 0, 0, 0, h_in / h_out, 0)); `divisor` = 255 for images (`ToTensor(...) / 255.0`), 1 for masks.
+// `mirror[b]` != 0: the source frame is read left-right mirrored (data/dexycb.py:427-430,479-481: left hands are flipped with
+// `img[:, ::-1, :]` before the warp) -- the same pixels as warping a mirrored copy, without making one.
 // HBM-bound byte work: 3 bytes read (scattered rows, contiguous along x for the crop) and 12 bytes written per output pixel.
 #include "common.cuh"
 
@@ -49,7 +51,8 @@ __global__ void crop_tables_kernel(const double* __restrict__ coef, int size, in
 // one thread per output pixel; grid (ceil(size * size / 256), batch)
 __global__ void __launch_bounds__(256)
 affine_crop_kernel(const uint8_t* __restrict__ src, int64_t src_pitch, int64_t src_stride, int src_w, int src_h, int channels,
-                   const double* __restrict__ coef, const int* __restrict__ tables, int size, float divisor,
+                   const double* __restrict__ coef, const int32_t* __restrict__ mirror, const int* __restrict__ tables,
+                   int size, float divisor,
                    float* __restrict__ out_f32, uint8_t* __restrict__ out_u8) {
   const int b = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -74,6 +77,7 @@ affine_crop_kernel(const uint8_t* __restrict__ src, int64_t src_pitch, int64_t s
   }
   uint8_t px[3] = {0, 0, 0};
   if (xin >= 0 && yin >= 0) {
+    if (mirror != nullptr && mirror[b] != 0) xin = src_w - 1 - xin;      // the warp reads the frame's mirror image
     const uint8_t* p = src + b * src_stride + yin * src_pitch + static_cast<int64_t>(xin) * channels;
     for (int c = 0; c < channels; ++c) px[c] = p[c];
   }
@@ -146,8 +150,8 @@ __global__ void __launch_bounds__(256) sdf_rows_kernel(SdfRowsArgs a) {
 using namespace hoisdf;
 
 HOISDF_API int hoisdf_image_crop_fwd(const uint8_t* src, int64_t batch, int64_t src_h, int64_t src_w, int64_t channels,
-                                     int64_t src_pitch, int64_t src_stride, const double* coef, int64_t size, float divisor,
-                                     float* out_f32, uint8_t* out_u8, int32_t* tables, void* stream) {
+                                     int64_t src_pitch, int64_t src_stride, const double* coef, const int32_t* mirror,
+                                     int64_t size, float divisor, float* out_f32, uint8_t* out_u8, int32_t* tables, void* stream) {
   if (src == nullptr || coef == nullptr || tables == nullptr || (out_f32 == nullptr && out_u8 == nullptr)) return HOISDF_E_NULL;
   if (batch <= 0 || batch > 65535 || src_h <= 0 || src_w <= 0 || src_h > 32767 || src_w > 32767 || size <= 0 || size > 8192 ||
       (channels != 1 && channels != 3) || !(divisor > 0.0f) || src_pitch < channels * src_w || src_stride < src_pitch * src_h)
@@ -157,7 +161,7 @@ HOISDF_API int hoisdf_image_crop_fwd(const uint8_t* src, int64_t batch, int64_t 
                 static_cast<int>(src_h), tables);
   const dim3 grid(static_cast<unsigned>(ceil_div(size * size, 256)), static_cast<unsigned>(batch));
   HOISDF_LAUNCH(affine_crop_kernel, grid, 256, s, src, src_pitch, src_stride, static_cast<int>(src_w), static_cast<int>(src_h),
-                static_cast<int>(channels), coef, tables, static_cast<int>(size), divisor, out_f32, out_u8);
+                static_cast<int>(channels), coef, mirror, tables, static_cast<int>(size), divisor, out_f32, out_u8);
   return launch_status();
 }
 

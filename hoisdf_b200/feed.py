@@ -26,7 +26,7 @@ from . import ops
 from ._capi import check, lib
 
 __all__ = ["bbox_from_points", "fuse_boxes", "crop_affine", "apply_affine", "pil_coefficients", "resize_coefficients",
-           "crop_geometry", "crop_images", "crop_masks", "data_crop", "draw_sdf_indices", "sdf_point_sets"]
+           "crop_geometry", "crop_geometry_dexycb", "crop_images", "crop_masks", "data_crop", "draw_sdf_indices", "sdf_point_sets"]
 
 
 def bbox_from_points(points2d: np.ndarray, factor: float = 1.1) -> np.ndarray:
@@ -97,7 +97,7 @@ def _fixed_point_ok(a: np.ndarray, size: int) -> bool:
     return True
 
 
-def _warp(frames: torch.Tensor, coefficients: np.ndarray, res: int, divisor: float, as_bytes: bool) -> torch.Tensor:
+def _warp(frames: torch.Tensor, coefficients: np.ndarray, res: int, divisor: float, as_bytes: bool, mirror=None) -> torch.Tensor:
     if not frames.is_cuda:
         raise RuntimeError("hoisdf_b200.feed runs on the GPU; got a %s tensor (no CPU fallback)" % frames.device)
     if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[3] not in (1, 3) or frames.stride(3) != 1 or \
@@ -114,6 +114,9 @@ def _warp(frames: torch.Tensor, coefficients: np.ndarray, res: int, divisor: flo
     with torch.cuda.device(dev):
         coef_d = torch.from_numpy(coef).to(dev)
         tables = torch.empty(b, 2, res, device=dev, dtype=torch.int32)
+        mirror_d = None
+        if mirror is not None:
+            mirror_d = torch.as_tensor(np.asarray(mirror).astype(np.int32).reshape(b)).to(dev)
         if as_bytes:
             out = torch.empty(b, res, res, ch, device=dev, dtype=torch.uint8)
             args = (None, out.data_ptr())
@@ -122,29 +125,30 @@ def _warp(frames: torch.Tensor, coefficients: np.ndarray, res: int, divisor: flo
             args = (out.data_ptr(), None)
         ops._count(2)
         check(lib.hoisdf_image_crop_fwd(frames.data_ptr(), b, h, w, ch, frames.stride(1), frames.stride(0), coef_d.data_ptr(),
-                                        res, float(divisor), args[0], args[1], tables.data_ptr(), ops._stream()),
+                                        ops._ptr(mirror_d), res, float(divisor), args[0], args[1], tables.data_ptr(), ops._stream()),
               "hoisdf_image_crop_fwd")
     return out
 
 
-def crop_images(frames: torch.Tensor, coefficients: np.ndarray, res: int, as_bytes: bool = False) -> torch.Tensor:
+def crop_images(frames: torch.Tensor, coefficients: np.ndarray, res: int, as_bytes: bool = False, mirror=None) -> torch.Tensor:
     """frames: (B, H, W, 3) uint8 CUDA tensor (row-contiguous); coefficients: (B, 6) PIL AFFINE data (`pil_coefficients`).
     -> (B, 3, res, res) float32 in [0, 1] = `ToTensor()(np.asarray(img.transform(...)).astype(np.float32)) / 255.0`
     (ho3d.py:550,624), or with `as_bytes` the (B, res, res, 3) uint8 PIL images themselves (what the training feed hands to
-    its blur / colour-jitter filters)."""
+    its blur / colour-jitter filters).  `mirror` (B,) bool: warp the left-right mirrored frame (dexycb.py:427-430, left
+    hands) -- identical to warping `frames.flip(2)`."""
     if frames.dim() != 4 or frames.shape[3] != 3:
         raise ValueError("frames must be (B, H, W, 3) uint8")
-    return _warp(frames, coefficients, res, 255.0, as_bytes)
+    return _warp(frames, coefficients, res, 255.0, as_bytes, mirror)
 
 
-def crop_masks(masks: torch.Tensor, coefficients: np.ndarray, res: int, out_res: int) -> torch.Tensor:
+def crop_masks(masks: torch.Tensor, coefficients: np.ndarray, res: int, out_res: int, mirror=None) -> torch.Tensor:
     """The segmentation masks of the training feed (ho3d.py:366-381, :551-552): masks (B, H, W) uint8 (mode "L") on the GPU ->
     `transform_img` to (res, res) with the frame's coefficients, `.resize((out_res, out_res), Image.NEAREST)`,
     `.astype(np.float32)` -> (B, out_res, out_res) float32."""
     if masks.dim() != 3:
         raise ValueError("masks must be (B, H, W) uint8")
     b = masks.shape[0]
-    warped = _warp(masks.unsqueeze(3), coefficients, res, 1.0, True)
+    warped = _warp(masks.unsqueeze(3), coefficients, res, 1.0, True, mirror)      # (dexycb.py:479-481)
     shrink = np.tile(resize_coefficients(res, out_res), (b, 1))
     return _warp(warped, shrink, out_res, 1.0, False).squeeze(1)
 
@@ -172,6 +176,42 @@ def crop_geometry(cam_intr: np.ndarray, bbox_hand: np.ndarray, obj_p2d: np.ndarr
         K_out[i] = affine.dot(np.asarray(cam_intr[i]))
         coef[i] = pil_coefficients(affine)
     return coef, {"cam_intr": K_out, "bbox_hand": hand_out, "bbox_obj": obj_out}
+
+
+def crop_geometry_dexycb(cam_intr: np.ndarray, joints_uv: np.ndarray, obj_p2d: np.ndarray, img_size: Sequence[int],
+                         res: int = 256, heatmap_res: int = 64) -> Tuple[np.ndarray, Dict[str, np.ndarray]]:
+    """The host half of DexYCB's `data_crop` (data/dexycb.py:355-404) for a batch: the window comes from the 2-D hand joints
+    (factor 1.5; hand box factor 1.1), the intrinsics go through `get_affine_transform(..., K=K)`'s second matrix
+    (dataset_util.py:67-91: the crop of the centre carried around the principal point -- without rotation the same centre up
+    to float64 rounding, which is kept), the joints are scaled to heat-map pixels and the object corners normalised to the
+    object box.  -> ((B, 6) PIL coefficients, {"cam_intr" (B, 3, 3) float64 as upstream, "bbox_hand", "bbox_obj" (B, 4),
+    "joints_uv" (B, J, 2), "p2d" (B, N, 2)})."""
+    b = len(cam_intr)
+    coef = np.empty((b, 6), np.float64)
+    out = {"cam_intr": [], "bbox_hand": [], "bbox_obj": [], "joints_uv": [], "p2d": []}
+    for i in range(b):
+        K = np.asarray(cam_intr[i])
+        uv, p2d = np.asarray(joints_uv[i]), np.asarray(obj_p2d[i])
+        centre, scale = fuse_boxes(bbox_from_points(uv, 1.5), bbox_from_points(p2d, 1.5), img_size)
+        affine = crop_affine(centre, scale, res)
+        # the principal-point form of the same crop: T^-1 R T centre with R = identity, evaluated as upstream does
+        shift = np.eye(3)
+        shift[0, 2], shift[1, 2] = -K[0, 2], -K[1, 2]
+        back = shift.copy()
+        back[:2, 2] *= -1
+        carried = back.dot(np.eye(3)).dot(shift).dot(np.asarray(centre).tolist() + [1])
+        post = crop_affine(carried[:2], scale, res)
+        box_hand = apply_affine(bbox_from_points(uv, 1.1).reshape(2, 2), affine).flatten()
+        box_obj = apply_affine(bbox_from_points(p2d, 1.0).reshape(2, 2), affine).flatten()
+        corners = apply_affine(p2d, affine)
+        span = box_obj.reshape(2, 2)
+        out["cam_intr"].append(post.dot(K))
+        out["bbox_hand"].append(box_hand)
+        out["bbox_obj"].append(box_obj)
+        out["joints_uv"].append(apply_affine(uv, affine) / res * heatmap_res)
+        out["p2d"].append((corners - span[0, :]) / (span[1, :] - span[0, :]))
+        coef[i] = pil_coefficients(affine)
+    return coef, {k: np.stack(v) for k, v in out.items()}
 
 
 def data_crop(frames: torch.Tensor, cam_intr: np.ndarray, bbox_hand: np.ndarray, obj_p2d: np.ndarray, res: int = 256

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 34
+#define HOISDF_ABI_VERSION 35
 
 enum {
   HOISDF_OK = 0,
@@ -649,6 +649,7 @@ int hoisdf_gemm_f32_batched(const float* a, int64_t lda, int32_t trans_a, int64_
  *   src: (batch, src_h, src_w, channels) bytes, channels = 3 (RGB) or 1 (mode "L" masks), row pitch src_pitch bytes, frame
  *        pitch src_stride bytes;
  *   coef: 6 doubles per sample, PIL's `data` = the first two rows of the INVERSE affine (output pixel -> source pixel);
+ *   mirror: NULL or one int32 per sample, != 0: warp the left-right mirrored frame (data/dexycb.py:427-430,479-481: left hands);
  *   out_f32 (batch, channels, size, size) = pixel / divisor in fp32 (divisor 255: upstream's ToTensor(...) / 255.0,
  *        ho3d.py:550,624; divisor 1: the masks' astype(float32), :551-552) and / or
  *   out_u8 (batch, size, size, channels) = the PIL image; pixels that map outside the source are 0;
@@ -657,8 +658,8 @@ int hoisdf_gemm_f32_batched(const float* a, int64_t lda, int32_t trans_a, int64_
  * restated: the caller checks (hoisdf_b200/feed.py raises).
  * ------------------------------------------------------------------------------------------------- */
 int hoisdf_image_crop_fwd(const uint8_t* src, int64_t batch, int64_t src_h, int64_t src_w, int64_t channels, int64_t src_pitch,
-                          int64_t src_stride, const double* coef, int64_t size, float divisor, float* out_f32, uint8_t* out_u8,
-                          int32_t* tables, void* stream);
+                          int64_t src_stride, const double* coef, const int32_t* mirror, int64_t size, float divisor, float* out_f32,
+                          uint8_t* out_u8, int32_t* tables, void* stream);
 
 /* Data feed, SDF point sets (upstream data/ho3d.py:484-486 `sdf_data[all_idx]`, :333 the augmentation's
  * rotation, :524-548 normalisation, :561-579 the `inputs` / `targets` entries; data/dexycb.py:515-548 incl. the mirror flip):

@@ -296,6 +296,19 @@ def feed_case(name, seed, n_eval, n_aug):
     for d in (ev, au):
         for k, v in d.items():
             fix[k] = np.stack(v)
+    # DexYCB's `data_crop` (data/dexycb.py:355-404): geometry outputs + the warped frame's checksum rows
+    import data.dexycb as D
+
+    class SelfD:
+        inp_res, heatmap_res = 256, 64
+
+    img, K32, _, p2d = FO.synthetic_frame(seed)
+    _, hs, os_, _, _, _ = FO.synthetic_aug(seed)
+    uv = (p2d.mean(0) + np.random.default_rng(seed).uniform(-60, 60, (21, 2))).astype(np.float32)
+    ref = D.Dataset.data_crop(SelfD(), Image.fromarray(img), K32.astype(np.float64), uv, p2d, Image.fromarray(hs),
+                              Image.fromarray(os_))
+    fix.update(dex_uv_in=uv, dex_bbox_hand=ref[1], dex_bbox_obj=ref[2], dex_K=ref[3], dex_joints_uv=ref[4], dex_p2d=ref[5],
+               dex_hand_seg=ref[6], dex_obj_seg=ref[7], dex_img_rows=np.asarray(ref[0])[::32].copy())
     # one whole training sample through the unmodified `Dataset.__getitem__` (oracle/reference_shim.py:ho3d_train_item): the
     # SDF point sets + masks it returns and the draws / augmentation arguments needed to reproduce them
     inputs, targets, meta, taps = rs.ho3d_train_item(seed)

@@ -24,12 +24,12 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fee
 def emu():
     lib = build_emulated("feed")
     vp, i64 = C.c_void_p, C.c_int64
-    lib.hoisdf_image_crop_fwd.argtypes = [vp, i64, i64, i64, i64, i64, i64, vp, i64, C.c_float, vp, vp, vp, vp]
+    lib.hoisdf_image_crop_fwd.argtypes = [vp, i64, i64, i64, i64, i64, i64, vp, vp, i64, C.c_float, vp, vp, vp, vp]
     lib.hoisdf_image_crop_fwd.restype = C.c_int
     return lib
 
 
-def emu_warp(lib, frames, coef, size, divisor=255.0):
+def emu_warp(lib, frames, coef, size, divisor=255.0, mirror=None):
     """frames (B, H, W, C) uint8 -> (out_f32 (B, C, size, size), out_u8 (B, size, size, C)) from ONE call with both outputs."""
     frames = np.ascontiguousarray(frames)
     b, h, w, ch = frames.shape
@@ -37,7 +37,9 @@ def emu_warp(lib, frames, coef, size, divisor=255.0):
     of = np.full((b, ch, size, size), np.nan, np.float32)
     ou = np.full((b, size, size, ch), 7, np.uint8)
     tables = np.zeros((b, 2, size), np.int32)
-    rc = lib.hoisdf_image_crop_fwd(frames.ctypes.data, b, h, w, ch, w * ch, h * w * ch, coef.ctypes.data, size, divisor,
+    mirror = None if mirror is None else np.ascontiguousarray(mirror, dtype=np.int32)
+    rc = lib.hoisdf_image_crop_fwd(frames.ctypes.data, b, h, w, ch, w * ch, h * w * ch, coef.ctypes.data,
+                                   None if mirror is None else mirror.ctypes.data, size, divisor,
                                    of.ctypes.data, ou.ctypes.data, tables.ctypes.data, None)
     assert rc == 0
     return of, ou
@@ -177,11 +179,11 @@ def test_argument_checks(emu):
     coef = np.array([1.0, 0, 0, 0, 1, 0])
     t = np.zeros(8, np.int32)
     call = emu.hoisdf_image_crop_fwd
-    assert call(None, 1, 2, 2, 3, 6, 12, coef.ctypes.data, 2, 255.0, buf.ctypes.data, None, t.ctypes.data, None) == -1
-    assert call(buf.ctypes.data, 1, 2, 2, 3, 6, 12, coef.ctypes.data, 2, 255.0, None, None, t.ctypes.data, None) == -1
-    assert call(buf.ctypes.data, 1, 2, 2, 2, 6, 12, coef.ctypes.data, 2, 255.0, buf.ctypes.data, None, t.ctypes.data, None) == -2
-    assert call(buf.ctypes.data, 1, 2, 2, 3, 5, 12, coef.ctypes.data, 2, 255.0, buf.ctypes.data, None, t.ctypes.data, None) == -2
-    assert call(buf.ctypes.data, 1, 2, 2, 3, 6, 12, coef.ctypes.data, 2, 0.0, buf.ctypes.data, None, t.ctypes.data, None) == -2
+    assert call(None, 1, 2, 2, 3, 6, 12, coef.ctypes.data, None, 2, 255.0, buf.ctypes.data, None, t.ctypes.data, None) == -1
+    assert call(buf.ctypes.data, 1, 2, 2, 3, 6, 12, coef.ctypes.data, None, 2, 255.0, None, None, t.ctypes.data, None) == -1
+    assert call(buf.ctypes.data, 1, 2, 2, 2, 6, 12, coef.ctypes.data, None, 2, 255.0, buf.ctypes.data, None, t.ctypes.data, None) == -2
+    assert call(buf.ctypes.data, 1, 2, 2, 3, 5, 12, coef.ctypes.data, None, 2, 255.0, buf.ctypes.data, None, t.ctypes.data, None) == -2
+    assert call(buf.ctypes.data, 1, 2, 2, 3, 6, 12, coef.ctypes.data, None, 2, 0.0, buf.ctypes.data, None, t.ctypes.data, None) == -2
 
 
 # ---------------------------------------------------------------------------------------------- SDF point sets
@@ -321,3 +323,62 @@ def test_sdf_rows_kernel_flags_bad_indices_and_arguments(emu_rows):
     assert not np.isnan(out["hand_sdf_points"][0, :3]).any()
     rc, _, _ = emu_point_sets(emu_rows, [(rows, idx[:-1], rot, root, centre)], 8, 4, 1.0, 1.0, False)
     assert rc == -2
+
+
+def test_mirrored_warp_equals_warping_the_mirrored_frame(emu):
+    """data/dexycb.py:427-430,479-481: left-hand frames and masks are flipped left-right before the warp."""
+    for s in range(3):
+        img, hs, _, center, scale, rot = FO.synthetic_aug(20 + s)
+        rot = rot if s else 0.0                                                # s = 0: the scale-only path
+        coef = feed.pil_coefficients(feed.crop_affine(center, scale, 256, rot))[None]
+        _, got = emu_warp(emu, img[None], coef, 256, mirror=[1])
+        assert np.array_equal(got[0], pil_warp(np.ascontiguousarray(img[:, ::-1, :]), coef[0], 256))
+        _, plain = emu_warp(emu, img[None], coef, 256, mirror=[0])
+        assert np.array_equal(plain[0], pil_warp(img, coef[0], 256))
+        _, got = emu_warp(emu, hs[None, :, :, None], coef, 256, divisor=1.0, mirror=[1])
+        assert np.array_equal(got[0], pil_warp(np.ascontiguousarray(hs[:, ::-1])[:, :, None], coef[0], 256))
+
+
+@pytest.mark.skipif(not rs.available(), reason="upstream reference not mounted")
+def test_dexycb_crop_geometry_and_warp_match_upstream_live(emu):
+    """The UNMODIFIED `data.dexycb.Dataset.data_crop` (dexycb.py:355-404) against the host geometry + the emulated kernel:
+    every returned array bit-equal (image, boxes, intrinsics, heat-map joints, normalised corners, both masks)."""
+    rs.load_data_modules()
+    import data.dexycb as D
+
+    class Self:
+        inp_res, heatmap_res = 256, 64
+
+    for seed in range(70, 76):
+        img, K32, _, p2d = FO.synthetic_frame(seed)
+        _, hs, os_, _, _, _ = FO.synthetic_aug(seed)
+        rng = np.random.default_rng(seed)
+        K = K32.astype(np.float64)                                            # dexycb.py:421-426 builds K in float64
+        uv = (p2d.mean(0) + rng.uniform(-60, 60, (21, 2))).astype(np.float32)
+        ref = D.Dataset.data_crop(Self(), Image.fromarray(img), K, uv, p2d, Image.fromarray(hs), Image.fromarray(os_))
+        r_img, r_hand, r_obj, r_K, r_uv, r_p2d, r_hs, r_os = ref
+        coef, meta = feed.crop_geometry_dexycb(K[None], uv[None], p2d[None], (640, 480), 256, 64)
+        assert np.array_equal(meta["bbox_hand"][0], r_hand) and np.array_equal(meta["bbox_obj"][0], r_obj)
+        assert np.array_equal(meta["cam_intr"][0], r_K) and meta["cam_intr"].dtype == r_K.dtype
+        assert np.array_equal(meta["joints_uv"][0], r_uv) and np.array_equal(meta["p2d"][0], r_p2d)
+        _, got = emu_warp(emu, img[None], coef, 256)
+        assert np.array_equal(got[0], np.asarray(r_img))
+        _, warped = emu_warp(emu, np.stack([hs, os_])[:, :, :, None], np.tile(coef, (2, 1)), 256, divisor=1.0)
+        small, _ = emu_warp(emu, warped, np.tile(feed.resize_coefficients(256, 64), (2, 1)), 64, divisor=1.0)
+        assert np.array_equal(small[0, 0], r_hs.astype(np.float32)) and np.array_equal(small[1, 0], r_os.astype(np.float32))
+
+
+def test_dexycb_crop_matches_golden(emu):
+    g = np.load(GOLDEN)
+    seed = int(g["seed"])
+    img, K32, _, p2d = FO.synthetic_frame(seed)
+    _, hs, os_, _, _, _ = FO.synthetic_aug(seed)
+    coef, meta = feed.crop_geometry_dexycb(K32.astype(np.float64)[None], g["dex_uv_in"][None], p2d[None], (640, 480), 256, 64)
+    for k, name in (("bbox_hand", "dex_bbox_hand"), ("bbox_obj", "dex_bbox_obj"), ("cam_intr", "dex_K"),
+                    ("joints_uv", "dex_joints_uv"), ("p2d", "dex_p2d")):
+        assert np.array_equal(meta[k][0], g[name]), k
+    _, got = emu_warp(emu, img[None], coef, 256)
+    assert np.array_equal(got[0][::32], g["dex_img_rows"])
+    _, warped = emu_warp(emu, np.stack([hs, os_])[:, :, :, None], np.tile(coef, (2, 1)), 256, divisor=1.0)
+    small, _ = emu_warp(emu, warped, np.tile(feed.resize_coefficients(256, 64), (2, 1)), 64, divisor=1.0)
+    assert np.array_equal(small[0, 0], g["dex_hand_seg"]) and np.array_equal(small[1, 0], g["dex_obj_seg"])

@@ -143,3 +143,23 @@ def test_training_item_reproduces_the_upstream_fixture(cuda):
                                           float(g["item_obj_sdf_scale"]), rot=torch.from_numpy(g["item_rot_mat"])[None])
     for k, v in {**inputs, **targets}.items():
         assert _close32(v[0].cpu().numpy(), g["item_" + k]), k
+
+
+def test_mirrored_warp_equals_warping_the_mirrored_frame(cuda):
+    """data/dexycb.py:427-430,479-481 (left hands): `mirror` reads the frame flipped left-right, in both of Pillow's paths."""
+    from hoisdf_b200 import feed
+    draws = [FO.synthetic_aug(20 + s) for s in range(4)]
+    coef = np.stack([feed.pil_coefficients(feed.crop_affine(c, sc, 256, r if i else 0.0))
+                     for i, (_, _, _, c, sc, r) in enumerate(draws)])
+    frames = torch.from_numpy(np.stack([d[0] for d in draws])).to(cuda)
+    mirror = np.array([1, 1, 0, 1])
+    got = feed.crop_images(frames, coef, 256, as_bytes=True, mirror=mirror)
+    want = feed.crop_images(torch.where(torch.from_numpy(mirror).to(cuda).bool()[:, None, None, None], frames.flip(2), frames),
+                            coef, 256, as_bytes=True)
+    assert torch.equal(got, want)
+    for i, d in enumerate(draws):
+        src = np.ascontiguousarray(d[0][:, ::-1, :]) if mirror[i] else d[0]
+        pil = np.asarray(Image.fromarray(src).transform((256, 256), Image.AFFINE, tuple(float(c) for c in coef[i])))
+        assert np.array_equal(got[i].cpu().numpy(), pil), i
+    masks = torch.from_numpy(np.stack([d[1] for d in draws])).to(cuda)
+    assert torch.equal(feed.crop_masks(masks, coef, 256, 64, mirror=np.ones(4)), feed.crop_masks(masks.flip(2).contiguous(), coef, 256, 64))
