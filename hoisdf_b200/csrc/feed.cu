@@ -49,8 +49,9 @@ __global__ void crop_tables_kernel(const double* __restrict__ coef, int size, in
 }
 
 // one thread per output pixel; grid (ceil(size * size / 256), batch)
+template <int channels>
 __global__ void __launch_bounds__(256)
-affine_crop_kernel(const uint8_t* __restrict__ src, int64_t src_pitch, int64_t src_stride, int src_w, int src_h, int channels,
+affine_crop_kernel(const uint8_t* __restrict__ src, int64_t src_pitch, int64_t src_stride, int src_w, int src_h,
                    const double* __restrict__ coef, const int32_t* __restrict__ mirror, const int* __restrict__ tables,
                    int size, float divisor,
                    float* __restrict__ out_f32, uint8_t* __restrict__ out_u8) {
@@ -75,19 +76,22 @@ affine_crop_kernel(const uint8_t* __restrict__ src, int64_t src_pitch, int64_t s
     yin = yy >> 16;
     if (xin < 0 || xin >= src_w || yin < 0 || yin >= src_h) xin = yin = -1;
   }
-  uint8_t px[3] = {0, 0, 0};
+  uint8_t px[channels] = {};
   if (xin >= 0 && yin >= 0) {
     if (mirror != nullptr && mirror[b] != 0) xin = src_w - 1 - xin;      // the warp reads the frame's mirror image
     const uint8_t* p = src + b * src_stride + yin * src_pitch + static_cast<int64_t>(xin) * channels;
+#pragma unroll
     for (int c = 0; c < channels; ++c) px[c] = p[c];
   }
   const int64_t plane = static_cast<int64_t>(size) * size;
   if (out_f32 != nullptr) {          // ToTensor layout (channels, size, size), value / divisor in fp32 (IEEE division)
     float* o = out_f32 + static_cast<int64_t>(b) * channels * plane + i;
+#pragma unroll
     for (int c = 0; c < channels; ++c) o[c * plane] = __fdiv_rn(static_cast<float>(px[c]), divisor);
   }
   if (out_u8 != nullptr) {           // the PIL image itself: (size, size, channels) bytes
     uint8_t* o = out_u8 + (static_cast<int64_t>(b) * plane + i) * channels;
+#pragma unroll
     for (int c = 0; c < channels; ++c) o[c] = px[c];
   }
 }
@@ -160,8 +164,12 @@ HOISDF_API int hoisdf_image_crop_fwd(const uint8_t* src, int64_t batch, int64_t 
   HOISDF_LAUNCH(crop_tables_kernel, static_cast<unsigned>(batch), 64, s, coef, static_cast<int>(size), static_cast<int>(src_w),
                 static_cast<int>(src_h), tables);
   const dim3 grid(static_cast<unsigned>(ceil_div(size * size, 256)), static_cast<unsigned>(batch));
-  HOISDF_LAUNCH(affine_crop_kernel, grid, 256, s, src, src_pitch, src_stride, static_cast<int>(src_w), static_cast<int>(src_h),
-                static_cast<int>(channels), coef, mirror, tables, static_cast<int>(size), divisor, out_f32, out_u8);
+  if (channels == 3)
+    HOISDF_LAUNCH(affine_crop_kernel<3>, grid, 256, s, src, src_pitch, src_stride, static_cast<int>(src_w),
+                  static_cast<int>(src_h), coef, mirror, tables, static_cast<int>(size), divisor, out_f32, out_u8);
+  else
+    HOISDF_LAUNCH(affine_crop_kernel<1>, grid, 256, s, src, src_pitch, src_stride, static_cast<int>(src_w),
+                  static_cast<int>(src_h), coef, mirror, tables, static_cast<int>(size), divisor, out_f32, out_u8);
   return launch_status();
 }
 
