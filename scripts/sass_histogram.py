@@ -11,7 +11,7 @@ for line in txt.splitlines():
     m = re.search(r"Function : (\S+)", line)
     if m:
         kern = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
-        kern = re.sub(r"\(.*", "", kern).replace("void ", "")
+        kern = re.sub(r"\(.*", "", kern.replace("(anonymous namespace)::", "")).replace("void ", "")
         hist[kern] = collections.Counter()
         continue
     m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", line)
