@@ -21,7 +21,7 @@ ROOT = os.path.dirname(PKG)
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(PKG, "libhoisdf_b200.so")
 
-SOURCES = ["api.cu", "linear.cu", "linear_tc.cu", "linear_tc2.cu", "linear_h3.cu", "resnet.cu", "narrow.cu", "lattice.cu", "gather.cu", "sdf.cu", "sdf_chain.cu", "sdf_infer.cu", "topk.cu", "attention.cu", "attention_tc.cu", "layernorm.cu", "transformer.cu", "heads.cu", "metrics.cu", "backward.cu", "train_prep.cu", "feed.cu"]
+SOURCES = ["api.cu", "linear.cu", "linear_tc.cu", "linear_tc2.cu", "linear_h3.cu", "resnet.cu", "narrow.cu", "lattice.cu", "gather.cu", "sdf.cu", "sdf_chain.cu", "sdf_infer.cu", "topk.cu", "attention.cu", "attention_tc.cu", "layernorm.cu", "transformer.cu", "heads.cu", "metrics.cu", "backward.cu", "train_prep.cu", "feed.cu", "augment.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "--fmad=true",

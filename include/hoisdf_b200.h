@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 35
+#define HOISDF_ABI_VERSION 36
 
 enum {
   HOISDF_OK = 0,
@@ -677,6 +677,18 @@ int hoisdf_sdf_rows_fwd(const float* rows, const int64_t* row_offsets, const int
                         int64_t n_hand, int64_t n_obj, const float* rot, const int32_t* flip, const float* hand_root,
                         const float* obj_centre, float hand_scale, float obj_scale, float* hand_points, float* obj_points,
                         float* hand_pre, float* obj_pre, float* hand_sdf, float* obj_sdf, int32_t* status, void* stream);
+
+/* Data feed, photometric augmentation of the training sample (upstream data/ho3d.py:355-364, data/dexycb.py:310-321):
+ * `img.filter(ImageFilter.GaussianBlur(radius))` on a batch of 8-bit images in device memory, bit-exact with Pillow 12.2.0
+ * (libImaging/BoxBlur.c: three box blurs per axis with fixed-point weights, bytes rounded after every pass).
+ *   hoisdf_gaussian_blur_params (HOST function, no GPU work): Pillow's `_gaussian_blur_radius` and box weights for one radius,
+ *     out[3] = {n, ww, fw}; the caller uploads one triple per sample;
+ *   hoisdf_gaussian_blur_u8: src / dst / scratch (batch, h, w, channels) bytes, packed; params (batch, 3) uint32 on the device;
+ *     passes = 3 for GaussianBlur.  2 * w * channels <= 48 KB and 8 * h <= 48 KB (HOISDF_E_SHAPE otherwise).  src may equal dst.
+ * ------------------------------------------------------------------------------------------------- */
+int hoisdf_gaussian_blur_params(float radius, int32_t passes, uint32_t* out);
+int hoisdf_gaussian_blur_u8(const uint8_t* src, uint8_t* dst, uint8_t* scratch, int64_t batch, int64_t h, int64_t w,
+                            int64_t channels, const uint32_t* params, int32_t passes, void* stream);
 
 /* One Linear of the training step per call (what hoisdf_b200/autograd.py:LinearFn runs; upstream main/train.py:108-131 through
  * every nn.Linear of the hot path), fp32 in / fp32 out on the FP16x3 tensor-core GEMM, caller-owned workspace of

@@ -23,7 +23,7 @@ EMU = os.path.join(ROOT, "tests", "emu")
 
 
 EMULATED = ("metrics", "lattice", "topk", "heads", "gather", "layernorm", "sdf", "linear", "attention", "narrow", "backward",
-            "feed")
+            "feed", "augment")
 STUBS = ("stubs_linear.cpp", "stubs_attention.cpp", "stubs_h3.cpp")
 _LIB = {}
 
