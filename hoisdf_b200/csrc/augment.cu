@@ -15,6 +15,7 @@
 // direct taps from shared memory -- all three passes of an axis in one kernel, the line (or a strip of columns) resident in
 // shared memory between them; intermediate results are rounded to bytes after every pass as in Pillow.
 // Upstream's radius is < 0.5 (n = 0: a 3-tap filter); larger radii cost 2 n + 3 taps per byte and pass.
+#include <algorithm>
 #include <cmath>
 
 #include "common.cuh"
@@ -85,6 +86,113 @@ blur_cols_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int
   }
 }
 
+// ---- colour jitter (data/dataset_util.py:167-201: up to four torchvision adjustments in a shuffled order) -------------------
+// op codes of one step, in upstream's creation order; factor = the adjustment's factor (hue: the byte added to H, 0..255)
+enum { JIT_NONE = 0, JIT_BRIGHTNESS = 1, JIT_SATURATION = 2, JIT_HUE = 3, JIT_CONTRAST = 4 };
+
+// Pillow's RGB -> L (Convert.c `L24`)
+__device__ inline int luma(int r, int g, int b) { return (r * 19595 + g * 38470 + b * 7471 + 0x8000) >> 16; }
+
+// Pillow's ImagingBlend on one byte (Blend.c): in1 + alpha * (in2 - in1) in float, truncated; clipped when alpha is outside [0, 1]
+__device__ inline uint8_t blend(int degenerate, int value, float alpha, bool inside) {
+  const float t = __fadd_rn(static_cast<float>(degenerate), __fmul_rn(alpha, static_cast<float>(value - degenerate)));
+  if (inside) return static_cast<uint8_t>(t);
+  return t <= 0.0f ? 0 : (t >= 255.0f ? 255 : static_cast<uint8_t>(t));
+}
+
+__device__ inline int clip8(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
+
+// Pillow's rgb2hsv_row (Convert.c): float variables, double constants
+__device__ inline void rgb_to_hsv(int r, int g, int b, int& uh, int& us, int& uv) {
+  const int maxc = max(r, max(g, b)), minc = min(r, min(g, b));
+  uv = maxc;
+  if (minc == maxc) { uh = 0; us = 0; return; }
+  const float cr = static_cast<float>(maxc - minc);
+  const float s = __fdiv_rn(cr, static_cast<float>(maxc));
+  const float rc = __fdiv_rn(static_cast<float>(maxc - r), cr), gc = __fdiv_rn(static_cast<float>(maxc - g), cr),
+              bc = __fdiv_rn(static_cast<float>(maxc - b), cr);
+  float h;
+  if (r == maxc) h = __fsub_rn(bc, gc);
+  else if (g == maxc) h = __double2float_rn(__dsub_rn(__dadd_rn(2.0, static_cast<double>(rc)), static_cast<double>(bc)));
+  else h = __double2float_rn(__dsub_rn(__dadd_rn(4.0, static_cast<double>(gc)), static_cast<double>(rc)));
+  h = __double2float_rn(fmod(__dadd_rn(__ddiv_rn(static_cast<double>(h), 6.0), 1.0), 1.0));
+  uh = clip8(static_cast<int>(__dmul_rn(static_cast<double>(h), 255.0)));
+  us = clip8(static_cast<int>(__dmul_rn(static_cast<double>(s), 255.0)));
+}
+
+// Pillow's hsv2rgb (Convert.c)
+__device__ inline void hsv_to_rgb(int h, int s, int v, int& r, int& g, int& b) {
+  if (s == 0) { r = g = b = v; return; }
+  const double h6 = __ddiv_rn(__dmul_rn(static_cast<double>(static_cast<float>(h)), 6.0), 255.0);
+  const int i = static_cast<int>(floor(h6));
+  const float f = __double2float_rn(__dsub_rn(h6, static_cast<double>(static_cast<float>(i))));
+  const float fs = __double2float_rn(__ddiv_rn(static_cast<double>(static_cast<float>(s)), 255.0));
+  const double vd = static_cast<double>(static_cast<float>(v)), fsd = static_cast<double>(fs), fd = static_cast<double>(f);
+  const int p = clip8(static_cast<int>(round(__dmul_rn(vd, __dsub_rn(1.0, fsd)))));
+  const int q = clip8(static_cast<int>(round(__dmul_rn(vd, __dsub_rn(1.0, __dmul_rn(fsd, fd))))));
+  const int t = clip8(static_cast<int>(round(__dmul_rn(vd, __dsub_rn(1.0, __dmul_rn(fsd, __dsub_rn(1.0, fd)))))));
+  switch (i % 6) {
+    case 0: r = v; g = t; b = p; break;
+    case 1: r = q; g = v; b = p; break;
+    case 2: r = p; g = v; b = t; break;
+    case 3: r = p; g = q; b = v; break;
+    case 4: r = t; g = p; b = v; break;
+    default: r = v; g = p; b = q; break;
+  }
+}
+
+// sum of L over the image for the samples whose op at `step` is the contrast adjustment (ImageEnhance.Contrast needs the
+// mean of the CURRENT image's grey version); integer partial sums -> one 64-bit atomic per block: order-independent
+__global__ void __launch_bounds__(256)
+jitter_luma_sum_kernel(const uint8_t* __restrict__ img, int64_t pixels, const int32_t* __restrict__ ops, int step,
+                       unsigned long long* __restrict__ sums) {
+  const int b = blockIdx.y;
+  if (ops[b * 4 + step] != JIT_CONTRAST) return;
+  __shared__ unsigned int warp_sums[8];
+  unsigned int local = 0;
+  const uint8_t* p = img + static_cast<int64_t>(b) * pixels * 3;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < pixels;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    local += static_cast<unsigned int>(luma(p[i * 3], p[i * 3 + 1], p[i * 3 + 2]));
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long total = 0;
+    for (int w = 0; w < 8; ++w) total += warp_sums[w];
+    atomicAdd(&sums[b], total);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+jitter_apply_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int64_t pixels, const int32_t* __restrict__ ops,
+                    const float* __restrict__ factors, int step, const unsigned long long* __restrict__ sums) {
+  const int b = blockIdx.y;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= pixels) return;
+  const int op = ops[b * 4 + step];
+  const float factor = factors[b * 4 + step];
+  const uint8_t* p = src + (static_cast<int64_t>(b) * pixels + i) * 3;
+  uint8_t* o = dst + (static_cast<int64_t>(b) * pixels + i) * 3;
+  int r = p[0], g = p[1], bl = p[2];
+  const bool inside = factor >= 0.0f && factor <= 1.0f;
+  if (op == JIT_BRIGHTNESS) {                       // ImageEnhance.Brightness: blend with black
+    r = blend(0, r, factor, inside); g = blend(0, g, factor, inside); bl = blend(0, bl, factor, inside);
+  } else if (op == JIT_SATURATION) {                // ImageEnhance.Color: blend with the grey version
+    const int l = luma(r, g, bl);
+    r = blend(l, r, factor, inside); g = blend(l, g, factor, inside); bl = blend(l, bl, factor, inside);
+  } else if (op == JIT_CONTRAST) {                  // ImageEnhance.Contrast: blend with the mean grey, int(mean + 0.5)
+    const int m = static_cast<int>(__dadd_rn(__ddiv_rn(static_cast<double>(sums[b]), static_cast<double>(pixels)), 0.5));
+    r = blend(m, r, factor, inside); g = blend(m, g, factor, inside); bl = blend(m, bl, factor, inside);
+  } else if (op == JIT_HUE) {                       // torchvision adjust_hue: H of Pillow's HSV shifted with byte wrap-around
+    int h, s, v;
+    rgb_to_hsv(r, g, bl, h, s, v);
+    h = (h + static_cast<int>(factor)) & 255;
+    hsv_to_rgb(h, s, v, r, g, bl);
+  }
+  o[0] = static_cast<uint8_t>(r); o[1] = static_cast<uint8_t>(g); o[2] = static_cast<uint8_t>(bl);
+}
+
 }  // namespace
 }  // namespace hoisdf
 
@@ -133,5 +241,27 @@ HOISDF_API int hoisdf_gaussian_blur_u8(const uint8_t* src, uint8_t* dst, uint8_t
   const dim3 g2(static_cast<unsigned>(ceil_div(line, static_cast<int64_t>(strip))), static_cast<unsigned>(batch));
   HOISDF_LAUNCH_SMEM(blur_cols_kernel, g2, 256, static_cast<size_t>(2 * h * strip), s, scratch, dst, static_cast<int>(h),
                      static_cast<int>(line), strip, params, passes);
+  return launch_status();
+}
+
+HOISDF_API int hoisdf_color_jitter_u8(const uint8_t* src, uint8_t* dst, int64_t batch, int64_t h, int64_t w, const int32_t* ops,
+                                      const float* factors, uint64_t* sums, void* stream) {
+  if (src == nullptr || dst == nullptr || ops == nullptr || factors == nullptr || sums == nullptr) return HOISDF_E_NULL;
+  if (batch <= 0 || batch > 65535 || h <= 0 || w <= 0 || h * w > (int64_t{1} << 24)) return HOISDF_E_SHAPE;   // 32-bit block sums
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t pixels = h * w;
+  cudaError_t e = cudaMemsetAsync(sums, 0, static_cast<size_t>(4 * batch) * sizeof(uint64_t), s);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  const dim3 grid(static_cast<unsigned>(ceil_div(pixels, static_cast<int64_t>(256))), static_cast<unsigned>(batch));
+  const dim3 sum_grid(static_cast<unsigned>(std::min<int64_t>(ceil_div(pixels, static_cast<int64_t>(256 * 16)), 64)),
+                      static_cast<unsigned>(batch));
+  const uint8_t* cur = src;
+  for (int step = 0; step < 4; ++step) {
+    unsigned long long* step_sums = reinterpret_cast<unsigned long long*>(sums) + static_cast<int64_t>(step) * batch;
+    HOISDF_LAUNCH(jitter_luma_sum_kernel, sum_grid, 256, s, cur, pixels, ops, step, step_sums);
+    HOISDF_LAUNCH(jitter_apply_kernel, grid, 256, s, cur, dst, pixels, ops, factors, step,
+                  static_cast<const unsigned long long*>(step_sums));
+    cur = dst;
+  }
   return launch_status();
 }

@@ -11,9 +11,13 @@ operations per frame and stays on the host in numpy, with the arithmetic (float6
 casts) of data/dataset_util.py so that `cam_intr`, `bbox_hand`, `bbox_obj` and the crop coefficients are the numbers upstream's
 dataset returns.
 
-Not covered: decoding the image files, the random draws of the augmentation (the caller passes centre, scale and angle), the
-training-only filters after the warp (PIL GaussianBlur, colour jitter), the MANO / object pose rotation (cv2.Rodrigues) and
-the random SDF point sampling (`np.random.choice`, ho3d.py:462-478), whose outcome is defined by numpy's generator state.
+The training-only filters between the warp and the tensor conversion (ho3d.py:355-364: PIL GaussianBlur, then
+`dataset_util.color_jitter` = torchvision's four PIL adjustments in a shuffled order) run on the warped bytes on the GPU as
+well (`gaussian_blur`, `color_jitter`; csrc/augment.cu), bit-exact with Pillow / torchvision.
+
+Not covered: decoding the image files, the random draws of the geometric augmentation (the caller passes centre, scale and
+angle; `draw_sdf_indices` / `draw_color_jitter` reproduce upstream's draws of the point indices and the jitter from the same
+generator state), the MANO / object pose rotation (cv2.Rodrigues).
 """
 from __future__ import annotations
 
@@ -26,7 +30,8 @@ from . import ops
 from ._capi import check, lib
 
 __all__ = ["bbox_from_points", "fuse_boxes", "crop_affine", "apply_affine", "pil_coefficients", "resize_coefficients",
-           "crop_geometry", "crop_geometry_dexycb", "crop_images", "crop_masks", "data_crop", "draw_sdf_indices", "sdf_point_sets"]
+           "crop_geometry", "crop_geometry_dexycb", "crop_images", "crop_masks", "data_crop", "draw_sdf_indices", "sdf_point_sets",
+           "gaussian_blur", "draw_color_jitter", "color_jitter", "to_tensor"]
 
 
 def bbox_from_points(points2d: np.ndarray, factor: float = 1.1) -> np.ndarray:
@@ -299,3 +304,88 @@ def sdf_point_sets(rows: torch.Tensor, row_offsets: torch.Tensor, index: torch.T
     if pre:
         inputs.update(hand_pre_points=hpre, obj_pre_points=opre)
     return inputs, {"hand_sdf": hs, "obj_sdf": os_}
+
+
+# ---------------------------------------------------------------------------------------------- photometric augmentation
+JITTER_OPS = {"brightness": 1, "saturation": 2, "hue": 3, "contrast": 4}
+
+
+def _bytes_image(images: torch.Tensor, channels=(1, 3)) -> Tuple[int, int, int, int]:
+    if not images.is_cuda:
+        raise RuntimeError("hoisdf_b200.feed runs on the GPU; got a %s tensor (no CPU fallback)" % images.device)
+    if images.dtype != torch.uint8 or images.dim() != 4 or images.shape[3] not in channels or not images.is_contiguous():
+        raise ValueError("images must be a contiguous (B, H, W, C) uint8 tensor, C in %s" % (channels,))
+    return tuple(images.shape)
+
+
+def gaussian_blur(images: torch.Tensor, radii: Sequence[float]) -> torch.Tensor:
+    """`img.filter(ImageFilter.GaussianBlur(radius))` (ho3d.py:355-357) per sample: images (B, H, W, C) uint8 on the GPU, radii (B,)
+    = upstream's `random.random() * self.blur_radius` draws.  -> the blurred bytes, as Pillow produces them."""
+    b, h, w, ch = _bytes_image(images)
+    import ctypes
+    params = np.zeros((b, 3), np.uint32)
+    for i, r in enumerate(np.asarray(radii, dtype=np.float64).reshape(b)):
+        check(lib.hoisdf_gaussian_blur_params(float(r), 3, params[i].ctypes.data_as(ctypes.c_void_p)), "hoisdf_gaussian_blur_params")
+    dev = images.device
+    with torch.cuda.device(dev):
+        params_d = torch.from_numpy(params.view(np.int32)).to(dev)
+        out, scratch = torch.empty_like(images), torch.empty_like(images)
+        ops._count(2)
+        check(lib.hoisdf_gaussian_blur_u8(images.data_ptr(), out.data_ptr(), scratch.data_ptr(), b, h, w, ch,
+                                          params_d.data_ptr(), 3, ops._stream()), "hoisdf_gaussian_blur_u8")
+    return out
+
+
+def draw_color_jitter(brightness: float = 0, contrast: float = 0, saturation: float = 0, hue: float = 0):
+    """The draws of `dataset_util.color_jitter` (data/dataset_util.py:144-201) from Python's GLOBAL `random` generator, in
+    upstream's order: four `random.uniform` factors (brightness, contrast, saturation, hue; a range of 0 draws nothing), then
+    `random.shuffle` of the adjustments listed as (brightness, saturation, hue, contrast) -- after the same `random.seed` the
+    sequence IS upstream's.  -> list of (name, factor) in application order, the `steps` entry of `color_jitter`."""
+    import random
+    b = random.uniform(max(0, 1 - brightness), 1 + brightness) if brightness > 0 else None
+    c = random.uniform(max(0, 1 - contrast), 1 + contrast) if contrast > 0 else None
+    sat = random.uniform(max(0, 1 - saturation), 1 + saturation) if saturation > 0 else None
+    hu = random.uniform(-hue, hue) if hue > 0 else None
+    steps = [(name, f) for name, f in (("brightness", b), ("saturation", sat), ("hue", hu), ("contrast", c)) if f is not None]
+    random.shuffle(steps)
+    return steps
+
+
+def color_jitter(images: torch.Tensor, steps: Sequence[Sequence[Tuple[str, float]]]) -> torch.Tensor:
+    """`dataset_util.color_jitter` for a batch: images (B, H, W, 3) uint8 on the GPU, steps[b] = that sample's adjustments in
+    application order (`draw_color_jitter`), each ("brightness" | "saturation" | "hue" | "contrast", factor as torchvision's
+    `adjust_*` receives it).  -> the jittered bytes, as torchvision's PIL branch produces them."""
+    b, h, w, _ = _bytes_image(images, (3,))
+    if len(steps) != b:
+        raise ValueError("one step list per sample")
+    codes = np.zeros((b, 4), np.int32)
+    factors = np.zeros((b, 4), np.float32)
+    for i, seq in enumerate(steps):
+        if len(seq) > 4:
+            raise ValueError("at most four adjustments per sample")
+        for j, (name, f) in enumerate(seq):
+            codes[i, j] = JITTER_OPS[name]
+            if name == "hue":
+                if not -0.5 <= f <= 0.5:
+                    raise ValueError("hue_factor (%s) is not in [-0.5, 0.5]." % f)       # torchvision raises the same
+                factors[i, j] = float(np.int32(f * 255).astype(np.uint8))                # torchvision's byte shift of H
+            else:
+                factors[i, j] = f
+    dev = images.device
+    with torch.cuda.device(dev):
+        out = torch.empty_like(images)
+        sums = torch.empty(4 * b, device=dev, dtype=torch.int64)
+        ops._count(8)
+        check(lib.hoisdf_color_jitter_u8(images.data_ptr(), out.data_ptr(), b, h, w, torch.from_numpy(codes).to(dev).data_ptr(),
+                                         torch.from_numpy(factors).to(dev).data_ptr(), sums.data_ptr(), ops._stream()),
+              "hoisdf_color_jitter_u8")
+    return out
+
+
+def to_tensor(images: torch.Tensor) -> torch.Tensor:
+    """`ToTensor()(np.asarray(img).astype(np.float32)) / 255.0` (ho3d.py:550) for square (B, S, S, 3) uint8 images on the GPU:
+    -> (B, 3, S, S) float32 with IEEE division (torch's CUDA division by a scalar multiplies by the reciprocal instead)."""
+    b, h, w, _ = _bytes_image(images, (3,))
+    if h != w:
+        raise ValueError("to_tensor takes the square crops of the feed")
+    return _warp(images, np.tile(np.array([1.0, 0, 0, 0, 1.0, 0]), (b, 1)), h, 255.0, False)

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 36
+#define HOISDF_ABI_VERSION 37
 
 enum {
   HOISDF_OK = 0,
@@ -689,6 +689,19 @@ int hoisdf_sdf_rows_fwd(const float* rows, const int64_t* row_offsets, const int
 int hoisdf_gaussian_blur_params(float radius, int32_t passes, uint32_t* out);
 int hoisdf_gaussian_blur_u8(const uint8_t* src, uint8_t* dst, uint8_t* scratch, int64_t batch, int64_t h, int64_t w,
                             int64_t channels, const uint32_t* params, int32_t passes, void* stream);
+
+/* `dataset_util.color_jitter` (upstream data/dataset_util.py:144-201, called from ho3d.py:358-364): up to four torchvision
+ * adjustments of a PIL image in a shuffled order, on a batch of 8-bit RGB images in device memory, bit-exact with torchvision's
+ * PIL branch over Pillow 12.2.0 (ImageEnhance = ImagingBlend with black / the grey version / the mean grey; adjust_hue =
+ * Pillow's RGB -> HSV, H shifted with byte wrap-around, HSV -> RGB).
+ *   src / dst (batch, h, w, 3) bytes, packed (src may equal dst); h * w <= 2^24;
+ *   ops (batch, 4) int32: the adjustment of each of the four steps, 0 none, 1 brightness, 2 saturation, 3 hue, 4 contrast;
+ *   factors (batch, 4) float: that step's factor as torchvision receives it (hue: the byte added to H,
+ *     np.int32(hue_factor * 255).astype(np.uint8), as a float 0..255);
+ *   sums: 4 * batch uint64 of scratch (the grey sums behind the contrast adjustment's mean; cleared by the call).
+ * ------------------------------------------------------------------------------------------------- */
+int hoisdf_color_jitter_u8(const uint8_t* src, uint8_t* dst, int64_t batch, int64_t h, int64_t w, const int32_t* ops,
+                           const float* factors, uint64_t* sums, void* stream);
 
 /* One Linear of the training step per call (what hoisdf_b200/autograd.py:LinearFn runs; upstream main/train.py:108-131 through
  * every nn.Linear of the hot path), fp32 in / fp32 out on the FP16x3 tensor-core GEMM, caller-owned workspace of

@@ -322,6 +322,18 @@ def feed_case(name, seed, n_eval, n_aug):
     assert np.array_equal(fix["u8_to_f32"][fix["item_img_bytes"]].transpose(2, 0, 1), inputs["img"].numpy())
     for k in ("hand_sdf_points", "obj_sdf_points", "hand_pre_points", "obj_pre_points"):
         fix["item_" + k] = inputs[k]
+    # the same sample with upstream's blur + colour jitter ON (constructor defaults): every 8th row of the network input, and
+    # the draws the filters made (re-derived from the same seed through upstream's own get_color_params / shuffle order)
+    import random
+    from hoisdf_b200 import feed
+    inputs, _, _, taps = rs.ho3d_train_item(seed, filters=True)
+    a = taps["affine"][0]
+    random.seed(seed)
+    radius = random.random() * 0.5
+    steps = feed.draw_color_jitter(brightness=0.5, contrast=0.5, saturation=0.5, hue=0.15)
+    fix.update(filt_center=a["center"], filt_scale=a["scale"], filt_rot=a["rot"], filt_radius=radius,
+               filt_order=np.array([n for n, _ in steps]), filt_factors=np.array([f for _, f in steps]),
+               filt_img_rows=inputs["img"].numpy()[:, ::8].copy())
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **fix)
     print(name, {k: np.asarray(v).shape for k, v in fix.items()})
 

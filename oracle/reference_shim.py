@@ -158,12 +158,13 @@ def load_data_modules():
     return _loaded["data"]
 
 
-def ho3d_train_item(seed, n_hand=24, n_obj=8):
+def ho3d_train_item(seed, n_hand=24, n_obj=8, filters=False):
     """ONE training sample through the UNMODIFIED upstream `data.ho3d.Dataset.__getitem__` (data/ho3d.py:432-589, mode "train"),
     on a synthetic frame written to a scratch directory (PNG + packed SDF .npy in upstream's layouts).  The dataset object is
     made with `__new__` (its constructor reads the HO3D tree, absent here) and given exactly the attributes `__getitem__` /
-    `data_aug` read; blur and colour jitter are switched off through upstream's own parameters (radius / ranges 0: PIL's
-    GaussianBlur(0) and the empty jitter list are identities), every other random draw is upstream's, from seeded generators.
+    `data_aug` read; with `filters=False` blur and colour jitter are switched off through upstream's own parameters (radius /
+    ranges 0: PIL's GaussianBlur(0) and the empty jitter list are identities), with `filters=True` they run with the
+    constructor's defaults (ho3d.py:34-41); every random draw is upstream's, from generators seeded with `seed`.
     Returns (inputs, targets, meta_info, taps): taps = the draws (`np.random.choice` results, affine arguments) and the raw
     arrays a restatement needs to reproduce the item."""
     import random
@@ -211,6 +212,8 @@ def ho3d_train_item(seed, n_hand=24, n_obj=8):
     ds.coord_change_mat = np.array([[1.0, 0.0, 0.0], [0, -1.0, 0.0], [0.0, 0.0, -1.0]], dtype=np.float32)
     ds.hue = ds.contrast = ds.brightness = ds.saturation = 0
     ds.blur_radius = 0
+    if filters:
+        ds.hue, ds.saturation, ds.contrast, ds.brightness, ds.blur_radius = 0.15, 0.5, 0.5, 0.5, 0.5
     ds.scale_jittering, ds.center_jittering, ds.max_rot = 0.2, 0.1, np.pi
     taps = {"draws": [], "affine": [], "sdf": sdf, "n_hand_rows": nh, "frame": img, "hand_mask": hand_mask,
             "obj_mask": obj_mask, "hand_sdf_scale": ds.hand_sdf_scale, "obj_sdf_scale": ds.obj_sdf_scale}

@@ -163,3 +163,66 @@ def test_mirrored_warp_equals_warping_the_mirrored_frame(cuda):
         assert np.array_equal(got[i].cpu().numpy(), pil), i
     masks = torch.from_numpy(np.stack([d[1] for d in draws])).to(cuda)
     assert torch.equal(feed.crop_masks(masks, coef, 256, 64, mirror=np.ones(4)), feed.crop_masks(masks.flip(2).contiguous(), coef, 256, 64))
+
+
+# ---------------------------------------------------------------------------------------------- photometric augmentation
+def test_gaussian_blur_vs_pillow(cuda):
+    from PIL import ImageFilter
+    from hoisdf_b200 import feed
+    rng = np.random.default_rng(11)
+    for (h, w, ch), radii in (((256, 256, 3), list(rng.uniform(0, 0.5, 14)) + [0.0, 0.5]), ((37, 53, 3), [0.3, 0.9, 2.0, 6.0]),
+                              ((64, 48, 1), [0.45, 3.7])):
+        imgs = rng.integers(0, 256, (len(radii), h, w, ch), dtype=np.uint8)
+        got = feed.gaussian_blur(torch.from_numpy(imgs).to(cuda), radii).cpu().numpy()
+        for i, r in enumerate(radii):
+            pil = Image.fromarray(imgs[i] if ch == 3 else imgs[i, :, :, 0])
+            want = np.asarray(pil.filter(ImageFilter.GaussianBlur(float(r)))).reshape(h, w, ch)
+            assert np.array_equal(got[i], want), (h, w, r)
+
+
+def test_color_jitter_vs_torchvision(cuda):
+    import itertools
+    import torchvision.transforms.functional as TF
+    from hoisdf_b200 import feed
+    fn = {"brightness": TF.adjust_brightness, "saturation": TF.adjust_saturation, "hue": TF.adjust_hue,
+          "contrast": TF.adjust_contrast}
+    rng = np.random.default_rng(12)
+    orders = list(itertools.permutations(fn))
+    imgs = rng.integers(0, 256, (len(orders), 96, 80, 3), dtype=np.uint8)
+    imgs[1] //= 4
+    steps = []
+    for order in orders:
+        f = {"brightness": rng.uniform(0.5, 1.5), "saturation": rng.uniform(0.5, 1.5), "contrast": rng.uniform(0.5, 1.5),
+             "hue": rng.uniform(-0.15, 0.15)}
+        steps.append([(n, float(f[n])) for n in order])
+    steps[3] = steps[3][:1]
+    steps[4] = []
+    got = feed.color_jitter(torch.from_numpy(imgs).to(cuda), steps).cpu().numpy()
+    for i, seq in enumerate(steps):
+        pil = Image.fromarray(imgs[i])
+        for n, f in seq:
+            pil = fn[n](pil, f)
+        assert np.array_equal(got[i], np.asarray(pil)), seq
+    # the colour cube (a 64^3 lattice) through the hue round trip
+    v = np.arange(0, 256, 4, dtype=np.uint8)
+    cube = np.stack(np.meshgrid(v, v, v, indexing="ij"), -1).reshape(512, 512, 3)
+    got = feed.color_jitter(torch.from_numpy(cube[None]).to(cuda), [[("hue", -0.12)]]).cpu().numpy()
+    assert np.array_equal(got[0], np.asarray(TF.adjust_hue(Image.fromarray(cube), -0.12)))
+
+
+def test_training_image_reproduces_the_upstream_fixture(cuda):
+    """warp -> blur -> jitter -> tensor of ONE sample of the unmodified upstream `Dataset.__getitem__` with its filters on."""
+    import random
+    from hoisdf_b200 import feed
+    g = np.load(GOLDEN)
+    seed = int(g["seed"])
+    state = random.getstate()
+    random.seed(seed)
+    radius = random.random() * 0.5
+    steps = feed.draw_color_jitter(brightness=0.5, contrast=0.5, saturation=0.5, hue=0.15)
+    random.setstate(state)
+    coef = feed.pil_coefficients(feed.crop_affine(g["filt_center"], float(g["filt_scale"]), 256, float(g["filt_rot"])))[None]
+    frame = torch.from_numpy(FO.synthetic_aug(seed)[0][None]).to(cuda)
+    img = feed.to_tensor(feed.color_jitter(feed.gaussian_blur(feed.crop_images(frame, coef, 256, as_bytes=True), [radius]),
+                                           [steps]))
+    assert np.array_equal(img[0].cpu().numpy()[:, ::8], g["filt_img_rows"])
