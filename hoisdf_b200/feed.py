@@ -375,10 +375,10 @@ def color_jitter(images: torch.Tensor, steps: Sequence[Sequence[Tuple[str, float
     with torch.cuda.device(dev):
         out = torch.empty_like(images)
         sums = torch.empty(4 * b, device=dev, dtype=torch.int64)
+        codes_d, factors_d = torch.from_numpy(codes).to(dev), torch.from_numpy(factors).to(dev)     # (kept alive past the launch)
         ops._count(8)
-        check(lib.hoisdf_color_jitter_u8(images.data_ptr(), out.data_ptr(), b, h, w, torch.from_numpy(codes).to(dev).data_ptr(),
-                                         torch.from_numpy(factors).to(dev).data_ptr(), sums.data_ptr(), ops._stream()),
-              "hoisdf_color_jitter_u8")
+        check(lib.hoisdf_color_jitter_u8(images.data_ptr(), out.data_ptr(), b, h, w, codes_d.data_ptr(), factors_d.data_ptr(),
+                                         sums.data_ptr(), ops._stream()), "hoisdf_color_jitter_u8")
     return out
 
 
