@@ -31,7 +31,8 @@ from ._capi import check, lib
 
 __all__ = ["bbox_from_points", "fuse_boxes", "crop_affine", "apply_affine", "pil_coefficients", "resize_coefficients",
            "crop_geometry", "crop_geometry_dexycb", "crop_images", "crop_masks", "data_crop", "draw_sdf_indices", "sdf_point_sets",
-           "gaussian_blur", "draw_color_jitter", "color_jitter", "to_tensor"]
+           "gaussian_blur", "draw_color_jitter", "color_jitter", "to_tensor",
+           "draw_train_geometry", "train_geometry", "train_batch"]
 
 
 def bbox_from_points(points2d: np.ndarray, factor: float = 1.1) -> np.ndarray:
@@ -389,3 +390,101 @@ def to_tensor(images: torch.Tensor) -> torch.Tensor:
     if h != w:
         raise ValueError("to_tensor takes the square crops of the feed")
     return _warp(images, np.tile(np.array([1.0, 0, 0, 0, 1.0, 0]), (b, 1)), h, 255.0, False)
+
+
+# ---------------------------------------------------------------------------------------------- training sample, host geometry
+def _affine_about_principal_point(centre, scale, res, turn, K) -> np.ndarray:
+    """The second matrix of `get_affine_transform(..., K=K)` (dataset_util.py:67-91): the un-rotated crop of the centre after
+    it was turned about the principal point (T^-1 R T centre) -- what the intrinsics are multiplied with."""
+    shift = np.eye(3)
+    shift[0, 2], shift[1, 2] = -K[0, 2], -K[1, 2]
+    back = shift.copy()
+    back[:2, 2] *= -1
+    carried = back.dot(turn).dot(shift).dot(np.asarray(centre).tolist() + [1])
+    return crop_affine(carried[:2], scale, res)
+
+
+def draw_train_geometry(centre: np.ndarray, scale: float, center_jittering: float = 0.1, scale_jittering: float = 0.2,
+                        max_rot: float = np.pi) -> Tuple[np.ndarray, float, float]:
+    """The three geometric draws of `data_aug` (ho3d.py:306-319) from numpy's GLOBAL generator in upstream's order (centre
+    offsets, scale factor, angle) applied to the fused window -> (centre, scale, rot)."""
+    centre = centre + center_jittering * scale * np.random.uniform(low=-1, high=1, size=2)
+    factor = np.clip(scale_jittering * np.random.randn() + 1, 1 - scale_jittering, 1 + scale_jittering)
+    return centre, scale * factor, np.random.uniform(low=-max_rot, high=max_rot)
+
+
+def train_geometry(cam_intr: np.ndarray, joints_uv: np.ndarray, joints_3d: np.ndarray, mano_param: np.ndarray,
+                   obj_p2d: np.ndarray, obj_p3d: np.ndarray, obj_rot: np.ndarray, obj_trans: np.ndarray, centre: np.ndarray,
+                   scale: float, rot: float, obj_depth_mean_value: float, res: int = 256, heatmap_res: int = 64,
+                   coord_change: Optional[np.ndarray] = None) -> Dict[str, np.ndarray]:
+    """Everything of one HO3D training sample that is not pixels or SDF rows (data_aug, ho3d.py:318-349, and the tail of
+    `__getitem__`, :519-523,553,568-587), for the drawn (centre, scale, rot): a few dozen floating-point operations in upstream's
+    own precision mixture (float64 matrices cast to float32, cv2.Rodrigues for the two rotations), kept on the host.
+    -> {"coef" (6,) PIL coefficients of the warp, "rot_mat" (3, 3) for `sdf_point_sets`, and upstream's entries: `joint_coord`,
+    `joint_cam_no_trans`, `mano_param`, `obj_rot`, `rel_obj_trans` (targets); `cam_intr`, `mano_root`, `obj_center_cam`,
+    `bbox_hand`, `bbox_obj` (meta_info); `p2d`, `p3d` (the normalised corners upstream computes and drops)}."""
+    import cv2
+    if coord_change is None:
+        coord_change = np.array([[1.0, 0.0, 0.0], [0, -1.0, 0.0], [0.0, 0.0, -1.0]], dtype=np.float32)     # ho3d.py:70-72
+    K = np.asarray(cam_intr).copy()
+    mano_param = np.asarray(mano_param).copy()
+    sn, cs = np.sin(rot), np.cos(rot)
+    turn = np.zeros((3, 3))
+    turn[0, :2] = [cs, -sn]
+    turn[1, :2] = [sn, cs]
+    turn[2, 2] = 1
+    affine = crop_affine(centre, scale, res, rot)
+    post = _affine_about_principal_point(centre, scale, res, turn, K)
+    rot_mat = turn.astype(np.float32)
+    # `dataset_util.rotation_angle` (:106-111): global hand rotation from OpenGL to camera axes, then the augmentation's turn
+    per_rdg, _ = cv2.Rodrigues(mano_param[:3])
+    resrot, _ = cv2.Rodrigues(np.dot(np.dot(rot_mat, coord_change), per_rdg))
+    mano_param[:3] = resrot[:, 0].astype(np.float32)
+    uv = apply_affine(joints_uv, affine)
+    joints_3d = np.asarray(joints_3d).dot(rot_mat.T)
+    p3d = np.asarray(obj_p3d).dot(rot_mat.T)
+    new_obj_rot = cv2.Rodrigues(rot_mat.dot(cv2.Rodrigues(np.asarray(obj_rot))[0]))[0].squeeze()
+    new_obj_trans = rot_mat.dot(np.asarray(obj_trans))
+    K = post.dot(K)
+    p2d = apply_affine(obj_p2d, affine)
+    bbox_hand = bbox_from_points(uv, 1.2)
+    uv = uv / res * heatmap_res
+    bbox_obj = bbox_from_points(p2d, 1.0)
+    span = bbox_obj.reshape(2, 2)
+    p2d = (p2d - span[0, :]) / (span[1, :] - span[0, :])
+    hand_root = joints_3d[0].copy()
+    joints_3d = joints_3d - hand_root[None]
+    # `get_center_cam` (:343-350): back-projection of the object box centre at the mean object depth
+    c = np.asarray([int((bbox_obj[2] + bbox_obj[0]) / 2), int((bbox_obj[3] + bbox_obj[1]) / 2), obj_depth_mean_value])
+    centre_cam = np.array([(c[0] - K[0, 2]) / K[0, 0] * c[2], (c[1] - K[1, 2]) / K[1, 1] * c[2], c[2]]).astype(np.float32)
+    return {"coef": pil_coefficients(affine), "rot_mat": rot_mat, "joint_coord": uv.astype(np.float32),
+            "joint_cam_no_trans": joints_3d * 1000, "mano_param": mano_param, "obj_rot": new_obj_rot,
+            "rel_obj_trans": new_obj_trans.astype(np.float32) - centre_cam, "cam_intr": K, "mano_root": hand_root,
+            "obj_center_cam": centre_cam, "bbox_hand": bbox_hand, "bbox_obj": bbox_obj, "p2d": p2d, "p3d": p3d - centre_cam[None]}
+
+
+def train_batch(frames: torch.Tensor, hand_masks: torch.Tensor, obj_masks: torch.Tensor, rows: torch.Tensor,
+                row_offsets: torch.Tensor, samples: Sequence[Dict], n_hand: int, n_obj: int, hand_sdf_scale: float,
+                obj_sdf_scale: float, res: int = 256, heatmap_res: int = 64):
+    """One collated HO3D training batch -- what upstream's DataLoader hands to `main/train.py:104-108` -- from the raw material
+    on the GPU: frames (B, H, W, 3) uint8, hand / object masks (B, H, W) uint8 (the unpacked bits), the frames' packed SDF rows
+    (`sdf_point_sets`), and per frame the host results `samples[b]` = `train_geometry(...)`'s dict + "index" (`draw_sdf_indices`),
+    "blur_radius" (`random.random() * blur_radius`) and "jitter" (`draw_color_jitter(...)`).
+    -> (inputs, targets, meta_info): dicts of CUDA tensors with upstream's keys (ho3d.py:561-587), batch-first."""
+    dev = frames.device
+    b = frames.shape[0]
+    if len(samples) != b:
+        raise ValueError("one sample dict per frame")
+    coef = np.stack([s["coef"] for s in samples])
+    warped = crop_images(frames, coef, res, as_bytes=True)
+    img = to_tensor(color_jitter(gaussian_blur(warped, [s["blur_radius"] for s in samples]), [s["jitter"] for s in samples]))
+    stack = lambda key, dtype=np.float32: torch.from_numpy(np.stack([np.asarray(s[key]) for s in samples]).astype(dtype)).to(dev)  # noqa: E731
+    inputs, targets = sdf_point_sets(rows, row_offsets, torch.from_numpy(np.stack([s["index"] for s in samples])), n_hand, n_obj,
+                                     stack("mano_root"), stack("obj_center_cam"), hand_sdf_scale, obj_sdf_scale,
+                                     rot=stack("rot_mat"))
+    inputs["img"] = img
+    targets.update(hand_seg=crop_masks(hand_masks, coef, res, heatmap_res), obj_seg=crop_masks(obj_masks, coef, res, heatmap_res))
+    for key in ("joint_coord", "joint_cam_no_trans", "obj_rot", "rel_obj_trans", "mano_param"):
+        targets[key] = stack(key)
+    meta = {key: stack(key) for key in ("cam_intr", "mano_root", "obj_center_cam", "bbox_hand", "bbox_obj")}
+    return inputs, targets, meta

@@ -168,3 +168,17 @@ def synthetic_sdf_frame(seed, n_hand, n_obj, train=True, dist=0.02):
     root = rng.uniform(-0.1, 0.1, 3).astype(np.float32)
     centre = rng.uniform(-0.1, 0.1, 3).astype(np.float32)
     return data, nh, np.concatenate(draws).astype(np.int64), rot, root, centre
+
+
+def synthetic_annotation(seed):
+    """The per-frame annotation arrays `ho3d.Dataset.__getitem__` reads in training mode (ho3d.py:436-459), synthetic and
+    deterministic: intrinsics, 2-D / 3-D hand joints, MANO parameters, projected / 3-D object corners, object pose."""
+    _, K, _, p2d = synthetic_frame(seed)
+    rng = np.random.default_rng(3000 + seed)
+    joints_3d = rng.uniform(-0.1, 0.1, (21, 3)).astype(np.float32) + np.array([0, 0, 0.6], np.float32)
+    uvw = joints_3d.dot(K.T)
+    return {"cam_intr": K, "joints_uv": (uvw[:, :2] / uvw[:, 2:]).astype(np.float32), "joints_3d": joints_3d,
+            "mano_param": rng.uniform(-0.5, 0.5, 61).astype(np.float32), "obj_p2d": p2d,
+            "obj_p3d": rng.uniform(-0.1, 0.1, (21, 3)).astype(np.float32) + np.array([0, 0, 0.6], np.float32),
+            "obj_rot": rng.uniform(-1, 1, 3).astype(np.float32), "obj_trans": np.array([0.02, -0.03, 0.6], np.float32),
+            "obj_depth_mean_value": 0.7}

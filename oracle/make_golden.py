@@ -326,11 +326,20 @@ def feed_case(name, seed, n_eval, n_aug):
     # the draws the filters made (re-derived from the same seed through upstream's own get_color_params / shuffle order)
     import random
     from hoisdf_b200 import feed
-    inputs, _, _, taps = rs.ho3d_train_item(seed, filters=True)
+    inputs, _t, _m, taps = rs.ho3d_train_item(seed, filters=True)
     a = taps["affine"][0]
     random.seed(seed)
     radius = random.random() * 0.5
     steps = feed.draw_color_jitter(brightness=0.5, contrast=0.5, saturation=0.5, hue=0.15)
+    inputs_f, targets_f, meta_f = inputs, _t, _m
+    for k in ("joint_coord", "joint_cam_no_trans", "obj_rot", "rel_obj_trans", "mano_param"):
+        fix["filt_t_" + k] = np.asarray(targets_f[k])
+    for k in ("cam_intr", "mano_root", "obj_center_cam", "bbox_hand", "bbox_obj"):
+        fix["filt_m_" + k] = np.asarray(meta_f[k])
+    for k in ("hand_sdf_points", "obj_sdf_points", "hand_pre_points", "obj_pre_points"):
+        fix["filt_i_" + k] = inputs_f[k]
+    fix.update(filt_t_hand_sdf=targets_f["hand_sdf"], filt_t_obj_sdf=targets_f["obj_sdf"],
+               filt_t_hand_seg=targets_f["hand_seg"].numpy(), filt_t_obj_seg=targets_f["obj_seg"].numpy())
     fix.update(filt_center=a["center"], filt_scale=a["scale"], filt_rot=a["rot"], filt_radius=radius,
                filt_order=np.array([n for n, _ in steps]), filt_factors=np.array([f for _, f in steps]),
                filt_img_rows=inputs["img"].numpy()[:, ::8].copy())

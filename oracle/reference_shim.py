@@ -179,34 +179,31 @@ def ho3d_train_item(seed, n_hand=24, n_obj=8, filters=False):
     DU, H = mods["dataset_util"], mods["ho3d"]
     scratch = tempfile.mkdtemp(prefix="hoisdf_feed_")
     img, hand_mask, obj_mask, _, _, _ = FO.synthetic_aug(seed)
-    _, K, _, p2d = FO.synthetic_frame(seed)
     sdf, nh, _, _, _, _ = FO.synthetic_sdf_frame(seed, n_hand, n_obj)
     no = len(sdf) - nh
-    rng = np.random.default_rng(3000 + seed)
+    ann = FO.synthetic_annotation(seed)
     Image.fromarray(img).save(os.path.join(scratch, "frame.png"))
     np.save(os.path.join(scratch, "sdf.npy"), sdf)
-    joints_3d = rng.uniform(-0.1, 0.1, (21, 3)).astype(np.float32) + np.array([0, 0, 0.6], np.float32)
-    uvw = joints_3d.dot(K.T)
     ds = H.Dataset.__new__(H.Dataset)
     ds.mode = "train"
     ds.image_paths = [os.path.join(scratch, "frame.png")]
-    ds.K = [K]
-    ds.joints_uv = [(uvw[:, :2] / uvw[:, 2:]).astype(np.float32)]
-    ds.mano_params = [rng.uniform(-0.5, 0.5, 61).astype(np.float32)]
-    ds.joints_3d = [joints_3d]
+    ds.K = [ann["cam_intr"]]
+    ds.joints_uv = [ann["joints_uv"]]
+    ds.mano_params = [ann["mano_param"]]
+    ds.joints_3d = [ann["joints_3d"]]
     ds.hand_segs = [np.packbits(hand_mask)]
     ds.obj_segs = [np.packbits(obj_mask)]
-    ds.obj_p2ds = [p2d]
-    ds.obj_p3ds = [rng.uniform(-0.1, 0.1, (21, 3)).astype(np.float32) + np.array([0, 0, 0.6], np.float32)]
-    ds.obj_rot_list = [rng.uniform(-1, 1, 3).astype(np.float32)]
-    ds.obj_trans_list = [np.array([0.02, -0.03, 0.6], np.float32)]
+    ds.obj_p2ds = [ann["obj_p2d"]]
+    ds.obj_p3ds = [ann["obj_p3d"]]
+    ds.obj_rot_list = [ann["obj_rot"]]
+    ds.obj_trans_list = [ann["obj_trans"]]
     ds.obj_cls_list = ["003_cracker_box"]
     ds.sdf_paths = [os.path.join(scratch, "sdf.npy")]
     ds.sdf_indexes = [np.array([nh, no])]
     ds.num_samp_hand, ds.num_samp_obj = n_hand, n_obj
     ds.dist = 0.02
     ds.hand_sdf_scale, ds.obj_sdf_scale = 6.2, 5.8
-    ds.obj_depth_mean_value = 0.7
+    ds.obj_depth_mean_value = ann["obj_depth_mean_value"]
     ds.inp_res, ds.heatmap_res = 256, 64
     ds.transform = transforms.ToTensor()
     ds.coord_change_mat = np.array([[1.0, 0.0, 0.0], [0, -1.0, 0.0], [0.0, 0.0, -1.0]], dtype=np.float32)
@@ -217,6 +214,10 @@ def ho3d_train_item(seed, n_hand=24, n_obj=8, filters=False):
     ds.scale_jittering, ds.center_jittering, ds.max_rot = 0.2, 0.1, np.pi
     taps = {"draws": [], "affine": [], "sdf": sdf, "n_hand_rows": nh, "frame": img, "hand_mask": hand_mask,
             "obj_mask": obj_mask, "hand_sdf_scale": ds.hand_sdf_scale, "obj_sdf_scale": ds.obj_sdf_scale}
+    taps["raw"] = {"cam_intr": ds.K[0].copy(), "joints_uv": ds.joints_uv[0].copy(), "joints_3d": ds.joints_3d[0].copy(),
+                   "mano_param": ds.mano_params[0].copy(), "obj_p2d": ds.obj_p2ds[0].copy(), "obj_p3d": ds.obj_p3ds[0].copy(),
+                   "obj_rot": ds.obj_rot_list[0].copy(), "obj_trans": ds.obj_trans_list[0].copy(),
+                   "obj_depth_mean_value": ds.obj_depth_mean_value}
     real_choice, real_affine = np.random.choice, DU.get_affine_transform
 
     def tap_choice(*a, **k):

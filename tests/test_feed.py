@@ -382,3 +382,57 @@ def test_dexycb_crop_matches_golden(emu):
     _, warped = emu_warp(emu, np.stack([hs, os_])[:, :, :, None], np.tile(coef, (2, 1)), 256, divisor=1.0)
     small, _ = emu_warp(emu, warped, np.tile(feed.resize_coefficients(256, 64), (2, 1)), 64, divisor=1.0)
     assert np.array_equal(small[0, 0], g["dex_hand_seg"]) and np.array_equal(small[1, 0], g["dex_obj_seg"])
+
+
+# ---------------------------------------------------------------------------------------------- training sample, host side
+def product_sample(seed, n_hand=N_HAND, n_obj=N_OBJ):
+    """The host half of one training sample as the product computes it: seeds both generators like the upstream run, then
+    draws in upstream's order (point indices, geometry, blur radius, jitter)."""
+    import random
+    ann = FO.synthetic_annotation(seed)
+    sdf, nh = FO.synthetic_sdf_frame(seed, n_hand, n_obj)[:2]
+    np.random.seed(seed)
+    random.seed(seed)
+    index = feed.draw_sdf_indices(sdf, nh, n_hand, n_obj, 0.02)
+    centre, scale = feed.fuse_boxes(feed.bbox_from_points(ann["joints_uv"], 1.5), feed.bbox_from_points(ann["obj_p2d"], 1.5),
+                                    (640, 480))
+    centre, scale, rot = feed.draw_train_geometry(centre, scale)
+    sample = feed.train_geometry(ann["cam_intr"], ann["joints_uv"], ann["joints_3d"], ann["mano_param"], ann["obj_p2d"],
+                                 ann["obj_p3d"], ann["obj_rot"], ann["obj_trans"], centre, scale, rot,
+                                 ann["obj_depth_mean_value"])
+    sample.update(index=index, blur_radius=random.random() * 0.5,
+                  jitter=feed.draw_color_jitter(brightness=0.5, contrast=0.5, saturation=0.5, hue=0.15))
+    return sample, sdf
+
+
+TARGET_KEYS = ("joint_coord", "joint_cam_no_trans", "obj_rot", "rel_obj_trans", "mano_param")
+META_KEYS = ("cam_intr", "mano_root", "obj_center_cam", "bbox_hand", "bbox_obj")
+
+
+@pytest.mark.skipif(not rs.available(), reason="upstream reference not mounted")
+def test_training_sample_host_geometry_matches_upstream_live():
+    """`train_geometry` + the product's draws against the unmodified `Dataset.__getitem__`: every non-pixel entry of the item
+    (targets and meta_info) equal in value AND dtype; the draws equal upstream's."""
+    state = np.random.get_state()
+    for seed in (0, 5, 13):
+        inputs, targets, meta, taps = rs.ho3d_train_item(seed, filters=True)
+        sample, _ = product_sample(seed)
+        a = taps["affine"][0]
+        assert np.array_equal(sample["index"], np.concatenate(taps["draws"])) and np.array_equal(sample["rot_mat"], a["rot_mat"])
+        for k in TARGET_KEYS:
+            assert np.array_equal(sample[k], targets[k]) and sample[k].dtype == targets[k].dtype, k
+        for k in META_KEYS:
+            assert np.array_equal(sample[k], meta[k]) and sample[k].dtype == meta[k].dtype, k
+    np.random.set_state(state)
+
+
+def test_training_sample_host_geometry_matches_golden():
+    g = np.load(GOLDEN)
+    state = np.random.get_state()
+    sample, _ = product_sample(int(g["seed"]))
+    np.random.set_state(state)
+    for k in TARGET_KEYS:
+        assert np.array_equal(sample[k], g["filt_t_" + k]), k
+    for k in META_KEYS:
+        assert np.array_equal(sample[k], g["filt_m_" + k]), k
+    assert sample["blur_radius"] == float(g["filt_radius"]) and [n for n, _ in sample["jitter"]] == [str(n) for n in g["filt_order"]]
