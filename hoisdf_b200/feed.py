@@ -35,6 +35,19 @@ __all__ = ["bbox_from_points", "fuse_boxes", "crop_affine", "apply_affine", "pil
            "draw_train_geometry", "train_geometry", "train_batch"]
 
 
+
+def _require_gpu(t: torch.Tensor) -> None:
+    if not t.is_cuda:
+        raise RuntimeError("hoisdf_b200.feed runs on the GPU; got a %s tensor (no CPU fallback)" % t.device)
+
+
+def _on(dev):
+    return torch.cuda.device(dev)
+
+
+def _stream() -> int:
+    return ops._stream()
+
 def bbox_from_points(points2d: np.ndarray, factor: float = 1.1) -> np.ndarray:
     """`dataset_util.get_bbox_joints` (data/dataset_util.py:106-116): box around 2-D points, centre truncated to an integer,
     half extents scaled by `factor`; float32 [x0, y0, x1, y1]."""
@@ -104,12 +117,12 @@ def _fixed_point_ok(a: np.ndarray, size: int) -> bool:
 
 
 def _warp(frames: torch.Tensor, coefficients: np.ndarray, res: int, divisor: float, as_bytes: bool, mirror=None) -> torch.Tensor:
-    if not frames.is_cuda:
-        raise RuntimeError("hoisdf_b200.feed runs on the GPU; got a %s tensor (no CPU fallback)" % frames.device)
+    _require_gpu(frames)
     if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[3] not in (1, 3) or frames.stride(3) != 1 or \
             frames.stride(2) != frames.shape[3]:
         raise ValueError("frames must be (B, H, W, C) uint8 with packed pixels, C = 1 or 3")
     b, h, w, ch = frames.shape
+    frame_pitch = frames.stride(0) if b > 1 else h * frames.stride(1)       # (a size-1 batch axis may carry any stride)
     coef = np.ascontiguousarray(np.asarray(coefficients, dtype=np.float64).reshape(b, 6))
     if not np.isfinite(coef).all():
         raise ValueError("non-finite crop coefficients")
@@ -117,7 +130,7 @@ def _warp(frames: torch.Tensor, coefficients: np.ndarray, res: int, divisor: flo
         if (a[1] != 0.0 or a[3] != 0.0) and not _fixed_point_ok(a, res):
             raise ValueError("crop transform outside Pillow's fixed-point range (|source coordinate| >= 32768)")
     dev = frames.device
-    with torch.cuda.device(dev):
+    with _on(dev):
         coef_d = torch.from_numpy(coef).to(dev)
         tables = torch.empty(b, 2, res, device=dev, dtype=torch.int32)
         mirror_d = None
@@ -130,8 +143,8 @@ def _warp(frames: torch.Tensor, coefficients: np.ndarray, res: int, divisor: flo
             out = torch.empty(b, ch, res, res, device=dev, dtype=torch.float32)
             args = (out.data_ptr(), None)
         ops._count(2)
-        check(lib.hoisdf_image_crop_fwd(frames.data_ptr(), b, h, w, ch, frames.stride(1), frames.stride(0), coef_d.data_ptr(),
-                                        ops._ptr(mirror_d), res, float(divisor), args[0], args[1], tables.data_ptr(), ops._stream()),
+        check(lib.hoisdf_image_crop_fwd(frames.data_ptr(), b, h, w, ch, frames.stride(1), frame_pitch, coef_d.data_ptr(),
+                                        ops._ptr(mirror_d), res, float(divisor), args[0], args[1], tables.data_ptr(), _stream()),
               "hoisdf_image_crop_fwd")
     return out
 
@@ -261,8 +274,7 @@ def sdf_point_sets(rows: torch.Tensor, row_offsets: torch.Tensor, index: torch.T
     `obj_center_cam`); rot (B, 3, 3) float32 = the augmentation's `rot_mat` or None; flip (B,) = dexycb's `do_flip` or None.
     -> (inputs, targets) with upstream's keys: `hand_sdf_points`, `obj_sdf_points` (, `hand_pre_points`, `obj_pre_points`)
     (B, n, 3); `hand_sdf`, `obj_sdf` (B, n)."""
-    if not rows.is_cuda:
-        raise RuntimeError("hoisdf_b200.feed runs on the GPU; got a %s tensor (no CPU fallback)" % rows.device)
+    _require_gpu(rows)
     dev = rows.device
     if rows.dtype != torch.float32 or rows.dim() != 2 or rows.shape[1] != 6 or not rows.is_contiguous():
         raise ValueError("rows must be a contiguous (total, 6) float32 tensor")
@@ -287,7 +299,7 @@ def sdf_point_sets(rows: torch.Tensor, row_offsets: torch.Tensor, index: torch.T
     obj_centre = prep(obj_centre, torch.float32, (b, 3), "obj_centre")
     rot = prep(rot, torch.float32, (b, 3, 3), "rot")
     flip = prep(flip, torch.int32, (b,), "flip")
-    with torch.cuda.device(dev):
+    with _on(dev):
         new = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float32)      # noqa: E731
         hp, op_, hs, os_ = new(b, n_hand, 3), new(b, n_obj, 3), new(b, n_hand), new(b, n_obj)
         pre = n_sel == 2 * per
@@ -297,7 +309,7 @@ def sdf_point_sets(rows: torch.Tensor, row_offsets: torch.Tensor, index: torch.T
         check(lib.hoisdf_sdf_rows_fwd(rows.data_ptr(), row_offsets.data_ptr(), index.data_ptr(), b, n_sel, n_hand, n_obj,
                                       ops._ptr(rot), ops._ptr(flip), hand_root.data_ptr(), obj_centre.data_ptr(),
                                       float(hand_scale), float(obj_scale), hp.data_ptr(), op_.data_ptr(), ops._ptr(hpre),
-                                      ops._ptr(opre), hs.data_ptr(), os_.data_ptr(), status.data_ptr(), ops._stream()),
+                                      ops._ptr(opre), hs.data_ptr(), os_.data_ptr(), status.data_ptr(), _stream()),
               "hoisdf_sdf_rows_fwd")
         if int(status.item()) != 0:
             raise IndexError("sdf_point_sets: an index lies outside its frame's rows")
@@ -312,8 +324,7 @@ JITTER_OPS = {"brightness": 1, "saturation": 2, "hue": 3, "contrast": 4}
 
 
 def _bytes_image(images: torch.Tensor, channels=(1, 3)) -> Tuple[int, int, int, int]:
-    if not images.is_cuda:
-        raise RuntimeError("hoisdf_b200.feed runs on the GPU; got a %s tensor (no CPU fallback)" % images.device)
+    _require_gpu(images)
     if images.dtype != torch.uint8 or images.dim() != 4 or images.shape[3] not in channels or not images.is_contiguous():
         raise ValueError("images must be a contiguous (B, H, W, C) uint8 tensor, C in %s" % (channels,))
     return tuple(images.shape)
@@ -328,12 +339,12 @@ def gaussian_blur(images: torch.Tensor, radii: Sequence[float]) -> torch.Tensor:
     for i, r in enumerate(np.asarray(radii, dtype=np.float64).reshape(b)):
         check(lib.hoisdf_gaussian_blur_params(float(r), 3, params[i].ctypes.data_as(ctypes.c_void_p)), "hoisdf_gaussian_blur_params")
     dev = images.device
-    with torch.cuda.device(dev):
+    with _on(dev):
         params_d = torch.from_numpy(params.view(np.int32)).to(dev)
         out, scratch = torch.empty_like(images), torch.empty_like(images)
         ops._count(2)
         check(lib.hoisdf_gaussian_blur_u8(images.data_ptr(), out.data_ptr(), scratch.data_ptr(), b, h, w, ch,
-                                          params_d.data_ptr(), 3, ops._stream()), "hoisdf_gaussian_blur_u8")
+                                          params_d.data_ptr(), 3, _stream()), "hoisdf_gaussian_blur_u8")
     return out
 
 
@@ -373,13 +384,13 @@ def color_jitter(images: torch.Tensor, steps: Sequence[Sequence[Tuple[str, float
             else:
                 factors[i, j] = f
     dev = images.device
-    with torch.cuda.device(dev):
+    with _on(dev):
         out = torch.empty_like(images)
         sums = torch.empty(4 * b, device=dev, dtype=torch.int64)
         codes_d, factors_d = torch.from_numpy(codes).to(dev), torch.from_numpy(factors).to(dev)     # (kept alive past the launch)
         ops._count(8)
         check(lib.hoisdf_color_jitter_u8(images.data_ptr(), out.data_ptr(), b, h, w, codes_d.data_ptr(), factors_d.data_ptr(),
-                                         sums.data_ptr(), ops._stream()), "hoisdf_color_jitter_u8")
+                                         sums.data_ptr(), _stream()), "hoisdf_color_jitter_u8")
     return out
 
 

@@ -1,0 +1,79 @@
+"""hoisdf_b200/feed.py's tensor-level wrappers (argument marshalling, strides, temporaries, the order of the calls in
+`train_batch`) driven on the CPU: the C entry points are taken from the EMULATED library (the same .cu files compiled for the
+host, tests/emu) and the three GPU touch points of the module (`_require_gpu`, `_on`, `_stream`) are patched for the duration of
+a test, so host tensors flow through exactly the Python code the GPU path runs.  The bodies are the ones of
+tests/test_gpu_zzz_feed.py: each GPU test of the feed is executed here against the emulator with `cuda` = the CPU device.
+Test infrastructure: the product never loads the emulated library."""
+import contextlib
+import ctypes as C
+
+import pytest
+import torch
+
+import test_gpu_zzz_feed as G
+from hoisdf_b200 import _capi, feed, ops
+from test_kernel_emulation import build_emulated
+
+FEED_ENTRY_POINTS = ("hoisdf_image_crop_fwd", "hoisdf_sdf_rows_fwd", "hoisdf_gaussian_blur_params", "hoisdf_gaussian_blur_u8",
+                     "hoisdf_color_jitter_u8")
+
+
+@pytest.fixture()
+def host(monkeypatch):
+    emu = build_emulated("feed")
+    for name in FEED_ENTRY_POINTS:
+        restype, argtypes = _capi.SIGNATURES[name]
+        getattr(emu, name).restype, getattr(emu, name).argtypes = restype, argtypes
+    monkeypatch.setattr(feed, "lib", emu)
+    monkeypatch.setattr(feed, "_require_gpu", lambda t: None)
+    monkeypatch.setattr(feed, "_on", lambda dev: contextlib.nullcontext())
+    monkeypatch.setattr(feed, "_stream", lambda: None)
+    return torch.device("cpu")
+
+
+def test_evaluation_crop_batch(host):
+    G.test_evaluation_crop_batch_vs_oracle_and_fixture(host)
+
+
+def test_rotated_warp_and_masks(host):
+    G.test_rotated_warp_and_masks_vs_oracle_and_fixture(host)
+
+
+@pytest.mark.parametrize("h,w,size", [(37, 53, 19), (5, 7, 33)])
+def test_ragged_sizes(host, h, w, size):
+    G.test_ragged_sizes_and_out_of_frame_windows(host, h, w, size)
+
+
+def test_sdf_point_sets(host):
+    G.test_sdf_point_sets_vs_oracle(host, True, True, False)
+    G.test_sdf_point_sets_vs_oracle(host, False, False, True)
+
+
+def test_training_item(host):
+    G.test_training_item_reproduces_the_upstream_fixture(host)
+
+
+def test_mirrored_warp(host):
+    G.test_mirrored_warp_equals_warping_the_mirrored_frame(host)
+
+
+def test_gaussian_blur(host):
+    G.test_gaussian_blur_vs_pillow(host)
+
+
+def test_color_jitter(host):
+    G.test_color_jitter_vs_torchvision(host)
+
+
+def test_training_image(host):
+    G.test_training_image_reproduces_the_upstream_fixture(host)
+
+
+def test_train_batch(host):
+    G.test_train_batch_reproduces_the_upstream_item(host)
+
+
+def test_the_patches_are_gone_afterwards():
+    assert feed.lib is _capi.lib and feed._stream.__module__ == "hoisdf_b200.feed"
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        feed.to_tensor(torch.zeros(1, 4, 4, 3, dtype=torch.uint8))
