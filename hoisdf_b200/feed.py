@@ -32,7 +32,8 @@ from ._capi import check, lib
 __all__ = ["bbox_from_points", "fuse_boxes", "crop_affine", "apply_affine", "pil_coefficients", "resize_coefficients",
            "crop_geometry", "crop_geometry_dexycb", "crop_images", "crop_masks", "data_crop", "draw_sdf_indices", "sdf_point_sets",
            "gaussian_blur", "draw_color_jitter", "color_jitter", "to_tensor",
-           "draw_train_geometry", "train_geometry", "train_batch"]
+           "draw_train_geometry", "train_geometry", "train_batch",
+           "eval_geometry", "eval_batch"]
 
 
 
@@ -499,3 +500,57 @@ def train_batch(frames: torch.Tensor, hand_masks: torch.Tensor, obj_masks: torch
         targets[key] = stack(key)
     meta = {key: stack(key) for key in ("cam_intr", "mano_root", "obj_center_cam", "bbox_hand", "bbox_obj")}
     return inputs, targets, meta
+
+
+# ---------------------------------------------------------------------------------------------- evaluation sample (main/test.py's feed)
+def eval_geometry(annotation: Dict, obj_bbox3d: np.ndarray, img_size: Sequence[int], obj_depth_mean_value: float, res: int = 256
+                  ) -> Dict[str, np.ndarray]:
+    """Everything of one HO3D EVALUATION sample that is not pixels (the `else` branch of `__getitem__`, ho3d.py:591-660): from the
+    frame's annotation dict (`meta/*.pkl`: camMat, objRot, objTrans, handBoundingBox, handJoints3D, objName) and the object's 3-D
+    box corners -- corner projection (ho3d_util.py:44-63), `data_crop`'s geometry, the root joint in camera axes, the object
+    centre at the mean depth, the object pose in OpenCV axes (dataset_util.py:27-35).
+    -> {"coef" (6,), `obj_rot`, `rel_obj_trans` (targets), `cam_intr`, `mano_root`, `obj_center_cam`, `bbox_hand`, `bbox_obj`,
+    `obj_mask`, `obj_cls` (meta_info)}."""
+    import cv2
+    K = np.array(annotation["camMat"], dtype=np.float32)
+    pose = np.zeros((4, 4))
+    pose[:3, 3] = annotation["objTrans"]
+    pose[3, 3] = 1
+    pose[:3, :3] = cv2.Rodrigues(annotation["objRot"].reshape((3,)))[0]
+    pose[1, :] = -pose[1, :]                                   # OpenGL -> camera axes
+    pose[2, :] = -pose[2, :]
+    corners = np.array(obj_bbox3d)
+    uv = np.matmul(np.array(K), np.matmul(pose[:3, :3], corners.T) + pose[:3, 3].reshape(-1, 1)).T
+    p2d = uv[:, :2] / uv[:, -1:]
+    flip = np.array([[1.0, 0.0, 0.0], [0, -1.0, 0.0], [0.0, 0.0, -1.0]], dtype=np.float32)
+    root = np.array(annotation["handJoints3D"], dtype=np.float32).dot(flip.T)
+    coef, geo = crop_geometry(K[None], np.array(annotation["handBoundingBox"], dtype=np.float32)[None], p2d[None], img_size, res)
+    K, bbox_obj = geo["cam_intr"][0], geo["bbox_obj"][0]
+    c = np.asarray([int((bbox_obj[2] + bbox_obj[0]) / 2), int((bbox_obj[3] + bbox_obj[1]) / 2), obj_depth_mean_value])
+    centre_cam = np.array([(c[0] - K[0, 2]) / K[0, 0] * c[2], (c[1] - K[1, 2]) / K[1, 1] * c[2], c[2]]).astype(np.float32)
+    change = np.array([[1.0, 0.0, 0.0], [0.0, -1.0, 0.0], [0.0, 0.0, -1.0]])
+    obj_pose = annotation["objRot"].squeeze()
+    obj_rot = obj_pose.copy()
+    obj_rot[:3] = cv2.Rodrigues(change.dot(cv2.Rodrigues(obj_pose[:3])[0]))[0][:, 0]
+    obj_trans = annotation["objTrans"].copy().dot(change.T).astype(np.float32) - centre_cam
+    name = annotation["objName"]
+    return {"coef": coef[0], "obj_rot": obj_rot, "rel_obj_trans": obj_trans.astype(np.float32), "cam_intr": K, "mano_root": root,
+            "obj_center_cam": centre_cam, "bbox_hand": geo["bbox_hand"][0], "bbox_obj": bbox_obj, "obj_cls": name,
+            "obj_mask": name in ("021_bleach_cleanser", "006_mustard_bottle", "010_potted_meat_can")}
+
+
+def eval_batch(frames: torch.Tensor, samples: Sequence[Dict], res: int = 256):
+    """One collated HO3D evaluation batch -- what `main/test.py:120-126` feeds to `model(inputs, targets, meta_info, "eval")` --
+    from the decoded frames (B, H, W, 3) uint8 on the GPU and `eval_geometry`'s per-frame dicts.
+    -> (inputs {"img"}, targets {"obj_rot", "rel_obj_trans"}, meta_info {"cam_intr", "mano_root", "obj_center_cam", "bbox_hand",
+    "bbox_obj", "obj_mask" (tensors), "obj_cls", "hand_type" (lists, as default_collate leaves strings)})."""
+    dev = frames.device
+    if len(samples) != frames.shape[0]:
+        raise ValueError("one sample dict per frame")
+    img = crop_images(frames, np.stack([s["coef"] for s in samples]), res)
+    stack = lambda key: torch.from_numpy(np.stack([np.asarray(s[key], dtype=np.float32) for s in samples])).to(dev)  # noqa: E731
+    meta = {key: stack(key) for key in ("cam_intr", "mano_root", "obj_center_cam", "bbox_hand", "bbox_obj")}
+    meta["obj_mask"] = torch.tensor([bool(s["obj_mask"]) for s in samples], device=dev)
+    meta["obj_cls"] = [s["obj_cls"] for s in samples]
+    meta["hand_type"] = ["right"] * len(samples)
+    return {"img": img}, {"obj_rot": stack("obj_rot"), "rel_obj_trans": stack("rel_obj_trans")}, meta

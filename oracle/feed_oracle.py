@@ -182,3 +182,18 @@ def synthetic_annotation(seed):
             "obj_p3d": rng.uniform(-0.1, 0.1, (21, 3)).astype(np.float32) + np.array([0, 0, 0.6], np.float32),
             "obj_rot": rng.uniform(-1, 1, 3).astype(np.float32), "obj_trans": np.array([0.02, -0.03, 0.6], np.float32),
             "obj_depth_mean_value": 0.7}
+
+
+def synthetic_eval_annotation(seed):
+    """One `meta/*.pkl` dict of an HO3D evaluation frame (the keys ho3d.py:606-631 reads) + the object's 3-D box corners,
+    synthetic: OpenGL-axes object pose in front of the camera, a hand box, a root joint."""
+    img, K, bbox_hand, _ = synthetic_frame(seed)
+    rng = np.random.default_rng(4000 + seed)
+    half = rng.uniform(0.03, 0.09, 3)
+    signs = np.array([[x, y, z] for x in (-1, 1) for y in (-1, 1) for z in (-1, 1)], dtype=np.float64)
+    corners = np.concatenate([signs * half, np.zeros((1, 3))]).astype(np.float32)          # 8 corners + the centre
+    ann = {"camMat": K.astype(np.float64), "objName": ["003_cracker_box", "021_bleach_cleanser"][seed % 2],
+           "objRot": rng.uniform(-1.5, 1.5, (3, 1)), "objTrans": np.array([rng.uniform(-0.08, 0.08), rng.uniform(-0.08, 0.08),
+                                                                            -rng.uniform(0.5, 0.8)]),
+           "handBoundingBox": [float(v) for v in bbox_hand], "handJoints3D": rng.uniform(-0.1, 0.1, 3) + np.array([0, 0, -0.6])}
+    return img, ann, corners

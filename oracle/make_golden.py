@@ -309,6 +309,12 @@ def feed_case(name, seed, n_eval, n_aug):
                               Image.fromarray(os_))
     fix.update(dex_uv_in=uv, dex_bbox_hand=ref[1], dex_bbox_obj=ref[2], dex_K=ref[3], dex_joints_uv=ref[4], dex_p2d=ref[5],
                dex_hand_seg=ref[6], dex_obj_seg=ref[7], dex_img_rows=np.asarray(ref[0])[::32].copy())
+    # one EVALUATION sample through the unmodified `Dataset.__getitem__` (oracle/reference_shim.py:ho3d_eval_item)
+    e_in, e_t, e_m = rs.ho3d_eval_item(seed)
+    fix.update(evi_img_rows=e_in["img"].numpy()[:, ::8].copy(), evi_obj_rot=e_t["obj_rot"], evi_rel_obj_trans=e_t["rel_obj_trans"],
+               evi_obj_mask=e_m["obj_mask"], evi_obj_cls=np.array(e_m["obj_cls"]))
+    for k in ("cam_intr", "mano_root", "obj_center_cam", "bbox_hand", "bbox_obj"):
+        fix["evi_" + k] = e_m[k]
     # one whole training sample through the unmodified `Dataset.__getitem__` (oracle/reference_shim.py:ho3d_train_item): the
     # SDF point sets + masks it returns and the draws / augmentation arguments needed to reproduce them
     inputs, targets, meta, taps = rs.ho3d_train_item(seed)

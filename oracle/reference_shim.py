@@ -241,3 +241,37 @@ def ho3d_train_item(seed, n_hand=24, n_obj=8, filters=False):
         import shutil
         shutil.rmtree(scratch, ignore_errors=True)
     return inputs, targets, meta, taps
+
+
+def ho3d_eval_item(seed):
+    """ONE evaluation sample through the UNMODIFIED upstream `data.ho3d.Dataset.__getitem__` (the `else` branch, ho3d.py:591-660;
+    what main/test.py's loader yields): a synthetic sequence directory (rgb/0000.png + meta/0000.pkl) in a scratch root, the
+    dataset object made with `__new__` and given the attributes that branch reads.  Returns (inputs, targets, meta_info)."""
+    import pickle
+    import shutil
+
+    import numpy as np
+    from PIL import Image
+    import torchvision.transforms as transforms
+
+    from oracle import feed_oracle as FO
+
+    H = load_data_modules()["ho3d"]
+    img, ann, corners = FO.synthetic_eval_annotation(seed)
+    root = tempfile.mkdtemp(prefix="hoisdf_feed_eval_")
+    seq = os.path.join(root, "evaluation", "SEQ1")
+    os.makedirs(os.path.join(seq, "rgb"))
+    os.makedirs(os.path.join(seq, "meta"))
+    Image.fromarray(img).save(os.path.join(seq, "rgb", "0000.png"))
+    with open(os.path.join(seq, "meta", "0000.pkl"), "wb") as f:
+        pickle.dump(ann, f)
+    ds = H.Dataset.__new__(H.Dataset)
+    ds.mode, ds.root, ds.set_list = "evaluation", root, ["SEQ1/0000"]
+    ds.obj_bbox3d = {ann["objName"]: corners}
+    ds.coord_change_mat = np.array([[1.0, 0.0, 0.0], [0, -1.0, 0.0], [0.0, 0.0, -1.0]], dtype=np.float32)
+    ds.obj_depth_mean_value, ds.inp_res = 0.7, 256
+    ds.transform = transforms.ToTensor()
+    try:
+        return ds[0]
+    finally:
+        shutil.rmtree(root, ignore_errors=True)

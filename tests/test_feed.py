@@ -436,3 +436,35 @@ def test_training_sample_host_geometry_matches_golden():
     for k in META_KEYS:
         assert np.array_equal(sample[k], g["filt_m_" + k]), k
     assert sample["blur_radius"] == float(g["filt_radius"]) and [n for n, _ in sample["jitter"]] == [str(n) for n in g["filt_order"]]
+
+
+# ---------------------------------------------------------------------------------------------- evaluation sample
+EVAL_META = ("cam_intr", "mano_root", "obj_center_cam", "bbox_hand", "bbox_obj")
+
+
+@pytest.mark.skipif(not rs.available(), reason="upstream reference not mounted")
+def test_evaluation_sample_matches_upstream_live(emu):
+    """The unmodified `Dataset.__getitem__` in evaluation mode (what main/test.py's loader yields) on a synthetic sequence
+    directory against `eval_geometry` + the emulated crop kernel: image, targets and meta_info, values and dtypes."""
+    for seed in range(4):
+        inputs, targets, meta = rs.ho3d_eval_item(seed)
+        img, ann, corners = FO.synthetic_eval_annotation(seed)
+        g = feed.eval_geometry(ann, corners, (640, 480), 0.7)
+        for k in ("obj_rot", "rel_obj_trans"):
+            assert np.array_equal(g[k], targets[k]) and g[k].dtype == targets[k].dtype, k
+        for k in EVAL_META:
+            assert np.array_equal(g[k], meta[k]) and g[k].dtype == meta[k].dtype, k
+        assert g["obj_mask"] == meta["obj_mask"] and g["obj_cls"] == meta["obj_cls"]
+        got, _ = emu_warp(emu, img[None], g["coef"][None], 256)
+        assert np.array_equal(got[0], inputs["img"].numpy())
+
+
+def test_evaluation_sample_matches_golden(emu):
+    g = np.load(GOLDEN)
+    img, ann, corners = FO.synthetic_eval_annotation(int(g["seed"]))
+    s = feed.eval_geometry(ann, corners, (640, 480), 0.7)
+    for k in ("obj_rot", "rel_obj_trans") + EVAL_META:
+        assert np.array_equal(s[k], g["evi_" + k]), k
+    assert s["obj_mask"] == bool(g["evi_obj_mask"]) and s["obj_cls"] == str(g["evi_obj_cls"])
+    got, _ = emu_warp(emu, img[None], s["coef"][None], 256)
+    assert np.array_equal(got[0][:, ::8], g["evi_img_rows"])

@@ -264,3 +264,39 @@ def test_train_batch_reproduces_the_upstream_item(cuda):
     for d in (inputs, targets, meta):
         for k, v in d.items():
             assert torch.equal(v[0], v[2]), k
+
+
+def test_eval_batch_reproduces_the_upstream_item(cuda):
+    """`feed.eval_batch` at BASELINE configs[1]'s batch (32 frames; the fixture's frame first and last) against one sample of
+    the unmodified upstream `Dataset.__getitem__` in evaluation mode -- the feed of main/test.py's loop."""
+    from hoisdf_b200 import feed
+    g = np.load(GOLDEN)
+    seed = int(g["seed"])
+    picks = [seed] + list(range(100, 130)) + [seed]
+    raw = [FO.synthetic_eval_annotation(s) for s in picks]
+    samples = [feed.eval_geometry(ann, corners, (640, 480), 0.7) for _, ann, corners in raw]
+    inputs, targets, meta = feed.eval_batch(torch.from_numpy(np.stack([r[0] for r in raw])).to(cuda), samples)
+    assert inputs["img"].shape == (32, 3, 256, 256) and meta["obj_mask"].dtype == torch.bool and len(meta["obj_cls"]) == 32
+    for i in (0, 31):
+        assert np.array_equal(inputs["img"][i].cpu().numpy()[:, ::8], g["evi_img_rows"])
+        for k in ("obj_rot", "rel_obj_trans"):
+            assert np.allclose(targets[k][i].cpu().numpy(), g["evi_" + k], rtol=1e-5, atol=1e-5), k
+        for k in ("cam_intr", "mano_root", "obj_center_cam", "bbox_hand", "bbox_obj"):
+            assert np.allclose(meta[k][i].cpu().numpy(), g["evi_" + k], rtol=1e-5, atol=1e-4), k
+        assert bool(meta["obj_mask"][i]) == bool(g["evi_obj_mask"]) and meta["obj_cls"][i] == str(g["evi_obj_cls"])
+    for i, (img, ann, corners) in enumerate(raw):                     # every frame against the oracle's data_crop
+        K = np.array(ann["camMat"], dtype=np.float32)
+        want = FO.data_crop(img, K, np.array(ann["handBoundingBox"], dtype=np.float32), _project(ann, corners, K))[0]
+        assert np.array_equal(inputs["img"][i].cpu().numpy(), want), i
+
+
+def _project(ann, corners, K):
+    """data/ho3d_util.py:44-63 (test-side restatement for the oracle call above)."""
+    import cv2
+    pose = np.zeros((4, 4))
+    pose[:3, 3] = ann["objTrans"]
+    pose[:3, :3] = cv2.Rodrigues(ann["objRot"].reshape((3,)))[0]
+    pose[1, :] = -pose[1, :]
+    pose[2, :] = -pose[2, :]
+    uv = np.matmul(np.array(K), np.matmul(pose[:3, :3], np.array(corners).T) + pose[:3, 3].reshape(-1, 1)).T
+    return uv[:, :2] / uv[:, -1:]
