@@ -4,7 +4,7 @@ data/dexycb.py likewise -- for a whole batch of frames that are already in devic
 
 Upstream warps every frame with PIL (`dataset_util.transform_img`, data/dataset_util.py:44-51: an affine `Image.transform` with
 PIL's default NEAREST resampling), shrinks the two segmentation masks with `Image.resize((64, 64), NEAREST)` and ships float
-tensors; here the raw 8-bit frames are uploaded once (3 bytes per pixel instead of 12) and `hoisdf_image_crop_fwd` produces the
+tensors; here the raw 8-bit frames are uploaded once and `hoisdf_image_crop_fwd` produces the
 `(B, 3, res, res)` network input and the `(B, 64, 64)` masks, bit-exact with Pillow.  The geometry that comes with the crop --
 bounding boxes, the fused crop window, the affine matrix, the updated camera intrinsics -- is a few dozen floating-point
 operations per frame and stays on the host in numpy, with the arithmetic (float64 intermediates, `int()` truncations, float32
