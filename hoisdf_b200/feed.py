@@ -490,7 +490,7 @@ def train_batch(frames: torch.Tensor, hand_masks: torch.Tensor, obj_masks: torch
     coef = np.stack([s["coef"] for s in samples])
     warped = crop_images(frames, coef, res, as_bytes=True)
     img = to_tensor(color_jitter(gaussian_blur(warped, [s["blur_radius"] for s in samples]), [s["jitter"] for s in samples]))
-    stack = lambda key, dtype=np.float32: torch.from_numpy(np.stack([np.asarray(s[key]) for s in samples]).astype(dtype)).to(dev)  # noqa: E731
+    stack = lambda key: torch.from_numpy(np.stack([np.asarray(s[key]) for s in samples])).to(dev)  # noqa: E731  (dtypes as upstream's collate)
     inputs, targets = sdf_point_sets(rows, row_offsets, torch.from_numpy(np.stack([s["index"] for s in samples])), n_hand, n_obj,
                                      stack("mano_root"), stack("obj_center_cam"), hand_sdf_scale, obj_sdf_scale,
                                      rot=stack("rot_mat"))
@@ -548,7 +548,7 @@ def eval_batch(frames: torch.Tensor, samples: Sequence[Dict], res: int = 256):
     if len(samples) != frames.shape[0]:
         raise ValueError("one sample dict per frame")
     img = crop_images(frames, np.stack([s["coef"] for s in samples]), res)
-    stack = lambda key: torch.from_numpy(np.stack([np.asarray(s[key], dtype=np.float32) for s in samples])).to(dev)  # noqa: E731
+    stack = lambda key: torch.from_numpy(np.stack([np.asarray(s[key]) for s in samples])).to(dev)  # noqa: E731  (dtypes as upstream's collate)
     meta = {key: stack(key) for key in ("cam_intr", "mano_root", "obj_center_cam", "bbox_hand", "bbox_obj")}
     meta["obj_mask"] = torch.tensor([bool(s["obj_mask"]) for s in samples], device=dev)
     meta["obj_cls"] = [s["obj_cls"] for s in samples]
