@@ -300,3 +300,37 @@ def _project(ann, corners, K):
     pose[2, :] = -pose[2, :]
     uv = np.matmul(np.array(K), np.matmul(pose[:3, :3], np.array(corners).T) + pose[:3, 3].reshape(-1, 1)).T
     return uv[:, :2] / uv[:, -1:]
+
+
+def test_eval_batch_feeds_the_model(cuda):
+    """Raw frames -> `feed.eval_batch` -> `Model.forward(..., "eval")`: the collated dicts are consumable as they are (upstream's
+    keys and dtypes, incl. the float64 `obj_rot` target and the string entries of meta_info), and the outputs equal those of
+    the same forward on an image batch assembled from the ORACLE's `data_crop` -- main/test.py:120-126 end to end."""
+    from hoisdf_b200 import feed, synthetic as syn
+    from hoisdf_b200.config import cfg
+    from hoisdf_b200.model import get_model
+    old = (cfg.setting, cfg.dataset, cfg.num_samp_hand, cfg.num_samp_obj)
+    try:
+        cfg.set_setting("ho3d")
+        type(cfg).dataset = "ho3d"
+        type(cfg).num_samp_hand, type(cfg).num_samp_obj = 96, 40
+        model = get_model("test", mano_buffers=syn.mano_buffers(5))
+        model.load_state_dict(syn.full_state_dict(5, "ho3d"), strict=True)
+        model = model.to(cuda).eval()
+        raw = [FO.synthetic_eval_annotation(s) for s in (100, 101, 102, 103)]
+        samples = [feed.eval_geometry(ann, corners, (640, 480), 0.7) for _, ann, corners in raw]
+        inputs, targets, meta = feed.eval_batch(torch.from_numpy(np.stack([r[0] for r in raw])).to(cuda), samples)
+        out = model(inputs, targets, meta, "eval")
+        crops = []
+        for img, ann, corners in raw:
+            K = np.array(ann["camMat"], dtype=np.float32)
+            crops.append(FO.data_crop(img, K, np.array(ann["handBoundingBox"], dtype=np.float32), _project(ann, corners, K))[0])
+        want = model({"img": torch.from_numpy(np.stack(crops)).to(cuda)}, targets, meta, "eval")
+        for k in ("hand_joints_out", "mano_joints_out", "mano_mesh_out", "obj_rot_out", "obj_trans_out"):
+            assert out[k].shape[0] == 4 and torch.isfinite(out[k]).all(), k
+            err = float((out[k] - want[k]).abs().max()) / max(float(want[k].abs().max()), 1e-12)
+            assert err < 1e-5, (k, err)
+    finally:
+        cfg.set_setting(old[0])
+        type(cfg).dataset = old[1]
+        type(cfg).num_samp_hand, type(cfg).num_samp_obj = old[2], old[3]
