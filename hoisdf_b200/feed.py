@@ -33,7 +33,7 @@ __all__ = ["bbox_from_points", "fuse_boxes", "crop_affine", "apply_affine", "pil
            "crop_geometry", "crop_geometry_dexycb", "crop_images", "crop_masks", "data_crop", "draw_sdf_indices", "sdf_point_sets",
            "gaussian_blur", "draw_color_jitter", "color_jitter", "to_tensor",
            "draw_train_geometry", "train_geometry", "train_batch",
-           "eval_geometry", "eval_batch"]
+           "eval_geometry", "eval_batch", "dexycb_eval_geometry", "dexycb_eval_batch"]
 
 
 
@@ -554,3 +554,88 @@ def eval_batch(frames: torch.Tensor, samples: Sequence[Dict], res: int = 256):
     meta["obj_cls"] = [s["obj_cls"] for s in samples]
     meta["hand_type"] = ["right"] * len(samples)
     return {"img": img}, {"obj_rot": stack("obj_rot"), "rel_obj_trans": stack("rel_obj_trans")}, meta
+
+
+# ---------------------------------------------------------------------------------------------- DexYCB evaluation sample
+def dexycb_eval_geometry(sample_info: Dict, components_right: np.ndarray, components_left: np.ndarray, handmean: np.ndarray,
+                         obj_bbox3d: np.ndarray, img_size: Sequence[int], res: int = 256, heatmap_res: int = 64
+                         ) -> Dict[str, np.ndarray]:
+    """Everything of one DexYCB TEST sample that is not pixels or SDF rows (data/dexycb.py:409-514,584-596,627-655): intrinsics
+    from the annotation, the MANO pose from PCA to axis-angle (right or left components), the left-hand mirror (x-flip of the
+    joints, principal point, object pose; re-projection of the object corners), `data_crop`'s geometry, root joint, object centre
+    at the ROOT's depth.  `sample_info` = the entry of DexYCB's `sample_dict`; `obj_bbox3d` = the grasped object's box corners.
+    -> {"coef" (6,), "flip" (bool: pass as `mirror` to the warps and `flip` to `sdf_point_sets`), and upstream's entries:
+    `joint_coord`, `joint_cam_no_trans`, `obj_rot`, `rel_obj_trans`, `mano_param` (targets), `cam_intr`, `mano_root`,
+    `obj_center_cam`, `bbox_hand`, `bbox_obj` (float64 here, as upstream), `obj_cls` (meta_info)}."""
+    import cv2
+    flip = sample_info["mano_side"] == "left"
+    width = img_size[0]
+    intr = sample_info["intrinsics"]
+    K = np.zeros((3, 3))
+    K[0, 0], K[1, 1], K[0, 2], K[1, 2], K[2, 2] = intr["fx"], intr["fy"], intr["ppx"], intr["ppy"], 1
+    pca = np.array(sample_info["pose_m"], dtype=np.float32).squeeze()
+    betas = np.array(sample_info["mano_betas"], dtype=np.float32)
+    joints_3d = np.array(sample_info["joint_3d"], dtype=np.float32).squeeze()
+    joints_uv = np.array(sample_info["joint_2d"], dtype=np.float32).squeeze()
+    comps = components_left if flip else components_right
+    pose = np.concatenate((pca[0:3], np.matmul(pca[3:48], comps.copy()), pca[48:]), axis=0)
+    if flip:
+        turned = pose[:48].reshape(-1, 3)
+        turned[:, 1:] *= -1
+        pose[0:48] = turned.reshape(-1)
+        joints_3d[:, 0] *= -1
+        joints_uv[:, 0] = np.array(width, dtype=np.float32) - joints_uv[:, 0] - 1
+    mano_param = np.concatenate((np.concatenate((pose[:3], pose[3:48] + handmean.copy()), axis=0), betas))
+    grasp = np.array(sample_info["pose_y"][sample_info["ycb_grasp_ind"]], dtype=np.float32)
+    corners = np.asarray(obj_bbox3d).copy()
+
+    def project(rt):
+        cam = (np.matmul(rt[:3, :3], corners.T) + rt[:3, 3].reshape(-1, 1)).T
+        uv = np.matmul(K, np.matmul(rt[:3, :3], corners.T) + rt[:3, 3].reshape(-1, 1)).T
+        return cam, uv[:, :2] / uv[:, -1:]
+
+    p3d, p2d = project(grasp)
+    obj_rot = cv2.Rodrigues(grasp[:, :3])[0].squeeze()
+    obj_trans = grasp[:, 3]
+    if flip:
+        K[0, 2] = width - K[0, 2] - 1
+        obj_trans[0] *= -1
+        obj_rot[1:] *= -1
+        p3d, p2d = project(np.concatenate([cv2.Rodrigues(obj_rot)[0], obj_trans[:, None]], axis=1))
+    coef, geo = crop_geometry_dexycb(K[None], joints_uv[None], p2d[None], img_size, res, heatmap_res)
+    K, bbox_obj = geo["cam_intr"][0], geo["bbox_obj"][0]
+    root = joints_3d[0].copy()
+    c = np.asarray([int((bbox_obj[2] + bbox_obj[0]) / 2), int((bbox_obj[3] + bbox_obj[1]) / 2), root[-1]])
+    centre_cam = np.array([(c[0] - K[0, 2]) / K[0, 0] * c[2], (c[1] - K[1, 2]) / K[1, 1] * c[2], c[2]]).astype(np.float32)
+    return {"coef": coef[0], "flip": flip, "joint_coord": geo["joints_uv"][0].astype(np.float32),
+            "joint_cam_no_trans": (joints_3d - root[None]) * 1000, "obj_rot": obj_rot,
+            "rel_obj_trans": (obj_trans.astype(np.float32) - centre_cam).astype(np.float32),
+            "mano_param": mano_param.astype(np.float32), "cam_intr": K.astype(np.float32), "mano_root": root,
+            "obj_center_cam": centre_cam, "bbox_hand": geo["bbox_hand"][0], "bbox_obj": bbox_obj,
+            "obj_cls": sample_info["ycb_ids"][sample_info["ycb_grasp_ind"]], "p2d": geo["p2d"][0], "p3d": p3d - centre_cam[None]}
+
+
+def dexycb_eval_batch(frames: torch.Tensor, hand_masks: torch.Tensor, obj_masks: torch.Tensor, rows: torch.Tensor,
+                      row_offsets: torch.Tensor, samples: Sequence[Dict], n_hand: int, n_obj: int, hand_sdf_scale: float,
+                      obj_sdf_scale: float, res: int = 256, heatmap_res: int = 64):
+    """One collated DexYCB test batch (BASELINE configs[2]'s feed; data/dexycb.py:627-657) from the raw material on the GPU:
+    frames (B, H, W, 3) uint8 and masks (B, H, W) uint8 UN-mirrored, the frames' packed SDF rows, and per frame
+    `dexycb_eval_geometry(...)`'s dict + "index" (`draw_sdf_indices(rows, n_hand_rows, n_hand, n_obj)`).
+    -> (inputs, targets, meta_info) with upstream's keys (`hand_pre_points` / `obj_pre_points` are False, as upstream)."""
+    dev = frames.device
+    if len(samples) != frames.shape[0]:
+        raise ValueError("one sample dict per frame")
+    coef = np.stack([s["coef"] for s in samples])
+    mirror = np.array([bool(s["flip"]) for s in samples])
+    stack = lambda key: torch.from_numpy(np.stack([np.asarray(s[key]) for s in samples])).to(dev)  # noqa: E731
+    inputs, targets = sdf_point_sets(rows, row_offsets, torch.from_numpy(np.stack([s["index"] for s in samples])), n_hand, n_obj,
+                                     stack("mano_root"), stack("obj_center_cam"), hand_sdf_scale, obj_sdf_scale,
+                                     flip=torch.from_numpy(mirror.astype(np.int32)))
+    inputs.update(img=crop_images(frames, coef, res, mirror=mirror), hand_pre_points=False, obj_pre_points=False)
+    targets.update(hand_seg=crop_masks(hand_masks, coef, res, heatmap_res, mirror=mirror),
+                   obj_seg=crop_masks(obj_masks, coef, res, heatmap_res, mirror=mirror))
+    for key in ("joint_coord", "joint_cam_no_trans", "obj_rot", "rel_obj_trans", "mano_param"):
+        targets[key] = stack(key)
+    meta = {key: stack(key) for key in ("cam_intr", "mano_root", "obj_center_cam", "bbox_hand", "bbox_obj")}
+    meta["obj_cls"] = torch.tensor([int(s["obj_cls"]) for s in samples], device=dev)
+    return inputs, targets, meta

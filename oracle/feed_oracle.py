@@ -197,3 +197,31 @@ def synthetic_eval_annotation(seed):
                                                                             -rng.uniform(0.5, 0.8)]),
            "handBoundingBox": [float(v) for v in bbox_hand], "handJoints3D": rng.uniform(-0.1, 0.1, 3) + np.array([0, 0, -0.6])}
     return img, ann, corners
+
+
+def synthetic_dexycb_sample(seed, left=None):
+    """One `sample_dict` entry of DexYCB in the layout `dexycb.Dataset.__getitem__` reads (dexycb.py:411-418,434-437,487-498) +
+    the arrays the dataset object holds (MANO PCA components / mean, the object's 3-D box corners), synthetic and deterministic.
+    -> (frame (480, 640, 3) uint8, hand mask, obj mask, sample_info dict, holders dict)."""
+    img, hand_mask, obj_mask = synthetic_aug(seed)[:3]
+    _, K, _, _ = synthetic_frame(seed)
+    rng = np.random.default_rng(5000 + seed)
+    left = bool(seed % 2) if left is None else left
+    joints_3d = rng.uniform(-0.09, 0.09, (21, 3)) + np.array([rng.uniform(-0.05, 0.05), rng.uniform(-0.05, 0.05), 0.65])
+    uvw = joints_3d.dot(K.astype(np.float64).T)
+    half = rng.uniform(0.03, 0.08, 3)
+    signs = np.array([[x, y, z] for x in (-1, 1) for y in (-1, 1) for z in (-1, 1)], dtype=np.float64)
+    corners = np.concatenate([signs * half, np.zeros((1, 3))]).astype(np.float32)
+    th = rng.uniform(-1, 1, 3)
+    import cv2
+    R = cv2.Rodrigues(th)[0]
+    pose_y = np.concatenate([R, np.array([[rng.uniform(-0.06, 0.06)], [rng.uniform(-0.06, 0.06)], [0.7]])], axis=1)
+    info = {"mano_side": "left" if left else "right", "color_file": "frame_%d.jpg.png" % seed,
+            "intrinsics": {"fx": float(K[0, 0]), "fy": float(K[1, 1]), "ppx": float(K[0, 2]), "ppy": float(K[1, 2])},
+            "pose_m": rng.uniform(-0.6, 0.6, (1, 51)).tolist(), "mano_betas": rng.uniform(-1, 1, 10).tolist(),
+            "joint_3d": joints_3d[None].tolist(), "joint_2d": (uvw[:, :2] / uvw[:, 2:])[None].tolist(),
+            "pose_y": [np.zeros((3, 4)).tolist(), pose_y.tolist()], "ycb_grasp_ind": 1, "ycb_ids": [7, 3 + seed % 5]}
+    holders = {"components_right": rng.standard_normal((45, 45)).astype(np.float32) * 0.2,
+               "components_left": rng.standard_normal((45, 45)).astype(np.float32) * 0.2,
+               "handmean": rng.uniform(-0.2, 0.2, 45).astype(np.float32), "obj_bbox3d": {info["ycb_ids"][1]: corners}}
+    return img, hand_mask, obj_mask, info, holders

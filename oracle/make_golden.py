@@ -315,6 +315,16 @@ def feed_case(name, seed, n_eval, n_aug):
                evi_obj_mask=e_m["obj_mask"], evi_obj_cls=np.array(e_m["obj_cls"]))
     for k in ("cam_intr", "mano_root", "obj_center_cam", "bbox_hand", "bbox_obj"):
         fix["evi_" + k] = e_m[k]
+    # one DexYCB TEST sample of a LEFT hand (mirror path) through the unmodified `dexycb.Dataset.__getitem__`
+    d_in, d_t, d_m, d_taps = rs.dexycb_test_item(seed, left=True)
+    fix.update(dxi_img_rows=d_in["img"].numpy()[:, ::8].copy(), dxi_draws=np.concatenate(d_taps["draws"]).astype(np.int64),
+               dxi_hand_seg=d_t["hand_seg"].numpy(), dxi_obj_seg=d_t["obj_seg"].numpy(), dxi_obj_cls=d_m["obj_cls"])
+    for k in ("hand_sdf_points", "obj_sdf_points"):
+        fix["dxi_" + k] = d_in[k]
+    for k in ("joint_coord", "joint_cam_no_trans", "obj_rot", "rel_obj_trans", "mano_param", "hand_sdf", "obj_sdf"):
+        fix["dxi_" + k] = d_t[k]
+    for k in ("cam_intr", "mano_root", "obj_center_cam", "bbox_hand", "bbox_obj"):
+        fix["dxi_" + k] = d_m[k]
     # one whole training sample through the unmodified `Dataset.__getitem__` (oracle/reference_shim.py:ho3d_train_item): the
     # SDF point sets + masks it returns and the draws / augmentation arguments needed to reproduce them
     inputs, targets, meta, taps = rs.ho3d_train_item(seed)

@@ -275,3 +275,54 @@ def ho3d_eval_item(seed):
         return ds[0]
     finally:
         shutil.rmtree(root, ignore_errors=True)
+
+
+def dexycb_test_item(seed, n_hand=24, n_obj=8, left=None):
+    """ONE sample through the UNMODIFIED upstream `data.dexycb.Dataset.__getitem__` in test mode (dexycb.py:409-657; the feed
+    of BASELINE configs[2]'s evaluation): synthetic colour file + packed SDF .npy in a scratch directory, dataset object made
+    with `__new__` and given the attributes that method reads.  Returns (inputs, targets, meta_info, taps) -- taps: the draws."""
+    import shutil
+
+    import numpy as np
+    from PIL import Image
+    import torchvision.transforms as transforms
+
+    from oracle import feed_oracle as FO
+
+    load_data_modules()
+    import data.dexycb as D
+
+    img, hand_mask, obj_mask, info, holders = FO.synthetic_dexycb_sample(seed, left)
+    sdf, nh = FO.synthetic_sdf_frame(seed, n_hand, n_obj)[:2]
+    scratch = tempfile.mkdtemp(prefix="hoisdf_feed_dex_")
+    Image.fromarray(img).save(os.path.join(scratch, info["color_file"]))
+    np.save(os.path.join(scratch, "sdf.npy"), sdf)
+    ds = D.Dataset.__new__(D.Dataset)
+    ds.mode = "test"
+    ds.sample_dict, ds.sample_list_processed = {"k": info}, ["k"]
+    ds.image_fast_path = scratch
+    ds.mano_handcomponent_right, ds.mano_handcomponent_left = holders["components_right"], holders["components_left"]
+    ds.mano_handmean = holders["handmean"]
+    ds.hand_segs, ds.obj_segs = [np.packbits(hand_mask)], [np.packbits(obj_mask)]
+    ds.obj_bbox3d = holders["obj_bbox3d"]
+    ds.sdf_path_list, ds.sdf_index_list = [os.path.join(scratch, "sdf.npy")], [np.array([nh, len(sdf) - nh])]
+    ds.num_samp_hand, ds.num_samp_obj = n_hand, n_obj
+    ds.inp_res, ds.heatmap_res = 256, 64
+    ds.hand_sdf_scale, ds.obj_sdf_scale = 6.2, 5.8
+    ds.transform = transforms.ToTensor()
+    taps = {"draws": [], "sdf": sdf, "n_hand_rows": nh}
+    real_choice = np.random.choice
+
+    def tap_choice(*a, **k):
+        out = real_choice(*a, **k)
+        taps["draws"].append(np.asarray(out).copy())
+        return out
+
+    np.random.seed(seed)
+    np.random.choice = tap_choice
+    try:
+        inputs, targets, meta = ds[0]
+    finally:
+        np.random.choice = real_choice
+        shutil.rmtree(scratch, ignore_errors=True)
+    return inputs, targets, meta, taps

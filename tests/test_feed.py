@@ -468,3 +468,61 @@ def test_evaluation_sample_matches_golden(emu):
     assert s["obj_mask"] == bool(g["evi_obj_mask"]) and s["obj_cls"] == str(g["evi_obj_cls"])
     got, _ = emu_warp(emu, img[None], s["coef"][None], 256)
     assert np.array_equal(got[0][:, ::8], g["evi_img_rows"])
+
+
+# ---------------------------------------------------------------------------------------------- DexYCB test sample
+DEX_TARGETS = ("joint_coord", "joint_cam_no_trans", "obj_rot", "rel_obj_trans", "mano_param")
+
+
+def dexycb_product_sample(seed, left=None):
+    img, hm, om, info, hold = FO.synthetic_dexycb_sample(seed, left)
+    sdf, nh = FO.synthetic_sdf_frame(seed, N_HAND, N_OBJ)[:2]
+    s = feed.dexycb_eval_geometry(info, hold["components_right"], hold["components_left"], hold["handmean"],
+                                  hold["obj_bbox3d"][info["ycb_ids"][1]], (640, 480))
+    state = np.random.get_state()
+    np.random.seed(seed)
+    s["index"] = feed.draw_sdf_indices(sdf, nh, N_HAND, N_OBJ)
+    np.random.set_state(state)
+    return s, img, hm, om, sdf
+
+
+def emu_dexycb_pixels(lib, s, img, hm, om):
+    mirror = [int(s["flip"])]
+    as_float, _ = emu_warp(lib, img[None], s["coef"][None], 256, mirror=mirror)
+    _, warped = emu_warp(lib, np.stack([hm, om])[:, :, :, None], np.tile(s["coef"], (2, 1)), 256, divisor=1.0, mirror=mirror * 2)
+    small, _ = emu_warp(lib, warped, np.tile(feed.resize_coefficients(256, 64), (2, 1)), 64, divisor=1.0)
+    return as_float[0], small[0, 0], small[1, 0]
+
+
+@pytest.mark.skipif(not rs.available(), reason="upstream reference not mounted")
+def test_dexycb_test_sample_matches_upstream_live(emu):
+    """The unmodified `dexycb.Dataset.__getitem__` in test mode (BASELINE configs[2]'s feed), right AND left hands (the mirror
+    path), against `dexycb_eval_geometry`, the product's draws and the emulated kernels: every entry, values and dtypes."""
+    for seed in range(4):
+        inputs, targets, meta, taps = rs.dexycb_test_item(seed)
+        s, img, hm, om, sdf = dexycb_product_sample(seed)
+        assert s["flip"] == bool(seed % 2) and np.array_equal(s["index"], np.concatenate(taps["draws"]))
+        for k in DEX_TARGETS:
+            assert np.array_equal(s[k], targets[k]) and s[k].dtype == targets[k].dtype, k
+        for k in EVAL_META:
+            assert np.array_equal(s[k], meta[k]) and s[k].dtype == meta[k].dtype, k
+        assert s["obj_cls"] == meta["obj_cls"] and inputs["hand_pre_points"] is False
+        got_img, got_hs, got_os = emu_dexycb_pixels(emu, s, img, hm, om)
+        assert np.array_equal(got_img, inputs["img"].numpy())
+        assert np.array_equal(got_hs, targets["hand_seg"].numpy()) and np.array_equal(got_os, targets["obj_seg"].numpy())
+        want_in, want_t = FO.sdf_point_sets(sdf, s["index"], N_HAND, N_OBJ, s["mano_root"], s["obj_center_cam"], 6.2, 5.8,
+                                            do_flip=s["flip"])
+        for k in ("hand_sdf_points", "obj_sdf_points"):
+            assert np.array_equal(want_in[k], inputs[k]), k
+        assert np.array_equal(want_t["hand_sdf"], targets["hand_sdf"]) and np.array_equal(want_t["obj_sdf"], targets["obj_sdf"])
+
+
+def test_dexycb_test_sample_matches_golden(emu):
+    g = np.load(GOLDEN)
+    s, img, hm, om, sdf = dexycb_product_sample(int(g["seed"]), left=True)
+    assert np.array_equal(s["index"], g["dxi_draws"]) and s["flip"] and s["obj_cls"] == int(g["dxi_obj_cls"])
+    for k in DEX_TARGETS + EVAL_META:
+        assert np.array_equal(s[k], g["dxi_" + k]), k
+    got_img, got_hs, got_os = emu_dexycb_pixels(emu, s, img, hm, om)
+    assert np.array_equal(got_img[:, ::8], g["dxi_img_rows"])
+    assert np.array_equal(got_hs, g["dxi_hand_seg"]) and np.array_equal(got_os, g["dxi_obj_seg"])

@@ -334,3 +334,41 @@ def test_eval_batch_feeds_the_model(cuda):
         cfg.set_setting(old[0])
         type(cfg).dataset = old[1]
         type(cfg).num_samp_hand, type(cfg).num_samp_obj = old[2], old[3]
+
+
+def test_dexycb_eval_batch_reproduces_the_upstream_item(cuda):
+    """`feed.dexycb_eval_batch` (BASELINE configs[2]'s feed) on a batch mixing right and left hands, the fixture's LEFT-hand
+    sample first and last: image (mirrored warp), masks, point sets (x-flipped), SDF targets and the host geometry of one
+    sample of the unmodified upstream `dexycb.Dataset.__getitem__` in test mode."""
+    from hoisdf_b200 import feed
+    from test_feed import dexycb_product_sample, DEX_TARGETS, EVAL_META
+    g = np.load(GOLDEN)
+    seed = int(g["seed"])
+    made = [dexycb_product_sample(seed, left=True)] + [dexycb_product_sample(s) for s in range(200, 206)] + \
+           [dexycb_product_sample(seed, left=True)]
+    frames = torch.from_numpy(np.stack([m[1] for m in made])).to(cuda)
+    hand_masks = torch.from_numpy(np.stack([m[2] for m in made])).to(cuda)
+    obj_masks = torch.from_numpy(np.stack([m[3] for m in made])).to(cuda)
+    rows = torch.from_numpy(np.concatenate([m[4] for m in made])).to(cuda)
+    offsets = torch.from_numpy(np.cumsum([0] + [len(m[4]) for m in made]).astype(np.int64))
+    inputs, targets, meta = feed.dexycb_eval_batch(frames, hand_masks, obj_masks, rows, offsets, [m[0] for m in made], 24, 8,
+                                                   6.2, 5.8)
+    assert inputs["img"].shape == (8, 3, 256, 256) and inputs["hand_pre_points"] is False and meta["bbox_hand"].dtype == torch.float64
+    for i in (0, 7):
+        assert np.array_equal(inputs["img"][i].cpu().numpy()[:, ::8], g["dxi_img_rows"])
+        assert np.array_equal(targets["hand_seg"][i].cpu().numpy(), g["dxi_hand_seg"])
+        assert np.array_equal(targets["obj_seg"][i].cpu().numpy(), g["dxi_obj_seg"])
+        for k in ("hand_sdf_points", "obj_sdf_points"):
+            assert _close32(inputs[k][i].cpu().numpy(), g["dxi_" + k]), k
+        for k in ("hand_sdf", "obj_sdf"):
+            assert _close32(targets[k][i].cpu().numpy(), g["dxi_" + k]), k
+        for k in DEX_TARGETS:
+            assert np.allclose(targets[k][i].cpu().numpy(), g["dxi_" + k], rtol=1e-5, atol=1e-4), k
+        for k in EVAL_META:
+            assert np.allclose(meta[k][i].cpu().numpy(), g["dxi_" + k], rtol=1e-5, atol=1e-4), k
+        assert int(meta["obj_cls"][i]) == int(g["dxi_obj_cls"])
+    for i, (s, img, hm, om, sdf) in enumerate(made):                  # every frame against Pillow on the mirrored source
+        src = np.ascontiguousarray(img[:, ::-1, :]) if s["flip"] else img
+        pil = np.asarray(Image.fromarray(src).transform((256, 256), Image.AFFINE, tuple(float(c) for c in s["coef"])))
+        want = np.ascontiguousarray(pil.astype(np.float32).transpose(2, 0, 1)) / np.float32(255.0)
+        assert np.array_equal(inputs["img"][i].cpu().numpy(), want), i
