@@ -15,7 +15,7 @@
 //     hoisdf_b200/feed.py); its floating-point loop for larger coordinates is not restated.
 // Pixels that map outside the source are 0 (PIL fills a new image with zeros).
 // `channels` = 3 (RGB frames) or 1 (mode "L": the hand / object segmentation masks of the training feed, ho3d.py:366-381,
-// which upstream warps with the same call and then shrinks with `resize((64, 64), Image.NEAREST)` = the scale-only path again
+// which upstream warps with the same call and then shrinks with `resize((128, 128), Image.NEAREST)` = the scale-only path again
 // with coefficients (w_in / w_out, 0, 0, 0, h_in / h_out, 0)); `divisor` = 255 for images (`ToTensor(...) / 255.0`), 1 for masks.
 // `mirror[b]` != 0: the source frame is read left-right mirrored (data/dexycb.py:427-430,479-481: left hands are flipped with
 // `img[:, ::-1, :]` before the warp) -- the same pixels as warping a mirrored copy, without making one.

@@ -3,9 +3,9 @@ worker -- `data_crop` (data/ho3d.py:399-427, evaluation) and the image / mask pa
 data/dexycb.py likewise -- for a whole batch of frames that are already in device memory.
 
 Upstream warps every frame with PIL (`dataset_util.transform_img`, data/dataset_util.py:44-51: an affine `Image.transform` with
-PIL's default NEAREST resampling), shrinks the two segmentation masks with `Image.resize((64, 64), NEAREST)` and ships float
+PIL's default NEAREST resampling), shrinks the two segmentation masks with `Image.resize((128, 128), NEAREST)` (cfg.output_hm_shape) and ships float
 tensors; here the raw 8-bit frames are uploaded once and `hoisdf_image_crop_fwd` produces the
-`(B, 3, res, res)` network input and the `(B, 64, 64)` masks, bit-exact with Pillow.  The geometry that comes with the crop --
+`(B, 3, res, res)` network input and the `(B, 128, 128)` masks, bit-exact with Pillow.  The geometry that comes with the crop --
 bounding boxes, the fused crop window, the affine matrix, the updated camera intrinsics -- is a few dozen floating-point
 operations per frame and stays on the host in numpy, with the arithmetic (float64 intermediates, `int()` truncations, float32
 casts) of data/dataset_util.py so that `cam_intr`, `bbox_hand`, `bbox_obj` and the crop coefficients are the numbers upstream's
@@ -199,7 +199,7 @@ def crop_geometry(cam_intr: np.ndarray, bbox_hand: np.ndarray, obj_p2d: np.ndarr
 
 
 def crop_geometry_dexycb(cam_intr: np.ndarray, joints_uv: np.ndarray, obj_p2d: np.ndarray, img_size: Sequence[int],
-                         res: int = 256, heatmap_res: int = 64) -> Tuple[np.ndarray, Dict[str, np.ndarray]]:
+                         res: int = 256, heatmap_res: int = 128) -> Tuple[np.ndarray, Dict[str, np.ndarray]]:
     """The host half of DexYCB's `data_crop` (data/dexycb.py:355-404) for a batch: the window comes from the 2-D hand joints
     (factor 1.5; hand box factor 1.1), the intrinsics go through `get_affine_transform(..., K=K)`'s second matrix
     (dataset_util.py:67-91: the crop of the centre carried around the principal point -- without rotation the same centre up
@@ -427,7 +427,7 @@ def draw_train_geometry(centre: np.ndarray, scale: float, center_jittering: floa
 
 def train_geometry(cam_intr: np.ndarray, joints_uv: np.ndarray, joints_3d: np.ndarray, mano_param: np.ndarray,
                    obj_p2d: np.ndarray, obj_p3d: np.ndarray, obj_rot: np.ndarray, obj_trans: np.ndarray, centre: np.ndarray,
-                   scale: float, rot: float, obj_depth_mean_value: float, res: int = 256, heatmap_res: int = 64,
+                   scale: float, rot: float, obj_depth_mean_value: float, res: int = 256, heatmap_res: int = 128,
                    coord_change: Optional[np.ndarray] = None) -> Dict[str, np.ndarray]:
     """Everything of one HO3D training sample that is not pixels or SDF rows (data_aug, ho3d.py:318-349, and the tail of
     `__getitem__`, :519-523,553,568-587), for the drawn (centre, scale, rot): a few dozen floating-point operations in upstream's
@@ -477,7 +477,7 @@ def train_geometry(cam_intr: np.ndarray, joints_uv: np.ndarray, joints_3d: np.nd
 
 def train_batch(frames: torch.Tensor, hand_masks: torch.Tensor, obj_masks: torch.Tensor, rows: torch.Tensor,
                 row_offsets: torch.Tensor, samples: Sequence[Dict], n_hand: int, n_obj: int, hand_sdf_scale: float,
-                obj_sdf_scale: float, res: int = 256, heatmap_res: int = 64):
+                obj_sdf_scale: float, res: int = 256, heatmap_res: int = 128):
     """One collated HO3D training batch -- what upstream's DataLoader hands to `main/train.py:104-108` -- from the raw material
     on the GPU: frames (B, H, W, 3) uint8, hand / object masks (B, H, W) uint8 (the unpacked bits), the frames' packed SDF rows
     (`sdf_point_sets`), and per frame the host results `samples[b]` = `train_geometry(...)`'s dict + "index" (`draw_sdf_indices`),
@@ -558,7 +558,7 @@ def eval_batch(frames: torch.Tensor, samples: Sequence[Dict], res: int = 256):
 
 # ---------------------------------------------------------------------------------------------- DexYCB evaluation sample
 def dexycb_eval_geometry(sample_info: Dict, components_right: np.ndarray, components_left: np.ndarray, handmean: np.ndarray,
-                         obj_bbox3d: np.ndarray, img_size: Sequence[int], res: int = 256, heatmap_res: int = 64
+                         obj_bbox3d: np.ndarray, img_size: Sequence[int], res: int = 256, heatmap_res: int = 128
                          ) -> Dict[str, np.ndarray]:
     """Everything of one DexYCB TEST sample that is not pixels or SDF rows (data/dexycb.py:409-514,584-596,627-655): intrinsics
     from the annotation, the MANO pose from PCA to axis-angle (right or left components), the left-hand mirror (x-flip of the
@@ -617,7 +617,7 @@ def dexycb_eval_geometry(sample_info: Dict, components_right: np.ndarray, compon
 
 def dexycb_eval_batch(frames: torch.Tensor, hand_masks: torch.Tensor, obj_masks: torch.Tensor, rows: torch.Tensor,
                       row_offsets: torch.Tensor, samples: Sequence[Dict], n_hand: int, n_obj: int, hand_sdf_scale: float,
-                      obj_sdf_scale: float, res: int = 256, heatmap_res: int = 64):
+                      obj_sdf_scale: float, res: int = 256, heatmap_res: int = 128):
     """One collated DexYCB test batch (BASELINE configs[2]'s feed; data/dexycb.py:627-657) from the raw material on the GPU:
     frames (B, H, W, 3) uint8 and masks (B, H, W) uint8 UN-mirrored, the frames' packed SDF rows, and per frame
     `dexycb_eval_geometry(...)`'s dict + "index" (`draw_sdf_indices(rows, n_hand_rows, n_hand, n_obj)`).

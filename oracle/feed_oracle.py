@@ -89,7 +89,7 @@ def synthetic_frame(seed, h=480, w=640):
     return img, K, bbox_hand, p2d
 
 
-def aug_warp(img_u8, hand_seg_u8, obj_seg_u8, center, scale, rot, inp_res=256, heatmap_res=64):
+def aug_warp(img_u8, hand_seg_u8, obj_seg_u8, center, scale, rot, inp_res=256, heatmap_res=128):
     """The image / mask part of the training augmentation, data/ho3d.py:318-321 (affine with the drawn rotation), :351-353
     (frame warp + crop), :366-381 (mask warp + crop + NEAREST shrink), :550-552 (tensor conversion) -- without the random
     blur / colour jitter between them (ho3d.py:355-364).  -> (pil_bytes (res, res, 3) uint8 = the image handed to the blur,

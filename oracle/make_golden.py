@@ -292,7 +292,7 @@ def feed_case(name, seed, n_eval, n_aug):
         au["aug_bytes"].append(np.asarray(DU.transform_img(Image.fromarray(img), affine, [256, 256]).crop((0, 0, 256, 256))))
         for key, seg in (("aug_hand_seg", hs), ("aug_obj_seg", os_)):
             w = DU.transform_img(Image.fromarray(seg), affine, [256, 256]).crop((0, 0, 256, 256))
-            au[key].append(np.asarray(w.resize((64, 64), Image.NEAREST)).astype(np.float32))
+            au[key].append(np.asarray(w.resize((128, 128), Image.NEAREST)).astype(np.float32))
     for d in (ev, au):
         for k, v in d.items():
             fix[k] = np.stack(v)
@@ -300,7 +300,7 @@ def feed_case(name, seed, n_eval, n_aug):
     import data.dexycb as D
 
     class SelfD:
-        inp_res, heatmap_res = 256, 64
+        inp_res, heatmap_res = 256, 128
 
     img, K32, _, p2d = FO.synthetic_frame(seed)
     _, hs, os_, _, _, _ = FO.synthetic_aug(seed)

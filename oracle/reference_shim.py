@@ -204,7 +204,7 @@ def ho3d_train_item(seed, n_hand=24, n_obj=8, filters=False):
     ds.dist = 0.02
     ds.hand_sdf_scale, ds.obj_sdf_scale = 6.2, 5.8
     ds.obj_depth_mean_value = ann["obj_depth_mean_value"]
-    ds.inp_res, ds.heatmap_res = 256, 64
+    ds.inp_res, ds.heatmap_res = 256, 128          # main/config.py:111-112
     ds.transform = transforms.ToTensor()
     ds.coord_change_mat = np.array([[1.0, 0.0, 0.0], [0, -1.0, 0.0], [0.0, 0.0, -1.0]], dtype=np.float32)
     ds.hue = ds.contrast = ds.brightness = ds.saturation = 0
@@ -307,7 +307,7 @@ def dexycb_test_item(seed, n_hand=24, n_obj=8, left=None):
     ds.obj_bbox3d = holders["obj_bbox3d"]
     ds.sdf_path_list, ds.sdf_index_list = [os.path.join(scratch, "sdf.npy")], [np.array([nh, len(sdf) - nh])]
     ds.num_samp_hand, ds.num_samp_obj = n_hand, n_obj
-    ds.inp_res, ds.heatmap_res = 256, 64
+    ds.inp_res, ds.heatmap_res = 256, 128          # main/config.py:111-112
     ds.hand_sdf_scale, ds.obj_sdf_scale = 6.2, 5.8
     ds.transform = transforms.ToTensor()
     taps = {"draws": [], "sdf": sdf, "n_hand_rows": nh}

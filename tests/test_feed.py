@@ -74,7 +74,7 @@ def test_feed_oracle_matches_upstream_live():
         affine, _ = DU.get_affine_transform(center, scale, [256, 256], rot=rot)
         ref_img = DU.transform_img(Image.fromarray(img), affine, [256, 256]).crop((0, 0, 256, 256))
         ref_seg = DU.transform_img(Image.fromarray(hs), affine, [256, 256]).crop((0, 0, 256, 256))
-        ref_seg = np.asarray(ref_seg.resize((64, 64), Image.NEAREST)).astype(np.float32)
+        ref_seg = np.asarray(ref_seg.resize((128, 128), Image.NEAREST)).astype(np.float32)
         pil_bytes, tensor, hand_seg, _, aff = FO.aug_warp(img, hs, os_, center, scale, rot)
         assert np.array_equal(affine, aff)
         assert np.array_equal(np.asarray(ref_img), pil_bytes) and np.array_equal(ref_seg, hand_seg)
@@ -116,7 +116,7 @@ def test_host_geometry_is_bit_equal_to_the_oracle():
         _, _, _, center, scale, rot = FO.synthetic_aug(s)
         want, _ = FO.get_affine_transform(center, scale, [256, 256], rot=rot)
         assert np.array_equal(feed.crop_affine(center, scale, 256, rot), want)
-    assert np.array_equal(feed.resize_coefficients(256, 64), [4.0, 0, 0, 0, 4.0, 0])
+    assert np.array_equal(feed.resize_coefficients(256, 128), [2.0, 0, 0, 0, 2.0, 0])
 
 
 def test_crop_refuses_host_tensors_and_bad_layouts():
@@ -155,7 +155,7 @@ def test_rotated_warp_and_masks_are_bit_exact_with_pillow(emu):
         assert np.array_equal(ou[0], pil_bytes) and np.array_equal(of[0], tensor)
         masks = np.stack([hs, os_])[:, :, :, None]
         _, warped = emu_warp(emu, masks, np.tile(coef, (2, 1)), 256, divisor=1.0)
-        small, _ = emu_warp(emu, warped, np.tile(feed.resize_coefficients(256, 64), (2, 1)), 64, divisor=1.0)
+        small, _ = emu_warp(emu, warped, np.tile(feed.resize_coefficients(256, 128), (2, 1)), 128, divisor=1.0)
         assert np.array_equal(small[0, 0], hand_seg) and np.array_equal(small[1, 0], obj_seg)
 
 
@@ -347,7 +347,7 @@ def test_dexycb_crop_geometry_and_warp_match_upstream_live(emu):
     import data.dexycb as D
 
     class Self:
-        inp_res, heatmap_res = 256, 64
+        inp_res, heatmap_res = 256, 128
 
     for seed in range(70, 76):
         img, K32, _, p2d = FO.synthetic_frame(seed)
@@ -357,14 +357,14 @@ def test_dexycb_crop_geometry_and_warp_match_upstream_live(emu):
         uv = (p2d.mean(0) + rng.uniform(-60, 60, (21, 2))).astype(np.float32)
         ref = D.Dataset.data_crop(Self(), Image.fromarray(img), K, uv, p2d, Image.fromarray(hs), Image.fromarray(os_))
         r_img, r_hand, r_obj, r_K, r_uv, r_p2d, r_hs, r_os = ref
-        coef, meta = feed.crop_geometry_dexycb(K[None], uv[None], p2d[None], (640, 480), 256, 64)
+        coef, meta = feed.crop_geometry_dexycb(K[None], uv[None], p2d[None], (640, 480), 256, 128)
         assert np.array_equal(meta["bbox_hand"][0], r_hand) and np.array_equal(meta["bbox_obj"][0], r_obj)
         assert np.array_equal(meta["cam_intr"][0], r_K) and meta["cam_intr"].dtype == r_K.dtype
         assert np.array_equal(meta["joints_uv"][0], r_uv) and np.array_equal(meta["p2d"][0], r_p2d)
         _, got = emu_warp(emu, img[None], coef, 256)
         assert np.array_equal(got[0], np.asarray(r_img))
         _, warped = emu_warp(emu, np.stack([hs, os_])[:, :, :, None], np.tile(coef, (2, 1)), 256, divisor=1.0)
-        small, _ = emu_warp(emu, warped, np.tile(feed.resize_coefficients(256, 64), (2, 1)), 64, divisor=1.0)
+        small, _ = emu_warp(emu, warped, np.tile(feed.resize_coefficients(256, 128), (2, 1)), 128, divisor=1.0)
         assert np.array_equal(small[0, 0], r_hs.astype(np.float32)) and np.array_equal(small[1, 0], r_os.astype(np.float32))
 
 
@@ -373,14 +373,14 @@ def test_dexycb_crop_matches_golden(emu):
     seed = int(g["seed"])
     img, K32, _, p2d = FO.synthetic_frame(seed)
     _, hs, os_, _, _, _ = FO.synthetic_aug(seed)
-    coef, meta = feed.crop_geometry_dexycb(K32.astype(np.float64)[None], g["dex_uv_in"][None], p2d[None], (640, 480), 256, 64)
+    coef, meta = feed.crop_geometry_dexycb(K32.astype(np.float64)[None], g["dex_uv_in"][None], p2d[None], (640, 480), 256, 128)
     for k, name in (("bbox_hand", "dex_bbox_hand"), ("bbox_obj", "dex_bbox_obj"), ("cam_intr", "dex_K"),
                     ("joints_uv", "dex_joints_uv"), ("p2d", "dex_p2d")):
         assert np.array_equal(meta[k][0], g[name]), k
     _, got = emu_warp(emu, img[None], coef, 256)
     assert np.array_equal(got[0][::32], g["dex_img_rows"])
     _, warped = emu_warp(emu, np.stack([hs, os_])[:, :, :, None], np.tile(coef, (2, 1)), 256, divisor=1.0)
-    small, _ = emu_warp(emu, warped, np.tile(feed.resize_coefficients(256, 64), (2, 1)), 64, divisor=1.0)
+    small, _ = emu_warp(emu, warped, np.tile(feed.resize_coefficients(256, 128), (2, 1)), 128, divisor=1.0)
     assert np.array_equal(small[0, 0], g["dex_hand_seg"]) and np.array_equal(small[1, 0], g["dex_obj_seg"])
 
 
@@ -490,7 +490,7 @@ def emu_dexycb_pixels(lib, s, img, hm, om):
     mirror = [int(s["flip"])]
     as_float, _ = emu_warp(lib, img[None], s["coef"][None], 256, mirror=mirror)
     _, warped = emu_warp(lib, np.stack([hm, om])[:, :, :, None], np.tile(s["coef"], (2, 1)), 256, divisor=1.0, mirror=mirror * 2)
-    small, _ = emu_warp(lib, warped, np.tile(feed.resize_coefficients(256, 64), (2, 1)), 64, divisor=1.0)
+    small, _ = emu_warp(lib, warped, np.tile(feed.resize_coefficients(256, 128), (2, 1)), 128, divisor=1.0)
     return as_float[0], small[0, 0], small[1, 0]
 
 

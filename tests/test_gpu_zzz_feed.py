@@ -50,8 +50,8 @@ def test_rotated_warp_and_masks_vs_oracle_and_fixture(cuda):
     frames = torch.from_numpy(np.stack([d[0] for d in draws])).to(cuda)
     as_bytes = feed.crop_images(frames, coef, 256, as_bytes=True).cpu().numpy()
     as_float = feed.crop_images(frames, coef, 256).cpu().numpy()
-    hand = feed.crop_masks(torch.from_numpy(np.stack([d[1] for d in draws])).to(cuda), coef, 256, 64).cpu().numpy()
-    obj = feed.crop_masks(torch.from_numpy(np.stack([d[2] for d in draws])).to(cuda), coef, 256, 64).cpu().numpy()
+    hand = feed.crop_masks(torch.from_numpy(np.stack([d[1] for d in draws])).to(cuda), coef, 256, 128).cpu().numpy()
+    obj = feed.crop_masks(torch.from_numpy(np.stack([d[2] for d in draws])).to(cuda), coef, 256, 128).cpu().numpy()
     for i, (img, hs, os_, c, sc, r) in enumerate(draws):
         pil_bytes, tensor, hand_seg, obj_seg, _ = FO.aug_warp(img, hs, os_, c, sc, r)
         assert np.array_equal(as_bytes[i], pil_bytes) and np.array_equal(as_float[i], tensor), i
@@ -135,7 +135,7 @@ def test_training_item_reproduces_the_upstream_fixture(cuda):
     coef = feed.pil_coefficients(feed.crop_affine(g["item_center"], float(g["item_scale"]), 256, float(g["item_rot"])))[None]
     img = feed.crop_images(torch.from_numpy(frame[None]).to(cuda), coef, 256)
     assert np.array_equal(img[0].cpu().numpy(), g["u8_to_f32"][g["item_img_bytes"]].transpose(2, 0, 1))
-    masks = feed.crop_masks(torch.from_numpy(np.stack([hand_mask, obj_mask])).to(cuda), np.tile(coef, (2, 1)), 256, 64)
+    masks = feed.crop_masks(torch.from_numpy(np.stack([hand_mask, obj_mask])).to(cuda), np.tile(coef, (2, 1)), 256, 128)
     assert np.array_equal(masks[0].cpu().numpy(), g["item_hand_seg"]) and np.array_equal(masks[1].cpu().numpy(), g["item_obj_seg"])
     inputs, targets = feed.sdf_point_sets(torch.from_numpy(sdf).to(cuda), torch.tensor([0, len(sdf)]),
                                           torch.from_numpy(g["item_draws"])[None], 24, 8,
@@ -163,7 +163,7 @@ def test_mirrored_warp_equals_warping_the_mirrored_frame(cuda):
         pil = np.asarray(Image.fromarray(src).transform((256, 256), Image.AFFINE, tuple(float(c) for c in coef[i])))
         assert np.array_equal(got[i].cpu().numpy(), pil), i
     masks = torch.from_numpy(np.stack([d[1] for d in draws])).to(cuda)
-    assert torch.equal(feed.crop_masks(masks, coef, 256, 64, mirror=np.ones(4)), feed.crop_masks(masks.flip(2).contiguous(), coef, 256, 64))
+    assert torch.equal(feed.crop_masks(masks, coef, 256, 128, mirror=np.ones(4)), feed.crop_masks(masks.flip(2).contiguous(), coef, 256, 128))
 
 
 # ---------------------------------------------------------------------------------------------- photometric augmentation
@@ -248,7 +248,7 @@ def test_train_batch_reproduces_the_upstream_item(cuda):
     rows = torch.from_numpy(np.concatenate([h[1] for h in host])).to(cuda)
     offsets = torch.from_numpy(np.cumsum([0] + [len(h[1]) for h in host]).astype(np.int64))
     inputs, targets, meta = feed.train_batch(frames, hand_masks, obj_masks, rows, offsets, [h[0] for h in host], 24, 8, 6.2, 5.8)
-    assert inputs["img"].shape == (3, 3, 256, 256) and targets["hand_seg"].shape == (3, 64, 64)
+    assert inputs["img"].shape == (3, 3, 256, 256) and targets["hand_seg"].shape == (3, 128, 128)
     for i in (0, 2):
         assert np.array_equal(inputs["img"][i].cpu().numpy()[:, ::8], g["filt_img_rows"])
         assert np.array_equal(targets["hand_seg"][i].cpu().numpy(), g["filt_t_hand_seg"])
