@@ -474,14 +474,14 @@ def test_evaluation_sample_matches_golden(emu):
 DEX_TARGETS = ("joint_coord", "joint_cam_no_trans", "obj_rot", "rel_obj_trans", "mano_param")
 
 
-def dexycb_product_sample(seed, left=None):
+def dexycb_product_sample(seed, left=None, n_hand=N_HAND, n_obj=N_OBJ):
     img, hm, om, info, hold = FO.synthetic_dexycb_sample(seed, left)
-    sdf, nh = FO.synthetic_sdf_frame(seed, N_HAND, N_OBJ)[:2]
+    sdf, nh = FO.synthetic_sdf_frame(seed, n_hand, n_obj)[:2]
     s = feed.dexycb_eval_geometry(info, hold["components_right"], hold["components_left"], hold["handmean"],
                                   hold["obj_bbox3d"][info["ycb_ids"][1]], (640, 480))
     state = np.random.get_state()
     np.random.seed(seed)
-    s["index"] = feed.draw_sdf_indices(sdf, nh, N_HAND, N_OBJ)
+    s["index"] = feed.draw_sdf_indices(sdf, nh, n_hand, n_obj)
     np.random.set_state(state)
     return s, img, hm, om, sdf
 
