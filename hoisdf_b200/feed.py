@@ -33,7 +33,8 @@ __all__ = ["bbox_from_points", "fuse_boxes", "crop_affine", "apply_affine", "pil
            "crop_geometry", "crop_geometry_dexycb", "crop_images", "crop_masks", "data_crop", "draw_sdf_indices", "sdf_point_sets",
            "gaussian_blur", "draw_color_jitter", "color_jitter", "to_tensor",
            "draw_train_geometry", "train_geometry", "train_batch",
-           "eval_geometry", "eval_batch", "dexycb_eval_geometry", "dexycb_eval_batch"]
+           "eval_geometry", "eval_batch", "dexycb_annotation", "dexycb_eval_geometry", "dexycb_eval_batch",
+           "dexycb_train_geometry"]
 
 
 
@@ -417,24 +418,32 @@ def _affine_about_principal_point(centre, scale, res, turn, K) -> np.ndarray:
 
 
 def draw_train_geometry(centre: np.ndarray, scale: float, center_jittering: float = 0.1, scale_jittering: float = 0.2,
-                        max_rot: float = np.pi) -> Tuple[np.ndarray, float, float]:
-    """The three geometric draws of `data_aug` (ho3d.py:306-319) from numpy's GLOBAL generator in upstream's order (centre
-    offsets, scale factor, angle) applied to the fused window -> (centre, scale, rot)."""
+                        max_rot: float = np.pi, dataset: str = "ho3d") -> Tuple[np.ndarray, float, float]:
+    """The three geometric draws of `data_aug` (ho3d.py:306-319, dexycb.py:253-274) from the GLOBAL generators in upstream's
+    order (centre offsets, scale factor, angle) applied to the fused window -> (centre, scale, rot).  HO3D draws the angle
+    uniformly in +-max_rot; DexYCB takes a clipped normal (x 30 degrees, scaled by max_rot / 180) with probability 0.6 --
+    that coin is Python's `random.random()`, drawn BEFORE the blur radius -- and no rotation otherwise."""
+    import random
     centre = centre + center_jittering * scale * np.random.uniform(low=-1, high=1, size=2)
     factor = np.clip(scale_jittering * np.random.randn() + 1, 1 - scale_jittering, 1 + scale_jittering)
+    if dataset == "dexycb":
+        rot = np.clip(np.random.randn(), -2.0, 2.0) * 30 if random.random() <= 0.6 else 0
+        return centre, scale * factor, rot * max_rot / 180
     return centre, scale * factor, np.random.uniform(low=-max_rot, high=max_rot)
 
 
 def train_geometry(cam_intr: np.ndarray, joints_uv: np.ndarray, joints_3d: np.ndarray, mano_param: np.ndarray,
                    obj_p2d: np.ndarray, obj_p3d: np.ndarray, obj_rot: np.ndarray, obj_trans: np.ndarray, centre: np.ndarray,
-                   scale: float, rot: float, obj_depth_mean_value: float, res: int = 256, heatmap_res: int = 128,
-                   coord_change: Optional[np.ndarray] = None) -> Dict[str, np.ndarray]:
+                   scale: float, rot: float, obj_depth_mean_value: Optional[float], res: int = 256, heatmap_res: int = 128,
+                   coord_change: Optional[np.ndarray] = None, hand_box_factor: float = 1.2) -> Dict[str, np.ndarray]:
     """Everything of one HO3D training sample that is not pixels or SDF rows (data_aug, ho3d.py:318-349, and the tail of
     `__getitem__`, :519-523,553,568-587), for the drawn (centre, scale, rot): a few dozen floating-point operations in upstream's
     own precision mixture (float64 matrices cast to float32, cv2.Rodrigues for the two rotations), kept on the host.
     -> {"coef" (6,) PIL coefficients of the warp, "rot_mat" (3, 3) for `sdf_point_sets`, and upstream's entries: `joint_coord`,
     `joint_cam_no_trans`, `mano_param`, `obj_rot`, `rel_obj_trans` (targets); `cam_intr`, `mano_root`, `obj_center_cam`,
-    `bbox_hand`, `bbox_obj` (meta_info); `p2d`, `p3d` (the normalised corners upstream computes and drops)}."""
+    `bbox_hand`, `bbox_obj` (meta_info); `p2d`, `p3d` (the normalised corners upstream computes and drops)}.
+    DexYCB's `data_aug` (dexycb.py:219-354) is the same with `coord_change = np.eye(3)`, `hand_box_factor = 1.1` and the
+    object centre at the ROOT joint's depth (`obj_depth_mean_value = None`; dexycb.py:589-592)."""
     import cv2
     if coord_change is None:
         coord_change = np.array([[1.0, 0.0, 0.0], [0, -1.0, 0.0], [0.0, 0.0, -1.0]], dtype=np.float32)     # ho3d.py:70-72
@@ -459,7 +468,7 @@ def train_geometry(cam_intr: np.ndarray, joints_uv: np.ndarray, joints_3d: np.nd
     new_obj_trans = rot_mat.dot(np.asarray(obj_trans))
     K = post.dot(K)
     p2d = apply_affine(obj_p2d, affine)
-    bbox_hand = bbox_from_points(uv, 1.2)
+    bbox_hand = bbox_from_points(uv, hand_box_factor)
     uv = uv / res * heatmap_res
     bbox_obj = bbox_from_points(p2d, 1.0)
     span = bbox_obj.reshape(2, 2)
@@ -467,7 +476,8 @@ def train_geometry(cam_intr: np.ndarray, joints_uv: np.ndarray, joints_3d: np.nd
     hand_root = joints_3d[0].copy()
     joints_3d = joints_3d - hand_root[None]
     # `get_center_cam` (:343-350): back-projection of the object box centre at the mean object depth
-    c = np.asarray([int((bbox_obj[2] + bbox_obj[0]) / 2), int((bbox_obj[3] + bbox_obj[1]) / 2), obj_depth_mean_value])
+    depth = hand_root[-1] if obj_depth_mean_value is None else obj_depth_mean_value
+    c = np.asarray([int((bbox_obj[2] + bbox_obj[0]) / 2), int((bbox_obj[3] + bbox_obj[1]) / 2), depth])
     centre_cam = np.array([(c[0] - K[0, 2]) / K[0, 0] * c[2], (c[1] - K[1, 2]) / K[1, 1] * c[2], c[2]]).astype(np.float32)
     return {"coef": pil_coefficients(affine), "rot_mat": rot_mat, "joint_coord": uv.astype(np.float32),
             "joint_cam_no_trans": joints_3d * 1000, "mano_param": mano_param, "obj_rot": new_obj_rot,
@@ -478,7 +488,8 @@ def train_geometry(cam_intr: np.ndarray, joints_uv: np.ndarray, joints_3d: np.nd
 def train_batch(frames: torch.Tensor, hand_masks: torch.Tensor, obj_masks: torch.Tensor, rows: torch.Tensor,
                 row_offsets: torch.Tensor, samples: Sequence[Dict], n_hand: int, n_obj: int, hand_sdf_scale: float,
                 obj_sdf_scale: float, res: int = 256, heatmap_res: int = 128):
-    """One collated HO3D training batch -- what upstream's DataLoader hands to `main/train.py:104-108` -- from the raw material
+    """One collated training batch (HO3D, or DexYCB when the sample dicts come from `dexycb_train_geometry` and carry "flip")
+    -- what upstream's DataLoader hands to `main/train.py:104-108` -- from the raw material
     on the GPU: frames (B, H, W, 3) uint8, hand / object masks (B, H, W) uint8 (the unpacked bits), the frames' packed SDF rows
     (`sdf_point_sets`), and per frame the host results `samples[b]` = `train_geometry(...)`'s dict + "index" (`draw_sdf_indices`),
     "blur_radius" (`random.random() * blur_radius`) and "jitter" (`draw_color_jitter(...)`).
@@ -488,17 +499,21 @@ def train_batch(frames: torch.Tensor, hand_masks: torch.Tensor, obj_masks: torch
     if len(samples) != b:
         raise ValueError("one sample dict per frame")
     coef = np.stack([s["coef"] for s in samples])
-    warped = crop_images(frames, coef, res, as_bytes=True)
+    mirror = np.array([bool(s.get("flip", False)) for s in samples])           # DexYCB left hands (dexycb.py:427-430,479-481,547)
+    warped = crop_images(frames, coef, res, as_bytes=True, mirror=mirror)
     img = to_tensor(color_jitter(gaussian_blur(warped, [s["blur_radius"] for s in samples]), [s["jitter"] for s in samples]))
     stack = lambda key: torch.from_numpy(np.stack([np.asarray(s[key]) for s in samples])).to(dev)  # noqa: E731  (dtypes as upstream's collate)
     inputs, targets = sdf_point_sets(rows, row_offsets, torch.from_numpy(np.stack([s["index"] for s in samples])), n_hand, n_obj,
                                      stack("mano_root"), stack("obj_center_cam"), hand_sdf_scale, obj_sdf_scale,
-                                     rot=stack("rot_mat"))
+                                     rot=stack("rot_mat"), flip=torch.from_numpy(mirror.astype(np.int32)))
     inputs["img"] = img
-    targets.update(hand_seg=crop_masks(hand_masks, coef, res, heatmap_res), obj_seg=crop_masks(obj_masks, coef, res, heatmap_res))
+    targets.update(hand_seg=crop_masks(hand_masks, coef, res, heatmap_res, mirror=mirror),
+                   obj_seg=crop_masks(obj_masks, coef, res, heatmap_res, mirror=mirror))
     for key in ("joint_coord", "joint_cam_no_trans", "obj_rot", "rel_obj_trans", "mano_param"):
         targets[key] = stack(key)
     meta = {key: stack(key) for key in ("cam_intr", "mano_root", "obj_center_cam", "bbox_hand", "bbox_obj")}
+    if "obj_cls" in samples[0]:
+        meta["obj_cls"] = torch.tensor([int(s["obj_cls"]) for s in samples], device=dev)
     return inputs, targets, meta
 
 
@@ -557,19 +572,15 @@ def eval_batch(frames: torch.Tensor, samples: Sequence[Dict], res: int = 256):
 
 
 # ---------------------------------------------------------------------------------------------- DexYCB evaluation sample
-def dexycb_eval_geometry(sample_info: Dict, components_right: np.ndarray, components_left: np.ndarray, handmean: np.ndarray,
-                         obj_bbox3d: np.ndarray, img_size: Sequence[int], res: int = 256, heatmap_res: int = 128
-                         ) -> Dict[str, np.ndarray]:
-    """Everything of one DexYCB TEST sample that is not pixels or SDF rows (data/dexycb.py:409-514,584-596,627-655): intrinsics
-    from the annotation, the MANO pose from PCA to axis-angle (right or left components), the left-hand mirror (x-flip of the
-    joints, principal point, object pose; re-projection of the object corners), `data_crop`'s geometry, root joint, object centre
-    at the ROOT's depth.  `sample_info` = the entry of DexYCB's `sample_dict`; `obj_bbox3d` = the grasped object's box corners.
-    -> {"coef" (6,), "flip" (bool: pass as `mirror` to the warps and `flip` to `sdf_point_sets`), and upstream's entries:
-    `joint_coord`, `joint_cam_no_trans`, `obj_rot`, `rel_obj_trans`, `mano_param` (targets), `cam_intr`, `mano_root`,
-    `obj_center_cam`, `bbox_hand`, `bbox_obj` (float64 here, as upstream), `obj_cls` (meta_info)}."""
+def dexycb_annotation(sample_info: Dict, components_right: np.ndarray, components_left: np.ndarray, handmean: np.ndarray,
+                      obj_bbox3d: np.ndarray, width: int) -> Dict:
+    """The annotation algebra at the head of DexYCB's `__getitem__` (data/dexycb.py:409-514), before any crop: intrinsics from
+    the annotation, the MANO pose from PCA to axis-angle (right or left components), the left-hand mirror (x-flip of the joints,
+    principal point and object pose; re-projection of the object corners).  `sample_info` = the entry of DexYCB's `sample_dict`;
+    `obj_bbox3d` = the grasped object's box corners.  -> {"flip", "cam_intr" (float64), "joints_uv", "joints_3d", "mano_param"
+    (58,), "obj_p2d", "obj_p3d", "obj_rot", "obj_trans", "obj_cls"}."""
     import cv2
     flip = sample_info["mano_side"] == "left"
-    width = img_size[0]
     intr = sample_info["intrinsics"]
     K = np.zeros((3, 3))
     K[0, 0], K[1, 1], K[0, 2], K[1, 2], K[2, 2] = intr["fx"], intr["fy"], intr["ppx"], intr["ppy"], 1
@@ -602,17 +613,50 @@ def dexycb_eval_geometry(sample_info: Dict, components_right: np.ndarray, compon
         obj_trans[0] *= -1
         obj_rot[1:] *= -1
         p3d, p2d = project(np.concatenate([cv2.Rodrigues(obj_rot)[0], obj_trans[:, None]], axis=1))
-    coef, geo = crop_geometry_dexycb(K[None], joints_uv[None], p2d[None], img_size, res, heatmap_res)
+    return {"flip": flip, "cam_intr": K, "joints_uv": joints_uv, "joints_3d": joints_3d, "mano_param": mano_param, "obj_p2d": p2d,
+            "obj_p3d": p3d, "obj_rot": obj_rot, "obj_trans": obj_trans,
+            "obj_cls": sample_info["ycb_ids"][sample_info["ycb_grasp_ind"]]}
+
+
+def dexycb_eval_geometry(sample_info: Dict, components_right: np.ndarray, components_left: np.ndarray, handmean: np.ndarray,
+                         obj_bbox3d: np.ndarray, img_size: Sequence[int], res: int = 256, heatmap_res: int = 128
+                         ) -> Dict[str, np.ndarray]:
+    """Everything of one DexYCB TEST sample that is not pixels or SDF rows (data/dexycb.py:409-514,584-596,627-655):
+    `dexycb_annotation`, then `data_crop`'s geometry, root joint, object centre at the ROOT's depth.
+    -> {"coef" (6,), "flip" (bool: pass as `mirror` to the warps and `flip` to `sdf_point_sets`), and upstream's entries:
+    `joint_coord`, `joint_cam_no_trans`, `obj_rot`, `rel_obj_trans`, `mano_param` (targets), `cam_intr`, `mano_root`,
+    `obj_center_cam`, `bbox_hand`, `bbox_obj` (float64 here, as upstream), `obj_cls` (meta_info)}."""
+    a = dexycb_annotation(sample_info, components_right, components_left, handmean, obj_bbox3d, img_size[0])
+    joints_3d = a["joints_3d"]
+    coef, geo = crop_geometry_dexycb(a["cam_intr"][None], a["joints_uv"][None], a["obj_p2d"][None], img_size, res, heatmap_res)
     K, bbox_obj = geo["cam_intr"][0], geo["bbox_obj"][0]
     root = joints_3d[0].copy()
     c = np.asarray([int((bbox_obj[2] + bbox_obj[0]) / 2), int((bbox_obj[3] + bbox_obj[1]) / 2), root[-1]])
     centre_cam = np.array([(c[0] - K[0, 2]) / K[0, 0] * c[2], (c[1] - K[1, 2]) / K[1, 1] * c[2], c[2]]).astype(np.float32)
-    return {"coef": coef[0], "flip": flip, "joint_coord": geo["joints_uv"][0].astype(np.float32),
-            "joint_cam_no_trans": (joints_3d - root[None]) * 1000, "obj_rot": obj_rot,
-            "rel_obj_trans": (obj_trans.astype(np.float32) - centre_cam).astype(np.float32),
-            "mano_param": mano_param.astype(np.float32), "cam_intr": K.astype(np.float32), "mano_root": root,
-            "obj_center_cam": centre_cam, "bbox_hand": geo["bbox_hand"][0], "bbox_obj": bbox_obj,
-            "obj_cls": sample_info["ycb_ids"][sample_info["ycb_grasp_ind"]], "p2d": geo["p2d"][0], "p3d": p3d - centre_cam[None]}
+    return {"coef": coef[0], "flip": a["flip"], "joint_coord": geo["joints_uv"][0].astype(np.float32),
+            "joint_cam_no_trans": (joints_3d - root[None]) * 1000, "obj_rot": a["obj_rot"],
+            "rel_obj_trans": (a["obj_trans"].astype(np.float32) - centre_cam).astype(np.float32),
+            "mano_param": a["mano_param"].astype(np.float32), "cam_intr": K.astype(np.float32), "mano_root": root,
+            "obj_center_cam": centre_cam, "bbox_hand": geo["bbox_hand"][0], "bbox_obj": bbox_obj, "obj_cls": a["obj_cls"],
+            "p2d": geo["p2d"][0], "p3d": a["obj_p3d"] - centre_cam[None]}
+
+
+def dexycb_train_geometry(sample_info: Dict, components_right: np.ndarray, components_left: np.ndarray, handmean: np.ndarray,
+                          obj_bbox3d: np.ndarray, img_size: Sequence[int], res: int = 256, heatmap_res: int = 128,
+                          center_jittering: float = 0.1, scale_jittering: float = 0.2, max_rot: float = np.pi
+                          ) -> Dict[str, np.ndarray]:
+    """The host half of one DexYCB TRAINING sample (dexycb.py:409-514, `data_aug` :219-354, :584-657): `dexycb_annotation`, the
+    fused window, the geometric draws in upstream's order (`draw_train_geometry(dataset="dexycb")` -- call AFTER
+    `draw_sdf_indices`, BEFORE the blur / jitter draws) and `train_geometry` with DexYCB's constants.  -> `train_geometry`'s
+    dict + "flip", "obj_cls"; `cam_intr` / `mano_param` cast to float32 as upstream's dict does (:645,649)."""
+    a = dexycb_annotation(sample_info, components_right, components_left, handmean, obj_bbox3d, img_size[0])
+    centre, scale = fuse_boxes(bbox_from_points(a["joints_uv"], 1.5), bbox_from_points(a["obj_p2d"], 1.5), img_size)
+    centre, scale, rot = draw_train_geometry(centre, scale, center_jittering, scale_jittering, max_rot, "dexycb")
+    g = train_geometry(a["cam_intr"], a["joints_uv"], a["joints_3d"], a["mano_param"], a["obj_p2d"], a["obj_p3d"], a["obj_rot"],
+                       a["obj_trans"], centre, scale, rot, None, res, heatmap_res, np.eye(3), 1.1)
+    g.update(flip=a["flip"], obj_cls=a["obj_cls"], cam_intr=g["cam_intr"].astype(np.float32),
+             mano_param=g["mano_param"].astype(np.float32))
+    return g
 
 
 def dexycb_eval_batch(frames: torch.Tensor, hand_masks: torch.Tensor, obj_masks: torch.Tensor, rows: torch.Tensor,

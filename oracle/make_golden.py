@@ -325,6 +325,17 @@ def feed_case(name, seed, n_eval, n_aug):
         fix["dxi_" + k] = d_t[k]
     for k in ("cam_intr", "mano_root", "obj_center_cam", "bbox_hand", "bbox_obj"):
         fix["dxi_" + k] = d_m[k]
+    # one DexYCB TRAINING sample of a LEFT hand with blur + jitter on, through the unmodified `dexycb.Dataset.__getitem__`
+    x_in, x_t, x_m, x_taps = rs.dexycb_test_item(seed, left=True, mode="train", filters=True)
+    fix.update(dxt_img_rows=x_in["img"].numpy()[:, ::8].copy(), dxt_draws=np.concatenate(x_taps["draws"]).astype(np.int64),
+               dxt_hand_seg=np.packbits(x_t["hand_seg"].numpy().astype(np.uint8)),
+               dxt_obj_seg=np.packbits(x_t["obj_seg"].numpy().astype(np.uint8)))
+    for k in ("hand_sdf_points", "obj_sdf_points", "hand_pre_points", "obj_pre_points"):
+        fix["dxt_" + k] = x_in[k]
+    for k in ("joint_coord", "joint_cam_no_trans", "obj_rot", "rel_obj_trans", "mano_param", "hand_sdf", "obj_sdf"):
+        fix["dxt_" + k] = x_t[k]
+    for k in ("cam_intr", "mano_root", "obj_center_cam", "bbox_hand", "bbox_obj"):
+        fix["dxt_" + k] = x_m[k]
     # one whole training sample through the unmodified `Dataset.__getitem__` (oracle/reference_shim.py:ho3d_train_item): the
     # SDF point sets + masks it returns and the draws / augmentation arguments needed to reproduce them
     inputs, targets, meta, taps = rs.ho3d_train_item(seed)

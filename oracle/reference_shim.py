@@ -277,7 +277,7 @@ def ho3d_eval_item(seed):
         shutil.rmtree(root, ignore_errors=True)
 
 
-def dexycb_test_item(seed, n_hand=24, n_obj=8, left=None):
+def dexycb_test_item(seed, n_hand=24, n_obj=8, left=None, mode="test", filters=False):
     """ONE sample through the UNMODIFIED upstream `data.dexycb.Dataset.__getitem__` in test mode (dexycb.py:409-657; the feed
     of BASELINE configs[2]'s evaluation): synthetic colour file + packed SDF .npy in a scratch directory, dataset object made
     with `__new__` and given the attributes that method reads.  Returns (inputs, targets, meta_info, taps) -- taps: the draws."""
@@ -298,7 +298,12 @@ def dexycb_test_item(seed, n_hand=24, n_obj=8, left=None):
     Image.fromarray(img).save(os.path.join(scratch, info["color_file"]))
     np.save(os.path.join(scratch, "sdf.npy"), sdf)
     ds = D.Dataset.__new__(D.Dataset)
-    ds.mode = "test"
+    ds.mode = mode                      # "test", or "train": data_aug with the constructor's defaults (dexycb.py:29-40)
+    ds.dist = 0.02
+    ds.scale_jittering, ds.center_jittering, ds.max_rot = 0.2, 0.1, np.pi
+    ds.hue = ds.contrast = ds.brightness = ds.saturation = ds.blur_radius = 0
+    if filters:
+        ds.hue, ds.saturation, ds.contrast, ds.brightness, ds.blur_radius = 0.15, 0.5, 0.5, 0.5, 0.5
     ds.sample_dict, ds.sample_list_processed = {"k": info}, ["k"]
     ds.image_fast_path = scratch
     ds.mano_handcomponent_right, ds.mano_handcomponent_left = holders["components_right"], holders["components_left"]
@@ -318,7 +323,9 @@ def dexycb_test_item(seed, n_hand=24, n_obj=8, left=None):
         taps["draws"].append(np.asarray(out).copy())
         return out
 
+    import random
     np.random.seed(seed)
+    random.seed(seed)
     np.random.choice = tap_choice
     try:
         inputs, targets, meta = ds[0]

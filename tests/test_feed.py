@@ -526,3 +526,41 @@ def test_dexycb_test_sample_matches_golden(emu):
     got_img, got_hs, got_os = emu_dexycb_pixels(emu, s, img, hm, om)
     assert np.array_equal(got_img[:, ::8], g["dxi_img_rows"])
     assert np.array_equal(got_hs, g["dxi_hand_seg"]) and np.array_equal(got_os, g["dxi_obj_seg"])
+
+
+# ---------------------------------------------------------------------------------------------- DexYCB training sample
+def dexycb_train_product_sample(seed, left=None):
+    """Host half of one DexYCB training sample as the product computes it, draws in upstream's order after the same seeds."""
+    import random
+    img, hm, om, info, hold = FO.synthetic_dexycb_sample(seed, left)
+    sdf, nh = FO.synthetic_sdf_frame(seed, N_HAND, N_OBJ)[:2]
+    state = np.random.get_state()
+    np.random.seed(seed)
+    random.seed(seed)
+    index = feed.draw_sdf_indices(sdf, nh, N_HAND, N_OBJ, 0.02)
+    s = feed.dexycb_train_geometry(info, hold["components_right"], hold["components_left"], hold["handmean"],
+                                   hold["obj_bbox3d"][info["ycb_ids"][1]], (640, 480))
+    s.update(index=index, blur_radius=random.random() * 0.5,
+             jitter=feed.draw_color_jitter(brightness=0.5, contrast=0.5, saturation=0.5, hue=0.15))
+    np.random.set_state(state)
+    return s, img, hm, om, sdf
+
+
+@pytest.mark.skipif(not rs.available(), reason="upstream reference not mounted")
+def test_dexycb_training_sample_host_geometry_matches_upstream_live():
+    for seed in range(6):
+        inputs, targets, meta, taps = rs.dexycb_test_item(seed, mode="train", filters=True)
+        s = dexycb_train_product_sample(seed)[0]
+        assert np.array_equal(s["index"], np.concatenate(taps["draws"]))
+        for k in DEX_TARGETS:
+            assert np.array_equal(s[k], targets[k]) and s[k].dtype == targets[k].dtype, k
+        for k in EVAL_META:
+            assert np.array_equal(s[k], meta[k]) and s[k].dtype == meta[k].dtype, k
+
+
+def test_dexycb_training_sample_host_geometry_matches_golden():
+    g = np.load(GOLDEN)
+    s = dexycb_train_product_sample(int(g["seed"]), left=True)[0]
+    assert np.array_equal(s["index"], g["dxt_draws"]) and s["flip"]
+    for k in DEX_TARGETS + EVAL_META:
+        assert np.array_equal(s[k], g["dxt_" + k]), k

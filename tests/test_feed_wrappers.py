@@ -81,6 +81,10 @@ def test_dexycb_eval_batch(host):
     G.test_dexycb_eval_batch_reproduces_the_upstream_item(host)
 
 
+def test_train_batch_dexycb(host):
+    G.test_train_batch_reproduces_the_upstream_dexycb_item(host)
+
+
 def test_the_patches_are_gone_afterwards():
     assert feed.lib is _capi.lib and feed._stream.__module__ == "hoisdf_b200.feed"
     with pytest.raises(RuntimeError, match="no CPU fallback"):

@@ -407,3 +407,30 @@ def test_dexycb_eval_batch_feeds_the_model(cuda):
         cfg.set_setting(old[0])
         type(cfg).dataset = old[1]
         type(cfg).num_samp_hand, type(cfg).num_samp_obj = old[2], old[3]
+
+
+def test_train_batch_reproduces_the_upstream_dexycb_item(cuda):
+    """`feed.train_batch` on DexYCB material (the fixture's LEFT-hand sample + a right-hand one): mirrored warp -> blur ->
+    jitter -> tensor, mirrored masks, x-flipped + rotated point sets incl. the `*_pre` sets, and the host geometry of one
+    training sample of the unmodified upstream `dexycb.Dataset.__getitem__` with its filters on."""
+    from hoisdf_b200 import feed
+    from test_feed import dexycb_train_product_sample, DEX_TARGETS, EVAL_META
+    g = np.load(GOLDEN)
+    made = [dexycb_train_product_sample(int(g["seed"]), left=True), dexycb_train_product_sample(300, left=False)]
+    rows = torch.from_numpy(np.concatenate([m[4] for m in made])).to(cuda)
+    offsets = torch.from_numpy(np.cumsum([0] + [len(m[4]) for m in made]).astype(np.int64))
+    inputs, targets, meta = feed.train_batch(
+        torch.from_numpy(np.stack([m[1] for m in made])).to(cuda), torch.from_numpy(np.stack([m[2] for m in made])).to(cuda),
+        torch.from_numpy(np.stack([m[3] for m in made])).to(cuda), rows, offsets, [m[0] for m in made], 24, 8, 6.2, 5.8)
+    assert np.array_equal(inputs["img"][0].cpu().numpy()[:, ::8], g["dxt_img_rows"])
+    assert np.array_equal(np.packbits(targets["hand_seg"][0].cpu().numpy().astype(np.uint8)), g["dxt_hand_seg"])
+    assert np.array_equal(np.packbits(targets["obj_seg"][0].cpu().numpy().astype(np.uint8)), g["dxt_obj_seg"])
+    for k in ("hand_sdf_points", "obj_sdf_points", "hand_pre_points", "obj_pre_points"):
+        assert _close32(inputs[k][0].cpu().numpy(), g["dxt_" + k]), k
+    for k in ("hand_sdf", "obj_sdf"):
+        assert _close32(targets[k][0].cpu().numpy(), g["dxt_" + k]), k
+    for k in DEX_TARGETS:
+        assert np.allclose(targets[k][0].cpu().numpy(), g["dxt_" + k], rtol=1e-5, atol=1e-4), k
+    for k in EVAL_META:
+        assert np.allclose(meta[k][0].cpu().numpy(), g["dxt_" + k], rtol=1e-5, atol=1e-4), k
+    assert meta["obj_cls"].shape == (2,)
