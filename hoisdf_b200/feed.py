@@ -514,6 +514,8 @@ def train_batch(frames: torch.Tensor, hand_masks: torch.Tensor, obj_masks: torch
     meta = {key: stack(key) for key in ("cam_intr", "mano_root", "obj_center_cam", "bbox_hand", "bbox_obj")}
     if "obj_cls" in samples[0]:
         meta["obj_cls"] = torch.tensor([int(s["obj_cls"]) for s in samples], device=dev)
+    if "obj_mask" in samples[0]:                                               # ho3d.py:554-558,583 (caller-provided flag)
+        meta["obj_mask"] = torch.tensor([bool(s["obj_mask"]) for s in samples], device=dev)
     return inputs, targets, meta
 
 

@@ -529,15 +529,15 @@ def test_dexycb_test_sample_matches_golden(emu):
 
 
 # ---------------------------------------------------------------------------------------------- DexYCB training sample
-def dexycb_train_product_sample(seed, left=None):
+def dexycb_train_product_sample(seed, left=None, n_hand=N_HAND, n_obj=N_OBJ):
     """Host half of one DexYCB training sample as the product computes it, draws in upstream's order after the same seeds."""
     import random
     img, hm, om, info, hold = FO.synthetic_dexycb_sample(seed, left)
-    sdf, nh = FO.synthetic_sdf_frame(seed, N_HAND, N_OBJ)[:2]
+    sdf, nh = FO.synthetic_sdf_frame(seed, n_hand, n_obj)[:2]
     state = np.random.get_state()
     np.random.seed(seed)
     random.seed(seed)
-    index = feed.draw_sdf_indices(sdf, nh, N_HAND, N_OBJ, 0.02)
+    index = feed.draw_sdf_indices(sdf, nh, n_hand, n_obj, 0.02)
     s = feed.dexycb_train_geometry(info, hold["components_right"], hold["components_left"], hold["handmean"],
                                    hold["obj_bbox3d"][info["ycb_ids"][1]], (640, 480))
     s.update(index=index, blur_radius=random.random() * 0.5,
