@@ -302,40 +302,6 @@ def _project(ann, corners, K):
     return uv[:, :2] / uv[:, -1:]
 
 
-def test_eval_batch_feeds_the_model(cuda):
-    """Raw frames -> `feed.eval_batch` -> `Model.forward(..., "eval")`: the collated dicts are consumable as they are (upstream's
-    keys and dtypes, incl. the float64 `obj_rot` target and the string entries of meta_info), and the outputs equal those of
-    the same forward on an image batch assembled from the ORACLE's `data_crop` -- main/test.py:120-126 end to end."""
-    from hoisdf_b200 import feed, synthetic as syn
-    from hoisdf_b200.config import cfg
-    from hoisdf_b200.model import get_model
-    old = (cfg.setting, cfg.dataset, cfg.num_samp_hand, cfg.num_samp_obj)
-    try:
-        cfg.set_setting("ho3d")
-        type(cfg).dataset = "ho3d"
-        type(cfg).num_samp_hand, type(cfg).num_samp_obj = 96, 40
-        model = get_model("test", mano_buffers=syn.mano_buffers(5))
-        model.load_state_dict(syn.full_state_dict(5, "ho3d"), strict=True)
-        model = model.to(cuda).eval()
-        raw = [FO.synthetic_eval_annotation(s) for s in (100, 101, 102, 103)]
-        samples = [feed.eval_geometry(ann, corners, (640, 480), 0.7) for _, ann, corners in raw]
-        inputs, targets, meta = feed.eval_batch(torch.from_numpy(np.stack([r[0] for r in raw])).to(cuda), samples)
-        out = model(inputs, targets, meta, "eval")
-        crops = []
-        for img, ann, corners in raw:
-            K = np.array(ann["camMat"], dtype=np.float32)
-            crops.append(FO.data_crop(img, K, np.array(ann["handBoundingBox"], dtype=np.float32), _project(ann, corners, K))[0])
-        want = model({"img": torch.from_numpy(np.stack(crops)).to(cuda)}, targets, meta, "eval")
-        for k in ("hand_joints_out", "mano_joints_out", "mano_mesh_out", "obj_rot_out", "obj_trans_out"):
-            assert out[k].shape[0] == 4 and torch.isfinite(out[k]).all(), k
-            err = float((out[k] - want[k]).abs().max()) / max(float(want[k].abs().max()), 1e-12)
-            assert err < 1e-5, (k, err)
-    finally:
-        cfg.set_setting(old[0])
-        type(cfg).dataset = old[1]
-        type(cfg).num_samp_hand, type(cfg).num_samp_obj = old[2], old[3]
-
-
 def test_dexycb_eval_batch_reproduces_the_upstream_item(cuda):
     """`feed.dexycb_eval_batch` (BASELINE configs[2]'s feed) on a batch mixing right and left hands, the fixture's LEFT-hand
     sample first and last: image (mirrored warp), masks, point sets (x-flipped), SDF targets and the host geometry of one
@@ -374,6 +340,69 @@ def test_dexycb_eval_batch_reproduces_the_upstream_item(cuda):
         assert np.array_equal(inputs["img"][i].cpu().numpy(), want), i
 
 
+def test_train_batch_reproduces_the_upstream_dexycb_item(cuda):
+    """`feed.train_batch` on DexYCB material (the fixture's LEFT-hand sample + a right-hand one): mirrored warp -> blur ->
+    jitter -> tensor, mirrored masks, x-flipped + rotated point sets incl. the `*_pre` sets, and the host geometry of one
+    training sample of the unmodified upstream `dexycb.Dataset.__getitem__` with its filters on."""
+    from hoisdf_b200 import feed
+    from test_feed import dexycb_train_product_sample, DEX_TARGETS, EVAL_META
+    g = np.load(GOLDEN)
+    made = [dexycb_train_product_sample(int(g["seed"]), left=True), dexycb_train_product_sample(300, left=False)]
+    rows = torch.from_numpy(np.concatenate([m[4] for m in made])).to(cuda)
+    offsets = torch.from_numpy(np.cumsum([0] + [len(m[4]) for m in made]).astype(np.int64))
+    inputs, targets, meta = feed.train_batch(
+        torch.from_numpy(np.stack([m[1] for m in made])).to(cuda), torch.from_numpy(np.stack([m[2] for m in made])).to(cuda),
+        torch.from_numpy(np.stack([m[3] for m in made])).to(cuda), rows, offsets, [m[0] for m in made], 24, 8, 6.2, 5.8)
+    assert np.array_equal(inputs["img"][0].cpu().numpy()[:, ::8], g["dxt_img_rows"])
+    assert np.array_equal(np.packbits(targets["hand_seg"][0].cpu().numpy().astype(np.uint8)), g["dxt_hand_seg"])
+    assert np.array_equal(np.packbits(targets["obj_seg"][0].cpu().numpy().astype(np.uint8)), g["dxt_obj_seg"])
+    for k in ("hand_sdf_points", "obj_sdf_points", "hand_pre_points", "obj_pre_points"):
+        assert _close32(inputs[k][0].cpu().numpy(), g["dxt_" + k]), k
+    for k in ("hand_sdf", "obj_sdf"):
+        assert _close32(targets[k][0].cpu().numpy(), g["dxt_" + k]), k
+    for k in DEX_TARGETS:
+        assert np.allclose(targets[k][0].cpu().numpy(), g["dxt_" + k], rtol=1e-5, atol=1e-4), k
+    for k in EVAL_META:
+        assert np.allclose(meta[k][0].cpu().numpy(), g["dxt_" + k], rtol=1e-5, atol=1e-4), k
+    assert meta["obj_cls"].shape == (2,)
+
+
+# ---------------------------------------------------------------------------------------------- feed -> model (last: they build whole models)
+
+def test_eval_batch_feeds_the_model(cuda):
+    """Raw frames -> `feed.eval_batch` -> `Model.forward(..., "eval")`: the collated dicts are consumable as they are (upstream's
+    keys and dtypes, incl. the float64 `obj_rot` target and the string entries of meta_info), and the outputs equal those of
+    the same forward on an image batch assembled from the ORACLE's `data_crop` -- main/test.py:120-126 end to end."""
+    from hoisdf_b200 import feed, synthetic as syn
+    from hoisdf_b200.config import cfg
+    from hoisdf_b200.model import get_model
+    old = (cfg.setting, cfg.dataset, cfg.num_samp_hand, cfg.num_samp_obj)
+    try:
+        cfg.set_setting("ho3d")
+        type(cfg).dataset = "ho3d"
+        type(cfg).num_samp_hand, type(cfg).num_samp_obj = 96, 40
+        model = get_model("test", mano_buffers=syn.mano_buffers(5))
+        model.load_state_dict(syn.full_state_dict(5, "ho3d"), strict=True)
+        model = model.to(cuda).eval()
+        raw = [FO.synthetic_eval_annotation(s) for s in (100, 101, 102, 103)]
+        samples = [feed.eval_geometry(ann, corners, (640, 480), 0.7) for _, ann, corners in raw]
+        inputs, targets, meta = feed.eval_batch(torch.from_numpy(np.stack([r[0] for r in raw])).to(cuda), samples)
+        out = model(inputs, targets, meta, "eval")
+        crops = []
+        for img, ann, corners in raw:
+            K = np.array(ann["camMat"], dtype=np.float32)
+            crops.append(FO.data_crop(img, K, np.array(ann["handBoundingBox"], dtype=np.float32), _project(ann, corners, K))[0])
+        want = model({"img": torch.from_numpy(np.stack(crops)).to(cuda)}, targets, meta, "eval")
+        for k in ("hand_joints_out", "mano_joints_out", "mano_mesh_out", "obj_rot_out", "obj_trans_out"):
+            assert out[k].shape[0] == 4 and torch.isfinite(out[k]).all(), k
+            err = float((out[k] - want[k]).abs().max()) / max(float(want[k].abs().max()), 1e-12)
+            assert err < 1e-5, (k, err)
+    finally:
+        cfg.set_setting(old[0])
+        type(cfg).dataset = old[1]
+        type(cfg).num_samp_hand, type(cfg).num_samp_obj = old[2], old[3]
+
+
 def test_dexycb_eval_batch_feeds_the_model(cuda):
     """Raw DexYCB material -> `feed.dexycb_eval_batch` -> `Model.forward(..., "eval")` with cfg.dataset = "dexycb" (BASELINE
     configs[2]'s path from the frames on): the collated dicts are consumable as they are -- every key the dataset branch reads
@@ -407,33 +436,6 @@ def test_dexycb_eval_batch_feeds_the_model(cuda):
         cfg.set_setting(old[0])
         type(cfg).dataset = old[1]
         type(cfg).num_samp_hand, type(cfg).num_samp_obj = old[2], old[3]
-
-
-def test_train_batch_reproduces_the_upstream_dexycb_item(cuda):
-    """`feed.train_batch` on DexYCB material (the fixture's LEFT-hand sample + a right-hand one): mirrored warp -> blur ->
-    jitter -> tensor, mirrored masks, x-flipped + rotated point sets incl. the `*_pre` sets, and the host geometry of one
-    training sample of the unmodified upstream `dexycb.Dataset.__getitem__` with its filters on."""
-    from hoisdf_b200 import feed
-    from test_feed import dexycb_train_product_sample, DEX_TARGETS, EVAL_META
-    g = np.load(GOLDEN)
-    made = [dexycb_train_product_sample(int(g["seed"]), left=True), dexycb_train_product_sample(300, left=False)]
-    rows = torch.from_numpy(np.concatenate([m[4] for m in made])).to(cuda)
-    offsets = torch.from_numpy(np.cumsum([0] + [len(m[4]) for m in made]).astype(np.int64))
-    inputs, targets, meta = feed.train_batch(
-        torch.from_numpy(np.stack([m[1] for m in made])).to(cuda), torch.from_numpy(np.stack([m[2] for m in made])).to(cuda),
-        torch.from_numpy(np.stack([m[3] for m in made])).to(cuda), rows, offsets, [m[0] for m in made], 24, 8, 6.2, 5.8)
-    assert np.array_equal(inputs["img"][0].cpu().numpy()[:, ::8], g["dxt_img_rows"])
-    assert np.array_equal(np.packbits(targets["hand_seg"][0].cpu().numpy().astype(np.uint8)), g["dxt_hand_seg"])
-    assert np.array_equal(np.packbits(targets["obj_seg"][0].cpu().numpy().astype(np.uint8)), g["dxt_obj_seg"])
-    for k in ("hand_sdf_points", "obj_sdf_points", "hand_pre_points", "obj_pre_points"):
-        assert _close32(inputs[k][0].cpu().numpy(), g["dxt_" + k]), k
-    for k in ("hand_sdf", "obj_sdf"):
-        assert _close32(targets[k][0].cpu().numpy(), g["dxt_" + k]), k
-    for k in DEX_TARGETS:
-        assert np.allclose(targets[k][0].cpu().numpy(), g["dxt_" + k], rtol=1e-5, atol=1e-4), k
-    for k in EVAL_META:
-        assert np.allclose(meta[k][0].cpu().numpy(), g["dxt_" + k], rtol=1e-5, atol=1e-4), k
-    assert meta["obj_cls"].shape == (2,)
 
 
 def test_train_batch_feeds_the_training_step(cuda):
