@@ -193,6 +193,149 @@ jitter_apply_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, 
   o[0] = static_cast<uint8_t>(r); o[1] = static_cast<uint8_t>(g); o[2] = static_cast<uint8_t>(bl);
 }
 
+// ---- the whole training image in ONE kernel ------------------------------------------------------------------------------
+// frame -> affine warp -> GaussianBlur -> colour jitter -> ToTensor / 255 (upstream ho3d.py:351-364,550) with ONE CTA per
+// image and the warped res x res x 3 image RESIDENT IN SHARED MEMORY from the gather to the final store: 256 x 772 bytes =
+// 193 KB of the SM's 227 KB (rows padded to an odd number of 32-bit words so that walking a column is bank-conflict free).
+// HBM traffic per image: the gathered source bytes in, 12 bytes per pixel out -- against 13 launches and ~ 40 bytes per pixel
+// through L2 / HBM for the step-by-step entry points above (which stay: masks, other sizes, box radii >= 1).  Same arithmetic,
+// same bytes: the blur's three passes per axis run IN PLACE with a sliding (previous, current, next) window per row / byte
+// column (box radius < 1: a 3-tap filter, all of upstream's radii), the jitter steps run element-wise with a block-wide
+// integer reduction for the contrast mean.
+struct TrainImageArgs {
+  const uint8_t* src; int64_t src_pitch, src_stride; int src_w, src_h;
+  const double* coef; const int32_t* mirror; const uint32_t* blur; const int32_t* ops; const float* factors;
+  int res, row; float* out_f32; uint8_t* out_u8;
+};
+
+__device__ inline int aug_floor(double v) { return v < 0.0 ? static_cast<int>(floor(v)) : static_cast<int>(v); }
+__device__ inline int aug_fix(double v) { return aug_floor(v * 65536.0 + 0.5); }          // Pillow's FIX (Geometry.c)
+
+__device__ inline void blur_line_in_place(uint8_t* p, int len, int step, uint32_t ww, uint32_t fw) {
+  uint32_t prev = p[0], cur = p[0];
+  for (int i = 0; i < len; ++i) {
+    const uint32_t nxt = p[min(i + 1, len - 1) * step];
+    p[i * step] = static_cast<uint8_t>((cur * ww + (prev + nxt) * fw + (1u << 23)) >> 24);
+    prev = cur;
+    cur = nxt;
+  }
+}
+
+__global__ void __launch_bounds__(1024) train_image_kernel(TrainImageArgs a) {
+  HOISDF_DYNAMIC_SMEM(uint8_t, smem);
+  __shared__ unsigned int warp_sums[32];
+  __shared__ int mean_grey;
+  const int b = blockIdx.x, res = a.res, row = a.row, tid = threadIdx.x, nthr = blockDim.x;
+  int* tab = reinterpret_cast<int*>(smem + static_cast<size_t>(res) * row);      // 2 * res source columns / rows (scale-only crops)
+  const double* c = a.coef + static_cast<int64_t>(b) * 6;
+  const bool scale_only = c[1] == 0.0 && c[3] == 0.0;
+  // 1. Pillow's ImagingScaleAffine tables: repeated double additions, one thread per table
+  if (scale_only && (tid == 0 || tid == 32)) {
+    const bool rows = tid == 32;
+    const double stepd = rows ? c[4] : c[0];
+    double o = (rows ? c[5] : c[2]) + stepd * 0.5;
+    const int lim = rows ? a.src_h : a.src_w;
+    for (int i = 0; i < res; ++i) {
+      const int v = o < 0.0 ? -1 : static_cast<int>(o);
+      tab[(rows ? res : 0) + i] = (v >= 0 && v < lim) ? v : -1;
+      o += stepd;
+    }
+  }
+  __syncthreads();
+  // 2. the warp: gather the frame's bytes into shared memory
+  const bool flip = a.mirror != nullptr && a.mirror[b] != 0;
+  const unsigned a0 = static_cast<unsigned>(aug_fix(c[0])), a1 = static_cast<unsigned>(aug_fix(c[1]));
+  const unsigned a3 = static_cast<unsigned>(aug_fix(c[3])), a4 = static_cast<unsigned>(aug_fix(c[4]));
+  const unsigned a2 = static_cast<unsigned>(aug_fix(c[2] + (c[0] * 0.5 + c[1] * 0.5)));
+  const unsigned a5 = static_cast<unsigned>(aug_fix(c[5] + (c[3] * 0.5 + c[4] * 0.5)));
+  for (int i = tid; i < res * res; i += nthr) {
+    const int y = i / res, x = i - y * res;
+    int xin, yin;
+    if (scale_only) {
+      xin = tab[x];
+      yin = tab[res + y];
+    } else {
+      xin = static_cast<int>(a2 + static_cast<unsigned>(y) * a1 + static_cast<unsigned>(x) * a0) >> 16;
+      yin = static_cast<int>(a5 + static_cast<unsigned>(y) * a4 + static_cast<unsigned>(x) * a3) >> 16;
+      if (xin < 0 || xin >= a.src_w || yin < 0 || yin >= a.src_h) xin = yin = -1;
+    }
+    uint8_t* o = smem + y * row + x * 3;
+    if (xin >= 0 && yin >= 0) {
+      if (flip) xin = a.src_w - 1 - xin;
+      const uint8_t* p = a.src + b * a.src_stride + yin * a.src_pitch + static_cast<int64_t>(xin) * 3;
+      o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+    } else {
+      o[0] = o[1] = o[2] = 0;
+    }
+  }
+  __syncthreads();
+  // 3. GaussianBlur: three box passes along x, then three along y, in place
+  const uint32_t ww = a.blur[b * 3 + 1], fw = a.blur[b * 3 + 2];
+  if (fw != 0) {                                                     // (fw == 0: radius 0, the identity)
+    for (int pass = 0; pass < 3; ++pass) {
+      for (int t = tid; t < res * 3; t += nthr) blur_line_in_place(smem + (t / 3) * row + (t % 3), res, 3, ww, fw);
+      __syncthreads();
+    }
+    for (int pass = 0; pass < 3; ++pass) {
+      for (int t = tid; t < res * 3; t += nthr) blur_line_in_place(smem + t, res, row, ww, fw);
+      __syncthreads();
+    }
+  }
+  // 4. colour jitter: up to four adjustments in the sample's order
+  for (int step = 0; step < 4; ++step) {
+    const int op = a.ops[b * 4 + step];
+    if (op == JIT_NONE) continue;                                     // (uniform over the block)
+    const float factor = a.factors[b * 4 + step];
+    const bool inside = factor >= 0.0f && factor <= 1.0f;
+    if (op == JIT_CONTRAST) {
+      unsigned int local = 0;
+      for (int i = tid; i < res * res; i += nthr) {
+        const uint8_t* p = smem + (i / res) * row + (i % res) * 3;
+        local += static_cast<unsigned int>(luma(p[0], p[1], p[2]));
+      }
+      for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+      if ((tid & 31) == 0) warp_sums[tid >> 5] = local;
+      __syncthreads();
+      if (tid == 0) {
+        unsigned long long total = 0;
+        for (int w = 0; w < (nthr >> 5); ++w) total += warp_sums[w];
+        mean_grey = static_cast<int>(__dadd_rn(__ddiv_rn(static_cast<double>(total), static_cast<double>(res * res)), 0.5));
+      }
+      __syncthreads();
+    }
+    const int shift = static_cast<int>(factor);
+    for (int i = tid; i < res * res; i += nthr) {
+      uint8_t* p = smem + (i / res) * row + (i % res) * 3;
+      int r = p[0], g = p[1], bl = p[2];
+      if (op == JIT_HUE) {
+        int h, s, v;
+        rgb_to_hsv(r, g, bl, h, s, v);
+        hsv_to_rgb((h + shift) & 255, s, v, r, g, bl);
+      } else {
+        const int l = op == JIT_BRIGHTNESS ? 0 : (op == JIT_SATURATION ? luma(r, g, bl) : mean_grey);
+        r = blend(l, r, factor, inside); g = blend(l, g, factor, inside); bl = blend(l, bl, factor, inside);
+      }
+      p[0] = static_cast<uint8_t>(r); p[1] = static_cast<uint8_t>(g); p[2] = static_cast<uint8_t>(bl);
+    }
+    __syncthreads();
+  }
+  // 5. ToTensor / 255: three fp32 planes, coalesced along x (and / or the bytes themselves)
+  const int64_t plane = static_cast<int64_t>(res) * res;
+  for (int i = tid; i < res * res; i += nthr) {
+    const uint8_t* p = smem + (i / res) * row + (i % res) * 3;
+    if (a.out_f32 != nullptr) {
+      float* o = a.out_f32 + static_cast<int64_t>(b) * 3 * plane + i;
+      o[0] = __fdiv_rn(static_cast<float>(p[0]), 255.0f);
+      o[plane] = __fdiv_rn(static_cast<float>(p[1]), 255.0f);
+      o[2 * plane] = __fdiv_rn(static_cast<float>(p[2]), 255.0f);
+    }
+    if (a.out_u8 != nullptr) {
+      uint8_t* o = a.out_u8 + (static_cast<int64_t>(b) * plane + i) * 3;
+      o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+    }
+  }
+}
+
 }  // namespace
 }  // namespace hoisdf
 
@@ -263,5 +406,40 @@ HOISDF_API int hoisdf_color_jitter_u8(const uint8_t* src, uint8_t* dst, int64_t 
                   static_cast<const unsigned long long*>(step_sums));
     cur = dst;
   }
+  return launch_status();
+}
+
+// row pitch of the shared-memory image: res * 3 rounded up to whole 32-bit words, an ODD number of them (bank-conflict-free columns)
+static int train_image_row_bytes(int64_t res) {
+  int64_t words = (res * 3 + 3) / 4;
+  if ((words & 1) == 0) ++words;
+  return static_cast<int>(words * 4);
+}
+
+HOISDF_API int64_t hoisdf_train_image_smem_bytes(int64_t res) {
+  if (res <= 0 || res > 4096) return HOISDF_E_SHAPE;
+  return res * train_image_row_bytes(res) + 2 * res * static_cast<int64_t>(sizeof(int));
+}
+
+HOISDF_API int hoisdf_train_image_fwd(const uint8_t* src, int64_t batch, int64_t src_h, int64_t src_w, int64_t src_pitch,
+                                      int64_t src_stride, const double* coef, const int32_t* mirror, const uint32_t* blur,
+                                      const int32_t* ops, const float* factors, int64_t res, float* out_f32, uint8_t* out_u8,
+                                      void* stream) {
+  if (src == nullptr || coef == nullptr || blur == nullptr || ops == nullptr || factors == nullptr ||
+      (out_f32 == nullptr && out_u8 == nullptr))
+    return HOISDF_E_NULL;
+  if (batch <= 0 || src_h <= 0 || src_w <= 0 || src_h > 32767 || src_w > 32767 || res <= 0 || src_pitch < 3 * src_w ||
+      src_stride < src_pitch * src_h)
+    return HOISDF_E_SHAPE;
+  const int64_t smem = hoisdf_train_image_smem_bytes(res);
+  if (smem < 0 || smem > 227 * 1024) return HOISDF_E_UNSUPPORTED;        // the image does not fit one SM: use the step-by-step calls
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#ifndef HOISDF_EMULATE
+  cudaError_t e = cudaFuncSetAttribute(train_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return static_cast<int>(e);
+#endif
+  TrainImageArgs a{src, src_pitch, src_stride, static_cast<int>(src_w), static_cast<int>(src_h), coef, mirror, blur, ops, factors,
+                   static_cast<int>(res), train_image_row_bytes(res), out_f32, out_u8};
+  HOISDF_LAUNCH_SMEM(train_image_kernel, static_cast<unsigned>(batch), 1024, static_cast<size_t>(smem), s, a);
   return launch_status();
 }

@@ -31,7 +31,7 @@ from ._capi import check, lib
 
 __all__ = ["bbox_from_points", "fuse_boxes", "crop_affine", "apply_affine", "pil_coefficients", "resize_coefficients",
            "crop_geometry", "crop_geometry_dexycb", "crop_images", "crop_masks", "data_crop", "draw_sdf_indices", "sdf_point_sets",
-           "gaussian_blur", "draw_color_jitter", "color_jitter", "to_tensor",
+           "gaussian_blur", "draw_color_jitter", "color_jitter", "to_tensor", "train_images",
            "draw_train_geometry", "train_geometry", "train_batch",
            "eval_geometry", "eval_batch", "dexycb_annotation", "dexycb_eval_geometry", "dexycb_eval_batch",
            "dexycb_train_geometry"]
@@ -336,10 +336,7 @@ def gaussian_blur(images: torch.Tensor, radii: Sequence[float]) -> torch.Tensor:
     """`img.filter(ImageFilter.GaussianBlur(radius))` (ho3d.py:355-357) per sample: images (B, H, W, C) uint8 on the GPU, radii (B,)
     = upstream's `random.random() * self.blur_radius` draws.  -> the blurred bytes, as Pillow produces them."""
     b, h, w, ch = _bytes_image(images)
-    import ctypes
-    params = np.zeros((b, 3), np.uint32)
-    for i, r in enumerate(np.asarray(radii, dtype=np.float64).reshape(b)):
-        check(lib.hoisdf_gaussian_blur_params(float(r), 3, params[i].ctypes.data_as(ctypes.c_void_p)), "hoisdf_gaussian_blur_params")
+    params = _blur_tables(radii, b)
     dev = images.device
     with _on(dev):
         params_d = torch.from_numpy(params.view(np.int32)).to(dev)
@@ -365,11 +362,8 @@ def draw_color_jitter(brightness: float = 0, contrast: float = 0, saturation: fl
     return steps
 
 
-def color_jitter(images: torch.Tensor, steps: Sequence[Sequence[Tuple[str, float]]]) -> torch.Tensor:
-    """`dataset_util.color_jitter` for a batch: images (B, H, W, 3) uint8 on the GPU, steps[b] = that sample's adjustments in
-    application order (`draw_color_jitter`), each ("brightness" | "saturation" | "hue" | "contrast", factor as torchvision's
-    `adjust_*` receives it).  -> the jittered bytes, as torchvision's PIL branch produces them."""
-    b, h, w, _ = _bytes_image(images, (3,))
+def _jitter_tables(steps, b: int) -> Tuple[np.ndarray, np.ndarray]:
+    """(B, 4) op codes and factors of `hoisdf_color_jitter_u8` / `hoisdf_train_image_fwd` from per-sample (name, factor) lists."""
     if len(steps) != b:
         raise ValueError("one step list per sample")
     codes = np.zeros((b, 4), np.int32)
@@ -385,6 +379,62 @@ def color_jitter(images: torch.Tensor, steps: Sequence[Sequence[Tuple[str, float
                 factors[i, j] = float(np.int32(f * 255).astype(np.uint8))                # torchvision's byte shift of H
             else:
                 factors[i, j] = f
+    return codes, factors
+
+
+def _blur_tables(radii, b: int) -> np.ndarray:
+    """(B, 3) uint32 {n, ww, fw} of `hoisdf_gaussian_blur_params` for the samples' radii."""
+    import ctypes
+    params = np.zeros((b, 3), np.uint32)
+    for i, r in enumerate(np.asarray(radii, dtype=np.float64).reshape(b)):
+        check(lib.hoisdf_gaussian_blur_params(float(r), 3, params[i].ctypes.data_as(ctypes.c_void_p)), "hoisdf_gaussian_blur_params")
+    return params
+
+
+def train_images(frames: torch.Tensor, coefficients: np.ndarray, radii: Sequence[float], steps, res: int = 256, mirror=None
+                 ) -> torch.Tensor:
+    """The network input of a batch of TRAINING frames (ho3d.py:351-364,550): warp -> GaussianBlur -> colour jitter ->
+    ToTensor / 255 -- in ONE launch (`hoisdf_train_image_fwd`: one CTA per frame, the warped image resident in shared memory)
+    when the crop fits an SM's shared memory and every blur has box radius < 1 (all of upstream's draws), otherwise through
+    the step-by-step calls; the bytes are the same either way.  frames (B, H, W, 3) uint8 on the GPU; coefficients (B, 6);
+    radii (B,); steps[b] = `draw_color_jitter(...)`; mirror (B,) bool or None.  -> (B, 3, res, res) float32."""
+    _require_gpu(frames)
+    if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[3] != 3 or frames.stride(3) != 1 or frames.stride(2) != 3:
+        raise ValueError("frames must be (B, H, W, 3) uint8 with packed RGB pixels")
+    b, h, w, _ = frames.shape
+    blur = _blur_tables(radii, b)
+    codes, factors = _jitter_tables(steps, b)
+    smem = lib.hoisdf_train_image_smem_bytes(res)
+    if (blur[:, 0] != 0).any() or smem < 0 or smem > 227 * 1024:
+        warped = crop_images(frames, coefficients, res, as_bytes=True, mirror=mirror)
+        return to_tensor(color_jitter(gaussian_blur(warped, radii), steps))
+    coef = np.ascontiguousarray(np.asarray(coefficients, dtype=np.float64).reshape(b, 6))
+    if not np.isfinite(coef).all():
+        raise ValueError("non-finite crop coefficients")
+    for a in coef:
+        if (a[1] != 0.0 or a[3] != 0.0) and not _fixed_point_ok(a, res):
+            raise ValueError("crop transform outside Pillow's fixed-point range (|source coordinate| >= 32768)")
+    frame_pitch = frames.stride(0) if b > 1 else h * frames.stride(1)
+    dev = frames.device
+    with _on(dev):
+        coef_d = torch.from_numpy(coef).to(dev)
+        mirror_d = None if mirror is None else torch.as_tensor(np.asarray(mirror).astype(np.int32).reshape(b)).to(dev)
+        blur_d = torch.from_numpy(blur.view(np.int32)).to(dev)
+        codes_d, factors_d = torch.from_numpy(codes).to(dev), torch.from_numpy(factors).to(dev)
+        out = torch.empty(b, 3, res, res, device=dev, dtype=torch.float32)
+        ops._count(1)
+        check(lib.hoisdf_train_image_fwd(frames.data_ptr(), b, h, w, frames.stride(1), frame_pitch, coef_d.data_ptr(),
+                                         ops._ptr(mirror_d), blur_d.data_ptr(), codes_d.data_ptr(), factors_d.data_ptr(), res,
+                                         out.data_ptr(), None, _stream()), "hoisdf_train_image_fwd")
+    return out
+
+
+def color_jitter(images: torch.Tensor, steps: Sequence[Sequence[Tuple[str, float]]]) -> torch.Tensor:
+    """`dataset_util.color_jitter` for a batch: images (B, H, W, 3) uint8 on the GPU, steps[b] = that sample's adjustments in
+    application order (`draw_color_jitter`), each ("brightness" | "saturation" | "hue" | "contrast", factor as torchvision's
+    `adjust_*` receives it).  -> the jittered bytes, as torchvision's PIL branch produces them."""
+    b, h, w, _ = _bytes_image(images, (3,))
+    codes, factors = _jitter_tables(steps, b)
     dev = images.device
     with _on(dev):
         out = torch.empty_like(images)
@@ -500,8 +550,7 @@ def train_batch(frames: torch.Tensor, hand_masks: torch.Tensor, obj_masks: torch
         raise ValueError("one sample dict per frame")
     coef = np.stack([s["coef"] for s in samples])
     mirror = np.array([bool(s.get("flip", False)) for s in samples])           # DexYCB left hands (dexycb.py:427-430,479-481,547)
-    warped = crop_images(frames, coef, res, as_bytes=True, mirror=mirror)
-    img = to_tensor(color_jitter(gaussian_blur(warped, [s["blur_radius"] for s in samples]), [s["jitter"] for s in samples]))
+    img = train_images(frames, coef, [s["blur_radius"] for s in samples], [s["jitter"] for s in samples], res, mirror)
     stack = lambda key: torch.from_numpy(np.stack([np.asarray(s[key]) for s in samples])).to(dev)  # noqa: E731  (dtypes as upstream's collate)
     inputs, targets = sdf_point_sets(rows, row_offsets, torch.from_numpy(np.stack([s["index"] for s in samples])), n_hand, n_obj,
                                      stack("mano_root"), stack("obj_center_cam"), hand_sdf_scale, obj_sdf_scale,

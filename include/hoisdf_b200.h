@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 37
+#define HOISDF_ABI_VERSION 38
 
 enum {
   HOISDF_OK = 0,
@@ -702,6 +702,20 @@ int hoisdf_gaussian_blur_u8(const uint8_t* src, uint8_t* dst, uint8_t* scratch, 
  * ------------------------------------------------------------------------------------------------- */
 int hoisdf_color_jitter_u8(const uint8_t* src, uint8_t* dst, int64_t batch, int64_t h, int64_t w, const int32_t* ops,
                            const float* factors, uint64_t* sums, void* stream);
+
+/* The whole training image in ONE launch (upstream data/ho3d.py:351-364,550: transform_img + crop, GaussianBlur, color_jitter,
+ * ToTensor / 255): one CTA per frame, the warped res x res x 3 image resident in shared memory from the gather to the final
+ * store (hoisdf_train_image_smem_bytes(res): 193 KB at res = 256, of the SM's 227 KB) -- the same bytes as
+ * hoisdf_image_crop_fwd -> hoisdf_gaussian_blur_u8 -> hoisdf_color_jitter_u8 -> the float conversion, in 1 launch instead of 13.
+ *   src / coef / mirror as hoisdf_image_crop_fwd (RGB); blur (batch, 3) uint32 = hoisdf_gaussian_blur_params triples, box radius
+ *   n = 0 only (Gaussian radius < ~1.4: every radius upstream draws; the caller checks, hoisdf_b200/feed.py falls back);
+ *   ops / factors as hoisdf_color_jitter_u8; out_f32 (batch, 3, res, res) and / or out_u8 (batch, res, res, 3).
+ *   HOISDF_E_UNSUPPORTED when the image does not fit one SM's shared memory (res > 256).
+ * ------------------------------------------------------------------------------------------------- */
+int64_t hoisdf_train_image_smem_bytes(int64_t res);
+int hoisdf_train_image_fwd(const uint8_t* src, int64_t batch, int64_t src_h, int64_t src_w, int64_t src_pitch, int64_t src_stride,
+                           const double* coef, const int32_t* mirror, const uint32_t* blur, const int32_t* ops,
+                           const float* factors, int64_t res, float* out_f32, uint8_t* out_u8, void* stream);
 
 /* One Linear of the training step per call (what hoisdf_b200/autograd.py:LinearFn runs; upstream main/train.py:108-131 through
  * every nn.Linear of the hot path), fp32 in / fp32 out on the FP16x3 tensor-core GEMM, caller-owned workspace of

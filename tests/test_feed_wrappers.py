@@ -15,7 +15,7 @@ from hoisdf_b200 import _capi, feed, ops
 from test_kernel_emulation import build_emulated
 
 FEED_ENTRY_POINTS = ("hoisdf_image_crop_fwd", "hoisdf_sdf_rows_fwd", "hoisdf_gaussian_blur_params", "hoisdf_gaussian_blur_u8",
-                     "hoisdf_color_jitter_u8")
+                     "hoisdf_color_jitter_u8", "hoisdf_train_image_smem_bytes", "hoisdf_train_image_fwd")
 
 
 @pytest.fixture()
@@ -83,6 +83,10 @@ def test_dexycb_eval_batch(host):
 
 def test_train_batch_dexycb(host):
     G.test_train_batch_reproduces_the_upstream_dexycb_item(host)
+
+
+def test_fused_training_image(host):
+    G.test_fused_training_image_equals_the_step_by_step_calls(host)
 
 
 def test_the_patches_are_gone_afterwards():

@@ -367,6 +367,38 @@ def test_train_batch_reproduces_the_upstream_dexycb_item(cuda):
     assert meta["obj_cls"].shape == (2,)
 
 
+
+def test_fused_training_image_equals_the_step_by_step_calls(cuda):
+    """`hoisdf_train_image_fwd` (one CTA per frame, the image resident in shared memory) against warp -> blur -> jitter ->
+    tensor through the separate entry points: rotated and scale-only warps, mirrored frames, windows leaving the frame, radius
+    0, fewer than four adjustments, every adjustment first -- bit-identical; a box radius >= 1 takes the fallback."""
+    import itertools
+    from hoisdf_b200 import feed
+    rng = np.random.default_rng(21)
+    draws = [FO.synthetic_aug(40 + s) for s in range(8)]
+    coef = np.stack([feed.pil_coefficients(feed.crop_affine(c, sc, 256, r if i % 4 else 0.0))
+                     for i, (_, _, _, c, sc, r) in enumerate(draws)])
+    coef[5] = [3.1, 0, -200.0, 0, 2.4, 150.0]                            # mostly outside the frame
+    frames = torch.from_numpy(np.stack([d[0] for d in draws])).to(cuda)
+    mirror = np.array([0, 1, 0, 1, 1, 0, 0, 1])
+    radii = [0.0, 0.49, 0.2, 0.31, 0.05, 0.44, 0.13, 0.38]
+    orders = list(itertools.permutations(["brightness", "saturation", "hue", "contrast"]))
+    steps = []
+    for i in range(8):
+        f = {"brightness": rng.uniform(0.5, 1.5), "saturation": rng.uniform(0.5, 1.5), "contrast": rng.uniform(0.5, 1.5),
+             "hue": rng.uniform(-0.15, 0.15)}
+        steps.append([(n, float(f[n])) for n in orders[(i * 7) % 24]])
+    steps[2], steps[3] = steps[2][:2], []
+    fused = feed.train_images(frames, coef, radii, steps, 256, mirror)
+    warped = feed.crop_images(frames, coef, 256, as_bytes=True, mirror=mirror)
+    separate = feed.to_tensor(feed.color_jitter(feed.gaussian_blur(warped, radii), steps))
+    assert fused.shape == (8, 3, 256, 256) and torch.equal(fused, separate)
+    radii[1] = 2.5                                                       # box radius 1: the fused kernel is not taken
+    again = feed.train_images(frames, coef, radii, steps, 256, mirror)
+    assert torch.equal(again[0], fused[0]) and not torch.equal(again[1], fused[1])
+    assert torch.equal(again, feed.to_tensor(feed.color_jitter(feed.gaussian_blur(warped, radii), steps)))
+
+
 # ---------------------------------------------------------------------------------------------- feed -> model (last: they build whole models)
 
 def test_eval_batch_feeds_the_model(cuda):
