@@ -229,43 +229,6 @@ def test_training_image_reproduces_the_upstream_fixture(cuda):
     assert np.array_equal(img[0].cpu().numpy()[:, ::8], g["filt_img_rows"])
 
 
-def test_train_batch_reproduces_the_upstream_item(cuda):
-    """`feed.train_batch` on a batch holding the fixture's sample twice (+ one other frame in between): every entry of the
-    unmodified upstream `Dataset.__getitem__` item with its filters on -- image, masks, point sets, SDF targets (GPU) and the
-    host geometry -- at the fixture's position, and identical results for the repeated sample."""
-    from hoisdf_b200 import feed
-    from test_feed import product_sample, TARGET_KEYS, META_KEYS
-    g = np.load(GOLDEN)
-    seed = int(g["seed"])
-    state = np.random.get_state()
-    picks = [seed, seed + 1, seed]
-    host = [product_sample(s) for s in picks]
-    np.random.set_state(state)
-    aug = [FO.synthetic_aug(s) for s in picks]
-    frames = torch.from_numpy(np.stack([a[0] for a in aug])).to(cuda)
-    hand_masks = torch.from_numpy(np.stack([a[1] for a in aug])).to(cuda)
-    obj_masks = torch.from_numpy(np.stack([a[2] for a in aug])).to(cuda)
-    rows = torch.from_numpy(np.concatenate([h[1] for h in host])).to(cuda)
-    offsets = torch.from_numpy(np.cumsum([0] + [len(h[1]) for h in host]).astype(np.int64))
-    inputs, targets, meta = feed.train_batch(frames, hand_masks, obj_masks, rows, offsets, [h[0] for h in host], 24, 8, 6.2, 5.8)
-    assert inputs["img"].shape == (3, 3, 256, 256) and targets["hand_seg"].shape == (3, 128, 128)
-    for i in (0, 2):
-        assert np.array_equal(inputs["img"][i].cpu().numpy()[:, ::8], g["filt_img_rows"])
-        assert np.array_equal(targets["hand_seg"][i].cpu().numpy(), g["filt_t_hand_seg"])
-        assert np.array_equal(targets["obj_seg"][i].cpu().numpy(), g["filt_t_obj_seg"])
-        for k in ("hand_sdf_points", "obj_sdf_points", "hand_pre_points", "obj_pre_points"):
-            assert _close32(inputs[k][i].cpu().numpy(), g["filt_i_" + k]), k
-        assert _close32(targets["hand_sdf"][i].cpu().numpy(), g["filt_t_hand_sdf"])
-        assert _close32(targets["obj_sdf"][i].cpu().numpy(), g["filt_t_obj_sdf"])
-        for k in TARGET_KEYS:
-            assert np.allclose(targets[k][i].cpu().numpy(), g["filt_t_" + k], rtol=1e-5, atol=1e-5), k
-        for k in META_KEYS:
-            assert np.allclose(meta[k][i].cpu().numpy(), g["filt_m_" + k], rtol=1e-5, atol=1e-4), k
-    for d in (inputs, targets, meta):
-        for k, v in d.items():
-            assert torch.equal(v[0], v[2]), k
-
-
 def test_eval_batch_reproduces_the_upstream_item(cuda):
     """`feed.eval_batch` at BASELINE configs[1]'s batch (32 frames; the fixture's frame first and last) against one sample of
     the unmodified upstream `Dataset.__getitem__` in evaluation mode -- the feed of main/test.py's loop."""
@@ -340,65 +303,6 @@ def test_dexycb_eval_batch_reproduces_the_upstream_item(cuda):
         assert np.array_equal(inputs["img"][i].cpu().numpy(), want), i
 
 
-def test_train_batch_reproduces_the_upstream_dexycb_item(cuda):
-    """`feed.train_batch` on DexYCB material (the fixture's LEFT-hand sample + a right-hand one): mirrored warp -> blur ->
-    jitter -> tensor, mirrored masks, x-flipped + rotated point sets incl. the `*_pre` sets, and the host geometry of one
-    training sample of the unmodified upstream `dexycb.Dataset.__getitem__` with its filters on."""
-    from hoisdf_b200 import feed
-    from test_feed import dexycb_train_product_sample, DEX_TARGETS, EVAL_META
-    g = np.load(GOLDEN)
-    made = [dexycb_train_product_sample(int(g["seed"]), left=True), dexycb_train_product_sample(300, left=False)]
-    rows = torch.from_numpy(np.concatenate([m[4] for m in made])).to(cuda)
-    offsets = torch.from_numpy(np.cumsum([0] + [len(m[4]) for m in made]).astype(np.int64))
-    inputs, targets, meta = feed.train_batch(
-        torch.from_numpy(np.stack([m[1] for m in made])).to(cuda), torch.from_numpy(np.stack([m[2] for m in made])).to(cuda),
-        torch.from_numpy(np.stack([m[3] for m in made])).to(cuda), rows, offsets, [m[0] for m in made], 24, 8, 6.2, 5.8)
-    assert np.array_equal(inputs["img"][0].cpu().numpy()[:, ::8], g["dxt_img_rows"])
-    assert np.array_equal(np.packbits(targets["hand_seg"][0].cpu().numpy().astype(np.uint8)), g["dxt_hand_seg"])
-    assert np.array_equal(np.packbits(targets["obj_seg"][0].cpu().numpy().astype(np.uint8)), g["dxt_obj_seg"])
-    for k in ("hand_sdf_points", "obj_sdf_points", "hand_pre_points", "obj_pre_points"):
-        assert _close32(inputs[k][0].cpu().numpy(), g["dxt_" + k]), k
-    for k in ("hand_sdf", "obj_sdf"):
-        assert _close32(targets[k][0].cpu().numpy(), g["dxt_" + k]), k
-    for k in DEX_TARGETS:
-        assert np.allclose(targets[k][0].cpu().numpy(), g["dxt_" + k], rtol=1e-5, atol=1e-4), k
-    for k in EVAL_META:
-        assert np.allclose(meta[k][0].cpu().numpy(), g["dxt_" + k], rtol=1e-5, atol=1e-4), k
-    assert meta["obj_cls"].shape == (2,)
-
-
-
-def test_fused_training_image_equals_the_step_by_step_calls(cuda):
-    """`hoisdf_train_image_fwd` (one CTA per frame, the image resident in shared memory) against warp -> blur -> jitter ->
-    tensor through the separate entry points: rotated and scale-only warps, mirrored frames, windows leaving the frame, radius
-    0, fewer than four adjustments, every adjustment first -- bit-identical; a box radius >= 1 takes the fallback."""
-    import itertools
-    from hoisdf_b200 import feed
-    rng = np.random.default_rng(21)
-    draws = [FO.synthetic_aug(40 + s) for s in range(8)]
-    coef = np.stack([feed.pil_coefficients(feed.crop_affine(c, sc, 256, r if i % 4 else 0.0))
-                     for i, (_, _, _, c, sc, r) in enumerate(draws)])
-    coef[5] = [3.1, 0, -200.0, 0, 2.4, 150.0]                            # mostly outside the frame
-    frames = torch.from_numpy(np.stack([d[0] for d in draws])).to(cuda)
-    mirror = np.array([0, 1, 0, 1, 1, 0, 0, 1])
-    radii = [0.0, 0.49, 0.2, 0.31, 0.05, 0.44, 0.13, 0.38]
-    orders = list(itertools.permutations(["brightness", "saturation", "hue", "contrast"]))
-    steps = []
-    for i in range(8):
-        f = {"brightness": rng.uniform(0.5, 1.5), "saturation": rng.uniform(0.5, 1.5), "contrast": rng.uniform(0.5, 1.5),
-             "hue": rng.uniform(-0.15, 0.15)}
-        steps.append([(n, float(f[n])) for n in orders[(i * 7) % 24]])
-    steps[2], steps[3] = steps[2][:2], []
-    fused = feed.train_images(frames, coef, radii, steps, 256, mirror)
-    warped = feed.crop_images(frames, coef, 256, as_bytes=True, mirror=mirror)
-    separate = feed.to_tensor(feed.color_jitter(feed.gaussian_blur(warped, radii), steps))
-    assert fused.shape == (8, 3, 256, 256) and torch.equal(fused, separate)
-    radii[1] = 2.5                                                       # box radius 1: the fused kernel is not taken
-    again = feed.train_images(frames, coef, radii, steps, 256, mirror)
-    assert torch.equal(again[0], fused[0]) and not torch.equal(again[1], fused[1])
-    assert torch.equal(again, feed.to_tensor(feed.color_jitter(feed.gaussian_blur(warped, radii), steps)))
-
-
 # ---------------------------------------------------------------------------------------------- feed -> model (last: they build whole models)
 
 def test_eval_batch_feeds_the_model(cuda):
@@ -468,6 +372,104 @@ def test_dexycb_eval_batch_feeds_the_model(cuda):
         cfg.set_setting(old[0])
         type(cfg).dataset = old[1]
         type(cfg).num_samp_hand, type(cfg).num_samp_obj = old[2], old[3]
+
+
+# ---------------------------------------------------------------------------------------------- the fused training-image kernel and its users (last)
+
+
+def test_fused_training_image_equals_the_step_by_step_calls(cuda):
+    """`hoisdf_train_image_fwd` (one CTA per frame, the image resident in shared memory) against warp -> blur -> jitter ->
+    tensor through the separate entry points: rotated and scale-only warps, mirrored frames, windows leaving the frame, radius
+    0, fewer than four adjustments, every adjustment first -- bit-identical; a box radius >= 1 takes the fallback."""
+    import itertools
+    from hoisdf_b200 import feed
+    rng = np.random.default_rng(21)
+    draws = [FO.synthetic_aug(40 + s) for s in range(8)]
+    coef = np.stack([feed.pil_coefficients(feed.crop_affine(c, sc, 256, r if i % 4 else 0.0))
+                     for i, (_, _, _, c, sc, r) in enumerate(draws)])
+    coef[5] = [3.1, 0, -200.0, 0, 2.4, 150.0]                            # mostly outside the frame
+    frames = torch.from_numpy(np.stack([d[0] for d in draws])).to(cuda)
+    mirror = np.array([0, 1, 0, 1, 1, 0, 0, 1])
+    radii = [0.0, 0.49, 0.2, 0.31, 0.05, 0.44, 0.13, 0.38]
+    orders = list(itertools.permutations(["brightness", "saturation", "hue", "contrast"]))
+    steps = []
+    for i in range(8):
+        f = {"brightness": rng.uniform(0.5, 1.5), "saturation": rng.uniform(0.5, 1.5), "contrast": rng.uniform(0.5, 1.5),
+             "hue": rng.uniform(-0.15, 0.15)}
+        steps.append([(n, float(f[n])) for n in orders[(i * 7) % 24]])
+    steps[2], steps[3] = steps[2][:2], []
+    fused = feed.train_images(frames, coef, radii, steps, 256, mirror)
+    warped = feed.crop_images(frames, coef, 256, as_bytes=True, mirror=mirror)
+    separate = feed.to_tensor(feed.color_jitter(feed.gaussian_blur(warped, radii), steps))
+    assert fused.shape == (8, 3, 256, 256) and torch.equal(fused, separate)
+    radii[1] = 2.5                                                       # box radius 1: the fused kernel is not taken
+    again = feed.train_images(frames, coef, radii, steps, 256, mirror)
+    assert torch.equal(again[0], fused[0]) and not torch.equal(again[1], fused[1])
+    assert torch.equal(again, feed.to_tensor(feed.color_jitter(feed.gaussian_blur(warped, radii), steps)))
+
+
+def test_train_batch_reproduces_the_upstream_item(cuda):
+    """`feed.train_batch` on a batch holding the fixture's sample twice (+ one other frame in between): every entry of the
+    unmodified upstream `Dataset.__getitem__` item with its filters on -- image, masks, point sets, SDF targets (GPU) and the
+    host geometry -- at the fixture's position, and identical results for the repeated sample."""
+    from hoisdf_b200 import feed
+    from test_feed import product_sample, TARGET_KEYS, META_KEYS
+    g = np.load(GOLDEN)
+    seed = int(g["seed"])
+    state = np.random.get_state()
+    picks = [seed, seed + 1, seed]
+    host = [product_sample(s) for s in picks]
+    np.random.set_state(state)
+    aug = [FO.synthetic_aug(s) for s in picks]
+    frames = torch.from_numpy(np.stack([a[0] for a in aug])).to(cuda)
+    hand_masks = torch.from_numpy(np.stack([a[1] for a in aug])).to(cuda)
+    obj_masks = torch.from_numpy(np.stack([a[2] for a in aug])).to(cuda)
+    rows = torch.from_numpy(np.concatenate([h[1] for h in host])).to(cuda)
+    offsets = torch.from_numpy(np.cumsum([0] + [len(h[1]) for h in host]).astype(np.int64))
+    inputs, targets, meta = feed.train_batch(frames, hand_masks, obj_masks, rows, offsets, [h[0] for h in host], 24, 8, 6.2, 5.8)
+    assert inputs["img"].shape == (3, 3, 256, 256) and targets["hand_seg"].shape == (3, 128, 128)
+    for i in (0, 2):
+        assert np.array_equal(inputs["img"][i].cpu().numpy()[:, ::8], g["filt_img_rows"])
+        assert np.array_equal(targets["hand_seg"][i].cpu().numpy(), g["filt_t_hand_seg"])
+        assert np.array_equal(targets["obj_seg"][i].cpu().numpy(), g["filt_t_obj_seg"])
+        for k in ("hand_sdf_points", "obj_sdf_points", "hand_pre_points", "obj_pre_points"):
+            assert _close32(inputs[k][i].cpu().numpy(), g["filt_i_" + k]), k
+        assert _close32(targets["hand_sdf"][i].cpu().numpy(), g["filt_t_hand_sdf"])
+        assert _close32(targets["obj_sdf"][i].cpu().numpy(), g["filt_t_obj_sdf"])
+        for k in TARGET_KEYS:
+            assert np.allclose(targets[k][i].cpu().numpy(), g["filt_t_" + k], rtol=1e-5, atol=1e-5), k
+        for k in META_KEYS:
+            assert np.allclose(meta[k][i].cpu().numpy(), g["filt_m_" + k], rtol=1e-5, atol=1e-4), k
+    for d in (inputs, targets, meta):
+        for k, v in d.items():
+            assert torch.equal(v[0], v[2]), k
+
+
+def test_train_batch_reproduces_the_upstream_dexycb_item(cuda):
+    """`feed.train_batch` on DexYCB material (the fixture's LEFT-hand sample + a right-hand one): mirrored warp -> blur ->
+    jitter -> tensor, mirrored masks, x-flipped + rotated point sets incl. the `*_pre` sets, and the host geometry of one
+    training sample of the unmodified upstream `dexycb.Dataset.__getitem__` with its filters on."""
+    from hoisdf_b200 import feed
+    from test_feed import dexycb_train_product_sample, DEX_TARGETS, EVAL_META
+    g = np.load(GOLDEN)
+    made = [dexycb_train_product_sample(int(g["seed"]), left=True), dexycb_train_product_sample(300, left=False)]
+    rows = torch.from_numpy(np.concatenate([m[4] for m in made])).to(cuda)
+    offsets = torch.from_numpy(np.cumsum([0] + [len(m[4]) for m in made]).astype(np.int64))
+    inputs, targets, meta = feed.train_batch(
+        torch.from_numpy(np.stack([m[1] for m in made])).to(cuda), torch.from_numpy(np.stack([m[2] for m in made])).to(cuda),
+        torch.from_numpy(np.stack([m[3] for m in made])).to(cuda), rows, offsets, [m[0] for m in made], 24, 8, 6.2, 5.8)
+    assert np.array_equal(inputs["img"][0].cpu().numpy()[:, ::8], g["dxt_img_rows"])
+    assert np.array_equal(np.packbits(targets["hand_seg"][0].cpu().numpy().astype(np.uint8)), g["dxt_hand_seg"])
+    assert np.array_equal(np.packbits(targets["obj_seg"][0].cpu().numpy().astype(np.uint8)), g["dxt_obj_seg"])
+    for k in ("hand_sdf_points", "obj_sdf_points", "hand_pre_points", "obj_pre_points"):
+        assert _close32(inputs[k][0].cpu().numpy(), g["dxt_" + k]), k
+    for k in ("hand_sdf", "obj_sdf"):
+        assert _close32(targets[k][0].cpu().numpy(), g["dxt_" + k]), k
+    for k in DEX_TARGETS:
+        assert np.allclose(targets[k][0].cpu().numpy(), g["dxt_" + k], rtol=1e-5, atol=1e-4), k
+    for k in EVAL_META:
+        assert np.allclose(meta[k][0].cpu().numpy(), g["dxt_" + k], rtol=1e-5, atol=1e-4), k
+    assert meta["obj_cls"].shape == (2,)
 
 
 def test_train_batch_feeds_the_training_step(cuda):
