@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhoisdf_b200.so")
 
-ABI_VERSION = 38
+ABI_VERSION = 39
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2      # ACT_SIGMOID: hoisdf_linear_narrow_split_fwd only
 GATHER_CONCAT, GATHER_SUM = 0, 1
 
@@ -196,6 +196,7 @@ SIGNATURES = {
     "hoisdf_color_jitter_u8": (C.c_int, [vp, vp, i64, i64, i64, vp, vp, vp, vp]),
     "hoisdf_train_image_smem_bytes": (i64, [i64]),
     "hoisdf_train_image_fwd": (C.c_int, [vp, i64, i64, i64, i64, i64, vp, vp, vp, vp, vp, i64, vp, vp, vp]),
+    "hoisdf_mask_crop_fwd": (C.c_int, [vp, i64, i64, i64, i64, i64, vp, vp, i64, i64, vp, vp]),
     "hoisdf_sdf_rows_fwd": (C.c_int, [vp, vp, vp, i64, i64, i64, i64, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp, vp, vp,
                                       vp, vp, vp, vp]),
     "hoisdf_linear_train_workspace_bytes": (i64, [i64, i64, i64]),

@@ -148,6 +148,71 @@ __global__ void __launch_bounds__(256) sdf_rows_kernel(SdfRowsArgs a) {
   }
 }
 
+// ---- segmentation masks of a training / DexYCB sample in ONE launch: `transform_img(mask)` to (res, res), then
+// `.resize((out_res, out_res), Image.NEAREST)`, then `.astype(float32)` (ho3d.py:366-381,551-552; dexycb.py:323-336,389-402).
+// One CTA per mask.  The shrink is Pillow's scale-only path with step res / out_res: its two tables (which warped column / row
+// each output column / row takes) and, for an un-rotated warp, the warp's two tables are built in shared memory by four threads
+// (repeated double-precision additions, as Pillow builds them); every output pixel is then ONE byte gathered from the frame.
+__global__ void __launch_bounds__(1024)
+mask_crop_kernel(const uint8_t* __restrict__ src, int64_t src_pitch, int64_t src_stride, int src_w, int src_h,
+                 const double* __restrict__ coef, const int32_t* __restrict__ mirror, int res, int out_res,
+                 float* __restrict__ out) {
+  HOISDF_DYNAMIC_SMEM(int, tabs);                 // [0, out_res): mid column, [out_res, 2 out_res): mid row, then 2 * res warp tables
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const double* a = coef + static_cast<int64_t>(b) * 6;
+  const bool scale_only = a[1] == 0.0 && a[3] == 0.0;
+  if (tid < 128 && (tid & 31) == 0) {
+    const int which = tid >> 5;                   // 0, 1: shrink columns / rows; 2, 3: warp columns / rows
+    if (which < 2) {
+      const double step = static_cast<double>(res) / static_cast<double>(out_res);
+      double o = 0.0 + step * 0.5;
+      for (int i = 0; i < out_res; ++i) {
+        const int v = pil_coord(o);
+        tabs[which * out_res + i] = (v >= 0 && v < res) ? v : -1;
+        o += step;
+      }
+    } else if (scale_only) {
+      const bool rows = which == 3;
+      const double step = rows ? a[4] : a[0];
+      double o = (rows ? a[5] : a[2]) + step * 0.5;
+      const int lim = rows ? src_h : src_w;
+      int* t = tabs + 2 * out_res + (rows ? res : 0);
+      for (int i = 0; i < res; ++i) {
+        const int v = pil_coord(o);
+        t[i] = (v >= 0 && v < lim) ? v : -1;
+        o += step;
+      }
+    }
+  }
+  __syncthreads();
+  const unsigned a0 = static_cast<unsigned>(pil_fix(a[0])), a1 = static_cast<unsigned>(pil_fix(a[1]));
+  const unsigned a3 = static_cast<unsigned>(pil_fix(a[3])), a4 = static_cast<unsigned>(pil_fix(a[4]));
+  const unsigned a2 = static_cast<unsigned>(pil_fix(a[2] + (a[0] * 0.5 + a[1] * 0.5)));
+  const unsigned a5 = static_cast<unsigned>(pil_fix(a[5] + (a[3] * 0.5 + a[4] * 0.5)));
+  const bool flip = mirror != nullptr && mirror[b] != 0;
+  for (int i = tid; i < out_res * out_res; i += blockDim.x) {
+    const int oy = i / out_res, ox = i - oy * out_res;
+    const int mx = tabs[ox], my = tabs[out_res + oy];                 // pixel of the (res, res) warp this output takes
+    uint8_t v = 0;
+    if (mx >= 0 && my >= 0) {
+      int xin, yin;
+      if (scale_only) {
+        xin = tabs[2 * out_res + mx];
+        yin = tabs[2 * out_res + res + my];
+      } else {
+        xin = static_cast<int>(a2 + static_cast<unsigned>(my) * a1 + static_cast<unsigned>(mx) * a0) >> 16;
+        yin = static_cast<int>(a5 + static_cast<unsigned>(my) * a4 + static_cast<unsigned>(mx) * a3) >> 16;
+        if (xin < 0 || xin >= src_w || yin < 0 || yin >= src_h) xin = yin = -1;
+      }
+      if (xin >= 0 && yin >= 0) {
+        if (flip) xin = src_w - 1 - xin;
+        v = src[b * src_stride + yin * src_pitch + xin];
+      }
+    }
+    out[static_cast<int64_t>(b) * out_res * out_res + i] = static_cast<float>(v);
+  }
+}
+
 }  // namespace
 }  // namespace hoisdf
 
@@ -190,5 +255,25 @@ HOISDF_API int hoisdf_sdf_rows_fwd(const float* rows, const int64_t* row_offsets
                 obj_centre, hand_scale, obj_scale, hand_points, obj_points, hand_pre, obj_pre, hand_sdf, obj_sdf, status};
   const dim3 grid(static_cast<unsigned>(ceil_div(n_sel, 256)), static_cast<unsigned>(batch));
   HOISDF_LAUNCH(sdf_rows_kernel, grid, 256, s, a);
+  return launch_status();
+}
+
+HOISDF_API int hoisdf_mask_crop_fwd(const uint8_t* src, int64_t batch, int64_t src_h, int64_t src_w, int64_t src_pitch,
+                                    int64_t src_stride, const double* coef, const int32_t* mirror, int64_t res, int64_t out_res,
+                                    float* out, void* stream) {
+  if (src == nullptr || coef == nullptr || out == nullptr) return HOISDF_E_NULL;
+  if (batch <= 0 || src_h <= 0 || src_w <= 0 || src_h > 32767 || src_w > 32767 || res <= 0 || res > 4096 || out_res <= 0 ||
+      out_res > res || src_pitch < src_w || src_stride < src_pitch * src_h)
+    return HOISDF_E_SHAPE;
+  const size_t smem = static_cast<size_t>(2 * out_res + 2 * res) * sizeof(int);       // <= 64 KB
+#ifndef HOISDF_EMULATE
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(mask_crop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+#endif
+  HOISDF_LAUNCH_SMEM(mask_crop_kernel, static_cast<unsigned>(batch), 1024, smem, static_cast<cudaStream_t>(stream), src, src_pitch,
+                     src_stride, static_cast<int>(src_w), static_cast<int>(src_h), coef, mirror, static_cast<int>(res),
+                     static_cast<int>(out_res), out);
   return launch_status();
 }

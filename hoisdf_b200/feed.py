@@ -165,13 +165,30 @@ def crop_images(frames: torch.Tensor, coefficients: np.ndarray, res: int, as_byt
 def crop_masks(masks: torch.Tensor, coefficients: np.ndarray, res: int, out_res: int, mirror=None) -> torch.Tensor:
     """The segmentation masks of the training feed (ho3d.py:366-381, :551-552): masks (B, H, W) uint8 (mode "L") on the GPU ->
     `transform_img` to (res, res) with the frame's coefficients, `.resize((out_res, out_res), Image.NEAREST)`,
-    `.astype(np.float32)` -> (B, out_res, out_res) float32."""
+    `.astype(np.float32)` -> (B, out_res, out_res) float32.  ONE launch (`hoisdf_mask_crop_fwd`: one CTA per mask, Pillow's
+    tables of both steps in shared memory); the same values as the two-step route through `hoisdf_image_crop_fwd`."""
     if masks.dim() != 3:
         raise ValueError("masks must be (B, H, W) uint8")
-    b = masks.shape[0]
-    warped = _warp(masks.unsqueeze(3), coefficients, res, 1.0, True, mirror)      # (dexycb.py:479-481)
-    shrink = np.tile(resize_coefficients(res, out_res), (b, 1))
-    return _warp(warped, shrink, out_res, 1.0, False).squeeze(1)
+    _require_gpu(masks)
+    if masks.dtype != torch.uint8 or masks.stride(2) != 1:
+        raise ValueError("masks must be (B, H, W) uint8 with packed rows")
+    b, h, w = masks.shape
+    coef = np.ascontiguousarray(np.asarray(coefficients, dtype=np.float64).reshape(b, 6))
+    if not np.isfinite(coef).all():
+        raise ValueError("non-finite crop coefficients")
+    for a in coef:
+        if (a[1] != 0.0 or a[3] != 0.0) and not _fixed_point_ok(a, res):
+            raise ValueError("crop transform outside Pillow's fixed-point range (|source coordinate| >= 32768)")
+    frame_pitch = masks.stride(0) if b > 1 else h * masks.stride(1)
+    dev = masks.device
+    with _on(dev):
+        coef_d = torch.from_numpy(coef).to(dev)
+        mirror_d = None if mirror is None else torch.as_tensor(np.asarray(mirror).astype(np.int32).reshape(b)).to(dev)
+        out = torch.empty(b, out_res, out_res, device=dev, dtype=torch.float32)
+        ops._count(1)
+        check(lib.hoisdf_mask_crop_fwd(masks.data_ptr(), b, h, w, masks.stride(1), frame_pitch, coef_d.data_ptr(),
+                                       ops._ptr(mirror_d), res, out_res, out.data_ptr(), _stream()), "hoisdf_mask_crop_fwd")
+    return out
 
 
 def crop_geometry(cam_intr: np.ndarray, bbox_hand: np.ndarray, obj_p2d: np.ndarray, img_size: Sequence[int], res: int = 256
@@ -556,8 +573,9 @@ def train_batch(frames: torch.Tensor, hand_masks: torch.Tensor, obj_masks: torch
                                      stack("mano_root"), stack("obj_center_cam"), hand_sdf_scale, obj_sdf_scale,
                                      rot=stack("rot_mat"), flip=torch.from_numpy(mirror.astype(np.int32)))
     inputs["img"] = img
-    targets.update(hand_seg=crop_masks(hand_masks, coef, res, heatmap_res, mirror=mirror),
-                   obj_seg=crop_masks(obj_masks, coef, res, heatmap_res, mirror=mirror))
+    segs = crop_masks(torch.cat([hand_masks, obj_masks]), np.concatenate([coef, coef]), res, heatmap_res,
+                      mirror=np.concatenate([mirror, mirror]))                 # both mask sets in one launch
+    targets.update(hand_seg=segs[:len(samples)], obj_seg=segs[len(samples):])
     for key in ("joint_coord", "joint_cam_no_trans", "obj_rot", "rel_obj_trans", "mano_param"):
         targets[key] = stack(key)
     meta = {key: stack(key) for key in ("cam_intr", "mano_root", "obj_center_cam", "bbox_hand", "bbox_obj")}
@@ -727,8 +745,9 @@ def dexycb_eval_batch(frames: torch.Tensor, hand_masks: torch.Tensor, obj_masks:
                                      stack("mano_root"), stack("obj_center_cam"), hand_sdf_scale, obj_sdf_scale,
                                      flip=torch.from_numpy(mirror.astype(np.int32)))
     inputs.update(img=crop_images(frames, coef, res, mirror=mirror), hand_pre_points=False, obj_pre_points=False)
-    targets.update(hand_seg=crop_masks(hand_masks, coef, res, heatmap_res, mirror=mirror),
-                   obj_seg=crop_masks(obj_masks, coef, res, heatmap_res, mirror=mirror))
+    segs = crop_masks(torch.cat([hand_masks, obj_masks]), np.concatenate([coef, coef]), res, heatmap_res,
+                      mirror=np.concatenate([mirror, mirror]))                 # both mask sets in one launch
+    targets.update(hand_seg=segs[:len(samples)], obj_seg=segs[len(samples):])
     for key in ("joint_coord", "joint_cam_no_trans", "obj_rot", "rel_obj_trans", "mano_param"):
         targets[key] = stack(key)
     meta = {key: stack(key) for key in ("cam_intr", "mano_root", "obj_center_cam", "bbox_hand", "bbox_obj")}

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HOISDF_ABI_VERSION 38
+#define HOISDF_ABI_VERSION 39
 
 enum {
   HOISDF_OK = 0,
@@ -716,6 +716,16 @@ int64_t hoisdf_train_image_smem_bytes(int64_t res);
 int hoisdf_train_image_fwd(const uint8_t* src, int64_t batch, int64_t src_h, int64_t src_w, int64_t src_pitch, int64_t src_stride,
                            const double* coef, const int32_t* mirror, const uint32_t* blur, const int32_t* ops,
                            const float* factors, int64_t res, float* out_f32, uint8_t* out_u8, void* stream);
+
+/* The segmentation masks of a sample in ONE launch (upstream data/ho3d.py:366-381,551-552; data/dexycb.py:323-336,389-402):
+ * `transform_img(mask)` to (res, res), `.resize((out_res, out_res), Image.NEAREST)`, `.astype(np.float32)` -- one CTA per mask,
+ * Pillow's tables built in shared memory, one byte gathered from the frame per output pixel; the same values as two
+ * hoisdf_image_crop_fwd calls (channels = 1, divisor 1) per mask.
+ *   src (batch, src_h, src_w) bytes (mode "L"), row pitch src_pitch, frame pitch src_stride; coef / mirror as
+ *   hoisdf_image_crop_fwd; out (batch, out_res, out_res) float32; out_res <= res <= 4096.
+ * ------------------------------------------------------------------------------------------------- */
+int hoisdf_mask_crop_fwd(const uint8_t* src, int64_t batch, int64_t src_h, int64_t src_w, int64_t src_pitch, int64_t src_stride,
+                         const double* coef, const int32_t* mirror, int64_t res, int64_t out_res, float* out, void* stream);
 
 /* One Linear of the training step per call (what hoisdf_b200/autograd.py:LinearFn runs; upstream main/train.py:108-131 through
  * every nn.Linear of the hot path), fp32 in / fp32 out on the FP16x3 tensor-core GEMM, caller-owned workspace of

@@ -15,7 +15,7 @@ from hoisdf_b200 import _capi, feed, ops
 from test_kernel_emulation import build_emulated
 
 FEED_ENTRY_POINTS = ("hoisdf_image_crop_fwd", "hoisdf_sdf_rows_fwd", "hoisdf_gaussian_blur_params", "hoisdf_gaussian_blur_u8",
-                     "hoisdf_color_jitter_u8", "hoisdf_train_image_smem_bytes", "hoisdf_train_image_fwd")
+                     "hoisdf_color_jitter_u8", "hoisdf_train_image_smem_bytes", "hoisdf_train_image_fwd", "hoisdf_mask_crop_fwd")
 
 
 @pytest.fixture()
@@ -87,6 +87,10 @@ def test_train_batch_dexycb(host):
 
 def test_fused_training_image(host):
     G.test_fused_training_image_equals_the_step_by_step_calls(host)
+
+
+def test_fused_masks(host):
+    G.test_fused_mask_crop_equals_the_two_step_route(host)
 
 
 def test_the_patches_are_gone_afterwards():

@@ -166,6 +166,30 @@ def test_mirrored_warp_equals_warping_the_mirrored_frame(cuda):
     assert torch.equal(feed.crop_masks(masks, coef, 256, 128, mirror=np.ones(4)), feed.crop_masks(masks.flip(2).contiguous(), coef, 256, 128))
 
 
+
+def test_fused_mask_crop_equals_the_two_step_route(cuda):
+    """`hoisdf_mask_crop_fwd` (warp + NEAREST shrink + float in one launch) against two `hoisdf_image_crop_fwd` calls and against
+    Pillow: rotated and un-rotated warps, mirrored masks, windows leaving the frame, shrink ratios 2, 4 and a non-integer one."""
+    from hoisdf_b200 import feed
+    draws = [FO.synthetic_aug(50 + s) for s in range(6)]
+    coef = np.stack([feed.pil_coefficients(feed.crop_affine(c, sc, 256, r if i % 2 else 0.0))
+                     for i, (_, _, _, c, sc, r) in enumerate(draws)])
+    coef[4] = [3.1, 0, -200.0, 0, 2.4, 150.0]
+    masks_np = np.stack([d[1] for d in draws])
+    masks = torch.from_numpy(masks_np).to(cuda)
+    mirror = np.array([0, 1, 1, 0, 1, 0])
+    for out_res in (128, 64, 100):
+        got = feed.crop_masks(masks, coef, 256, out_res, mirror=mirror)
+        warped = feed._warp(masks.unsqueeze(3), coef, 256, 1.0, True, mirror)
+        two_step = feed._warp(warped, np.tile(feed.resize_coefficients(256, out_res), (6, 1)), out_res, 1.0, False).squeeze(1)
+        assert got.shape == (6, out_res, out_res) and torch.equal(got, two_step), out_res
+        for i in range(6):
+            src = np.ascontiguousarray(masks_np[i][:, ::-1]) if mirror[i] else masks_np[i]
+            pil = Image.fromarray(src).transform((256, 256), Image.AFFINE, tuple(float(c) for c in coef[i]))
+            want = np.asarray(pil.resize((out_res, out_res), Image.NEAREST)).astype(np.float32)
+            assert np.array_equal(got[i].cpu().numpy(), want), (out_res, i)
+
+
 # ---------------------------------------------------------------------------------------------- photometric augmentation
 def test_gaussian_blur_vs_pillow(cuda):
     from PIL import ImageFilter
