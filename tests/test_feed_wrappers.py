@@ -93,6 +93,12 @@ def test_fused_masks(host):
     G.test_fused_mask_crop_equals_the_two_step_route(host)
 
 
+def test_smoke_feed(host):
+    """`__graft_entry__.smoke_feed` (the feed's line of the driver's smoke run) on the emulator."""
+    import __graft_entry__ as entry
+    entry.smoke_feed(host)
+
+
 def test_the_patches_are_gone_afterwards():
     assert feed.lib is _capi.lib and feed._stream.__module__ == "hoisdf_b200.feed"
     with pytest.raises(RuntimeError, match="no CPU fallback"):
