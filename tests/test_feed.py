@@ -564,3 +564,62 @@ def test_dexycb_training_sample_host_geometry_matches_golden():
     assert np.array_equal(s["index"], g["dxt_draws"]) and s["flip"]
     for k in DEX_TARGETS + EVAL_META:
         assert np.array_equal(s[k], g["dxt_" + k]), k
+
+
+# ---------------------------------------------------------------------------------------------- randomized sweeps against Pillow
+def _random_coefficients(rng, h, w):
+    kind = int(rng.integers(0, 4))
+    if kind == 0:           # scale-only, any sign / magnitude of the scales
+        return np.array([rng.uniform(-3, 3), 0, rng.uniform(-w, 2 * w), 0, rng.uniform(-3, 3), rng.uniform(-h, 2 * h)])
+    if kind == 1:           # degenerate scales and integer shifts
+        pick = [0.0, 1.0, -1.0, 0.5, 2.0]
+        return np.array([rng.choice(pick), 0, float(rng.integers(-5, w + 5)), 0, rng.choice(pick), float(rng.integers(-5, h + 5))])
+    if kind == 2:           # general affine
+        return rng.uniform(-2, 2, 6) * np.array([1, 1, w, 1, 1, h])
+    return np.array([rng.uniform(-1e3, 1e3), rng.uniform(-1e-3, 1e-3), rng.uniform(-1e3, 1e3), rng.uniform(-1e-3, 1e-3),
+                     rng.uniform(-1e3, 1e3), rng.uniform(-1e3, 1e3)])            # almost everything outside the frame
+
+
+def test_randomized_warps_match_pillow(emu):
+    """300 seeded draws of frame size, output size, channel count and coefficients (negative, zero and huge scales, shears,
+    integer shifts): the emulated kernel against `Image.transform(..., AFFINE)`, every byte."""
+    rng = np.random.default_rng(123)
+    n = 0
+    for _ in range(300):
+        h, w, size, ch = int(rng.integers(1, 40)), int(rng.integers(1, 40)), int(rng.integers(1, 40)), int(rng.choice([1, 3]))
+        img = rng.integers(1, 256, (1, h, w, ch), dtype=np.uint8)
+        coef = _random_coefficients(rng, h, w)
+        if (coef[1] != 0 or coef[3] != 0) and not feed._fixed_point_ok(coef, size):
+            continue
+        n += 1
+        _, got = emu_warp(emu, img, coef[None], size)
+        assert np.array_equal(got[0], pil_warp(img[0], coef, size)), (h, w, size, ch, coef)
+    assert n > 250
+
+
+def test_randomized_mask_crops_match_pillow(emu):
+    """The one-launch mask kernel against `transform` + `resize(NEAREST)` for 120 seeded draws of sizes (incl. non-integer
+    shrink ratios and out_res = res) and coefficients."""
+    vp, i64 = C.c_void_p, C.c_int64
+    emu.hoisdf_mask_crop_fwd.argtypes = [vp, i64, i64, i64, i64, i64, vp, vp, i64, i64, vp, vp]
+    rng = np.random.default_rng(321)
+    n = 0
+    for _ in range(120):
+        h, w = int(rng.integers(1, 40)), int(rng.integers(1, 40))
+        res = int(rng.integers(1, 48))
+        out_res = int(rng.integers(1, res + 1))
+        mask = np.ascontiguousarray(rng.integers(1, 256, (h, w), dtype=np.uint8))
+        coef = _random_coefficients(rng, h, w)
+        if (coef[1] != 0 or coef[3] != 0) and not feed._fixed_point_ok(coef, res):
+            continue
+        n += 1
+        flip = np.array([int(rng.integers(0, 2))], np.int32)
+        out = np.full((out_res, out_res), np.nan, np.float32)
+        c = np.ascontiguousarray(coef, dtype=np.float64)
+        assert emu.hoisdf_mask_crop_fwd(mask.ctypes.data, 1, h, w, w, h * w, c.ctypes.data, flip.ctypes.data, res, out_res,
+                                        out.ctypes.data, None) == 0
+        src = np.ascontiguousarray(mask[:, ::-1]) if flip[0] else mask
+        pil = Image.fromarray(src).transform((res, res), Image.AFFINE, tuple(float(v) for v in coef))
+        want = np.asarray(pil.resize((out_res, out_res), Image.NEAREST)).astype(np.float32)
+        assert np.array_equal(out, want), (h, w, res, out_res, coef, flip)
+    assert n > 90

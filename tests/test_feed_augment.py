@@ -244,3 +244,47 @@ def test_training_image_matches_the_upstream_fixture(emu_jitter):
     got = emu_training_image(emu_jitter, FO.synthetic_aug(seed)[0], g["filt_center"], float(g["filt_scale"]),
                              float(g["filt_rot"]), radius, steps)
     assert np.array_equal(got[:, ::8], g["filt_img_rows"])
+
+
+def test_randomized_fused_training_images_equal_the_step_route(emu_jitter):
+    """`hoisdf_train_image_fwd` at 60 seeded draws of frame size, crop size (row pitches with and without padding), warp
+    coefficients, mirror flag, blur radius (every box radius < 1) and jitter sequence against the emulated step-by-step route
+    (crop -> blur -> jitter -> float), bytes and floats."""
+    import itertools
+    from test_feed import emu_warp, _random_coefficients
+    from hoisdf_b200 import feed
+    lib = emu_jitter
+    vp, i64 = C.c_void_p, C.c_int64
+    lib.hoisdf_image_crop_fwd.argtypes = [vp, i64, i64, i64, i64, i64, i64, vp, vp, i64, C.c_float, vp, vp, vp, vp]
+    lib.hoisdf_train_image_fwd.argtypes = [vp, i64, i64, i64, i64, i64, vp, vp, vp, vp, vp, i64, vp, vp, vp]
+    rng = np.random.default_rng(77)
+    orders = list(itertools.permutations([BRIGHTNESS, SATURATION, HUE, CONTRAST]))
+    n = 0
+    for _ in range(60):
+        h, w, res = int(rng.integers(2, 40)), int(rng.integers(2, 40)), int(rng.integers(1, 36))
+        img = rng.integers(0, 256, (1, h, w, 3), dtype=np.uint8)
+        coef = _random_coefficients(rng, h, w)
+        if (coef[1] != 0 or coef[3] != 0) and not feed._fixed_point_ok(coef, res):
+            continue
+        n += 1
+        mirror = np.array([int(rng.integers(0, 2))], np.int32)
+        radius = float(rng.choice([0.0, rng.uniform(0, 0.5), rng.uniform(0.5, 1.3)]))
+        blur = blur_params(lib, [radius])
+        assert blur[0, 0] == 0
+        seq = [(op, float(rng.uniform(-0.5, 0.5) if op == HUE else rng.uniform(0.3, 1.7)))
+               for op in orders[int(rng.integers(0, 24))]][:int(rng.integers(0, 5))]
+        ops = np.zeros((1, 4), np.int32)
+        fac = np.zeros((1, 4), np.float32)
+        for j, (op, f) in enumerate(seq):
+            ops[0, j], fac[0, j] = op, (float(np.int32(f * 255).astype(np.uint8)) if op == HUE else f)
+        of = np.full((1, 3, res, res), np.nan, np.float32)
+        ou = np.full((1, res, res, 3), 9, np.uint8)
+        c = np.ascontiguousarray(coef[None], dtype=np.float64)
+        rc = lib.hoisdf_train_image_fwd(img.ctypes.data, 1, h, w, w * 3, h * w * 3, c.ctypes.data, mirror.ctypes.data,
+                                        blur.ctypes.data, ops.ctypes.data, fac.ctypes.data, res, of.ctypes.data, ou.ctypes.data, None)
+        assert rc == 0
+        _, warped = emu_warp(lib, img, c, res, mirror=mirror)
+        want = emu_jitter_run(lib, emu_blur(lib, warped, [radius]), [seq])
+        assert np.array_equal(ou, want), (h, w, res, coef, radius, seq)
+        assert np.array_equal(of[0], want[0].astype(np.float32).transpose(2, 0, 1) / np.float32(255.0))
+    assert n > 45
