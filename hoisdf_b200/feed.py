@@ -473,6 +473,9 @@ def to_tensor(images: torch.Tensor) -> torch.Tensor:
 
 
 # ---------------------------------------------------------------------------------------------- training sample, host geometry
+HO3D_MASKED_OBJECTS = ("021_bleach_cleanser", "006_mustard_bottle", "010_potted_meat_can")        # ho3d.py:554-558,631-635
+
+
 def _affine_about_principal_point(centre, scale, res, turn, K) -> np.ndarray:
     """The second matrix of `get_affine_transform(..., K=K)` (dataset_util.py:67-91): the un-rotated crop of the centre after
     it was turned about the principal point (T^-1 R T centre) -- what the intrinsics are multiplied with."""
@@ -502,13 +505,15 @@ def draw_train_geometry(centre: np.ndarray, scale: float, center_jittering: floa
 def train_geometry(cam_intr: np.ndarray, joints_uv: np.ndarray, joints_3d: np.ndarray, mano_param: np.ndarray,
                    obj_p2d: np.ndarray, obj_p3d: np.ndarray, obj_rot: np.ndarray, obj_trans: np.ndarray, centre: np.ndarray,
                    scale: float, rot: float, obj_depth_mean_value: Optional[float], res: int = 256, heatmap_res: int = 128,
-                   coord_change: Optional[np.ndarray] = None, hand_box_factor: float = 1.2) -> Dict[str, np.ndarray]:
+                   coord_change: Optional[np.ndarray] = None, hand_box_factor: float = 1.2, obj_name: Optional[str] = None
+                   ) -> Dict[str, np.ndarray]:
     """Everything of one HO3D training sample that is not pixels or SDF rows (data_aug, ho3d.py:318-349, and the tail of
     `__getitem__`, :519-523,553,568-587), for the drawn (centre, scale, rot): a few dozen floating-point operations in upstream's
     own precision mixture (float64 matrices cast to float32, cv2.Rodrigues for the two rotations), kept on the host.
     -> {"coef" (6,) PIL coefficients of the warp, "rot_mat" (3, 3) for `sdf_point_sets`, and upstream's entries: `joint_coord`,
     `joint_cam_no_trans`, `mano_param`, `obj_rot`, `rel_obj_trans` (targets); `cam_intr`, `mano_root`, `obj_center_cam`,
-    `bbox_hand`, `bbox_obj` (meta_info); `p2d`, `p3d` (the normalised corners upstream computes and drops)}.
+    `bbox_hand`, `bbox_obj` (meta_info; + `obj_mask` when `obj_name` is given); `p2d`, `p3d` (the normalised corners upstream
+    computes and drops)}.
     DexYCB's `data_aug` (dexycb.py:219-354) is the same with `coord_change = np.eye(3)`, `hand_box_factor = 1.1` and the
     object centre at the ROOT joint's depth (`obj_depth_mean_value = None`; dexycb.py:589-592)."""
     import cv2
@@ -546,7 +551,8 @@ def train_geometry(cam_intr: np.ndarray, joints_uv: np.ndarray, joints_3d: np.nd
     depth = hand_root[-1] if obj_depth_mean_value is None else obj_depth_mean_value
     c = np.asarray([int((bbox_obj[2] + bbox_obj[0]) / 2), int((bbox_obj[3] + bbox_obj[1]) / 2), depth])
     centre_cam = np.array([(c[0] - K[0, 2]) / K[0, 0] * c[2], (c[1] - K[1, 2]) / K[1, 1] * c[2], c[2]]).astype(np.float32)
-    return {"coef": pil_coefficients(affine), "rot_mat": rot_mat, "joint_coord": uv.astype(np.float32),
+    extra = {} if obj_name is None else {"obj_mask": obj_name in HO3D_MASKED_OBJECTS}                     # ho3d.py:554-558
+    return {**extra, "coef": pil_coefficients(affine), "rot_mat": rot_mat, "joint_coord": uv.astype(np.float32),
             "joint_cam_no_trans": joints_3d * 1000, "mano_param": mano_param, "obj_rot": new_obj_rot,
             "rel_obj_trans": new_obj_trans.astype(np.float32) - centre_cam, "cam_intr": K, "mano_root": hand_root,
             "obj_center_cam": centre_cam, "bbox_hand": bbox_hand, "bbox_obj": bbox_obj, "p2d": p2d, "p3d": p3d - centre_cam[None]}
@@ -620,7 +626,7 @@ def eval_geometry(annotation: Dict, obj_bbox3d: np.ndarray, img_size: Sequence[i
     name = annotation["objName"]
     return {"coef": coef[0], "obj_rot": obj_rot, "rel_obj_trans": obj_trans.astype(np.float32), "cam_intr": K, "mano_root": root,
             "obj_center_cam": centre_cam, "bbox_hand": geo["bbox_hand"][0], "bbox_obj": bbox_obj, "obj_cls": name,
-            "obj_mask": name in ("021_bleach_cleanser", "006_mustard_bottle", "010_potted_meat_can")}
+            "obj_mask": name in HO3D_MASKED_OBJECTS}
 
 
 def eval_batch(frames: torch.Tensor, samples: Sequence[Dict], res: int = 256):

@@ -399,7 +399,7 @@ def product_sample(seed, n_hand=N_HAND, n_obj=N_OBJ):
     centre, scale, rot = feed.draw_train_geometry(centre, scale)
     sample = feed.train_geometry(ann["cam_intr"], ann["joints_uv"], ann["joints_3d"], ann["mano_param"], ann["obj_p2d"],
                                  ann["obj_p3d"], ann["obj_rot"], ann["obj_trans"], centre, scale, rot,
-                                 ann["obj_depth_mean_value"])
+                                 ann["obj_depth_mean_value"], obj_name="003_cracker_box")
     sample.update(index=index, blur_radius=random.random() * 0.5,
                   jitter=feed.draw_color_jitter(brightness=0.5, contrast=0.5, saturation=0.5, hue=0.15))
     return sample, sdf
@@ -423,6 +423,7 @@ def test_training_sample_host_geometry_matches_upstream_live():
             assert np.array_equal(sample[k], targets[k]) and sample[k].dtype == targets[k].dtype, k
         for k in META_KEYS:
             assert np.array_equal(sample[k], meta[k]) and sample[k].dtype == meta[k].dtype, k
+        assert sample["obj_mask"] == meta["obj_mask"]
     np.random.set_state(state)
 
 
