@@ -99,6 +99,19 @@ def test_smoke_feed(host):
     entry.smoke_feed(host)
 
 
+def test_feed_bench_script(host):
+    """scripts/feed_bench.py (the GPU timing of the feed, not yet run on a GPU) driven on the emulator at a tiny size."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("feed_bench", os.path.join(os.path.dirname(os.path.dirname(
+        os.path.abspath(__file__))), "scripts", "feed_bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    line = mod.run(host, eval_frames=2, train_frames=2, steps=1, warmup=0, n_hand=24, n_obj=8, cpu_samples=1)
+    assert line["train_batch"]["launches"] == 3 and line["eval_batch"]["frames_per_s"] > 0
+    assert line["cpu_reference"]["ms_per_train_sample"] > 0
+
+
 def test_the_patches_are_gone_afterwards():
     assert feed.lib is _capi.lib and feed._stream.__module__ == "hoisdf_b200.feed"
     with pytest.raises(RuntimeError, match="no CPU fallback"):
