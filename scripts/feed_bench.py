@@ -37,7 +37,6 @@ def _timed(fn, device, steps, warmup):
 
 
 def run(device, eval_frames=32, train_frames=64, steps=20, warmup=3, n_hand=600, n_obj=200, cpu_samples=4):
-    import random
     from PIL import Image, ImageFilter
     import torchvision.transforms.functional as TF
     from hoisdf_b200 import feed, ops

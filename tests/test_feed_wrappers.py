@@ -5,13 +5,12 @@ a test, so host tensors flow through exactly the Python code the GPU path runs. 
 tests/test_gpu_zzz_feed.py: each GPU test of the feed is executed here against the emulator with `cuda` = the CPU device.
 Test infrastructure: the product never loads the emulated library."""
 import contextlib
-import ctypes as C
 
 import pytest
 import torch
 
 import test_gpu_zzz_feed as G
-from hoisdf_b200 import _capi, feed, ops
+from hoisdf_b200 import _capi, feed
 from test_kernel_emulation import build_emulated
 
 FEED_ENTRY_POINTS = ("hoisdf_image_crop_fwd", "hoisdf_sdf_rows_fwd", "hoisdf_gaussian_blur_params", "hoisdf_gaussian_blur_u8",
