@@ -94,8 +94,20 @@ def test_fused_masks(host):
 
 def test_smoke_feed(host):
     """`__graft_entry__.smoke_feed` (the feed's line of the driver's smoke run) on the emulator."""
+    import time
     import __graft_entry__ as entry
+    from oracle import feed_oracle as FO
     entry.smoke_feed(host)
+
+    def once(fn):
+        t0 = time.perf_counter()
+        fn()
+        return 1e3 * (time.perf_counter() - t0)
+
+    img, _, _, centre, scale, rot = FO.synthetic_aug(2)
+    frame, K, bbox_hand, p2d = FO.synthetic_frame(2)
+    coef = feed.pil_coefficients(feed.crop_affine(centre, scale, 256, rot))[None]
+    entry.smoke_feed_timing(host, img, coef, 0.37, [("hue", 0.1)], frame, K, bbox_hand, p2d, n_train=2, n_eval=2, timed=once)
 
 
 def test_feed_bench_script(host):
